@@ -1,0 +1,472 @@
+"""Model compiler: MJCF robot -> flat articulation / collision tables.
+
+Flattens the reference's robot description files (``mocca_envs/data/robots/*.xml``,
+loaded by the reference at ``mocca_envs/robots.py:101-105`` via ``loadMJCF``) into the
+struct-of-arrays tables that the CUDA kernels and the CPU oracle consume.
+
+The compiler restates the conventions of Bullet's MJCF importer + ``URDF2Bullet`` multibody
+conversion (third-party ``pybullet``; un-pinned dependency of the reference, ``setup.py:11``;
+conventions listed in SURVEY.md App. B.1):
+
+* top-level body without a free joint  -> floating base
+* a body with k hinge joints           -> k links (k-1 massless dummies + the body itself),
+  link frames at the joint positions, PyBullet joint index == link index in DFS pre-order
+* a body with no joint                 -> link attached by a fixed joint (``jointfix_*``)
+* ``inertiafromgeom``                  -> mass = 1000 kg/m^3 * sum(geom volumes),
+  inertial frame == body frame (no COM recomputation),
+  inertia diagonal = box inertia of the AABB of the link's compound collision shape
+* MJCF ``damping`` / ``armature``       -> ignored by the importer (switchable here)
+* geom ``friction``'s first entry      -> lateral friction; condim 3 -> no spinning/rolling rows
+* ``contype``/``conaffinity``           -> collision filter group/mask of the link
+
+Everything here is host-side, one-time work.  Output is a plain dict of
+lists (JSON-serialisable, human-diffable) so that a host with PyBullet can diff it against
+``getJointInfo`` / ``getDynamicsInfo`` dumps.
+"""
+from __future__ import annotations
+
+import json
+import math
+import xml.etree.ElementTree as ET
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+
+GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX = 0, 1, 2
+JOINT_FIXED, JOINT_REVOLUTE = 0, 1
+
+DENSITY = 1000.0  # Bullet MJCF importer default when no <inertial> is given
+CONTACT_BREAKING_THRESHOLD = 0.02  # Bullet gContactBreakingThreshold
+
+
+# ----------------------------------------------------------------------------- small math
+def quat_to_mat(q):
+    """xyzw quaternion (normalised on the fly, as btMatrix3x3::setRotation does) -> 3x3."""
+    x, y, z, w = [float(v) for v in q]
+    d = x * x + y * y + z * z + w * w
+    s = 2.0 / d
+    xs, ys, zs = x * s, y * s, z * s
+    wx, wy, wz = w * xs, w * ys, w * zs
+    xx, xy, xz = x * xs, x * ys, x * zs
+    yy, yz, zz = y * ys, y * zs, z * zs
+    return np.array(
+        [
+            [1.0 - (yy + zz), xy - wz, xz + wy],
+            [xy + wz, 1.0 - (xx + zz), yz - wx],
+            [xz - wy, yz + wx, 1.0 - (xx + yy)],
+        ]
+    )
+
+
+def mat_to_quat(m):
+    """3x3 rotation -> xyzw quaternion (w >= 0)."""
+    m = np.asarray(m, dtype=np.float64)
+    tr = m[0, 0] + m[1, 1] + m[2, 2]
+    if tr > 0:
+        s = math.sqrt(tr + 1.0) * 2
+        w = 0.25 * s
+        x = (m[2, 1] - m[1, 2]) / s
+        y = (m[0, 2] - m[2, 0]) / s
+        z = (m[1, 0] - m[0, 1]) / s
+    elif m[0, 0] > m[1, 1] and m[0, 0] > m[2, 2]:
+        s = math.sqrt(1.0 + m[0, 0] - m[1, 1] - m[2, 2]) * 2
+        w = (m[2, 1] - m[1, 2]) / s
+        x = 0.25 * s
+        y = (m[0, 1] + m[1, 0]) / s
+        z = (m[0, 2] + m[2, 0]) / s
+    elif m[1, 1] > m[2, 2]:
+        s = math.sqrt(1.0 + m[1, 1] - m[0, 0] - m[2, 2]) * 2
+        w = (m[0, 2] - m[2, 0]) / s
+        x = (m[0, 1] + m[1, 0]) / s
+        y = 0.25 * s
+        z = (m[1, 2] + m[2, 1]) / s
+    else:
+        s = math.sqrt(1.0 + m[2, 2] - m[0, 0] - m[1, 1]) * 2
+        w = (m[1, 0] - m[0, 1]) / s
+        x = (m[0, 2] + m[2, 0]) / s
+        y = (m[1, 2] + m[2, 1]) / s
+        z = 0.25 * s
+    q = np.array([x, y, z, w])
+    if w < 0:
+        q = -q
+    return q / np.linalg.norm(q)
+
+
+def shortest_arc_quat(v0, v1):
+    """Bullet's shortestArcQuat(v0, v1): rotation taking unit v0 onto unit v1 (xyzw)."""
+    v0 = np.asarray(v0, dtype=np.float64)
+    v1 = np.asarray(v1, dtype=np.float64)
+    c = np.cross(v0, v1)
+    d = float(np.dot(v0, v1))
+    if d < -1.0 + 1e-7:
+        # opposite vectors: any perpendicular axis (btPlaneSpace1 picks one)
+        n = np.array([0.0, -v0[2], v0[1]]) if abs(v0[2]) > 0.7071 else np.array([-v0[1], v0[0], 0.0])
+        n /= np.linalg.norm(n)
+        return np.array([n[0], n[1], n[2], 0.0])
+    s = math.sqrt((1.0 + d) * 2.0)
+    rs = 1.0 / s
+    return np.array([c[0] * rs, c[1] * rs, c[2] * rs, s * 0.5])
+
+
+# ----------------------------------------------------------------------------- data classes
+@dataclass
+class Geom:
+    name: str
+    type: int
+    pos: np.ndarray  # centre in the link's inertial frame
+    quat: np.ndarray  # xyzw, orientation in the link's inertial frame
+    size: np.ndarray  # sphere [r,0,0]; capsule [r, half_len, 0] (axis = local z); box half extents
+    group: int
+    mask: int
+    friction: float
+
+    def volume(self) -> float:
+        if self.type == GEOM_SPHERE:
+            r = self.size[0]
+            return 4.0 / 3.0 * math.pi * r ** 3
+        if self.type == GEOM_CAPSULE:
+            r, hl = self.size[0], self.size[1]
+            return 4.0 / 3.0 * math.pi * r ** 3 + math.pi * r * r * (2 * hl)
+        hx, hy, hz = self.size
+        return 8.0 * hx * hy * hz
+
+    def aabb(self):
+        """AABB in the link frame, following btSphereShape/btCapsuleShape/btBoxShape::getAabb."""
+        R = quat_to_mat(self.quat)
+        if self.type == GEOM_SPHERE:
+            he = np.array([self.size[0]] * 3)
+            ext = he
+        elif self.type == GEOM_CAPSULE:
+            he = np.array([self.size[0], self.size[0], self.size[0] + self.size[1]])
+            ext = np.abs(R) @ he
+        else:
+            he = np.array(self.size, dtype=np.float64)
+            ext = np.abs(R) @ he
+        return self.pos - ext, self.pos + ext
+
+
+@dataclass
+class Link:
+    name: str
+    parent: int  # index into links, -1 = base
+    joint_name: str
+    joint_type: int
+    axis: np.ndarray  # joint axis in this link's frame
+    rot_parent_to_this: np.ndarray  # xyzw; Bullet's zeroRotParentToThis
+    e_vec: np.ndarray  # parent COM -> pivot, in parent frame
+    d_vec: np.ndarray  # pivot -> this COM, in this frame
+    mass: float = 0.0
+    inertia: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    lower: float = 0.0
+    upper: float = 0.0
+    damping: float = 0.0
+    armature: float = 0.0
+    geoms: List[Geom] = field(default_factory=list)
+    is_dummy: bool = False
+
+
+def _floats(s: Optional[str], default=None):
+    if s is None:
+        return default
+    return np.array([float(t) for t in s.split()], dtype=np.float64)
+
+
+class MJCFCompiler:
+    """Parse an MJCF humanoid-style file into Bullet-convention links."""
+
+    def __init__(self, path: str, use_mjcf_damping: bool = False, use_mjcf_armature: bool = False):
+        self.path = path
+        self.use_mjcf_damping = use_mjcf_damping
+        self.use_mjcf_armature = use_mjcf_armature
+        self.links: List[Link] = []
+        self.base: Optional[Link] = None
+        self.anon = 0
+
+        root = ET.parse(path).getroot()
+        comp = root.find("compiler")
+        self.degrees = comp is None or comp.get("angle", "degree") == "degree"
+        dflt = root.find("default")
+        dj = dflt.find("joint") if dflt is not None else None
+        dg = dflt.find("geom") if dflt is not None else None
+        self.d_limited = (dj.get("limited", "false") == "true") if dj is not None else False
+        self.d_damping = float(dj.get("damping", 0.0)) if dj is not None else 0.0
+        self.d_armature = float(dj.get("armature", 0.0)) if dj is not None else 0.0
+        self.d_contype = int(dg.get("contype", 1)) if dg is not None else 1
+        self.d_conaffinity = int(dg.get("conaffinity", 1)) if dg is not None else 1
+        fr = _floats(dg.get("friction")) if dg is not None and dg.get("friction") else None
+        self.d_friction = float(fr[0]) if fr is not None else 0.5
+
+        world = root.find("worldbody")
+        top = world.find("body")
+        self.base_name = top.get("name")
+        self.base_pos = _floats(top.get("pos"), np.zeros(3))
+        self._parse_body(top, parent_link=-1, is_root=True)
+        self._finalize_inertia()
+
+    # ---- geoms
+    def _parse_geom(self, g, shift: np.ndarray) -> Geom:
+        """``shift`` = body-frame origin expressed in the link inertial frame (zero here:
+        inertial frame == body frame for MJCF bodies without <inertial>)."""
+        gtype = g.get("type", "sphere")
+        name = g.get("name", "geom%d" % self.anon)
+        group = int(g.get("contype", self.d_contype))
+        mask = int(g.get("conaffinity", self.d_conaffinity))
+        fr = _floats(g.get("friction"))
+        friction = float(fr[0]) if fr is not None else self.d_friction
+        size = _floats(g.get("size"))
+        if gtype == "sphere":
+            pos = _floats(g.get("pos"), np.zeros(3)) + shift
+            return Geom(name, GEOM_SPHERE, pos, np.array([0, 0, 0, 1.0]), np.array([size[0], 0, 0]), group, mask, friction)
+        if gtype == "capsule":
+            ft = _floats(g.get("fromto"))
+            assert ft is not None, "only fromto capsules occur in the in-scope models"
+            f, t = ft[:3], ft[3:]
+            diff = t - f
+            h = float(np.linalg.norm(diff))
+            quat = shortest_arc_quat([0, 0, 1.0], diff / h) if h > 1e-12 else np.array([0, 0, 0, 1.0])
+            return Geom(name, GEOM_CAPSULE, 0.5 * (f + t) + shift, quat, np.array([size[0], 0.5 * h, 0]), group, mask, friction)
+        if gtype == "box":
+            pos = _floats(g.get("pos"), np.zeros(3)) + shift
+            quat = np.array([0, 0, 0, 1.0])
+            return Geom(name, GEOM_BOX, pos, quat, np.array(size[:3]), group, mask, friction)
+        raise ValueError("unsupported geom type %s" % gtype)
+
+    # ---- bodies
+    def _parse_body(self, body, parent_link: int, is_root: bool):
+        name = body.get("name")
+        if name is None:
+            name = "anon_body_%d" % self.anon
+            self.anon += 1
+        pos = _floats(body.get("pos"), np.zeros(3))
+        q = _floats(body.get("quat"))  # MJCF order w x y z
+        quat = np.array([q[1], q[2], q[3], q[0]]) if q is not None else np.array([0, 0, 0, 1.0])
+        R_body = quat_to_mat(quat)  # body axes in parent-body axes
+
+        joints = [c for c in body if c.tag == "joint"]
+        geoms = [c for c in body if c.tag == "geom"]
+        children = [c for c in body if c.tag == "body"]
+
+        if is_root:
+            assert not joints, "root body with joints is not a floating base"
+            link = Link(name, -2, "", JOINT_FIXED, np.zeros(3), np.array([0, 0, 0, 1.0]), np.zeros(3), np.zeros(3))
+            link.geoms = [self._parse_geom(g, np.zeros(3)) for g in geoms]
+            self.base = link
+            my_index = -1
+        else:
+            rot_p2t = mat_to_quat(R_body.T)
+            if not joints:
+                link = Link(name, parent_link, "jointfix_%s" % name, JOINT_FIXED, np.zeros(3), rot_p2t, pos.copy(), np.zeros(3))
+                self.links.append(link)
+                my_index = len(self.links) - 1
+            else:
+                prev_pivot = None
+                cur_parent = parent_link
+                for k, j in enumerate(joints):
+                    jpos = _floats(j.get("pos"), np.zeros(3))  # in body frame
+                    axis = _floats(j.get("axis"), np.array([1.0, 0, 0]))
+                    axis = axis / np.linalg.norm(axis)
+                    limited = j.get("limited")
+                    limited = self.d_limited if limited is None else (limited == "true")
+                    rng = _floats(j.get("range"), np.array([0.0, 0.0]))
+                    if self.degrees:
+                        rng = rng * math.pi / 180.0
+                    if not limited:
+                        rng = np.array([1.0, -1.0])  # Bullet: lower > upper == unlimited
+                    last = k == len(joints) - 1
+                    if k == 0:
+                        e = pos + R_body @ jpos
+                        r = rot_p2t
+                    else:
+                        e = jpos - prev_pivot
+                        r = np.array([0, 0, 0, 1.0])
+                    d = -jpos if last else np.zeros(3)
+                    lname = name if last else "link_dummy_%s_%d" % (name, k)
+                    link = Link(lname, cur_parent, j.get("name"), JOINT_REVOLUTE, axis, r, e, d, is_dummy=not last)
+                    link.lower, link.upper = float(rng[0]), float(rng[1])
+                    dmp = j.get("damping")
+                    arm = j.get("armature")
+                    if self.use_mjcf_damping:
+                        link.damping = float(dmp) if dmp is not None else self.d_damping
+                    if self.use_mjcf_armature:
+                        link.armature = float(arm) if arm is not None else self.d_armature
+                    self.links.append(link)
+                    cur_parent = len(self.links) - 1
+                    prev_pivot = jpos
+                my_index = cur_parent
+                link = self.links[my_index]
+            link.geoms = [self._parse_geom(g, np.zeros(3)) for g in geoms]
+
+        for c in children:
+            self._parse_body(c, my_index, False)
+
+    def _finalize_inertia(self):
+        for link in [self.base] + self.links:
+            vol = sum(g.volume() for g in link.geoms)
+            link.mass = DENSITY * vol
+            if link.geoms:
+                lo = np.min([g.aabb()[0] for g in link.geoms], axis=0)
+                hi = np.max([g.aabb()[1] for g in link.geoms], axis=0)
+                l = hi - lo
+                m = link.mass
+                link.inertia = m / 12.0 * np.array([l[1] ** 2 + l[2] ** 2, l[0] ** 2 + l[2] ** 2, l[0] ** 2 + l[1] ** 2])
+                link.aabb = (lo, hi)
+            else:
+                link.inertia = np.zeros(3)
+                link.aabb = None
+
+
+# ----------------------------------------------------------------------------- flat table
+def compile_mjcf(path: str, name: str, power_coef: Dict[str, float], base_power: float,
+                 foot_names: List[str], use_mjcf_damping=False, use_mjcf_armature=False) -> dict:
+    """Return the flat, JSON-serialisable articulation + collision table.
+
+    ``power_coef`` / ``base_power`` / ``foot_names`` restate the robot classes of the reference
+    (``mocca_envs/robots.py:230-256`` Walker3D, ``:407-436`` Monkey3D).
+    """
+    c = MJCFCompiler(path, use_mjcf_damping, use_mjcf_armature)
+    links = c.links
+    nl = len(links)
+    dof_of_link = []
+    nd = 0
+    for l in links:
+        if l.joint_type == JOINT_REVOLUTE:
+            dof_of_link.append(nd)
+            nd += 1
+        else:
+            dof_of_link.append(-1)
+    joint_names = [l.joint_name for l in links if l.joint_type == JOINT_REVOLUTE]
+    gains = [base_power * power_coef[n] for n in joint_names]
+
+    geoms = []
+    for li, l in enumerate([c.base] + links):
+        for g in l.geoms:
+            R = quat_to_mat(g.quat)
+            if g.type == GEOM_CAPSULE:
+                p0 = g.pos - R @ np.array([0, 0, g.size[1]])
+                p1 = g.pos + R @ np.array([0, 0, g.size[1]])
+            else:
+                p0 = p1 = g.pos
+            geoms.append(dict(name=g.name, link=li - 1, type=g.type, pos=g.pos.tolist(), quat=g.quat.tolist(),
+                              size=g.size.tolist(), p0=p0.tolist(), p1=p1.tolist(), group=g.group, mask=g.mask,
+                              friction=g.friction))
+
+    def thresh(l):
+        if l.aabb is None:
+            return 0.0
+        lo, hi = l.aabb
+        return CONTACT_BREAKING_THRESHOLD * (0.5 * float(np.linalg.norm(hi - lo)) + float(np.linalg.norm(0.5 * (lo + hi))))
+
+    def link_filter(l):
+        # BulletMJCFImporter::getCollisionGroupAndMask: the last collision geom wins
+        if not l.geoms:
+            return (0, 0)
+        return (l.geoms[-1].group, l.geoms[-1].mask)
+
+    table = dict(
+        name=name,
+        source=path.split("/mocca_envs/")[-1],
+        conventions=dict(density=DENSITY, mjcf_damping=use_mjcf_damping, mjcf_armature=use_mjcf_armature,
+                         inertia="aabb-of-compound", com="body-origin"),
+        base=dict(name=c.base.name, mass=c.base.mass, inertia=c.base.inertia.tolist(), init_pos=c.base_pos.tolist(),
+                  contact_threshold=thresh(c.base), group=link_filter(c.base)[0], mask=link_filter(c.base)[1]),
+        n_links=nl,
+        n_dof=nd,
+        link_names=[l.name for l in links],
+        joint_names_all=[l.joint_name for l in links],
+        parent=[l.parent for l in links],
+        joint_type=[l.joint_type for l in links],
+        dof_of_link=dof_of_link,
+        axis=[l.axis.tolist() for l in links],
+        rot_parent_to_this=[l.rot_parent_to_this.tolist() for l in links],
+        e_vec=[l.e_vec.tolist() for l in links],
+        d_vec=[l.d_vec.tolist() for l in links],
+        mass=[l.mass for l in links],
+        inertia=[l.inertia.tolist() for l in links],
+        contact_threshold=[thresh(l) for l in links],
+        group=[link_filter(l)[0] for l in links],
+        mask=[link_filter(l)[1] for l in links],
+        # per-dof (ordered joints of robots.py:163-172)
+        joint_names=joint_names,
+        link_of_dof=[i for i, l in enumerate(links) if l.joint_type == JOINT_REVOLUTE],
+        lower=[l.lower for l in links if l.joint_type == JOINT_REVOLUTE],
+        upper=[l.upper for l in links if l.joint_type == JOINT_REVOLUTE],
+        damping=[l.damping for l in links if l.joint_type == JOINT_REVOLUTE],
+        armature=[l.armature for l in links if l.joint_type == JOINT_REVOLUTE],
+        gain=gains,
+        foot_links=[[l.name for l in links].index(f) for f in foot_names],
+        foot_names=list(foot_names),
+        geoms=geoms,
+        total_mass=c.base.mass + sum(l.mass for l in links),
+    )
+    return table
+
+
+# ----------------------------------------------------------------------------- robot classes
+WALKER3D_POWER = {  # mocca_envs/robots.py:234-256
+    "abdomen_z": 60, "abdomen_y": 80, "abdomen_x": 60,
+    "right_hip_x": 80, "right_hip_z": 60, "right_hip_y": 100, "right_knee": 90, "right_ankle": 60,
+    "left_hip_x": 80, "left_hip_z": 60, "left_hip_y": 100, "left_knee": 90, "left_ankle": 60,
+    "right_shoulder_x": 60, "right_shoulder_z": 60, "right_shoulder_y": 50, "right_elbow": 60,
+    "left_shoulder_x": 60, "left_shoulder_z": 60, "left_shoulder_y": 50, "left_elbow": 60,
+}
+
+MONKEY3D_POWER = {  # mocca_envs/robots.py:410-434
+    "abdomen_z": 60, "abdomen_y": 60, "abdomen_x": 60,
+    "right_hip_x": 50, "right_hip_z": 50, "right_hip_y": 50, "right_knee": 30, "right_ankle": 10,
+    "left_hip_x": 50, "left_hip_z": 50, "left_hip_y": 50, "left_knee": 30, "left_ankle": 10,
+    "right_shoulder_x": 100, "right_shoulder_y": 100, "right_elbow_z": 60, "right_elbow_y": 100, "right_hand": 80,
+    "left_shoulder_x": 100, "left_shoulder_y": 100, "left_elbow_z": 60, "left_elbow_y": 100, "left_hand": 80,
+}
+
+
+def compile_walker3d(data_dir: str, **kw) -> dict:
+    t = compile_mjcf(data_dir + "/robots/walker3d.xml", "walker3d", WALKER3D_POWER, 1.0,
+                     ["right_foot", "left_foot"], **kw)
+    # robots.py:275-302 -- T-pose base + "running_start" joint pose used by both Walker3D envs
+    pose = [0.0] * 21
+    for i in (5, 6):
+        pose[i] = -math.pi / 8
+    pose[10] = math.pi / 10
+    pose[13] = pose[17] = math.pi / 3
+    pose[14] = -math.pi / 6
+    pose[18] = math.pi / 6
+    pose[16] = pose[20] = math.pi / 3
+    t["base_joint_angles"] = pose
+    t["base_position"] = [0.0, 0.0, 1.32]
+    t["right_joint_indices"] = [3, 4, 5, 6, 7, 13, 14, 15, 16]  # robots.py:282-284
+    t["left_joint_indices"] = [8, 9, 10, 11, 12, 17, 18, 19, 20]  # robots.py:285-287
+    t["negation_joint_indices"] = [0, 2]  # robots.py:288
+    return t
+
+
+def compile_monkey3d(data_dir: str, **kw) -> dict:
+    t = compile_mjcf(data_dir + "/robots/monkey3d.xml", "monkey3d", MONKEY3D_POWER, 0.7,
+                     ["right_hand", "left_hand"], **kw)
+    d = math.pi / 180
+    pose = [0.0] * 23  # robots.py:462-470 "monkey_start"
+    pose[14] = -140 * d
+    pose[15] = 180 * d
+    pose[17] = -90 * d
+    pose[19] = -170 * d
+    pose[20] = 180 * d
+    pose[22] = -90 * d
+    pose[6] = pose[11] = -90 * d
+    pose[7] = pose[12] = -90 * d
+    t["base_joint_angles"] = pose
+    t["base_position"] = [0.0, 0.0, 0.7]
+    t["right_joint_indices"] = [3, 4, 5, 6, 7, 13, 14, 15, 16, 17]
+    t["left_joint_indices"] = [8, 9, 10, 11, 12, 18, 19, 20, 21, 22]
+    t["negation_joint_indices"] = [0, 2]
+    return t
+
+
+def save_table(table: dict, path: str):
+    with open(path, "w") as f:
+        json.dump(table, f, indent=1)
+        f.write("\n")
+
+
+def load_table(path: str) -> dict:
+    with open(path) as f:
+        return json.load(f)

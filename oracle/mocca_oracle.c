@@ -1,0 +1,1179 @@
+/*
+ * mocca_oracle.c -- CPU float64 restatement of the mocca_envs hot path.  TEST INFRASTRUCTURE ONLY.
+ * See mocca_oracle.h for the "parity unpinned" statement and the list of what may call this file.
+ *
+ * Layout of this file
+ *   1. small linear algebra
+ *   2. kinematics (btMultiBody link conventions: COM-centred link frames, parent->this rotations)
+ *   3. articulated-body forward dynamics (btMultiBody::computeAccelerationsArticulatedBodyAlgorithmMultiDof)
+ *      and unit-impulse response (calcAccelerationDeltasMultiDof)
+ *   4. world-frame RNEA + mass matrix (independent formulation, used to cross-check 3)
+ *   5. narrow phase (sphere/capsule vs plane z=0 and vs static boxes)
+ *   6. constraint rows + projected Gauss-Seidel (btMultiBodyConstraintSolver semantics)
+ *   7. integration (btMultiBody::stepPositionsMultiDof) and the stepSimulation driver
+ *   8. MT19937 / NumPy legacy RandomState draws
+ *   9. Walker3DCustomEnv (reference mocca_envs/env_locomotion.py:37-222, robots.py:31-95,179-227)
+ */
+#include "mocca_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define PI 3.14159265358979323846
+
+typedef double v3[3];
+typedef double m3[3][3];
+typedef double v6[6];
+typedef double m6[6][6];
+
+/* ------------------------------------------------------------------ 1. linear algebra */
+static void v3set(v3 a, double x, double y, double z) { a[0] = x; a[1] = y; a[2] = z; }
+static void v3copy(v3 a, const v3 b) { a[0] = b[0]; a[1] = b[1]; a[2] = b[2]; }
+static double v3dot(const v3 a, const v3 b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static double v3norm(const v3 a) { return sqrt(v3dot(a, a)); }
+static void v3cross(const v3 a, const v3 b, v3 c) {
+  double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  c[0] = x; c[1] = y; c[2] = z;
+}
+static void m3vec(const m3 R, const v3 a, v3 out) {
+  double x = R[0][0] * a[0] + R[0][1] * a[1] + R[0][2] * a[2];
+  double y = R[1][0] * a[0] + R[1][1] * a[1] + R[1][2] * a[2];
+  double z = R[2][0] * a[0] + R[2][1] * a[1] + R[2][2] * a[2];
+  out[0] = x; out[1] = y; out[2] = z;
+}
+static void m3Tvec(const m3 R, const v3 a, v3 out) {
+  double x = R[0][0] * a[0] + R[1][0] * a[1] + R[2][0] * a[2];
+  double y = R[0][1] * a[0] + R[1][1] * a[1] + R[2][1] * a[2];
+  double z = R[0][2] * a[0] + R[1][2] * a[1] + R[2][2] * a[2];
+  out[0] = x; out[1] = y; out[2] = z;
+}
+static void m3mul(const m3 A, const m3 B, m3 C) {
+  m3 T;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) T[i][j] = A[i][0] * B[0][j] + A[i][1] * B[1][j] + A[i][2] * B[2][j];
+  memcpy(C, T, sizeof(m3));
+}
+/* xyzw quaternion -> rotation matrix (btMatrix3x3::setRotation; normalises implicitly) */
+static void quat_to_mat(const double q[4], m3 R) {
+  double x = q[0], y = q[1], z = q[2], w = q[3];
+  double d = x * x + y * y + z * z + w * w, s = 2.0 / d;
+  double xs = x * s, ys = y * s, zs = z * s;
+  double wx = w * xs, wy = w * ys, wz = w * zs, xx = x * xs, xy = x * ys, xz = x * zs;
+  double yy = y * ys, yz = y * zs, zz = z * zs;
+  R[0][0] = 1 - (yy + zz); R[0][1] = xy - wz; R[0][2] = xz + wy;
+  R[1][0] = xy + wz; R[1][1] = 1 - (xx + zz); R[1][2] = yz - wx;
+  R[2][0] = xz - wy; R[2][1] = yz + wx; R[2][2] = 1 - (xx + yy);
+}
+/* rotation about unit axis by angle (Rodrigues) */
+static void axis_angle_mat(const v3 a, double ang, m3 R) {
+  double c = cos(ang), s = sin(ang), t = 1 - c;
+  R[0][0] = t * a[0] * a[0] + c; R[0][1] = t * a[0] * a[1] - s * a[2]; R[0][2] = t * a[0] * a[2] + s * a[1];
+  R[1][0] = t * a[0] * a[1] + s * a[2]; R[1][1] = t * a[1] * a[1] + c; R[1][2] = t * a[1] * a[2] - s * a[0];
+  R[2][0] = t * a[0] * a[2] - s * a[1]; R[2][1] = t * a[1] * a[2] + s * a[0]; R[2][2] = t * a[2] * a[2] + c;
+}
+static double v6dot(const v6 a, const v6 b) {
+  double s = 0;
+  for (int i = 0; i < 6; i++) s += a[i] * b[i];
+  return s;
+}
+static void m6vec(const m6 A, const v6 x, v6 y) {
+  v6 t;
+  for (int i = 0; i < 6; i++) {
+    double s = 0;
+    for (int j = 0; j < 6; j++) s += A[i][j] * x[j];
+    t[i] = s;
+  }
+  memcpy(y, t, sizeof(v6));
+}
+/* Gaussian elimination with partial pivoting: solve A x = b (n<=6), A destroyed */
+static void solve_n(int n, double A[6][6], double* b, double* x) {
+  for (int c = 0; c < n; c++) {
+    int piv = c;
+    for (int r = c + 1; r < n; r++)
+      if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+    if (piv != c) {
+      for (int k = 0; k < n; k++) { double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
+      double t = b[c]; b[c] = b[piv]; b[piv] = t;
+    }
+    for (int r = c + 1; r < n; r++) {
+      double f = A[r][c] / A[c][c];
+      for (int k = c; k < n; k++) A[r][k] -= f * A[c][k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = n - 1; r >= 0; r--) {
+    double s = b[r];
+    for (int k = r + 1; k < n; k++) s -= A[r][k] * x[k];
+    x[r] = s / A[r][r];
+  }
+}
+static void invert6(const m6 A, m6 Ainv) {
+  for (int c = 0; c < 6; c++) {
+    double T[6][6], b[6] = {0, 0, 0, 0, 0, 0}, x[6];
+    memcpy(T, A, sizeof(T));
+    b[c] = 1;
+    solve_n(6, T, b, x);
+    for (int r = 0; r < 6; r++) Ainv[r][c] = x[r];
+  }
+}
+
+/* ------------------------------------------------------------------ 2. kinematics */
+typedef struct {
+  m3 R0;               /* world -> base (Bullet rot_from_parent[0]) */
+  m3 Rp[ORC_MAXL];     /* parent -> this */
+  v3 r[ORC_MAXL];      /* parent COM -> this COM, in this frame (m_cachedRVector) */
+  m3 Rw[ORC_MAXL + 1]; /* world -> link, [0] = base */
+  v3 pw[ORC_MAXL + 1]; /* link COM in world */
+  v6 S[ORC_MAXL];      /* joint motion subspace in link frame (m_axisTop, m_axisBottom) */
+  /* ABA cache (valid after aba()) */
+  m6 IA[ORC_MAXL + 1];
+  v6 h[ORC_MAXL];
+  double Dinv[ORC_MAXL];
+  m6 IA0inv;
+} orc_cache;
+
+static void kin(const orc_model* m, const orc_state* s, orc_cache* c) {
+  m3 Q;
+  quat_to_mat(s->quat, Q); /* local -> world */
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) c->R0[i][j] = Q[j][i];
+  memcpy(c->Rw[0], c->R0, sizeof(m3));
+  v3copy(c->pw[0], s->pos);
+  for (int i = 0; i < m->n_links; i++) {
+    m3 Rz;
+    quat_to_mat(m->rot_p2t[i], Rz);
+    if (m->joint_type[i] == ORC_JOINT_REVOLUTE) {
+      /* m_cachedRotParentToThis = btQuaternion(axis, -q) * m_zeroRotParentToThis */
+      m3 Rj;
+      axis_angle_mat(m->axis[i], -s->q[m->dof_of_link[i]], Rj);
+      m3mul(Rj, Rz, c->Rp[i]);
+      v3copy(c->S[i], m->axis[i]);
+      v3cross(m->axis[i], m->d_vec[i], &c->S[i][3]);
+    } else {
+      memcpy(c->Rp[i], Rz, sizeof(m3));
+      memset(c->S[i], 0, sizeof(v6));
+    }
+    /* m_cachedRVector = quatRotate(rotParentToThis, eVector) + dVector */
+    m3vec(c->Rp[i], m->e_vec[i], c->r[i]);
+    for (int k = 0; k < 3; k++) c->r[i][k] += m->d_vec[i][k];
+    int p = m->parent[i] + 1;
+    m3mul(c->Rp[i], c->Rw[p], c->Rw[i + 1]);
+    v3 rw;
+    m3Tvec(c->Rw[i + 1], c->r[i], rw);
+    for (int k = 0; k < 3; k++) c->pw[i + 1][k] = c->pw[p][k] + rw[k];
+  }
+}
+
+void orc_fk(const orc_model* m, const orc_state* s, double link_pos[][3], double link_rot[][9]) {
+  orc_cache* c = (orc_cache*)malloc(sizeof(orc_cache));
+  kin(m, s, c);
+  for (int i = 0; i <= m->n_links; i++) {
+    v3copy(link_pos[i], c->pw[i]);
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) link_rot[i][3 * a + b] = c->Rw[i][b][a]; /* local -> world, row-major */
+  }
+  free(c);
+}
+
+/* spatial transforms; vectors are (angular[3], linear[3]) */
+static void xform_motion(const m3 R, const v3 r, const v6 in, v6 out) {
+  v3 w, v, t;
+  m3vec(R, in, w);
+  m3vec(R, in + 3, v);
+  v3cross(r, w, t);
+  out[0] = w[0]; out[1] = w[1]; out[2] = w[2];
+  out[3] = v[0] - t[0]; out[4] = v[1] - t[1]; out[5] = v[2] - t[2];
+}
+static void xform_force_T(const m3 R, const v3 r, const v6 in, v6 out) {
+  /* child -> parent: torque about parent COM = n + r x f */
+  v3 t, n;
+  v3cross(r, in + 3, t);
+  for (int k = 0; k < 3; k++) n[k] = in[k] + t[k];
+  m3Tvec(R, n, out);
+  m3Tvec(R, in + 3, out + 3);
+}
+static void xform_matrix(const m3 R, const v3 r, m6 X) {
+  /* motion transform parent -> child as 6x6: [[R,0],[-[r]x R, R]] */
+  memset(X, 0, sizeof(m6));
+  double rx[3][3] = {{0, -r[2], r[1]}, {r[2], 0, -r[0]}, {-r[1], r[0], 0}};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      X[i][j] = R[i][j];
+      X[i + 3][j + 3] = R[i][j];
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += rx[i][k] * R[k][j];
+      X[i + 3][j] = -s;
+    }
+}
+static void motion_cross(const v6 a, const v6 b, v6 out) {
+  v3 t1, t2, t3;
+  v3cross(a, b, t1);
+  v3cross(a + 3, b, t2);
+  v3cross(a, b + 3, t3);
+  for (int k = 0; k < 3; k++) { out[k] = t1[k]; out[3 + k] = t2[k] + t3[k]; }
+}
+
+/* ------------------------------------------------------------------ 3. ABA */
+static void rigid_bias(double mass, const v3 I, const v6 vel, const v3 fext_local, const orc_params* p,
+                       int with_damping, v6 Z) {
+  /* zero-acceleration force of one link: -external + damping + gyroscopic + m w x v */
+  const double* w = vel;
+  const double* v = vel + 3;
+  v3 Iw = {I[0] * w[0], I[1] * w[1], I[2] * w[2]};
+  for (int k = 0; k < 3; k++) { Z[k] = 0; Z[3 + k] = -fext_local[k]; }
+  if (with_damping) {
+    double wn = v3norm(w), vn = v3norm(v);
+    for (int k = 0; k < 3; k++) {
+      Z[k] += Iw[k] * (p->ang_damping + p->ang_damping * wn);
+      Z[3 + k] += mass * v[k] * (p->lin_damping + p->lin_damping * vn);
+    }
+  }
+  if (p->gyro) {
+    v3 g;
+    v3cross(w, Iw, g);
+    for (int k = 0; k < 3; k++) Z[k] += g[k];
+  }
+  v3 wv;
+  v3cross(w, v, wv);
+  for (int k = 0; k < 3; k++) Z[3 + k] += mass * wv[k];
+}
+
+static void aba(const orc_model* m, const orc_params* p, const orc_state* s, const double* tau, int with_damping,
+                orc_cache* c, double* acc) {
+  int nl = m->n_links;
+  static _Thread_local v6 vel[ORC_MAXL + 1], Z[ORC_MAXL + 1], cor[ORC_MAXL], a[ORC_MAXL + 1];
+  static _Thread_local double Y[ORC_MAXL];
+  v3 gw = {0, 0, -p->gravity};
+  /* base */
+  m3vec(c->R0, s->omega, vel[0]);
+  m3vec(c->R0, s->vel, vel[0] + 3);
+  v3 f, fl;
+  for (int k = 0; k < 3; k++) f[k] = gw[k] * m->base_mass;
+  m3vec(c->R0, f, fl);
+  rigid_bias(m->base_mass, m->base_inertia, vel[0], fl, p, with_damping, Z[0]);
+  memset(c->IA[0], 0, sizeof(m6));
+  for (int k = 0; k < 3; k++) { c->IA[0][k][k] = m->base_inertia[k]; c->IA[0][3 + k][3 + k] = m->base_mass; }
+  for (int i = 0; i < nl; i++) {
+    int pp = m->parent[i] + 1;
+    xform_motion(c->Rp[i], c->r[i], vel[pp], vel[i + 1]);
+    v6 vj;
+    double qd = m->joint_type[i] == ORC_JOINT_REVOLUTE ? s->qd[m->dof_of_link[i]] : 0.0;
+    for (int k = 0; k < 6; k++) { vj[k] = c->S[i][k] * qd; vel[i + 1][k] += vj[k]; }
+    motion_cross(vel[i + 1], vj, cor[i]);
+    for (int k = 0; k < 3; k++) f[k] = gw[k] * m->mass[i];
+    m3vec(c->Rw[i + 1], f, fl);
+    rigid_bias(m->mass[i], m->inertia[i], vel[i + 1], fl, p, with_damping, Z[i + 1]);
+    memset(c->IA[i + 1], 0, sizeof(m6));
+    for (int k = 0; k < 3; k++) { c->IA[i + 1][k][k] = m->inertia[i][k]; c->IA[i + 1][3 + k][3 + k] = m->mass[i]; }
+  }
+  /* inward pass */
+  for (int i = nl - 1; i >= 0; i--) {
+    int pp = m->parent[i] + 1;
+    m6 Ia;
+    v6 Za, Ic;
+    memcpy(Ia, c->IA[i + 1], sizeof(m6));
+    m6vec(c->IA[i + 1], cor[i], Ic);
+    for (int k = 0; k < 6; k++) Za[k] = Z[i + 1][k] + Ic[k];
+    if (m->joint_type[i] == ORC_JOINT_REVOLUTE) {
+      int d = m->dof_of_link[i];
+      m6vec(c->IA[i + 1], c->S[i], c->h[i]);
+      double D = v6dot(c->S[i], c->h[i]) + m->armature[d];
+      c->Dinv[i] = 1.0 / D;
+      Y[i] = tau[d] - v6dot(c->S[i], Z[i + 1]) - v6dot(cor[i], c->h[i]);
+      for (int a_ = 0; a_ < 6; a_++) {
+        for (int b = 0; b < 6; b++) Ia[a_][b] -= c->h[i][a_] * c->h[i][b] * c->Dinv[i];
+        Za[a_] += c->h[i][a_] * Y[i] * c->Dinv[i];
+      }
+    }
+    /* IA[parent] += X^T Ia X ; Z[parent] += X^T Za */
+    m6 X, T;
+    xform_matrix(c->Rp[i], c->r[i], X);
+    for (int a_ = 0; a_ < 6; a_++)
+      for (int b = 0; b < 6; b++) {
+        double sum = 0;
+        for (int k = 0; k < 6; k++) sum += Ia[a_][k] * X[k][b];
+        T[a_][b] = sum;
+      }
+    for (int a_ = 0; a_ < 6; a_++)
+      for (int b = 0; b < 6; b++) {
+        double sum = 0;
+        for (int k = 0; k < 6; k++) sum += X[k][a_] * T[k][b];
+        c->IA[pp][a_][b] += sum;
+      }
+    v6 Zp;
+    xform_force_T(c->Rp[i], c->r[i], Za, Zp);
+    for (int k = 0; k < 6; k++) Z[pp][k] += Zp[k];
+  }
+  invert6(c->IA[0], c->IA0inv);
+  for (int k = 0; k < 6; k++) {
+    double sum = 0;
+    for (int j = 0; j < 6; j++) sum += c->IA0inv[k][j] * Z[0][j];
+    a[0][k] = -sum;
+  }
+  /* outward pass */
+  for (int i = 0; i < nl; i++) {
+    int pp = m->parent[i] + 1;
+    xform_motion(c->Rp[i], c->r[i], a[pp], a[i + 1]);
+    if (m->joint_type[i] == ORC_JOINT_REVOLUTE) {
+      int d = m->dof_of_link[i];
+      double qdd = (Y[i] - v6dot(c->h[i], a[i + 1])) * c->Dinv[i];
+      acc[6 + d] = qdd;
+      for (int k = 0; k < 6; k++) a[i + 1][k] += cor[i][k] + c->S[i][k] * qdd;
+    }
+  }
+  /* base acceleration back to world; classical linear acceleration = spatial + w x v */
+  v3 wv, lin;
+  v3cross(vel[0], vel[0] + 3, wv);
+  for (int k = 0; k < 3; k++) lin[k] = a[0][3 + k] + wv[k];
+  m3Tvec(c->R0, a[0], acc);
+  m3Tvec(c->R0, lin, acc + 3);
+}
+
+/* M^-1 f using the cached articulated inertias (calcAccelerationDeltasMultiDof) */
+static void minv(const orc_model* m, const orc_cache* c, const double* f, double* out) {
+  int nl = m->n_links;
+  static _Thread_local v6 Z[ORC_MAXL + 1], a[ORC_MAXL + 1];
+  static _Thread_local double Y[ORC_MAXL];
+  v3 t;
+  m3vec(c->R0, f, t);
+  for (int k = 0; k < 3; k++) Z[0][k] = -t[k];
+  m3vec(c->R0, f + 3, t);
+  for (int k = 0; k < 3; k++) Z[0][3 + k] = -t[k];
+  for (int i = 0; i < nl; i++) memset(Z[i + 1], 0, sizeof(v6));
+  for (int i = nl - 1; i >= 0; i--) {
+    int pp = m->parent[i] + 1;
+    v6 Za, Zp;
+    memcpy(Za, Z[i + 1], sizeof(v6));
+    if (m->joint_type[i] == ORC_JOINT_REVOLUTE) {
+      Y[i] = f[6 + m->dof_of_link[i]] - v6dot(c->S[i], Z[i + 1]);
+      for (int k = 0; k < 6; k++) Za[k] += c->h[i][k] * Y[i] * c->Dinv[i];
+    }
+    xform_force_T(c->Rp[i], c->r[i], Za, Zp);
+    for (int k = 0; k < 6; k++) Z[pp][k] += Zp[k];
+  }
+  for (int k = 0; k < 6; k++) {
+    double sum = 0;
+    for (int j = 0; j < 6; j++) sum += c->IA0inv[k][j] * Z[0][j];
+    a[0][k] = -sum;
+  }
+  for (int i = 0; i < nl; i++) {
+    int pp = m->parent[i] + 1;
+    xform_motion(c->Rp[i], c->r[i], a[pp], a[i + 1]);
+    if (m->joint_type[i] == ORC_JOINT_REVOLUTE) {
+      double qdd = (Y[i] - v6dot(c->h[i], a[i + 1])) * c->Dinv[i];
+      out[6 + m->dof_of_link[i]] = qdd;
+      for (int k = 0; k < 6; k++) a[i + 1][k] += c->S[i][k] * qdd;
+    }
+  }
+  m3Tvec(c->R0, a[0], out);
+  m3Tvec(c->R0, a[0] + 3, out + 3);
+}
+
+void orc_default_params(orc_params* p) {
+  p->gravity = 9.8;
+  p->dt = 1.0 / 240.0;
+  p->substeps = 4;
+  p->iterations = 5;
+  p->erp_contact = 0.9;
+  p->erp_joint = 0.2;
+  p->linear_slop = 1e-5;
+  p->lin_damping = 0.04;
+  p->ang_damping = 0.04;
+  p->max_coord_vel = 100.0;
+  p->warmstart = 0.0;
+  p->limit_max_impulse = 100.0;
+  p->split_threshold = -0.04;
+  p->residual_threshold = 1e-7;
+  p->limit_rows_always = 0;
+  p->gyro = 1;
+  p->has_ground = 1;
+  p->ground_friction = 0.8;
+  p->self_collision = 0;
+}
+
+void orc_forward_dynamics(const orc_model* m, const orc_params* p, const orc_state* s, const double* tau,
+                          int with_damping, double* acc) {
+  orc_cache* c = (orc_cache*)malloc(sizeof(orc_cache));
+  kin(m, s, c);
+  aba(m, p, s, tau, with_damping, c, acc);
+  free(c);
+}
+
+void orc_minv_mult(const orc_model* m, const orc_params* p, const orc_state* s, const double* f, double* out) {
+  orc_cache* c = (orc_cache*)malloc(sizeof(orc_cache));
+  double tau[ORC_MAXD] = {0}, acc[ORC_MAXU];
+  kin(m, s, c);
+  aba(m, p, s, tau, 0, c, acc);
+  minv(m, c, f, out);
+  free(c);
+}
+
+/* ------------------------------------------------------------------ 4. world-frame RNEA / mass matrix */
+/* Independent of section 3: spatial vectors about the WORLD origin, world axes.
+ * Generalised coordinates u = [omega_world, v_baseCOM_world, qd];  tau = M(q) udot + C(q,u) + G(q). */
+void orc_rnea(const orc_model* m, const orc_state* s, const double* acc, double gravity, double* tau) {
+  int nl = m->n_links;
+  orc_cache* c = (orc_cache*)malloc(sizeof(orc_cache));
+  kin(m, s, c);
+  static _Thread_local v6 V[ORC_MAXL + 1], A[ORC_MAXL + 1], F[ORC_MAXL + 1], Sw[ORC_MAXL];
+  v3 t;
+  /* base: V = (w, v - w x p), A = (wd, vd - wd x p - w x v) + gravity trick */
+  v3cross(s->omega, s->pos, t);
+  for (int k = 0; k < 3; k++) { V[0][k] = s->omega[k]; V[0][3 + k] = s->vel[k] - t[k]; }
+  v3 t2;
+  v3cross(acc, s->pos, t);
+  v3cross(s->omega, s->vel, t2);
+  for (int k = 0; k < 3; k++) { A[0][k] = acc[k]; A[0][3 + k] = acc[3 + k] - t[k] - t2[k]; }
+  A[0][5] += gravity;
+  for (int i = 0; i < nl; i++) {
+    int pp = m->parent[i] + 1;
+    memcpy(V[i + 1], V[pp], sizeof(v6));
+    memcpy(A[i + 1], A[pp], sizeof(v6));
+    memset(Sw[i], 0, sizeof(v6));
+    if (m->joint_type[i] == ORC_JOINT_REVOLUTE) {
+      int d = m->dof_of_link[i];
+      v3 aw, dw, piv;
+      m3Tvec(c->Rw[i + 1], m->axis[i], aw);
+      m3Tvec(c->Rw[i + 1], m->d_vec[i], dw);
+      for (int k = 0; k < 3; k++) piv[k] = c->pw[i + 1][k] - dw[k];
+      v3copy(Sw[i], aw);
+      v3cross(piv, aw, &Sw[i][3]);
+      v6 vj, cr;
+      for (int k = 0; k < 6; k++) { vj[k] = Sw[i][k] * s->qd[d]; V[i + 1][k] += vj[k]; }
+      motion_cross(V[i + 1], vj, cr);
+      for (int k = 0; k < 6; k++) A[i + 1][k] += Sw[i][k] * acc[6 + d] + cr[k];
+    }
+  }
+  for (int i = 0; i <= nl; i++) {
+    double mass = i == 0 ? m->base_mass : m->mass[i - 1];
+    const double* Id = i == 0 ? m->base_inertia : m->inertia[i - 1];
+    /* world inertia about COM: R^T diag R with R = world->link */
+    m3 Iw;
+    for (int a_ = 0; a_ < 3; a_++)
+      for (int b = 0; b < 3; b++) {
+        double sum = 0;
+        for (int k = 0; k < 3; k++) sum += c->Rw[i][k][a_] * Id[k] * c->Rw[i][k][b];
+        Iw[a_][b] = sum;
+      }
+    /* momentum about origin: h = (Iw w + m c x vc, m vc), vc = v_O + w x c */
+    const double* pc = c->pw[i];
+    v3 vc, wc, ac, tmp;
+    v3cross(V[i], pc, wc);
+    for (int k = 0; k < 3; k++) vc[k] = V[i][3 + k] + wc[k];
+    /* classical COM acceleration: a_O + wd x c + w x (w x c) + w x v_O ... use spatial form:
+       f = I A + V x* (I V) with I about origin */
+    /* I*X for X = (w, vO): lin = m (vO + w x c) ; ang = Iw w + m c x (vO + w x c) */
+    v6 IV, IAc;
+    m3vec(Iw, V[i], tmp);
+    v3 cxv;
+    v3cross(pc, vc, cxv);
+    for (int k = 0; k < 3; k++) { IV[k] = tmp[k] + mass * cxv[k]; IV[3 + k] = mass * vc[k]; }
+    v3cross(A[i], pc, wc);
+    for (int k = 0; k < 3; k++) ac[k] = A[i][3 + k] + wc[k];
+    m3vec(Iw, A[i], tmp);
+    v3cross(pc, ac, cxv);
+    for (int k = 0; k < 3; k++) { IAc[k] = tmp[k] + mass * cxv[k]; IAc[3 + k] = mass * ac[k]; }
+    /* force cross: V x* F = (w x n + v x f, w x f) */
+    v3 c1, c2, c3;
+    v3cross(V[i], IV, c1);
+    v3cross(V[i] + 3, IV + 3, c2);
+    v3cross(V[i], IV + 3, c3);
+    for (int k = 0; k < 3; k++) { F[i][k] = IAc[k] + c1[k] + c2[k]; F[i][3 + k] = IAc[3 + k] + c3[k]; }
+  }
+  for (int i = nl - 1; i >= 0; i--) {
+    int pp = m->parent[i] + 1;
+    if (m->joint_type[i] == ORC_JOINT_REVOLUTE) tau[6 + m->dof_of_link[i]] = v6dot(Sw[i], F[i + 1]);
+    for (int k = 0; k < 6; k++) F[pp][k] += F[i + 1][k];
+  }
+  v3cross(s->pos, F[0] + 3, t);
+  for (int k = 0; k < 3; k++) { tau[k] = F[0][k] - t[k]; tau[3 + k] = F[0][3 + k]; }
+  free(c);
+}
+
+void orc_mass_matrix(const orc_model* m, const orc_state* s, double* M) {
+  int nu = 6 + m->n_dof;
+  orc_state z = *s;
+  memset(z.omega, 0, sizeof(z.omega));
+  memset(z.vel, 0, sizeof(z.vel));
+  memset(z.qd, 0, sizeof(z.qd));
+  for (int cidx = 0; cidx < nu; cidx++) {
+    double acc[ORC_MAXU] = {0}, tau[ORC_MAXU];
+    acc[cidx] = 1.0;
+    orc_rnea(m, &z, acc, 0.0, tau);
+    for (int r = 0; r < nu; r++) M[r * nu + cidx] = tau[r];
+  }
+}
+
+void orc_energy_momentum(const orc_model* m, const orc_state* s, double gravity, double* out) {
+  orc_cache* c = (orc_cache*)malloc(sizeof(orc_cache));
+  kin(m, s, c);
+  static _Thread_local v6 vel[ORC_MAXL + 1];
+  m3vec(c->R0, s->omega, vel[0]);
+  m3vec(c->R0, s->vel, vel[0] + 3);
+  double KE = 0, PE = 0, P[3] = {0, 0, 0}, L[3] = {0, 0, 0};
+  for (int i = 0; i <= m->n_links; i++) {
+    if (i > 0) {
+      int l = i - 1, pp = m->parent[l] + 1;
+      xform_motion(c->Rp[l], c->r[l], vel[pp], vel[i]);
+      double qd = m->joint_type[l] == ORC_JOINT_REVOLUTE ? s->qd[m->dof_of_link[l]] : 0.0;
+      for (int k = 0; k < 6; k++) vel[i][k] += c->S[l][k] * qd;
+    }
+    double mass = i == 0 ? m->base_mass : m->mass[i - 1];
+    const double* Id = i == 0 ? m->base_inertia : m->inertia[i - 1];
+    v3 Iw_l = {Id[0] * vel[i][0], Id[1] * vel[i][1], Id[2] * vel[i][2]}, Iw, vw, t;
+    KE += 0.5 * (v3dot(vel[i], Iw_l) + mass * v3dot(vel[i] + 3, vel[i] + 3));
+    PE += mass * gravity * c->pw[i][2];
+    m3Tvec(c->Rw[i], Iw_l, Iw);
+    m3Tvec(c->Rw[i], vel[i] + 3, vw);
+    v3cross(c->pw[i], vw, t);
+    for (int k = 0; k < 3; k++) { P[k] += mass * vw[k]; L[k] += Iw[k] + mass * t[k]; }
+  }
+  out[0] = KE; out[1] = PE;
+  for (int k = 0; k < 3; k++) { out[2 + k] = P[k]; out[5 + k] = L[k]; }
+  free(c);
+}
+
+/* ------------------------------------------------------------------ 5. narrow phase */
+static void add_point(orc_contacts* c, int pid, int link, int partner, const v3 pa, const v3 n, double dist,
+                      double mu, double erp, double cfm) {
+  if (c->n >= ORC_MAXP) return;
+  int k = c->n++;
+  c->point_id[k] = pid; c->link[k] = link; c->partner[k] = partner;
+  v3copy(c->pos_a[k], pa); v3copy(c->normal[k], n);
+  c->dist[k] = dist; c->friction[k] = mu; c->erp[k] = erp; c->cfm[k] = cfm; c->impulse[k] = 0;
+}
+
+/* sphere (centre cw, radius r) vs static box; returns 1 and fills (pa, n, dist) if dist < thresh */
+static int sphere_box(const v3 cw, double r, const orc_box* b, double thresh, v3 pa, v3 n, double* dist) {
+  v3 d, cl, q, nl;
+  for (int k = 0; k < 3; k++) d[k] = cw[k] - b->center[k];
+  for (int k = 0; k < 3; k++) cl[k] = b->R[0][k] * d[0] + b->R[1][k] * d[1] + b->R[2][k] * d[2];
+  int inside = 1;
+  for (int k = 0; k < 3; k++) {
+    q[k] = cl[k];
+    if (q[k] > b->half[k]) { q[k] = b->half[k]; inside = 0; }
+    if (q[k] < -b->half[k]) { q[k] = -b->half[k]; inside = 0; }
+  }
+  if (!inside) {
+    v3 diff = {cl[0] - q[0], cl[1] - q[1], cl[2] - q[2]};
+    double len = v3norm(diff);
+    *dist = len - r;
+    if (*dist >= thresh) return 0;
+    for (int k = 0; k < 3; k++) nl[k] = diff[k] / len;
+  } else {
+    int ax = 0;
+    double best = 1e30;
+    for (int k = 0; k < 3; k++) {
+      double pen = b->half[k] - fabs(cl[k]);
+      if (pen < best) { best = pen; ax = k; }
+    }
+    v3set(nl, 0, 0, 0);
+    nl[ax] = cl[ax] >= 0 ? 1.0 : -1.0;
+    *dist = -best - r;
+  }
+  for (int k = 0; k < 3; k++) n[k] = b->R[k][0] * nl[0] + b->R[k][1] * nl[1] + b->R[k][2] * nl[2];
+  for (int k = 0; k < 3; k++) pa[k] = cw[k] - r * n[k];
+  return 1;
+}
+
+int orc_collide_cached(const orc_model* m, const orc_params* p, const orc_cache* c, const orc_box* boxes,
+                       int n_boxes, orc_contacts* out) {
+  out->n = 0;
+  for (int g = 0; g < m->n_geoms; g++) {
+    int link = m->geom_link[g];
+    if (m->geom_type[g] == ORC_GEOM_BOX) continue; /* robot box geoms (Monkey3D) not handled yet */
+    int nends = m->geom_type[g] == ORC_GEOM_CAPSULE ? 2 : 1;
+    double r = m->geom_size[g][0];
+    double thresh = m->link_thresh[link + 1];
+    for (int e = 0; e < nends; e++) {
+      const double* pl = e == 0 ? m->geom_p0[g] : m->geom_p1[g];
+      v3 cw, t;
+      m3Tvec(c->Rw[link + 1], pl, t);
+      for (int k = 0; k < 3; k++) cw[k] = c->pw[link + 1][k] + t[k];
+      if (p->has_ground) {
+        double dist = cw[2] - r;
+        if (dist < thresh) {
+          v3 n = {0, 0, 1}, pa = {cw[0], cw[1], cw[2] - r};
+          add_point(out, 2 * g + e, link, 0, pa, n, dist, m->geom_friction[g] * p->ground_friction,
+                    p->erp_contact, 0.0);
+        }
+      }
+      for (int b = 0; b < n_boxes; b++) {
+        v3 pa, n;
+        double dist;
+        if (sphere_box(cw, r, &boxes[b], thresh, pa, n, &dist)) {
+          double erp = p->erp_contact, cfm = 0.0;
+          if (boxes[b].stiffness > 0) {
+            /* soft contact, SURVEY App. B.4 (bullet_objects.py:64-72) */
+            double denom = p->dt * boxes[b].stiffness + boxes[b].damping;
+            if (denom < 1.1920929e-07) denom = 1.1920929e-07;
+            cfm = 1.0 / denom;
+            erp = p->dt * boxes[b].stiffness / denom;
+          }
+          add_point(out, 2 * g + e, link, boxes[b].id, pa, n, dist, m->geom_friction[g] * boxes[b].friction, erp,
+                    cfm);
+        }
+      }
+    }
+  }
+  return out->n;
+}
+
+int orc_collide(const orc_model* m, const orc_params* p, const orc_state* s, const orc_box* boxes, int n_boxes,
+                orc_contacts* out) {
+  orc_cache* c = (orc_cache*)malloc(sizeof(orc_cache));
+  kin(m, s, c);
+  int n = orc_collide_cached(m, p, c, boxes, n_boxes, out);
+  free(c);
+  return n;
+}
+
+/* ------------------------------------------------------------------ 6. rows + PGS */
+typedef struct {
+  double J[ORC_MAXU];
+  double MinvJ[ORC_MAXU];
+  double rhs, cfm, lo, hi, jinv, applied, mu;
+  int normal_index; /* friction rows: index of their normal row */
+} orc_row;
+
+/* btPlaneSpace1 */
+static void plane_space(const v3 n, v3 p, v3 q) {
+  if (fabs(n[2]) > 0.7071067811865475244008443621048490) {
+    double a = n[1] * n[1] + n[2] * n[2], k = 1.0 / sqrt(a);
+    p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k;
+    q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+  } else {
+    double a = n[0] * n[0] + n[1] * n[1], k = 1.0 / sqrt(a);
+    p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0;
+    q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
+  }
+}
+
+static void point_jacobian(const orc_model* m, const orc_state* s, const orc_cache* c, int link, const v3 pt,
+                           const v3 dir, double* J) {
+  int nu = 6 + m->n_dof;
+  for (int k = 0; k < nu; k++) J[k] = 0;
+  v3 rel, t;
+  for (int k = 0; k < 3; k++) rel[k] = pt[k] - s->pos[k];
+  v3cross(rel, dir, t);
+  for (int k = 0; k < 3; k++) { J[k] = t[k]; J[3 + k] = dir[k]; }
+  for (int l = link; l >= 0; l = m->parent[l]) {
+    if (m->joint_type[l] != ORC_JOINT_REVOLUTE) continue;
+    v3 aw, dw, piv, arm, vel;
+    m3Tvec(c->Rw[l + 1], m->axis[l], aw);
+    m3Tvec(c->Rw[l + 1], m->d_vec[l], dw);
+    for (int k = 0; k < 3; k++) { piv[k] = c->pw[l + 1][k] - dw[k]; arm[k] = pt[k] - piv[k]; }
+    v3cross(aw, arm, vel);
+    J[6 + m->dof_of_link[l]] = v3dot(dir, vel);
+  }
+}
+
+static double dotn(const double* a, const double* b, int n) {
+  double s = 0;
+  for (int i = 0; i < n; i++) s += a[i] * b[i];
+  return s;
+}
+
+/* one contact/friction row (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint) */
+static void setup_contact_row(const orc_model* m, const orc_params* p, const orc_state* s, const orc_cache* c,
+                              const double* u, const orc_contacts* ct, int k, const v3 dir, int is_friction,
+                              orc_row* row) {
+  int nu = 6 + m->n_dof;
+  double inv_dt = 1.0 / p->dt;
+  double cfm = is_friction ? 0.0 : ct->cfm[k] * inv_dt;
+  double erp = ct->erp[k];
+  point_jacobian(m, s, c, ct->link[k], ct->pos_a[k], dir, row->J);
+  minv(m, c, row->J, row->MinvJ);
+  double d = dotn(row->J, row->MinvJ, nu) + cfm;
+  row->jinv = d > 1.1920929e-07 ? 1.0 / d : 0.0;
+  double rel_vel = dotn(row->J, u, nu);
+  double distance = is_friction ? 0.0 : ct->dist[k] + p->linear_slop;
+  double positional = 0.0, velocity_err = -rel_vel; /* combined restitution = 0 (robot links) */
+  if (is_friction) {
+    positional = 0.0;
+  } else if (distance > 0) {
+    velocity_err -= distance * inv_dt;
+  } else {
+    positional = -distance * erp * inv_dt;
+  }
+  row->rhs = positional * row->jinv + velocity_err * row->jinv;
+  row->cfm = cfm * row->jinv;
+  row->applied = 0.0;
+  row->mu = ct->friction[k];
+  if (is_friction) { row->lo = -row->mu; row->hi = row->mu; }
+  else { row->lo = 0.0; row->hi = 1e10; }
+}
+
+typedef struct {
+  orc_row limit[2 * ORC_MAXD];
+  orc_row normal[ORC_MAXP];
+  orc_row fric[2 * ORC_MAXP];
+} orc_rows;
+
+static void apply_row(double* dv, const orc_row* r, double imp, int nu) {
+  for (int i = 0; i < nu; i++) dv[i] += r->MinvJ[i] * imp;
+}
+
+static double resolve_single(orc_row* r, double* dv, int nu) {
+  double delta = r->rhs - r->applied * r->cfm;
+  delta -= dotn(r->J, dv, nu) * r->jinv;
+  double sum = r->applied + delta;
+  if (sum < r->lo) { delta = r->lo - r->applied; r->applied = r->lo; }
+  else if (sum > r->hi) { delta = r->hi - r->applied; r->applied = r->hi; }
+  else r->applied = sum;
+  apply_row(dv, r, delta, nu);
+  return r->jinv != 0.0 ? delta / r->jinv : 0.0;
+}
+
+/* btMultiBodyConstraintSolver::resolveConeFrictionConstraintRows */
+static double resolve_cone(orc_row* a, orc_row* b, double* dv, int nu) {
+  double dB = b->rhs - b->applied * b->cfm - dotn(b->J, dv, nu) * b->jinv;
+  double sumB = b->applied + dB;
+  double dA = a->rhs - a->applied * a->cfm - dotn(a->J, dv, nu) * a->jinv;
+  double sumA = a->applied + dA;
+  if (sumA * sumA + sumB * sumB >= a->lo * b->lo) {
+    double angle = atan2(sumA, sumB);
+    double clipA = fabs(a->lo * sin(angle)), clipB = fabs(b->lo * cos(angle));
+    if (sumA < -clipA) { dA = -clipA - a->applied; a->applied = -clipA; }
+    else if (sumA > clipA) { dA = clipA - a->applied; a->applied = clipA; }
+    else a->applied = sumA;
+    if (sumB < -clipB) { dB = -clipB - b->applied; b->applied = -clipB; }
+    else if (sumB > clipB) { dB = clipB - b->applied; b->applied = clipB; }
+    else b->applied = sumB;
+  } else {
+    a->applied = sumA;
+    b->applied = sumB;
+  }
+  apply_row(dv, a, dA, nu);
+  apply_row(dv, b, dB, nu);
+  double res = 0;
+  if (a->jinv != 0.0) res += dA / a->jinv;
+  if (b->jinv != 0.0) res += dB / b->jinv;
+  return res;
+}
+
+static void clamp_u(double* u, int nu, double vmax) {
+  for (int i = 0; i < nu; i++) {
+    if (u[i] > vmax) u[i] = vmax;
+    if (u[i] < -vmax) u[i] = -vmax;
+  }
+}
+
+static void pack_u(const orc_model* m, const orc_state* s, double* u) {
+  for (int k = 0; k < 3; k++) { u[k] = s->omega[k]; u[3 + k] = s->vel[k]; }
+  for (int d = 0; d < m->n_dof; d++) u[6 + d] = s->qd[d];
+}
+static void unpack_u(const orc_model* m, orc_state* s, const double* u) {
+  for (int k = 0; k < 3; k++) { s->omega[k] = u[k]; s->vel[k] = u[3 + k]; }
+  for (int d = 0; d < m->n_dof; d++) s->qd[d] = u[6 + d];
+}
+
+/* ------------------------------------------------------------------ 7. integration + driver */
+static void integrate_positions(const orc_model* m, const orc_params* p, orc_state* s) {
+  double dt = p->dt;
+  for (int k = 0; k < 3; k++) s->pos[k] += dt * s->vel[k];
+  /* btMultiBody::stepPositionsMultiDof quaternion exponential (world-frame angular velocity) */
+  double ang = v3norm(s->omega);
+  if (ang * dt > 0.25 * PI) ang = 0.25 * PI / dt;
+  double f;
+  if (ang < 0.001) f = 0.5 * dt - dt * dt * dt * 0.020833333333 * ang * ang;
+  else f = sin(0.5 * ang * dt) / ang;
+  double ax = s->omega[0] * f, ay = s->omega[1] * f, az = s->omega[2] * f, aw = cos(ang * dt * 0.5);
+  double x = s->quat[0], y = s->quat[1], z = s->quat[2], w = s->quat[3];
+  /* q_new = dq * q */
+  double nx = aw * x + ax * w + ay * z - az * y;
+  double ny = aw * y - ax * z + ay * w + az * x;
+  double nz = aw * z + ax * y - ay * x + az * w;
+  double nw = aw * w - ax * x - ay * y - az * z;
+  double n = sqrt(nx * nx + ny * ny + nz * nz + nw * nw);
+  s->quat[0] = nx / n; s->quat[1] = ny / n; s->quat[2] = nz / n; s->quat[3] = nw / n;
+  for (int d = 0; d < m->n_dof; d++) s->q[d] += dt * s->qd[d];
+}
+
+void orc_substep(const orc_model* m, const orc_params* p, orc_state* s, const double* tau, const orc_box* boxes,
+                 int n_boxes, double* warm, orc_contacts* ct, int* out_rows) {
+  int nu = 6 + m->n_dof;
+  orc_cache* c = (orc_cache*)malloc(sizeof(orc_cache));
+  orc_rows* rows = (orc_rows*)malloc(sizeof(orc_rows));
+  double u[ORC_MAXU], acc[ORC_MAXU], dv[ORC_MAXU];
+  /* collision detection at start-of-substep poses */
+  kin(m, s, c);
+  orc_collide_cached(m, p, c, boxes, n_boxes, ct);
+  /* forward dynamics, velocity update */
+  aba(m, p, s, tau, 1, c, acc);
+  pack_u(m, s, u);
+  for (int i = 0; i < nu; i++) u[i] += acc[i] * p->dt;
+  clamp_u(u, nu, p->max_coord_vel);
+  for (int i = 0; i < nu; i++) dv[i] = 0;
+  /* non-contact rows: joint limits (btMultiBodyJointLimitConstraint::createConstraintRows) */
+  int nlim = 0;
+  for (int d = 0; d < m->n_dof; d++) {
+    if (m->lower[d] > m->upper[d]) continue;
+    for (int r = 0; r < 2; r++) {
+      double pen = r == 0 ? s->q[d] - m->lower[d] : m->upper[d] - s->q[d];
+      if (pen > 0 && !p->limit_rows_always) continue;
+      orc_row* row = &rows->limit[nlim++];
+      double dir = r ? -1.0 : 1.0;
+      for (int k = 0; k < nu; k++) row->J[k] = 0;
+      row->J[6 + d] = dir;
+      minv(m, c, row->J, row->MinvJ);
+      double dd = dotn(row->J, row->MinvJ, nu);
+      row->jinv = dd > 1.1920929e-07 ? 1.0 / dd : 0.0;
+      double rel_vel = dotn(row->J, u, nu);
+      double positional = 0, velocity_err = -rel_vel;
+      double erp = pen > p->split_threshold ? p->erp_joint : p->erp_contact;
+      int split = !(pen > p->split_threshold); /* position part goes to the (unapplied) split impulse */
+      if (pen > 0) velocity_err = -pen / p->dt;
+      else positional = -pen * erp / p->dt;
+      row->rhs = velocity_err * row->jinv + (split ? 0.0 : positional * row->jinv);
+      row->cfm = 0; row->lo = 0; row->hi = p->limit_max_impulse; row->applied = 0; row->mu = 0;
+    }
+  }
+  /* contact rows */
+  int nc = ct->n;
+  for (int k = 0; k < nc; k++) {
+    v3 t1, t2;
+    setup_contact_row(m, p, s, c, u, ct, k, ct->normal[k], 0, &rows->normal[k]);
+    if (p->warmstart > 0 && warm) {
+      double imp = warm[ct->point_id[k]] * p->warmstart;
+      rows->normal[k].applied = imp;
+      if (imp != 0.0) apply_row(dv, &rows->normal[k], imp, nu);
+    }
+    plane_space(ct->normal[k], t1, t2);
+    setup_contact_row(m, p, s, c, u, ct, k, t1, 1, &rows->fric[2 * k]);
+    setup_contact_row(m, p, s, c, u, ct, k, t2, 1, &rows->fric[2 * k + 1]);
+    rows->fric[2 * k].normal_index = rows->fric[2 * k + 1].normal_index = k;
+  }
+  /* PGS (btMultiBodyConstraintSolver::solveSingleIteration order) */
+  for (int it = 0; it < p->iterations; it++) {
+    double res2 = 0;
+    for (int j = 0; j < nlim; j++) {
+      int idx = (it & 1) ? j : nlim - 1 - j;
+      double r = resolve_single(&rows->limit[idx], dv, nu);
+      if (r * r > res2) res2 = r * r;
+    }
+    for (int k = 0; k < nc; k++) {
+      double r = resolve_single(&rows->normal[k], dv, nu);
+      if (r * r > res2) res2 = r * r;
+    }
+    for (int k = 0; k < nc; k++) {
+      orc_row *a = &rows->fric[2 * k], *b = &rows->fric[2 * k + 1];
+      double total = rows->normal[k].applied;
+      a->lo = -(a->mu * total); a->hi = a->mu * total;
+      b->lo = -(b->mu * total); b->hi = b->mu * total;
+      double r = resolve_cone(a, b, dv, nu);
+      if (r * r > res2) res2 = r * r;
+    }
+    if (res2 <= p->residual_threshold) break;
+  }
+  for (int i = 0; i < nu; i++) u[i] += dv[i];
+  clamp_u(u, nu, p->max_coord_vel);
+  unpack_u(m, s, u);
+  if (warm) {
+    for (int i = 0; i < ORC_MAXP; i++) warm[i] = 0;
+    for (int k = 0; k < nc; k++) warm[ct->point_id[k]] = rows->normal[k].applied;
+  }
+  for (int k = 0; k < nc; k++) ct->impulse[k] = rows->normal[k].applied;
+  if (out_rows) *out_rows = nlim + 3 * nc;
+  integrate_positions(m, p, s);
+  free(rows);
+  free(c);
+}
+
+/* one pybullet.stepSimulation(): applied torques + PyBullet's joint damping torque are computed once and
+ * held over the substeps */
+void orc_step_physics(const orc_model* m, const orc_params* p, orc_state* s, const double* tau_applied,
+                      const orc_box* boxes, int n_boxes, double* warm, orc_contacts* last, int* rows_sum) {
+  double tau[ORC_MAXD];
+  for (int d = 0; d < m->n_dof; d++) tau[d] = tau_applied[d] - m->damping[d] * s->qd[d];
+  orc_contacts* ct = last ? last : (orc_contacts*)malloc(sizeof(orc_contacts));
+  int total = 0;
+  for (int k = 0; k < p->substeps; k++) {
+    int r = 0;
+    orc_substep(m, p, s, tau, boxes, n_boxes, warm, ct, &r);
+    total += r;
+  }
+  if (rows_sum) *rows_sum = total;
+  if (!last) free(ct);
+}
+
+/* ------------------------------------------------------------------ 8. MT19937 */
+static void mt_init_genrand(orc_rng* r, uint32_t s) {
+  r->mt[0] = s;
+  for (int i = 1; i < 624; i++) r->mt[i] = 1812433253U * (r->mt[i - 1] ^ (r->mt[i - 1] >> 30)) + (uint32_t)i;
+  r->pos = 624;
+}
+void orc_rng_seed_array(orc_rng* r, const uint32_t* key, int len) {
+  mt_init_genrand(r, 19650218U);
+  int i = 1, j = 0, k = 624 > len ? 624 : len;
+  for (; k; k--) {
+    r->mt[i] = (r->mt[i] ^ ((r->mt[i - 1] ^ (r->mt[i - 1] >> 30)) * 1664525U)) + key[j] + (uint32_t)j;
+    i++; j++;
+    if (i >= 624) { r->mt[0] = r->mt[623]; i = 1; }
+    if (j >= len) j = 0;
+  }
+  for (k = 623; k; k--) {
+    r->mt[i] = (r->mt[i] ^ ((r->mt[i - 1] ^ (r->mt[i - 1] >> 30)) * 1566083941U)) - (uint32_t)i;
+    i++;
+    if (i >= 624) { r->mt[0] = r->mt[623]; i = 1; }
+  }
+  r->mt[0] = 0x80000000U;
+  r->pos = 624;
+}
+uint32_t orc_rng_u32(orc_rng* r) {
+  if (r->pos >= 624) {
+    uint32_t* mt = r->mt;
+    int kk;
+    for (kk = 0; kk < 624 - 397; kk++) {
+      uint32_t y = (mt[kk] & 0x80000000U) | (mt[kk + 1] & 0x7fffffffU);
+      mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
+    }
+    for (; kk < 623; kk++) {
+      uint32_t y = (mt[kk] & 0x80000000U) | (mt[kk + 1] & 0x7fffffffU);
+      mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
+    }
+    uint32_t y = (mt[623] & 0x80000000U) | (mt[0] & 0x7fffffffU);
+    mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
+    r->pos = 0;
+  }
+  uint32_t y = r->mt[r->pos++];
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680U;
+  y ^= (y << 15) & 0xefc60000U;
+  y ^= (y >> 18);
+  return y;
+}
+double orc_rng_double(orc_rng* r) { /* RandomState.random_sample / rand() */
+  uint32_t a = orc_rng_u32(r) >> 5, b = orc_rng_u32(r) >> 6;
+  return (a * 67108864.0 + b) / 9007199254740992.0;
+}
+double orc_rng_uniform(orc_rng* r, double lo, double hi) { return lo + (hi - lo) * orc_rng_double(r); }
+
+/* ------------------------------------------------------------------ 9. Walker3DCustomEnv */
+/* pybullet.getEulerFromQuaternion */
+static void euler_from_quat(const double qin[4], double rpy[3]) {
+  double len = sqrt(qin[0] * qin[0] + qin[1] * qin[1] + qin[2] * qin[2] + qin[3] * qin[3]);
+  double q[4] = {qin[0] / len, qin[1] / len, qin[2] / len, qin[3] / len};
+  double sqx = q[0] * q[0], sqy = q[1] * q[1], sqz = q[2] * q[2], squ = q[3] * q[3];
+  double sarg = -2 * (q[0] * q[2] - q[3] * q[1]);
+  if (sarg <= -0.99999) {
+    rpy[0] = 0; rpy[1] = -0.5 * PI; rpy[2] = 2 * atan2(q[0], -q[1]);
+  } else if (sarg >= 0.99999) {
+    rpy[0] = 0; rpy[1] = 0.5 * PI; rpy[2] = 2 * atan2(-q[0], q[1]);
+  } else {
+    rpy[0] = atan2(2 * (q[1] * q[2] + q[3] * q[0]), squ - sqx - sqy + sqz);
+    rpy[1] = asin(sarg);
+    rpy[2] = atan2(2 * (q[0] * q[1] + q[3] * q[2]), squ + sqx - sqy - sqz);
+  }
+}
+
+static orc_rng* robot_rng(orc_w3d_env* e) { return e->rng_aliased ? &e->env_rng : &e->robot_rng; }
+
+void orc_w3d_seed(orc_w3d_env* e, const uint32_t* key, int len, int at_construction) {
+  /* env_base.py:164-166: seed() rebinds only the env's RandomState; the robot keeps the object it was
+   * given at construction (env_base.py:93) -- quirk Q1 */
+  if (!at_construction && e->rng_aliased) {
+    e->robot_rng = e->env_rng;
+    e->rng_aliased = 0;
+  }
+  orc_rng_seed_array(&e->env_rng, key, len);
+  if (at_construction) e->rng_aliased = 1;
+}
+
+static double f32(double x) { return (double)(float)x; }
+
+/* robots.py:42-95 */
+static void w3d_calc_state(const orc_model* m, orc_w3d_env* e, const orc_contacts* ground_contacts) {
+  int A = m->n_dof, F = m->n_feet;
+  orc_cache* c = (orc_cache*)malloc(sizeof(orc_cache));
+  kin(m, &e->s, c);
+  double* st = e->robot_state;
+  e->joints_at_limit = 0;
+  for (int d = 0; d < A; d++) {
+    float q = (float)e->s.q[d], qd = (float)e->s.qd[d];
+    float bias = (float)m->lower[d], weight = (float)(m->upper[d] - m->lower[d]);
+    float nrm = 2.0f * (q - bias) / weight - 1.0f;
+    float sp = 0.1f * qd;
+    st[6 + d] = nrm;
+    st[6 + A + d] = sp;
+    e->joint_speeds[d] = sp;
+    if (fabsf(nrm) > 0.99f) e->joints_at_limit++;
+  }
+  v3copy(e->body_xyz, e->s.pos);
+  euler_from_quat(e->s.quat, e->body_rpy);
+  double yaw = e->body_rpy[2];
+  double cy = cos(-yaw), sy = sin(-yaw);
+  e->body_vel[0] = cy * e->s.vel[0] - sy * e->s.vel[1];
+  e->body_vel[1] = sy * e->s.vel[0] + cy * e->s.vel[1];
+  e->body_vel[2] = e->s.vel[2];
+  double minz = 1e30;
+  for (int f = 0; f < F; f++) {
+    v3copy(e->feet_xyz[f], c->pw[m->foot_link[f] + 1]);
+    if (e->feet_xyz[f][2] < minz) minz = e->feet_xyz[f][2];
+  }
+  if (ground_contacts) {
+    for (int f = 0; f < F; f++) {
+      e->feet_contact[f] = 0;
+      for (int k = 0; k < ground_contacts->n; k++)
+        if (ground_contacts->link[k] == m->foot_link[f] && ground_contacts->partner[k] == 0) e->feet_contact[f] = 1;
+    }
+  }
+  st[0] = f32(e->body_xyz[2] - minz);
+  st[1] = f32(e->body_vel[0]); st[2] = f32(e->body_vel[1]); st[3] = f32(e->body_vel[2]);
+  st[4] = f32(e->body_rpy[0]); st[5] = f32(e->body_rpy[1]);
+  for (int f = 0; f < F; f++) st[6 + 2 * A + f] = e->feet_contact[f];
+  for (int k = 0; k < 6 + 2 * A + F; k++) {
+    if (st[k] > 5) st[k] = 5;
+    if (st[k] < -5) st[k] = -5;
+  }
+  free(c);
+}
+
+/* robots.py:179-210 */
+static void w3d_robot_reset(const orc_model* m, orc_w3d_env* e, const double* pos) {
+  int A = m->n_dof;
+  double ang[ORC_MAXD];
+  for (int d = 0; d < A; d++) ang[d] = m->base_joint_angles[d];
+  orc_rng* rr = robot_rng(e);
+  if (orc_rng_double(rr) < 0.5) {
+    e->mirrored = 1;
+    double tmp[ORC_MAXD];
+    memcpy(tmp, ang, sizeof(tmp));
+    for (int k = 0; k < m->n_right; k++) {
+      ang[m->right_idx[k]] = tmp[m->left_idx[k]];
+      ang[m->left_idx[k]] = tmp[m->right_idx[k]];
+    }
+    for (int k = 0; k < m->n_neg; k++) ang[m->neg_idx[k]] *= -1;
+  } else {
+    e->mirrored = 0;
+  }
+  /* random_pose=True: +-0.1 rad noise, clipped to +-0.95 of the normalised range (robots.py:190-194) */
+  double ds[ORC_MAXD];
+  for (int d = 0; d < A; d++) ds[d] = orc_rng_uniform(rr, -0.1, 0.1);
+  for (int d = 0; d < A; d++) {
+    double bias = (double)(float)m->lower[d], weight = (double)(float)(m->upper[d] - m->lower[d]);
+    double ps = 2 * (ang[d] + ds[d] - bias) / weight - 1;
+    if (ps > 0.95) ps = 0.95;
+    if (ps < -0.95) ps = -0.95;
+    e->s.q[d] = weight * (ps + 1) / 2 + bias;
+    e->s.qd[d] = 0;
+  }
+  for (int k = 0; k < 3; k++) { e->s.pos[k] = pos[k]; e->s.omega[k] = 0; e->s.vel[k] = 0; }
+  e->s.quat[0] = e->s.quat[1] = e->s.quat[2] = 0; e->s.quat[3] = 1;
+  for (int f = 0; f < 4; f++) { e->feet_contact[f] = 0; v3set(e->feet_xyz[f], 0, 0, 0); }
+  for (int i = 0; i < ORC_MAXP; i++) e->warm[i] = 0;
+  w3d_calc_state(m, e, NULL);
+}
+
+static void w3d_randomize_target(orc_w3d_env* e) { /* env_locomotion.py:67-74 */
+  if (e->eval_mode) { e->dist = 4; e->angle = 0; }
+  else {
+    e->dist = orc_rng_uniform(&e->env_rng, 3, 5);
+    e->angle = orc_rng_uniform(&e->env_rng, -PI / 2, PI / 2);
+  }
+  e->stop_frames = (orc_rng_u32(&e->env_rng) & 1U) ? 60.0 : 30.0;
+}
+
+static void w3d_calc_potential(orc_w3d_env* e, double scene_dt) { /* env_locomotion.py:143-158 */
+  double dx = e->walk_target[0] - e->body_xyz[0], dy = e->walk_target[1] - e->body_xyz[1];
+  e->angle_to_target = atan2(dy, dx) - e->body_rpy[2];
+  e->distance_to_target = sqrt(dx * dx + dy * dy);
+  e->linear_potential = -e->distance_to_target / scene_dt;
+  e->angular_potential = cos(e->angle_to_target);
+}
+
+static void w3d_obs(const orc_model* m, const orc_w3d_env* e, double* obs) {
+  int n = 6 + 2 * m->n_dof + m->n_feet;
+  for (int k = 0; k < n; k++) obs[k] = e->robot_state[k];
+  double s_ = e->distance_to_target * sin(e->angle_to_target);
+  double c_ = e->distance_to_target * cos(e->angle_to_target);
+  obs[n] = s_ / (1 + fabs(s_));
+  obs[n + 1] = c_ / (1 + fabs(c_));
+}
+
+void orc_w3d_reset(const orc_model* m, const orc_params* p, orc_w3d_env* e, double* obs) {
+  e->done = 0;
+  e->elapsed = 0;
+  w3d_randomize_target(e);
+  e->walk_target[0] = e->dist * cos(e->angle);
+  e->walk_target[1] = e->dist * sin(e->angle);
+  e->walk_target[2] = 1.0;
+  e->close_count = 0;
+  w3d_robot_reset(m, e, m->base_position);
+  w3d_calc_potential(e, p->dt * p->substeps);
+  w3d_obs(m, e, obs);
+}
+
+void orc_w3d_step(const orc_model* m, const orc_params* p, orc_w3d_env* e, const double* action, double* obs,
+                  double* reward, int* done, int* truncated) {
+  int A = m->n_dof;
+  double tau[ORC_MAXD];
+  /* robots.py:31-40 apply_action (applied_gain = 1 for Walker3DCustomEnv) */
+  for (int d = 0; d < A; d++) {
+    double a = action[d];
+    if (a > 1) a = 1;
+    if (a < -1) a = -1;
+    tau[d] = m->gain[d] * a;
+  }
+  int rows = 0;
+  orc_step_physics(m, p, &e->s, tau, NULL, 0, e->warm, &e->last_contacts, &rows);
+  e->rows_sum = rows;
+  if (e->eval_mode) { /* env_locomotion.py:115-116 uses the body_xyz of the previous calc_state */
+    e->walk_target[0] = e->body_xyz[0] + 4; e->walk_target[1] = 0; e->walk_target[2] = 1.0;
+  }
+  w3d_calc_state(m, e, &e->last_contacts);
+  /* calc_env_state (env_locomotion.py:204-222) */
+  int nstate = 6 + 2 * A + m->n_feet;
+  for (int k = 0; k < nstate; k++)
+    if (!isfinite(e->robot_state[k])) e->done = 1;
+  double old_lin = e->linear_potential;
+  w3d_calc_potential(e, p->dt * p->substeps);
+  e->progress = e->linear_potential - old_lin;
+  e->posture_penalty = 0;
+  double pitch = e->body_rpy[1], roll = e->body_rpy[0];
+  if (!(-0.2 < pitch && pitch < 0.4)) e->posture_penalty = fabs(pitch);
+  if (!(-0.4 < roll && roll < 0.4)) e->posture_penalty += fabs(roll);
+  double s1 = 0, s2 = 0;
+  for (int d = 0; d < A; d++) { s1 += fabs(action[d] * e->joint_speeds[d]); s2 += action[d] * action[d]; }
+  e->energy_penalty = 4.5 * (s1 / A) + 0.225 * (s2 / A);
+  e->joints_penalty = 0.1 * e->joints_at_limit;
+  e->tall_bonus = e->robot_state[0] > 0.7 ? 2.0 : -1.0;
+  if (e->tall_bonus < 0) e->done = 1;
+  e->target_bonus = 0;
+  if (e->distance_to_target < 0.15) { e->close_count++; e->target_bonus = 2; }
+  if (e->close_count >= e->stop_frames) {
+    e->close_count = 0;
+    w3d_randomize_target(e);
+    e->walk_target[0] += e->dist * cos(e->angle);
+    e->walk_target[1] += e->dist * sin(e->angle);
+    w3d_calc_potential(e, p->dt * p->substeps);
+  }
+  *reward = e->progress + e->target_bonus - e->energy_penalty + e->tall_bonus - e->posture_penalty - e->joints_penalty;
+  w3d_obs(m, e, obs);
+  /* gym TimeLimit(max_episode_steps=1000), reference mocca_envs/__init__.py:52-56 */
+  e->elapsed++;
+  *truncated = 0;
+  *done = e->done;
+  if (e->elapsed >= 1000) { *truncated = !e->done; *done = 1; }
+}
+
+void orc_w3d_step_batch(const orc_model* m, const orc_params* p, orc_w3d_env* envs, int n, const double* actions,
+                        double* obs, double* rewards, int* dones, int n_threads) {
+  int A = m->n_dof, O = 6 + 2 * A + m->n_feet + 2;
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+  for (int i = 0; i < n; i++) {
+    int trunc;
+    orc_w3d_step(m, p, &envs[i], actions + (size_t)i * A, obs + (size_t)i * O, &rewards[i], &dones[i], &trunc);
+    if (dones[i]) orc_w3d_reset(m, p, &envs[i], obs + (size_t)i * O);
+  }
+}
+
+int orc_sizeof_w3d_env(void) { return (int)sizeof(orc_w3d_env); }
+int orc_sizeof_model(void) { return (int)sizeof(orc_model); }

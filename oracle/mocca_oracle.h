@@ -1,0 +1,178 @@
+/*
+ * mocca_oracle.h -- CPU float64 restatement of the mocca_envs hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * PARITY UNPINNED: the arithmetic of the reference's hot path lives in the third-party `pybullet`
+ * C-extension (reference setup.py:11, un-pinned, not vendored, not installable here), reached through
+ * `stepSimulation` (reference mocca_envs/bullet_utils.py:352-353).  The reference ships no tests or golden
+ * vectors.  This file restates Bullet's published multibody pipeline (btMultiBody ABA,
+ * btMultiBodyConstraintSolver PGS, semi-implicit Euler) and the reference's Python
+ * env logic (robots.py, env_locomotion.py).  It is pinned against: NumPy RandomState streams (bit-exact),
+ * an independent Jacobian-based mass matrix, ID(FD(tau)) round trips and conservation laws
+ * (tests/test_oracle_*.py) -- NOT against PyBullet outputs.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
+ */
+#ifndef MOCCA_ORACLE_H
+#define MOCCA_ORACLE_H
+#include <stdint.h>
+
+#define ORC_MAXL 40   /* links (without base) */
+#define ORC_MAXD 40   /* joint dofs */
+#define ORC_MAXG 48   /* geoms */
+#define ORC_MAXP 96   /* candidate contact points (2 per geom) */
+#define ORC_MAXROW (3 * ORC_MAXP + 2 * ORC_MAXD)
+#define ORC_MAXU (6 + ORC_MAXD)
+#define ORC_MAXSTEPS 32 /* stepping stones / bars in a terrain table */
+
+enum { ORC_GEOM_SPHERE = 0, ORC_GEOM_CAPSULE = 1, ORC_GEOM_BOX = 2 };
+enum { ORC_JOINT_FIXED = 0, ORC_JOINT_REVOLUTE = 1 };
+
+typedef struct {
+  int n_links, n_dof, n_geoms, n_feet;
+  int parent[ORC_MAXL];      /* -1 = base */
+  int joint_type[ORC_MAXL];
+  int dof_of_link[ORC_MAXL]; /* -1 for fixed */
+  int link_of_dof[ORC_MAXD];
+  double axis[ORC_MAXL][3];     /* joint axis, link frame */
+  double rot_p2t[ORC_MAXL][4];  /* xyzw, parent->this at q=0 (Bullet zeroRotParentToThis) */
+  double e_vec[ORC_MAXL][3];    /* parent COM -> pivot, parent frame */
+  double d_vec[ORC_MAXL][3];    /* pivot -> COM, this frame */
+  double mass[ORC_MAXL];
+  double inertia[ORC_MAXL][3];
+  double base_mass;
+  double base_inertia[3];
+  double lower[ORC_MAXD], upper[ORC_MAXD], damping[ORC_MAXD], armature[ORC_MAXD], gain[ORC_MAXD];
+  double link_thresh[ORC_MAXL + 1]; /* contact breaking threshold; [0] = base, [i+1] = link i */
+  int link_group[ORC_MAXL + 1], link_mask[ORC_MAXL + 1];
+  int geom_link[ORC_MAXG];  /* -1 = base */
+  int geom_type[ORC_MAXG];
+  double geom_p0[ORC_MAXG][3], geom_p1[ORC_MAXG][3]; /* sphere centre / capsule ends, link frame */
+  double geom_quat[ORC_MAXG][4];
+  double geom_size[ORC_MAXG][3];
+  double geom_friction[ORC_MAXG];
+  int foot_link[4];
+  double base_joint_angles[ORC_MAXD];
+  double base_position[3];
+  int n_right, right_idx[ORC_MAXD], left_idx[ORC_MAXD]; /* mirroring tables robots.py:282-290 */
+  int n_neg, neg_idx[8];
+} orc_model;
+
+typedef struct {
+  double gravity;        /* 9.8   env_base.py:80 */
+  double dt;             /* 1/240 env_base.py:81 */
+  int substeps;          /* 4     bullet_utils.py:349 */
+  int iterations;        /* 5     bullet_utils.py:340 */
+  double erp_contact;    /* 0.9   bullet_utils.py:345 (m_erp2) */
+  double erp_joint;      /* 0.2   Bullet m_erp */
+  double linear_slop;    /* 1e-5  PyBullet createEmptyDynamicsWorld */
+  double lin_damping;    /* 0.04  btMultiBody m_linearDamping */
+  double ang_damping;    /* 0.04 */
+  double max_coord_vel;  /* 100   btMultiBody m_maxCoordinateVelocity */
+  double warmstart;      /* 0.1   PyBullet m_warmstartingFactor; 0 disables */
+  double limit_max_impulse; /* 100 btMultiBodyConstraint m_maxAppliedImpulse */
+  double split_threshold;   /* -0.04 m_splitImpulsePenetrationThreshold (limit rows) */
+  double residual_threshold; /* 1e-7 m_leastSquaresResidualThreshold */
+  int limit_rows_always;     /* 0: rows only when the limit is violated (Bullet >= 2.88) */
+  int gyro;                  /* 1 */
+  int has_ground;            /* 1: infinite plane z=0 (plane_stadium.sdf) */
+  double ground_friction;    /* 0.8 bullet_utils.py:371 */
+  int self_collision;        /* robots.py:260-264; 0 until SURVEY §8 f1 lands */
+} orc_params;
+
+typedef struct {
+  double pos[3];   /* base COM, world */
+  double quat[4];  /* xyzw, base orientation local->world (as PyBullet reports it) */
+  double omega[3]; /* world */
+  double vel[3];   /* world, base COM */
+  double q[ORC_MAXD];
+  double qd[ORC_MAXD];
+} orc_state;
+
+typedef struct {
+  int n;                  /* number of contact points this substep */
+  int point_id[ORC_MAXP]; /* candidate id: geom*2 + end */
+  int link[ORC_MAXP];     /* -1 = base */
+  int partner[ORC_MAXP];  /* 0 = ground plane, 1+k = box k (base), 100+k = box k cover */
+  double pos_a[ORC_MAXP][3];
+  double normal[ORC_MAXP][3]; /* on B, pointing towards A */
+  double dist[ORC_MAXP];
+  double friction[ORC_MAXP];
+  double erp[ORC_MAXP], cfm[ORC_MAXP]; /* per-contact (soft contacts on planks) */
+  double impulse[ORC_MAXP];            /* applied normal impulse after the solve */
+} orc_contacts;
+
+/* static box obstacle (plank base / cover), world frame */
+typedef struct {
+  double center[3];
+  double R[3][3]; /* box axes as columns */
+  double half[3];
+  double friction;
+  double stiffness, damping; /* <=0: rigid */
+  int id;                    /* partner code reported in orc_contacts */
+} orc_box;
+
+typedef struct {
+  uint32_t mt[624];
+  int pos;
+} orc_rng;
+
+/* ---- dynamics primitives (tests) ---- */
+void orc_default_params(orc_params* p);
+void orc_fk(const orc_model* m, const orc_state* s, double link_pos[][3], double link_rot[][9]);
+void orc_forward_dynamics(const orc_model* m, const orc_params* p, const orc_state* s, const double* tau,
+                          int with_damping, double* acc /* [6+n] */);
+void orc_rnea(const orc_model* m, const orc_state* s, const double* acc, double gravity, double* tau /* [6+n] */);
+void orc_mass_matrix(const orc_model* m, const orc_state* s, double* M /* [(6+n)^2] row-major */);
+void orc_minv_mult(const orc_model* m, const orc_params* p, const orc_state* s, const double* f, double* out);
+int orc_collide(const orc_model* m, const orc_params* p, const orc_state* s, const orc_box* boxes, int n_boxes,
+                orc_contacts* c);
+void orc_substep(const orc_model* m, const orc_params* p, orc_state* s, const double* tau, const orc_box* boxes,
+                 int n_boxes, double* warm /* [ORC_MAXP] */, orc_contacts* out_contacts, int* out_rows);
+void orc_step_physics(const orc_model* m, const orc_params* p, orc_state* s, const double* tau_applied,
+                      const orc_box* boxes, int n_boxes, double* warm, orc_contacts* last_contacts, int* rows_sum);
+void orc_energy_momentum(const orc_model* m, const orc_state* s, double gravity, double* out /* KE,PE,P[3],L[3] */);
+
+/* ---- RNG (NumPy legacy RandomState compatible) ---- */
+void orc_rng_seed_array(orc_rng* r, const uint32_t* key, int len);
+uint32_t orc_rng_u32(orc_rng* r);
+double orc_rng_double(orc_rng* r);
+double orc_rng_uniform(orc_rng* r, double lo, double hi);
+
+/* ---- Walker3DCustomEnv (env_locomotion.py:37-282) ---- */
+typedef struct {
+  orc_state s;
+  double warm[ORC_MAXP];
+  /* robot (robots.py:13-227) */
+  double feet_contact[4];
+  double feet_xyz[4][3];
+  double body_xyz[3], body_rpy[3], body_vel[3];
+  double joint_speeds[ORC_MAXD];
+  int joints_at_limit;
+  int mirrored;
+  double robot_state[6 + 2 * ORC_MAXD + 4];
+  /* env */
+  double dist, angle, stop_frames;
+  double walk_target[3];
+  int close_count;
+  double linear_potential, angular_potential, distance_to_target, angle_to_target;
+  int done;
+  int eval_mode;
+  int elapsed;  /* gym TimeLimit counter (__init__.py:55) */
+  double progress, posture_penalty, energy_penalty, joints_penalty, tall_bonus, target_bonus;
+  orc_rng env_rng, robot_rng;
+  int rng_aliased; /* env_base.py:93 quirk Q1: robot draws from the env stream until seed() rebinds */
+  double rows_sum; /* diagnostics: constraint rows over the last step */
+  orc_contacts last_contacts;
+} orc_w3d_env;
+
+void orc_w3d_seed(orc_w3d_env* e, const uint32_t* key, int len, int at_construction);
+void orc_w3d_reset(const orc_model* m, const orc_params* p, orc_w3d_env* e, double* obs /* [52] */);
+void orc_w3d_step(const orc_model* m, const orc_params* p, orc_w3d_env* e, const double* action, double* obs,
+                  double* reward, int* done, int* truncated);
+/* batched convenience for the CPU baseline: n independent envs, OpenMP over envs, auto-reset on done */
+void orc_w3d_step_batch(const orc_model* m, const orc_params* p, orc_w3d_env* envs, int n, const double* actions,
+                        double* obs, double* rewards, int* dones, int n_threads);
+int orc_sizeof_w3d_env(void);
+int orc_sizeof_model(void);
+
+#endif

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Regenerate the committed model tables from the reference's data files.
+
+Reads  /root/reference/mocca_envs/data/robots/*.xml  (only available in the build container)
+Writes mocca_envs_b200/models/<robot>.json            (committed; what the GPU box uses)
+       mocca_envs_b200/csrc/generated/<robot>_model.h (committed; compile-time tables for the CUDA kernels)
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from mocca_envs_b200 import model_compiler as mc  # noqa: E402
+
+
+def main(data_dir="/root/reference/mocca_envs/data"):
+    out = os.path.join(os.path.dirname(HERE), "mocca_envs_b200", "models")
+    os.makedirs(out, exist_ok=True)
+    w = mc.compile_walker3d(data_dir)
+    mc.save_table(w, os.path.join(out, "walker3d.json"))
+    m = mc.compile_monkey3d(data_dir)
+    mc.save_table(m, os.path.join(out, "monkey3d.json"))
+    try:
+        from mocca_envs_b200 import codegen
+        codegen.emit_all(os.path.dirname(HERE))
+    except ImportError:
+        pass
+    print("walker3d: links=%d dof=%d mass=%.3f" % (w["n_links"], w["n_dof"], w["total_mass"]))
+    print("monkey3d: links=%d dof=%d mass=%.3f" % (m["n_links"], m["n_dof"], m["total_mass"]))
+
+
+if __name__ == "__main__":
+    main(*sys.argv[1:])
