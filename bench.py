@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched Walker3DCustomEnv-v0 hot path (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--actions random|pd] [--impl reference]
+
+One "step" = one fused kernel launch stepping E envs per GPU through one control step (4 Bullet substeps +
+obs/reward/done/auto-reset).  Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "Walker3DCustomEnv-v0 batched 16384 envs/GPU, flat ground"
+METRIC = "env-steps/sec (Walker3DCustomEnv-v0, 16384 envs/GPU, random actions)"
+
+
+def flops_per_env_step(rows_per_substep, S=4, n=27, L=17, G=22, I=5):
+    """F = S*[60L + 430n + 30G + R*150n + I*R*(4n+10) + 20n] + 1000."""
+    R = rows_per_substep
+    return S * (60 * L + 430 * n + 30 * G + R * 150 * n + I * R * (4 * n + 10) + 20 * n) + 1000
+
+
+def bytes_per_env_step(S_state=55, A=21, O=52, S_env=12):
+    """B = 4*(2*S_state + A + O + 2*S_env) + 6."""
+    return 4 * (2 * S_state + A + O + 2 * S_env) + 6
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower() == "active":
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(n_envs, steps, warmup, threads, time_budget=None):
+    """The reference-side CPU implementation of the path: the float64 oracle port (oracle/mocca_oracle.c; the
+    reference's own arithmetic is the un-installable third-party pybullet), OpenMP over envs."""
+    import ctypes as C
+
+    import numpy as np
+
+    from mocca_envs_b200.model_compiler import load_table
+    from oracle import oracle as O
+
+    t = load_table(os.path.join(ROOT, "mocca_envs_b200", "models", "walker3d.json"))
+    m = O.model_from_table(t)
+    p = O.default_params()
+    L = O.lib()
+    envs = (O.W3DEnv * n_envs)()
+    A, OB = 21, 52
+    obs = np.zeros((n_envs, OB))
+    for i in range(n_envs):
+        words = O.gym_seed_words(1000 + i)
+        key = (C.c_uint32 * len(words))(*words)
+        L.orc_w3d_seed(C.byref(envs[i]), key, len(words), 1)
+        L.orc_w3d_reset(C.byref(m), C.byref(p), C.byref(envs[i]), obs[i].ctypes.data_as(C.c_void_p))
+    rew = np.zeros(n_envs)
+    done = np.zeros(n_envs, dtype=np.int32)
+    rng = np.random.RandomState(1)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def one():
+        a = rng.uniform(-1, 1, (n_envs, A))
+        L.orc_w3d_step_batch(C.byref(m), C.byref(p), envs, n_envs, vp(a), vp(obs), vp(rew), vp(done), threads)
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    done_steps = 0
+    for _ in range(steps):
+        one()
+        done_steps += 1
+        if time_budget and time.perf_counter() - t0 > time_budget:
+            break
+    dt = time.perf_counter() - t0
+    return n_envs * done_steps / dt, dt, done_steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--envs", type=int, default=16384, help="envs per GPU")
+    ap.add_argument("--actions", default="random", choices=["random", "pd"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample_envs = 2048
+        v, dt, ks = cpu_reference_run(sample_envs, args.steps, max(args.warmup, 1), cores)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": ks, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(ks, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs, "actions": "random-uniform U(-1,1)^21"},
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                             "sample": "%d envs x %d control steps per step-sample, OpenMP over envs; float64 oracle "
+                                       "port (PyBullet itself is not installable: no wheel, no network)" % (sample_envs, ks)},
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+
+    from mocca_envs_b200 import _lib
+    from mocca_envs_b200.vec_env import Walker3DCustomVecEnv
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    N, K, W = args.envs, args.steps, max(args.warmup, 3)
+    # env i of rank r is global env r*N + i: seeds are independent of the GPU count
+    env = Walker3DCustomVecEnv(N, device=dev, seed=1234 + rank * N)
+    env.reset()
+    A = env.act_dim
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pool = 64
+    act_pool = torch.rand(pool, N, A, device=dev, generator=gen) * 2 - 1
+    q_ref = torch.tensor(env.table["base_joint_angles"], device=dev, dtype=torch.float32)
+    lo = torch.tensor(env.table["lower"], device=dev, dtype=torch.float32)
+    hi = torch.tensor(env.table["upper"], device=dev, dtype=torch.float32)
+    ref_norm = 2 * (q_ref - lo) / (hi - lo) - 1
+
+    def action(i, obs):
+        if args.actions == "random":
+            return act_pool[i % pool]
+        # scripted PD toward the running_start pose in normalised units (kp=1, kd=0.1)
+        return torch.clamp(1.0 * (ref_norm - obs[:, 6:6 + A]) - 0.1 * (obs[:, 6 + A:6 + 2 * A] * 10.0), -1, 1)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    obs = env.obs
+    for i in range(W):
+        obs, _, _, _ = env.step(action(i, obs))
+    torch.cuda.synchronize(dev)
+    rec0 = env.get_record()
+    rows0 = float(rec0[:, 15].double().sum())
+    cont0 = float(rec0[:, 16].double().sum())
+    env.stats(reset=True)
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    if rank == 0:
+        sampler.start()
+    launches0 = env.launch_count()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    wall0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()  # evict L2 between timed steps (not inside the event pair)
+        a = action(W + i, obs)
+        evs[i][0].record()
+        obs, rew, done, info = env.step(a)
+        evs[i][1].record()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - wall0
+    launches = env.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    rec1 = env.get_record()
+    rows = float(rec1[:, 15].double().sum()) - rows0
+    conts = float(rec1[:, 16].double().sum()) - cont0
+    st = env.stats()
+    # the path's only collective: all-reduce of episode statistics over NCCL
+    stat_vec = torch.tensor([st["episodes"], st["return_sum"], st["length_sum"], st["nonfinite"], st["overflow"],
+                             rows, conts], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(stat_vec, op=dist.ReduceOp.SUM)
+    episodes, ret_sum, len_sum, nonfinite, overflow, rows_all, conts_all = [float(x) for x in stat_vec.tolist()]
+
+    # ---- e2e: same step through the host-buffer C-ABI entry point (pinned host memory, H2D + D2H in the timed region)
+    Ke = max(10, min(K, 100))
+    h_act = torch.empty(N, A, dtype=torch.float32).pin_memory()
+    h_act.copy_(act_pool[0].cpu())
+    h_obs = torch.empty(N, env.obs_dim, dtype=torch.float32).pin_memory()
+    h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(N, dtype=torch.uint8).pin_memory()
+    h_trunc = torch.empty(N, dtype=torch.uint8).pin_memory()
+    outs = (h_obs.numpy(), h_rew.numpy(), h_done.numpy(), h_trunc.numpy())
+    h_act_np = h_act.numpy()
+    for _ in range(3):
+        env.step_host(h_act_np, outs)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        env.step_host(h_act_np, outs)  # returns after the D2H copies completed (stream synchronised inside)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = N * world * Ke / float(te.item())
+    h2d = N * A * 4
+    d2h = N * (env.obs_dim * 4 + 4 + 1 + 1)
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = total_ms_max / K
+    value = N * world * K / (total_ms_max * 1e-3)
+    R_mean = rows_all / (K * N * world * env.physics.substeps)
+    F = flops_per_env_step(R_mean)
+    kernel_s = (total_ms / K) * 1e-3  # this rank's average launch duration (one kernel per step)
+    achieved_tf = F * N / kernel_s / 1e12
+    peak = C_peak(_lib, local_rank)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_ach = bytes_per_env_step() * N / kernel_s / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "envs_per_gpu": N, "actions": "random-uniform U(-1,1)^21 (device pool)"
+                   if args.actions == "random" else "scripted PD toward running_start (kp=1, kd=0.1, normalised)",
+                   "frame_skip": 4, "solver_iterations": 5, "rng": "mt19937 (NumPy-compatible)",
+                   "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs)",
+                   "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks",
+                   "parallelism": "env-sharded x%d, no data-path collective" % world},
+        "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved_tf / peak if peak else None, "traffic": None,
+                     "peak_source": "FP32 FMA probe kernel measured in this run (mb200_measure_fp32_peak)",
+                     "flops_per_env_step": F, "rows_per_substep": R_mean,
+                     "contacts_per_substep": conts_all / (K * N * world * env.physics.substeps),
+                     "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                             "bytes_per_env_step": bytes_per_env_step(),
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": Ke, "api": "mb200_step_host (pinned host buffers, stream-synchronised)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "episodes": {"finished": episodes, "mean_return": ret_sum / episodes if episodes else None,
+                     "mean_length": len_sum / episodes if episodes else None, "nonfinite": nonfinite,
+                     "cap_overflows": overflow, "reduced_with": "nccl all_reduce" if dist else "single rank"},
+        "wall_s": wall,
+    }
+    if not args.no_cpu_baseline:
+        v, dt, ks = cpu_reference_run(1024, 1000, 2, cores, time_budget=12.0)
+        line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                "sample": "1024 envs x %d control steps (%.1f s), same action distribution; float64 "
+                                          "oracle port with OpenMP over envs (PyBullet not installable here)" % (ks, dt)}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+def C_peak(_lib, device):
+    import ctypes as C
+
+    out = C.c_double(0.0)
+    _lib.check(_lib.lib().mb200_measure_fp32_peak(device, C.byref(out)))
+    return out.value
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,113 @@
+/*
+ * mocca_b200.h -- C ABI of libmocca_b200.so, the B200-native batched replacement for the mocca_envs hot path.
+ *
+ * The reference has no FFI of its own for this path: its "plugin API" is the gym.Env protocol implemented by
+ * EnvBase subclasses, and all arithmetic is reached through pybullet.  Every entry point
+ * below cites the reference interface it replaces.  Conventions:
+ *   - plain pointers and sizes only; *_dev pointers are DEVICE pointers owned by the caller (e.g. torch tensors),
+ *     *_host pointers are host memory; the library owns only the opaque handle and its internal state arrays;
+ *   - row-major [n_envs, dim] float32 at the boundary;
+ *   - return 0 on success, negative on error, message via mb200_last_error(); no exceptions cross the ABI;
+ *   - asynchronous on the given cudaStream_t (passed as void*; NULL = default stream) unless stated;
+ *   - no CPU fallback: mb200_create fails unless the device is compute capability 10.x (sm_100a code only).
+ */
+#ifndef MOCCA_B200_H
+#define MOCCA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mb200_env mb200_env;
+
+/* Physics constants of the reference's Bullet world; mb200_default_physics() fills the reference values. */
+typedef struct mb200_physics {
+  float dt;                 /* 1/240  env_base.py:81 (control_step / llc_frame_skip / sim_frame_skip)      */
+  int substeps;             /* 4      bullet_utils.py:346-350 numSubSteps = frame_skip                     */
+  int iterations;           /* 5      bullet_utils.py:340 numSolverIterations                             */
+  float gravity;            /* 9.8    env_base.py:80, bullet_utils.py:344                                 */
+  float erp_contact;        /* 0.9    bullet_utils.py:345 setDefaultContactERP                            */
+  float erp_joint;          /* 0.2    Bullet m_erp (joint-limit rows)                                     */
+  float linear_slop;        /* 1e-5   PyBullet world default                                              */
+  float lin_damping;        /* 0.04   btMultiBody default linear damping                                  */
+  float ang_damping;        /* 0.04   btMultiBody default angular damping                                 */
+  float max_coord_vel;      /* 100    btMultiBody m_maxCoordinateVelocity                                 */
+  float limit_max_impulse;  /* 100    btMultiBodyConstraint m_maxAppliedImpulse                           */
+  float split_threshold;    /* -0.04  m_splitImpulsePenetrationThreshold (limit rows)                     */
+  float residual_threshold; /* 1e-7   m_leastSquaresResidualThreshold (PGS early exit)                    */
+  float ground_friction;    /* 0.8    bullet_utils.py:371 changeDynamics(lateralFriction=0.8)             */
+  int has_ground;           /* 1      bullet_utils.py:361-371 plane_stadium.sdf (0 = remove_ground)       */
+} mb200_physics;
+
+void mb200_default_physics(mb200_physics* p);
+
+/* gym.make("mocca_envs:<env_id>") x n_envs  (reference mocca_envs/__init__.py:18-116, env_base.py:16-42).
+ * env_id: "Walker3DCustomEnv-v0".  physics may be NULL (reference values). */
+int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics* physics, mb200_env** out);
+/* EnvBase.close (env_base.py:44-47) */
+void mb200_destroy(mb200_env* env);
+
+/* observation_space.shape[0], action_space.shape[0] (robots.py:22-29, env_locomotion.py:58-60); state_dim is the
+ * width of the get/set_state vector [pos3 quat4(xyzw) omega3 vel3 q qd]; nu = 6 + action dim. */
+int mb200_dims(const mb200_env* env, int* n_envs, int* obs_dim, int* act_dim, int* state_dim, int* nu);
+
+/* EnvBase.seed (env_base.py:164-166): mt_host is [n_envs][625] uint32 -- the 624 MT19937 key words of
+ * numpy.random.RandomState(gym_seed_words(seed_i)) followed by its position (624).  at_construction != 0 also
+ * binds the robot's stream to the env's (env_base.py:93); later calls rebind only the env stream (quirk Q1).
+ * Synchronous. */
+int mb200_seed(mb200_env* env, const uint32_t* mt_host, int at_construction);
+
+/* Env.reset (env_locomotion.py:79-109) for every env whose mask byte is non-zero (mask_dev NULL = all). */
+int mb200_reset(mb200_env* env, const uint8_t* mask_dev, float* obs_dev, void* stream);
+
+/* Env.step (env_locomotion.py:111-141) for all envs, fused with gym TimeLimit and VecEnv auto-reset:
+ * where done is set, obs is the first observation of the next episode and, if final_obs_dev is not NULL, the
+ * terminal observation is written there.  trunc = info["TimeLimit.truncated"]. */
+int mb200_step(mb200_env* env, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev,
+               uint8_t* trunc_dev, float* final_obs_dev, void* stream);
+
+/* Same call with HOST buffers (what a gym/SubprocVecEnv user holds): H2D of the actions, the step kernel,
+ * D2H of obs/reward/done/trunc, then a stream synchronise.  Pinned host memory makes the copies asynchronous. */
+int mb200_step_host(mb200_env* env, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host,
+                    uint8_t* trunc_host, void* stream);
+
+/* resetJointState / resetBasePositionAndOrientation / resetBaseVelocity and the matching getters
+ * (robots.py:212-216, bullet_utils.py:100-146,157-175): rows are [pos3 quat4 omega3 vel3 q[A] qd[A]]. */
+int mb200_get_state(mb200_env* env, float* state_dev, void* stream);
+int mb200_set_state(mb200_env* env, const float* state_dev, void* stream);
+/* per-env bookkeeping record (walk_target, potentials, counters ...), 32 x 4-byte words per env, see ER_* in
+ * csrc/mb_env.cuh; used by tests and checkpointing. */
+int mb200_get_record(mb200_env* env, float* rec_dev, void* stream);
+int mb200_set_record(mb200_env* env, const float* rec_dev, void* stream);
+
+/* stepSimulation only (bullet_utils.py:352-353): hold tau_dev [n][A] over `substeps` substeps, no env logic.
+ * Outputs per env: rows_dev (constraint rows summed over the substeps) and contacts_dev (contact points of the
+ * last substep); either may be NULL. */
+int mb200_step_physics(mb200_env* env, const float* tau_dev, int* rows_dev, int* contacts_dev, void* stream);
+
+/* pybullet.calculateMassMatrix / calculateInverseDynamics analogues at the current state, in PyBullet's
+ * generalised coordinates u = [omega_world, v_world, qd]:  M_dev [n][nu][nu];  tau = M acc + C + G, [n][nu]. */
+int mb200_mass_matrix(mb200_env* env, float* M_dev, void* stream);
+int mb200_inverse_dynamics(mb200_env* env, const float* acc_dev, float* tau_dev, void* stream);
+
+/* EnvBase.set_env_params analogue (env_base.py:103-106): "eval_mode" (env_locomotion.py:76-77). */
+int mb200_set_param(mb200_env* env, const char* key, float value);
+
+/* Episode statistics accumulated on the device since the last call with reset != 0 (synchronous):
+ * out = {episodes, sum_return, sum_length, nonfinite_events, cap_overflows, 0, 0, 0}. */
+int mb200_stats(mb200_env* env, double out[8], int reset);
+
+/* number of kernel launches issued through this handle (bench.py's gpu_launches) */
+long long mb200_launch_count(const mb200_env* env);
+
+/* FP32 FMA throughput of `device` in TFLOP/s (synchronous probe kernel, ~10 ms): the measured denominator of the
+ * CUDA-core roofline bench.py reports for this path. */
+int mb200_measure_fp32_peak(int device, double* tflops_out);
+
+const char* mb200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,14 @@
+"""mocca_envs_b200 -- B200-native batched replacement for the mocca_envs hot path.
+
+Public surface mirrors the reference's: ``make(env_id)`` (gym.make analogue, reference mocca_envs/__init__.py),
+gym-style ``reset/step/seed`` plus a batched VecEnv returning torch CUDA tensors.
+"""
+ENV_IDS = ["Walker3DCustomEnv-v0"]
+
+
+def __getattr__(name):
+    if name in ("make", "Walker3DCustomVecEnv", "Walker3DCustomEnv"):
+        from . import vec_env
+
+        return getattr(vec_env, name)
+    raise AttributeError(name)

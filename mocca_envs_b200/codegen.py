@@ -1,0 +1,203 @@
+"""Reduce a Bullet-convention model table (model_compiler.py) to the kernel's articulation tables and emit
+them as a C header (``csrc/generated/<robot>_model.h``) consumed by the CUDA kernels.
+
+Kernel-side representation (all constant, derived at q = 0):
+
+* joints j = 0..NJ-1  : the revolute links in PyBullet joint order (== action order, robots.py:163-172).
+  ``jparent`` (-1 = base), the joint frame's pose in its parent joint frame (``joff``, ``jrot``), the axis.
+  Frames sit at the joint pivots; fixed links between revolute links are folded into these constants.
+* bodies b = 0..NB-1  : every Bullet link with mass (base first, DFS order) attached to its owner joint frame:
+  COM offset, inertia (symmetric 3x3 in owner axes), mass.  Kept un-merged because Bullet's velocity damping is
+  per link and non-linear in |v|.
+* points              : contact candidates -- sphere centres and both capsule end-sphere centres.
+* generalised coordinates u = [omega_world, v_baseCOM_world, qd] (PyBullet/btMultiBody order), NU = 6 + NJ.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from .model_compiler import JOINT_REVOLUTE, GEOM_SPHERE, GEOM_CAPSULE, load_table, quat_to_mat
+
+
+def reduce_table(t: dict) -> dict:
+    nl = t["n_links"]
+    parent = t["parent"]
+    # pose of every Bullet link COM frame in the base frame at q = 0
+    Rl = [np.eye(3)] * (nl + 1)
+    pl = [np.zeros(3)] * (nl + 1)
+    piv = [np.zeros(3)] * (nl + 1)
+    for i in range(nl):
+        Rz = quat_to_mat(t["rot_parent_to_this"][i])  # parent -> this
+        p = parent[i] + 1
+        Rl[i + 1] = Rl[p] @ Rz.T
+        piv[i + 1] = pl[p] + Rl[p] @ np.array(t["e_vec"][i])
+        pl[i + 1] = piv[i + 1] + Rl[i + 1] @ np.array(t["d_vec"][i])
+
+    jlink = [i for i in range(nl) if t["joint_type"][i] == JOINT_REVOLUTE]
+    nj = len(jlink)
+    joint_of_link = {l: j for j, l in enumerate(jlink)}
+
+    def owner_joint(link):  # nearest revolute ancestor-or-self, -1 = base
+        l = link
+        while l >= 0:
+            if l in joint_of_link:
+                return joint_of_link[l]
+            l = parent[l]
+        return -1
+
+    def frame(j):  # joint frame (origin at pivot, link axes) in base coords at q = 0
+        if j < 0:
+            return np.eye(3), np.zeros(3)
+        return Rl[jlink[j] + 1], piv[jlink[j] + 1]
+
+    jparent, joff, jrot, jaxis, jlevel, janc = [], [], [], [], [], []
+    for j, l in enumerate(jlink):
+        pj = owner_joint(parent[l])
+        Rp, op = frame(pj)
+        Rj, oj = frame(j)
+        jparent.append(pj)
+        joff.append(Rp.T @ (oj - op))
+        jrot.append(Rp.T @ Rj)
+        jaxis.append(np.array(t["axis"][l]))
+        jlevel.append(0 if pj < 0 else jlevel[pj] + 1)
+        janc.append((1 << j) | (0 if pj < 0 else janc[pj]))
+
+    bodies = []
+    masses = [t["base"]["mass"]] + t["mass"]
+    inertias = [t["base"]["inertia"]] + t["inertia"]
+    names = [t["base"]["name"]] + t["link_names"]
+    for li in range(nl + 1):
+        if masses[li] <= 0:
+            continue
+        link = li - 1
+        oj = owner_joint(link) if link >= 0 else -1
+        Ro, oo = frame(oj)
+        Rrel = Ro.T @ Rl[li]
+        I = Rrel @ np.diag(inertias[li]) @ Rrel.T
+        bodies.append(dict(name=names[li], link=link, owner=oj, com=Ro.T @ (pl[li] - oo), mass=masses[li],
+                           inertia=[I[0, 0], I[1, 1], I[2, 2], I[0, 1], I[0, 2], I[1, 2]]))
+    nb = len(bodies)
+    # subtree body ranges (bodies are in DFS order -> contiguous)
+    bstart, bend = [], []
+    for j in range(nj):
+        idx = [k for k, b in enumerate(bodies) if b["owner"] >= 0 and (janc[b["owner"]] >> j) & 1]
+        assert idx == list(range(idx[0], idx[-1] + 1)), "subtree bodies must be contiguous"
+        bstart.append(idx[0])
+        bend.append(idx[-1] + 1)
+
+    thresh = [t["base"]["contact_threshold"]] + t["contact_threshold"]
+    foot_links = t["foot_links"]
+    points = []
+    for gi, g in enumerate(t["geoms"]):
+        if g["type"] not in (GEOM_SPHERE, GEOM_CAPSULE):
+            continue
+        link = g["link"]
+        oj = owner_joint(link) if link >= 0 else -1
+        Ro, oo = frame(oj)
+        ends = [g["p0"]] if g["type"] == GEOM_SPHERE else [g["p0"], g["p1"]]
+        for e, pe in enumerate(ends):
+            pw = pl[link + 1] + Rl[link + 1] @ np.array(pe)
+            points.append(dict(geom=gi, end=e, link=link, owner=oj, pos=Ro.T @ (pw - oo), radius=g["size"][0],
+                               friction=g["friction"], thresh=thresh[link + 1],
+                               foot=foot_links.index(link) if link in foot_links else -1))
+    foot_body = [[b["link"] for b in bodies].index(f) for f in foot_links]
+    return dict(name=t["name"], nj=nj, nb=nb, nu=6 + nj, npt=len(points), nlevel=max(jlevel) + 1,
+                jparent=jparent, joff=joff, jrot=jrot, jaxis=jaxis, jlevel=jlevel, janc=janc,
+                lower=t["lower"], upper=t["upper"], gain=t["gain"], damping=t["damping"], armature=t["armature"],
+                bodies=bodies, bstart=bstart, bend=bend, points=points, foot_body=foot_body,
+                nfeet=len(foot_links), base_joint_angles=t["base_joint_angles"], base_position=t["base_position"],
+                right=t["right_joint_indices"], left=t["left_joint_indices"], neg=t["negation_joint_indices"])
+
+
+def _f(v) -> str:
+    s = "%.9g" % float(v)
+    if "." not in s and "e" not in s and "n" not in s:
+        s += ".0"
+    return s + "f"
+
+
+def _farr(name, rows, width=None):
+    rows = np.asarray(rows, dtype=np.float64)
+    if rows.ndim == 1:
+        body = ", ".join(_f(v) for v in rows)
+        return "MB_TABLE float %s[%d] = {%s};\n" % (name, len(rows), body)
+    body = ",\n  ".join("{" + ", ".join(_f(v) for v in r) + "}" for r in rows)
+    return "MB_TABLE float %s[%d][%d] = {\n  %s};\n" % (name, rows.shape[0], rows.shape[1], body)
+
+
+def _darr(name, vals):
+    return "MB_TABLE double %s[%d] = {%s};\n" % (name, len(vals), ", ".join("%.17g" % float(v) for v in vals))
+
+
+def _iarr(name, vals, ctype="int"):
+    fmt = "%du" if ctype == "unsigned" else "%d"
+    return "MB_TABLE %s %s[%d] = {%s};\n" % (ctype, name, len(vals), ", ".join(fmt % v for v in vals))
+
+
+def emit_header(t: dict, prefix: str) -> str:
+    r = reduce_table(t)
+    P = prefix
+    out = []
+    out.append("// GENERATED by mocca_envs_b200/codegen.py from mocca_envs_b200/models/%s.json -- do not edit.\n" % r["name"])
+    out.append("// Source model: reference mocca_envs/%s (loaded at mocca_envs/robots.py:101-105).\n" % t["source"])
+    out.append("#pragma once\n#include \"../mb_tables.h\"\n\n")
+    out.append(_iarr(P + "_jparent", r["jparent"]))
+    out.append(_iarr(P + "_jlevel", r["jlevel"]))
+    out.append(_iarr(P + "_janc", r["janc"], "unsigned"))
+    out.append(_farr(P + "_joff", r["joff"]))
+    out.append(_farr(P + "_jrot", [np.asarray(m).reshape(9) for m in r["jrot"]]))
+    out.append(_farr(P + "_jaxis", r["jaxis"]))
+    # float32 limits exactly as robots.py:126-130 builds them (weight = f32(upper - lower), bias = f32(lower))
+    out.append(_farr(P + "_lower", r["lower"]))
+    out.append(_farr(P + "_upper", r["upper"]))
+    out.append(_farr(P + "_weight", [np.float32(u - l) for u, l in zip(r["upper"], r["lower"])]))
+    out.append(_farr(P + "_gain", r["gain"]))
+    out.append(_farr(P + "_damping", r["damping"]))
+    out.append(_farr(P + "_armature", r["armature"]))
+    out.append(_iarr(P + "_bstart", r["bstart"]))
+    out.append(_iarr(P + "_bend", r["bend"]))
+    out.append(_iarr(P + "_bowner", [b["owner"] for b in r["bodies"]]))
+    out.append(_farr(P + "_bcom", [b["com"] for b in r["bodies"]]))
+    out.append(_farr(P + "_bmass", [b["mass"] for b in r["bodies"]]))
+    out.append(_farr(P + "_binertia", [b["inertia"] for b in r["bodies"]]))
+    out.append(_iarr(P + "_powner", [p["owner"] for p in r["points"]]))
+    out.append(_iarr(P + "_pfoot", [p["foot"] for p in r["points"]]))
+    out.append(_iarr(P + "_pid", [2 * p["geom"] + p["end"] for p in r["points"]]))
+    out.append(_farr(P + "_ppos", [p["pos"] for p in r["points"]]))
+    out.append(_farr(P + "_pradius", [p["radius"] for p in r["points"]]))
+    out.append(_farr(P + "_pfriction", [p["friction"] for p in r["points"]]))
+    out.append(_farr(P + "_pthresh", [p["thresh"] for p in r["points"]]))
+    out.append(_iarr(P + "_foot_body", r["foot_body"]))
+    out.append(_darr(P + "_base_angles", r["base_joint_angles"]))
+    out.append(_iarr(P + "_right", r["right"]))
+    out.append(_iarr(P + "_left", r["left"]))
+    out.append(_iarr(P + "_neg", r["neg"]))
+    out.append("\nstruct %s_Model {\n" % P)
+    out.append("  enum { NJ = %d, NB = %d, NU = %d, NPT = %d, NLEVEL = %d, NFEET = %d, NMIRROR = %d, NNEG = %d };\n"
+               % (r["nj"], r["nb"], r["nu"], r["npt"], r["nlevel"], r["nfeet"], len(r["right"]), len(r["neg"])))
+    for fld, ctype in [("jparent", "int"), ("jlevel", "int"), ("janc", "unsigned"), ("bstart", "int"), ("bend", "int"),
+                       ("bowner", "int"), ("powner", "int"), ("pfoot", "int"), ("pid", "int"), ("foot_body", "int"),
+                       ("right", "int"), ("left", "int"), ("neg", "int")]:
+        out.append("  MB_HD static %s %s(int i) { return %s_%s[i]; }\n" % (ctype, fld, P, fld))
+    out.append("  MB_HD static double base_angles(int i) { return %s_base_angles[i]; }\n" % P)
+    for fld in ["lower", "upper", "weight", "gain", "damping", "armature", "bmass", "pradius", "pfriction", "pthresh"]:
+        out.append("  MB_HD static float %s(int i) { return %s_%s[i]; }\n" % (fld, P, fld))
+    for fld in ["joff", "jrot", "jaxis", "bcom", "binertia", "ppos"]:
+        out.append("  MB_HD static float %s(int i, int k) { return %s_%s[i][k]; }\n" % (fld, P, fld))
+    out.append("  MB_HD static float base_x() { return %s; }\n" % _f(r["base_position"][0]))
+    out.append("  MB_HD static float base_y() { return %s; }\n" % _f(r["base_position"][1]))
+    out.append("  MB_HD static float base_z() { return %s; }\n" % _f(r["base_position"][2]))
+    out.append("};\n")
+    return "".join(out)
+
+
+def emit_all(repo_root: str):
+    gen = os.path.join(repo_root, "mocca_envs_b200", "csrc", "generated")
+    os.makedirs(gen, exist_ok=True)
+    models = os.path.join(repo_root, "mocca_envs_b200", "models")
+    for name, prefix in (("walker3d", "W3D"),):
+        t = load_table(os.path.join(models, name + ".json"))
+        with open(os.path.join(gen, name + "_model.h"), "w") as f:
+            f.write(emit_header(t, prefix))

@@ -1,0 +1,469 @@
+// mb200.cu -- sm_100a kernels + the C ABI declared in include/mocca_b200.h.
+// One warp per environment, MB_WARPS warps per CTA; per-env working set lives in shared memory (WarpMem).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/mocca_b200.h"
+#include "generated/walker3d_model.h"
+#include "mb_env.cuh"
+
+#define MB_WARPS 4
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return -1; }
+#define CUDA_OK(x)                                                                                       \
+  do {                                                                                                   \
+    cudaError_t e_ = (x);                                                                                \
+    if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_));                 \
+  } while (0)
+
+struct mb200_env {
+  int n, device;
+  int obs_dim, act_dim, state_dim, nu;
+  MbPhysics phys;
+  float* state;     // [n][MB_STATE_STRIDE]
+  float* rec;       // [n][MB_REC_STRIDE]
+  uint32_t* mt;     // [n][2][MB_MT_STRIDE]
+  MbStats* stats;   // device
+  float* stage_act; // device staging for the host-buffer entry point
+  float* stage_obs;
+  float* stage_rew;
+  uint8_t* stage_done;
+  uint8_t* stage_trunc;
+  long long launches;
+  size_t smem;
+};
+
+typedef W3D_Model WM;
+typedef W3DEnv<WM> WEnv;
+typedef WarpMem<WM> WMem;
+
+// ------------------------------------------------------------------------------------------------ kernels
+struct StepArgs {
+  int n;
+  MbPhysics phys;
+  float* state;
+  float* rec;
+  uint32_t* mt;
+  const float* act;
+  float* obs;
+  float* rew;
+  uint8_t* done;
+  uint8_t* trunc;
+  float* final_obs;
+  MbStats* stats;
+};
+
+__global__ void __launch_bounds__(MB_WARPS * 32) k_step_walker3d_custom(StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * MB_WARPS + warp;
+  if (env >= a.n) return;
+  WMem& S = reinterpret_cast<WMem*>(smem_raw)[warp];
+  WEnv::step(S, a.phys, a.state + (size_t)env * MB_STATE_STRIDE, a.rec + (size_t)env * MB_REC_STRIDE,
+             a.mt + (size_t)env * 2 * MB_MT_STRIDE, a.mt + ((size_t)env * 2 + 1) * MB_MT_STRIDE,
+             a.act + (size_t)env * WM::NJ, a.obs + (size_t)env * WEnv::OBS, a.rew + env, a.done + env, a.trunc + env,
+             a.final_obs ? a.final_obs + (size_t)env * WEnv::OBS : nullptr, a.stats);
+}
+
+__global__ void __launch_bounds__(MB_WARPS * 32)
+    k_reset_walker3d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
+                            float* obs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * MB_WARPS + warp;
+  if (env >= n) return;
+  if (mask && !mask[env]) return;
+  WMem& S = reinterpret_cast<WMem*>(smem_raw)[warp];
+  WEnv::reset(S, phys, rec + (size_t)env * MB_REC_STRIDE, mt + (size_t)env * 2 * MB_MT_STRIDE,
+              mt + ((size_t)env * 2 + 1) * MB_MT_STRIDE, obs + (size_t)env * WEnv::OBS);
+  WEnv::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
+}
+
+__global__ void __launch_bounds__(MB_WARPS * 32)
+    k_step_physics_walker3d(int n, MbPhysics phys, float* state, const float* tau, int* rows_out, int* contacts_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * MB_WARPS + warp;
+  if (env >= n) return;
+  WMem& S = reinterpret_cast<WMem*>(smem_raw)[warp];
+  WEnv::load_state(S, state + (size_t)env * MB_STATE_STRIDE);
+  MB_LANES(l)
+    if (l < WM::NJ) S.tau[l] = tau[(size_t)env * WM::NJ + l];
+  MB_END
+  int rows = 0, nc = 0, overflow = 0;
+  for (int k = 0; k < phys.substeps; ++k) rows += Sim<WM>::substep(S, phys, &nc, &overflow);
+  WEnv::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
+  if ((threadIdx.x & 31) == 0) {
+    if (rows_out) rows_out[env] = rows;
+    if (contacts_out) contacts_out[env] = nc;
+  }
+}
+
+// mode 0: M (full symmetric, [nu][nu]);  mode 1: tau = M acc - rhs (rhs = -bias with zero applied torque)
+__global__ void __launch_bounds__(MB_WARPS * 32)
+    k_dynamics_debug_walker3d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * MB_WARPS + warp;
+  if (env >= n) return;
+  WMem& S = reinterpret_cast<WMem*>(smem_raw)[warp];
+  const int NU = WM::NU;
+  WEnv::load_state(S, state + (size_t)env * MB_STATE_STRIDE);
+  MB_LANES(l)
+    S.tau[l] = 0.0f;
+  MB_END
+  Sim<WM>::kinematics(S, phys, true);
+  Sim<WM>::bodies(S, phys);
+  Sim<WM>::mass_matrix_and_rhs(S);
+  MB_LANES(l)
+    if (l < NU) {
+      if (mode == 0) {
+        for (int j = 0; j < NU; ++j) out[((size_t)env * NU + l) * NU + j] = l >= j ? S.L[tri(l, j)] : S.L[tri(j, l)];
+      } else {
+        float t = -S.rhs[l];
+        for (int j = 0; j < NU; ++j) t += (l >= j ? S.L[tri(l, j)] : S.L[tri(j, l)]) * acc[(size_t)env * NU + j];
+        out[(size_t)env * NU + l] = t;
+      }
+    }
+  MB_END
+}
+
+__global__ void k_copy_strided(int n, int width, const float* src, int src_stride, float* dst, int dst_stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * width) return;
+  const int e = i / width, k = i % width;
+  dst[(size_t)e * dst_stride + k] = src[(size_t)e * src_stride + k];
+}
+
+// FP32 FMA throughput probe: the roofline denominator for this (CUDA-core bound) path, measured on the same
+// device in the same process as the benchmark (MEASURED_PEAKS.json only carries HBM and tensor-core peaks).
+__global__ void __launch_bounds__(256) k_fma_probe(float* out, int iters, float b, float c) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
+        a6 = a0 + 6.f, a7 = a0 + 7.f;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+    a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* mb200_last_error(void) { return g_err.c_str(); }
+
+void mb200_default_physics(mb200_physics* p) {
+  p->dt = 1.0f / 240.0f;
+  p->substeps = 4;
+  p->iterations = 5;
+  p->gravity = 9.8f;
+  p->erp_contact = 0.9f;
+  p->erp_joint = 0.2f;
+  p->linear_slop = 1e-5f;
+  p->lin_damping = 0.04f;
+  p->ang_damping = 0.04f;
+  p->max_coord_vel = 100.0f;
+  p->limit_max_impulse = 100.0f;
+  p->split_threshold = -0.04f;
+  p->residual_threshold = 1e-7f;
+  p->ground_friction = 0.8f;
+  p->has_ground = 1;
+}
+
+static void to_internal(const mb200_physics& p, MbPhysics* q) {
+  q->dt = p.dt; q->substeps = p.substeps; q->iterations = p.iterations; q->gravity = p.gravity;
+  q->erp_contact = p.erp_contact; q->erp_joint = p.erp_joint; q->linear_slop = p.linear_slop;
+  q->lin_damping = p.lin_damping; q->ang_damping = p.ang_damping; q->max_coord_vel = p.max_coord_vel;
+  q->limit_max_impulse = p.limit_max_impulse; q->split_threshold = p.split_threshold;
+  q->residual_threshold = p.residual_threshold; q->ground_friction = p.ground_friction; q->has_ground = p.has_ground;
+}
+
+static int grid_for(int n) { return (n + MB_WARPS - 1) / MB_WARPS; }
+
+int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics* physics, mb200_env** out) {
+  if (!out) return fail("mb200_create: out is NULL");
+  *out = nullptr;
+  if (!env_id || strcmp(env_id, "Walker3DCustomEnv-v0") != 0)
+    return fail(std::string("mb200_create: unsupported env id '") + (env_id ? env_id : "(null)") +
+                "' (built: Walker3DCustomEnv-v0)");
+  if (n_envs <= 0) return fail("mb200_create: n_envs must be positive");
+  int count = 0;
+  CUDA_OK(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail("mb200_create: no such CUDA device");
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail("mb200_create: device is not compute capability 10.x; this library carries sm_100a code only and has "
+                "no CPU or other-arch fallback");
+  CUDA_OK(cudaSetDevice(device));
+  mb200_env* e = new mb200_env();
+  memset(e, 0, sizeof(*e));
+  e->n = n_envs;
+  e->device = device;
+  e->obs_dim = WEnv::OBS;
+  e->act_dim = WM::NJ;
+  e->state_dim = 13 + 2 * WM::NJ;
+  e->nu = WM::NU;
+  mb200_physics p;
+  mb200_default_physics(&p);
+  if (physics) p = *physics;
+  to_internal(p, &e->phys);
+  e->smem = sizeof(WMem) * MB_WARPS;
+  CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_custom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  CUDA_OK(cudaFuncSetAttribute(k_reset_walker3d_custom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_walker3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  const size_t n = (size_t)n_envs;
+  CUDA_OK(cudaMalloc(&e->state, n * MB_STATE_STRIDE * sizeof(float)));
+  CUDA_OK(cudaMalloc(&e->rec, n * MB_REC_STRIDE * sizeof(float)));
+  CUDA_OK(cudaMalloc(&e->mt, n * 2 * MB_MT_STRIDE * sizeof(uint32_t)));
+  CUDA_OK(cudaMalloc(&e->stats, sizeof(MbStats)));
+  CUDA_OK(cudaMalloc(&e->stage_act, n * e->act_dim * sizeof(float)));
+  CUDA_OK(cudaMalloc(&e->stage_obs, n * e->obs_dim * sizeof(float)));
+  CUDA_OK(cudaMalloc(&e->stage_rew, n * sizeof(float)));
+  CUDA_OK(cudaMalloc(&e->stage_done, n));
+  CUDA_OK(cudaMalloc(&e->stage_trunc, n));
+  CUDA_OK(cudaMemset(e->state, 0, n * MB_STATE_STRIDE * sizeof(float)));
+  CUDA_OK(cudaMemset(e->rec, 0, n * MB_REC_STRIDE * sizeof(float)));
+  CUDA_OK(cudaMemset(e->mt, 0, n * 2 * MB_MT_STRIDE * sizeof(uint32_t)));
+  CUDA_OK(cudaMemset(e->stats, 0, sizeof(MbStats)));
+  *out = e;
+  return 0;
+}
+
+void mb200_destroy(mb200_env* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaFree(e->state); cudaFree(e->rec); cudaFree(e->mt); cudaFree(e->stats);
+  cudaFree(e->stage_act); cudaFree(e->stage_obs); cudaFree(e->stage_rew); cudaFree(e->stage_done);
+  cudaFree(e->stage_trunc);
+  delete e;
+}
+
+int mb200_dims(const mb200_env* e, int* n_envs, int* obs_dim, int* act_dim, int* state_dim, int* nu) {
+  if (!e) return fail("mb200_dims: NULL handle");
+  if (n_envs) *n_envs = e->n;
+  if (obs_dim) *obs_dim = e->obs_dim;
+  if (act_dim) *act_dim = e->act_dim;
+  if (state_dim) *state_dim = e->state_dim;
+  if (nu) *nu = e->nu;
+  return 0;
+}
+
+int mb200_seed(mb200_env* e, const uint32_t* mt_host, int at_construction) {
+  if (!e || !mt_host) return fail("mb200_seed: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  const size_t n = (size_t)e->n;
+  if (!at_construction) {
+    // EnvBase.seed rebinds only the env's RandomState: an aliased robot keeps drawing from the OLD stream,
+    // which therefore moves to the robot slot (quirk Q1)
+    uint32_t* tmp = (uint32_t*)malloc(n * 2 * MB_MT_STRIDE * sizeof(uint32_t));
+    float* rec = (float*)malloc(n * MB_REC_STRIDE * sizeof(float));
+    if (!tmp || !rec) { free(tmp); free(rec); return fail("mb200_seed: host allocation failed"); }
+    CUDA_OK(cudaMemcpy(tmp, e->mt, n * 2 * MB_MT_STRIDE * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(rec, e->rec, n * MB_REC_STRIDE * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) {
+      int* ri = reinterpret_cast<int*>(rec + i * MB_REC_STRIDE);
+      if (ri[ER_ALIASED]) {
+        memcpy(tmp + (i * 2 + 1) * MB_MT_STRIDE, tmp + (i * 2) * MB_MT_STRIDE, 625 * sizeof(uint32_t));
+        ri[ER_ALIASED] = 0;
+      }
+      memcpy(tmp + (i * 2) * MB_MT_STRIDE, mt_host + i * 625, 625 * sizeof(uint32_t));
+    }
+    CUDA_OK(cudaMemcpy(e->mt, tmp, n * 2 * MB_MT_STRIDE * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->rec, rec, n * MB_REC_STRIDE * sizeof(float), cudaMemcpyHostToDevice));
+    free(tmp);
+    free(rec);
+  } else {
+    uint32_t* tmp = (uint32_t*)calloc(n * 2 * MB_MT_STRIDE, sizeof(uint32_t));
+    float* rec = (float*)malloc(n * MB_REC_STRIDE * sizeof(float));
+    if (!tmp || !rec) { free(tmp); free(rec); return fail("mb200_seed: host allocation failed"); }
+    CUDA_OK(cudaMemcpy(rec, e->rec, n * MB_REC_STRIDE * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) {
+      memcpy(tmp + (i * 2) * MB_MT_STRIDE, mt_host + i * 625, 625 * sizeof(uint32_t));
+      tmp[(i * 2 + 1) * MB_MT_STRIDE + 624] = 624;
+      reinterpret_cast<int*>(rec + i * MB_REC_STRIDE)[ER_ALIASED] = 1;
+    }
+    CUDA_OK(cudaMemcpy(e->mt, tmp, n * 2 * MB_MT_STRIDE * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->rec, rec, n * MB_REC_STRIDE * sizeof(float), cudaMemcpyHostToDevice));
+    free(tmp);
+    free(rec);
+  }
+  return 0;
+}
+
+int mb200_reset(mb200_env* e, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+  if (!e || !obs_dev) return fail("mb200_reset: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  k_reset_walker3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+      e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev);
+  e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int mb200_step(mb200_env* e, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev,
+               uint8_t* trunc_dev, float* final_obs_dev, void* stream) {
+  if (!e || !act_dev || !obs_dev || !rew_dev || !done_dev || !trunc_dev) return fail("mb200_step: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  StepArgs a;
+  a.n = e->n; a.phys = e->phys; a.state = e->state; a.rec = e->rec; a.mt = e->mt; a.act = act_dev; a.obs = obs_dev;
+  a.rew = rew_dev; a.done = done_dev; a.trunc = trunc_dev; a.final_obs = final_obs_dev; a.stats = e->stats;
+  k_step_walker3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
+  e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int mb200_step_host(mb200_env* e, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host,
+                    uint8_t* trunc_host, void* stream) {
+  if (!e || !act_host || !obs_host || !rew_host || !done_host || !trunc_host)
+    return fail("mb200_step_host: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)e->n;
+  CUDA_OK(cudaMemcpyAsync(e->stage_act, act_host, n * e->act_dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = mb200_step(e, e->stage_act, e->stage_obs, e->stage_rew, e->stage_done, e->stage_trunc, nullptr, stream);
+  if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(obs_host, e->stage_obs, n * e->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(rew_host, e->stage_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(done_host, e->stage_done, n, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(trunc_host, e->stage_trunc, n, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static int copy_rows(mb200_env* e, const float* src, int ss, float* dst, int ds, int width, void* stream) {
+  const int total = e->n * width;
+  k_copy_strided<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->n, width, src, ss, dst, ds);
+  e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int mb200_get_state(mb200_env* e, float* state_dev, void* stream) {
+  if (!e || !state_dev) return fail("mb200_get_state: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  return copy_rows(e, e->state, MB_STATE_STRIDE, state_dev, e->state_dim, e->state_dim, stream);
+}
+int mb200_set_state(mb200_env* e, const float* state_dev, void* stream) {
+  if (!e || !state_dev) return fail("mb200_set_state: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  return copy_rows(e, state_dev, e->state_dim, e->state, MB_STATE_STRIDE, e->state_dim, stream);
+}
+int mb200_get_record(mb200_env* e, float* rec_dev, void* stream) {
+  if (!e || !rec_dev) return fail("mb200_get_record: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaMemcpyAsync(rec_dev, e->rec, (size_t)e->n * MB_REC_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice,
+                          (cudaStream_t)stream));
+  return 0;
+}
+int mb200_set_record(mb200_env* e, const float* rec_dev, void* stream) {
+  if (!e || !rec_dev) return fail("mb200_set_record: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaMemcpyAsync(e->rec, rec_dev, (size_t)e->n * MB_REC_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice,
+                          (cudaStream_t)stream));
+  return 0;
+}
+
+int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* contacts_dev, void* stream) {
+  if (!e || !tau_dev) return fail("mb200_step_physics: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  k_step_physics_walker3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+      e->n, e->phys, e->state, tau_dev, rows_dev, contacts_dev);
+  e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int mb200_mass_matrix(mb200_env* e, float* M_dev, void* stream) {
+  if (!e || !M_dev) return fail("mb200_mass_matrix: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  k_dynamics_debug_walker3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+      e->n, e->phys, e->state, 0, nullptr, M_dev);
+  e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int mb200_inverse_dynamics(mb200_env* e, const float* acc_dev, float* tau_dev, void* stream) {
+  if (!e || !acc_dev || !tau_dev) return fail("mb200_inverse_dynamics: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  MbPhysics p = e->phys;
+  p.lin_damping = 0.0f;  // calculateInverseDynamics has no velocity-damping term
+  p.ang_damping = 0.0f;
+  k_dynamics_debug_walker3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+      e->n, p, e->state, 1, acc_dev, tau_dev);
+  e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int mb200_set_param(mb200_env* e, const char* key, float value) {
+  if (!e || !key) return fail("mb200_set_param: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  if (strcmp(key, "eval_mode") == 0) {
+    CUDA_OK(cudaDeviceSynchronize());
+    const size_t n = (size_t)e->n;
+    float* rec = (float*)malloc(n * MB_REC_STRIDE * sizeof(float));
+    if (!rec) return fail("mb200_set_param: host allocation failed");
+    CUDA_OK(cudaMemcpy(rec, e->rec, n * MB_REC_STRIDE * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) reinterpret_cast<int*>(rec + i * MB_REC_STRIDE)[ER_EVAL] = value != 0.0f;
+    CUDA_OK(cudaMemcpy(e->rec, rec, n * MB_REC_STRIDE * sizeof(float), cudaMemcpyHostToDevice));
+    free(rec);
+    return 0;
+  }
+  return fail(std::string("mb200_set_param: unknown key '") + key + "'");
+}
+
+int mb200_stats(mb200_env* e, double out[8], int reset) {
+  if (!e || !out) return fail("mb200_stats: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  MbStats s;
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(&s, e->stats, sizeof(s), cudaMemcpyDeviceToHost));
+  out[0] = (double)s.episodes; out[1] = s.ret_sum; out[2] = s.len_sum; out[3] = (double)s.nonfinite;
+  out[4] = (double)s.overflow; out[5] = out[6] = out[7] = 0.0;
+  if (reset) CUDA_OK(cudaMemset(e->stats, 0, sizeof(MbStats)));
+  return 0;
+}
+
+long long mb200_launch_count(const mb200_env* e) { return e ? e->launches : 0; }
+
+int mb200_measure_fp32_peak(int device, double* tflops_out) {
+  if (!tflops_out) return fail("mb200_measure_fp32_peak: NULL argument");
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  float* buf = nullptr;
+  CUDA_OK(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(float)));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_OK(cudaEventRecord(e0));
+    k_fma_probe<<<blocks, threads>>>(buf, iters, 0.999f, 1e-3f);
+    CUDA_OK(cudaEventRecord(e1));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *tflops_out = best;
+  return 0;
+}
+
+}  // extern "C"

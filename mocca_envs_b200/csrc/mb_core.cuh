@@ -1,0 +1,724 @@
+// mb_core.cuh -- batched articulated-body simulator core, one environment per warp.
+//
+// Replaces, for the batched path, what the reference reaches through pybullet.stepSimulation()
+// (reference mocca_envs/bullet_utils.py:352-353, physics parameters :343-350): per substep
+//   collision -> forward dynamics -> PGS over limits/contacts -> semi-implicit Euler.
+// It is NOT a port of btMultiBody.  Mathematically equivalent formulation chosen for a 32-lane warp:
+//   * world-frame spatial algebra about the base COM (no per-link frame transforms),
+//   * CRBA mass matrix + RNEA bias instead of ABA, factorised leaf-to-root as M = L^T L (no fill-in on a tree),
+//   * constraint rows r are half-solved once, Y_r = L^-T J_r^T, and the projected Gauss-Seidel runs in the
+//     transformed space z = L dv:  J_r dv = Y_r . z,  dv = L^-1 z.  Same row order / clamps / cone projection as
+//     btMultiBodyConstraintSolver, so results equal Bullet's velocity-space PGS up to rounding.
+//
+// SPMD style: code inside MB_LANES(l) ... MB_END is per-lane; code outside is warp-uniform.  Under nvcc the
+// lane loop is the hardware warp; under g++ (tests/emu only) it is a 32-iteration loop, which lets the very same
+// source be diffed against the CPU oracle on a box without a GPU.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "mb_tables.h"
+
+#ifdef __CUDACC__
+#define MB_LANES(l) { const int l = (int)(threadIdx.x & 31);
+#define MB_END } __syncwarp();
+template <typename T> struct LaneVar {
+  T v;
+  MB_HD T& operator[](int) { return v; }
+  MB_HD const T& operator[](int) const { return v; }
+};
+MB_HD float warp_sum(const LaneVar<float>& x) {
+  float v = x.v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+MB_HD float warp_bcast(const LaneVar<float>& x, int src) { return __shfl_sync(0xffffffffu, x.v, src); }
+MB_HD unsigned warp_ballot(const LaneVar<int>& p) { return __ballot_sync(0xffffffffu, p.v != 0); }
+MB_HD int mb_popc(unsigned x) { return __popc(x); }
+MB_HD void mb_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+#else
+#define MB_LANES(l) for (int l = 0; l < 32; ++l) {
+#define MB_END }
+template <typename T> struct LaneVar {
+  T v[32];
+  T& operator[](int l) { return v[l]; }
+  const T& operator[](int l) const { return v[l]; }
+};
+inline float warp_sum(const LaneVar<float>& x) {
+  float t[32];
+  for (int l = 0; l < 32; ++l) t[l] = x.v[l];
+  for (int o = 16; o > 0; o >>= 1) {
+    float n[32];
+    for (int l = 0; l < 32; ++l) n[l] = t[l] + t[l ^ o];
+    for (int l = 0; l < 32; ++l) t[l] = n[l];
+  }
+  return t[0];
+}
+inline float warp_bcast(const LaneVar<float>& x, int src) { return x.v[src]; }
+inline unsigned warp_ballot(const LaneVar<int>& p) {
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l)
+    if (p.v[l]) m |= 1u << l;
+  return m;
+}
+inline int mb_popc(unsigned x) { return __builtin_popcount(x); }
+inline void mb_sincos(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
+#endif
+
+#define MB_MAXC 20   /* contact points kept per substep */
+#define MB_MAXROW 64 /* constraint rows per substep (limits + 3 per contact) */
+#define MB_PI_F 3.14159265358979323846f
+
+// Physics constants of the reference's Bullet world (citations in include/mocca_b200.h: mb200_physics)
+struct MbPhysics {
+  float dt;              // env_base.py:81  control_step / llc_frame_skip / sim_frame_skip
+  int substeps;          // bullet_utils.py:349 numSubSteps
+  int iterations;        // bullet_utils.py:340 numSolverIterations
+  float gravity;         // env_base.py:80
+  float erp_contact;     // bullet_utils.py:345 setDefaultContactERP (m_erp2)
+  float erp_joint;       // Bullet m_erp
+  float linear_slop;     // PyBullet m_linearSlop
+  float lin_damping;     // btMultiBody m_linearDamping
+  float ang_damping;     // btMultiBody m_angularDamping
+  float max_coord_vel;   // btMultiBody m_maxCoordinateVelocity
+  float limit_max_impulse;
+  float split_threshold;
+  float residual_threshold;
+  float ground_friction; // bullet_utils.py:371
+  int has_ground;
+};
+
+MB_HD int tri(int i, int j) { return (i * (i + 1)) / 2 + j; }
+MB_HD bool mb_finite(float x) { return fabsf(x) <= 3.402823466e38f; }  // false for NaN and +-inf  // packed lower-triangular index, j <= i
+
+template <class M> struct WarpMem {
+  // ---- state (generalised velocity u = [omega_w, v_w, qd])
+  float u[32];
+  float q[32];
+  float tau[32];
+  float quat[4];
+  float pos[4];
+  float Rb[9];
+  // ---- kinematics (world axes, positions relative to the base COM)
+  float jR[M::NJ][9];
+  float jp[M::NJ][3];
+  float js[M::NJ][6];
+  float jV[M::NJ + 1][6];  // [0] = base
+  float jA[M::NJ + 1][6];
+  // ---- bodies
+  float bI[M::NB][10];  // m, h[3], I_O{xx,yy,zz,xy,xz,yz}
+  float bF[M::NB][6];   // bias wrench about O (n, f)
+  // ---- dynamics
+  float L[(M::NU * (M::NU + 1)) / 2];
+  float Ldinv[32];
+  float rhs[32];
+  // ---- contacts
+  float cP[MB_MAXC][3];
+  float cn[MB_MAXC][3];
+  float cdist[MB_MAXC];
+  float cmu[MB_MAXC];
+  float cerp[MB_MAXC];
+  float ccfm[MB_MAXC];
+  int clink[MB_MAXC];
+  int cfoot[MB_MAXC];
+  int cpartner[MB_MAXC];
+  // ---- rows
+  float Y[MB_MAXROW][M::NU];
+  float r_rhs[MB_MAXROW];
+  float r_cfm[MB_MAXROW];
+  float r_jinv[MB_MAXROW];
+  float r_app[MB_MAXROW];
+  float r_mu[MB_MAXROW];
+  int r_dof[32];
+  float r_dir[32];
+  // ---- scratch for the epilogue
+  float scratch[64];
+};
+
+// ------------------------------------------------------------------------------------------------ helpers
+MB_HD void mb_cross(const float* a, const float* b, float* c) {
+  float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  c[0] = x; c[1] = y; c[2] = z;
+}
+MB_HD float mb_dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+MB_HD void mb_matvec(const float* R, const float* a, float* o) {  // row-major 3x3
+  float x = R[0] * a[0] + R[1] * a[1] + R[2] * a[2];
+  float y = R[3] * a[0] + R[4] * a[1] + R[5] * a[2];
+  float z = R[6] * a[0] + R[7] * a[1] + R[8] * a[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+MB_HD void mb_matmul(const float* A, const float* B, float* C) {
+  float T[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) T[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) C[i] = T[i];
+}
+MB_HD void mb_quat_to_mat(const float* q, float* R) {  // xyzw, local->world, row-major
+  float x = q[0], y = q[1], z = q[2], w = q[3];
+  float d = x * x + y * y + z * z + w * w, s = 2.0f / d;
+  float xs = x * s, ys = y * s, zs = z * s;
+  float wx = w * xs, wy = w * ys, wz = w * zs, xx = x * xs, xy = x * ys, xz = x * zs;
+  float yy = y * ys, yz = y * zs, zz = z * zs;
+  R[0] = 1 - (yy + zz); R[1] = xy - wz; R[2] = xz + wy;
+  R[3] = xy + wz; R[4] = 1 - (xx + zz); R[5] = yz - wx;
+  R[6] = xz - wy; R[7] = yz + wx; R[8] = 1 - (xx + yy);
+}
+// btPlaneSpace1
+MB_HD void mb_plane_space(const float* n, float* p, float* q) {
+  if (fabsf(n[2]) > 0.70710678f) {
+    float a = n[1] * n[1] + n[2] * n[2], k = 1.0f / sqrtf(a);
+    p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k;
+    q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+  } else {
+    float a = n[0] * n[0] + n[1] * n[1], k = 1.0f / sqrtf(a);
+    p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0;
+    q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ simulator
+template <class M> struct Sim {
+  typedef WarpMem<M> Mem;
+  enum { NJ = M::NJ, NB = M::NB, NU = M::NU, NPT = M::NPT };
+
+  // ---- A. kinematics (+ velocities / bias accelerations when with_vel) --------------------------------------
+  MB_HD static void kinematics(Mem& S, const MbPhysics& P, bool with_vel) {
+    MB_LANES(l)
+      if (l == 0) {
+        mb_quat_to_mat(S.quat, S.Rb);
+        if (with_vel) {
+          // base spatial velocity about O = base COM; bias acceleration with udot = 0 and the gravity trick:
+          // A0 = (0, -w x v - g_vec)
+          float wv[3];
+          mb_cross(&S.u[0], &S.u[3], wv);
+          for (int k = 0; k < 3; ++k) {
+            S.jV[0][k] = S.u[k]; S.jV[0][3 + k] = S.u[3 + k];
+            S.jA[0][k] = 0.0f; S.jA[0][3 + k] = -wv[k];
+          }
+          S.jA[0][5] += P.gravity;
+        }
+      }
+    MB_END
+    for (int lev = 0; lev < M::NLEVEL; ++lev) {
+      MB_LANES(l)
+        if (l < NJ && M::jlevel(l) == lev) {
+          const int pj = M::jparent(l);
+          const float* Rp = pj < 0 ? S.Rb : S.jR[pj];
+          float off[3] = {M::joff(l, 0), M::joff(l, 1), M::joff(l, 2)};
+          float p[3];
+          mb_matvec(Rp, off, p);
+          if (pj >= 0) { p[0] += S.jp[pj][0]; p[1] += S.jp[pj][1]; p[2] += S.jp[pj][2]; }
+          // R = Rp * R0 * Rot(axis, q)
+          float ax[3] = {M::jaxis(l, 0), M::jaxis(l, 1), M::jaxis(l, 2)};
+          float sn, cs;
+          mb_sincos(S.q[l], &sn, &cs);
+          float t = 1.0f - cs;
+          float Rq[9] = {t * ax[0] * ax[0] + cs, t * ax[0] * ax[1] - sn * ax[2], t * ax[0] * ax[2] + sn * ax[1],
+                         t * ax[0] * ax[1] + sn * ax[2], t * ax[1] * ax[1] + cs, t * ax[1] * ax[2] - sn * ax[0],
+                         t * ax[0] * ax[2] - sn * ax[1], t * ax[1] * ax[2] + sn * ax[0], t * ax[2] * ax[2] + cs};
+          float R0[9], T[9], R[9];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) R0[k] = M::jrot(l, k);
+          mb_matmul(R0, Rq, T);
+          mb_matmul(Rp, T, R);
+          float a[3], s[6];
+          mb_matvec(R, ax, a);
+          s[0] = a[0]; s[1] = a[1]; s[2] = a[2];
+          mb_cross(p, a, &s[3]);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) S.jR[l][k] = R[k];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) S.jp[l][k] = p[k];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) S.js[l][k] = s[k];
+          if (with_vel) {
+            const float qd = S.u[6 + l];
+            const float* Vp = S.jV[pj + 1];
+            const float* Ap = S.jA[pj + 1];
+            float vj[6], c1[3], c2[3], c3[3];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) vj[k] = s[k] * qd;
+            // A = Ap + Vp x vj   (motion cross; vj x vj = 0)
+            mb_cross(Vp, vj, c1);
+            mb_cross(Vp, vj + 3, c2);
+            mb_cross(Vp + 3, vj, c3);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              S.jV[l + 1][k] = Vp[k] + vj[k];
+              S.jV[l + 1][3 + k] = Vp[3 + k] + vj[3 + k];
+              S.jA[l + 1][k] = Ap[k] + c1[k];
+              S.jA[l + 1][3 + k] = Ap[3 + k] + c2[k] + c3[k];
+            }
+          }
+        }
+      MB_END
+    }
+  }
+
+  // ---- B. per-body spatial inertia about O and bias wrench (gyroscopic + Bullet velocity damping + gravity) --
+  MB_HD static void bodies(Mem& S, const MbPhysics& P) {
+    MB_LANES(l)
+      if (l < NB) {
+        const int o = M::bowner(l);
+        const float* R = o < 0 ? S.Rb : S.jR[o];
+        float com[3] = {M::bcom(l, 0), M::bcom(l, 1), M::bcom(l, 2)};
+        float c[3];
+        mb_matvec(R, com, c);
+        if (o >= 0) { c[0] += S.jp[o][0]; c[1] += S.jp[o][1]; c[2] += S.jp[o][2]; }
+        // Ic = R Ib R^T
+        const float ixx = M::binertia(l, 0), iyy = M::binertia(l, 1), izz = M::binertia(l, 2);
+        const float ixy = M::binertia(l, 3), ixz = M::binertia(l, 4), iyz = M::binertia(l, 5);
+        float Ib[9] = {ixx, ixy, ixz, ixy, iyy, iyz, ixz, iyz, izz};
+        float T[9], Ic[9];
+        mb_matmul(R, Ib, T);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) Ic[3 * i + j] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
+        const float m = M::bmass(l);
+        const float* V = S.jV[o + 1];
+        const float* A = S.jA[o + 1];
+        const float* w = V;
+        float wxc[3], vc[3], t1[3], t2[3], t3[3], ac[3], Iw[3], Ia[3], g[3], f[3], nc[3], nO[3];
+        mb_cross(w, c, wxc);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) vc[k] = V[3 + k] + wxc[k];
+        mb_cross(A, c, t1);
+        mb_cross(w, V + 3, t2);
+        mb_cross(w, wxc, t3);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ac[k] = A[3 + k] + t1[k] + t2[k] + t3[k];
+        mb_matvec(Ic, w, Iw);
+        mb_matvec(Ic, A, Ia);
+        mb_cross(w, Iw, g);
+        const float wn = sqrtf(mb_dot3(w, w)), vn = sqrtf(mb_dot3(vc, vc));
+        const float kl = P.lin_damping + P.lin_damping * vn, ka = P.ang_damping + P.ang_damping * wn;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          f[k] = m * ac[k] + m * vc[k] * kl;
+          nc[k] = Ia[k] + g[k] + Iw[k] * ka;
+        }
+        mb_cross(c, f, nO);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { S.bF[l][k] = nc[k] + nO[k]; S.bF[l][3 + k] = f[k]; }
+        const float cc = mb_dot3(c, c);
+        S.bI[l][0] = m;
+        S.bI[l][1] = m * c[0]; S.bI[l][2] = m * c[1]; S.bI[l][3] = m * c[2];
+        S.bI[l][4] = Ic[0] + m * (cc - c[0] * c[0]);
+        S.bI[l][5] = Ic[4] + m * (cc - c[1] * c[1]);
+        S.bI[l][6] = Ic[8] + m * (cc - c[2] * c[2]);
+        S.bI[l][7] = Ic[1] - m * c[0] * c[1];
+        S.bI[l][8] = Ic[2] - m * c[0] * c[2];
+        S.bI[l][9] = Ic[5] - m * c[1] * c[2];
+      }
+    MB_END
+  }
+
+  // ---- C. composite inertias -> mass matrix rows (packed lower) and generalised rhs = tau - bias ------------
+  MB_HD static void mass_matrix_and_rhs(Mem& S) {
+    MB_LANES(l)
+      if (l <= NJ) {
+        const int b0 = l < NJ ? M::bstart(l) : 0, b1 = l < NJ ? M::bend(l) : NB;
+        float I[10], F[6];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) I[k] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) F[k] = 0.0f;
+        for (int b = b0; b < b1; ++b) {
+#pragma unroll
+          for (int k = 0; k < 10; ++k) I[k] += S.bI[b][k];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) F[k] += S.bF[b][k];
+        }
+        const float m = I[0];
+        const float* h = &I[1];
+        if (l < NJ) {
+          const float* s = S.js[l];
+          // G = I^c s : n = I_O a + h x lv ; f = m lv + a x h
+          float G[6], hx[3], ah[3];
+          float IOa[3] = {I[4] * s[0] + I[7] * s[1] + I[8] * s[2], I[7] * s[0] + I[5] * s[1] + I[9] * s[2],
+                          I[8] * s[0] + I[9] * s[1] + I[6] * s[2]};
+          mb_cross(h, s + 3, hx);
+          mb_cross(s, h, ah);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { G[k] = IOa[k] + hx[k]; G[3 + k] = m * s[3 + k] + ah[k]; }
+          float bias = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) bias += s[k] * F[k];
+          const int row = 6 + l;
+          float* Lr = &S.L[tri(row, 0)];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) Lr[k] = G[k];
+          const unsigned anc = M::janc(l);
+          for (int i = 0; i <= l; ++i) {
+            float v = 0.0f;
+            if ((anc >> i) & 1u) {
+              const float* si = S.js[i];
+#pragma unroll
+              for (int k = 0; k < 6; ++k) v += si[k] * G[k];
+            }
+            Lr[6 + i] = v;
+          }
+          Lr[6 + l] += M::armature(l);
+          S.rhs[row] = S.tau[l] - bias;
+        } else {
+          // base 6x6 block: [[I_O, [h]x], [-[h]x, m 1]], lower triangle
+          float* L0 = S.L;
+          L0[tri(0, 0)] = I[4];
+          L0[tri(1, 0)] = I[7]; L0[tri(1, 1)] = I[5];
+          L0[tri(2, 0)] = I[8]; L0[tri(2, 1)] = I[9]; L0[tri(2, 2)] = I[6];
+          L0[tri(3, 0)] = 0.0f; L0[tri(3, 1)] = h[2]; L0[tri(3, 2)] = -h[1]; L0[tri(3, 3)] = m;
+          L0[tri(4, 0)] = -h[2]; L0[tri(4, 1)] = 0.0f; L0[tri(4, 2)] = h[0]; L0[tri(4, 3)] = 0.0f; L0[tri(4, 4)] = m;
+          L0[tri(5, 0)] = h[1]; L0[tri(5, 1)] = -h[0]; L0[tri(5, 2)] = 0.0f; L0[tri(5, 3)] = 0.0f; L0[tri(5, 4)] = 0.0f;
+          L0[tri(5, 5)] = m;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) S.rhs[k] = -F[k];
+        }
+      }
+    MB_END
+  }
+
+  // ---- D. M = L^T L, processed leaf-to-root so the tree sparsity of M is preserved (no fill-in) -------------
+  MB_HD static void factorize(Mem& S) {
+    for (int k = NU - 1; k >= 0; --k) {
+      const float d = sqrtf(S.L[tri(k, k)]);
+      const float inv = 1.0f / d;
+      MB_LANES(l)
+        if (l < k) S.L[tri(k, l)] *= inv;
+        else if (l == k) { S.L[tri(k, k)] = d; S.Ldinv[k] = inv; }
+      MB_END
+      MB_LANES(l)
+        if (l < k) {
+          const float Lkl = S.L[tri(k, l)];
+          if (Lkl != 0.0f) {
+            float* Ll = &S.L[tri(l, 0)];
+            const float* Lk = &S.L[tri(k, 0)];
+            for (int j = 0; j <= l; ++j) Ll[j] -= Lkl * Lk[j];
+          }
+        }
+      MB_END
+    }
+  }
+
+  // ---- E. single right-hand-side solves, one generalised coordinate per lane ---------------------------------
+  MB_HD static void solve_Lt(Mem& S, LaneVar<float>& x) {  // L^T y = x
+    for (int i = NU - 1; i >= 0; --i) {
+      const float yi = warp_bcast(x, i) * S.Ldinv[i];
+      MB_LANES(l)
+        if (l == i) x[l] = yi;
+        else if (l < i) x[l] -= S.L[tri(i, l)] * yi;
+      MB_END
+    }
+  }
+  MB_HD static void solve_L(Mem& S, LaneVar<float>& x) {  // L y = x
+    for (int i = 0; i < NU; ++i) {
+      const float xi = warp_bcast(x, i) * S.Ldinv[i];
+      MB_LANES(l)
+        if (l == i) x[l] = xi;
+        else if (l > i && l < NU) x[l] -= S.L[tri(l, i)] * xi;
+      MB_END
+    }
+  }
+
+  MB_HD static void clamp_u(Mem& S, const MbPhysics& P) {
+    MB_LANES(l)
+      if (l < NU) S.u[l] = fminf(fmaxf(S.u[l], -P.max_coord_vel), P.max_coord_vel);
+    MB_END
+  }
+
+  // ---- F. narrow phase: sphere / capsule-end candidates vs the ground plane z = 0 ---------------------------
+  MB_HD static int collide(Mem& S, const MbPhysics& P, int* overflow) {
+    int nc = 0;
+    for (int pass = 0; pass * 32 < NPT; ++pass) {
+      LaneVar<int> hit;
+      LaneVar<float> px, py, pz, dd;
+      MB_LANES(l)
+        const int pt = pass * 32 + l;
+        hit[l] = 0;
+        if (pt < NPT && P.has_ground) {
+          const int o = M::powner(pt);
+          const float* R = o < 0 ? S.Rb : S.jR[o];
+          float loc[3] = {M::ppos(pt, 0), M::ppos(pt, 1), M::ppos(pt, 2)};
+          float c[3];
+          mb_matvec(R, loc, c);
+          if (o >= 0) { c[0] += S.jp[o][0]; c[1] += S.jp[o][1]; c[2] += S.jp[o][2]; }
+          const float r = M::pradius(pt);
+          const float dist = (S.pos[2] + c[2]) - r;
+          if (dist < M::pthresh(pt)) {
+            hit[l] = 1;
+            px[l] = c[0]; py[l] = c[1]; pz[l] = c[2] - r; dd[l] = dist;
+          }
+        }
+      MB_END
+      const unsigned mask = warp_ballot(hit);
+      MB_LANES(l)
+        if (hit[l]) {
+          const int pt = pass * 32 + l;
+          const int k = nc + mb_popc(mask & ((1u << l) - 1u));
+          if (k < MB_MAXC) {
+            S.cP[k][0] = px[l]; S.cP[k][1] = py[l]; S.cP[k][2] = pz[l];
+            S.cn[k][0] = 0.0f; S.cn[k][1] = 0.0f; S.cn[k][2] = 1.0f;
+            S.cdist[k] = dd[l];
+            S.cmu[k] = M::pfriction(pt) * P.ground_friction;
+            S.cerp[k] = P.erp_contact;
+            S.ccfm[k] = 0.0f;
+            S.clink[k] = M::powner(pt);
+            S.cfoot[k] = M::pfoot(pt);
+            S.cpartner[k] = 0;
+          }
+        }
+      MB_END
+      nc += mb_popc(mask);
+    }
+    if (nc > MB_MAXC) { *overflow += 1; nc = MB_MAXC; }
+    return nc;
+  }
+
+  // ---- G. constraint rows: J, Y = L^-T J^T, effective mass, rhs ---------------------------------------------
+  // rows [0, nlim) joint limits, [nlim, nlim+nc) contact normals, then 2 friction rows per contact.
+  MB_HD static int find_limits(Mem& S) {
+    LaneVar<int> lim;
+    MB_LANES(l)
+      lim[l] = 0;
+      if (l < NJ) {
+        const float lo = M::lower(l), hi = M::upper(l), q = S.q[l];
+        if (lo <= hi) {
+          if (q - lo <= 0.0f) lim[l] = 1;
+          else if (hi - q <= 0.0f) lim[l] = 2;
+        }
+      }
+    MB_END
+    const unsigned mask = warp_ballot(lim);
+    MB_LANES(l)
+      if (lim[l]) {
+        const int k = mb_popc(mask & ((1u << l) - 1u));
+        S.r_dof[k] = l;
+        S.r_dir[k] = lim[l] == 1 ? 1.0f : -1.0f;
+      }
+    MB_END
+    return mb_popc(mask);
+  }
+
+  MB_HD static void setup_rows(Mem& S, const MbPhysics& P, int nlim, int nc) {
+    const int R = nlim + 3 * nc;
+    const float inv_dt = 1.0f / P.dt;
+    for (int base = 0; base < R; base += 32) {
+      MB_LANES(l)
+        const int r = base + l;
+        if (r < R) {
+          float b[NU];
+          float cfm = 0.0f, rhs, mu = 0.0f;
+          float pen = 0.0f, dist = 0.0f, erp = 0.0f;
+          int kind;  // 0 limit, 1 normal, 2 friction
+          if (r < nlim) {
+            kind = 0;
+            const int d = S.r_dof[r];
+            const float dir = S.r_dir[r];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) b[i] = (i == 6 + d) ? dir : 0.0f;
+            pen = dir > 0.0f ? S.q[d] - M::lower(d) : M::upper(d) - S.q[d];
+          } else {
+            int k;
+            float dirv[3];
+            if (r < nlim + nc) {
+              kind = 1; k = r - nlim;
+              dirv[0] = S.cn[k][0]; dirv[1] = S.cn[k][1]; dirv[2] = S.cn[k][2];
+              cfm = S.ccfm[k] * inv_dt; erp = S.cerp[k]; dist = S.cdist[k] + P.linear_slop;
+            } else {
+              kind = 2; k = (r - nlim - nc) >> 1;
+              float t1[3], t2[3];
+              mb_plane_space(S.cn[k], t1, t2);
+              const bool second = ((r - nlim - nc) & 1) != 0;
+              dirv[0] = second ? t2[0] : t1[0]; dirv[1] = second ? t2[1] : t1[1]; dirv[2] = second ? t2[2] : t1[2];
+            }
+            mu = S.cmu[k];
+            float W[6];
+            mb_cross(S.cP[k], dirv, W);
+            W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) b[i] = W[i];
+            const int link = S.clink[k];
+            const unsigned anc = link < 0 ? 0u : M::janc(link);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+              const float* s = S.js[j];
+              float v = s[0] * W[0] + s[1] * W[1] + s[2] * W[2] + s[3] * W[3] + s[4] * W[4] + s[5] * W[5];
+              b[6 + j] = ((anc >> j) & 1u) ? v : 0.0f;
+            }
+          }
+          float rel_vel = 0.0f;
+#pragma unroll
+          for (int i = 0; i < NU; ++i) rel_vel += b[i] * S.u[i];
+          // half solve L^T y = J^T (column-oriented back substitution over the packed factor)
+#pragma unroll
+          for (int i = NU - 1; i >= 0; --i) {
+            const float yi = b[i] * S.Ldinv[i];
+            b[i] = yi;
+            const float* Li = &S.L[tri(i, 0)];
+#pragma unroll
+            for (int j = 0; j < i; ++j) b[j] -= Li[j] * yi;
+          }
+          float dd = cfm;
+#pragma unroll
+          for (int i = 0; i < NU; ++i) dd += b[i] * b[i];
+          const float jinv = dd > 1.1920929e-07f ? 1.0f / dd : 0.0f;
+          float positional = 0.0f, verr = -rel_vel;
+          if (kind == 0) {
+            // btMultiBodyJointLimitConstraint: erp = m_erp unless deeper than the split-impulse threshold, in
+            // which case the positional part is routed to the (never applied) split impulse
+            if (pen > 0.0f) verr = -pen * inv_dt;
+            else if (pen > P.split_threshold) positional = -pen * P.erp_joint * inv_dt;
+          } else if (kind == 1) {
+            if (dist > 0.0f) verr -= dist * inv_dt;
+            else positional = -dist * erp * inv_dt;
+          }
+          rhs = (positional + verr) * jinv;
+#pragma unroll
+          for (int i = 0; i < NU; ++i) S.Y[r][i] = b[i];
+          S.r_rhs[r] = rhs;
+          S.r_cfm[r] = cfm * jinv;
+          S.r_jinv[r] = jinv;
+          S.r_app[r] = 0.0f;
+          S.r_mu[r] = mu;
+        }
+      MB_END
+    }
+  }
+
+  // ---- H. projected Gauss-Seidel in z-space (btMultiBodyConstraintSolver::solveSingleIteration order) --------
+  MB_HD static float row_dot(Mem& S, int r, const LaneVar<float>& z) {
+    LaneVar<float> t;
+    MB_LANES(l)
+      t[l] = l < NU ? S.Y[r][l] * z[l] : 0.0f;
+    MB_END
+    return warp_sum(t);
+  }
+  MB_HD static void row_apply(Mem& S, int r, float imp, float new_app, LaneVar<float>& z) {
+    MB_LANES(l)
+      if (l < NU) z[l] += S.Y[r][l] * imp;
+      if (l == 0) S.r_app[r] = new_app;
+    MB_END
+  }
+  MB_HD static float resolve_single(Mem& S, int r, float lo, float hi, LaneVar<float>& z) {
+    const float app = S.r_app[r], jinv = S.r_jinv[r];
+    float delta = S.r_rhs[r] - app * S.r_cfm[r];
+    delta -= row_dot(S, r, z) * jinv;
+    const float sum = app + delta;
+    float napp;
+    if (sum < lo) { delta = lo - app; napp = lo; }
+    else if (sum > hi) { delta = hi - app; napp = hi; }
+    else napp = sum;
+    row_apply(S, r, delta, napp, z);
+    return jinv != 0.0f ? delta / jinv : 0.0f;
+  }
+  MB_HD static float resolve_cone(Mem& S, int ra, int rb, float lim, LaneVar<float>& z) {
+    const float appA = S.r_app[ra], appB = S.r_app[rb], jA = S.r_jinv[ra], jB = S.r_jinv[rb];
+    float dB = S.r_rhs[rb] - appB * S.r_cfm[rb] - row_dot(S, rb, z) * jB;
+    float dA = S.r_rhs[ra] - appA * S.r_cfm[ra] - row_dot(S, ra, z) * jA;
+    const float sumA = appA + dA, sumB = appB + dB;
+    float nA = sumA, nB = sumB;
+    if (sumA * sumA + sumB * sumB >= lim * lim) {
+      const float angle = atan2f(sumA, sumB);
+      const float clipA = fabsf(lim * sinf(angle)), clipB = fabsf(lim * cosf(angle));
+      if (sumA < -clipA) { dA = -clipA - appA; nA = -clipA; }
+      else if (sumA > clipA) { dA = clipA - appA; nA = clipA; }
+      if (sumB < -clipB) { dB = -clipB - appB; nB = -clipB; }
+      else if (sumB > clipB) { dB = clipB - appB; nB = clipB; }
+    }
+    row_apply(S, ra, dA, nA, z);
+    row_apply(S, rb, dB, nB, z);
+    float res = 0.0f;
+    if (jA != 0.0f) res += dA / jA;
+    if (jB != 0.0f) res += dB / jB;
+    return res;
+  }
+
+  MB_HD static void solve_constraints(Mem& S, const MbPhysics& P, int nlim, int nc, LaneVar<float>& z) {
+    MB_LANES(l)
+      z[l] = 0.0f;
+    MB_END
+    for (int it = 0; it < P.iterations; ++it) {
+      float res2 = 0.0f;
+      for (int j = 0; j < nlim; ++j) {
+        const int r = (it & 1) ? j : nlim - 1 - j;
+        const float rr = resolve_single(S, r, 0.0f, P.limit_max_impulse, z);
+        res2 = fmaxf(res2, rr * rr);
+      }
+      for (int k = 0; k < nc; ++k) {
+        const float rr = resolve_single(S, nlim + k, 0.0f, 1e10f, z);
+        res2 = fmaxf(res2, rr * rr);
+      }
+      for (int k = 0; k < nc; ++k) {
+        const int ra = nlim + nc + 2 * k;
+        const float lim = S.r_mu[ra] * S.r_app[nlim + k];
+        const float rr = resolve_cone(S, ra, ra + 1, lim, z);
+        res2 = fmaxf(res2, rr * rr);
+      }
+      if (res2 <= P.residual_threshold) break;
+    }
+  }
+
+  // ---- I. integrate positions (btMultiBody::stepPositionsMultiDof) --------------------------------------------
+  MB_HD static void integrate(Mem& S, const MbPhysics& P) {
+    MB_LANES(l)
+      if (l < NJ) S.q[l] += P.dt * S.u[6 + l];
+      if (l == 31) {
+        const float dt = P.dt;
+        S.pos[0] += dt * S.u[3]; S.pos[1] += dt * S.u[4]; S.pos[2] += dt * S.u[5];
+        const float wx = S.u[0], wy = S.u[1], wz = S.u[2];
+        float ang = sqrtf(wx * wx + wy * wy + wz * wz);
+        if (ang * dt > 0.25f * MB_PI_F) ang = 0.25f * MB_PI_F / dt;
+        float f;
+        if (ang < 0.001f) f = 0.5f * dt - dt * dt * dt * 0.020833333333f * ang * ang;
+        else f = sinf(0.5f * ang * dt) / ang;
+        const float ax = wx * f, ay = wy * f, az = wz * f, aw = cosf(ang * dt * 0.5f);
+        const float x = S.quat[0], y = S.quat[1], zq = S.quat[2], w = S.quat[3];
+        float nx = aw * x + ax * w + ay * zq - az * y;
+        float ny = aw * y - ax * zq + ay * w + az * x;
+        float nz = aw * zq + ax * y - ay * x + az * w;
+        float nw = aw * w - ax * x - ay * y - az * zq;
+        const float n = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+        S.quat[0] = nx * n; S.quat[1] = ny * n; S.quat[2] = nz * n; S.quat[3] = nw * n;
+      }
+    MB_END
+  }
+
+  // ---- one Bullet substep.  Returns the number of constraint rows; contact list of this substep stays in S ----
+  MB_HD static int substep(Mem& S, const MbPhysics& P, int* nc_out, int* overflow) {
+    kinematics(S, P, true);
+    const int nc_all = collide(S, P, overflow);
+    bodies(S, P);
+    mass_matrix_and_rhs(S);
+    factorize(S);
+    // forward dynamics: udot = M^-1 (tau - bias); u += dt udot (clamped like btMultiBody::applyDeltaVeeMultiDof)
+    LaneVar<float> x;
+    MB_LANES(l)
+      x[l] = l < NU ? S.rhs[l] : 0.0f;
+    MB_END
+    solve_Lt(S, x);
+    solve_L(S, x);
+    MB_LANES(l)
+      if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + P.dt * x[l], -P.max_coord_vel), P.max_coord_vel);
+    MB_END
+    const int nlim = find_limits(S);
+    int nc = nc_all;
+    if (nlim + 3 * nc > MB_MAXROW) { nc = (MB_MAXROW - nlim) / 3; *overflow += 1; }
+    const int R = nlim + 3 * nc;
+    if (R > 0) {
+      setup_rows(S, P, nlim, nc);
+      LaneVar<float> z;
+      solve_constraints(S, P, nlim, nc, z);
+      solve_L(S, z);
+      MB_LANES(l)
+        if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + z[l], -P.max_coord_vel), P.max_coord_vel);
+      MB_END
+    }
+    integrate(S, P);
+    *nc_out = nc_all < MB_MAXC ? nc_all : MB_MAXC;
+    return R;
+  }
+};

@@ -1,0 +1,412 @@
+// mb_env.cuh -- env layer fused around the simulator core: action -> torque, frame_skip substeps,
+// observation / reward / termination, gym TimeLimit, auto-reset with NumPy-compatible MT19937 streams.
+//
+// Restates (per environment, one warp each):
+//   WalkerBase.apply_action / calc_state / reset      reference mocca_envs/robots.py:31-95,179-227
+//   Walker3DCustomEnv.reset/step/calc_*               reference mocca_envs/env_locomotion.py:67-222
+//   gym TimeLimit(max_episode_steps=1000)             reference mocca_envs/__init__.py:52-56
+#pragma once
+#include "mb_core.cuh"
+
+// ---- HBM record layout (array-of-records: one warp streams its env's record with coalesced 128 B lines) ----
+#define MB_STATE_STRIDE 64 /* floats: pos3 quat4 omega3 vel3 q[NJ] qd[NJ] */
+#define MB_REC_STRIDE 32   /* floats/ints, see ER_* */
+#define MB_MT_STRIDE 640   /* uint32: 624 state words + [624] position */
+enum {
+  ER_TX = 0, ER_TY, ER_TZ,      // walk_target
+  ER_DIST, ER_ANGLE, ER_STOP,   // randomize_target() draws
+  ER_CLOSE,                     // close_count (int)
+  ER_LINPOT,                    // linear_potential
+  ER_ELAPSED,                   // TimeLimit counter (int)
+  ER_FEET0, ER_FEET1,           // feet_contact
+  ER_ALIASED,                   // robot RNG still aliased to env RNG (int)  -- env_base.py:93 quirk Q1
+  ER_EPRET, ER_EPLEN,           // running episode return / length (float, int)
+  ER_MIRRORED,                  // robots.py:182-188 (int)
+  ER_ROWS,                      // diagnostics: constraint rows accumulated (float)
+  ER_CONTACTS,                  // diagnostics: contact points accumulated (float)
+  ER_BODYX,                     // body_xyz[0] of the previous calc_state (eval mode, env_locomotion.py:115-116)
+  ER_EVAL,                      // eval_mode (int)
+  ER_LAST_EPRET, ER_LAST_EPLEN, // return / length of the last finished episode
+  ER_OVERFLOW,                  // contact/row cap hits (int)
+};
+
+struct MbStats {  // per-device accumulators, all-reduced across ranks by the host (NCCL) when asked
+  unsigned long long episodes;
+  unsigned long long steps;
+  unsigned long long nonfinite;
+  unsigned long long overflow;
+  double ret_sum;
+  double len_sum;
+};
+
+MB_HD int& rec_i(float* rec, int k) { return reinterpret_cast<int*>(rec)[k]; }
+
+// ------------------------------------------------------------------------------------------------ MT19937
+// NumPy legacy RandomState stream, warp-cooperative.  mt[0..623] state words, mt[624] position.
+MB_HD void mt_twist(uint32_t* mt) {
+  for (int g = 0; g < 624; g += 32) {
+    LaneVar<uint32_t> nv;
+    MB_LANES(l)
+      const int k = g + l;
+      nv[l] = 0;
+      if (k < 624) {
+        const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+        nv[l] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+    MB_END
+    MB_LANES(l)
+      const int k = g + l;
+      if (k < 624) mt[k] = nv[l];
+    MB_END
+  }
+}
+MB_HD uint32_t mt_temper(uint32_t y) {
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= (y >> 18);
+  return y;
+}
+MB_HD void mt_fill(uint32_t* mt, uint32_t* out, int count) {
+  int pos = (int)mt[624];
+  int produced = 0;
+  while (produced < count) {
+    if (pos >= 624) { mt_twist(mt); pos = 0; }
+    int take = 624 - pos;
+    if (take > count - produced) take = count - produced;
+    MB_LANES(l)
+      for (int i = l; i < take; i += 32) out[produced + i] = mt_temper(mt[pos + i]);
+    MB_END
+    pos += take;
+    produced += take;
+  }
+  MB_LANES(l)
+    if (l == 0) mt[624] = (uint32_t)pos;
+  MB_END
+}
+// RandomState.random_sample(): 53-bit double from two 32-bit outputs
+MB_HD double mt_double(const uint32_t* w) { return ((double)(w[0] >> 5) * 67108864.0 + (double)(w[1] >> 6)) / 9007199254740992.0; }
+
+// ------------------------------------------------------------------------------------------------ Walker3DCustom
+struct W3DObsScalars {
+  float height, vx, vy, vz, roll, pitch, yaw;
+  int joints_at_limit;
+  int nonfinite;
+};
+
+// pybullet.getEulerFromQuaternion (reference bullet_utils.py:83-84)
+MB_HD void mb_euler(const float* qin, float* rpy) {
+  const float len = sqrtf(qin[0] * qin[0] + qin[1] * qin[1] + qin[2] * qin[2] + qin[3] * qin[3]);
+  const float q0 = qin[0] / len, q1 = qin[1] / len, q2 = qin[2] / len, q3 = qin[3] / len;
+  const float sqx = q0 * q0, sqy = q1 * q1, sqz = q2 * q2, squ = q3 * q3;
+  const float sarg = -2.0f * (q0 * q2 - q3 * q1);
+  if (sarg <= -0.99999f) { rpy[0] = 0; rpy[1] = -0.5f * MB_PI_F; rpy[2] = 2 * atan2f(q0, -q1); }
+  else if (sarg >= 0.99999f) { rpy[0] = 0; rpy[1] = 0.5f * MB_PI_F; rpy[2] = 2 * atan2f(-q0, q1); }
+  else {
+    rpy[0] = atan2f(2 * (q1 * q2 + q3 * q0), squ - sqx - sqy + sqz);
+    rpy[1] = asinf(sarg);
+    rpy[2] = atan2f(2 * (q0 * q1 + q3 * q2), squ + sqx - sqy - sqz);
+  }
+}
+MB_HD float mb_clip5(float x) { return fminf(fmaxf(x, -5.0f), 5.0f); }
+
+template <class M> struct W3DEnv {
+  typedef WarpMem<M> Mem;
+  typedef Sim<M> S_;
+  enum { NJ = M::NJ, NU = M::NU, OBS = 6 + 2 * M::NJ + M::NFEET + 2, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET };
+
+  // HBM <-> shared
+  MB_HD static void load_state(Mem& S, const float* st) {
+    MB_LANES(l)
+      for (int i = l; i < 13 + 2 * NJ; i += 32) {
+        const float v = st[i];
+        if (i < 3) S.pos[i] = v;
+        else if (i < 7) S.quat[i - 3] = v;
+        else if (i < 13) S.u[i - 7] = v;
+        else if (i < 13 + NJ) S.q[i - 13] = v;
+        else S.u[6 + i - 13 - NJ] = v;
+      }
+    MB_END
+  }
+  MB_HD static void store_state(const Mem& S, float* st) {
+    MB_LANES(l)
+      for (int i = l; i < 13 + 2 * NJ; i += 32) {
+        float v;
+        if (i < 3) v = S.pos[i];
+        else if (i < 7) v = S.quat[i - 3];
+        else if (i < 13) v = S.u[i - 7];
+        else if (i < 13 + NJ) v = S.q[i - 13];
+        else v = S.u[6 + i - 13 - NJ];
+        st[i] = v;
+      }
+    MB_END
+  }
+
+  // robots.py:42-95 calc_state: writes robot_state (clipped to +-5) into obs[0 .. ROBOT_OBS) and returns the
+  // unclipped scalars the reward needs.  Requires kinematics(S, P, false) at the current pose.
+  MB_HD static W3DObsScalars observe(Mem& S, const float* rec, float* obs, const LaneVar<float>& araw, float* s1,
+                                     float* s2) {
+    W3DObsScalars o;
+    LaneVar<float> e1, e2;
+    LaneVar<int> atl, bad;
+    MB_LANES(l)
+      e1[l] = 0.0f; e2[l] = 0.0f; atl[l] = 0; bad[l] = 0;
+      if (l < NJ) {
+        const float q = S.q[l], qd = S.u[6 + l];
+        const float nrm = 2.0f * (q - M::lower(l)) / M::weight(l) - 1.0f;
+        const float sp = 0.1f * qd;
+        obs[6 + l] = mb_clip5(nrm);
+        obs[6 + NJ + l] = mb_clip5(sp);
+        atl[l] = fabsf(nrm) > 0.99f;
+        bad[l] = !(mb_finite(nrm) && mb_finite(sp));
+        const float a = araw[l];
+        e1[l] = fabsf(a * sp);
+        e2[l] = a * a;
+      }
+    MB_END
+    o.joints_at_limit = mb_popc(warp_ballot(atl));
+    *s1 = warp_sum(e1);
+    *s2 = warp_sum(e2);
+    float rpy[3];
+    mb_euler(S.quat, rpy);
+    o.roll = rpy[0]; o.pitch = rpy[1]; o.yaw = rpy[2];
+    const float cy = cosf(-o.yaw), sy = sinf(-o.yaw);
+    o.vx = cy * S.u[3] - sy * S.u[4];
+    o.vy = sy * S.u[3] + cy * S.u[4];
+    o.vz = S.u[5];
+    float minz = 1e30f;
+    for (int f = 0; f < M::NFEET; ++f) {
+      const int b = M::foot_body(f), ow = M::bowner(b);
+      const float* R = S.jR[ow];
+      const float z = S.jp[ow][2] + R[6] * M::bcom(b, 0) + R[7] * M::bcom(b, 1) + R[8] * M::bcom(b, 2);
+      minz = fminf(minz, z);
+    }
+    o.height = -minz;  // body_z - min(feet_z), both relative to the base COM
+    o.nonfinite = warp_ballot(bad) != 0u ||
+                  !(mb_finite(o.height) && mb_finite(o.vx) && mb_finite(o.vy) && mb_finite(o.vz) && mb_finite(o.roll) &&
+                    mb_finite(o.pitch));
+    MB_LANES(l)
+      if (l == 0) {
+        obs[0] = mb_clip5(o.height); obs[1] = mb_clip5(o.vx); obs[2] = mb_clip5(o.vy); obs[3] = mb_clip5(o.vz);
+        obs[4] = mb_clip5(o.roll); obs[5] = mb_clip5(o.pitch);
+        obs[6 + 2 * NJ] = rec[ER_FEET0];
+        obs[6 + 2 * NJ + 1] = rec[ER_FEET1];
+      }
+    MB_END
+    return o;
+  }
+
+  // env_locomotion.py:143-158
+  MB_HD static void potential(const Mem& S, const float* rec, float yaw, float scene_dt, float* dist, float* ang,
+                              float* linpot) {
+    const float dx = rec[ER_TX] - S.pos[0], dy = rec[ER_TY] - S.pos[1];
+    *ang = atan2f(dy, dx) - yaw;
+    *dist = sqrtf(dx * dx + dy * dy);
+    *linpot = -(*dist) / scene_dt;
+  }
+  MB_HD static void target_obs(float dist, float ang, float* obs) {  // env_locomotion.py:124-129
+    const float s_ = dist * sinf(ang), c_ = dist * cosf(ang);
+    MB_LANES(l)
+      if (l == 0) {
+        obs[ROBOT_OBS] = s_ / (1.0f + fabsf(s_));
+        obs[ROBOT_OBS + 1] = c_ / (1.0f + fabsf(c_));
+      }
+    MB_END
+  }
+
+  // env_locomotion.py:67-74 -- consumes 5 words of the env stream
+  MB_HD static void randomize_target(float* rec, const uint32_t* w, double* dist, double* angle) {
+    if (rec_i(rec, ER_EVAL)) { *dist = 4.0; *angle = 0.0; }
+    else {
+      *dist = 3.0 + (5.0 - 3.0) * mt_double(w);
+      const double lo = -3.14159265358979323846 / 2, hi = 3.14159265358979323846 / 2;
+      *angle = lo + (hi - lo) * mt_double(w + 2);
+    }
+    const float stop = (w[4] & 1u) ? 60.0f : 30.0f;
+    MB_LANES(l)
+      if (l == 0) { rec[ER_DIST] = (float)*dist; rec[ER_ANGLE] = (float)*angle; rec[ER_STOP] = stop; }
+    MB_END
+  }
+
+  // Walker3DCustomEnv.reset (env_locomotion.py:79-109) + WalkerBase.reset (robots.py:179-210)
+  MB_HD static void reset(Mem& S, const MbPhysics& P, float* rec, uint32_t* mt_env, uint32_t* mt_robot, float* obs) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(S.scratch);
+    const int aliased = rec_i(rec, ER_ALIASED);
+    const int nrobot = 2 + 2 * NJ;
+    if (aliased) mt_fill(mt_env, w, 5 + nrobot);
+    else { mt_fill(mt_env, w, 5); mt_fill(mt_robot, w + 5, nrobot); }
+    double dist, angle;
+    randomize_target(rec, w, &dist, &angle);
+    const uint32_t* wr = w + 5;
+    const int mirrored = mt_double(wr) < 0.5;
+    MB_LANES(l)
+      if (l == 0) {
+        rec[ER_TX] = (float)(dist * cos(angle)); rec[ER_TY] = (float)(dist * sin(angle)); rec[ER_TZ] = 1.0f;
+        rec_i(rec, ER_CLOSE) = 0; rec_i(rec, ER_ELAPSED) = 0; rec[ER_FEET0] = 0.0f; rec[ER_FEET1] = 0.0f;
+        rec_i(rec, ER_MIRRORED) = mirrored; rec[ER_EPRET] = 0.0f; rec_i(rec, ER_EPLEN) = 0;
+      }
+      if (l < NJ) {
+        // mirrored base pose (robots.py:182-188), +-0.1 rad noise clipped to +-0.95 normalised (robots.py:190-194)
+        int src = l;
+        double sign = 1.0;
+        if (mirrored) {
+          for (int k = 0; k < M::NMIRROR; ++k) {
+            if (M::right(k) == l) src = M::left(k);
+            if (M::left(k) == l) src = M::right(k);
+          }
+          for (int k = 0; k < M::NNEG; ++k)
+            if (M::neg(k) == l) sign = -1.0;
+        }
+        const double ang = sign * (double)M::base_angles(src);
+        const double ds = -0.1 + (0.1 - -0.1) * mt_double(wr + 2 + 2 * l);
+        const double bias = (double)M::lower(l), weight = (double)M::weight(l);
+        double ps = 2 * (ang + ds - bias) / weight - 1;
+        ps = ps > 0.95 ? 0.95 : (ps < -0.95 ? -0.95 : ps);
+        S.q[l] = (float)(weight * (ps + 1) / 2 + bias);
+      }
+      if (l < NU) S.u[l] = 0.0f;
+      if (l == 31) {
+        S.pos[0] = M::base_x(); S.pos[1] = M::base_y(); S.pos[2] = M::base_z();
+        S.quat[0] = 0.0f; S.quat[1] = 0.0f; S.quat[2] = 0.0f; S.quat[3] = 1.0f;
+      }
+    MB_END
+    S_::kinematics(S, P, false);
+    LaneVar<float> zero;
+    MB_LANES(l)
+      zero[l] = 0.0f;
+    MB_END
+    float s1, s2;
+    W3DObsScalars o = observe(S, rec, obs, zero, &s1, &s2);
+    float d, a, lp;
+    potential(S, rec, o.yaw, P.dt * P.substeps, &d, &a, &lp);
+    MB_LANES(l)
+      if (l == 0) { rec[ER_LINPOT] = lp; rec[ER_BODYX] = S.pos[0]; }
+    MB_END
+    target_obs(d, a, obs);
+  }
+
+  // Walker3DCustomEnv.step (env_locomotion.py:111-141) for one env; obs/reward/done follow the VecEnv
+  // convention: on done the env is reset in place and obs is the first observation of the next episode
+  // (the terminal observation goes to final_obs when that pointer is non-null).
+  MB_HD static void step(Mem& S, const MbPhysics& P, float* state, float* rec, uint32_t* mt_env, uint32_t* mt_robot,
+                         const float* act, float* obs, float* rew, uint8_t* done, uint8_t* trunc, float* final_obs,
+                         MbStats* stats) {
+    load_state(S, state);
+    LaneVar<float> araw;
+    LaneVar<int> badact;
+    MB_LANES(l)
+      araw[l] = 0.0f; badact[l] = 0;
+      if (l < NJ) {
+        float a = act[l];
+        if (!mb_finite(a)) { a = 0.0f; badact[l] = 1; }  // reference asserts (robots.py:32); we count and zero
+        araw[l] = a;
+        const float ac = fminf(fmaxf(a, -1.0f), 1.0f);
+        // torque is applied once and held for all substeps, as is PyBullet's -damping*qd
+        S.tau[l] = M::gain(l) * ac - M::damping(l) * S.u[6 + l];
+      }
+    MB_END
+    const unsigned anybad = warp_ballot(badact);
+    int rows = 0, nc = 0, overflow = 0, ncsum = 0;
+    for (int k = 0; k < P.substeps; ++k) {
+      rows += S_::substep(S, P, &nc, &overflow);
+      ncsum += nc;
+    }
+    // feet_contact from the last collision pass (robots.py:74-86 via getContactPoints)
+    float fc0 = 0.0f, fc1 = 0.0f;
+    for (int k = 0; k < nc; ++k) {
+      if (S.cpartner[k] == 0 && S.cfoot[k] == 0) fc0 = 1.0f;
+      if (S.cpartner[k] == 0 && S.cfoot[k] == 1) fc1 = 1.0f;
+    }
+    const float prev_bodyx = rec[ER_BODYX];
+    const int eval_mode = rec_i(rec, ER_EVAL);
+    MB_LANES(l)
+      if (l == 0) {
+        rec[ER_FEET0] = fc0; rec[ER_FEET1] = fc1;
+        if (eval_mode) { rec[ER_TX] = prev_bodyx + 4.0f; rec[ER_TY] = 0.0f; rec[ER_TZ] = 1.0f; }
+      }
+    MB_END
+    S_::kinematics(S, P, false);
+    float s1, s2;
+    W3DObsScalars o = observe(S, rec, obs, araw, &s1, &s2);
+    int env_done = o.nonfinite ? 1 : 0;
+    const float old_lp = rec[ER_LINPOT];
+    float dist, ang, lp;
+    const float scene_dt = P.dt * P.substeps;
+    potential(S, rec, o.yaw, scene_dt, &dist, &ang, &lp);
+    const float progress = lp - old_lp;
+    float posture = 0.0f;
+    if (!(-0.2f < o.pitch && o.pitch < 0.4f)) posture = fabsf(o.pitch);
+    if (!(-0.4f < o.roll && o.roll < 0.4f)) posture += fabsf(o.roll);
+    const float energy = 4.5f * (s1 / NJ) + 0.225f * (s2 / NJ);
+    const float joints_pen = 0.1f * o.joints_at_limit;
+    const float height_obs = mb_clip5(o.height);
+    const float tall = height_obs > 0.7f ? 2.0f : -1.0f;
+    if (tall < 0.0f) env_done = 1;
+    float target_bonus = 0.0f;
+    int close = rec_i(rec, ER_CLOSE);
+    if (dist < 0.15f) { close += 1; target_bonus = 2.0f; }
+    if ((float)close >= rec[ER_STOP]) {
+      // env_locomotion.py:214-222 -- re-sample the target mid-episode from the env stream
+      close = 0;
+      uint32_t* w = reinterpret_cast<uint32_t*>(S.scratch);
+      mt_fill(mt_env, w, 5);
+      double nd, na;
+      randomize_target(rec, w, &nd, &na);
+      MB_LANES(l)
+        if (l == 0) { rec[ER_TX] += (float)(nd * cos(na)); rec[ER_TY] += (float)(nd * sin(na)); }
+      MB_END
+      potential(S, rec, o.yaw, scene_dt, &dist, &ang, &lp);
+    }
+    const float reward = progress + target_bonus - energy + tall - posture - joints_pen;
+    target_obs(dist, ang, obs);
+    const int elapsed = rec_i(rec, ER_ELAPSED) + 1;
+    int truncated = 0, any_done = env_done;
+    if (elapsed >= 1000) { truncated = !env_done; any_done = 1; }
+    const float epret = rec[ER_EPRET] + reward;
+    const int eplen = rec_i(rec, ER_EPLEN) + 1;
+    MB_LANES(l)
+      if (l == 0) {
+        rec_i(rec, ER_CLOSE) = close; rec[ER_LINPOT] = lp; rec_i(rec, ER_ELAPSED) = elapsed;
+        rec[ER_BODYX] = S.pos[0];
+        rec[ER_EPRET] = epret; rec_i(rec, ER_EPLEN) = eplen;
+        rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum;
+        rec_i(rec, ER_OVERFLOW) += overflow;
+        *rew = reward; *done = (uint8_t)any_done; *trunc = (uint8_t)truncated;
+      }
+    MB_END
+    if (any_done) {
+      if (final_obs) {
+        MB_LANES(l)
+          for (int i = l; i < OBS; i += 32) final_obs[i] = obs[i];
+        MB_END
+      }
+      MB_LANES(l)
+        if (l == 0) {
+          rec[ER_LAST_EPRET] = epret; rec_i(rec, ER_LAST_EPLEN) = eplen;
+#ifdef __CUDACC__
+          atomicAdd(&stats->episodes, 1ull);
+          atomicAdd(&stats->ret_sum, (double)epret);
+          atomicAdd(&stats->len_sum, (double)eplen);
+          if (o.nonfinite) atomicAdd(&stats->nonfinite, 1ull);
+#else
+          stats->episodes += 1; stats->ret_sum += epret; stats->len_sum += eplen;
+          if (o.nonfinite) stats->nonfinite += 1;
+#endif
+        }
+      MB_END
+      reset(S, P, rec, mt_env, mt_robot, obs);
+    }
+    if (anybad) {
+      MB_LANES(l)
+        if (l == 0) {
+#ifdef __CUDACC__
+          atomicAdd(&stats->nonfinite, 1ull);
+#else
+          stats->nonfinite += 1;
+#endif
+        }
+      MB_END
+    }
+    store_state(S, state);
+  }
+};

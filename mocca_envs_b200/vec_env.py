@@ -1,0 +1,283 @@
+"""Batched, GPU-resident drop-in for the reference's env classes.
+
+``Walker3DCustomVecEnv`` runs ``num_envs`` independent copies of ``Walker3DCustomEnv-v0``
+(reference mocca_envs/env_locomotion.py:37-282, registered at mocca_envs/__init__.py:52-56 with
+``max_episode_steps=1000``) inside one CUDA kernel launch per ``step``.  Observations, rewards and dones are
+torch CUDA tensors (zero-copy; ``torch.utils.dlpack.to_dlpack`` works on them).  Auto-reset follows the baselines
+VecEnv convention the reference's downstream trainers use.
+
+``Walker3DCustomEnv`` is the N=1 gym-protocol facade: ``reset() -> obs``, ``step(a) -> (obs, reward, done, info)``
+with NumPy float64 observations, like the reference.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic is in libmocca_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from .seeding import create_seed, mt_state_rows
+
+ENV_ID = "Walker3DCustomEnv-v0"
+_MODELS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models")
+
+
+class Box:
+    """Minimal stand-in for gym.spaces.Box (gym is not a dependency of the batched path)."""
+
+    def __init__(self, low, high, dtype=np.float32):
+        self.low = np.asarray(low, dtype=dtype)
+        self.high = np.asarray(high, dtype=dtype)
+        self.shape = self.low.shape
+        self.dtype = np.dtype(dtype)
+
+    def sample(self, rng=np.random):
+        lo = np.where(np.isfinite(self.low), self.low, -1.0)
+        hi = np.where(np.isfinite(self.high), self.high, 1.0)
+        return rng.uniform(lo, hi).astype(self.dtype)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Walker3DCustomVecEnv:
+    env_id = ENV_ID
+    control_step = 1 / 60  # env_locomotion.py:39
+    llc_frame_skip = 1  # env_locomotion.py:40
+    sim_frame_skip = 4  # env_locomotion.py:41
+    max_episode_steps = 1000  # __init__.py:55
+
+    def __init__(self, num_envs: int, device="cuda:0", seed: int | None = None, physics: dict | None = None,
+                 return_final_obs: bool = False):
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("mocca_envs_b200 has no CPU path; device must be a CUDA device")
+        L = _lib.lib()
+        phys = _lib.Physics()
+        L.mb200_default_physics(C.byref(phys))
+        for k, v in (physics or {}).items():
+            if not hasattr(phys, k):
+                raise KeyError(k)
+            setattr(phys, k, v)
+        self.physics = phys
+        h = C.c_void_p()
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _lib.check(L.mb200_create(ENV_ID.encode(), self.num_envs, idx, C.byref(phys), C.byref(h)))
+        self._h = h
+        self._L = L
+        dims = [C.c_int() for _ in range(5)]
+        _lib.check(L.mb200_dims(h, *[C.byref(d) for d in dims]))
+        _, self.obs_dim, self.act_dim, self.state_dim, self.nu = [d.value for d in dims]
+        with open(os.path.join(_MODELS, "walker3d.json")) as f:
+            self.table = json.load(f)
+        # spaces as the reference builds them (robots.py:22-29, env_locomotion.py:58-60)
+        self.observation_space = Box(-np.inf * np.ones(self.obs_dim), np.inf * np.ones(self.obs_dim))
+        self.action_space = Box(-np.ones(self.act_dim), np.ones(self.act_dim))
+        kw = dict(device=self.device)
+        n = self.num_envs
+        self.obs = torch.zeros(n, self.obs_dim, dtype=torch.float32, **kw)
+        self.rew = torch.zeros(n, dtype=torch.float32, **kw)
+        self.done = torch.zeros(n, dtype=torch.uint8, **kw)
+        self.trunc = torch.zeros(n, dtype=torch.uint8, **kw)
+        self.final_obs = torch.zeros(n, self.obs_dim, dtype=torch.float32, **kw) if return_final_obs else None
+        self._seeded = False
+        self.seed(seed, _at_construction=True)
+
+    # ---- lifecycle
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._L.mb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- EnvBase.seed (env_base.py:164-166): env i is seeded with seed + i
+    def seed(self, seed=None, _at_construction=False):
+        base = create_seed(seed)
+        seeds = [(base + i) % 2 ** 64 for i in range(self.num_envs)]
+        rows = np.ascontiguousarray(mt_state_rows(seeds))
+        _lib.check(self._L.mb200_seed(self._h, rows.ctypes.data_as(C.c_void_p), int(_at_construction)))
+        self._seeded = True
+        return seeds
+
+    # ---- gym / VecEnv protocol
+    def reset(self, mask: torch.Tensor | None = None) -> torch.Tensor:
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _lib.check(self._L.mb200_reset(self._h, _ptr(mask), _ptr(self.obs), self._stream()))
+        return self.obs
+
+    def step(self, actions: torch.Tensor):
+        if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        assert actions.shape == (self.num_envs, self.act_dim)
+        _lib.check(self._L.mb200_step(self._h, _ptr(actions), _ptr(self.obs), _ptr(self.rew), _ptr(self.done),
+                                      _ptr(self.trunc), _ptr(self.final_obs), self._stream()))
+        info = {"TimeLimit.truncated": self.trunc}
+        if self.final_obs is not None:
+            info["terminal_observation"] = self.final_obs
+        return self.obs, self.rew, self.done, info
+
+    def step_host(self, actions: np.ndarray, out=None):
+        """Host-buffer entry point (what a SubprocVecEnv user holds): H2D, kernel, D2H, sync in one C call."""
+        n = self.num_envs
+        if out is None:
+            out = (np.empty((n, self.obs_dim), np.float32), np.empty(n, np.float32), np.empty(n, np.uint8),
+                   np.empty(n, np.uint8))
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        vp = lambda x: x.ctypes.data_as(C.c_void_p)
+        _lib.check(self._L.mb200_step_host(self._h, vp(a), vp(out[0]), vp(out[1]), vp(out[2]), vp(out[3]),
+                                           self._stream()))
+        return out
+
+    # ---- state access (parity tests, checkpoint/resume)
+    def get_state(self) -> torch.Tensor:
+        s = torch.empty(self.num_envs, self.state_dim, dtype=torch.float32, device=self.device)
+        _lib.check(self._L.mb200_get_state(self._h, _ptr(s), self._stream()))
+        return s
+
+    def set_state(self, s: torch.Tensor):
+        s = s.to(device=self.device, dtype=torch.float32).contiguous()
+        assert s.shape == (self.num_envs, self.state_dim)
+        _lib.check(self._L.mb200_set_state(self._h, _ptr(s), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def get_record(self) -> torch.Tensor:
+        r = torch.empty(self.num_envs, 32, dtype=torch.float32, device=self.device)
+        _lib.check(self._L.mb200_get_record(self._h, _ptr(r), self._stream()))
+        return r
+
+    def set_record(self, r: torch.Tensor):
+        r = r.to(device=self.device, dtype=torch.float32).contiguous()
+        _lib.check(self._L.mb200_set_record(self._h, _ptr(r), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def state_dict(self):
+        return {"state": self.get_state().cpu(), "record": self.get_record().cpu()}
+
+    def load_state_dict(self, d):
+        self.set_state(d["state"])
+        self.set_record(d["record"])
+
+    def step_physics(self, tau: torch.Tensor):
+        """stepSimulation only (bullet_utils.py:352-353): hold tau over the substeps; returns (rows, contacts)."""
+        tau = tau.to(device=self.device, dtype=torch.float32).contiguous()
+        rows = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        nc = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        _lib.check(self._L.mb200_step_physics(self._h, _ptr(tau), _ptr(rows), _ptr(nc), self._stream()))
+        return rows, nc
+
+    def mass_matrix(self) -> torch.Tensor:
+        M = torch.empty(self.num_envs, self.nu, self.nu, dtype=torch.float32, device=self.device)
+        _lib.check(self._L.mb200_mass_matrix(self._h, _ptr(M), self._stream()))
+        return M
+
+    def inverse_dynamics(self, acc: torch.Tensor) -> torch.Tensor:
+        acc = acc.to(device=self.device, dtype=torch.float32).contiguous()
+        tau = torch.empty(self.num_envs, self.nu, dtype=torch.float32, device=self.device)
+        _lib.check(self._L.mb200_inverse_dynamics(self._h, _ptr(acc), _ptr(tau), self._stream()))
+        return tau
+
+    # ---- trainer-facing extras (env_base.py:103-118, env_locomotion.py:76-77,224-282)
+    def evaluation_mode(self):
+        _lib.check(self._L.mb200_set_param(self._h, b"eval_mode", 1.0))
+
+    def set_env_params(self, params: dict):
+        for k, v in params.items():
+            if k == "eval_mode":
+                _lib.check(self._L.mb200_set_param(self._h, b"eval_mode", float(bool(v))))
+
+    def stats(self, reset=False) -> dict:
+        out = (C.c_double * 8)()
+        _lib.check(self._L.mb200_stats(self._h, out, int(reset)))
+        return {"episodes": out[0], "return_sum": out[1], "length_sum": out[2], "nonfinite": out[3],
+                "overflow": out[4]}
+
+    def launch_count(self) -> int:
+        return int(self._L.mb200_launch_count(self._h))
+
+    def get_mirror_indices(self):
+        """Walker3DCustomEnv.get_mirror_indices (env_locomotion.py:224-282) -- static index tables."""
+        A = self.act_dim
+        right_j = np.array(self.table["right_joint_indices"], dtype=np.int64)
+        left_j = np.array(self.table["left_joint_indices"], dtype=np.int64)
+        neg_j = np.array(self.table["negation_joint_indices"], dtype=np.int64)
+        nfeet = len(self.table["foot_links"])
+        right = np.concatenate((right_j + 6, right_j + 6 + A, [6 + 2 * A + 2 * i for i in range(nfeet // 2)]))
+        left = np.concatenate((left_j + 6, left_j + 6 + A, [6 + 2 * A + 2 * i + 1 for i in range(nfeet // 2)]))
+        neg_obs = np.concatenate(([2, 4], 6 + neg_j, 6 + neg_j + A, [6 + 2 * A + nfeet]))
+        return neg_obs, right, left, neg_j, right_j, left_j
+
+
+class Walker3DCustomEnv:
+    """gym-protocol facade over a 1-env batch; NumPy float64 observations like the reference."""
+
+    metadata = {"render.modes": []}
+
+    def __init__(self, device="cuda:0", seed=None, render=False, **kwargs):
+        if render:
+            raise NotImplementedError("rendering is out of scope for the GPU path (SURVEY.md section 2, row 2)")
+        self.vec = Walker3DCustomVecEnv(1, device=device, seed=seed, return_final_obs=True)
+        self.observation_space = self.vec.observation_space
+        self.action_space = self.vec.action_space
+        self._pending_reset_obs = None
+
+    def seed(self, seed=None):
+        return [self.vec.seed(seed)[0]]
+
+    def reset(self):
+        if self._pending_reset_obs is not None:
+            # the kernel already reset this env (same RNG draws reset() would make) when the episode ended
+            obs, self._pending_reset_obs = self._pending_reset_obs, None
+            return obs
+        return self.vec.reset()[0].double().cpu().numpy()
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.float64)
+        assert np.isfinite(a).all()  # robots.py:32
+        self._pending_reset_obs = None
+        act = torch.as_tensor(a, dtype=torch.float32).reshape(1, -1)
+        obs, rew, done, info = self.vec.step(act)
+        d = bool(done[0].item())
+        out_info = {}
+        if d:
+            self._pending_reset_obs = obs[0].double().cpu().numpy()
+            o = info["terminal_observation"][0].double().cpu().numpy()
+            if bool(info["TimeLimit.truncated"][0].item()):
+                out_info["TimeLimit.truncated"] = True
+        else:
+            o = obs[0].double().cpu().numpy()
+        return o, float(rew[0].item()), d, out_info
+
+    def evaluation_mode(self):
+        self.vec.evaluation_mode()
+
+    def get_mirror_indices(self):
+        return self.vec.get_mirror_indices()
+
+    def close(self):
+        self.vec.close()
+
+
+def make(env_id: str, num_envs: int | None = None, **kwargs):
+    """gym.make analogue: ``make("Walker3DCustomEnv-v0")`` -> gym-style env, ``make(id, num_envs=N)`` -> VecEnv."""
+    eid = env_id.split(":")[-1]
+    if eid != ENV_ID:
+        raise KeyError("env id %r is not built yet (available: %s)" % (env_id, ENV_ID))
+    if num_envs is None:
+        return Walker3DCustomEnv(**kwargs)
+    return Walker3DCustomVecEnv(num_envs, **kwargs)

@@ -1,0 +1,69 @@
+// Lane-loop emulation of the kernel source (mb_core.cuh / mb_env.cuh compiled by g++ with MB_LANES as a
+// 32-iteration loop).  DEBUG/TEST HARNESS ONLY: lets the exact kernel source be diffed against the CPU oracle on
+// a box without a GPU.  Never loaded by the mocca_envs_b200 package; the product path is libmocca_b200.so.
+#include <string.h>
+
+#include "../../mocca_envs_b200/csrc/generated/walker3d_model.h"
+#include "../../mocca_envs_b200/csrc/mb_env.cuh"
+
+typedef W3D_Model WM;
+typedef W3DEnv<WM> WEnv;
+typedef WarpMem<WM> WMem;
+
+static void default_phys(MbPhysics* p) {
+  p->dt = 1.0f / 240.0f; p->substeps = 4; p->iterations = 5; p->gravity = 9.8f; p->erp_contact = 0.9f;
+  p->erp_joint = 0.2f; p->linear_slop = 1e-5f; p->lin_damping = 0.04f; p->ang_damping = 0.04f;
+  p->max_coord_vel = 100.0f; p->limit_max_impulse = 100.0f; p->split_threshold = -0.04f;
+  p->residual_threshold = 1e-7f; p->ground_friction = 0.8f; p->has_ground = 1;
+}
+
+extern "C" {
+int emu_sizeof_phys() { return (int)sizeof(MbPhysics); }
+int emu_sizeof_warpmem() { return (int)sizeof(WMem); }
+void emu_default_phys(MbPhysics* p) { default_phys(p); }
+
+void emu_step_physics(const MbPhysics* p, float* state, const float* tau, int* rows, int* contacts) {
+  static WMem S;
+  memset(&S, 0, sizeof(S));
+  WEnv::load_state(S, state);
+  for (int j = 0; j < WM::NJ; ++j) S.tau[j] = tau[j];
+  int r = 0, nc = 0, ov = 0;
+  for (int k = 0; k < p->substeps; ++k) r += Sim<WM>::substep(S, *p, &nc, &ov);
+  WEnv::store_state(S, state);
+  *rows = r;
+  *contacts = nc;
+}
+
+void emu_mass_matrix(const MbPhysics* p, const float* state, float* Mout, float* bias) {
+  static WMem S;
+  memset(&S, 0, sizeof(S));
+  WEnv::load_state(S, state);
+  Sim<WM>::kinematics(S, *p, true);
+  Sim<WM>::bodies(S, *p);
+  Sim<WM>::mass_matrix_and_rhs(S);
+  const int NU = WM::NU;
+  for (int i = 0; i < NU; ++i) {
+    for (int j = 0; j < NU; ++j) Mout[i * NU + j] = i >= j ? S.L[tri(i, j)] : S.L[tri(j, i)];
+    bias[i] = -S.rhs[i];
+  }
+}
+
+void emu_w3d_reset(const MbPhysics* p, float* state, float* rec, uint32_t* mt_env, uint32_t* mt_robot, float* obs) {
+  static WMem S;
+  memset(&S, 0, sizeof(S));
+  WEnv::reset(S, *p, rec, mt_env, mt_robot, obs);
+  WEnv::store_state(S, state);
+}
+
+void emu_w3d_step(const MbPhysics* p, float* state, float* rec, uint32_t* mt_env, uint32_t* mt_robot,
+                  const float* act, float* obs, float* rew, uint8_t* done, uint8_t* trunc, float* final_obs,
+                  double* stats_out) {
+  static WMem S;
+  memset(&S, 0, sizeof(S));
+  MbStats st;
+  memset(&st, 0, sizeof(st));
+  WEnv::step(S, *p, state, rec, mt_env, mt_robot, act, obs, rew, done, trunc, final_obs, &st);
+  stats_out[0] = (double)st.episodes; stats_out[1] = st.ret_sum; stats_out[2] = st.len_sum;
+  stats_out[3] = (double)st.nonfinite;
+}
+}

@@ -1,0 +1,95 @@
+"""ctypes binding of the lane-loop emulation of the kernel source (tests only; see emu.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libmb_emu.so")
+_SRC = [os.path.join(_HERE, "emu.cpp")] + [
+    os.path.join(_HERE, "..", "..", "mocca_envs_b200", "csrc", f)
+    for f in ("mb_core.cuh", "mb_env.cuh", "mb_tables.h", "generated/walker3d_model.h")]
+
+
+class Phys(C.Structure):
+    _fields_ = [("dt", C.c_float), ("substeps", C.c_int), ("iterations", C.c_int), ("gravity", C.c_float),
+                ("erp_contact", C.c_float), ("erp_joint", C.c_float), ("linear_slop", C.c_float),
+                ("lin_damping", C.c_float), ("ang_damping", C.c_float), ("max_coord_vel", C.c_float),
+                ("limit_max_impulse", C.c_float), ("split_threshold", C.c_float), ("residual_threshold", C.c_float),
+                ("ground_friction", C.c_float), ("has_ground", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        stale = (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in _SRC)
+        if stale:
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                                   "-Wno-unused-variable", "-o", _LIB, _SRC[0]])
+        _lib = C.CDLL(_LIB)
+        assert _lib.emu_sizeof_phys() == C.sizeof(Phys)
+    return _lib
+
+
+def default_phys():
+    p = Phys()
+    lib().emu_default_phys(C.byref(p))
+    return p
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def step_physics(p, state, tau):
+    state = np.ascontiguousarray(state, dtype=np.float32).copy()
+    buf = np.zeros(64, dtype=np.float32)
+    buf[: len(state)] = state
+    tau = np.ascontiguousarray(tau, dtype=np.float32)
+    rows, nc = C.c_int(0), C.c_int(0)
+    lib().emu_step_physics(C.byref(p), _fp(buf), _fp(tau), C.byref(rows), C.byref(nc))
+    return buf[: len(state)].copy(), rows.value, nc.value
+
+
+def mass_matrix(p, state, nu):
+    buf = np.zeros(64, dtype=np.float32)
+    buf[: len(state)] = state
+    M = np.zeros((nu, nu), dtype=np.float32)
+    b = np.zeros(nu, dtype=np.float32)
+    lib().emu_mass_matrix(C.byref(p), _fp(buf), _fp(M), _fp(b))
+    return M, b
+
+
+class EmuW3D:
+    def __init__(self, mt_state, obs_dim=52, act_dim=21, phys=None):
+        self.p = phys or default_phys()
+        self.state = np.zeros(64, dtype=np.float32)
+        self.rec = np.zeros(32, dtype=np.float32)
+        self.mt = np.zeros((2, 640), dtype=np.uint32)
+        self.mt[0, :625] = mt_state
+        self.mt[1, 624] = 624
+        self.rec.view(np.int32)[11] = 1  # ER_ALIASED
+        self.obs_dim, self.act_dim = obs_dim, act_dim
+        self.stats = np.zeros(4)
+
+    def reset(self):
+        obs = np.zeros(self.obs_dim, dtype=np.float32)
+        lib().emu_w3d_reset(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(self.mt[0]), _fp(self.mt[1]), _fp(obs))
+        return obs
+
+    def step(self, act):
+        act = np.ascontiguousarray(act, dtype=np.float32)
+        obs = np.zeros(self.obs_dim, dtype=np.float32)
+        fin = np.zeros(self.obs_dim, dtype=np.float32)
+        rew = np.zeros(1, dtype=np.float32)
+        done = np.zeros(1, dtype=np.uint8)
+        trunc = np.zeros(1, dtype=np.uint8)
+        st = np.zeros(4)
+        lib().emu_w3d_step(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(self.mt[0]), _fp(self.mt[1]), _fp(act),
+                           _fp(obs), _fp(rew), _fp(done), _fp(trunc), _fp(fin), _fp(st))
+        self.stats += st
+        return obs, float(rew[0]), bool(done[0]), bool(trunc[0]), fin

@@ -1,0 +1,46 @@
+"""Shared helpers for parity tests (oracle vs kernel source)."""
+import numpy as np
+
+
+def random_states(table, rng, n, airborne=True, spin=1.0, margin=0.15):
+    """[n, 13+2A] float64 rows: pos3 quat4 omega3 vel3 q qd, joints strictly inside their limits."""
+    A = table["n_dof"]
+    lo, hi = np.array(table["lower"]), np.array(table["upper"])
+    out = np.zeros((n, 13 + 2 * A))
+    for i in range(n):
+        quat = rng.randn(4)
+        quat /= np.linalg.norm(quat)
+        out[i, 0:3] = rng.uniform(-1, 1, 3) + [0, 0, 3.0 if airborne else 1.3]
+        out[i, 3:7] = quat
+        out[i, 7:10] = spin * rng.randn(3)
+        out[i, 10:13] = rng.randn(3)
+        out[i, 13:13 + A] = lo + (hi - lo) * rng.uniform(margin, 1 - margin, A)
+        out[i, 13 + A:] = spin * rng.uniform(-3, 3, A)
+    return out
+
+
+def oracle_state(O, A, row):
+    return O.make_state(A, row[0:3], row[3:7], row[7:10], row[10:13], row[13:13 + A], row[13 + A:13 + 2 * A])
+
+
+def contact_states(O, table, rng, n, steps=(6, 30)):
+    """States sampled from oracle rollouts that are in ground contact (random bounded torques)."""
+    A = table["n_dof"]
+    m = O.model_from_table(table)
+    p = O.default_params()
+    gain = np.array(table["gain"])
+    out = []
+    while len(out) < n:
+        q0 = np.array(table["base_joint_angles"]) + rng.uniform(-0.1, 0.1, A)
+        s = O.make_state(A, [0, 0, 1.32], [0, 0, 0, 1], [0] * 3, [0] * 3, q0, np.zeros(A))
+        k = rng.randint(*steps)
+        for _ in range(k):
+            c, _ = O.step_physics(m, p, s, 0.3 * gain * rng.uniform(-1, 1, A))
+        if c.n > 0 and s.pos[2] > 0.5:
+            out.append(O.state_vector(s, A))
+    return np.array(out)
+
+
+def state_error(out, ref):
+    """max abs error scaled per component by max(1, |ref|)."""
+    return float(np.max(np.abs(out - ref) / np.maximum(1.0, np.abs(ref))))

@@ -1,0 +1,266 @@
+"""GPU parity tests proper: the sm_100a kernels, called through the C ABI (libmocca_b200.so via ctypes), against
+the float64 CPU oracle on identical seeded inputs.  Oracle = our restatement of Bullet's pipeline (PyBullet golden
+vectors unavailable: "vs restatement").  Tolerances follow BASELINE.json's north_star."""
+import numpy as np
+import pytest
+
+from tests.helpers import contact_states, oracle_state, random_states, state_error
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _env(n, seed=0, **kw):
+    from mocca_envs_b200.vec_env import Walker3DCustomVecEnv
+
+    return Walker3DCustomVecEnv(n, device="cuda:0", seed=seed, **kw)
+
+
+def test_mass_matrix_and_inverse_dynamics(walker_table, oracle_mod, torch_mod):
+    """north_star: mass matrix and inverse dynamics within 1e-4 relative error."""
+    torch, O, t = torch_mod, oracle_mod, walker_table
+    A = t["n_dof"]
+    m = O.model_from_table(t)
+    rng = np.random.RandomState(0)
+    N = 64
+    st = random_states(t, rng, N)
+    env = _env(N)
+    env.set_state(torch.tensor(st, dtype=torch.float32))
+    M = env.mass_matrix().cpu().numpy()
+    acc = rng.randn(N, 6 + A)
+    tau = env.inverse_dynamics(torch.tensor(acc, dtype=torch.float32)).cpu().numpy()
+    for i in range(N):
+        s = oracle_state(O, A, st[i].astype(np.float32).astype(np.float64))
+        Mref = O.mass_matrix(m, s)
+        assert np.abs(M[i] - Mref).max() / np.abs(Mref).max() < 1e-4
+        assert np.allclose(M[i], M[i].T)
+        ref = O.rnea(m, s, acc[i].astype(np.float32).astype(np.float64), 9.8)
+        assert np.abs(tau[i] - ref).max() / np.abs(ref).max() < 1e-4
+    env.close()
+
+
+def test_contact_free_single_step(walker_table, oracle_mod, torch_mod):
+    """north_star: contact-free single-step state within 1e-4."""
+    torch, O, t = torch_mod, oracle_mod, walker_table
+    A = t["n_dof"]
+    m = O.model_from_table(t)
+    p = O.default_params()
+    rng = np.random.RandomState(1)
+    N = 64
+    st = random_states(t, rng, N, spin=0.5, margin=0.35).astype(np.float32)
+    tau = (np.array(t["gain"]) * rng.uniform(-1, 1, (N, A))).astype(np.float32)
+    env = _env(N)
+    env.set_state(torch.tensor(st))
+    rows, nc = env.step_physics(torch.tensor(tau))
+    out = env.get_state().cpu().numpy()
+    assert int(rows.sum()) == 0 and int(nc.sum()) == 0
+    worst = 0.0
+    for i in range(N):
+        s = oracle_state(O, A, st[i].astype(np.float64))
+        O.step_physics(m, p, s, tau[i].astype(np.float64))
+        worst = max(worst, state_error(out[i], O.state_vector(s, A)))
+    assert worst < 1e-4, worst
+    env.close()
+
+
+def test_contact_single_frame(walker_table, oracle_mod, torch_mod):
+    """north_star: per-step contact rollouts within a stated tolerance over 1 frame.
+    Stated tolerance: 2e-3 of max(1, |x|) per state component (f32 PGS in the factor-transformed space vs f64
+    velocity-space PGS), identical contact counts."""
+    torch, O, t = torch_mod, oracle_mod, walker_table
+    A = t["n_dof"]
+    m = O.model_from_table(t)
+    p = O.default_params()
+    rng = np.random.RandomState(2)
+    N = 32
+    st = contact_states(O, t, rng, N).astype(np.float32)
+    tau = (0.3 * np.array(t["gain"]) * rng.uniform(-1, 1, (N, A))).astype(np.float32)
+    env = _env(N)
+    env.set_state(torch.tensor(st))
+    rows, nc = env.step_physics(torch.tensor(tau))
+    out = env.get_state().cpu().numpy()
+    rows, nc = rows.cpu().numpy(), nc.cpu().numpy()
+    worst = 0.0
+    for i in range(N):
+        s = oracle_state(O, A, st[i].astype(np.float64))
+        c, r = O.step_physics(m, p, s, tau[i].astype(np.float64))
+        assert c.n == nc[i]
+        assert abs(r - rows[i]) <= 2
+        worst = max(worst, state_error(out[i], O.state_vector(s, A)))
+    assert worst < 2e-3, worst
+    env.close()
+
+
+def test_reset_bit_exact_vs_numpy(walker_table, oracle_mod, torch_mod):
+    """north_star: bit-exact reset-state generation from the same seed (values rounded to the f32 state)."""
+    torch, O, t = torch_mod, oracle_mod, walker_table
+    N = 16
+    env = _env(N, seed=100)
+    oracles = [O.Walker3DCustomOracle(t, seed=100 + i) for i in range(N)]
+    for episode in range(3):
+        obs = env.reset().cpu().numpy()
+        st = env.get_state().cpu().numpy()
+        rec = env.get_record().cpu().numpy()
+        for i, o in enumerate(oracles):
+            oref = o.reset()
+            assert np.array_equal(st[i, 13:34], np.array(o.e.s.q[:21]).astype(np.float32))
+            assert np.array_equal(st[i, 0:7], np.array([0, 0, 1.32, 0, 0, 0, 1], dtype=np.float32))
+            assert np.array_equal(rec[i, 0:3], np.array(o.e.walk_target[:], dtype=np.float32))
+            assert rec[i, 5] == o.e.stop_frames
+            assert np.abs(obs[i] - oref).max() < 1e-5
+    env.close()
+
+
+def test_env_step_teacher_forced(walker_table, oracle_mod, torch_mod):
+    """Walker3DCustomEnv.step obs / reward / done from identical states, 16 envs x 40 steps."""
+    torch, O, t = torch_mod, oracle_mod, walker_table
+    N = 16
+    env = _env(N, seed=7, return_final_obs=True)
+    oracles = [O.Walker3DCustomOracle(t, seed=7 + i) for i in range(N)]
+    env.reset()
+    for o in oracles:
+        o.reset()
+    arng = np.random.RandomState(3)
+    for step in range(40):
+        a = arng.uniform(-1.2, 1.2, (N, 21)).astype(np.float32)
+        st = np.stack([o.state_vector() for o in oracles]).astype(np.float32)
+        env.set_state(torch.tensor(st))
+        rec = env.get_record()
+        rec[:, 7] = torch.tensor([o.e.linear_potential for o in oracles], dtype=torch.float32)
+        env.set_record(rec)
+        obs, rew, done, info = env.step(torch.tensor(a))
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        fin = info["terminal_observation"].cpu().numpy()
+        for i, o in enumerate(oracles):
+            # the oracle sees the same f32-rounded state the kernel saw
+            sv = st[i].astype(np.float64)
+            for k in range(3):
+                o.e.s.pos[k] = sv[k]; o.e.s.omega[k] = sv[7 + k]; o.e.s.vel[k] = sv[10 + k]
+            for k in range(4):
+                o.e.s.quat[k] = sv[3 + k]
+            for k in range(21):
+                o.e.s.q[k] = sv[13 + k]; o.e.s.qd[k] = sv[34 + k]
+            o1, r1, d1, _ = o.step(a[i].astype(np.float64))
+            assert bool(done[i]) == d1, (step, i)
+            ocmp = fin[i] if d1 else obs[i]
+            assert np.abs(o1 - ocmp).max() < 5e-3, (step, i, int(np.abs(o1 - ocmp).argmax()))
+            assert abs(r1 - rew[i]) < 5e-2 + 1e-3 * abs(r1)
+            if d1:
+                o.reset()
+    env.close()
+
+
+def test_rollout_statistics_vs_oracle(walker_table, oracle_mod, torch_mod):
+    """north_star: episode return and length for fixed random policies statistically indistinguishable.
+    Stated bound: |mean_gpu - mean_oracle| < 4 standard errors (pooled) for episode length and return,
+    random-uniform policy, >= 256 oracle episodes vs >= 4096 GPU episodes."""
+    torch, O, t = torch_mod, oracle_mod, walker_table
+    N = 2048
+    env = _env(N, seed=11)
+    env.reset()
+    g = torch.Generator(device="cuda:0").manual_seed(5)
+    lens, rets = [], []
+    for _ in range(120):
+        a = torch.rand(N, 21, device="cuda:0", generator=g) * 2 - 1
+        obs, rew, done, info = env.step(a)
+        d = done.bool()
+        if d.any():
+            rec = env.get_record()
+            lens.append(rec[d, 20].view(torch.int32).float().cpu().numpy())
+            rets.append(rec[d, 19].cpu().numpy())
+    lens, rets = np.concatenate(lens), np.concatenate(rets)
+    assert len(lens) >= 4096
+    olens, orets = [], []
+    arng = np.random.RandomState(9)
+    o = O.Walker3DCustomOracle(t, seed=12345)
+    while len(olens) < 256:
+        o.reset()
+        L, R = 0, 0.0
+        while True:
+            _, r, d, _ = o.step(arng.uniform(-1, 1, 21))
+            L += 1
+            R += r
+            if d:
+                break
+        olens.append(L)
+        orets.append(R)
+    olens, orets = np.array(olens), np.array(orets)
+    for a_, b_ in ((lens, olens), (rets, orets)):
+        se = np.sqrt(a_.var() / len(a_) + b_.var() / len(b_))
+        assert abs(a_.mean() - b_.mean()) < 4 * se + 1e-6, (a_.mean(), b_.mean(), se)
+    env.close()
+
+
+def test_full_size_properties(torch_mod):
+    """BASELINE config 2 size (16384 envs): determinism, finiteness, auto-reset bookkeeping, host path == device."""
+    torch = torch_mod
+    N = 16384
+    outs = []
+    for rep in range(2):
+        env = _env(N, seed=3)
+        env.reset()
+        g = torch.Generator(device="cuda:0").manual_seed(1)
+        tot_done = 0
+        for _ in range(40):
+            a = torch.rand(N, 21, device="cuda:0", generator=g) * 2 - 1
+            obs, rew, done, info = env.step(a)
+            tot_done += int(done.sum())
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        st = env.stats()
+        assert st["episodes"] == tot_done and st["nonfinite"] == 0
+        assert tot_done > 0
+        outs.append((obs.clone(), env.get_state().clone()))
+        env.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_step_host_matches_device(torch_mod):
+    torch = torch_mod
+    N = 256
+    e1, e2 = _env(N, seed=21), _env(N, seed=21)
+    e1.reset(); e2.reset()
+    rng = np.random.RandomState(0)
+    for _ in range(5):
+        a = rng.uniform(-1, 1, (N, 21)).astype(np.float32)
+        o1, r1, d1, _ = e1.step(torch.tensor(a))
+        o2, r2, d2, t2 = e2.step_host(a)
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(d1.cpu().numpy(), d2)
+    e1.close(); e2.close()
+
+
+def test_gym_facade(torch_mod):
+    from mocca_envs_b200 import make
+
+    env = make("mocca_envs:Walker3DCustomEnv-v0", seed=0)
+    obs = env.reset()
+    assert obs.shape == (52,) and obs.dtype == np.float64
+    total, steps = 0.0, 0
+    done = False
+    while not done and steps < 1000:
+        obs, r, done, info = env.step(np.zeros(21))
+        total += r
+        steps += 1
+    assert done and steps < 200  # the passive walker collapses (oracle: 33 steps with seed 0)
+    assert env.reset().shape == (52,)
+    env.close()
+
+
+def test_abi_errors(torch_mod):
+    import ctypes as C
+
+    from mocca_envs_b200 import _lib
+
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.mb200_create(b"Nope-v0", 4, 0, None, C.byref(h)) != 0
+    assert L.mb200_create(b"Walker3DCustomEnv-v0", 0, 0, None, C.byref(h)) != 0
+    assert L.mb200_create(b"Walker3DCustomEnv-v0", 4, 99, None, C.byref(h)) != 0
+    assert L.mb200_step(None, None, None, None, None, None, None, None) != 0
