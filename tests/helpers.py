@@ -44,3 +44,33 @@ def contact_states(O, table, rng, n, steps=(6, 30)):
 def state_error(out, ref):
     """max abs error scaled per component by max(1, |ref|)."""
     return float(np.max(np.abs(out - ref) / np.maximum(1.0, np.abs(ref))))
+
+
+def oracle_record(o, rec_row):
+    """Teacher-force the per-env bookkeeping record (ER_* in csrc/mb_env.cuh) from an oracle env."""
+    e = o.e
+    rec_row[0:3] = np.array(e.walk_target[:], dtype=np.float32)
+    rec_row[3] = e.dist
+    rec_row[4] = e.angle
+    rec_row[5] = e.stop_frames
+    rec_row.view(np.int32)[6] = e.close_count
+    rec_row[7] = e.linear_potential
+    rec_row.view(np.int32)[8] = e.elapsed
+    rec_row[9] = e.feet_contact[0]
+    rec_row[10] = e.feet_contact[1]
+    rec_row[17] = e.body_xyz[0]
+    return rec_row
+
+
+def force_oracle_state(o, sv):
+    """Overwrite the oracle env's physics state with the (f32-rounded) row the kernel sees."""
+    A = o.A
+    for k in range(3):
+        o.e.s.pos[k] = sv[k]
+        o.e.s.omega[k] = sv[7 + k]
+        o.e.s.vel[k] = sv[10 + k]
+    for k in range(4):
+        o.e.s.quat[k] = sv[3 + k]
+    for k in range(A):
+        o.e.s.q[k] = sv[13 + k]
+        o.e.s.qd[k] = sv[13 + A + k]
