@@ -103,12 +103,28 @@ def reduce_table(t: dict) -> dict:
                                friction=g["friction"], thresh=thresh[link + 1],
                                foot=foot_links.index(link) if link in foot_links else -1))
     foot_body = [[b["link"] for b in bodies].index(f) for f in foot_links]
+    # ancestor chains (root -> self) packed 5 bits per entry, and the compact (chain-ordered) factor layout:
+    # row i of L stores only its support [base block | ancestors root->parent | diagonal]
+    chains = []
+    for j in range(nj):
+        c = [j]
+        while jparent[c[0]] >= 0:
+            c.insert(0, jparent[c[0]])
+        chains.append(c)
+    jdepth = [len(c) - 1 for c in chains]
+    assert max(jdepth) + 1 <= 12 and nj <= 32
+    chainpack = [sum(a << (5 * t) for t, a in enumerate(c)) for c in chains]
+    rowlen = [i + 1 for i in range(6)] + [6 + jdepth[j] + 1 for j in range(nj)]
+    rowoff = [sum(rowlen[:i]) for i in range(6 + nj)]
+    rowmask_rt = [(1 << i) - 1 for i in range(6)] + [0x3F | ((janc[j] & ~(1 << j)) << 6) for j in range(nj)]
     return dict(name=t["name"], nj=nj, nb=nb, nu=6 + nj, npt=len(points), nlevel=max(jlevel) + 1,
                 jparent=jparent, joff=joff, jrot=jrot, jaxis=jaxis, jlevel=jlevel, janc=janc,
                 lower=t["lower"], upper=t["upper"], gain=t["gain"], damping=t["damping"], armature=t["armature"],
                 bodies=bodies, bstart=bstart, bend=bend, points=points, foot_body=foot_body,
                 nfeet=len(foot_links), base_joint_angles=t["base_joint_angles"], base_position=t["base_position"],
-                right=t["right_joint_indices"], left=t["left_joint_indices"], neg=t["negation_joint_indices"])
+                right=t["right_joint_indices"], left=t["left_joint_indices"], neg=t["negation_joint_indices"],
+                jdepth=jdepth, chainpack=chainpack, rowlen=rowlen, rowoff=rowoff, rowmask_rt=rowmask_rt,
+                lsize=sum(rowlen), maxsup=max(rowlen))
 
 
 def _f(v) -> str:
@@ -146,6 +162,12 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append(_iarr(P + "_jparent", r["jparent"]))
     out.append(_iarr(P + "_jlevel", r["jlevel"]))
     out.append(_iarr(P + "_janc", r["janc"], "unsigned"))
+    out.append(_iarr(P + "_jdepth", r["jdepth"]))
+    out.append("MB_TABLE unsigned long long %s_chainpack[%d] = {%s};\n"
+               % (P, len(r["chainpack"]), ", ".join("%dull" % v for v in r["chainpack"])))
+    out.append(_iarr(P + "_rowoff", r["rowoff"]))
+    out.append(_iarr(P + "_rowlen", r["rowlen"]))
+    out.append(_iarr(P + "_rowmask", r["rowmask_rt"], "unsigned"))
     out.append(_farr(P + "_joff", r["joff"]))
     out.append(_farr(P + "_jrot", [np.asarray(m).reshape(9) for m in r["jrot"]]))
     out.append(_farr(P + "_jaxis", r["jaxis"]))
@@ -174,10 +196,24 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append(_iarr(P + "_right", r["right"]))
     out.append(_iarr(P + "_left", r["left"]))
     out.append(_iarr(P + "_neg", r["neg"]))
+    # support of row i of the mass matrix / its L^T L factor (columns j < i): base block + ancestors
+    rowmask = []
+    for i in range(r["nu"]):
+        if i < 6:
+            rowmask.append((1 << i) - 1)
+        else:
+            j = i - 6
+            rowmask.append(0x3F | (((r["janc"][j] & ~(1 << j))) << 6))
     out.append("\nstruct %s_Model {\n" % P)
-    out.append("  enum { NJ = %d, NB = %d, NU = %d, NPT = %d, NLEVEL = %d, NFEET = %d, NMIRROR = %d, NNEG = %d };\n"
-               % (r["nj"], r["nb"], r["nu"], r["npt"], r["nlevel"], r["nfeet"], len(r["right"]), len(r["neg"])))
+    out.append("  MB_HD static constexpr unsigned rowmask_c(int i) {\n    return " +
+               " ".join("i == %d ? %du :" % (i, m) for i, m in enumerate(rowmask)) + " 0u;\n  }\n")
+    out.append("  enum { NJ = %d, NB = %d, NU = %d, NPT = %d, NLEVEL = %d, NFEET = %d, NMIRROR = %d, NNEG = %d,\n"
+               "         LSIZE = %d, MAXSUP = %d };\n"
+               % (r["nj"], r["nb"], r["nu"], r["npt"], r["nlevel"], r["nfeet"], len(r["right"]), len(r["neg"]),
+                  r["lsize"], r["maxsup"]))
+    out.append("  MB_HD static unsigned long long chainpack(int j) { return %s_chainpack[j]; }\n" % P)
     for fld, ctype in [("jparent", "int"), ("jlevel", "int"), ("janc", "unsigned"), ("bstart", "int"), ("bend", "int"),
+                       ("jdepth", "int"), ("rowoff", "int"), ("rowlen", "int"), ("rowmask", "unsigned"),
                        ("bowner", "int"), ("powner", "int"), ("pfoot", "int"), ("pid", "int"), ("foot_body", "int"),
                        ("right", "int"), ("left", "int"), ("neg", "int")]:
         out.append("  MB_HD static %s %s(int i) { return %s_%s[i]; }\n" % (ctype, fld, P, fld))

@@ -57,7 +57,7 @@ struct StepArgs {
   MbStats* stats;
 };
 
-__global__ void __launch_bounds__(MB_WARPS * 32) k_step_walker3d_custom(StepArgs a) {
+__global__ void __launch_bounds__(MB_WARPS * 32, 6) k_step_walker3d_custom(StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * MB_WARPS + warp;
@@ -122,10 +122,10 @@ __global__ void __launch_bounds__(MB_WARPS * 32)
   MB_LANES(l)
     if (l < NU) {
       if (mode == 0) {
-        for (int j = 0; j < NU; ++j) out[((size_t)env * NU + l) * NU + j] = l >= j ? S.L[tri(l, j)] : S.L[tri(j, l)];
+        for (int j = 0; j < NU; ++j) out[((size_t)env * NU + l) * NU + j] = mb_Lget<WM>(S.L, l, j);
       } else {
         float t = -S.rhs[l];
-        for (int j = 0; j < NU; ++j) t += (l >= j ? S.L[tri(l, j)] : S.L[tri(j, l)]) * acc[(size_t)env * NU + j];
+        for (int j = 0; j < NU; ++j) t += mb_Lget<WM>(S.L, l, j) * acc[(size_t)env * NU + j];
         out[(size_t)env * NU + l] = t;
       }
     }

@@ -20,6 +20,7 @@
 #include "mb_tables.h"
 
 #ifdef __CUDACC__
+#define MB_NOINLINE __device__ __noinline__
 #define MB_LANES(l) { const int l = (int)(threadIdx.x & 31);
 #define MB_END } __syncwarp();
 template <typename T> struct LaneVar {
@@ -38,6 +39,7 @@ MB_HD unsigned warp_ballot(const LaneVar<int>& p) { return __ballot_sync(0xfffff
 MB_HD int mb_popc(unsigned x) { return __popc(x); }
 MB_HD void mb_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
 #else
+#define MB_NOINLINE
 #define MB_LANES(l) for (int l = 0; l < 32; ++l) {
 #define MB_END }
 template <typename T> struct LaneVar {
@@ -66,8 +68,9 @@ inline int mb_popc(unsigned x) { return __builtin_popcount(x); }
 inline void mb_sincos(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
 #endif
 
-#define MB_MAXC 20   /* contact points kept per substep */
-#define MB_MAXROW 64 /* constraint rows per substep (limits + 3 per contact) */
+#define MB_MAXC 16    /* contact points kept per substep */
+#define MB_MAXROW 48  /* constraint rows per substep (limits + 3 per contact) */
+#define MB_YSTRIDE 15 /* compact row: 6 base + <= 8 chain entries (+1 pad, odd stride = conflict-free) */
 #define MB_PI_F 3.14159265358979323846f
 
 // Physics constants of the reference's Bullet world (citations in include/mocca_b200.h: mb200_physics)
@@ -89,8 +92,9 @@ struct MbPhysics {
   int has_ground;
 };
 
-MB_HD int tri(int i, int j) { return (i * (i + 1)) / 2 + j; }
-MB_HD bool mb_finite(float x) { return fabsf(x) <= 3.402823466e38f; }  // false for NaN and +-inf  // packed lower-triangular index, j <= i
+MB_HD constexpr int tri(int i, int j) { return (i * (i + 1)) / 2 + j; }  // packed lower-triangular index, j <= i
+MB_HD int chain_at(unsigned long long pack, int t) { return (int)((pack >> (5 * t)) & 31ull); }
+MB_HD bool mb_finite(float x) { return fabsf(x) <= 3.402823466e38f; }   // false for NaN and +-inf
 
 template <class M> struct WarpMem {
   // ---- state (generalised velocity u = [omega_w, v_w, qd])
@@ -100,17 +104,27 @@ template <class M> struct WarpMem {
   float quat[4];
   float pos[4];
   float Rb[9];
-  // ---- kinematics (world axes, positions relative to the base COM)
-  float jR[M::NJ][9];
-  float jp[M::NJ][3];
-  float js[M::NJ][6];
-  float jV[M::NJ + 1][6];  // [0] = base
-  float jA[M::NJ + 1][6];
-  // ---- bodies
-  float bI[M::NB][10];  // m, h[3], I_O{xx,yy,zz,xy,xz,yz}
-  float bF[M::NB][6];   // bias wrench about O (n, f)
+  float js[M::NJ][6];  // joint motion subspaces about O (needed until the rows are built)
+  // Kinematics / body scratch is dead once the mass matrix is assembled; the constraint rows are born after
+  // the factorisation.  They share storage.
+  union {
+    struct {
+      // ---- kinematics (world axes, positions relative to the base COM)
+      float jR[M::NJ][9];
+      float jp[M::NJ][3];
+      float jV[M::NJ + 1][6];  // [0] = base
+      float jA[M::NJ + 1][6];
+      // ---- bodies
+      float bI[M::NB][10];  // m, h[3], I_O{xx,yy,zz,xy,xz,yz}
+      float bF[M::NB][6];   // bias wrench about O (n, f)
+    } k;
+    // ---- rows: Y_r = L^-T J_r^T stored compactly over its support (base block + ancestor chain)
+    float Yc[MB_MAXROW][MB_YSTRIDE];
+  } w;
   // ---- dynamics
-  float L[(M::NU * (M::NU + 1)) / 2];
+  // M, then its factor L (M = L^T L), compact: row i keeps only its support in chain order
+  // [base block 0..5 | ancestors root->parent | diagonal]; an ancestor's support is a prefix of its descendants'
+  float L[M::LSIZE];
   float Ldinv[32];
   float rhs[32];
   // ---- contacts
@@ -123,13 +137,13 @@ template <class M> struct WarpMem {
   int clink[MB_MAXC];
   int cfoot[MB_MAXC];
   int cpartner[MB_MAXC];
-  // ---- rows
-  float Y[MB_MAXROW][M::NU];
+  // ---- row parameters
   float r_rhs[MB_MAXROW];
   float r_cfm[MB_MAXROW];
   float r_jinv[MB_MAXROW];
   float r_app[MB_MAXROW];
   float r_mu[MB_MAXROW];
+  unsigned r_mask[MB_MAXROW];  // support of the row over the generalised coordinates
   int r_dof[32];
   float r_dir[32];
   // ---- scratch for the epilogue
@@ -180,6 +194,14 @@ MB_HD void mb_plane_space(const float* n, float* p, float* q) {
   }
 }
 
+// dense view of the compact symmetric storage (debug / parity kernels only)
+template <class M> MB_HD float mb_Lget(const float* L, int i, int j) {
+  if (j > i) { const int t = i; i = j; j = t; }
+  if (i == j) return L[M::rowoff(i) + M::rowlen(i) - 1];
+  const unsigned sup = M::rowmask(i);
+  return ((sup >> j) & 1u) ? L[M::rowoff(i) + mb_popc(sup & ((1u << j) - 1u))] : 0.0f;
+}
+
 // ------------------------------------------------------------------------------------------------ simulator
 template <class M> struct Sim {
   typedef WarpMem<M> Mem;
@@ -196,22 +218,23 @@ template <class M> struct Sim {
           float wv[3];
           mb_cross(&S.u[0], &S.u[3], wv);
           for (int k = 0; k < 3; ++k) {
-            S.jV[0][k] = S.u[k]; S.jV[0][3 + k] = S.u[3 + k];
-            S.jA[0][k] = 0.0f; S.jA[0][3 + k] = -wv[k];
+            S.w.k.jV[0][k] = S.u[k]; S.w.k.jV[0][3 + k] = S.u[3 + k];
+            S.w.k.jA[0][k] = 0.0f; S.w.k.jA[0][3 + k] = -wv[k];
           }
-          S.jA[0][5] += P.gravity;
+          S.w.k.jA[0][5] += P.gravity;
         }
       }
     MB_END
+#pragma unroll 1
     for (int lev = 0; lev < M::NLEVEL; ++lev) {
       MB_LANES(l)
         if (l < NJ && M::jlevel(l) == lev) {
           const int pj = M::jparent(l);
-          const float* Rp = pj < 0 ? S.Rb : S.jR[pj];
+          const float* Rp = pj < 0 ? S.Rb : S.w.k.jR[pj];
           float off[3] = {M::joff(l, 0), M::joff(l, 1), M::joff(l, 2)};
           float p[3];
           mb_matvec(Rp, off, p);
-          if (pj >= 0) { p[0] += S.jp[pj][0]; p[1] += S.jp[pj][1]; p[2] += S.jp[pj][2]; }
+          if (pj >= 0) { p[0] += S.w.k.jp[pj][0]; p[1] += S.w.k.jp[pj][1]; p[2] += S.w.k.jp[pj][2]; }
           // R = Rp * R0 * Rot(axis, q)
           float ax[3] = {M::jaxis(l, 0), M::jaxis(l, 1), M::jaxis(l, 2)};
           float sn, cs;
@@ -230,15 +253,15 @@ template <class M> struct Sim {
           s[0] = a[0]; s[1] = a[1]; s[2] = a[2];
           mb_cross(p, a, &s[3]);
 #pragma unroll
-          for (int k = 0; k < 9; ++k) S.jR[l][k] = R[k];
+          for (int k = 0; k < 9; ++k) S.w.k.jR[l][k] = R[k];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) S.jp[l][k] = p[k];
+          for (int k = 0; k < 3; ++k) S.w.k.jp[l][k] = p[k];
 #pragma unroll
           for (int k = 0; k < 6; ++k) S.js[l][k] = s[k];
           if (with_vel) {
             const float qd = S.u[6 + l];
-            const float* Vp = S.jV[pj + 1];
-            const float* Ap = S.jA[pj + 1];
+            const float* Vp = S.w.k.jV[pj + 1];
+            const float* Ap = S.w.k.jA[pj + 1];
             float vj[6], c1[3], c2[3], c3[3];
 #pragma unroll
             for (int k = 0; k < 6; ++k) vj[k] = s[k] * qd;
@@ -248,10 +271,10 @@ template <class M> struct Sim {
             mb_cross(Vp + 3, vj, c3);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-              S.jV[l + 1][k] = Vp[k] + vj[k];
-              S.jV[l + 1][3 + k] = Vp[3 + k] + vj[3 + k];
-              S.jA[l + 1][k] = Ap[k] + c1[k];
-              S.jA[l + 1][3 + k] = Ap[3 + k] + c2[k] + c3[k];
+              S.w.k.jV[l + 1][k] = Vp[k] + vj[k];
+              S.w.k.jV[l + 1][3 + k] = Vp[3 + k] + vj[3 + k];
+              S.w.k.jA[l + 1][k] = Ap[k] + c1[k];
+              S.w.k.jA[l + 1][3 + k] = Ap[3 + k] + c2[k] + c3[k];
             }
           }
         }
@@ -264,11 +287,11 @@ template <class M> struct Sim {
     MB_LANES(l)
       if (l < NB) {
         const int o = M::bowner(l);
-        const float* R = o < 0 ? S.Rb : S.jR[o];
+        const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
         float com[3] = {M::bcom(l, 0), M::bcom(l, 1), M::bcom(l, 2)};
         float c[3];
         mb_matvec(R, com, c);
-        if (o >= 0) { c[0] += S.jp[o][0]; c[1] += S.jp[o][1]; c[2] += S.jp[o][2]; }
+        if (o >= 0) { c[0] += S.w.k.jp[o][0]; c[1] += S.w.k.jp[o][1]; c[2] += S.w.k.jp[o][2]; }
         // Ic = R Ib R^T
         const float ixx = M::binertia(l, 0), iyy = M::binertia(l, 1), izz = M::binertia(l, 2);
         const float ixy = M::binertia(l, 3), ixz = M::binertia(l, 4), iyz = M::binertia(l, 5);
@@ -280,8 +303,8 @@ template <class M> struct Sim {
 #pragma unroll
           for (int j = 0; j < 3; ++j) Ic[3 * i + j] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
         const float m = M::bmass(l);
-        const float* V = S.jV[o + 1];
-        const float* A = S.jA[o + 1];
+        const float* V = S.w.k.jV[o + 1];
+        const float* A = S.w.k.jA[o + 1];
         const float* w = V;
         float wxc[3], vc[3], t1[3], t2[3], t3[3], ac[3], Iw[3], Ia[3], g[3], f[3], nc[3], nO[3];
         mb_cross(w, c, wxc);
@@ -304,16 +327,16 @@ template <class M> struct Sim {
         }
         mb_cross(c, f, nO);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { S.bF[l][k] = nc[k] + nO[k]; S.bF[l][3 + k] = f[k]; }
+        for (int k = 0; k < 3; ++k) { S.w.k.bF[l][k] = nc[k] + nO[k]; S.w.k.bF[l][3 + k] = f[k]; }
         const float cc = mb_dot3(c, c);
-        S.bI[l][0] = m;
-        S.bI[l][1] = m * c[0]; S.bI[l][2] = m * c[1]; S.bI[l][3] = m * c[2];
-        S.bI[l][4] = Ic[0] + m * (cc - c[0] * c[0]);
-        S.bI[l][5] = Ic[4] + m * (cc - c[1] * c[1]);
-        S.bI[l][6] = Ic[8] + m * (cc - c[2] * c[2]);
-        S.bI[l][7] = Ic[1] - m * c[0] * c[1];
-        S.bI[l][8] = Ic[2] - m * c[0] * c[2];
-        S.bI[l][9] = Ic[5] - m * c[1] * c[2];
+        S.w.k.bI[l][0] = m;
+        S.w.k.bI[l][1] = m * c[0]; S.w.k.bI[l][2] = m * c[1]; S.w.k.bI[l][3] = m * c[2];
+        S.w.k.bI[l][4] = Ic[0] + m * (cc - c[0] * c[0]);
+        S.w.k.bI[l][5] = Ic[4] + m * (cc - c[1] * c[1]);
+        S.w.k.bI[l][6] = Ic[8] + m * (cc - c[2] * c[2]);
+        S.w.k.bI[l][7] = Ic[1] - m * c[0] * c[1];
+        S.w.k.bI[l][8] = Ic[2] - m * c[0] * c[2];
+        S.w.k.bI[l][9] = Ic[5] - m * c[1] * c[2];
       }
     MB_END
   }
@@ -330,9 +353,9 @@ template <class M> struct Sim {
         for (int k = 0; k < 6; ++k) F[k] = 0.0f;
         for (int b = b0; b < b1; ++b) {
 #pragma unroll
-          for (int k = 0; k < 10; ++k) I[k] += S.bI[b][k];
+          for (int k = 0; k < 10; ++k) I[k] += S.w.k.bI[b][k];
 #pragma unroll
-          for (int k = 0; k < 6; ++k) F[k] += S.bF[b][k];
+          for (int k = 0; k < 6; ++k) F[k] += S.w.k.bF[b][k];
         }
         const float m = I[0];
         const float* h = &I[1];
@@ -350,20 +373,19 @@ template <class M> struct Sim {
 #pragma unroll
           for (int k = 0; k < 6; ++k) bias += s[k] * F[k];
           const int row = 6 + l;
-          float* Lr = &S.L[tri(row, 0)];
+          float* Lr = &S.L[M::rowoff(row)];
 #pragma unroll
           for (int k = 0; k < 6; ++k) Lr[k] = G[k];
-          const unsigned anc = M::janc(l);
-          for (int i = 0; i <= l; ++i) {
+          const unsigned long long pack = M::chainpack(l);
+          const int depth = M::jdepth(l);
+          for (int t = 0; t <= depth; ++t) {
+            const float* si = S.js[chain_at(pack, t)];
             float v = 0.0f;
-            if ((anc >> i) & 1u) {
-              const float* si = S.js[i];
 #pragma unroll
-              for (int k = 0; k < 6; ++k) v += si[k] * G[k];
-            }
-            Lr[6 + i] = v;
+            for (int k = 0; k < 6; ++k) v += si[k] * G[k];
+            Lr[6 + t] = v;
           }
-          Lr[6 + l] += M::armature(l);
+          Lr[6 + depth] += M::armature(l);
           S.rhs[row] = S.tau[l] - bias;
         } else {
           // base 6x6 block: [[I_O, [h]x], [-[h]x, m 1]], lower triangle
@@ -383,22 +405,31 @@ template <class M> struct Sim {
   }
 
   // ---- D. M = L^T L, processed leaf-to-root so the tree sparsity of M is preserved (no fill-in) -------------
+  // Compact rows: entry t of row k belongs to column i_t = (t < 6 ? t : 6 + chain_k[t-6]), and row i_t has exactly
+  // t off-diagonal entries occupying the same slots 0..t-1 -- every update is a contiguous prefix.
+  enum { MAXOFF = M::MAXSUP - 1 };
   MB_HD static void factorize(Mem& S) {
+#pragma unroll 1
     for (int k = NU - 1; k >= 0; --k) {
-      const float d = sqrtf(S.L[tri(k, k)]);
+      const int offk = M::rowoff(k), nk = M::rowlen(k) - 1;
+      const float d = sqrtf(S.L[offk + nk]);
       const float inv = 1.0f / d;
+      const unsigned long long pack = k >= 6 ? M::chainpack(k - 6) : 0ull;
       MB_LANES(l)
-        if (l < k) S.L[tri(k, l)] *= inv;
-        else if (l == k) { S.L[tri(k, k)] = d; S.Ldinv[k] = inv; }
+        if (l < nk) S.L[offk + l] *= inv;
+        else if (l == nk) { S.L[offk + nk] = d; S.Ldinv[k] = inv; }
       MB_END
-      MB_LANES(l)
-        if (l < k) {
-          const float Lkl = S.L[tri(k, l)];
-          if (Lkl != 0.0f) {
-            float* Ll = &S.L[tri(l, 0)];
-            const float* Lk = &S.L[tri(k, 0)];
-            for (int j = 0; j <= l; ++j) Ll[j] -= Lkl * Lk[j];
-          }
+      float lk[MAXOFF];
+#pragma unroll
+      for (int s2 = 0; s2 < MAXOFF; ++s2) lk[s2] = s2 < nk ? S.L[offk + s2] : 0.0f;
+      MB_LANES(t)
+        if (t < nk) {
+          const int it = t < 6 ? t : 6 + chain_at(pack, t - 6);
+          float* Li = &S.L[M::rowoff(it)];
+          const float Lkt = S.L[offk + t];
+#pragma unroll
+          for (int s2 = 0; s2 < MAXOFF; ++s2)
+            if (s2 <= t) Li[s2] -= Lkt * lk[s2];
         }
       MB_END
     }
@@ -406,20 +437,30 @@ template <class M> struct Sim {
 
   // ---- E. single right-hand-side solves, one generalised coordinate per lane ---------------------------------
   MB_HD static void solve_Lt(Mem& S, LaneVar<float>& x) {  // L^T y = x
+#pragma unroll 1
     for (int i = NU - 1; i >= 0; --i) {
       const float yi = warp_bcast(x, i) * S.Ldinv[i];
+      const unsigned sup = M::rowmask(i);
+      const int off = M::rowoff(i);
       MB_LANES(l)
         if (l == i) x[l] = yi;
-        else if (l < i) x[l] -= S.L[tri(i, l)] * yi;
+        else if ((sup >> l) & 1u) x[l] -= S.L[off + mb_popc(sup & ((1u << l) - 1u))] * yi;
       MB_END
     }
   }
   MB_HD static void solve_L(Mem& S, LaneVar<float>& x) {  // L y = x
+    LaneVar<unsigned> sup;
+    LaneVar<int> off;
+    MB_LANES(l)
+      sup[l] = l < NU ? M::rowmask(l) : 0u;
+      off[l] = l < NU ? M::rowoff(l) : 0;
+    MB_END
+#pragma unroll 1
     for (int i = 0; i < NU; ++i) {
       const float xi = warp_bcast(x, i) * S.Ldinv[i];
       MB_LANES(l)
         if (l == i) x[l] = xi;
-        else if (l > i && l < NU) x[l] -= S.L[tri(l, i)] * xi;
+        else if ((sup[l] >> i) & 1u) x[l] -= S.L[off[l] + mb_popc(sup[l] & ((1u << i) - 1u))] * xi;
       MB_END
     }
   }
@@ -441,11 +482,11 @@ template <class M> struct Sim {
         hit[l] = 0;
         if (pt < NPT && P.has_ground) {
           const int o = M::powner(pt);
-          const float* R = o < 0 ? S.Rb : S.jR[o];
+          const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
           float loc[3] = {M::ppos(pt, 0), M::ppos(pt, 1), M::ppos(pt, 2)};
           float c[3];
           mb_matvec(R, loc, c);
-          if (o >= 0) { c[0] += S.jp[o][0]; c[1] += S.jp[o][1]; c[2] += S.jp[o][2]; }
+          if (o >= 0) { c[0] += S.w.k.jp[o][0]; c[1] += S.w.k.jp[o][1]; c[2] += S.w.k.jp[o][2]; }
           const float r = M::pradius(pt);
           const float dist = (S.pos[2] + c[2]) - r;
           if (dist < M::pthresh(pt)) {
@@ -506,21 +547,24 @@ template <class M> struct Sim {
   MB_HD static void setup_rows(Mem& S, const MbPhysics& P, int nlim, int nc) {
     const int R = nlim + 3 * nc;
     const float inv_dt = 1.0f / P.dt;
+#pragma unroll 1
     for (int base = 0; base < R; base += 32) {
       MB_LANES(l)
         const int r = base + l;
         if (r < R) {
-          float b[NU];
-          float cfm = 0.0f, rhs, mu = 0.0f;
-          float pen = 0.0f, dist = 0.0f, erp = 0.0f;
+          // everything lives on the row's support: base block + chain (root -> constrained joint)
+          float b[M::MAXSUP];
+          float W[6];
+          float cfm = 0.0f, mu = 0.0f, pen = 0.0f, dist = 0.0f, erp = 0.0f, dir = 0.0f;
           int kind;  // 0 limit, 1 normal, 2 friction
+          int cj;    // constrained joint, -1 = base link
           if (r < nlim) {
             kind = 0;
-            const int d = S.r_dof[r];
-            const float dir = S.r_dir[r];
+            cj = S.r_dof[r];
+            dir = S.r_dir[r];
+            pen = dir > 0.0f ? S.q[cj] - M::lower(cj) : M::upper(cj) - S.q[cj];
 #pragma unroll
-            for (int i = 0; i < NU; ++i) b[i] = (i == 6 + d) ? dir : 0.0f;
-            pen = dir > 0.0f ? S.q[d] - M::lower(d) : M::upper(d) - S.q[d];
+            for (int i = 0; i < 6; ++i) W[i] = 0.0f;
           } else {
             int k;
             float dirv[3];
@@ -536,35 +580,45 @@ template <class M> struct Sim {
               dirv[0] = second ? t2[0] : t1[0]; dirv[1] = second ? t2[1] : t1[1]; dirv[2] = second ? t2[2] : t1[2];
             }
             mu = S.cmu[k];
-            float W[6];
             mb_cross(S.cP[k], dirv, W);
             W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) b[i] = W[i];
-            const int link = S.clink[k];
-            const unsigned anc = link < 0 ? 0u : M::janc(link);
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-              const float* s = S.js[j];
-              float v = s[0] * W[0] + s[1] * W[1] + s[2] * W[2] + s[3] * W[3] + s[4] * W[4] + s[5] * W[5];
-              b[6 + j] = ((anc >> j) & 1u) ? v : 0.0f;
-            }
+            cj = S.clink[k];
           }
+          const unsigned long long pack = cj >= 0 ? M::chainpack(cj) : 0ull;
+          const int depth = cj >= 0 ? M::jdepth(cj) : -1;
+          const int n = 7 + depth;  // support size
           float rel_vel = 0.0f;
 #pragma unroll
-          for (int i = 0; i < NU; ++i) rel_vel += b[i] * S.u[i];
-          // half solve L^T y = J^T (column-oriented back substitution over the packed factor)
+          for (int t = 0; t < 6; ++t) { b[t] = W[t]; rel_vel += W[t] * S.u[t]; }
 #pragma unroll
-          for (int i = NU - 1; i >= 0; --i) {
-            const float yi = b[i] * S.Ldinv[i];
-            b[i] = yi;
-            const float* Li = &S.L[tri(i, 0)];
+          for (int t = 0; t < M::MAXSUP - 6; ++t) {
+            float v = 0.0f;
+            if (t <= depth) {
+              const int a = chain_at(pack, t);
+              if (kind == 0) v = t == depth ? dir : 0.0f;
+              else {
+                const float* sj = S.js[a];
+                v = sj[0] * W[0] + sj[1] * W[1] + sj[2] * W[2] + sj[3] * W[3] + sj[4] * W[4] + sj[5] * W[5];
+              }
+              rel_vel += v * S.u[6 + a];
+            }
+            b[6 + t] = v;
+          }
+          // half solve L^T y = J^T restricted to the support (prefix property of the compact factor)
 #pragma unroll
-            for (int j = 0; j < i; ++j) b[j] -= Li[j] * yi;
+          for (int t = M::MAXSUP - 1; t >= 0; --t) {
+            if (t < n) {
+              const int it = t < 6 ? t : 6 + chain_at(pack, t - 6);
+              const float yi = b[t] * S.Ldinv[it];
+              b[t] = yi;
+              const float* Li = &S.L[M::rowoff(it)];
+#pragma unroll
+              for (int s2 = 0; s2 < t; ++s2) b[s2] -= Li[s2] * yi;
+            }
           }
           float dd = cfm;
 #pragma unroll
-          for (int i = 0; i < NU; ++i) dd += b[i] * b[i];
+          for (int t = 0; t < M::MAXSUP; ++t) dd += b[t] * b[t];
           const float jinv = dd > 1.1920929e-07f ? 1.0f / dd : 0.0f;
           float positional = 0.0f, verr = -rel_vel;
           if (kind == 0) {
@@ -576,10 +630,12 @@ template <class M> struct Sim {
             if (dist > 0.0f) verr -= dist * inv_dt;
             else positional = -dist * erp * inv_dt;
           }
-          rhs = (positional + verr) * jinv;
+          float* Yr = S.w.Yc[r];
 #pragma unroll
-          for (int i = 0; i < NU; ++i) S.Y[r][i] = b[i];
-          S.r_rhs[r] = rhs;
+          for (int t = 0; t < M::MAXSUP; ++t)
+            if (t < n) Yr[t] = b[t];
+          S.r_mask[r] = 0x3Fu | (cj >= 0 ? (M::janc(cj) << 6) : 0u);
+          S.r_rhs[r] = (positional + verr) * jinv;
           S.r_cfm[r] = cfm * jinv;
           S.r_jinv[r] = jinv;
           S.r_app[r] = 0.0f;
@@ -592,14 +648,16 @@ template <class M> struct Sim {
   // ---- H. projected Gauss-Seidel in z-space (btMultiBodyConstraintSolver::solveSingleIteration order) --------
   MB_HD static float row_dot(Mem& S, int r, const LaneVar<float>& z) {
     LaneVar<float> t;
+    const unsigned sup = S.r_mask[r];
     MB_LANES(l)
-      t[l] = l < NU ? S.Y[r][l] * z[l] : 0.0f;
+      t[l] = ((sup >> l) & 1u) ? S.w.Yc[r][mb_popc(sup & ((1u << l) - 1u))] * z[l] : 0.0f;
     MB_END
     return warp_sum(t);
   }
   MB_HD static void row_apply(Mem& S, int r, float imp, float new_app, LaneVar<float>& z) {
+    const unsigned sup = S.r_mask[r];
     MB_LANES(l)
-      if (l < NU) z[l] += S.Y[r][l] * imp;
+      if ((sup >> l) & 1u) z[l] += S.w.Yc[r][mb_popc(sup & ((1u << l) - 1u))] * imp;
       if (l == 0) S.r_app[r] = new_app;
     MB_END
   }

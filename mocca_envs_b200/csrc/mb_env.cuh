@@ -177,8 +177,8 @@ template <class M> struct W3DEnv {
     float minz = 1e30f;
     for (int f = 0; f < M::NFEET; ++f) {
       const int b = M::foot_body(f), ow = M::bowner(b);
-      const float* R = S.jR[ow];
-      const float z = S.jp[ow][2] + R[6] * M::bcom(b, 0) + R[7] * M::bcom(b, 1) + R[8] * M::bcom(b, 2);
+      const float* R = S.w.k.jR[ow];
+      const float z = S.w.k.jp[ow][2] + R[6] * M::bcom(b, 0) + R[7] * M::bcom(b, 1) + R[8] * M::bcom(b, 2);
       minz = fminf(minz, z);
     }
     o.height = -minz;  // body_z - min(feet_z), both relative to the base COM

@@ -43,7 +43,7 @@ void emu_mass_matrix(const MbPhysics* p, const float* state, float* Mout, float*
   Sim<WM>::mass_matrix_and_rhs(S);
   const int NU = WM::NU;
   for (int i = 0; i < NU; ++i) {
-    for (int j = 0; j < NU; ++j) Mout[i * NU + j] = i >= j ? S.L[tri(i, j)] : S.L[tri(j, i)];
+    for (int j = 0; j < NU; ++j) Mout[i * NU + j] = mb_Lget<WM>(S.L, i, j);
     bias[i] = -S.rhs[i];
   }
 }
