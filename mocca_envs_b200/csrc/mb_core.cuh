@@ -19,6 +19,16 @@
 
 #include "mb_tables.h"
 
+#if defined(__CUDACC__) && defined(MB_SYNC) && MB_SYNC
+#define MB_BLOCK_BARRIER() __syncthreads()
+#else
+#define MB_BLOCK_BARRIER()
+#endif
+#if defined(__CUDACC__) && defined(MB_SYNC) && MB_SYNC >= 2
+#define MB_BLOCK_BARRIER2() __syncthreads()
+#else
+#define MB_BLOCK_BARRIER2()
+#endif
 #ifdef __CUDACC__
 #define MB_NOINLINE __device__ __noinline__
 #define MB_LANES(l) { const int l = (int)(threadIdx.x & 31);
@@ -419,17 +429,14 @@ template <class M> struct Sim {
         if (l < nk) S.L[offk + l] *= inv;
         else if (l == nk) { S.L[offk + nk] = d; S.Ldinv[k] = inv; }
       MB_END
-      float lk[MAXOFF];
-#pragma unroll
-      for (int s2 = 0; s2 < MAXOFF; ++s2) lk[s2] = s2 < nk ? S.L[offk + s2] : 0.0f;
       MB_LANES(t)
         if (t < nk) {
           const int it = t < 6 ? t : 6 + chain_at(pack, t - 6);
-          float* Li = &S.L[M::rowoff(it)];
-          const float Lkt = S.L[offk + t];
-#pragma unroll
-          for (int s2 = 0; s2 < MAXOFF; ++s2)
-            if (s2 <= t) Li[s2] -= Lkt * lk[s2];
+          float* __restrict__ Li = &S.L[M::rowoff(it)];
+          const float* __restrict__ Lk = &S.L[offk];
+          const float Lkt = Lk[t];
+#pragma unroll 4
+          for (int s2 = 0; s2 <= t; ++s2) Li[s2] -= Lkt * Lk[s2];
         }
       MB_END
     }
@@ -747,6 +754,7 @@ template <class M> struct Sim {
 
   // ---- one Bullet substep.  Returns the number of constraint rows; contact list of this substep stays in S ----
   MB_HD static int substep(Mem& S, const MbPhysics& P, int* nc_out, int* overflow) {
+    MB_BLOCK_BARRIER();  // keeps the warps of a CTA in the same phase so instruction-cache lines are shared
     kinematics(S, P, true);
     const int nc_all = collide(S, P, overflow);
     bodies(S, P);
@@ -762,6 +770,7 @@ template <class M> struct Sim {
     MB_LANES(l)
       if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + P.dt * x[l], -P.max_coord_vel), P.max_coord_vel);
     MB_END
+    MB_BLOCK_BARRIER2();
     const int nlim = find_limits(S);
     int nc = nc_all;
     if (nlim + 3 * nc > MB_MAXROW) { nc = (MB_MAXROW - nlim) / 3; *overflow += 1; }

@@ -227,6 +227,29 @@ def test_full_size_properties(torch_mod):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
+def test_batch_size_independence(torch_mod):
+    """Env i evolves identically whatever the batch size (CTA padding / tail warps must have no side effects):
+    N = 5, 13 and 24 with the same per-env seeds and actions."""
+    torch = torch_mod
+    rng = np.random.RandomState(4)
+    acts = rng.uniform(-1, 1, (30, 24, 21)).astype(np.float32)
+    results = {}
+    for N in (5, 13, 24):
+        env = _env(N, seed=50)
+        env.reset()
+        done_total = 0
+        for k in range(30):
+            obs, rew, done, _ = env.step(torch.tensor(acts[k, :N]))
+            done_total += int(done.sum())
+        results[N] = (obs.cpu().numpy().copy(), env.get_state().cpu().numpy().copy(), done_total, env.stats()["episodes"])
+        env.close()
+    for N in (13, 24):
+        assert np.array_equal(results[5][0], results[N][0][:5])
+        assert np.array_equal(results[5][1], results[N][1][:5])
+    for N in (5, 13, 24):
+        assert results[N][2] == results[N][3]  # pad envs never leak into the statistics
+
+
 def test_step_host_matches_device(torch_mod):
     torch = torch_mod
     N = 256
