@@ -171,6 +171,18 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append(_farr(P + "_joff", r["joff"]))
     out.append(_farr(P + "_jrot", [np.asarray(m).reshape(9) for m in r["jrot"]]))
     out.append(_farr(P + "_jaxis", r["jaxis"]))
+    # fast paths: coordinate-aligned joint axes (index, sign; -1 = generic) and identity zero-pose rotations
+    jaxk, jsgn, jident = [], [], []
+    for ax, R0 in zip(r["jaxis"], r["jrot"]):
+        ax = np.asarray(ax)
+        k = int(np.argmax(np.abs(ax)))
+        aligned = abs(abs(ax[k]) - 1.0) < 1e-12 and np.abs(np.delete(ax, k)).max() < 1e-12
+        jaxk.append(k if aligned else -1)
+        jsgn.append(float(np.sign(ax[k])) if aligned else 0.0)
+        jident.append(1 if np.abs(np.asarray(R0) - np.eye(3)).max() < 1e-12 else 0)
+    out.append(_iarr(P + "_jaxk", jaxk))
+    out.append(_farr(P + "_jsgn", jsgn))
+    out.append(_iarr(P + "_jident", jident))
     # float32 limits exactly as robots.py:126-130 builds them (weight = f32(upper - lower), bias = f32(lower))
     out.append(_farr(P + "_lower", r["lower"]))
     out.append(_farr(P + "_upper", r["upper"]))
@@ -214,11 +226,13 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append("  MB_HD static unsigned long long chainpack(int j) { return %s_chainpack[j]; }\n" % P)
     for fld, ctype in [("jparent", "int"), ("jlevel", "int"), ("janc", "unsigned"), ("bstart", "int"), ("bend", "int"),
                        ("jdepth", "int"), ("rowoff", "int"), ("rowlen", "int"), ("rowmask", "unsigned"),
+                       ("jaxk", "int"), ("jident", "int"),
                        ("bowner", "int"), ("powner", "int"), ("pfoot", "int"), ("pid", "int"), ("foot_body", "int"),
                        ("right", "int"), ("left", "int"), ("neg", "int")]:
         out.append("  MB_HD static %s %s(int i) { return %s_%s[i]; }\n" % (ctype, fld, P, fld))
     out.append("  MB_HD static double base_angles(int i) { return %s_base_angles[i]; }\n" % P)
-    for fld in ["lower", "upper", "weight", "gain", "damping", "armature", "bmass", "pradius", "pfriction", "pthresh"]:
+    for fld in ["lower", "upper", "weight", "gain", "damping", "armature", "bmass", "pradius", "pfriction", "pthresh",
+                "jsgn"]:
         out.append("  MB_HD static float %s(int i) { return %s_%s[i]; }\n" % (fld, P, fld))
     for fld in ["joff", "jrot", "jaxis", "bcom", "binertia", "ppos"]:
         out.append("  MB_HD static float %s(int i, int k) { return %s_%s[i][k]; }\n" % (fld, P, fld))

@@ -245,19 +245,39 @@ template <class M> struct Sim {
           float p[3];
           mb_matvec(Rp, off, p);
           if (pj >= 0) { p[0] += S.w.k.jp[pj][0]; p[1] += S.w.k.jp[pj][1]; p[2] += S.w.k.jp[pj][2]; }
-          // R = Rp * R0 * Rot(axis, q)
+          // R = Rp * R0 * Rot(axis, q); fast paths: identity R0, coordinate-aligned axis (two columns mix)
           float ax[3] = {M::jaxis(l, 0), M::jaxis(l, 1), M::jaxis(l, 2)};
           float sn, cs;
           mb_sincos(S.q[l], &sn, &cs);
-          float t = 1.0f - cs;
-          float Rq[9] = {t * ax[0] * ax[0] + cs, t * ax[0] * ax[1] - sn * ax[2], t * ax[0] * ax[2] + sn * ax[1],
-                         t * ax[0] * ax[1] + sn * ax[2], t * ax[1] * ax[1] + cs, t * ax[1] * ax[2] - sn * ax[0],
-                         t * ax[0] * ax[2] - sn * ax[1], t * ax[1] * ax[2] + sn * ax[0], t * ax[2] * ax[2] + cs};
-          float R0[9], T[9], R[9];
+          float B[9], R[9];
 #pragma unroll
-          for (int k = 0; k < 9; ++k) R0[k] = M::jrot(l, k);
-          mb_matmul(R0, Rq, T);
-          mb_matmul(Rp, T, R);
+          for (int k = 0; k < 9; ++k) B[k] = Rp[k];
+          if (!M::jident(l)) {
+            float R0[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) R0[k] = M::jrot(l, k);
+            mb_matmul(B, R0, B);
+          }
+          const int kax = M::jaxk(l);
+          if (kax >= 0) {
+            const float sg = sn * M::jsgn(l);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const float c0 = B[3 * r], c1 = B[3 * r + 1], c2 = B[3 * r + 2];
+              const float ci = kax == 0 ? c1 : (kax == 1 ? c2 : c0);
+              const float cj = kax == 0 ? c2 : (kax == 1 ? c0 : c1);
+              const float ni = cs * ci + sg * cj, nj = cs * cj - sg * ci;
+              R[3 * r] = kax == 0 ? c0 : (kax == 1 ? nj : ni);
+              R[3 * r + 1] = kax == 0 ? ni : (kax == 1 ? c1 : nj);
+              R[3 * r + 2] = kax == 0 ? nj : (kax == 1 ? ni : c2);
+            }
+          } else {
+            const float t = 1.0f - cs;
+            float Rq[9] = {t * ax[0] * ax[0] + cs, t * ax[0] * ax[1] - sn * ax[2], t * ax[0] * ax[2] + sn * ax[1],
+                           t * ax[0] * ax[1] + sn * ax[2], t * ax[1] * ax[1] + cs, t * ax[1] * ax[2] - sn * ax[0],
+                           t * ax[0] * ax[2] - sn * ax[1], t * ax[1] * ax[2] + sn * ax[0], t * ax[2] * ax[2] + cs};
+            mb_matmul(B, Rq, R);
+          }
           float a[3], s[6];
           mb_matvec(R, ax, a);
           s[0] = a[0]; s[1] = a[1]; s[2] = a[2];
@@ -653,52 +673,53 @@ template <class M> struct Sim {
   }
 
   // ---- H. projected Gauss-Seidel in z-space (btMultiBodyConstraintSolver::solveSingleIteration order) --------
-  MB_HD static float row_dot(Mem& S, int r, const LaneVar<float>& z) {
-    LaneVar<float> t;
-    const unsigned sup = S.r_mask[r];
+  // One visit resolves row ra, or the friction pair (ra, rb) with btMultiBodyConstraintSolver's cone projection.
+  // A single code path serves limit, normal and friction rows (code size matters: see DESIGN.md, I-cache).
+  MB_HD static float pgs_visit(Mem& S, int ra, int rb, float lo, float hi, float cone, LaneVar<float>& z) {
+    const bool pair = rb >= 0;
+    const unsigned supA = S.r_mask[ra];
+    const unsigned supB = pair ? S.r_mask[rb] : 0u;
+    LaneVar<float> ya, yb, ta, tb;
     MB_LANES(l)
-      t[l] = ((sup >> l) & 1u) ? S.w.Yc[r][mb_popc(sup & ((1u << l) - 1u))] * z[l] : 0.0f;
+      const unsigned lt = (1u << l) - 1u;
+      ya[l] = ((supA >> l) & 1u) ? S.w.Yc[ra][mb_popc(supA & lt)] : 0.0f;
+      yb[l] = ((supB >> l) & 1u) ? S.w.Yc[rb][mb_popc(supB & lt)] : 0.0f;
+      ta[l] = ya[l] * z[l];
+      tb[l] = yb[l] * z[l];
     MB_END
-    return warp_sum(t);
-  }
-  MB_HD static void row_apply(Mem& S, int r, float imp, float new_app, LaneVar<float>& z) {
-    const unsigned sup = S.r_mask[r];
-    MB_LANES(l)
-      if ((sup >> l) & 1u) z[l] += S.w.Yc[r][mb_popc(sup & ((1u << l) - 1u))] * imp;
-      if (l == 0) S.r_app[r] = new_app;
-    MB_END
-  }
-  MB_HD static float resolve_single(Mem& S, int r, float lo, float hi, LaneVar<float>& z) {
-    const float app = S.r_app[r], jinv = S.r_jinv[r];
-    float delta = S.r_rhs[r] - app * S.r_cfm[r];
-    delta -= row_dot(S, r, z) * jinv;
-    const float sum = app + delta;
-    float napp;
-    if (sum < lo) { delta = lo - app; napp = lo; }
-    else if (sum > hi) { delta = hi - app; napp = hi; }
-    else napp = sum;
-    row_apply(S, r, delta, napp, z);
-    return jinv != 0.0f ? delta / jinv : 0.0f;
-  }
-  MB_HD static float resolve_cone(Mem& S, int ra, int rb, float lim, LaneVar<float>& z) {
-    const float appA = S.r_app[ra], appB = S.r_app[rb], jA = S.r_jinv[ra], jB = S.r_jinv[rb];
-    float dB = S.r_rhs[rb] - appB * S.r_cfm[rb] - row_dot(S, rb, z) * jB;
-    float dA = S.r_rhs[ra] - appA * S.r_cfm[ra] - row_dot(S, ra, z) * jA;
-    const float sumA = appA + dA, sumB = appB + dB;
-    float nA = sumA, nB = sumB;
-    if (sumA * sumA + sumB * sumB >= lim * lim) {
-      const float angle = atan2f(sumA, sumB);
-      const float clipA = fabsf(lim * sinf(angle)), clipB = fabsf(lim * cosf(angle));
-      if (sumA < -clipA) { dA = -clipA - appA; nA = -clipA; }
-      else if (sumA > clipA) { dA = clipA - appA; nA = clipA; }
-      if (sumB < -clipB) { dB = -clipB - appB; nB = -clipB; }
-      else if (sumB > clipB) { dB = clipB - appB; nB = clipB; }
+    const float dotA = warp_sum(ta);
+    const float appA = S.r_app[ra], jA = S.r_jinv[ra];
+    float dA = S.r_rhs[ra] - appA * S.r_cfm[ra] - dotA * jA;
+    const float sumA = appA + dA;
+    float nA = sumA, nB = 0.0f, dB = 0.0f, jB = 0.0f;
+    if (!pair) {
+      if (sumA < lo) { dA = lo - appA; nA = lo; }
+      else if (sumA > hi) { dA = hi - appA; nA = hi; }
+    } else {
+      const float dotB = warp_sum(tb);
+      const float appB = S.r_app[rb];
+      jB = S.r_jinv[rb];
+      dB = S.r_rhs[rb] - appB * S.r_cfm[rb] - dotB * jB;
+      const float sumB = appB + dB;
+      nB = sumB;
+      if (sumA * sumA + sumB * sumB >= cone * cone) {
+        const float angle = atan2f(sumA, sumB);
+        const float clipA = fabsf(cone * sinf(angle)), clipB = fabsf(cone * cosf(angle));
+        if (sumA < -clipA) { dA = -clipA - appA; nA = -clipA; }
+        else if (sumA > clipA) { dA = clipA - appA; nA = clipA; }
+        if (sumB < -clipB) { dB = -clipB - appB; nB = -clipB; }
+        else if (sumB > clipB) { dB = clipB - appB; nB = clipB; }
+      }
     }
-    row_apply(S, ra, dA, nA, z);
-    row_apply(S, rb, dB, nB, z);
-    float res = 0.0f;
-    if (jA != 0.0f) res += dA / jA;
-    if (jB != 0.0f) res += dB / jB;
+    MB_LANES(l)
+      z[l] += ya[l] * dA + yb[l] * dB;
+      if (l == 0) {
+        S.r_app[ra] = nA;
+        if (pair) S.r_app[rb] = nB;
+      }
+    MB_END
+    float res = jA != 0.0f ? dA / jA : 0.0f;
+    if (pair && jB != 0.0f) res += dB / jB;
     return res;
   }
 
@@ -706,21 +727,23 @@ template <class M> struct Sim {
     MB_LANES(l)
       z[l] = 0.0f;
     MB_END
+    const int nvis = nlim + 2 * nc;
+#pragma unroll 1
     for (int it = 0; it < P.iterations; ++it) {
       float res2 = 0.0f;
-      for (int j = 0; j < nlim; ++j) {
-        const int r = (it & 1) ? j : nlim - 1 - j;
-        const float rr = resolve_single(S, r, 0.0f, P.limit_max_impulse, z);
-        res2 = fmaxf(res2, rr * rr);
-      }
-      for (int k = 0; k < nc; ++k) {
-        const float rr = resolve_single(S, nlim + k, 0.0f, 1e10f, z);
-        res2 = fmaxf(res2, rr * rr);
-      }
-      for (int k = 0; k < nc; ++k) {
-        const int ra = nlim + nc + 2 * k;
-        const float lim = S.r_mu[ra] * S.r_app[nlim + k];
-        const float rr = resolve_cone(S, ra, ra + 1, lim, z);
+#pragma unroll 1
+      for (int v = 0; v < nvis; ++v) {
+        int ra, rb = -1;
+        float lo = 0.0f, hi = 1e10f, cone = 0.0f;
+        if (v < nlim) { ra = (it & 1) ? v : nlim - 1 - v; hi = P.limit_max_impulse; }
+        else if (v < nlim + nc) ra = v;
+        else {
+          const int k = v - nlim - nc;
+          ra = nlim + nc + 2 * k;
+          rb = ra + 1;
+          cone = S.r_mu[ra] * S.r_app[nlim + k];
+        }
+        const float rr = pgs_visit(S, ra, rb, lo, hi, cone, z);
         res2 = fmaxf(res2, rr * rr);
       }
       if (res2 <= P.residual_threshold) break;
@@ -737,10 +760,12 @@ template <class M> struct Sim {
         const float wx = S.u[0], wy = S.u[1], wz = S.u[2];
         float ang = sqrtf(wx * wx + wy * wy + wz * wz);
         if (ang * dt > 0.25f * MB_PI_F) ang = 0.25f * MB_PI_F / dt;
-        float f;
-        if (ang < 0.001f) f = 0.5f * dt - dt * dt * dt * 0.020833333333f * ang * ang;
-        else f = sinf(0.5f * ang * dt) / ang;
-        const float ax = wx * f, ay = wy * f, az = wz * f, aw = cosf(ang * dt * 0.5f);
+        // half angle h <= pi/8: sin(h)/ang = (dt/2) sinc(h), cos(h) -- short Taylor polynomials (rel. err < 1e-8;
+        // Bullet's own small-angle branch is the first two terms of the same series)
+        const float h = 0.5f * ang * dt, h2 = h * h;
+        const float f = 0.5f * dt * (1.0f + h2 * (-1.0f / 6.0f + h2 * (1.0f / 120.0f + h2 * (-1.0f / 5040.0f))));
+        const float aw = 1.0f + h2 * (-0.5f + h2 * (1.0f / 24.0f + h2 * (-1.0f / 720.0f + h2 * (1.0f / 40320.0f))));
+        const float ax = wx * f, ay = wy * f, az = wz * f;
         const float x = S.quat[0], y = S.quat[1], zq = S.quat[2], w = S.quat[3];
         float nx = aw * x + ax * w + ay * zq - az * y;
         float ny = aw * y - ax * zq + ay * w + az * x;
