@@ -123,7 +123,10 @@ __global__ void __launch_bounds__(MB_WARPS * 32)
     if (l < WM::NJ) S.tau[l] = tail ? 0.0f : tau[(size_t)env * WM::NJ + l];
   MB_END
   int rows = 0, nc = 0, overflow = 0;
-  for (int k = 0; k < phys.substeps; ++k) rows += Sim<WM>::substep(S, phys, &nc, &overflow);
+  Sim<WM>::LaneConst C;
+  Sim<WM>::init_lane_const(C);
+#pragma unroll 1
+  for (int k = 0; k < phys.substeps; ++k) rows += Sim<WM>::substep(S, phys, C, &nc, &overflow);
   WEnv::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
   if (tail) return;
   if ((threadIdx.x & 31) == 0) {
@@ -145,7 +148,9 @@ __global__ void __launch_bounds__(MB_WARPS * 32)
   MB_LANES(l)
     S.tau[l] = 0.0f;
   MB_END
-  Sim<WM>::kinematics(S, phys, true);
+  Sim<WM>::LaneConst C;
+  Sim<WM>::init_lane_const(C);
+  Sim<WM>::kinematics(S, phys, C, true);
   Sim<WM>::bodies(S, phys);
   Sim<WM>::mass_matrix_and_rhs(S);
   MB_LANES(l)

@@ -76,6 +76,7 @@ inline unsigned warp_ballot(const LaneVar<int>& p) {
 }
 inline int mb_popc(unsigned x) { return __builtin_popcount(x); }
 inline void mb_sincos(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #endif
 
 #define MB_MAXC 16    /* contact points kept per substep */
@@ -217,8 +218,41 @@ template <class M> struct Sim {
   typedef WarpMem<M> Mem;
   enum { NJ = M::NJ, NB = M::NB, NU = M::NU, NPT = M::NPT };
 
+  // ---- lane constants: computed once per kernel, live in registers -------------------------------------------
+  struct LaneConst {
+    LaneVar<int> tl;        // |support(l)| = slot of column l in every descendant's compact row = rowlen(l) - 1
+    LaneVar<int> off;       // rowoff(l)
+    LaneVar<unsigned> sup;  // rowmask(l)
+    LaneVar<int> pairs;     // (t, s) of the lower-triangle entries p = l, l + 32, l + 64 (4 bits each)
+    LaneVar<int> kin;       // joint l: (parent+1) | level<<6 | (axis index+1)<<10 | negative axis<<12 | identity R0<<13
+    LaneVar<float> ox, oy, oz;  // joint l: pivot offset in the parent joint frame
+  };
+  MB_HD static void init_lane_const(LaneConst& C) {
+    MB_LANES(l)
+      C.tl[l] = l < NU ? M::rowlen(l) - 1 : 0;
+      C.off[l] = l < NU ? M::rowoff(l) : 0;
+      C.sup[l] = l < NU ? M::rowmask(l) : 0u;
+      int packed = 0;
+      for (int r = 0; r < 3; ++r) {
+        const int pidx = l + 32 * r;
+        int t = 0;
+        while ((t + 1) * (t + 2) / 2 <= pidx) ++t;
+        const int s2 = pidx - t * (t + 1) / 2;
+        packed |= (t | (s2 << 4)) << (8 * r);
+      }
+      C.pairs[l] = packed;
+      C.kin[l] = -1;
+      C.ox[l] = C.oy[l] = C.oz[l] = 0.0f;
+      if (l < NJ) {
+        C.kin[l] = (M::jparent(l) + 1) | (M::jlevel(l) << 6) | ((M::jaxk(l) + 1) << 10) |
+                   ((M::jsgn(l) < 0.0f ? 1 : 0) << 12) | (M::jident(l) << 13);
+        C.ox[l] = M::joff(l, 0); C.oy[l] = M::joff(l, 1); C.oz[l] = M::joff(l, 2);
+      }
+    MB_END
+  }
+
   // ---- A. kinematics (+ velocities / bias accelerations when with_vel) --------------------------------------
-  MB_HD static void kinematics(Mem& S, const MbPhysics& P, bool with_vel) {
+  MB_HD static void kinematics(Mem& S, const MbPhysics& P, const LaneConst& C, bool with_vel) {
     MB_LANES(l)
       if (l == 0) {
         mb_quat_to_mat(S.quat, S.Rb);
@@ -238,10 +272,11 @@ template <class M> struct Sim {
 #pragma unroll 1
     for (int lev = 0; lev < M::NLEVEL; ++lev) {
       MB_LANES(l)
-        if (l < NJ && M::jlevel(l) == lev) {
-          const int pj = M::jparent(l);
+        const int kc = C.kin[l];
+        if (kc >= 0 && ((kc >> 6) & 15) == lev) {
+          const int pj = (kc & 63) - 1;
           const float* Rp = pj < 0 ? S.Rb : S.w.k.jR[pj];
-          float off[3] = {M::joff(l, 0), M::joff(l, 1), M::joff(l, 2)};
+          float off[3] = {C.ox[l], C.oy[l], C.oz[l]};
           float p[3];
           mb_matvec(Rp, off, p);
           if (pj >= 0) { p[0] += S.w.k.jp[pj][0]; p[1] += S.w.k.jp[pj][1]; p[2] += S.w.k.jp[pj][2]; }
@@ -252,15 +287,15 @@ template <class M> struct Sim {
           float B[9], R[9];
 #pragma unroll
           for (int k = 0; k < 9; ++k) B[k] = Rp[k];
-          if (!M::jident(l)) {
+          if (!((kc >> 13) & 1)) {
             float R0[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) R0[k] = M::jrot(l, k);
             mb_matmul(B, R0, B);
           }
-          const int kax = M::jaxk(l);
+          const int kax = ((kc >> 10) & 3) - 1;
           if (kax >= 0) {
-            const float sg = sn * M::jsgn(l);
+            const float sg = ((kc >> 12) & 1) ? -sn : sn;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
               const float c0 = B[3 * r], c1 = B[3 * r + 1], c2 = B[3 * r + 2];
@@ -279,7 +314,14 @@ template <class M> struct Sim {
             mb_matmul(B, Rq, R);
           }
           float a[3], s[6];
-          mb_matvec(R, ax, a);
+          if (kax >= 0) {
+            const float sgn = ((kc >> 12) & 1) ? -1.0f : 1.0f;
+            a[0] = sgn * (kax == 0 ? R[0] : (kax == 1 ? R[1] : R[2]));
+            a[1] = sgn * (kax == 0 ? R[3] : (kax == 1 ? R[4] : R[5]));
+            a[2] = sgn * (kax == 0 ? R[6] : (kax == 1 ? R[7] : R[8]));
+          } else {
+            mb_matvec(R, ax, a);
+          }
           s[0] = a[0]; s[1] = a[1]; s[2] = a[2];
           mb_cross(p, a, &s[3]);
 #pragma unroll
@@ -436,34 +478,36 @@ template <class M> struct Sim {
 
   // ---- D. M = L^T L, processed leaf-to-root so the tree sparsity of M is preserved (no fill-in) -------------
   // Compact rows: entry t of row k belongs to column i_t = (t < 6 ? t : 6 + chain_k[t-6]), and row i_t has exactly
-  // t off-diagonal entries occupying the same slots 0..t-1 -- every update is a contiguous prefix.
-  enum { MAXOFF = M::MAXSUP - 1 };
-  MB_HD static void factorize(Mem& S) {
+  // t off-diagonal entries occupying the same slots 0..t-1 -- every update L[i_t][s] -= L[k][t] L[k][s] (s <= t)
+  // is a contiguous prefix.  The nk(nk+1)/2 updates of step k are spread over the 32 lanes (<= 3 rounds).
+  MB_HD static void factorize(Mem& S, const LaneConst& C) {
 #pragma unroll 1
     for (int k = NU - 1; k >= 0; --k) {
       const int offk = M::rowoff(k), nk = M::rowlen(k) - 1;
-      const float d = sqrtf(S.L[offk + nk]);
-      const float inv = 1.0f / d;
+      const float dkk = S.L[offk + nk];
+      const float inv = rsqrtf(dkk);
       const unsigned long long pack = k >= 6 ? M::chainpack(k - 6) : 0ull;
       MB_LANES(l)
         if (l < nk) S.L[offk + l] *= inv;
-        else if (l == nk) { S.L[offk + nk] = d; S.Ldinv[k] = inv; }
+        else if (l == nk) { S.L[offk + nk] = dkk * inv; S.Ldinv[k] = inv; }
       MB_END
-      MB_LANES(t)
-        if (t < nk) {
-          const int it = t < 6 ? t : 6 + chain_at(pack, t - 6);
-          float* __restrict__ Li = &S.L[M::rowoff(it)];
-          const float* __restrict__ Lk = &S.L[offk];
-          const float Lkt = Lk[t];
-#pragma unroll 4
-          for (int s2 = 0; s2 <= t; ++s2) Li[s2] -= Lkt * Lk[s2];
+      const int npairs = (nk * (nk + 1)) >> 1;
+      MB_LANES(l)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          if (l + 32 * r < npairs) {
+            const int t = (C.pairs[l] >> (8 * r)) & 15, s2 = (C.pairs[l] >> (8 * r + 4)) & 15;
+            const int it = t < 6 ? t : 6 + chain_at(pack, t - 6);
+            S.L[M::rowoff(it) + s2] -= S.L[offk + t] * S.L[offk + s2];
+          }
         }
       MB_END
     }
   }
 
   // ---- E. single right-hand-side solves, one generalised coordinate per lane ---------------------------------
-  MB_HD static void solve_Lt(Mem& S, LaneVar<float>& x) {  // L^T y = x
+  // L[i][l] sits at rowoff(i) + tl(l) for every i whose support contains l (prefix property): no index math.
+  MB_HD static void solve_Lt(Mem& S, const LaneConst& C, LaneVar<float>& x) {  // L^T y = x
 #pragma unroll 1
     for (int i = NU - 1; i >= 0; --i) {
       const float yi = warp_bcast(x, i) * S.Ldinv[i];
@@ -471,23 +515,18 @@ template <class M> struct Sim {
       const int off = M::rowoff(i);
       MB_LANES(l)
         if (l == i) x[l] = yi;
-        else if ((sup >> l) & 1u) x[l] -= S.L[off + mb_popc(sup & ((1u << l) - 1u))] * yi;
+        else if ((sup >> l) & 1u) x[l] -= S.L[off + C.tl[l]] * yi;
       MB_END
     }
   }
-  MB_HD static void solve_L(Mem& S, LaneVar<float>& x) {  // L y = x
-    LaneVar<unsigned> sup;
-    LaneVar<int> off;
-    MB_LANES(l)
-      sup[l] = l < NU ? M::rowmask(l) : 0u;
-      off[l] = l < NU ? M::rowoff(l) : 0;
-    MB_END
+  MB_HD static void solve_L(Mem& S, const LaneConst& C, LaneVar<float>& x) {  // L y = x
 #pragma unroll 1
     for (int i = 0; i < NU; ++i) {
       const float xi = warp_bcast(x, i) * S.Ldinv[i];
+      const int ti = M::rowlen(i) - 1;
       MB_LANES(l)
         if (l == i) x[l] = xi;
-        else if ((sup[l] >> i) & 1u) x[l] -= S.L[off[l] + mb_popc(sup[l] & ((1u << i) - 1u))] * xi;
+        else if ((C.sup[l] >> i) & 1u) x[l] -= S.L[C.off[l] + ti] * xi;
       MB_END
     }
   }
@@ -673,77 +712,85 @@ template <class M> struct Sim {
   }
 
   // ---- H. projected Gauss-Seidel in z-space (btMultiBodyConstraintSolver::solveSingleIteration order) --------
-  // One visit resolves row ra, or the friction pair (ra, rb) with btMultiBodyConstraintSolver's cone projection.
-  // A single code path serves limit, normal and friction rows (code size matters: see DESIGN.md, I-cache).
-  MB_HD static float pgs_visit(Mem& S, int ra, int rb, float lo, float hi, float cone, LaneVar<float>& z) {
-    const bool pair = rb >= 0;
+  // Row r of Y is stored over its support; the entry of coordinate l sits at slot tl(l) (prefix property).
+  MB_HD static float pgs_single(Mem& S, const LaneConst& C, int ra, float lo, float hi, LaneVar<float>& z) {
     const unsigned supA = S.r_mask[ra];
-    const unsigned supB = pair ? S.r_mask[rb] : 0u;
-    LaneVar<float> ya, yb, ta, tb;
+    LaneVar<float> ya, ta;
     MB_LANES(l)
-      const unsigned lt = (1u << l) - 1u;
-      ya[l] = ((supA >> l) & 1u) ? S.w.Yc[ra][mb_popc(supA & lt)] : 0.0f;
-      yb[l] = ((supB >> l) & 1u) ? S.w.Yc[rb][mb_popc(supB & lt)] : 0.0f;
+      ya[l] = ((supA >> l) & 1u) ? S.w.Yc[ra][C.tl[l]] : 0.0f;
       ta[l] = ya[l] * z[l];
-      tb[l] = yb[l] * z[l];
     MB_END
     const float dotA = warp_sum(ta);
     const float appA = S.r_app[ra], jA = S.r_jinv[ra];
     float dA = S.r_rhs[ra] - appA * S.r_cfm[ra] - dotA * jA;
     const float sumA = appA + dA;
-    float nA = sumA, nB = 0.0f, dB = 0.0f, jB = 0.0f;
-    if (!pair) {
-      if (sumA < lo) { dA = lo - appA; nA = lo; }
-      else if (sumA > hi) { dA = hi - appA; nA = hi; }
-    } else {
-      const float dotB = warp_sum(tb);
-      const float appB = S.r_app[rb];
-      jB = S.r_jinv[rb];
-      dB = S.r_rhs[rb] - appB * S.r_cfm[rb] - dotB * jB;
-      const float sumB = appB + dB;
-      nB = sumB;
-      if (sumA * sumA + sumB * sumB >= cone * cone) {
-        const float angle = atan2f(sumA, sumB);
-        const float clipA = fabsf(cone * sinf(angle)), clipB = fabsf(cone * cosf(angle));
-        if (sumA < -clipA) { dA = -clipA - appA; nA = -clipA; }
-        else if (sumA > clipA) { dA = clipA - appA; nA = clipA; }
-        if (sumB < -clipB) { dB = -clipB - appB; nB = -clipB; }
-        else if (sumB > clipB) { dB = clipB - appB; nB = clipB; }
-      }
+    float nA = sumA;
+    if (sumA < lo) { dA = lo - appA; nA = lo; }
+    else if (sumA > hi) { dA = hi - appA; nA = hi; }
+    MB_LANES(l)
+      z[l] += ya[l] * dA;
+      if (l == 0) S.r_app[ra] = nA;
+    MB_END
+    return jA != 0.0f ? dA / jA : 0.0f;
+  }
+  // friction pair with btMultiBodyConstraintSolver::resolveConeFrictionConstraintRows' projection;
+  // sin/cos(atan2(a, b)) are written as a/|(a,b)|, b/|(a,b)|
+  MB_HD static float pgs_pair(Mem& S, const LaneConst& C, int ra, float cone, LaneVar<float>& z) {
+    const int rb = ra + 1;
+    const unsigned supA = S.r_mask[ra];  // both rows of a contact share the support
+    LaneVar<float> ya, yb, ta, tb;
+    MB_LANES(l)
+      const bool in = ((supA >> l) & 1u) != 0u;
+      ya[l] = in ? S.w.Yc[ra][C.tl[l]] : 0.0f;
+      yb[l] = in ? S.w.Yc[rb][C.tl[l]] : 0.0f;
+      ta[l] = ya[l] * z[l];
+      tb[l] = yb[l] * z[l];
+    MB_END
+    const float dotA = warp_sum(ta), dotB = warp_sum(tb);
+    const float appA = S.r_app[ra], jA = S.r_jinv[ra], appB = S.r_app[rb], jB = S.r_jinv[rb];
+    float dA = S.r_rhs[ra] - appA * S.r_cfm[ra] - dotA * jA;
+    float dB = S.r_rhs[rb] - appB * S.r_cfm[rb] - dotB * jB;
+    const float sumA = appA + dA, sumB = appB + dB;
+    float nA = sumA, nB = sumB;
+    const float n2 = sumA * sumA + sumB * sumB;
+    if (n2 >= cone * cone) {
+      const float sc = n2 > 0.0f ? fabsf(cone) * rsqrtf(n2) : 0.0f;
+      const float clipA = fabsf(sumA) * sc, clipB = fabsf(sumB) * sc;
+      if (sumA < -clipA) { dA = -clipA - appA; nA = -clipA; }
+      else if (sumA > clipA) { dA = clipA - appA; nA = clipA; }
+      if (sumB < -clipB) { dB = -clipB - appB; nB = -clipB; }
+      else if (sumB > clipB) { dB = clipB - appB; nB = clipB; }
     }
     MB_LANES(l)
       z[l] += ya[l] * dA + yb[l] * dB;
-      if (l == 0) {
-        S.r_app[ra] = nA;
-        if (pair) S.r_app[rb] = nB;
-      }
+      if (l == 0) { S.r_app[ra] = nA; S.r_app[rb] = nB; }
     MB_END
     float res = jA != 0.0f ? dA / jA : 0.0f;
-    if (pair && jB != 0.0f) res += dB / jB;
+    if (jB != 0.0f) res += dB / jB;
     return res;
   }
 
-  MB_HD static void solve_constraints(Mem& S, const MbPhysics& P, int nlim, int nc, LaneVar<float>& z) {
+  // btMultiBodyConstraintSolver::solveSingleIteration order: limits (alternating direction), normals, friction
+  MB_HD static void solve_constraints(Mem& S, const MbPhysics& P, const LaneConst& C, int nlim, int nc,
+                                      LaneVar<float>& z) {
     MB_LANES(l)
       z[l] = 0.0f;
     MB_END
-    const int nvis = nlim + 2 * nc;
+    const int nsingle = nlim + nc;
 #pragma unroll 1
     for (int it = 0; it < P.iterations; ++it) {
       float res2 = 0.0f;
 #pragma unroll 1
-      for (int v = 0; v < nvis; ++v) {
-        int ra, rb = -1;
-        float lo = 0.0f, hi = 1e10f, cone = 0.0f;
-        if (v < nlim) { ra = (it & 1) ? v : nlim - 1 - v; hi = P.limit_max_impulse; }
-        else if (v < nlim + nc) ra = v;
-        else {
-          const int k = v - nlim - nc;
-          ra = nlim + nc + 2 * k;
-          rb = ra + 1;
-          cone = S.r_mu[ra] * S.r_app[nlim + k];
-        }
-        const float rr = pgs_visit(S, ra, rb, lo, hi, cone, z);
+      for (int v = 0; v < nsingle; ++v) {
+        const bool lim = v < nlim;
+        const int ra = lim ? ((it & 1) ? v : nlim - 1 - v) : v;
+        const float rr = pgs_single(S, C, ra, 0.0f, lim ? P.limit_max_impulse : 1e10f, z);
+        res2 = fmaxf(res2, rr * rr);
+      }
+#pragma unroll 1
+      for (int k = 0; k < nc; ++k) {
+        const int ra = nsingle + 2 * k;
+        const float rr = pgs_pair(S, C, ra, S.r_mu[ra] * S.r_app[nlim + k], z);
         res2 = fmaxf(res2, rr * rr);
       }
       if (res2 <= P.residual_threshold) break;
@@ -778,20 +825,20 @@ template <class M> struct Sim {
   }
 
   // ---- one Bullet substep.  Returns the number of constraint rows; contact list of this substep stays in S ----
-  MB_HD static int substep(Mem& S, const MbPhysics& P, int* nc_out, int* overflow) {
+  MB_HD static int substep(Mem& S, const MbPhysics& P, const LaneConst& C, int* nc_out, int* overflow) {
     MB_BLOCK_BARRIER();  // keeps the warps of a CTA in the same phase so instruction-cache lines are shared
-    kinematics(S, P, true);
+    kinematics(S, P, C, true);
     const int nc_all = collide(S, P, overflow);
     bodies(S, P);
     mass_matrix_and_rhs(S);
-    factorize(S);
+    factorize(S, C);
     // forward dynamics: udot = M^-1 (tau - bias); u += dt udot (clamped like btMultiBody::applyDeltaVeeMultiDof)
     LaneVar<float> x;
     MB_LANES(l)
       x[l] = l < NU ? S.rhs[l] : 0.0f;
     MB_END
-    solve_Lt(S, x);
-    solve_L(S, x);
+    solve_Lt(S, C, x);
+    solve_L(S, C, x);
     MB_LANES(l)
       if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + P.dt * x[l], -P.max_coord_vel), P.max_coord_vel);
     MB_END
@@ -803,8 +850,8 @@ template <class M> struct Sim {
     if (R > 0) {
       setup_rows(S, P, nlim, nc);
       LaneVar<float> z;
-      solve_constraints(S, P, nlim, nc, z);
-      solve_L(S, z);
+      solve_constraints(S, P, C, nlim, nc, z);
+      solve_L(S, C, z);
       MB_LANES(l)
         if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + z[l], -P.max_coord_vel), P.max_coord_vel);
       MB_END

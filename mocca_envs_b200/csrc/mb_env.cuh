@@ -270,7 +270,9 @@ template <class M> struct W3DEnv {
         S.quat[0] = 0.0f; S.quat[1] = 0.0f; S.quat[2] = 0.0f; S.quat[3] = 1.0f;
       }
     MB_END
-    S_::kinematics(S, P, false);
+    typename S_::LaneConst C;
+    S_::init_lane_const(C);
+    S_::kinematics(S, P, C, false);
     LaneVar<float> zero;
     MB_LANES(l)
       zero[l] = 0.0f;
@@ -307,8 +309,11 @@ template <class M> struct W3DEnv {
     MB_END
     const unsigned anybad = warp_ballot(badact);
     int rows = 0, nc = 0, overflow = 0, ncsum = 0;
+    typename S_::LaneConst C;
+    S_::init_lane_const(C);
+#pragma unroll 1
     for (int k = 0; k < P.substeps; ++k) {
-      rows += S_::substep(S, P, &nc, &overflow);
+      rows += S_::substep(S, P, C, &nc, &overflow);
       ncsum += nc;
     }
     // feet_contact from the last collision pass (robots.py:74-86 via getContactPoints)
@@ -325,7 +330,7 @@ template <class M> struct W3DEnv {
         if (eval_mode) { rec[ER_TX] = prev_bodyx + 4.0f; rec[ER_TY] = 0.0f; rec[ER_TZ] = 1.0f; }
       }
     MB_END
-    S_::kinematics(S, P, false);
+    S_::kinematics(S, P, C, false);
     float s1, s2;
     W3DObsScalars o = observe(S, rec, obs, araw, &s1, &s2);
     int env_done = o.nonfinite ? 1 : 0;

@@ -28,7 +28,9 @@ void emu_step_physics(const MbPhysics* p, float* state, const float* tau, int* r
   WEnv::load_state(S, state);
   for (int j = 0; j < WM::NJ; ++j) S.tau[j] = tau[j];
   int r = 0, nc = 0, ov = 0;
-  for (int k = 0; k < p->substeps; ++k) r += Sim<WM>::substep(S, *p, &nc, &ov);
+  Sim<WM>::LaneConst C;
+  Sim<WM>::init_lane_const(C);
+  for (int k = 0; k < p->substeps; ++k) r += Sim<WM>::substep(S, *p, C, &nc, &ov);
   WEnv::store_state(S, state);
   *rows = r;
   *contacts = nc;
@@ -38,7 +40,9 @@ void emu_mass_matrix(const MbPhysics* p, const float* state, float* Mout, float*
   static WMem S;
   memset(&S, 0, sizeof(S));
   WEnv::load_state(S, state);
-  Sim<WM>::kinematics(S, *p, true);
+  Sim<WM>::LaneConst C;
+  Sim<WM>::init_lane_const(C);
+  Sim<WM>::kinematics(S, *p, C, true);
   Sim<WM>::bodies(S, *p);
   Sim<WM>::mass_matrix_and_rhs(S);
   const int NU = WM::NU;
