@@ -166,6 +166,7 @@ def main():
     import torch
 
     from mocca_envs_b200 import _lib
+    from mocca_envs_b200.distributed import shard_seed
     from mocca_envs_b200.vec_env import Walker3DCustomVecEnv
 
     if not torch.cuda.is_available():
@@ -180,7 +181,7 @@ def main():
     torch.cuda.set_device(dev)
     N, K, W = args.envs, args.steps, max(args.warmup, 3)
     # env i of rank r is global env r*N + i: seeds are independent of the GPU count
-    env = Walker3DCustomVecEnv(N, device=dev, seed=1234 + rank * N)
+    env = Walker3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N))
     env.reset()
     A = env.act_dim
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
