@@ -136,6 +136,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--envs", type=int, default=16384, help="envs per GPU")
     ap.add_argument("--actions", default="random", choices=["random", "pd"])
+    ap.add_argument("--env", default="custom", choices=["custom", "stepper"],
+                    help="custom = BASELINE configs[1] (headline); stepper = configs[2] (curriculum 0/5/9 per env)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -167,7 +169,7 @@ def main():
 
     from mocca_envs_b200 import _lib
     from mocca_envs_b200.distributed import shard_seed
-    from mocca_envs_b200.vec_env import Walker3DCustomVecEnv
+    from mocca_envs_b200.vec_env import Walker3DCustomVecEnv, Walker3DStepperVecEnv
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
@@ -181,7 +183,11 @@ def main():
     torch.cuda.set_device(dev)
     N, K, W = args.envs, args.steps, max(args.warmup, 3)
     # env i of rank r is global env r*N + i: seeds are independent of the GPU count
-    env = Walker3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N))
+    if args.env == "stepper":
+        env = Walker3DStepperVecEnv(N, device=dev, seed=shard_seed(1234, rank, N))
+        env.set_env_params({"curriculum": np.array([0, 5, 9] * (N // 3 + 1))[:N]})
+    else:
+        env = Walker3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N))
     env.reset()
     A = env.act_dim
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -294,10 +300,13 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_ach = bytes_per_env_step() * N / kernel_s / 1e9
     line = {
-        "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC if args.env == "custom" else METRIC.replace("Walker3DCustomEnv", "Walker3DStepperEnv"),
+        "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": N, "actions": "random-uniform U(-1,1)^21 (device pool)"
+        "config": {"workload": WORKLOAD if args.env == "custom" else
+                   "Walker3DStepperEnv-v0 batched 16384 envs/GPU, seeded stepping stones, curriculum 0/5/9",
+                   "envs_per_gpu": N, "actions": "random-uniform U(-1,1)^21 (device pool)"
                    if args.actions == "random" else "scripted PD toward running_start (kp=1, kd=0.1, normalised)",
                    "frame_skip": 4, "solver_iterations": 5, "rng": "mt19937 (NumPy-compatible)",
                    "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs)",

@@ -43,7 +43,8 @@ typedef struct mb200_physics {
 void mb200_default_physics(mb200_physics* p);
 
 /* gym.make("mocca_envs:<env_id>") x n_envs  (reference mocca_envs/__init__.py:18-116, env_base.py:16-42).
- * env_id: "Walker3DCustomEnv-v0".  physics may be NULL (reference values). */
+ * env_id: "Walker3DCustomEnv-v0" (__init__.py:52-56) or "Walker3DStepperEnv-v0" (__init__.py:58-62).
+ * physics may be NULL (reference values). */
 int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics* physics, mb200_env** out);
 /* EnvBase.close (env_base.py:44-47) */
 void mb200_destroy(mb200_env* env);
@@ -76,8 +77,9 @@ int mb200_step_host(mb200_env* env, const float* act_host, float* obs_host, floa
  * (robots.py:212-216, bullet_utils.py:100-146,157-175): rows are [pos3 quat4 omega3 vel3 q[A] qd[A]]. */
 int mb200_get_state(mb200_env* env, float* state_dev, void* stream);
 int mb200_set_state(mb200_env* env, const float* state_dev, void* stream);
-/* per-env bookkeeping record (walk_target, potentials, counters ...), 32 x 4-byte words per env, see ER_* in
- * csrc/mb_env.cuh; used by tests and checkpointing. */
+/* per-env bookkeeping record (walk_target, potentials, counters, terrain ...), mb200_record_stride() 4-byte words
+ * per env, see ER_* / ES_* in csrc/mb_env.cuh; used by tests and checkpointing. */
+int mb200_record_stride(const mb200_env* env);
 int mb200_get_record(mb200_env* env, float* rec_dev, void* stream);
 int mb200_set_record(mb200_env* env, const float* rec_dev, void* stream);
 
@@ -91,11 +93,15 @@ int mb200_step_physics(mb200_env* env, const float* tau_dev, int* rows_dev, int*
 int mb200_mass_matrix(mb200_env* env, float* M_dev, void* stream);
 int mb200_inverse_dynamics(mb200_env* env, const float* acc_dev, float* tau_dev, void* stream);
 
-/* EnvBase.set_env_params analogue (env_base.py:103-106): "eval_mode" (env_locomotion.py:76-77). */
+/* EnvBase.set_env_params analogue (env_base.py:103-106): "eval_mode" (Walker3DCustomEnv, env_locomotion.py:76-77),
+ * "curriculum" 0..9 (Walker3DStepperEnv, env_locomotion.py:362-369; takes effect at the next reset like the
+ * reference, whose terrain / gain / terminal height are read in reset() and step()).  The array variant sets one
+ * value per env (values_host[count], count == n_envs).  Synchronous. */
 int mb200_set_param(mb200_env* env, const char* key, float value);
+int mb200_set_param_array(mb200_env* env, const char* key, const float* values_host, int count);
 
 /* Episode statistics accumulated on the device since the last call with reset != 0 (synchronous):
- * out = {episodes, sum_return, sum_length, nonfinite_events, cap_overflows, 0, 0, 0}. */
+ * out = {episodes, sum_return, sum_length, nonfinite_events, cap_overflows, sum_steps_reached (Stepper), 0, 0}. */
 int mb200_stats(mb200_env* env, double out[8], int reset);
 
 /* number of kernel launches issued through this handle (bench.py's gpu_launches) */

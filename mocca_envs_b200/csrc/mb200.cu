@@ -32,7 +32,11 @@ static int fail(const std::string& m) { g_err = m; return -1; }
     if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_));                 \
   } while (0)
 
+enum { KIND_CUSTOM = 0, KIND_STEPPER = 1 };
+
 struct mb200_env {
+  int kind;        // KIND_*
+  int rec_stride;  // floats per env in `rec`
   int n, device;
   int obs_dim, act_dim, state_dim, nu;
   MbPhysics phys;
@@ -58,6 +62,7 @@ struct mb200_env {
 
 typedef W3D_Model WM;
 typedef W3DEnv<WM> WEnv;
+typedef StepperEnv<WM> SEnv;
 typedef WarpMem<WM> WMem;
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -80,45 +85,65 @@ struct StepArgs {
   MbStats* dummy_stats;
 };
 
-__global__ void __launch_bounds__(MB_WARPS * 32, MB_MINBLOCKS) k_step_walker3d_custom(StepArgs a) {
+template <class Env>
+__device__ __forceinline__ void step_body(const StepArgs& a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * MB_WARPS + warp;  // < n_pad by construction of the grid
   const bool tail = env >= a.n;
   WMem& S = reinterpret_cast<WMem*>(smem_raw)[warp];
-  float* obs = tail ? a.dummy_obs + (size_t)warp * WEnv::OBS : a.obs + (size_t)env * WEnv::OBS;
-  float* fin = tail ? a.dummy_obs + (size_t)(MB_WARPS + warp) * WEnv::OBS
-                    : (a.final_obs ? a.final_obs + (size_t)env * WEnv::OBS : nullptr);
-  WEnv::step(S, a.phys, a.state + (size_t)env * MB_STATE_STRIDE, a.rec + (size_t)env * MB_REC_STRIDE,
-             a.mt + (size_t)env * 2 * MB_MT_STRIDE, a.mt + ((size_t)env * 2 + 1) * MB_MT_STRIDE,
-             a.act + (size_t)(tail ? 0 : env) * WM::NJ, obs, tail ? a.dummy_rew + warp : a.rew + env,
-             tail ? a.dummy_flag + warp : a.done + env, tail ? a.dummy_flag + MB_WARPS + warp : a.trunc + env, fin,
-             tail ? a.dummy_stats : a.stats);
+  float* obs = tail ? a.dummy_obs + (size_t)warp * Env::OBS : a.obs + (size_t)env * Env::OBS;
+  float* fin = tail ? a.dummy_obs + (size_t)(MB_WARPS + warp) * Env::OBS
+                    : (a.final_obs ? a.final_obs + (size_t)env * Env::OBS : nullptr);
+  Env::step(S, a.phys, a.state + (size_t)env * MB_STATE_STRIDE, a.rec + (size_t)env * Env::REC_STRIDE,
+            a.mt + (size_t)env * 2 * MB_MT_STRIDE, a.mt + ((size_t)env * 2 + 1) * MB_MT_STRIDE,
+            a.act + (size_t)(tail ? 0 : env) * WM::NJ, obs, tail ? a.dummy_rew + warp : a.rew + env,
+            tail ? a.dummy_flag + warp : a.done + env, tail ? a.dummy_flag + MB_WARPS + warp : a.trunc + env, fin,
+            tail ? a.dummy_stats : a.stats);
+}
+__global__ void __launch_bounds__(MB_WARPS * 32, MB_MINBLOCKS) k_step_walker3d_custom(StepArgs a) {
+  step_body<WEnv>(a);
+}
+__global__ void __launch_bounds__(MB_WARPS * 32, MB_MINBLOCKS) k_step_walker3d_stepper(StepArgs a) {
+  step_body<SEnv>(a);
 }
 
-__global__ void __launch_bounds__(MB_WARPS * 32)
-    k_reset_walker3d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
-                            float* obs, float* dummy_obs) {
+template <class Env>
+__device__ __forceinline__ void reset_body(int n, const MbPhysics& phys, float* state, float* rec, uint32_t* mt,
+                                           const uint8_t* mask, float* obs, float* dummy_obs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * MB_WARPS + warp;
   const bool tail = env >= n;
   if (!tail && mask && !mask[env]) return;  // no CTA barrier inside reset, early exit is fine
   WMem& S = reinterpret_cast<WMem*>(smem_raw)[warp];
-  WEnv::reset(S, phys, rec + (size_t)env * MB_REC_STRIDE, mt + (size_t)env * 2 * MB_MT_STRIDE,
-              mt + ((size_t)env * 2 + 1) * MB_MT_STRIDE,
-              tail ? dummy_obs + (size_t)warp * WEnv::OBS : obs + (size_t)env * WEnv::OBS);
+  Env::reset(S, phys, rec + (size_t)env * Env::REC_STRIDE, mt + (size_t)env * 2 * MB_MT_STRIDE,
+             mt + ((size_t)env * 2 + 1) * MB_MT_STRIDE,
+             tail ? dummy_obs + (size_t)warp * Env::OBS : obs + (size_t)env * Env::OBS);
   WEnv::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
 }
-
 __global__ void __launch_bounds__(MB_WARPS * 32)
-    k_step_physics_walker3d(int n, MbPhysics phys, float* state, const float* tau, int* rows_out, int* contacts_out) {
+    k_reset_walker3d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
+                            float* obs, float* dummy_obs) {
+  reset_body<WEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
+}
+__global__ void __launch_bounds__(MB_WARPS * 32)
+    k_reset_walker3d_stepper(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
+                             float* obs, float* dummy_obs) {
+  reset_body<SEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
+}
+
+// stepSimulation only; rec (may be NULL) supplies the static obstacles of the env kind
+template <class Env>
+__device__ __forceinline__ void physics_body(int n, const MbPhysics& phys, float* state, const float* rec,
+                                             const float* tau, int* rows_out, int* contacts_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * MB_WARPS + warp;
   const bool tail = env >= n;  // pad env: steps with zero torque, outputs discarded
   WMem& S = reinterpret_cast<WMem*>(smem_raw)[warp];
   WEnv::load_state(S, state + (size_t)env * MB_STATE_STRIDE);
+  Env::load_obstacles(S, rec + (size_t)env * Env::REC_STRIDE);
   MB_LANES(l)
     if (l < WM::NJ) S.tau[l] = tail ? 0.0f : tau[(size_t)env * WM::NJ + l];
   MB_END
@@ -133,6 +158,16 @@ __global__ void __launch_bounds__(MB_WARPS * 32)
     if (rows_out) rows_out[env] = rows;
     if (contacts_out) contacts_out[env] = nc;
   }
+}
+__global__ void __launch_bounds__(MB_WARPS * 32)
+    k_step_physics_walker3d(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
+                            int* contacts_out) {
+  physics_body<WEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
+}
+__global__ void __launch_bounds__(MB_WARPS * 32)
+    k_step_physics_walker3d_stepper(int n, MbPhysics phys, float* state, const float* rec, const float* tau,
+                                    int* rows_out, int* contacts_out) {
+  physics_body<SEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
 }
 
 // mode 0: M (full symmetric, [nu][nu]);  mode 1: tau = M acc - rhs (rhs = -bias with zero applied torque)
@@ -215,6 +250,7 @@ static void to_internal(const mb200_physics& p, MbPhysics* q) {
   q->lin_damping = p.lin_damping; q->ang_damping = p.ang_damping; q->max_coord_vel = p.max_coord_vel;
   q->limit_max_impulse = p.limit_max_impulse; q->split_threshold = p.split_threshold;
   q->residual_threshold = p.residual_threshold; q->ground_friction = p.ground_friction; q->has_ground = p.has_ground;
+  q->box_friction = 1.0f; q->box_erp = p.erp_contact; q->box_cfm = 0.0f;
 }
 
 static int grid_for(int n) { return (n + MB_WARPS - 1) / MB_WARPS; }
@@ -222,9 +258,12 @@ static int grid_for(int n) { return (n + MB_WARPS - 1) / MB_WARPS; }
 int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics* physics, mb200_env** out) {
   if (!out) return fail("mb200_create: out is NULL");
   *out = nullptr;
-  if (!env_id || strcmp(env_id, "Walker3DCustomEnv-v0") != 0)
+  int kind = -1;
+  if (env_id && strcmp(env_id, "Walker3DCustomEnv-v0") == 0) kind = KIND_CUSTOM;
+  if (env_id && strcmp(env_id, "Walker3DStepperEnv-v0") == 0) kind = KIND_STEPPER;
+  if (kind < 0)
     return fail(std::string("mb200_create: unsupported env id '") + (env_id ? env_id : "(null)") +
-                "' (built: Walker3DCustomEnv-v0)");
+                "' (built: Walker3DCustomEnv-v0, Walker3DStepperEnv-v0)");
   if (n_envs <= 0) return fail("mb200_create: n_envs must be positive");
   int count = 0;
   CUDA_OK(cudaGetDeviceCount(&count));
@@ -239,7 +278,9 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   memset(e, 0, sizeof(*e));
   e->n = n_envs;
   e->device = device;
-  e->obs_dim = WEnv::OBS;
+  e->kind = kind;
+  e->rec_stride = kind == KIND_STEPPER ? (int)SEnv::REC_STRIDE : (int)WEnv::REC_STRIDE;
+  e->obs_dim = kind == KIND_STEPPER ? (int)SEnv::OBS : (int)WEnv::OBS;
   e->act_dim = WM::NJ;
   e->state_dim = 13 + 2 * WM::NJ;
   e->nu = WM::NU;
@@ -247,7 +288,21 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   mb200_default_physics(&p);
   if (physics) p = *physics;
   to_internal(p, &e->phys);
+  if (kind == KIND_STEPPER) {
+    // remove_ground=True (env_locomotion.py:359); planks: lateralFriction 1.0, contactStiffness 30000,
+    // contactDamping 1000 (bullet_objects.py:64-72) -> per-contact erp / cfm; Bullet sums both
+    // bodies' contact damping and a link's default is 0.1
+    e->phys.has_ground = 0;
+    const float kp = 30000.0f, kd = 1000.0f + 0.1f, denom = e->phys.dt * kp + kd;
+    e->phys.box_friction = 1.0f;
+    e->phys.box_erp = e->phys.dt * kp / denom;
+    e->phys.box_cfm = 1.0f / denom;
+  }
   e->smem = sizeof(WMem) * MB_WARPS;
+  CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_stepper, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  CUDA_OK(cudaFuncSetAttribute(k_reset_walker3d_stepper, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d_stepper, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)e->smem));
   CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_custom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   CUDA_OK(cudaFuncSetAttribute(k_reset_walker3d_custom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
@@ -260,7 +315,7 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   CUDA_OK(cudaMalloc(&e->dummy_stats, sizeof(MbStats)));
   CUDA_OK(cudaMemset(e->dummy_stats, 0, sizeof(MbStats)));
   CUDA_OK(cudaMalloc(&e->state, n * MB_STATE_STRIDE * sizeof(float)));
-  CUDA_OK(cudaMalloc(&e->rec, n * MB_REC_STRIDE * sizeof(float)));
+  CUDA_OK(cudaMalloc(&e->rec, n * e->rec_stride * sizeof(float)));
   CUDA_OK(cudaMalloc(&e->mt, n * 2 * MB_MT_STRIDE * sizeof(uint32_t)));
   CUDA_OK(cudaMalloc(&e->stats, sizeof(MbStats)));
   CUDA_OK(cudaMalloc(&e->stage_act, n * e->act_dim * sizeof(float)));
@@ -269,7 +324,7 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   CUDA_OK(cudaMalloc(&e->stage_done, n));
   CUDA_OK(cudaMalloc(&e->stage_trunc, n));
   CUDA_OK(cudaMemset(e->state, 0, n * MB_STATE_STRIDE * sizeof(float)));
-  CUDA_OK(cudaMemset(e->rec, 0, n * MB_REC_STRIDE * sizeof(float)));
+  CUDA_OK(cudaMemset(e->rec, 0, n * e->rec_stride * sizeof(float)));
   CUDA_OK(cudaMemset(e->mt, 0, n * 2 * MB_MT_STRIDE * sizeof(uint32_t)));
   CUDA_OK(cudaMemset(e->stats, 0, sizeof(MbStats)));
   *out = e;
@@ -305,12 +360,12 @@ int mb200_seed(mb200_env* e, const uint32_t* mt_host, int at_construction) {
     // EnvBase.seed rebinds only the env's RandomState: an aliased robot keeps drawing from the OLD stream,
     // which therefore moves to the robot slot (quirk Q1)
     uint32_t* tmp = (uint32_t*)malloc(n * 2 * MB_MT_STRIDE * sizeof(uint32_t));
-    float* rec = (float*)malloc(n * MB_REC_STRIDE * sizeof(float));
+    float* rec = (float*)malloc(n * e->rec_stride * sizeof(float));
     if (!tmp || !rec) { free(tmp); free(rec); return fail("mb200_seed: host allocation failed"); }
     CUDA_OK(cudaMemcpy(tmp, e->mt, n * 2 * MB_MT_STRIDE * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    CUDA_OK(cudaMemcpy(rec, e->rec, n * MB_REC_STRIDE * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(rec, e->rec, n * e->rec_stride * sizeof(float), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < n; ++i) {
-      int* ri = reinterpret_cast<int*>(rec + i * MB_REC_STRIDE);
+      int* ri = reinterpret_cast<int*>(rec + i * e->rec_stride);
       if (ri[ER_ALIASED]) {
         memcpy(tmp + (i * 2 + 1) * MB_MT_STRIDE, tmp + (i * 2) * MB_MT_STRIDE, 625 * sizeof(uint32_t));
         ri[ER_ALIASED] = 0;
@@ -318,21 +373,21 @@ int mb200_seed(mb200_env* e, const uint32_t* mt_host, int at_construction) {
       memcpy(tmp + (i * 2) * MB_MT_STRIDE, mt_host + (i % nreal) * 625, 625 * sizeof(uint32_t));
     }
     CUDA_OK(cudaMemcpy(e->mt, tmp, n * 2 * MB_MT_STRIDE * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(e->rec, rec, n * MB_REC_STRIDE * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->rec, rec, n * e->rec_stride * sizeof(float), cudaMemcpyHostToDevice));
     free(tmp);
     free(rec);
   } else {
     uint32_t* tmp = (uint32_t*)calloc(n * 2 * MB_MT_STRIDE, sizeof(uint32_t));
-    float* rec = (float*)malloc(n * MB_REC_STRIDE * sizeof(float));
+    float* rec = (float*)malloc(n * e->rec_stride * sizeof(float));
     if (!tmp || !rec) { free(tmp); free(rec); return fail("mb200_seed: host allocation failed"); }
-    CUDA_OK(cudaMemcpy(rec, e->rec, n * MB_REC_STRIDE * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(rec, e->rec, n * e->rec_stride * sizeof(float), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < n; ++i) {
       memcpy(tmp + (i * 2) * MB_MT_STRIDE, mt_host + (i % nreal) * 625, 625 * sizeof(uint32_t));
       tmp[(i * 2 + 1) * MB_MT_STRIDE + 624] = 624;
-      reinterpret_cast<int*>(rec + i * MB_REC_STRIDE)[ER_ALIASED] = 1;
+      reinterpret_cast<int*>(rec + i * e->rec_stride)[ER_ALIASED] = 1;
     }
     CUDA_OK(cudaMemcpy(e->mt, tmp, n * 2 * MB_MT_STRIDE * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(e->rec, rec, n * MB_REC_STRIDE * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->rec, rec, n * e->rec_stride * sizeof(float), cudaMemcpyHostToDevice));
     free(tmp);
     free(rec);
   }
@@ -342,8 +397,12 @@ int mb200_seed(mb200_env* e, const uint32_t* mt_host, int at_construction) {
 int mb200_reset(mb200_env* e, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (!e || !obs_dev) return fail("mb200_reset: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
-  k_reset_walker3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
-      e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
+  if (e->kind == KIND_STEPPER)
+    k_reset_walker3d_stepper<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
+  else
+    k_reset_walker3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
   e->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -357,7 +416,10 @@ int mb200_step(mb200_env* e, const float* act_dev, float* obs_dev, float* rew_de
   a.n = e->n; a.phys = e->phys; a.state = e->state; a.rec = e->rec; a.mt = e->mt; a.act = act_dev; a.obs = obs_dev;
   a.rew = rew_dev; a.done = done_dev; a.trunc = trunc_dev; a.final_obs = final_obs_dev; a.stats = e->stats;
   a.dummy_obs = e->dummy_obs; a.dummy_rew = e->dummy_rew; a.dummy_flag = e->dummy_flag; a.dummy_stats = e->dummy_stats;
-  k_step_walker3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
+  if (e->kind == KIND_STEPPER)
+    k_step_walker3d_stepper<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
+  else
+    k_step_walker3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
   e->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -402,14 +464,14 @@ int mb200_set_state(mb200_env* e, const float* state_dev, void* stream) {
 int mb200_get_record(mb200_env* e, float* rec_dev, void* stream) {
   if (!e || !rec_dev) return fail("mb200_get_record: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
-  CUDA_OK(cudaMemcpyAsync(rec_dev, e->rec, (size_t)e->n * MB_REC_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice,
+  CUDA_OK(cudaMemcpyAsync(rec_dev, e->rec, (size_t)e->n * e->rec_stride * sizeof(float), cudaMemcpyDeviceToDevice,
                           (cudaStream_t)stream));
   return 0;
 }
 int mb200_set_record(mb200_env* e, const float* rec_dev, void* stream) {
   if (!e || !rec_dev) return fail("mb200_set_record: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
-  CUDA_OK(cudaMemcpyAsync(e->rec, rec_dev, (size_t)e->n * MB_REC_STRIDE * sizeof(float), cudaMemcpyDeviceToDevice,
+  CUDA_OK(cudaMemcpyAsync(e->rec, rec_dev, (size_t)e->n * e->rec_stride * sizeof(float), cudaMemcpyDeviceToDevice,
                           (cudaStream_t)stream));
   return 0;
 }
@@ -417,8 +479,12 @@ int mb200_set_record(mb200_env* e, const float* rec_dev, void* stream) {
 int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* contacts_dev, void* stream) {
   if (!e || !tau_dev) return fail("mb200_step_physics: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
-  k_step_physics_walker3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
-      e->n, e->phys, e->state, tau_dev, rows_dev, contacts_dev);
+  if (e->kind == KIND_STEPPER)
+    k_step_physics_walker3d_stepper<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
+  else
+    k_step_physics_walker3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
   e->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -447,21 +513,51 @@ int mb200_inverse_dynamics(mb200_env* e, const float* acc_dev, float* tau_dev, v
   return 0;
 }
 
+static int set_record_int(mb200_env* e, int field, const float* values, int count, float scalar) {
+  CUDA_OK(cudaDeviceSynchronize());
+  const size_t n = (size_t)e->n_pad;
+  float* rec = (float*)malloc(n * e->rec_stride * sizeof(float));
+  if (!rec) return fail("mb200_set_param: host allocation failed");
+  CUDA_OK(cudaMemcpy(rec, e->rec, n * e->rec_stride * sizeof(float), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) {
+    const float v = values ? values[i % (size_t)count] : scalar;
+    reinterpret_cast<int*>(rec + i * e->rec_stride)[field] = (int)v;
+  }
+  CUDA_OK(cudaMemcpy(e->rec, rec, n * e->rec_stride * sizeof(float), cudaMemcpyHostToDevice));
+  free(rec);
+  return 0;
+}
+
+static int param_field(mb200_env* e, const char* key, float lo, float hi, const float* values, int count, float scalar,
+                       int* field) {
+  if (strcmp(key, "eval_mode") == 0 && e->kind == KIND_CUSTOM) { *field = ER_EVAL; return 0; }
+  if (strcmp(key, "curriculum") == 0 && e->kind == KIND_STEPPER) {
+    for (int i = 0; i < (values ? count : 1); ++i) {
+      const float v = values ? values[i] : scalar;
+      if (!(v >= 0.0f && v <= 9.0f)) return fail("mb200_set_param: curriculum must be in [0, 9]");
+    }
+    *field = ES_CURRIC;
+    return 0;
+  }
+  (void)lo; (void)hi;
+  return fail(std::string("mb200_set_param: unknown key '") + key + "' for this env");
+}
+
 int mb200_set_param(mb200_env* e, const char* key, float value) {
   if (!e || !key) return fail("mb200_set_param: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
-  if (strcmp(key, "eval_mode") == 0) {
-    CUDA_OK(cudaDeviceSynchronize());
-    const size_t n = (size_t)e->n_pad;
-    float* rec = (float*)malloc(n * MB_REC_STRIDE * sizeof(float));
-    if (!rec) return fail("mb200_set_param: host allocation failed");
-    CUDA_OK(cudaMemcpy(rec, e->rec, n * MB_REC_STRIDE * sizeof(float), cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < n; ++i) reinterpret_cast<int*>(rec + i * MB_REC_STRIDE)[ER_EVAL] = value != 0.0f;
-    CUDA_OK(cudaMemcpy(e->rec, rec, n * MB_REC_STRIDE * sizeof(float), cudaMemcpyHostToDevice));
-    free(rec);
-    return 0;
-  }
-  return fail(std::string("mb200_set_param: unknown key '") + key + "'");
+  int field = 0;
+  if (param_field(e, key, 0, 0, nullptr, 0, value, &field)) return -1;
+  return set_record_int(e, field, nullptr, 0, field == ER_EVAL && e->kind == KIND_CUSTOM ? (value != 0.0f) : value);
+}
+
+int mb200_set_param_array(mb200_env* e, const char* key, const float* values_host, int count) {
+  if (!e || !key || !values_host) return fail("mb200_set_param_array: NULL argument");
+  if (count != e->n) return fail("mb200_set_param_array: count must equal the number of envs");
+  CUDA_OK(cudaSetDevice(e->device));
+  int field = 0;
+  if (param_field(e, key, 0, 0, values_host, count, 0.0f, &field)) return -1;
+  return set_record_int(e, field, values_host, count, 0.0f);
 }
 
 int mb200_stats(mb200_env* e, double out[8], int reset) {
@@ -471,12 +567,13 @@ int mb200_stats(mb200_env* e, double out[8], int reset) {
   CUDA_OK(cudaDeviceSynchronize());
   CUDA_OK(cudaMemcpy(&s, e->stats, sizeof(s), cudaMemcpyDeviceToHost));
   out[0] = (double)s.episodes; out[1] = s.ret_sum; out[2] = s.len_sum; out[3] = (double)s.nonfinite;
-  out[4] = (double)s.overflow; out[5] = out[6] = out[7] = 0.0;
+  out[4] = (double)s.overflow; out[5] = (double)s.steps; out[6] = out[7] = 0.0;
   if (reset) CUDA_OK(cudaMemset(e->stats, 0, sizeof(MbStats)));
   return 0;
 }
 
 long long mb200_launch_count(const mb200_env* e) { return e ? e->launches : 0; }
+int mb200_record_stride(const mb200_env* e) { return e ? e->rec_stride : 0; }
 
 int mb200_measure_fp32_peak(int device, double* tflops_out) {
   if (!tflops_out) return fail("mb200_measure_fp32_peak: NULL argument");

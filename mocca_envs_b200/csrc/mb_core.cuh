@@ -82,6 +82,7 @@ inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #define MB_MAXC 16    /* contact points kept per substep */
 #define MB_MAXROW 48  /* constraint rows per substep (limits + 3 per contact) */
 #define MB_YSTRIDE 15 /* compact row: 6 base + <= 8 chain entries (+1 pad, odd stride = conflict-free) */
+#define MB_MAXBOX 6   /* static box obstacles per env (3 planks x {base, cover}) */
 #define MB_PI_F 3.14159265358979323846f
 
 // Physics constants of the reference's Bullet world (citations in include/mocca_b200.h: mb200_physics)
@@ -101,6 +102,11 @@ struct MbPhysics {
   float residual_threshold;
   float ground_friction; // bullet_utils.py:371
   int has_ground;
+  // static box obstacles (stepping-stone planks, bullet_objects.py:64-72): friction and the per-contact ERP / CFM
+  // Bullet derives from contactStiffness / contactDamping
+  float box_friction;
+  float box_erp;
+  float box_cfm;
 };
 
 MB_HD constexpr int tri(int i, int j) { return (i * (i + 1)) / 2 + j; }  // packed lower-triangular index, j <= i
@@ -125,9 +131,14 @@ template <class M> struct WarpMem {
       float jp[M::NJ][3];
       float jV[M::NJ + 1][6];  // [0] = base
       float jA[M::NJ + 1][6];
-      // ---- bodies
-      float bI[M::NB][10];  // m, h[3], I_O{xx,yy,zz,xy,xz,yz}
-      float bF[M::NB][6];   // bias wrench about O (n, f)
+      union {
+        struct {
+          // ---- bodies
+          float bI[M::NB][10];  // m, h[3], I_O{xx,yy,zz,xy,xz,yz}
+          float bF[M::NB][6];   // bias wrench about O (n, f)
+        } b;
+        float pt[M::NPT][3];  // contact candidate points (collision runs before the body pass)
+      } u2;
     } k;
     // ---- rows: Y_r = L^-T J_r^T stored compactly over its support (base block + ancestor chain)
     float Yc[MB_MAXROW][MB_YSTRIDE];
@@ -157,6 +168,9 @@ template <class M> struct WarpMem {
   unsigned r_mask[MB_MAXROW];  // support of the row over the generalised coordinates
   int r_dof[32];
   float r_dir[32];
+  // ---- static box obstacles of this env: centre[3], axes R[9] (row-major, columns = box axes), half[3], pad
+  float box[MB_MAXBOX][16];
+  int nbox;
   // ---- scratch for the epilogue
   float scratch[64];
 };
@@ -399,16 +413,16 @@ template <class M> struct Sim {
         }
         mb_cross(c, f, nO);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { S.w.k.bF[l][k] = nc[k] + nO[k]; S.w.k.bF[l][3 + k] = f[k]; }
+        for (int k = 0; k < 3; ++k) { S.w.k.u2.b.bF[l][k] = nc[k] + nO[k]; S.w.k.u2.b.bF[l][3 + k] = f[k]; }
         const float cc = mb_dot3(c, c);
-        S.w.k.bI[l][0] = m;
-        S.w.k.bI[l][1] = m * c[0]; S.w.k.bI[l][2] = m * c[1]; S.w.k.bI[l][3] = m * c[2];
-        S.w.k.bI[l][4] = Ic[0] + m * (cc - c[0] * c[0]);
-        S.w.k.bI[l][5] = Ic[4] + m * (cc - c[1] * c[1]);
-        S.w.k.bI[l][6] = Ic[8] + m * (cc - c[2] * c[2]);
-        S.w.k.bI[l][7] = Ic[1] - m * c[0] * c[1];
-        S.w.k.bI[l][8] = Ic[2] - m * c[0] * c[2];
-        S.w.k.bI[l][9] = Ic[5] - m * c[1] * c[2];
+        S.w.k.u2.b.bI[l][0] = m;
+        S.w.k.u2.b.bI[l][1] = m * c[0]; S.w.k.u2.b.bI[l][2] = m * c[1]; S.w.k.u2.b.bI[l][3] = m * c[2];
+        S.w.k.u2.b.bI[l][4] = Ic[0] + m * (cc - c[0] * c[0]);
+        S.w.k.u2.b.bI[l][5] = Ic[4] + m * (cc - c[1] * c[1]);
+        S.w.k.u2.b.bI[l][6] = Ic[8] + m * (cc - c[2] * c[2]);
+        S.w.k.u2.b.bI[l][7] = Ic[1] - m * c[0] * c[1];
+        S.w.k.u2.b.bI[l][8] = Ic[2] - m * c[0] * c[2];
+        S.w.k.u2.b.bI[l][9] = Ic[5] - m * c[1] * c[2];
       }
     MB_END
   }
@@ -425,9 +439,9 @@ template <class M> struct Sim {
         for (int k = 0; k < 6; ++k) F[k] = 0.0f;
         for (int b = b0; b < b1; ++b) {
 #pragma unroll
-          for (int k = 0; k < 10; ++k) I[k] += S.w.k.bI[b][k];
+          for (int k = 0; k < 10; ++k) I[k] += S.w.k.u2.b.bI[b][k];
 #pragma unroll
-          for (int k = 0; k < 6; ++k) F[k] += S.w.k.bF[b][k];
+          for (int k = 0; k < 6; ++k) F[k] += S.w.k.u2.b.bF[b][k];
         }
         const float m = I[0];
         const float* h = &I[1];
@@ -537,49 +551,128 @@ template <class M> struct Sim {
     MB_END
   }
 
-  // ---- F. narrow phase: sphere / capsule-end candidates vs the ground plane z = 0 ---------------------------
+  // ---- F. narrow phase: sphere / capsule-end candidates vs the ground plane z = 0 and static boxes ------------
+  // Contacts are listed obstacle-major (ground for every point, then box 0, ...) like the oracle.
+  MB_HD static bool sphere_box(const float* c, float r, const float* bx, float thresh, float* pa, float* n,
+                               float* dist) {
+    const float* R = bx + 3;
+    const float* half = bx + 12;
+    const float d[3] = {c[0] - bx[0], c[1] - bx[1], c[2] - bx[2]};
+    float cl[3], q[3], nl[3];
+    bool inside = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      cl[k] = R[k] * d[0] + R[3 + k] * d[1] + R[6 + k] * d[2];
+      q[k] = fminf(fmaxf(cl[k], -half[k]), half[k]);
+      if (q[k] != cl[k]) inside = false;
+    }
+    if (!inside) {
+      const float df[3] = {cl[0] - q[0], cl[1] - q[1], cl[2] - q[2]};
+      const float len = sqrtf(df[0] * df[0] + df[1] * df[1] + df[2] * df[2]);
+      *dist = len - r;
+      if (*dist >= thresh) return false;
+      const float il = 1.0f / len;
+      nl[0] = df[0] * il; nl[1] = df[1] * il; nl[2] = df[2] * il;
+    } else {
+      int ax = 0;
+      float best = 1e30f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float pen = half[k] - fabsf(cl[k]);
+        if (pen < best) { best = pen; ax = k; }
+      }
+      nl[0] = nl[1] = nl[2] = 0.0f;
+      const float sgn = (ax == 0 ? cl[0] : (ax == 1 ? cl[1] : cl[2])) >= 0.0f ? 1.0f : -1.0f;
+      if (ax == 0) nl[0] = sgn; else if (ax == 1) nl[1] = sgn; else nl[2] = sgn;
+      *dist = -best - r;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      n[k] = R[3 * k] * nl[0] + R[3 * k + 1] * nl[1] + R[3 * k + 2] * nl[2];
+      pa[k] = c[k] - r * n[k];
+    }
+    return true;
+  }
+
   MB_HD static int collide(Mem& S, const MbPhysics& P, int* overflow) {
+    // world positions of the candidate points (relative to the base COM)
+    MB_LANES(l)
+      for (int pt = l; pt < NPT; pt += 32) {
+        const int o = M::powner(pt);
+        const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
+        float loc[3] = {M::ppos(pt, 0), M::ppos(pt, 1), M::ppos(pt, 2)};
+        float c[3];
+        mb_matvec(R, loc, c);
+        if (o >= 0) { c[0] += S.w.k.jp[o][0]; c[1] += S.w.k.jp[o][1]; c[2] += S.w.k.jp[o][2]; }
+        S.w.k.u2.pt[pt][0] = c[0]; S.w.k.u2.pt[pt][1] = c[1]; S.w.k.u2.pt[pt][2] = c[2];
+      }
+    MB_END
     int nc = 0;
-    for (int pass = 0; pass * 32 < NPT; ++pass) {
-      LaneVar<int> hit;
-      LaneVar<float> px, py, pz, dd;
-      MB_LANES(l)
-        const int pt = pass * 32 + l;
-        hit[l] = 0;
-        if (pt < NPT && P.has_ground) {
-          const int o = M::powner(pt);
-          const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
-          float loc[3] = {M::ppos(pt, 0), M::ppos(pt, 1), M::ppos(pt, 2)};
-          float c[3];
-          mb_matvec(R, loc, c);
-          if (o >= 0) { c[0] += S.w.k.jp[o][0]; c[1] += S.w.k.jp[o][1]; c[2] += S.w.k.jp[o][2]; }
-          const float r = M::pradius(pt);
-          const float dist = (S.pos[2] + c[2]) - r;
-          if (dist < M::pthresh(pt)) {
-            hit[l] = 1;
-            px[l] = c[0]; py[l] = c[1]; pz[l] = c[2] - r; dd[l] = dist;
-          }
+    const int nbox = S.nbox;
+#pragma unroll 1
+    for (int ob = P.has_ground ? -1 : 0; ob < nbox; ++ob) {
+      if (ob >= 0) {
+        // cheap uniform cull: the robot (all points within ~1.2 m of the base) cannot reach a plank whose local
+        // x / z slab is farther away than that
+        const float* bx = S.box[ob];
+        const float d[3] = {S.pos[0] - bx[0], S.pos[1] - bx[1], S.pos[2] - bx[2]};
+        bool far = false;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float cl = bx[3 + k] * d[0] + bx[6 + k] * d[1] + bx[9 + k] * d[2];
+          if (fabsf(cl) > bx[12 + k] + 1.6f) far = true;
         }
-      MB_END
-      const unsigned mask = warp_ballot(hit);
-      MB_LANES(l)
-        if (hit[l]) {
+        if (far) continue;
+      }
+#pragma unroll 1
+      for (int pass = 0; pass * 32 < NPT; ++pass) {
+        LaneVar<int> hit;
+        LaneVar<float> px, py, pz, nx, ny, nz, dd;
+        MB_LANES(l)
           const int pt = pass * 32 + l;
-          const int k = nc + mb_popc(mask & ((1u << l) - 1u));
-          if (k < MB_MAXC) {
-            S.cP[k][0] = px[l]; S.cP[k][1] = py[l]; S.cP[k][2] = pz[l];
-            S.cn[k][0] = 0.0f; S.cn[k][1] = 0.0f; S.cn[k][2] = 1.0f;
-            S.cdist[k] = dd[l];
-            S.cmu[k] = M::pfriction(pt) * P.ground_friction;
-            S.cerp[k] = P.erp_contact;
-            S.ccfm[k] = 0.0f;
-            S.clink[k] = M::powner(pt);
-            S.cfoot[k] = M::pfoot(pt);
-            S.cpartner[k] = 0;
+          hit[l] = 0;
+          if (pt < NPT) {
+            const float r = M::pradius(pt);
+            const float* c = S.w.k.u2.pt[pt];
+            if (ob < 0) {
+              const float dist = (S.pos[2] + c[2]) - r;
+              if (dist < M::pthresh(pt)) {
+                hit[l] = 1;
+                px[l] = c[0]; py[l] = c[1]; pz[l] = c[2] - r; dd[l] = dist;
+                nx[l] = 0.0f; ny[l] = 0.0f; nz[l] = 1.0f;
+              }
+            } else {
+              const float cw[3] = {c[0] + S.pos[0], c[1] + S.pos[1], c[2] + S.pos[2]};
+              float pa[3], n[3], dist;
+              if (sphere_box(cw, r, S.box[ob], M::pthresh(pt), pa, n, &dist)) {
+                hit[l] = 1;
+                px[l] = pa[0] - S.pos[0]; py[l] = pa[1] - S.pos[1]; pz[l] = pa[2] - S.pos[2]; dd[l] = dist;
+                nx[l] = n[0]; ny[l] = n[1]; nz[l] = n[2];
+              }
+            }
           }
-        }
-      MB_END
-      nc += mb_popc(mask);
+        MB_END
+        const unsigned mask = warp_ballot(hit);
+        if (mask == 0u) continue;
+        MB_LANES(l)
+          if (hit[l]) {
+            const int pt = pass * 32 + l;
+            const int k = nc + mb_popc(mask & ((1u << l) - 1u));
+            if (k < MB_MAXC) {
+              S.cP[k][0] = px[l]; S.cP[k][1] = py[l]; S.cP[k][2] = pz[l];
+              S.cn[k][0] = nx[l]; S.cn[k][1] = ny[l]; S.cn[k][2] = nz[l];
+              S.cdist[k] = dd[l];
+              S.cmu[k] = M::pfriction(pt) * (ob < 0 ? P.ground_friction : P.box_friction);
+              S.cerp[k] = ob < 0 ? P.erp_contact : P.box_erp;
+              S.ccfm[k] = ob < 0 ? 0.0f : P.box_cfm;
+              S.clink[k] = M::powner(pt);
+              S.cfoot[k] = M::pfoot(pt);
+              S.cpartner[k] = ob < 0 ? 0 : 10 + ob;
+            }
+          }
+        MB_END
+        nc += mb_popc(mask);
+      }
     }
     if (nc > MB_MAXC) { *overflow += 1; nc = MB_MAXC; }
     return nc;

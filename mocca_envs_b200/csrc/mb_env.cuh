@@ -10,7 +10,8 @@
 
 // ---- HBM record layout (array-of-records: one warp streams its env's record with coalesced 128 B lines) ----
 #define MB_STATE_STRIDE 64 /* floats: pos3 quat4 omega3 vel3 q[NJ] qd[NJ] */
-#define MB_REC_STRIDE 32   /* floats/ints, see ER_* */
+#define MB_REC_STRIDE 32   /* floats/ints, see ER_* (Walker3DCustomEnv) */
+#define MB_REC_STRIDE_STEPPER 192 /* ER_* + ES_* (Walker3DStepperEnv) */
 #define MB_MT_STRIDE 640   /* uint32: 624 state words + [624] position */
 enum {
   ER_TX = 0, ER_TY, ER_TZ,      // walk_target
@@ -28,6 +29,20 @@ enum {
   ER_EVAL,                      // eval_mode (int)
   ER_LAST_EPRET, ER_LAST_EPLEN, // return / length of the last finished episode
   ER_OVERFLOW,                  // contact/row cap hits (int)
+};
+
+enum {  // Walker3DStepperEnv additions (env_locomotion.py:330-840)
+  ES_NEXT = 22,       // next_step_index (int)
+  ES_COUNT,           // target_reached_count (int)
+  ES_STOP,            // stop_on_next_step (int)
+  ES_SETSTOP,         // set_stop_on_next_step (int)
+  ES_TIMESTEP,        // timestep (int)
+  ES_CURRIC,          // curriculum 0..9 (int)
+  ES_PLANKIDX,        // [3] terrain row shown by each physical plank (int)
+  ES_STEPS_REACHED = 31,  // info["steps_reached"] of the last step, -1 = not reported (int)
+  ES_GAIN_CURRIC = 6,     // curriculum the applied_gain was taken from at reset (env_locomotion.py:489) (int)
+  ES_BOX = 32,        // [3][12] plank base-box centre + axes
+  ES_TERRAIN = 68,    // [20][6] x y z phi x_tilt y_tilt
 };
 
 struct MbStats {  // per-device accumulators, all-reduced across ranks by the host (NCCL) when asked
@@ -113,11 +128,14 @@ MB_HD float mb_clip5(float x) { return fminf(fmaxf(x, -5.0f), 5.0f); }
 template <class M> struct W3DEnv {
   typedef WarpMem<M> Mem;
   typedef Sim<M> S_;
-  enum { NJ = M::NJ, NU = M::NU, OBS = 6 + 2 * M::NJ + M::NFEET + 2, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET };
+  enum { NJ = M::NJ, NU = M::NU, OBS = 6 + 2 * M::NJ + M::NFEET + 2, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET,
+         REC_STRIDE = MB_REC_STRIDE };
+  MB_HD static void load_obstacles(WarpMem<M>&, const float*) {}
 
   // HBM <-> shared
   MB_HD static void load_state(Mem& S, const float* st) {
     MB_LANES(l)
+      if (l == 0) S.nbox = 0;
       for (int i = l; i < 13 + 2 * NJ; i += 32) {
         const float v = st[i];
         if (i < 3) S.pos[i] = v;
@@ -413,5 +431,349 @@ template <class M> struct W3DEnv {
       MB_END
     }
     store_state(S, state);
+  }
+};
+
+// ================================================================================================ Stepper
+// Walker3DStepperEnv (reference env_locomotion.py:330-840) with 3 recycled LargePlanks (bullet_objects.py:47-103).
+template <class M> struct StepperEnv {
+  typedef WarpMem<M> Mem;
+  typedef Sim<M> S_;
+  typedef W3DEnv<M> B_;
+  enum { NJ = M::NJ, NU = M::NU, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET, OBS = ROBOT_OBS + 15, NSTEPS = 20,
+         REC_STRIDE = MB_REC_STRIDE_STEPPER };
+  MB_HD static void load_obstacles(Mem& S, const float* rec) { load_boxes(S, rec); }
+  MB_HD static void load_state(Mem& S, const float* st) { B_::load_state(S, st); }
+  MB_HD static void store_state(const Mem& S, float* st) { B_::store_state(S, st); }
+
+  MB_HD static float lin10(float a, float b, int i) { return i >= 9 ? b : a + i * ((b - a) / 9.0f); }
+
+  // plank p -> two boxes in shared memory (base, cover): bullet_objects.py:98-103 scaled by 2*step_radius = 0.5
+  MB_HD static void load_boxes(Mem& S, const float* rec) {
+    MB_LANES(l)
+      if (l < 6) {
+        const int p = l >> 1, cover = l & 1;
+        const float* b = rec + ES_BOX + 12 * p;
+        float* bx = S.box[l];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) bx[k] = b[k];
+        if (cover) { bx[0] += b[3 + 2] * 0.125f; bx[1] += b[3 + 5] * 0.125f; bx[2] += b[3 + 8] * 0.125f; }
+        bx[12] = 0.25f; bx[13] = 5.0f; bx[14] = cover ? 0.0125f : 0.1125f; bx[15] = 0.0f;
+      }
+      if (l == 0) S.nbox = 6;
+    MB_END
+  }
+
+  // BaseStep.set_position via set_step_state (env_locomotion.py:461-465, bullet_objects.py:77-83):
+  // base box centre = pos + (0, 0, -0.1375) (not rotated, quirk Q15), R = euler(x_tilt, y_tilt, phi)
+  MB_HD static void place_plank(float* rec, int info, int plank) {
+    MB_LANES(l)
+      if (l == 0) {
+        const float* t = rec + ES_TERRAIN + 6 * info;
+        const float roll = t[4], pitch = t[5], yaw = t[3];
+        const float cr = cosf(roll * 0.5f), sr = sinf(roll * 0.5f), cp = cosf(pitch * 0.5f), sp = sinf(pitch * 0.5f);
+        const float cy = cosf(yaw * 0.5f), sy = sinf(yaw * 0.5f);
+        const float q[4] = {sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy,
+                            cr * cp * cy + sr * sp * sy};
+        float* b = rec + ES_BOX + 12 * plank;
+        b[0] = t[0]; b[1] = t[1]; b[2] = t[2] - 0.1375f;
+        mb_quat_to_mat(q, b + 3);
+        rec_i(rec, ES_PLANKIDX + plank) = info;
+      }
+    MB_END
+  }
+
+  // delta_to_k_targets (env_locomotion.py:712-759): writes obs[ROBOT_OBS .. +15) and walk_target
+  MB_HD static void targets(const Mem& S, float* rec, float yaw, float* obs) {
+    const int N = rec_i(rec, ES_NEXT), stop = rec_i(rec, ES_STOP);
+    MB_LANES(l)
+      if (l < 3) {
+        int idx = stop ? (l == 0 ? N - 1 : N) : N - 1 + l;
+        if (idx > NSTEPS - 1) idx = NSTEPS - 1;
+        const float* t = rec + ES_TERRAIN + 6 * idx;
+        const float dx = t[0] - S.pos[0], dy = t[1] - S.pos[1], dz = t[2] - S.pos[2];
+        const float ang = atan2f(dy, dx) - yaw, d = sqrtf(dx * dx + dy * dy);
+        float* o = obs + ROBOT_OBS + 5 * l;
+        o[0] = sinf(ang) * d; o[1] = cosf(ang) * d; o[2] = dz; o[3] = t[4]; o[4] = t[5];
+        if (l == 2) { rec[ER_TX] = t[0]; rec[ER_TY] = t[1]; rec[ER_TZ] = t[2]; }
+      }
+    MB_END
+  }
+
+  // generate_step_placements (env_locomotion.py:395-441) in float64 from 200 words of the env stream
+  MB_HD static void generate_terrain(Mem& S, float* rec, const uint32_t* w, double* dbuf) {
+    const int c = rec_i(rec, ES_CURRIC);
+    const double PI_D = 3.14159265358979323846, D2R = PI_D / 180;
+    const double ratio = c / 9.0;
+    const double dist_hi = c >= 9 ? 1.25 : 0.65 + c * ((1.25 - 0.65) / 9.0);
+    const double yaw_lo = -20 * ratio * D2R, yaw_hi = 20 * ratio * D2R;
+    const double pit_lo = -30 * ratio * D2R + PI_D / 2, pit_hi = 30 * ratio * D2R + PI_D / 2;
+    const double til_lo = -15 * ratio * D2R, til_hi = 15 * ratio * D2R;
+    double* dphi = dbuf;            // [20]
+    double* dx = dbuf + 20;         // [20]
+    double* dy = dbuf + 40;
+    double* dz = dbuf + 60;
+    double* tilt = dbuf + 80;       // [40] x_tilt, y_tilt
+    MB_LANES(l)
+      if (l < NSTEPS) {
+        double dr = 0.65 + (dist_hi - 0.65) * mt_double(w + 2 * l);
+        double dp = yaw_lo + (yaw_hi - yaw_lo) * mt_double(w + 40 + 2 * l);
+        double dt = pit_lo + (pit_hi - pit_lo) * mt_double(w + 80 + 2 * l);
+        double xt = til_lo + (til_hi - til_lo) * mt_double(w + 120 + 2 * l);
+        double yt = til_lo + (til_hi - til_lo) * mt_double(w + 160 + 2 * l);
+        if (l == 0) { dr = 0.0; dp = 0.0; dt = PI_D / 2; }
+        if (l == 1 || l == 2) { dr = 0.75; dp = 0.0; dt = PI_D / 2; }
+        if (l < 3) { xt = 0.0; yt = 0.0; }
+        dphi[l] = dp; dx[l] = dr; dy[l] = dt; tilt[l] = xt; tilt[20 + l] = yt;
+      }
+    MB_END
+    MB_LANES(l)
+      if (l < NSTEPS) {
+        double phi = 0.0;
+        for (int j = 0; j <= l; ++j) phi += dphi[j];  // np.cumsum order
+        const double dr = dx[l], dt = dy[l];
+        double ddx = dr * sin(dt) * cos(phi);
+        const double ddy = dr * sin(dt) * sin(phi);
+        const double ddz = dr * cos(dt);
+        if (l >= 2) {
+          const double ax = fabs(ddx), mx = ax > 0.25 * 2.5 ? ax : 0.25 * 2.5;
+          const double sg = ddx > 0 ? 1.0 : (ddx < 0 ? -1.0 : 0.0);
+          ddx = sg * (mx < 1.25 ? mx : 1.25);
+        }
+        dz[l] = ddz;
+        rec[ES_TERRAIN + 6 * l + 3] = (float)phi;
+        rec[ES_TERRAIN + 6 * l + 4] = (float)tilt[l];
+        rec[ES_TERRAIN + 6 * l + 5] = (float)tilt[20 + l];
+        tilt[l] = ddx;        // reuse: dx increments
+        tilt[20 + l] = ddy;   //        dy increments
+      }
+    MB_END
+    MB_LANES(l)
+      if (l < NSTEPS) {
+        double x = 0.0, y = 0.0, z = 0.0;
+        for (int j = 0; j <= l; ++j) { x += tilt[j]; y += tilt[20 + j]; z += dz[j]; }
+        rec[ES_TERRAIN + 6 * l + 0] = (float)x;
+        rec[ES_TERRAIN + 6 * l + 1] = (float)y;
+        rec[ES_TERRAIN + 6 * l + 2] = (float)z;
+      }
+    MB_END
+  }
+
+  // Walker3DStepperEnv.reset (env_locomotion.py:481-513)
+  MB_HD static void reset(Mem& S, const MbPhysics& P, float* rec, uint32_t* mt_env, uint32_t* mt_robot, float* obs) {
+    // 44 robot words + 200 terrain words; the row storage is free between steps and serves as scratch
+    uint32_t* w = reinterpret_cast<uint32_t*>(&S.w);
+    double* dbuf = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(w + 256) + 7) & ~(uintptr_t)7);
+    const int aliased = rec_i(rec, ER_ALIASED);
+    const int nrobot = 2 + 2 * NJ;
+    if (aliased) mt_fill(mt_env, w, nrobot + 200);
+    else { mt_fill(mt_robot, w, nrobot); mt_fill(mt_env, w + nrobot, 200); }
+    const int mirrored = mt_double(w) < 0.5;
+    MB_LANES(l)
+      if (l == 0) {
+        rec_i(rec, ER_ELAPSED) = 0; rec[ER_FEET0] = 0.0f; rec[ER_FEET1] = 0.0f;
+        rec_i(rec, ER_MIRRORED) = mirrored; rec[ER_EPRET] = 0.0f; rec_i(rec, ER_EPLEN) = 0;
+        rec_i(rec, ES_TIMESTEP) = 0; rec_i(rec, ES_COUNT) = 0; rec_i(rec, ES_STOP) = 0; rec_i(rec, ES_SETSTOP) = 0;
+        rec_i(rec, ES_NEXT) = 1; rec_i(rec, ES_STEPS_REACHED) = -1;
+        rec_i(rec, ES_GAIN_CURRIC) = rec_i(rec, ES_CURRIC);
+      }
+      if (l < NJ) {
+        int src = l;
+        double sign = 1.0;
+        if (mirrored) {
+          for (int k = 0; k < M::NMIRROR; ++k) {
+            if (M::right(k) == l) src = M::left(k);
+            if (M::left(k) == l) src = M::right(k);
+          }
+          for (int k = 0; k < M::NNEG; ++k)
+            if (M::neg(k) == l) sign = -1.0;
+        }
+        const double ang = sign * M::base_angles(src);
+        const double ds = -0.1 + (0.1 - -0.1) * mt_double(w + 2 + 2 * l);
+        const double bias = (double)M::lower(l), weight = (double)M::weight(l);
+        double ps = 2 * (ang + ds - bias) / weight - 1;
+        ps = ps > 0.95 ? 0.95 : (ps < -0.95 ? -0.95 : ps);
+        S.q[l] = (float)(weight * (ps + 1) / 2 + bias);
+      }
+      if (l < NU) S.u[l] = 0.0f;
+      if (l == 31) {
+        S.pos[0] = 0.3f; S.pos[1] = 0.0f; S.pos[2] = 1.32f;  // robot_init_position, env_locomotion.py:339
+        S.quat[0] = 0.0f; S.quat[1] = 0.0f; S.quat[2] = 0.0f; S.quat[3] = 1.0f;
+      }
+    MB_END
+    generate_terrain(S, rec, w + nrobot, dbuf);
+    for (int k = 0; k < 3; ++k) place_plank(rec, k, k);
+    typename S_::LaneConst C;
+    S_::init_lane_const(C);
+    S_::kinematics(S, P, C, false);
+    LaneVar<float> zero;
+    MB_LANES(l)
+      zero[l] = 0.0f;
+    MB_END
+    float s1, s2;
+    W3DObsScalars o = B_::observe(S, rec, obs, zero, &s1, &s2);
+    targets(S, rec, o.yaw, obs);
+    float d, a, lp;
+    B_::potential(S, rec, o.yaw, P.dt * P.substeps, &d, &a, &lp);
+    MB_LANES(l)
+      if (l == 0) rec[ER_LINPOT] = lp;
+    MB_END
+  }
+
+  // Walker3DStepperEnv.step (env_locomotion.py:515-568)
+  MB_HD static void step(Mem& S, const MbPhysics& P, float* state, float* rec, uint32_t* mt_env, uint32_t* mt_robot,
+                         const float* act, float* obs, float* rew, uint8_t* done, uint8_t* trunc, float* final_obs,
+                         MbStats* stats) {
+    B_::load_state(S, state);
+    load_boxes(S, rec);
+    const int cur_c = rec_i(rec, ES_CURRIC);  // terminal height follows the attribute immediately (:628)
+    const float applied_gain = lin10(1.0f, 1.2f, rec_i(rec, ES_GAIN_CURRIC));  // gain is latched at reset (:489)
+    LaneVar<float> araw;
+    LaneVar<int> badact;
+    MB_LANES(l)
+      araw[l] = 0.0f; badact[l] = 0;
+      if (l < NJ) {
+        float a = act[l];
+        if (!mb_finite(a)) { a = 0.0f; badact[l] = 1; }
+        araw[l] = a;
+        const float ac = fminf(fmaxf(a, -1.0f), 1.0f);
+        S.tau[l] = M::gain(l) * (applied_gain * ac) - M::damping(l) * S.u[6 + l];
+      }
+    MB_END
+    const unsigned anybad = warp_ballot(badact);
+    int rows = 0, nc = 0, overflow = 0, ncsum = 0;
+    typename S_::LaneConst C;
+    S_::init_lane_const(C);
+#pragma unroll 1
+    for (int k = 0; k < P.substeps; ++k) {
+      rows += S_::substep(S, P, C, &nc, &overflow);
+      ncsum += nc;
+    }
+    const int timestep = rec_i(rec, ES_TIMESTEP) + 1;
+    int next = rec_i(rec, ES_NEXT);
+    int set_stop = (next == 6 || next == 7 || next == 13 || next == 14) ? 1 : 0;
+    // foot contacts from the last collision pass: any partner; target = cover of plank next % 3
+    const int cover_id = 10 + 2 * (next % 3) + 1;
+    float fc0 = 0.0f, fc1 = 0.0f;
+    int reached = 0;
+    for (int k = 0; k < nc; ++k) {
+      if (S.cfoot[k] == 0) fc0 = 1.0f;
+      if (S.cfoot[k] == 1) fc1 = 1.0f;
+      if (S.cfoot[k] >= 0 && S.cpartner[k] == cover_id) reached = 1;
+    }
+    S_::kinematics(S, P, C, false);
+    float s1, s2;
+    W3DObsScalars o = B_::observe(S, rec, obs, araw, &s1, &s2);  // foot contacts lag one step (quirk Q6)
+    int env_done = o.nonfinite ? 1 : 0;
+    const int cur_index = next;
+    // calc_feet_state (env_locomotion.py:632-674)
+    float fdist[2];
+    for (int f = 0; f < 2; ++f) {
+      const int b = M::foot_body(f), ow = M::bowner(b);
+      const float* R = S.w.k.jR[ow];
+      const float fx = S.pos[0] + S.w.k.jp[ow][0] + R[0] * M::bcom(b, 0) + R[1] * M::bcom(b, 1) + R[2] * M::bcom(b, 2);
+      const float fy = S.pos[1] + S.w.k.jp[ow][1] + R[3] * M::bcom(b, 0) + R[4] * M::bcom(b, 1) + R[5] * M::bcom(b, 2);
+      const float dx = fx - rec[ES_TERRAIN + 6 * next], dy = fy - rec[ES_TERRAIN + 6 * next + 1];
+      fdist[f] = sqrtf(dx * dx + dy * dy);
+    }
+    int count = rec_i(rec, ES_COUNT), stop = rec_i(rec, ES_STOP);
+    int place_info = -1, place_plank_id = 0;
+    if (reached) {
+      count += 1;
+      if (count > 120) { stop = 0; set_stop = 0; }
+      if (count >= 2) {
+        if (!stop) {
+          next += 1;
+          count = 0;
+          if (next >= 3) { place_plank_id = next % 3; place_info = next < NSTEPS - 1 ? next : NSTEPS - 1; }
+        }
+        stop = set_stop;
+      }
+      if (next >= NSTEPS) next -= 1;
+    }
+    MB_LANES(l)
+      if (l == 0) {
+        rec[ER_FEET0] = fc0; rec[ER_FEET1] = fc1;
+        rec_i(rec, ES_NEXT) = next; rec_i(rec, ES_COUNT) = count; rec_i(rec, ES_STOP) = stop;
+        rec_i(rec, ES_SETSTOP) = set_stop; rec_i(rec, ES_TIMESTEP) = timestep;
+      }
+    MB_END
+    if (place_info >= 0) place_plank(rec, place_info, place_plank_id);
+    // calc_base_reward (env_locomotion.py:598-630)
+    const float old_lp = rec[ER_LINPOT];
+    float dist, ang, lp;
+    const float scene_dt = P.dt * P.substeps;
+    B_::potential(S, rec, o.yaw, scene_dt, &dist, &ang, &lp);
+    const float progress = lp - old_lp;
+    float posture = 0.0f;
+    if (!(-0.2f < o.pitch && o.pitch < 0.4f)) posture = fabsf(o.pitch);
+    if (!(-0.4f < o.roll && o.roll < 0.4f)) posture += fabsf(o.roll);
+    const float energy = 4.5f * (s1 / NJ) + 0.225f * (s2 / NJ);
+    const float joints_pen = 0.1f * o.joints_at_limit;
+    const float tall = mb_clip5(o.height) > lin10(0.75f, 0.45f, cur_c) ? 2.0f : -1.0f;
+    if (tall < 0.0f) env_done = 1;
+    // calc_step_reward (env_locomotion.py:676-693); 2.718 is the reference's literal (quirk Q13)
+    float step_bonus = 0.0f;
+    if (reached && count == 1 && next != NSTEPS - 1)
+      step_bonus = 50.0f * powf(2.718f, -fminf(fdist[0], fdist[1]) / 0.25f);
+    float target_bonus = 0.0f;
+    if ((next == NSTEPS - 1 || stop) && dist < 0.15f) target_bonus = 2.0f;
+    targets(S, rec, o.yaw, obs);
+    if (cur_index != next) B_::potential(S, rec, o.yaw, scene_dt, &dist, &ang, &lp);
+    const float reward = progress - energy + step_bonus + target_bonus + tall - posture - joints_pen;
+    const int elapsed = rec_i(rec, ER_ELAPSED) + 1;
+    int truncated = 0, any_done = env_done;
+    if (elapsed >= 1000) { truncated = !env_done; any_done = 1; }
+    const float epret = rec[ER_EPRET] + reward;
+    const int eplen = rec_i(rec, ER_EPLEN) + 1;
+    MB_LANES(l)
+      if (l == 0) {
+        rec[ER_LINPOT] = lp; rec_i(rec, ER_ELAPSED) = elapsed;
+        rec[ER_EPRET] = epret; rec_i(rec, ER_EPLEN) = eplen;
+        rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum;
+        rec_i(rec, ER_OVERFLOW) += overflow;
+        rec_i(rec, ES_STEPS_REACHED) = (env_done || timestep == 999) ? next : -1;
+        *rew = reward; *done = (uint8_t)any_done; *trunc = (uint8_t)truncated;
+      }
+    MB_END
+    if (any_done) {
+      if (final_obs) {
+        MB_LANES(l)
+          for (int i = l; i < OBS; i += 32) final_obs[i] = obs[i];
+        MB_END
+      }
+      MB_LANES(l)
+        if (l == 0) {
+          rec[ER_LAST_EPRET] = epret; rec_i(rec, ER_LAST_EPLEN) = eplen;
+#ifdef __CUDACC__
+          atomicAdd(&stats->episodes, 1ull);
+          atomicAdd(&stats->ret_sum, (double)epret);
+          atomicAdd(&stats->len_sum, (double)eplen);
+          atomicAdd(&stats->steps, (unsigned long long)next);
+          if (o.nonfinite) atomicAdd(&stats->nonfinite, 1ull);
+#else
+          stats->episodes += 1; stats->ret_sum += epret; stats->len_sum += eplen; stats->steps += next;
+          if (o.nonfinite) stats->nonfinite += 1;
+#endif
+        }
+      MB_END
+      const int keep = rec_i(rec, ES_STEPS_REACHED);
+      reset(S, P, rec, mt_env, mt_robot, obs);
+      MB_LANES(l)
+        if (l == 0) rec_i(rec, ES_STEPS_REACHED) = keep;  // info of the finished episode stays readable
+      MB_END
+    }
+    if (anybad) {
+      MB_LANES(l)
+        if (l == 0) {
+#ifdef __CUDACC__
+          atomicAdd(&stats->nonfinite, 1ull);
+#else
+          stats->nonfinite += 1;
+#endif
+        }
+      MB_END
+    }
+    B_::store_state(S, state);
   }
 };

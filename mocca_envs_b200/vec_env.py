@@ -24,6 +24,7 @@ from . import _lib
 from .seeding import create_seed, mt_state_rows
 
 ENV_ID = "Walker3DCustomEnv-v0"
+STEPPER_ID = "Walker3DStepperEnv-v0"
 _MODELS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models")
 
 
@@ -47,6 +48,8 @@ def _ptr(t):
 
 
 class Walker3DCustomVecEnv:
+    """Batched Walker3DCustomEnv-v0; also the base class of the other batched envs (env_id selects the kernels)."""
+
     env_id = ENV_ID
     control_step = 1 / 60  # env_locomotion.py:39
     llc_frame_skip = 1  # env_locomotion.py:40
@@ -69,12 +72,13 @@ class Walker3DCustomVecEnv:
         self.physics = phys
         h = C.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        _lib.check(L.mb200_create(ENV_ID.encode(), self.num_envs, idx, C.byref(phys), C.byref(h)))
+        _lib.check(L.mb200_create(self.env_id.encode(), self.num_envs, idx, C.byref(phys), C.byref(h)))
         self._h = h
         self._L = L
         dims = [C.c_int() for _ in range(5)]
         _lib.check(L.mb200_dims(h, *[C.byref(d) for d in dims]))
         _, self.obs_dim, self.act_dim, self.state_dim, self.nu = [d.value for d in dims]
+        self.rec_stride = int(L.mb200_record_stride(h))
         with open(os.path.join(_MODELS, "walker3d.json")) as f:
             self.table = json.load(f)
         # spaces as the reference builds them (robots.py:22-29, env_locomotion.py:58-60)
@@ -157,12 +161,13 @@ class Walker3DCustomVecEnv:
         torch.cuda.current_stream(self.device).synchronize()
 
     def get_record(self) -> torch.Tensor:
-        r = torch.empty(self.num_envs, 32, dtype=torch.float32, device=self.device)
+        r = torch.empty(self.num_envs, self.rec_stride, dtype=torch.float32, device=self.device)
         _lib.check(self._L.mb200_get_record(self._h, _ptr(r), self._stream()))
         return r
 
     def set_record(self, r: torch.Tensor):
         r = r.to(device=self.device, dtype=torch.float32).contiguous()
+        assert r.shape == (self.num_envs, self.rec_stride)
         _lib.check(self._L.mb200_set_record(self._h, _ptr(r), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()
 
@@ -223,15 +228,69 @@ class Walker3DCustomVecEnv:
         return neg_obs, right, left, neg_j, right_j, left_j
 
 
+class Walker3DStepperVecEnv(Walker3DCustomVecEnv):
+    """Batched Walker3DStepperEnv-v0 (reference env_locomotion.py:330-840): seeded stepping-stone terrain, three
+    recycled LargePlanks with soft contacts, fixed-order curriculum 0..9 (per env)."""
+
+    env_id = STEPPER_ID
+    ES_NEXT, ES_CURRIC, ES_STEPS_REACHED, ES_TERRAIN = 22, 27, 31, 68
+    max_curriculum = 9
+
+    def set_env_params(self, params: dict):
+        """``{"curriculum": c}`` with an int or one value per env (env_base.py:103-106); used at the next reset
+        for the terrain and immediately for gain / terminal height, like the reference's attribute."""
+        for k, v in params.items():
+            if k != "curriculum":
+                continue
+            if np.isscalar(v):
+                _lib.check(self._L.mb200_set_param(self._h, b"curriculum", float(min(int(v), self.max_curriculum))))
+            else:
+                arr = np.ascontiguousarray(np.minimum(np.asarray(v), self.max_curriculum), dtype=np.float32)
+                _lib.check(self._L.mb200_set_param_array(self._h, b"curriculum", arr.ctypes.data_as(C.c_void_p),
+                                                         len(arr)))
+
+    def evaluation_mode(self):
+        raise AttributeError("Walker3DStepperEnv has no evaluation_mode (reference: only Walker3DCustomEnv)")
+
+    def steps_reached(self) -> torch.Tensor:
+        """info["steps_reached"] per env of the last step (env_locomotion.py:562-566), -1 where not reported."""
+        return self.get_record()[:, self.ES_STEPS_REACHED].contiguous().view(torch.int32)
+
+    def terrain_info(self) -> torch.Tensor:
+        return self.get_record()[:, self.ES_TERRAIN:self.ES_TERRAIN + 120].reshape(self.num_envs, 20, 6)
+
+    def stats(self, reset=False) -> dict:
+        out = (C.c_double * 8)()
+        _lib.check(self._L.mb200_stats(self._h, out, int(reset)))
+        return {"episodes": out[0], "return_sum": out[1], "length_sum": out[2], "nonfinite": out[3],
+                "overflow": out[4], "steps_reached_sum": out[5]}
+
+    def get_mirror_indices(self):
+        """Walker3DStepperEnv.get_mirror_indices (env_locomotion.py:761-840)."""
+        A = self.act_dim
+        right_j = np.array(self.table["right_joint_indices"], dtype=np.int64)
+        left_j = np.array(self.table["left_joint_indices"], dtype=np.int64)
+        neg_j = np.array(self.table["negation_joint_indices"], dtype=np.int64)
+        nfeet = len(self.table["foot_links"])
+        robot_obs = 6 + 2 * A + nfeet
+        right = np.concatenate((6 + right_j, 6 + right_j + A, [6 + 2 * A + 2 * i for i in range(nfeet // 2)]))
+        left = np.concatenate((6 + left_j, 6 + left_j + A, [6 + 2 * A + 2 * i + 1 for i in range(nfeet // 2)]))
+        robot_neg = np.concatenate(([2, 4], 6 + neg_j, 6 + neg_j + A))
+        steps_neg = np.array([(i * 5 + 0, i * 5 + 3) for i in range(3)], dtype=np.int64).flatten()
+        neg_obs = np.concatenate((robot_neg, steps_neg + robot_obs))
+        return neg_obs, right, left, neg_j, right_j, left_j
+
+
 class Walker3DCustomEnv:
     """gym-protocol facade over a 1-env batch; NumPy float64 observations like the reference."""
 
     metadata = {"render.modes": []}
+    vec_class = Walker3DCustomVecEnv
 
     def __init__(self, device="cuda:0", seed=None, render=False, **kwargs):
         if render:
             raise NotImplementedError("rendering is out of scope for the GPU path (SURVEY.md section 2, row 2)")
-        self.vec = Walker3DCustomVecEnv(1, device=device, seed=seed, return_final_obs=True)
+        self.vec = self.vec_class(1, device=device, seed=seed, return_final_obs=True)
         self.observation_space = self.vec.observation_space
         self.action_space = self.vec.action_space
         self._pending_reset_obs = None
@@ -261,7 +320,14 @@ class Walker3DCustomEnv:
                 out_info["TimeLimit.truncated"] = True
         else:
             o = obs[0].double().cpu().numpy()
+        self._extra_info(out_info)
         return o, float(rew[0].item()), d, out_info
+
+    def _extra_info(self, info):
+        pass
+
+    def set_env_params(self, params):
+        self.vec.set_env_params(params)
 
     def evaluation_mode(self):
         self.vec.evaluation_mode()
@@ -273,11 +339,29 @@ class Walker3DCustomEnv:
         self.vec.close()
 
 
+class Walker3DStepperEnv(Walker3DCustomEnv):
+    """gym-protocol facade of Walker3DStepperEnv-v0; info carries "steps_reached" like the reference."""
+
+    vec_class = Walker3DStepperVecEnv
+
+    def _extra_info(self, info):
+        sr = int(self.vec.steps_reached()[0].item())
+        if sr >= 0:
+            info["steps_reached"] = sr
+
+    def evaluation_mode(self):
+        raise AttributeError("Walker3DStepperEnv has no evaluation_mode")
+
+
+_REGISTRY = {ENV_ID: (Walker3DCustomEnv, Walker3DCustomVecEnv), STEPPER_ID: (Walker3DStepperEnv, Walker3DStepperVecEnv)}
+
+
 def make(env_id: str, num_envs: int | None = None, **kwargs):
     """gym.make analogue: ``make("Walker3DCustomEnv-v0")`` -> gym-style env, ``make(id, num_envs=N)`` -> VecEnv."""
     eid = env_id.split(":")[-1]
-    if eid != ENV_ID:
-        raise KeyError("env id %r is not built yet (available: %s)" % (env_id, ENV_ID))
+    if eid not in _REGISTRY:
+        raise KeyError("env id %r is not built yet (available: %s)" % (env_id, ", ".join(_REGISTRY)))
+    single, vec = _REGISTRY[eid]
     if num_envs is None:
-        return Walker3DCustomEnv(**kwargs)
-    return Walker3DCustomVecEnv(num_envs, **kwargs)
+        return single(**kwargs)
+    return vec(num_envs, **kwargs)

@@ -580,42 +580,52 @@ static int sphere_box(const v3 cw, double r, const orc_box* b, double thresh, v3
   return 1;
 }
 
+static void point_world(const orc_model* m, const orc_cache* c, int g, int e, v3 cw) {
+  int link = m->geom_link[g];
+  const double* pl = e == 0 ? m->geom_p0[g] : m->geom_p1[g];
+  v3 t;
+  m3Tvec(c->Rw[link + 1], pl, t);
+  for (int k = 0; k < 3; k++) cw[k] = c->pw[link + 1][k] + t[k];
+}
+
+/* Candidate points: sphere centres and both capsule end spheres.  Contacts are listed obstacle-major:
+ * the ground plane for every point, then box 0 for every point, ... (the CUDA kernel uses the same order). */
 int orc_collide_cached(const orc_model* m, const orc_params* p, const orc_cache* c, const orc_box* boxes,
                        int n_boxes, orc_contacts* out) {
   out->n = 0;
-  for (int g = 0; g < m->n_geoms; g++) {
-    int link = m->geom_link[g];
-    if (m->geom_type[g] == ORC_GEOM_BOX) continue; /* robot box geoms (Monkey3D) not handled yet */
-    int nends = m->geom_type[g] == ORC_GEOM_CAPSULE ? 2 : 1;
-    double r = m->geom_size[g][0];
-    double thresh = m->link_thresh[link + 1];
-    for (int e = 0; e < nends; e++) {
-      const double* pl = e == 0 ? m->geom_p0[g] : m->geom_p1[g];
-      v3 cw, t;
-      m3Tvec(c->Rw[link + 1], pl, t);
-      for (int k = 0; k < 3; k++) cw[k] = c->pw[link + 1][k] + t[k];
-      if (p->has_ground) {
-        double dist = cw[2] - r;
-        if (dist < thresh) {
-          v3 n = {0, 0, 1}, pa = {cw[0], cw[1], cw[2] - r};
-          add_point(out, 2 * g + e, link, 0, pa, n, dist, m->geom_friction[g] * p->ground_friction,
-                    p->erp_contact, 0.0);
-        }
-      }
-      for (int b = 0; b < n_boxes; b++) {
-        v3 pa, n;
-        double dist;
-        if (sphere_box(cw, r, &boxes[b], thresh, pa, n, &dist)) {
-          double erp = p->erp_contact, cfm = 0.0;
-          if (boxes[b].stiffness > 0) {
-            /* soft contact, SURVEY App. B.4 (bullet_objects.py:64-72) */
-            double denom = p->dt * boxes[b].stiffness + boxes[b].damping;
-            if (denom < 1.1920929e-07) denom = 1.1920929e-07;
-            cfm = 1.0 / denom;
-            erp = p->dt * boxes[b].stiffness / denom;
+  for (int ob = -1; ob < n_boxes; ob++) {
+    if (ob < 0 && !p->has_ground) continue;
+    for (int g = 0; g < m->n_geoms; g++) {
+      int link = m->geom_link[g];
+      if (m->geom_type[g] == ORC_GEOM_BOX) continue; /* robot box geoms (Monkey3D) not handled yet */
+      int nends = m->geom_type[g] == ORC_GEOM_CAPSULE ? 2 : 1;
+      double r = m->geom_size[g][0];
+      double thresh = m->link_thresh[link + 1];
+      for (int e = 0; e < nends; e++) {
+        v3 cw;
+        point_world(m, c, g, e, cw);
+        if (ob < 0) {
+          double dist = cw[2] - r;
+          if (dist < thresh) {
+            v3 n = {0, 0, 1}, pa = {cw[0], cw[1], cw[2] - r};
+            add_point(out, 2 * g + e, link, 0, pa, n, dist, m->geom_friction[g] * p->ground_friction,
+                      p->erp_contact, 0.0);
           }
-          add_point(out, 2 * g + e, link, boxes[b].id, pa, n, dist, m->geom_friction[g] * boxes[b].friction, erp,
-                    cfm);
+        } else {
+          v3 pa, n;
+          double dist;
+          if (sphere_box(cw, r, &boxes[ob], thresh, pa, n, &dist)) {
+            double erp = p->erp_contact, cfm = 0.0;
+            if (boxes[ob].stiffness > 0) {
+              /* soft contact, SURVEY App. B.4 (bullet_objects.py:64-72) */
+              double denom = p->dt * boxes[ob].stiffness + boxes[ob].damping;
+              if (denom < 1.1920929e-07) denom = 1.1920929e-07;
+              cfm = 1.0 / denom;
+              erp = p->dt * boxes[ob].stiffness / denom;
+            }
+            add_point(out, 2 * g + e, link, boxes[ob].id, pa, n, dist, m->geom_friction[g] * boxes[ob].friction,
+                      erp, cfm);
+          }
         }
       }
     }
@@ -1175,5 +1185,246 @@ void orc_w3d_step_batch(const orc_model* m, const orc_params* p, orc_w3d_env* en
   }
 }
 
+/* ------------------------------------------------------------------ 10. Walker3DStepperEnv */
+static double linspace10(double a, double b, int i) { /* np.linspace(a, b, 10)[i] */
+  if (i >= 9) return b;
+  return a + i * ((b - a) / 9.0);
+}
+
+/* pybullet.getQuaternionFromEuler([roll, pitch, yaw]) -> rotation matrix (local -> world) */
+static void euler_to_mat(double roll, double pitch, double yaw, m3 R) {
+  double cr = cos(roll * 0.5), sr = sin(roll * 0.5), cp = cos(pitch * 0.5), sp = sin(pitch * 0.5);
+  double cy = cos(yaw * 0.5), sy = sin(yaw * 0.5);
+  double q[4] = {sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy,
+                 cr * cp * cy + sr * sp * sy};
+  quat_to_mat(q, R);
+}
+
+/* Walker3DStepperEnv.set_step_state + BaseStep.set_position (env_locomotion.py:461-465, bullet_objects.py:77-83):
+ * LargePlank scaled by 2*step_radius = 0.5; base box centre = pos + (0,0,-0.1375) (offset NOT rotated, quirk Q15),
+ * cover centre = base centre + R (0,0,0.125); friction 1.0, contactStiffness 30000, contactDamping 1000. */
+static void stepper_place_plank(orc_stepper_env* e, int info_index, int plank) {
+  const double* t = e->terrain[info_index];
+  m3 R;
+  euler_to_mat(t[4], t[5], t[3], R);
+  orc_box* b = &e->boxes[2 * plank];
+  orc_box* c = &e->boxes[2 * plank + 1];
+  b->center[0] = t[0]; b->center[1] = t[1]; b->center[2] = t[2] - 0.1375;
+  memcpy(b->R, R, sizeof(m3));
+  b->half[0] = 0.25; b->half[1] = 5.0; b->half[2] = 0.1125;
+  memcpy(c->R, R, sizeof(m3));
+  for (int k = 0; k < 3; k++) c->center[k] = b->center[k] + R[k][2] * 0.125;
+  c->half[0] = 0.25; c->half[1] = 5.0; c->half[2] = 0.0125;
+  for (int k = 0; k < 2; k++) {
+    orc_box* x = k ? c : b;
+    x->friction = 1.0;
+    x->stiffness = 30000.0;
+    x->damping = 1000.0 + 0.1; /* Bullet sums both bodies' contact damping; a link's default is 0.1 */
+    x->id = 10 + 2 * plank + k;
+  }
+  e->plank_index[plank] = info_index;
+}
+
+/* env_locomotion.py:395-441 */
+static void stepper_generate_placements(orc_stepper_env* e) {
+  orc_rng* r = &e->base.env_rng;
+  int c = e->curriculum > 9 ? 9 : e->curriculum;
+  e->curriculum = c;
+  const double D2R = PI / 180;
+  double ratio = c / 9.0;
+  double dist_lo = 0.65, dist_hi = linspace10(0.65, 1.25, c);
+  double yaw_lo = -20 * ratio * D2R, yaw_hi = 20 * ratio * D2R;
+  double pit_lo = -30 * ratio * D2R + PI / 2, pit_hi = 30 * ratio * D2R + PI / 2;
+  double til_lo = -15 * ratio * D2R, til_hi = 15 * ratio * D2R;
+  double dr[ORC_NSTEPS], dphi[ORC_NSTEPS], dth[ORC_NSTEPS], xt[ORC_NSTEPS], yt[ORC_NSTEPS];
+  for (int i = 0; i < ORC_NSTEPS; i++) dr[i] = orc_rng_uniform(r, dist_lo, dist_hi);
+  for (int i = 0; i < ORC_NSTEPS; i++) dphi[i] = orc_rng_uniform(r, yaw_lo, yaw_hi);
+  for (int i = 0; i < ORC_NSTEPS; i++) dth[i] = orc_rng_uniform(r, pit_lo, pit_hi);
+  for (int i = 0; i < ORC_NSTEPS; i++) xt[i] = orc_rng_uniform(r, til_lo, til_hi);
+  for (int i = 0; i < ORC_NSTEPS; i++) yt[i] = orc_rng_uniform(r, til_lo, til_hi);
+  dr[0] = 0; dphi[0] = 0; dth[0] = PI / 2;
+  for (int i = 1; i < 3; i++) { dr[i] = 0.75; dphi[i] = 0; dth[i] = PI / 2; }
+  for (int i = 0; i < 3; i++) { xt[i] = 0; yt[i] = 0; }
+  double acc = 0;
+  for (int i = 0; i < ORC_NSTEPS; i++) { acc += dphi[i]; dphi[i] = acc; }
+  double dx[ORC_NSTEPS], dy[ORC_NSTEPS], dz[ORC_NSTEPS];
+  for (int i = 0; i < ORC_NSTEPS; i++) {
+    dx[i] = dr[i] * sin(dth[i]) * cos(dphi[i]);
+    dy[i] = dr[i] * sin(dth[i]) * sin(dphi[i]);
+    dz[i] = dr[i] * cos(dth[i]);
+  }
+  for (int i = 2; i < ORC_NSTEPS; i++) {
+    double ax = fabs(dx[i]);
+    double mx = ax > 0.25 * 2.5 ? ax : 0.25 * 2.5;
+    double sg = dx[i] > 0 ? 1.0 : (dx[i] < 0 ? -1.0 : 0.0);
+    dx[i] = sg * (mx < 1.25 ? mx : 1.25);
+  }
+  double x = 0, y = 0, z = 0;
+  for (int i = 0; i < ORC_NSTEPS; i++) {
+    x += dx[i]; y += dy[i]; z += dz[i];
+    e->terrain[i][0] = x; e->terrain[i][1] = y; e->terrain[i][2] = z;
+    e->terrain[i][3] = dphi[i]; e->terrain[i][4] = xt[i]; e->terrain[i][5] = yt[i];
+  }
+}
+
+/* env_locomotion.py:712-759 */
+static void stepper_targets(orc_stepper_env* e) {
+  int N = e->next_step_index, idx[3];
+  if (!e->stop_on_next_step) {
+    for (int k = 0; k < 3; k++) { idx[k] = N - 1 + k; if (idx[k] > ORC_NSTEPS - 1) idx[k] = ORC_NSTEPS - 1; }
+  } else {
+    idx[0] = N - 1; idx[1] = N; idx[2] = N;
+  }
+  orc_w3d_env* b = &e->base;
+  for (int k = 0; k < 3; k++) b->walk_target[k] = e->terrain[idx[2]][k];
+  for (int k = 0; k < 3; k++) {
+    const double* t = e->terrain[idx[k]];
+    double dx = t[0] - b->body_xyz[0], dy = t[1] - b->body_xyz[1], dz = t[2] - b->body_xyz[2];
+    double ang = atan2(dy, dx) - b->body_rpy[2], d = sqrt(dx * dx + dy * dy);
+    e->targets[k][0] = sin(ang) * d; e->targets[k][1] = cos(ang) * d; e->targets[k][2] = dz;
+    e->targets[k][3] = t[4]; e->targets[k][4] = t[5];
+  }
+}
+
+static void stepper_obs(const orc_model* m, const orc_stepper_env* e, double* obs) {
+  int n = 6 + 2 * m->n_dof + m->n_feet;
+  for (int k = 0; k < n; k++) obs[k] = e->base.robot_state[k];
+  for (int k = 0; k < 3; k++)
+    for (int j = 0; j < 5; j++) obs[n + 5 * k + j] = e->targets[k][j];
+}
+
+void orc_stepper_seed(orc_stepper_env* e, const uint32_t* key, int len, int at_construction) {
+  orc_w3d_seed(&e->base, key, len, at_construction);
+}
+
+void orc_stepper_reset(const orc_model* m, const orc_params* p, orc_stepper_env* e, double* obs) {
+  orc_w3d_env* b = &e->base;
+  e->timestep = 0; b->done = 0; b->elapsed = 0; e->target_reached_count = 0;
+  e->set_stop_on_next_step = 0; e->stop_on_next_step = 0; e->steps_reached = -1;
+  e->gain_curriculum = e->curriculum > 9 ? 9 : e->curriculum;
+  double pos[3] = {0.3, 0.0, 1.32}; /* env_locomotion.py:339 */
+  w3d_robot_reset(m, b, pos);
+  /* quirk Q5: the reference runs calc_feet_state() here on Bullet's STALE contact points of the previous episode;
+   * the batched simulator defines "no contacts after reset" (documented deviation) */
+  e->target_reached = 0;
+  stepper_generate_placements(e);
+  for (int k = 0; k < 3; k++) stepper_place_plank(e, k, k);
+  e->next_step_index = 1;
+  stepper_targets(e);
+  w3d_calc_potential(b, p->dt * p->substeps);
+  stepper_obs(m, e, obs);
+}
+
+void orc_stepper_step(const orc_model* m, const orc_params* p, orc_stepper_env* e, const double* action,
+                      double* obs, double* reward, int* done, int* truncated) {
+  orc_w3d_env* b = &e->base;
+  int A = m->n_dof;
+  double tau[ORC_MAXD];
+  double gain = linspace10(1.0, 1.2, e->gain_curriculum);
+  e->timestep += 1;
+  for (int d = 0; d < A; d++) {
+    double a = action[d];
+    if (a > 1) a = 1;
+    if (a < -1) a = -1;
+    tau[d] = m->gain[d] * (gain * a);
+  }
+  orc_params pp = *p;
+  pp.has_ground = 0; /* remove_ground=True (env_locomotion.py:359) */
+  int rows = 0;
+  orc_step_physics(m, &pp, &b->s, tau, e->boxes, 6, b->warm, &b->last_contacts, &rows);
+  b->rows_sum = rows;
+  e->set_stop_on_next_step = (e->next_step_index == 6 || e->next_step_index == 7 || e->next_step_index == 13 ||
+                              e->next_step_index == 14);
+  w3d_calc_state(m, b, NULL); /* obs foot contacts lag one step (quirk Q6) */
+  int nstate = 6 + 2 * A + m->n_feet;
+  for (int k = 0; k < nstate; k++)
+    if (!isfinite(b->robot_state[k])) b->done = 1;
+  int cur = e->next_step_index;
+  /* calc_feet_state (env_locomotion.py:632-674) */
+  int cover_id = 10 + 2 * (e->next_step_index % 3) + 1;
+  e->target_reached = 0;
+  for (int f = 0; f < 2; f++) {
+    double dx = b->feet_xyz[f][0] - e->terrain[e->next_step_index][0];
+    double dy = b->feet_xyz[f][1] - e->terrain[e->next_step_index][1];
+    e->foot_dist_to_target[f] = sqrt(dx * dx + dy * dy);
+    int contact = 0;
+    for (int k = 0; k < b->last_contacts.n; k++)
+      if (b->last_contacts.link[k] == m->foot_link[f]) {
+        contact = 1;
+        if (b->last_contacts.partner[k] == cover_id) e->target_reached = 1;
+      }
+    b->feet_contact[f] = contact;
+  }
+  if (e->target_reached) {
+    e->target_reached_count += 1;
+    if (e->target_reached_count > 120) { e->stop_on_next_step = 0; e->set_stop_on_next_step = 0; }
+    if (e->target_reached_count >= 2) {
+      if (!e->stop_on_next_step) {
+        e->next_step_index += 1;
+        e->target_reached_count = 0;
+        if (e->next_step_index >= 3) { /* update_steps (env_locomotion.py:472-479) */
+          int oldest = e->next_step_index % 3;
+          int nxt = e->next_step_index < ORC_NSTEPS - 1 ? e->next_step_index : ORC_NSTEPS - 1;
+          stepper_place_plank(e, nxt, oldest);
+        }
+      }
+      e->stop_on_next_step = e->set_stop_on_next_step;
+    }
+    if (e->next_step_index >= ORC_NSTEPS) e->next_step_index -= 1;
+  }
+  /* calc_base_reward (env_locomotion.py:598-630) */
+  double old_lin = b->linear_potential;
+  w3d_calc_potential(b, p->dt * p->substeps);
+  b->progress = b->linear_potential - old_lin;
+  b->posture_penalty = 0;
+  double pitch = b->body_rpy[1], roll = b->body_rpy[0];
+  if (!(-0.2 < pitch && pitch < 0.4)) b->posture_penalty = fabs(pitch);
+  if (!(-0.4 < roll && roll < 0.4)) b->posture_penalty += fabs(roll);
+  double sp = sqrt(b->body_vel[0] * b->body_vel[0] + b->body_vel[1] * b->body_vel[1] + b->body_vel[2] * b->body_vel[2]);
+  e->speed_penalty = sp - 1.6 > 0 ? sp - 1.6 : 0;
+  double s1 = 0, s2 = 0;
+  for (int d = 0; d < A; d++) { s1 += fabs(action[d] * b->joint_speeds[d]); s2 += action[d] * action[d]; }
+  b->energy_penalty = 4.5 * (s1 / A) + 0.225 * (s2 / A);
+  b->joints_penalty = 0.1 * b->joints_at_limit;
+  double terminal_height = linspace10(0.75, 0.45, e->curriculum);
+  b->tall_bonus = b->robot_state[0] > terminal_height ? 2.0 : -1.0;
+  if (b->tall_bonus < 0) b->done = 1;
+  /* calc_step_reward (env_locomotion.py:676-693) */
+  e->step_bonus = 0;
+  if (e->target_reached && e->target_reached_count == 1 && e->next_step_index != ORC_NSTEPS - 1) {
+    double dist = e->foot_dist_to_target[0] < e->foot_dist_to_target[1] ? e->foot_dist_to_target[0]
+                                                                        : e->foot_dist_to_target[1];
+    e->step_bonus = 50 * pow(2.718, -dist / 0.25);
+  }
+  b->target_bonus = 0;
+  int last_step = e->next_step_index == ORC_NSTEPS - 1;
+  if ((last_step || e->stop_on_next_step) && b->distance_to_target < 0.15) b->target_bonus = 2.0;
+  stepper_targets(e);
+  if (cur != e->next_step_index) w3d_calc_potential(b, p->dt * p->substeps);
+  *reward = b->progress - b->energy_penalty + e->step_bonus + b->target_bonus - e->speed_penalty * 0 + b->tall_bonus -
+            b->posture_penalty - b->joints_penalty;
+  stepper_obs(m, e, obs);
+  e->steps_reached = (b->done || e->timestep == 999) ? e->next_step_index : -1;
+  b->elapsed++;
+  *truncated = 0;
+  *done = b->done;
+  if (b->elapsed >= 1000) { *truncated = !b->done; *done = 1; }
+}
+
+void orc_stepper_step_batch(const orc_model* m, const orc_params* p, orc_stepper_env* envs, int n,
+                            const double* actions, double* obs, double* rewards, int* dones, int n_threads) {
+  int A = m->n_dof, O = 6 + 2 * A + m->n_feet + 15;
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+  for (int i = 0; i < n; i++) {
+    int trunc;
+    orc_stepper_step(m, p, &envs[i], actions + (size_t)i * A, obs + (size_t)i * O, &rewards[i], &dones[i], &trunc);
+    if (dones[i]) orc_stepper_reset(m, p, &envs[i], obs + (size_t)i * O);
+  }
+}
+
+int orc_sizeof_stepper_env(void) { return (int)sizeof(orc_stepper_env); }
 int orc_sizeof_w3d_env(void) { return (int)sizeof(orc_w3d_env); }
 int orc_sizeof_model(void) { return (int)sizeof(orc_model); }

@@ -172,6 +172,29 @@ void orc_w3d_step(const orc_model* m, const orc_params* p, orc_w3d_env* e, const
 /* batched convenience for the CPU baseline: n independent envs, OpenMP over envs, auto-reset on done */
 void orc_w3d_step_batch(const orc_model* m, const orc_params* p, orc_w3d_env* envs, int n, const double* actions,
                         double* obs, double* rewards, int* dones, int n_threads);
+/* ---- Walker3DStepperEnv (env_locomotion.py:330-840; planks bullet_objects.py:47-103) ---- */
+#define ORC_NSTEPS 20
+typedef struct {
+  orc_w3d_env base; /* robot + physics state + RNG streams (walk_target / potentials reused) */
+  int curriculum;   /* 0..9, set through set_env_params (env_locomotion.py:362-369) */
+  int gain_curriculum; /* curriculum latched for robot.applied_gain at reset (env_locomotion.py:489) */
+  double terrain[ORC_NSTEPS][6]; /* x y z phi x_tilt y_tilt (env_locomotion.py:395-441) */
+  int plank_index[3];            /* which terrain row each of the 3 physical planks shows */
+  orc_box boxes[6];              /* plank p: boxes[2p] = base, boxes[2p+1] = cover */
+  int next_step_index, target_reached_count, stop_on_next_step, set_stop_on_next_step, timestep, target_reached;
+  double foot_dist_to_target[2];
+  double targets[3][5];
+  double step_bonus, speed_penalty;
+  int steps_reached; /* info["steps_reached"] when reported, else -1 */
+} orc_stepper_env;
+
+void orc_stepper_seed(orc_stepper_env* e, const uint32_t* key, int len, int at_construction);
+void orc_stepper_reset(const orc_model* m, const orc_params* p, orc_stepper_env* e, double* obs /* [65] */);
+void orc_stepper_step(const orc_model* m, const orc_params* p, orc_stepper_env* e, const double* action,
+                      double* obs, double* reward, int* done, int* truncated);
+void orc_stepper_step_batch(const orc_model* m, const orc_params* p, orc_stepper_env* envs, int n,
+                            const double* actions, double* obs, double* rewards, int* dones, int n_threads);
+int orc_sizeof_stepper_env(void);
 int orc_sizeof_w3d_env(void);
 int orc_sizeof_model(void);
 

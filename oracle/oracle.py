@@ -87,6 +87,18 @@ class W3DEnv(C.Structure):
     ]
 
 
+class StepperEnv(C.Structure):
+    _fields_ = [
+        ("base", W3DEnv), ("curriculum", i32), ("gain_curriculum", i32), ("terrain", (d * 6) * 20),
+        ("plank_index", i32 * 3),
+        ("boxes", Box * 6),
+        ("next_step_index", i32), ("target_reached_count", i32), ("stop_on_next_step", i32),
+        ("set_stop_on_next_step", i32), ("timestep", i32), ("target_reached", i32),
+        ("foot_dist_to_target", d * 2), ("targets", (d * 5) * 3), ("step_bonus", d), ("speed_penalty", d),
+        ("steps_reached", i32),
+    ]
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "mocca_oracle.c")
     hdr = os.path.join(_HERE, "mocca_oracle.h")
@@ -107,6 +119,7 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         assert L.orc_sizeof_model() == C.sizeof(Model), (L.orc_sizeof_model(), C.sizeof(Model))
         assert L.orc_sizeof_w3d_env() == C.sizeof(W3DEnv), (L.orc_sizeof_w3d_env(), C.sizeof(W3DEnv))
+        assert L.orc_sizeof_stepper_env() == C.sizeof(StepperEnv), (L.orc_sizeof_stepper_env(), C.sizeof(StepperEnv))
         L.orc_rng_double.restype = d
         L.orc_rng_uniform.restype = d
         L.orc_rng_uniform.argtypes = [C.c_void_p, d, d]
@@ -316,3 +329,53 @@ class Walker3DCustomOracle:
 
     def state_vector(self):
         return state_vector(self.e.s, self.A)
+
+
+class Walker3DStepperOracle:
+    """Single-env restatement of Walker3DStepperEnv (reference env_locomotion.py:330-840)."""
+
+    def __init__(self, table: dict, seed: int = 0, curriculum: int = 0, params: Params | None = None):
+        self.table = table
+        self.m = model_from_table(table)
+        self.p = params or default_params()
+        self.e = StepperEnv()
+        self.e.curriculum = curriculum
+        self.A = table["n_dof"]
+        self.obs_dim = 6 + 2 * self.A + len(table["foot_links"]) + 15
+        self._seed(seed, True)
+
+    def _seed(self, seed, at_construction):
+        words = gym_seed_words(seed)
+        key = (C.c_uint32 * len(words))(*words)
+        lib().orc_stepper_seed(C.byref(self.e), key, len(words), int(at_construction))
+
+    def seed(self, seed):
+        self._seed(seed, False)
+        return [seed]
+
+    def set_env_params(self, params):
+        if "curriculum" in params:
+            self.e.curriculum = int(params["curriculum"])
+
+    def reset(self):
+        obs = (d * self.obs_dim)()
+        lib().orc_stepper_reset(C.byref(self.m), C.byref(self.p), C.byref(self.e), obs)
+        return np.array(obs)
+
+    def step(self, action):
+        a = (d * MAXD)(*[float(x) for x in action])
+        obs = (d * self.obs_dim)()
+        r = d(0)
+        done = i32(0)
+        trunc = i32(0)
+        lib().orc_stepper_step(C.byref(self.m), C.byref(self.p), C.byref(self.e), a, obs, C.byref(r), C.byref(done),
+                               C.byref(trunc))
+        info = {}
+        if self.e.steps_reached >= 0:
+            info["steps_reached"] = self.e.steps_reached
+        if trunc.value:
+            info["TimeLimit.truncated"] = True
+        return np.array(obs), r.value, bool(done.value), info
+
+    def state_vector(self):
+        return state_vector(self.e.base.s, self.A)

@@ -8,6 +8,7 @@
 
 typedef W3D_Model WM;
 typedef W3DEnv<WM> WEnv;
+typedef StepperEnv<WM> SEnv;
 typedef WarpMem<WM> WMem;
 
 static void default_phys(MbPhysics* p) {
@@ -15,6 +16,7 @@ static void default_phys(MbPhysics* p) {
   p->erp_joint = 0.2f; p->linear_slop = 1e-5f; p->lin_damping = 0.04f; p->ang_damping = 0.04f;
   p->max_coord_vel = 100.0f; p->limit_max_impulse = 100.0f; p->split_threshold = -0.04f;
   p->residual_threshold = 1e-7f; p->ground_friction = 0.8f; p->has_ground = 1;
+  p->box_friction = 1.0f; p->box_erp = 0.9f; p->box_cfm = 0.0f;
 }
 
 extern "C" {
@@ -69,5 +71,50 @@ void emu_w3d_step(const MbPhysics* p, float* state, float* rec, uint32_t* mt_env
   WEnv::step(S, *p, state, rec, mt_env, mt_robot, act, obs, rew, done, trunc, final_obs, &st);
   stats_out[0] = (double)st.episodes; stats_out[1] = st.ret_sum; stats_out[2] = st.len_sum;
   stats_out[3] = (double)st.nonfinite;
+}
+
+// ---- Walker3DStepperEnv
+void emu_stepper_phys(MbPhysics* p) {
+  default_phys(p);
+  p->has_ground = 0;
+  const float kp = 30000.0f, kd = 1000.0f + 0.1f, denom = p->dt * kp + kd;
+  p->box_friction = 1.0f; p->box_erp = p->dt * kp / denom; p->box_cfm = 1.0f / denom;
+}
+int emu_stepper_rec_stride() { return (int)SEnv::REC_STRIDE; }
+
+void emu_stepper_reset(const MbPhysics* p, float* state, float* rec, uint32_t* mt_env, uint32_t* mt_robot, float* obs) {
+  static WMem S;
+  memset(&S, 0, sizeof(S));
+  SEnv::reset(S, *p, rec, mt_env, mt_robot, obs);
+  WEnv::store_state(S, state);
+}
+
+void emu_stepper_step(const MbPhysics* p, float* state, float* rec, uint32_t* mt_env, uint32_t* mt_robot,
+                      const float* act, float* obs, float* rew, uint8_t* done, uint8_t* trunc, float* final_obs,
+                      double* stats_out) {
+  static WMem S;
+  memset(&S, 0, sizeof(S));
+  MbStats st;
+  memset(&st, 0, sizeof(st));
+  SEnv::step(S, *p, state, rec, mt_env, mt_robot, act, obs, rew, done, trunc, final_obs, &st);
+  stats_out[0] = (double)st.episodes; stats_out[1] = st.ret_sum; stats_out[2] = st.len_sum;
+  stats_out[3] = (double)st.nonfinite;
+}
+
+// stepSimulation with the planks described by a Stepper record
+void emu_stepper_step_physics(const MbPhysics* p, float* state, const float* rec, const float* tau, int* rows,
+                              int* contacts) {
+  static WMem S;
+  memset(&S, 0, sizeof(S));
+  WEnv::load_state(S, state);
+  SEnv::load_obstacles(S, rec);
+  for (int j = 0; j < WM::NJ; ++j) S.tau[j] = tau[j];
+  int r = 0, nc = 0, ov = 0;
+  Sim<WM>::LaneConst C;
+  Sim<WM>::init_lane_const(C);
+  for (int k = 0; k < p->substeps; ++k) r += Sim<WM>::substep(S, *p, C, &nc, &ov);
+  WEnv::store_state(S, state);
+  *rows = r;
+  *contacts = nc;
 }
 }

@@ -17,7 +17,8 @@ class Phys(C.Structure):
                 ("erp_contact", C.c_float), ("erp_joint", C.c_float), ("linear_slop", C.c_float),
                 ("lin_damping", C.c_float), ("ang_damping", C.c_float), ("max_coord_vel", C.c_float),
                 ("limit_max_impulse", C.c_float), ("split_threshold", C.c_float), ("residual_threshold", C.c_float),
-                ("ground_friction", C.c_float), ("has_ground", C.c_int)]
+                ("ground_friction", C.c_float), ("has_ground", C.c_int), ("box_friction", C.c_float),
+                ("box_erp", C.c_float), ("box_cfm", C.c_float)]
 
 
 _lib = None
@@ -93,3 +94,54 @@ class EmuW3D:
                            _fp(obs), _fp(rew), _fp(done), _fp(trunc), _fp(fin), _fp(st))
         self.stats += st
         return obs, float(rew[0]), bool(done[0]), bool(trunc[0]), fin
+
+
+def stepper_phys():
+    p = Phys()
+    lib().emu_stepper_phys(C.byref(p))
+    return p
+
+
+class EmuStepper:
+    """Walker3DStepperEnv through the emulated kernel source (record layout: ER_* / ES_* in mb_env.cuh)."""
+
+    ES_NEXT, ES_COUNT, ES_STOP, ES_SETSTOP, ES_TIMESTEP, ES_CURRIC, ES_PLANKIDX, ES_STEPS = 22, 23, 24, 25, 26, 27, 28, 31
+    ES_BOX, ES_TERRAIN = 32, 68
+
+    def __init__(self, mt_state, curriculum=0):
+        self.p = stepper_phys()
+        self.state = np.zeros(64, dtype=np.float32)
+        self.stride = lib().emu_stepper_rec_stride()
+        self.rec = np.zeros(self.stride, dtype=np.float32)
+        self.mt = np.zeros((2, 640), dtype=np.uint32)
+        self.mt[0, :625] = mt_state
+        self.mt[1, 624] = 624
+        self.rec.view(np.int32)[11] = 1  # ER_ALIASED
+        self.rec.view(np.int32)[self.ES_CURRIC] = curriculum
+        self.obs_dim = 65
+
+    def reset(self):
+        obs = np.zeros(self.obs_dim, dtype=np.float32)
+        lib().emu_stepper_reset(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(self.mt[0]), _fp(self.mt[1]), _fp(obs))
+        return obs
+
+    def step(self, act):
+        act = np.ascontiguousarray(act, dtype=np.float32)
+        obs = np.zeros(self.obs_dim, dtype=np.float32)
+        fin = np.zeros(self.obs_dim, dtype=np.float32)
+        rew = np.zeros(1, dtype=np.float32)
+        done = np.zeros(1, dtype=np.uint8)
+        trunc = np.zeros(1, dtype=np.uint8)
+        st = np.zeros(4)
+        lib().emu_stepper_step(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(self.mt[0]), _fp(self.mt[1]),
+                               _fp(act), _fp(obs), _fp(rew), _fp(done), _fp(trunc), _fp(fin), _fp(st))
+        return obs, float(rew[0]), bool(done[0]), bool(trunc[0]), fin
+
+    def terrain(self):
+        return self.rec[self.ES_TERRAIN:self.ES_TERRAIN + 120].reshape(20, 6)
+
+    def step_physics(self, tau):
+        tau = np.ascontiguousarray(tau, dtype=np.float32)
+        rows, nc = C.c_int(0), C.c_int(0)
+        lib().emu_stepper_step_physics(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(tau), C.byref(rows), C.byref(nc))
+        return rows.value, nc.value

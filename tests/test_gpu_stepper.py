@@ -1,0 +1,150 @@
+"""GPU parity tests for Walker3DStepperEnv-v0 (BASELINE config 3) through the C ABI, against the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _env(n, seed=0, **kw):
+    from mocca_envs_b200.vec_env import Walker3DStepperVecEnv
+
+    return Walker3DStepperVecEnv(n, device="cuda:0", seed=seed, **kw)
+
+
+def test_stepper_reset_and_terrain_bit_exact(walker_table, oracle_mod, torch_mod):
+    """north_star: bit-exact terrain, stepping-stone layout and reset state from the same seed (per-env
+    curriculum 0 / 5 / 9), compared after rounding to the f32 record."""
+    torch, O, t = torch_mod, oracle_mod, walker_table
+    N = 12
+    curs = [0, 5, 9] * 4
+    env = _env(N, seed=200)
+    env.set_env_params({"curriculum": curs})
+    oracles = [O.Walker3DStepperOracle(t, seed=200 + i, curriculum=curs[i]) for i in range(N)]
+    for _ in range(2):
+        obs = env.reset().cpu().numpy()
+        st = env.get_state().cpu().numpy()
+        ter = env.terrain_info().cpu().numpy()
+        for i, o in enumerate(oracles):
+            oref = o.reset()
+            assert np.array_equal(ter[i], np.array(o.e.terrain[:]).astype(np.float32))
+            assert np.array_equal(st[i, 13:34], np.array(o.e.base.s.q[:21]).astype(np.float32))
+            assert np.array_equal(st[i, 0:3], np.array([0.3, 0.0, 1.32], dtype=np.float32))
+            assert np.abs(obs[i] - oref).max() < 1e-5
+    env.close()
+
+
+def test_stepper_env_step_teacher_forced(walker_table, oracle_mod, torch_mod):
+    """Walker3DStepperEnv.step from identical states and bookkeeping: box contacts on soft planks, target advance,
+    plank recycling, step bonus, look-ahead targets.  >= 97 % of env-steps within 5e-3 (obs) / 5e-2 (reward)."""
+    from tests.helpers import force_oracle_state
+
+    torch, O, t = torch_mod, oracle_mod, walker_table
+    N = 12
+    curs = [0, 5, 9] * 4
+    env = _env(N, seed=300, return_final_obs=True)
+    env.set_env_params({"curriculum": curs})
+    oracles = [O.Walker3DStepperOracle(t, seed=300 + i, curriculum=curs[i]) for i in range(N)]
+    env.reset()
+    for o in oracles:
+        o.reset()
+    arng = np.random.RandomState(5)
+    bad, total, errs, advanced = 0, 0, [], 0
+    for step in range(50):
+        a = (0.3 * arng.uniform(-1, 1, (N, 21))).astype(np.float32)
+        st = np.stack([o.state_vector() for o in oracles]).astype(np.float32)
+        env.set_state(torch.tensor(st))
+        rec = env.get_record().cpu().numpy()
+        ri = rec.view(np.int32)
+        for i, o in enumerate(oracles):
+            b = o.e.base
+            sv = st[i].astype(np.float64)
+            for k in range(3):
+                b.s.pos[k] = sv[k]; b.s.omega[k] = sv[7 + k]; b.s.vel[k] = sv[10 + k]
+            for k in range(4):
+                b.s.quat[k] = sv[3 + k]
+            for k in range(21):
+                b.s.q[k] = sv[13 + k]; b.s.qd[k] = sv[34 + k]
+            rec[i, 0:3] = np.array(b.walk_target[:], dtype=np.float32)
+            rec[i, 7] = b.linear_potential
+            rec[i, 9], rec[i, 10] = b.feet_contact[0], b.feet_contact[1]
+            ri[i, 8] = b.elapsed
+            ri[i, 22:27] = (o.e.next_step_index, o.e.target_reached_count, o.e.stop_on_next_step,
+                            o.e.set_stop_on_next_step, o.e.timestep)
+            ri[i, 6] = o.e.gain_curriculum
+            for p in range(3):
+                bx = o.e.boxes[2 * p]
+                rec[i, 32 + 12 * p:32 + 12 * p + 3] = np.array(bx.center[:], dtype=np.float32)
+                rec[i, 32 + 12 * p + 3:32 + 12 * p + 12] = np.array([list(r) for r in bx.R], dtype=np.float32).ravel()
+            rec[i, 68:188] = np.array(o.e.terrain[:], dtype=np.float32).ravel()
+        env.set_record(torch.tensor(rec))
+        obs, rew, done, info = env.step(torch.tensor(a))
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        fin = info["terminal_observation"].cpu().numpy()
+        for i, o in enumerate(oracles):
+            n0 = o.e.next_step_index
+            o1, r1, d1, _ = o.step(a[i].astype(np.float64))
+            advanced += o.e.next_step_index != n0
+            ocmp = fin[i] if done[i] else obs[i]
+            e_obs = float(np.abs(o1 - ocmp).max())
+            ok = bool(done[i]) == d1 and e_obs < 5e-3 and abs(r1 - rew[i]) < 5e-2 + 1e-3 * abs(r1)
+            total += 1
+            bad += 0 if ok else 1
+            errs.append(e_obs)
+            if d1:
+                o.reset()
+    assert advanced >= 4
+    assert bad <= 0.03 * total, (bad, total)
+    assert np.median(errs) < 2e-4
+    env.close()
+
+
+def test_stepper_full_size_properties(torch_mod):
+    """BASELINE config 3 size: 16384 envs, curriculum {0,5,9}: determinism, finiteness, steps_reached bookkeeping."""
+    torch = torch_mod
+    N = 16384
+    curs = np.array([0, 5, 9] * (N // 3 + 1))[:N]
+    outs = []
+    for rep in range(2):
+        env = _env(N, seed=9)
+        env.set_env_params({"curriculum": curs})
+        env.reset()
+        g = torch.Generator(device="cuda:0").manual_seed(2)
+        tot_done = 0
+        for _ in range(40):
+            a = torch.rand(N, 21, device="cuda:0", generator=g) * 2 - 1
+            obs, rew, done, info = env.step(a)
+            tot_done += int(done.sum())
+            sr = env.steps_reached()
+            assert bool(((sr >= 1) & (sr <= 19))[done.bool()].all())
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        st = env.stats()
+        assert st["episodes"] == tot_done > 0 and st["nonfinite"] == 0
+        assert st["steps_reached_sum"] >= st["episodes"]
+        outs.append((obs.clone(), env.get_state().clone()))
+        env.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_stepper_gym_facade(torch_mod):
+    from mocca_envs_b200 import make
+
+    env = make("mocca_envs:Walker3DStepperEnv-v0", seed=0)
+    env.set_env_params({"curriculum": 5})
+    obs = env.reset()
+    assert obs.shape == (65,) and obs.dtype == np.float64
+    done, steps, info = False, 0, {}
+    while not done and steps < 1000:
+        obs, r, done, info = env.step(np.zeros(21))
+        steps += 1
+    assert done and "steps_reached" in info and 1 <= info["steps_reached"] <= 19
+    neg, right, left, na, ra, la = env.get_mirror_indices()
+    assert neg.max() < 65 and right.max() < 65 and left.max() < 65
+    env.close()

@@ -121,3 +121,74 @@ def test_env_step_teacher_forced(walker_table, oracle_mod):
                 o.reset()
     assert bad <= 0.03 * total, (bad, total)
     assert np.median(errs) < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------ Stepper
+def test_stepper_reset_terrain_bit_exact(walker_table, oracle_mod):
+    """north_star: bit-exact terrain, stepping-stone layout and reset-state generation from the same seed
+    (float64 generator on the device path, compared after rounding to the f32 record)."""
+    O, t = oracle_mod, walker_table
+    for seed, cur in ((0, 0), (1, 5), (2, 9)):
+        env = O.Walker3DStepperOracle(t, seed=seed, curriculum=cur)
+        emu = E.EmuStepper(_mt_row(O, seed), curriculum=cur)
+        for _ in range(2):
+            o1, o2 = env.reset(), emu.reset()
+            assert np.array_equal(emu.terrain(), np.array(env.e.terrain[:]).astype(np.float32))
+            assert np.array_equal(emu.state[13:34], np.array(env.e.base.s.q[:21]).astype(np.float32))
+            assert np.array_equal(emu.state[0:3], np.array([0.3, 0.0, 1.32], dtype=np.float32))
+            assert np.abs(o1 - o2).max() < 1e-6
+
+
+def test_stepper_env_step_teacher_forced(walker_table, oracle_mod):
+    """Walker3DStepperEnv.step (box contacts with soft-contact planks, target advance, step bonus, look-ahead
+    targets) from identical states; same >= 97 % criterion as the flat-ground env."""
+    from tests.helpers import force_oracle_state
+
+    O, t = oracle_mod, walker_table
+    bad, total, errs, advanced = 0, 0, [], 0
+    for seed, cur in ((3, 5), (4, 0), (5, 9)):
+        env = O.Walker3DStepperOracle(t, seed=seed, curriculum=cur)
+        emu = E.EmuStepper(_mt_row(O, seed), curriculum=cur)
+        env.reset()
+        emu.reset()
+        arng = np.random.RandomState(seed)
+        for i in range(60):
+            a = 0.3 * arng.uniform(-1, 1, 21)
+            sv = env.state_vector().astype(np.float32)
+            emu.state[:55] = sv
+            b = env.e.base
+            for k in range(3):
+                b.s.pos[k] = float(sv[k]); b.s.omega[k] = float(sv[7 + k]); b.s.vel[k] = float(sv[10 + k])
+            for k in range(4):
+                b.s.quat[k] = float(sv[3 + k])
+            for k in range(21):
+                b.s.q[k] = float(sv[13 + k]); b.s.qd[k] = float(sv[34 + k])
+            # bookkeeping is teacher-forced too
+            ri = emu.rec.view(np.int32)
+            emu.rec[0:3] = np.array(b.walk_target[:], dtype=np.float32)
+            emu.rec[7] = b.linear_potential
+            emu.rec[9], emu.rec[10] = b.feet_contact[0], b.feet_contact[1]
+            ri[8] = b.elapsed
+            ri[22], ri[23], ri[24], ri[25], ri[26] = (env.e.next_step_index, env.e.target_reached_count,
+                                                      env.e.stop_on_next_step, env.e.set_stop_on_next_step,
+                                                      env.e.timestep)
+            for p in range(3):
+                bx = env.e.boxes[2 * p]
+                emu.rec[32 + 12 * p:32 + 12 * p + 3] = np.array(bx.center[:], dtype=np.float32)
+                emu.rec[32 + 12 * p + 3:32 + 12 * p + 12] = np.array([list(r) for r in bx.R], dtype=np.float32).ravel()
+            n0 = env.e.next_step_index
+            o1, r1, d1, _ = env.step(a)
+            o2, r2, d2, tr2, fin = emu.step(a)
+            advanced += env.e.next_step_index != n0
+            ocmp = fin if d2 else o2
+            err = float(np.abs(o1 - ocmp).max())
+            ok = d1 == d2 and err < 5e-3 and abs(r1 - r2) < 5e-2 + 1e-3 * abs(r1)
+            total += 1
+            bad += 0 if ok else 1
+            errs.append(err)
+            if d1:
+                env.reset()
+                emu.reset() if not d2 else None
+    assert advanced >= 2  # the target-advance / plank-recycling path was exercised
+    assert bad <= 0.03 * total, (bad, total)
+    assert np.median(errs) < 2e-4
