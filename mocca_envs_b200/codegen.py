@@ -168,6 +168,18 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append(_iarr(P + "_rowoff", r["rowoff"]))
     out.append(_iarr(P + "_rowlen", r["rowlen"]))
     out.append(_iarr(P + "_rowmask", r["rowmask_rt"], "unsigned"))
+    # uniform-indexed copies in constant memory (one LDC instead of a global load in the sequential loops)
+    out.append(_iarr(P + "_c_rowoff", r["rowoff"]).replace("MB_TABLE", "MB_CTABLE"))
+    out.append(_iarr(P + "_c_rowlen", r["rowlen"]).replace("MB_TABLE", "MB_CTABLE"))
+    out.append(_iarr(P + "_c_rowmask", r["rowmask_rt"], "unsigned").replace("MB_TABLE", "MB_CTABLE"))
+    # facoff[k][t]: offset of the compact row that entry t of row k updates (its column index' own row)
+    maxoff = r["maxsup"] - 1
+    fac = []
+    for k in range(r["nu"]):
+        cols = sorted(j for j in range(k) if (r["rowmask_rt"][k] >> j) & 1)
+        fac.append([r["rowoff"][c] for c in cols] + [0] * (maxoff - len(cols)))
+    out.append("MB_TABLE int %s_facoff[%d][%d] = {\n  %s};\n" % (
+        P, r["nu"], maxoff, ",\n  ".join("{" + ", ".join(str(v) for v in row) + "}" for row in fac)))
     out.append(_farr(P + "_joff", r["joff"]))
     out.append(_farr(P + "_jrot", [np.asarray(m).reshape(9) for m in r["jrot"]]))
     out.append(_farr(P + "_jaxis", r["jaxis"]))
@@ -224,6 +236,10 @@ def emit_header(t: dict, prefix: str) -> str:
                % (r["nj"], r["nb"], r["nu"], r["npt"], r["nlevel"], r["nfeet"], len(r["right"]), len(r["neg"]),
                   r["lsize"], r["maxsup"]))
     out.append("  MB_HD static unsigned long long chainpack(int j) { return %s_chainpack[j]; }\n" % P)
+    out.append("  MB_HD static int facoff(int k, int t) { return %s_facoff[k][t]; }\n" % P)
+    out.append("  MB_HD static int c_rowoff(int i) { return %s_c_rowoff[i]; }\n" % P)
+    out.append("  MB_HD static int c_rowlen(int i) { return %s_c_rowlen[i]; }\n" % P)
+    out.append("  MB_HD static unsigned c_rowmask(int i) { return %s_c_rowmask[i]; }\n" % P)
     for fld, ctype in [("jparent", "int"), ("jlevel", "int"), ("janc", "unsigned"), ("bstart", "int"), ("bend", "int"),
                        ("jdepth", "int"), ("rowoff", "int"), ("rowlen", "int"), ("rowmask", "unsigned"),
                        ("jaxk", "int"), ("jident", "int"),

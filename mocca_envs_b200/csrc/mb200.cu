@@ -151,7 +151,7 @@ __device__ __forceinline__ void physics_body(int n, const MbPhysics& phys, float
   Sim<WM>::LaneConst C;
   Sim<WM>::init_lane_const(C);
 #pragma unroll 1
-  for (int k = 0; k < phys.substeps; ++k) rows += Sim<WM>::substep(S, phys, C, &nc, &overflow);
+  for (int k = 0; k < phys.substeps; ++k) rows += Sim<WM>::substep<Env::HAS_BOXES != 0>(S, phys, C, &nc, &overflow);
   WEnv::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
   if (tail) return;
   if ((threadIdx.x & 31) == 0) {

@@ -33,6 +33,7 @@
 #define MB_NOINLINE __device__ __noinline__
 #define MB_LANES(l) { const int l = (int)(threadIdx.x & 31);
 #define MB_END } __syncwarp();
+#define MB_END_REG }  /* the block touched registers only: no memory ordering needed */
 template <typename T> struct LaneVar {
   T v;
   MB_HD T& operator[](int) { return v; }
@@ -52,6 +53,7 @@ MB_HD void mb_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
 #define MB_NOINLINE
 #define MB_LANES(l) for (int l = 0; l < 32; ++l) {
 #define MB_END }
+#define MB_END_REG }
 template <typename T> struct LaneVar {
   T v[32];
   T& operator[](int l) { return v[l]; }
@@ -497,10 +499,9 @@ template <class M> struct Sim {
   MB_HD static void factorize(Mem& S, const LaneConst& C) {
 #pragma unroll 1
     for (int k = NU - 1; k >= 0; --k) {
-      const int offk = M::rowoff(k), nk = M::rowlen(k) - 1;
+      const int offk = M::c_rowoff(k), nk = M::c_rowlen(k) - 1;
       const float dkk = S.L[offk + nk];
       const float inv = rsqrtf(dkk);
-      const unsigned long long pack = k >= 6 ? M::chainpack(k - 6) : 0ull;
       MB_LANES(l)
         if (l < nk) S.L[offk + l] *= inv;
         else if (l == nk) { S.L[offk + nk] = dkk * inv; S.Ldinv[k] = inv; }
@@ -511,8 +512,7 @@ template <class M> struct Sim {
         for (int r = 0; r < 3; ++r) {
           if (l + 32 * r < npairs) {
             const int t = (C.pairs[l] >> (8 * r)) & 15, s2 = (C.pairs[l] >> (8 * r + 4)) & 15;
-            const int it = t < 6 ? t : 6 + chain_at(pack, t - 6);
-            S.L[M::rowoff(it) + s2] -= S.L[offk + t] * S.L[offk + s2];
+            S.L[M::facoff(k, t) + s2] -= S.L[offk + t] * S.L[offk + s2];
           }
         }
       MB_END
@@ -522,26 +522,26 @@ template <class M> struct Sim {
   // ---- E. single right-hand-side solves, one generalised coordinate per lane ---------------------------------
   // L[i][l] sits at rowoff(i) + tl(l) for every i whose support contains l (prefix property): no index math.
   MB_HD static void solve_Lt(Mem& S, const LaneConst& C, LaneVar<float>& x) {  // L^T y = x
-#pragma unroll 1
+#pragma unroll 3
     for (int i = NU - 1; i >= 0; --i) {
       const float yi = warp_bcast(x, i) * S.Ldinv[i];
-      const unsigned sup = M::rowmask(i);
-      const int off = M::rowoff(i);
+      const unsigned sup = M::c_rowmask(i);
+      const int off = M::c_rowoff(i);
       MB_LANES(l)
         if (l == i) x[l] = yi;
         else if ((sup >> l) & 1u) x[l] -= S.L[off + C.tl[l]] * yi;
-      MB_END
+      MB_END_REG
     }
   }
   MB_HD static void solve_L(Mem& S, const LaneConst& C, LaneVar<float>& x) {  // L y = x
-#pragma unroll 1
+#pragma unroll 3
     for (int i = 0; i < NU; ++i) {
       const float xi = warp_bcast(x, i) * S.Ldinv[i];
-      const int ti = M::rowlen(i) - 1;
+      const int ti = M::c_rowlen(i) - 1;
       MB_LANES(l)
         if (l == i) x[l] = xi;
         else if ((C.sup[l] >> i) & 1u) x[l] -= S.L[C.off[l] + ti] * xi;
-      MB_END
+      MB_END_REG
     }
   }
 
@@ -594,7 +594,7 @@ template <class M> struct Sim {
     return true;
   }
 
-  MB_HD static int collide(Mem& S, const MbPhysics& P, int* overflow) {
+  template <bool BOXES> MB_HD static int collide(Mem& S, const MbPhysics& P, int* overflow) {
     // world positions of the candidate points (relative to the base COM)
     MB_LANES(l)
       for (int pt = l; pt < NPT; pt += 32) {
@@ -608,7 +608,7 @@ template <class M> struct Sim {
       }
     MB_END
     int nc = 0;
-    const int nbox = S.nbox;
+    const int nbox = BOXES ? S.nbox : 0;
 #pragma unroll 1
     for (int ob = P.has_ground ? -1 : 0; ob < nbox; ++ob) {
       if (ob >= 0) {
@@ -812,7 +812,7 @@ template <class M> struct Sim {
     MB_LANES(l)
       ya[l] = ((supA >> l) & 1u) ? S.w.Yc[ra][C.tl[l]] : 0.0f;
       ta[l] = ya[l] * z[l];
-    MB_END
+    MB_END_REG
     const float dotA = warp_sum(ta);
     const float appA = S.r_app[ra], jA = S.r_jinv[ra];
     float dA = S.r_rhs[ra] - appA * S.r_cfm[ra] - dotA * jA;
@@ -838,7 +838,7 @@ template <class M> struct Sim {
       yb[l] = in ? S.w.Yc[rb][C.tl[l]] : 0.0f;
       ta[l] = ya[l] * z[l];
       tb[l] = yb[l] * z[l];
-    MB_END
+    MB_END_REG
     const float dotA = warp_sum(ta), dotB = warp_sum(tb);
     const float appA = S.r_app[ra], jA = S.r_jinv[ra], appB = S.r_app[rb], jB = S.r_jinv[rb];
     float dA = S.r_rhs[ra] - appA * S.r_cfm[ra] - dotA * jA;
@@ -866,9 +866,6 @@ template <class M> struct Sim {
   // btMultiBodyConstraintSolver::solveSingleIteration order: limits (alternating direction), normals, friction
   MB_HD static void solve_constraints(Mem& S, const MbPhysics& P, const LaneConst& C, int nlim, int nc,
                                       LaneVar<float>& z) {
-    MB_LANES(l)
-      z[l] = 0.0f;
-    MB_END
     const int nsingle = nlim + nc;
 #pragma unroll 1
     for (int it = 0; it < P.iterations; ++it) {
@@ -918,14 +915,17 @@ template <class M> struct Sim {
   }
 
   // ---- one Bullet substep.  Returns the number of constraint rows; contact list of this substep stays in S ----
+  template <bool BOXES>
   MB_HD static int substep(Mem& S, const MbPhysics& P, const LaneConst& C, int* nc_out, int* overflow) {
     MB_BLOCK_BARRIER();  // keeps the warps of a CTA in the same phase so instruction-cache lines are shared
     kinematics(S, P, C, true);
-    const int nc_all = collide(S, P, overflow);
+    const int nc_all = collide<BOXES>(S, P, overflow);
     bodies(S, P);
     mass_matrix_and_rhs(S);
     factorize(S, C);
-    // forward dynamics: udot = M^-1 (tau - bias); u += dt udot (clamped like btMultiBody::applyDeltaVeeMultiDof)
+    // forward dynamics: udot = M^-1 (tau - bias); u += dt udot, clamped like btMultiBody::applyDeltaVeeMultiDof.
+    // (The clamp is live in practice: Bullet ignores the MJCF armature, so the light arm links reach 100 rad/s
+    // under full torque -- which is why the two forward substitutions of a substep cannot be merged into one.)
     LaneVar<float> x;
     MB_LANES(l)
       x[l] = l < NU ? S.rhs[l] : 0.0f;
@@ -935,7 +935,6 @@ template <class M> struct Sim {
     MB_LANES(l)
       if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + P.dt * x[l], -P.max_coord_vel), P.max_coord_vel);
     MB_END
-    MB_BLOCK_BARRIER2();
     const int nlim = find_limits(S);
     int nc = nc_all;
     if (nlim + 3 * nc > MB_MAXROW) { nc = (MB_MAXROW - nlim) / 3; *overflow += 1; }
@@ -943,6 +942,9 @@ template <class M> struct Sim {
     if (R > 0) {
       setup_rows(S, P, nlim, nc);
       LaneVar<float> z;
+      MB_LANES(l)
+        z[l] = 0.0f;
+      MB_END
       solve_constraints(S, P, C, nlim, nc, z);
       solve_L(S, C, z);
       MB_LANES(l)

@@ -129,7 +129,7 @@ template <class M> struct W3DEnv {
   typedef WarpMem<M> Mem;
   typedef Sim<M> S_;
   enum { NJ = M::NJ, NU = M::NU, OBS = 6 + 2 * M::NJ + M::NFEET + 2, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET,
-         REC_STRIDE = MB_REC_STRIDE };
+         REC_STRIDE = MB_REC_STRIDE, HAS_BOXES = 0 };
   MB_HD static void load_obstacles(WarpMem<M>&, const float*) {}
 
   // HBM <-> shared
@@ -331,7 +331,7 @@ template <class M> struct W3DEnv {
     S_::init_lane_const(C);
 #pragma unroll 1
     for (int k = 0; k < P.substeps; ++k) {
-      rows += S_::substep(S, P, C, &nc, &overflow);
+      rows += S_::template substep<false>(S, P, C, &nc, &overflow);
       ncsum += nc;
     }
     // feet_contact from the last collision pass (robots.py:74-86 via getContactPoints)
@@ -441,7 +441,7 @@ template <class M> struct StepperEnv {
   typedef Sim<M> S_;
   typedef W3DEnv<M> B_;
   enum { NJ = M::NJ, NU = M::NU, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET, OBS = ROBOT_OBS + 15, NSTEPS = 20,
-         REC_STRIDE = MB_REC_STRIDE_STEPPER };
+         REC_STRIDE = MB_REC_STRIDE_STEPPER, HAS_BOXES = 1 };
   MB_HD static void load_obstacles(Mem& S, const float* rec) { load_boxes(S, rec); }
   MB_HD static void load_state(Mem& S, const float* st) { B_::load_state(S, st); }
   MB_HD static void store_state(const Mem& S, float* st) { B_::store_state(S, st); }
@@ -646,7 +646,7 @@ template <class M> struct StepperEnv {
     S_::init_lane_const(C);
 #pragma unroll 1
     for (int k = 0; k < P.substeps; ++k) {
-      rows += S_::substep(S, P, C, &nc, &overflow);
+      rows += S_::template substep<true>(S, P, C, &nc, &overflow);
       ncsum += nc;
     }
     const int timestep = rec_i(rec, ES_TIMESTEP) + 1;

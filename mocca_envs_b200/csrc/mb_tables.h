@@ -5,7 +5,9 @@
 #ifdef __CUDACC__
 #define MB_HD __device__ __forceinline__
 #define MB_TABLE static __device__ const
+#define MB_CTABLE static __constant__ const
 #else
 #define MB_HD inline
 #define MB_TABLE static const
+#define MB_CTABLE static const
 #endif

@@ -32,7 +32,7 @@ void emu_step_physics(const MbPhysics* p, float* state, const float* tau, int* r
   int r = 0, nc = 0, ov = 0;
   Sim<WM>::LaneConst C;
   Sim<WM>::init_lane_const(C);
-  for (int k = 0; k < p->substeps; ++k) r += Sim<WM>::substep(S, *p, C, &nc, &ov);
+  for (int k = 0; k < p->substeps; ++k) r += Sim<WM>::substep<false>(S, *p, C, &nc, &ov);
   WEnv::store_state(S, state);
   *rows = r;
   *contacts = nc;
@@ -112,7 +112,7 @@ void emu_stepper_step_physics(const MbPhysics* p, float* state, const float* rec
   int r = 0, nc = 0, ov = 0;
   Sim<WM>::LaneConst C;
   Sim<WM>::init_lane_const(C);
-  for (int k = 0; k < p->substeps; ++k) r += Sim<WM>::substep(S, *p, C, &nc, &ov);
+  for (int k = 0; k < p->substeps; ++k) r += Sim<WM>::substep<true>(S, *p, C, &nc, &ov);
   WEnv::store_state(S, state);
   *rows = r;
   *contacts = nc;
