@@ -192,6 +192,12 @@ def emit_header(t: dict, prefix: str) -> str:
         jaxk.append(k if aligned else -1)
         jsgn.append(float(np.sign(ax[k])) if aligned else 0.0)
         jident.append(1 if np.abs(np.asarray(R0) - np.eye(3)).max() < 1e-12 else 0)
+    # joints of each kinematic level (component-parallel kinematics: lane = 3 * slot + component)
+    lv = [[j for j in range(r["nj"]) if r["jlevel"][j] == L] for L in range(r["nlevel"])]
+    maxslot = 10
+    assert max(len(x) for x in lv) <= maxslot
+    out.append("MB_TABLE int %s_lvjoint[%d][%d] = {\n  %s};\n" % (
+        P, r["nlevel"], maxslot, ",\n  ".join("{" + ", ".join(str(v) for v in (x + [-1] * (maxslot - len(x)))) + "}" for x in lv)))
     out.append(_iarr(P + "_jaxk", jaxk))
     out.append(_farr(P + "_jsgn", jsgn))
     out.append(_iarr(P + "_jident", jident))
@@ -237,6 +243,7 @@ def emit_header(t: dict, prefix: str) -> str:
                   r["lsize"], r["maxsup"]))
     out.append("  MB_HD static unsigned long long chainpack(int j) { return %s_chainpack[j]; }\n" % P)
     out.append("  MB_HD static int facoff(int k, int t) { return %s_facoff[k][t]; }\n" % P)
+    out.append("  MB_HD static int lvjoint(int lev, int slot) { return %s_lvjoint[lev][slot]; }\n" % P)
     out.append("  MB_HD static int c_rowoff(int i) { return %s_c_rowoff[i]; }\n" % P)
     out.append("  MB_HD static int c_rowlen(int i) { return %s_c_rowlen[i]; }\n" % P)
     out.append("  MB_HD static unsigned c_rowmask(int i) { return %s_c_rowmask[i]; }\n" % P)

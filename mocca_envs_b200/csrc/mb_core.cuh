@@ -240,8 +240,6 @@ template <class M> struct Sim {
     LaneVar<int> off;       // rowoff(l)
     LaneVar<unsigned> sup;  // rowmask(l)
     LaneVar<int> pairs;     // (t, s) of the lower-triangle entries p = l, l + 32, l + 64 (4 bits each)
-    LaneVar<int> kin;       // joint l: (parent+1) | level<<6 | (axis index+1)<<10 | negative axis<<12 | identity R0<<13
-    LaneVar<float> ox, oy, oz;  // joint l: pivot offset in the parent joint frame
   };
   MB_HD static void init_lane_const(LaneConst& C) {
     MB_LANES(l)
@@ -251,19 +249,13 @@ template <class M> struct Sim {
       int packed = 0;
       for (int r = 0; r < 3; ++r) {
         const int pidx = l + 32 * r;
-        int t = 0;
-        while ((t + 1) * (t + 2) / 2 <= pidx) ++t;
+        int t = (int)((sqrtf(8.0f * (float)pidx + 1.0f) - 1.0f) * 0.5f);
+        if ((t + 1) * (t + 2) / 2 <= pidx) ++t;
+        if (t * (t + 1) / 2 > pidx) --t;
         const int s2 = pidx - t * (t + 1) / 2;
         packed |= (t | (s2 << 4)) << (8 * r);
       }
       C.pairs[l] = packed;
-      C.kin[l] = -1;
-      C.ox[l] = C.oy[l] = C.oz[l] = 0.0f;
-      if (l < NJ) {
-        C.kin[l] = (M::jparent(l) + 1) | (M::jlevel(l) << 6) | ((M::jaxk(l) + 1) << 10) |
-                   ((M::jsgn(l) < 0.0f ? 1 : 0) << 12) | (M::jident(l) << 13);
-        C.ox[l] = M::joff(l, 0); C.oy[l] = M::joff(l, 1); C.oz[l] = M::joff(l, 2);
-      }
     MB_END
   }
 
@@ -285,85 +277,80 @@ template <class M> struct Sim {
         }
       }
     MB_END
+    // Level by level down the tree; within a level lane 3*slot + c handles component c (matrix row / vector
+    // entry) of the slot-th joint of that level -- three lanes per joint, lanes of a warp are free.
 #pragma unroll 1
     for (int lev = 0; lev < M::NLEVEL; ++lev) {
+      LaneVar<int> jj;
       MB_LANES(l)
-        const int kc = C.kin[l];
-        if (kc >= 0 && ((kc >> 6) & 15) == lev) {
-          const int pj = (kc & 63) - 1;
+        const int slot = l / 3, c = l - 3 * slot;
+        const int j = slot < 10 ? M::lvjoint(lev, slot) : -1;
+        jj[l] = j;
+        if (j >= 0) {
+          const int pj = M::jparent(j);
           const float* Rp = pj < 0 ? S.Rb : S.w.k.jR[pj];
-          float off[3] = {C.ox[l], C.oy[l], C.oz[l]};
-          float p[3];
-          mb_matvec(Rp, off, p);
-          if (pj >= 0) { p[0] += S.w.k.jp[pj][0]; p[1] += S.w.k.jp[pj][1]; p[2] += S.w.k.jp[pj][2]; }
-          // R = Rp * R0 * Rot(axis, q); fast paths: identity R0, coordinate-aligned axis (two columns mix)
-          float ax[3] = {M::jaxis(l, 0), M::jaxis(l, 1), M::jaxis(l, 2)};
+          float b0 = Rp[3 * c], b1 = Rp[3 * c + 1], b2 = Rp[3 * c + 2];  // row c of the parent rotation
+          float pc = b0 * M::joff(j, 0) + b1 * M::joff(j, 1) + b2 * M::joff(j, 2);
+          if (pj >= 0) pc += S.w.k.jp[pj][c];
+          if (!M::jident(j)) {  // row c of Rp * R0
+            const float n0 = b0 * M::jrot(j, 0) + b1 * M::jrot(j, 3) + b2 * M::jrot(j, 6);
+            const float n1 = b0 * M::jrot(j, 1) + b1 * M::jrot(j, 4) + b2 * M::jrot(j, 7);
+            const float n2 = b0 * M::jrot(j, 2) + b1 * M::jrot(j, 5) + b2 * M::jrot(j, 8);
+            b0 = n0; b1 = n1; b2 = n2;
+          }
           float sn, cs;
-          mb_sincos(S.q[l], &sn, &cs);
-          float B[9], R[9];
-#pragma unroll
-          for (int k = 0; k < 9; ++k) B[k] = Rp[k];
-          if (!((kc >> 13) & 1)) {
-            float R0[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) R0[k] = M::jrot(l, k);
-            mb_matmul(B, R0, B);
+          mb_sincos(S.q[j], &sn, &cs);
+          const int kax = M::jaxk(j);
+          float r0, r1, r2, ac;
+          if (kax >= 0) {  // coordinate-aligned axis: two columns mix
+            const float sgn = M::jsgn(j), sg = sn * sgn;
+            const float ci = kax == 0 ? b1 : (kax == 1 ? b2 : b0);
+            const float cj = kax == 0 ? b2 : (kax == 1 ? b0 : b1);
+            const float ni = cs * ci + sg * cj, nj = cs * cj - sg * ci;
+            r0 = kax == 0 ? b0 : (kax == 1 ? nj : ni);
+            r1 = kax == 0 ? ni : (kax == 1 ? b1 : nj);
+            r2 = kax == 0 ? nj : (kax == 1 ? ni : b2);
+            ac = sgn * (kax == 0 ? r0 : (kax == 1 ? r1 : r2));
+          } else {  // generic axis: row c of B * Rodrigues(ax, q)
+            const float ax0 = M::jaxis(j, 0), ax1 = M::jaxis(j, 1), ax2 = M::jaxis(j, 2), t = 1.0f - cs;
+            r0 = b0 * (t * ax0 * ax0 + cs) + b1 * (t * ax0 * ax1 + sn * ax2) + b2 * (t * ax0 * ax2 - sn * ax1);
+            r1 = b0 * (t * ax0 * ax1 - sn * ax2) + b1 * (t * ax1 * ax1 + cs) + b2 * (t * ax1 * ax2 + sn * ax0);
+            r2 = b0 * (t * ax0 * ax2 + sn * ax1) + b1 * (t * ax1 * ax2 - sn * ax0) + b2 * (t * ax2 * ax2 + cs);
+            ac = r0 * ax0 + r1 * ax1 + r2 * ax2;
           }
-          const int kax = ((kc >> 10) & 3) - 1;
-          if (kax >= 0) {
-            const float sg = ((kc >> 12) & 1) ? -sn : sn;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              const float c0 = B[3 * r], c1 = B[3 * r + 1], c2 = B[3 * r + 2];
-              const float ci = kax == 0 ? c1 : (kax == 1 ? c2 : c0);
-              const float cj = kax == 0 ? c2 : (kax == 1 ? c0 : c1);
-              const float ni = cs * ci + sg * cj, nj = cs * cj - sg * ci;
-              R[3 * r] = kax == 0 ? c0 : (kax == 1 ? nj : ni);
-              R[3 * r + 1] = kax == 0 ? ni : (kax == 1 ? c1 : nj);
-              R[3 * r + 2] = kax == 0 ? nj : (kax == 1 ? ni : c2);
-            }
-          } else {
-            const float t = 1.0f - cs;
-            float Rq[9] = {t * ax[0] * ax[0] + cs, t * ax[0] * ax[1] - sn * ax[2], t * ax[0] * ax[2] + sn * ax[1],
-                           t * ax[0] * ax[1] + sn * ax[2], t * ax[1] * ax[1] + cs, t * ax[1] * ax[2] - sn * ax[0],
-                           t * ax[0] * ax[2] - sn * ax[1], t * ax[1] * ax[2] + sn * ax[0], t * ax[2] * ax[2] + cs};
-            mb_matmul(B, Rq, R);
-          }
-          float a[3], s[6];
-          if (kax >= 0) {
-            const float sgn = ((kc >> 12) & 1) ? -1.0f : 1.0f;
-            a[0] = sgn * (kax == 0 ? R[0] : (kax == 1 ? R[1] : R[2]));
-            a[1] = sgn * (kax == 0 ? R[3] : (kax == 1 ? R[4] : R[5]));
-            a[2] = sgn * (kax == 0 ? R[6] : (kax == 1 ? R[7] : R[8]));
-          } else {
-            mb_matvec(R, ax, a);
-          }
-          s[0] = a[0]; s[1] = a[1]; s[2] = a[2];
-          mb_cross(p, a, &s[3]);
-#pragma unroll
-          for (int k = 0; k < 9; ++k) S.w.k.jR[l][k] = R[k];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) S.w.k.jp[l][k] = p[k];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) S.js[l][k] = s[k];
+          S.w.k.jR[j][3 * c] = r0; S.w.k.jR[j][3 * c + 1] = r1; S.w.k.jR[j][3 * c + 2] = r2;
+          S.w.k.jp[j][c] = pc;
+          S.js[j][c] = ac;
+        }
+      MB_END
+      MB_LANES(l)
+        const int j = jj[l];
+        if (j >= 0) {
+          const int slot = l / 3, c = l - 3 * slot;
+          const float* p = S.w.k.jp[j];
+          const float* a = S.js[j];
+          float sl[3];
+          mb_cross(p, a, sl);  // linear part of the motion subspace, all three entries (needed by the crosses)
+          const float slc = c == 0 ? sl[0] : (c == 1 ? sl[1] : sl[2]);
+          S.js[j][3 + c] = slc;
           if (with_vel) {
-            const float qd = S.u[6 + l];
+            const int pj = M::jparent(j);
+            const float qd = S.u[6 + j];
             const float* Vp = S.w.k.jV[pj + 1];
             const float* Ap = S.w.k.jA[pj + 1];
-            float vj[6], c1[3], c2[3], c3[3];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) vj[k] = s[k] * qd;
-            // A = Ap + Vp x vj   (motion cross; vj x vj = 0)
-            mb_cross(Vp, vj, c1);
-            mb_cross(Vp, vj + 3, c2);
-            mb_cross(Vp + 3, vj, c3);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              S.w.k.jV[l + 1][k] = Vp[k] + vj[k];
-              S.w.k.jV[l + 1][3 + k] = Vp[3 + k] + vj[3 + k];
-              S.w.k.jA[l + 1][k] = Ap[k] + c1[k];
-              S.w.k.jA[l + 1][3 + k] = Ap[3 + k] + c2[k] + c3[k];
-            }
+            const float vw[3] = {a[0] * qd, a[1] * qd, a[2] * qd};
+            const float vv[3] = {sl[0] * qd, sl[1] * qd, sl[2] * qd};
+            float c1[3], c2[3], c3[3];
+            mb_cross(Vp, vw, c1);      // A = Ap + Vp x vj   (motion cross; vj x vj = 0)
+            mb_cross(Vp, vv, c2);
+            mb_cross(Vp + 3, vw, c3);
+            const float c1c = c == 0 ? c1[0] : (c == 1 ? c1[1] : c1[2]);
+            const float c23 = c == 0 ? c2[0] + c3[0] : (c == 1 ? c2[1] + c3[1] : c2[2] + c3[2]);
+            const float vwc = c == 0 ? vw[0] : (c == 1 ? vw[1] : vw[2]);
+            S.w.k.jV[j + 1][c] = Vp[c] + vwc;
+            S.w.k.jV[j + 1][3 + c] = Vp[3 + c] + slc * qd;
+            S.w.k.jA[j + 1][c] = Ap[c] + c1c;
+            S.w.k.jA[j + 1][3 + c] = Ap[3 + c] + c23;
           }
         }
       MB_END
@@ -510,9 +497,11 @@ template <class M> struct Sim {
       MB_LANES(l)
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          if (l + 32 * r < npairs) {
-            const int t = (C.pairs[l] >> (8 * r)) & 15, s2 = (C.pairs[l] >> (8 * r + 4)) & 15;
-            S.L[M::facoff(k, t) + s2] -= S.L[offk + t] * S.L[offk + s2];
+          if (32 * r < npairs) {  // uniform: whole rounds are skipped for short rows
+            if (l + 32 * r < npairs) {
+              const int t = (C.pairs[l] >> (8 * r)) & 15, s2 = (C.pairs[l] >> (8 * r + 4)) & 15;
+              S.L[M::facoff(k, t) + s2] -= S.L[offk + t] * S.L[offk + s2];
+            }
           }
         }
       MB_END
