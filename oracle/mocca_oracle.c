@@ -590,6 +590,86 @@ static void point_world(const orc_model* m, const orc_cache* c, int g, int e, v3
 
 /* Candidate points: sphere centres and both capsule end spheres.  Contacts are listed obstacle-major:
  * the ground plane for every point, then box 0 for every point, ... (the CUDA kernel uses the same order). */
+/* sphere (centre cw, radius r) vs bar-as-capsule */
+static int sphere_bar(const v3 cw, double r, const orc_bar* b, double thresh, v3 pa, v3 n, double* dist) {
+  v3 d = {cw[0] - b->center[0], cw[1] - b->center[1], cw[2] - b->center[2]};
+  double t = v3dot(d, b->axis);
+  if (t > b->halflen) t = b->halflen;
+  if (t < -b->halflen) t = -b->halflen;
+  v3 q = {b->center[0] + t * b->axis[0], b->center[1] + t * b->axis[1], b->center[2] + t * b->axis[2]};
+  v3 df = {cw[0] - q[0], cw[1] - q[1], cw[2] - q[2]};
+  double len = v3norm(df);
+  *dist = len - r - b->radius;
+  if (*dist >= thresh || len < 1e-12) return 0;
+  for (int k = 0; k < 3; k++) { n[k] = df[k] / len; pa[k] = cw[k] - r * n[k]; }
+  return 1;
+}
+
+/* robot box geom vs bar.  Bullet runs GJK/EPA (one point per frame); restated as the deepest of 5 spheres of the
+ * bar's radius sampled 3 cm apart along its axis around the point nearest to the box centre (documented
+ * approximation). */
+static int box_bar(const orc_box* bx, const orc_bar* b, double thresh, v3 pa, v3 n, double* dist) {
+  v3 d = {bx->center[0] - b->center[0], bx->center[1] - b->center[1], bx->center[2] - b->center[2]};
+  double t0 = v3dot(d, b->axis);
+  int found = 0;
+  double best = 1e30;
+  for (int k = -2; k <= 2; k++) {
+    double t = t0 + 0.03 * k;
+    if (t > b->halflen) t = b->halflen;
+    if (t < -b->halflen) t = -b->halflen;
+    v3 q = {b->center[0] + t * b->axis[0], b->center[1] + t * b->axis[1], b->center[2] + t * b->axis[2]};
+    v3 ps, ns;
+    double ds;
+    if (sphere_box(q, b->radius, bx, thresh, ps, ns, &ds) && ds < best) {
+      best = ds;
+      found = 1;
+      for (int i = 0; i < 3; i++) { n[i] = -ns[i]; pa[i] = ps[i] - ds * ns[i]; }
+    }
+  }
+  *dist = best;
+  return found;
+}
+
+static int collide_bars(const orc_model* m, const orc_params* p, const orc_cache* c, const orc_bar* bars, int n_bars,
+                        orc_contacts* out) {
+  for (int ob = 0; ob < n_bars; ob++) {
+    for (int g = 0; g < m->n_geoms; g++) {
+      int link = m->geom_link[g];
+      double thresh = m->link_thresh[link + 1];
+      if (m->geom_type[g] == ORC_GEOM_BOX) continue;
+      int nends = m->geom_type[g] == ORC_GEOM_CAPSULE ? 2 : 1;
+      for (int e = 0; e < nends; e++) {
+        v3 cw, pa, n;
+        double dist;
+        point_world(m, c, g, e, cw);
+        if (sphere_bar(cw, m->geom_size[g][0], &bars[ob], thresh, pa, n, &dist))
+          add_point(out, 2 * g + e, link, bars[ob].id, pa, n, dist, m->geom_friction[g] * bars[ob].friction,
+                    p->erp_contact, 0.0);
+      }
+    }
+    for (int g = 0; g < m->n_geoms; g++) {
+      if (m->geom_type[g] != ORC_GEOM_BOX) continue;
+      int link = m->geom_link[g];
+      orc_box bx;
+      v3 t;
+      m3 Rg, Rl;
+      m3Tvec(c->Rw[link + 1], m->geom_p0[g], t);
+      for (int k = 0; k < 3; k++) bx.center[k] = c->pw[link + 1][k] + t[k];
+      quat_to_mat(m->geom_quat[g], Rg);
+      for (int a = 0; a < 3; a++)
+        for (int b2 = 0; b2 < 3; b2++) Rl[a][b2] = c->Rw[link + 1][b2][a]; /* link -> world */
+      m3mul(Rl, Rg, bx.R);
+      for (int k = 0; k < 3; k++) bx.half[k] = m->geom_size[g][k];
+      v3 pa, n;
+      double dist;
+      if (box_bar(&bx, &bars[ob], m->link_thresh[link + 1], pa, n, &dist))
+        add_point(out, 2 * g, link, bars[ob].id, pa, n, dist, m->geom_friction[g] * bars[ob].friction,
+                  p->erp_contact, 0.0);
+    }
+  }
+  return out->n;
+}
+
 int orc_collide_cached(const orc_model* m, const orc_params* p, const orc_cache* c, const orc_box* boxes,
                        int n_boxes, orc_contacts* out) {
   out->n = 0;
@@ -804,8 +884,18 @@ static void integrate_positions(const orc_model* m, const orc_params* p, orc_sta
   for (int d = 0; d < m->n_dof; d++) s->q[d] += dt * s->qd[d];
 }
 
+static void substep_impl(const orc_model* m, const orc_params* p, orc_state* s, const double* tau,
+                         const orc_box* boxes, int n_boxes, const orc_bar* bars, int n_bars, double* warm,
+                         orc_contacts* ct, int* out_rows);
+
 void orc_substep(const orc_model* m, const orc_params* p, orc_state* s, const double* tau, const orc_box* boxes,
                  int n_boxes, double* warm, orc_contacts* ct, int* out_rows) {
+  substep_impl(m, p, s, tau, boxes, n_boxes, NULL, 0, warm, ct, out_rows);
+}
+
+static void substep_impl(const orc_model* m, const orc_params* p, orc_state* s, const double* tau,
+                         const orc_box* boxes, int n_boxes, const orc_bar* bars, int n_bars, double* warm,
+                         orc_contacts* ct, int* out_rows) {
   int nu = 6 + m->n_dof;
   orc_cache* c = (orc_cache*)malloc(sizeof(orc_cache));
   orc_rows* rows = (orc_rows*)malloc(sizeof(orc_rows));
@@ -813,6 +903,7 @@ void orc_substep(const orc_model* m, const orc_params* p, orc_state* s, const do
   /* collision detection at start-of-substep poses */
   kin(m, s, c);
   orc_collide_cached(m, p, c, boxes, n_boxes, ct);
+  if (n_bars > 0) collide_bars(m, p, c, bars, n_bars, ct);
   /* forward dynamics, velocity update */
   aba(m, p, s, tau, 1, c, acc);
   pack_u(m, s, u);
@@ -909,6 +1000,19 @@ void orc_step_physics(const orc_model* m, const orc_params* p, orc_state* s, con
   }
   if (rows_sum) *rows_sum = total;
   if (!last) free(ct);
+}
+
+void orc_step_physics_bars(const orc_model* m, const orc_params* p, orc_state* s, const double* tau_applied,
+                           const orc_bar* bars, int n_bars, orc_contacts* last, int* rows_sum) {
+  double tau[ORC_MAXD];
+  for (int d = 0; d < m->n_dof; d++) tau[d] = tau_applied[d] - m->damping[d] * s->qd[d];
+  int total = 0;
+  for (int k = 0; k < p->substeps; k++) {
+    int r = 0;
+    substep_impl(m, p, s, tau, NULL, 0, bars, n_bars, NULL, last, &r);
+    total += r;
+  }
+  if (rows_sum) *rows_sum = total;
 }
 
 /* ------------------------------------------------------------------ 8. MT19937 */
@@ -1044,7 +1148,11 @@ static void w3d_calc_state(const orc_model* m, orc_w3d_env* e, const orc_contact
 }
 
 /* robots.py:179-210 */
+static void robot_reset_ex(const orc_model* m, orc_w3d_env* e, const double* pos, const double* vel, int random_pose);
 static void w3d_robot_reset(const orc_model* m, orc_w3d_env* e, const double* pos) {
+  robot_reset_ex(m, e, pos, NULL, 1);
+}
+static void robot_reset_ex(const orc_model* m, orc_w3d_env* e, const double* pos, const double* vel, int random_pose) {
   int A = m->n_dof;
   double ang[ORC_MAXD];
   for (int d = 0; d < A; d++) ang[d] = m->base_joint_angles[d];
@@ -1062,17 +1170,19 @@ static void w3d_robot_reset(const orc_model* m, orc_w3d_env* e, const double* po
     e->mirrored = 0;
   }
   /* random_pose=True: +-0.1 rad noise, clipped to +-0.95 of the normalised range (robots.py:190-194) */
-  double ds[ORC_MAXD];
-  for (int d = 0; d < A; d++) ds[d] = orc_rng_uniform(rr, -0.1, 0.1);
-  for (int d = 0; d < A; d++) {
-    double bias = (double)(float)m->lower[d], weight = (double)(float)(m->upper[d] - m->lower[d]);
-    double ps = 2 * (ang[d] + ds[d] - bias) / weight - 1;
-    if (ps > 0.95) ps = 0.95;
-    if (ps < -0.95) ps = -0.95;
-    e->s.q[d] = weight * (ps + 1) / 2 + bias;
-    e->s.qd[d] = 0;
+  if (random_pose) {
+    double ds[ORC_MAXD];
+    for (int d = 0; d < A; d++) ds[d] = orc_rng_uniform(rr, -0.1, 0.1);
+    for (int d = 0; d < A; d++) {
+      double bias = (double)(float)m->lower[d], weight = (double)(float)(m->upper[d] - m->lower[d]);
+      double ps = 2 * (ang[d] + ds[d] - bias) / weight - 1;
+      if (ps > 0.95) ps = 0.95;
+      if (ps < -0.95) ps = -0.95;
+      ang[d] = weight * (ps + 1) / 2 + bias;
+    }
   }
-  for (int k = 0; k < 3; k++) { e->s.pos[k] = pos[k]; e->s.omega[k] = 0; e->s.vel[k] = 0; }
+  for (int d = 0; d < A; d++) { e->s.q[d] = ang[d]; e->s.qd[d] = 0; }
+  for (int k = 0; k < 3; k++) { e->s.pos[k] = pos[k]; e->s.omega[k] = 0; e->s.vel[k] = vel ? vel[k] : 0; }
   e->s.quat[0] = e->s.quat[1] = e->s.quat[2] = 0; e->s.quat[3] = 1;
   for (int f = 0; f < 4; f++) { e->feet_contact[f] = 0; v3set(e->feet_xyz[f], 0, 0, 0); }
   for (int i = 0; i < ORC_MAXP; i++) e->warm[i] = 0;

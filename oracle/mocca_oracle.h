@@ -55,6 +55,7 @@ typedef struct {
   double base_position[3];
   int n_right, right_idx[ORC_MAXD], left_idx[ORC_MAXD]; /* mirroring tables robots.py:282-290 */
   int n_neg, neg_idx[8];
+  int palm_link[2]; /* Monkey3D: right_palm, left_palm (env_locomotion.py:1269,1424); -1 otherwise */
 } orc_model;
 
 typedef struct {
@@ -111,6 +112,14 @@ typedef struct {
   int id;                    /* partner code reported in orc_contacts */
 } orc_box;
 
+/* static thin cylinder (MonkeyBar, bullet_objects.py:148-187), treated as a capsule around its axis segment */
+typedef struct {
+  double center[3];
+  double axis[3]; /* unit */
+  double halflen, radius, friction;
+  int id;
+} orc_bar;
+
 typedef struct {
   uint32_t mt[624];
   int pos;
@@ -126,6 +135,8 @@ void orc_mass_matrix(const orc_model* m, const orc_state* s, double* M /* [(6+n)
 void orc_minv_mult(const orc_model* m, const orc_params* p, const orc_state* s, const double* f, double* out);
 int orc_collide(const orc_model* m, const orc_params* p, const orc_state* s, const orc_box* boxes, int n_boxes,
                 orc_contacts* c);
+void orc_step_physics_bars(const orc_model* m, const orc_params* p, orc_state* s, const double* tau_applied,
+                           const orc_bar* bars, int n_bars, orc_contacts* last_contacts, int* rows_sum);
 void orc_substep(const orc_model* m, const orc_params* p, orc_state* s, const double* tau, const orc_box* boxes,
                  int n_boxes, double* warm /* [ORC_MAXP] */, orc_contacts* out_contacts, int* out_rows);
 void orc_step_physics(const orc_model* m, const orc_params* p, orc_state* s, const double* tau_applied,
@@ -194,6 +205,25 @@ void orc_stepper_step(const orc_model* m, const orc_params* p, orc_stepper_env* 
                       double* obs, double* reward, int* done, int* truncated);
 void orc_stepper_step_batch(const orc_model* m, const orc_params* p, orc_stepper_env* envs, int n,
                             const double* actions, double* obs, double* rewards, int* dones, int n_threads);
+/* ---- Monkey3DCustomEnv (env_locomotion.py:1136-1516) ---- */
+#define ORC_NBARS 32
+typedef struct {
+  orc_w3d_env base;
+  double terrain[ORC_NBARS][4]; /* x y z phi */
+  orc_bar bars[4];
+  int bar_index[4];
+  int next_step_index, target_reached_count, free_fall_count, timestep, swing_leg, pivot_leg, target_reached;
+  double foot_dist_to_target, swing_potential;
+  double targets[2][3];
+  double palm_xyz[2][3], palm_quat[2][4];
+  double step_bonus;
+} orc_monkey_env;
+
+void orc_monkey_seed(orc_monkey_env* e, const uint32_t* key, int len, int at_construction);
+void orc_monkey_reset(const orc_model* m, const orc_params* p, orc_monkey_env* e, double* obs /* [69] */);
+void orc_monkey_step(const orc_model* m, const orc_params* p, orc_monkey_env* e, const double* action, double* obs,
+                     double* reward, int* done, int* truncated);
+int orc_sizeof_monkey_env(void);
 int orc_sizeof_stepper_env(void);
 int orc_sizeof_w3d_env(void);
 int orc_sizeof_model(void);

@@ -38,6 +38,7 @@ class Model(C.Structure):
         ("base_joint_angles", d * MAXD), ("base_position", d * 3),
         ("n_right", i32), ("right_idx", i32 * MAXD), ("left_idx", i32 * MAXD),
         ("n_neg", i32), ("neg_idx", i32 * 8),
+        ("palm_link", i32 * 2),
     ]
 
 
@@ -176,6 +177,8 @@ def model_from_table(t: dict) -> Model:
     _fill(m.left_idx, np.array(t["left_joint_indices"], dtype=np.int64))
     m.n_neg = len(t["negation_joint_indices"])
     _fill(m.neg_idx, np.array(t["negation_joint_indices"], dtype=np.int64))
+    palms = t.get("palm_links", [-1, -1])
+    m.palm_link[0], m.palm_link[1] = int(palms[0]), int(palms[1])
     return m
 
 
