@@ -33,32 +33,89 @@ def bytes_per_env_step(S_state=55, A=21, O=52, S_env=12):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): an in-process NVML
+    poll every 10 ms (so that even a sub-second timed region is covered), nvidia-smi -lms as the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self.proc = None
         self.gpu = gpu_index
+        self.uuid = uuid
+        self.nvml = None
+        self.handle = None
+        self.stop_flag = False
+        self.source = None
 
     def start(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid if isinstance(self.uuid, bytes) else self.uuid.encode())
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml, self.handle = pynvml, h
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            self.source = "nvml poll 10 ms"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 20"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def sample(self):
+        if self.nvml is None:
+            return
+        n, h = self.nvml, self.handle
+        try:
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+            try:
+                r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for bit, nm in self.BITS.items():
+                if r & bit:
+                    self.reasons.add(nm)
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self.stop_flag:
+            self.sample()
+            time.sleep(0.01)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=2)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": self.source}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -82,10 +139,10 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
-def cpu_reference_run(n_envs, steps, warmup, threads, time_budget=None):
+def cpu_reference_run(n_envs, steps, warmup, threads, time_budget=None, kind="custom"):
     """The reference-side CPU implementation of the path: the float64 oracle port (oracle/mocca_oracle.c; the
     reference's own arithmetic is the un-installable third-party pybullet), OpenMP over envs."""
     import ctypes as C
@@ -95,18 +152,23 @@ def cpu_reference_run(n_envs, steps, warmup, threads, time_budget=None):
     from mocca_envs_b200.model_compiler import load_table
     from oracle import oracle as O
 
-    t = load_table(os.path.join(ROOT, "mocca_envs_b200", "models", "walker3d.json"))
+    model, struct, pre, A, OB = {"custom": ("walker3d", O.W3DEnv, "orc_w3d", 21, 52),
+                                 "stepper": ("walker3d", O.StepperEnv, "orc_stepper", 21, 65),
+                                 "monkey": ("monkey3d", O.MonkeyEnv, "orc_monkey", 23, 69)}[kind]
+    t = load_table(os.path.join(ROOT, "mocca_envs_b200", "models", model + ".json"))
     m = O.model_from_table(t)
     p = O.default_params()
     L = O.lib()
-    envs = (O.W3DEnv * n_envs)()
-    A, OB = 21, 52
+    envs = (struct * n_envs)()
     obs = np.zeros((n_envs, OB))
+    seed_fn, reset_fn, batch_fn = (getattr(L, pre + sfx) for sfx in ("_seed", "_reset", "_step_batch"))
     for i in range(n_envs):
         words = O.gym_seed_words(1000 + i)
         key = (C.c_uint32 * len(words))(*words)
-        L.orc_w3d_seed(C.byref(envs[i]), key, len(words), 1)
-        L.orc_w3d_reset(C.byref(m), C.byref(p), C.byref(envs[i]), obs[i].ctypes.data_as(C.c_void_p))
+        if kind == "stepper":
+            envs[i].curriculum = (0, 5, 9)[i % 3]
+        seed_fn(C.byref(envs[i]), key, len(words), 1)
+        reset_fn(C.byref(m), C.byref(p), C.byref(envs[i]), obs[i].ctypes.data_as(C.c_void_p))
     rew = np.zeros(n_envs)
     done = np.zeros(n_envs, dtype=np.int32)
     rng = np.random.RandomState(1)
@@ -114,7 +176,7 @@ def cpu_reference_run(n_envs, steps, warmup, threads, time_budget=None):
 
     def one():
         a = rng.uniform(-1, 1, (n_envs, A))
-        L.orc_w3d_step_batch(C.byref(m), C.byref(p), envs, n_envs, vp(a), vp(obs), vp(rew), vp(done), threads)
+        batch_fn(C.byref(m), C.byref(p), envs, n_envs, vp(a), vp(obs), vp(rew), vp(done), threads)
 
     for _ in range(warmup):
         one()
@@ -132,12 +194,13 @@ def cpu_reference_run(n_envs, steps, warmup, threads, time_budget=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--envs", type=int, default=16384, help="envs per GPU")
     ap.add_argument("--actions", default="random", choices=["random", "pd"])
-    ap.add_argument("--env", default="custom", choices=["custom", "stepper"],
-                    help="custom = BASELINE configs[1] (headline); stepper = configs[2] (curriculum 0/5/9 per env)")
+    ap.add_argument("--env", default="custom", choices=["custom", "stepper", "monkey"],
+                    help="custom = BASELINE configs[1] (headline); stepper = configs[2] (curriculum 0/5/9 per env); "
+                         "monkey = configs[4] (Monkey3DCustomEnv-v0)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -149,10 +212,15 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sample_envs = 2048
-        v, dt, ks = cpu_reference_run(sample_envs, args.steps, max(args.warmup, 1), cores)
+        # size the per-step sample so that K steps take about a minute on this box's cores
+        v0, _, _ = cpu_reference_run(256, 8, 1, cores, kind=args.env)
+        sample_envs = int(min(4096, max(64, v0 * 60.0 / max(args.steps, 1))))
+        v, dt, ks = cpu_reference_run(sample_envs, args.steps, min(max(args.warmup, 1), 10), cores, kind=args.env)
         line = {
-            "impl": "reference", "metric": METRIC, "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "impl": "reference",
+            "metric": METRIC.replace("Walker3DCustomEnv", {"custom": "Walker3DCustomEnv", "stepper": "Walker3DStepperEnv",
+                                                           "monkey": "Monkey3DCustomEnv"}[args.env]),
+            "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": ks, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(ks, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs, "actions": "random-uniform U(-1,1)^21"},
@@ -169,7 +237,7 @@ def main():
 
     from mocca_envs_b200 import _lib
     from mocca_envs_b200.distributed import shard_seed
-    from mocca_envs_b200.vec_env import Walker3DCustomVecEnv, Walker3DStepperVecEnv
+    from mocca_envs_b200.vec_env import Monkey3DCustomVecEnv, Walker3DCustomVecEnv, Walker3DStepperVecEnv
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
@@ -186,6 +254,8 @@ def main():
     if args.env == "stepper":
         env = Walker3DStepperVecEnv(N, device=dev, seed=shard_seed(1234, rank, N))
         env.set_env_params({"curriculum": np.array([0, 5, 9] * (N // 3 + 1))[:N]})
+    elif args.env == "monkey":
+        env = Monkey3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N))
     else:
         env = Walker3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N))
     env.reset()
@@ -213,14 +283,21 @@ def main():
     rows0 = float(rec0[:, 15].double().sum())
     cont0 = float(rec0[:, 16].double().sum())
     env.stats(reset=True)
-    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
-    if rank == 0:
-        sampler.start()
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        uuid = None
+    try:
+        gpu_index = int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])
+    except Exception:
+        gpu_index = local_rank
+    sampler = ClockSampler(gpu_index, uuid)
     launches0 = env.launch_count()
     if dist:
         dist.barrier()
     torch.cuda.synchronize(dev)
+    if rank == 0:
+        sampler.start()  # polls from here to the closing synchronize: the timed region only
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     wall0 = time.perf_counter()
     for i in range(K):
@@ -229,6 +306,8 @@ def main():
         evs[i][0].record()
         obs, rew, done, info = env.step(a)
         evs[i][1].record()
+    if rank == 0:
+        sampler.sample()  # the GPU is still draining the queued steps here
     if dist:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -287,7 +366,15 @@ def main():
     ms_per_step = total_ms_max / K
     value = N * world * K / (total_ms_max * 1e-3)
     R_mean = rows_all / (K * N * world * env.physics.substeps)
-    F = flops_per_env_step(R_mean)
+    if args.env == "monkey":  # Monkey3D: n = 29 generalised coordinates, 20 massive links, 29 geoms, obs 69
+        F = flops_per_env_step(R_mean, n=29, L=20, G=29)
+        B_step = bytes_per_env_step(S_state=59, A=23, O=69, S_env=40)
+    elif args.env == "stepper":
+        F = flops_per_env_step(R_mean)
+        B_step = bytes_per_env_step(O=65, S_env=40)
+    else:
+        F = flops_per_env_step(R_mean)
+        B_step = bytes_per_env_step()
     kernel_s = (total_ms / K) * 1e-3  # this rank's average launch duration (one kernel per step)
     achieved_tf = F * N / kernel_s / 1e12
     peak = C_peak(_lib, local_rank)
@@ -298,15 +385,18 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_ach = bytes_per_env_step() * N / kernel_s / 1e9
+    hbm_ach = B_step * N / kernel_s / 1e9
     line = {
-        "metric": METRIC if args.env == "custom" else METRIC.replace("Walker3DCustomEnv", "Walker3DStepperEnv"),
+        "metric": METRIC.replace("Walker3DCustomEnv", {"custom": "Walker3DCustomEnv", "stepper": "Walker3DStepperEnv",
+                                                       "monkey": "Monkey3DCustomEnv"}[args.env]),
         "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD if args.env == "custom" else
-                   "Walker3DStepperEnv-v0 batched 16384 envs/GPU, seeded stepping stones, curriculum 0/5/9",
-                   "envs_per_gpu": N, "actions": "random-uniform U(-1,1)^21 (device pool)"
+        "config": {"workload": {"custom": WORKLOAD,
+                                "stepper": "Walker3DStepperEnv-v0 batched 16384 envs/GPU, seeded stepping stones, "
+                                           "curriculum 0/5/9",
+                                "monkey": "Monkey3DCustomEnv-v0 batched, seeded monkey bars"}[args.env],
+                   "envs_per_gpu": N, "actions": "random-uniform U(-1,1)^%d (device pool)" % A
                    if args.actions == "random" else "scripted PD toward running_start (kp=1, kd=0.1, normalised)",
                    "frame_skip": 4, "solver_iterations": 5, "rng": "mt19937 (NumPy-compatible)",
                    "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs)",
@@ -318,7 +408,7 @@ def main():
                      "flops_per_env_step": F, "rows_per_substep": R_mean,
                      "contacts_per_substep": conts_all / (K * N * world * env.physics.substeps),
                      "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                             "bytes_per_env_step": bytes_per_env_step(),
+                             "bytes_per_env_step": B_step,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "api": "mb200_step_host (pinned host buffers, stream-synchronised)"},
@@ -330,9 +420,9 @@ def main():
         "wall_s": wall,
     }
     if not args.no_cpu_baseline:
-        v, dt, ks = cpu_reference_run(1024, 1000, 2, cores, time_budget=12.0)
+        v, dt, ks = cpu_reference_run(2048, 2000, 2, cores, time_budget=15.0, kind=args.env)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                "sample": "1024 envs x %d control steps (%.1f s), same action distribution; float64 "
+                                "sample": "2048 envs x %d control steps (%.1f s), same action distribution; float64 "
                                           "oracle port with OpenMP over envs (PyBullet not installable here)" % (ks, dt)}
     print(json.dumps(line))
     if dist:

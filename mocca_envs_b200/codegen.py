@@ -18,7 +18,7 @@ import os
 
 import numpy as np
 
-from .model_compiler import JOINT_REVOLUTE, GEOM_SPHERE, GEOM_CAPSULE, load_table, quat_to_mat
+from .model_compiler import JOINT_REVOLUTE, GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX, load_table, quat_to_mat
 
 
 def reduce_table(t: dict) -> dict:
@@ -89,8 +89,20 @@ def reduce_table(t: dict) -> dict:
 
     thresh = [t["base"]["contact_threshold"]] + t["contact_threshold"]
     foot_links = t["foot_links"]
+    palm_links = t.get("palm_links", [])
     points = []
+    xboxes = []  # robot box geoms (Monkey3D fingers / hands): collide with the monkey bars only
     for gi, g in enumerate(t["geoms"]):
+        if g["type"] == GEOM_BOX:
+            link = g["link"]
+            oj = owner_joint(link) if link >= 0 else -1
+            Ro, oo = frame(oj)
+            cw = pl[link + 1] + Rl[link + 1] @ np.array(g["pos"])
+            Rg = Rl[link + 1] @ quat_to_mat(g["quat"])
+            xboxes.append(dict(geom=gi, link=link, owner=oj, pos=Ro.T @ (cw - oo), rot=(Ro.T @ Rg).reshape(9),
+                               half=g["size"], friction=g["friction"], thresh=thresh[link + 1],
+                               foot=foot_links.index(link) if link in foot_links else -1))
+            continue
         if g["type"] not in (GEOM_SPHERE, GEOM_CAPSULE):
             continue
         link = g["link"]
@@ -101,7 +113,8 @@ def reduce_table(t: dict) -> dict:
             pw = pl[link + 1] + Rl[link + 1] @ np.array(pe)
             points.append(dict(geom=gi, end=e, link=link, owner=oj, pos=Ro.T @ (pw - oo), radius=g["size"][0],
                                friction=g["friction"], thresh=thresh[link + 1],
-                               foot=foot_links.index(link) if link in foot_links else -1))
+                               foot=foot_links.index(link) if link in foot_links else
+                               (2 + palm_links.index(link) if link in palm_links else -1)))
     foot_body = [[b["link"] for b in bodies].index(f) for f in foot_links]
     # ancestor chains (root -> self) packed 5 bits per entry, and the compact (chain-ordered) factor layout:
     # row i of L stores only its support [base block | ancestors root->parent | diagonal]
@@ -117,7 +130,9 @@ def reduce_table(t: dict) -> dict:
     rowlen = [i + 1 for i in range(6)] + [6 + jdepth[j] + 1 for j in range(nj)]
     rowoff = [sum(rowlen[:i]) for i in range(6 + nj)]
     rowmask_rt = [(1 << i) - 1 for i in range(6)] + [0x3F | ((janc[j] & ~(1 << j)) << 6) for j in range(nj)]
+    palm_body = [[b["link"] for b in bodies].index(f) for f in palm_links]
     return dict(name=t["name"], nj=nj, nb=nb, nu=6 + nj, npt=len(points), nlevel=max(jlevel) + 1,
+                xboxes=xboxes, palm_body=palm_body,
                 jparent=jparent, joff=joff, jrot=jrot, jaxis=jaxis, jlevel=jlevel, janc=janc,
                 lower=t["lower"], upper=t["upper"], gain=t["gain"], damping=t["damping"], armature=t["armature"],
                 bodies=bodies, bstart=bstart, bend=bend, points=points, foot_body=foot_body,
@@ -222,6 +237,16 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append(_farr(P + "_pfriction", [p["friction"] for p in r["points"]]))
     out.append(_farr(P + "_pthresh", [p["thresh"] for p in r["points"]]))
     out.append(_iarr(P + "_foot_body", r["foot_body"]))
+    out.append(_iarr(P + "_palm_body", r["palm_body"] or [-1]))
+    xb = r["xboxes"] or [dict(owner=-1, foot=-1, pos=[0, 0, 0], rot=np.eye(3).reshape(9), half=[0, 0, 0], friction=0,
+                              thresh=0)]
+    out.append(_iarr(P + "_xowner", [b["owner"] for b in xb]))
+    out.append(_iarr(P + "_xfoot", [b["foot"] for b in xb]))
+    out.append(_farr(P + "_xpos", [b["pos"] for b in xb]))
+    out.append(_farr(P + "_xrot", [b["rot"] for b in xb]))
+    out.append(_farr(P + "_xhalf", [b["half"] for b in xb]))
+    out.append(_farr(P + "_xfriction", [b["friction"] for b in xb]))
+    out.append(_farr(P + "_xthresh", [b["thresh"] for b in xb]))
     out.append(_darr(P + "_base_angles", r["base_joint_angles"]))
     out.append(_iarr(P + "_right", r["right"]))
     out.append(_iarr(P + "_left", r["left"]))
@@ -238,9 +263,9 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append("  MB_HD static constexpr unsigned rowmask_c(int i) {\n    return " +
                " ".join("i == %d ? %du :" % (i, m) for i, m in enumerate(rowmask)) + " 0u;\n  }\n")
     out.append("  enum { NJ = %d, NB = %d, NU = %d, NPT = %d, NLEVEL = %d, NFEET = %d, NMIRROR = %d, NNEG = %d,\n"
-               "         LSIZE = %d, MAXSUP = %d };\n"
+               "         LSIZE = %d, MAXSUP = %d, NXBOX = %d };\n"
                % (r["nj"], r["nb"], r["nu"], r["npt"], r["nlevel"], r["nfeet"], len(r["right"]), len(r["neg"]),
-                  r["lsize"], r["maxsup"]))
+                  r["lsize"], r["maxsup"], len(r["xboxes"])))
     out.append("  MB_HD static unsigned long long chainpack(int j) { return %s_chainpack[j]; }\n" % P)
     out.append("  MB_HD static int facoff(int k, int t) { return %s_facoff[k][t]; }\n" % P)
     out.append("  MB_HD static int lvjoint(int lev, int slot) { return %s_lvjoint[lev][slot]; }\n" % P)
@@ -251,13 +276,14 @@ def emit_header(t: dict, prefix: str) -> str:
                        ("jdepth", "int"), ("rowoff", "int"), ("rowlen", "int"), ("rowmask", "unsigned"),
                        ("jaxk", "int"), ("jident", "int"),
                        ("bowner", "int"), ("powner", "int"), ("pfoot", "int"), ("pid", "int"), ("foot_body", "int"),
+                       ("palm_body", "int"), ("xowner", "int"), ("xfoot", "int"),
                        ("right", "int"), ("left", "int"), ("neg", "int")]:
         out.append("  MB_HD static %s %s(int i) { return %s_%s[i]; }\n" % (ctype, fld, P, fld))
     out.append("  MB_HD static double base_angles(int i) { return %s_base_angles[i]; }\n" % P)
     for fld in ["lower", "upper", "weight", "gain", "damping", "armature", "bmass", "pradius", "pfriction", "pthresh",
-                "jsgn"]:
+                "jsgn", "xfriction", "xthresh"]:
         out.append("  MB_HD static float %s(int i) { return %s_%s[i]; }\n" % (fld, P, fld))
-    for fld in ["joff", "jrot", "jaxis", "bcom", "binertia", "ppos"]:
+    for fld in ["joff", "jrot", "jaxis", "bcom", "binertia", "ppos", "xpos", "xrot", "xhalf"]:
         out.append("  MB_HD static float %s(int i, int k) { return %s_%s[i][k]; }\n" % (fld, P, fld))
     out.append("  MB_HD static float base_x() { return %s; }\n" % _f(r["base_position"][0]))
     out.append("  MB_HD static float base_y() { return %s; }\n" % _f(r["base_position"][1]))
@@ -270,7 +296,7 @@ def emit_all(repo_root: str):
     gen = os.path.join(repo_root, "mocca_envs_b200", "csrc", "generated")
     os.makedirs(gen, exist_ok=True)
     models = os.path.join(repo_root, "mocca_envs_b200", "models")
-    for name, prefix in (("walker3d", "W3D"),):
+    for name, prefix in (("walker3d", "W3D"), ("monkey3d", "MK3D")):
         t = load_table(os.path.join(models, name + ".json"))
         with open(os.path.join(gen, name + "_model.h"), "w") as f:
             f.write(emit_header(t, prefix))

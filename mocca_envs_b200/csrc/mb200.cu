@@ -21,6 +21,7 @@
 
 #include "../../include/mocca_b200.h"
 #include "generated/walker3d_model.h"
+#include "generated/monkey3d_model.h"
 #include "mb_env.cuh"
 
 
@@ -32,7 +33,7 @@ static int fail(const std::string& m) { g_err = m; return -1; }
     if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_));                 \
   } while (0)
 
-enum { KIND_CUSTOM = 0, KIND_STEPPER = 1 };
+enum { KIND_CUSTOM = 0, KIND_STEPPER = 1, KIND_MONKEY = 2 };
 
 struct mb200_env {
   int kind;        // KIND_*
@@ -61,8 +62,10 @@ struct mb200_env {
 };
 
 typedef W3D_Model WM;
+typedef MK3D_Model MM;
 typedef W3DEnv<WM> WEnv;
 typedef StepperEnv<WM> SEnv;
+typedef MonkeyEnv<MM> MEnv;
 typedef WarpMem<WM> WMem;
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -91,13 +94,13 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * MB_WARPS + warp;  // < n_pad by construction of the grid
   const bool tail = env >= a.n;
-  WMem& S = reinterpret_cast<WMem*>(smem_raw)[warp];
+  typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
   float* obs = tail ? a.dummy_obs + (size_t)warp * Env::OBS : a.obs + (size_t)env * Env::OBS;
   float* fin = tail ? a.dummy_obs + (size_t)(MB_WARPS + warp) * Env::OBS
                     : (a.final_obs ? a.final_obs + (size_t)env * Env::OBS : nullptr);
   Env::step(S, a.phys, a.state + (size_t)env * MB_STATE_STRIDE, a.rec + (size_t)env * Env::REC_STRIDE,
             a.mt + (size_t)env * 2 * MB_MT_STRIDE, a.mt + ((size_t)env * 2 + 1) * MB_MT_STRIDE,
-            a.act + (size_t)(tail ? 0 : env) * WM::NJ, obs, tail ? a.dummy_rew + warp : a.rew + env,
+            a.act + (size_t)(tail ? 0 : env) * Env::NJ, obs, tail ? a.dummy_rew + warp : a.rew + env,
             tail ? a.dummy_flag + warp : a.done + env, tail ? a.dummy_flag + MB_WARPS + warp : a.trunc + env, fin,
             tail ? a.dummy_stats : a.stats);
 }
@@ -106,6 +109,9 @@ __global__ void __launch_bounds__(MB_WARPS * 32, MB_MINBLOCKS) k_step_walker3d_c
 }
 __global__ void __launch_bounds__(MB_WARPS * 32, MB_MINBLOCKS) k_step_walker3d_stepper(StepArgs a) {
   step_body<SEnv>(a);
+}
+__global__ void __launch_bounds__(MB_WARPS * 32, MB_MINBLOCKS) k_step_monkey3d_custom(StepArgs a) {
+  step_body<MEnv>(a);
 }
 
 template <class Env>
@@ -116,11 +122,11 @@ __device__ __forceinline__ void reset_body(int n, const MbPhysics& phys, float* 
   const int env = blockIdx.x * MB_WARPS + warp;
   const bool tail = env >= n;
   if (!tail && mask && !mask[env]) return;  // no CTA barrier inside reset, early exit is fine
-  WMem& S = reinterpret_cast<WMem*>(smem_raw)[warp];
+  typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
   Env::reset(S, phys, rec + (size_t)env * Env::REC_STRIDE, mt + (size_t)env * 2 * MB_MT_STRIDE,
              mt + ((size_t)env * 2 + 1) * MB_MT_STRIDE,
              tail ? dummy_obs + (size_t)warp * Env::OBS : obs + (size_t)env * Env::OBS);
-  WEnv::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
+  Env::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
 }
 __global__ void __launch_bounds__(MB_WARPS * 32)
     k_reset_walker3d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
@@ -132,6 +138,11 @@ __global__ void __launch_bounds__(MB_WARPS * 32)
                              float* obs, float* dummy_obs) {
   reset_body<SEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
 }
+__global__ void __launch_bounds__(MB_WARPS * 32)
+    k_reset_monkey3d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
+                            float* obs, float* dummy_obs) {
+  reset_body<MEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
+}
 
 // stepSimulation only; rec (may be NULL) supplies the static obstacles of the env kind
 template <class Env>
@@ -141,18 +152,20 @@ __device__ __forceinline__ void physics_body(int n, const MbPhysics& phys, float
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * MB_WARPS + warp;
   const bool tail = env >= n;  // pad env: steps with zero torque, outputs discarded
-  WMem& S = reinterpret_cast<WMem*>(smem_raw)[warp];
-  WEnv::load_state(S, state + (size_t)env * MB_STATE_STRIDE);
+  typedef typename Env::Model EM;
+  typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
+  Env::load_state(S, state + (size_t)env * MB_STATE_STRIDE);
   Env::load_obstacles(S, rec + (size_t)env * Env::REC_STRIDE);
   MB_LANES(l)
-    if (l < WM::NJ) S.tau[l] = tail ? 0.0f : tau[(size_t)env * WM::NJ + l];
+    if (l < EM::NJ) S.tau[l] = tail ? 0.0f : tau[(size_t)env * EM::NJ + l];
   MB_END
   int rows = 0, nc = 0, overflow = 0;
-  Sim<WM>::LaneConst C;
-  Sim<WM>::init_lane_const(C);
+  typename Sim<EM>::LaneConst C;
+  Sim<EM>::init_lane_const(C);
 #pragma unroll 1
-  for (int k = 0; k < phys.substeps; ++k) rows += Sim<WM>::substep<Env::HAS_BOXES != 0>(S, phys, C, &nc, &overflow);
-  WEnv::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
+  for (int k = 0; k < phys.substeps; ++k)
+    rows += Sim<EM>::template substep<Env::OBST>(S, phys, C, &nc, &overflow);
+  Env::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
   if (tail) return;
   if ((threadIdx.x & 31) == 0) {
     if (rows_out) rows_out[env] = rows;
@@ -169,36 +182,51 @@ __global__ void __launch_bounds__(MB_WARPS * 32)
                                     int* rows_out, int* contacts_out) {
   physics_body<SEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
 }
+__global__ void __launch_bounds__(MB_WARPS * 32)
+    k_step_physics_monkey3d(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
+                            int* contacts_out) {
+  physics_body<MEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
+}
 
 // mode 0: M (full symmetric, [nu][nu]);  mode 1: tau = M acc - rhs (rhs = -bias with zero applied torque)
-__global__ void __launch_bounds__(MB_WARPS * 32)
-    k_dynamics_debug_walker3d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
+template <class Env>
+__device__ __forceinline__ void dynamics_debug_body(int n, const MbPhysics& phys, const float* state, int mode,
+                                                    const float* acc, float* out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef typename Env::Model EM;
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * MB_WARPS + warp;
   if (env >= n) return;
-  WMem& S = reinterpret_cast<WMem*>(smem_raw)[warp];
-  const int NU = WM::NU;
-  WEnv::load_state(S, state + (size_t)env * MB_STATE_STRIDE);
+  typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
+  const int NU = EM::NU;
+  Env::load_state(S, state + (size_t)env * MB_STATE_STRIDE);
   MB_LANES(l)
     S.tau[l] = 0.0f;
   MB_END
-  Sim<WM>::LaneConst C;
-  Sim<WM>::init_lane_const(C);
-  Sim<WM>::kinematics(S, phys, C, true);
-  Sim<WM>::bodies(S, phys);
-  Sim<WM>::mass_matrix_and_rhs(S);
+  typename Sim<EM>::LaneConst C;
+  Sim<EM>::init_lane_const(C);
+  Sim<EM>::kinematics(S, phys, C, true);
+  Sim<EM>::bodies(S, phys);
+  Sim<EM>::mass_matrix_and_rhs(S);
   MB_LANES(l)
     if (l < NU) {
       if (mode == 0) {
-        for (int j = 0; j < NU; ++j) out[((size_t)env * NU + l) * NU + j] = mb_Lget<WM>(S.L, l, j);
+        for (int j = 0; j < NU; ++j) out[((size_t)env * NU + l) * NU + j] = mb_Lget<EM>(S.L, l, j);
       } else {
         float t = -S.rhs[l];
-        for (int j = 0; j < NU; ++j) t += mb_Lget<WM>(S.L, l, j) * acc[(size_t)env * NU + j];
+        for (int j = 0; j < NU; ++j) t += mb_Lget<EM>(S.L, l, j) * acc[(size_t)env * NU + j];
         out[(size_t)env * NU + l] = t;
       }
     }
   MB_END
+}
+__global__ void __launch_bounds__(MB_WARPS * 32)
+    k_dynamics_debug_walker3d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
+  dynamics_debug_body<WEnv>(n, phys, state, mode, acc, out);
+}
+__global__ void __launch_bounds__(MB_WARPS * 32)
+    k_dynamics_debug_monkey3d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
+  dynamics_debug_body<MEnv>(n, phys, state, mode, acc, out);
 }
 
 __global__ void k_copy_strided(int n, int width, const float* src, int src_stride, float* dst, int dst_stride) {
@@ -250,7 +278,7 @@ static void to_internal(const mb200_physics& p, MbPhysics* q) {
   q->lin_damping = p.lin_damping; q->ang_damping = p.ang_damping; q->max_coord_vel = p.max_coord_vel;
   q->limit_max_impulse = p.limit_max_impulse; q->split_threshold = p.split_threshold;
   q->residual_threshold = p.residual_threshold; q->ground_friction = p.ground_friction; q->has_ground = p.has_ground;
-  q->box_friction = 1.0f; q->box_erp = p.erp_contact; q->box_cfm = 0.0f;
+  q->box_friction = 1.0f; q->box_erp = p.erp_contact; q->box_cfm = 0.0f; q->bar_friction = 0.5f;
 }
 
 static int grid_for(int n) { return (n + MB_WARPS - 1) / MB_WARPS; }
@@ -261,9 +289,10 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   int kind = -1;
   if (env_id && strcmp(env_id, "Walker3DCustomEnv-v0") == 0) kind = KIND_CUSTOM;
   if (env_id && strcmp(env_id, "Walker3DStepperEnv-v0") == 0) kind = KIND_STEPPER;
+  if (env_id && strcmp(env_id, "Monkey3DCustomEnv-v0") == 0) kind = KIND_MONKEY;
   if (kind < 0)
     return fail(std::string("mb200_create: unsupported env id '") + (env_id ? env_id : "(null)") +
-                "' (built: Walker3DCustomEnv-v0, Walker3DStepperEnv-v0)");
+                "' (built: Walker3DCustomEnv-v0, Walker3DStepperEnv-v0, Monkey3DCustomEnv-v0)");
   if (n_envs <= 0) return fail("mb200_create: n_envs must be positive");
   int count = 0;
   CUDA_OK(cudaGetDeviceCount(&count));
@@ -279,11 +308,12 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   e->n = n_envs;
   e->device = device;
   e->kind = kind;
-  e->rec_stride = kind == KIND_STEPPER ? (int)SEnv::REC_STRIDE : (int)WEnv::REC_STRIDE;
-  e->obs_dim = kind == KIND_STEPPER ? (int)SEnv::OBS : (int)WEnv::OBS;
-  e->act_dim = WM::NJ;
-  e->state_dim = 13 + 2 * WM::NJ;
-  e->nu = WM::NU;
+  e->rec_stride = kind == KIND_STEPPER ? (int)SEnv::REC_STRIDE
+                  : kind == KIND_MONKEY ? (int)MEnv::REC_STRIDE : (int)WEnv::REC_STRIDE;
+  e->obs_dim = kind == KIND_STEPPER ? (int)SEnv::OBS : kind == KIND_MONKEY ? (int)MEnv::OBS : (int)WEnv::OBS;
+  e->act_dim = kind == KIND_MONKEY ? (int)MM::NJ : (int)WM::NJ;
+  e->state_dim = 13 + 2 * e->act_dim;
+  e->nu = 6 + e->act_dim;
   mb200_physics p;
   mb200_default_physics(&p);
   if (physics) p = *physics;
@@ -298,7 +328,13 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
     e->phys.box_erp = e->phys.dt * kp / denom;
     e->phys.box_cfm = 1.0f / denom;
   }
-  e->smem = sizeof(WMem) * MB_WARPS;
+  e->smem = (kind == KIND_MONKEY ? sizeof(WarpMem<MM>) : sizeof(WMem)) * MB_WARPS;
+  if (kind == KIND_MONKEY) {
+    CUDA_OK(cudaFuncSetAttribute(k_step_monkey3d_custom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    CUDA_OK(cudaFuncSetAttribute(k_reset_monkey3d_custom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    CUDA_OK(cudaFuncSetAttribute(k_step_physics_monkey3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_monkey3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  } else {
   CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_stepper, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   CUDA_OK(cudaFuncSetAttribute(k_reset_walker3d_stepper, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d_stepper, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -307,6 +343,7 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   CUDA_OK(cudaFuncSetAttribute(k_reset_walker3d_custom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_walker3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  }
   e->n_pad = grid_for(n_envs) * MB_WARPS;
   const size_t n = (size_t)e->n_pad;
   CUDA_OK(cudaMalloc(&e->dummy_obs, (size_t)2 * MB_WARPS * e->obs_dim * sizeof(float)));
@@ -397,7 +434,10 @@ int mb200_seed(mb200_env* e, const uint32_t* mt_host, int at_construction) {
 int mb200_reset(mb200_env* e, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (!e || !obs_dev) return fail("mb200_reset: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
-  if (e->kind == KIND_STEPPER)
+  if (e->kind == KIND_MONKEY)
+    k_reset_monkey3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
+  else if (e->kind == KIND_STEPPER)
     k_reset_walker3d_stepper<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
   else
@@ -416,7 +456,9 @@ int mb200_step(mb200_env* e, const float* act_dev, float* obs_dev, float* rew_de
   a.n = e->n; a.phys = e->phys; a.state = e->state; a.rec = e->rec; a.mt = e->mt; a.act = act_dev; a.obs = obs_dev;
   a.rew = rew_dev; a.done = done_dev; a.trunc = trunc_dev; a.final_obs = final_obs_dev; a.stats = e->stats;
   a.dummy_obs = e->dummy_obs; a.dummy_rew = e->dummy_rew; a.dummy_flag = e->dummy_flag; a.dummy_stats = e->dummy_stats;
-  if (e->kind == KIND_STEPPER)
+  if (e->kind == KIND_MONKEY)
+    k_step_monkey3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
+  else if (e->kind == KIND_STEPPER)
     k_step_walker3d_stepper<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
   else
     k_step_walker3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
@@ -479,7 +521,10 @@ int mb200_set_record(mb200_env* e, const float* rec_dev, void* stream) {
 int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* contacts_dev, void* stream) {
   if (!e || !tau_dev) return fail("mb200_step_physics: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
-  if (e->kind == KIND_STEPPER)
+  if (e->kind == KIND_MONKEY)
+    k_step_physics_monkey3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
+  else if (e->kind == KIND_STEPPER)
     k_step_physics_walker3d_stepper<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
   else
@@ -493,8 +538,12 @@ int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* c
 int mb200_mass_matrix(mb200_env* e, float* M_dev, void* stream) {
   if (!e || !M_dev) return fail("mb200_mass_matrix: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
-  k_dynamics_debug_walker3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
-      e->n, e->phys, e->state, 0, nullptr, M_dev);
+  if (e->kind == KIND_MONKEY)
+    k_dynamics_debug_monkey3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, 0, nullptr, M_dev);
+  else
+    k_dynamics_debug_walker3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, 0, nullptr, M_dev);
   e->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -506,8 +555,12 @@ int mb200_inverse_dynamics(mb200_env* e, const float* acc_dev, float* tau_dev, v
   MbPhysics p = e->phys;
   p.lin_damping = 0.0f;  // calculateInverseDynamics has no velocity-damping term
   p.ang_damping = 0.0f;
-  k_dynamics_debug_walker3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
-      e->n, p, e->state, 1, acc_dev, tau_dev);
+  if (e->kind == KIND_MONKEY)
+    k_dynamics_debug_monkey3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, p, e->state, 1, acc_dev, tau_dev);
+  else
+    k_dynamics_debug_walker3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, p, e->state, 1, acc_dev, tau_dev);
   e->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

@@ -85,6 +85,9 @@ inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #define MB_MAXROW 48  /* constraint rows per substep (limits + 3 per contact) */
 #define MB_YSTRIDE 15 /* compact row: 6 base + <= 8 chain entries (+1 pad, odd stride = conflict-free) */
 #define MB_MAXBOX 6   /* static box obstacles per env (3 planks x {base, cover}) */
+#define MB_MAXBAR 4   /* static bars per env (Monkey3D rendered_step_count, env_locomotion.py:1149) */
+#define MB_OBST_BOXES 1
+#define MB_OBST_BARS 2
 #define MB_PI_F 3.14159265358979323846f
 
 // Physics constants of the reference's Bullet world (citations in include/mocca_b200.h: mb200_physics)
@@ -109,6 +112,7 @@ struct MbPhysics {
   float box_friction;
   float box_erp;
   float box_cfm;
+  float bar_friction;  // MonkeyBar keeps Bullet's default lateral friction (bullet_objects.py:172-179 is commented out)
 };
 
 MB_HD constexpr int tri(int i, int j) { return (i * (i + 1)) / 2 + j; }  // packed lower-triangular index, j <= i
@@ -173,6 +177,9 @@ template <class M> struct WarpMem {
   // ---- static box obstacles of this env: centre[3], axes R[9] (row-major, columns = box axes), half[3], pad
   float box[MB_MAXBOX][16];
   int nbox;
+  // ---- static bars (MonkeyBar, bullet_objects.py:148-187): centre[3], unit axis[3], half length, radius
+  float bar[MB_MAXBAR][8];
+  int nbar;
   // ---- scratch for the epilogue
   float scratch[64];
 };
@@ -583,7 +590,53 @@ template <class M> struct Sim {
     return true;
   }
 
-  template <bool BOXES> MB_HD static int collide(Mem& S, const MbPhysics& P, int* overflow) {
+  // sphere (centre c, radius r) vs bar treated as a capsule around its axis segment; everything relative to the
+  // base COM (bc = bar centre - base position) so that a world far from the origin costs no precision
+  MB_HD static bool sphere_bar(const float* c, float r, const float* bc, const float* bar, float thresh, float* pa,
+                               float* n, float* dist) {
+    const float d[3] = {c[0] - bc[0], c[1] - bc[1], c[2] - bc[2]};
+    float t = d[0] * bar[3] + d[1] * bar[4] + d[2] * bar[5];
+    t = fminf(fmaxf(t, -bar[6]), bar[6]);
+    const float df[3] = {d[0] - t * bar[3], d[1] - t * bar[4], d[2] - t * bar[5]};
+    const float len = sqrtf(df[0] * df[0] + df[1] * df[1] + df[2] * df[2]);
+    *dist = len - r - bar[7];
+    if (*dist >= thresh || len < 1e-12f) return false;
+    const float il = 1.0f / len;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { n[k] = df[k] * il; pa[k] = c[k] - r * n[k]; }
+    return true;
+  }
+
+  // robot box geom (Monkey3D fingers / hands) vs bar.  Bullet runs GJK/EPA (one point per frame); restated as the
+  // deepest of 5 spheres of the bar's radius sampled 3 cm apart along its axis around the point nearest to the box
+  // centre (same restatement as the oracle's box_bar)
+  MB_HD static bool box_bar(const float* bx, const float* bc, const float* bar, float thresh, float* pa, float* n,
+                            float* dist) {
+    const float d[3] = {bx[0] - bc[0], bx[1] - bc[1], bx[2] - bc[2]};
+    const float t0 = d[0] * bar[3] + d[1] * bar[4] + d[2] * bar[5];
+    bool found = false;
+    float best = 1e30f;
+#pragma unroll 1
+    for (int kk = 0; kk < 5; ++kk) {
+      // visiting order 0, -1, +1, -2, +2; an outer sample wins only if deeper by more than 1e-5 m, so a bar lying
+      // parallel to a box face (all samples equally deep) yields the central point
+      const int k = kk == 0 ? 0 : ((kk & 1) ? -((kk + 1) >> 1) : (kk >> 1));
+      const float t = fminf(fmaxf(t0 + 0.03f * k, -bar[6]), bar[6]);
+      const float q[3] = {bc[0] + t * bar[3], bc[1] + t * bar[4], bc[2] + t * bar[5]};
+      float ps[3], ns[3], ds;
+      if (sphere_box(q, bar[7], bx, thresh, ps, ns, &ds) && ds < best - 1e-5f) {
+        best = ds;
+        found = true;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { n[i] = -ns[i]; pa[i] = ps[i] - ds * ns[i]; }
+      }
+    }
+    *dist = best;
+    return found;
+  }
+
+  template <int OBST> MB_HD static int collide(Mem& S, const MbPhysics& P, int* overflow) {
+    constexpr bool BOXES = (OBST & MB_OBST_BOXES) != 0;
     // world positions of the candidate points (relative to the base COM)
     MB_LANES(l)
       for (int pt = l; pt < NPT; pt += 32) {
@@ -661,6 +714,101 @@ template <class M> struct Sim {
           }
         MB_END
         nc += mb_popc(mask);
+      }
+    }
+    if (OBST & MB_OBST_BARS) {
+#pragma unroll 1
+      for (int ob = 0; ob < S.nbar; ++ob) {
+        const float* bar = S.bar[ob];
+        const float bc[3] = {bar[0] - S.pos[0], bar[1] - S.pos[1], bar[2] - S.pos[2]};
+        // uniform cull: every robot point lies within ~1.3 m of the base COM; compare with the distance from the
+        // base to the bar's axis line
+        const float ta = bc[0] * bar[3] + bc[1] * bar[4] + bc[2] * bar[5];
+        const float px0 = bc[0] - ta * bar[3], py0 = bc[1] - ta * bar[4], pz0 = bc[2] - ta * bar[5];
+        if (px0 * px0 + py0 * py0 + pz0 * pz0 > 1.5f * 1.5f) continue;
+#pragma unroll 1
+        for (int pass = 0; pass * 32 < NPT; ++pass) {
+          LaneVar<int> hit;
+          LaneVar<float> px, py, pz, nx, ny, nz, dd;
+          MB_LANES(l)
+            const int pt = pass * 32 + l;
+            hit[l] = 0;
+            if (pt < NPT) {
+              float pa[3], n[3], dist;
+              if (sphere_bar(S.w.k.u2.pt[pt], M::pradius(pt), bc, bar, M::pthresh(pt), pa, n, &dist)) {
+                hit[l] = 1;
+                px[l] = pa[0]; py[l] = pa[1]; pz[l] = pa[2]; dd[l] = dist;
+                nx[l] = n[0]; ny[l] = n[1]; nz[l] = n[2];
+              }
+            }
+          MB_END
+          const unsigned mask = warp_ballot(hit);
+          if (mask == 0u) continue;
+          MB_LANES(l)
+            if (hit[l]) {
+              const int pt = pass * 32 + l;
+              const int k = nc + mb_popc(mask & ((1u << l) - 1u));
+              if (k < MB_MAXC) {
+                S.cP[k][0] = px[l]; S.cP[k][1] = py[l]; S.cP[k][2] = pz[l];
+                S.cn[k][0] = nx[l]; S.cn[k][1] = ny[l]; S.cn[k][2] = nz[l];
+                S.cdist[k] = dd[l];
+                S.cmu[k] = M::pfriction(pt) * P.bar_friction;
+                S.cerp[k] = P.erp_contact;
+                S.ccfm[k] = 0.0f;
+                S.clink[k] = M::powner(pt);
+                S.cfoot[k] = M::pfoot(pt);
+                S.cpartner[k] = 20 + ob;
+              }
+            }
+          MB_END
+          nc += mb_popc(mask);
+        }
+        if (M::NXBOX > 0) {
+          LaneVar<int> hit;
+          LaneVar<float> px, py, pz, nx, ny, nz, dd;
+          MB_LANES(l)
+            hit[l] = 0;
+            if (l < M::NXBOX) {
+              const int o = M::xowner(l);
+              const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
+              float bx[16];
+              const float loc[3] = {M::xpos(l, 0), M::xpos(l, 1), M::xpos(l, 2)};
+              mb_matvec(R, loc, bx);
+              if (o >= 0) { bx[0] += S.w.k.jp[o][0]; bx[1] += S.w.k.jp[o][1]; bx[2] += S.w.k.jp[o][2]; }
+              float Rx[9];
+#pragma unroll
+              for (int i = 0; i < 9; ++i) Rx[i] = M::xrot(l, i);
+              mb_matmul(R, Rx, bx + 3);
+              bx[12] = M::xhalf(l, 0); bx[13] = M::xhalf(l, 1); bx[14] = M::xhalf(l, 2);
+              float pa[3], n[3], dist;
+              if (box_bar(bx, bc, bar, M::xthresh(l), pa, n, &dist)) {
+                hit[l] = 1;
+                px[l] = pa[0]; py[l] = pa[1]; pz[l] = pa[2]; dd[l] = dist;
+                nx[l] = n[0]; ny[l] = n[1]; nz[l] = n[2];
+              }
+            }
+          MB_END
+          const unsigned mask = warp_ballot(hit);
+          if (mask != 0u) {
+            MB_LANES(l)
+              if (hit[l]) {
+                const int k = nc + mb_popc(mask & ((1u << l) - 1u));
+                if (k < MB_MAXC) {
+                  S.cP[k][0] = px[l]; S.cP[k][1] = py[l]; S.cP[k][2] = pz[l];
+                  S.cn[k][0] = nx[l]; S.cn[k][1] = ny[l]; S.cn[k][2] = nz[l];
+                  S.cdist[k] = dd[l];
+                  S.cmu[k] = M::xfriction(l) * P.bar_friction;
+                  S.cerp[k] = P.erp_contact;
+                  S.ccfm[k] = 0.0f;
+                  S.clink[k] = M::xowner(l);
+                  S.cfoot[k] = M::xfoot(l);
+                  S.cpartner[k] = 20 + ob;
+                }
+              }
+            MB_END
+            nc += mb_popc(mask);
+          }
+        }
       }
     }
     if (nc > MB_MAXC) { *overflow += 1; nc = MB_MAXC; }
@@ -904,11 +1052,11 @@ template <class M> struct Sim {
   }
 
   // ---- one Bullet substep.  Returns the number of constraint rows; contact list of this substep stays in S ----
-  template <bool BOXES>
+  template <int OBST>
   MB_HD static int substep(Mem& S, const MbPhysics& P, const LaneConst& C, int* nc_out, int* overflow) {
     MB_BLOCK_BARRIER();  // keeps the warps of a CTA in the same phase so instruction-cache lines are shared
     kinematics(S, P, C, true);
-    const int nc_all = collide<BOXES>(S, P, overflow);
+    const int nc_all = collide<OBST>(S, P, overflow);
     bodies(S, P);
     mass_matrix_and_rhs(S);
     factorize(S, C);

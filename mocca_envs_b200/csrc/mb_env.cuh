@@ -31,6 +31,19 @@ enum {
   ER_OVERFLOW,                  // contact/row cap hits (int)
 };
 
+enum {  // Monkey3DCustomEnv additions (env_locomotion.py:1136-1516)
+  EM_NEXT = 22,      // next_step_index (int)
+  EM_FREEFALL,       // free_fall_count (int)
+  EM_TIMESTEP,       // timestep (int)
+  EM_SWING,          // swing_leg (int)
+  EM_PIVOT,          // pivot_leg (int)
+  EM_SWINGPOT,       // swing_potential
+  EM_BARIDX,         // [4] terrain row shown by each physical bar (int)
+  EM_BAR = 32,       // [4][8] bar centre, unit axis, half length, radius
+  EM_TERRAIN = 64,   // [32][4] x y z phi
+};
+#define MB_REC_STRIDE_MONKEY 192
+
 enum {  // Walker3DStepperEnv additions (env_locomotion.py:330-840)
   ES_NEXT = 22,       // next_step_index (int)
   ES_COUNT,           // target_reached_count (int)
@@ -55,6 +68,7 @@ struct MbStats {  // per-device accumulators, all-reduced across ranks by the ho
 };
 
 MB_HD int& rec_i(float* rec, int k) { return reinterpret_cast<int*>(rec)[k]; }
+MB_HD int rec_i(const float* rec, int k) { return reinterpret_cast<const int*>(rec)[k]; }
 
 // ------------------------------------------------------------------------------------------------ MT19937
 // NumPy legacy RandomState stream, warp-cooperative.  mt[0..623] state words, mt[624] position.
@@ -128,14 +142,15 @@ MB_HD float mb_clip5(float x) { return fminf(fmaxf(x, -5.0f), 5.0f); }
 template <class M> struct W3DEnv {
   typedef WarpMem<M> Mem;
   typedef Sim<M> S_;
+  typedef M Model;
   enum { NJ = M::NJ, NU = M::NU, OBS = 6 + 2 * M::NJ + M::NFEET + 2, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET,
-         REC_STRIDE = MB_REC_STRIDE, HAS_BOXES = 0 };
+         REC_STRIDE = MB_REC_STRIDE, OBST = 0 };
   MB_HD static void load_obstacles(WarpMem<M>&, const float*) {}
 
   // HBM <-> shared
   MB_HD static void load_state(Mem& S, const float* st) {
     MB_LANES(l)
-      if (l == 0) S.nbox = 0;
+      if (l == 0) { S.nbox = 0; S.nbar = 0; }
       for (int i = l; i < 13 + 2 * NJ; i += 32) {
         const float v = st[i];
         if (i < 3) S.pos[i] = v;
@@ -331,7 +346,7 @@ template <class M> struct W3DEnv {
     S_::init_lane_const(C);
 #pragma unroll 1
     for (int k = 0; k < P.substeps; ++k) {
-      rows += S_::template substep<false>(S, P, C, &nc, &overflow);
+      rows += S_::template substep<0>(S, P, C, &nc, &overflow);
       ncsum += nc;
     }
     // feet_contact from the last collision pass (robots.py:74-86 via getContactPoints)
@@ -440,8 +455,9 @@ template <class M> struct StepperEnv {
   typedef WarpMem<M> Mem;
   typedef Sim<M> S_;
   typedef W3DEnv<M> B_;
+  typedef M Model;
   enum { NJ = M::NJ, NU = M::NU, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET, OBS = ROBOT_OBS + 15, NSTEPS = 20,
-         REC_STRIDE = MB_REC_STRIDE_STEPPER, HAS_BOXES = 1 };
+         REC_STRIDE = MB_REC_STRIDE_STEPPER, OBST = MB_OBST_BOXES };
   MB_HD static void load_obstacles(Mem& S, const float* rec) { load_boxes(S, rec); }
   MB_HD static void load_state(Mem& S, const float* st) { B_::load_state(S, st); }
   MB_HD static void store_state(const Mem& S, float* st) { B_::store_state(S, st); }
@@ -646,7 +662,7 @@ template <class M> struct StepperEnv {
     S_::init_lane_const(C);
 #pragma unroll 1
     for (int k = 0; k < P.substeps; ++k) {
-      rows += S_::template substep<true>(S, P, C, &nc, &overflow);
+      rows += S_::template substep<MB_OBST_BOXES>(S, P, C, &nc, &overflow);
       ncsum += nc;
     }
     const int timestep = rec_i(rec, ES_TIMESTEP) + 1;
@@ -762,6 +778,368 @@ template <class M> struct StepperEnv {
       MB_LANES(l)
         if (l == 0) rec_i(rec, ES_STEPS_REACHED) = keep;  // info of the finished episode stays readable
       MB_END
+    }
+    if (anybad) {
+      MB_LANES(l)
+        if (l == 0) {
+#ifdef __CUDACC__
+          atomicAdd(&stats->nonfinite, 1ull);
+#else
+          stats->nonfinite += 1;
+#endif
+        }
+      MB_END
+    }
+    B_::store_state(S, state);
+  }
+};
+
+// ================================================================================================ Monkey3D
+// Monkey3DCustomEnv (reference env_locomotion.py:1136-1516) with 4 recycled MonkeyBars (bullet_objects.py:148-187).
+// btMatrix3x3::getRotation of a row-major local->world rotation (xyzw)
+MB_HD void mb_mat_to_quat(const float* R, float* q) {
+  const float tr = R[0] + R[4] + R[8];
+  if (tr > 0.0f) {
+    float s = sqrtf(tr + 1.0f);
+    q[3] = s * 0.5f;
+    s = 0.5f / s;
+    q[0] = (R[7] - R[5]) * s; q[1] = (R[2] - R[6]) * s; q[2] = (R[3] - R[1]) * s;
+  } else {
+    const int i = R[0] < R[4] ? (R[4] < R[8] ? 2 : 1) : (R[0] < R[8] ? 2 : 0);
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    float s = sqrtf(R[4 * i] - R[4 * j] - R[4 * k] + 1.0f);
+    float t[4];
+    t[i] = s * 0.5f;
+    s = 0.5f / s;
+    t[3] = (R[3 * k + j] - R[3 * j + k]) * s; t[j] = (R[3 * j + i] + R[3 * i + j]) * s;
+    t[k] = (R[3 * k + i] + R[3 * i + k]) * s;
+    q[0] = t[0]; q[1] = t[1]; q[2] = t[2]; q[3] = t[3];
+  }
+}
+
+template <class M> struct MonkeyEnv {
+  typedef WarpMem<M> Mem;
+  typedef Sim<M> S_;
+  typedef W3DEnv<M> B_;
+  typedef M Model;
+  enum { NJ = M::NJ, NU = M::NU, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET, OBS = ROBOT_OBS + 15, NSTEPS = 32, NBARS = 4,
+         REC_STRIDE = MB_REC_STRIDE_MONKEY, OBST = MB_OBST_BARS };
+  MB_HD static void load_obstacles(Mem& S, const float* rec) { load_bars(S, rec); }
+  MB_HD static void load_state(Mem& S, const float* st) { B_::load_state(S, st); }
+  MB_HD static void store_state(const Mem& S, float* st) { B_::store_state(S, st); }
+
+  MB_HD static void load_bars(Mem& S, const float* rec) {
+    MB_LANES(l)
+      S.bar[l >> 3][l & 7] = rec[EM_BAR + l];
+      if (l == 0) S.nbar = NBARS;
+    MB_END
+  }
+
+  // set_step_state (env_locomotion.py:1244-1248): cylinder axis = euler(90 deg, 0, phi) applied to local z
+  MB_HD static void place_bar(float* rec, int info, int bar) {
+    MB_LANES(l)
+      if (l == 0) {
+        const float* t = rec + EM_TERRAIN + 4 * info;
+        float* b = rec + EM_BAR + 8 * bar;
+        b[0] = t[0]; b[1] = t[1]; b[2] = t[2];
+        b[3] = sinf(t[3]); b[4] = -cosf(t[3]); b[5] = 0.0f;
+        b[6] = 2.5f;    // bar_length / 2 (env_locomotion.py:1143)
+        b[7] = 0.015f;  // step_radius (env_locomotion.py:1148)
+        rec_i(rec, EM_BARIDX + bar) = info;
+      }
+    MB_END
+  }
+
+  // palm link pose relative to the base COM (BodyPart.pose() of right_palm / left_palm, env_locomotion.py:1269-1272)
+  MB_HD static void palm_rel(const Mem& S, int h, float* p) {
+    const int b = M::palm_body(h), ow = M::bowner(b);
+    const float* R = S.w.k.jR[ow];
+    const float c[3] = {M::bcom(b, 0), M::bcom(b, 1), M::bcom(b, 2)};
+    mb_matvec(R, c, p);
+    p[0] += S.w.k.jp[ow][0]; p[1] += S.w.k.jp[ow][1]; p[2] += S.w.k.jp[ow][2];
+  }
+  MB_HD static void foot_rel(const Mem& S, int f, float* p) {
+    const int b = M::foot_body(f), ow = M::bowner(b);
+    const float* R = S.w.k.jR[ow];
+    const float c[3] = {M::bcom(b, 0), M::bcom(b, 1), M::bcom(b, 2)};
+    mb_matvec(R, c, p);
+    p[0] += S.w.k.jp[ow][0]; p[1] += S.w.k.jp[ow][1]; p[2] += S.w.k.jp[ow][2];
+  }
+
+  // calc_potential (env_locomotion.py:1351-1364): only swing_potential is used by the reward
+  MB_HD static float swing_potential(const Mem& S, const float* rec, int swing, float scene_dt) {
+    float p[3];
+    palm_rel(S, swing == 0 ? 0 : 1, p);
+    // (target - base) - palm_rel: both differences are small, no cancellation at 20 m altitude
+    const float dx = (rec[ER_TX] - S.pos[0]) - p[0], dy = (rec[ER_TY] - S.pos[1]) - p[1];
+    const float dz = (rec[ER_TZ] - S.pos[2]) - p[2];
+    return -sqrtf(dx * dx + dy * dy + dz * dz) / scene_dt;
+  }
+
+  // delta_to_k_targets(k=2) (env_locomotion.py:1489-1516): obs[ROBOT_OBS .. +6) and walk_target
+  MB_HD static void targets(const Mem& S, float* rec, float yaw, float* obs) {
+    const int N = rec_i(rec, EM_NEXT);
+    MB_LANES(l)
+      if (l < 2) {
+        int idx = N + l;
+        if (idx > NSTEPS - 1) idx = NSTEPS - 1;
+        const float* t = rec + EM_TERRAIN + 4 * idx;
+        const float dx = t[0] - S.pos[0], dy = t[1] - S.pos[1], dz = t[2] - S.pos[2];
+        const float ang = atan2f(dy, dx) - yaw, d = sqrtf(dx * dx + dy * dy);
+        float* o = obs + ROBOT_OBS + 3 * l;
+        o[0] = sinf(ang) * d; o[1] = cosf(ang) * d; o[2] = dz;
+        if (l == 0) { rec[ER_TX] = t[0]; rec[ER_TY] = t[1]; rec[ER_TZ] = t[2]; }
+      }
+    MB_END
+  }
+
+  // get_observation_component tail (env_locomotion.py:1268-1281)
+  MB_HD static void tail_obs(const Mem& S, const float* rec, float* obs) {
+    const int swing = rec_i(rec, EM_SWING), pivot = rec_i(rec, EM_PIVOT);
+    const int h = swing == 0 ? 0 : 1;
+    float p[3], q[4];
+    palm_rel(S, h, p);
+    mb_mat_to_quat(S.w.k.jR[M::bowner(M::palm_body(h))], q);
+    MB_LANES(l)
+      if (l == 0) {
+        float* o = obs + ROBOT_OBS + 6;
+        o[0] = (float)swing; o[1] = (float)pivot;
+        o[2] = (rec[ER_TX] - S.pos[0]) - p[0]; o[3] = (rec[ER_TY] - S.pos[1]) - p[1];
+        o[4] = (rec[ER_TZ] - S.pos[2]) - p[2];
+        o[5] = q[0]; o[6] = q[1]; o[7] = q[2]; o[8] = q[3];
+      }
+    MB_END
+  }
+
+  // generate_step_placements (env_locomotion.py:1183-1228), n_steps = 32, yaw_limit = pitch_limit = 0:
+  // 96 float64 draws (192 words) of the env stream; rows 0 / 1 are pinned to the rear / front hand
+  MB_HD static void generate_terrain(const Mem& S, float* rec, const uint32_t* w, double* dbuf, int mirrored) {
+    const double PI_D = 3.14159265358979323846, D2R = PI_D / 180;
+    double* dx = dbuf;        // [32]
+    double* dy = dbuf + 32;
+    double* dz = dbuf + 64;
+    float f0[3], f1[3];
+    foot_rel(S, 0, f0);
+    foot_rel(S, 1, f1);
+    const double fx[2] = {(double)S.pos[0] + f0[0], (double)S.pos[0] + f1[0]};
+    const double fy[2] = {(double)S.pos[1] + f0[1], (double)S.pos[1] + f1[1]};
+    const double fz[2] = {(double)S.pos[2] + f0[2], (double)S.pos[2] + f1[2]};
+    const int i0 = fx[1] < fx[0] ? 1 : 0, j0 = fx[1] > fx[0] ? 1 : 0;
+    MB_LANES(l)
+      {
+        const double dr = 0.3 + (0.5 - 0.3) * mt_double(w + 2 * l);
+        const double dth = (90 - 0) * D2R + ((90 + 0) * D2R - (90 - 0) * D2R) * mt_double(w + 128 + 2 * l);
+        const double deg = l == 0 ? -10.0 : (l == NSTEPS - 1 ? 10.0 : ((l & 1) ? 20.0 : -20.0));
+        const double bp = (D2R * deg) * (mirrored ? -1.0 : 1.0);  // phi = cumsum(0) = 0
+        double x = dr * sin(dth) * cos(0.0 + bp);
+        const double ax = fabs(x), mx = ax > 0.015 * 2.5 ? ax : 0.015 * 2.5;
+        const double sg = x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0);
+        x = sg * (mx < 0.5 ? mx : 0.5);
+        double y = dr * sin(dth) * sin(0.0 + bp);
+        double z = dr * cos(dth);
+        if (l == 0) { x = fx[i0] + 0.04; y = fy[i0]; z = fz[i0] + (-20 + 0.04); }
+        if (l == 1) { x = fx[j0] - fx[i0] + 0.01; y = fy[j0] - fy[i0]; z = fz[j0] - fz[i0] - 0.02; }
+        dx[l] = x; dy[l] = y; dz[l] = z;
+      }
+    MB_END
+    MB_LANES(l)
+      {
+        double x = 0.0, y = 0.0, z = 0.0;
+        for (int j = 0; j <= l; ++j) { x += dx[j]; y += dy[j]; z += dz[j]; }
+        rec[EM_TERRAIN + 4 * l + 0] = (float)x;
+        rec[EM_TERRAIN + 4 * l + 1] = (float)y;
+        rec[EM_TERRAIN + 4 * l + 2] = (float)(z + 20);
+        rec[EM_TERRAIN + 4 * l + 3] = 0.0f;
+        if (l == 0) { rec_i(rec, EM_SWING) = i0; rec_i(rec, EM_PIVOT) = j0; }
+      }
+    MB_END
+  }
+
+  // Monkey3DCustomEnv.reset (env_locomotion.py:1283-1316); robot.reset(random_pose=False) still draws the coin
+  MB_HD static void reset(Mem& S, const MbPhysics& P, float* rec, uint32_t* mt_env, uint32_t* mt_robot, float* obs) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(S.L);  // 2 + 192 words; the factor storage is free between steps
+    // kinematics(with_vel = false) writes jR / jp / js only: the body scratch behind them is free for the doubles
+    double* dbuf = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(&S.w.k.u2) + 7) & ~(uintptr_t)7);
+    static_assert(sizeof(S.L) >= 200 * sizeof(uint32_t), "factor storage too small for the reset scratch");
+    static_assert(sizeof(S.w.k.u2) >= 97 * sizeof(double), "body scratch too small for the terrain doubles");
+    const int aliased = rec_i(rec, ER_ALIASED);
+    if (aliased) mt_fill(mt_env, w, 2 + 192);
+    else { mt_fill(mt_robot, w, 2); mt_fill(mt_env, w + 2, 192); }
+    const int mirrored = mt_double(w) < 0.5;
+    MB_LANES(l)
+      if (l == 0) {
+        rec_i(rec, ER_ELAPSED) = 0; rec[ER_FEET0] = 0.0f; rec[ER_FEET1] = 0.0f;
+        rec_i(rec, ER_MIRRORED) = mirrored; rec[ER_EPRET] = 0.0f; rec_i(rec, ER_EPLEN) = 0;
+        rec_i(rec, EM_TIMESTEP) = 0; rec_i(rec, EM_FREEFALL) = 0; rec_i(rec, EM_NEXT) = 2;
+      }
+      if (l < NJ) {
+        int src = l;
+        float sign = 1.0f;
+        if (mirrored) {
+          for (int k = 0; k < M::NMIRROR; ++k) {
+            if (M::right(k) == l) src = M::left(k);
+            if (M::left(k) == l) src = M::right(k);
+          }
+          for (int k = 0; k < M::NNEG; ++k)
+            if (M::neg(k) == l) sign = -1.0f;
+        }
+        S.q[l] = sign * (float)M::base_angles(src);
+      }
+      if (l < NU) S.u[l] = 0.0f;
+      if (l == 31) {
+        S.pos[0] = 0.0f; S.pos[1] = 0.0f; S.pos[2] = 20.0f;  // initial_height (env_locomotion.py:1142,1153)
+        S.quat[0] = 0.0f; S.quat[1] = 0.0f; S.quat[2] = 0.0f; S.quat[3] = 1.0f;
+        S.u[3] = 3.0f; S.u[4] = 0.0f; S.u[5] = -1.0f;        // base_velocity (env_locomotion.py:1154)
+      }
+    MB_END
+    typename S_::LaneConst C;
+    S_::init_lane_const(C);
+    S_::kinematics(S, P, C, false);
+    generate_terrain(S, rec, w + 2, dbuf, mirrored);
+    for (int k = 0; k < NBARS; ++k) place_bar(rec, k, k);
+    LaneVar<float> zero;
+    MB_LANES(l)
+      zero[l] = 0.0f;
+    MB_END
+    float s1, s2;
+    W3DObsScalars o = B_::observe(S, rec, obs, zero, &s1, &s2);
+    targets(S, rec, o.yaw, obs);
+    const float sp = swing_potential(S, rec, rec_i(rec, EM_SWING), P.dt * P.substeps);
+    MB_LANES(l)
+      if (l == 0) rec[EM_SWINGPOT] = sp;
+    MB_END
+    tail_obs(S, rec, obs);
+  }
+
+  // Monkey3DCustomEnv.step (env_locomotion.py:1318-1349)
+  MB_HD static void step(Mem& S, const MbPhysics& P, float* state, float* rec, uint32_t* mt_env, uint32_t* mt_robot,
+                         const float* act, float* obs, float* rew, uint8_t* done, uint8_t* trunc, float* final_obs,
+                         MbStats* stats) {
+    B_::load_state(S, state);
+    load_bars(S, rec);
+    int swing = rec_i(rec, EM_SWING), pivot = rec_i(rec, EM_PIVOT);
+    const int jswing = swing == 0 ? 17 : 22, jpivot = pivot == 0 ? 17 : 22;
+    LaneVar<float> araw;
+    LaneVar<int> badact;
+    MB_LANES(l)
+      araw[l] = 0.0f; badact[l] = 0;
+      if (l < NJ) {
+        float a = act[l];
+        if (!mb_finite(a)) { a = 0.0f; badact[l] = 1; }
+        // the finger joints are scripted: swing hand opens, pivot hand closes (env_locomotion.py:1322-1323)
+        if (l == jswing) a = 1.0f;
+        if (l == jpivot) a = -1.0f;
+        araw[l] = a;
+        const float ac = fminf(fmaxf(a, -1.0f), 1.0f);
+        S.tau[l] = M::gain(l) * ac - M::damping(l) * S.u[6 + l];
+      }
+    MB_END
+    const unsigned anybad = warp_ballot(badact);
+    int rows = 0, nc = 0, overflow = 0, ncsum = 0;
+    typename S_::LaneConst C;
+    S_::init_lane_const(C);
+#pragma unroll 1
+    for (int k = 0; k < P.substeps; ++k) {
+      rows += S_::template substep<MB_OBST_BARS>(S, P, C, &nc, &overflow);
+      ncsum += nc;
+    }
+    const int timestep = rec_i(rec, EM_TIMESTEP) + 1;
+    int next = rec_i(rec, EM_NEXT);
+    const int cur_index = next;
+    // calc_feet_state (env_locomotion.py:1404-1452) on the contact list of the last collision pass
+    const int target_id = 20 + (next % NBARS);
+    float fc[2] = {0.0f, 0.0f};
+    int palm_hit[2] = {0, 0};
+    for (int k = 0; k < nc; ++k) {
+      const int f = S.cfoot[k];
+      if (f == 0 || f == 1) fc[f] = 1.0f;
+      if ((f == 2 || f == 3) && S.cpartner[k] == target_id) palm_hit[f - 2] = 1;
+    }
+    S_::kinematics(S, P, C, false);
+    // next_step / p_xyz are bound before the loop over the feet and stay stale if the index advances at i == 0
+    const float tpx = rec[EM_TERRAIN + 4 * next], tpy = rec[EM_TERRAIN + 4 * next + 1];
+    int reached = 0, place_info = -1, place_id = 0;
+    float foot_dist = 0.0f;
+    for (int i = 0; i < 2; ++i) {
+      if (i != swing) continue;
+      float fp[3];
+      foot_rel(S, swing, fp);
+      const float dx = (S.pos[0] - tpx) + fp[0], dy = (S.pos[1] - tpy) + fp[1];
+      foot_dist = sqrtf(dx * dx + dy * dy);
+      reached = palm_hit[swing == 0 ? 0 : 1];
+      if (!reached) continue;
+      next = next + 1 > NSTEPS - 1 ? NSTEPS - 1 : next + 1;
+      if (next >= NBARS) {  // update_steps (env_locomotion.py:1255-1266)
+        if (place_info >= 0) place_bar(rec, place_info, place_id);
+        place_id = next % NBARS;
+        place_info = next;
+      }
+      pivot = swing;
+      swing = (swing + 1) % 2;
+    }
+    MB_LANES(l)
+      if (l == 0) {
+        rec[ER_FEET0] = fc[0]; rec[ER_FEET1] = fc[1];
+        rec_i(rec, EM_NEXT) = next; rec_i(rec, EM_SWING) = swing; rec_i(rec, EM_PIVOT) = pivot;
+        rec_i(rec, EM_TIMESTEP) = timestep;
+      }
+    MB_END
+    if (place_info >= 0) place_bar(rec, place_info, place_id);
+    float s1, s2;
+    W3DObsScalars o = B_::observe(S, rec, obs, araw, &s1, &s2);
+    int env_done = o.nonfinite ? 1 : 0;
+    // calc_base_reward (env_locomotion.py:1366-1402): the swing progress and the free-fall test are what survives
+    // the zero weights in step()
+    const float scene_dt = P.dt * P.substeps;
+    const float old_sp = rec[EM_SWINGPOT];
+    float sp = swing_potential(S, rec, swing, scene_dt);
+    const float progress = sp - old_sp;
+    int freefall = rec_i(rec, EM_FREEFALL);
+    if (freefall > 30) env_done = 1;
+    const float step_bonus = reached ? 50.0f * expf(-foot_dist / 0.25f) : 0.0f;  // env_locomotion.py:1454-1458
+    targets(S, rec, o.yaw, obs);
+    const int airborne = (fc[0] + fc[1]) == 0.0f;
+    freefall = airborne ? freefall + 1 : 0;
+    if (cur_index != next) sp = swing_potential(S, rec, swing, scene_dt);
+    const float reward = progress + step_bonus - fc[swing];
+    if (timestep > 180 && next <= 2) env_done = 1;
+    tail_obs(S, rec, obs);
+    const int elapsed = rec_i(rec, ER_ELAPSED) + 1;
+    int truncated = 0, any_done = env_done;
+    if (elapsed >= 1000) { truncated = !env_done; any_done = 1; }
+    const float epret = rec[ER_EPRET] + reward;
+    const int eplen = rec_i(rec, ER_EPLEN) + 1;
+    MB_LANES(l)
+      if (l == 0) {
+        rec[EM_SWINGPOT] = sp; rec_i(rec, EM_FREEFALL) = freefall; rec_i(rec, ER_ELAPSED) = elapsed;
+        rec[ER_EPRET] = epret; rec_i(rec, ER_EPLEN) = eplen;
+        rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum;
+        rec_i(rec, ER_OVERFLOW) += overflow;
+        *rew = reward; *done = (uint8_t)any_done; *trunc = (uint8_t)truncated;
+      }
+    MB_END
+    if (any_done) {
+      if (final_obs) {
+        MB_LANES(l)
+          for (int i = l; i < OBS; i += 32) final_obs[i] = obs[i];
+        MB_END
+      }
+      MB_LANES(l)
+        if (l == 0) {
+          rec[ER_LAST_EPRET] = epret; rec_i(rec, ER_LAST_EPLEN) = eplen;
+#ifdef __CUDACC__
+          atomicAdd(&stats->episodes, 1ull);
+          atomicAdd(&stats->ret_sum, (double)epret);
+          atomicAdd(&stats->len_sum, (double)eplen);
+          atomicAdd(&stats->steps, (unsigned long long)next);
+          if (o.nonfinite) atomicAdd(&stats->nonfinite, 1ull);
+#else
+          stats->episodes += 1; stats->ret_sum += epret; stats->len_sum += eplen; stats->steps += next;
+          if (o.nonfinite) stats->nonfinite += 1;
+#endif
+        }
+      MB_END
+      reset(S, P, rec, mt_env, mt_robot, obs);
     }
     if (anybad) {
       MB_LANES(l)

@@ -458,6 +458,8 @@ def compile_monkey3d(data_dir: str, **kw) -> dict:
     t["right_joint_indices"] = [3, 4, 5, 6, 7, 13, 14, 15, 16, 17]
     t["left_joint_indices"] = [8, 9, 10, 11, 12, 18, 19, 20, 21, 22]
     t["negation_joint_indices"] = [0, 2]
+    # env_locomotion.py:1269,1424: the palm spheres whose contact with the target bar advances the step index
+    t["palm_links"] = [t["link_names"].index("right_palm"), t["link_names"].index("left_palm")]
     return t
 
 

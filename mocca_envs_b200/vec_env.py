@@ -25,6 +25,7 @@ from .seeding import create_seed, mt_state_rows
 
 ENV_ID = "Walker3DCustomEnv-v0"
 STEPPER_ID = "Walker3DStepperEnv-v0"
+MONKEY_ID = "Monkey3DCustomEnv-v0"
 _MODELS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models")
 
 
@@ -51,6 +52,7 @@ class Walker3DCustomVecEnv:
     """Batched Walker3DCustomEnv-v0; also the base class of the other batched envs (env_id selects the kernels)."""
 
     env_id = ENV_ID
+    model = "walker3d"
     control_step = 1 / 60  # env_locomotion.py:39
     llc_frame_skip = 1  # env_locomotion.py:40
     sim_frame_skip = 4  # env_locomotion.py:41
@@ -79,11 +81,11 @@ class Walker3DCustomVecEnv:
         _lib.check(L.mb200_dims(h, *[C.byref(d) for d in dims]))
         _, self.obs_dim, self.act_dim, self.state_dim, self.nu = [d.value for d in dims]
         self.rec_stride = int(L.mb200_record_stride(h))
-        with open(os.path.join(_MODELS, "walker3d.json")) as f:
+        with open(os.path.join(_MODELS, self.model + ".json")) as f:
             self.table = json.load(f)
         # spaces as the reference builds them (robots.py:22-29, env_locomotion.py:58-60)
         self.observation_space = Box(-np.inf * np.ones(self.obs_dim), np.inf * np.ones(self.obs_dim))
-        self.action_space = Box(-np.ones(self.act_dim), np.ones(self.act_dim))
+        self.action_space = self._action_space()
         kw = dict(device=self.device)
         n = self.num_envs
         self.obs = torch.zeros(n, self.obs_dim, dtype=torch.float32, **kw)
@@ -93,6 +95,9 @@ class Walker3DCustomVecEnv:
         self.final_obs = torch.zeros(n, self.obs_dim, dtype=torch.float32, **kw) if return_final_obs else None
         self._seeded = False
         self.seed(seed, _at_construction=True)
+
+    def _action_space(self):
+        return Box(-np.ones(self.act_dim), np.ones(self.act_dim))
 
     # ---- lifecycle
     def close(self):
@@ -281,6 +286,40 @@ class Walker3DStepperVecEnv(Walker3DCustomVecEnv):
         return neg_obs, right, left, neg_j, right_j, left_j
 
 
+class Monkey3DCustomVecEnv(Walker3DCustomVecEnv):
+    """Batched Monkey3DCustomEnv-v0 (reference env_locomotion.py:1136-1516): 23-DoF brachiator released at 20 m
+    with both hands on the first two of 32 seeded monkey bars (4 physical bars, recycled); the finger joints are
+    scripted by the env (swing hand opens, pivot hand closes)."""
+
+    env_id = MONKEY_ID
+    model = "monkey3d"
+    EM_NEXT, EM_FREEFALL, EM_TIMESTEP, EM_SWING, EM_PIVOT, EM_BAR, EM_TERRAIN = 22, 23, 24, 25, 26, 32, 64
+
+    def _action_space(self):  # env_locomotion.py:1179-1181: unbounded torque space
+        return Box(-np.inf * np.ones(self.act_dim), np.inf * np.ones(self.act_dim))
+
+    def evaluation_mode(self):
+        raise AttributeError("Monkey3DCustomEnv has no evaluation_mode (reference: only Walker3DCustomEnv)")
+
+    def set_env_params(self, params: dict):
+        pass
+
+    def terrain_info(self) -> torch.Tensor:
+        return self.get_record()[:, self.EM_TERRAIN:self.EM_TERRAIN + 128].reshape(self.num_envs, 32, 4)
+
+    def next_step_index(self) -> torch.Tensor:
+        return self.get_record()[:, self.EM_NEXT].contiguous().view(torch.int32)
+
+    def stats(self, reset=False) -> dict:
+        out = (C.c_double * 8)()
+        _lib.check(self._L.mb200_stats(self._h, out, int(reset)))
+        return {"episodes": out[0], "return_sum": out[1], "length_sum": out[2], "nonfinite": out[3],
+                "overflow": out[4], "steps_reached_sum": out[5]}
+
+    def get_mirror_indices(self):
+        raise AttributeError("Monkey3DCustomEnv defines no get_mirror_indices in the reference")
+
+
 class Walker3DCustomEnv:
     """gym-protocol facade over a 1-env batch; NumPy float64 observations like the reference."""
 
@@ -353,7 +392,29 @@ class Walker3DStepperEnv(Walker3DCustomEnv):
         raise AttributeError("Walker3DStepperEnv has no evaluation_mode")
 
 
-_REGISTRY = {ENV_ID: (Walker3DCustomEnv, Walker3DCustomVecEnv), STEPPER_ID: (Walker3DStepperEnv, Walker3DStepperVecEnv)}
+class Monkey3DCustomEnv(Walker3DCustomEnv):
+    """gym-protocol facade of Monkey3DCustomEnv-v0.  The reference overwrites the two finger entries of the caller's
+    action array in place (env_locomotion.py:1322-1323, quirk Q11); the kernel applies the same override internally
+    and this facade mirrors the visible side effect."""
+
+    vec_class = Monkey3DCustomVecEnv
+
+    def step(self, action):
+        rec = self.vec.get_record()[0]
+        swing = int(rec[self.vec.EM_SWING].view(torch.int32).item())
+        pivot = int(rec[self.vec.EM_PIVOT].view(torch.int32).item())
+        out = super().step(action)
+        if isinstance(action, np.ndarray):
+            action[17 if swing == 0 else 22] = 1
+            action[17 if pivot == 0 else 22] = -1
+        return out
+
+    def evaluation_mode(self):
+        raise AttributeError("Monkey3DCustomEnv has no evaluation_mode")
+
+
+_REGISTRY = {ENV_ID: (Walker3DCustomEnv, Walker3DCustomVecEnv), STEPPER_ID: (Walker3DStepperEnv, Walker3DStepperVecEnv),
+             MONKEY_ID: (Monkey3DCustomEnv, Monkey3DCustomVecEnv)}
 
 
 def make(env_id: str, num_envs: int | None = None, **kwargs):

@@ -613,14 +613,18 @@ static int box_bar(const orc_box* bx, const orc_bar* b, double thresh, v3 pa, v3
   double t0 = v3dot(d, b->axis);
   int found = 0;
   double best = 1e30;
-  for (int k = -2; k <= 2; k++) {
+  /* visiting order 0, -1, +1, -2, +2; an outer sample replaces the current one only if it is deeper by more than
+   * 1e-5 m, so that a bar lying parallel to a box face (all samples equally deep) yields the central point */
+  static const int order[5] = {0, -1, 1, -2, 2};
+  for (int kk = 0; kk < 5; kk++) {
+    int k = order[kk];
     double t = t0 + 0.03 * k;
     if (t > b->halflen) t = b->halflen;
     if (t < -b->halflen) t = -b->halflen;
     v3 q = {b->center[0] + t * b->axis[0], b->center[1] + t * b->axis[1], b->center[2] + t * b->axis[2]};
     v3 ps, ns;
     double ds;
-    if (sphere_box(q, b->radius, bx, thresh, ps, ns, &ds) && ds < best) {
+    if (sphere_box(q, b->radius, bx, thresh, ps, ns, &ds) && ds < best - 1e-5) {
       best = ds;
       found = 1;
       for (int i = 0; i < 3; i++) { n[i] = -ns[i]; pa[i] = ps[i] - ds * ns[i]; }
@@ -1534,6 +1538,256 @@ void orc_stepper_step_batch(const orc_model* m, const orc_params* p, orc_stepper
     if (dones[i]) orc_stepper_reset(m, p, &envs[i], obs + (size_t)i * O);
   }
 }
+
+/* ------------------------------------------------------------------ 11. Monkey3DCustomEnv */
+/* btMatrix3x3::getRotation on the link->world rotation */
+static void mat_to_quat(m3 R, double q[4]) {
+  double tr = R[0][0] + R[1][1] + R[2][2];
+  if (tr > 0) {
+    double s = sqrt(tr + 1.0);
+    q[3] = s * 0.5;
+    s = 0.5 / s;
+    q[0] = (R[2][1] - R[1][2]) * s; q[1] = (R[0][2] - R[2][0]) * s; q[2] = (R[1][0] - R[0][1]) * s;
+  } else {
+    int i = R[0][0] < R[1][1] ? (R[1][1] < R[2][2] ? 2 : 1) : (R[0][0] < R[2][2] ? 2 : 0);
+    int j = (i + 1) % 3, k = (i + 2) % 3;
+    double s = sqrt(R[i][i] - R[j][j] - R[k][k] + 1.0);
+    q[i] = s * 0.5;
+    s = 0.5 / s;
+    q[3] = (R[k][j] - R[j][k]) * s; q[j] = (R[j][i] + R[i][j]) * s; q[k] = (R[k][i] + R[i][k]) * s;
+  }
+}
+
+/* BodyPart.pose() of the palm links (bullet_utils.py:100-107): COM frame == body frame for these MJCF bodies */
+static void monkey_palms(const orc_model* m, orc_monkey_env* e) {
+  orc_cache* c = (orc_cache*)malloc(sizeof(orc_cache));
+  kin(m, &e->base.s, c);
+  for (int h = 0; h < 2; h++) {
+    int li = m->palm_link[h] + 1;
+    v3copy(e->palm_xyz[h], c->pw[li]);
+    m3 Rl;
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) Rl[a][b] = c->Rw[li][b][a];
+    mat_to_quat(Rl, e->palm_quat[h]);
+  }
+  free(c);
+}
+
+/* set_step_state (env_locomotion.py:1244-1248): cylinder axis = local z rotated by euler(90 deg, 0, phi) */
+static void monkey_place_bar(orc_monkey_env* e, int info_index, int bar) {
+  const double* t = e->terrain[info_index];
+  orc_bar* b = &e->bars[bar];
+  m3 R;
+  euler_to_mat(90 * (PI / 180), 0.0, t[3], R);
+  for (int k = 0; k < 3; k++) { b->center[k] = t[k]; b->axis[k] = R[k][2]; }
+  b->halflen = 2.5;   /* bar_length = 5 (env_locomotion.py:1143) */
+  b->radius = 0.015;  /* step_radius (env_locomotion.py:1148) */
+  b->friction = 0.5;  /* Bullet default: the changeDynamics call is commented out (bullet_objects.py:172-179) */
+  b->id = 20 + bar;
+  e->bar_index[bar] = info_index;
+}
+
+/* env_locomotion.py:1183-1228 with n_steps=32, yaw_limit=pitch_limit=0 */
+static void monkey_generate_placements(orc_monkey_env* e) {
+  orc_rng* r = &e->base.env_rng;
+  const double D2R = PI / 180;
+  double dr[ORC_NBARS], dphi[ORC_NBARS], dth[ORC_NBARS], dx[ORC_NBARS], dy[ORC_NBARS], dz[ORC_NBARS], phi[ORC_NBARS];
+  double ylo = -0.0 * D2R, yhi = 0.0 * D2R, plo = (90 - 0) * D2R, phi_ = (90 + 0) * D2R;
+  for (int i = 0; i < ORC_NBARS; i++) dr[i] = orc_rng_uniform(r, 0.3, 0.5);
+  for (int i = 0; i < ORC_NBARS; i++) dphi[i] = orc_rng_uniform(r, ylo, yhi);
+  for (int i = 0; i < ORC_NBARS; i++) dth[i] = orc_rng_uniform(r, plo, phi_);
+  dphi[0] = 0; dphi[1] = 0;
+  double acc = 0;
+  for (int i = 0; i < ORC_NBARS; i++) { acc += dphi[i]; phi[i] = acc; }
+  /* base_phi (env_locomotion.py:1298-1301) */
+  double sgn = e->base.mirrored ? -1.0 : 1.0;
+  for (int i = 0; i < ORC_NBARS; i++) {
+    double deg = i == 0 ? -10 : (i == ORC_NBARS - 1 ? 10 : ((i & 1) ? 20 : -20));
+    double bp = (D2R * deg) * sgn;
+    dx[i] = dr[i] * sin(dth[i]) * cos(phi[i] + bp);
+    double ax = fabs(dx[i]), mx = ax > 0.015 * 2.5 ? ax : 0.015 * 2.5;
+    double sg = dx[i] > 0 ? 1.0 : (dx[i] < 0 ? -1.0 : 0.0);
+    dx[i] = sg * (mx < 0.5 ? mx : 0.5);
+    dy[i] = dr[i] * sin(dth[i]) * sin(phi[i] + bp);
+    dz[i] = dr[i] * cos(dth[i]);
+  }
+  const double (*f)[3] = e->base.feet_xyz;
+  int i0 = f[1][0] < f[0][0] ? 1 : 0; /* np.argmin: first minimum */
+  int j0 = f[1][0] > f[0][0] ? 1 : 0; /* np.argmax: first maximum */
+  dx[0] = f[i0][0]; dy[0] = f[i0][1]; dz[0] = f[i0][2];
+  dx[1] = f[j0][0] - dx[0] + 0.01;
+  dy[1] = f[j0][1] - dy[0];
+  dz[1] = f[j0][2] - dz[0] - 0.02;
+  dx[0] += 0.04;
+  dz[0] += -20 + 0.04;
+  double x = 0, y = 0, z = 0;
+  for (int i = 0; i < ORC_NBARS; i++) {
+    x += dx[i]; y += dy[i]; z += dz[i];
+    e->terrain[i][0] = x; e->terrain[i][1] = y; e->terrain[i][2] = z + 20; e->terrain[i][3] = phi[i];
+  }
+  e->swing_leg = i0;
+  e->pivot_leg = j0;
+}
+
+/* delta_to_k_targets(k=2) (env_locomotion.py:1489-1516) */
+static void monkey_targets(orc_monkey_env* e) {
+  orc_w3d_env* b = &e->base;
+  for (int k = 0; k < 2; k++) {
+    int idx = e->next_step_index + k;
+    if (idx > ORC_NBARS - 1) idx = ORC_NBARS - 1;
+    const double* t = e->terrain[idx];
+    if (k == 0) v3copy(b->walk_target, t);
+    double dx = t[0] - b->body_xyz[0], dy = t[1] - b->body_xyz[1], dz = t[2] - b->body_xyz[2];
+    double ang = atan2(dy, dx) - b->body_rpy[2], d = sqrt(dx * dx + dy * dy);
+    e->targets[k][0] = sin(ang) * d; e->targets[k][1] = cos(ang) * d; e->targets[k][2] = dz;
+  }
+}
+
+/* env_locomotion.py:1351-1364 */
+static void monkey_calc_potential(const orc_model* m, orc_monkey_env* e, double scene_dt) {
+  orc_w3d_env* b = &e->base;
+  double dx = b->walk_target[0] - b->body_xyz[0], dy = b->walk_target[1] - b->body_xyz[1];
+  b->distance_to_target = sqrt(dx * dx + dy * dy);
+  monkey_palms(m, e);
+  const double* pxyz = e->palm_xyz[e->swing_leg == 0 ? 0 : 1];
+  double d[3] = {b->walk_target[0] - pxyz[0], b->walk_target[1] - pxyz[1], b->walk_target[2] - pxyz[2]};
+  b->linear_potential = -b->distance_to_target / scene_dt;
+  e->swing_potential = -sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) / scene_dt;
+}
+
+/* get_observation_component (env_locomotion.py:1268-1281) */
+static void monkey_obs(const orc_model* m, orc_monkey_env* e, double* obs) {
+  orc_w3d_env* b = &e->base;
+  int n = 6 + 2 * m->n_dof; /* robot_state[:-2] */
+  for (int k = 0; k < n; k++) obs[k] = b->robot_state[k];
+  obs[n] = b->feet_contact[0]; obs[n + 1] = b->feet_contact[1];
+  for (int k = 0; k < 2; k++)
+    for (int j = 0; j < 3; j++) obs[n + 2 + 3 * k + j] = e->targets[k][j];
+  obs[n + 8] = e->swing_leg; obs[n + 9] = e->pivot_leg;
+  monkey_palms(m, e);
+  int h = e->swing_leg == 0 ? 0 : 1;
+  for (int k = 0; k < 3; k++) obs[n + 10 + k] = b->walk_target[k] - e->palm_xyz[h][k];
+  for (int k = 0; k < 4; k++) obs[n + 13 + k] = e->palm_quat[h][k];
+}
+
+void orc_monkey_seed(orc_monkey_env* e, const uint32_t* key, int len, int at_construction) {
+  orc_w3d_seed(&e->base, key, len, at_construction);
+}
+
+/* calc_feet_state (env_locomotion.py:1404-1452).  contacts == NULL: the reset-time call, which in the reference
+ * reads Bullet's STALE contact points of the previous episode; the batched simulator defines "no contacts after
+ * reset" (documented deviation, same policy as the Stepper's quirk Q5). */
+static void monkey_feet_state(const orc_model* m, orc_monkey_env* e, const orc_contacts* ct) {
+  orc_w3d_env* b = &e->base;
+  /* next_step and p_xyz are bound BEFORE the loop and stay stale if the index advances at i == 0 */
+  int target_id = 20 + (e->next_step_index % 4);
+  double px = e->terrain[e->next_step_index][0], py = e->terrain[e->next_step_index][1];
+  for (int i = 0; i < 2; i++) {
+    int contact = 0;
+    if (ct)
+      for (int k = 0; k < ct->n; k++)
+        if (ct->link[k] == m->foot_link[i]) contact = 1; /* every partner (bars, ground) is in all_contact_object_ids */
+    b->feet_contact[i] = contact;
+    if (i != e->swing_leg) continue;
+    double dx = b->feet_xyz[e->swing_leg][0] - px, dy = b->feet_xyz[e->swing_leg][1] - py;
+    e->foot_dist_to_target = sqrt(dx * dx + dy * dy);
+    int palm = m->palm_link[e->swing_leg == 0 ? 0 : 1];
+    int hit = 0;
+    if (ct)
+      for (int k = 0; k < ct->n; k++)
+        if (ct->link[k] == palm && ct->partner[k] == target_id) hit = 1;
+    e->target_reached_count += hit;
+    e->target_reached = e->target_reached_count >= 1;
+    if (!e->target_reached) continue;
+    e->target_reached_count = 0;
+    e->next_step_index += 1;
+    if (e->next_step_index > ORC_NBARS - 1) e->next_step_index = ORC_NBARS - 1;
+    if (e->next_step_index >= 4) { /* update_steps (env_locomotion.py:1255-1266) */
+      int oldest = e->next_step_index % 4;
+      int nxt = e->next_step_index < ORC_NBARS - 1 ? e->next_step_index : ORC_NBARS - 1;
+      monkey_place_bar(e, nxt, oldest);
+    }
+    e->pivot_leg = e->swing_leg;
+    e->swing_leg = (e->swing_leg + 1) % 2;
+  }
+}
+
+void orc_monkey_reset(const orc_model* m, const orc_params* p, orc_monkey_env* e, double* obs) {
+  orc_w3d_env* b = &e->base;
+  b->done = 0; b->elapsed = 0;
+  e->free_fall_count = 0; e->target_reached_count = 0; e->timestep = 0; e->target_reached = 0;
+  e->next_step_index = 2;
+  double pos[3] = {0, 0, 20}, vel[3] = {3, 0, -1}; /* env_locomotion.py:1153-1154 */
+  robot_reset_ex(m, b, pos, vel, 0);
+  monkey_generate_placements(e);
+  for (int k = 0; k < 4; k++) monkey_place_bar(e, k, k);
+  monkey_feet_state(m, e, NULL);
+  monkey_targets(e);
+  monkey_calc_potential(m, e, p->dt * p->substeps);
+  monkey_obs(m, e, obs);
+}
+
+void orc_monkey_step(const orc_model* m, const orc_params* p, orc_monkey_env* e, const double* action_in, double* obs,
+                     double* reward, int* done, int* truncated) {
+  orc_w3d_env* b = &e->base;
+  int A = m->n_dof;
+  double action[ORC_MAXD], tau[ORC_MAXD];
+  for (int d = 0; d < A; d++) action[d] = action_in[d];
+  e->timestep += 1;
+  /* env_locomotion.py:1322-1323 (the reference mutates the caller's array, quirk Q11) */
+  action[e->swing_leg == 0 ? 17 : 22] = 1;
+  action[e->pivot_leg == 0 ? 17 : 22] = -1;
+  for (int d = 0; d < A; d++) {
+    double a = action[d];
+    if (a > 1) a = 1;
+    if (a < -1) a = -1;
+    tau[d] = m->gain[d] * a;
+  }
+  int rows = 0;
+  orc_step_physics_bars(m, p, &b->s, tau, e->bars, 4, &b->last_contacts, &rows);
+  b->rows_sum = rows;
+  w3d_calc_state(m, b, NULL);
+  int nstate = 6 + 2 * A + m->n_feet;
+  for (int k = 0; k < nstate; k++)
+    if (!isfinite(b->robot_state[k])) b->done = 1;
+  int cur = e->next_step_index;
+  monkey_feet_state(m, e, &b->last_contacts);
+  /* calc_base_reward (env_locomotion.py:1366-1402): only the swing progress and the free-fall test survive the
+   * zero weights of step() */
+  double old_swing = e->swing_potential;
+  monkey_calc_potential(m, e, p->dt * p->substeps);
+  b->progress = e->swing_potential - old_swing;
+  if (e->free_fall_count > 30) b->done = 1;
+  /* calc_step_reward (env_locomotion.py:1454-1466) */
+  e->step_bonus = e->target_reached ? 50 * exp(-e->foot_dist_to_target / 0.25) : 0.0;
+  monkey_targets(e);
+  int mask = (b->feet_contact[0] + b->feet_contact[1]) == 0;
+  e->free_fall_count = mask * e->free_fall_count + mask;
+  if (cur != e->next_step_index) monkey_calc_potential(m, e, p->dt * p->substeps);
+  *reward = b->progress + e->step_bonus - b->feet_contact[e->swing_leg];
+  if (e->timestep > 180 && e->next_step_index <= 2) b->done = 1;
+  monkey_obs(m, e, obs);
+  b->elapsed++;
+  *truncated = 0;
+  *done = b->done;
+  if (b->elapsed >= 1000) { *truncated = !b->done; *done = 1; }
+}
+
+void orc_monkey_step_batch(const orc_model* m, const orc_params* p, orc_monkey_env* envs, int n,
+                           const double* actions, double* obs, double* rewards, int* dones, int n_threads) {
+  int A = m->n_dof, O = 6 + 2 * A + 17;
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+  for (int i = 0; i < n; i++) {
+    int trunc;
+    orc_monkey_step(m, p, &envs[i], actions + (size_t)i * A, obs + (size_t)i * O, &rewards[i], &dones[i], &trunc);
+    if (dones[i]) orc_monkey_reset(m, p, &envs[i], obs + (size_t)i * O);
+  }
+}
+
+int orc_sizeof_monkey_env(void) { return (int)sizeof(orc_monkey_env); }
 
 int orc_sizeof_stepper_env(void) { return (int)sizeof(orc_stepper_env); }
 int orc_sizeof_w3d_env(void) { return (int)sizeof(orc_w3d_env); }

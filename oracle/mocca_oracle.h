@@ -223,6 +223,8 @@ void orc_monkey_seed(orc_monkey_env* e, const uint32_t* key, int len, int at_con
 void orc_monkey_reset(const orc_model* m, const orc_params* p, orc_monkey_env* e, double* obs /* [69] */);
 void orc_monkey_step(const orc_model* m, const orc_params* p, orc_monkey_env* e, const double* action, double* obs,
                      double* reward, int* done, int* truncated);
+void orc_monkey_step_batch(const orc_model* m, const orc_params* p, orc_monkey_env* envs, int n,
+                           const double* actions, double* obs, double* rewards, int* dones, int n_threads);
 int orc_sizeof_monkey_env(void);
 int orc_sizeof_stepper_env(void);
 int orc_sizeof_w3d_env(void);

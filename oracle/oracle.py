@@ -100,6 +100,20 @@ class StepperEnv(C.Structure):
     ]
 
 
+class Bar(C.Structure):
+    _fields_ = [("center", d * 3), ("axis", d * 3), ("halflen", d), ("radius", d), ("friction", d), ("id", i32)]
+
+
+class MonkeyEnv(C.Structure):
+    _fields_ = [
+        ("base", W3DEnv), ("terrain", (d * 4) * 32), ("bars", Bar * 4), ("bar_index", i32 * 4),
+        ("next_step_index", i32), ("target_reached_count", i32), ("free_fall_count", i32), ("timestep", i32),
+        ("swing_leg", i32), ("pivot_leg", i32), ("target_reached", i32),
+        ("foot_dist_to_target", d), ("swing_potential", d), ("targets", (d * 3) * 2),
+        ("palm_xyz", (d * 3) * 2), ("palm_quat", (d * 4) * 2), ("step_bonus", d),
+    ]
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "mocca_oracle.c")
     hdr = os.path.join(_HERE, "mocca_oracle.h")
@@ -121,6 +135,7 @@ def lib():
         assert L.orc_sizeof_model() == C.sizeof(Model), (L.orc_sizeof_model(), C.sizeof(Model))
         assert L.orc_sizeof_w3d_env() == C.sizeof(W3DEnv), (L.orc_sizeof_w3d_env(), C.sizeof(W3DEnv))
         assert L.orc_sizeof_stepper_env() == C.sizeof(StepperEnv), (L.orc_sizeof_stepper_env(), C.sizeof(StepperEnv))
+        assert L.orc_sizeof_monkey_env() == C.sizeof(MonkeyEnv), (L.orc_sizeof_monkey_env(), C.sizeof(MonkeyEnv))
         L.orc_rng_double.restype = d
         L.orc_rng_uniform.restype = d
         L.orc_rng_uniform.argtypes = [C.c_void_p, d, d]
@@ -266,6 +281,15 @@ def step_physics(m, p, s, tau, boxes=None, warm=None):
     return c, rows.value
 
 
+def step_physics_bars(m, p, s, tau, bars):
+    """One stepSimulation with static bars (Monkey3D). Mutates s. Returns (last contacts, total rows)."""
+    t = (d * MAXD)(*[float(x) for x in tau])
+    c = Contacts()
+    rows = i32(0)
+    lib().orc_step_physics_bars(C.byref(m), C.byref(p), C.byref(s), t, bars, len(bars), C.byref(c), C.byref(rows))
+    return c, rows.value
+
+
 def energy_momentum(m, s, gravity):
     out = (d * 8)()
     lib().orc_energy_momentum(C.byref(m), C.byref(s), float(gravity), out)
@@ -378,6 +402,47 @@ class Walker3DStepperOracle:
             info["steps_reached"] = self.e.steps_reached
         if trunc.value:
             info["TimeLimit.truncated"] = True
+        return np.array(obs), r.value, bool(done.value), info
+
+    def state_vector(self):
+        return state_vector(self.e.base.s, self.A)
+
+
+class Monkey3DOracle:
+    """Single-env restatement of Monkey3DCustomEnv (reference env_locomotion.py:1136-1516)."""
+
+    def __init__(self, table: dict, seed: int = 0, params: Params | None = None):
+        self.table = table
+        self.m = model_from_table(table)
+        self.p = params or default_params()
+        self.e = MonkeyEnv()
+        self.A = table["n_dof"]
+        self.obs_dim = 6 + 2 * self.A + 17
+        self._seed(seed, True)
+
+    def _seed(self, seed, at_construction):
+        words = gym_seed_words(seed)
+        key = (C.c_uint32 * len(words))(*words)
+        lib().orc_monkey_seed(C.byref(self.e), key, len(words), int(at_construction))
+
+    def seed(self, seed):
+        self._seed(seed, False)
+        return [seed]
+
+    def reset(self):
+        obs = (d * self.obs_dim)()
+        lib().orc_monkey_reset(C.byref(self.m), C.byref(self.p), C.byref(self.e), obs)
+        return np.array(obs)
+
+    def step(self, action):
+        a = (d * MAXD)(*[float(x) for x in action])
+        obs = (d * self.obs_dim)()
+        r = d(0)
+        done = i32(0)
+        trunc = i32(0)
+        lib().orc_monkey_step(C.byref(self.m), C.byref(self.p), C.byref(self.e), a, obs, C.byref(r), C.byref(done),
+                              C.byref(trunc))
+        info = {"TimeLimit.truncated": True} if trunc.value else {}
         return np.array(obs), r.value, bool(done.value), info
 
     def state_vector(self):

@@ -25,3 +25,10 @@ def oracle_mod():
 
     O.build()
     return O
+
+
+@pytest.fixture(scope="session")
+def monkey_table():
+    from mocca_envs_b200.model_compiler import load_table
+
+    return load_table(os.path.join(ROOT, "mocca_envs_b200", "models", "monkey3d.json"))

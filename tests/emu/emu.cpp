@@ -4,19 +4,23 @@
 #include <string.h>
 
 #include "../../mocca_envs_b200/csrc/generated/walker3d_model.h"
+#include "../../mocca_envs_b200/csrc/generated/monkey3d_model.h"
 #include "../../mocca_envs_b200/csrc/mb_env.cuh"
 
 typedef W3D_Model WM;
 typedef W3DEnv<WM> WEnv;
 typedef StepperEnv<WM> SEnv;
 typedef WarpMem<WM> WMem;
+typedef MK3D_Model MM;
+typedef MonkeyEnv<MM> MEnv;
+typedef WarpMem<MM> MMem;
 
 static void default_phys(MbPhysics* p) {
   p->dt = 1.0f / 240.0f; p->substeps = 4; p->iterations = 5; p->gravity = 9.8f; p->erp_contact = 0.9f;
   p->erp_joint = 0.2f; p->linear_slop = 1e-5f; p->lin_damping = 0.04f; p->ang_damping = 0.04f;
   p->max_coord_vel = 100.0f; p->limit_max_impulse = 100.0f; p->split_threshold = -0.04f;
   p->residual_threshold = 1e-7f; p->ground_friction = 0.8f; p->has_ground = 1;
-  p->box_friction = 1.0f; p->box_erp = 0.9f; p->box_cfm = 0.0f;
+  p->box_friction = 1.0f; p->box_erp = 0.9f; p->box_cfm = 0.0f; p->bar_friction = 0.5f;
 }
 
 extern "C" {
@@ -32,7 +36,7 @@ void emu_step_physics(const MbPhysics* p, float* state, const float* tau, int* r
   int r = 0, nc = 0, ov = 0;
   Sim<WM>::LaneConst C;
   Sim<WM>::init_lane_const(C);
-  for (int k = 0; k < p->substeps; ++k) r += Sim<WM>::substep<false>(S, *p, C, &nc, &ov);
+  for (int k = 0; k < p->substeps; ++k) r += Sim<WM>::substep<0>(S, *p, C, &nc, &ov);
   WEnv::store_state(S, state);
   *rows = r;
   *contacts = nc;
@@ -112,9 +116,65 @@ void emu_stepper_step_physics(const MbPhysics* p, float* state, const float* rec
   int r = 0, nc = 0, ov = 0;
   Sim<WM>::LaneConst C;
   Sim<WM>::init_lane_const(C);
-  for (int k = 0; k < p->substeps; ++k) r += Sim<WM>::substep<true>(S, *p, C, &nc, &ov);
+  for (int k = 0; k < p->substeps; ++k) r += Sim<WM>::substep<MB_OBST_BOXES>(S, *p, C, &nc, &ov);
   WEnv::store_state(S, state);
   *rows = r;
   *contacts = nc;
+}
+
+// ---- Monkey3DCustomEnv
+int emu_monkey_rec_stride() { return (int)MEnv::REC_STRIDE; }
+int emu_sizeof_monkey_warpmem() { return (int)sizeof(MMem); }
+
+void emu_monkey_reset(const MbPhysics* p, float* state, float* rec, uint32_t* mt_env, uint32_t* mt_robot, float* obs) {
+  static MMem S;
+  memset(&S, 0, sizeof(S));
+  MEnv::reset(S, *p, rec, mt_env, mt_robot, obs);
+  MEnv::store_state(S, state);
+}
+
+void emu_monkey_step(const MbPhysics* p, float* state, float* rec, uint32_t* mt_env, uint32_t* mt_robot,
+                     const float* act, float* obs, float* rew, uint8_t* done, uint8_t* trunc, float* final_obs,
+                     double* stats_out) {
+  static MMem S;
+  memset(&S, 0, sizeof(S));
+  MbStats st;
+  memset(&st, 0, sizeof(st));
+  MEnv::step(S, *p, state, rec, mt_env, mt_robot, act, obs, rew, done, trunc, final_obs, &st);
+  stats_out[0] = (double)st.episodes; stats_out[1] = st.ret_sum; stats_out[2] = st.len_sum;
+  stats_out[3] = (double)st.nonfinite;
+}
+
+// stepSimulation with the bars described by a Monkey record
+void emu_monkey_step_physics(const MbPhysics* p, float* state, const float* rec, const float* tau, int* rows,
+                             int* contacts) {
+  static MMem S;
+  memset(&S, 0, sizeof(S));
+  MEnv::load_state(S, state);
+  MEnv::load_obstacles(S, rec);
+  for (int j = 0; j < MM::NJ; ++j) S.tau[j] = tau[j];
+  int r = 0, nc = 0, ov = 0;
+  Sim<MM>::LaneConst C;
+  Sim<MM>::init_lane_const(C);
+  for (int k = 0; k < p->substeps; ++k) r += Sim<MM>::substep<MB_OBST_BARS>(S, *p, C, &nc, &ov);
+  MEnv::store_state(S, state);
+  *rows = r;
+  *contacts = nc;
+}
+
+void emu_monkey_mass_matrix(const MbPhysics* p, const float* state, float* Mout, float* bias) {
+  static MMem S;
+  memset(&S, 0, sizeof(S));
+  MEnv::load_state(S, state);
+  Sim<MM>::LaneConst C;
+  Sim<MM>::init_lane_const(C);
+  Sim<MM>::kinematics(S, *p, C, true);
+  Sim<MM>::bodies(S, *p);
+  Sim<MM>::mass_matrix_and_rhs(S);
+  const int NU = MM::NU;
+  for (int i = 0; i < NU; ++i) {
+    for (int j = 0; j < NU; ++j) Mout[i * NU + j] = mb_Lget<MM>(S.L, i, j);
+    bias[i] = -S.rhs[i];
+  }
 }
 }

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libmb_emu.so")
 _SRC = [os.path.join(_HERE, "emu.cpp")] + [
     os.path.join(_HERE, "..", "..", "mocca_envs_b200", "csrc", f)
-    for f in ("mb_core.cuh", "mb_env.cuh", "mb_tables.h", "generated/walker3d_model.h")]
+    for f in ("mb_core.cuh", "mb_env.cuh", "mb_tables.h", "generated/walker3d_model.h", "generated/monkey3d_model.h")]
 
 
 class Phys(C.Structure):
@@ -18,7 +18,7 @@ class Phys(C.Structure):
                 ("lin_damping", C.c_float), ("ang_damping", C.c_float), ("max_coord_vel", C.c_float),
                 ("limit_max_impulse", C.c_float), ("split_threshold", C.c_float), ("residual_threshold", C.c_float),
                 ("ground_friction", C.c_float), ("has_ground", C.c_int), ("box_friction", C.c_float),
-                ("box_erp", C.c_float), ("box_cfm", C.c_float)]
+                ("box_erp", C.c_float), ("box_cfm", C.c_float), ("bar_friction", C.c_float)]
 
 
 _lib = None
@@ -145,3 +145,56 @@ class EmuStepper:
         rows, nc = C.c_int(0), C.c_int(0)
         lib().emu_stepper_step_physics(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(tau), C.byref(rows), C.byref(nc))
         return rows.value, nc.value
+
+
+class EmuMonkey:
+    """Monkey3DCustomEnv through the emulated kernel source (record layout: ER_* / EM_* in mb_env.cuh)."""
+
+    EM_NEXT, EM_FREEFALL, EM_TIMESTEP, EM_SWING, EM_PIVOT, EM_SWINGPOT, EM_BARIDX, EM_BAR, EM_TERRAIN = \
+        22, 23, 24, 25, 26, 27, 28, 32, 64
+
+    def __init__(self, mt_state):
+        self.p = default_phys()
+        self.state = np.zeros(64, dtype=np.float32)
+        self.stride = lib().emu_monkey_rec_stride()
+        self.rec = np.zeros(self.stride, dtype=np.float32)
+        self.mt = np.zeros((2, 640), dtype=np.uint32)
+        self.mt[0, :625] = mt_state
+        self.mt[1, 624] = 624
+        self.rec.view(np.int32)[11] = 1  # ER_ALIASED
+        self.obs_dim, self.act_dim = 69, 23
+
+    def reset(self):
+        obs = np.zeros(self.obs_dim, dtype=np.float32)
+        lib().emu_monkey_reset(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(self.mt[0]), _fp(self.mt[1]), _fp(obs))
+        return obs
+
+    def step(self, act):
+        act = np.ascontiguousarray(act, dtype=np.float32)
+        obs = np.zeros(self.obs_dim, dtype=np.float32)
+        fin = np.zeros(self.obs_dim, dtype=np.float32)
+        rew = np.zeros(1, dtype=np.float32)
+        done = np.zeros(1, dtype=np.uint8)
+        trunc = np.zeros(1, dtype=np.uint8)
+        st = np.zeros(4)
+        lib().emu_monkey_step(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(self.mt[0]), _fp(self.mt[1]),
+                              _fp(act), _fp(obs), _fp(rew), _fp(done), _fp(trunc), _fp(fin), _fp(st))
+        return obs, float(rew[0]), bool(done[0]), bool(trunc[0]), fin
+
+    def terrain(self):
+        return self.rec[self.EM_TERRAIN:self.EM_TERRAIN + 128].reshape(32, 4)
+
+    def step_physics(self, tau):
+        tau = np.ascontiguousarray(tau, dtype=np.float32)
+        rows, nc = C.c_int(0), C.c_int(0)
+        lib().emu_monkey_step_physics(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(tau), C.byref(rows), C.byref(nc))
+        return rows.value, nc.value
+
+
+def monkey_mass_matrix(p, state, nu=29):
+    buf = np.zeros(64, dtype=np.float32)
+    buf[: len(state)] = state
+    M = np.zeros((nu, nu), dtype=np.float32)
+    b = np.zeros(nu, dtype=np.float32)
+    lib().emu_monkey_mass_matrix(C.byref(p), _fp(buf), _fp(M), _fp(b))
+    return M, b
