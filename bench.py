@@ -152,22 +152,25 @@ def cpu_reference_run(n_envs, steps, warmup, threads, time_budget=None, kind="cu
     from mocca_envs_b200.model_compiler import load_table
     from oracle import oracle as O
 
-    model, struct, pre, A, OB = {"custom": ("walker3d", O.W3DEnv, "orc_w3d", 21, 52),
+    model, struct, pre, A, OB = {"cassie": ("cassie", O.CassieEnvS, "orc_cassie", 10, 36),
+                                 "custom": ("walker3d", O.W3DEnv, "orc_w3d", 21, 52),
                                  "stepper": ("walker3d", O.StepperEnv, "orc_stepper", 21, 65),
                                  "monkey": ("monkey3d", O.MonkeyEnv, "orc_monkey", 23, 69)}[kind]
     t = load_table(os.path.join(ROOT, "mocca_envs_b200", "models", model + ".json"))
     m = O.model_from_table(t)
-    p = O.default_params()
+    p = O.cassie_params() if kind == "cassie" else O.default_params()
     L = O.lib()
     envs = (struct * n_envs)()
     obs = np.zeros((n_envs, OB))
-    seed_fn, reset_fn, batch_fn = (getattr(L, pre + sfx) for sfx in ("_seed", "_reset", "_step_batch"))
+    seed_fn = getattr(L, pre + "_seed", None)  # CassieEnv draws no random numbers
+    reset_fn, batch_fn = getattr(L, pre + "_reset"), getattr(L, pre + "_step_batch")
     for i in range(n_envs):
         words = O.gym_seed_words(1000 + i)
         key = (C.c_uint32 * len(words))(*words)
         if kind == "stepper":
             envs[i].curriculum = (0, 5, 9)[i % 3]
-        seed_fn(C.byref(envs[i]), key, len(words), 1)
+        if seed_fn is not None:
+            seed_fn(C.byref(envs[i]), key, len(words), 1)
         reset_fn(C.byref(m), C.byref(p), C.byref(envs[i]), obs[i].ctypes.data_as(C.c_void_p))
     rew = np.zeros(n_envs)
     done = np.zeros(n_envs, dtype=np.int32)
@@ -175,7 +178,7 @@ def cpu_reference_run(n_envs, steps, warmup, threads, time_budget=None, kind="cu
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
 
     def one():
-        a = rng.uniform(-1, 1, (n_envs, A))
+        a = rng.uniform(-1, 1, (n_envs, A)) * (0.1 if kind == "cassie" else 1.0)
         batch_fn(C.byref(m), C.byref(p), envs, n_envs, vp(a), vp(obs), vp(rew), vp(done), threads)
 
     for _ in range(warmup):
@@ -198,9 +201,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--envs", type=int, default=16384, help="envs per GPU")
     ap.add_argument("--actions", default="random", choices=["random", "pd"])
-    ap.add_argument("--env", default="custom", choices=["custom", "stepper", "monkey"],
+    ap.add_argument("--env", default="custom", choices=["custom", "stepper", "monkey", "cassie"],
                     help="custom = BASELINE configs[1] (headline); stepper = configs[2] (curriculum 0/5/9 per env); "
-                         "monkey = configs[4] (Monkey3DCustomEnv-v0)")
+                         "monkey = configs[4] (Monkey3DCustomEnv-v0); cassie = configs[3] (CassieEnv-v0, 50 substeps per step)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -219,7 +222,7 @@ def main():
         line = {
             "impl": "reference",
             "metric": METRIC.replace("Walker3DCustomEnv", {"custom": "Walker3DCustomEnv", "stepper": "Walker3DStepperEnv",
-                                                           "monkey": "Monkey3DCustomEnv"}[args.env]),
+                                                           "monkey": "Monkey3DCustomEnv", "cassie": "CassieEnv"}[args.env]),
             "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": ks, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(ks, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -237,7 +240,7 @@ def main():
 
     from mocca_envs_b200 import _lib
     from mocca_envs_b200.distributed import shard_seed
-    from mocca_envs_b200.vec_env import Monkey3DCustomVecEnv, Walker3DCustomVecEnv, Walker3DStepperVecEnv
+    from mocca_envs_b200.vec_env import CassieVecEnv, Monkey3DCustomVecEnv, Walker3DCustomVecEnv, Walker3DStepperVecEnv
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
@@ -256,6 +259,8 @@ def main():
         env.set_env_params({"curriculum": np.array([0, 5, 9] * (N // 3 + 1))[:N]})
     elif args.env == "monkey":
         env = Monkey3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N))
+    elif args.env == "cassie":
+        env = CassieVecEnv(N, device=dev, seed=shard_seed(1234, rank, N))
     else:
         env = Walker3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N))
     env.reset()
@@ -263,10 +268,13 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     pool = 64
     act_pool = torch.rand(pool, N, A, device=dev, generator=gen) * 2 - 1
-    q_ref = torch.tensor(env.table["base_joint_angles"], device=dev, dtype=torch.float32)
-    lo = torch.tensor(env.table["lower"], device=dev, dtype=torch.float32)
-    hi = torch.tensor(env.table["upper"], device=dev, dtype=torch.float32)
-    ref_norm = 2 * (q_ref - lo) / (hi - lo) - 1
+    if args.env == "cassie":
+        act_pool *= 0.1  # a ~ U(-0.1, 0.1)^10 residual on the PD targets
+    if args.actions == "pd":
+        q_ref = torch.tensor(env.table["base_joint_angles"], device=dev, dtype=torch.float32)
+        lo = torch.tensor(env.table["lower"], device=dev, dtype=torch.float32)
+        hi = torch.tensor(env.table["upper"], device=dev, dtype=torch.float32)
+        ref_norm = 2 * (q_ref - lo) / (hi - lo) - 1
 
     def action(i, obs):
         if args.actions == "random":
@@ -365,8 +373,12 @@ def main():
 
     ms_per_step = total_ms_max / K
     value = N * world * K / (total_ms_max * 1e-3)
-    R_mean = rows_all / (K * N * world * env.physics.substeps)
-    if args.env == "monkey":  # Monkey3D: n = 29 generalised coordinates, 20 massive links, 29 geoms, obs 69
+    S_sub = 50 * env.physics.substeps if args.env == "cassie" else env.physics.substeps  # substeps per env step
+    R_mean = rows_all / (K * N * world * S_sub)
+    if args.env == "cassie":  # Cassie: 50 x 1 substeps, n = 24 generalised coordinates, 17 massive links, 158 points
+        F = flops_per_env_step(R_mean, S=S_sub, n=24, L=17, G=158)
+        B_step = bytes_per_env_step(S_state=49, A=10, O=36, S_env=20)
+    elif args.env == "monkey":  # Monkey3D: n = 29 generalised coordinates, 20 massive links, 29 geoms, obs 69
         F = flops_per_env_step(R_mean, n=29, L=20, G=29)
         B_step = bytes_per_env_step(S_state=59, A=23, O=69, S_env=40)
     elif args.env == "stepper":
@@ -388,17 +400,18 @@ def main():
     hbm_ach = B_step * N / kernel_s / 1e9
     line = {
         "metric": METRIC.replace("Walker3DCustomEnv", {"custom": "Walker3DCustomEnv", "stepper": "Walker3DStepperEnv",
-                                                       "monkey": "Monkey3DCustomEnv"}[args.env]),
+                                                       "monkey": "Monkey3DCustomEnv", "cassie": "CassieEnv"}[args.env]),
         "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": {"custom": WORKLOAD,
                                 "stepper": "Walker3DStepperEnv-v0 batched 16384 envs/GPU, seeded stepping stones, "
                                            "curriculum 0/5/9",
-                                "monkey": "Monkey3DCustomEnv-v0 batched, seeded monkey bars"}[args.env],
+                                "monkey": "Monkey3DCustomEnv-v0 batched, seeded monkey bars",
+                                "cassie": "CassieEnv-v0 batched, residual PD control, 50 substeps per env step"}[args.env],
                    "envs_per_gpu": N, "actions": "random-uniform U(-1,1)^%d (device pool)" % A
                    if args.actions == "random" else "scripted PD toward running_start (kp=1, kd=0.1, normalised)",
-                   "frame_skip": 4, "solver_iterations": 5, "rng": "mt19937 (NumPy-compatible)",
+                   "frame_skip": S_sub, "solver_iterations": 5, "rng": "mt19937 (NumPy-compatible)",
                    "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs)",
                    "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks",
                    "parallelism": "env-sharded x%d, no data-path collective" % world},
@@ -406,7 +419,7 @@ def main():
                      "frac": achieved_tf / peak if peak else None, "traffic": None,
                      "peak_source": "FP32 FMA probe kernel measured in this run (mb200_measure_fp32_peak)",
                      "flops_per_env_step": F, "rows_per_substep": R_mean,
-                     "contacts_per_substep": conts_all / (K * N * world * env.physics.substeps),
+                     "contacts_per_substep": conts_all / (K * N * world * S_sub),
                      "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                              "bytes_per_env_step": B_step,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
@@ -420,9 +433,10 @@ def main():
         "wall_s": wall,
     }
     if not args.no_cpu_baseline:
-        v, dt, ks = cpu_reference_run(2048, 2000, 2, cores, time_budget=15.0, kind=args.env)
+        ce = 256 if args.env == "cassie" else 2048
+        v, dt, ks = cpu_reference_run(ce, 2000, 2, cores, time_budget=15.0, kind=args.env)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                "sample": "2048 envs x %d control steps (%.1f s), same action distribution; float64 "
+                                "sample": str(ce) + " envs x %d control steps (%.1f s), same action distribution; float64 "
                                           "oracle port with OpenMP over envs (PyBullet not installable here)" % (ks, dt)}
     print(json.dumps(line))
     if dist:

@@ -41,10 +41,14 @@ typedef struct mb200_physics {
 } mb200_physics;
 
 void mb200_default_physics(mb200_physics* p);
+/* the same with the env's own timing: CassieEnv-v0 runs dt = 0.03 / 50 with one substep per stepSimulation and 50
+ * PD-controlled stepSimulations per env step (env_cassie.py:287-289,450-465) */
+void mb200_default_physics_for(const char* env_id, mb200_physics* p);
 
 /* gym.make("mocca_envs:<env_id>") x n_envs  (reference mocca_envs/__init__.py:18-116, env_base.py:16-42).
  * env_id: "Walker3DCustomEnv-v0" (__init__.py:52-56), "Walker3DStepperEnv-v0" (__init__.py:58-62) or
- * "Monkey3DCustomEnv-v0" (__init__.py:94-98; env_locomotion.py:1136-1516).
+ * "Monkey3DCustomEnv-v0" (__init__.py:94-98; env_locomotion.py:1136-1516) or "CassieEnv-v0" (__init__.py:18-22;
+ * env_cassie.py:285-479).
  * physics may be NULL (reference values). */
 int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics* physics, mb200_env** out);
 /* EnvBase.close (env_base.py:44-47) */
@@ -84,7 +88,7 @@ int mb200_record_stride(const mb200_env* env);
 int mb200_get_record(mb200_env* env, float* rec_dev, void* stream);
 int mb200_set_record(mb200_env* env, const float* rec_dev, void* stream);
 
-/* stepSimulation only (bullet_utils.py:352-353): hold tau_dev [n][A] over `substeps` substeps, no env logic.
+/* stepSimulation only (bullet_utils.py:352-353): hold tau_dev [n][nu - 6] over `substeps` substeps, no env logic.
  * Outputs per env: rows_dev (constraint rows summed over the substeps) and contacts_dev (contact points of the
  * last substep); either may be NULL. */
 int mb200_step_physics(mb200_env* env, const float* tau_dev, int* rows_dev, int* contacts_dev, void* stream);

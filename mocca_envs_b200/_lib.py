@@ -10,12 +10,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MB200_LIB") or os.path.join(_HERE, "libmocca_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in
            ("mb200.cu", "mb_core.cuh", "mb_env.cuh", "mb_tables.h", "generated/walker3d_model.h",
-            "generated/monkey3d_model.h")]
+            "generated/monkey3d_model.h", "generated/cassie_model.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 SYMBOLS = [
-    "mb200_default_physics", "mb200_create", "mb200_destroy", "mb200_dims", "mb200_seed", "mb200_reset",
+    "mb200_default_physics", "mb200_default_physics_for", "mb200_create", "mb200_destroy", "mb200_dims", "mb200_seed", "mb200_reset",
     "mb200_step", "mb200_step_host", "mb200_get_state", "mb200_set_state", "mb200_get_record", "mb200_set_record",
     "mb200_step_physics", "mb200_mass_matrix", "mb200_inverse_dynamics", "mb200_set_param",
     "mb200_set_param_array", "mb200_record_stride", "mb200_stats",
@@ -58,6 +58,7 @@ def lib():
         L.mb200_launch_count.restype = C.c_longlong
         L.mb200_launch_count.argtypes = [vp]
         L.mb200_default_physics.argtypes = [C.POINTER(Physics)]
+        L.mb200_default_physics_for.argtypes = [C.c_char_p, C.POINTER(Physics)]
         L.mb200_create.argtypes = [C.c_char_p, ip, ip, C.POINTER(Physics), C.POINTER(vp)]
         L.mb200_destroy.argtypes = [vp]
         L.mb200_destroy.restype = None

@@ -131,8 +131,24 @@ def reduce_table(t: dict) -> dict:
     rowoff = [sum(rowlen[:i]) for i in range(6 + nj)]
     rowmask_rt = [(1 << i) - 1 for i in range(6)] + [0x3F | ((janc[j] & ~(1 << j)) << 6) for j in range(nj)]
     palm_body = [[b["link"] for b in bodies].index(f) for f in palm_links]
+    # loop closures (Cassie): pivots re-expressed in the owner joint frames of the two links
+    p2p = []
+    for c in t.get("p2p", []):
+        sides = []
+        for link, pivot in ((c["link_a"], c["pivot_a"]), (c["link_b"], c["pivot_b"])):
+            oj = owner_joint(link)
+            Ro, oo = frame(oj)
+            pw = pl[link + 1] + Rl[link + 1] @ np.array(pivot)
+            sides.append(dict(owner=oj, pos=Ro.T @ (pw - oo)))
+        p2p.append(dict(sides=sides, max_impulse=c["max_impulse"]))
+    dof_of_rev_link = {l: j for j, l in enumerate(jlink)}
+    extras = {}
+    if "ordered_dofs" in t:
+        pd = t["powered_joint_inds"] + t["spring_joint_inds"]
+        extras = dict(ordered=t["ordered_dofs"], pd_dof=[t["ordered_dofs"][k] for k in pd], pd_ordered=pd,
+                      pd_kp=t["pd_kp"], pd_kd=t["pd_kd"], npowered=len(t["powered_joint_inds"]))
     return dict(name=t["name"], nj=nj, nb=nb, nu=6 + nj, npt=len(points), nlevel=max(jlevel) + 1,
-                xboxes=xboxes, palm_body=palm_body,
+                xboxes=xboxes, palm_body=palm_body, p2p=p2p, extras=extras,
                 jparent=jparent, joff=joff, jrot=jrot, jaxis=jaxis, jlevel=jlevel, janc=janc,
                 lower=t["lower"], upper=t["upper"], gain=t["gain"], damping=t["damping"], armature=t["armature"],
                 bodies=bodies, bstart=bstart, bend=bend, points=points, foot_body=foot_body,
@@ -159,10 +175,12 @@ def _farr(name, rows, width=None):
 
 
 def _darr(name, vals):
+    vals = list(vals) or [0.0]
     return "MB_TABLE double %s[%d] = {%s};\n" % (name, len(vals), ", ".join("%.17g" % float(v) for v in vals))
 
 
 def _iarr(name, vals, ctype="int"):
+    vals = list(vals) or [-1 if ctype == "int" else 0]  # zero-length arrays are not C
     fmt = "%du" if ctype == "unsigned" else "%d"
     return "MB_TABLE %s %s[%d] = {%s};\n" % (ctype, name, len(vals), ", ".join(fmt % v for v in vals))
 
@@ -172,7 +190,7 @@ def emit_header(t: dict, prefix: str) -> str:
     P = prefix
     out = []
     out.append("// GENERATED by mocca_envs_b200/codegen.py from mocca_envs_b200/models/%s.json -- do not edit.\n" % r["name"])
-    out.append("// Source model: reference mocca_envs/%s (loaded at mocca_envs/robots.py:101-105).\n" % t["source"])
+    out.append("// Source model: reference mocca_envs/%s.\n" % t["source"])
     out.append("#pragma once\n#include \"../mb_tables.h\"\n\n")
     out.append(_iarr(P + "_jparent", r["jparent"]))
     out.append(_iarr(P + "_jlevel", r["jlevel"]))
@@ -237,6 +255,16 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append(_farr(P + "_pfriction", [p["friction"] for p in r["points"]]))
     out.append(_farr(P + "_pthresh", [p["thresh"] for p in r["points"]]))
     out.append(_iarr(P + "_foot_body", r["foot_body"]))
+    sides = [sd for c in r["p2p"] for sd in c["sides"]]
+    out.append(_iarr(P + "_lc_owner", [sd["owner"] for sd in sides]))
+    out.append(_farr(P + "_lc_pos", [sd["pos"] for sd in sides] or [[0, 0, 0]]))
+    out.append(_farr(P + "_lc_maximp", [c["max_impulse"] for c in r["p2p"]] or [0]))
+    ex = r["extras"]
+    out.append(_iarr(P + "_ordered", ex.get("ordered", [])))
+    out.append(_iarr(P + "_pd_dof", ex.get("pd_dof", [])))
+    out.append(_iarr(P + "_pd_ordered", ex.get("pd_ordered", [])))
+    out.append(_farr(P + "_pd_kp", ex.get("pd_kp", [0])))
+    out.append(_farr(P + "_pd_kd", ex.get("pd_kd", [0])))
     out.append(_iarr(P + "_palm_body", r["palm_body"] or [-1]))
     xb = r["xboxes"] or [dict(owner=-1, foot=-1, pos=[0, 0, 0], rot=np.eye(3).reshape(9), half=[0, 0, 0], friction=0,
                               thresh=0)]
@@ -263,9 +291,10 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append("  MB_HD static constexpr unsigned rowmask_c(int i) {\n    return " +
                " ".join("i == %d ? %du :" % (i, m) for i, m in enumerate(rowmask)) + " 0u;\n  }\n")
     out.append("  enum { NJ = %d, NB = %d, NU = %d, NPT = %d, NLEVEL = %d, NFEET = %d, NMIRROR = %d, NNEG = %d,\n"
-               "         LSIZE = %d, MAXSUP = %d, NXBOX = %d };\n"
+               "         LSIZE = %d, MAXSUP = %d, NXBOX = %d, NLOOP = %d, NORDERED = %d, NPD = %d, NPOWERED = %d };\n"
                % (r["nj"], r["nb"], r["nu"], r["npt"], r["nlevel"], r["nfeet"], len(r["right"]), len(r["neg"]),
-                  r["lsize"], r["maxsup"], len(r["xboxes"])))
+                  r["lsize"], r["maxsup"], len(r["xboxes"]), len(r["p2p"]), len(ex.get("ordered", [])),
+                  len(ex.get("pd_dof", [])), ex.get("npowered", 0)))
     out.append("  MB_HD static unsigned long long chainpack(int j) { return %s_chainpack[j]; }\n" % P)
     out.append("  MB_HD static int facoff(int k, int t) { return %s_facoff[k][t]; }\n" % P)
     out.append("  MB_HD static int lvjoint(int lev, int slot) { return %s_lvjoint[lev][slot]; }\n" % P)
@@ -277,13 +306,14 @@ def emit_header(t: dict, prefix: str) -> str:
                        ("jaxk", "int"), ("jident", "int"),
                        ("bowner", "int"), ("powner", "int"), ("pfoot", "int"), ("pid", "int"), ("foot_body", "int"),
                        ("palm_body", "int"), ("xowner", "int"), ("xfoot", "int"),
+                       ("lc_owner", "int"), ("ordered", "int"), ("pd_dof", "int"), ("pd_ordered", "int"),
                        ("right", "int"), ("left", "int"), ("neg", "int")]:
         out.append("  MB_HD static %s %s(int i) { return %s_%s[i]; }\n" % (ctype, fld, P, fld))
     out.append("  MB_HD static double base_angles(int i) { return %s_base_angles[i]; }\n" % P)
     for fld in ["lower", "upper", "weight", "gain", "damping", "armature", "bmass", "pradius", "pfriction", "pthresh",
-                "jsgn", "xfriction", "xthresh"]:
+                "jsgn", "xfriction", "xthresh", "lc_maximp", "pd_kp", "pd_kd"]:
         out.append("  MB_HD static float %s(int i) { return %s_%s[i]; }\n" % (fld, P, fld))
-    for fld in ["joff", "jrot", "jaxis", "bcom", "binertia", "ppos", "xpos", "xrot", "xhalf"]:
+    for fld in ["joff", "jrot", "jaxis", "bcom", "binertia", "ppos", "xpos", "xrot", "xhalf", "lc_pos"]:
         out.append("  MB_HD static float %s(int i, int k) { return %s_%s[i][k]; }\n" % (fld, P, fld))
     out.append("  MB_HD static float base_x() { return %s; }\n" % _f(r["base_position"][0]))
     out.append("  MB_HD static float base_y() { return %s; }\n" % _f(r["base_position"][1]))
@@ -296,7 +326,7 @@ def emit_all(repo_root: str):
     gen = os.path.join(repo_root, "mocca_envs_b200", "csrc", "generated")
     os.makedirs(gen, exist_ok=True)
     models = os.path.join(repo_root, "mocca_envs_b200", "models")
-    for name, prefix in (("walker3d", "W3D"), ("monkey3d", "MK3D")):
+    for name, prefix in (("walker3d", "W3D"), ("monkey3d", "MK3D"), ("cassie", "CAS")):
         t = load_table(os.path.join(models, name + ".json"))
         with open(os.path.join(gen, name + "_model.h"), "w") as f:
             f.write(emit_header(t, prefix))

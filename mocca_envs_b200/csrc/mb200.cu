@@ -22,6 +22,7 @@
 #include "../../include/mocca_b200.h"
 #include "generated/walker3d_model.h"
 #include "generated/monkey3d_model.h"
+#include "generated/cassie_model.h"
 #include "mb_env.cuh"
 
 
@@ -33,7 +34,7 @@ static int fail(const std::string& m) { g_err = m; return -1; }
     if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_));                 \
   } while (0)
 
-enum { KIND_CUSTOM = 0, KIND_STEPPER = 1, KIND_MONKEY = 2 };
+enum { KIND_CUSTOM = 0, KIND_STEPPER = 1, KIND_MONKEY = 2, KIND_CASSIE = 3 };
 
 struct mb200_env {
   int kind;        // KIND_*
@@ -66,6 +67,8 @@ typedef MK3D_Model MM;
 typedef W3DEnv<WM> WEnv;
 typedef StepperEnv<WM> SEnv;
 typedef MonkeyEnv<MM> MEnv;
+typedef CAS_Model CM;
+typedef CassieEnv<CM> CEnv;
 typedef WarpMem<WM> WMem;
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -100,7 +103,7 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
                     : (a.final_obs ? a.final_obs + (size_t)env * Env::OBS : nullptr);
   Env::step(S, a.phys, a.state + (size_t)env * MB_STATE_STRIDE, a.rec + (size_t)env * Env::REC_STRIDE,
             a.mt + (size_t)env * 2 * MB_MT_STRIDE, a.mt + ((size_t)env * 2 + 1) * MB_MT_STRIDE,
-            a.act + (size_t)(tail ? 0 : env) * Env::NJ, obs, tail ? a.dummy_rew + warp : a.rew + env,
+            a.act + (size_t)(tail ? 0 : env) * Env::ACT, obs, tail ? a.dummy_rew + warp : a.rew + env,
             tail ? a.dummy_flag + warp : a.done + env, tail ? a.dummy_flag + MB_WARPS + warp : a.trunc + env, fin,
             tail ? a.dummy_stats : a.stats);
 }
@@ -112,6 +115,9 @@ __global__ void __launch_bounds__(MB_WARPS * 32, MB_MINBLOCKS) k_step_walker3d_s
 }
 __global__ void __launch_bounds__(MB_WARPS * 32, MB_MINBLOCKS) k_step_monkey3d_custom(StepArgs a) {
   step_body<MEnv>(a);
+}
+__global__ void __launch_bounds__(MB_WARPS * 32, MB_MINBLOCKS) k_step_cassie(StepArgs a) {
+  step_body<CEnv>(a);
 }
 
 template <class Env>
@@ -142,6 +148,11 @@ __global__ void __launch_bounds__(MB_WARPS * 32)
     k_reset_monkey3d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
                             float* obs, float* dummy_obs) {
   reset_body<MEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
+}
+__global__ void __launch_bounds__(MB_WARPS * 32)
+    k_reset_cassie(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask, float* obs,
+                   float* dummy_obs) {
+  reset_body<CEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
 }
 
 // stepSimulation only; rec (may be NULL) supplies the static obstacles of the env kind
@@ -187,6 +198,11 @@ __global__ void __launch_bounds__(MB_WARPS * 32)
                             int* contacts_out) {
   physics_body<MEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
 }
+__global__ void __launch_bounds__(MB_WARPS * 32)
+    k_step_physics_cassie(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
+                          int* contacts_out) {
+  physics_body<CEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
+}
 
 // mode 0: M (full symmetric, [nu][nu]);  mode 1: tau = M acc - rhs (rhs = -bias with zero applied torque)
 template <class Env>
@@ -227,6 +243,10 @@ __global__ void __launch_bounds__(MB_WARPS * 32)
 __global__ void __launch_bounds__(MB_WARPS * 32)
     k_dynamics_debug_monkey3d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
   dynamics_debug_body<MEnv>(n, phys, state, mode, acc, out);
+}
+__global__ void __launch_bounds__(MB_WARPS * 32)
+    k_dynamics_debug_cassie(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
+  dynamics_debug_body<CEnv>(n, phys, state, mode, acc, out);
 }
 
 __global__ void k_copy_strided(int n, int width, const float* src, int src_stride, float* dst, int dst_stride) {
@@ -272,6 +292,16 @@ void mb200_default_physics(mb200_physics* p) {
   p->has_ground = 1;
 }
 
+void mb200_default_physics_for(const char* env_id, mb200_physics* p) {
+  mb200_default_physics(p);
+  if (env_id && strcmp(env_id, "CassieEnv-v0") == 0) {
+    // control_step 0.03 / llc_frame_skip 50 / sim_frame_skip 1 (env_cassie.py:287-289, env_base.py:81); one
+    // stepSimulation = one substep, 50 of them per env step
+    p->dt = 0.03f / 50.0f;
+    p->substeps = 1;
+  }
+}
+
 static void to_internal(const mb200_physics& p, MbPhysics* q) {
   q->dt = p.dt; q->substeps = p.substeps; q->iterations = p.iterations; q->gravity = p.gravity;
   q->erp_contact = p.erp_contact; q->erp_joint = p.erp_joint; q->linear_slop = p.linear_slop;
@@ -290,9 +320,10 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   if (env_id && strcmp(env_id, "Walker3DCustomEnv-v0") == 0) kind = KIND_CUSTOM;
   if (env_id && strcmp(env_id, "Walker3DStepperEnv-v0") == 0) kind = KIND_STEPPER;
   if (env_id && strcmp(env_id, "Monkey3DCustomEnv-v0") == 0) kind = KIND_MONKEY;
+  if (env_id && strcmp(env_id, "CassieEnv-v0") == 0) kind = KIND_CASSIE;
   if (kind < 0)
     return fail(std::string("mb200_create: unsupported env id '") + (env_id ? env_id : "(null)") +
-                "' (built: Walker3DCustomEnv-v0, Walker3DStepperEnv-v0, Monkey3DCustomEnv-v0)");
+                "' (built: Walker3DCustomEnv-v0, Walker3DStepperEnv-v0, Monkey3DCustomEnv-v0, CassieEnv-v0)");
   if (n_envs <= 0) return fail("mb200_create: n_envs must be positive");
   int count = 0;
   CUDA_OK(cudaGetDeviceCount(&count));
@@ -308,14 +339,17 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   e->n = n_envs;
   e->device = device;
   e->kind = kind;
-  e->rec_stride = kind == KIND_STEPPER ? (int)SEnv::REC_STRIDE
-                  : kind == KIND_MONKEY ? (int)MEnv::REC_STRIDE : (int)WEnv::REC_STRIDE;
-  e->obs_dim = kind == KIND_STEPPER ? (int)SEnv::OBS : kind == KIND_MONKEY ? (int)MEnv::OBS : (int)WEnv::OBS;
-  e->act_dim = kind == KIND_MONKEY ? (int)MM::NJ : (int)WM::NJ;
-  e->state_dim = 13 + 2 * e->act_dim;
-  e->nu = 6 + e->act_dim;
+  int nj = WM::NJ;
+  switch (kind) {
+    case KIND_STEPPER: e->rec_stride = SEnv::REC_STRIDE; e->obs_dim = SEnv::OBS; e->act_dim = SEnv::ACT; break;
+    case KIND_MONKEY: e->rec_stride = MEnv::REC_STRIDE; e->obs_dim = MEnv::OBS; e->act_dim = MEnv::ACT; nj = MM::NJ; break;
+    case KIND_CASSIE: e->rec_stride = CEnv::REC_STRIDE; e->obs_dim = CEnv::OBS; e->act_dim = CEnv::ACT; nj = CM::NJ; break;
+    default: e->rec_stride = WEnv::REC_STRIDE; e->obs_dim = WEnv::OBS; e->act_dim = WEnv::ACT; break;
+  }
+  e->state_dim = 13 + 2 * nj;
+  e->nu = 6 + nj;
   mb200_physics p;
-  mb200_default_physics(&p);
+  mb200_default_physics_for(env_id, &p);
   if (physics) p = *physics;
   to_internal(p, &e->phys);
   if (kind == KIND_STEPPER) {
@@ -328,8 +362,14 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
     e->phys.box_erp = e->phys.dt * kp / denom;
     e->phys.box_cfm = 1.0f / denom;
   }
-  e->smem = (kind == KIND_MONKEY ? sizeof(WarpMem<MM>) : sizeof(WMem)) * MB_WARPS;
-  if (kind == KIND_MONKEY) {
+  e->smem = (kind == KIND_MONKEY ? sizeof(WarpMem<MM>) : kind == KIND_CASSIE ? sizeof(WarpMem<CM>) : sizeof(WMem)) *
+            MB_WARPS;
+  if (kind == KIND_CASSIE) {
+    CUDA_OK(cudaFuncSetAttribute(k_step_cassie, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    CUDA_OK(cudaFuncSetAttribute(k_reset_cassie, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    CUDA_OK(cudaFuncSetAttribute(k_step_physics_cassie, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_cassie, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  } else if (kind == KIND_MONKEY) {
     CUDA_OK(cudaFuncSetAttribute(k_step_monkey3d_custom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     CUDA_OK(cudaFuncSetAttribute(k_reset_monkey3d_custom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     CUDA_OK(cudaFuncSetAttribute(k_step_physics_monkey3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
@@ -434,7 +474,10 @@ int mb200_seed(mb200_env* e, const uint32_t* mt_host, int at_construction) {
 int mb200_reset(mb200_env* e, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (!e || !obs_dev) return fail("mb200_reset: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
-  if (e->kind == KIND_MONKEY)
+  if (e->kind == KIND_CASSIE)
+    k_reset_cassie<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
+  else if (e->kind == KIND_MONKEY)
     k_reset_monkey3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
   else if (e->kind == KIND_STEPPER)
@@ -456,7 +499,9 @@ int mb200_step(mb200_env* e, const float* act_dev, float* obs_dev, float* rew_de
   a.n = e->n; a.phys = e->phys; a.state = e->state; a.rec = e->rec; a.mt = e->mt; a.act = act_dev; a.obs = obs_dev;
   a.rew = rew_dev; a.done = done_dev; a.trunc = trunc_dev; a.final_obs = final_obs_dev; a.stats = e->stats;
   a.dummy_obs = e->dummy_obs; a.dummy_rew = e->dummy_rew; a.dummy_flag = e->dummy_flag; a.dummy_stats = e->dummy_stats;
-  if (e->kind == KIND_MONKEY)
+  if (e->kind == KIND_CASSIE)
+    k_step_cassie<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
+  else if (e->kind == KIND_MONKEY)
     k_step_monkey3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
   else if (e->kind == KIND_STEPPER)
     k_step_walker3d_stepper<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
@@ -521,7 +566,10 @@ int mb200_set_record(mb200_env* e, const float* rec_dev, void* stream) {
 int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* contacts_dev, void* stream) {
   if (!e || !tau_dev) return fail("mb200_step_physics: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
-  if (e->kind == KIND_MONKEY)
+  if (e->kind == KIND_CASSIE)
+    k_step_physics_cassie<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
+  else if (e->kind == KIND_MONKEY)
     k_step_physics_monkey3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
   else if (e->kind == KIND_STEPPER)
@@ -538,7 +586,10 @@ int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* c
 int mb200_mass_matrix(mb200_env* e, float* M_dev, void* stream) {
   if (!e || !M_dev) return fail("mb200_mass_matrix: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
-  if (e->kind == KIND_MONKEY)
+  if (e->kind == KIND_CASSIE)
+    k_dynamics_debug_cassie<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, 0, nullptr, M_dev);
+  else if (e->kind == KIND_MONKEY)
     k_dynamics_debug_monkey3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, 0, nullptr, M_dev);
   else
@@ -555,7 +606,10 @@ int mb200_inverse_dynamics(mb200_env* e, const float* acc_dev, float* tau_dev, v
   MbPhysics p = e->phys;
   p.lin_damping = 0.0f;  // calculateInverseDynamics has no velocity-damping term
   p.ang_damping = 0.0f;
-  if (e->kind == KIND_MONKEY)
+  if (e->kind == KIND_CASSIE)
+    k_dynamics_debug_cassie<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, p, e->state, 1, acc_dev, tau_dev);
+  else if (e->kind == KIND_MONKEY)
     k_dynamics_debug_monkey3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, p, e->state, 1, acc_dev, tau_dev);
   else

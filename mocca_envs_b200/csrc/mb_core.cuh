@@ -143,7 +143,9 @@ template <class M> struct WarpMem {
           float bI[M::NB][10];  // m, h[3], I_O{xx,yy,zz,xy,xz,yz}
           float bF[M::NB][6];   // bias wrench about O (n, f)
         } b;
-        float pt[M::NPT][3];  // contact candidate points (collision runs before the body pass)
+        // contact candidate points (collision runs before the body pass); models with many candidates (hull
+        // vertices, Cassie) test them on the fly against the ground plane and store nothing
+        float pt[(M::NPT <= 64 ? M::NPT : 1)][3];
       } u2;
     } k;
     // ---- rows: Y_r = L^-T J_r^T stored compactly over its support (base block + ancestor chain)
@@ -180,6 +182,9 @@ template <class M> struct WarpMem {
   // ---- static bars (MonkeyBar, bullet_objects.py:148-187): centre[3], unit axis[3], half length, radius
   float bar[MB_MAXBAR][8];
   int nbar;
+  // ---- loop-closure pivots (btMultiBodyPoint2Point, Cassie): world axes, relative to the base COM; [2c] on link A,
+  // [2c + 1] on link B
+  float lcP[(M::NLOOP > 0 ? 2 * M::NLOOP : 1)][3];
   // ---- scratch for the epilogue
   float scratch[64];
 };
@@ -637,9 +642,11 @@ template <class M> struct Sim {
 
   template <int OBST> MB_HD static int collide(Mem& S, const MbPhysics& P, int* overflow) {
     constexpr bool BOXES = (OBST & MB_OBST_BOXES) != 0;
+    constexpr bool STORE = NPT <= 64;  // else: ground plane only, points are transformed inside the test pass
+    static_assert(STORE || OBST == 0, "on-the-fly candidate points support the ground plane only");
     // world positions of the candidate points (relative to the base COM)
     MB_LANES(l)
-      for (int pt = l; pt < NPT; pt += 32) {
+      for (int pt = l; STORE && pt < NPT; pt += 32) {
         const int o = M::powner(pt);
         const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
         float loc[3] = {M::ppos(pt, 0), M::ppos(pt, 1), M::ppos(pt, 2)};
@@ -675,7 +682,15 @@ template <class M> struct Sim {
           hit[l] = 0;
           if (pt < NPT) {
             const float r = M::pradius(pt);
-            const float* c = S.w.k.u2.pt[pt];
+            float cfly[3];
+            if (!STORE) {
+              const int o = M::powner(pt);
+              const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
+              const float loc[3] = {M::ppos(pt, 0), M::ppos(pt, 1), M::ppos(pt, 2)};
+              mb_matvec(R, loc, cfly);
+              if (o >= 0) { cfly[0] += S.w.k.jp[o][0]; cfly[1] += S.w.k.jp[o][1]; cfly[2] += S.w.k.jp[o][2]; }
+            }
+            const float* c = STORE ? S.w.k.u2.pt[STORE ? pt : 0] : cfly;
             if (ob < 0) {
               const float dist = (S.pos[2] + c[2]) - r;
               if (dist < M::pthresh(pt)) {
@@ -815,6 +830,22 @@ template <class M> struct Sim {
     return nc;
   }
 
+  // ---- F2. loop-closure pivots in world axes (needs the kinematics of this substep) ---------------------------
+  MB_HD static void loop_pivots(Mem& S) {
+    if (M::NLOOP == 0) return;
+    MB_LANES(l)
+      if (l < 2 * M::NLOOP) {
+        const int o = M::lc_owner(l);
+        const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
+        const float loc[3] = {M::lc_pos(l, 0), M::lc_pos(l, 1), M::lc_pos(l, 2)};
+        float c[3];
+        mb_matvec(R, loc, c);
+        if (o >= 0) { c[0] += S.w.k.jp[o][0]; c[1] += S.w.k.jp[o][1]; c[2] += S.w.k.jp[o][2]; }
+        S.lcP[l][0] = c[0]; S.lcP[l][1] = c[1]; S.lcP[l][2] = c[2];
+      }
+    MB_END
+  }
+
   // ---- G. constraint rows: J, Y = L^-T J^T, effective mass, rhs ---------------------------------------------
   // rows [0, nlim) joint limits, [nlim, nlim+nc) contact normals, then 2 friction rows per contact.
   MB_HD static int find_limits(Mem& S) {
@@ -840,8 +871,13 @@ template <class M> struct Sim {
     return mb_popc(mask);
   }
 
+  // rows [0, nlim) joint limits; [nlim, nlim + NLC) loop closures: three world axes per constraint, each stored
+  // as TWO compact rows (the part on link A and the part on link B -- their union is a tree, not a chain) that share
+  // one multiplier; then contact normals and friction pairs.
+  enum { NLC = 6 * M::NLOOP };
   MB_HD static void setup_rows(Mem& S, const MbPhysics& P, int nlim, int nc) {
-    const int R = nlim + 3 * nc;
+    const int n0 = nlim + NLC;
+    const int R = n0 + 3 * nc;
     const float inv_dt = 1.0f / P.dt;
 #pragma unroll 1
     for (int base = 0; base < R; base += 32) {
@@ -861,18 +897,28 @@ template <class M> struct Sim {
             pen = dir > 0.0f ? S.q[cj] - M::lower(cj) : M::upper(cj) - S.q[cj];
 #pragma unroll
             for (int i = 0; i < 6; ++i) W[i] = 0.0f;
+          } else if (r < n0) {
+            // btMultiBodyPoint2Point::createConstraintRows: contactNormalOnB = -e_ax for link A, +e_ax for link B
+            kind = 3;
+            const int i = r - nlim, side = i & 1, ax = (i % 6) >> 1, sd = 2 * (i / 6) + side;
+            float dirv[3] = {0.0f, 0.0f, 0.0f};
+            const float sg = side ? 1.0f : -1.0f;
+            if (ax == 0) dirv[0] = sg; else if (ax == 1) dirv[1] = sg; else dirv[2] = sg;
+            mb_cross(S.lcP[sd], dirv, W);
+            W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
+            cj = M::lc_owner(sd);
           } else {
             int k;
             float dirv[3];
-            if (r < nlim + nc) {
-              kind = 1; k = r - nlim;
+            if (r < n0 + nc) {
+              kind = 1; k = r - n0;
               dirv[0] = S.cn[k][0]; dirv[1] = S.cn[k][1]; dirv[2] = S.cn[k][2];
               cfm = S.ccfm[k] * inv_dt; erp = S.cerp[k]; dist = S.cdist[k] + P.linear_slop;
             } else {
-              kind = 2; k = (r - nlim - nc) >> 1;
+              kind = 2; k = (r - n0 - nc) >> 1;
               float t1[3], t2[3];
               mb_plane_space(S.cn[k], t1, t2);
-              const bool second = ((r - nlim - nc) & 1) != 0;
+              const bool second = ((r - n0 - nc) & 1) != 0;
               dirv[0] = second ? t2[0] : t1[0]; dirv[1] = second ? t2[1] : t1[1]; dirv[2] = second ? t2[2] : t1[2];
             }
             mu = S.cmu[k];
@@ -931,11 +977,33 @@ template <class M> struct Sim {
           for (int t = 0; t < M::MAXSUP; ++t)
             if (t < n) Yr[t] = b[t];
           S.r_mask[r] = 0x3Fu | (cj >= 0 ? (M::janc(cj) << 6) : 0u);
-          S.r_rhs[r] = (positional + verr) * jinv;
+          if (kind == 3) {  // partial sums; the two parts of a loop row are combined below
+            S.r_rhs[r] = rel_vel;
+            S.r_jinv[r] = dd;
+          } else {
+            S.r_rhs[r] = (positional + verr) * jinv;
+            S.r_jinv[r] = jinv;
+          }
           S.r_cfm[r] = cfm * jinv;
-          S.r_jinv[r] = jinv;
           S.r_app[r] = 0.0f;
           S.r_mu[r] = mu;
+        }
+      MB_END
+    }
+    if (NLC > 0) {
+      // fillMultiBodyConstraint: denominator = JA M^-1 JA^T + JB M^-1 JB^T (no coupling term, even for two links of
+      // the same multibody), erp = m_erp, impulse bounds +-maxAppliedImpulse
+      MB_LANES(l)
+        if (l < NLC / 2) {
+          const int ra = nlim + 2 * l, ax = l % 3, c = l / 3;
+          const float dd = S.r_jinv[ra] + S.r_jinv[ra + 1];
+          const float jinv = dd > 1.1920929e-07f ? 1.0f / dd : 0.0f;
+          const float rel_vel = S.r_rhs[ra] + S.r_rhs[ra + 1];
+          const float pos_error = -(S.lcP[2 * c][ax] - S.lcP[2 * c + 1][ax]);
+          const float positional = -pos_error * P.erp_joint * inv_dt;
+          S.r_rhs[ra] = (positional - rel_vel) * jinv;
+          S.r_jinv[ra] = jinv;
+          S.r_mu[ra] = M::lc_maximp(c);
         }
       MB_END
     }
@@ -1000,24 +1068,55 @@ template <class M> struct Sim {
     return res;
   }
 
-  // btMultiBodyConstraintSolver::solveSingleIteration order: limits (alternating direction), normals, friction
+  // loop-closure row: two compact rows (ra on link A, ra + 1 on link B) sharing one multiplier
+  MB_HD static float pgs_dual(Mem& S, const LaneConst& C, int ra, LaneVar<float>& z) {
+    const int rb = ra + 1;
+    const unsigned supA = S.r_mask[ra], supB = S.r_mask[rb];
+    LaneVar<float> y, t;
+    MB_LANES(l)
+      const float ya = ((supA >> l) & 1u) ? S.w.Yc[ra][C.tl[l]] : 0.0f;
+      const float yb = ((supB >> l) & 1u) ? S.w.Yc[rb][C.tl[l]] : 0.0f;
+      y[l] = ya + yb;
+      t[l] = y[l] * z[l];
+    MB_END_REG
+    const float dot = warp_sum(t);
+    const float app = S.r_app[ra], jinv = S.r_jinv[ra], lim = S.r_mu[ra];
+    float d = S.r_rhs[ra] - dot * jinv;
+    const float sum = app + d;
+    float na = sum;
+    if (sum < -lim) { d = -lim - app; na = -lim; }
+    else if (sum > lim) { d = lim - app; na = lim; }
+    MB_LANES(l)
+      z[l] += y[l] * d;
+      if (l == 0) S.r_app[ra] = na;
+    MB_END
+    return jinv != 0.0f ? d / jinv : 0.0f;
+  }
+
+  // btMultiBodyConstraintSolver::solveSingleIteration order: non-contact rows (limits, then loop closures;
+  // alternating direction), normals, friction
   MB_HD static void solve_constraints(Mem& S, const MbPhysics& P, const LaneConst& C, int nlim, int nc,
                                       LaneVar<float>& z) {
-    const int nsingle = nlim + nc;
+    const int nnc = nlim + NLC / 2, n0 = nlim + NLC;
 #pragma unroll 1
     for (int it = 0; it < P.iterations; ++it) {
       float res2 = 0.0f;
 #pragma unroll 1
-      for (int v = 0; v < nsingle; ++v) {
-        const bool lim = v < nlim;
-        const int ra = lim ? ((it & 1) ? v : nlim - 1 - v) : v;
-        const float rr = pgs_single(S, C, ra, 0.0f, lim ? P.limit_max_impulse : 1e10f, z);
+      for (int v = 0; v < nnc; ++v) {
+        const int idx = (it & 1) ? v : nnc - 1 - v;
+        const float rr = idx < nlim ? pgs_single(S, C, idx, 0.0f, P.limit_max_impulse, z)
+                                    : pgs_dual(S, C, nlim + 2 * (idx - nlim), z);
         res2 = fmaxf(res2, rr * rr);
       }
 #pragma unroll 1
       for (int k = 0; k < nc; ++k) {
-        const int ra = nsingle + 2 * k;
-        const float rr = pgs_pair(S, C, ra, S.r_mu[ra] * S.r_app[nlim + k], z);
+        const float rr = pgs_single(S, C, n0 + k, 0.0f, 1e10f, z);
+        res2 = fmaxf(res2, rr * rr);
+      }
+#pragma unroll 1
+      for (int k = 0; k < nc; ++k) {
+        const int ra = n0 + nc + 2 * k;
+        const float rr = pgs_pair(S, C, ra, S.r_mu[ra] * S.r_app[n0 + k], z);
         res2 = fmaxf(res2, rr * rr);
       }
       if (res2 <= P.residual_threshold) break;
@@ -1057,6 +1156,7 @@ template <class M> struct Sim {
     MB_BLOCK_BARRIER();  // keeps the warps of a CTA in the same phase so instruction-cache lines are shared
     kinematics(S, P, C, true);
     const int nc_all = collide<OBST>(S, P, overflow);
+    loop_pivots(S);
     bodies(S, P);
     mass_matrix_and_rhs(S);
     factorize(S, C);
@@ -1074,8 +1174,8 @@ template <class M> struct Sim {
     MB_END
     const int nlim = find_limits(S);
     int nc = nc_all;
-    if (nlim + 3 * nc > MB_MAXROW) { nc = (MB_MAXROW - nlim) / 3; *overflow += 1; }
-    const int R = nlim + 3 * nc;
+    if (nlim + NLC + 3 * nc > MB_MAXROW) { nc = (MB_MAXROW - nlim - NLC) / 3; *overflow += 1; }
+    const int R = nlim + NLC / 2 + 3 * nc;  // as Bullet counts them (a loop row is one row)
     if (R > 0) {
       setup_rows(S, P, nlim, nc);
       LaneVar<float> z;

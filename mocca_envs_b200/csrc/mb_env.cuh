@@ -31,6 +31,13 @@ enum {
   ER_OVERFLOW,                  // contact/row cap hits (int)
 };
 
+enum {  // CassieEnv additions (env_cassie.py:285-479)
+  EC_POTENTIAL = 22,  // potential = -distance / control_step (kept for inspection; f32 ulp at -33333 is 4e-3)
+  EC_PREVX, EC_PREVY, // body x, y at the previous calc_potential: the progress reward is formed from exact differences
+  EC_JVEL = 32,       // [14] low-pass joint velocity of the ordered joints (env_cassie.py:319,451-453,467-468)
+};
+#define MB_REC_STRIDE_CASSIE 64
+
 enum {  // Monkey3DCustomEnv additions (env_locomotion.py:1136-1516)
   EM_NEXT = 22,      // next_step_index (int)
   EM_FREEFALL,       // free_fall_count (int)
@@ -144,7 +151,7 @@ template <class M> struct W3DEnv {
   typedef Sim<M> S_;
   typedef M Model;
   enum { NJ = M::NJ, NU = M::NU, OBS = 6 + 2 * M::NJ + M::NFEET + 2, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET,
-         REC_STRIDE = MB_REC_STRIDE, OBST = 0 };
+         REC_STRIDE = MB_REC_STRIDE, OBST = 0, ACT = M::NJ };
   MB_HD static void load_obstacles(WarpMem<M>&, const float*) {}
 
   // HBM <-> shared
@@ -457,7 +464,7 @@ template <class M> struct StepperEnv {
   typedef W3DEnv<M> B_;
   typedef M Model;
   enum { NJ = M::NJ, NU = M::NU, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET, OBS = ROBOT_OBS + 15, NSTEPS = 20,
-         REC_STRIDE = MB_REC_STRIDE_STEPPER, OBST = MB_OBST_BOXES };
+         REC_STRIDE = MB_REC_STRIDE_STEPPER, OBST = MB_OBST_BOXES, ACT = M::NJ };
   MB_HD static void load_obstacles(Mem& S, const float* rec) { load_boxes(S, rec); }
   MB_HD static void load_state(Mem& S, const float* st) { B_::load_state(S, st); }
   MB_HD static void store_state(const Mem& S, float* st) { B_::store_state(S, st); }
@@ -823,7 +830,7 @@ template <class M> struct MonkeyEnv {
   typedef W3DEnv<M> B_;
   typedef M Model;
   enum { NJ = M::NJ, NU = M::NU, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET, OBS = ROBOT_OBS + 15, NSTEPS = 32, NBARS = 4,
-         REC_STRIDE = MB_REC_STRIDE_MONKEY, OBST = MB_OBST_BARS };
+         REC_STRIDE = MB_REC_STRIDE_MONKEY, OBST = MB_OBST_BARS, ACT = M::NJ };
   MB_HD static void load_obstacles(Mem& S, const float* rec) { load_bars(S, rec); }
   MB_HD static void load_state(Mem& S, const float* st) { B_::load_state(S, st); }
   MB_HD static void store_state(const Mem& S, float* st) { B_::store_state(S, st); }
@@ -1136,6 +1143,230 @@ template <class M> struct MonkeyEnv {
 #else
           stats->episodes += 1; stats->ret_sum += epret; stats->len_sum += eplen; stats->steps += next;
           if (o.nonfinite) stats->nonfinite += 1;
+#endif
+        }
+      MB_END
+      reset(S, P, rec, mt_env, mt_robot, obs);
+    }
+    if (anybad) {
+      MB_LANES(l)
+        if (l == 0) {
+#ifdef __CUDACC__
+          atomicAdd(&stats->nonfinite, 1ull);
+#else
+          stats->nonfinite += 1;
+#endif
+        }
+      MB_END
+    }
+    B_::store_state(S, state);
+  }
+};
+
+// ================================================================================================ Cassie
+// CassieEnv-v0 (reference env_cassie.py:285-479; its defects fixed by intent): 10 residual PD
+// targets, 50 x { low-pass joint velocity, PD torque, clip, one 0.6 ms Bullet step with two point-to-point loop
+// closures } per env step.  No random draws: reset restores the saved state (env_cassie.py:363-378).
+template <class M> struct CassieEnv {
+  typedef WarpMem<M> Mem;
+  typedef Sim<M> S_;
+  typedef W3DEnv<M> B_;
+  typedef M Model;
+  enum { NJ = M::NJ, NU = M::NU, NO = M::NORDERED, ROBOT_OBS = 6 + 2 * M::NORDERED, OBS = ROBOT_OBS + 2,
+         ACT = M::NPOWERED, REC_STRIDE = MB_REC_STRIDE_CASSIE, OBST = 0, LLC_FRAME_SKIP = 50 };
+  MB_HD static void load_obstacles(Mem&, const float*) {}
+  MB_HD static void load_state(Mem& S, const float* st) { B_::load_state(S, st); }
+  MB_HD static void store_state(const Mem& S, float* st) { B_::store_state(S, st); }
+  MB_HD static float control_step() { return 0.03f; }  // env_cassie.py:287
+
+  // Joint.current_relative_position + to_radians (bullet_utils.py:212-215, env_cassie.py:204-212): lane k < 14
+  MB_HD static float rad_angle(const Mem& S, int k, float* nrm_out) {
+    const int d = M::ordered(k);
+    const float lo = M::lower(d), hi = M::upper(d), mid = 0.5f * (lo + hi);
+    const float nrm = 2.0f * (S.q[d] - mid) / (hi - lo);
+    *nrm_out = nrm;
+    return (hi - lo) * (nrm + 1.0f) * 0.5f + lo;
+  }
+
+  // Cassie.calc_state + CassieEnv.get_obs (env_cassie.py:238-276,416-431).  Needs kinematics(S, P, C, false).
+  // Returns body_z - min(feet_z) and whether the state is finite.
+  MB_HD static float observe(Mem& S, const float* rec, float* obs, int* nonfinite) {
+    LaneVar<int> bad;
+    MB_LANES(l)
+      bad[l] = 0;
+      if (l < NO) {
+        float nrm;
+        rad_angle(S, l, &nrm);
+        const float sp = S.u[6 + M::ordered(l)];
+        obs[6 + l] = nrm;
+        obs[6 + NO + l] = sp;
+        bad[l] = !(mb_finite(nrm) && mb_finite(sp));
+      }
+    MB_END
+    float rpy[3];
+    mb_euler(S.quat, rpy);
+    const float cy = cosf(-rpy[2]), sy = sinf(-rpy[2]);
+    const float vx = cy * S.u[3] - sy * S.u[4], vy = sy * S.u[3] + cy * S.u[4], vz = S.u[5];
+    const float dz = S.pos[2] - M::base_z();  // initial_z is the reset height (env_cassie.py:252-254)
+    float minz = 1e30f;
+    for (int f = 0; f < M::NFEET; ++f) {
+      const int b = M::foot_body(f), ow = M::bowner(b);
+      const float* R = S.w.k.jR[ow];
+      minz = fminf(minz, S.w.k.jp[ow][2] + R[6] * M::bcom(b, 0) + R[7] * M::bcom(b, 1) + R[8] * M::bcom(b, 2));
+    }
+    *nonfinite = warp_ballot(bad) != 0u ||
+                 !(mb_finite(dz) && mb_finite(vx) && mb_finite(vy) && mb_finite(vz) && mb_finite(rpy[0]) && mb_finite(rpy[1]));
+    // get_obs: R_z(-dtheta) walk_target, walk_target = (1000, 0, 0)
+    const float tx = rec[ER_TX], ty = rec[ER_TY];
+    const float dth = atan2f(ty - S.pos[1], tx - S.pos[0]) - rpy[2];
+    const float cs = cosf(-dth), sn = sinf(-dth);
+    MB_LANES(l)
+      if (l == 0) {
+        obs[0] = dz; obs[1] = vx; obs[2] = vy; obs[3] = vz; obs[4] = rpy[0]; obs[5] = rpy[1];
+        obs[ROBOT_OBS] = cs * tx - sn * ty;
+        obs[ROBOT_OBS + 1] = sn * tx + cs * ty;
+      }
+    MB_END
+    return -minz;  // feet relative to the base COM
+  }
+
+  MB_HD static float potential(const Mem& S, const float* rec) {  // env_cassie.py:348-354
+    const float dx = rec[ER_TX] - S.pos[0], dy = rec[ER_TY] - S.pos[1];
+    return -sqrtf(dy * dy + dx * dx) / control_step();
+  }
+
+  MB_HD static void reset(Mem& S, const MbPhysics& P, float* rec, uint32_t*, uint32_t*, float* obs) {
+    MB_LANES(l)
+      if (l == 0) {
+        rec[ER_TX] = 1000.0f; rec[ER_TY] = 0.0f; rec[ER_TZ] = 0.0f;
+        rec_i(rec, ER_ELAPSED) = 0; rec[ER_EPRET] = 0.0f; rec_i(rec, ER_EPLEN) = 0;
+      }
+      if (l < NO) rec[EC_JVEL + l] = 0.0f;
+      if (l < NJ) S.q[l] = (float)M::base_angles(l);
+      if (l < NU) S.u[l] = 0.0f;
+      if (l == 31) {
+        // the saved state holds the base INERTIAL frame at base_position, identity orientation
+        // (resetBasePositionAndOrientation, env_cassie.py:104-106)
+        S.pos[0] = M::base_x(); S.pos[1] = M::base_y(); S.pos[2] = M::base_z();
+        S.quat[0] = 0.0f; S.quat[1] = 0.0f; S.quat[2] = 0.0f; S.quat[3] = 1.0f;
+      }
+    MB_END
+    typename S_::LaneConst C;
+    S_::init_lane_const(C);
+    S_::kinematics(S, P, C, false);
+    int nonfinite;
+    observe(S, rec, obs, &nonfinite);
+    const float pot = potential(S, rec);
+    MB_LANES(l)
+      if (l == 0) { rec[EC_POTENTIAL] = pot; rec[EC_PREVX] = S.pos[0]; rec[EC_PREVY] = S.pos[1]; }
+    MB_END
+  }
+
+  MB_HD static void step(Mem& S, const MbPhysics& P, float* state, float* rec, uint32_t* mt_env, uint32_t* mt_robot,
+                         const float* act, float* obs, float* rew, uint8_t* done, uint8_t* trunc, float* final_obs,
+                         MbStats* stats) {
+    B_::load_state(S, state);
+    // PD targets, one lane per PD joint: base angle + residual action for the 10 powered joints, 0 for the two
+    // knee_to_shin "springs" (env_cassie.py:434-443)
+    LaneVar<float> target, jvel, kp, kd, lim, jpos0;
+    LaneVar<int> pdo, pdd, badact;
+    MB_LANES(l)
+      target[l] = 0.0f; kp[l] = 0.0f; kd[l] = 0.0f; lim[l] = 0.0f; pdo[l] = 0; pdd[l] = 0; badact[l] = 0;
+      if (l < M::NPD) {
+        pdo[l] = M::pd_ordered(l); pdd[l] = M::pd_dof(l);
+        kp[l] = M::pd_kp(l); kd[l] = M::pd_kd(l); lim[l] = M::gain(pdd[l]);
+        if (l < M::NPOWERED) {
+          float a = act[l];
+          if (!mb_finite(a)) { a = 0.0f; badact[l] = 1; }
+          target[l] = (float)M::base_angles(pdd[l]) + a;
+        }
+      }
+      float nrm;
+      jpos0[l] = l < NO ? rad_angle(S, l, &nrm) : 0.0f;
+      jvel[l] = l < NO ? rec[EC_JVEL + l] : 0.0f;  // lane k < 14 holds ordered joint k
+    MB_END
+    const unsigned anybad = warp_ballot(badact);
+    int rows = 0, nc = 0, overflow = 0, ncsum = 0;
+    typename S_::LaneConst C;
+    S_::init_lane_const(C);
+#pragma unroll 1
+    for (int it = 0; it < LLC_FRAME_SKIP; ++it) {
+      // jvel <- 0.8 jvel + 0.2 joint_speeds (env_cassie.py:319,451-453); the filtered value of PD joint l lives in
+      // lane pd_ordered(l) and is fetched through shared memory
+      MB_LANES(l)
+        if (l < NO) {
+          jvel[l] = (1.0f - 0.2f) * jvel[l] + 0.2f * S.u[6 + M::ordered(l)];
+          S.scratch[l] = jvel[l];
+        }
+        if (l < NJ) S.tau[l] = -M::damping(l) * S.u[6 + l];  // PyBullet's joint damping, once per stepSimulation
+      MB_END
+      MB_LANES(l)
+        if (l < M::NPD) {
+          float nrm;
+          const float q = rad_angle(S, pdo[l], &nrm);
+          const float verr = fminf(fmaxf(0.0f - S.scratch[pdo[l]], -5.0f), 5.0f);  // env_cassie.py:380-393
+          const float t = kp[l] * (target[l] - q) + kd[l] * verr;
+          S.tau[pdd[l]] += fminf(fmaxf(t, -lim[l]), lim[l]);                       // apply_action clip (:225-230)
+        }
+      MB_END
+      rows += S_::template substep<0>(S, P, C, &nc, &overflow);
+      ncsum += nc;
+    }
+    S_::kinematics(S, P, C, false);
+    MB_LANES(l)
+      if (l < NO) {  // jvel = (jpos_end - jpos_start) / control_step (env_cassie.py:467-468)
+        float nrm;
+        rec[EC_JVEL + l] = (rad_angle(S, l, &nrm) - jpos0[l]) / control_step();
+      }
+    MB_END
+    int nonfinite;
+    const float height = observe(S, rec, obs, &nonfinite);
+    int env_done = nonfinite ? 1 : 0;
+    // compute_rewards (env_cassie.py:401-414)
+    // progress = potential_new - potential_old = -(d_new - d_old) / control_step with the target 1000 m away:
+    // d_new - d_old = (d_new^2 - d_old^2) / (d_new + d_old), the squares' difference factored through the exact
+    // position differences (the potentials themselves only resolve 4e-3 in f32)
+    const float pot = potential(S, rec);
+    const float dxn = rec[ER_TX] - S.pos[0], dyn = rec[ER_TY] - S.pos[1];
+    const float dxo = rec[ER_TX] - rec[EC_PREVX], dyo = rec[ER_TY] - rec[EC_PREVY];
+    const float dn = sqrtf(dxn * dxn + dyn * dyn), dold = sqrtf(dxo * dxo + dyo * dyo);
+    const float num = (rec[EC_PREVX] - S.pos[0]) * (dxn + dxo) + (rec[EC_PREVY] - S.pos[1]) * (dyn + dyo);
+    const float progress = (dn + dold) > 0.0f ? -(num / (dn + dold)) / control_step() : 0.0f;
+    const float tall = height > 0.6f ? 2.0f : -1.0f;
+    if (tall < 0.0f) env_done = 1;
+    const float reward = tall + progress;
+    const int elapsed = rec_i(rec, ER_ELAPSED) + 1;
+    int truncated = 0, any_done = env_done;
+    if (elapsed >= 1000) { truncated = !env_done; any_done = 1; }
+    const float epret = rec[ER_EPRET] + reward;
+    const int eplen = rec_i(rec, ER_EPLEN) + 1;
+    MB_LANES(l)
+      if (l == 0) {
+        rec[EC_POTENTIAL] = pot; rec[EC_PREVX] = S.pos[0]; rec[EC_PREVY] = S.pos[1];
+        rec_i(rec, ER_ELAPSED) = elapsed;
+        rec[ER_EPRET] = epret; rec_i(rec, ER_EPLEN) = eplen;
+        rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum;
+        rec_i(rec, ER_OVERFLOW) += overflow;
+        *rew = reward; *done = (uint8_t)any_done; *trunc = (uint8_t)truncated;
+      }
+    MB_END
+    if (any_done) {
+      if (final_obs) {
+        MB_LANES(l)
+          for (int i = l; i < OBS; i += 32) final_obs[i] = obs[i];
+        MB_END
+      }
+      MB_LANES(l)
+        if (l == 0) {
+          rec[ER_LAST_EPRET] = epret; rec_i(rec, ER_LAST_EPLEN) = eplen;
+#ifdef __CUDACC__
+          atomicAdd(&stats->episodes, 1ull);
+          atomicAdd(&stats->ret_sum, (double)epret);
+          atomicAdd(&stats->len_sum, (double)eplen);
+          if (nonfinite) atomicAdd(&stats->nonfinite, 1ull);
+#else
+          stats->episodes += 1; stats->ret_sum += epret; stats->len_sum += eplen;
+          if (nonfinite) stats->nonfinite += 1;
 #endif
         }
       MB_END

@@ -26,6 +26,7 @@ from .seeding import create_seed, mt_state_rows
 ENV_ID = "Walker3DCustomEnv-v0"
 STEPPER_ID = "Walker3DStepperEnv-v0"
 MONKEY_ID = "Monkey3DCustomEnv-v0"
+CASSIE_ID = "CassieEnv-v0"
 _MODELS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models")
 
 
@@ -66,7 +67,7 @@ class Walker3DCustomVecEnv:
             raise RuntimeError("mocca_envs_b200 has no CPU path; device must be a CUDA device")
         L = _lib.lib()
         phys = _lib.Physics()
-        L.mb200_default_physics(C.byref(phys))
+        L.mb200_default_physics_for(self.env_id.encode(), C.byref(phys))
         for k, v in (physics or {}).items():
             if not hasattr(phys, k):
                 raise KeyError(k)
@@ -320,6 +321,36 @@ class Monkey3DCustomVecEnv(Walker3DCustomVecEnv):
         raise AttributeError("Monkey3DCustomEnv defines no get_mirror_indices in the reference")
 
 
+class CassieVecEnv(Walker3DCustomVecEnv):
+    """Batched CassieEnv-v0 (reference env_cassie.py:285-479, registered at __init__.py:18-22): 10 residual PD targets
+    per env step, 50 PD-controlled 0.6 ms physics steps inside the kernel, two point-to-point loop closures
+    (achilles rods).  The reference file does not import as shipped; this is its intended
+    behaviour.  The env draws no random numbers: reset restores the saved initial state."""
+
+    env_id = CASSIE_ID
+    model = "cassie"
+    control_step = 0.03  # env_cassie.py:287
+    llc_frame_skip = 50  # env_cassie.py:288
+    sim_frame_skip = 1  # env_cassie.py:289
+    EC_POTENTIAL, EC_JVEL = 22, 32
+
+    def evaluation_mode(self):
+        raise AttributeError("CassieEnv has no evaluation_mode")
+
+    def set_env_params(self, params: dict):
+        pass
+
+    def get_mirror_indices(self):
+        raise AttributeError("CassieEnv-v0 defines no get_mirror_indices in the reference")
+
+    def rewards_info(self, obs_rew: torch.Tensor | None = None) -> dict:
+        """The reference returns the reward terms as ``info`` (env_cassie.py:479): AliveRew = +2 / -1,
+        ProgressRew = reward - AliveRew."""
+        rew = self.rew if obs_rew is None else obs_rew
+        alive = torch.where(self.done.bool() & ~self.trunc.bool(), -1.0, 2.0)
+        return {"AliveRew": alive, "ProgressRew": rew - alive}
+
+
 class Walker3DCustomEnv:
     """gym-protocol facade over a 1-env batch; NumPy float64 observations like the reference."""
 
@@ -413,8 +444,22 @@ class Monkey3DCustomEnv(Walker3DCustomEnv):
         raise AttributeError("Monkey3DCustomEnv has no evaluation_mode")
 
 
+class CassieEnv(Walker3DCustomEnv):
+    """gym-protocol facade of CassieEnv-v0; ``info`` carries the reward terms like the reference."""
+
+    vec_class = CassieVecEnv
+
+    def _extra_info(self, info):
+        r = self.vec.rewards_info()
+        info["AliveRew"] = float(r["AliveRew"][0].item())
+        info["ProgressRew"] = float(r["ProgressRew"][0].item())
+
+    def evaluation_mode(self):
+        raise AttributeError("CassieEnv has no evaluation_mode")
+
+
 _REGISTRY = {ENV_ID: (Walker3DCustomEnv, Walker3DCustomVecEnv), STEPPER_ID: (Walker3DStepperEnv, Walker3DStepperVecEnv),
-             MONKEY_ID: (Monkey3DCustomEnv, Monkey3DCustomVecEnv)}
+             MONKEY_ID: (Monkey3DCustomEnv, Monkey3DCustomVecEnv), CASSIE_ID: (CassieEnv, CassieVecEnv)}
 
 
 def make(env_id: str, num_envs: int | None = None, **kwargs):

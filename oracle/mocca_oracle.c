@@ -938,6 +938,37 @@ static void substep_impl(const orc_model* m, const orc_params* p, orc_state* s, 
       row->cfm = 0; row->lo = 0; row->hi = p->limit_max_impulse; row->applied = 0; row->mu = 0;
     }
   }
+  /* loop closures: btMultiBodyPoint2Point::createConstraintRows -- three world-axis rows per constraint, appended to
+   * the non-contact list after the limit rows (PyBullet creates them after the URDF's limit constraints).  The
+   * denominator is JA M^-1 JA^T + JB M^-1 JB^T: fillMultiBodyConstraint sums the two bodies' terms and ignores their
+   * coupling even when both links belong to the same multibody; erp = m_erp. */
+  for (int cidx = 0; cidx < m->n_p2p; cidx++) {
+    int la = m->p2p_link_a[cidx], lb = m->p2p_link_b[cidx];
+    v3 pa, pb, t;
+    m3Tvec(c->Rw[la + 1], m->p2p_pivot_a[cidx], t);
+    for (int k = 0; k < 3; k++) pa[k] = c->pw[la + 1][k] + t[k];
+    m3Tvec(c->Rw[lb + 1], m->p2p_pivot_b[cidx], t);
+    for (int k = 0; k < 3; k++) pb[k] = c->pw[lb + 1][k] + t[k];
+    for (int ax = 0; ax < 3; ax++) {
+      orc_row* row = &rows->limit[nlim++];
+      v3 nrm = {0, 0, 0}, neg = {0, 0, 0};
+      nrm[ax] = -1.0; neg[ax] = 1.0;
+      double JA[ORC_MAXU], JB[ORC_MAXU], MA[ORC_MAXU], MB[ORC_MAXU];
+      point_jacobian(m, s, c, la, pa, nrm, JA);
+      point_jacobian(m, s, c, lb, pb, neg, JB);
+      minv(m, c, JA, MA);
+      minv(m, c, JB, MB);
+      double dd = dotn(JA, MA, nu) + dotn(JB, MB, nu);
+      for (int k = 0; k < nu; k++) { row->J[k] = JA[k] + JB[k]; row->MinvJ[k] = MA[k] + MB[k]; }
+      row->jinv = dd > 1.1920929e-07 ? 1.0 / dd : 0.0;
+      double rel_vel = dotn(row->J, u, nu);
+      double pos_error = (pa[0] - pb[0]) * nrm[0] + (pa[1] - pb[1]) * nrm[1] + (pa[2] - pb[2]) * nrm[2];
+      double positional = -pos_error * p->erp_joint / p->dt;
+      row->rhs = (positional - rel_vel) * row->jinv;
+      row->cfm = 0; row->lo = -m->p2p_max_impulse[cidx]; row->hi = m->p2p_max_impulse[cidx];
+      row->applied = 0; row->mu = 0;
+    }
+  }
   /* contact rows */
   int nc = ct->n;
   for (int k = 0; k < nc; k++) {
@@ -979,7 +1010,7 @@ static void substep_impl(const orc_model* m, const orc_params* p, orc_state* s, 
   clamp_u(u, nu, p->max_coord_vel);
   unpack_u(m, s, u);
   if (warm) {
-    for (int i = 0; i < ORC_MAXP; i++) warm[i] = 0;
+    for (int i = 0; i < ORC_MAXW; i++) warm[i] = 0;
     for (int k = 0; k < nc; k++) warm[ct->point_id[k]] = rows->normal[k].applied;
   }
   for (int k = 0; k < nc; k++) ct->impulse[k] = rows->normal[k].applied;
@@ -1189,7 +1220,7 @@ static void robot_reset_ex(const orc_model* m, orc_w3d_env* e, const double* pos
   for (int k = 0; k < 3; k++) { e->s.pos[k] = pos[k]; e->s.omega[k] = 0; e->s.vel[k] = vel ? vel[k] : 0; }
   e->s.quat[0] = e->s.quat[1] = e->s.quat[2] = 0; e->s.quat[3] = 1;
   for (int f = 0; f < 4; f++) { e->feet_contact[f] = 0; v3set(e->feet_xyz[f], 0, 0, 0); }
-  for (int i = 0; i < ORC_MAXP; i++) e->warm[i] = 0;
+  for (int i = 0; i < ORC_MAXW; i++) e->warm[i] = 0;
   w3d_calc_state(m, e, NULL);
 }
 
@@ -1788,6 +1819,150 @@ void orc_monkey_step_batch(const orc_model* m, const orc_params* p, orc_monkey_e
 }
 
 int orc_sizeof_monkey_env(void) { return (int)sizeof(orc_monkey_env); }
+
+/* ------------------------------------------------------------------ 12. CassieEnv (env_cassie.py) */
+void orc_cassie_params(orc_params* p) {
+  orc_default_params(p);
+  p->dt = 0.03 / 50 / 1; /* control_step / llc_frame_skip / sim_frame_skip (env_cassie.py:287-289, env_base.py:81) */
+  p->substeps = 1;
+}
+
+/* Cassie.calc_state (env_cassie.py:238-276) */
+static void cassie_calc_state(const orc_model* m, orc_cassie_env* e) {
+  orc_w3d_env* b = &e->base;
+  orc_cache* c = (orc_cache*)malloc(sizeof(orc_cache));
+  kin(m, &b->s, c);
+  int A = m->n_ordered;
+  double* st = e->robot_state;
+  b->joints_at_limit = 0;
+  for (int k = 0; k < A; k++) {
+    int d = m->ordered_dof[k];
+    double lo = m->lower[d], hi = m->upper[d], mid = 0.5 * (lo + hi);
+    float nrm = (float)(2 * (b->s.q[d] - mid) / (hi - lo));
+    float sp = (float)b->s.qd[d];
+    st[6 + k] = nrm;
+    st[6 + A + k] = sp;
+    e->rad_angles[k] = (hi - lo) * ((double)nrm + 1) / 2 + lo; /* to_radians, float64 weights */
+    e->speeds[k] = sp;
+    if (fabsf(nrm) > 0.99f) b->joints_at_limit++;
+  }
+  v3copy(b->body_xyz, b->s.pos);
+  if (isnan(e->initial_z)) e->initial_z = b->body_xyz[2];
+  euler_from_quat(b->s.quat, b->body_rpy);
+  double yaw = b->body_rpy[2], cy = cos(-yaw), sy = sin(-yaw);
+  b->body_vel[0] = cy * b->s.vel[0] - sy * b->s.vel[1];
+  b->body_vel[1] = sy * b->s.vel[0] + cy * b->s.vel[1];
+  b->body_vel[2] = b->s.vel[2];
+  st[0] = f32(b->body_xyz[2] - e->initial_z);
+  st[1] = f32(b->body_vel[0]); st[2] = f32(b->body_vel[1]); st[3] = f32(b->body_vel[2]);
+  st[4] = f32(b->body_rpy[0]); st[5] = f32(b->body_rpy[1]);
+  for (int f = 0; f < m->n_feet; f++) v3copy(b->feet_xyz[f], c->pw[m->foot_link[f] + 1]);
+  free(c);
+}
+
+static double cassie_potential(const orc_cassie_env* e) { /* env_cassie.py:348-354 */
+  const orc_w3d_env* b = &e->base;
+  double dx = b->walk_target[0] - b->body_xyz[0], dy = b->walk_target[1] - b->body_xyz[1];
+  return -sqrt(dy * dy + dx * dx) / 0.03;
+}
+
+static void cassie_obs(const orc_model* m, const orc_cassie_env* e, double* obs) { /* env_cassie.py:416-431 */
+  const orc_w3d_env* b = &e->base;
+  int n = 6 + 2 * m->n_ordered;
+  for (int k = 0; k < n; k++) obs[k] = e->robot_state[k];
+  double dx = b->walk_target[0] - b->body_xyz[0], dy = b->walk_target[1] - b->body_xyz[1];
+  double dth = atan2(dy, dx) - b->body_rpy[2];
+  double cs = cos(-dth), sn = sin(-dth);
+  obs[n] = cs * b->walk_target[0] - sn * b->walk_target[1];
+  obs[n + 1] = sn * b->walk_target[0] + cs * b->walk_target[1];
+}
+
+void orc_cassie_reset(const orc_model* m, const orc_params* p, orc_cassie_env* e, double* obs) {
+  (void)p;
+  orc_w3d_env* b = &e->base;
+  b->done = 0; b->elapsed = 0;
+  b->walk_target[0] = 1000.0; b->walk_target[1] = 0.0; b->walk_target[2] = 0.0;
+  /* restoreState + resetJoints + reset_velocity (env_cassie.py:363-370): the saved state has the base INERTIAL
+   * frame at base_position with identity orientation (resetBasePositionAndOrientation, env_cassie.py:104-106) */
+  for (int d = 0; d < m->n_dof; d++) { b->s.q[d] = m->base_joint_angles[d]; b->s.qd[d] = 0; }
+  for (int k = 0; k < 3; k++) { b->s.pos[k] = m->base_position[k]; b->s.omega[k] = 0; b->s.vel[k] = 0; }
+  b->s.quat[0] = b->s.quat[1] = b->s.quat[2] = 0; b->s.quat[3] = 1;
+  for (int i = 0; i < ORC_MAXW; i++) b->warm[i] = 0;
+  for (int k = 0; k < 16; k++) e->jvel[k] = 0;
+  e->initial_z = NAN;
+  cassie_calc_state(m, e);
+  e->potential = cassie_potential(e);
+  cassie_obs(m, e, obs);
+}
+
+void orc_cassie_step(const orc_model* m, const orc_params* p, orc_cassie_env* e, const double* action, double* obs,
+                     double* reward, int* done, int* truncated) {
+  orc_w3d_env* b = &e->base;
+  int A = m->n_ordered, NP = m->n_pd;
+  double target[16], jpos0[16];
+  /* residual control: base angles of the powered joints + a; 0 for the springs (env_cassie.py:434-443) */
+  for (int k = 0; k < NP; k++) {
+    int oj = m->pd_ordered_index[k];
+    target[k] = k < NP - 2 ? m->base_joint_angles[m->ordered_dof[oj]] + action[k] : 0.0;
+  }
+  for (int k = 0; k < A; k++) jpos0[k] = e->rad_angles[k];
+  int rows_total = 0;
+  for (int it = 0; it < 50; it++) { /* llc_frame_skip (env_cassie.py:288,450) */
+    for (int k = 0; k < A; k++) e->jvel[k] = (1 - 0.2) * e->jvel[k] + 0.2 * e->speeds[k]; /* jvel_alpha = 10/50 */
+    double tau[ORC_MAXD];
+    for (int d = 0; d < m->n_dof; d++) tau[d] = 0;
+    for (int k = 0; k < NP; k++) { /* pd_control (env_cassie.py:380-393) + apply_action clip (:225-230) */
+      int oj = m->pd_ordered_index[k], d = m->ordered_dof[oj];
+      double perr = target[k] - e->rad_angles[oj];
+      double verr = 0.0 - e->jvel[oj];
+      if (verr > 5) verr = 5;
+      if (verr < -5) verr = -5;
+      double t = m->pd_kp[k] * perr + m->pd_kd[k] * verr;
+      double lim = m->gain[d];
+      if (t > lim) t = lim;
+      if (t < -lim) t = -lim;
+      tau[d] = t;
+    }
+    int rows = 0;
+    orc_step_physics(m, p, &b->s, tau, NULL, 0, b->warm, &b->last_contacts, &rows);
+    rows_total += rows;
+    cassie_calc_state(m, e);
+  }
+  b->rows_sum = rows_total;
+  for (int k = 0; k < A; k++) e->jvel[k] = (e->rad_angles[k] - jpos0[k]) / 0.03;
+  int n = 6 + 2 * A;
+  for (int k = 0; k < n; k++)
+    if (!isfinite(e->robot_state[k])) b->done = 1;
+  /* compute_rewards (env_cassie.py:401-414) */
+  double old = e->potential;
+  e->potential = cassie_potential(e);
+  e->progress_rew = e->potential - old;
+  double minz = b->feet_xyz[0][2] < b->feet_xyz[1][2] ? b->feet_xyz[0][2] : b->feet_xyz[1][2];
+  e->alive_rew = b->body_xyz[2] - minz > 0.6 ? 2.0 : -1.0;
+  if (e->alive_rew < 0) b->done = 1;
+  *reward = e->alive_rew + e->progress_rew;
+  cassie_obs(m, e, obs);
+  b->elapsed++;
+  *truncated = 0;
+  *done = b->done;
+  if (b->elapsed >= 1000) { *truncated = !b->done; *done = 1; }
+}
+
+void orc_cassie_step_batch(const orc_model* m, const orc_params* p, orc_cassie_env* envs, int n,
+                           const double* actions, double* obs, double* rewards, int* dones, int n_threads) {
+  int A = 10, O = 36;
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+  for (int i = 0; i < n; i++) {
+    int trunc;
+    orc_cassie_step(m, p, &envs[i], actions + (size_t)i * A, obs + (size_t)i * O, &rewards[i], &dones[i], &trunc);
+    if (dones[i]) orc_cassie_reset(m, p, &envs[i], obs + (size_t)i * O);
+  }
+}
+
+int orc_sizeof_cassie_env(void) { return (int)sizeof(orc_cassie_env); }
 
 int orc_sizeof_stepper_env(void) { return (int)sizeof(orc_stepper_env); }
 int orc_sizeof_w3d_env(void) { return (int)sizeof(orc_w3d_env); }

@@ -18,8 +18,9 @@
 
 #define ORC_MAXL 40   /* links (without base) */
 #define ORC_MAXD 40   /* joint dofs */
-#define ORC_MAXG 48   /* geoms */
-#define ORC_MAXP 96   /* candidate contact points (2 per geom) */
+#define ORC_MAXG 192  /* geoms (Cassie: 158 hull support vertices) */
+#define ORC_MAXP 96   /* contact points kept per substep */
+#define ORC_MAXW (2 * ORC_MAXG) /* warm-start slots, indexed by candidate id = 2 * geom + end */
 #define ORC_MAXROW (3 * ORC_MAXP + 2 * ORC_MAXD)
 #define ORC_MAXU (6 + ORC_MAXD)
 #define ORC_MAXSTEPS 32 /* stepping stones / bars in a terrain table */
@@ -56,6 +57,14 @@ typedef struct {
   int n_right, right_idx[ORC_MAXD], left_idx[ORC_MAXD]; /* mirroring tables robots.py:282-290 */
   int n_neg, neg_idx[8];
   int palm_link[2]; /* Monkey3D: right_palm, left_palm (env_locomotion.py:1269,1424); -1 otherwise */
+  /* loop closures: btMultiBodyPoint2Point between two links of the robot (Cassie, env_cassie.py:114-137);
+   * pivots in the links' inertial frames */
+  int n_p2p, p2p_link_a[2], p2p_link_b[2];
+  double p2p_pivot_a[2][3], p2p_pivot_b[2][3], p2p_max_impulse[2];
+  /* Cassie bookkeeping (env_cassie.py:59-60,192-202): dofs of the 14 ordered joints, PD joint list, gains */
+  int n_ordered, ordered_dof[ORC_MAXD];
+  int n_pd, pd_ordered_index[16]; /* powered + spring joints, as indices into the ordered joints */
+  double pd_kp[16], pd_kd[16];
 } orc_model;
 
 typedef struct {
@@ -138,7 +147,7 @@ int orc_collide(const orc_model* m, const orc_params* p, const orc_state* s, con
 void orc_step_physics_bars(const orc_model* m, const orc_params* p, orc_state* s, const double* tau_applied,
                            const orc_bar* bars, int n_bars, orc_contacts* last_contacts, int* rows_sum);
 void orc_substep(const orc_model* m, const orc_params* p, orc_state* s, const double* tau, const orc_box* boxes,
-                 int n_boxes, double* warm /* [ORC_MAXP] */, orc_contacts* out_contacts, int* out_rows);
+                 int n_boxes, double* warm /* [ORC_MAXW] */, orc_contacts* out_contacts, int* out_rows);
 void orc_step_physics(const orc_model* m, const orc_params* p, orc_state* s, const double* tau_applied,
                       const orc_box* boxes, int n_boxes, double* warm, orc_contacts* last_contacts, int* rows_sum);
 void orc_energy_momentum(const orc_model* m, const orc_state* s, double gravity, double* out /* KE,PE,P[3],L[3] */);
@@ -152,7 +161,7 @@ double orc_rng_uniform(orc_rng* r, double lo, double hi);
 /* ---- Walker3DCustomEnv (env_locomotion.py:37-282) ---- */
 typedef struct {
   orc_state s;
-  double warm[ORC_MAXP];
+  double warm[ORC_MAXW];
   /* robot (robots.py:13-227) */
   double feet_contact[4];
   double feet_xyz[4][3];
@@ -226,6 +235,23 @@ void orc_monkey_step(const orc_model* m, const orc_params* p, orc_monkey_env* e,
 void orc_monkey_step_batch(const orc_model* m, const orc_params* p, orc_monkey_env* envs, int n,
                            const double* actions, double* obs, double* rewards, int* dones, int n_threads);
 int orc_sizeof_monkey_env(void);
+/* ---- CassieEnv (env_cassie.py:285-479) ---- */
+typedef struct {
+  orc_w3d_env base;
+  double jvel[16];       /* low-pass joint velocity of the ordered joints (env_cassie.py:319,451-453) */
+  double rad_angles[16]; /* robot.rad_joint_angles of the last calc_state */
+  double speeds[16];     /* robot.joint_speeds (raw rad/s) */
+  double potential, initial_z;
+  double alive_rew, progress_rew;
+  double robot_state[40];
+} orc_cassie_env;
+void orc_cassie_params(orc_params* p); /* dt = 0.03 / 50, one substep per stepSimulation */
+void orc_cassie_reset(const orc_model* m, const orc_params* p, orc_cassie_env* e, double* obs /* [36] */);
+void orc_cassie_step(const orc_model* m, const orc_params* p, orc_cassie_env* e, const double* action /* [10] */,
+                     double* obs, double* reward, int* done, int* truncated);
+void orc_cassie_step_batch(const orc_model* m, const orc_params* p, orc_cassie_env* envs, int n,
+                           const double* actions, double* obs, double* rewards, int* dones, int n_threads);
+int orc_sizeof_cassie_env(void);
 int orc_sizeof_stepper_env(void);
 int orc_sizeof_w3d_env(void);
 int orc_sizeof_model(void);

@@ -15,7 +15,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmocca_oracle.so")
 
-MAXL, MAXD, MAXG, MAXP = 40, 40, 48, 96
+MAXL, MAXD, MAXG, MAXP = 40, 40, 192, 96
+MAXW = 2 * MAXG
 MAXU = 6 + MAXD
 
 d = C.c_double
@@ -39,6 +40,10 @@ class Model(C.Structure):
         ("n_right", i32), ("right_idx", i32 * MAXD), ("left_idx", i32 * MAXD),
         ("n_neg", i32), ("neg_idx", i32 * 8),
         ("palm_link", i32 * 2),
+        ("n_p2p", i32), ("p2p_link_a", i32 * 2), ("p2p_link_b", i32 * 2),
+        ("p2p_pivot_a", (d * 3) * 2), ("p2p_pivot_b", (d * 3) * 2), ("p2p_max_impulse", d * 2),
+        ("n_ordered", i32), ("ordered_dof", i32 * MAXD),
+        ("n_pd", i32), ("pd_ordered_index", i32 * 16), ("pd_kp", d * 16), ("pd_kd", d * 16),
     ]
 
 
@@ -75,7 +80,7 @@ class Rng(C.Structure):
 
 class W3DEnv(C.Structure):
     _fields_ = [
-        ("s", State), ("warm", d * MAXP),
+        ("s", State), ("warm", d * MAXW),
         ("feet_contact", d * 4), ("feet_xyz", (d * 3) * 4), ("body_xyz", d * 3), ("body_rpy", d * 3),
         ("body_vel", d * 3), ("joint_speeds", d * MAXD), ("joints_at_limit", i32), ("mirrored", i32),
         ("robot_state", d * (6 + 2 * MAXD + 4)),
@@ -114,6 +119,11 @@ class MonkeyEnv(C.Structure):
     ]
 
 
+class CassieEnvS(C.Structure):
+    _fields_ = [("base", W3DEnv), ("jvel", d * 16), ("rad_angles", d * 16), ("speeds", d * 16), ("potential", d),
+                ("initial_z", d), ("alive_rew", d), ("progress_rew", d), ("robot_state", d * 40)]
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "mocca_oracle.c")
     hdr = os.path.join(_HERE, "mocca_oracle.h")
@@ -136,6 +146,7 @@ def lib():
         assert L.orc_sizeof_w3d_env() == C.sizeof(W3DEnv), (L.orc_sizeof_w3d_env(), C.sizeof(W3DEnv))
         assert L.orc_sizeof_stepper_env() == C.sizeof(StepperEnv), (L.orc_sizeof_stepper_env(), C.sizeof(StepperEnv))
         assert L.orc_sizeof_monkey_env() == C.sizeof(MonkeyEnv), (L.orc_sizeof_monkey_env(), C.sizeof(MonkeyEnv))
+        assert L.orc_sizeof_cassie_env() == C.sizeof(CassieEnvS), (L.orc_sizeof_cassie_env(), C.sizeof(CassieEnvS))
         L.orc_rng_double.restype = d
         L.orc_rng_uniform.restype = d
         L.orc_rng_uniform.argtypes = [C.c_void_p, d, d]
@@ -194,6 +205,21 @@ def model_from_table(t: dict) -> Model:
     _fill(m.neg_idx, np.array(t["negation_joint_indices"], dtype=np.int64))
     palms = t.get("palm_links", [-1, -1])
     m.palm_link[0], m.palm_link[1] = int(palms[0]), int(palms[1])
+    m.n_p2p = len(t.get("p2p", []))
+    for k, c in enumerate(t.get("p2p", [])):
+        m.p2p_link_a[k], m.p2p_link_b[k] = c["link_a"], c["link_b"]
+        for j in range(3):
+            m.p2p_pivot_a[k][j] = c["pivot_a"][j]
+            m.p2p_pivot_b[k][j] = c["pivot_b"][j]
+        m.p2p_max_impulse[k] = c["max_impulse"]
+    if "ordered_dofs" in t:
+        m.n_ordered = len(t["ordered_dofs"])
+        _fill(m.ordered_dof, np.array(t["ordered_dofs"], dtype=np.int64))
+        pd = t["powered_joint_inds"] + t["spring_joint_inds"]
+        m.n_pd = len(pd)
+        _fill(m.pd_ordered_index, np.array(pd, dtype=np.int64))
+        _fill(m.pd_kp, np.array(t["pd_kp"], dtype=np.float64))
+        _fill(m.pd_kd, np.array(t["pd_kd"], dtype=np.float64))
     return m
 
 
@@ -447,3 +473,47 @@ class Monkey3DOracle:
 
     def state_vector(self):
         return state_vector(self.e.base.s, self.A)
+
+
+def cassie_params() -> Params:
+    p = Params()
+    lib().orc_cassie_params(C.byref(p))
+    return p
+
+
+class CassieOracle:
+    """Single-env restatement of CassieEnv-v0 (reference env_cassie.py:285-479, defects fixed by intent: SURVEY App. D
+    Q7-Q9)."""
+
+    def __init__(self, table: dict, seed: int = 0, params: Params | None = None):
+        self.table = table
+        self.m = model_from_table(table)
+        self.p = params or cassie_params()
+        self.e = CassieEnvS()
+        self.A = 10
+        self.n_dof = table["n_dof"]
+        self.obs_dim = 36
+
+    def seed(self, seed):
+        return [seed]
+
+    def reset(self):
+        obs = (d * self.obs_dim)()
+        lib().orc_cassie_reset(C.byref(self.m), C.byref(self.p), C.byref(self.e), obs)
+        return np.array(obs)
+
+    def step(self, action):
+        a = (d * 16)(*[float(x) for x in action])
+        obs = (d * self.obs_dim)()
+        r = d(0)
+        done = i32(0)
+        trunc = i32(0)
+        lib().orc_cassie_step(C.byref(self.m), C.byref(self.p), C.byref(self.e), a, obs, C.byref(r), C.byref(done),
+                              C.byref(trunc))
+        info = {"AliveRew": self.e.alive_rew, "ProgressRew": self.e.progress_rew}
+        if trunc.value:
+            info["TimeLimit.truncated"] = True
+        return np.array(obs), r.value, bool(done.value), info
+
+    def state_vector(self):
+        return state_vector(self.e.base.s, self.n_dof)

@@ -32,3 +32,10 @@ def monkey_table():
     from mocca_envs_b200.model_compiler import load_table
 
     return load_table(os.path.join(ROOT, "mocca_envs_b200", "models", "monkey3d.json"))
+
+
+@pytest.fixture(scope="session")
+def cassie_table():
+    from mocca_envs_b200.model_compiler import load_table
+
+    return load_table(os.path.join(ROOT, "mocca_envs_b200", "models", "cassie.json"))

@@ -5,6 +5,7 @@
 
 #include "../../mocca_envs_b200/csrc/generated/walker3d_model.h"
 #include "../../mocca_envs_b200/csrc/generated/monkey3d_model.h"
+#include "../../mocca_envs_b200/csrc/generated/cassie_model.h"
 #include "../../mocca_envs_b200/csrc/mb_env.cuh"
 
 typedef W3D_Model WM;
@@ -14,6 +15,9 @@ typedef WarpMem<WM> WMem;
 typedef MK3D_Model MM;
 typedef MonkeyEnv<MM> MEnv;
 typedef WarpMem<MM> MMem;
+typedef CAS_Model CM;
+typedef CassieEnv<CM> CEnv;
+typedef WarpMem<CM> CMem;
 
 static void default_phys(MbPhysics* p) {
   p->dt = 1.0f / 240.0f; p->substeps = 4; p->iterations = 5; p->gravity = 9.8f; p->erp_contact = 0.9f;
@@ -174,6 +178,63 @@ void emu_monkey_mass_matrix(const MbPhysics* p, const float* state, float* Mout,
   const int NU = MM::NU;
   for (int i = 0; i < NU; ++i) {
     for (int j = 0; j < NU; ++j) Mout[i * NU + j] = mb_Lget<MM>(S.L, i, j);
+    bias[i] = -S.rhs[i];
+  }
+}
+
+// ---- CassieEnv
+void emu_cassie_phys(MbPhysics* p) {
+  default_phys(p);
+  p->dt = 0.03f / 50.0f;
+  p->substeps = 1;
+}
+int emu_cassie_rec_stride() { return (int)CEnv::REC_STRIDE; }
+int emu_sizeof_cassie_warpmem() { return (int)sizeof(CMem); }
+
+void emu_cassie_reset(const MbPhysics* p, float* state, float* rec, float* obs) {
+  static CMem S;
+  memset(&S, 0, sizeof(S));
+  CEnv::reset(S, *p, rec, nullptr, nullptr, obs);
+  CEnv::store_state(S, state);
+}
+
+void emu_cassie_step(const MbPhysics* p, float* state, float* rec, const float* act, float* obs, float* rew,
+                     uint8_t* done, uint8_t* trunc, float* final_obs, double* stats_out) {
+  static CMem S;
+  memset(&S, 0, sizeof(S));
+  MbStats st;
+  memset(&st, 0, sizeof(st));
+  CEnv::step(S, *p, state, rec, nullptr, nullptr, act, obs, rew, done, trunc, final_obs, &st);
+  stats_out[0] = (double)st.episodes; stats_out[1] = st.ret_sum; stats_out[2] = st.len_sum;
+  stats_out[3] = (double)st.nonfinite;
+}
+
+void emu_cassie_step_physics(const MbPhysics* p, float* state, const float* tau, int* rows, int* contacts) {
+  static CMem S;
+  memset(&S, 0, sizeof(S));
+  CEnv::load_state(S, state);
+  for (int j = 0; j < CM::NJ; ++j) S.tau[j] = tau[j];
+  int r = 0, nc = 0, ov = 0;
+  Sim<CM>::LaneConst C;
+  Sim<CM>::init_lane_const(C);
+  for (int k = 0; k < p->substeps; ++k) r += Sim<CM>::substep<0>(S, *p, C, &nc, &ov);
+  CEnv::store_state(S, state);
+  *rows = r;
+  *contacts = nc;
+}
+
+void emu_cassie_mass_matrix(const MbPhysics* p, const float* state, float* Mout, float* bias) {
+  static CMem S;
+  memset(&S, 0, sizeof(S));
+  CEnv::load_state(S, state);
+  Sim<CM>::LaneConst C;
+  Sim<CM>::init_lane_const(C);
+  Sim<CM>::kinematics(S, *p, C, true);
+  Sim<CM>::bodies(S, *p);
+  Sim<CM>::mass_matrix_and_rhs(S);
+  const int NU = CM::NU;
+  for (int i = 0; i < NU; ++i) {
+    for (int j = 0; j < NU; ++j) Mout[i * NU + j] = mb_Lget<CM>(S.L, i, j);
     bias[i] = -S.rhs[i];
   }
 }

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libmb_emu.so")
 _SRC = [os.path.join(_HERE, "emu.cpp")] + [
     os.path.join(_HERE, "..", "..", "mocca_envs_b200", "csrc", f)
-    for f in ("mb_core.cuh", "mb_env.cuh", "mb_tables.h", "generated/walker3d_model.h", "generated/monkey3d_model.h")]
+    for f in ("mb_core.cuh", "mb_env.cuh", "mb_tables.h", "generated/walker3d_model.h", "generated/monkey3d_model.h", "generated/cassie_model.h")]
 
 
 class Phys(C.Structure):
@@ -197,4 +197,55 @@ def monkey_mass_matrix(p, state, nu=29):
     M = np.zeros((nu, nu), dtype=np.float32)
     b = np.zeros(nu, dtype=np.float32)
     lib().emu_monkey_mass_matrix(C.byref(p), _fp(buf), _fp(M), _fp(b))
+    return M, b
+
+
+def cassie_phys():
+    p = Phys()
+    lib().emu_cassie_phys(C.byref(p))
+    return p
+
+
+class EmuCassie:
+    """CassieEnv-v0 through the emulated kernel source (record layout: ER_* / EC_* in mb_env.cuh)."""
+
+    EC_POTENTIAL, EC_JVEL = 22, 32
+
+    def __init__(self):
+        self.p = cassie_phys()
+        self.state = np.zeros(64, dtype=np.float32)
+        self.stride = lib().emu_cassie_rec_stride()
+        self.rec = np.zeros(self.stride, dtype=np.float32)
+        self.obs_dim, self.act_dim, self.n_dof = 36, 10, 18
+
+    def reset(self):
+        obs = np.zeros(self.obs_dim, dtype=np.float32)
+        lib().emu_cassie_reset(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(obs))
+        return obs
+
+    def step(self, act):
+        act = np.ascontiguousarray(act, dtype=np.float32)
+        obs = np.zeros(self.obs_dim, dtype=np.float32)
+        fin = np.zeros(self.obs_dim, dtype=np.float32)
+        rew = np.zeros(1, dtype=np.float32)
+        done = np.zeros(1, dtype=np.uint8)
+        trunc = np.zeros(1, dtype=np.uint8)
+        st = np.zeros(4)
+        lib().emu_cassie_step(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(act), _fp(obs), _fp(rew), _fp(done),
+                              _fp(trunc), _fp(fin), _fp(st))
+        return obs, float(rew[0]), bool(done[0]), bool(trunc[0]), fin
+
+    def step_physics(self, tau):
+        tau = np.ascontiguousarray(tau, dtype=np.float32)
+        rows, nc = C.c_int(0), C.c_int(0)
+        lib().emu_cassie_step_physics(C.byref(self.p), _fp(self.state), _fp(tau), C.byref(rows), C.byref(nc))
+        return rows.value, nc.value
+
+
+def cassie_mass_matrix(p, state, nu=24):
+    buf = np.zeros(64, dtype=np.float32)
+    buf[: len(state)] = state
+    M = np.zeros((nu, nu), dtype=np.float32)
+    b = np.zeros(nu, dtype=np.float32)
+    lib().emu_cassie_mass_matrix(C.byref(p), _fp(buf), _fp(M), _fp(b))
     return M, b

@@ -1,0 +1,125 @@
+"""GPU parity tests for CassieEnv-v0 (BASELINE config 4) through the C ABI, against the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _env(n, **kw):
+    from mocca_envs_b200.vec_env import CassieVecEnv
+
+    return CassieVecEnv(n, device="cuda:0", **kw)
+
+
+def test_cassie_mass_matrix_and_inverse_dynamics(cassie_table, oracle_mod, torch_mod):
+    """north_star: mass matrix and inverse dynamics within 1e-4 relative error (Cassie, 24 generalised coords)."""
+    from tests.helpers import oracle_state, random_states
+    from tests.test_cassie_emulation import _rand_table
+
+    torch, O, t = torch_mod, oracle_mod, cassie_table
+    A, N = t["n_dof"], 16
+    m = O.model_from_table(t)
+    rows = random_states(_rand_table(t), np.random.RandomState(0), N)
+    env = _env(N)
+    assert (env.obs_dim, env.act_dim, env.state_dim, env.nu) == (36, 10, 49, 24)
+    env.set_state(torch.tensor(rows, dtype=torch.float32))
+    M = env.mass_matrix().cpu().numpy()
+    acc = np.random.RandomState(1).randn(N, 6 + A)
+    tau = env.inverse_dynamics(torch.tensor(acc, dtype=torch.float32)).cpu().numpy()
+    for i in range(N):
+        s = oracle_state(O, A, rows[i].astype(np.float32).astype(np.float64))
+        Mref = O.mass_matrix(m, s)
+        assert np.abs(M[i] - Mref).max() / np.abs(Mref).max() < 1e-4
+        tref = O.rnea(m, s, acc[i].astype(np.float32).astype(np.float64), 9.8)
+        assert np.abs(tau[i] - tref).max() / np.abs(tref).max() < 1e-4
+    env.close()
+
+
+def test_cassie_airborne_step_with_loop_closures(cassie_table, oracle_mod, torch_mod):
+    """One 0.6 ms step away from the ground: forward dynamics + the loop-closure rows; state within 1e-4."""
+    from tests.helpers import oracle_state, state_error
+
+    torch, O, t = torch_mod, oracle_mod, cassie_table
+    A, N = t["n_dof"], 16
+    m = O.model_from_table(t)
+    p = O.cassie_params()
+    rng = np.random.RandomState(1)
+    base = np.array(t["base_joint_angles"])
+    rows = np.zeros((N, 13 + 2 * A))
+    for k in range(N):
+        rows[k] = np.concatenate([[0, 0, 3.0], [0, 0, 0, 1], 0.3 * rng.randn(3), 0.3 * rng.randn(3),
+                                  base + 0.01 * rng.randn(A), 0.2 * rng.randn(A)])
+    rows = rows.astype(np.float32).astype(np.float64)
+    taus = 20 * rng.uniform(-1, 1, (N, A))
+    env = _env(N)
+    env.set_state(torch.tensor(rows, dtype=torch.float32))
+    held = taus - np.array(t["damping"]) * rows[:, 13 + A:]
+    nrows, nc = env.step_physics(torch.tensor(held, dtype=torch.float32))
+    out = env.get_state().cpu().numpy()
+    for i in range(N):
+        s = oracle_state(O, A, rows[i])
+        _, r = O.step_physics(m, p, s, taus[i])
+        assert int(nc[i]) == 0 and abs(int(nrows[i]) - r) <= 1
+        assert state_error(out[i], O.state_vector(s, A)) < 1e-4
+    env.close()
+
+
+def test_cassie_env_free_running(cassie_table, oracle_mod, torch_mod):
+    """CassieEnv.step free-running from reset for 8 different action streams: obs within 1e-2 (raw joint speeds in
+    rad/s dominate), reward within 1e-3, identical done flags over the first 10 steps."""
+    torch, O, t = torch_mod, oracle_mod, cassie_table
+    N = 8
+    env = _env(N, return_final_obs=True)
+    obs0 = env.reset().cpu().numpy()
+    oracles = [O.CassieOracle(t) for _ in range(N)]
+    for i, o in enumerate(oracles):
+        assert np.abs(o.reset() - obs0[i]).max() < 1e-5
+    rng = np.random.RandomState(0)
+    alive = [True] * N
+    for step in range(10):
+        acts = 0.1 * rng.uniform(-1, 1, (N, 10))
+        obs, rew, done, info = env.step(torch.tensor(acts, dtype=torch.float32))
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        fin = info["terminal_observation"].cpu().numpy()
+        for i, o in enumerate(oracles):
+            if not alive[i]:
+                continue
+            o1, r1, d1, _ = o.step(acts[i])
+            assert bool(d1) == bool(done[i])
+            assert np.abs(o1 - (fin[i] if done[i] else obs[i])).max() < 1e-2
+            assert abs(r1 - rew[i]) < 1e-3
+            if d1:
+                alive[i] = False
+    env.close()
+
+
+def test_cassie_determinism_and_gym_facade(torch_mod):
+    import mocca_envs_b200 as mb
+
+    torch = torch_mod
+    a = _env(64)
+    b = _env(7)
+    a.reset()
+    b.reset()
+    g = torch.Generator(device="cuda:0").manual_seed(0)
+    for _ in range(5):
+        act = 0.2 * (torch.rand(64, 10, device="cuda:0", generator=g) * 2 - 1)
+        oa, ra, da, _ = a.step(act)
+        ob, rb, db, _ = b.step(act[:7])
+        assert torch.equal(oa[:7], ob) and torch.equal(ra[:7], rb)  # batch-size independence, bit-exact
+    a.close()
+    b.close()
+    env = mb.make("mocca_envs:CassieEnv-v0")
+    obs = env.reset()
+    assert obs.shape == (36,) and obs.dtype == np.float64
+    o, r, d, info = env.step(np.zeros(10))
+    assert set(info) >= {"AliveRew", "ProgressRew"} and abs(info["AliveRew"] + info["ProgressRew"] - r) < 1e-6
+    env.close()

@@ -21,6 +21,11 @@ def main(data_dir="/root/reference/mocca_envs/data"):
     mc.save_table(w, os.path.join(out, "walker3d.json"))
     m = mc.compile_monkey3d(data_dir)
     mc.save_table(m, os.path.join(out, "monkey3d.json"))
+    from mocca_envs_b200 import urdf_compiler as uc
+
+    c = uc.compile_cassie(data_dir)
+    mc.save_table(c, os.path.join(out, "cassie.json"))
+    print("cassie:   links=%d dof=%d mass=%.3f points=%d" % (c["n_links"], c["n_dof"], c["total_mass"], len(c["geoms"])))
     try:
         from mocca_envs_b200 import codegen
         codegen.emit_all(os.path.dirname(HERE))
