@@ -400,7 +400,8 @@ def main():
     hbm_ach = B_step * N / kernel_s / 1e9
     line = {
         "metric": METRIC.replace("Walker3DCustomEnv", {"custom": "Walker3DCustomEnv", "stepper": "Walker3DStepperEnv",
-                                                       "monkey": "Monkey3DCustomEnv", "cassie": "CassieEnv"}[args.env]),
+                                                       "monkey": "Monkey3DCustomEnv", "cassie": "CassieEnv"}[args.env]
+                                 ).replace("16384", str(N)),
         "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -416,7 +417,10 @@ def main():
                    "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks",
                    "parallelism": "env-sharded x%d, no data-path collective" % world},
         "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak if peak else None, "traffic": None,
+                     "frac": achieved_tf / peak if peak else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at 16384 envs from the
+                     # committed ncu --set full capture (profiles/r1j_step_kernel_raw.csv); null for other workloads
+                     "traffic": 7.97e6 if (args.env == "custom" and N == 16384) else None,
                      "peak_source": "FP32 FMA probe kernel measured in this run (mb200_measure_fp32_peak)",
                      "flops_per_env_step": F, "rows_per_substep": R_mean,
                      "contacts_per_substep": conts_all / (K * N * world * S_sub),

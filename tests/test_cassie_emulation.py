@@ -78,7 +78,8 @@ def test_cassie_mass_matrix_and_bias(cassie_table, oracle_mod):
 
 def test_cassie_airborne_step_with_loop_closures(cassie_table, oracle_mod):
     """One 0.6 ms Bullet step away from the ground: forward dynamics + the six loop-closure rows (two compact rows
-    per multiplier in the kernel) against the oracle's velocity-space PGS; state within 1e-4."""
+    per multiplier in the kernel) against the oracle's velocity-space PGS; state within 3e-4 (the ERP term
+    divides the f32 pivot gap by dt = 0.6 ms: 1e-7 m of rounding is 1.7e-4 m/s)."""
     O, t = oracle_mod, cassie_table
     A = t["n_dof"]
     m = O.model_from_table(t)
@@ -96,7 +97,7 @@ def test_cassie_airborne_step_with_loop_closures(cassie_table, oracle_mod):
         emu.state[:13 + 2 * A] = row.astype(np.float32)
         erows, enc = emu.step_physics(tau - np.array(t["damping"]) * row[13 + A:])
         assert enc == 0 and abs(rows - erows) <= 1
-        assert state_error(emu.state[:13 + 2 * A], O.state_vector(s, A)) < 1e-4
+        assert state_error(emu.state[:13 + 2 * A], O.state_vector(s, A)) < 3e-4
 
 
 def test_cassie_env_free_running(cassie_table, oracle_mod):
