@@ -213,6 +213,28 @@ def emit_header(t: dict, prefix: str) -> str:
         fac.append([r["rowoff"][c] for c in cols] + [0] * (maxoff - len(cols)))
     out.append("MB_TABLE int %s_facoff[%d][%d] = {\n  %s};\n" % (
         P, r["nu"], maxoff, ",\n  ".join("{" + ", ".join(str(v) for v in row) + "}" for row in fac)))
+    # fcol[k][t]: generalised coordinate whose column sits in slot t of compact row k
+    fcol = []
+    for k in range(r["nu"]):
+        cols = sorted(j for j in range(k) if (r["rowmask_rt"][k] >> j) & 1)
+        fcol.append(cols + [0] * (maxoff - len(cols)))
+    out.append("MB_TABLE int %s_fcol[%d][%d] = {\n  %s};\n" % (
+        P, r["nu"], maxoff, ",\n  ".join("{" + ", ".join(str(v) for v in row) + "}" for row in fcol)))
+    # per coordinate: depth in the joint tree (-1 for the six base coordinates) and its ancestors' coordinate
+    # indices by level, 5 bits each (levels 0-5 in word 0, 6-11 in word 1)
+    cdepth = [-1] * 6 + list(r["jdepth"])
+    anc0, anc1 = [0] * 6, [0] * 6
+    for j in range(r["nj"]):
+        c = [j]
+        while r["jparent"][c[0]] >= 0:
+            c.insert(0, r["jparent"][c[0]])
+        w0 = sum((6 + a) << (5 * t) for t, a in enumerate(c[:6]))
+        w1 = sum((6 + a) << (5 * t) for t, a in enumerate(c[6:12]))
+        anc0.append(w0)
+        anc1.append(w1)
+    out.append(_iarr(P + "_cdepth", cdepth))
+    out.append(_iarr(P + "_canc0", anc0, "unsigned"))
+    out.append(_iarr(P + "_canc1", anc1, "unsigned"))
     out.append(_farr(P + "_joff", r["joff"]))
     out.append(_farr(P + "_jrot", [np.asarray(m).reshape(9) for m in r["jrot"]]))
     out.append(_farr(P + "_jaxis", r["jaxis"]))
@@ -297,12 +319,14 @@ def emit_header(t: dict, prefix: str) -> str:
                   len(ex.get("pd_dof", [])), ex.get("npowered", 0)))
     out.append("  MB_HD static unsigned long long chainpack(int j) { return %s_chainpack[j]; }\n" % P)
     out.append("  MB_HD static int facoff(int k, int t) { return %s_facoff[k][t]; }\n" % P)
+    out.append("  MB_HD static int fcol(int k, int t) { return %s_fcol[k][t]; }\n" % P)
     out.append("  MB_HD static int lvjoint(int lev, int slot) { return %s_lvjoint[lev][slot]; }\n" % P)
     out.append("  MB_HD static int c_rowoff(int i) { return %s_c_rowoff[i]; }\n" % P)
     out.append("  MB_HD static int c_rowlen(int i) { return %s_c_rowlen[i]; }\n" % P)
     out.append("  MB_HD static unsigned c_rowmask(int i) { return %s_c_rowmask[i]; }\n" % P)
     for fld, ctype in [("jparent", "int"), ("jlevel", "int"), ("janc", "unsigned"), ("bstart", "int"), ("bend", "int"),
                        ("jdepth", "int"), ("rowoff", "int"), ("rowlen", "int"), ("rowmask", "unsigned"),
+                       ("cdepth", "int"), ("canc0", "unsigned"), ("canc1", "unsigned"),
                        ("jaxk", "int"), ("jident", "int"),
                        ("bowner", "int"), ("powner", "int"), ("pfoot", "int"), ("pid", "int"), ("foot_body", "int"),
                        ("palm_body", "int"), ("xowner", "int"), ("xfoot", "int"),

@@ -2,6 +2,7 @@
 // One warp per environment, MB_WARPS warps per CTA; per-env working set lives in shared memory (WarpMem).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -58,6 +59,14 @@ struct mb200_env {
   float* dummy_rew;    // [MB_WARPS]
   uint8_t* dummy_flag; // [2][MB_WARPS]
   MbStats* dummy_stats;
+  // work-sorted slot -> env map: the warps of a CTA meet at one barrier per substep, so a CTA runs at the pace of
+  // its slowest env; grouping envs with similar constraint-row counts (of the previous step) removes most of that
+  // wait, and heavy CTAs are scheduled first.  Pure scheduling: every env's arithmetic is unchanged.
+  int* order;      // [n_pad]
+  int* work;       // [n_pad] running constraint-row sum per env
+  int* work_prev;  // [n_pad] the same one sort earlier
+  int sort_every;  // re-sort period in steps (0 = never, identity order)
+  long long steps;
   long long launches;
   size_t smem;
 };
@@ -89,13 +98,15 @@ struct StepArgs {
   float* dummy_rew;
   uint8_t* dummy_flag;
   MbStats* dummy_stats;
+  const int* order;
+  int* work;
 };
 
 template <class Env>
 __device__ __forceinline__ void step_body(const StepArgs& a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
-  const int env = blockIdx.x * MB_WARPS + warp;  // < n_pad by construction of the grid
+  const int env = a.order[blockIdx.x * MB_WARPS + warp];  // a permutation of [0, n_pad)
   const bool tail = env >= a.n;
   typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
   float* obs = tail ? a.dummy_obs + (size_t)warp * Env::OBS : a.obs + (size_t)env * Env::OBS;
@@ -106,6 +117,63 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
             a.act + (size_t)(tail ? 0 : env) * Env::ACT, obs, tail ? a.dummy_rew + warp : a.rew + env,
             tail ? a.dummy_flag + warp : a.done + env, tail ? a.dummy_flag + MB_WARPS + warp : a.trunc + env, fin,
             tail ? a.dummy_stats : a.stats);
+  // work estimate for the scheduler: constraint rows accumulated by this step (ER_ROWS is a running sum)
+  if ((threadIdx.x & 31) == 0) {
+    const float* rec = a.rec + (size_t)env * Env::REC_STRIDE;
+    a.work[env] = (int)rec[ER_ROWS];
+  }
+}
+
+// Counting sort of the envs by the rows of their last step, heaviest first (one CTA; keys clamp at 255).
+// `work` holds the running row sum; prev holds the sum one step earlier (updated here).
+__global__ void __launch_bounds__(1024) k_sort_by_work(int n_pad, const int* work, int* prev, int* order) {
+  __shared__ int hist[256];
+  __shared__ int start[256];
+  const unsigned lane = threadIdx.x & 31u;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int rounds = (n_pad + blockDim.x - 1) / blockDim.x;  // uniform trip count: __match_any_sync needs full warps
+  for (int r = 0; r < rounds; ++r) {
+    const int e = r * blockDim.x + threadIdx.x;
+    int k = 256;  // out of range: no bin
+    if (e < n_pad) {
+      k = work[e] - prev[e];
+      k = 255 - (k < 0 ? 0 : (k > 255 ? 255 : k));
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, k);  // warp-aggregated shared-memory atomics
+    if (k < 256 && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[k], __popc(peers));
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {  // exclusive scan of the 256 bins by one warp, 8 bins per lane
+    int loc[8], sum = 0;
+    for (int i = 0; i < 8; ++i) { loc[i] = sum; sum += hist[8 * lane + i]; }
+    int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (unsigned)o) incl += v;
+    }
+    const int base = incl - sum;
+    for (int i = 0; i < 8; ++i) start[8 * lane + i] = base + loc[i];
+  }
+  __syncthreads();
+  for (int r = 0; r < rounds; ++r) {
+    const int e = r * blockDim.x + threadIdx.x;
+    int k = 256, w = 0;
+    if (e < n_pad) {
+      w = work[e];
+      k = w - prev[e];
+      k = 255 - (k < 0 ? 0 : (k > 255 ? 255 : k));
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, k);
+    int base = 0;
+    const int leader = __ffs(peers) - 1;
+    if (k < 256 && lane == (unsigned)leader) base = atomicAdd(&start[k], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (k < 256) {
+      order[base + __popc(peers & ((1u << lane) - 1u))] = e;
+      prev[e] = w;
+    }
+  }
 }
 __global__ void __launch_bounds__(MB_WARPS * 32, MB_MINBLOCKS) k_step_walker3d_custom(StepArgs a) {
   step_body<WEnv>(a);
@@ -395,6 +463,21 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   CUDA_OK(cudaMalloc(&e->rec, n * e->rec_stride * sizeof(float)));
   CUDA_OK(cudaMalloc(&e->mt, n * 2 * MB_MT_STRIDE * sizeof(uint32_t)));
   CUDA_OK(cudaMalloc(&e->stats, sizeof(MbStats)));
+  CUDA_OK(cudaMalloc(&e->order, n * sizeof(int)));
+  CUDA_OK(cudaMalloc(&e->work, n * sizeof(int)));
+  CUDA_OK(cudaMalloc(&e->work_prev, n * sizeof(int)));
+  CUDA_OK(cudaMemset(e->work, 0, n * sizeof(int)));
+  CUDA_OK(cudaMemset(e->work_prev, 0, n * sizeof(int)));
+  {
+    int* ident = (int*)malloc(n * sizeof(int));
+    if (!ident) return fail("mb200_create: host allocation failed");
+    for (size_t i = 0; i < n; ++i) ident[i] = (int)i;
+    cudaError_t ce = cudaMemcpy(e->order, ident, n * sizeof(int), cudaMemcpyHostToDevice);
+    free(ident);
+    CUDA_OK(ce);
+  }
+  e->sort_every = 1;
+  if (const char* sv = getenv("MB200_SORT_EVERY")) e->sort_every = atoi(sv);
   CUDA_OK(cudaMalloc(&e->stage_act, n * e->act_dim * sizeof(float)));
   CUDA_OK(cudaMalloc(&e->stage_obs, n * e->obs_dim * sizeof(float)));
   CUDA_OK(cudaMalloc(&e->stage_rew, n * sizeof(float)));
@@ -415,6 +498,7 @@ void mb200_destroy(mb200_env* e) {
   cudaFree(e->stage_act); cudaFree(e->stage_obs); cudaFree(e->stage_rew); cudaFree(e->stage_done);
   cudaFree(e->stage_trunc);
   cudaFree(e->dummy_obs); cudaFree(e->dummy_rew); cudaFree(e->dummy_flag); cudaFree(e->dummy_stats);
+  cudaFree(e->order); cudaFree(e->work); cudaFree(e->work_prev);
   delete e;
 }
 
@@ -499,6 +583,7 @@ int mb200_step(mb200_env* e, const float* act_dev, float* obs_dev, float* rew_de
   a.n = e->n; a.phys = e->phys; a.state = e->state; a.rec = e->rec; a.mt = e->mt; a.act = act_dev; a.obs = obs_dev;
   a.rew = rew_dev; a.done = done_dev; a.trunc = trunc_dev; a.final_obs = final_obs_dev; a.stats = e->stats;
   a.dummy_obs = e->dummy_obs; a.dummy_rew = e->dummy_rew; a.dummy_flag = e->dummy_flag; a.dummy_stats = e->dummy_stats;
+  a.order = e->order; a.work = e->work;
   if (e->kind == KIND_CASSIE)
     k_step_cassie<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
   else if (e->kind == KIND_MONKEY)
@@ -508,6 +593,11 @@ int mb200_step(mb200_env* e, const float* act_dev, float* obs_dev, float* rew_de
   else
     k_step_walker3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
   e->launches++;
+  e->steps++;
+  if (e->sort_every > 0 && e->steps % e->sort_every == 0 && grid_for(e->n) > 1) {
+    k_sort_by_work<<<1, 1024, 0, (cudaStream_t)stream>>>(e->n_pad, e->work, e->work_prev, e->order);
+    e->launches++;
+  }
   CUDA_OK(cudaGetLastError());
   return 0;
 }

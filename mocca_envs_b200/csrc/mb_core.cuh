@@ -46,6 +46,9 @@ MB_HD float warp_sum(const LaneVar<float>& x) {
   return v;
 }
 MB_HD float warp_bcast(const LaneVar<float>& x, int src) { return __shfl_sync(0xffffffffu, x.v, src); }
+MB_HD void warp_gather(const LaneVar<float>& x, const LaneVar<int>& src, LaneVar<float>& out) {
+  out.v = __shfl_sync(0xffffffffu, x.v, src.v);
+}
 MB_HD unsigned warp_ballot(const LaneVar<int>& p) { return __ballot_sync(0xffffffffu, p.v != 0); }
 MB_HD int mb_popc(unsigned x) { return __popc(x); }
 MB_HD void mb_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
@@ -70,6 +73,11 @@ inline float warp_sum(const LaneVar<float>& x) {
   return t[0];
 }
 inline float warp_bcast(const LaneVar<float>& x, int src) { return x.v[src]; }
+inline void warp_gather(const LaneVar<float>& x, const LaneVar<int>& src, LaneVar<float>& out) {
+  float t[32];
+  for (int l = 0; l < 32; ++l) t[l] = x.v[src.v[l] & 31];
+  for (int l = 0; l < 32; ++l) out.v[l] = t[l];
+}
 inline unsigned warp_ballot(const LaneVar<int>& p) {
   unsigned m = 0;
   for (int l = 0; l < 32; ++l)
@@ -252,12 +260,17 @@ template <class M> struct Sim {
     LaneVar<int> off;       // rowoff(l)
     LaneVar<unsigned> sup;  // rowmask(l)
     LaneVar<int> pairs;     // (t, s) of the lower-triangle entries p = l, l + 32, l + 64 (4 bits each)
+    LaneVar<int> dep;       // tree depth of coordinate l (-1 base block, 99 unused lane)
+    LaneVar<unsigned> anc0, anc1;  // coordinate index of l's ancestor at each level, 5 bits per level
   };
   MB_HD static void init_lane_const(LaneConst& C) {
     MB_LANES(l)
       C.tl[l] = l < NU ? M::rowlen(l) - 1 : 0;
       C.off[l] = l < NU ? M::rowoff(l) : 0;
       C.sup[l] = l < NU ? M::rowmask(l) : 0u;
+      C.dep[l] = l < NU ? M::cdepth(l) : 99;
+      C.anc0[l] = l < NU ? M::canc0(l) : 0u;
+      C.anc1[l] = l < NU ? M::canc1(l) : 0u;
       int packed = 0;
       for (int r = 0; r < 3; ++r) {
         const int pidx = l + 32 * r;
@@ -495,15 +508,25 @@ template <class M> struct Sim {
   // Compact rows: entry t of row k belongs to column i_t = (t < 6 ? t : 6 + chain_k[t-6]), and row i_t has exactly
   // t off-diagonal entries occupying the same slots 0..t-1 -- every update L[i_t][s] -= L[k][t] L[k][s] (s <= t)
   // is a contiguous prefix.  The nk(nk+1)/2 updates of step k are spread over the 32 lanes (<= 3 rounds).
-  MB_HD static void factorize(Mem& S, const LaneConst& C) {
+  // With RHS the backward substitution L^T y = rhs rides along: row k of L is final once it has been scaled, and
+  // the substitution visits the rows in the same order (k descending), so y_k = rhs_k / L_kk and
+  // rhs_col -= L[k][col] y_k are issued by the lanes that just scaled the row (S.rhs is overwritten by y).
+  template <bool RHS> MB_HD static void factorize(Mem& S, const LaneConst& C) {
 #pragma unroll 1
     for (int k = NU - 1; k >= 0; --k) {
       const int offk = M::c_rowoff(k), nk = M::c_rowlen(k) - 1;
       const float dkk = S.L[offk + nk];
       const float inv = rsqrtf(dkk);
+      const float yk = RHS ? S.rhs[k] * inv : 0.0f;
       MB_LANES(l)
-        if (l < nk) S.L[offk + l] *= inv;
-        else if (l == nk) { S.L[offk + nk] = dkk * inv; S.Ldinv[k] = inv; }
+        if (l < nk) {
+          const float v = S.L[offk + l] * inv;
+          S.L[offk + l] = v;
+          if (RHS) S.rhs[M::fcol(k, l)] -= v * yk;
+        } else if (l == nk) {
+          S.L[offk + nk] = dkk * inv; S.Ldinv[k] = inv;
+          if (RHS) S.rhs[k] = yk;
+        }
       MB_END
       const int npairs = (nk * (nk + 1)) >> 1;
       MB_LANES(l)
@@ -520,28 +543,35 @@ template <class M> struct Sim {
     }
   }
 
-  // ---- E. single right-hand-side solves, one generalised coordinate per lane ---------------------------------
-  // L[i][l] sits at rowoff(i) + tl(l) for every i whose support contains l (prefix property): no index math.
-  MB_HD static void solve_Lt(Mem& S, const LaneConst& C, LaneVar<float>& x) {  // L^T y = x
-#pragma unroll 3
-    for (int i = NU - 1; i >= 0; --i) {
-      const float yi = warp_bcast(x, i) * S.Ldinv[i];
-      const unsigned sup = M::c_rowmask(i);
-      const int off = M::c_rowoff(i);
-      MB_LANES(l)
-        if (l == i) x[l] = yi;
-        else if ((sup >> l) & 1u) x[l] -= S.L[off + C.tl[l]] * yi;
-      MB_END_REG
-    }
-  }
-  MB_HD static void solve_L(Mem& S, const LaneConst& C, LaneVar<float>& x) {  // L y = x
-#pragma unroll 3
-    for (int i = 0; i < NU; ++i) {
+  // ---- E. single right-hand-side solve, one generalised coordinate per lane ----------------------------------
+  // L y = x, forward substitution.  The six base coordinates go one by one; after that the joints of one tree
+  // level are independent of each other, so a level is one step: its lanes finalise, every deeper lane fetches
+  // the value of ITS ancestor on that level (one indexed shuffle) and subtracts L[l][ancestor], which sits at slot
+  // 6 + level of the lane's own compact row.
+  MB_HD static void solve_L(Mem& S, const LaneConst& C, LaneVar<float>& x) {
+    LaneVar<float> dinv;
+    MB_LANES(l)
+      dinv[l] = S.Ldinv[l];
+    MB_END_REG
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
       const float xi = warp_bcast(x, i) * S.Ldinv[i];
-      const int ti = M::c_rowlen(i) - 1;
       MB_LANES(l)
         if (l == i) x[l] = xi;
-        else if ((C.sup[l] >> i) & 1u) x[l] -= S.L[C.off[l] + ti] * xi;
+        else if (l > i && l < NU) x[l] -= S.L[C.off[l] + i] * xi;
+      MB_END_REG
+    }
+#pragma unroll
+    for (int d = 0; d < M::NLEVEL; ++d) {
+      LaneVar<int> src;
+      LaneVar<float> xa;
+      MB_LANES(l)
+        if (C.dep[l] == d) x[l] *= dinv[l];
+        src[l] = (int)(((d < 6 ? C.anc0[l] >> (5 * d) : C.anc1[l] >> (5 * (d - 6)))) & 31u);
+      MB_END_REG
+      warp_gather(x, src, xa);
+      MB_LANES(l)
+        if (C.dep[l] > d && C.dep[l] < 99) x[l] -= S.L[C.off[l] + 6 + d] * xa[l];
       MB_END_REG
     }
   }
@@ -1159,7 +1189,7 @@ template <class M> struct Sim {
     loop_pivots(S);
     bodies(S, P);
     mass_matrix_and_rhs(S);
-    factorize(S, C);
+    factorize<true>(S, C);  // also turns S.rhs into L^-T rhs
     // forward dynamics: udot = M^-1 (tau - bias); u += dt udot, clamped like btMultiBody::applyDeltaVeeMultiDof.
     // (The clamp is live in practice: Bullet ignores the MJCF armature, so the light arm links reach 100 rad/s
     // under full torque -- which is why the two forward substitutions of a substep cannot be merged into one.)
@@ -1167,7 +1197,6 @@ template <class M> struct Sim {
     MB_LANES(l)
       x[l] = l < NU ? S.rhs[l] : 0.0f;
     MB_END
-    solve_Lt(S, C, x);
     solve_L(S, C, x);
     MB_LANES(l)
       if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + P.dt * x[l], -P.max_coord_vel), P.max_coord_vel);
