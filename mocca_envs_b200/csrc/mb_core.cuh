@@ -127,6 +127,14 @@ MB_HD constexpr int tri(int i, int j) { return (i * (i + 1)) / 2 + j; }  // pack
 MB_HD int chain_at(unsigned long long pack, int t) { return (int)((pack >> (5 * t)) & 31ull); }
 MB_HD bool mb_finite(float x) { return fabsf(x) <= 3.402823466e38f; }   // false for NaN and +-inf
 
+// per-row solver constants, read with one 128-bit shared-memory load per row visit
+struct alignas(16) MbRowPar {
+  float rhs;   // (positional + velocity error) * jinv
+  float cfm;   // cfm * jinv
+  float jinv;  // 1 / (J M^-1 J^T + cfm)
+  float den;   // J M^-1 J^T + cfm (0 for a degenerate row): residual = delta impulse * den
+};
+
 template <class M> struct WarpMem {
   // ---- state (generalised velocity u = [omega_w, v_w, qd])
   float u[32];
@@ -176,9 +184,7 @@ template <class M> struct WarpMem {
   int cfoot[MB_MAXC];
   int cpartner[MB_MAXC];
   // ---- row parameters
-  float r_rhs[MB_MAXROW];
-  float r_cfm[MB_MAXROW];
-  float r_jinv[MB_MAXROW];
+  MbRowPar r_par[MB_MAXROW];
   float r_app[MB_MAXROW];
   float r_mu[MB_MAXROW];
   unsigned r_mask[MB_MAXROW];  // support of the row over the generalised coordinates
@@ -1007,14 +1013,14 @@ template <class M> struct Sim {
           for (int t = 0; t < M::MAXSUP; ++t)
             if (t < n) Yr[t] = b[t];
           S.r_mask[r] = 0x3Fu | (cj >= 0 ? (M::janc(cj) << 6) : 0u);
+          MbRowPar par;
           if (kind == 3) {  // partial sums; the two parts of a loop row are combined below
-            S.r_rhs[r] = rel_vel;
-            S.r_jinv[r] = dd;
+            par.rhs = rel_vel; par.jinv = dd; par.den = 0.0f;
           } else {
-            S.r_rhs[r] = (positional + verr) * jinv;
-            S.r_jinv[r] = jinv;
+            par.rhs = (positional + verr) * jinv; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
           }
-          S.r_cfm[r] = cfm * jinv;
+          par.cfm = cfm * jinv;
+          S.r_par[r] = par;
           S.r_app[r] = 0.0f;
           S.r_mu[r] = mu;
         }
@@ -1026,13 +1032,14 @@ template <class M> struct Sim {
       MB_LANES(l)
         if (l < NLC / 2) {
           const int ra = nlim + 2 * l, ax = l % 3, c = l / 3;
-          const float dd = S.r_jinv[ra] + S.r_jinv[ra + 1];
+          const float dd = S.r_par[ra].jinv + S.r_par[ra + 1].jinv;
           const float jinv = dd > 1.1920929e-07f ? 1.0f / dd : 0.0f;
-          const float rel_vel = S.r_rhs[ra] + S.r_rhs[ra + 1];
+          const float rel_vel = S.r_par[ra].rhs + S.r_par[ra + 1].rhs;
           const float pos_error = -(S.lcP[2 * c][ax] - S.lcP[2 * c + 1][ax]);
           const float positional = -pos_error * P.erp_joint * inv_dt;
-          S.r_rhs[ra] = (positional - rel_vel) * jinv;
-          S.r_jinv[ra] = jinv;
+          MbRowPar par;
+          par.rhs = (positional - rel_vel) * jinv; par.cfm = 0.0f; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
+          S.r_par[ra] = par;
           S.r_mu[ra] = M::lc_maximp(c);
         }
       MB_END
@@ -1049,8 +1056,9 @@ template <class M> struct Sim {
       ta[l] = ya[l] * z[l];
     MB_END_REG
     const float dotA = warp_sum(ta);
-    const float appA = S.r_app[ra], jA = S.r_jinv[ra];
-    float dA = S.r_rhs[ra] - appA * S.r_cfm[ra] - dotA * jA;
+    const MbRowPar pA = S.r_par[ra];
+    const float appA = S.r_app[ra];
+    float dA = pA.rhs - appA * pA.cfm - dotA * pA.jinv;
     const float sumA = appA + dA;
     float nA = sumA;
     if (sumA < lo) { dA = lo - appA; nA = lo; }
@@ -1059,7 +1067,7 @@ template <class M> struct Sim {
       z[l] += ya[l] * dA;
       if (l == 0) S.r_app[ra] = nA;
     MB_END
-    return jA != 0.0f ? dA / jA : 0.0f;
+    return dA * pA.den;  // deltaImpulse * (1 / jacDiagABInv)
   }
   // friction pair with btMultiBodyConstraintSolver::resolveConeFrictionConstraintRows' projection;
   // sin/cos(atan2(a, b)) are written as a/|(a,b)|, b/|(a,b)|
@@ -1075,9 +1083,10 @@ template <class M> struct Sim {
       tb[l] = yb[l] * z[l];
     MB_END_REG
     const float dotA = warp_sum(ta), dotB = warp_sum(tb);
-    const float appA = S.r_app[ra], jA = S.r_jinv[ra], appB = S.r_app[rb], jB = S.r_jinv[rb];
-    float dA = S.r_rhs[ra] - appA * S.r_cfm[ra] - dotA * jA;
-    float dB = S.r_rhs[rb] - appB * S.r_cfm[rb] - dotB * jB;
+    const MbRowPar pA = S.r_par[ra], pB = S.r_par[rb];
+    const float appA = S.r_app[ra], appB = S.r_app[rb];
+    float dA = pA.rhs - appA * pA.cfm - dotA * pA.jinv;
+    float dB = pB.rhs - appB * pB.cfm - dotB * pB.jinv;
     const float sumA = appA + dA, sumB = appB + dB;
     float nA = sumA, nB = sumB;
     const float n2 = sumA * sumA + sumB * sumB;
@@ -1093,9 +1102,7 @@ template <class M> struct Sim {
       z[l] += ya[l] * dA + yb[l] * dB;
       if (l == 0) { S.r_app[ra] = nA; S.r_app[rb] = nB; }
     MB_END
-    float res = jA != 0.0f ? dA / jA : 0.0f;
-    if (jB != 0.0f) res += dB / jB;
-    return res;
+    return dA * pA.den + dB * pB.den;
   }
 
   // loop-closure row: two compact rows (ra on link A, ra + 1 on link B) sharing one multiplier
@@ -1110,8 +1117,9 @@ template <class M> struct Sim {
       t[l] = y[l] * z[l];
     MB_END_REG
     const float dot = warp_sum(t);
-    const float app = S.r_app[ra], jinv = S.r_jinv[ra], lim = S.r_mu[ra];
-    float d = S.r_rhs[ra] - dot * jinv;
+    const MbRowPar pA = S.r_par[ra];
+    const float app = S.r_app[ra], lim = S.r_mu[ra];
+    float d = pA.rhs - dot * pA.jinv;
     const float sum = app + d;
     float na = sum;
     if (sum < -lim) { d = -lim - app; na = -lim; }
@@ -1120,7 +1128,7 @@ template <class M> struct Sim {
       z[l] += y[l] * d;
       if (l == 0) S.r_app[ra] = na;
     MB_END
-    return jinv != 0.0f ? d / jinv : 0.0f;
+    return d * pA.den;
   }
 
   // btMultiBodyConstraintSolver::solveSingleIteration order: non-contact rows (limits, then loop closures;
