@@ -170,8 +170,12 @@ template <class M> struct WarpMem {
   // ---- dynamics
   // M, then its factor L (M = L^T L), compact: row i keeps only its support in chain order
   // [base block 0..5 | ancestors root->parent | diagonal]; an ancestor's support is a prefix of its descendants'
+  // After factorize(): rows are left UNSCALED (U[k][t] = pivot-time M entries, diagonal slot = pivot d_k) with
+  // Ldinv = d^-1/2 and Ldi2 = 1/d beside them; L = diag(Ldinv) U.  Nothing ever reads a scaled row, so the
+  // factorisation has no scaling pass and one warp barrier per pivot.
   float L[M::LSIZE];
   float Ldinv[32];
+  float Ldi2[32];
   float rhs[32];
   // ---- contacts
   float cP[MB_MAXC][3];
@@ -514,34 +518,26 @@ template <class M> struct Sim {
   // Compact rows: entry t of row k belongs to column i_t = (t < 6 ? t : 6 + chain_k[t-6]), and row i_t has exactly
   // t off-diagonal entries occupying the same slots 0..t-1 -- every update L[i_t][s] -= L[k][t] L[k][s] (s <= t)
   // is a contiguous prefix.  The nk(nk+1)/2 updates of step k are spread over the 32 lanes (<= 3 rounds).
-  // With RHS the backward substitution L^T y = rhs rides along: row k of L is final once it has been scaled, and
-  // the substitution visits the rows in the same order (k descending), so y_k = rhs_k / L_kk and
-  // rhs_col -= L[k][col] y_k are issued by the lanes that just scaled the row (S.rhs is overwritten by y).
+  // With RHS the backward substitution L^T y = rhs rides along (same visiting order, k descending): the pivot row
+  // pushes rhs_col -= U[k][col] rhs_k / d_k.  S.rhs is left holding d^1/2 y, which is exactly the pre-scaled input
+  // solve_L<true> wants, so the forward-dynamics solve never touches a square root besides the pivot's rsqrt.
   template <bool RHS> MB_HD static void factorize(Mem& S, const LaneConst& C) {
 #pragma unroll 1
     for (int k = NU - 1; k >= 0; --k) {
       const int offk = M::c_rowoff(k), nk = M::c_rowlen(k) - 1;
       const float dkk = S.L[offk + nk];
-      const float inv = rsqrtf(dkk);
-      const float yk = RHS ? S.rhs[k] * inv : 0.0f;
-      MB_LANES(l)
-        if (l < nk) {
-          const float v = S.L[offk + l] * inv;
-          S.L[offk + l] = v;
-          if (RHS) S.rhs[M::fcol(k, l)] -= v * yk;
-        } else if (l == nk) {
-          S.L[offk + nk] = dkk * inv; S.Ldinv[k] = inv;
-          if (RHS) S.rhs[k] = yk;
-        }
-      MB_END
+      const float inv = rsqrtf(dkk), invd = inv * inv;
+      const float ck = RHS ? S.rhs[k] * invd : 0.0f;
       const int npairs = (nk * (nk + 1)) >> 1;
       MB_LANES(l)
+        if (l == 31) { S.Ldinv[k] = inv; S.Ldi2[k] = invd; }
+        if (RHS && l < nk) S.rhs[M::fcol(k, l)] -= S.L[offk + l] * ck;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           if (32 * r < npairs) {  // uniform: whole rounds are skipped for short rows
             if (l + 32 * r < npairs) {
               const int t = (C.pairs[l] >> (8 * r)) & 15, s2 = (C.pairs[l] >> (8 * r + 4)) & 15;
-              S.L[M::facoff(k, t) + s2] -= S.L[offk + t] * S.L[offk + s2];
+              S.L[M::facoff(k, t) + s2] -= (S.L[offk + t] * invd) * S.L[offk + s2];
             }
           }
         }
@@ -550,18 +546,20 @@ template <class M> struct Sim {
   }
 
   // ---- E. single right-hand-side solve, one generalised coordinate per lane ----------------------------------
-  // L y = x, forward substitution.  The six base coordinates go one by one; after that the joints of one tree
-  // level are independent of each other, so a level is one step: its lanes finalise, every deeper lane fetches
-  // the value of ITS ancestor on that level (one indexed shuffle) and subtracts L[l][ancestor], which sits at slot
-  // 6 + level of the lane's own compact row.
-  MB_HD static void solve_L(Mem& S, const LaneConst& C, LaneVar<float>& x) {
-    LaneVar<float> dinv;
+  // L y = x, forward substitution on the unscaled rows: with xs = d^1/2 x the recurrence is
+  // y_i = xs_i / d_i, xs_l -= U[l][i] y_i.  PRESCALED: x already holds xs (the fused factorisation leaves it so).
+  // The six base coordinates go one by one; after that the joints of one tree level are independent of each other,
+  // so a level is one step: its lanes finalise, every deeper lane fetches the value of ITS ancestor on that level
+  // (one indexed shuffle) and subtracts U[l][ancestor], which sits at slot 6 + level of the lane's own compact row.
+  template <bool PRESCALED> MB_HD static void solve_L(Mem& S, const LaneConst& C, LaneVar<float>& x) {
+    LaneVar<float> di2;
     MB_LANES(l)
-      dinv[l] = S.Ldinv[l];
+      di2[l] = S.Ldi2[l];
+      if (!PRESCALED && l < NU) x[l] *= S.L[C.off[l] + C.tl[l]] * S.Ldinv[l];
     MB_END_REG
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      const float xi = warp_bcast(x, i) * S.Ldinv[i];
+      const float xi = warp_bcast(x, i) * S.Ldi2[i];
       MB_LANES(l)
         if (l == i) x[l] = xi;
         else if (l > i && l < NU) x[l] -= S.L[C.off[l] + i] * xi;
@@ -572,7 +570,7 @@ template <class M> struct Sim {
       LaneVar<int> src;
       LaneVar<float> xa;
       MB_LANES(l)
-        if (C.dep[l] == d) x[l] *= dinv[l];
+        if (C.dep[l] == d) x[l] *= di2[l];
         src[l] = (int)(((d < 6 ? C.anc0[l] >> (5 * d) : C.anc1[l] >> (5 * (d - 6)))) & 31u);
       MB_END_REG
       warp_gather(x, src, xa);
@@ -987,11 +985,11 @@ template <class M> struct Sim {
           for (int t = M::MAXSUP - 1; t >= 0; --t) {
             if (t < n) {
               const int it = t < 6 ? t : 6 + chain_at(pack, t - 6);
-              const float yi = b[t] * S.Ldinv[it];
-              b[t] = yi;
+              const float ci = b[t] * S.Ldi2[it];  // rows are unscaled: L[it][s] y = U[it][s] (b_t / d_it)
+              b[t] *= S.Ldinv[it];
               const float* Li = &S.L[M::rowoff(it)];
 #pragma unroll
-              for (int s2 = 0; s2 < t; ++s2) b[s2] -= Li[s2] * yi;
+              for (int s2 = 0; s2 < t; ++s2) b[s2] -= Li[s2] * ci;
             }
           }
           float dd = cfm;
@@ -1197,7 +1195,7 @@ template <class M> struct Sim {
     loop_pivots(S);
     bodies(S, P);
     mass_matrix_and_rhs(S);
-    factorize<true>(S, C);  // also turns S.rhs into L^-T rhs
+    factorize<true>(S, C);  // also turns S.rhs into d^1/2 L^-T rhs
     // forward dynamics: udot = M^-1 (tau - bias); u += dt udot, clamped like btMultiBody::applyDeltaVeeMultiDof.
     // (The clamp is live in practice: Bullet ignores the MJCF armature, so the light arm links reach 100 rad/s
     // under full torque -- which is why the two forward substitutions of a substep cannot be merged into one.)
@@ -1205,7 +1203,7 @@ template <class M> struct Sim {
     MB_LANES(l)
       x[l] = l < NU ? S.rhs[l] : 0.0f;
     MB_END
-    solve_L(S, C, x);
+    solve_L<true>(S, C, x);
     MB_LANES(l)
       if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + P.dt * x[l], -P.max_coord_vel), P.max_coord_vel);
     MB_END
@@ -1220,7 +1218,7 @@ template <class M> struct Sim {
         z[l] = 0.0f;
       MB_END
       solve_constraints(S, P, C, nlim, nc, z);
-      solve_L(S, C, z);
+      solve_L<false>(S, C, z);
       MB_LANES(l)
         if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + z[l], -P.max_coord_vel), P.max_coord_vel);
       MB_END

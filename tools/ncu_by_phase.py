@@ -1,6 +1,6 @@
 import csv,re,subprocess,bisect
 from collections import defaultdict
-csv_path="gpurun_out/src_r1j.csv"; cubin="gpurun_out/sass/mb200.sm_100a.cubin"; kname="_Z22k_step_walker3d_custom8StepArgs"
+csv_path="gpurun_out/src_r1k.csv"; cubin="gpurun_out/sass/mb200.sm_100a.cubin"; kname="_Z22k_step_walker3d_custom8StepArgs"
 dis = subprocess.run(["nvdisasm","-g","-c",cubin],capture_output=True,text=True).stdout.splitlines()
 start = next(i for i,l in enumerate(dis) if l.startswith(".text."+kname+":"))
 lines=[]; cur=("?",0)
@@ -20,7 +20,7 @@ for k in range(min(len(body),len(lines))):
     key=f
     if f=="mb_core.cuh": key="core:"+funcs[bisect.bisect_right(starts,ln)-1][1]
     agg[key][0]+=inst; agg[key][1]+=samp; agg[key][2]+=thr; agg[key][3]+=1; ti+=inst; ts+=samp
-print("k_step_walker3d_custom, 16384 envs, ncu --set full (prof_r1j): %d SASS instructions, %d warp-instructions executed = %.0f per env-substep"%(len(body),ti,ti/65536))
+print("k_step_walker3d_custom, 16384 envs, ncu --set full (prof_r1k): %d SASS instructions, %d warp-instructions executed = %.0f per env-substep"%(len(body),ti,ti/65536))
 print("%-60s %8s %14s %9s %7s %7s"%("source function","static","warp-inst/substep","inst%","stall%","lanes"))
 for k,a in sorted(agg.items(), key=lambda kv:-kv[1][0])[:24]:
     print("%-60s %8d %14.0f %8.2f%% %6.2f%% %7.1f" % (k,a[3],a[0]/65536,100*a[0]/ti,100*a[1]/ts,a[2]/max(a[0],1)))
