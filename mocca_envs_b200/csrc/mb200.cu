@@ -7,12 +7,25 @@
 
 #include <string>
 
-// 12 warps (envs) per CTA, 2 CTAs per SM, and one CTA barrier per substep (MB_SYNC): the barrier keeps the warps
-// of a CTA in the same phase of the (large) step code so instruction-cache lines are shared -- measured
-// 7.1M -> 10.1M env-steps/s at 16384 envs (profiles/README.md).
-#ifndef MB_WARPS
-#define MB_WARPS 12
+// 12 or 14 warps (envs) per CTA, 2 CTAs per SM, and one CTA barrier per substep (MB_SYNC): the barrier keeps the
+// warps of a CTA in the same phase of the (large) step code so instruction-cache lines are shared -- measured
+// 7.1M -> 10.1M env-steps/s at 16384 envs (profiles/README.md).  Walker3DCustom runs 14: 28 resident warps per SM
+// (72 registers) make 16384 envs exactly 4 waves of 148 x 28 (3.95) where 24 needed 4.6, measured +3 %; the
+// other kernels lose more to the extra spills than they gain (measured -1 % .. -3.5 %) and stay at 12.
+#ifndef MB_WARPS_CUSTOM
+#define MB_WARPS_CUSTOM 14
 #endif
+#ifndef MB_WARPS_STEPPER
+#define MB_WARPS_STEPPER 12
+#endif
+#ifndef MB_WARPS_MONKEY
+#define MB_WARPS_MONKEY 12
+#endif
+#ifndef MB_WARPS_CASSIE
+#define MB_WARPS_CASSIE 12
+#endif
+#define MB_WARPS_MAX 16
+#define MB_WARPS ((int)(blockDim.x >> 5)) /* device code: warps of this launch */
 #ifndef MB_MINBLOCKS
 #define MB_MINBLOCKS 2
 #endif
@@ -39,6 +52,7 @@ enum { KIND_CUSTOM = 0, KIND_STEPPER = 1, KIND_MONKEY = 2, KIND_CASSIE = 3 };
 
 struct mb200_env {
   int kind;        // KIND_*
+  int warps;       // envs per CTA of this kind's kernels
   int rec_stride;  // floats per env in `rec`
   int n, device;
   int obs_dim, act_dim, state_dim, nu;
@@ -55,9 +69,9 @@ struct mb200_env {
   // CTA barriers require every warp of a CTA to run: the state arrays are padded to a whole number of CTAs and
   // the pad envs ("tail") step like any other env but write their outputs/statistics to these dummies
   int n_pad;
-  float* dummy_obs;    // [MB_WARPS][obs_dim] x2 (obs, final_obs)
-  float* dummy_rew;    // [MB_WARPS]
-  uint8_t* dummy_flag; // [2][MB_WARPS]
+  float* dummy_obs;    // [MB_WARPS_MAX][obs_dim] x2 (obs, final_obs)
+  float* dummy_rew;    // [MB_WARPS_MAX]
+  uint8_t* dummy_flag; // [2][MB_WARPS_MAX]
   MbStats* dummy_stats;
   // work-sorted slot -> env map: the warps of a CTA meet at one barrier per substep, so a CTA runs at the pace of
   // its slowest env; grouping envs with similar constraint-row counts (of the previous step) removes most of that
@@ -110,12 +124,12 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   const bool tail = env >= a.n;
   typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
   float* obs = tail ? a.dummy_obs + (size_t)warp * Env::OBS : a.obs + (size_t)env * Env::OBS;
-  float* fin = tail ? a.dummy_obs + (size_t)(MB_WARPS + warp) * Env::OBS
+  float* fin = tail ? a.dummy_obs + (size_t)(MB_WARPS_MAX + warp) * Env::OBS
                     : (a.final_obs ? a.final_obs + (size_t)env * Env::OBS : nullptr);
   Env::step(S, a.phys, a.state + (size_t)env * MB_STATE_STRIDE, a.rec + (size_t)env * Env::REC_STRIDE,
             a.mt + (size_t)env * 2 * MB_MT_STRIDE, a.mt + ((size_t)env * 2 + 1) * MB_MT_STRIDE,
             a.act + (size_t)(tail ? 0 : env) * Env::ACT, obs, tail ? a.dummy_rew + warp : a.rew + env,
-            tail ? a.dummy_flag + warp : a.done + env, tail ? a.dummy_flag + MB_WARPS + warp : a.trunc + env, fin,
+            tail ? a.dummy_flag + warp : a.done + env, tail ? a.dummy_flag + MB_WARPS_MAX + warp : a.trunc + env, fin,
             tail ? a.dummy_stats : a.stats);
   // work estimate for the scheduler: constraint rows accumulated by this step (ER_ROWS is a running sum)
   if ((threadIdx.x & 31) == 0) {
@@ -175,16 +189,16 @@ __global__ void __launch_bounds__(1024) k_sort_by_work(int n_pad, const int* wor
     }
   }
 }
-__global__ void __launch_bounds__(MB_WARPS * 32, MB_MINBLOCKS) k_step_walker3d_custom(StepArgs a) {
+__global__ void __launch_bounds__(MB_WARPS_CUSTOM * 32, MB_MINBLOCKS) k_step_walker3d_custom(StepArgs a) {
   step_body<WEnv>(a);
 }
-__global__ void __launch_bounds__(MB_WARPS * 32, MB_MINBLOCKS) k_step_walker3d_stepper(StepArgs a) {
+__global__ void __launch_bounds__(MB_WARPS_STEPPER * 32, MB_MINBLOCKS) k_step_walker3d_stepper(StepArgs a) {
   step_body<SEnv>(a);
 }
-__global__ void __launch_bounds__(MB_WARPS * 32, MB_MINBLOCKS) k_step_monkey3d_custom(StepArgs a) {
+__global__ void __launch_bounds__(MB_WARPS_MONKEY * 32, MB_MINBLOCKS) k_step_monkey3d_custom(StepArgs a) {
   step_body<MEnv>(a);
 }
-__global__ void __launch_bounds__(MB_WARPS * 32, MB_MINBLOCKS) k_step_cassie(StepArgs a) {
+__global__ void __launch_bounds__(MB_WARPS_CASSIE * 32, MB_MINBLOCKS) k_step_cassie(StepArgs a) {
   step_body<CEnv>(a);
 }
 
@@ -202,22 +216,22 @@ __device__ __forceinline__ void reset_body(int n, const MbPhysics& phys, float* 
              tail ? dummy_obs + (size_t)warp * Env::OBS : obs + (size_t)env * Env::OBS);
   Env::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
 }
-__global__ void __launch_bounds__(MB_WARPS * 32)
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_reset_walker3d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
                             float* obs, float* dummy_obs) {
   reset_body<WEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
 }
-__global__ void __launch_bounds__(MB_WARPS * 32)
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_reset_walker3d_stepper(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
                              float* obs, float* dummy_obs) {
   reset_body<SEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
 }
-__global__ void __launch_bounds__(MB_WARPS * 32)
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_reset_monkey3d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
                             float* obs, float* dummy_obs) {
   reset_body<MEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
 }
-__global__ void __launch_bounds__(MB_WARPS * 32)
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_reset_cassie(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask, float* obs,
                    float* dummy_obs) {
   reset_body<CEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
@@ -234,7 +248,6 @@ __device__ __forceinline__ void physics_body(int n, const MbPhysics& phys, float
   typedef typename Env::Model EM;
   typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
   Env::load_state(S, state + (size_t)env * MB_STATE_STRIDE);
-  Env::load_obstacles(S, rec + (size_t)env * Env::REC_STRIDE);
   MB_LANES(l)
     if (l < EM::NJ) S.tau[l] = tail ? 0.0f : tau[(size_t)env * EM::NJ + l];
   MB_END
@@ -242,8 +255,10 @@ __device__ __forceinline__ void physics_body(int n, const MbPhysics& phys, float
   typename Sim<EM>::LaneConst C;
   Sim<EM>::init_lane_const(C);
 #pragma unroll 1
-  for (int k = 0; k < phys.substeps; ++k)
+  for (int k = 0; k < phys.substeps; ++k) {
+    Env::load_obstacles(S, rec + (size_t)env * Env::REC_STRIDE);
     rows += Sim<EM>::template substep<Env::OBST>(S, phys, C, &nc, &overflow);
+  }
   Env::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
   if (tail) return;
   if ((threadIdx.x & 31) == 0) {
@@ -251,22 +266,22 @@ __device__ __forceinline__ void physics_body(int n, const MbPhysics& phys, float
     if (contacts_out) contacts_out[env] = nc;
   }
 }
-__global__ void __launch_bounds__(MB_WARPS * 32)
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_step_physics_walker3d(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
                             int* contacts_out) {
   physics_body<WEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
 }
-__global__ void __launch_bounds__(MB_WARPS * 32)
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_step_physics_walker3d_stepper(int n, MbPhysics phys, float* state, const float* rec, const float* tau,
                                     int* rows_out, int* contacts_out) {
   physics_body<SEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
 }
-__global__ void __launch_bounds__(MB_WARPS * 32)
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_step_physics_monkey3d(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
                             int* contacts_out) {
   physics_body<MEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
 }
-__global__ void __launch_bounds__(MB_WARPS * 32)
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_step_physics_cassie(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
                           int* contacts_out) {
   physics_body<CEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
@@ -304,15 +319,15 @@ __device__ __forceinline__ void dynamics_debug_body(int n, const MbPhysics& phys
     }
   MB_END
 }
-__global__ void __launch_bounds__(MB_WARPS * 32)
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_dynamics_debug_walker3d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
   dynamics_debug_body<WEnv>(n, phys, state, mode, acc, out);
 }
-__global__ void __launch_bounds__(MB_WARPS * 32)
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_dynamics_debug_monkey3d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
   dynamics_debug_body<MEnv>(n, phys, state, mode, acc, out);
 }
-__global__ void __launch_bounds__(MB_WARPS * 32)
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_dynamics_debug_cassie(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
   dynamics_debug_body<CEnv>(n, phys, state, mode, acc, out);
 }
@@ -379,7 +394,7 @@ static void to_internal(const mb200_physics& p, MbPhysics* q) {
   q->box_friction = 1.0f; q->box_erp = p.erp_contact; q->box_cfm = 0.0f; q->bar_friction = 0.5f;
 }
 
-static int grid_for(int n) { return (n + MB_WARPS - 1) / MB_WARPS; }
+static int grid_for(const mb200_env* e) { return (e->n + e->warps - 1) / e->warps; }
 
 int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics* physics, mb200_env** out) {
   if (!out) return fail("mb200_create: out is NULL");
@@ -414,6 +429,8 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
     case KIND_CASSIE: e->rec_stride = CEnv::REC_STRIDE; e->obs_dim = CEnv::OBS; e->act_dim = CEnv::ACT; nj = CM::NJ; break;
     default: e->rec_stride = WEnv::REC_STRIDE; e->obs_dim = WEnv::OBS; e->act_dim = WEnv::ACT; break;
   }
+  e->warps = kind == KIND_MONKEY ? MB_WARPS_MONKEY : kind == KIND_CASSIE ? MB_WARPS_CASSIE
+             : kind == KIND_STEPPER ? MB_WARPS_STEPPER : MB_WARPS_CUSTOM;
   e->state_dim = 13 + 2 * nj;
   e->nu = 6 + nj;
   mb200_physics p;
@@ -431,7 +448,7 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
     e->phys.box_cfm = 1.0f / denom;
   }
   e->smem = (kind == KIND_MONKEY ? sizeof(WarpMem<MM>) : kind == KIND_CASSIE ? sizeof(WarpMem<CM>) : sizeof(WMem)) *
-            MB_WARPS;
+            e->warps;
   if (kind == KIND_CASSIE) {
     CUDA_OK(cudaFuncSetAttribute(k_step_cassie, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     CUDA_OK(cudaFuncSetAttribute(k_reset_cassie, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
@@ -452,11 +469,11 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_walker3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   }
-  e->n_pad = grid_for(n_envs) * MB_WARPS;
+  e->n_pad = grid_for(e) * e->warps;
   const size_t n = (size_t)e->n_pad;
-  CUDA_OK(cudaMalloc(&e->dummy_obs, (size_t)2 * MB_WARPS * e->obs_dim * sizeof(float)));
-  CUDA_OK(cudaMalloc(&e->dummy_rew, MB_WARPS * sizeof(float)));
-  CUDA_OK(cudaMalloc(&e->dummy_flag, 2 * MB_WARPS));
+  CUDA_OK(cudaMalloc(&e->dummy_obs, (size_t)2 * MB_WARPS_MAX * e->obs_dim * sizeof(float)));
+  CUDA_OK(cudaMalloc(&e->dummy_rew, MB_WARPS_MAX * sizeof(float)));
+  CUDA_OK(cudaMalloc(&e->dummy_flag, 2 * MB_WARPS_MAX));
   CUDA_OK(cudaMalloc(&e->dummy_stats, sizeof(MbStats)));
   CUDA_OK(cudaMemset(e->dummy_stats, 0, sizeof(MbStats)));
   CUDA_OK(cudaMalloc(&e->state, n * MB_STATE_STRIDE * sizeof(float)));
@@ -559,16 +576,16 @@ int mb200_reset(mb200_env* e, const uint8_t* mask_dev, float* obs_dev, void* str
   if (!e || !obs_dev) return fail("mb200_reset: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
   if (e->kind == KIND_CASSIE)
-    k_reset_cassie<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+    k_reset_cassie<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
   else if (e->kind == KIND_MONKEY)
-    k_reset_monkey3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+    k_reset_monkey3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
   else if (e->kind == KIND_STEPPER)
-    k_reset_walker3d_stepper<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+    k_reset_walker3d_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
   else
-    k_reset_walker3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+    k_reset_walker3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
   e->launches++;
   CUDA_OK(cudaGetLastError());
@@ -585,16 +602,16 @@ int mb200_step(mb200_env* e, const float* act_dev, float* obs_dev, float* rew_de
   a.dummy_obs = e->dummy_obs; a.dummy_rew = e->dummy_rew; a.dummy_flag = e->dummy_flag; a.dummy_stats = e->dummy_stats;
   a.order = e->order; a.work = e->work;
   if (e->kind == KIND_CASSIE)
-    k_step_cassie<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
+    k_step_cassie<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
   else if (e->kind == KIND_MONKEY)
-    k_step_monkey3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
+    k_step_monkey3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
   else if (e->kind == KIND_STEPPER)
-    k_step_walker3d_stepper<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
+    k_step_walker3d_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
   else
-    k_step_walker3d_custom<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(a);
+    k_step_walker3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
   e->launches++;
   e->steps++;
-  if (e->sort_every > 0 && e->steps % e->sort_every == 0 && grid_for(e->n) > 1) {
+  if (e->sort_every > 0 && e->steps % e->sort_every == 0 && grid_for(e) > 1) {
     k_sort_by_work<<<1, 1024, 0, (cudaStream_t)stream>>>(e->n_pad, e->work, e->work_prev, e->order);
     e->launches++;
   }
@@ -657,16 +674,16 @@ int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* c
   if (!e || !tau_dev) return fail("mb200_step_physics: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
   if (e->kind == KIND_CASSIE)
-    k_step_physics_cassie<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+    k_step_physics_cassie<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
   else if (e->kind == KIND_MONKEY)
-    k_step_physics_monkey3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+    k_step_physics_monkey3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
   else if (e->kind == KIND_STEPPER)
-    k_step_physics_walker3d_stepper<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+    k_step_physics_walker3d_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
   else
-    k_step_physics_walker3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+    k_step_physics_walker3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
   e->launches++;
   CUDA_OK(cudaGetLastError());
@@ -677,13 +694,13 @@ int mb200_mass_matrix(mb200_env* e, float* M_dev, void* stream) {
   if (!e || !M_dev) return fail("mb200_mass_matrix: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
   if (e->kind == KIND_CASSIE)
-    k_dynamics_debug_cassie<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+    k_dynamics_debug_cassie<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, 0, nullptr, M_dev);
   else if (e->kind == KIND_MONKEY)
-    k_dynamics_debug_monkey3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+    k_dynamics_debug_monkey3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, 0, nullptr, M_dev);
   else
-    k_dynamics_debug_walker3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+    k_dynamics_debug_walker3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, 0, nullptr, M_dev);
   e->launches++;
   CUDA_OK(cudaGetLastError());
@@ -697,13 +714,13 @@ int mb200_inverse_dynamics(mb200_env* e, const float* acc_dev, float* tau_dev, v
   p.lin_damping = 0.0f;  // calculateInverseDynamics has no velocity-damping term
   p.ang_damping = 0.0f;
   if (e->kind == KIND_CASSIE)
-    k_dynamics_debug_cassie<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+    k_dynamics_debug_cassie<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, p, e->state, 1, acc_dev, tau_dev);
   else if (e->kind == KIND_MONKEY)
-    k_dynamics_debug_monkey3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+    k_dynamics_debug_monkey3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, p, e->state, 1, acc_dev, tau_dev);
   else
-    k_dynamics_debug_walker3d<<<grid_for(e->n), MB_WARPS * 32, e->smem, (cudaStream_t)stream>>>(
+    k_dynamics_debug_walker3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, p, e->state, 1, acc_dev, tau_dev);
   e->launches++;
   CUDA_OK(cudaGetLastError());

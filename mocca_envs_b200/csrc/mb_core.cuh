@@ -188,23 +188,29 @@ template <class M> struct WarpMem {
   int cfoot[MB_MAXC];
   int cpartner[MB_MAXC];
   // ---- row parameters
-  MbRowPar r_par[MB_MAXROW];
-  float r_app[MB_MAXROW];
-  float r_mu[MB_MAXROW];
-  unsigned r_mask[MB_MAXROW];  // support of the row over the generalised coordinates
+  // The row parameters live from setup_rows() to the end of the substep.  Before that (collision) the same bytes
+  // hold the env's static obstacles, re-staged from the record at the start of every substep; between steps they
+  // are scratch for the epilogue / reset.
+  union {
+    struct {
+      MbRowPar r_par[MB_MAXROW];
+      float r_app[MB_MAXROW];
+      float r_mu[MB_MAXROW];
+      unsigned r_mask[MB_MAXROW];  // support of the row over the generalised coordinates
+    } r;
+    // static box obstacles: centre[3], axes R[9] (row-major, columns = box axes), half[3], pad
+    float box[MB_MAXBOX][16];
+    // static bars (MonkeyBar, bullet_objects.py:148-187): centre[3], unit axis[3], half length, radius
+    float bar[MB_MAXBAR][8];
+    float scratch[64];
+  } rc;
   int r_dof[32];
   float r_dir[32];
-  // ---- static box obstacles of this env: centre[3], axes R[9] (row-major, columns = box axes), half[3], pad
-  float box[MB_MAXBOX][16];
   int nbox;
-  // ---- static bars (MonkeyBar, bullet_objects.py:148-187): centre[3], unit axis[3], half length, radius
-  float bar[MB_MAXBAR][8];
   int nbar;
   // ---- loop-closure pivots (btMultiBodyPoint2Point, Cassie): world axes, relative to the base COM; [2c] on link A,
   // [2c + 1] on link B
   float lcP[(M::NLOOP > 0 ? 2 * M::NLOOP : 1)][3];
-  // ---- scratch for the epilogue
-  float scratch[64];
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -697,7 +703,7 @@ template <class M> struct Sim {
       if (ob >= 0) {
         // cheap uniform cull: the robot (all points within ~1.2 m of the base) cannot reach a plank whose local
         // x / z slab is farther away than that
-        const float* bx = S.box[ob];
+        const float* bx = S.rc.box[ob];
         const float d[3] = {S.pos[0] - bx[0], S.pos[1] - bx[1], S.pos[2] - bx[2]};
         bool far = false;
 #pragma unroll
@@ -735,7 +741,7 @@ template <class M> struct Sim {
             } else {
               const float cw[3] = {c[0] + S.pos[0], c[1] + S.pos[1], c[2] + S.pos[2]};
               float pa[3], n[3], dist;
-              if (sphere_box(cw, r, S.box[ob], M::pthresh(pt), pa, n, &dist)) {
+              if (sphere_box(cw, r, S.rc.box[ob], M::pthresh(pt), pa, n, &dist)) {
                 hit[l] = 1;
                 px[l] = pa[0] - S.pos[0]; py[l] = pa[1] - S.pos[1]; pz[l] = pa[2] - S.pos[2]; dd[l] = dist;
                 nx[l] = n[0]; ny[l] = n[1]; nz[l] = n[2];
@@ -768,7 +774,7 @@ template <class M> struct Sim {
     if (OBST & MB_OBST_BARS) {
 #pragma unroll 1
       for (int ob = 0; ob < S.nbar; ++ob) {
-        const float* bar = S.bar[ob];
+        const float* bar = S.rc.bar[ob];
         const float bc[3] = {bar[0] - S.pos[0], bar[1] - S.pos[1], bar[2] - S.pos[2]};
         // uniform cull: every robot point lies within ~1.3 m of the base COM; compare with the distance from the
         // base to the bar's axis line
@@ -1010,7 +1016,7 @@ template <class M> struct Sim {
 #pragma unroll
           for (int t = 0; t < M::MAXSUP; ++t)
             if (t < n) Yr[t] = b[t];
-          S.r_mask[r] = 0x3Fu | (cj >= 0 ? (M::janc(cj) << 6) : 0u);
+          S.rc.r.r_mask[r] = 0x3Fu | (cj >= 0 ? (M::janc(cj) << 6) : 0u);
           MbRowPar par;
           if (kind == 3) {  // partial sums; the two parts of a loop row are combined below
             par.rhs = rel_vel; par.jinv = dd; par.den = 0.0f;
@@ -1018,9 +1024,9 @@ template <class M> struct Sim {
             par.rhs = (positional + verr) * jinv; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
           }
           par.cfm = cfm * jinv;
-          S.r_par[r] = par;
-          S.r_app[r] = 0.0f;
-          S.r_mu[r] = mu;
+          S.rc.r.r_par[r] = par;
+          S.rc.r.r_app[r] = 0.0f;
+          S.rc.r.r_mu[r] = mu;
         }
       MB_END
     }
@@ -1030,15 +1036,15 @@ template <class M> struct Sim {
       MB_LANES(l)
         if (l < NLC / 2) {
           const int ra = nlim + 2 * l, ax = l % 3, c = l / 3;
-          const float dd = S.r_par[ra].jinv + S.r_par[ra + 1].jinv;
+          const float dd = S.rc.r.r_par[ra].jinv + S.rc.r.r_par[ra + 1].jinv;
           const float jinv = dd > 1.1920929e-07f ? 1.0f / dd : 0.0f;
-          const float rel_vel = S.r_par[ra].rhs + S.r_par[ra + 1].rhs;
+          const float rel_vel = S.rc.r.r_par[ra].rhs + S.rc.r.r_par[ra + 1].rhs;
           const float pos_error = -(S.lcP[2 * c][ax] - S.lcP[2 * c + 1][ax]);
           const float positional = -pos_error * P.erp_joint * inv_dt;
           MbRowPar par;
           par.rhs = (positional - rel_vel) * jinv; par.cfm = 0.0f; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
-          S.r_par[ra] = par;
-          S.r_mu[ra] = M::lc_maximp(c);
+          S.rc.r.r_par[ra] = par;
+          S.rc.r.r_mu[ra] = M::lc_maximp(c);
         }
       MB_END
     }
@@ -1047,15 +1053,15 @@ template <class M> struct Sim {
   // ---- H. projected Gauss-Seidel in z-space (btMultiBodyConstraintSolver::solveSingleIteration order) --------
   // Row r of Y is stored over its support; the entry of coordinate l sits at slot tl(l) (prefix property).
   MB_HD static float pgs_single(Mem& S, const LaneConst& C, int ra, float lo, float hi, LaneVar<float>& z) {
-    const unsigned supA = S.r_mask[ra];
+    const unsigned supA = S.rc.r.r_mask[ra];
     LaneVar<float> ya, ta;
     MB_LANES(l)
       ya[l] = ((supA >> l) & 1u) ? S.w.Yc[ra][C.tl[l]] : 0.0f;
       ta[l] = ya[l] * z[l];
     MB_END_REG
     const float dotA = warp_sum(ta);
-    const MbRowPar pA = S.r_par[ra];
-    const float appA = S.r_app[ra];
+    const MbRowPar pA = S.rc.r.r_par[ra];
+    const float appA = S.rc.r.r_app[ra];
     float dA = pA.rhs - appA * pA.cfm - dotA * pA.jinv;
     const float sumA = appA + dA;
     float nA = sumA;
@@ -1063,7 +1069,7 @@ template <class M> struct Sim {
     else if (sumA > hi) { dA = hi - appA; nA = hi; }
     MB_LANES(l)
       z[l] += ya[l] * dA;
-      if (l == 0) S.r_app[ra] = nA;
+      if (l == 0) S.rc.r.r_app[ra] = nA;
     MB_END
     return dA * pA.den;  // deltaImpulse * (1 / jacDiagABInv)
   }
@@ -1071,7 +1077,7 @@ template <class M> struct Sim {
   // sin/cos(atan2(a, b)) are written as a/|(a,b)|, b/|(a,b)|
   MB_HD static float pgs_pair(Mem& S, const LaneConst& C, int ra, float cone, LaneVar<float>& z) {
     const int rb = ra + 1;
-    const unsigned supA = S.r_mask[ra];  // both rows of a contact share the support
+    const unsigned supA = S.rc.r.r_mask[ra];  // both rows of a contact share the support
     LaneVar<float> ya, yb, ta, tb;
     MB_LANES(l)
       const bool in = ((supA >> l) & 1u) != 0u;
@@ -1081,8 +1087,8 @@ template <class M> struct Sim {
       tb[l] = yb[l] * z[l];
     MB_END_REG
     const float dotA = warp_sum(ta), dotB = warp_sum(tb);
-    const MbRowPar pA = S.r_par[ra], pB = S.r_par[rb];
-    const float appA = S.r_app[ra], appB = S.r_app[rb];
+    const MbRowPar pA = S.rc.r.r_par[ra], pB = S.rc.r.r_par[rb];
+    const float appA = S.rc.r.r_app[ra], appB = S.rc.r.r_app[rb];
     float dA = pA.rhs - appA * pA.cfm - dotA * pA.jinv;
     float dB = pB.rhs - appB * pB.cfm - dotB * pB.jinv;
     const float sumA = appA + dA, sumB = appB + dB;
@@ -1098,7 +1104,7 @@ template <class M> struct Sim {
     }
     MB_LANES(l)
       z[l] += ya[l] * dA + yb[l] * dB;
-      if (l == 0) { S.r_app[ra] = nA; S.r_app[rb] = nB; }
+      if (l == 0) { S.rc.r.r_app[ra] = nA; S.rc.r.r_app[rb] = nB; }
     MB_END
     return dA * pA.den + dB * pB.den;
   }
@@ -1106,7 +1112,7 @@ template <class M> struct Sim {
   // loop-closure row: two compact rows (ra on link A, ra + 1 on link B) sharing one multiplier
   MB_HD static float pgs_dual(Mem& S, const LaneConst& C, int ra, LaneVar<float>& z) {
     const int rb = ra + 1;
-    const unsigned supA = S.r_mask[ra], supB = S.r_mask[rb];
+    const unsigned supA = S.rc.r.r_mask[ra], supB = S.rc.r.r_mask[rb];
     LaneVar<float> y, t;
     MB_LANES(l)
       const float ya = ((supA >> l) & 1u) ? S.w.Yc[ra][C.tl[l]] : 0.0f;
@@ -1115,8 +1121,8 @@ template <class M> struct Sim {
       t[l] = y[l] * z[l];
     MB_END_REG
     const float dot = warp_sum(t);
-    const MbRowPar pA = S.r_par[ra];
-    const float app = S.r_app[ra], lim = S.r_mu[ra];
+    const MbRowPar pA = S.rc.r.r_par[ra];
+    const float app = S.rc.r.r_app[ra], lim = S.rc.r.r_mu[ra];
     float d = pA.rhs - dot * pA.jinv;
     const float sum = app + d;
     float na = sum;
@@ -1124,7 +1130,7 @@ template <class M> struct Sim {
     else if (sum > lim) { d = lim - app; na = lim; }
     MB_LANES(l)
       z[l] += y[l] * d;
-      if (l == 0) S.r_app[ra] = na;
+      if (l == 0) S.rc.r.r_app[ra] = na;
     MB_END
     return d * pA.den;
   }
@@ -1152,7 +1158,7 @@ template <class M> struct Sim {
 #pragma unroll 1
       for (int k = 0; k < nc; ++k) {
         const int ra = n0 + nc + 2 * k;
-        const float rr = pgs_pair(S, C, ra, S.r_mu[ra] * S.r_app[n0 + k], z);
+        const float rr = pgs_pair(S, C, ra, S.rc.r.r_mu[ra] * S.rc.r.r_app[n0 + k], z);
         res2 = fmaxf(res2, rr * rr);
       }
       if (res2 <= P.residual_threshold) break;

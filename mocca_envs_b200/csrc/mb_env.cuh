@@ -270,7 +270,7 @@ template <class M> struct W3DEnv {
 
   // Walker3DCustomEnv.reset (env_locomotion.py:79-109) + WalkerBase.reset (robots.py:179-210)
   MB_HD static void reset(Mem& S, const MbPhysics& P, float* rec, uint32_t* mt_env, uint32_t* mt_robot, float* obs) {
-    uint32_t* w = reinterpret_cast<uint32_t*>(S.scratch);
+    uint32_t* w = reinterpret_cast<uint32_t*>(S.rc.scratch);
     const int aliased = rec_i(rec, ER_ALIASED);
     const int nrobot = 2 + 2 * NJ;
     if (aliased) mt_fill(mt_env, w, 5 + nrobot);
@@ -393,7 +393,7 @@ template <class M> struct W3DEnv {
     if ((float)close >= rec[ER_STOP]) {
       // env_locomotion.py:214-222 -- re-sample the target mid-episode from the env stream
       close = 0;
-      uint32_t* w = reinterpret_cast<uint32_t*>(S.scratch);
+      uint32_t* w = reinterpret_cast<uint32_t*>(S.rc.scratch);
       mt_fill(mt_env, w, 5);
       double nd, na;
       randomize_target(rec, w, &nd, &na);
@@ -477,7 +477,7 @@ template <class M> struct StepperEnv {
       if (l < 6) {
         const int p = l >> 1, cover = l & 1;
         const float* b = rec + ES_BOX + 12 * p;
-        float* bx = S.box[l];
+        float* bx = S.rc.box[l];
 #pragma unroll
         for (int k = 0; k < 12; ++k) bx[k] = b[k];
         if (cover) { bx[0] += b[3 + 2] * 0.125f; bx[1] += b[3 + 5] * 0.125f; bx[2] += b[3 + 8] * 0.125f; }
@@ -648,7 +648,6 @@ template <class M> struct StepperEnv {
                          const float* act, float* obs, float* rew, uint8_t* done, uint8_t* trunc, float* final_obs,
                          MbStats* stats) {
     B_::load_state(S, state);
-    load_boxes(S, rec);
     const int cur_c = rec_i(rec, ES_CURRIC);  // terminal height follows the attribute immediately (:628)
     const float applied_gain = lin10(1.0f, 1.2f, rec_i(rec, ES_GAIN_CURRIC));  // gain is latched at reset (:489)
     LaneVar<float> araw;
@@ -669,6 +668,7 @@ template <class M> struct StepperEnv {
     S_::init_lane_const(C);
 #pragma unroll 1
     for (int k = 0; k < P.substeps; ++k) {
+      load_boxes(S, rec);  // the obstacle staging area is reused by the constraint rows of every substep
       rows += S_::template substep<MB_OBST_BOXES>(S, P, C, &nc, &overflow);
       ncsum += nc;
     }
@@ -837,7 +837,7 @@ template <class M> struct MonkeyEnv {
 
   MB_HD static void load_bars(Mem& S, const float* rec) {
     MB_LANES(l)
-      S.bar[l >> 3][l & 7] = rec[EM_BAR + l];
+      S.rc.bar[l >> 3][l & 7] = rec[EM_BAR + l];
       if (l == 0) S.nbar = NBARS;
     MB_END
   }
@@ -1023,7 +1023,6 @@ template <class M> struct MonkeyEnv {
                          const float* act, float* obs, float* rew, uint8_t* done, uint8_t* trunc, float* final_obs,
                          MbStats* stats) {
     B_::load_state(S, state);
-    load_bars(S, rec);
     int swing = rec_i(rec, EM_SWING), pivot = rec_i(rec, EM_PIVOT);
     const int jswing = swing == 0 ? 17 : 22, jpivot = pivot == 0 ? 17 : 22;
     LaneVar<float> araw;
@@ -1047,6 +1046,7 @@ template <class M> struct MonkeyEnv {
     S_::init_lane_const(C);
 #pragma unroll 1
     for (int k = 0; k < P.substeps; ++k) {
+      load_bars(S, rec);  // the obstacle staging area is reused by the constraint rows of every substep
       rows += S_::template substep<MB_OBST_BARS>(S, P, C, &nc, &overflow);
       ncsum += nc;
     }
@@ -1296,7 +1296,7 @@ template <class M> struct CassieEnv {
       MB_LANES(l)
         if (l < NO) {
           jvel[l] = (1.0f - 0.2f) * jvel[l] + 0.2f * S.u[6 + M::ordered(l)];
-          S.scratch[l] = jvel[l];
+          S.rc.scratch[l] = jvel[l];
         }
         if (l < NJ) S.tau[l] = -M::damping(l) * S.u[6 + l];  // PyBullet's joint damping, once per stepSimulation
       MB_END
@@ -1304,7 +1304,7 @@ template <class M> struct CassieEnv {
         if (l < M::NPD) {
           float nrm;
           const float q = rad_angle(S, pdo[l], &nrm);
-          const float verr = fminf(fmaxf(0.0f - S.scratch[pdo[l]], -5.0f), 5.0f);  // env_cassie.py:380-393
+          const float verr = fminf(fmaxf(0.0f - S.rc.scratch[pdo[l]], -5.0f), 5.0f);  // env_cassie.py:380-393
           const float t = kp[l] * (target[l] - q) + kd[l] * verr;
           S.tau[pdd[l]] += fminf(fmaxf(t, -lim[l]), lim[l]);                       // apply_action clip (:225-230)
         }

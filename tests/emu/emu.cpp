@@ -115,12 +115,14 @@ void emu_stepper_step_physics(const MbPhysics* p, float* state, const float* rec
   static WMem S;
   memset(&S, 0, sizeof(S));
   WEnv::load_state(S, state);
-  SEnv::load_obstacles(S, rec);
   for (int j = 0; j < WM::NJ; ++j) S.tau[j] = tau[j];
   int r = 0, nc = 0, ov = 0;
   Sim<WM>::LaneConst C;
   Sim<WM>::init_lane_const(C);
-  for (int k = 0; k < p->substeps; ++k) r += Sim<WM>::substep<MB_OBST_BOXES>(S, *p, C, &nc, &ov);
+  for (int k = 0; k < p->substeps; ++k) {
+    SEnv::load_obstacles(S, rec);
+    r += Sim<WM>::substep<MB_OBST_BOXES>(S, *p, C, &nc, &ov);
+  }
   WEnv::store_state(S, state);
   *rows = r;
   *contacts = nc;
@@ -155,12 +157,14 @@ void emu_monkey_step_physics(const MbPhysics* p, float* state, const float* rec,
   static MMem S;
   memset(&S, 0, sizeof(S));
   MEnv::load_state(S, state);
-  MEnv::load_obstacles(S, rec);
   for (int j = 0; j < MM::NJ; ++j) S.tau[j] = tau[j];
   int r = 0, nc = 0, ov = 0;
   Sim<MM>::LaneConst C;
   Sim<MM>::init_lane_const(C);
-  for (int k = 0; k < p->substeps; ++k) r += Sim<MM>::substep<MB_OBST_BARS>(S, *p, C, &nc, &ov);
+  for (int k = 0; k < p->substeps; ++k) {
+    MEnv::load_obstacles(S, rec);
+    r += Sim<MM>::substep<MB_OBST_BARS>(S, *p, C, &nc, &ov);
+  }
   MEnv::store_state(S, state);
   *rows = r;
   *contacts = nc;
