@@ -449,25 +449,27 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   }
   e->smem = (kind == KIND_MONKEY ? sizeof(WarpMem<MM>) : kind == KIND_CASSIE ? sizeof(WarpMem<CM>) : sizeof(WMem)) *
             e->warps;
-  if (kind == KIND_CASSIE) {
-    CUDA_OK(cudaFuncSetAttribute(k_step_cassie, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    CUDA_OK(cudaFuncSetAttribute(k_reset_cassie, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    CUDA_OK(cudaFuncSetAttribute(k_step_physics_cassie, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_cassie, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-  } else if (kind == KIND_MONKEY) {
-    CUDA_OK(cudaFuncSetAttribute(k_step_monkey3d_custom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    CUDA_OK(cudaFuncSetAttribute(k_reset_monkey3d_custom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    CUDA_OK(cudaFuncSetAttribute(k_step_physics_monkey3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_monkey3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-  } else {
-  CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_stepper, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-  CUDA_OK(cudaFuncSetAttribute(k_reset_walker3d_stepper, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-  CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d_stepper, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)e->smem));
-  CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_custom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-  CUDA_OK(cudaFuncSetAttribute(k_reset_walker3d_custom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-  CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-  CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_walker3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  {
+    // opt every kernel in to the largest dynamic shared memory any env kind may launch it with (several env kinds
+    // can live in one process; the attribute is per kernel, not per handle)
+    const int sw = (int)(sizeof(WMem) * MB_WARPS_MAX), sm = (int)(sizeof(WarpMem<MM>) * MB_WARPS_MAX),
+              sc = (int)(sizeof(WarpMem<CM>) * MB_WARPS_MAX);
+    const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    CUDA_OK(cudaFuncSetAttribute(k_step_cassie, at, sc));
+    CUDA_OK(cudaFuncSetAttribute(k_reset_cassie, at, sc));
+    CUDA_OK(cudaFuncSetAttribute(k_step_physics_cassie, at, sc));
+    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_cassie, at, sc));
+    CUDA_OK(cudaFuncSetAttribute(k_step_monkey3d_custom, at, sm));
+    CUDA_OK(cudaFuncSetAttribute(k_reset_monkey3d_custom, at, sm));
+    CUDA_OK(cudaFuncSetAttribute(k_step_physics_monkey3d, at, sm));
+    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_monkey3d, at, sm));
+    CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_stepper, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_reset_walker3d_stepper, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d_stepper, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_custom, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_reset_walker3d_custom, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_walker3d, at, sw));
   }
   e->n_pad = grid_for(e) * e->warps;
   const size_t n = (size_t)e->n_pad;
