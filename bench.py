@@ -21,10 +21,11 @@ WORKLOAD = "Walker3DCustomEnv-v0 batched 16384 envs/GPU, flat ground"
 METRIC = "env-steps/sec (Walker3DCustomEnv-v0, 16384 envs/GPU, random actions)"
 
 
-def flops_per_env_step(rows_per_substep, S=4, n=27, L=17, G=22, I=5):
-    """F = S*[60L + 430n + 30G + R*150n + I*R*(4n+10) + 20n] + 1000."""
+def flops_per_env_step(rows_per_substep, S=4, n=27, L=17, G=22, I=5, P=0):
+    """F = S*[60L + 430n + 30G + 60P + R*150n + I*R*(4n+10) + 20n] + 1000
+    (P = self-collision candidate pairs tested per substep)."""
     R = rows_per_substep
-    return S * (60 * L + 430 * n + 30 * G + R * 150 * n + I * R * (4 * n + 10) + 20 * n) + 1000
+    return S * (60 * L + 430 * n + 30 * G + 60 * P + R * 150 * n + I * R * (4 * n + 10) + 20 * n) + 1000
 
 
 def bytes_per_env_step(S_state=55, A=21, O=52, S_env=12):
@@ -206,6 +207,8 @@ def main():
                          "monkey = configs[4] (Monkey3DCustomEnv-v0); cassie = configs[3] (CassieEnv-v0, 50 substeps per step)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--self-collision", type=int, default=1, choices=[0, 1],
+                    help="1 = the reference's URDF_USE_SELF_COLLISION flags (robots.py:259-264); 0 = ablation")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -254,15 +257,16 @@ def main():
     torch.cuda.set_device(dev)
     N, K, W = args.envs, args.steps, max(args.warmup, 3)
     # env i of rank r is global env r*N + i: seeds are independent of the GPU count
+    phys = {"self_collision": args.self_collision}
     if args.env == "stepper":
-        env = Walker3DStepperVecEnv(N, device=dev, seed=shard_seed(1234, rank, N))
+        env = Walker3DStepperVecEnv(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
         env.set_env_params({"curriculum": np.array([0, 5, 9] * (N // 3 + 1))[:N]})
     elif args.env == "monkey":
-        env = Monkey3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N))
+        env = Monkey3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
     elif args.env == "cassie":
-        env = CassieVecEnv(N, device=dev, seed=shard_seed(1234, rank, N))
+        env = CassieVecEnv(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
     else:
-        env = Walker3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N))
+        env = Walker3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
     env.reset()
     A = env.act_dim
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -375,17 +379,18 @@ def main():
     value = N * world * K / (total_ms_max * 1e-3)
     S_sub = 50 * env.physics.substeps if args.env == "cassie" else env.physics.substeps  # substeps per env step
     R_mean = rows_all / (K * N * world * S_sub)
+    n_self = len(env.table.get("self_pairs", [])) if args.self_collision else 0
     if args.env == "cassie":  # Cassie: 50 x 1 substeps, n = 24 generalised coordinates, 17 massive links, 158 points
         F = flops_per_env_step(R_mean, S=S_sub, n=24, L=17, G=158)
         B_step = bytes_per_env_step(S_state=49, A=10, O=36, S_env=20)
     elif args.env == "monkey":  # Monkey3D: n = 29 generalised coordinates, 20 massive links, 29 geoms, obs 69
-        F = flops_per_env_step(R_mean, n=29, L=20, G=29)
+        F = flops_per_env_step(R_mean, n=29, L=20, G=29, P=n_self)
         B_step = bytes_per_env_step(S_state=59, A=23, O=69, S_env=40)
     elif args.env == "stepper":
-        F = flops_per_env_step(R_mean)
+        F = flops_per_env_step(R_mean, P=n_self)
         B_step = bytes_per_env_step(O=65, S_env=40)
     else:
-        F = flops_per_env_step(R_mean)
+        F = flops_per_env_step(R_mean, P=n_self)
         B_step = bytes_per_env_step()
     kernel_s = (total_ms / K) * 1e-3  # this rank's average launch duration (one kernel per step)
     achieved_tf = F * N / kernel_s / 1e12
@@ -412,7 +417,8 @@ def main():
                                 "cassie": "CassieEnv-v0 batched, residual PD control, 50 substeps per env step"}[args.env],
                    "envs_per_gpu": N, "actions": "random-uniform U(-1,1)^%d (device pool)" % A
                    if args.actions == "random" else "scripted PD toward running_start (kp=1, kd=0.1, normalised)",
-                   "frame_skip": S_sub, "solver_iterations": 5, "rng": "mt19937 (NumPy-compatible)",
+                   "frame_skip": S_sub, "solver_iterations": 5,
+                   "self_collision": "on, %d candidate geom pairs per substep" % n_self if n_self else "off", "rng": "mt19937 (NumPy-compatible)",
                    "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs)",
                    "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks",
                    "parallelism": "env-sharded x%d, no data-path collective" % world},

@@ -38,6 +38,8 @@ typedef struct mb200_physics {
   float residual_threshold; /* 1e-7   m_leastSquaresResidualThreshold (PGS early exit)                    */
   float ground_friction;    /* 0.8    bullet_utils.py:371 changeDynamics(lateralFriction=0.8)             */
   int has_ground;           /* 1      bullet_utils.py:361-371 plane_stadium.sdf (0 = remove_ground)       */
+  int self_collision;       /* 1      robots.py:259-264 URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS (Walker3D,
+                                      Monkey3D sphere / capsule geoms; Cassie's mesh hulls: not modelled)          */
 } mb200_physics;
 
 void mb200_default_physics(mb200_physics* p);

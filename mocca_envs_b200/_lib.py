@@ -29,7 +29,7 @@ class Physics(C.Structure):
                 ("erp_contact", C.c_float), ("erp_joint", C.c_float), ("linear_slop", C.c_float),
                 ("lin_damping", C.c_float), ("ang_damping", C.c_float), ("max_coord_vel", C.c_float),
                 ("limit_max_impulse", C.c_float), ("split_threshold", C.c_float), ("residual_threshold", C.c_float),
-                ("ground_friction", C.c_float), ("has_ground", C.c_int)]
+                ("ground_friction", C.c_float), ("has_ground", C.c_int), ("self_collision", C.c_int)]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -116,6 +116,20 @@ def reduce_table(t: dict) -> dict:
                                foot=foot_links.index(link) if link in foot_links else
                                (2 + palm_links.index(link) if link in palm_links else -1)))
     foot_body = [[b["link"] for b in bodies].index(f) for f in foot_links]
+    # self-collision candidate pairs (model_compiler.self_collision_pairs): candidate-point indices of the two core
+    # segments (a sphere is a zero-length segment), the smaller breaking threshold, the product friction
+    # (btManifoldResult::calculateCombinedFriction) and which feet the two links are (Stepper feet_contact)
+    pts_of_geom = {}
+    for k, pnt in enumerate(points):
+        pts_of_geom.setdefault(pnt["geom"], []).append(k)
+    spairs = []
+    for ga, gb in t.get("self_pairs", []):
+        pa, pb = pts_of_geom[ga], pts_of_geom[gb]
+        A, B = points[pa[0]], points[pb[0]]
+        feet = sum(1 << f for f in range(2) for x in (A, B) if x["foot"] == f)
+        spairs.append(dict(pack=pa[0] | (pa[-1] << 8) | (pb[0] << 16) | (pb[-1] << 24), thresh=min(A["thresh"], B["thresh"]),
+                           mu=A["friction"] * B["friction"], own_a=A["owner"], own_b=B["owner"], feet=feet))
+        assert A["owner"] != B["owner"]
     # ancestor chains (root -> self) packed 5 bits per entry, and the compact (chain-ordered) factor layout:
     # row i of L stores only its support [base block | ancestors root->parent | diagonal]
     chains = []
@@ -148,7 +162,7 @@ def reduce_table(t: dict) -> dict:
         extras = dict(ordered=t["ordered_dofs"], pd_dof=[t["ordered_dofs"][k] for k in pd], pd_ordered=pd,
                       pd_kp=t["pd_kp"], pd_kd=t["pd_kd"], npowered=len(t["powered_joint_inds"]))
     return dict(name=t["name"], nj=nj, nb=nb, nu=6 + nj, npt=len(points), nlevel=max(jlevel) + 1,
-                xboxes=xboxes, palm_body=palm_body, p2p=p2p, extras=extras,
+                xboxes=xboxes, palm_body=palm_body, p2p=p2p, extras=extras, spairs=spairs,
                 jparent=jparent, joff=joff, jrot=jrot, jaxis=jaxis, jlevel=jlevel, janc=janc,
                 lower=t["lower"], upper=t["upper"], gain=t["gain"], damping=t["damping"], armature=t["armature"],
                 bodies=bodies, bstart=bstart, bend=bend, points=points, foot_body=foot_body,
@@ -281,6 +295,11 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append(_iarr(P + "_lc_owner", [sd["owner"] for sd in sides]))
     out.append(_farr(P + "_lc_pos", [sd["pos"] for sd in sides] or [[0, 0, 0]]))
     out.append(_farr(P + "_lc_maximp", [c["max_impulse"] for c in r["p2p"]] or [0]))
+    sp = r["spairs"]
+    out.append(_iarr(P + "_sp_pack", [x["pack"] for x in sp] or [0], "unsigned"))
+    out.append(_iarr(P + "_sp_own", [(x["own_a"] + 1) | ((x["own_b"] + 1) << 8) | (x["feet"] << 16) for x in sp] or [0]))
+    out.append(_farr(P + "_sp_thresh", [x["thresh"] for x in sp] or [0]))
+    out.append(_farr(P + "_sp_mu", [x["mu"] for x in sp] or [0]))
     ex = r["extras"]
     out.append(_iarr(P + "_ordered", ex.get("ordered", [])))
     out.append(_iarr(P + "_pd_dof", ex.get("pd_dof", [])))
@@ -313,10 +332,10 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append("  MB_HD static constexpr unsigned rowmask_c(int i) {\n    return " +
                " ".join("i == %d ? %du :" % (i, m) for i, m in enumerate(rowmask)) + " 0u;\n  }\n")
     out.append("  enum { NJ = %d, NB = %d, NU = %d, NPT = %d, NLEVEL = %d, NFEET = %d, NMIRROR = %d, NNEG = %d,\n"
-               "         LSIZE = %d, MAXSUP = %d, NXBOX = %d, NLOOP = %d, NORDERED = %d, NPD = %d, NPOWERED = %d };\n"
+               "         LSIZE = %d, MAXSUP = %d, NXBOX = %d, NLOOP = %d, NORDERED = %d, NPD = %d, NPOWERED = %d, NSELF = %d };\n"
                % (r["nj"], r["nb"], r["nu"], r["npt"], r["nlevel"], r["nfeet"], len(r["right"]), len(r["neg"]),
                   r["lsize"], r["maxsup"], len(r["xboxes"]), len(r["p2p"]), len(ex.get("ordered", [])),
-                  len(ex.get("pd_dof", [])), ex.get("npowered", 0)))
+                  len(ex.get("pd_dof", [])), ex.get("npowered", 0), len(sp)))
     out.append("  MB_HD static unsigned long long chainpack(int j) { return %s_chainpack[j]; }\n" % P)
     out.append("  MB_HD static int facoff(int k, int t) { return %s_facoff[k][t]; }\n" % P)
     out.append("  MB_HD static int fcol(int k, int t) { return %s_fcol[k][t]; }\n" % P)
@@ -331,11 +350,11 @@ def emit_header(t: dict, prefix: str) -> str:
                        ("bowner", "int"), ("powner", "int"), ("pfoot", "int"), ("pid", "int"), ("foot_body", "int"),
                        ("palm_body", "int"), ("xowner", "int"), ("xfoot", "int"),
                        ("lc_owner", "int"), ("ordered", "int"), ("pd_dof", "int"), ("pd_ordered", "int"),
-                       ("right", "int"), ("left", "int"), ("neg", "int")]:
+                       ("right", "int"), ("left", "int"), ("neg", "int"), ("sp_pack", "unsigned"), ("sp_own", "int")]:
         out.append("  MB_HD static %s %s(int i) { return %s_%s[i]; }\n" % (ctype, fld, P, fld))
     out.append("  MB_HD static double base_angles(int i) { return %s_base_angles[i]; }\n" % P)
     for fld in ["lower", "upper", "weight", "gain", "damping", "armature", "bmass", "pradius", "pfriction", "pthresh",
-                "jsgn", "xfriction", "xthresh", "lc_maximp", "pd_kp", "pd_kd"]:
+                "jsgn", "xfriction", "xthresh", "lc_maximp", "pd_kp", "pd_kd", "sp_thresh", "sp_mu"]:
         out.append("  MB_HD static float %s(int i) { return %s_%s[i]; }\n" % (fld, P, fld))
     for fld in ["joff", "jrot", "jaxis", "bcom", "binertia", "ppos", "xpos", "xrot", "xhalf", "lc_pos"]:
         out.append("  MB_HD static float %s(int i, int k) { return %s_%s[i][k]; }\n" % (fld, P, fld))

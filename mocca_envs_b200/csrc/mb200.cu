@@ -373,6 +373,7 @@ void mb200_default_physics(mb200_physics* p) {
   p->residual_threshold = 1e-7f;
   p->ground_friction = 0.8f;
   p->has_ground = 1;
+  p->self_collision = 1;
 }
 
 void mb200_default_physics_for(const char* env_id, mb200_physics* p) {
@@ -392,6 +393,7 @@ static void to_internal(const mb200_physics& p, MbPhysics* q) {
   q->limit_max_impulse = p.limit_max_impulse; q->split_threshold = p.split_threshold;
   q->residual_threshold = p.residual_threshold; q->ground_friction = p.ground_friction; q->has_ground = p.has_ground;
   q->box_friction = 1.0f; q->box_erp = p.erp_contact; q->box_cfm = 0.0f; q->bar_friction = 0.5f;
+  q->self_collision = p.self_collision;
 }
 
 static int grid_for(const mb200_env* e) { return (e->n + e->warps - 1) / e->warps; }

@@ -121,6 +121,7 @@ struct MbPhysics {
   float box_erp;
   float box_cfm;
   float bar_friction;  // MonkeyBar keeps Bullet's default lateral friction (bullet_objects.py:172-179 is commented out)
+  int self_collision;  // robots.py:259-264 URDF_USE_SELF_COLLISION | URDF_USE_SELF_COLLISION_EXCLUDE_ALL_PARENTS
 };
 
 MB_HD constexpr int tri(int i, int j) { return (i * (i + 1)) / 2 + j; }  // packed lower-triangular index, j <= i
@@ -680,7 +681,85 @@ template <class M> struct Sim {
     return found;
   }
 
-  template <int OBST> MB_HD static int collide(Mem& S, const MbPhysics& P, int* overflow) {
+  // closest points of two segments (Ericson, Real-Time Collision Detection 5.1.9; same restatement as the oracle's
+  // seg_seg): Bullet's sphere-sphere, capsuleCapsuleDistance and GJK on two capsules all reduce to this
+  MB_HD static void seg_seg(const float* p1, const float* q1, const float* p2, const float* q2, float* c1, float* c2) {
+    const float d1[3] = {q1[0] - p1[0], q1[1] - p1[1], q1[2] - p1[2]};
+    const float d2[3] = {q2[0] - p2[0], q2[1] - p2[1], q2[2] - p2[2]};
+    const float r[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+    const float a = mb_dot3(d1, d1), e = mb_dot3(d2, d2), f = mb_dot3(d2, r), c = mb_dot3(d1, r);
+    const float EPS = 1e-12f;
+    float s2 = 0.0f, t = 0.0f;
+    if (a <= EPS && e <= EPS) {
+    } else if (a <= EPS) {
+      t = fminf(fmaxf(f / e, 0.0f), 1.0f);
+    } else if (e <= EPS) {
+      s2 = fminf(fmaxf(-c / a, 0.0f), 1.0f);
+    } else {
+      const float b = mb_dot3(d1, d2), den = a * e - b * b;
+      s2 = den > EPS ? fminf(fmaxf((b * f - c * e) / den, 0.0f), 1.0f) : 0.0f;
+      t = (b * s2 + f) / e;
+      if (t < 0.0f) { t = 0.0f; s2 = fminf(fmaxf(-c / a, 0.0f), 1.0f); }
+      else if (t > 1.0f) { t = 1.0f; s2 = fminf(fmaxf((b - c) / a, 0.0f), 1.0f); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { c1[k] = p1[k] + d1[k] * s2; c2[k] = p2[k] + d2[k] * t; }
+  }
+
+  // self-collision (robots.py:259-264): one point per candidate geom pair, listed after the contacts with the
+  // static world.  cP = point on link A, cn = normal on B towards A; the point on B is cP - cdist * cn.
+  // cpartner = 1000 + pair index.  Returns the number of self-contacts appended at slot nc.
+  MB_HD static int collide_self(Mem& S, const MbPhysics& P, int nc) {
+    int ns = 0;
+#pragma unroll 1
+    for (int pass = 0; pass * 32 < M::NSELF; ++pass) {
+      LaneVar<int> hit;
+      LaneVar<float> px, py, pz, nx, ny, nz, dd;
+      MB_LANES(l)
+        const int k = pass * 32 + l;
+        hit[l] = 0;
+        if (k < M::NSELF) {
+          const unsigned pk = M::sp_pack(k);
+          const int a0 = pk & 255u, a1 = (pk >> 8) & 255u, b0 = (pk >> 16) & 255u, b1 = pk >> 24;
+          float c1[3], c2[3];
+          seg_seg(S.w.k.u2.pt[a0], S.w.k.u2.pt[a1], S.w.k.u2.pt[b0], S.w.k.u2.pt[b1], c1, c2);
+          const float d[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
+          const float len = sqrtf(mb_dot3(d, d)), ra = M::pradius(a0), rb = M::pradius(b0);
+          const float dist = len - ra - rb;
+          if (dist < M::sp_thresh(k) && len >= 1e-9f) {
+            const float il = 1.0f / len;
+            hit[l] = 1;
+            nx[l] = d[0] * il; ny[l] = d[1] * il; nz[l] = d[2] * il;
+            px[l] = c1[0] - ra * nx[l]; py[l] = c1[1] - ra * ny[l]; pz[l] = c1[2] - ra * nz[l];
+            dd[l] = dist;
+          }
+        }
+      MB_END
+      const unsigned mask = warp_ballot(hit);
+      if (mask == 0u) continue;
+      MB_LANES(l)
+        if (hit[l]) {
+          const int pr = pass * 32 + l;
+          const int k = nc + ns + mb_popc(mask & ((1u << l) - 1u));
+          if (k < MB_MAXC) {
+            S.cP[k][0] = px[l]; S.cP[k][1] = py[l]; S.cP[k][2] = pz[l];
+            S.cn[k][0] = nx[l]; S.cn[k][1] = ny[l]; S.cn[k][2] = nz[l];
+            S.cdist[k] = dd[l];
+            S.cmu[k] = M::sp_mu(pr);
+            S.cerp[k] = P.erp_contact;
+            S.ccfm[k] = 0.0f;
+            S.clink[k] = (M::sp_own(pr) & 255) - 1;
+            S.cfoot[k] = -1;
+            S.cpartner[k] = 1000 + pr;
+          }
+        }
+      MB_END
+      ns += mb_popc(mask);
+    }
+    return ns;
+  }
+
+  template <int OBST> MB_HD static int collide(Mem& S, const MbPhysics& P, int* overflow, int* ns_out) {
     constexpr bool BOXES = (OBST & MB_OBST_BOXES) != 0;
     constexpr bool STORE = NPT <= 64;  // else: ground plane only, points are transformed inside the test pass
     static_assert(STORE || OBST == 0, "on-the-fly candidate points support the ground plane only");
@@ -867,7 +946,13 @@ template <class M> struct Sim {
       }
     }
     if (nc > MB_MAXC) { *overflow += 1; nc = MB_MAXC; }
-    return nc;
+    int ns = 0;
+    if (M::NSELF > 0 && STORE && P.self_collision) {
+      ns = collide_self(S, P, nc);
+      if (nc + ns > MB_MAXC) { *overflow += 1; ns = MB_MAXC - nc; }
+    }
+    *ns_out = ns;
+    return nc + ns;
   }
 
   // ---- F2. loop-closure pivots in world axes (needs the kinematics of this substep) ---------------------------
@@ -915,9 +1000,13 @@ template <class M> struct Sim {
   // as TWO compact rows (the part on link A and the part on link B -- their union is a tree, not a chain) that share
   // one multiplier; then contact normals and friction pairs.
   enum { NLC = 6 * M::NLOOP };
-  MB_HD static void setup_rows(Mem& S, const MbPhysics& P, int nlim, int nc) {
+  // Self-contacts (ncs of them, contact slots [nc, nc + ncs)) couple two links, so like a loop row each of their
+  // three rows is stored as two compact rows sharing one multiplier: normals at S0 + 2s + side, friction at
+  // S0 + 2 ncs + 4s + 2 dir + side, with S0 = n0 + 3 nc.
+  MB_HD static void setup_rows(Mem& S, const MbPhysics& P, int nlim, int nc, int ncs) {
     const int n0 = nlim + NLC;
-    const int R = n0 + 3 * nc;
+    const int S0 = n0 + 3 * nc;
+    const int R = S0 + 6 * ncs;
     const float inv_dt = 1.0f / P.dt;
 #pragma unroll 1
     for (int base = 0; base < R; base += 32) {
@@ -950,21 +1039,38 @@ template <class M> struct Sim {
           } else {
             int k;
             float dirv[3];
+            int fr = -1;     // friction direction (0 / 1), -1 = normal
+            bool sideB = false;
             if (r < n0 + nc) {
               kind = 1; k = r - n0;
-              dirv[0] = S.cn[k][0]; dirv[1] = S.cn[k][1]; dirv[2] = S.cn[k][2];
               cfm = S.ccfm[k] * inv_dt; erp = S.cerp[k]; dist = S.cdist[k] + P.linear_slop;
+            } else if (r < S0) {
+              kind = 2; k = (r - n0 - nc) >> 1; fr = (r - n0 - nc) & 1;
+            } else if (r < S0 + 2 * ncs) {
+              kind = 4; k = nc + ((r - S0) >> 1); sideB = ((r - S0) & 1) != 0;
             } else {
-              kind = 2; k = (r - n0 - nc) >> 1;
+              const int i = r - S0 - 2 * ncs;
+              kind = 4; k = nc + (i >> 2); fr = (i >> 1) & 1; sideB = (i & 1) != 0;
+            }
+            if (fr < 0) {
+              dirv[0] = S.cn[k][0]; dirv[1] = S.cn[k][1]; dirv[2] = S.cn[k][2];
+            } else {
               float t1[3], t2[3];
               mb_plane_space(S.cn[k], t1, t2);
-              const bool second = ((r - n0 - nc) & 1) != 0;
-              dirv[0] = second ? t2[0] : t1[0]; dirv[1] = second ? t2[1] : t1[1]; dirv[2] = second ? t2[2] : t1[2];
+              dirv[0] = fr ? t2[0] : t1[0]; dirv[1] = fr ? t2[1] : t1[1]; dirv[2] = fr ? t2[2] : t1[2];
             }
             mu = S.cmu[k];
-            mb_cross(S.cP[k], dirv, W);
-            W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
             cj = S.clink[k];
+            float pc[3] = {S.cP[k][0], S.cP[k][1], S.cP[k][2]};
+            if (M::NSELF > 0 && sideB) {
+              // setupMultiBodyContactConstraint: jacobian B is built with -direction at the point on B
+              const float dk = S.cdist[k];
+              pc[0] -= dk * S.cn[k][0]; pc[1] -= dk * S.cn[k][1]; pc[2] -= dk * S.cn[k][2];
+              dirv[0] = -dirv[0]; dirv[1] = -dirv[1]; dirv[2] = -dirv[2];
+              cj = ((M::sp_own(S.cpartner[k] - 1000) >> 8) & 255) - 1;
+            }
+            mb_cross(pc, dirv, W);
+            W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
           }
           const unsigned long long pack = cj >= 0 ? M::chainpack(cj) : 0ull;
           const int depth = cj >= 0 ? M::jdepth(cj) : -1;
@@ -1018,7 +1124,7 @@ template <class M> struct Sim {
             if (t < n) Yr[t] = b[t];
           S.rc.r.r_mask[r] = 0x3Fu | (cj >= 0 ? (M::janc(cj) << 6) : 0u);
           MbRowPar par;
-          if (kind == 3) {  // partial sums; the two parts of a loop row are combined below
+          if (kind >= 3) {  // partial sums; the two parts of a loop / self-contact row are combined below
             par.rhs = rel_vel; par.jinv = dd; par.den = 0.0f;
           } else {
             par.rhs = (positional + verr) * jinv; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
@@ -1045,6 +1151,27 @@ template <class M> struct Sim {
           par.rhs = (positional - rel_vel) * jinv; par.cfm = 0.0f; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
           S.rc.r.r_par[ra] = par;
           S.rc.r.r_mu[ra] = M::lc_maximp(c);
+        }
+      MB_END
+    }
+    if (M::NSELF > 0 && ncs > 0) {
+      // same denominator rule for a contact between two links of the multibody
+      MB_LANES(l)
+        for (int i = l; i < 3 * ncs; i += 32) {
+          const int sidx = i / 3, w = i - 3 * sidx;  // w: 0 normal, 1 / 2 friction directions
+          const int ra = w == 0 ? S0 + 2 * sidx : S0 + 2 * ncs + 4 * sidx + 2 * (w - 1);
+          const float dd = S.rc.r.r_par[ra].jinv + S.rc.r.r_par[ra + 1].jinv;
+          const float jinv = dd > 1.1920929e-07f ? 1.0f / dd : 0.0f;
+          const float rel_vel = S.rc.r.r_par[ra].rhs + S.rc.r.r_par[ra + 1].rhs;
+          float positional = 0.0f, verr = -rel_vel;
+          if (w == 0) {
+            const float dist = S.cdist[nc + sidx] + P.linear_slop;
+            if (dist > 0.0f) verr -= dist * inv_dt;
+            else positional = -dist * S.cerp[nc + sidx] * inv_dt;
+          }
+          MbRowPar par;
+          par.rhs = (positional + verr) * jinv; par.cfm = 0.0f; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
+          S.rc.r.r_par[ra] = par;
         }
       MB_END
     }
@@ -1110,7 +1237,7 @@ template <class M> struct Sim {
   }
 
   // loop-closure row: two compact rows (ra on link A, ra + 1 on link B) sharing one multiplier
-  MB_HD static float pgs_dual(Mem& S, const LaneConst& C, int ra, LaneVar<float>& z) {
+  MB_HD static float pgs_dual(Mem& S, const LaneConst& C, int ra, float lo, float hi, LaneVar<float>& z) {
     const int rb = ra + 1;
     const unsigned supA = S.rc.r.r_mask[ra], supB = S.rc.r.r_mask[rb];
     LaneVar<float> y, t;
@@ -1122,32 +1249,70 @@ template <class M> struct Sim {
     MB_END_REG
     const float dot = warp_sum(t);
     const MbRowPar pA = S.rc.r.r_par[ra];
-    const float app = S.rc.r.r_app[ra], lim = S.rc.r.r_mu[ra];
+    const float app = S.rc.r.r_app[ra];
     float d = pA.rhs - dot * pA.jinv;
     const float sum = app + d;
     float na = sum;
-    if (sum < -lim) { d = -lim - app; na = -lim; }
-    else if (sum > lim) { d = lim - app; na = lim; }
+    if (sum < lo) { d = lo - app; na = lo; }
+    else if (sum > hi) { d = hi - app; na = hi; }
     MB_LANES(l)
       z[l] += y[l] * d;
       if (l == 0) S.rc.r.r_app[ra] = na;
     MB_END
     return d * pA.den;
   }
+  // friction pair of a self-contact: rows ra, ra + 1 = first direction on link A / B, ra + 2, ra + 3 = second
+  MB_HD static float pgs_pair_dual(Mem& S, const LaneConst& C, int ra, float cone, LaneVar<float>& z) {
+    const unsigned supA = S.rc.r.r_mask[ra], supB = S.rc.r.r_mask[ra + 1];
+    LaneVar<float> ya, yb, ta, tb;
+    MB_LANES(l)
+      const bool inA = ((supA >> l) & 1u) != 0u, inB = ((supB >> l) & 1u) != 0u;
+      ya[l] = (inA ? S.w.Yc[ra][C.tl[l]] : 0.0f) + (inB ? S.w.Yc[ra + 1][C.tl[l]] : 0.0f);
+      yb[l] = (inA ? S.w.Yc[ra + 2][C.tl[l]] : 0.0f) + (inB ? S.w.Yc[ra + 3][C.tl[l]] : 0.0f);
+      ta[l] = ya[l] * z[l];
+      tb[l] = yb[l] * z[l];
+    MB_END_REG
+    const float dotA = warp_sum(ta), dotB = warp_sum(tb);
+    const MbRowPar pA = S.rc.r.r_par[ra], pB = S.rc.r.r_par[ra + 2];
+    const float appA = S.rc.r.r_app[ra], appB = S.rc.r.r_app[ra + 2];
+    float dA = pA.rhs - dotA * pA.jinv;
+    float dB = pB.rhs - dotB * pB.jinv;
+    const float sumA = appA + dA, sumB = appB + dB;
+    float nA = sumA, nB = sumB;
+    const float n2 = sumA * sumA + sumB * sumB;
+    if (n2 >= cone * cone) {
+      const float sc = n2 > 0.0f ? fabsf(cone) * rsqrtf(n2) : 0.0f;
+      const float clipA = fabsf(sumA) * sc, clipB = fabsf(sumB) * sc;
+      if (sumA < -clipA) { dA = -clipA - appA; nA = -clipA; }
+      else if (sumA > clipA) { dA = clipA - appA; nA = clipA; }
+      if (sumB < -clipB) { dB = -clipB - appB; nB = -clipB; }
+      else if (sumB > clipB) { dB = clipB - appB; nB = clipB; }
+    }
+    MB_LANES(l)
+      z[l] += ya[l] * dA + yb[l] * dB;
+      if (l == 0) { S.rc.r.r_app[ra] = nA; S.rc.r.r_app[ra + 2] = nB; }
+    MB_END
+    return dA * pA.den + dB * pB.den;
+  }
 
   // btMultiBodyConstraintSolver::solveSingleIteration order: non-contact rows (limits, then loop closures;
   // alternating direction), normals, friction
-  MB_HD static void solve_constraints(Mem& S, const MbPhysics& P, const LaneConst& C, int nlim, int nc,
+  MB_HD static void solve_constraints(Mem& S, const MbPhysics& P, const LaneConst& C, int nlim, int nc, int ncs,
                                       LaneVar<float>& z) {
-    const int nnc = nlim + NLC / 2, n0 = nlim + NLC;
+    const int nnc = nlim + NLC / 2, n0 = nlim + NLC, S0 = n0 + 3 * nc;
 #pragma unroll 1
     for (int it = 0; it < P.iterations; ++it) {
       float res2 = 0.0f;
 #pragma unroll 1
       for (int v = 0; v < nnc; ++v) {
         const int idx = (it & 1) ? v : nnc - 1 - v;
-        const float rr = idx < nlim ? pgs_single(S, C, idx, 0.0f, P.limit_max_impulse, z)
-                                    : pgs_dual(S, C, nlim + 2 * (idx - nlim), z);
+        float rr;
+        if (idx < nlim) rr = pgs_single(S, C, idx, 0.0f, P.limit_max_impulse, z);
+        else {
+          const int ra = nlim + 2 * (idx - nlim);
+          const float lim = S.rc.r.r_mu[ra];
+          rr = pgs_dual(S, C, ra, -lim, lim, z);
+        }
         res2 = fmaxf(res2, rr * rr);
       }
 #pragma unroll 1
@@ -1155,11 +1320,26 @@ template <class M> struct Sim {
         const float rr = pgs_single(S, C, n0 + k, 0.0f, 1e10f, z);
         res2 = fmaxf(res2, rr * rr);
       }
+      if (M::NSELF > 0) {
+#pragma unroll 1
+        for (int k = 0; k < ncs; ++k) {
+          const float rr = pgs_dual(S, C, S0 + 2 * k, 0.0f, 1e10f, z);
+          res2 = fmaxf(res2, rr * rr);
+        }
+      }
 #pragma unroll 1
       for (int k = 0; k < nc; ++k) {
         const int ra = n0 + nc + 2 * k;
         const float rr = pgs_pair(S, C, ra, S.rc.r.r_mu[ra] * S.rc.r.r_app[n0 + k], z);
         res2 = fmaxf(res2, rr * rr);
+      }
+      if (M::NSELF > 0) {
+#pragma unroll 1
+        for (int k = 0; k < ncs; ++k) {
+          const int ra = S0 + 2 * ncs + 4 * k;
+          const float rr = pgs_pair_dual(S, C, ra, S.rc.r.r_mu[ra] * S.rc.r.r_app[S0 + 2 * k], z);
+          res2 = fmaxf(res2, rr * rr);
+        }
       }
       if (res2 <= P.residual_threshold) break;
     }
@@ -1197,7 +1377,8 @@ template <class M> struct Sim {
   MB_HD static int substep(Mem& S, const MbPhysics& P, const LaneConst& C, int* nc_out, int* overflow) {
     MB_BLOCK_BARRIER();  // keeps the warps of a CTA in the same phase so instruction-cache lines are shared
     kinematics(S, P, C, true);
-    const int nc_all = collide<OBST>(S, P, overflow);
+    int ns_all = 0;
+    const int nc_all = collide<OBST>(S, P, overflow, &ns_all);  // static-world contacts, then ns_all self-contacts
     loop_pivots(S);
     bodies(S, P);
     mass_matrix_and_rhs(S);
@@ -1214,16 +1395,21 @@ template <class M> struct Sim {
       if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + P.dt * x[l], -P.max_coord_vel), P.max_coord_vel);
     MB_END
     const int nlim = find_limits(S);
-    int nc = nc_all;
-    if (nlim + NLC + 3 * nc > MB_MAXROW) { nc = (MB_MAXROW - nlim - NLC) / 3; *overflow += 1; }
-    const int R = nlim + NLC / 2 + 3 * nc;  // as Bullet counts them (a loop row is one row)
+    int nc = nc_all - ns_all, ncs = ns_all;
+    if (nlim + NLC + 3 * nc + 6 * ncs > MB_MAXROW) {  // self-contacts are dropped first
+      const int avail = MB_MAXROW - nlim - NLC;
+      if (3 * nc > avail) { nc = avail / 3; ncs = 0; }
+      else ncs = (avail - 3 * nc) / 6;
+      *overflow += 1;
+    }
+    const int R = nlim + NLC / 2 + 3 * (nc + ncs);  // as Bullet counts them (a loop / self-contact row is one row)
     if (R > 0) {
-      setup_rows(S, P, nlim, nc);
+      setup_rows(S, P, nlim, nc, ncs);
       LaneVar<float> z;
       MB_LANES(l)
         z[l] = 0.0f;
       MB_END
-      solve_constraints(S, P, C, nlim, nc, z);
+      solve_constraints(S, P, C, nlim, nc, ncs, z);
       solve_L<false>(S, C, z);
       MB_LANES(l)
         if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + z[l], -P.max_coord_vel), P.max_coord_vel);

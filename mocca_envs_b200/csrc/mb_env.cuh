@@ -683,6 +683,12 @@ template <class M> struct StepperEnv {
       if (S.cfoot[k] == 0) fc0 = 1.0f;
       if (S.cfoot[k] == 1) fc1 = 1.0f;
       if (S.cfoot[k] >= 0 && S.cpartner[k] == cover_id) reached = 1;
+      if (M::NSELF > 0 && S.cpartner[k] >= 1000) {
+        // "contact = 1.0 if contact_ids" (env_locomotion.py:645-646): a self-contact of the foot link counts too
+        const int feet = M::sp_own(S.cpartner[k] - 1000) >> 16;
+        if (feet & 1) fc0 = 1.0f;
+        if (feet & 2) fc1 = 1.0f;
+      }
     }
     S_::kinematics(S, P, C, false);
     float s1, s2;

@@ -402,6 +402,109 @@ def compile_mjcf(path: str, name: str, power_coef: Dict[str, float], base_power:
     return table
 
 
+# ----------------------------------------------------------------------------- self-collision pairs
+def fk_links(t: dict, q):
+    """Forward kinematics of a compiled table at joint angles q (base at the origin, identity orientation):
+    returns (pos[n_links + 1, 3], rot[n_links + 1, 3, 3]) of the link COM frames (local -> world), index 0 = base.
+    Same recurrence as btMultiBody: R_parent_to_this = R(axis, -q) * zeroRotParentToThis."""
+    nl = t["n_links"]
+    pos = np.zeros((nl + 1, 3))
+    rot = np.zeros((nl + 1, 3, 3))
+    rot[0] = np.eye(3)
+    for i in range(nl):
+        p = t["parent"][i] + 1
+        Rz = quat_to_mat(t["rot_parent_to_this"][i])  # parent -> this at q = 0
+        if t["joint_type"][i] == JOINT_REVOLUTE:
+            ax = np.array(t["axis"][i])
+            a = -q[t["dof_of_link"][i]]
+            K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+            Rq = np.eye(3) + math.sin(a) * K + (1 - math.cos(a)) * (K @ K)
+            Rp2t = Rq @ Rz
+        else:
+            Rp2t = Rz
+        rot[i + 1] = rot[p] @ Rp2t.T
+        pos[i + 1] = pos[p] + rot[p] @ np.array(t["e_vec"][i]) + rot[i + 1] @ np.array(t["d_vec"][i])
+    return pos, rot
+
+
+def _seg_dist(p1, q1, p2, q2):
+    """Closest distance between segments p1q1 and p2q2 (Ericson, Real-Time Collision Detection 5.1.9)."""
+    d1, d2, r = q1 - p1, q2 - p2, p1 - p2
+    a, e, f = d1 @ d1, d2 @ d2, d2 @ r
+    if a <= 1e-12 and e <= 1e-12:
+        return float(np.linalg.norm(r))
+    if a <= 1e-12:
+        s, tt = 0.0, min(max(f / e, 0.0), 1.0)
+    else:
+        c = d1 @ r
+        if e <= 1e-12:
+            tt, s = 0.0, min(max(-c / a, 0.0), 1.0)
+        else:
+            b = d1 @ d2
+            den = a * e - b * b
+            s = min(max((b * f - c * e) / den, 0.0), 1.0) if den > 1e-12 else 0.0
+            tt = (b * s + f) / e
+            if tt < 0:
+                tt, s = 0.0, min(max(-c / a, 0.0), 1.0)
+            elif tt > 1:
+                tt, s = 1.0, min(max((b - c) / a, 0.0), 1.0)
+    return float(np.linalg.norm(p1 + d1 * s - p2 - d2 * tt))
+
+
+def self_collision_pairs(t: dict, samples: int = 4000, margin: float = 0.05, seed: int = 0):
+    """Geom pairs that can touch under URDF_USE_SELF_COLLISION | URDF_USE_SELF_COLLISION_EXCLUDE_ALL_PARENTS
+    (robots.py:259-264): different links, neither an ancestor of the other, Bullet's two-way group/mask filter
+    (BulletMJCFImporter: group = contype, mask = conaffinity of the link's last geom), sphere / capsule geoms only,
+    links not rigidly attached to the same joint frame.  Pairs that never come within ``margin`` of each other in
+    ``samples`` uniformly drawn poses inside the joint limits are dropped (documented reduction)."""
+    par = t["parent"]
+    nl = t["n_links"]
+
+    def ancestors(l):
+        out = set()
+        while l >= 0:
+            l = par[l]
+            out.add(l)
+        return out
+
+    def owner(l):
+        while l >= 0 and t["joint_type"][l] != JOINT_REVOLUTE:
+            l = par[l]
+        return l
+
+    groups = [t["base"]["group"]] + t["group"]
+    masks = [t["base"]["mask"]] + t["mask"]
+    G = t["geoms"]
+    cand = []
+    for i in range(len(G)):
+        for j in range(i + 1, len(G)):
+            a, b = G[i]["link"], G[j]["link"]
+            if a == b or a in ancestors(b) or b in ancestors(a) or owner(a) == owner(b):
+                continue
+            if G[i]["type"] == GEOM_BOX or G[j]["type"] == GEOM_BOX:
+                continue
+            if not ((groups[a + 1] & masks[b + 1]) and (groups[b + 1] & masks[a + 1])):
+                continue
+            cand.append((i, j))
+    rng = np.random.RandomState(seed)
+    lo, hi = np.array(t["lower"]), np.array(t["upper"])
+    un = lo > hi
+    lo, hi = np.where(un, -math.pi, lo), np.where(un, math.pi, hi)
+    mind = np.full(len(cand), np.inf)
+    for _ in range(samples):
+        q = lo + (hi - lo) * rng.uniform(0, 1, len(lo))
+        pos, rot = fk_links(t, q)
+        ends = []
+        for g in G:
+            li = g["link"] + 1
+            ends.append((pos[li] + rot[li] @ np.array(g["p0"]), pos[li] + rot[li] @ np.array(g["p1"])))
+        for k, (i, j) in enumerate(cand):
+            d = _seg_dist(ends[i][0], ends[i][1], ends[j][0], ends[j][1]) - G[i]["size"][0] - G[j]["size"][0]
+            if d < mind[k]:
+                mind[k] = d
+    return [[i, j] for k, (i, j) in enumerate(cand) if mind[k] < margin], len(cand)
+
+
 # ----------------------------------------------------------------------------- robot classes
 WALKER3D_POWER = {  # mocca_envs/robots.py:234-256
     "abdomen_z": 60, "abdomen_y": 80, "abdomen_x": 60,
@@ -437,6 +540,7 @@ def compile_walker3d(data_dir: str, **kw) -> dict:
     t["right_joint_indices"] = [3, 4, 5, 6, 7, 13, 14, 15, 16]  # robots.py:282-284
     t["left_joint_indices"] = [8, 9, 10, 11, 12, 17, 18, 19, 20]  # robots.py:285-287
     t["negation_joint_indices"] = [0, 2]  # robots.py:288
+    t["self_pairs"], t["self_pairs_candidates"] = self_collision_pairs(t)
     return t
 
 
@@ -460,6 +564,7 @@ def compile_monkey3d(data_dir: str, **kw) -> dict:
     t["negation_joint_indices"] = [0, 2]
     # env_locomotion.py:1269,1424: the palm spheres whose contact with the target bar advances the step index
     t["palm_links"] = [t["link_names"].index("right_palm"), t["link_names"].index("left_palm")]
+    t["self_pairs"], t["self_pairs_candidates"] = self_collision_pairs(t)
     return t
 
 

@@ -392,7 +392,7 @@ void orc_default_params(orc_params* p) {
   p->gyro = 1;
   p->has_ground = 1;
   p->ground_friction = 0.8;
-  p->self_collision = 0;
+  p->self_collision = 1;
 }
 
 void orc_forward_dynamics(const orc_model* m, const orc_params* p, const orc_state* s, const double* tau,
@@ -542,7 +542,8 @@ static void add_point(orc_contacts* c, int pid, int link, int partner, const v3 
                       double mu, double erp, double cfm) {
   if (c->n >= ORC_MAXP) return;
   int k = c->n++;
-  c->point_id[k] = pid; c->link[k] = link; c->partner[k] = partner;
+  c->point_id[k] = pid; c->link[k] = link; c->partner[k] = partner; c->link_b[k] = -2;
+  v3set(c->pos_b[k], 0, 0, 0);
   v3copy(c->pos_a[k], pa); v3copy(c->normal[k], n);
   c->dist[k] = dist; c->friction[k] = mu; c->erp[k] = erp; c->cfm[k] = cfm; c->impulse[k] = 0;
 }
@@ -674,6 +675,56 @@ static int collide_bars(const orc_model* m, const orc_params* p, const orc_cache
   return out->n;
 }
 
+/* closest points of two segments (Ericson, Real-Time Collision Detection 5.1.9); a sphere is a zero-length segment */
+static void seg_seg(const v3 p1, const v3 q1, const v3 p2, const v3 q2, v3 c1, v3 c2) {
+  v3 d1 = {q1[0] - p1[0], q1[1] - p1[1], q1[2] - p1[2]}, d2 = {q2[0] - p2[0], q2[1] - p2[1], q2[2] - p2[2]};
+  v3 r = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+  double a = v3dot(d1, d1), e = v3dot(d2, d2), f = v3dot(d2, r), s, t;
+  const double EPS = 1e-12;
+  if (a <= EPS && e <= EPS) { s = t = 0; }
+  else if (a <= EPS) { s = 0; t = f / e; t = t < 0 ? 0 : (t > 1 ? 1 : t); }
+  else {
+    double c = v3dot(d1, r);
+    if (e <= EPS) { t = 0; s = -c / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+    else {
+      double b = v3dot(d1, d2), den = a * e - b * b;
+      s = den > EPS ? (b * f - c * e) / den : 0.0;
+      s = s < 0 ? 0 : (s > 1 ? 1 : s);
+      t = (b * s + f) / e;
+      if (t < 0) { t = 0; s = -c / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+      else if (t > 1) { t = 1; s = (b - c) / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+    }
+  }
+  for (int k = 0; k < 3; k++) { c1[k] = p1[k] + d1[k] * s; c2[k] = p2[k] + d2[k] * t; }
+}
+
+/* Self-collision (robots.py:259-264).  Bullet: sphere-sphere, capsule-capsule (capsuleCapsuleDistance) and the GJK
+ * pairs all yield the closest points of the two core segments; one point per geom pair and substep.  Contact while
+ * the distance is below the smaller of the two links' breaking thresholds; combined friction = product. */
+static void collide_self(const orc_model* m, const orc_params* p, const orc_cache* c, orc_contacts* out) {
+  for (int k = 0; k < m->n_self; k++) {
+    int ga = m->self_a[k], gb = m->self_b[k];
+    int la = m->geom_link[ga], lb = m->geom_link[gb];
+    v3 a0, a1, b0, b1, c1, c2;
+    point_world(m, c, ga, 0, a0); point_world(m, c, ga, 1, a1);
+    point_world(m, c, gb, 0, b0); point_world(m, c, gb, 1, b1);
+    seg_seg(a0, a1, b0, b1, c1, c2);
+    v3 d = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
+    double len = v3norm(d), ra = m->geom_size[ga][0], rb = m->geom_size[gb][0];
+    double dist = len - ra - rb;
+    double thresh = m->link_thresh[la + 1] < m->link_thresh[lb + 1] ? m->link_thresh[la + 1] : m->link_thresh[lb + 1];
+    if (dist >= thresh || len < 1e-9) continue;
+    v3 n = {d[0] / len, d[1] / len, d[2] / len}; /* on B, pointing towards A */
+    v3 pa = {c1[0] - ra * n[0], c1[1] - ra * n[1], c1[2] - ra * n[2]};
+    if (out->n >= ORC_MAXP) return;
+    int idx = out->n;
+    add_point(out, 2 * ga, la, 1000 + lb + 1, pa, n, dist, m->geom_friction[ga] * m->geom_friction[gb],
+              p->erp_contact, 0.0);
+    out->link_b[idx] = lb;
+    for (int i = 0; i < 3; i++) out->pos_b[idx][i] = c2[i] + rb * n[i];
+  }
+}
+
 int orc_collide_cached(const orc_model* m, const orc_params* p, const orc_cache* c, const orc_box* boxes,
                        int n_boxes, orc_contacts* out) {
   out->n = 0;
@@ -721,9 +772,10 @@ int orc_collide(const orc_model* m, const orc_params* p, const orc_state* s, con
                 orc_contacts* out) {
   orc_cache* c = (orc_cache*)malloc(sizeof(orc_cache));
   kin(m, s, c);
-  int n = orc_collide_cached(m, p, c, boxes, n_boxes, out);
+  orc_collide_cached(m, p, c, boxes, n_boxes, out);
+  if (p->self_collision) collide_self(m, p, c, out);
   free(c);
-  return n;
+  return out->n;
 }
 
 /* ------------------------------------------------------------------ 6. rows + PGS */
@@ -783,6 +835,16 @@ static void setup_contact_row(const orc_model* m, const orc_params* p, const orc
   point_jacobian(m, s, c, ct->link[k], ct->pos_a[k], dir, row->J);
   minv(m, c, row->J, row->MinvJ);
   double d = dotn(row->J, row->MinvJ, nu) + cfm;
+  if (ct->link_b[k] > -2) {
+    /* both bodies are links of the multibody: setupMultiBodyContactConstraint fills jacobian B with -dir and sums
+     * the two denominators (no coupling term) */
+    double JB[ORC_MAXU], MB[ORC_MAXU];
+    v3 neg = {-dir[0], -dir[1], -dir[2]};
+    point_jacobian(m, s, c, ct->link_b[k], ct->pos_b[k], neg, JB);
+    minv(m, c, JB, MB);
+    d += dotn(JB, MB, nu);
+    for (int i = 0; i < nu; i++) { row->J[i] += JB[i]; row->MinvJ[i] += MB[i]; }
+  }
   row->jinv = d > 1.1920929e-07 ? 1.0 / d : 0.0;
   double rel_vel = dotn(row->J, u, nu);
   double distance = is_friction ? 0.0 : ct->dist[k] + p->linear_slop;
@@ -908,6 +970,7 @@ static void substep_impl(const orc_model* m, const orc_params* p, orc_state* s, 
   kin(m, s, c);
   orc_collide_cached(m, p, c, boxes, n_boxes, ct);
   if (n_bars > 0) collide_bars(m, p, c, bars, n_bars, ct);
+  if (p->self_collision) collide_self(m, p, c, ct);
   /* forward dynamics, velocity update */
   aba(m, p, s, tau, 1, c, acc);
   pack_u(m, s, u);
@@ -1493,11 +1556,14 @@ void orc_stepper_step(const orc_model* m, const orc_params* p, orc_stepper_env* 
     double dy = b->feet_xyz[f][1] - e->terrain[e->next_step_index][1];
     e->foot_dist_to_target[f] = sqrt(dx * dx + dy * dy);
     int contact = 0;
-    for (int k = 0; k < b->last_contacts.n; k++)
+    for (int k = 0; k < b->last_contacts.n; k++) {
+      /* "contact = 1.0 if contact_ids" (env_locomotion.py:645-646): any contact point of the foot link counts, a
+       * self-contact included (either side) */
       if (b->last_contacts.link[k] == m->foot_link[f]) {
         contact = 1;
         if (b->last_contacts.partner[k] == cover_id) e->target_reached = 1;
-      }
+      } else if (b->last_contacts.link_b[k] == m->foot_link[f]) contact = 1;
+    }
     b->feet_contact[f] = contact;
   }
   if (e->target_reached) {
@@ -1717,7 +1783,8 @@ static void monkey_feet_state(const orc_model* m, orc_monkey_env* e, const orc_c
     int contact = 0;
     if (ct)
       for (int k = 0; k < ct->n; k++)
-        if (ct->link[k] == m->foot_link[i]) contact = 1; /* every partner (bars, ground) is in all_contact_object_ids */
+        /* every static partner (bars, ground) is in all_contact_object_ids; robot links are not */
+        if (ct->link[k] == m->foot_link[i] && ct->partner[k] < 1000) contact = 1;
     b->feet_contact[i] = contact;
     if (i != e->swing_leg) continue;
     double dx = b->feet_xyz[e->swing_leg][0] - px, dy = b->feet_xyz[e->swing_leg][1] - py;

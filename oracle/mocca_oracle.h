@@ -23,6 +23,7 @@
 #define ORC_MAXW (2 * ORC_MAXG) /* warm-start slots, indexed by candidate id = 2 * geom + end */
 #define ORC_MAXROW (3 * ORC_MAXP + 2 * ORC_MAXD)
 #define ORC_MAXU (6 + ORC_MAXD)
+#define ORC_MAXSP 256 /* self-collision candidate pairs */
 #define ORC_MAXSTEPS 32 /* stepping stones / bars in a terrain table */
 
 enum { ORC_GEOM_SPHERE = 0, ORC_GEOM_CAPSULE = 1, ORC_GEOM_BOX = 2 };
@@ -62,6 +63,8 @@ typedef struct {
   int n_p2p, p2p_link_a[2], p2p_link_b[2];
   double p2p_pivot_a[2][3], p2p_pivot_b[2][3], p2p_max_impulse[2];
   /* Cassie bookkeeping (env_cassie.py:59-60,192-202): dofs of the 14 ordered joints, PD joint list, gains */
+  /* self-collision candidate geom pairs (robots.py:259-264; compiled by model_compiler.self_collision_pairs) */
+  int n_self, self_a[ORC_MAXSP], self_b[ORC_MAXSP];
   int n_ordered, ordered_dof[ORC_MAXD];
   int n_pd, pd_ordered_index[16]; /* powered + spring joints, as indices into the ordered joints */
   double pd_kp[16], pd_kd[16];
@@ -86,7 +89,7 @@ typedef struct {
   int gyro;                  /* 1 */
   int has_ground;            /* 1: infinite plane z=0 (plane_stadium.sdf) */
   double ground_friction;    /* 0.8 bullet_utils.py:371 */
-  int self_collision;        /* robots.py:260-264; 0 until SURVEY §8 f1 lands */
+  int self_collision;        /* 1: URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS (robots.py:259-264) */
 } orc_params;
 
 typedef struct {
@@ -102,8 +105,10 @@ typedef struct {
   int n;                  /* number of contact points this substep */
   int point_id[ORC_MAXP]; /* candidate id: geom*2 + end */
   int link[ORC_MAXP];     /* -1 = base */
-  int partner[ORC_MAXP];  /* 0 = ground plane, 1+k = box k (base), 100+k = box k cover */
+  int partner[ORC_MAXP];  /* 0 = ground plane, 10+k = box k, 20+k = bar k, 1000 + (link_b + 1) = robot link */
+  int link_b[ORC_MAXP];   /* self-contact: the other robot link (-1 = base); -2 = static partner */
   double pos_a[ORC_MAXP][3];
+  double pos_b[ORC_MAXP][3]; /* self-contact: contact point on link_b */
   double normal[ORC_MAXP][3]; /* on B, pointing towards A */
   double dist[ORC_MAXP];
   double friction[ORC_MAXP];

@@ -18,6 +18,7 @@ _LIB_PATH = os.path.join(_HERE, "libmocca_oracle.so")
 MAXL, MAXD, MAXG, MAXP = 40, 40, 192, 96
 MAXW = 2 * MAXG
 MAXU = 6 + MAXD
+MAXSP = 256
 
 d = C.c_double
 i32 = C.c_int
@@ -42,6 +43,7 @@ class Model(C.Structure):
         ("palm_link", i32 * 2),
         ("n_p2p", i32), ("p2p_link_a", i32 * 2), ("p2p_link_b", i32 * 2),
         ("p2p_pivot_a", (d * 3) * 2), ("p2p_pivot_b", (d * 3) * 2), ("p2p_max_impulse", d * 2),
+        ("n_self", i32), ("self_a", i32 * MAXSP), ("self_b", i32 * MAXSP),
         ("n_ordered", i32), ("ordered_dof", i32 * MAXD),
         ("n_pd", i32), ("pd_ordered_index", i32 * 16), ("pd_kp", d * 16), ("pd_kd", d * 16),
     ]
@@ -64,7 +66,7 @@ class State(C.Structure):
 class Contacts(C.Structure):
     _fields_ = [
         ("n", i32), ("point_id", i32 * MAXP), ("link", i32 * MAXP), ("partner", i32 * MAXP),
-        ("pos_a", (d * 3) * MAXP), ("normal", (d * 3) * MAXP), ("dist", d * MAXP), ("friction", d * MAXP),
+        ("link_b", i32 * MAXP), ("pos_a", (d * 3) * MAXP), ("pos_b", (d * 3) * MAXP), ("normal", (d * 3) * MAXP), ("dist", d * MAXP), ("friction", d * MAXP),
         ("erp", d * MAXP), ("cfm", d * MAXP), ("impulse", d * MAXP),
     ]
 
@@ -212,6 +214,11 @@ def model_from_table(t: dict) -> Model:
             m.p2p_pivot_a[k][j] = c["pivot_a"][j]
             m.p2p_pivot_b[k][j] = c["pivot_b"][j]
         m.p2p_max_impulse[k] = c["max_impulse"]
+    pairs = t.get("self_pairs", [])
+    assert len(pairs) <= MAXSP
+    m.n_self = len(pairs)
+    for k, (a, b) in enumerate(pairs):
+        m.self_a[k], m.self_b[k] = a, b
     if "ordered_dofs" in t:
         m.n_ordered = len(t["ordered_dofs"])
         _fill(m.ordered_dof, np.array(t["ordered_dofs"], dtype=np.int64))

@@ -25,6 +25,7 @@ static void default_phys(MbPhysics* p) {
   p->max_coord_vel = 100.0f; p->limit_max_impulse = 100.0f; p->split_threshold = -0.04f;
   p->residual_threshold = 1e-7f; p->ground_friction = 0.8f; p->has_ground = 1;
   p->box_friction = 1.0f; p->box_erp = 0.9f; p->box_cfm = 0.0f; p->bar_friction = 0.5f;
+  p->self_collision = 1;
 }
 
 extern "C" {

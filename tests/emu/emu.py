@@ -18,7 +18,7 @@ class Phys(C.Structure):
                 ("lin_damping", C.c_float), ("ang_damping", C.c_float), ("max_coord_vel", C.c_float),
                 ("limit_max_impulse", C.c_float), ("split_threshold", C.c_float), ("residual_threshold", C.c_float),
                 ("ground_friction", C.c_float), ("has_ground", C.c_int), ("box_friction", C.c_float),
-                ("box_erp", C.c_float), ("box_cfm", C.c_float), ("bar_friction", C.c_float)]
+                ("box_erp", C.c_float), ("box_cfm", C.c_float), ("bar_friction", C.c_float), ("self_collision", C.c_int)]
 
 
 _lib = None

@@ -74,3 +74,27 @@ def force_oracle_state(o, sv):
     for k in range(A):
         o.e.s.q[k] = sv[13 + k]
         o.e.s.qd[k] = sv[13 + A + k]
+
+
+def self_contact_states(O, table, rng, n, max_tries=4000):
+    """Airborne f32-rounded states (random held torques from the base pose) whose next physics step sees at least
+    one self-contact (robots.py:259-264) according to the oracle."""
+    A = table["n_dof"]
+    m = O.model_from_table(table)
+    p = O.default_params()
+    gain = np.array(table["gain"])
+    out = []
+    for _ in range(max_tries):
+        q0 = np.array(table["base_joint_angles"]) + rng.uniform(-0.1, 0.1, A)
+        s = O.make_state(A, [0, 0, 3.0], [0, 0, 0, 1], [0] * 3, [0] * 3, q0, np.zeros(A))
+        a = rng.uniform(-1, 1, A)
+        for _k in range(rng.randint(3, 25)):
+            O.step_physics(m, p, s, gain * a)
+        row = O.state_vector(s, A).astype(np.float32).astype(np.float64)
+        c = O.collide(m, p, oracle_state(O, A, row))
+        if any(c.partner[k] >= 1000 for k in range(c.n)):
+            out.append(row)
+            if len(out) == n:
+                break
+    assert len(out) == n
+    return np.array(out)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from tests.emu import emu as E
-from tests.helpers import contact_states, oracle_state, random_states, state_error
+from tests.helpers import contact_states, oracle_state, random_states, self_contact_states, state_error
 
 
 def test_mass_matrix_and_bias(walker_table, oracle_mod):
@@ -63,6 +63,34 @@ def test_contact_step(walker_table, oracle_mod):
         assert abs(rows - erows) <= 2  # a limit row can flip at an exact boundary
         worst = max(worst, state_error(out, O.state_vector(s, A)))
     assert worst < 2e-3, worst
+
+
+def test_self_contact_step(walker_table, oracle_mod):
+    """SURVEY 8 f1: self-collision (robots.py:259-264).  Limb-vs-limb contacts couple two links of the multibody;
+    same 2e-3 one-frame tolerance and identical contact / row counts as the ground-contact test.  Switching the
+    kernel's self-collision off must break the agreement (the test is sensitive to the feature)."""
+    O, t = oracle_mod, walker_table
+    A = t["n_dof"]
+    m = O.model_from_table(t)
+    p = O.default_params()
+    ep = E.default_phys()
+    off = E.default_phys()
+    off.self_collision = 0
+    rng = np.random.RandomState(3)
+    gain = np.array(t["gain"])
+    worst, worst_off = 0.0, 0.0
+    for row in self_contact_states(O, t, rng, 16):
+        tau = gain * rng.uniform(-1, 1, A)
+        s = oracle_state(O, A, row)
+        c, rows = O.step_physics(m, p, s, tau)
+        out, erows, enc = E.step_physics(ep, row.astype(np.float32), tau)
+        assert enc == c.n
+        assert abs(rows - erows) <= 2
+        worst = max(worst, state_error(out, O.state_vector(s, A)))
+        out2, _, _ = E.step_physics(off, row.astype(np.float32), tau)
+        worst_off = max(worst_off, state_error(out2, O.state_vector(s, A)))
+    assert worst < 2e-3, worst
+    assert worst_off > 0.1, worst_off
 
 
 def _mt_row(O, seed):

@@ -113,6 +113,7 @@ def test_free_flight_conservation(walker_table, oracle_mod):
         p.gravity = 0.0
         p.lin_damping = p.ang_damping = 0.0
         p.has_ground = 0
+        p.self_collision = 0  # random joint angles beyond the limits interpenetrate the limbs
         p.dt = 1.0 / 240.0 / sub
         p.substeps = sub
         for d in range(n):  # take joint limits out of play
@@ -144,3 +145,48 @@ def test_free_fall_analytic(walker_table, oracle_mod):
     e = O.energy_momentum(m, s, p.gravity)
     vz = e["P"][2] / t["total_mass"]
     assert abs(vz - (-p.gravity * 4 * p.dt)) < 1e-9
+
+
+def test_self_contact_is_an_internal_force(walker_table, oracle_mod):
+    """Self-collision rows apply equal and opposite impulses to two links of the same multibody:
+    without gravity, damping and ground the total linear momentum must not change, and the angular momentum only by
+    the friction couple over the contact gap (the penetration depth)."""
+    from tests.helpers import oracle_state, self_contact_states
+
+    O, t = oracle_mod, walker_table
+    n = t["n_dof"]
+    m = O.model_from_table(t)
+    rng = np.random.RandomState(11)
+    changed = 0
+    for row in self_contact_states(O, t, rng, 6):
+        p = O.default_params()
+        p.gravity = 0.0
+        p.lin_damping = p.ang_damping = 0.0
+        p.has_ground = 0
+        p.substeps = 1
+        p.max_coord_vel = 1e9  # the +-100 clamp of btMultiBody is not momentum-conserving
+        for d in range(n):
+            m.lower[d], m.upper[d] = 1.0, -1.0
+        s = oracle_state(O, n, row)
+        e0 = O.energy_momentum(m, s, 0.0)
+        c, rows = O.step_physics(m, p, s, np.zeros(n))
+        assert rows >= 3 and any(c.partner[k] >= 1000 for k in range(c.n))
+        p.self_collision = 0
+        s2 = oracle_state(O, n, row)
+        O.step_physics(m, p, s2, np.zeros(n))
+        # the contact changes the motion ...
+        v1, v2 = O.state_vector(s, n), O.state_vector(s2, n)
+        changed += np.abs(v1 - v2).max() > 1e-4  # (a separating speculative contact applies no impulse)
+        # ... but not the momentum.  Evaluated at the start-of-step configuration with the two end-of-step
+        # velocities (the position update that follows has its own O(dt |u|^2) drift, different for the two runs).
+        mom = []
+        for v in (v1, v2):
+            mixed = row.copy()
+            mixed[7:13] = v[7:13]
+            mixed[13 + n:] = v[13 + n:]
+            mom.append(O.energy_momentum(m, oracle_state(O, n, mixed), 0.0))
+        scale = np.abs(e0["P"]).max() + 1.0
+        assert np.abs(mom[0]["P"] - mom[1]["P"]).max() / scale < 1e-9
+        # the friction impulses act at the two surface points, |penetration| apart: a small couple remains
+        assert np.abs(mom[0]["L"] - mom[1]["L"]).max() / (np.abs(e0["L"]).max() + 1.0) < 5e-2
+    assert changed >= 3
