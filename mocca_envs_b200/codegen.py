@@ -127,7 +127,9 @@ def reduce_table(t: dict) -> dict:
         pa, pb = pts_of_geom[ga], pts_of_geom[gb]
         A, B = points[pa[0]], points[pb[0]]
         feet = sum(1 << f for f in range(2) for x in (A, B) if x["foot"] == f)
-        spairs.append(dict(pack=pa[0] | (pa[-1] << 8) | (pb[0] << 16) | (pb[-1] << 24), thresh=min(A["thresh"], B["thresh"]),
+        half = lambda ids: 0.5 * float(np.linalg.norm(np.asarray(points[ids[0]]["pos"]) - np.asarray(points[ids[-1]]["pos"])))
+        reach = half(pa) + half(pb) + A["radius"] + B["radius"] + min(A["thresh"], B["thresh"])
+        spairs.append(dict(reach=reach * (1 + 1e-5) + 1e-6, pack=pa[0] | (pa[-1] << 8) | (pb[0] << 16) | (pb[-1] << 24), thresh=min(A["thresh"], B["thresh"]),
                            mu=A["friction"] * B["friction"], own_a=A["owner"], own_b=B["owner"], feet=feet))
         assert A["owner"] != B["owner"]
     # ancestor chains (root -> self) packed 5 bits per entry, and the compact (chain-ordered) factor layout:
@@ -300,6 +302,7 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append(_iarr(P + "_sp_own", [(x["own_a"] + 1) | ((x["own_b"] + 1) << 8) | (x["feet"] << 16) for x in sp] or [0]))
     out.append(_farr(P + "_sp_thresh", [x["thresh"] for x in sp] or [0]))
     out.append(_farr(P + "_sp_mu", [x["mu"] for x in sp] or [0]))
+    out.append(_farr(P + "_sp_reach", [x["reach"] for x in sp] or [0]))
     ex = r["extras"]
     out.append(_iarr(P + "_ordered", ex.get("ordered", [])))
     out.append(_iarr(P + "_pd_dof", ex.get("pd_dof", [])))
@@ -354,7 +357,7 @@ def emit_header(t: dict, prefix: str) -> str:
         out.append("  MB_HD static %s %s(int i) { return %s_%s[i]; }\n" % (ctype, fld, P, fld))
     out.append("  MB_HD static double base_angles(int i) { return %s_base_angles[i]; }\n" % P)
     for fld in ["lower", "upper", "weight", "gain", "damping", "armature", "bmass", "pradius", "pfriction", "pthresh",
-                "jsgn", "xfriction", "xthresh", "lc_maximp", "pd_kp", "pd_kd", "sp_thresh", "sp_mu"]:
+                "jsgn", "xfriction", "xthresh", "lc_maximp", "pd_kp", "pd_kd", "sp_thresh", "sp_mu", "sp_reach"]:
         out.append("  MB_HD static float %s(int i) { return %s_%s[i]; }\n" % (fld, P, fld))
     for fld in ["joff", "jrot", "jaxis", "bcom", "binertia", "ppos", "xpos", "xrot", "xhalf", "lc_pos"]:
         out.append("  MB_HD static float %s(int i, int k) { return %s_%s[i][k]; }\n" % (fld, P, fld))

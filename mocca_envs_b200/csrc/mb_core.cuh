@@ -89,6 +89,19 @@ inline void mb_sincos(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x);
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #endif
 
+#define MB_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#if defined(MB_COLD_INLINE) && MB_COLD_INLINE
+#define MB_COLD MB_HD
+#else
+#define MB_COLD MB_NOINLINE
+#endif
+#ifdef __CUDACC__
+#define MB_ASSUME_SHARED(S) __builtin_assume(__isShared(&(S)))  /* out-of-line helpers keep LDS/STS addressing */
+#define MB_FDIV(a, b) __fdividef((a), (b))
+#else
+#define MB_ASSUME_SHARED(S)
+#define MB_FDIV(a, b) ((a) / (b))
+#endif
 #define MB_MAXC 16    /* contact points kept per substep */
 #define MB_MAXROW 48  /* constraint rows per substep (limits + 3 per contact) */
 #define MB_YSTRIDE 15 /* compact row: 6 base + <= 8 chain entries (+1 pad, odd stride = conflict-free) */
@@ -269,7 +282,11 @@ template <class M> MB_HD float mb_Lget(const float* L, int i, int j) {
 // ------------------------------------------------------------------------------------------------ simulator
 template <class M> struct Sim {
   typedef WarpMem<M> Mem;
-  enum { NJ = M::NJ, NB = M::NB, NU = M::NU, NPT = M::NPT };
+#if defined(MB_DISABLE_SELF) && MB_DISABLE_SELF
+  enum { NJ = M::NJ, NB = M::NB, NU = M::NU, NPT = M::NPT, NSELF = 0 };  // ablation build (tools/abbench.sh)
+#else
+  enum { NJ = M::NJ, NB = M::NB, NU = M::NU, NPT = M::NPT, NSELF = M::NSELF };
+#endif
 
   // ---- lane constants: computed once per kernel, live in registers -------------------------------------------
   struct LaneConst {
@@ -692,70 +709,105 @@ template <class M> struct Sim {
     float s2 = 0.0f, t = 0.0f;
     if (a <= EPS && e <= EPS) {
     } else if (a <= EPS) {
-      t = fminf(fmaxf(f / e, 0.0f), 1.0f);
+      t = fminf(fmaxf(MB_FDIV(f, e), 0.0f), 1.0f);
     } else if (e <= EPS) {
-      s2 = fminf(fmaxf(-c / a, 0.0f), 1.0f);
+      s2 = fminf(fmaxf(MB_FDIV(-c, a), 0.0f), 1.0f);
     } else {
       const float b = mb_dot3(d1, d2), den = a * e - b * b;
-      s2 = den > EPS ? fminf(fmaxf((b * f - c * e) / den, 0.0f), 1.0f) : 0.0f;
-      t = (b * s2 + f) / e;
-      if (t < 0.0f) { t = 0.0f; s2 = fminf(fmaxf(-c / a, 0.0f), 1.0f); }
-      else if (t > 1.0f) { t = 1.0f; s2 = fminf(fmaxf((b - c) / a, 0.0f), 1.0f); }
+      s2 = den > EPS ? fminf(fmaxf(MB_FDIV(b * f - c * e, den), 0.0f), 1.0f) : 0.0f;
+      t = MB_FDIV(b * s2 + f, e);
+      if (t < 0.0f) { t = 0.0f; s2 = fminf(fmaxf(MB_FDIV(-c, a), 0.0f), 1.0f); }
+      else if (t > 1.0f) { t = 1.0f; s2 = fminf(fmaxf(MB_FDIV(b - c, a), 0.0f), 1.0f); }
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) { c1[k] = p1[k] + d1[k] * s2; c2[k] = p2[k] + d2[k] * t; }
   }
 
+  // narrow phase over the (<= 32) candidate pairs listed in S.r_dof; appends at contact slot `at`
+  MB_HD static int collide_self_narrow(Mem& S, int cnt, int at, float erp) {
+    LaneVar<int> hit, pair;
+    LaneVar<float> px, py, pz, nx, ny, nz, dd;
+    MB_LANES(l)
+      hit[l] = 0;
+      if (l < cnt) {
+        const int k = S.r_dof[l];
+        pair[l] = k;
+        const unsigned pk = M::sp_pack(k);
+        const int a0 = pk & 255u, a1 = (pk >> 8) & 255u, b0 = (pk >> 16) & 255u, b1 = pk >> 24;
+        float c1[3], c2[3];
+        seg_seg(S.w.k.u2.pt[a0], S.w.k.u2.pt[a1], S.w.k.u2.pt[b0], S.w.k.u2.pt[b1], c1, c2);
+        const float d[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
+        const float len = sqrtf(mb_dot3(d, d)), ra = M::pradius(a0), rb = M::pradius(b0);
+        const float dist = len - ra - rb;
+        if (dist < M::sp_thresh(k) && len >= 1e-9f) {
+          const float il = 1.0f / len;
+          hit[l] = 1;
+          nx[l] = d[0] * il; ny[l] = d[1] * il; nz[l] = d[2] * il;
+          px[l] = c1[0] - ra * nx[l]; py[l] = c1[1] - ra * ny[l]; pz[l] = c1[2] - ra * nz[l];
+          dd[l] = dist;
+        }
+      }
+    MB_END
+    const unsigned mask = warp_ballot(hit);
+    if (mask == 0u) return 0;
+    MB_LANES(l)
+      if (hit[l]) {
+        const int pr = pair[l];
+        const int k = at + mb_popc(mask & ((1u << l) - 1u));
+        if (k < MB_MAXC) {
+          S.cP[k][0] = px[l]; S.cP[k][1] = py[l]; S.cP[k][2] = pz[l];
+          S.cn[k][0] = nx[l]; S.cn[k][1] = ny[l]; S.cn[k][2] = nz[l];
+          S.cdist[k] = dd[l];
+          S.cmu[k] = M::sp_mu(pr);
+          S.cerp[k] = erp;
+          S.ccfm[k] = 0.0f;
+          S.clink[k] = (M::sp_own(pr) & 255) - 1;
+          S.cfoot[k] = -1;
+          S.cpartner[k] = 1000 + pr;
+        }
+      }
+    MB_END
+    return mb_popc(mask);
+  }
+
   // self-collision (robots.py:259-264): one point per candidate geom pair, listed after the contacts with the
-  // static world.  cP = point on link A, cn = normal on B towards A; the point on B is cP - cdist * cn.
-  // cpartner = 1000 + pair index.  Returns the number of self-contacts appended at slot nc.
+  // static world in pair order.  cP = point on link A, cn = normal on B towards A; the point on B is cP - cdist cn;
+  // cpartner = 1000 + pair index.  Broad phase: bounding spheres of the two core segments (+ radii + breaking
+  // threshold, tabulated as sp_reach); the survivors are compacted into S.r_dof (free until find_limits) so that
+  // the closest-point routine usually runs once per substep instead of NSELF / 32 times.
   MB_HD static int collide_self(Mem& S, const MbPhysics& P, int nc) {
-    int ns = 0;
+    int ns = 0, cnt = 0;
 #pragma unroll 1
-    for (int pass = 0; pass * 32 < M::NSELF; ++pass) {
-      LaneVar<int> hit;
-      LaneVar<float> px, py, pz, nx, ny, nz, dd;
+    for (int pass = 0; pass * 32 < NSELF; ++pass) {
+      LaneVar<int> near;
       MB_LANES(l)
         const int k = pass * 32 + l;
-        hit[l] = 0;
-        if (k < M::NSELF) {
+        near[l] = 0;
+        if (k < NSELF) {
           const unsigned pk = M::sp_pack(k);
-          const int a0 = pk & 255u, a1 = (pk >> 8) & 255u, b0 = (pk >> 16) & 255u, b1 = pk >> 24;
-          float c1[3], c2[3];
-          seg_seg(S.w.k.u2.pt[a0], S.w.k.u2.pt[a1], S.w.k.u2.pt[b0], S.w.k.u2.pt[b1], c1, c2);
-          const float d[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
-          const float len = sqrtf(mb_dot3(d, d)), ra = M::pradius(a0), rb = M::pradius(b0);
-          const float dist = len - ra - rb;
-          if (dist < M::sp_thresh(k) && len >= 1e-9f) {
-            const float il = 1.0f / len;
-            hit[l] = 1;
-            nx[l] = d[0] * il; ny[l] = d[1] * il; nz[l] = d[2] * il;
-            px[l] = c1[0] - ra * nx[l]; py[l] = c1[1] - ra * ny[l]; pz[l] = c1[2] - ra * nz[l];
-            dd[l] = dist;
-          }
+          const float* a0 = S.w.k.u2.pt[pk & 255u];
+          const float* a1 = S.w.k.u2.pt[(pk >> 8) & 255u];
+          const float* b0 = S.w.k.u2.pt[(pk >> 16) & 255u];
+          const float* b1 = S.w.k.u2.pt[pk >> 24];
+          const float dx = (a0[0] + a1[0]) - (b0[0] + b1[0]), dy = (a0[1] + a1[1]) - (b0[1] + b1[1]);
+          const float dz = (a0[2] + a1[2]) - (b0[2] + b1[2]);  // twice the centre distance
+          const float reach = M::sp_reach(k);
+          near[l] = dx * dx + dy * dy + dz * dz < 4.0f * reach * reach;
         }
-      MB_END
-      const unsigned mask = warp_ballot(hit);
+      MB_END_REG
+      const unsigned mask = warp_ballot(near);
       if (mask == 0u) continue;
+      const int add = mb_popc(mask);
+      if (cnt + add > 32) {  // flush (rare): keeps pair order
+        ns += collide_self_narrow(S, cnt, nc + ns, P.erp_contact);
+        cnt = 0;
+      }
       MB_LANES(l)
-        if (hit[l]) {
-          const int pr = pass * 32 + l;
-          const int k = nc + ns + mb_popc(mask & ((1u << l) - 1u));
-          if (k < MB_MAXC) {
-            S.cP[k][0] = px[l]; S.cP[k][1] = py[l]; S.cP[k][2] = pz[l];
-            S.cn[k][0] = nx[l]; S.cn[k][1] = ny[l]; S.cn[k][2] = nz[l];
-            S.cdist[k] = dd[l];
-            S.cmu[k] = M::sp_mu(pr);
-            S.cerp[k] = P.erp_contact;
-            S.ccfm[k] = 0.0f;
-            S.clink[k] = (M::sp_own(pr) & 255) - 1;
-            S.cfoot[k] = -1;
-            S.cpartner[k] = 1000 + pr;
-          }
-        }
+        if (near[l]) S.r_dof[cnt + mb_popc(mask & ((1u << l) - 1u))] = pass * 32 + l;
       MB_END
-      ns += mb_popc(mask);
+      cnt += add;
     }
+    if (cnt > 0) ns += collide_self_narrow(S, cnt, nc + ns, P.erp_contact);
     return ns;
   }
 
@@ -947,7 +999,7 @@ template <class M> struct Sim {
     }
     if (nc > MB_MAXC) { *overflow += 1; nc = MB_MAXC; }
     int ns = 0;
-    if (M::NSELF > 0 && STORE && P.self_collision) {
+    if (NSELF > 0 && STORE && P.self_collision) {
       ns = collide_self(S, P, nc);
       if (nc + ns > MB_MAXC) { *overflow += 1; ns = MB_MAXC - nc; }
     }
@@ -1000,13 +1052,112 @@ template <class M> struct Sim {
   // as TWO compact rows (the part on link A and the part on link B -- their union is a tree, not a chain) that share
   // one multiplier; then contact normals and friction pairs.
   enum { NLC = 6 * M::NLOOP };
-  // Self-contacts (ncs of them, contact slots [nc, nc + ncs)) couple two links, so like a loop row each of their
-  // three rows is stored as two compact rows sharing one multiplier: normals at S0 + 2s + side, friction at
-  // S0 + 2 ncs + 4s + 2 dir + side, with S0 = n0 + 3 nc.
-  MB_HD static void setup_rows(Mem& S, const MbPhysics& P, int nlim, int nc, int ncs) {
+  // ---- G2. self-contact rows (cold path: ~0.3 self-contacts per env step under random actions) --------------------
+  // A self-contact couples two links, so like a loop row each of its three rows is stored as two compact rows
+  // sharing one multiplier: normals at S0 + 2s + side, friction at S0 + 2 ncs + 4s + 2 dir + side (S0 = first row
+  // after the static-world contacts, s = self-contact index, contact slot nc + s).  Kept out of line so that the
+  // common path's code footprint stays what it was.
+  MB_HD static void setup_self_rows(Mem& S, int S0, int nc, int ncs, float slop, float inv_dt) {
+    const int R = 6 * ncs;
+#pragma unroll 1
+    for (int base = 0; base < R; base += 32) {
+      MB_LANES(l)
+        const int i = base + l;
+        if (i < R) {
+          float b[M::MAXSUP];
+          float W[6];
+          int k, fr = -1;
+          bool sideB;
+          if (i < 2 * ncs) { k = nc + (i >> 1); sideB = (i & 1) != 0; }
+          else { const int i2 = i - 2 * ncs; k = nc + (i2 >> 2); fr = (i2 >> 1) & 1; sideB = (i2 & 1) != 0; }
+          float dirv[3];
+          if (fr < 0) {
+            dirv[0] = S.cn[k][0]; dirv[1] = S.cn[k][1]; dirv[2] = S.cn[k][2];
+          } else {
+            float t1[3], t2[3];
+            mb_plane_space(S.cn[k], t1, t2);
+            dirv[0] = fr ? t2[0] : t1[0]; dirv[1] = fr ? t2[1] : t1[1]; dirv[2] = fr ? t2[2] : t1[2];
+          }
+          int cj = S.clink[k];
+          float pc[3] = {S.cP[k][0], S.cP[k][1], S.cP[k][2]};
+          if (sideB) {
+            // setupMultiBodyContactConstraint: jacobian B is built with -direction at the point on B = pA - dist n
+            const float dk = S.cdist[k];
+            pc[0] -= dk * S.cn[k][0]; pc[1] -= dk * S.cn[k][1]; pc[2] -= dk * S.cn[k][2];
+            dirv[0] = -dirv[0]; dirv[1] = -dirv[1]; dirv[2] = -dirv[2];
+            cj = ((M::sp_own(S.cpartner[k] - 1000) >> 8) & 255) - 1;
+          }
+          mb_cross(pc, dirv, W);
+          W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
+          const unsigned long long pack = cj >= 0 ? M::chainpack(cj) : 0ull;
+          const int depth = cj >= 0 ? M::jdepth(cj) : -1;
+          const int n = 7 + depth;
+          float rel_vel = 0.0f;
+#pragma unroll
+          for (int t = 0; t < 6; ++t) { b[t] = W[t]; rel_vel += W[t] * S.u[t]; }
+#pragma unroll
+          for (int t = 0; t < M::MAXSUP - 6; ++t) {
+            float v = 0.0f;
+            if (t <= depth) {
+              const int a = chain_at(pack, t);
+              const float* sj = S.js[a];
+              v = sj[0] * W[0] + sj[1] * W[1] + sj[2] * W[2] + sj[3] * W[3] + sj[4] * W[4] + sj[5] * W[5];
+              rel_vel += v * S.u[6 + a];
+            }
+            b[6 + t] = v;
+          }
+#pragma unroll
+          for (int t = M::MAXSUP - 1; t >= 0; --t) {
+            if (t < n) {
+              const int it = t < 6 ? t : 6 + chain_at(pack, t - 6);
+              const float ci = b[t] * S.Ldi2[it];
+              b[t] *= S.Ldinv[it];
+              const float* Li = &S.L[M::rowoff(it)];
+#pragma unroll
+              for (int s2 = 0; s2 < t; ++s2) b[s2] -= Li[s2] * ci;
+            }
+          }
+          float dd = 0.0f;
+#pragma unroll
+          for (int t = 0; t < M::MAXSUP; ++t) dd += b[t] * b[t];
+          const int r = S0 + i;
+          float* Yr = S.w.Yc[r];
+#pragma unroll
+          for (int t = 0; t < M::MAXSUP; ++t)
+            if (t < n) Yr[t] = b[t];
+          S.rc.r.r_mask[r] = 0x3Fu | (cj >= 0 ? (M::janc(cj) << 6) : 0u);
+          MbRowPar par;  // partial sums, combined below
+          par.rhs = rel_vel; par.cfm = 0.0f; par.jinv = dd; par.den = 0.0f;
+          S.rc.r.r_par[r] = par;
+          S.rc.r.r_app[r] = 0.0f;
+          S.rc.r.r_mu[r] = S.cmu[k];
+        }
+      MB_END
+    }
+    // fillMultiBodyConstraint: denominator = JA M^-1 JA^T + JB M^-1 JB^T (no coupling term, as for loop closures)
+    MB_LANES(l)
+      for (int i = l; i < 3 * ncs; i += 32) {
+        const int sidx = i / 3, w = i - 3 * sidx;  // w: 0 normal, 1 / 2 friction directions
+        const int ra = S0 + (w == 0 ? 2 * sidx : 2 * ncs + 4 * sidx + 2 * (w - 1));
+        const float dd = S.rc.r.r_par[ra].jinv + S.rc.r.r_par[ra + 1].jinv;
+        const float jinv = dd > 1.1920929e-07f ? 1.0f / dd : 0.0f;
+        const float rel_vel = S.rc.r.r_par[ra].rhs + S.rc.r.r_par[ra + 1].rhs;
+        float positional = 0.0f, verr = -rel_vel;
+        if (w == 0) {
+          const float dist = S.cdist[nc + sidx] + slop;
+          if (dist > 0.0f) verr -= dist * inv_dt;
+          else positional = -dist * S.cerp[nc + sidx] * inv_dt;
+        }
+        MbRowPar par;
+        par.rhs = (positional + verr) * jinv; par.cfm = 0.0f; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
+        S.rc.r.r_par[ra] = par;
+      }
+    MB_END
+  }
+
+  MB_HD static void setup_rows(Mem& S, const MbPhysics& P, int nlim, int nc) {
     const int n0 = nlim + NLC;
-    const int S0 = n0 + 3 * nc;
-    const int R = S0 + 6 * ncs;
+    const int R = n0 + 3 * nc;
     const float inv_dt = 1.0f / P.dt;
 #pragma unroll 1
     for (int base = 0; base < R; base += 32) {
@@ -1039,38 +1190,21 @@ template <class M> struct Sim {
           } else {
             int k;
             float dirv[3];
-            int fr = -1;     // friction direction (0 / 1), -1 = normal
-            bool sideB = false;
             if (r < n0 + nc) {
               kind = 1; k = r - n0;
-              cfm = S.ccfm[k] * inv_dt; erp = S.cerp[k]; dist = S.cdist[k] + P.linear_slop;
-            } else if (r < S0) {
-              kind = 2; k = (r - n0 - nc) >> 1; fr = (r - n0 - nc) & 1;
-            } else if (r < S0 + 2 * ncs) {
-              kind = 4; k = nc + ((r - S0) >> 1); sideB = ((r - S0) & 1) != 0;
-            } else {
-              const int i = r - S0 - 2 * ncs;
-              kind = 4; k = nc + (i >> 2); fr = (i >> 1) & 1; sideB = (i & 1) != 0;
-            }
-            if (fr < 0) {
               dirv[0] = S.cn[k][0]; dirv[1] = S.cn[k][1]; dirv[2] = S.cn[k][2];
+              cfm = S.ccfm[k] * inv_dt; erp = S.cerp[k]; dist = S.cdist[k] + P.linear_slop;
             } else {
+              kind = 2; k = (r - n0 - nc) >> 1;
               float t1[3], t2[3];
               mb_plane_space(S.cn[k], t1, t2);
-              dirv[0] = fr ? t2[0] : t1[0]; dirv[1] = fr ? t2[1] : t1[1]; dirv[2] = fr ? t2[2] : t1[2];
+              const bool second = ((r - n0 - nc) & 1) != 0;
+              dirv[0] = second ? t2[0] : t1[0]; dirv[1] = second ? t2[1] : t1[1]; dirv[2] = second ? t2[2] : t1[2];
             }
             mu = S.cmu[k];
-            cj = S.clink[k];
-            float pc[3] = {S.cP[k][0], S.cP[k][1], S.cP[k][2]};
-            if (M::NSELF > 0 && sideB) {
-              // setupMultiBodyContactConstraint: jacobian B is built with -direction at the point on B
-              const float dk = S.cdist[k];
-              pc[0] -= dk * S.cn[k][0]; pc[1] -= dk * S.cn[k][1]; pc[2] -= dk * S.cn[k][2];
-              dirv[0] = -dirv[0]; dirv[1] = -dirv[1]; dirv[2] = -dirv[2];
-              cj = ((M::sp_own(S.cpartner[k] - 1000) >> 8) & 255) - 1;
-            }
-            mb_cross(pc, dirv, W);
+            mb_cross(S.cP[k], dirv, W);
             W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
+            cj = S.clink[k];
           }
           const unsigned long long pack = cj >= 0 ? M::chainpack(cj) : 0ull;
           const int depth = cj >= 0 ? M::jdepth(cj) : -1;
@@ -1124,7 +1258,7 @@ template <class M> struct Sim {
             if (t < n) Yr[t] = b[t];
           S.rc.r.r_mask[r] = 0x3Fu | (cj >= 0 ? (M::janc(cj) << 6) : 0u);
           MbRowPar par;
-          if (kind >= 3) {  // partial sums; the two parts of a loop / self-contact row are combined below
+          if (kind == 3) {  // partial sums; the two parts of a loop row are combined below
             par.rhs = rel_vel; par.jinv = dd; par.den = 0.0f;
           } else {
             par.rhs = (positional + verr) * jinv; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
@@ -1151,27 +1285,6 @@ template <class M> struct Sim {
           par.rhs = (positional - rel_vel) * jinv; par.cfm = 0.0f; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
           S.rc.r.r_par[ra] = par;
           S.rc.r.r_mu[ra] = M::lc_maximp(c);
-        }
-      MB_END
-    }
-    if (M::NSELF > 0 && ncs > 0) {
-      // same denominator rule for a contact between two links of the multibody
-      MB_LANES(l)
-        for (int i = l; i < 3 * ncs; i += 32) {
-          const int sidx = i / 3, w = i - 3 * sidx;  // w: 0 normal, 1 / 2 friction directions
-          const int ra = w == 0 ? S0 + 2 * sidx : S0 + 2 * ncs + 4 * sidx + 2 * (w - 1);
-          const float dd = S.rc.r.r_par[ra].jinv + S.rc.r.r_par[ra + 1].jinv;
-          const float jinv = dd > 1.1920929e-07f ? 1.0f / dd : 0.0f;
-          const float rel_vel = S.rc.r.r_par[ra].rhs + S.rc.r.r_par[ra + 1].rhs;
-          float positional = 0.0f, verr = -rel_vel;
-          if (w == 0) {
-            const float dist = S.cdist[nc + sidx] + P.linear_slop;
-            if (dist > 0.0f) verr -= dist * inv_dt;
-            else positional = -dist * S.cerp[nc + sidx] * inv_dt;
-          }
-          MbRowPar par;
-          par.rhs = (positional + verr) * jinv; par.cfm = 0.0f; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
-          S.rc.r.r_par[ra] = par;
         }
       MB_END
     }
@@ -1237,13 +1350,13 @@ template <class M> struct Sim {
   }
 
   // loop-closure row: two compact rows (ra on link A, ra + 1 on link B) sharing one multiplier
-  MB_HD static float pgs_dual(Mem& S, const LaneConst& C, int ra, float lo, float hi, LaneVar<float>& z) {
+  MB_HD static float pgs_dual(Mem& S, const LaneVar<int>& tl, int ra, float lo, float hi, LaneVar<float>& z) {
     const int rb = ra + 1;
     const unsigned supA = S.rc.r.r_mask[ra], supB = S.rc.r.r_mask[rb];
     LaneVar<float> y, t;
     MB_LANES(l)
-      const float ya = ((supA >> l) & 1u) ? S.w.Yc[ra][C.tl[l]] : 0.0f;
-      const float yb = ((supB >> l) & 1u) ? S.w.Yc[rb][C.tl[l]] : 0.0f;
+      const float ya = ((supA >> l) & 1u) ? S.w.Yc[ra][tl[l]] : 0.0f;
+      const float yb = ((supB >> l) & 1u) ? S.w.Yc[rb][tl[l]] : 0.0f;
       y[l] = ya + yb;
       t[l] = y[l] * z[l];
     MB_END_REG
@@ -1262,13 +1375,13 @@ template <class M> struct Sim {
     return d * pA.den;
   }
   // friction pair of a self-contact: rows ra, ra + 1 = first direction on link A / B, ra + 2, ra + 3 = second
-  MB_HD static float pgs_pair_dual(Mem& S, const LaneConst& C, int ra, float cone, LaneVar<float>& z) {
+  MB_HD static float pgs_pair_dual(Mem& S, const LaneVar<int>& tl, int ra, float cone, LaneVar<float>& z) {
     const unsigned supA = S.rc.r.r_mask[ra], supB = S.rc.r.r_mask[ra + 1];
     LaneVar<float> ya, yb, ta, tb;
     MB_LANES(l)
       const bool inA = ((supA >> l) & 1u) != 0u, inB = ((supB >> l) & 1u) != 0u;
-      ya[l] = (inA ? S.w.Yc[ra][C.tl[l]] : 0.0f) + (inB ? S.w.Yc[ra + 1][C.tl[l]] : 0.0f);
-      yb[l] = (inA ? S.w.Yc[ra + 2][C.tl[l]] : 0.0f) + (inB ? S.w.Yc[ra + 3][C.tl[l]] : 0.0f);
+      ya[l] = (inA ? S.w.Yc[ra][tl[l]] : 0.0f) + (inB ? S.w.Yc[ra + 1][tl[l]] : 0.0f);
+      yb[l] = (inA ? S.w.Yc[ra + 2][tl[l]] : 0.0f) + (inB ? S.w.Yc[ra + 3][tl[l]] : 0.0f);
       ta[l] = ya[l] * z[l];
       tb[l] = yb[l] * z[l];
     MB_END_REG
@@ -1297,6 +1410,7 @@ template <class M> struct Sim {
 
   // btMultiBodyConstraintSolver::solveSingleIteration order: non-contact rows (limits, then loop closures;
   // alternating direction), normals, friction
+  template <bool SELF>
   MB_HD static void solve_constraints(Mem& S, const MbPhysics& P, const LaneConst& C, int nlim, int nc, int ncs,
                                       LaneVar<float>& z) {
     const int nnc = nlim + NLC / 2, n0 = nlim + NLC, S0 = n0 + 3 * nc;
@@ -1311,7 +1425,7 @@ template <class M> struct Sim {
         else {
           const int ra = nlim + 2 * (idx - nlim);
           const float lim = S.rc.r.r_mu[ra];
-          rr = pgs_dual(S, C, ra, -lim, lim, z);
+          rr = pgs_dual(S, C.tl, ra, -lim, lim, z);
         }
         res2 = fmaxf(res2, rr * rr);
       }
@@ -1320,10 +1434,10 @@ template <class M> struct Sim {
         const float rr = pgs_single(S, C, n0 + k, 0.0f, 1e10f, z);
         res2 = fmaxf(res2, rr * rr);
       }
-      if (M::NSELF > 0) {
+      if (SELF) {
 #pragma unroll 1
         for (int k = 0; k < ncs; ++k) {
-          const float rr = pgs_dual(S, C, S0 + 2 * k, 0.0f, 1e10f, z);
+          const float rr = pgs_dual(S, C.tl, S0 + 2 * k, 0.0f, 1e10f, z);
           res2 = fmaxf(res2, rr * rr);
         }
       }
@@ -1333,16 +1447,42 @@ template <class M> struct Sim {
         const float rr = pgs_pair(S, C, ra, S.rc.r.r_mu[ra] * S.rc.r.r_app[n0 + k], z);
         res2 = fmaxf(res2, rr * rr);
       }
-      if (M::NSELF > 0) {
+      if (SELF) {
 #pragma unroll 1
         for (int k = 0; k < ncs; ++k) {
           const int ra = S0 + 2 * ncs + 4 * k;
-          const float rr = pgs_pair_dual(S, C, ra, S.rc.r.r_mu[ra] * S.rc.r.r_app[S0 + 2 * k], z);
+          const float rr = pgs_pair_dual(S, C.tl, ra, S.rc.r.r_mu[ra] * S.rc.r.r_app[S0 + 2 * k], z);
           res2 = fmaxf(res2, rr * rr);
         }
       }
       if (res2 <= P.residual_threshold) break;
     }
+  }
+
+  // ---- H2. rows + PGS of a substep that has self-contacts, out of line ------------------------------------------
+  // About a quarter of the env steps under random actions see a self-contact.  Their whole constraint phase runs in
+  // this separate copy, so the common path keeps the code footprint (instruction cache) and the register budget it
+  // has without the feature; nothing but the few scalars below is live across the call -- the caller re-derives
+  // its lane constants afterwards instead of saving them.
+  struct SolverPar { float dt, slop, erp_joint, split_threshold, limit_max_impulse, residual_threshold; int iterations; };
+  MB_NOINLINE static LaneVar<float> constrain_self(Mem& S, SolverPar sp, int nlim, int nc, int ncs) {
+    MB_ASSUME_SHARED(S);
+    MbPhysics P;
+    P.dt = sp.dt; P.linear_slop = sp.slop; P.erp_joint = sp.erp_joint; P.split_threshold = sp.split_threshold;
+    P.limit_max_impulse = sp.limit_max_impulse; P.residual_threshold = sp.residual_threshold;
+    P.iterations = sp.iterations;
+    LaneConst C;
+    MB_LANES(l)
+      C.tl[l] = l < NU ? M::rowlen(l) - 1 : 0;
+    MB_END_REG
+    setup_rows(S, P, nlim, nc);
+    setup_self_rows(S, nlim + NLC + 3 * nc, nc, ncs, sp.slop, 1.0f / sp.dt);
+    LaneVar<float> z;
+    MB_LANES(l)
+      z[l] = 0.0f;
+    MB_END
+    solve_constraints<true>(S, P, C, nlim, nc, ncs, z);
+    return z;
   }
 
   // ---- I. integrate positions (btMultiBody::stepPositionsMultiDof) --------------------------------------------
@@ -1374,7 +1514,7 @@ template <class M> struct Sim {
 
   // ---- one Bullet substep.  Returns the number of constraint rows; contact list of this substep stays in S ----
   template <int OBST>
-  MB_HD static int substep(Mem& S, const MbPhysics& P, const LaneConst& C, int* nc_out, int* overflow) {
+  MB_HD static int substep(Mem& S, const MbPhysics& P, LaneConst& C, int* nc_out, int* overflow) {
     MB_BLOCK_BARRIER();  // keeps the warps of a CTA in the same phase so instruction-cache lines are shared
     kinematics(S, P, C, true);
     int ns_all = 0;
@@ -1404,12 +1544,21 @@ template <class M> struct Sim {
     }
     const int R = nlim + NLC / 2 + 3 * (nc + ncs);  // as Bullet counts them (a loop / self-contact row is one row)
     if (R > 0) {
-      setup_rows(S, P, nlim, nc, ncs);
       LaneVar<float> z;
-      MB_LANES(l)
-        z[l] = 0.0f;
-      MB_END
-      solve_constraints(S, P, C, nlim, nc, ncs, z);
+      if (NSELF > 0 && MB_UNLIKELY(ncs > 0)) {
+        SolverPar sp;
+        sp.dt = P.dt; sp.slop = P.linear_slop; sp.erp_joint = P.erp_joint; sp.split_threshold = P.split_threshold;
+        sp.limit_max_impulse = P.limit_max_impulse; sp.residual_threshold = P.residual_threshold;
+        sp.iterations = P.iterations;
+        z = constrain_self(S, sp, nlim, nc, ncs);
+        init_lane_const(C);  // dead across the call by construction: recomputed, not saved
+      } else {
+        setup_rows(S, P, nlim, nc);
+        MB_LANES(l)
+          z[l] = 0.0f;
+        MB_END
+        solve_constraints<false>(S, P, C, nlim, nc, 0, z);
+      }
       solve_L<false>(S, C, z);
       MB_LANES(l)
         if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + z[l], -P.max_coord_vel), P.max_coord_vel);
