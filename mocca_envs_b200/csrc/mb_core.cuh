@@ -105,6 +105,8 @@ inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #define MB_MAXC 16    /* contact points kept per substep */
 #define MB_MAXROW 48  /* constraint rows per substep (limits + 3 per contact) */
 #define MB_YSTRIDE 15 /* compact row: 6 base + <= 8 chain entries (+1 pad, odd stride = conflict-free) */
+#define MB_ROW_DUAL 0x80000000u /* r_mask flag: the row continues in a second compact row (other link, same multiplier) */
+#define MB_ROW_SUP 0x1FFFFFFFu  /* r_mask bits that are generalised coordinates (NU <= 29) */
 #define MB_MAXBOX 6   /* static box obstacles per env (3 planks x {base, cover}) */
 #define MB_MAXBAR 4   /* static bars per env (Monkey3D rendered_step_count, env_locomotion.py:1149) */
 #define MB_OBST_BOXES 1
@@ -775,7 +777,8 @@ template <class M> struct Sim {
   // cpartner = 1000 + pair index.  Broad phase: bounding spheres of the two core segments (+ radii + breaking
   // threshold, tabulated as sp_reach); the survivors are compacted into S.r_dof (free until find_limits) so that
   // the closest-point routine usually runs once per substep instead of NSELF / 32 times.
-  MB_HD static int collide_self(Mem& S, const MbPhysics& P, int nc) {
+  MB_NOINLINE static int collide_self(Mem& S, float erp_contact, int nc) {
+    MB_ASSUME_SHARED(S);
     int ns = 0, cnt = 0;
 #pragma unroll 1
     for (int pass = 0; pass * 32 < NSELF; ++pass) {
@@ -799,7 +802,7 @@ template <class M> struct Sim {
       if (mask == 0u) continue;
       const int add = mb_popc(mask);
       if (cnt + add > 32) {  // flush (rare): keeps pair order
-        ns += collide_self_narrow(S, cnt, nc + ns, P.erp_contact);
+        ns += collide_self_narrow(S, cnt, nc + ns, erp_contact);
         cnt = 0;
       }
       MB_LANES(l)
@@ -807,7 +810,7 @@ template <class M> struct Sim {
       MB_END
       cnt += add;
     }
-    if (cnt > 0) ns += collide_self_narrow(S, cnt, nc + ns, P.erp_contact);
+    if (cnt > 0) ns += collide_self_narrow(S, cnt, nc + ns, erp_contact);
     return ns;
   }
 
@@ -1000,7 +1003,7 @@ template <class M> struct Sim {
     if (nc > MB_MAXC) { *overflow += 1; nc = MB_MAXC; }
     int ns = 0;
     if (NSELF > 0 && STORE && P.self_collision) {
-      ns = collide_self(S, P, nc);
+      ns = collide_self(S, P.erp_contact, nc);
       if (nc + ns > MB_MAXC) { *overflow += 1; ns = MB_MAXC - nc; }
     }
     *ns_out = ns;
@@ -1054,26 +1057,26 @@ template <class M> struct Sim {
   enum { NLC = 6 * M::NLOOP };
   // ---- G2. self-contact rows (cold path: ~0.3 self-contacts per env step under random actions) --------------------
   // A self-contact couples two links, so like a loop row each of its three rows is stored as two compact rows
-  // sharing one multiplier: normals at S0 + 2s + side, friction at S0 + 2 ncs + 4s + 2 dir + side (S0 = first row
-  // after the static-world contacts, s = self-contact index, contact slot nc + s).  Kept out of line so that the
-  // common path's code footprint stays what it was.
-  MB_HD static void setup_self_rows(Mem& S, int S0, int nc, int ncs, float slop, float inv_dt) {
+  // sharing one multiplier (flag MB_ROW_DUAL on the first): normals at S0 + 2s + {A, B}, friction at
+  // S0 + 2 ncs + 4s + {t1 A, t2 A, t1 B, t2 B} (S0 = first row after the static-world contacts, s = self-contact
+  // index, contact slot nc + s).  Written for SIZE, not speed: the step kernel's hot loop already exceeds the 32 KB
+  // L1.5 instruction cache, so every instruction executed off the common path evicts hot code.  Rolled loops, the
+  // half solve runs in place in the row's own shared-memory slot; out of line, and the caller re-derives its lane
+  // constants afterwards instead of keeping them live across the call.
+  MB_NOINLINE static void setup_self_rows(Mem& S, int S0, int nc, int ncs, float slop, float inv_dt) {
+    MB_ASSUME_SHARED(S);
     const int R = 6 * ncs;
 #pragma unroll 1
     for (int base = 0; base < R; base += 32) {
       MB_LANES(l)
         const int i = base + l;
         if (i < R) {
-          float b[M::MAXSUP];
-          float W[6];
           int k, fr = -1;
           bool sideB;
           if (i < 2 * ncs) { k = nc + (i >> 1); sideB = (i & 1) != 0; }
-          else { const int i2 = i - 2 * ncs; k = nc + (i2 >> 2); fr = (i2 >> 1) & 1; sideB = (i2 & 1) != 0; }
-          float dirv[3];
-          if (fr < 0) {
-            dirv[0] = S.cn[k][0]; dirv[1] = S.cn[k][1]; dirv[2] = S.cn[k][2];
-          } else {
+          else { const int i2 = i - 2 * ncs; k = nc + (i2 >> 2); fr = i2 & 1; sideB = (i2 & 2) != 0; }
+          float dirv[3] = {S.cn[k][0], S.cn[k][1], S.cn[k][2]};
+          if (fr >= 0) {
             float t1[3], t2[3];
             mb_plane_space(S.cn[k], t1, t2);
             dirv[0] = fr ? t2[0] : t1[0]; dirv[1] = fr ? t2[1] : t1[1]; dirv[2] = fr ? t2[2] : t1[2];
@@ -1087,44 +1090,43 @@ template <class M> struct Sim {
             dirv[0] = -dirv[0]; dirv[1] = -dirv[1]; dirv[2] = -dirv[2];
             cj = ((M::sp_own(S.cpartner[k] - 1000) >> 8) & 255) - 1;
           }
+          float W[6];
           mb_cross(pc, dirv, W);
           W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
           const unsigned long long pack = cj >= 0 ? M::chainpack(cj) : 0ull;
           const int depth = cj >= 0 ? M::jdepth(cj) : -1;
           const int n = 7 + depth;
-          float rel_vel = 0.0f;
-#pragma unroll
-          for (int t = 0; t < 6; ++t) { b[t] = W[t]; rel_vel += W[t] * S.u[t]; }
-#pragma unroll
-          for (int t = 0; t < M::MAXSUP - 6; ++t) {
-            float v = 0.0f;
-            if (t <= depth) {
-              const int a = chain_at(pack, t);
-              const float* sj = S.js[a];
-              v = sj[0] * W[0] + sj[1] * W[1] + sj[2] * W[2] + sj[3] * W[3] + sj[4] * W[4] + sj[5] * W[5];
-              rel_vel += v * S.u[6 + a];
-            }
-            b[6 + t] = v;
-          }
-#pragma unroll
-          for (int t = M::MAXSUP - 1; t >= 0; --t) {
-            if (t < n) {
-              const int it = t < 6 ? t : 6 + chain_at(pack, t - 6);
-              const float ci = b[t] * S.Ldi2[it];
-              b[t] *= S.Ldinv[it];
-              const float* Li = &S.L[M::rowoff(it)];
-#pragma unroll
-              for (int s2 = 0; s2 < t; ++s2) b[s2] -= Li[s2] * ci;
-            }
-          }
-          float dd = 0.0f;
-#pragma unroll
-          for (int t = 0; t < M::MAXSUP; ++t) dd += b[t] * b[t];
           const int r = S0 + i;
           float* Yr = S.w.Yc[r];
-#pragma unroll
-          for (int t = 0; t < M::MAXSUP; ++t)
-            if (t < n) Yr[t] = b[t];
+          float rel_vel = 0.0f;
+#pragma unroll 1
+          for (int t = 0; t < n; ++t) {
+            float v, uu;
+            if (t < 6) {  // (a select chain: a dynamic index would push W into local memory)
+              v = t == 0 ? W[0] : (t == 1 ? W[1] : (t == 2 ? W[2] : (t == 3 ? W[3] : (t == 4 ? W[4] : W[5]))));
+              uu = S.u[t];
+            } else {
+              const int a = chain_at(pack, t - 6);
+              const float* sj = S.js[a];
+              v = sj[0] * W[0] + sj[1] * W[1] + sj[2] * W[2] + sj[3] * W[3] + sj[4] * W[4] + sj[5] * W[5];
+              uu = S.u[6 + a];
+            }
+            rel_vel += v * uu;
+            Yr[t] = v;
+          }
+          // half solve L^T y = J^T in place (prefix property of the compact factor)
+#pragma unroll 1
+          for (int t = n - 1; t >= 0; --t) {
+            const int it = t < 6 ? t : 6 + chain_at(pack, t - 6);
+            const float bt = Yr[t], ci = bt * S.Ldi2[it];
+            Yr[t] = bt * S.Ldinv[it];
+            const float* Li = &S.L[M::rowoff(it)];
+#pragma unroll 1
+            for (int s2 = 0; s2 < t; ++s2) Yr[s2] -= Li[s2] * ci;
+          }
+          float dd = 0.0f;
+#pragma unroll 1
+          for (int t = 0; t < n; ++t) dd += Yr[t] * Yr[t];
           S.rc.r.r_mask[r] = 0x3Fu | (cj >= 0 ? (M::janc(cj) << 6) : 0u);
           MbRowPar par;  // partial sums, combined below
           par.rhs = rel_vel; par.cfm = 0.0f; par.jinv = dd; par.den = 0.0f;
@@ -1138,10 +1140,11 @@ template <class M> struct Sim {
     MB_LANES(l)
       for (int i = l; i < 3 * ncs; i += 32) {
         const int sidx = i / 3, w = i - 3 * sidx;  // w: 0 normal, 1 / 2 friction directions
-        const int ra = S0 + (w == 0 ? 2 * sidx : 2 * ncs + 4 * sidx + 2 * (w - 1));
-        const float dd = S.rc.r.r_par[ra].jinv + S.rc.r.r_par[ra + 1].jinv;
+        const int ra = S0 + (w == 0 ? 2 * sidx : 2 * ncs + 4 * sidx + (w - 1));
+        const int rb = ra + (w == 0 ? 1 : 2);
+        const float dd = S.rc.r.r_par[ra].jinv + S.rc.r.r_par[rb].jinv;
         const float jinv = dd > 1.1920929e-07f ? 1.0f / dd : 0.0f;
-        const float rel_vel = S.rc.r.r_par[ra].rhs + S.rc.r.r_par[ra + 1].rhs;
+        const float rel_vel = S.rc.r.r_par[ra].rhs + S.rc.r.r_par[rb].rhs;
         float positional = 0.0f, verr = -rel_vel;
         if (w == 0) {
           const float dist = S.cdist[nc + sidx] + slop;
@@ -1151,6 +1154,7 @@ template <class M> struct Sim {
         MbRowPar par;
         par.rhs = (positional + verr) * jinv; par.cfm = 0.0f; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
         S.rc.r.r_par[ra] = par;
+        if (w < 2) S.rc.r.r_mask[ra] |= MB_ROW_DUAL;  // friction pairs carry the flag on their first row
       }
     MB_END
   }
@@ -1285,6 +1289,7 @@ template <class M> struct Sim {
           par.rhs = (positional - rel_vel) * jinv; par.cfm = 0.0f; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
           S.rc.r.r_par[ra] = par;
           S.rc.r.r_mu[ra] = M::lc_maximp(c);
+          S.rc.r.r_mask[ra] |= MB_ROW_DUAL;
         }
       MB_END
     }
@@ -1292,11 +1297,22 @@ template <class M> struct Sim {
 
   // ---- H. projected Gauss-Seidel in z-space (btMultiBodyConstraintSolver::solveSingleIteration order) --------
   // Row r of Y is stored over its support; the entry of coordinate l sits at slot tl(l) (prefix property).
+  // DUAL: 0 = the row is one compact row (joint limits; contacts of a model without self-collision), 1 = always two
+  // (loop closures), 2 = look at the row's MB_ROW_DUAL flag (contacts of a model with self-collision)
+  template <int DUAL>
   MB_HD static float pgs_single(Mem& S, const LaneConst& C, int ra, float lo, float hi, LaneVar<float>& z) {
     const unsigned supA = S.rc.r.r_mask[ra];
     LaneVar<float> ya, ta;
     MB_LANES(l)
-      ya[l] = ((supA >> l) & 1u) ? S.w.Yc[ra][C.tl[l]] : 0.0f;
+      ya[l] = (((DUAL ? supA & MB_ROW_SUP : supA) >> l) & 1u) ? S.w.Yc[ra][C.tl[l]] : 0.0f;
+    MB_END_REG
+    if (DUAL == 1 || (DUAL == 2 && (supA & MB_ROW_DUAL))) {  // loop closure / self-contact: part on the other link
+      const unsigned supB = S.rc.r.r_mask[ra + 1];
+      MB_LANES(l)
+        if ((supB >> l) & 1u) ya[l] += S.w.Yc[ra + 1][C.tl[l]];
+      MB_END_REG
+    }
+    MB_LANES(l)
       ta[l] = ya[l] * z[l];
     MB_END_REG
     const float dotA = warp_sum(ta);
@@ -1314,15 +1330,23 @@ template <class M> struct Sim {
     return dA * pA.den;  // deltaImpulse * (1 / jacDiagABInv)
   }
   // friction pair with btMultiBodyConstraintSolver::resolveConeFrictionConstraintRows' projection;
-  // sin/cos(atan2(a, b)) are written as a/|(a,b)|, b/|(a,b)|
+  // sin/cos(atan2(a, b)) are written as a/|(a,b)|, b/|(a,b)|.  A self-contact's pair continues in rows ra + 2, ra + 3.
   MB_HD static float pgs_pair(Mem& S, const LaneConst& C, int ra, float cone, LaneVar<float>& z) {
     const int rb = ra + 1;
     const unsigned supA = S.rc.r.r_mask[ra];  // both rows of a contact share the support
     LaneVar<float> ya, yb, ta, tb;
     MB_LANES(l)
-      const bool in = ((supA >> l) & 1u) != 0u;
+      const bool in = (((NSELF > 0 ? supA & MB_ROW_SUP : supA) >> l) & 1u) != 0u;
       ya[l] = in ? S.w.Yc[ra][C.tl[l]] : 0.0f;
       yb[l] = in ? S.w.Yc[rb][C.tl[l]] : 0.0f;
+    MB_END_REG
+    if (NSELF > 0 && (supA & MB_ROW_DUAL)) {
+      const unsigned supB = S.rc.r.r_mask[ra + 2];
+      MB_LANES(l)
+        if ((supB >> l) & 1u) { ya[l] += S.w.Yc[ra + 2][C.tl[l]]; yb[l] += S.w.Yc[ra + 3][C.tl[l]]; }
+      MB_END_REG
+    }
+    MB_LANES(l)
       ta[l] = ya[l] * z[l];
       tb[l] = yb[l] * z[l];
     MB_END_REG
@@ -1349,71 +1373,12 @@ template <class M> struct Sim {
     return dA * pA.den + dB * pB.den;
   }
 
-  // loop-closure row: two compact rows (ra on link A, ra + 1 on link B) sharing one multiplier
-  MB_HD static float pgs_dual(Mem& S, const LaneVar<int>& tl, int ra, float lo, float hi, LaneVar<float>& z) {
-    const int rb = ra + 1;
-    const unsigned supA = S.rc.r.r_mask[ra], supB = S.rc.r.r_mask[rb];
-    LaneVar<float> y, t;
-    MB_LANES(l)
-      const float ya = ((supA >> l) & 1u) ? S.w.Yc[ra][tl[l]] : 0.0f;
-      const float yb = ((supB >> l) & 1u) ? S.w.Yc[rb][tl[l]] : 0.0f;
-      y[l] = ya + yb;
-      t[l] = y[l] * z[l];
-    MB_END_REG
-    const float dot = warp_sum(t);
-    const MbRowPar pA = S.rc.r.r_par[ra];
-    const float app = S.rc.r.r_app[ra];
-    float d = pA.rhs - dot * pA.jinv;
-    const float sum = app + d;
-    float na = sum;
-    if (sum < lo) { d = lo - app; na = lo; }
-    else if (sum > hi) { d = hi - app; na = hi; }
-    MB_LANES(l)
-      z[l] += y[l] * d;
-      if (l == 0) S.rc.r.r_app[ra] = na;
-    MB_END
-    return d * pA.den;
-  }
-  // friction pair of a self-contact: rows ra, ra + 1 = first direction on link A / B, ra + 2, ra + 3 = second
-  MB_HD static float pgs_pair_dual(Mem& S, const LaneVar<int>& tl, int ra, float cone, LaneVar<float>& z) {
-    const unsigned supA = S.rc.r.r_mask[ra], supB = S.rc.r.r_mask[ra + 1];
-    LaneVar<float> ya, yb, ta, tb;
-    MB_LANES(l)
-      const bool inA = ((supA >> l) & 1u) != 0u, inB = ((supB >> l) & 1u) != 0u;
-      ya[l] = (inA ? S.w.Yc[ra][tl[l]] : 0.0f) + (inB ? S.w.Yc[ra + 1][tl[l]] : 0.0f);
-      yb[l] = (inA ? S.w.Yc[ra + 2][tl[l]] : 0.0f) + (inB ? S.w.Yc[ra + 3][tl[l]] : 0.0f);
-      ta[l] = ya[l] * z[l];
-      tb[l] = yb[l] * z[l];
-    MB_END_REG
-    const float dotA = warp_sum(ta), dotB = warp_sum(tb);
-    const MbRowPar pA = S.rc.r.r_par[ra], pB = S.rc.r.r_par[ra + 2];
-    const float appA = S.rc.r.r_app[ra], appB = S.rc.r.r_app[ra + 2];
-    float dA = pA.rhs - dotA * pA.jinv;
-    float dB = pB.rhs - dotB * pB.jinv;
-    const float sumA = appA + dA, sumB = appB + dB;
-    float nA = sumA, nB = sumB;
-    const float n2 = sumA * sumA + sumB * sumB;
-    if (n2 >= cone * cone) {
-      const float sc = n2 > 0.0f ? fabsf(cone) * rsqrtf(n2) : 0.0f;
-      const float clipA = fabsf(sumA) * sc, clipB = fabsf(sumB) * sc;
-      if (sumA < -clipA) { dA = -clipA - appA; nA = -clipA; }
-      else if (sumA > clipA) { dA = clipA - appA; nA = clipA; }
-      if (sumB < -clipB) { dB = -clipB - appB; nB = -clipB; }
-      else if (sumB > clipB) { dB = clipB - appB; nB = clipB; }
-    }
-    MB_LANES(l)
-      z[l] += ya[l] * dA + yb[l] * dB;
-      if (l == 0) { S.rc.r.r_app[ra] = nA; S.rc.r.r_app[ra + 2] = nB; }
-    MB_END
-    return dA * pA.den + dB * pB.den;
-  }
-
   // btMultiBodyConstraintSolver::solveSingleIteration order: non-contact rows (limits, then loop closures;
-  // alternating direction), normals, friction
-  template <bool SELF>
+  // alternating direction), normals, friction.  Contact k < nc is a static-world contact, nc <= k < nc + ncs a
+  // self-contact (rows behind S0, see setup_self_rows); one loop serves both so that the row code exists once.
   MB_HD static void solve_constraints(Mem& S, const MbPhysics& P, const LaneConst& C, int nlim, int nc, int ncs,
                                       LaneVar<float>& z) {
-    const int nnc = nlim + NLC / 2, n0 = nlim + NLC, S0 = n0 + 3 * nc;
+    const int nnc = nlim + NLC / 2, n0 = nlim + NLC, S0 = n0 + 3 * nc, nct = nc + (NSELF > 0 ? ncs : 0);
 #pragma unroll 1
     for (int it = 0; it < P.iterations; ++it) {
       float res2 = 0.0f;
@@ -1421,68 +1386,30 @@ template <class M> struct Sim {
       for (int v = 0; v < nnc; ++v) {
         const int idx = (it & 1) ? v : nnc - 1 - v;
         float rr;
-        if (idx < nlim) rr = pgs_single(S, C, idx, 0.0f, P.limit_max_impulse, z);
+        if (NLC == 0 || idx < nlim) rr = pgs_single<0>(S, C, idx, 0.0f, P.limit_max_impulse, z);
         else {
           const int ra = nlim + 2 * (idx - nlim);
           const float lim = S.rc.r.r_mu[ra];
-          rr = pgs_dual(S, C.tl, ra, -lim, lim, z);
+          rr = pgs_single<1>(S, C, ra, -lim, lim, z);
         }
         res2 = fmaxf(res2, rr * rr);
       }
 #pragma unroll 1
-      for (int k = 0; k < nc; ++k) {
-        const float rr = pgs_single(S, C, n0 + k, 0.0f, 1e10f, z);
+      for (int k = 0; k < nct; ++k) {
+        const int ra = (NSELF > 0 && k >= nc) ? S0 + 2 * (k - nc) : n0 + k;
+        const float rr = pgs_single<(NSELF > 0 ? 2 : 0)>(S, C, ra, 0.0f, 1e10f, z);
         res2 = fmaxf(res2, rr * rr);
       }
-      if (SELF) {
 #pragma unroll 1
-        for (int k = 0; k < ncs; ++k) {
-          const float rr = pgs_dual(S, C.tl, S0 + 2 * k, 0.0f, 1e10f, z);
-          res2 = fmaxf(res2, rr * rr);
-        }
-      }
-#pragma unroll 1
-      for (int k = 0; k < nc; ++k) {
-        const int ra = n0 + nc + 2 * k;
-        const float rr = pgs_pair(S, C, ra, S.rc.r.r_mu[ra] * S.rc.r.r_app[n0 + k], z);
+      for (int k = 0; k < nct; ++k) {
+        const bool self = NSELF > 0 && k >= nc;
+        const int ra = self ? S0 + 2 * ncs + 4 * (k - nc) : n0 + nc + 2 * k;
+        const int rn = self ? S0 + 2 * (k - nc) : n0 + k;
+        const float rr = pgs_pair(S, C, ra, S.rc.r.r_mu[ra] * S.rc.r.r_app[rn], z);
         res2 = fmaxf(res2, rr * rr);
-      }
-      if (SELF) {
-#pragma unroll 1
-        for (int k = 0; k < ncs; ++k) {
-          const int ra = S0 + 2 * ncs + 4 * k;
-          const float rr = pgs_pair_dual(S, C.tl, ra, S.rc.r.r_mu[ra] * S.rc.r.r_app[S0 + 2 * k], z);
-          res2 = fmaxf(res2, rr * rr);
-        }
       }
       if (res2 <= P.residual_threshold) break;
     }
-  }
-
-  // ---- H2. rows + PGS of a substep that has self-contacts, out of line ------------------------------------------
-  // About a quarter of the env steps under random actions see a self-contact.  Their whole constraint phase runs in
-  // this separate copy, so the common path keeps the code footprint (instruction cache) and the register budget it
-  // has without the feature; nothing but the few scalars below is live across the call -- the caller re-derives
-  // its lane constants afterwards instead of saving them.
-  struct SolverPar { float dt, slop, erp_joint, split_threshold, limit_max_impulse, residual_threshold; int iterations; };
-  MB_NOINLINE static LaneVar<float> constrain_self(Mem& S, SolverPar sp, int nlim, int nc, int ncs) {
-    MB_ASSUME_SHARED(S);
-    MbPhysics P;
-    P.dt = sp.dt; P.linear_slop = sp.slop; P.erp_joint = sp.erp_joint; P.split_threshold = sp.split_threshold;
-    P.limit_max_impulse = sp.limit_max_impulse; P.residual_threshold = sp.residual_threshold;
-    P.iterations = sp.iterations;
-    LaneConst C;
-    MB_LANES(l)
-      C.tl[l] = l < NU ? M::rowlen(l) - 1 : 0;
-    MB_END_REG
-    setup_rows(S, P, nlim, nc);
-    setup_self_rows(S, nlim + NLC + 3 * nc, nc, ncs, sp.slop, 1.0f / sp.dt);
-    LaneVar<float> z;
-    MB_LANES(l)
-      z[l] = 0.0f;
-    MB_END
-    solve_constraints<true>(S, P, C, nlim, nc, ncs, z);
-    return z;
   }
 
   // ---- I. integrate positions (btMultiBody::stepPositionsMultiDof) --------------------------------------------
@@ -1544,21 +1471,16 @@ template <class M> struct Sim {
     }
     const int R = nlim + NLC / 2 + 3 * (nc + ncs);  // as Bullet counts them (a loop / self-contact row is one row)
     if (R > 0) {
-      LaneVar<float> z;
+      setup_rows(S, P, nlim, nc);
       if (NSELF > 0 && MB_UNLIKELY(ncs > 0)) {
-        SolverPar sp;
-        sp.dt = P.dt; sp.slop = P.linear_slop; sp.erp_joint = P.erp_joint; sp.split_threshold = P.split_threshold;
-        sp.limit_max_impulse = P.limit_max_impulse; sp.residual_threshold = P.residual_threshold;
-        sp.iterations = P.iterations;
-        z = constrain_self(S, sp, nlim, nc, ncs);
+        setup_self_rows(S, nlim + NLC + 3 * nc, nc, ncs, P.linear_slop, 1.0f / P.dt);
         init_lane_const(C);  // dead across the call by construction: recomputed, not saved
-      } else {
-        setup_rows(S, P, nlim, nc);
-        MB_LANES(l)
-          z[l] = 0.0f;
-        MB_END
-        solve_constraints<false>(S, P, C, nlim, nc, 0, z);
       }
+      LaneVar<float> z;
+      MB_LANES(l)
+        z[l] = 0.0f;
+      MB_END
+      solve_constraints(S, P, C, nlim, nc, ncs, z);
       solve_L<false>(S, C, z);
       MB_LANES(l)
         if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + z[l], -P.max_coord_vel), P.max_coord_vel);
