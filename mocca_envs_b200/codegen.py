@@ -335,10 +335,12 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append("  MB_HD static constexpr unsigned rowmask_c(int i) {\n    return " +
                " ".join("i == %d ? %du :" % (i, m) for i, m in enumerate(rowmask)) + " 0u;\n  }\n")
     out.append("  enum { NJ = %d, NB = %d, NU = %d, NPT = %d, NLEVEL = %d, NFEET = %d, NMIRROR = %d, NNEG = %d,\n"
-               "         LSIZE = %d, MAXSUP = %d, NXBOX = %d, NLOOP = %d, NORDERED = %d, NPD = %d, NPOWERED = %d, NSELF = %d };\n"
+               "         LSIZE = %d, MAXSUP = %d, NXBOX = %d, NLOOP = %d, NORDERED = %d, NPD = %d, NPOWERED = %d, NSELF = %d,\n"
+               "         ALL_ALIGNED = %d, ALL_IDENT = %d };  // every joint axis is a coordinate axis / every zero-pose rotation is 1\n"
                % (r["nj"], r["nb"], r["nu"], r["npt"], r["nlevel"], r["nfeet"], len(r["right"]), len(r["neg"]),
                   r["lsize"], r["maxsup"], len(r["xboxes"]), len(r["p2p"]), len(ex.get("ordered", [])),
-                  len(ex.get("pd_dof", [])), ex.get("npowered", 0), len(sp)))
+                  len(ex.get("pd_dof", [])), ex.get("npowered", 0), len(sp),
+                  int(all(k >= 0 for k in jaxk)), int(all(jident))))
     out.append("  MB_HD static unsigned long long chainpack(int j) { return %s_chainpack[j]; }\n" % P)
     out.append("  MB_HD static int facoff(int k, int t) { return %s_facoff[k][t]; }\n" % P)
     out.append("  MB_HD static int fcol(int k, int t) { return %s_fcol[k][t]; }\n" % P)

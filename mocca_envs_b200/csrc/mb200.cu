@@ -759,6 +759,7 @@ static int param_field(mb200_env* e, const char* key, float lo, float hi, const 
     *field = ES_CURRIC;
     return 0;
   }
+  if (strcmp(key, "random_reward") == 0 && e->kind == KIND_STEPPER) { *field = ES_RANDOM_REWARD; return 0; }
   (void)lo; (void)hi;
   return fail(std::string("mb200_set_param: unknown key '") + key + "' for this env");
 }

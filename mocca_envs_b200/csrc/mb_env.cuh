@@ -61,6 +61,7 @@ enum {  // Walker3DStepperEnv additions (env_locomotion.py:330-840)
   ES_PLANKIDX,        // [3] terrain row shown by each physical plank (int)
   ES_STEPS_REACHED = 31,  // info["steps_reached"] of the last step, -1 = not reported (int)
   ES_GAIN_CURRIC = 6,     // curriculum the applied_gain was taken from at reset (env_locomotion.py:489) (int)
+  ES_RANDOM_REWARD = 3,   // random_reward kwarg (env_locomotion.py:355,528-547) (int; ER_DIST is unused by this env)
   ES_BOX = 32,        // [3][12] plank base-box centre + axes
   ES_TERRAIN = 68,    // [20][6] x y z phi x_tilt y_tilt
 };
@@ -749,7 +750,18 @@ template <class M> struct StepperEnv {
     if ((next == NSTEPS - 1 || stop) && dist < 0.15f) target_bonus = 2.0f;
     targets(S, rec, o.yaw, obs);
     if (cur_index != next) B_::potential(S, rec, o.yaw, scene_dt, &dist, &ang, &lp);
-    const float reward = progress - energy + step_bonus + target_bonus + tall - posture - joints_pen;
+    float reward = progress - energy + step_bonus + target_bonus + tall - posture - joints_pen;
+    if (rec_i(rec, ES_RANDOM_REWARD)) {
+      // np.dot(np_random.uniform(0.8, 1.2, 8), [progress, -energy, step_bonus, target_bonus, -speed_penalty * 0,
+      // tall_bonus, -posture_penalty, -joints_penalty]) (env_locomotion.py:532-547): eight draws of the env stream
+      // per step, the fifth multiplies zero
+      uint32_t* w = reinterpret_cast<uint32_t*>(S.rc.scratch);
+      mt_fill(mt_env, w, 16);
+      const float term[8] = {progress, -energy, step_bonus, target_bonus, 0.0f, tall, -posture, -joints_pen};
+      double acc = 0.0;
+      for (int i = 0; i < 8; ++i) acc += (0.8 + (1.2 - 0.8) * mt_double(w + 2 * i)) * (double)term[i];
+      reward = (float)acc;
+    }
     const int elapsed = rec_i(rec, ER_ELAPSED) + 1;
     int truncated = 0, any_done = env_done;
     if (elapsed >= 1000) { truncated = !env_done; any_done = 1; }

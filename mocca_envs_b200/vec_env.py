@@ -242,6 +242,15 @@ class Walker3DStepperVecEnv(Walker3DCustomVecEnv):
     ES_NEXT, ES_CURRIC, ES_STEPS_REACHED, ES_TERRAIN = 22, 27, 31, 68
     max_curriculum = 9
 
+    def __init__(self, num_envs: int, device="cuda:0", seed: int | None = None, physics: dict | None = None,
+                 return_final_obs: bool = False, random_reward: bool = False):
+        """``random_reward`` is the reference's constructor kwarg (env_locomotion.py:355): every reward term is
+        scaled by its own np_random.uniform(0.8, 1.2) draw each step (:532-547)."""
+        super().__init__(num_envs, device=device, seed=seed, physics=physics, return_final_obs=return_final_obs)
+        self.random_reward = bool(random_reward)
+        if self.random_reward:
+            _lib.check(self._L.mb200_set_param(self._h, b"random_reward", 1.0))
+
     def set_env_params(self, params: dict):
         """``{"curriculum": c}`` with an int or one value per env (env_base.py:103-106); used at the next reset
         for the terrain and immediately for gain / terminal height, like the reference's attribute."""

@@ -1614,6 +1614,13 @@ void orc_stepper_step(const orc_model* m, const orc_params* p, orc_stepper_env* 
   if (cur != e->next_step_index) w3d_calc_potential(b, p->dt * p->substeps);
   *reward = b->progress - b->energy_penalty + e->step_bonus + b->target_bonus - e->speed_penalty * 0 + b->tall_bonus -
             b->posture_penalty - b->joints_penalty;
+  if (e->random_reward) { /* env_locomotion.py:532-547 */
+    double term[8] = {b->progress, -b->energy_penalty, e->step_bonus, b->target_bonus, -e->speed_penalty * 0,
+                      b->tall_bonus, -b->posture_penalty, -b->joints_penalty};
+    double acc = 0;
+    for (int i = 0; i < 8; i++) acc += orc_rng_uniform(&b->env_rng, 0.8, 1.2) * term[i];
+    *reward = acc;
+  }
   stepper_obs(m, e, obs);
   e->steps_reached = (b->done || e->timestep == 999) ? e->next_step_index : -1;
   b->elapsed++;

@@ -211,6 +211,7 @@ typedef struct {
   double targets[3][5];
   double step_bonus, speed_penalty;
   int steps_reached; /* info["steps_reached"] when reported, else -1 */
+  int random_reward; /* constructor kwarg (env_locomotion.py:355) */
 } orc_stepper_env;
 
 void orc_stepper_seed(orc_stepper_env* e, const uint32_t* key, int len, int at_construction);

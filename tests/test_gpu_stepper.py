@@ -148,3 +148,37 @@ def test_stepper_gym_facade(torch_mod):
     neg, right, left, na, ra, la = env.get_mirror_indices()
     assert neg.max() < 65 and right.max() < 65 and left.max() < 65
     env.close()
+
+
+def test_stepper_random_reward(walker_table, oracle_mod, torch_mod):
+    """the random_reward constructor kwarg (env_locomotion.py:355,528-547).  Zero actions from the same
+    seeds: the first contact-free steps keep f32 and f64 together, so the randomly weighted rewards must agree, differ
+    from the plain reward, and leave the env stream in lockstep (bit-exact terrain at the next reset)."""
+    torch, O, t = torch_mod, oracle_mod, walker_table
+    N = 8
+    env = _env(N, seed=300, random_reward=True)
+    env.set_env_params({"curriculum": 5})
+    oracles = [O.Walker3DStepperOracle(t, seed=300 + i, curriculum=5, random_reward=True) for i in range(N)]
+    plain = [O.Walker3DStepperOracle(t, seed=300 + i, curriculum=5) for i in range(N)]
+    env.reset()
+    for o in oracles + plain:
+        o.reset()
+    a = torch.zeros(N, 21, device="cuda:0")
+    differs = 0
+    for step in range(6):
+        _, rew, done, _ = env.step(a)
+        rew = rew.cpu().numpy()
+        assert not done.any()
+        for i in range(N):
+            _, r1, d1, _ = oracles[i].step(np.zeros(21))
+            _, r0, _, _ = plain[i].step(np.zeros(21))
+            assert not d1
+            assert abs(r1 - rew[i]) < 2e-3 + 1e-3 * abs(r1), (step, i, r1, rew[i])
+            differs += abs(r1 - r0) > 1e-3 * abs(r0)
+    assert differs >= 5 * N
+    env.reset()
+    ter = env.terrain_info().cpu().numpy()
+    for i, o in enumerate(oracles):
+        o.reset()
+        assert np.array_equal(ter[i], np.array(o.e.terrain[:]).astype(np.float32))
+    env.close()

@@ -220,3 +220,29 @@ def test_stepper_env_step_teacher_forced(walker_table, oracle_mod):
     assert advanced >= 2  # the target-advance / plank-recycling path was exercised
     assert bad <= 0.03 * total, (bad, total)
     assert np.median(errs) < 2e-4
+
+
+def test_stepper_random_reward(walker_table, oracle_mod):
+    """SURVEY 8 f2, random_reward kwarg (env_locomotion.py:355,528-547): every reward term is scaled by its own
+    np_random.uniform(0.8, 1.2) draw.  Free-running from the same seed with zero actions (the first steps are
+    contact-free and the stones are far away, so f32 and f64 stay together): rewards agree, differ from the plain
+    reward, and the env stream stays in lockstep -- the terrain drawn at the next reset is bit-exact."""
+    O, t = oracle_mod, walker_table
+    seed, cur = 6, 5
+    env = O.Walker3DStepperOracle(t, seed=seed, curriculum=cur, random_reward=True)
+    plain = O.Walker3DStepperOracle(t, seed=seed, curriculum=cur)
+    emu = E.EmuStepper(_mt_row(O, seed), curriculum=cur)
+    emu.rec.view(np.int32)[3] = 1  # ES_RANDOM_REWARD
+    env.reset(), plain.reset(), emu.reset()
+    differs = 0
+    for i in range(6):
+        a = np.zeros(21)
+        _, r1, d1, _ = env.step(a)
+        _, r0, _, _ = plain.step(a)
+        _, r2, d2, _, _ = emu.step(a)
+        assert not d1 and not d2
+        assert abs(r1 - r2) < 2e-3 + 1e-3 * abs(r1), (i, r1, r2)
+        differs += abs(r1 - r0) > 1e-3 * abs(r0)
+    assert differs >= 5
+    env.reset(), emu.reset()
+    assert np.array_equal(emu.terrain(), np.array(env.e.terrain[:]).astype(np.float32))

@@ -31,7 +31,7 @@ for l in dis[start + 1:]:
 root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "mocca_envs_b200", "csrc")
 src = open(os.path.join(root, "mb_core.cuh")).read().splitlines()
 funcs = [(i + 1, l.strip()[:50]) for i, l in enumerate(src)
-         if "MB_HD static" in l or l.startswith("MB_HD") or l.startswith("template <class M> MB_HD")]
+         if "MB_HD static" in l or "MB_NOINLINE static" in l or l.startswith("MB_HD") or l.startswith("template <class M> MB_HD")]
 starts = [f[0] for f in funcs]
 hot, warm = Counter(), Counter()
 nh = nw = 0
