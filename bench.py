@@ -345,22 +345,23 @@ def main():
 
     # ---- e2e: same step through the host-buffer C-ABI entry point (pinned host memory, H2D + D2H in the timed region)
     Ke = max(10, min(K, 100))
-    h_act = torch.empty(N, A, dtype=torch.float32).pin_memory()
-    h_act.copy_(act_pool[0].cpu())
+    # the same action stream as the device-timed loop, held in pinned host memory (a constant action per env would
+    # be a different workload: joints pinned at their limits, more constraint rows)
+    h_pool = act_pool.cpu().pin_memory()
     h_obs = torch.empty(N, env.obs_dim, dtype=torch.float32).pin_memory()
     h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
     h_done = torch.empty(N, dtype=torch.uint8).pin_memory()
     h_trunc = torch.empty(N, dtype=torch.uint8).pin_memory()
     outs = (h_obs.numpy(), h_rew.numpy(), h_done.numpy(), h_trunc.numpy())
-    h_act_np = h_act.numpy()
-    for _ in range(3):
-        env.step_host(h_act_np, outs)
+    h_pool_np = [h_pool[k].numpy() for k in range(pool)]
+    for k in range(3):
+        env.step_host(h_pool_np[k % pool], outs)
     if dist:
         dist.barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     for i in range(Ke):
-        env.step_host(h_act_np, outs)  # returns after the D2H copies completed (stream synchronised inside)
+        env.step_host(h_pool_np[(W + i) % pool], outs)  # returns once the D2H copies have completed
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)

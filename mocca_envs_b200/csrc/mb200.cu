@@ -66,6 +66,7 @@ struct mb200_env {
   float* stage_rew;
   uint8_t* stage_done;
   uint8_t* stage_trunc;
+  cudaEvent_t host_done; // results of mb200_step_host have reached the host buffers
   // CTA barriers require every warp of a CTA to run: the state arrays are padded to a whole number of CTAs and
   // the pad envs ("tail") step like any other env but write their outputs/statistics to these dummies
   int n_pad;
@@ -506,6 +507,7 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   CUDA_OK(cudaMalloc(&e->stage_rew, n * sizeof(float)));
   CUDA_OK(cudaMalloc(&e->stage_done, n));
   CUDA_OK(cudaMalloc(&e->stage_trunc, n));
+  CUDA_OK(cudaEventCreateWithFlags(&e->host_done, cudaEventDisableTiming));
   CUDA_OK(cudaMemset(e->state, 0, n * MB_STATE_STRIDE * sizeof(float)));
   CUDA_OK(cudaMemset(e->rec, 0, n * e->rec_stride * sizeof(float)));
   CUDA_OK(cudaMemset(e->mt, 0, n * 2 * MB_MT_STRIDE * sizeof(uint32_t)));
@@ -520,6 +522,7 @@ void mb200_destroy(mb200_env* e) {
   cudaFree(e->state); cudaFree(e->rec); cudaFree(e->mt); cudaFree(e->stats);
   cudaFree(e->stage_act); cudaFree(e->stage_obs); cudaFree(e->stage_rew); cudaFree(e->stage_done);
   cudaFree(e->stage_trunc);
+  cudaEventDestroy(e->host_done);
   cudaFree(e->dummy_obs); cudaFree(e->dummy_rew); cudaFree(e->dummy_flag); cudaFree(e->dummy_stats);
   cudaFree(e->order); cudaFree(e->work); cudaFree(e->work_prev);
   delete e;
@@ -598,8 +601,17 @@ int mb200_reset(mb200_env* e, const uint8_t* mask_dev, float* obs_dev, void* str
   return 0;
 }
 
-int mb200_step(mb200_env* e, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev,
-               uint8_t* trunc_dev, float* final_obs_dev, void* stream) {
+static int launch_sort(mb200_env* e, void* stream) {
+  if (e->sort_every > 0 && e->steps % e->sort_every == 0 && grid_for(e) > 1) {
+    k_sort_by_work<<<1, 1024, 0, (cudaStream_t)stream>>>(e->n_pad, e->work, e->work_prev, e->order);
+    e->launches++;
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int step_impl(mb200_env* e, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev,
+                     uint8_t* trunc_dev, float* final_obs_dev, void* stream, bool sort_now) {
   if (!e || !act_dev || !obs_dev || !rew_dev || !done_dev || !trunc_dev) return fail("mb200_step: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
   StepArgs a;
@@ -617,12 +629,13 @@ int mb200_step(mb200_env* e, const float* act_dev, float* obs_dev, float* rew_de
     k_step_walker3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
   e->launches++;
   e->steps++;
-  if (e->sort_every > 0 && e->steps % e->sort_every == 0 && grid_for(e) > 1) {
-    k_sort_by_work<<<1, 1024, 0, (cudaStream_t)stream>>>(e->n_pad, e->work, e->work_prev, e->order);
-    e->launches++;
-  }
   CUDA_OK(cudaGetLastError());
-  return 0;
+  return sort_now ? launch_sort(e, stream) : 0;
+}
+
+int mb200_step(mb200_env* e, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev,
+               uint8_t* trunc_dev, float* final_obs_dev, void* stream) {
+  return step_impl(e, act_dev, obs_dev, rew_dev, done_dev, trunc_dev, final_obs_dev, stream, true);
 }
 
 int mb200_step_host(mb200_env* e, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host,
@@ -633,13 +646,18 @@ int mb200_step_host(mb200_env* e, const float* act_host, float* obs_host, float*
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)e->n;
   CUDA_OK(cudaMemcpyAsync(e->stage_act, act_host, n * e->act_dim * sizeof(float), cudaMemcpyHostToDevice, st));
-  int rc = mb200_step(e, e->stage_act, e->stage_obs, e->stage_rew, e->stage_done, e->stage_trunc, nullptr, stream);
+  int rc = step_impl(e, e->stage_act, e->stage_obs, e->stage_rew, e->stage_done, e->stage_trunc, nullptr, stream, false);
   if (rc) return rc;
   CUDA_OK(cudaMemcpyAsync(obs_host, e->stage_obs, n * e->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaMemcpyAsync(rew_host, e->stage_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaMemcpyAsync(done_host, e->stage_done, n, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaMemcpyAsync(trunc_host, e->stage_trunc, n, cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaStreamSynchronize(st));
+  // the caller needs the results, not the scheduler's re-sort: wait for the copies only and let the sort of the next
+  // step's launch order run while the host picks its actions
+  CUDA_OK(cudaEventRecord(e->host_done, st));
+  rc = launch_sort(e, stream);
+  if (rc) return rc;
+  CUDA_OK(cudaEventSynchronize(e->host_done));
   return 0;
 }
 

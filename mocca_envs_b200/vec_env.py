@@ -365,11 +365,13 @@ class Walker3DCustomEnv:
 
     metadata = {"render.modes": []}
     vec_class = Walker3DCustomVecEnv
+    vec_kwargs = ()  # reference constructor kwargs this env's VecEnv understands
 
     def __init__(self, device="cuda:0", seed=None, render=False, **kwargs):
         if render:
             raise NotImplementedError("rendering is out of scope for the GPU path (SURVEY.md section 2, row 2)")
-        self.vec = self.vec_class(1, device=device, seed=seed, return_final_obs=True)
+        extra = {k: kwargs[k] for k in self.vec_kwargs if k in kwargs}
+        self.vec = self.vec_class(1, device=device, seed=seed, return_final_obs=True, **extra)
         self.observation_space = self.vec.observation_space
         self.action_space = self.vec.action_space
         self._pending_reset_obs = None
@@ -422,6 +424,7 @@ class Walker3DStepperEnv(Walker3DCustomEnv):
     """gym-protocol facade of Walker3DStepperEnv-v0; info carries "steps_reached" like the reference."""
 
     vec_class = Walker3DStepperVecEnv
+    vec_kwargs = ("random_reward",)  # env_locomotion.py:355
 
     def _extra_info(self, info):
         sr = int(self.vec.steps_reached()[0].item())
