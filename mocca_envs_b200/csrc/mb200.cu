@@ -77,10 +77,15 @@ struct mb200_env {
   // work-sorted slot -> env map: the warps of a CTA meet at one barrier per substep, so a CTA runs at the pace of
   // its slowest env; grouping envs with similar constraint-row counts (of the previous step) removes most of that
   // wait, and heavy CTAs are scheduled first.  Pure scheduling: every env's arithmetic is unchanged.
+  // The step kernel itself classifies: each warp turns the rows of its step into a key (heaviest = 0), stores it and
+  // counts it in a 256-bin histogram (global atomics spread over the launch); a small multi-CTA kernel then scans
+  // the bins and scatters the env ids (k_order_by_key, ~10 us instead of the 38 us of a single-CTA counting sort).
   int* order;      // [n_pad]
-  int* work;       // [n_pad] running constraint-row sum per env
-  int* work_prev;  // [n_pad] the same one sort earlier
-  int sort_every;  // re-sort period in steps (0 = never, identity order)
+  int* work;       // [n_pad] running constraint-row sum per env (owned by the env's warp)
+  int* key;        // [n_pad] sort key of the last step
+  int* hist;       // [2][256] step t counts into hist[t & 1]; the scatter kernel zeroes the other half
+  int* cursor;     // [2][256] scatter cursors, same double buffering
+  int sort_every;  // 0 = never re-sort (identity order), otherwise after every step
   long long steps;
   long long launches;
   size_t smem;
@@ -115,6 +120,8 @@ struct StepArgs {
   MbStats* dummy_stats;
   const int* order;
   int* work;
+  int* key;
+  int* hist;  // this step's histogram half, nullptr = scheduler off
 };
 
 template <class Env>
@@ -135,63 +142,48 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
             tail ? a.dummy_flag + warp : a.done + env, tail ? a.dummy_flag + MB_WARPS_MAX + warp : a.trunc + env, fin,
             tail ? a.dummy_stats : a.stats);
   // work estimate for the scheduler: constraint rows accumulated by this step (ER_ROWS is a running sum)
-  if ((threadIdx.x & 31) == 0) {
+  if ((threadIdx.x & 31) == 0 && a.hist) {
     const float* rec = a.rec + (size_t)env * Env::REC_STRIDE;
-    a.work[env] = (int)rec[ER_ROWS];
+    const int w = (int)rec[ER_ROWS];
+    int k = w - a.work[env];
+    k = 255 - (k < 0 ? 0 : (k > 255 ? 255 : k));  // heaviest first
+    a.work[env] = w;
+    a.key[env] = k;
+    atomicAdd(&a.hist[k], 1);
   }
 }
 
-// Counting sort of the envs by the rows of their last step, heaviest first (one CTA; keys clamp at 255).
-// `work` holds the running row sum; prev holds the sum one step earlier (updated here).
-__global__ void __launch_bounds__(1024) k_sort_by_work(int n_pad, const int* work, int* prev, int* order) {
-  __shared__ int hist[256];
+// Second half of the counting sort (the histogram was filled by the step kernel): every CTA scans the 256 bins into
+// bin starts, then places its 256 envs with warp-aggregated global cursors.  Order inside a bin is arbitrary (pure
+// scheduling).  CTA 0 also clears the other halves of hist / cursor for the next step.
+__global__ void __launch_bounds__(256) k_order_by_key(int n_pad, const int* key, const int* hist, int* cursor,
+                                                       int* hist_next, int* cursor_next, int* order) {
   __shared__ int start[256];
-  const unsigned lane = threadIdx.x & 31u;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
-  __syncthreads();
-  const int rounds = (n_pad + blockDim.x - 1) / blockDim.x;  // uniform trip count: __match_any_sync needs full warps
-  for (int r = 0; r < rounds; ++r) {
-    const int e = r * blockDim.x + threadIdx.x;
-    int k = 256;  // out of range: no bin
-    if (e < n_pad) {
-      k = work[e] - prev[e];
-      k = 255 - (k < 0 ? 0 : (k > 255 ? 255 : k));
-    }
-    const unsigned peers = __match_any_sync(0xffffffffu, k);  // warp-aggregated shared-memory atomics
-    if (k < 256 && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[k], __popc(peers));
+  __shared__ int wsum[8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int h = hist[tid];
+  int incl = h;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
   }
+  if (lane == 31) wsum[wid] = incl;
   __syncthreads();
-  if (threadIdx.x < 32) {  // exclusive scan of the 256 bins by one warp, 8 bins per lane
-    int loc[8], sum = 0;
-    for (int i = 0; i < 8; ++i) { loc[i] = sum; sum += hist[8 * lane + i]; }
-    int incl = sum;
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (unsigned)o) incl += v;
-    }
-    const int base = incl - sum;
-    for (int i = 0; i < 8; ++i) start[8 * lane + i] = base + loc[i];
-  }
+  int base = 0;
+  for (int w = 0; w < wid; ++w) base += wsum[w];
+  start[tid] = base + incl - h;
+  if (blockIdx.x == 0) { hist_next[tid] = 0; cursor_next[tid] = 0; }
   __syncthreads();
-  for (int r = 0; r < rounds; ++r) {
-    const int e = r * blockDim.x + threadIdx.x;
-    int k = 256, w = 0;
-    if (e < n_pad) {
-      w = work[e];
-      k = w - prev[e];
-      k = 255 - (k < 0 ? 0 : (k > 255 ? 255 : k));
-    }
-    const unsigned peers = __match_any_sync(0xffffffffu, k);
-    int base = 0;
-    const int leader = __ffs(peers) - 1;
-    if (k < 256 && lane == (unsigned)leader) base = atomicAdd(&start[k], __popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (k < 256) {
-      order[base + __popc(peers & ((1u << lane) - 1u))] = e;
-      prev[e] = w;
-    }
-  }
+  const int e = blockIdx.x * 256 + tid;
+  const int k = e < n_pad ? key[e] : 256 + lane;  // out of range: a key nobody shares
+  const unsigned peers = __match_any_sync(0xffffffffu, k);
+  const int leader = __ffs(peers) - 1;
+  int off = 0;
+  if (k < 256 && lane == leader) off = atomicAdd(&cursor[k], __popc(peers));
+  off = __shfl_sync(0xffffffffu, off, leader);
+  if (k < 256) order[start[k] + off + __popc(peers & ((1u << lane) - 1u))] = e;
 }
+
 __global__ void __launch_bounds__(MB_WARPS_CUSTOM * 32, MB_MINBLOCKS) k_step_walker3d_custom(StepArgs a) {
   step_body<WEnv>(a);
 }
@@ -489,9 +481,13 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   CUDA_OK(cudaMalloc(&e->stats, sizeof(MbStats)));
   CUDA_OK(cudaMalloc(&e->order, n * sizeof(int)));
   CUDA_OK(cudaMalloc(&e->work, n * sizeof(int)));
-  CUDA_OK(cudaMalloc(&e->work_prev, n * sizeof(int)));
+  CUDA_OK(cudaMalloc(&e->key, n * sizeof(int)));
+  CUDA_OK(cudaMalloc(&e->hist, 2 * 256 * sizeof(int)));
+  CUDA_OK(cudaMalloc(&e->cursor, 2 * 256 * sizeof(int)));
   CUDA_OK(cudaMemset(e->work, 0, n * sizeof(int)));
-  CUDA_OK(cudaMemset(e->work_prev, 0, n * sizeof(int)));
+  CUDA_OK(cudaMemset(e->key, 0, n * sizeof(int)));
+  CUDA_OK(cudaMemset(e->hist, 0, 2 * 256 * sizeof(int)));
+  CUDA_OK(cudaMemset(e->cursor, 0, 2 * 256 * sizeof(int)));
   {
     int* ident = (int*)malloc(n * sizeof(int));
     if (!ident) return fail("mb200_create: host allocation failed");
@@ -524,7 +520,7 @@ void mb200_destroy(mb200_env* e) {
   cudaFree(e->stage_trunc);
   cudaEventDestroy(e->host_done);
   cudaFree(e->dummy_obs); cudaFree(e->dummy_rew); cudaFree(e->dummy_flag); cudaFree(e->dummy_stats);
-  cudaFree(e->order); cudaFree(e->work); cudaFree(e->work_prev);
+  cudaFree(e->order); cudaFree(e->work); cudaFree(e->key); cudaFree(e->hist); cudaFree(e->cursor);
   delete e;
 }
 
@@ -601,9 +597,15 @@ int mb200_reset(mb200_env* e, const uint8_t* mask_dev, float* obs_dev, void* str
   return 0;
 }
 
+static bool sorting(const mb200_env* e) { return e->sort_every > 0 && grid_for(e) > 1; }
+
+// scatter for the step that was just launched (e->steps already counts it)
 static int launch_sort(mb200_env* e, void* stream) {
-  if (e->sort_every > 0 && e->steps % e->sort_every == 0 && grid_for(e) > 1) {
-    k_sort_by_work<<<1, 1024, 0, (cudaStream_t)stream>>>(e->n_pad, e->work, e->work_prev, e->order);
+  if (sorting(e)) {
+    const int b = (int)((e->steps - 1) & 1);
+    k_order_by_key<<<(e->n_pad + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        e->n_pad, e->key, e->hist + 256 * b, e->cursor + 256 * b, e->hist + 256 * (b ^ 1), e->cursor + 256 * (b ^ 1),
+        e->order);
     e->launches++;
   }
   CUDA_OK(cudaGetLastError());
@@ -618,7 +620,8 @@ static int step_impl(mb200_env* e, const float* act_dev, float* obs_dev, float* 
   a.n = e->n; a.phys = e->phys; a.state = e->state; a.rec = e->rec; a.mt = e->mt; a.act = act_dev; a.obs = obs_dev;
   a.rew = rew_dev; a.done = done_dev; a.trunc = trunc_dev; a.final_obs = final_obs_dev; a.stats = e->stats;
   a.dummy_obs = e->dummy_obs; a.dummy_rew = e->dummy_rew; a.dummy_flag = e->dummy_flag; a.dummy_stats = e->dummy_stats;
-  a.order = e->order; a.work = e->work;
+  a.order = e->order; a.work = e->work; a.key = e->key;
+  a.hist = sorting(e) ? e->hist + 256 * (int)(e->steps & 1) : nullptr;
   if (e->kind == KIND_CASSIE)
     k_step_cassie<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
   else if (e->kind == KIND_MONKEY)

@@ -26,8 +26,11 @@ with open(os.path.join(out, tag + "_step_kernel_raw.csv"), "w") as f:
         if any(s in name for s in KEEP) and "pcsamp" not in name:
             w.writerow([name, units[k]] + [v[k] for v in vals])
 src_csv = os.path.join(ROOT, "gpurun_out", "src_" + tag + ".csv")
-with open(src_csv, "w") as f:
-    f.write(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout)
+with open(src_csv, "w") as f:  # the first captured launch only (the page repeats per launch)
+    page = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    lines = page.splitlines(True)
+    starts = [i for i, l in enumerate(lines) if l.startswith('"Kernel Name"')]
+    f.write("".join(lines[starts[0]:starts[1]] if len(starts) > 1 else lines))
 lib = os.path.join(ROOT, "mocca_envs_b200", "libmocca_b200.so")
 with open(os.path.join(out, tag + "_by_phase.txt"), "w") as f:
     f.write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_phase.py"), src_csv, lib],
