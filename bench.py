@@ -426,8 +426,9 @@ def main():
         "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak if peak else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at 16384 envs from the
-                     # committed ncu --set full capture (profiles/r1j_step_kernel_raw.csv); null for other workloads
-                     "traffic": 7.97e6 if (args.env == "custom" and N == 16384) else None,
+                     # committed ncu --set full capture (profiles/r1q_step_kernel_raw.csv: 8.14 MB read + 0.03 MB
+                     # written); null for other workloads
+                     "traffic": 8.17e6 if (args.env == "custom" and N == 16384 and args.self_collision) else None,
                      "peak_source": "FP32 FMA probe kernel measured in this run (mb200_measure_fp32_peak)",
                      "flops_per_env_step": F, "rows_per_substep": R_mean,
                      "contacts_per_substep": conts_all / (K * N * world * S_sub),
@@ -435,7 +436,8 @@ def main():
                              "bytes_per_env_step": B_step,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": Ke, "api": "mb200_step_host (pinned host buffers, stream-synchronised)"},
+                "steps": Ke, "api": "mb200_step_host (pinned host buffers, returns when the D2H copies have landed)",
+                "actions": "the device loop's random pool, read from pinned host memory"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "episodes": {"finished": episodes, "mean_return": ret_sum / episodes if episodes else None,
