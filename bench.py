@@ -21,6 +21,10 @@ WORKLOAD = "Walker3DCustomEnv-v0 batched 16384 envs/GPU, flat ground"
 METRIC = "env-steps/sec (Walker3DCustomEnv-v0, 16384 envs/GPU, random actions)"
 
 
+ENV_NAMES = {"custom": "Walker3DCustomEnv", "stepper": "Walker3DStepperEnv", "monkey": "Monkey3DCustomEnv",
+             "cassie": "CassieEnv", "child": "Child3DCustomEnv", "mike": "MikeStepperEnv"}
+
+
 def flops_per_env_step(rows_per_substep, S=4, n=27, L=17, G=22, I=5, P=0):
     """F = S*[60L + 430n + 30G + 60P + R*150n + I*R*(4n+10) + 20n] + 1000
     (P = self-collision candidate pairs tested per substep)."""
@@ -153,7 +157,9 @@ def cpu_reference_run(n_envs, steps, warmup, threads, time_budget=None, kind="cu
     from mocca_envs_b200.model_compiler import load_table
     from oracle import oracle as O
 
-    model, struct, pre, A, OB = {"cassie": ("cassie", O.CassieEnvS, "orc_cassie", 10, 36),
+    model, struct, pre, A, OB = {"child": ("child3d", O.W3DEnv, "orc_w3d", 21, 52),
+                                 "mike": ("mike", O.StepperEnv, "orc_stepper", 21, 65),
+                                 "cassie": ("cassie", O.CassieEnvS, "orc_cassie", 10, 36),
                                  "custom": ("walker3d", O.W3DEnv, "orc_w3d", 21, 52),
                                  "stepper": ("walker3d", O.StepperEnv, "orc_stepper", 21, 65),
                                  "monkey": ("monkey3d", O.MonkeyEnv, "orc_monkey", 23, 69)}[kind]
@@ -168,7 +174,7 @@ def cpu_reference_run(n_envs, steps, warmup, threads, time_budget=None, kind="cu
     for i in range(n_envs):
         words = O.gym_seed_words(1000 + i)
         key = (C.c_uint32 * len(words))(*words)
-        if kind == "stepper":
+        if kind in ("stepper", "mike"):
             envs[i].curriculum = (0, 5, 9)[i % 3]
         if seed_fn is not None:
             seed_fn(C.byref(envs[i]), key, len(words), 1)
@@ -202,9 +208,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--envs", type=int, default=16384, help="envs per GPU")
     ap.add_argument("--actions", default="random", choices=["random", "pd"])
-    ap.add_argument("--env", default="custom", choices=["custom", "stepper", "monkey", "cassie"],
+    ap.add_argument("--env", default="custom", choices=["custom", "stepper", "monkey", "cassie", "child", "mike"],
                     help="custom = BASELINE configs[1] (headline); stepper = configs[2] (curriculum 0/5/9 per env); "
-                         "monkey = configs[4] (Monkey3DCustomEnv-v0); cassie = configs[3] (CassieEnv-v0, 50 substeps per step)")
+                         "monkey = configs[4] (Monkey3DCustomEnv-v0); cassie = configs[3] (CassieEnv-v0, 50 substeps per step); "
+                         "child / mike = SURVEY 8 f3 (Child3DCustomEnv-v0, MikeStepperEnv-v0)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--self-collision", type=int, default=1, choices=[0, 1],
@@ -224,8 +231,7 @@ def main():
         v, dt, ks = cpu_reference_run(sample_envs, args.steps, min(max(args.warmup, 1), 10), cores, kind=args.env)
         line = {
             "impl": "reference",
-            "metric": METRIC.replace("Walker3DCustomEnv", {"custom": "Walker3DCustomEnv", "stepper": "Walker3DStepperEnv",
-                                                           "monkey": "Monkey3DCustomEnv", "cassie": "CassieEnv"}[args.env]),
+            "metric": METRIC.replace("Walker3DCustomEnv", ENV_NAMES[args.env]),
             "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": ks, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(ks, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -243,7 +249,8 @@ def main():
 
     from mocca_envs_b200 import _lib
     from mocca_envs_b200.distributed import shard_seed
-    from mocca_envs_b200.vec_env import CassieVecEnv, Monkey3DCustomVecEnv, Walker3DCustomVecEnv, Walker3DStepperVecEnv
+    from mocca_envs_b200.vec_env import (CassieVecEnv, Child3DCustomVecEnv, MikeStepperVecEnv, Monkey3DCustomVecEnv,
+                                         Walker3DCustomVecEnv, Walker3DStepperVecEnv)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
@@ -258,9 +265,12 @@ def main():
     N, K, W = args.envs, args.steps, max(args.warmup, 3)
     # env i of rank r is global env r*N + i: seeds are independent of the GPU count
     phys = {"self_collision": args.self_collision}
-    if args.env == "stepper":
-        env = Walker3DStepperVecEnv(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
+    if args.env in ("stepper", "mike"):
+        cls = Walker3DStepperVecEnv if args.env == "stepper" else MikeStepperVecEnv
+        env = cls(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
         env.set_env_params({"curriculum": np.array([0, 5, 9] * (N // 3 + 1))[:N]})
+    elif args.env == "child":
+        env = Child3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
     elif args.env == "monkey":
         env = Monkey3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
     elif args.env == "cassie":
@@ -387,8 +397,9 @@ def main():
     elif args.env == "monkey":  # Monkey3D: n = 29 generalised coordinates, 20 massive links, 29 geoms, obs 69
         F = flops_per_env_step(R_mean, n=29, L=20, G=29, P=n_self)
         B_step = bytes_per_env_step(S_state=59, A=23, O=69, S_env=40)
-    elif args.env == "stepper":
-        F = flops_per_env_step(R_mean, P=n_self)
+    elif args.env in ("stepper", "mike"):
+        F = flops_per_env_step(R_mean, L=len([x for x in env.table["mass"] if x > 0]) + 1, G=len(env.table["geoms"]),
+                               P=n_self)
         B_step = bytes_per_env_step(O=65, S_env=40)
     else:
         F = flops_per_env_step(R_mean, P=n_self)
@@ -405,8 +416,7 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_ach = B_step * N / kernel_s / 1e9
     line = {
-        "metric": METRIC.replace("Walker3DCustomEnv", {"custom": "Walker3DCustomEnv", "stepper": "Walker3DStepperEnv",
-                                                       "monkey": "Monkey3DCustomEnv", "cassie": "CassieEnv"}[args.env]
+        "metric": METRIC.replace("Walker3DCustomEnv", ENV_NAMES[args.env]
                                  ).replace("16384", str(N)),
         "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -415,7 +425,9 @@ def main():
                                 "stepper": "Walker3DStepperEnv-v0 batched 16384 envs/GPU, seeded stepping stones, "
                                            "curriculum 0/5/9",
                                 "monkey": "Monkey3DCustomEnv-v0 batched, seeded monkey bars",
-                                "cassie": "CassieEnv-v0 batched, residual PD control, 50 substeps per env step"}[args.env],
+                                "cassie": "CassieEnv-v0 batched, residual PD control, 50 substeps per env step",
+                                "child": "Child3DCustomEnv-v0 batched, flat ground, crawl start pose",
+                                "mike": "MikeStepperEnv-v0 batched, seeded stepping stones, curriculum 0/5/9"}[args.env],
                    "envs_per_gpu": N, "actions": "random-uniform U(-1,1)^%d (device pool)" % A
                    if args.actions == "random" else "scripted PD toward running_start (kp=1, kd=0.1, normalised)",
                    "frame_skip": S_sub, "solver_iterations": 5,

@@ -366,6 +366,16 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append("  MB_HD static float base_x() { return %s; }\n" % _f(r["base_position"][0]))
     out.append("  MB_HD static float base_y() { return %s; }\n" % _f(r["base_position"][1]))
     out.append("  MB_HD static float base_z() { return %s; }\n" % _f(r["base_position"][2]))
+    # base orientation of the start pose (robots.py:276,311-323; xyzw), the env's termination height
+    # (env_locomotion.py:44,320) and the stepper env's robot_init_position (env_locomotion.py:339,845)
+    bq = t.get("base_orientation", [0.0, 0.0, 0.0, 1.0])
+    out.append("  MB_HD static float base_quat(int k) { return k == 0 ? %s : (k == 1 ? %s : (k == 2 ? %s : %s)); }\n"
+               % tuple(_f(v) for v in bq))
+    out.append("  MB_HD static float term_height() { return %s; }\n" % _f(t.get("termination_height", 0.7)))
+    sp = t.get("stepper_init_position", [0.3, 0.0, 1.32])
+    out.append("  MB_HD static float stepper_x() { return %s; }\n" % _f(sp[0]))
+    out.append("  MB_HD static float stepper_y() { return %s; }\n" % _f(sp[1]))
+    out.append("  MB_HD static float stepper_z() { return %s; }\n" % _f(sp[2]))
     out.append("};\n")
     return "".join(out)
 
@@ -374,7 +384,8 @@ def emit_all(repo_root: str):
     gen = os.path.join(repo_root, "mocca_envs_b200", "csrc", "generated")
     os.makedirs(gen, exist_ok=True)
     models = os.path.join(repo_root, "mocca_envs_b200", "models")
-    for name, prefix in (("walker3d", "W3D"), ("monkey3d", "MK3D"), ("cassie", "CAS")):
+    for name, prefix in (("walker3d", "W3D"), ("monkey3d", "MK3D"), ("cassie", "CAS"), ("child3d", "CH3D"),
+                         ("mike", "MIKE")):
         t = load_table(os.path.join(models, name + ".json"))
         with open(os.path.join(gen, name + "_model.h"), "w") as f:
             f.write(emit_header(t, prefix))

@@ -37,6 +37,8 @@
 #include "generated/walker3d_model.h"
 #include "generated/monkey3d_model.h"
 #include "generated/cassie_model.h"
+#include "generated/child3d_model.h"
+#include "generated/mike_model.h"
 #include "mb_env.cuh"
 
 
@@ -48,7 +50,10 @@ static int fail(const std::string& m) { g_err = m; return -1; }
     if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_));                 \
   } while (0)
 
-enum { KIND_CUSTOM = 0, KIND_STEPPER = 1, KIND_MONKEY = 2, KIND_CASSIE = 3 };
+// KIND_CHILD / KIND_MIKE run the Walker3DCustomEnv / Walker3DStepperEnv templates on other model tables
+enum { KIND_CUSTOM = 0, KIND_STEPPER = 1, KIND_MONKEY = 2, KIND_CASSIE = 3, KIND_CHILD = 4, KIND_MIKE = 5 };
+static bool custom_family(int kind) { return kind == KIND_CUSTOM || kind == KIND_CHILD; }
+static bool stepper_family(int kind) { return kind == KIND_STEPPER || kind == KIND_MIKE; }
 
 struct mb200_env {
   int kind;        // KIND_*
@@ -98,6 +103,10 @@ typedef StepperEnv<WM> SEnv;
 typedef MonkeyEnv<MM> MEnv;
 typedef CAS_Model CM;
 typedef CassieEnv<CM> CEnv;
+typedef W3DEnv<CH3D_Model> ChEnv;       // Child3DCustomEnv-v0 (env_locomotion.py:317-327)
+typedef StepperEnv<MIKE_Model> MkEnv;   // MikeStepperEnv-v0 (env_locomotion.py:843-851)
+static_assert(sizeof(WarpMem<CH3D_Model>) <= sizeof(WarpMem<WM>) && sizeof(WarpMem<MIKE_Model>) <= sizeof(WarpMem<WM>),
+              "the shared-memory opt-in of the Walker3D-family kernels is sized for the Walker3D table");
 typedef WarpMem<WM> WMem;
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -196,6 +205,12 @@ __global__ void __launch_bounds__(MB_WARPS_MONKEY * 32, MB_MINBLOCKS) k_step_mon
 __global__ void __launch_bounds__(MB_WARPS_CASSIE * 32, MB_MINBLOCKS) k_step_cassie(StepArgs a) {
   step_body<CEnv>(a);
 }
+__global__ void __launch_bounds__(MB_WARPS_STEPPER * 32, MB_MINBLOCKS) k_step_child3d_custom(StepArgs a) {
+  step_body<ChEnv>(a);
+}
+__global__ void __launch_bounds__(MB_WARPS_STEPPER * 32, MB_MINBLOCKS) k_step_mike_stepper(StepArgs a) {
+  step_body<MkEnv>(a);
+}
 
 template <class Env>
 __device__ __forceinline__ void reset_body(int n, const MbPhysics& phys, float* state, float* rec, uint32_t* mt,
@@ -230,6 +245,16 @@ __global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_reset_cassie(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask, float* obs,
                    float* dummy_obs) {
   reset_body<CEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
+}
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
+    k_reset_child3d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
+                           float* obs, float* dummy_obs) {
+  reset_body<ChEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
+}
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
+    k_reset_mike_stepper(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
+                         float* obs, float* dummy_obs) {
+  reset_body<MkEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
 }
 
 // stepSimulation only; rec (may be NULL) supplies the static obstacles of the env kind
@@ -281,6 +306,16 @@ __global__ void __launch_bounds__(MB_WARPS_MAX * 32)
                           int* contacts_out) {
   physics_body<CEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
 }
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
+    k_step_physics_child3d(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
+                           int* contacts_out) {
+  physics_body<ChEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
+}
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
+    k_step_physics_mike_stepper(int n, MbPhysics phys, float* state, const float* rec, const float* tau,
+                                int* rows_out, int* contacts_out) {
+  physics_body<MkEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
+}
 
 // mode 0: M (full symmetric, [nu][nu]);  mode 1: tau = M acc - rhs (rhs = -bias with zero applied torque)
 template <class Env>
@@ -325,6 +360,14 @@ __global__ void __launch_bounds__(MB_WARPS_MAX * 32)
 __global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_dynamics_debug_cassie(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
   dynamics_debug_body<CEnv>(n, phys, state, mode, acc, out);
+}
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
+    k_dynamics_debug_child3d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
+  dynamics_debug_body<ChEnv>(n, phys, state, mode, acc, out);
+}
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
+    k_dynamics_debug_mike(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
+  dynamics_debug_body<MkEnv>(n, phys, state, mode, acc, out);
 }
 
 __global__ void k_copy_strided(int n, int width, const float* src, int src_stride, float* dst, int dst_stride) {
@@ -401,9 +444,12 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   if (env_id && strcmp(env_id, "Walker3DStepperEnv-v0") == 0) kind = KIND_STEPPER;
   if (env_id && strcmp(env_id, "Monkey3DCustomEnv-v0") == 0) kind = KIND_MONKEY;
   if (env_id && strcmp(env_id, "CassieEnv-v0") == 0) kind = KIND_CASSIE;
+  if (env_id && strcmp(env_id, "Child3DCustomEnv-v0") == 0) kind = KIND_CHILD;
+  if (env_id && strcmp(env_id, "MikeStepperEnv-v0") == 0) kind = KIND_MIKE;
   if (kind < 0)
     return fail(std::string("mb200_create: unsupported env id '") + (env_id ? env_id : "(null)") +
-                "' (built: Walker3DCustomEnv-v0, Walker3DStepperEnv-v0, Monkey3DCustomEnv-v0, CassieEnv-v0)");
+                "' (built: Walker3DCustomEnv-v0, Walker3DStepperEnv-v0, Monkey3DCustomEnv-v0, CassieEnv-v0, "
+                "Child3DCustomEnv-v0, MikeStepperEnv-v0)");
   if (n_envs <= 0) return fail("mb200_create: n_envs must be positive");
   int count = 0;
   CUDA_OK(cudaGetDeviceCount(&count));
@@ -421,20 +467,21 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   e->kind = kind;
   int nj = WM::NJ;
   switch (kind) {
+    case KIND_MIKE:
     case KIND_STEPPER: e->rec_stride = SEnv::REC_STRIDE; e->obs_dim = SEnv::OBS; e->act_dim = SEnv::ACT; break;
     case KIND_MONKEY: e->rec_stride = MEnv::REC_STRIDE; e->obs_dim = MEnv::OBS; e->act_dim = MEnv::ACT; nj = MM::NJ; break;
     case KIND_CASSIE: e->rec_stride = CEnv::REC_STRIDE; e->obs_dim = CEnv::OBS; e->act_dim = CEnv::ACT; nj = CM::NJ; break;
     default: e->rec_stride = WEnv::REC_STRIDE; e->obs_dim = WEnv::OBS; e->act_dim = WEnv::ACT; break;
   }
   e->warps = kind == KIND_MONKEY ? MB_WARPS_MONKEY : kind == KIND_CASSIE ? MB_WARPS_CASSIE
-             : kind == KIND_STEPPER ? MB_WARPS_STEPPER : MB_WARPS_CUSTOM;
+             : kind == KIND_CUSTOM ? MB_WARPS_CUSTOM : MB_WARPS_STEPPER;
   e->state_dim = 13 + 2 * nj;
   e->nu = 6 + nj;
   mb200_physics p;
   mb200_default_physics_for(env_id, &p);
   if (physics) p = *physics;
   to_internal(p, &e->phys);
-  if (kind == KIND_STEPPER) {
+  if (stepper_family(kind)) {
     // remove_ground=True (env_locomotion.py:359); planks: lateralFriction 1.0, contactStiffness 30000,
     // contactDamping 1000 (bullet_objects.py:64-72) -> per-contact erp / cfm; Bullet sums both
     // bodies' contact damping and a link's default is 0.1
@@ -444,8 +491,9 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
     e->phys.box_erp = e->phys.dt * kp / denom;
     e->phys.box_cfm = 1.0f / denom;
   }
-  e->smem = (kind == KIND_MONKEY ? sizeof(WarpMem<MM>) : kind == KIND_CASSIE ? sizeof(WarpMem<CM>) : sizeof(WMem)) *
-            e->warps;
+  e->smem = (kind == KIND_MONKEY ? sizeof(WarpMem<MM>) : kind == KIND_CASSIE ? sizeof(WarpMem<CM>)
+             : kind == KIND_CHILD ? sizeof(WarpMem<CH3D_Model>) : kind == KIND_MIKE ? sizeof(WarpMem<MIKE_Model>)
+             : sizeof(WMem)) * e->warps;
   {
     // opt every kernel in to the largest dynamic shared memory any env kind may launch it with (several env kinds
     // can live in one process; the attribute is per kernel, not per handle)
@@ -467,6 +515,14 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
     CUDA_OK(cudaFuncSetAttribute(k_reset_walker3d_custom, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_walker3d, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_child3d_custom, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_reset_child3d_custom, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_physics_child3d, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_child3d, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_mike_stepper, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_reset_mike_stepper, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_physics_mike_stepper, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_mike, at, sw));
   }
   e->n_pad = grid_for(e) * e->warps;
   const size_t n = (size_t)e->n_pad;
@@ -586,6 +642,12 @@ int mb200_reset(mb200_env* e, const uint8_t* mask_dev, float* obs_dev, void* str
   else if (e->kind == KIND_MONKEY)
     k_reset_monkey3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
+  else if (e->kind == KIND_CHILD)
+    k_reset_child3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
+  else if (e->kind == KIND_MIKE)
+    k_reset_mike_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
   else if (e->kind == KIND_STEPPER)
     k_reset_walker3d_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
@@ -626,6 +688,10 @@ static int step_impl(mb200_env* e, const float* act_dev, float* obs_dev, float* 
     k_step_cassie<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
   else if (e->kind == KIND_MONKEY)
     k_step_monkey3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
+  else if (e->kind == KIND_CHILD)
+    k_step_child3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
+  else if (e->kind == KIND_MIKE)
+    k_step_mike_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
   else if (e->kind == KIND_STEPPER)
     k_step_walker3d_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
   else
@@ -706,6 +772,12 @@ int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* c
   else if (e->kind == KIND_MONKEY)
     k_step_physics_monkey3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
+  else if (e->kind == KIND_CHILD)
+    k_step_physics_child3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
+  else if (e->kind == KIND_MIKE)
+    k_step_physics_mike_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
   else if (e->kind == KIND_STEPPER)
     k_step_physics_walker3d_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
@@ -726,6 +798,12 @@ int mb200_mass_matrix(mb200_env* e, float* M_dev, void* stream) {
   else if (e->kind == KIND_MONKEY)
     k_dynamics_debug_monkey3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, 0, nullptr, M_dev);
+  else if (e->kind == KIND_CHILD)
+    k_dynamics_debug_child3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, 0, nullptr, M_dev);
+  else if (e->kind == KIND_MIKE)
+    k_dynamics_debug_mike<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, 0, nullptr, M_dev);
   else
     k_dynamics_debug_walker3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, 0, nullptr, M_dev);
@@ -745,6 +823,12 @@ int mb200_inverse_dynamics(mb200_env* e, const float* acc_dev, float* tau_dev, v
         e->n, p, e->state, 1, acc_dev, tau_dev);
   else if (e->kind == KIND_MONKEY)
     k_dynamics_debug_monkey3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, p, e->state, 1, acc_dev, tau_dev);
+  else if (e->kind == KIND_CHILD)
+    k_dynamics_debug_child3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, p, e->state, 1, acc_dev, tau_dev);
+  else if (e->kind == KIND_MIKE)
+    k_dynamics_debug_mike<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, p, e->state, 1, acc_dev, tau_dev);
   else
     k_dynamics_debug_walker3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
@@ -771,8 +855,8 @@ static int set_record_int(mb200_env* e, int field, const float* values, int coun
 
 static int param_field(mb200_env* e, const char* key, float lo, float hi, const float* values, int count, float scalar,
                        int* field) {
-  if (strcmp(key, "eval_mode") == 0 && e->kind == KIND_CUSTOM) { *field = ER_EVAL; return 0; }
-  if (strcmp(key, "curriculum") == 0 && e->kind == KIND_STEPPER) {
+  if (strcmp(key, "eval_mode") == 0 && custom_family(e->kind)) { *field = ER_EVAL; return 0; }
+  if (strcmp(key, "curriculum") == 0 && stepper_family(e->kind)) {
     for (int i = 0; i < (values ? count : 1); ++i) {
       const float v = values ? values[i] : scalar;
       if (!(v >= 0.0f && v <= 9.0f)) return fail("mb200_set_param: curriculum must be in [0, 9]");
@@ -780,7 +864,7 @@ static int param_field(mb200_env* e, const char* key, float lo, float hi, const 
     *field = ES_CURRIC;
     return 0;
   }
-  if (strcmp(key, "random_reward") == 0 && e->kind == KIND_STEPPER) { *field = ES_RANDOM_REWARD; return 0; }
+  if (strcmp(key, "random_reward") == 0 && stepper_family(e->kind)) { *field = ES_RANDOM_REWARD; return 0; }
   (void)lo; (void)hi;
   return fail(std::string("mb200_set_param: unknown key '") + key + "' for this env");
 }
@@ -790,7 +874,7 @@ int mb200_set_param(mb200_env* e, const char* key, float value) {
   CUDA_OK(cudaSetDevice(e->device));
   int field = 0;
   if (param_field(e, key, 0, 0, nullptr, 0, value, &field)) return -1;
-  return set_record_int(e, field, nullptr, 0, field == ER_EVAL && e->kind == KIND_CUSTOM ? (value != 0.0f) : value);
+  return set_record_int(e, field, nullptr, 0, field == ER_EVAL && custom_family(e->kind) ? (value != 0.0f) : value);
 }
 
 int mb200_set_param_array(mb200_env* e, const char* key, const float* values_host, int count) {

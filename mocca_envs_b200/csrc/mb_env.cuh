@@ -308,7 +308,8 @@ template <class M> struct W3DEnv {
       if (l < NU) S.u[l] = 0.0f;
       if (l == 31) {
         S.pos[0] = M::base_x(); S.pos[1] = M::base_y(); S.pos[2] = M::base_z();
-        S.quat[0] = 0.0f; S.quat[1] = 0.0f; S.quat[2] = 0.0f; S.quat[3] = 1.0f;
+        // "quat = quat or self.base_orientation" (robots.py:199): the un-mirrored attribute
+        S.quat[0] = M::base_quat(0); S.quat[1] = M::base_quat(1); S.quat[2] = M::base_quat(2); S.quat[3] = M::base_quat(3);
       }
     MB_END
     typename S_::LaneConst C;
@@ -386,7 +387,7 @@ template <class M> struct W3DEnv {
     const float energy = 4.5f * (s1 / NJ) + 0.225f * (s2 / NJ);
     const float joints_pen = 0.1f * o.joints_at_limit;
     const float height_obs = mb_clip5(o.height);
-    const float tall = height_obs > 0.7f ? 2.0f : -1.0f;
+    const float tall = height_obs > M::term_height() ? 2.0f : -1.0f;  // env_locomotion.py:44,195,320
     if (tall < 0.0f) env_done = 1;
     float target_bonus = 0.0f;
     int close = rec_i(rec, ER_CLOSE);
@@ -621,7 +622,7 @@ template <class M> struct StepperEnv {
       }
       if (l < NU) S.u[l] = 0.0f;
       if (l == 31) {
-        S.pos[0] = 0.3f; S.pos[1] = 0.0f; S.pos[2] = 1.32f;  // robot_init_position, env_locomotion.py:339
+        S.pos[0] = M::stepper_x(); S.pos[1] = M::stepper_y(); S.pos[2] = M::stepper_z();  // robot_init_position, env_locomotion.py:339,845
         S.quat[0] = 0.0f; S.quat[1] = 0.0f; S.quat[2] = 0.0f; S.quat[3] = 1.0f;
       }
     MB_END

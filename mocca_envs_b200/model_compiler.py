@@ -544,6 +544,74 @@ def compile_walker3d(data_dir: str, **kw) -> dict:
     return t
 
 
+MIKE_POWER = {  # mocca_envs/robots.py:477-499
+    "abdomen_z": 0, "abdomen_y": 0, "abdomen_x": 0,
+    "right_hip_x": 80, "right_hip_z": 60, "right_hip_y": 100, "right_knee": 90, "right_ankle": 60,
+    "left_hip_x": 80, "left_hip_z": 60, "left_hip_y": 100, "left_knee": 90, "left_ankle": 60,
+    "right_shoulder_x": 30, "right_shoulder_z": 30, "right_shoulder_y": 25, "right_elbow": 30,
+    "left_shoulder_x": 30, "left_shoulder_z": 30, "left_shoulder_y": 25, "left_elbow": 30,
+}
+
+
+def _walker_family(t: dict) -> dict:
+    """Mirroring tables shared by the Walker3D subclasses (robots.py:280-290)."""
+    t["right_joint_indices"] = [3, 4, 5, 6, 7, 13, 14, 15, 16]
+    t["left_joint_indices"] = [8, 9, 10, 11, 12, 17, 18, 19, 20]
+    t["negation_joint_indices"] = [0, 2]
+    t["self_pairs"], t["self_pairs_candidates"] = self_collision_pairs(t)
+    return t
+
+
+def compile_child3d(data_dir: str, **kw) -> dict:
+    """Child3D (robots.py:326-335): Walker3D's joints on child3d.xml, power 0.4, base at z = 0.38;
+    Child3DCustomEnv (env_locomotion.py:317-327) starts it in the "crawl" pose (robots.py:314-323) and ends the
+    episode below a relative height of 0.1."""
+    t = compile_mjcf(data_dir + "/robots/child3d.xml", "child3d", WALKER3D_POWER, 0.4,
+                     ["right_foot", "left_foot"], **kw)
+    d = math.pi / 180
+    pose = [0.0] * 21
+    pose[13] = pose[17] = math.pi / 2
+    pose[14] = pose[18] = math.pi / 2
+    pose[16] = pose[20] = math.pi / 3
+    pose[5] = pose[10] = -math.pi / 2
+    pose[6] = pose[11] = -120 * d
+    pose[7] = pose[12] = -20 * d
+    t["base_joint_angles"] = pose
+    t["base_position"] = [0.0, 0.0, 0.38]
+    # pybullet.getQuaternionFromEuler([0, 90 deg, 0]) = (0, sin 45, 0, cos 45), xyzw
+    t["base_orientation"] = [0.0, math.sin(math.pi / 4), 0.0, math.cos(math.pi / 4)]
+    t["termination_height"] = 0.1  # env_locomotion.py:320
+    return _walker_family(t)
+
+
+def compile_mike(data_dir: str, **kw) -> dict:
+    """Mike (robots.py:474-513): Walker3D's joints on mike.xml with its own power table; the waist link's mass is set
+    to 8 after loading (changeDynamics, :506-510).  MikeStepperEnv (env_locomotion.py:843-851) starts it at
+    (0.3, 0, 1.0)."""
+    t = compile_mjcf(data_dir + "/robots/mike.xml", "mike", MIKE_POWER, 1.0, ["right_foot", "left_foot"], **kw)
+    w = t["link_names"].index("waist")
+    old = t["mass"][w]
+    # changeDynamics(mass=m) on a multibody link: Bullet re-derives the local inertia from the link's collision shape
+    # with the new mass; for the single sphere of this link that is the old diagonal scaled by m / m_old
+    # (hypothesis recorded in conventions; btCompoundShape's AABB approximation would differ)
+    t["mass"][w] = 8.0
+    t["inertia"][w] = [x * 8.0 / old for x in t["inertia"][w]]
+    t["total_mass"] = float(t["base"]["mass"] + sum(t["mass"]))
+    t.setdefault("conventions", {})["mike_waist_mass"] = "mass 8 (robots.py:510), inertia scaled by 8 / %.6g" % old
+    pose = [0.0] * 21  # MikeStepperEnv inherits Walker3DStepperEnv's set_base_pose("running_start")
+    for i in (5, 6):
+        pose[i] = -math.pi / 8
+    pose[10] = math.pi / 10
+    pose[13] = pose[17] = math.pi / 3
+    pose[14] = -math.pi / 6
+    pose[18] = math.pi / 6
+    pose[16] = pose[20] = math.pi / 3
+    t["base_joint_angles"] = pose
+    t["base_position"] = [0.0, 0.0, 1.32]           # Walker3D.set_base_pose default (robots.py:275)
+    t["stepper_init_position"] = [0.3, 0.0, 1.0]    # env_locomotion.py:845
+    return _walker_family(t)
+
+
 def compile_monkey3d(data_dir: str, **kw) -> dict:
     t = compile_mjcf(data_dir + "/robots/monkey3d.xml", "monkey3d", MONKEY3D_POWER, 0.7,
                      ["right_hand", "left_hand"], **kw)

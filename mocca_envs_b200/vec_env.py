@@ -27,6 +27,8 @@ ENV_ID = "Walker3DCustomEnv-v0"
 STEPPER_ID = "Walker3DStepperEnv-v0"
 MONKEY_ID = "Monkey3DCustomEnv-v0"
 CASSIE_ID = "CassieEnv-v0"
+CHILD_ID = "Child3DCustomEnv-v0"
+MIKE_ID = "MikeStepperEnv-v0"
 _MODELS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models")
 
 
@@ -296,6 +298,23 @@ class Walker3DStepperVecEnv(Walker3DCustomVecEnv):
         return neg_obs, right, left, neg_j, right_j, left_j
 
 
+class Child3DCustomVecEnv(Walker3DCustomVecEnv):
+    """Batched Child3DCustomEnv-v0 (reference env_locomotion.py:317-327, robots.py:326-335): Walker3DCustomEnv's
+    logic on the child3d model (power 0.4), started in the "crawl" pose at z = 0.38 with the base pitched by 90
+    degrees, episode over below a relative height of 0.1."""
+
+    env_id = CHILD_ID
+    model = "child3d"
+
+
+class MikeStepperVecEnv(Walker3DStepperVecEnv):
+    """Batched MikeStepperEnv-v0 (reference env_locomotion.py:843-851, robots.py:474-513): Walker3DStepperEnv's
+    logic on the mike model (own power table, waist mass 8), started at (0.3, 0, 1.0)."""
+
+    env_id = MIKE_ID
+    model = "mike"
+
+
 class Monkey3DCustomVecEnv(Walker3DCustomVecEnv):
     """Batched Monkey3DCustomEnv-v0 (reference env_locomotion.py:1136-1516): 23-DoF brachiator released at 20 m
     with both hands on the first two of 32 seeded monkey bars (4 physical bars, recycled); the finger joints are
@@ -435,6 +454,18 @@ class Walker3DStepperEnv(Walker3DCustomEnv):
         raise AttributeError("Walker3DStepperEnv has no evaluation_mode")
 
 
+class Child3DCustomEnv(Walker3DCustomEnv):
+    """gym-protocol facade of Child3DCustomEnv-v0."""
+
+    vec_class = Child3DCustomVecEnv
+
+
+class MikeStepperEnv(Walker3DStepperEnv):
+    """gym-protocol facade of MikeStepperEnv-v0."""
+
+    vec_class = MikeStepperVecEnv
+
+
 class Monkey3DCustomEnv(Walker3DCustomEnv):
     """gym-protocol facade of Monkey3DCustomEnv-v0.  The reference overwrites the two finger entries of the caller's
     action array in place (env_locomotion.py:1322-1323, quirk Q11); the kernel applies the same override internally
@@ -471,7 +502,8 @@ class CassieEnv(Walker3DCustomEnv):
 
 
 _REGISTRY = {ENV_ID: (Walker3DCustomEnv, Walker3DCustomVecEnv), STEPPER_ID: (Walker3DStepperEnv, Walker3DStepperVecEnv),
-             MONKEY_ID: (Monkey3DCustomEnv, Monkey3DCustomVecEnv), CASSIE_ID: (CassieEnv, CassieVecEnv)}
+             MONKEY_ID: (Monkey3DCustomEnv, Monkey3DCustomVecEnv), CASSIE_ID: (CassieEnv, CassieVecEnv),
+             CHILD_ID: (Child3DCustomEnv, Child3DCustomVecEnv), MIKE_ID: (MikeStepperEnv, MikeStepperVecEnv)}
 
 
 def make(env_id: str, num_envs: int | None = None, **kwargs):

@@ -1281,7 +1281,8 @@ static void robot_reset_ex(const orc_model* m, orc_w3d_env* e, const double* pos
   }
   for (int d = 0; d < A; d++) { e->s.q[d] = ang[d]; e->s.qd[d] = 0; }
   for (int k = 0; k < 3; k++) { e->s.pos[k] = pos[k]; e->s.omega[k] = 0; e->s.vel[k] = vel ? vel[k] : 0; }
-  e->s.quat[0] = e->s.quat[1] = e->s.quat[2] = 0; e->s.quat[3] = 1;
+  /* "quat = quat or self.base_orientation" (robots.py:199): the un-mirrored attribute, not the mirrored copy */
+  for (int k = 0; k < 4; k++) e->s.quat[k] = m->base_orientation[k];
   for (int f = 0; f < 4; f++) { e->feet_contact[f] = 0; v3set(e->feet_xyz[f], 0, 0, 0); }
   for (int i = 0; i < ORC_MAXW; i++) e->warm[i] = 0;
   w3d_calc_state(m, e, NULL);
@@ -1359,7 +1360,7 @@ void orc_w3d_step(const orc_model* m, const orc_params* p, orc_w3d_env* e, const
   for (int d = 0; d < A; d++) { s1 += fabs(action[d] * e->joint_speeds[d]); s2 += action[d] * action[d]; }
   e->energy_penalty = 4.5 * (s1 / A) + 0.225 * (s2 / A);
   e->joints_penalty = 0.1 * e->joints_at_limit;
-  e->tall_bonus = e->robot_state[0] > 0.7 ? 2.0 : -1.0;
+  e->tall_bonus = e->robot_state[0] > m->termination_height ? 2.0 : -1.0;
   if (e->tall_bonus < 0) e->done = 1;
   e->target_bonus = 0;
   if (e->distance_to_target < 0.15) { e->close_count++; e->target_bonus = 2; }
@@ -1510,7 +1511,8 @@ void orc_stepper_reset(const orc_model* m, const orc_params* p, orc_stepper_env*
   e->timestep = 0; b->done = 0; b->elapsed = 0; e->target_reached_count = 0;
   e->set_stop_on_next_step = 0; e->stop_on_next_step = 0; e->steps_reached = -1;
   e->gain_curriculum = e->curriculum > 9 ? 9 : e->curriculum;
-  double pos[3] = {0.3, 0.0, 1.32}; /* env_locomotion.py:339 */
+  double pos[3] = {m->stepper_init_position[0], m->stepper_init_position[1],
+                   m->stepper_init_position[2]}; /* env_locomotion.py:339,845 */
   w3d_robot_reset(m, b, pos);
   /* quirk Q5: the reference runs calc_feet_state() here on Bullet's STALE contact points of the previous episode;
    * the batched simulator defines "no contacts after reset" (documented deviation) */

@@ -55,6 +55,9 @@ typedef struct {
   int foot_link[4];
   double base_joint_angles[ORC_MAXD];
   double base_position[3];
+  double base_orientation[4];       /* xyzw; set_base_pose (robots.py:276,311-323) */
+  double termination_height;        /* env class attribute (env_locomotion.py:44,320) */
+  double stepper_init_position[3];  /* robot_init_position of the stepper env (env_locomotion.py:339,845) */
   int n_right, right_idx[ORC_MAXD], left_idx[ORC_MAXD]; /* mirroring tables robots.py:282-290 */
   int n_neg, neg_idx[8];
   int palm_link[2]; /* Monkey3D: right_palm, left_palm (env_locomotion.py:1269,1424); -1 otherwise */

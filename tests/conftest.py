@@ -35,6 +35,20 @@ def monkey_table():
 
 
 @pytest.fixture(scope="session")
+def child_table():
+    from mocca_envs_b200.model_compiler import load_table
+
+    return load_table(os.path.join(ROOT, "mocca_envs_b200", "models", "child3d.json"))
+
+
+@pytest.fixture(scope="session")
+def mike_table():
+    from mocca_envs_b200.model_compiler import load_table
+
+    return load_table(os.path.join(ROOT, "mocca_envs_b200", "models", "mike.json"))
+
+
+@pytest.fixture(scope="session")
 def cassie_table():
     from mocca_envs_b200.model_compiler import load_table
 

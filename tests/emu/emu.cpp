@@ -6,6 +6,8 @@
 #include "../../mocca_envs_b200/csrc/generated/walker3d_model.h"
 #include "../../mocca_envs_b200/csrc/generated/monkey3d_model.h"
 #include "../../mocca_envs_b200/csrc/generated/cassie_model.h"
+#include "../../mocca_envs_b200/csrc/generated/child3d_model.h"
+#include "../../mocca_envs_b200/csrc/generated/mike_model.h"
 #include "../../mocca_envs_b200/csrc/mb_env.cuh"
 
 typedef W3D_Model WM;
@@ -243,4 +245,59 @@ void emu_cassie_mass_matrix(const MbPhysics* p, const float* state, float* Mout,
     bias[i] = -S.rhs[i];
   }
 }
+
+// ---- more model tables through the same env templates (Child3DCustomEnv-v0, MikeStepperEnv-v0)
+#define EMU_ENV(PFX, MODEL, ENV, OBST)                                                                                \
+  void emu_##PFX##_reset(const MbPhysics* p, float* state, float* rec, uint32_t* mt_env, uint32_t* mt_robot,         \
+                         float* obs) {                                                                                \
+    static WarpMem<MODEL> S;                                                                                          \
+    memset(&S, 0, sizeof(S));                                                                                         \
+    ENV::reset(S, *p, rec, mt_env, mt_robot, obs);                                                                    \
+    W3DEnv<MODEL>::store_state(S, state);                                                                             \
+  }                                                                                                                   \
+  void emu_##PFX##_step(const MbPhysics* p, float* state, float* rec, uint32_t* mt_env, uint32_t* mt_robot,          \
+                        const float* act, float* obs, float* rew, uint8_t* done, uint8_t* trunc, float* final_obs,   \
+                        double* stats_out) {                                                                          \
+    static WarpMem<MODEL> S;                                                                                          \
+    memset(&S, 0, sizeof(S));                                                                                         \
+    MbStats st;                                                                                                       \
+    memset(&st, 0, sizeof(st));                                                                                       \
+    ENV::step(S, *p, state, rec, mt_env, mt_robot, act, obs, rew, done, trunc, final_obs, &st);                       \
+    stats_out[0] = (double)st.episodes; stats_out[1] = st.ret_sum; stats_out[2] = st.len_sum;                         \
+    stats_out[3] = (double)st.nonfinite;                                                                              \
+  }                                                                                                                   \
+  void emu_##PFX##_step_physics(const MbPhysics* p, float* state, const float* rec, const float* tau, int* rows,     \
+                                int* contacts) {                                                                      \
+    static WarpMem<MODEL> S;                                                                                          \
+    memset(&S, 0, sizeof(S));                                                                                         \
+    W3DEnv<MODEL>::load_state(S, state);                                                                              \
+    for (int j = 0; j < MODEL::NJ; ++j) S.tau[j] = tau[j];                                                            \
+    int r = 0, nc = 0, ov = 0;                                                                                        \
+    Sim<MODEL>::LaneConst C;                                                                                          \
+    Sim<MODEL>::init_lane_const(C);                                                                                   \
+    for (int k = 0; k < p->substeps; ++k) {                                                                           \
+      ENV::load_obstacles(S, rec);                                                                                    \
+      r += Sim<MODEL>::substep<OBST>(S, *p, C, &nc, &ov);                                                             \
+    }                                                                                                                 \
+    W3DEnv<MODEL>::store_state(S, state);                                                                             \
+    *rows = r;                                                                                                        \
+    *contacts = nc;                                                                                                   \
+  }                                                                                                                   \
+  void emu_##PFX##_mass_matrix(const MbPhysics* p, const float* state, float* Mout, float* bias) {                   \
+    static WarpMem<MODEL> S;                                                                                          \
+    memset(&S, 0, sizeof(S));                                                                                         \
+    W3DEnv<MODEL>::load_state(S, state);                                                                              \
+    Sim<MODEL>::LaneConst C;                                                                                          \
+    Sim<MODEL>::init_lane_const(C);                                                                                   \
+    Sim<MODEL>::kinematics(S, *p, C, true);                                                                           \
+    Sim<MODEL>::bodies(S, *p);                                                                                        \
+    Sim<MODEL>::mass_matrix_and_rhs(S);                                                                               \
+    const int NU = MODEL::NU;                                                                                         \
+    for (int i = 0; i < NU; ++i) {                                                                                    \
+      for (int j = 0; j < NU; ++j) Mout[i * NU + j] = mb_Lget<MODEL>(S.L, i, j);                                      \
+      bias[i] = -S.rhs[i];                                                                                            \
+    }                                                                                                                 \
+  }
+EMU_ENV(child, CH3D_Model, W3DEnv<CH3D_Model>, 0)
+EMU_ENV(mike, MIKE_Model, StepperEnv<MIKE_Model>, MB_OBST_BOXES)
 }

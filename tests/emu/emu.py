@@ -9,7 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libmb_emu.so")
 _SRC = [os.path.join(_HERE, "emu.cpp")] + [
     os.path.join(_HERE, "..", "..", "mocca_envs_b200", "csrc", f)
-    for f in ("mb_core.cuh", "mb_env.cuh", "mb_tables.h", "generated/walker3d_model.h", "generated/monkey3d_model.h", "generated/cassie_model.h")]
+    for f in ("mb_core.cuh", "mb_env.cuh", "mb_tables.h", "generated/walker3d_model.h", "generated/monkey3d_model.h",
+              "generated/cassie_model.h", "generated/child3d_model.h", "generated/mike_model.h")]
 
 
 class Phys(C.Structure):
@@ -66,6 +67,8 @@ def mass_matrix(p, state, nu):
 
 
 class EmuW3D:
+    prefix = "w3d"  # emu_<prefix>_reset / _step in emu.cpp
+
     def __init__(self, mt_state, obs_dim=52, act_dim=21, phys=None):
         self.p = phys or default_phys()
         self.state = np.zeros(64, dtype=np.float32)
@@ -79,7 +82,7 @@ class EmuW3D:
 
     def reset(self):
         obs = np.zeros(self.obs_dim, dtype=np.float32)
-        lib().emu_w3d_reset(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(self.mt[0]), _fp(self.mt[1]), _fp(obs))
+        getattr(lib(), "emu_%s_reset" % self.prefix)(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(self.mt[0]), _fp(self.mt[1]), _fp(obs))
         return obs
 
     def step(self, act):
@@ -90,10 +93,36 @@ class EmuW3D:
         done = np.zeros(1, dtype=np.uint8)
         trunc = np.zeros(1, dtype=np.uint8)
         st = np.zeros(4)
-        lib().emu_w3d_step(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(self.mt[0]), _fp(self.mt[1]), _fp(act),
-                           _fp(obs), _fp(rew), _fp(done), _fp(trunc), _fp(fin), _fp(st))
+        getattr(lib(), "emu_%s_step" % self.prefix)(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(self.mt[0]),
+                                                    _fp(self.mt[1]), _fp(act), _fp(obs), _fp(rew), _fp(done), _fp(trunc),
+                                                    _fp(fin), _fp(st))
         self.stats += st
         return obs, float(rew[0]), bool(done[0]), bool(trunc[0]), fin
+
+
+class EmuChild(EmuW3D):
+    """Child3DCustomEnv-v0: the Walker3DCustomEnv template on the child3d table."""
+    prefix = "child"
+
+
+def model_step_physics(prefix, p, state, tau, rec=None):
+    """stepSimulation through emu_<prefix>_step_physics (child: ground plane; mike: the planks of a Stepper record)."""
+    buf = np.zeros(64, dtype=np.float32)
+    buf[: len(state)] = state
+    tau = np.ascontiguousarray(tau, dtype=np.float32)
+    rec = np.zeros(192, dtype=np.float32) if rec is None else rec
+    rows, nc = C.c_int(0), C.c_int(0)
+    getattr(lib(), "emu_%s_step_physics" % prefix)(C.byref(p), _fp(buf), _fp(rec), _fp(tau), C.byref(rows), C.byref(nc))
+    return buf[: len(state)].copy(), rows.value, nc.value
+
+
+def model_mass_matrix(prefix, p, state, nu=27):
+    buf = np.zeros(64, dtype=np.float32)
+    buf[: len(state)] = state
+    M = np.zeros((nu, nu), dtype=np.float32)
+    b = np.zeros(nu, dtype=np.float32)
+    getattr(lib(), "emu_%s_mass_matrix" % prefix)(C.byref(p), _fp(buf), _fp(M), _fp(b))
+    return M, b
 
 
 def stepper_phys():
@@ -104,6 +133,8 @@ def stepper_phys():
 
 class EmuStepper:
     """Walker3DStepperEnv through the emulated kernel source (record layout: ER_* / ES_* in mb_env.cuh)."""
+
+    prefix = "stepper"
 
     ES_NEXT, ES_COUNT, ES_STOP, ES_SETSTOP, ES_TIMESTEP, ES_CURRIC, ES_PLANKIDX, ES_STEPS = 22, 23, 24, 25, 26, 27, 28, 31
     ES_BOX, ES_TERRAIN = 32, 68
@@ -122,7 +153,7 @@ class EmuStepper:
 
     def reset(self):
         obs = np.zeros(self.obs_dim, dtype=np.float32)
-        lib().emu_stepper_reset(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(self.mt[0]), _fp(self.mt[1]), _fp(obs))
+        getattr(lib(), "emu_%s_reset" % self.prefix)(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(self.mt[0]), _fp(self.mt[1]), _fp(obs))
         return obs
 
     def step(self, act):
@@ -133,8 +164,9 @@ class EmuStepper:
         done = np.zeros(1, dtype=np.uint8)
         trunc = np.zeros(1, dtype=np.uint8)
         st = np.zeros(4)
-        lib().emu_stepper_step(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(self.mt[0]), _fp(self.mt[1]),
-                               _fp(act), _fp(obs), _fp(rew), _fp(done), _fp(trunc), _fp(fin), _fp(st))
+        getattr(lib(), "emu_%s_step" % self.prefix)(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(self.mt[0]),
+                                                    _fp(self.mt[1]), _fp(act), _fp(obs), _fp(rew), _fp(done), _fp(trunc),
+                                                    _fp(fin), _fp(st))
         return obs, float(rew[0]), bool(done[0]), bool(trunc[0]), fin
 
     def terrain(self):
@@ -143,8 +175,13 @@ class EmuStepper:
     def step_physics(self, tau):
         tau = np.ascontiguousarray(tau, dtype=np.float32)
         rows, nc = C.c_int(0), C.c_int(0)
-        lib().emu_stepper_step_physics(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(tau), C.byref(rows), C.byref(nc))
+        getattr(lib(), "emu_%s_step_physics" % self.prefix)(C.byref(self.p), _fp(self.state), _fp(self.rec), _fp(tau), C.byref(rows), C.byref(nc))
         return rows.value, nc.value
+
+
+class EmuMike(EmuStepper):
+    """MikeStepperEnv-v0: the Walker3DStepperEnv template on the mike table."""
+    prefix = "mike"
 
 
 class EmuMonkey:
