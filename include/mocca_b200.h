@@ -48,9 +48,10 @@ void mb200_default_physics(mb200_physics* p);
 void mb200_default_physics_for(const char* env_id, mb200_physics* p);
 
 /* gym.make("mocca_envs:<env_id>") x n_envs  (reference mocca_envs/__init__.py:18-116, env_base.py:16-42).
- * env_id: "Walker3DCustomEnv-v0" (__init__.py:52-56), "Walker3DStepperEnv-v0" (__init__.py:58-62) or
- * "Monkey3DCustomEnv-v0" (__init__.py:94-98; env_locomotion.py:1136-1516) or "CassieEnv-v0" (__init__.py:18-22;
- * env_cassie.py:285-479).
+ * env_id: "Walker3DCustomEnv-v0" (__init__.py:52-56), "Walker3DStepperEnv-v0" (__init__.py:58-62),
+ * "Monkey3DCustomEnv-v0" (__init__.py:94-98; env_locomotion.py:1136-1516), "CassieEnv-v0" (__init__.py:18-22;
+ * env_cassie.py:285-479), "Child3DCustomEnv-v0" (__init__.py:45-49; env_locomotion.py:317-327) or
+ * "MikeStepperEnv-v0" (__init__.py:64-68; env_locomotion.py:843-851).
  * physics may be NULL (reference values). */
 int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics* physics, mb200_env** out);
 /* EnvBase.close (env_base.py:44-47) */
