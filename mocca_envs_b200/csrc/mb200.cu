@@ -864,6 +864,15 @@ static int param_field(mb200_env* e, const char* key, float lo, float hi, const 
     *field = ES_CURRIC;
     return 0;
   }
+  if (strcmp(key, "plank_class") == 0 && stepper_family(e->kind)) {
+    for (int i = 0; i < (values ? count : 1); ++i) {
+      const float v = values ? values[i] : scalar;
+      if (!(v == 0.0f || v == 1.0f))
+        return fail("mb200_set_param: plank_class must be 0 (LargePlank) or 1 (Plank); Pillar is not built");
+    }
+    *field = ES_PLANK_CLASS;
+    return 0;
+  }
   if (strcmp(key, "random_reward") == 0 && stepper_family(e->kind)) { *field = ES_RANDOM_REWARD; return 0; }
   (void)lo; (void)hi;
   return fail(std::string("mb200_set_param: unknown key '") + key + "' for this env");

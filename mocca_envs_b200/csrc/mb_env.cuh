@@ -61,6 +61,7 @@ enum {  // Walker3DStepperEnv additions (env_locomotion.py:330-840)
   ES_PLANKIDX,        // [3] terrain row shown by each physical plank (int)
   ES_STEPS_REACHED = 31,  // info["steps_reached"] of the last step, -1 = not reported (int)
   ES_GAIN_CURRIC = 6,     // curriculum the applied_gain was taken from at reset (env_locomotion.py:489) (int)
+  ES_PLANK_CLASS = 4,     // plank_class kwarg (env_locomotion.py:342,356-357): 0 LargePlank, 1 Plank (int; ER_ANGLE unused here)
   ES_RANDOM_REWARD = 3,   // random_reward kwarg (env_locomotion.py:355,528-547) (int; ER_DIST is unused by this env)
   ES_BOX = 32,        // [3][12] plank base-box centre + axes
   ES_TERRAIN = 68,    // [20][6] x y z phi x_tilt y_tilt
@@ -483,7 +484,9 @@ template <class M> struct StepperEnv {
 #pragma unroll
         for (int k = 0; k < 12; ++k) bx[k] = b[k];
         if (cover) { bx[0] += b[3 + 2] * 0.125f; bx[1] += b[3 + 5] * 0.125f; bx[2] += b[3 + 8] * 0.125f; }
-        bx[12] = 0.25f; bx[13] = 5.0f; bx[14] = cover ? 0.0125f : 0.1125f; bx[15] = 0.0f;
+        // plank_large.urdf: box 1 x 20 x (0.45 | 0.05), plank.urdf: 1 x 1.5 x (0.45 | 0.05); globalScaling 2 * 0.25
+        bx[12] = 0.25f; bx[13] = rec_i(rec, ES_PLANK_CLASS) == 1 ? 0.375f : 5.0f; bx[14] = cover ? 0.0125f : 0.1125f;
+        bx[15] = 0.0f;
       }
       if (l == 0) S.nbox = 6;
     MB_END

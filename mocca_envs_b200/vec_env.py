@@ -245,13 +245,19 @@ class Walker3DStepperVecEnv(Walker3DCustomVecEnv):
     max_curriculum = 9
 
     def __init__(self, num_envs: int, device="cuda:0", seed: int | None = None, physics: dict | None = None,
-                 return_final_obs: bool = False, random_reward: bool = False):
-        """``random_reward`` is the reference's constructor kwarg (env_locomotion.py:355): every reward term is
-        scaled by its own np_random.uniform(0.8, 1.2) draw each step (:532-547)."""
+                 return_final_obs: bool = False, random_reward: bool = False, plank_class: str | None = None):
+        """``random_reward`` and ``plank_class`` are the reference's constructor kwargs (env_locomotion.py:355-357):
+        every reward term scaled by its own np_random.uniform(0.8, 1.2) draw each step (:532-547); "LargePlank"
+        (default, 0.5 x 10 m) or "Plank" (0.5 x 0.75 m) stepping stones.  "Pillar" (cylinders) is not built."""
         super().__init__(num_envs, device=device, seed=seed, physics=physics, return_final_obs=return_final_obs)
         self.random_reward = bool(random_reward)
         if self.random_reward:
             _lib.check(self._L.mb200_set_param(self._h, b"random_reward", 1.0))
+        if plank_class not in (None, "LargePlank", "Plank"):
+            raise NotImplementedError("plank_class %r: only LargePlank and Plank are built" % (plank_class,))
+        self.plank_class = plank_class or "LargePlank"
+        if self.plank_class == "Plank":
+            _lib.check(self._L.mb200_set_param(self._h, b"plank_class", 1.0))
 
     def set_env_params(self, params: dict):
         """``{"curriculum": c}`` with an int or one value per env (env_base.py:103-106); used at the next reset
@@ -443,7 +449,7 @@ class Walker3DStepperEnv(Walker3DCustomEnv):
     """gym-protocol facade of Walker3DStepperEnv-v0; info carries "steps_reached" like the reference."""
 
     vec_class = Walker3DStepperVecEnv
-    vec_kwargs = ("random_reward",)  # env_locomotion.py:355
+    vec_kwargs = ("random_reward", "plank_class")  # env_locomotion.py:355-357
 
     def _extra_info(self, info):
         sr = int(self.vec.steps_reached()[0].item())

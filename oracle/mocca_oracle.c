@@ -1420,10 +1420,12 @@ static void stepper_place_plank(orc_stepper_env* e, int info_index, int plank) {
   orc_box* c = &e->boxes[2 * plank + 1];
   b->center[0] = t[0]; b->center[1] = t[1]; b->center[2] = t[2] - 0.1375;
   memcpy(b->R, R, sizeof(m3));
-  b->half[0] = 0.25; b->half[1] = 5.0; b->half[2] = 0.1125;
+  /* plank_large.urdf: box 1 x 20 x 0.45 / 0.05, plank.urdf: 1 x 1.5 x 0.45 / 0.05, globalScaling 2 * step_radius */
+  double half_y = e->plank_class == 1 ? 0.375 : 5.0;
+  b->half[0] = 0.25; b->half[1] = half_y; b->half[2] = 0.1125;
   memcpy(c->R, R, sizeof(m3));
   for (int k = 0; k < 3; k++) c->center[k] = b->center[k] + R[k][2] * 0.125;
-  c->half[0] = 0.25; c->half[1] = 5.0; c->half[2] = 0.0125;
+  c->half[0] = 0.25; c->half[1] = half_y; c->half[2] = 0.0125;
   for (int k = 0; k < 2; k++) {
     orc_box* x = k ? c : b;
     x->friction = 1.0;

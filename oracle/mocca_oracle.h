@@ -215,6 +215,7 @@ typedef struct {
   double step_bonus, speed_penalty;
   int steps_reached; /* info["steps_reached"] when reported, else -1 */
   int random_reward; /* constructor kwarg (env_locomotion.py:355) */
+  int plank_class;   /* constructor kwarg (env_locomotion.py:342,356-357): 0 LargePlank, 1 Plank */
 } orc_stepper_env;
 
 void orc_stepper_seed(orc_stepper_env* e, const uint32_t* key, int len, int at_construction);

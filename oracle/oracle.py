@@ -104,7 +104,7 @@ class StepperEnv(C.Structure):
         ("next_step_index", i32), ("target_reached_count", i32), ("stop_on_next_step", i32),
         ("set_stop_on_next_step", i32), ("timestep", i32), ("target_reached", i32),
         ("foot_dist_to_target", d * 2), ("targets", (d * 5) * 3), ("step_bonus", d), ("speed_penalty", d),
-        ("steps_reached", i32), ("random_reward", i32),
+        ("steps_reached", i32), ("random_reward", i32), ("plank_class", i32),
     ]
 
 
@@ -399,13 +399,14 @@ class Walker3DStepperOracle:
     """Single-env restatement of Walker3DStepperEnv (reference env_locomotion.py:330-840)."""
 
     def __init__(self, table: dict, seed: int = 0, curriculum: int = 0, params: Params | None = None,
-                 random_reward: bool = False):
+                 random_reward: bool = False, plank_class: str | None = None):
         self.table = table
         self.m = model_from_table(table)
         self.p = params or default_params()
         self.e = StepperEnv()
         self.e.curriculum = curriculum
         self.e.random_reward = int(random_reward)
+        self.e.plank_class = {None: 0, "LargePlank": 0, "Plank": 1}[plank_class]
         self.A = table["n_dof"]
         self.obs_dim = 6 + 2 * self.A + len(table["foot_links"]) + 15
         self._seed(seed, True)

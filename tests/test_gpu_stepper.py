@@ -182,3 +182,43 @@ def test_stepper_random_reward(walker_table, oracle_mod, torch_mod):
         o.reset()
         assert np.array_equal(ter[i], np.array(o.e.terrain[:]).astype(np.float32))
     env.close()
+
+
+def test_stepper_plank_class(walker_table, oracle_mod, torch_mod):
+    """plank_class constructor kwarg (env_locomotion.py:342,356-357; bullet_objects.py:92-103): "Plank" stones are
+    0.75 m wide instead of 10 m.  Walkers shifted 0.45 m off the path: one foot misses a Plank, both land on a
+    LargePlank.  Device and oracle agree frame by frame for each class (2e-3), and the classes differ."""
+    from tests.helpers import oracle_state, state_error
+
+    torch, O, t = torch_mod, oracle_mod, walker_table
+    N = 4
+    final = {}
+    for cls in ("LargePlank", "Plank"):
+        env = _env(N, seed=500, plank_class=cls)
+        env.set_env_params({"curriculum": 0})
+        oracles = [O.Walker3DStepperOracle(t, seed=500 + i, curriculum=0, plank_class=cls) for i in range(N)]
+        env.reset()
+        for o in oracles:
+            o.reset()
+        p = O.default_params()
+        p.has_ground = 0
+        st = np.stack([o.state_vector() for o in oracles])
+        st[:, 1] += 0.45
+        st = st.astype(np.float32)
+        boxes = [(O.Box * 6)(*o.e.boxes) for o in oracles]
+        zero = torch.zeros(N, 21, device="cuda:0")
+        worst = 0.0
+        for frame in range(30):
+            env.set_state(torch.tensor(st))
+            env.step_physics(zero)
+            out = env.get_state().cpu().numpy()
+            for i, o in enumerate(oracles):
+                s = oracle_state(O, 21, st[i].astype(np.float64))
+                O.step_physics(o.m, p, s, np.zeros(21), boxes=boxes[i])
+                ref = O.state_vector(s, 21)
+                worst = max(worst, state_error(out[i], ref))
+                st[i] = ref.astype(np.float32)
+        assert worst < 2e-3, (cls, worst)
+        final[cls] = st.copy()
+        env.close()
+    assert np.abs(final["Plank"] - final["LargePlank"]).max() > 1e-2

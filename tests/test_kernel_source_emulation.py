@@ -246,3 +246,38 @@ def test_stepper_random_reward(walker_table, oracle_mod):
     assert differs >= 5
     env.reset(), emu.reset()
     assert np.array_equal(emu.terrain(), np.array(env.e.terrain[:]).astype(np.float32))
+
+
+def test_stepper_plank_class(walker_table, oracle_mod):
+    """plank_class kwarg (env_locomotion.py:342,356-357; bullet_objects.py:92-103): "Plank" stones are 0.75 m wide
+    instead of 10 m.  A walker dropped 0.45 m to the side of the path lands with one foot off a Plank but with both
+    feet on a LargePlank: kernel source and oracle agree for each class, and the two classes differ."""
+    from tests.helpers import oracle_state, state_error
+
+    O, t = oracle_mod, walker_table
+    outs = {}
+    for cls, flag in (("LargePlank", 0), ("Plank", 1)):
+        env = O.Walker3DStepperOracle(t, seed=2, curriculum=0, plank_class=cls)
+        emu = E.EmuStepper(_mt_row(O, 2), curriculum=0)
+        emu.rec.view(np.int32)[4] = flag  # ES_PLANK_CLASS
+        env.reset()
+        emu.reset()
+        m, p = env.m, O.default_params()
+        p.has_ground = 0  # remove_ground=True (env_locomotion.py:359)
+        sv = env.state_vector()
+        sv[1] += 0.45
+        sv = sv.astype(np.float32)
+        emu.state[:55] = sv
+        s = oracle_state(O, 21, sv.astype(np.float64))
+        boxes = (O.Box * 6)(*env.e.boxes)
+        worst = 0.0
+        for frame in range(30):
+            c, rows = O.step_physics(m, p, s, np.zeros(21), boxes=boxes)
+            erows, enc = emu.step_physics(np.zeros(21, dtype=np.float32))
+            ref = O.state_vector(s, 21)
+            worst = max(worst, state_error(emu.state[:55], ref))
+            emu.state[:55] = ref.astype(np.float32)  # teacher-forced frame by frame
+            s = oracle_state(O, 21, emu.state[:55].astype(np.float64))
+        assert worst < 2e-3, (cls, worst)
+        outs[cls] = O.state_vector(s, 21)
+    assert np.abs(outs["Plank"] - outs["LargePlank"]).max() > 1e-2
