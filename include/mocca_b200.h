@@ -90,6 +90,12 @@ int mb200_set_state(mb200_env* env, const float* state_dev, void* stream);
 int mb200_record_stride(const mb200_env* env);
 int mb200_get_record(mb200_env* env, float* rec_dev, void* stream);
 int mb200_set_record(mb200_env* env, const float* rec_dev, void* stream);
+/* the env / robot MT19937 streams (np_random of env_base.py:164-166 and robots.py:182,192), [n_envs][2][640] uint32
+ * on the HOST: 624 key words, position, padding.  With get/set_state and get/set_record this is the complete
+ * checkpoint of a batch: a restored batch continues bit-exactly.  Synchronous. */
+int mb200_rng_words(const mb200_env* env);
+int mb200_get_rng(mb200_env* env, uint32_t* mt_host);
+int mb200_set_rng(mb200_env* env, const uint32_t* mt_host);
 
 /* stepSimulation only (bullet_utils.py:352-353): hold tau_dev [n][nu - 6] over `substeps` substeps, no env logic.
  * Outputs per env: rows_dev (constraint rows summed over the substeps) and contacts_dev (contact points of the

@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 SYMBOLS = [
     "mb200_default_physics", "mb200_default_physics_for", "mb200_create", "mb200_destroy", "mb200_dims", "mb200_seed", "mb200_reset",
     "mb200_step", "mb200_step_host", "mb200_get_state", "mb200_set_state", "mb200_get_record", "mb200_set_record",
-    "mb200_step_physics", "mb200_mass_matrix", "mb200_inverse_dynamics", "mb200_set_param",
+    "mb200_rng_words", "mb200_get_rng", "mb200_set_rng", "mb200_step_physics", "mb200_mass_matrix", "mb200_inverse_dynamics", "mb200_set_param",
     "mb200_set_param_array", "mb200_record_stride", "mb200_stats",
     "mb200_launch_count", "mb200_measure_fp32_peak", "mb200_last_error",
 ]
@@ -71,6 +71,9 @@ def lib():
         for f in ("mb200_get_state", "mb200_set_state", "mb200_get_record", "mb200_set_record", "mb200_mass_matrix"):
             getattr(L, f).argtypes = [vp, vp, vp]
         L.mb200_step_physics.argtypes = [vp, vp, vp, vp, vp]
+        L.mb200_rng_words.argtypes = [vp]
+        L.mb200_get_rng.argtypes = [vp, vp]
+        L.mb200_set_rng.argtypes = [vp, vp]
         L.mb200_inverse_dynamics.argtypes = [vp, vp, vp, vp]
         L.mb200_set_param.argtypes = [vp, C.c_char_p, C.c_float]
         L.mb200_set_param_array.argtypes = [vp, C.c_char_p, vp, ip]

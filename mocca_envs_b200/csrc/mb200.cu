@@ -763,6 +763,22 @@ int mb200_set_record(mb200_env* e, const float* rec_dev, void* stream) {
   return 0;
 }
 
+int mb200_rng_words(const mb200_env* e) { return e ? 2 * MB_MT_STRIDE : 0; }
+int mb200_get_rng(mb200_env* e, uint32_t* mt_host) {
+  if (!e || !mt_host) return fail("mb200_get_rng: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(mt_host, e->mt, (size_t)e->n * 2 * MB_MT_STRIDE * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
+int mb200_set_rng(mb200_env* e, const uint32_t* mt_host) {
+  if (!e || !mt_host) return fail("mb200_set_rng: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(e->mt, mt_host, (size_t)e->n * 2 * MB_MT_STRIDE * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* contacts_dev, void* stream) {
   if (!e || !tau_dev) return fail("mb200_step_physics: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));

@@ -179,12 +179,30 @@ class Walker3DCustomVecEnv:
         _lib.check(self._L.mb200_set_record(self._h, _ptr(r), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()
 
+    def get_rng(self) -> np.ndarray:
+        """The env / robot MT19937 streams, [num_envs, 2, 640] uint32 (624 key words, position, padding)."""
+        out = np.empty((self.num_envs, int(self._L.mb200_rng_words(self._h))), dtype=np.uint32)
+        _lib.check(self._L.mb200_get_rng(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out.reshape(self.num_envs, 2, -1)
+
+    def set_rng(self, mt: np.ndarray):
+        mt = np.ascontiguousarray(mt, dtype=np.uint32)
+        assert mt.size == self.num_envs * int(self._L.mb200_rng_words(self._h))
+        _lib.check(self._L.mb200_set_rng(self._h, mt.ctypes.data_as(C.c_void_p)))
+
     def state_dict(self):
-        return {"state": self.get_state().cpu(), "record": self.get_record().cpu()}
+        """Complete checkpoint of the batch (physics state, bookkeeping record, RNG streams, current observation):
+        a batch restored with load_state_dict continues bit-exactly."""
+        return {"state": self.get_state().cpu(), "record": self.get_record().cpu(), "rng": self.get_rng(),
+                "obs": self.obs.clone().cpu()}
 
     def load_state_dict(self, d):
         self.set_state(d["state"])
         self.set_record(d["record"])
+        if "rng" in d:
+            self.set_rng(d["rng"])
+        if "obs" in d:
+            self.obs.copy_(d["obs"].to(self.device))
 
     def step_physics(self, tau: torch.Tensor):
         """stepSimulation only (bullet_utils.py:352-353): hold tau over the substeps; returns (rows, contacts)."""
