@@ -292,6 +292,15 @@ template <class M> MB_HD float mb_Lget(const float* L, int i, int j) {
   return ((sup >> j) & 1u) ? L[M::rowoff(i) + mb_popc(sup & ((1u << j) - 1u))] : 0.0f;
 }
 
+// Per-CTA copy of the two factorisation tables (facoff: offset of the compact row an update lands in, fcol: column of
+// a slot), as bytes: [which][k][16].  They are read with a lane-dependent index at every pivot of every substep; from
+// global memory that was 470 of the 10 700 instructions of a substep (64-bit address arithmetic) and a 35-cycle L1 hit
+// on the critical path of a sequential 27-pivot loop: +3 % Walker3D, +5 % Monkey3D.  Filled by Sim::load_tables() at
+// kernel start.  (The same treatment of the per-joint kinematics tables measured within noise and was dropped.)
+#ifdef __CUDACC__
+static __shared__ unsigned char mb_s_fac[2 * 32 * 16];
+#endif
+
 // ------------------------------------------------------------------------------------------------ simulator
 template <class M> struct Sim {
   typedef WarpMem<M> Mem;
@@ -329,6 +338,34 @@ template <class M> struct Sim {
       }
       C.pairs[l] = packed;
     MB_END
+  }
+
+  // every kernel that runs substeps calls this once (all threads of the CTA)
+  MB_HD static void load_tables() {
+#ifdef __CUDACC__
+    static_assert(M::NU <= 32 && M::MAXSUP - 1 <= 16 && M::LSIZE <= 255, "byte tables");
+    for (int i = (int)threadIdx.x; i < 2 * 32 * 16; i += (int)blockDim.x) {
+      const int which = i >> 9, k = (i >> 4) & 31, t = i & 15;
+      int v = 0;
+      if (k < NU && t < M::MAXSUP - 1) v = which ? M::fcol(k, t) : M::facoff(k, t);
+      mb_s_fac[i] = (unsigned char)v;
+    }
+    __syncthreads();
+#endif
+  }
+  MB_HD static int t_facoff(int k, int t) {
+#ifdef __CUDACC__
+    return mb_s_fac[(k << 4) + t];
+#else
+    return M::facoff(k, t);
+#endif
+  }
+  MB_HD static int t_fcol(int k, int t) {
+#ifdef __CUDACC__
+    return mb_s_fac[512 + (k << 4) + t];
+#else
+    return M::fcol(k, t);
+#endif
   }
 
   // ---- A. kinematics (+ velocities / bias accelerations when with_vel) --------------------------------------
@@ -568,13 +605,13 @@ template <class M> struct Sim {
       const int npairs = (nk * (nk + 1)) >> 1;
       MB_LANES(l)
         if (l == 31) { S.Ldinv[k] = inv; S.Ldi2[k] = invd; }
-        if (RHS && l < nk) S.rhs[M::fcol(k, l)] -= S.L[offk + l] * ck;
+        if (RHS && l < nk) S.rhs[t_fcol(k, l)] -= S.L[offk + l] * ck;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           if (32 * r < npairs) {  // uniform: whole rounds are skipped for short rows
             if (l + 32 * r < npairs) {
               const int t = (C.pairs[l] >> (8 * r)) & 15, s2 = (C.pairs[l] >> (8 * r + 4)) & 15;
-              S.L[M::facoff(k, t) + s2] -= (S.L[offk + t] * invd) * S.L[offk + s2];
+              S.L[t_facoff(k, t) + s2] -= (S.L[offk + t] * invd) * S.L[offk + s2];
             }
           }
         }
