@@ -7,22 +7,24 @@
 
 #include <string>
 
-// 12 or 14 warps (envs) per CTA, 2 CTAs per SM, and one CTA barrier per substep (MB_SYNC): the barrier keeps the
-// warps of a CTA in the same phase of the (large) step code so instruction-cache lines are shared -- measured
-// 7.1M -> 10.1M env-steps/s at 16384 envs (profiles/README.md).  Walker3DCustom runs 14: 28 resident warps per SM
-// (72 registers) make 16384 envs exactly 4 waves of 148 x 28 (3.95) where 24 needed 4.6, measured +3 %; the
-// other kernels lose more to the extra spills than they gain (measured -1 % .. -3.5 %) and stay at 12.
+// 14 warps (envs) per CTA (12 for Monkey3D, whose 8.8 KB WarpMem does not fit 14), 2 CTAs per SM, and one CTA barrier
+// per substep (MB_SYNC): the barrier keeps the warps of a CTA in the same phase of the (large) step code so
+// instruction-cache lines are shared -- measured 7.1M -> 10.1M env-steps/s at 16384 envs (profiles/README.md).
+// 28 resident warps per SM (72 registers) make 16384 envs exactly 4 waves of 148 x 28 (3.95) where 24 needed 4.6.
+// Before the WarpMem base moved to a uniform register the 72-register budget cost the larger kernels more in spills
+// than the extra warps gave; since then 14 warps win everywhere they fit: Stepper +5 %, Child3D +5.6 %, Mike +6.6 %,
+// Cassie +7.7 % (A/B on one B200, r1s).
 #ifndef MB_WARPS_CUSTOM
 #define MB_WARPS_CUSTOM 14
 #endif
 #ifndef MB_WARPS_STEPPER
-#define MB_WARPS_STEPPER 12
+#define MB_WARPS_STEPPER 14
 #endif
 #ifndef MB_WARPS_MONKEY
 #define MB_WARPS_MONKEY 12
 #endif
 #ifndef MB_WARPS_CASSIE
-#define MB_WARPS_CASSIE 12
+#define MB_WARPS_CASSIE 14
 #endif
 #define MB_WARPS_MAX 16
 #define MB_WARPS ((int)(blockDim.x >> 5)) /* device code: warps of this launch */
