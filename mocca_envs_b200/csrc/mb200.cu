@@ -7,13 +7,13 @@
 
 #include <string>
 
-// 14 warps (envs) per CTA (12 for Monkey3D, whose 8.8 KB WarpMem does not fit 14), 2 CTAs per SM, and one CTA barrier
-// per substep (MB_SYNC): the barrier keeps the warps of a CTA in the same phase of the (large) step code so
+// 14 warps (envs) per CTA, 2 CTAs per SM (Monkey3D's 8 160-byte WarpMem fits with 896 bytes to spare since the
+// joint-limit list moved onto the dead tail of the kinematics scratch), and one CTA barrier per substep (MB_SYNC): the barrier keeps the warps of a CTA in the same phase of the (large) step code so
 // instruction-cache lines are shared -- measured 7.1M -> 10.1M env-steps/s at 16384 envs (profiles/README.md).
 // 28 resident warps per SM (72 registers) make 16384 envs exactly 4 waves of 148 x 28 (3.95) where 24 needed 4.6.
 // Before the WarpMem base moved to a uniform register the 72-register budget cost the larger kernels more in spills
 // than the extra warps gave; since then 14 warps win everywhere they fit: Stepper +5 %, Child3D +5.6 %, Mike +6.6 %,
-// Cassie +7.7 % (A/B on one B200, r1s).
+// Cassie +7.7 %, Monkey3D +10.6 % (A/B on one B200, r1s / r1t).
 #ifndef MB_WARPS_CUSTOM
 #define MB_WARPS_CUSTOM 14
 #endif
@@ -21,7 +21,7 @@
 #define MB_WARPS_STEPPER 14
 #endif
 #ifndef MB_WARPS_MONKEY
-#define MB_WARPS_MONKEY 12
+#define MB_WARPS_MONKEY 14
 #endif
 #ifndef MB_WARPS_CASSIE
 #define MB_WARPS_CASSIE 14

@@ -193,6 +193,14 @@ template <class M> struct WarpMem {
     } k;
     // ---- rows: Y_r = L^-T J_r^T stored compactly over its support (base block + ancestor chain)
     float Yc[MB_MAXROW][MB_YSTRIDE];
+    // ---- tail behind the rows: the list of violated joint limits (find_limits -> setup_rows; the kinematics / body
+    // scratch it overlaps is dead by then).  During collision the same words serve collide_self as its candidate list:
+    // there they alias the part of u2 behind the candidate points, unused until bodies() (checked in collide_self).
+    struct {
+      float rows_[MB_MAXROW * MB_YSTRIDE];
+      int r_dof[32];
+      float r_dir[32];
+    } t;
   } w;
   // ---- dynamics
   // M, then its factor L (M = L^T L), compact: row i keeps only its support in chain order
@@ -231,8 +239,6 @@ template <class M> struct WarpMem {
     float bar[MB_MAXBAR][8];
     float scratch[64];
   } rc;
-  int r_dof[32];
-  float r_dir[32];
   int nbox;
   int nbar;
   // ---- loop-closure pivots (btMultiBodyPoint2Point, Cassie): world axes, relative to the base COM; [2c] on link A,
@@ -773,14 +779,14 @@ template <class M> struct Sim {
     for (int k = 0; k < 3; ++k) { c1[k] = p1[k] + d1[k] * s2; c2[k] = p2[k] + d2[k] * t; }
   }
 
-  // narrow phase over the (<= 32) candidate pairs listed in S.r_dof; appends at contact slot `at`
+  // narrow phase over the (<= 32) candidate pairs listed in S.w.t.r_dof; appends at contact slot `at`
   MB_HD static int collide_self_narrow(Mem& S, int cnt, int at, float erp) {
     LaneVar<int> hit, pair;
     LaneVar<float> px, py, pz, nx, ny, nz, dd;
     MB_LANES(l)
       hit[l] = 0;
       if (l < cnt) {
-        const int k = S.r_dof[l];
+        const int k = S.w.t.r_dof[l];
         pair[l] = k;
         const unsigned pk = M::sp_pack(k);
         const int a0 = pk & 255u, a1 = (pk >> 8) & 255u, b0 = (pk >> 16) & 255u, b1 = pk >> 24;
@@ -823,10 +829,14 @@ template <class M> struct Sim {
   // self-collision (robots.py:259-264): one point per candidate geom pair, listed after the contacts with the
   // static world in pair order.  cP = point on link A, cn = normal on B towards A; the point on B is cP - cdist cn;
   // cpartner = 1000 + pair index.  Broad phase: bounding spheres of the two core segments (+ radii + breaking
-  // threshold, tabulated as sp_reach); the survivors are compacted into S.r_dof (free until find_limits) so that
+  // threshold, tabulated as sp_reach); the survivors are compacted into S.w.t.r_dof (free until find_limits) so that
   // the closest-point routine usually runs once per substep instead of NSELF / 32 times.
   MB_NOINLINE static int collide_self(Mem& S, float erp_contact, int nc) {
     MB_ASSUME_SHARED(S);
+    // the candidate list (w.t.r_dof) must not overlap the live kinematics arrays or the candidate points
+    static_assert(NSELF == 0 || sizeof(S.w.k.jR) + sizeof(S.w.k.jp) + sizeof(S.w.k.jV) + sizeof(S.w.k.jA) +
+                                        sizeof(float) * 3 * NPT <= sizeof(float) * MB_MAXROW * MB_YSTRIDE,
+                  "collide_self's candidate list would alias live kinematics data");
     int ns = 0, cnt = 0;
 #pragma unroll 1
     for (int pass = 0; pass * 32 < NSELF; ++pass) {
@@ -854,7 +864,7 @@ template <class M> struct Sim {
         cnt = 0;
       }
       MB_LANES(l)
-        if (near[l]) S.r_dof[cnt + mb_popc(mask & ((1u << l) - 1u))] = pass * 32 + l;
+        if (near[l]) S.w.t.r_dof[cnt + mb_popc(mask & ((1u << l) - 1u))] = pass * 32 + l;
       MB_END
       cnt += add;
     }
@@ -1092,8 +1102,8 @@ template <class M> struct Sim {
     MB_LANES(l)
       if (lim[l]) {
         const int k = mb_popc(mask & ((1u << l) - 1u));
-        S.r_dof[k] = l;
-        S.r_dir[k] = lim[l] == 1 ? 1.0f : -1.0f;
+        S.w.t.r_dof[k] = l;
+        S.w.t.r_dir[k] = lim[l] == 1 ? 1.0f : -1.0f;
       }
     MB_END
     return mb_popc(mask);
@@ -1224,8 +1234,8 @@ template <class M> struct Sim {
           int cj;    // constrained joint, -1 = base link
           if (r < nlim) {
             kind = 0;
-            cj = S.r_dof[r];
-            dir = S.r_dir[r];
+            cj = S.w.t.r_dof[r];
+            dir = S.w.t.r_dir[r];
             pen = dir > 0.0f ? S.q[cj] - M::lower(cj) : M::upper(cj) - S.q[cj];
 #pragma unroll
             for (int i = 0; i < 6; ++i) W[i] = 0.0f;
