@@ -173,7 +173,7 @@ template <class M> struct WarpMem {
   float js[M::NJ][6];  // joint motion subspaces about O (needed until the rows are built)
   // Kinematics / body scratch is dead once the mass matrix is assembled; the constraint rows are born after
   // the factorisation.  They share storage.
-  union {
+  union alignas(16) {
     struct {
       // ---- kinematics (world axes, positions relative to the base COM)
       float jR[M::NJ][9];
@@ -183,8 +183,9 @@ template <class M> struct WarpMem {
       union {
         struct {
           // ---- bodies
-          float bI[M::NB][10];  // m, h[3], I_O{xx,yy,zz,xy,xz,yz}
-          float bF[M::NB][6];   // bias wrench about O (n, f)
+          // per body, one 64-byte record read with four 128-bit loads by the subtree sums:
+          // [0..9] m, h[3], I_O{xx,yy,zz,xy,xz,yz};  [10..15] bias wrench about O (n, f)
+          alignas(16) float bIF[M::NB][16];
         } b;
         // contact candidate points (collision runs before the body pass); models with many candidates (hull
         // vertices, Cassie) test them on the fly against the ground plane and store nothing
@@ -517,16 +518,16 @@ template <class M> struct Sim {
         }
         mb_cross(c, f, nO);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { S.w.k.u2.b.bF[l][k] = nc[k] + nO[k]; S.w.k.u2.b.bF[l][3 + k] = f[k]; }
+        for (int k = 0; k < 3; ++k) { S.w.k.u2.b.bIF[l][10 + k] = nc[k] + nO[k]; S.w.k.u2.b.bIF[l][13 + k] = f[k]; }
         const float cc = mb_dot3(c, c);
-        S.w.k.u2.b.bI[l][0] = m;
-        S.w.k.u2.b.bI[l][1] = m * c[0]; S.w.k.u2.b.bI[l][2] = m * c[1]; S.w.k.u2.b.bI[l][3] = m * c[2];
-        S.w.k.u2.b.bI[l][4] = Ic[0] + m * (cc - c[0] * c[0]);
-        S.w.k.u2.b.bI[l][5] = Ic[4] + m * (cc - c[1] * c[1]);
-        S.w.k.u2.b.bI[l][6] = Ic[8] + m * (cc - c[2] * c[2]);
-        S.w.k.u2.b.bI[l][7] = Ic[1] - m * c[0] * c[1];
-        S.w.k.u2.b.bI[l][8] = Ic[2] - m * c[0] * c[2];
-        S.w.k.u2.b.bI[l][9] = Ic[5] - m * c[1] * c[2];
+        S.w.k.u2.b.bIF[l][0] = m;
+        S.w.k.u2.b.bIF[l][1] = m * c[0]; S.w.k.u2.b.bIF[l][2] = m * c[1]; S.w.k.u2.b.bIF[l][3] = m * c[2];
+        S.w.k.u2.b.bIF[l][4] = Ic[0] + m * (cc - c[0] * c[0]);
+        S.w.k.u2.b.bIF[l][5] = Ic[4] + m * (cc - c[1] * c[1]);
+        S.w.k.u2.b.bIF[l][6] = Ic[8] + m * (cc - c[2] * c[2]);
+        S.w.k.u2.b.bIF[l][7] = Ic[1] - m * c[0] * c[1];
+        S.w.k.u2.b.bIF[l][8] = Ic[2] - m * c[0] * c[2];
+        S.w.k.u2.b.bIF[l][9] = Ic[5] - m * c[1] * c[2];
       }
     MB_END
   }
@@ -542,10 +543,18 @@ template <class M> struct Sim {
 #pragma unroll
         for (int k = 0; k < 6; ++k) F[k] = 0.0f;
         for (int b = b0; b < b1; ++b) {
+          float v[16];
+#ifdef __CUDACC__
+          const float4* p4 = reinterpret_cast<const float4*>(S.w.k.u2.b.bIF[b]);
 #pragma unroll
-          for (int k = 0; k < 10; ++k) I[k] += S.w.k.u2.b.bI[b][k];
+          for (int k = 0; k < 4; ++k) { const float4 t = p4[k]; v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w; }
+#else
+          for (int k = 0; k < 16; ++k) v[k] = S.w.k.u2.b.bIF[b][k];
+#endif
 #pragma unroll
-          for (int k = 0; k < 6; ++k) F[k] += S.w.k.u2.b.bF[b][k];
+          for (int k = 0; k < 10; ++k) I[k] += v[k];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) F[k] += v[10 + k];
         }
         const float m = I[0];
         const float* h = &I[1];

@@ -173,3 +173,24 @@ def test_full_size_properties(name, torch_mod):
         outs.append((obs.clone(), rew.clone(), done.clone()))
         env.close()
     assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))
+
+
+def test_gym_facades_and_kwargs(torch_mod):
+    """make() ids and the reference's constructor kwargs: Child3D / Mike facades return float64 NumPy like the
+    reference; random_reward / plank_class reach the stepper-family envs; an unknown plank class is refused."""
+    from mocca_envs_b200 import make
+
+    for eid, obs_dim in (("mocca_envs:Child3DCustomEnv-v0", 52), ("MikeStepperEnv-v0", 65)):
+        env = make(eid, seed=3)
+        o = env.reset()
+        assert o.dtype == np.float64 and o.shape == (obs_dim,)
+        o, r, d, info = env.step(np.zeros(21))
+        assert o.shape == (obs_dim,) and isinstance(r, float) and isinstance(d, bool)
+        env.close()
+    env = make("MikeStepperEnv-v0", seed=3, random_reward=True, plank_class="Plank")
+    assert env.vec.random_reward and env.vec.plank_class == "Plank"
+    env.reset()
+    env.step(np.zeros(21))
+    env.close()
+    with pytest.raises(NotImplementedError):
+        make("Walker3DStepperEnv-v0", num_envs=2, plank_class="Pillar")

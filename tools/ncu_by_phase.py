@@ -2,7 +2,7 @@ import csv,re,subprocess,bisect
 from collections import defaultdict
 import sys, os, tempfile
 # usage: ncu_by_phase.py <source-page csv> <libmocca_b200.so | cubin> [mb_core.cuh of that build] [kernel symbol]
-csv_path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/src_r1k.csv"
+csv_path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/src_r1s.csv"
 cubin = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/sass/mb200.sm_100a.cubin"
 core_src = sys.argv[3] if len(sys.argv) > 3 else "mocca_envs_b200/csrc/mb_core.cuh"
 kname = sys.argv[4] if len(sys.argv) > 4 else "_Z22k_step_walker3d_custom8StepArgs"
