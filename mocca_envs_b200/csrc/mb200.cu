@@ -88,7 +88,6 @@ struct mb200_env {
   // counts it in a 256-bin histogram (global atomics spread over the launch); a small multi-CTA kernel then scans
   // the bins and scatters the env ids (k_order_by_key, ~10 us instead of the 38 us of a single-CTA counting sort).
   int* order;      // [n_pad]
-  int* work;       // [n_pad] running constraint-row sum per env (owned by the env's warp)
   int* key;        // [n_pad] sort key of the last step
   int* hist;       // [2][256] step t counts into hist[t & 1]; the scatter kernel zeroes the other half
   int* cursor;     // [2][256] scatter cursors, same double buffering
@@ -130,7 +129,6 @@ struct StepArgs {
   uint8_t* dummy_flag;
   MbStats* dummy_stats;
   const int* order;
-  int* work;
   int* key;
   int* hist;  // this step's histogram half, nullptr = scheduler off
 };
@@ -153,13 +151,12 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
             a.act + (size_t)(tail ? 0 : env) * Env::ACT, obs, tail ? a.dummy_rew + warp : a.rew + env,
             tail ? a.dummy_flag + warp : a.done + env, tail ? a.dummy_flag + MB_WARPS_MAX + warp : a.trunc + env, fin,
             tail ? a.dummy_stats : a.stats);
-  // work estimate for the scheduler: constraint rows accumulated by this step (ER_ROWS is a running sum)
+  // work estimate for the scheduler: constraint rows of this step
   if ((threadIdx.x & 31) == 0 && a.hist) {
-    const float* rec = a.rec + (size_t)env * Env::REC_STRIDE;
-    const int w = (int)rec[ER_ROWS];
-    int k = w - a.work[env];
+    // (taken from the step itself, not from the float running sum ER_ROWS, which stops resolving single steps after
+    // ~10^7 rows = a few hours of stepping)
+    int k = S.step_rows;
     k = 255 - (k < 0 ? 0 : (k > 255 ? 255 : k));  // heaviest first
-    a.work[env] = w;
     a.key[env] = k;
     atomicAdd(&a.hist[k], 1);
   }
@@ -540,11 +537,9 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   CUDA_OK(cudaMalloc(&e->mt, n * 2 * MB_MT_STRIDE * sizeof(uint32_t)));
   CUDA_OK(cudaMalloc(&e->stats, sizeof(MbStats)));
   CUDA_OK(cudaMalloc(&e->order, n * sizeof(int)));
-  CUDA_OK(cudaMalloc(&e->work, n * sizeof(int)));
   CUDA_OK(cudaMalloc(&e->key, n * sizeof(int)));
   CUDA_OK(cudaMalloc(&e->hist, 2 * 256 * sizeof(int)));
   CUDA_OK(cudaMalloc(&e->cursor, 2 * 256 * sizeof(int)));
-  CUDA_OK(cudaMemset(e->work, 0, n * sizeof(int)));
   CUDA_OK(cudaMemset(e->key, 0, n * sizeof(int)));
   CUDA_OK(cudaMemset(e->hist, 0, 2 * 256 * sizeof(int)));
   CUDA_OK(cudaMemset(e->cursor, 0, 2 * 256 * sizeof(int)));
@@ -580,7 +575,7 @@ void mb200_destroy(mb200_env* e) {
   cudaFree(e->stage_trunc);
   cudaEventDestroy(e->host_done);
   cudaFree(e->dummy_obs); cudaFree(e->dummy_rew); cudaFree(e->dummy_flag); cudaFree(e->dummy_stats);
-  cudaFree(e->order); cudaFree(e->work); cudaFree(e->key); cudaFree(e->hist); cudaFree(e->cursor);
+  cudaFree(e->order); cudaFree(e->key); cudaFree(e->hist); cudaFree(e->cursor);
   delete e;
 }
 
@@ -686,7 +681,7 @@ static int step_impl(mb200_env* e, const float* act_dev, float* obs_dev, float* 
   a.n = e->n; a.phys = e->phys; a.state = e->state; a.rec = e->rec; a.mt = e->mt; a.act = act_dev; a.obs = obs_dev;
   a.rew = rew_dev; a.done = done_dev; a.trunc = trunc_dev; a.final_obs = final_obs_dev; a.stats = e->stats;
   a.dummy_obs = e->dummy_obs; a.dummy_rew = e->dummy_rew; a.dummy_flag = e->dummy_flag; a.dummy_stats = e->dummy_stats;
-  a.order = e->order; a.work = e->work; a.key = e->key;
+  a.order = e->order; a.key = e->key;
   a.hist = sorting(e) ? e->hist + 256 * (int)(e->steps & 1) : nullptr;
   if (e->kind == KIND_CASSIE)
     k_step_cassie<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);

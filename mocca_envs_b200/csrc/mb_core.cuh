@@ -173,7 +173,7 @@ template <class M> struct WarpMem {
   float js[M::NJ][6];  // joint motion subspaces about O (needed until the rows are built)
   // Kinematics / body scratch is dead once the mass matrix is assembled; the constraint rows are born after
   // the factorisation.  They share storage.
-  union alignas(16) {
+  union {
     struct {
       // ---- kinematics (world axes, positions relative to the base COM)
       float jR[M::NJ][9];
@@ -183,9 +183,8 @@ template <class M> struct WarpMem {
       union {
         struct {
           // ---- bodies
-          // per body, one 64-byte record read with four 128-bit loads by the subtree sums:
-          // [0..9] m, h[3], I_O{xx,yy,zz,xy,xz,yz};  [10..15] bias wrench about O (n, f)
-          alignas(16) float bIF[M::NB][16];
+          float bI[M::NB][10];  // m, h[3], I_O{xx,yy,zz,xy,xz,yz}
+          float bF[M::NB][6];   // bias wrench about O (n, f)  (one 64-byte record + 128-bit loads measured no gain)
         } b;
         // contact candidate points (collision runs before the body pass); models with many candidates (hull
         // vertices, Cassie) test them on the fly against the ground plane and store nothing
@@ -242,6 +241,7 @@ template <class M> struct WarpMem {
   } rc;
   int nbox;
   int nbar;
+  int step_rows;  // constraint rows of the env step just taken: the scheduler's sort key (mb200.cu step_body)
   // ---- loop-closure pivots (btMultiBodyPoint2Point, Cassie): world axes, relative to the base COM; [2c] on link A,
   // [2c + 1] on link B
   float lcP[(M::NLOOP > 0 ? 2 * M::NLOOP : 1)][3];
@@ -518,16 +518,16 @@ template <class M> struct Sim {
         }
         mb_cross(c, f, nO);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { S.w.k.u2.b.bIF[l][10 + k] = nc[k] + nO[k]; S.w.k.u2.b.bIF[l][13 + k] = f[k]; }
+        for (int k = 0; k < 3; ++k) { S.w.k.u2.b.bF[l][k] = nc[k] + nO[k]; S.w.k.u2.b.bF[l][3 + k] = f[k]; }
         const float cc = mb_dot3(c, c);
-        S.w.k.u2.b.bIF[l][0] = m;
-        S.w.k.u2.b.bIF[l][1] = m * c[0]; S.w.k.u2.b.bIF[l][2] = m * c[1]; S.w.k.u2.b.bIF[l][3] = m * c[2];
-        S.w.k.u2.b.bIF[l][4] = Ic[0] + m * (cc - c[0] * c[0]);
-        S.w.k.u2.b.bIF[l][5] = Ic[4] + m * (cc - c[1] * c[1]);
-        S.w.k.u2.b.bIF[l][6] = Ic[8] + m * (cc - c[2] * c[2]);
-        S.w.k.u2.b.bIF[l][7] = Ic[1] - m * c[0] * c[1];
-        S.w.k.u2.b.bIF[l][8] = Ic[2] - m * c[0] * c[2];
-        S.w.k.u2.b.bIF[l][9] = Ic[5] - m * c[1] * c[2];
+        S.w.k.u2.b.bI[l][0] = m;
+        S.w.k.u2.b.bI[l][1] = m * c[0]; S.w.k.u2.b.bI[l][2] = m * c[1]; S.w.k.u2.b.bI[l][3] = m * c[2];
+        S.w.k.u2.b.bI[l][4] = Ic[0] + m * (cc - c[0] * c[0]);
+        S.w.k.u2.b.bI[l][5] = Ic[4] + m * (cc - c[1] * c[1]);
+        S.w.k.u2.b.bI[l][6] = Ic[8] + m * (cc - c[2] * c[2]);
+        S.w.k.u2.b.bI[l][7] = Ic[1] - m * c[0] * c[1];
+        S.w.k.u2.b.bI[l][8] = Ic[2] - m * c[0] * c[2];
+        S.w.k.u2.b.bI[l][9] = Ic[5] - m * c[1] * c[2];
       }
     MB_END
   }
@@ -543,18 +543,10 @@ template <class M> struct Sim {
 #pragma unroll
         for (int k = 0; k < 6; ++k) F[k] = 0.0f;
         for (int b = b0; b < b1; ++b) {
-          float v[16];
-#ifdef __CUDACC__
-          const float4* p4 = reinterpret_cast<const float4*>(S.w.k.u2.b.bIF[b]);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { const float4 t = p4[k]; v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w; }
-#else
-          for (int k = 0; k < 16; ++k) v[k] = S.w.k.u2.b.bIF[b][k];
-#endif
+          for (int k = 0; k < 10; ++k) I[k] += S.w.k.u2.b.bI[b][k];
 #pragma unroll
-          for (int k = 0; k < 10; ++k) I[k] += v[k];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) F[k] += v[10 + k];
+          for (int k = 0; k < 6; ++k) F[k] += S.w.k.u2.b.bF[b][k];
         }
         const float m = I[0];
         const float* h = &I[1];
@@ -1473,7 +1465,11 @@ template <class M> struct Sim {
         const bool self = NSELF > 0 && k >= nc;
         const int ra = self ? S0 + 2 * ncs + 4 * (k - nc) : n0 + nc + 2 * k;
         const int rn = self ? S0 + 2 * (k - nc) : n0 + k;
-        const float rr = pgs_pair(S, C, ra, S.rc.r.r_mu[ra] * S.rc.r.r_app[rn], z);
+        const float cone = S.rc.r.r_mu[ra] * S.rc.r.r_app[rn];
+        // a contact that carries no normal impulse has a zero friction cone: with nothing applied yet the projection
+        // returns exactly zero for both rows (deltas 0, residual 0), so the visit can be skipped -- bit-identical
+        if (cone == 0.0f && S.rc.r.r_app[ra] == 0.0f && S.rc.r.r_app[ra + 1] == 0.0f) continue;
+        const float rr = pgs_pair(S, C, ra, cone, z);
         res2 = fmaxf(res2, rr * rr);
       }
       if (res2 <= P.residual_threshold) break;

@@ -417,7 +417,7 @@ template <class M> struct W3DEnv {
         rec_i(rec, ER_CLOSE) = close; rec[ER_LINPOT] = lp; rec_i(rec, ER_ELAPSED) = elapsed;
         rec[ER_BODYX] = S.pos[0];
         rec[ER_EPRET] = epret; rec_i(rec, ER_EPLEN) = eplen;
-        rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum;
+        rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum; S.step_rows = rows;
         rec_i(rec, ER_OVERFLOW) += overflow;
         *rew = reward; *done = (uint8_t)any_done; *trunc = (uint8_t)truncated;
       }
@@ -775,7 +775,7 @@ template <class M> struct StepperEnv {
       if (l == 0) {
         rec[ER_LINPOT] = lp; rec_i(rec, ER_ELAPSED) = elapsed;
         rec[ER_EPRET] = epret; rec_i(rec, ER_EPLEN) = eplen;
-        rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum;
+        rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum; S.step_rows = rows;
         rec_i(rec, ER_OVERFLOW) += overflow;
         rec_i(rec, ES_STEPS_REACHED) = (env_done || timestep == 999) ? next : -1;
         *rew = reward; *done = (uint8_t)any_done; *trunc = (uint8_t)truncated;
@@ -1142,7 +1142,7 @@ template <class M> struct MonkeyEnv {
       if (l == 0) {
         rec[EM_SWINGPOT] = sp; rec_i(rec, EM_FREEFALL) = freefall; rec_i(rec, ER_ELAPSED) = elapsed;
         rec[ER_EPRET] = epret; rec_i(rec, ER_EPLEN) = eplen;
-        rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum;
+        rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum; S.step_rows = rows;
         rec_i(rec, ER_OVERFLOW) += overflow;
         *rew = reward; *done = (uint8_t)any_done; *trunc = (uint8_t)truncated;
       }
@@ -1367,7 +1367,7 @@ template <class M> struct CassieEnv {
         rec[EC_POTENTIAL] = pot; rec[EC_PREVX] = S.pos[0]; rec[EC_PREVY] = S.pos[1];
         rec_i(rec, ER_ELAPSED) = elapsed;
         rec[ER_EPRET] = epret; rec_i(rec, ER_EPLEN) = eplen;
-        rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum;
+        rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum; S.step_rows = rows;
         rec_i(rec, ER_OVERFLOW) += overflow;
         *rew = reward; *done = (uint8_t)any_done; *trunc = (uint8_t)truncated;
       }
