@@ -438,9 +438,9 @@ def main():
         "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak if peak else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at 16384 envs from the
-                     # committed ncu --set full capture (profiles/r1s_step_kernel_raw.csv: 8.12 MB read + 0.03 MB
+                     # committed ncu --set full capture (profiles/r1u_step_kernel_raw.csv: 8.05 MB read, < 0.01 MB
                      # written); null for other workloads
-                     "traffic": 8.15e6 if (args.env == "custom" and N == 16384 and args.self_collision) else None,
+                     "traffic": 8.05e6 if (args.env == "custom" and N == 16384 and args.self_collision) else None,
                      "peak_source": "FP32 FMA probe kernel measured in this run (mb200_measure_fp32_peak)",
                      "flops_per_env_step": F, "rows_per_substep": R_mean,
                      "contacts_per_substep": conts_all / (K * N * world * S_sub),
