@@ -231,6 +231,17 @@ class Walker3DCustomVecEnv:
         for k, v in params.items():
             if k == "eval_mode":
                 _lib.check(self._L.mb200_set_param(self._h, b"eval_mode", float(bool(v))))
+                self.eval_mode = bool(v)
+
+    def get_env_param(self, param_name, default):
+        """EnvBase.get_env_param (env_base.py:116-117): the host-side mirror of the env attribute, else ``default``."""
+        return getattr(self, param_name, default)
+
+    def set_robot_params(self, params: dict):
+        """EnvBase.set_robot_params (env_base.py:108-114) ends in ``self.robot.calc_torque_limits()``, a method no
+        robot class of the reference defines (quirk Q4): the reference raises AttributeError, and so does this."""
+        raise AttributeError("set_robot_params: the reference calls the undefined robot.calc_torque_limits() "
+                             "(env_base.py:114); no robot parameter can be changed after construction")
 
     def stats(self, reset=False) -> dict:
         out = (C.c_double * 8)()
@@ -261,6 +272,7 @@ class Walker3DStepperVecEnv(Walker3DCustomVecEnv):
     env_id = STEPPER_ID
     ES_NEXT, ES_CURRIC, ES_STEPS_REACHED, ES_TERRAIN = 22, 27, 31, 68
     max_curriculum = 9
+    curriculum = 0  # env_locomotion.py:363
 
     def __init__(self, num_envs: int, device="cuda:0", seed: int | None = None, physics: dict | None = None,
                  return_final_obs: bool = False, random_reward: bool = False, plank_class: str | None = None):
@@ -285,10 +297,12 @@ class Walker3DStepperVecEnv(Walker3DCustomVecEnv):
                 continue
             if np.isscalar(v):
                 _lib.check(self._L.mb200_set_param(self._h, b"curriculum", float(min(int(v), self.max_curriculum))))
+                self.curriculum = min(int(v), self.max_curriculum)
             else:
                 arr = np.ascontiguousarray(np.minimum(np.asarray(v), self.max_curriculum), dtype=np.float32)
                 _lib.check(self._L.mb200_set_param_array(self._h, b"curriculum", arr.ctypes.data_as(C.c_void_p),
                                                          len(arr)))
+                self.curriculum = arr.astype(np.int64)
 
     def evaluation_mode(self):
         raise AttributeError("Walker3DStepperEnv has no evaluation_mode (reference: only Walker3DCustomEnv)")
@@ -452,6 +466,12 @@ class Walker3DCustomEnv:
 
     def set_env_params(self, params):
         self.vec.set_env_params(params)
+
+    def get_env_param(self, param_name, default):
+        return self.vec.get_env_param(param_name, default)
+
+    def set_robot_params(self, params):
+        self.vec.set_robot_params(params)
 
     def evaluation_mode(self):
         self.vec.evaluation_mode()

@@ -194,3 +194,17 @@ def test_gym_facades_and_kwargs(torch_mod):
     env.close()
     with pytest.raises(NotImplementedError):
         make("Walker3DStepperEnv-v0", num_envs=2, plank_class="Pillar")
+
+
+def test_env_param_accessors(torch_mod):
+    """EnvBase.get_env_param / set_robot_params (env_base.py:108-117): the attribute mirror and quirk Q4."""
+    from mocca_envs_b200 import make
+
+    env = make("Walker3DStepperEnv-v0", num_envs=4, seed=0)
+    assert env.get_env_param("curriculum", -1) == 0 and env.get_env_param("max_curriculum", -1) == 9
+    env.set_env_params({"curriculum": 7})
+    assert env.get_env_param("curriculum", -1) == 7
+    assert env.get_env_param("no_such_param", "dflt") == "dflt"
+    with pytest.raises(AttributeError):
+        env.set_robot_params({"power": 0.5})
+    env.close()
