@@ -224,8 +224,11 @@ class Walker3DCustomVecEnv:
         return tau
 
     # ---- trainer-facing extras (env_base.py:103-118, env_locomotion.py:76-77,224-282)
+    eval_mode = False  # env_locomotion.py:52
+
     def evaluation_mode(self):
         _lib.check(self._L.mb200_set_param(self._h, b"eval_mode", 1.0))
+        self.eval_mode = True
 
     def set_env_params(self, params: dict):
         for k, v in params.items():
