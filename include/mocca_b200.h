@@ -110,8 +110,9 @@ int mb200_inverse_dynamics(mb200_env* env, const float* acc_dev, float* tau_dev,
 /* EnvBase.set_env_params analogue (env_base.py:103-106): "eval_mode" (Walker3DCustomEnv, env_locomotion.py:76-77),
  * "curriculum" 0..9 (Walker3DStepperEnv, env_locomotion.py:362-369; takes effect at the next reset like the
  * reference, whose terrain / gain / terminal height are read in reset() and step()), "random_reward" 0 / 1
- * and "plank_class" 0 = LargePlank / 1 = Plank (Walker3DStepperEnv constructor kwargs, env_locomotion.py:355-357,
- * 528-547; bullet_objects.py:86-103).  The array variant sets one value per env
+ * and "plank_class" 0 = LargePlank / 1 = Plank / 2 = Pillar (Walker3DStepperEnv constructor kwargs,
+ * env_locomotion.py:355-357, 528-547; bullet_objects.py:86-103; Pillar launches its own kernel instantiation, so it
+ * is set for the whole batch or not at all).  The array variant sets one value per env
  * (values_host[count], count == n_envs).  Synchronous. */
 int mb200_set_param(mb200_env* env, const char* key, float value);
 int mb200_set_param_array(mb200_env* env, const char* key, const float* values_host, int count);

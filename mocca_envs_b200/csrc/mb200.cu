@@ -59,6 +59,7 @@ static bool stepper_family(int kind) { return kind == KIND_STEPPER || kind == KI
 
 struct mb200_env {
   int kind;        // KIND_*
+  bool pillar;     // stepper family: plank_class = Pillar, launch the cylinder-stone instantiation
   int warps;       // envs per CTA of this kind's kernels
   int rec_stride;  // floats per env in `rec`
   int n, device;
@@ -106,6 +107,8 @@ typedef CAS_Model CM;
 typedef CassieEnv<CM> CEnv;
 typedef W3DEnv<CH3D_Model> ChEnv;       // Child3DCustomEnv-v0 (env_locomotion.py:317-327)
 typedef StepperEnv<MIKE_Model> MkEnv;   // MikeStepperEnv-v0 (env_locomotion.py:843-851)
+typedef StepperEnv<WM, true> SEnvP;     // plank_class = "Pillar" (bullet_objects.py:86-90): cylinder stones
+typedef StepperEnv<MIKE_Model, true> MkEnvP;
 static_assert(sizeof(WarpMem<CH3D_Model>) <= sizeof(WarpMem<WM>) && sizeof(WarpMem<MIKE_Model>) <= sizeof(WarpMem<WM>),
               "the shared-memory opt-in of the Walker3D-family kernels is sized for the Walker3D table");
 typedef WarpMem<WM> WMem;
@@ -210,6 +213,12 @@ __global__ void __launch_bounds__(MB_WARPS_STEPPER * 32, MB_MINBLOCKS) k_step_ch
 }
 __global__ void __launch_bounds__(MB_WARPS_STEPPER * 32, MB_MINBLOCKS) k_step_mike_stepper(StepArgs a) {
   step_body<MkEnv>(a);
+}
+__global__ void __launch_bounds__(MB_WARPS_STEPPER * 32, MB_MINBLOCKS) k_step_walker3d_stepper_pillar(StepArgs a) {
+  step_body<SEnvP>(a);
+}
+__global__ void __launch_bounds__(MB_WARPS_STEPPER * 32, MB_MINBLOCKS) k_step_mike_stepper_pillar(StepArgs a) {
+  step_body<MkEnvP>(a);
 }
 
 template <class Env>
@@ -316,6 +325,16 @@ __global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_step_physics_mike_stepper(int n, MbPhysics phys, float* state, const float* rec, const float* tau,
                                 int* rows_out, int* contacts_out) {
   physics_body<MkEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
+}
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
+    k_step_physics_walker3d_stepper_pillar(int n, MbPhysics phys, float* state, const float* rec, const float* tau,
+                                           int* rows_out, int* contacts_out) {
+  physics_body<SEnvP>(n, phys, state, rec, tau, rows_out, contacts_out);
+}
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
+    k_step_physics_mike_stepper_pillar(int n, MbPhysics phys, float* state, const float* rec, const float* tau,
+                                       int* rows_out, int* contacts_out) {
+  physics_body<MkEnvP>(n, phys, state, rec, tau, rows_out, contacts_out);
 }
 
 // mode 0: M (full symmetric, [nu][nu]);  mode 1: tau = M acc - rhs (rhs = -bias with zero applied torque)
@@ -466,6 +485,7 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   e->n = n_envs;
   e->device = device;
   e->kind = kind;
+  e->pillar = false;
   int nj = WM::NJ;
   switch (kind) {
     case KIND_MIKE:
@@ -524,6 +544,10 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
     CUDA_OK(cudaFuncSetAttribute(k_reset_mike_stepper, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_physics_mike_stepper, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_mike, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_stepper_pillar, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d_stepper_pillar, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_mike_stepper_pillar, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_physics_mike_stepper_pillar, at, sw));
   }
   e->n_pad = grid_for(e) * e->warps;
   const size_t n = (size_t)e->n_pad;
@@ -689,8 +713,12 @@ static int step_impl(mb200_env* e, const float* act_dev, float* obs_dev, float* 
     k_step_monkey3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
   else if (e->kind == KIND_CHILD)
     k_step_child3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
+  else if (e->kind == KIND_MIKE && e->pillar)
+    k_step_mike_stepper_pillar<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
   else if (e->kind == KIND_MIKE)
     k_step_mike_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
+  else if (e->kind == KIND_STEPPER && e->pillar)
+    k_step_walker3d_stepper_pillar<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
   else if (e->kind == KIND_STEPPER)
     k_step_walker3d_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
   else
@@ -790,8 +818,14 @@ int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* c
   else if (e->kind == KIND_CHILD)
     k_step_physics_child3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
+  else if (e->kind == KIND_MIKE && e->pillar)
+    k_step_physics_mike_stepper_pillar<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
   else if (e->kind == KIND_MIKE)
     k_step_physics_mike_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
+  else if (e->kind == KIND_STEPPER && e->pillar)
+    k_step_physics_walker3d_stepper_pillar<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
   else if (e->kind == KIND_STEPPER)
     k_step_physics_walker3d_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
@@ -882,8 +916,11 @@ static int param_field(mb200_env* e, const char* key, float lo, float hi, const 
   if (strcmp(key, "plank_class") == 0 && stepper_family(e->kind)) {
     for (int i = 0; i < (values ? count : 1); ++i) {
       const float v = values ? values[i] : scalar;
-      if (!(v == 0.0f || v == 1.0f))
-        return fail("mb200_set_param: plank_class must be 0 (LargePlank) or 1 (Plank); Pillar is not built");
+      if (!(v == 0.0f || v == 1.0f || v == 2.0f))
+        return fail("mb200_set_param: plank_class must be 0 (LargePlank), 1 (Plank) or 2 (Pillar)");
+      // Pillar runs its own kernel instantiation: the whole batch or none of it
+      if ((v == 2.0f) != ((values ? values[0] : scalar) == 2.0f))
+        return fail("mb200_set_param: plank_class 2 (Pillar) cannot be mixed with other classes in one batch");
     }
     *field = ES_PLANK_CLASS;
     return 0;
@@ -898,6 +935,7 @@ int mb200_set_param(mb200_env* e, const char* key, float value) {
   CUDA_OK(cudaSetDevice(e->device));
   int field = 0;
   if (param_field(e, key, 0, 0, nullptr, 0, value, &field)) return -1;
+  if (field == ES_PLANK_CLASS && stepper_family(e->kind)) e->pillar = value == 2.0f;
   return set_record_int(e, field, nullptr, 0, field == ER_EVAL && custom_family(e->kind) ? (value != 0.0f) : value);
 }
 
@@ -907,6 +945,7 @@ int mb200_set_param_array(mb200_env* e, const char* key, const float* values_hos
   CUDA_OK(cudaSetDevice(e->device));
   int field = 0;
   if (param_field(e, key, 0, 0, values_host, count, 0.0f, &field)) return -1;
+  if (field == ES_PLANK_CLASS && stepper_family(e->kind)) e->pillar = values_host[0] == 2.0f;
   return set_record_int(e, field, values_host, count, 0.0f);
 }
 

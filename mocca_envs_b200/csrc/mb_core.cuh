@@ -122,6 +122,7 @@ MB_HD void mb_sincos(float x, float* s, float* c) {
 #define MB_MAXBAR 4   /* static bars per env (Monkey3D rendered_step_count, env_locomotion.py:1149) */
 #define MB_OBST_BOXES 1
 #define MB_OBST_BARS 2
+#define MB_OBST_CYLS 4 /* the box records are capped cylinders about their local z axis (Pillar stepping stones) */
 #define MB_PI_F 3.14159265358979323846f
 
 // Physics constants of the reference's Bullet world (citations in include/mocca_b200.h: mb200_physics)
@@ -710,6 +711,42 @@ template <class M> struct Sim {
     return true;
   }
 
+  // sphere vs capped cylinder about the record's local z axis (Pillar, bullet_objects.py:86-90; pillar.urdf): radius
+  // half[0], half length half[2].  Same conventions as sphere_box; Bullet runs its convex-convex pipeline here.
+  MB_HD static bool sphere_cyl(const float* c, float r, const float* bx, float thresh, float* pa, float* n,
+                               float* dist) {
+    const float* R = bx + 3;
+    const float rad = bx[12], h = bx[14];
+    const float d[3] = {c[0] - bx[0], c[1] - bx[1], c[2] - bx[2]};
+    float cl[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cl[k] = R[k] * d[0] + R[3 + k] * d[1] + R[6 + k] * d[2];
+    const float rho = sqrtf(cl[0] * cl[0] + cl[1] * cl[1]);
+    const float ir = rho > 1e-12f ? 1.0f / rho : 0.0f;
+    const float ux = cl[0] * ir, uy = cl[1] * ir;  // radial unit vector (0 on the axis)
+    const bool in_r = rho <= rad, in_z = fabsf(cl[2]) <= h;
+    float nl[3];
+    if (!(in_r && in_z)) {
+      const float qr = fminf(rho, rad), qz = fminf(fmaxf(cl[2], -h), h);
+      const float dr = rho - qr, dz = cl[2] - qz;
+      const float len = sqrtf(dr * dr + dz * dz);
+      *dist = len - r;
+      if (*dist >= thresh) return false;
+      const float il = 1.0f / len;
+      nl[0] = ux * dr * il; nl[1] = uy * dr * il; nl[2] = dz * il;
+    } else {
+      const float pen_r = rad - rho, pen_z = h - fabsf(cl[2]);
+      if (pen_z <= pen_r) { nl[0] = 0.0f; nl[1] = 0.0f; nl[2] = cl[2] >= 0.0f ? 1.0f : -1.0f; *dist = -pen_z - r; }
+      else { nl[0] = ux; nl[1] = uy; nl[2] = 0.0f; *dist = -pen_r - r; }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      n[k] = R[3 * k] * nl[0] + R[3 * k + 1] * nl[1] + R[3 * k + 2] * nl[2];
+      pa[k] = c[k] - r * n[k];
+    }
+    return true;
+  }
+
   // sphere (centre c, radius r) vs bar treated as a capsule around its axis segment; everything relative to the
   // base COM (bc = bar centre - base position) so that a world far from the origin costs no precision
   MB_HD static bool sphere_bar(const float* c, float r, const float* bc, const float* bar, float thresh, float* pa,
@@ -874,7 +911,8 @@ template <class M> struct Sim {
   }
 
   template <int OBST> MB_HD static int collide(Mem& S, const MbPhysics& P, int* overflow, int* ns_out) {
-    constexpr bool BOXES = (OBST & MB_OBST_BOXES) != 0;
+    constexpr bool BOXES = (OBST & (MB_OBST_BOXES | MB_OBST_CYLS)) != 0;
+    constexpr bool CYLS = (OBST & MB_OBST_CYLS) != 0;
     constexpr bool STORE = NPT <= 64;  // else: ground plane only, points are transformed inside the test pass
     static_assert(STORE || OBST == 0, "on-the-fly candidate points support the ground plane only");
     // world positions of the candidate points (relative to the base COM)
@@ -934,7 +972,8 @@ template <class M> struct Sim {
             } else {
               const float cw[3] = {c[0] + S.pos[0], c[1] + S.pos[1], c[2] + S.pos[2]};
               float pa[3], n[3], dist;
-              if (sphere_box(cw, r, S.rc.box[ob], M::pthresh(pt), pa, n, &dist)) {
+              if (CYLS ? sphere_cyl(cw, r, S.rc.box[ob], M::pthresh(pt), pa, n, &dist)
+                       : sphere_box(cw, r, S.rc.box[ob], M::pthresh(pt), pa, n, &dist)) {
                 hit[l] = 1;
                 px[l] = pa[0] - S.pos[0]; py[l] = pa[1] - S.pos[1]; pz[l] = pa[2] - S.pos[2]; dd[l] = dist;
                 nx[l] = n[0]; ny[l] = n[1]; nz[l] = n[2];

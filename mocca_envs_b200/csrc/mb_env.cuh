@@ -61,7 +61,8 @@ enum {  // Walker3DStepperEnv additions (env_locomotion.py:330-840)
   ES_PLANKIDX,        // [3] terrain row shown by each physical plank (int)
   ES_STEPS_REACHED = 31,  // info["steps_reached"] of the last step, -1 = not reported (int)
   ES_GAIN_CURRIC = 6,     // curriculum the applied_gain was taken from at reset (env_locomotion.py:489) (int)
-  ES_PLANK_CLASS = 4,     // plank_class kwarg (env_locomotion.py:342,356-357): 0 LargePlank, 1 Plank (int; ER_ANGLE unused here)
+  ES_PLANK_CLASS = 4,     // plank_class kwarg (env_locomotion.py:342,356-357): 0 LargePlank, 1 Plank, 2 Pillar (the
+                          // library launches the PILLAR instantiation for 2) (int; ER_ANGLE unused here)
   ES_RANDOM_REWARD = 3,   // random_reward kwarg (env_locomotion.py:355,528-547) (int; ER_DIST is unused by this env)
   ES_BOX = 32,        // [3][12] plank base-box centre + axes
   ES_TERRAIN = 68,    // [20][6] x y z phi x_tilt y_tilt
@@ -461,13 +462,15 @@ template <class M> struct W3DEnv {
 
 // ================================================================================================ Stepper
 // Walker3DStepperEnv (reference env_locomotion.py:330-840) with 3 recycled LargePlanks (bullet_objects.py:47-103).
-template <class M> struct StepperEnv {
+// PILLAR: plank_class = "Pillar" (bullet_objects.py:86-90): the stones are capped cylinders of radius step_radius = 0.25
+// with the planks' heights; a separate instantiation so that the default kernel's hot loop carries no dead branch.
+template <class M, bool PILLAR = false> struct StepperEnv {
   typedef WarpMem<M> Mem;
   typedef Sim<M> S_;
   typedef W3DEnv<M> B_;
   typedef M Model;
   enum { NJ = M::NJ, NU = M::NU, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET, OBS = ROBOT_OBS + 15, NSTEPS = 20,
-         REC_STRIDE = MB_REC_STRIDE_STEPPER, OBST = MB_OBST_BOXES, ACT = M::NJ };
+         REC_STRIDE = MB_REC_STRIDE_STEPPER, OBST = PILLAR ? MB_OBST_CYLS : MB_OBST_BOXES, ACT = M::NJ };
   MB_HD static void load_obstacles(Mem& S, const float* rec) { load_boxes(S, rec); }
   MB_HD static void load_state(Mem& S, const float* st) { B_::load_state(S, st); }
   MB_HD static void store_state(const Mem& S, float* st) { B_::store_state(S, st); }
@@ -485,7 +488,10 @@ template <class M> struct StepperEnv {
         for (int k = 0; k < 12; ++k) bx[k] = b[k];
         if (cover) { bx[0] += b[3 + 2] * 0.125f; bx[1] += b[3 + 5] * 0.125f; bx[2] += b[3 + 8] * 0.125f; }
         // plank_large.urdf: box 1 x 20 x (0.45 | 0.05), plank.urdf: 1 x 1.5 x (0.45 | 0.05); globalScaling 2 * 0.25
-        bx[12] = 0.25f; bx[13] = rec_i(rec, ES_PLANK_CLASS) == 1 ? 0.375f : 5.0f; bx[14] = cover ? 0.0125f : 0.1125f;
+        // pillar.urdf: cylinders radius 1, length 0.9 / 0.1, globalScaling step_radius = 0.25 (bx[13] bounds the cull)
+        bx[12] = 0.25f;
+        bx[13] = PILLAR ? 0.25f : (rec_i(rec, ES_PLANK_CLASS) == 1 ? 0.375f : 5.0f);
+        bx[14] = cover ? 0.0125f : 0.1125f;
         bx[15] = 0.0f;
       }
       if (l == 0) S.nbox = 6;

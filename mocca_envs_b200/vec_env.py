@@ -281,16 +281,20 @@ class Walker3DStepperVecEnv(Walker3DCustomVecEnv):
                  return_final_obs: bool = False, random_reward: bool = False, plank_class: str | None = None):
         """``random_reward`` and ``plank_class`` are the reference's constructor kwargs (env_locomotion.py:355-357):
         every reward term scaled by its own np_random.uniform(0.8, 1.2) draw each step (:532-547); "LargePlank"
-        (default, 0.5 x 10 m) or "Plank" (0.5 x 0.75 m) stepping stones.  "Pillar" (cylinders) is not built."""
+        (default, 0.5 x 10 m), "Plank" (0.5 x 0.75 m) or "Pillar" (capped cylinders of radius 0.25, bullet_objects.py:86-90)
+        stepping stones."""
         super().__init__(num_envs, device=device, seed=seed, physics=physics, return_final_obs=return_final_obs)
         self.random_reward = bool(random_reward)
         if self.random_reward:
             _lib.check(self._L.mb200_set_param(self._h, b"random_reward", 1.0))
-        if plank_class not in (None, "LargePlank", "Plank"):
-            raise NotImplementedError("plank_class %r: only LargePlank and Plank are built" % (plank_class,))
+        classes = {"LargePlank": 0.0, "Plank": 1.0, "Pillar": 2.0}
+        if plank_class is not None and plank_class not in classes:
+            # the reference does globals().get(plank_class, LargePlank) (env_locomotion.py:356-357); a misspelt
+            # class silently becoming LargePlank is not reproduced
+            raise ValueError("plank_class %r: one of %s" % (plank_class, sorted(classes)))
         self.plank_class = plank_class or "LargePlank"
-        if self.plank_class == "Plank":
-            _lib.check(self._L.mb200_set_param(self._h, b"plank_class", 1.0))
+        if classes[self.plank_class]:
+            _lib.check(self._L.mb200_set_param(self._h, b"plank_class", classes[self.plank_class]))
 
     def set_env_params(self, params: dict):
         """``{"curriculum": c}`` with an int or one value per env (env_base.py:103-106); used at the next reset

@@ -549,7 +549,33 @@ static void add_point(orc_contacts* c, int pid, int link, int partner, const v3 
 }
 
 /* sphere (centre cw, radius r) vs static box; returns 1 and fills (pa, n, dist) if dist < thresh */
+/* sphere vs capped cylinder (Pillar, bullet_objects.py:86-90; pillar.urdf) in the record's local frame */
+static int sphere_cyl(const v3 cw, double r, const orc_box* b, double thresh, v3 pa, v3 n, double* dist) {
+  v3 d, cl, nl;
+  for (int k = 0; k < 3; k++) d[k] = cw[k] - b->center[k];
+  for (int k = 0; k < 3; k++) cl[k] = b->R[0][k] * d[0] + b->R[1][k] * d[1] + b->R[2][k] * d[2];
+  double rad = b->half[0], h = b->half[2];
+  double rho = sqrt(cl[0] * cl[0] + cl[1] * cl[1]);
+  double ux = rho > 1e-12 ? cl[0] / rho : 0.0, uy = rho > 1e-12 ? cl[1] / rho : 0.0;
+  int in_r = rho <= rad, in_z = fabs(cl[2]) <= h;
+  if (!(in_r && in_z)) {
+    double qr = rho < rad ? rho : rad, qz = cl[2] > h ? h : (cl[2] < -h ? -h : cl[2]);
+    double dr = rho - qr, dz = cl[2] - qz, len = sqrt(dr * dr + dz * dz);
+    *dist = len - r;
+    if (*dist >= thresh) return 0;
+    nl[0] = ux * dr / len; nl[1] = uy * dr / len; nl[2] = dz / len;
+  } else {
+    double pen_r = rad - rho, pen_z = h - fabs(cl[2]);
+    if (pen_z <= pen_r) { nl[0] = 0; nl[1] = 0; nl[2] = cl[2] >= 0 ? 1.0 : -1.0; *dist = -pen_z - r; }
+    else { nl[0] = ux; nl[1] = uy; nl[2] = 0; *dist = -pen_r - r; }
+  }
+  for (int k = 0; k < 3; k++) n[k] = b->R[k][0] * nl[0] + b->R[k][1] * nl[1] + b->R[k][2] * nl[2];
+  for (int k = 0; k < 3; k++) pa[k] = cw[k] - r * n[k];
+  return 1;
+}
+
 static int sphere_box(const v3 cw, double r, const orc_box* b, double thresh, v3 pa, v3 n, double* dist) {
+  if (b->cylinder) return sphere_cyl(cw, r, b, thresh, pa, n, dist);
   v3 d, cl, q, nl;
   for (int k = 0; k < 3; k++) d[k] = cw[k] - b->center[k];
   for (int k = 0; k < 3; k++) cl[k] = b->R[0][k] * d[0] + b->R[1][k] * d[1] + b->R[2][k] * d[2];
@@ -665,6 +691,7 @@ static int collide_bars(const orc_model* m, const orc_params* p, const orc_cache
         for (int b2 = 0; b2 < 3; b2++) Rl[a][b2] = c->Rw[link + 1][b2][a]; /* link -> world */
       m3mul(Rl, Rg, bx.R);
       for (int k = 0; k < 3; k++) bx.half[k] = m->geom_size[g][k];
+      bx.cylinder = 0;
       v3 pa, n;
       double dist;
       if (box_bar(&bx, &bars[ob], m->link_thresh[link + 1], pa, n, &dist))
@@ -1421,7 +1448,9 @@ static void stepper_place_plank(orc_stepper_env* e, int info_index, int plank) {
   b->center[0] = t[0]; b->center[1] = t[1]; b->center[2] = t[2] - 0.1375;
   memcpy(b->R, R, sizeof(m3));
   /* plank_large.urdf: box 1 x 20 x 0.45 / 0.05, plank.urdf: 1 x 1.5 x 0.45 / 0.05, globalScaling 2 * step_radius */
-  double half_y = e->plank_class == 1 ? 0.375 : 5.0;
+  /* pillar.urdf: cylinders radius 1, length 0.9 / 0.1, globalScaling step_radius = 0.25 */
+  double half_y = e->plank_class == 1 ? 0.375 : (e->plank_class == 2 ? 0.25 : 5.0);
+  b->cylinder = c->cylinder = e->plank_class == 2;
   b->half[0] = 0.25; b->half[1] = half_y; b->half[2] = 0.1125;
   memcpy(c->R, R, sizeof(m3));
   for (int k = 0; k < 3; k++) c->center[k] = b->center[k] + R[k][2] * 0.125;

@@ -127,6 +127,7 @@ typedef struct {
   double friction;
   double stiffness, damping; /* <=0: rigid */
   int id;                    /* partner code reported in orc_contacts */
+  int cylinder;              /* 1: capped cylinder about the local z axis, radius half[0], half length half[2] (Pillar) */
 } orc_box;
 
 /* static thin cylinder (MonkeyBar, bullet_objects.py:148-187), treated as a capsule around its axis segment */
@@ -215,7 +216,7 @@ typedef struct {
   double step_bonus, speed_penalty;
   int steps_reached; /* info["steps_reached"] when reported, else -1 */
   int random_reward; /* constructor kwarg (env_locomotion.py:355) */
-  int plank_class;   /* constructor kwarg (env_locomotion.py:342,356-357): 0 LargePlank, 1 Plank */
+  int plank_class;   /* constructor kwarg (env_locomotion.py:342,356-357): 0 LargePlank, 1 Plank, 2 Pillar */
 } orc_stepper_env;
 
 void orc_stepper_seed(orc_stepper_env* e, const uint32_t* key, int len, int at_construction);

@@ -74,7 +74,7 @@ class Contacts(C.Structure):
 
 class Box(C.Structure):
     _fields_ = [("center", d * 3), ("R", (d * 3) * 3), ("half", d * 3), ("friction", d), ("stiffness", d),
-                ("damping", d), ("id", i32)]
+                ("damping", d), ("id", i32), ("cylinder", i32)]
 
 
 class Rng(C.Structure):
@@ -406,7 +406,7 @@ class Walker3DStepperOracle:
         self.e = StepperEnv()
         self.e.curriculum = curriculum
         self.e.random_reward = int(random_reward)
-        self.e.plank_class = {None: 0, "LargePlank": 0, "Plank": 1}[plank_class]
+        self.e.plank_class = {None: 0, "LargePlank": 0, "Plank": 1, "Pillar": 2}[plank_class]
         self.A = table["n_dof"]
         self.obs_dim = 6 + 2 * self.A + len(table["foot_links"]) + 15
         self._seed(seed, True)

@@ -300,4 +300,7 @@ void emu_cassie_mass_matrix(const MbPhysics* p, const float* state, float* Mout,
   }
 EMU_ENV(child, CH3D_Model, W3DEnv<CH3D_Model>, 0)
 EMU_ENV(mike, MIKE_Model, StepperEnv<MIKE_Model>, MB_OBST_BOXES)
+// plank_class = "Pillar": the PILLAR instantiation of the stepper template
+typedef StepperEnv<WM, true> SEnvPillar;
+EMU_ENV(pillar, WM, SEnvPillar, MB_OBST_CYLS)
 }

@@ -192,8 +192,15 @@ def test_gym_facades_and_kwargs(torch_mod):
     env.reset()
     env.step(np.zeros(21))
     env.close()
-    with pytest.raises(NotImplementedError):
-        make("Walker3DStepperEnv-v0", num_envs=2, plank_class="Pillar")
+    env = make("MikeStepperEnv-v0", seed=3, plank_class="Pillar")  # cylinder stones (bullet_objects.py:86-90)
+    assert env.vec.plank_class == "Pillar"
+    o = env.reset()
+    for _ in range(5):
+        o, r, d, info = env.step(np.zeros(21))
+    assert np.isfinite(o).all() and np.isfinite(r)
+    env.close()
+    with pytest.raises(ValueError):
+        make("Walker3DStepperEnv-v0", num_envs=2, plank_class="Pilar")
 
 
 def test_env_param_accessors(torch_mod):

@@ -222,3 +222,51 @@ def test_stepper_plank_class(walker_table, oracle_mod, torch_mod):
         final[cls] = st.copy()
         env.close()
     assert np.abs(final["Plank"] - final["LargePlank"]).max() > 1e-2
+
+
+def test_stepper_pillar_class(walker_table, oracle_mod, torch_mod):
+    """plank_class = "Pillar" (bullet_objects.py:86-90, pillar.urdf): capped cylinders of radius 0.25 instead of 10 m
+    wide planks, run by the PILLAR kernel instantiation.  Walkers shifted 0.3 m sideways: one foot over the rim / off the
+    stone.  Device and oracle agree frame by frame (2e-3) and the result differs from the LargePlank run; then whole
+    env steps (terrain bookkeeping, obs, reward) stay finite and the pillar batch refuses a per-env class mix."""
+    from tests.helpers import oracle_state, state_error
+
+    torch, O, t = torch_mod, oracle_mod, walker_table
+    N = 4
+    final = {}
+    for cls in ("LargePlank", "Pillar"):
+        env = _env(N, seed=700, plank_class=cls)
+        env.set_env_params({"curriculum": 0})
+        oracles = [O.Walker3DStepperOracle(t, seed=700 + i, curriculum=0, plank_class=cls) for i in range(N)]
+        env.reset()
+        for o in oracles:
+            o.reset()
+        p = O.default_params()
+        p.has_ground = 0
+        st = np.stack([o.state_vector() for o in oracles])
+        st[:, 1] += 0.3
+        st = st.astype(np.float32)
+        boxes = [(O.Box * 6)(*o.e.boxes) for o in oracles]
+        zero = torch.zeros(N, 21, device="cuda:0")
+        worst, contacts = 0.0, 0
+        for frame in range(30):
+            env.set_state(torch.tensor(st))
+            env.step_physics(zero)
+            out = env.get_state().cpu().numpy()
+            for i, o in enumerate(oracles):
+                s = oracle_state(O, 21, st[i].astype(np.float64))
+                c, rows = O.step_physics(o.m, p, s, np.zeros(21), boxes=boxes[i])
+                contacts += c.n
+                ref = O.state_vector(s, 21)
+                worst = max(worst, state_error(out[i], ref))
+                st[i] = ref.astype(np.float32)
+        assert contacts > 0
+        assert worst < 2e-3, (cls, worst)
+        final[cls] = st.copy()
+        if cls == "Pillar":
+            env.reset()
+            for _ in range(20):
+                obs, rew, done, info = env.step(zero)
+            assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        env.close()
+    assert np.abs(final["Pillar"] - final["LargePlank"]).max() > 1e-2

@@ -281,3 +281,45 @@ def test_stepper_plank_class(walker_table, oracle_mod):
         assert worst < 2e-3, (cls, worst)
         outs[cls] = O.state_vector(s, 21)
     assert np.abs(outs["Plank"] - outs["LargePlank"]).max() > 1e-2
+
+
+def test_stepper_pillar_class(walker_table, oracle_mod):
+    """plank_class = "Pillar" (bullet_objects.py:86-90, pillar.urdf): capped cylinders of radius 0.25.  A walker
+    dropped 0.3 m to the side keeps one foot on a pillar and none... on the rim: kernel source (PILLAR instantiation)
+    and oracle agree frame by frame, and the result differs from the LargePlank run."""
+    from tests.helpers import oracle_state, state_error
+
+    O, t = oracle_mod, walker_table
+
+    class EmuPillar(E.EmuStepper):
+        prefix = "pillar"
+
+    outs = {}
+    for cls, emu_cls in (("LargePlank", E.EmuStepper), ("Pillar", EmuPillar)):
+        env = O.Walker3DStepperOracle(t, seed=2, curriculum=0, plank_class=cls)
+        emu = emu_cls(_mt_row(O, 2), curriculum=0)
+        env.reset()
+        emu.reset()
+        m, p = env.m, O.default_params()
+        p.has_ground = 0
+        sv = env.state_vector()
+        sv[1] += 0.3
+        sv = sv.astype(np.float32)
+        emu.state[:55] = sv
+        s = oracle_state(O, 21, sv.astype(np.float64))
+        boxes = (O.Box * 6)(*env.e.boxes)
+        assert all(bool(b.cylinder) == (cls == "Pillar") for b in boxes)
+        worst, contacts = 0.0, 0
+        for frame in range(30):
+            c, rows = O.step_physics(m, p, s, np.zeros(21), boxes=boxes)
+            erows, enc = emu.step_physics(np.zeros(21, dtype=np.float32))
+            assert enc == c.n
+            contacts += c.n
+            ref = O.state_vector(s, 21)
+            worst = max(worst, state_error(emu.state[:55], ref))
+            emu.state[:55] = ref.astype(np.float32)
+            s = oracle_state(O, 21, emu.state[:55].astype(np.float64))
+        assert contacts > 0
+        assert worst < 2e-3, (cls, worst)
+        outs[cls] = O.state_vector(s, 21)
+    assert np.abs(outs["Pillar"] - outs["LargePlank"]).max() > 1e-2
