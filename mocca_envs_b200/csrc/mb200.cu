@@ -134,9 +134,16 @@ struct StepArgs {
   const int* order;
   int* key;
   int* hist;  // this step's histogram half, nullptr = scheduler off
+  // mb200_step_host with pinned (device-mapped) result buffers: each warp forwards its env's finished rows from the
+  // device staging arrays to the host with coalesced zero-copy stores, so the D2H traffic overlaps the rest of the
+  // launch instead of following it; nullptr = staged cudaMemcpyAsync (pageable host memory) or device callers
+  float* host_obs;
+  float* host_rew;
+  uint8_t* host_done;
+  uint8_t* host_trunc;
 };
 
-template <class Env>
+template <class Env, bool HOST>
 __device__ __forceinline__ void step_body(const StepArgs& a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // broadcast from lane 0: tells the compiler the warp index is warp-uniform, so the WarpMem base lives in a uniform
@@ -154,6 +161,21 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
             a.act + (size_t)(tail ? 0 : env) * Env::ACT, obs, tail ? a.dummy_rew + warp : a.rew + env,
             tail ? a.dummy_flag + warp : a.done + env, tail ? a.dummy_flag + MB_WARPS_MAX + warp : a.trunc + env, fin,
             tail ? a.dummy_stats : a.stats);
+  if (HOST && !tail) {
+    // (separate kernel instantiation: the extra epilogue cost the device-buffer kernel 1 % through register
+    // allocation when it was a run-time branch)  the row is final here (auto-reset included); lanes read what other lanes of this warp wrote
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    const float* src = a.obs + (size_t)env * Env::OBS;
+    float* dst = a.host_obs + (size_t)env * Env::OBS;
+#pragma unroll
+    for (int i = lane; i < Env::OBS; i += 32) dst[i] = __ldcg(src + i);
+    if (lane == 0) {
+      a.host_rew[env] = __ldcg(a.rew + env);
+      a.host_done[env] = __ldcg(a.done + env);
+      a.host_trunc[env] = __ldcg(a.trunc + env);
+    }
+  }
   // work estimate for the scheduler: constraint rows of this step
   if ((threadIdx.x & 31) == 0 && a.hist) {
     // (taken from the step itself, not from the float running sum ER_ROWS, which stops resolving single steps after
@@ -196,30 +218,19 @@ __global__ void __launch_bounds__(256) k_order_by_key(int n_pad, const int* key,
   if (k < 256) order[start[k] + off + __popc(peers & ((1u << lane) - 1u))] = e;
 }
 
-__global__ void __launch_bounds__(MB_WARPS_CUSTOM * 32, MB_MINBLOCKS) k_step_walker3d_custom(StepArgs a) {
-  step_body<WEnv>(a);
-}
-__global__ void __launch_bounds__(MB_WARPS_STEPPER * 32, MB_MINBLOCKS) k_step_walker3d_stepper(StepArgs a) {
-  step_body<SEnv>(a);
-}
-__global__ void __launch_bounds__(MB_WARPS_MONKEY * 32, MB_MINBLOCKS) k_step_monkey3d_custom(StepArgs a) {
-  step_body<MEnv>(a);
-}
-__global__ void __launch_bounds__(MB_WARPS_CASSIE * 32, MB_MINBLOCKS) k_step_cassie(StepArgs a) {
-  step_body<CEnv>(a);
-}
-__global__ void __launch_bounds__(MB_WARPS_STEPPER * 32, MB_MINBLOCKS) k_step_child3d_custom(StepArgs a) {
-  step_body<ChEnv>(a);
-}
-__global__ void __launch_bounds__(MB_WARPS_STEPPER * 32, MB_MINBLOCKS) k_step_mike_stepper(StepArgs a) {
-  step_body<MkEnv>(a);
-}
-__global__ void __launch_bounds__(MB_WARPS_STEPPER * 32, MB_MINBLOCKS) k_step_walker3d_stepper_pillar(StepArgs a) {
-  step_body<SEnvP>(a);
-}
-__global__ void __launch_bounds__(MB_WARPS_STEPPER * 32, MB_MINBLOCKS) k_step_mike_stepper_pillar(StepArgs a) {
-  step_body<MkEnvP>(a);
-}
+// every step kernel exists twice: NAME (device result buffers) and NAME_host (mb200_step_host with pinned host buffers:
+// the same step plus the zero-copy forwarding of the finished rows)
+#define MB_STEP_KERNEL(NAME, WARPS, ENV)                                                        \
+  __global__ void __launch_bounds__(WARPS * 32, MB_MINBLOCKS) NAME(StepArgs a) { step_body<ENV, false>(a); } \
+  __global__ void __launch_bounds__(WARPS * 32, MB_MINBLOCKS) NAME##_host(StepArgs a) { step_body<ENV, true>(a); }
+MB_STEP_KERNEL(k_step_walker3d_custom, MB_WARPS_CUSTOM, WEnv)
+MB_STEP_KERNEL(k_step_walker3d_stepper, MB_WARPS_STEPPER, SEnv)
+MB_STEP_KERNEL(k_step_monkey3d_custom, MB_WARPS_MONKEY, MEnv)
+MB_STEP_KERNEL(k_step_cassie, MB_WARPS_CASSIE, CEnv)
+MB_STEP_KERNEL(k_step_child3d_custom, MB_WARPS_STEPPER, ChEnv)
+MB_STEP_KERNEL(k_step_mike_stepper, MB_WARPS_STEPPER, MkEnv)
+MB_STEP_KERNEL(k_step_walker3d_stepper_pillar, MB_WARPS_STEPPER, SEnvP)
+MB_STEP_KERNEL(k_step_mike_stepper_pillar, MB_WARPS_STEPPER, MkEnvP)
 
 template <class Env>
 __device__ __forceinline__ void reset_body(int n, const MbPhysics& phys, float* state, float* rec, uint32_t* mt,
@@ -522,31 +533,39 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
               sc = (int)(sizeof(WarpMem<CM>) * MB_WARPS_MAX);
     const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
     CUDA_OK(cudaFuncSetAttribute(k_step_cassie, at, sc));
+    CUDA_OK(cudaFuncSetAttribute(k_step_cassie_host, at, sc));
     CUDA_OK(cudaFuncSetAttribute(k_reset_cassie, at, sc));
     CUDA_OK(cudaFuncSetAttribute(k_step_physics_cassie, at, sc));
     CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_cassie, at, sc));
     CUDA_OK(cudaFuncSetAttribute(k_step_monkey3d_custom, at, sm));
+    CUDA_OK(cudaFuncSetAttribute(k_step_monkey3d_custom_host, at, sm));
     CUDA_OK(cudaFuncSetAttribute(k_reset_monkey3d_custom, at, sm));
     CUDA_OK(cudaFuncSetAttribute(k_step_physics_monkey3d, at, sm));
     CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_monkey3d, at, sm));
     CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_stepper, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_stepper_host, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_reset_walker3d_stepper, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d_stepper, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_custom, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_custom_host, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_reset_walker3d_custom, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_walker3d, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_child3d_custom, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_child3d_custom_host, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_reset_child3d_custom, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_physics_child3d, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_child3d, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_mike_stepper, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_mike_stepper_host, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_reset_mike_stepper, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_physics_mike_stepper, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_mike, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_stepper_pillar, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_stepper_pillar_host, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d_stepper_pillar, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_mike_stepper_pillar, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_mike_stepper_pillar_host, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_physics_mike_stepper_pillar, at, sw));
   }
   e->n_pad = grid_for(e) * e->warps;
@@ -697,8 +716,16 @@ static int launch_sort(mb200_env* e, void* stream) {
   return 0;
 }
 
+struct HostOut {
+  float* obs;
+  float* rew;
+  uint8_t* done;
+  uint8_t* trunc;
+};
+
 static int step_impl(mb200_env* e, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev,
-                     uint8_t* trunc_dev, float* final_obs_dev, void* stream, bool sort_now) {
+                     uint8_t* trunc_dev, float* final_obs_dev, void* stream, bool sort_now,
+                     const HostOut* host = nullptr) {
   if (!e || !act_dev || !obs_dev || !rew_dev || !done_dev || !trunc_dev) return fail("mb200_step: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
   StepArgs a;
@@ -707,22 +734,29 @@ static int step_impl(mb200_env* e, const float* act_dev, float* obs_dev, float* 
   a.dummy_obs = e->dummy_obs; a.dummy_rew = e->dummy_rew; a.dummy_flag = e->dummy_flag; a.dummy_stats = e->dummy_stats;
   a.order = e->order; a.key = e->key;
   a.hist = sorting(e) ? e->hist + 256 * (int)(e->steps & 1) : nullptr;
+  a.host_obs = host ? host->obs : nullptr; a.host_rew = host ? host->rew : nullptr;
+  a.host_done = host ? host->done : nullptr; a.host_trunc = host ? host->trunc : nullptr;
+#define MB_LAUNCH_STEP(NAME)                                                                   \
+  do {                                                                                         \
+    if (host) NAME##_host<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);   \
+    else NAME<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);               \
+  } while (0)
   if (e->kind == KIND_CASSIE)
-    k_step_cassie<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
+    MB_LAUNCH_STEP(k_step_cassie);
   else if (e->kind == KIND_MONKEY)
-    k_step_monkey3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
+    MB_LAUNCH_STEP(k_step_monkey3d_custom);
   else if (e->kind == KIND_CHILD)
-    k_step_child3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
+    MB_LAUNCH_STEP(k_step_child3d_custom);
   else if (e->kind == KIND_MIKE && e->pillar)
-    k_step_mike_stepper_pillar<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
+    MB_LAUNCH_STEP(k_step_mike_stepper_pillar);
   else if (e->kind == KIND_MIKE)
-    k_step_mike_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
+    MB_LAUNCH_STEP(k_step_mike_stepper);
   else if (e->kind == KIND_STEPPER && e->pillar)
-    k_step_walker3d_stepper_pillar<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
+    MB_LAUNCH_STEP(k_step_walker3d_stepper_pillar);
   else if (e->kind == KIND_STEPPER)
-    k_step_walker3d_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
+    MB_LAUNCH_STEP(k_step_walker3d_stepper);
   else
-    k_step_walker3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);
+    MB_LAUNCH_STEP(k_step_walker3d_custom);
   e->launches++;
   e->steps++;
   CUDA_OK(cudaGetLastError());
@@ -734,6 +768,25 @@ int mb200_step(mb200_env* e, const float* act_dev, float* obs_dev, float* rew_de
   return step_impl(e, act_dev, obs_dev, rew_dev, done_dev, trunc_dev, final_obs_dev, stream, true);
 }
 
+// device alias of a pinned / registered host buffer (UVA), nullptr for pageable memory
+static void* mapped_alias(const void* host) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type != cudaMemoryTypeHost) return nullptr;
+  return at.devicePointer;
+}
+
+// MB200_HOST_DIRECT: 0 = always stage through device buffers + cudaMemcpyAsync; 1 = results go to pinned host buffers
+// by zero-copy stores from the step kernel; 2 (default) = also read the actions from the pinned host buffer in place
+static int host_direct_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* s = getenv("MB200_HOST_DIRECT");
+    mode = s && *s ? atoi(s) : 2;
+  }
+  return mode;
+}
+
 int mb200_step_host(mb200_env* e, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host,
                     uint8_t* trunc_host, void* stream) {
   if (!e || !act_host || !obs_host || !rew_host || !done_host || !trunc_host)
@@ -741,15 +794,30 @@ int mb200_step_host(mb200_env* e, const float* act_host, float* obs_host, float*
   CUDA_OK(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)e->n;
-  CUDA_OK(cudaMemcpyAsync(e->stage_act, act_host, n * e->act_dim * sizeof(float), cudaMemcpyHostToDevice, st));
-  int rc = step_impl(e, e->stage_act, e->stage_obs, e->stage_rew, e->stage_done, e->stage_trunc, nullptr, stream, false);
+  const int mode = host_direct_mode();
+  HostOut ho = {nullptr, nullptr, nullptr, nullptr};
+  if (mode >= 1) {
+    ho.obs = (float*)mapped_alias(obs_host); ho.rew = (float*)mapped_alias(rew_host);
+    ho.done = (uint8_t*)mapped_alias(done_host); ho.trunc = (uint8_t*)mapped_alias(trunc_host);
+  }
+  const bool direct_out = ho.obs && ho.rew && ho.done && ho.trunc;
+  const float* act_dev = mode >= 2 && direct_out ? (const float*)mapped_alias(act_host) : nullptr;
+  if (!act_dev) {
+    CUDA_OK(cudaMemcpyAsync(e->stage_act, act_host, n * e->act_dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    act_dev = e->stage_act;
+  }
+  int rc = step_impl(e, act_dev, e->stage_obs, e->stage_rew, e->stage_done, e->stage_trunc, nullptr, stream, false,
+                     direct_out ? &ho : nullptr);
   if (rc) return rc;
-  CUDA_OK(cudaMemcpyAsync(obs_host, e->stage_obs, n * e->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaMemcpyAsync(rew_host, e->stage_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaMemcpyAsync(done_host, e->stage_done, n, cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaMemcpyAsync(trunc_host, e->stage_trunc, n, cudaMemcpyDeviceToHost, st));
-  // the caller needs the results, not the scheduler's re-sort: wait for the copies only and let the sort of the next
-  // step's launch order run while the host picks its actions
+  if (!direct_out) {
+    CUDA_OK(cudaMemcpyAsync(obs_host, e->stage_obs, n * e->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(rew_host, e->stage_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(done_host, e->stage_done, n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(trunc_host, e->stage_trunc, n, cudaMemcpyDeviceToHost, st));
+  }
+  // the caller needs the results, not the scheduler's re-sort: wait for the results only (the event completes when
+  // the kernel's zero-copy stores / the copies have landed) and let the sort of the next step's launch order run
+  // while the host picks its actions
   CUDA_OK(cudaEventRecord(e->host_done, st));
   rc = launch_sort(e, stream);
   if (rc) return rc;

@@ -215,3 +215,34 @@ def test_env_param_accessors(torch_mod):
     with pytest.raises(AttributeError):
         env.set_robot_params({"power": 0.5})
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id,kwargs", [("Walker3DStepperEnv-v0", {}), ("Walker3DStepperEnv-v0", {"plank_class": "Pillar"}),
+                                           ("Monkey3DCustomEnv-v0", {}), ("CassieEnv-v0", {}),
+                                           ("Child3DCustomEnv-v0", {}), ("MikeStepperEnv-v0", {})])
+def test_step_host_pinned_matches_device_every_env(env_id, kwargs):
+    """The `_host` instantiation of every step kernel (zero-copy result stores into pinned host buffers, actions read
+    from the pinned host buffer in place) returns exactly what the device-buffer step returns."""
+    import torch
+    from mocca_envs_b200 import make
+
+    N = 200
+    e1, e2 = make(env_id, num_envs=N, seed=9, **kwargs), make(env_id, num_envs=N, seed=9, **kwargs)
+    e1.reset(); e2.reset()
+    A, OB = e1.act_dim, e1.obs_dim
+    h_act = torch.empty(N, A).pin_memory()
+    outs = tuple(t.numpy() for t in (torch.empty(N, OB).pin_memory(), torch.empty(N).pin_memory(),
+                                     torch.empty(N, dtype=torch.uint8).pin_memory(),
+                                     torch.empty(N, dtype=torch.uint8).pin_memory()))
+    rng = np.random.RandomState(3)
+    for _ in range(12):
+        a = rng.uniform(-1, 1, (N, A)).astype(np.float32)
+        h_act.numpy()[:] = a
+        o1, r1, d1, _ = e1.step(torch.tensor(a))
+        for o in outs:
+            o.fill(0)
+        e2.step_host(h_act.numpy(), outs)
+        assert np.array_equal(o1.cpu().numpy(), outs[0]) and np.array_equal(r1.cpu().numpy(), outs[1])
+        assert np.array_equal(d1.cpu().numpy(), outs[2])
+    e1.close(); e2.close()

@@ -309,6 +309,35 @@ def test_step_host_matches_device(torch_mod):
     e1.close(); e2.close()
 
 
+def test_step_host_pinned_zero_copy_matches_device(torch_mod):
+    """Pinned host buffers take the zero-copy route of mb200_step_host (the step kernel reads the actions from and
+    stores obs / reward / done / trunc into the mapped host buffers itself); pageable buffers take the staged copies.
+    Both must equal the device-buffer step bit for bit, through auto-resets and with pad envs in the last CTA."""
+    torch = torch_mod
+    N = 1000
+    e1, e2 = _env(N, seed=33), _env(N, seed=33)
+    e1.reset(); e2.reset()
+    h_act = torch.empty(N, 21).pin_memory()
+    outs = (torch.empty(N, 52).pin_memory(), torch.empty(N).pin_memory(),
+            torch.empty(N, dtype=torch.uint8).pin_memory(), torch.empty(N, dtype=torch.uint8).pin_memory())
+    outs_np = tuple(o.numpy() for o in outs)
+    rng = np.random.RandomState(1)
+    dones = 0
+    for _ in range(60):
+        a = rng.uniform(-1, 1, (N, 21)).astype(np.float32)
+        h_act.numpy()[:] = a
+        o1, r1, d1, i1 = e1.step(torch.tensor(a))
+        for o in outs_np:
+            o.fill(0)
+        e2.step_host(h_act.numpy(), outs_np)
+        assert np.array_equal(o1.cpu().numpy(), outs_np[0]) and np.array_equal(r1.cpu().numpy(), outs_np[1])
+        assert np.array_equal(d1.cpu().numpy(), outs_np[2])
+        assert np.array_equal(i1["TimeLimit.truncated"].cpu().numpy().astype(np.uint8), outs_np[3])
+        dones += int(outs_np[2].sum())
+    assert dones > N // 2  # random actions: most walkers fell and were reset at least once
+    e1.close(); e2.close()
+
+
 def test_gym_facade(torch_mod):
     from mocca_envs_b200 import make
 
