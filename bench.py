@@ -22,7 +22,8 @@ METRIC = "env-steps/sec (Walker3DCustomEnv-v0, 16384 envs/GPU, random actions)"
 
 
 ENV_NAMES = {"custom": "Walker3DCustomEnv", "stepper": "Walker3DStepperEnv", "monkey": "Monkey3DCustomEnv",
-             "cassie": "CassieEnv", "child": "Child3DCustomEnv", "mike": "MikeStepperEnv"}
+             "cassie": "CassieEnv", "child": "Child3DCustomEnv", "mike": "MikeStepperEnv",
+             "walker2d": "Walker2DCustomEnv", "crab2d": "Crab2DCustomEnv"}
 
 
 def flops_per_env_step(rows_per_substep, S=4, n=27, L=17, G=22, I=5, P=0):
@@ -158,6 +159,8 @@ def cpu_reference_run(n_envs, steps, warmup, threads, time_budget=None, kind="cu
     from oracle import oracle as O
 
     model, struct, pre, A, OB = {"child": ("child3d", O.W3DEnv, "orc_w3d", 21, 52),
+                                 "walker2d": ("walker2d", O.W3DEnv, "orc_w3d", 7, 24),
+                                 "crab2d": ("crab2d", O.W3DEnv, "orc_w3d", 6, 22),
                                  "mike": ("mike", O.StepperEnv, "orc_stepper", 21, 65),
                                  "cassie": ("cassie", O.CassieEnvS, "orc_cassie", 10, 36),
                                  "custom": ("walker3d", O.W3DEnv, "orc_w3d", 21, 52),
@@ -208,7 +211,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--envs", type=int, default=16384, help="envs per GPU")
     ap.add_argument("--actions", default="random", choices=["random", "pd"])
-    ap.add_argument("--env", default="custom", choices=["custom", "stepper", "monkey", "cassie", "child", "mike"],
+    ap.add_argument("--env", default="custom", choices=["custom", "stepper", "monkey", "cassie", "child", "mike", "walker2d", "crab2d"],
                     help="custom = BASELINE configs[1] (headline); stepper = configs[2] (curriculum 0/5/9 per env); "
                          "monkey = configs[4] (Monkey3DCustomEnv-v0); cassie = configs[3] (CassieEnv-v0, 50 substeps per step); "
                          "child / mike = SURVEY 8 f3 (Child3DCustomEnv-v0, MikeStepperEnv-v0)")
@@ -271,6 +274,10 @@ def main():
         env.set_env_params({"curriculum": np.array([0, 5, 9] * (N // 3 + 1))[:N]})
     elif args.env == "child":
         env = Child3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
+    elif args.env in ("walker2d", "crab2d"):
+        from mocca_envs_b200.vec_env import Crab2DCustomVecEnv, Walker2DCustomVecEnv
+        cls = Walker2DCustomVecEnv if args.env == "walker2d" else Crab2DCustomVecEnv
+        env = cls(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
     elif args.env == "monkey":
         env = Monkey3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
     elif args.env == "cassie":
@@ -401,6 +408,9 @@ def main():
         F = flops_per_env_step(R_mean, L=len([x for x in env.table["mass"] if x > 0]) + 1, G=len(env.table["geoms"]),
                                P=n_self)
         B_step = bytes_per_env_step(O=65, S_env=40)
+    elif args.env in ("walker2d", "crab2d"):  # planar walkers: n = 6 + A, every link massive
+        F = flops_per_env_step(R_mean, n=6 + A, L=len(env.table["mass"]) + 1, G=len(env.table["geoms"]), P=n_self)
+        B_step = bytes_per_env_step(S_state=13 + 2 * A, A=A, O=env.obs_dim)
     else:
         F = flops_per_env_step(R_mean, P=n_self)
         B_step = bytes_per_env_step()
@@ -427,6 +437,8 @@ def main():
                                 "monkey": "Monkey3DCustomEnv-v0 batched, seeded monkey bars",
                                 "cassie": "CassieEnv-v0 batched, residual PD control, 50 substeps per env step",
                                 "child": "Child3DCustomEnv-v0 batched, flat ground, crawl start pose",
+                                "walker2d": "Walker2DCustomEnv-v0 batched, flat ground, planar base (SURVEY 8 f3)",
+                                "crab2d": "Crab2DCustomEnv-v0 batched, flat ground, planar base (SURVEY 8 f3)",
                                 "mike": "MikeStepperEnv-v0 batched, seeded stepping stones, curriculum 0/5/9"}[args.env],
                    "envs_per_gpu": N, "actions": "random-uniform U(-1,1)^%d (device pool)" % A
                    if args.actions == "random" else "scripted PD toward running_start (kp=1, kd=0.1, normalised)",

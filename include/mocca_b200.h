@@ -50,8 +50,9 @@ void mb200_default_physics_for(const char* env_id, mb200_physics* p);
 /* gym.make("mocca_envs:<env_id>") x n_envs  (reference mocca_envs/__init__.py:18-116, env_base.py:16-42).
  * env_id: "Walker3DCustomEnv-v0" (__init__.py:52-56), "Walker3DStepperEnv-v0" (__init__.py:58-62),
  * "Monkey3DCustomEnv-v0" (__init__.py:94-98; env_locomotion.py:1136-1516), "CassieEnv-v0" (__init__.py:18-22;
- * env_cassie.py:285-479), "Child3DCustomEnv-v0" (__init__.py:45-49; env_locomotion.py:317-327) or
- * "MikeStepperEnv-v0" (__init__.py:64-68; env_locomotion.py:843-851).
+ * env_cassie.py:285-479), "Child3DCustomEnv-v0" (__init__.py:45-49; env_locomotion.py:317-327),
+ * "MikeStepperEnv-v0" (__init__.py:64-68; env_locomotion.py:843-851), "Walker2DCustomEnv-v0" (__init__.py:106-110;
+ * env_locomotion.py:285-310) or "Crab2DCustomEnv-v0" (__init__.py:112-116; env_locomotion.py:312-314).
  * physics may be NULL (reference values). */
 int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics* physics, mb200_env** out);
 /* EnvBase.close (env_base.py:44-47) */
@@ -76,8 +77,11 @@ int mb200_reset(mb200_env* env, const uint8_t* mask_dev, float* obs_dev, void* s
 int mb200_step(mb200_env* env, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev,
                uint8_t* trunc_dev, float* final_obs_dev, void* stream);
 
-/* Same call with HOST buffers (what a gym/SubprocVecEnv user holds): H2D of the actions, the step kernel,
- * D2H of obs/reward/done/trunc, then a stream synchronise.  Pinned host memory makes the copies asynchronous. */
+/* Same call with HOST buffers (what a gym/SubprocVecEnv user holds); returns when the results are in the buffers.
+ * Pinned buffers (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory): the step kernel reads the actions from and
+ * stores obs/reward/done/trunc into the mapped host memory itself, so the transfers overlap the launch.  Pageable
+ * buffers: H2D of the actions, the step kernel, D2H of the results through device staging buffers.
+ * MB200_HOST_DIRECT=0 in the environment forces the staged path, =1 keeps only the result stores direct. */
 int mb200_step_host(mb200_env* env, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host,
                     uint8_t* trunc_host, void* stream);
 

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("MB200_LIB") or os.path.join(_HERE, "libmocca_b200.so"
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in
            ("mb200.cu", "mb_core.cuh", "mb_env.cuh", "mb_tables.h", "generated/walker3d_model.h",
             "generated/monkey3d_model.h", "generated/cassie_model.h", "generated/child3d_model.h",
-            "generated/mike_model.h")]
+            "generated/mike_model.h", "generated/walker2d_model.h", "generated/crab2d_model.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -372,6 +372,9 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append("  MB_HD static float base_quat(int k) { return k == 0 ? %s : (k == 1 ? %s : (k == 2 ? %s : %s)); }\n"
                % tuple(_f(v) for v in bq))
     out.append("  MB_HD static float term_height() { return %s; }\n" % _f(t.get("termination_height", 0.7)))
+    # Walker2DCustomEnv / Crab2DCustomEnv (env_locomotion.py:285-310): done is forced to False, reset() returns zeros
+    # in the two target slots
+    out.append("  MB_HD static constexpr bool planar_env() { return %s; }\n" % ("true" if t.get("planar") else "false"))
     sp = t.get("stepper_init_position", [0.3, 0.0, 1.32])
     out.append("  MB_HD static float stepper_x() { return %s; }\n" % _f(sp[0]))
     out.append("  MB_HD static float stepper_y() { return %s; }\n" % _f(sp[1]))
@@ -385,7 +388,7 @@ def emit_all(repo_root: str):
     os.makedirs(gen, exist_ok=True)
     models = os.path.join(repo_root, "mocca_envs_b200", "models")
     for name, prefix in (("walker3d", "W3D"), ("monkey3d", "MK3D"), ("cassie", "CAS"), ("child3d", "CH3D"),
-                         ("mike", "MIKE")):
+                         ("mike", "MIKE"), ("walker2d", "W2D"), ("crab2d", "CR2D")):
         t = load_table(os.path.join(models, name + ".json"))
         with open(os.path.join(gen, name + "_model.h"), "w") as f:
             f.write(emit_header(t, prefix))

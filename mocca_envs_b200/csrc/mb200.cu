@@ -40,6 +40,8 @@
 #include "generated/monkey3d_model.h"
 #include "generated/cassie_model.h"
 #include "generated/child3d_model.h"
+#include "generated/walker2d_model.h"
+#include "generated/crab2d_model.h"
 #include "generated/mike_model.h"
 #include "mb_env.cuh"
 
@@ -53,8 +55,12 @@ static int fail(const std::string& m) { g_err = m; return -1; }
   } while (0)
 
 // KIND_CHILD / KIND_MIKE run the Walker3DCustomEnv / Walker3DStepperEnv templates on other model tables
-enum { KIND_CUSTOM = 0, KIND_STEPPER = 1, KIND_MONKEY = 2, KIND_CASSIE = 3, KIND_CHILD = 4, KIND_MIKE = 5 };
-static bool custom_family(int kind) { return kind == KIND_CUSTOM || kind == KIND_CHILD; }
+// KIND_WALKER2D / KIND_CRAB2D: the planar walkers (free base that stays in the x-z plane) on the Walker3DCustomEnv template
+enum { KIND_CUSTOM = 0, KIND_STEPPER = 1, KIND_MONKEY = 2, KIND_CASSIE = 3, KIND_CHILD = 4, KIND_MIKE = 5,
+       KIND_WALKER2D = 6, KIND_CRAB2D = 7 };
+static bool custom_family(int kind) {
+  return kind == KIND_CUSTOM || kind == KIND_CHILD || kind == KIND_WALKER2D || kind == KIND_CRAB2D;
+}
 static bool stepper_family(int kind) { return kind == KIND_STEPPER || kind == KIND_MIKE; }
 
 struct mb200_env {
@@ -106,6 +112,10 @@ typedef MonkeyEnv<MM> MEnv;
 typedef CAS_Model CM;
 typedef CassieEnv<CM> CEnv;
 typedef W3DEnv<CH3D_Model> ChEnv;       // Child3DCustomEnv-v0 (env_locomotion.py:317-327)
+typedef W3DEnv<W2D_Model> W2Env;        // Walker2DCustomEnv-v0 (env_locomotion.py:285-310)
+typedef W3DEnv<CR2D_Model> CrEnv;       // Crab2DCustomEnv-v0 (env_locomotion.py:312-314)
+static_assert(sizeof(WarpMem<W2D_Model>) <= sizeof(WarpMem<W3D_Model>) &&
+              sizeof(WarpMem<CR2D_Model>) <= sizeof(WarpMem<W3D_Model>), "shared-memory opt-in is sized for Walker3D");
 typedef StepperEnv<MIKE_Model> MkEnv;   // MikeStepperEnv-v0 (env_locomotion.py:843-851)
 typedef StepperEnv<WM, true> SEnvP;     // plank_class = "Pillar" (bullet_objects.py:86-90): cylinder stones
 typedef StepperEnv<MIKE_Model, true> MkEnvP;
@@ -228,6 +238,8 @@ MB_STEP_KERNEL(k_step_walker3d_stepper, MB_WARPS_STEPPER, SEnv)
 MB_STEP_KERNEL(k_step_monkey3d_custom, MB_WARPS_MONKEY, MEnv)
 MB_STEP_KERNEL(k_step_cassie, MB_WARPS_CASSIE, CEnv)
 MB_STEP_KERNEL(k_step_child3d_custom, MB_WARPS_STEPPER, ChEnv)
+MB_STEP_KERNEL(k_step_walker2d_custom, MB_WARPS_STEPPER, W2Env)
+MB_STEP_KERNEL(k_step_crab2d_custom, MB_WARPS_STEPPER, CrEnv)
 MB_STEP_KERNEL(k_step_mike_stepper, MB_WARPS_STEPPER, MkEnv)
 MB_STEP_KERNEL(k_step_walker3d_stepper_pillar, MB_WARPS_STEPPER, SEnvP)
 MB_STEP_KERNEL(k_step_mike_stepper_pillar, MB_WARPS_STEPPER, MkEnvP)
@@ -270,6 +282,16 @@ __global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_reset_child3d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
                            float* obs, float* dummy_obs) {
   reset_body<ChEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
+}
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
+    k_reset_walker2d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
+                           float* obs, float* dummy_obs) {
+  reset_body<W2Env>(n, phys, state, rec, mt, mask, obs, dummy_obs);
+}
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
+    k_reset_crab2d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
+                           float* obs, float* dummy_obs) {
+  reset_body<CrEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
 }
 __global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_reset_mike_stepper(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
@@ -331,6 +353,16 @@ __global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_step_physics_child3d(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
                            int* contacts_out) {
   physics_body<ChEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
+}
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
+    k_step_physics_walker2d(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
+                           int* contacts_out) {
+  physics_body<W2Env>(n, phys, state, rec, tau, rows_out, contacts_out);
+}
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
+    k_step_physics_crab2d(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
+                           int* contacts_out) {
+  physics_body<CrEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
 }
 __global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_step_physics_mike_stepper(int n, MbPhysics phys, float* state, const float* rec, const float* tau,
@@ -395,6 +427,14 @@ __global__ void __launch_bounds__(MB_WARPS_MAX * 32)
 __global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_dynamics_debug_child3d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
   dynamics_debug_body<ChEnv>(n, phys, state, mode, acc, out);
+}
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
+    k_dynamics_debug_walker2d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
+  dynamics_debug_body<W2Env>(n, phys, state, mode, acc, out);
+}
+__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
+    k_dynamics_debug_crab2d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
+  dynamics_debug_body<CrEnv>(n, phys, state, mode, acc, out);
 }
 __global__ void __launch_bounds__(MB_WARPS_MAX * 32)
     k_dynamics_debug_mike(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
@@ -476,11 +516,13 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   if (env_id && strcmp(env_id, "Monkey3DCustomEnv-v0") == 0) kind = KIND_MONKEY;
   if (env_id && strcmp(env_id, "CassieEnv-v0") == 0) kind = KIND_CASSIE;
   if (env_id && strcmp(env_id, "Child3DCustomEnv-v0") == 0) kind = KIND_CHILD;
+  if (env_id && strcmp(env_id, "Walker2DCustomEnv-v0") == 0) kind = KIND_WALKER2D;
+  if (env_id && strcmp(env_id, "Crab2DCustomEnv-v0") == 0) kind = KIND_CRAB2D;
   if (env_id && strcmp(env_id, "MikeStepperEnv-v0") == 0) kind = KIND_MIKE;
   if (kind < 0)
     return fail(std::string("mb200_create: unsupported env id '") + (env_id ? env_id : "(null)") +
                 "' (built: Walker3DCustomEnv-v0, Walker3DStepperEnv-v0, Monkey3DCustomEnv-v0, CassieEnv-v0, "
-                "Child3DCustomEnv-v0, MikeStepperEnv-v0)");
+                "Child3DCustomEnv-v0, MikeStepperEnv-v0, Walker2DCustomEnv-v0, Crab2DCustomEnv-v0)");
   if (n_envs <= 0) return fail("mb200_create: n_envs must be positive");
   int count = 0;
   CUDA_OK(cudaGetDeviceCount(&count));
@@ -502,6 +544,8 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
     case KIND_MIKE:
     case KIND_STEPPER: e->rec_stride = SEnv::REC_STRIDE; e->obs_dim = SEnv::OBS; e->act_dim = SEnv::ACT; break;
     case KIND_MONKEY: e->rec_stride = MEnv::REC_STRIDE; e->obs_dim = MEnv::OBS; e->act_dim = MEnv::ACT; nj = MM::NJ; break;
+    case KIND_WALKER2D: e->rec_stride = W2Env::REC_STRIDE; e->obs_dim = W2Env::OBS; e->act_dim = W2Env::ACT; nj = W2D_Model::NJ; break;
+    case KIND_CRAB2D: e->rec_stride = CrEnv::REC_STRIDE; e->obs_dim = CrEnv::OBS; e->act_dim = CrEnv::ACT; nj = CR2D_Model::NJ; break;
     case KIND_CASSIE: e->rec_stride = CEnv::REC_STRIDE; e->obs_dim = CEnv::OBS; e->act_dim = CEnv::ACT; nj = CM::NJ; break;
     default: e->rec_stride = WEnv::REC_STRIDE; e->obs_dim = WEnv::OBS; e->act_dim = WEnv::ACT; break;
   }
@@ -524,6 +568,7 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
     e->phys.box_cfm = 1.0f / denom;
   }
   e->smem = (kind == KIND_MONKEY ? sizeof(WarpMem<MM>) : kind == KIND_CASSIE ? sizeof(WarpMem<CM>)
+             : kind == KIND_WALKER2D ? sizeof(WarpMem<W2D_Model>) : kind == KIND_CRAB2D ? sizeof(WarpMem<CR2D_Model>)
              : kind == KIND_CHILD ? sizeof(WarpMem<CH3D_Model>) : kind == KIND_MIKE ? sizeof(WarpMem<MIKE_Model>)
              : sizeof(WMem)) * e->warps;
   {
@@ -552,10 +597,20 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
     CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_walker3d, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_child3d_custom, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_walker2d_custom, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_crab2d_custom, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_child3d_custom_host, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_walker2d_custom_host, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_crab2d_custom_host, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_reset_child3d_custom, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_reset_walker2d_custom, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_reset_crab2d_custom, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_physics_child3d, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker2d, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_step_physics_crab2d, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_child3d, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_walker2d, at, sw));
+    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_crab2d, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_mike_stepper, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_step_mike_stepper_host, at, sw));
     CUDA_OK(cudaFuncSetAttribute(k_reset_mike_stepper, at, sw));
@@ -687,6 +742,12 @@ int mb200_reset(mb200_env* e, const uint8_t* mask_dev, float* obs_dev, void* str
   else if (e->kind == KIND_CHILD)
     k_reset_child3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
+  else if (e->kind == KIND_WALKER2D)
+    k_reset_walker2d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
+  else if (e->kind == KIND_CRAB2D)
+    k_reset_crab2d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
   else if (e->kind == KIND_MIKE)
     k_reset_mike_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
@@ -747,6 +808,10 @@ static int step_impl(mb200_env* e, const float* act_dev, float* obs_dev, float* 
     MB_LAUNCH_STEP(k_step_monkey3d_custom);
   else if (e->kind == KIND_CHILD)
     MB_LAUNCH_STEP(k_step_child3d_custom);
+  else if (e->kind == KIND_WALKER2D)
+    MB_LAUNCH_STEP(k_step_walker2d_custom);
+  else if (e->kind == KIND_CRAB2D)
+    MB_LAUNCH_STEP(k_step_crab2d_custom);
   else if (e->kind == KIND_MIKE && e->pillar)
     MB_LAUNCH_STEP(k_step_mike_stepper_pillar);
   else if (e->kind == KIND_MIKE)
@@ -886,6 +951,12 @@ int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* c
   else if (e->kind == KIND_CHILD)
     k_step_physics_child3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
+  else if (e->kind == KIND_WALKER2D)
+    k_step_physics_walker2d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
+  else if (e->kind == KIND_CRAB2D)
+    k_step_physics_crab2d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
   else if (e->kind == KIND_MIKE && e->pillar)
     k_step_physics_mike_stepper_pillar<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
@@ -918,6 +989,12 @@ int mb200_mass_matrix(mb200_env* e, float* M_dev, void* stream) {
   else if (e->kind == KIND_CHILD)
     k_dynamics_debug_child3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, 0, nullptr, M_dev);
+  else if (e->kind == KIND_WALKER2D)
+    k_dynamics_debug_walker2d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, 0, nullptr, M_dev);
+  else if (e->kind == KIND_CRAB2D)
+    k_dynamics_debug_crab2d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, e->phys, e->state, 0, nullptr, M_dev);
   else if (e->kind == KIND_MIKE)
     k_dynamics_debug_mike<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, e->phys, e->state, 0, nullptr, M_dev);
@@ -943,6 +1020,12 @@ int mb200_inverse_dynamics(mb200_env* e, const float* acc_dev, float* tau_dev, v
         e->n, p, e->state, 1, acc_dev, tau_dev);
   else if (e->kind == KIND_CHILD)
     k_dynamics_debug_child3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, p, e->state, 1, acc_dev, tau_dev);
+  else if (e->kind == KIND_WALKER2D)
+    k_dynamics_debug_walker2d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
+        e->n, p, e->state, 1, acc_dev, tau_dev);
+  else if (e->kind == KIND_CRAB2D)
+    k_dynamics_debug_crab2d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
         e->n, p, e->state, 1, acc_dev, tau_dev);
   else if (e->kind == KIND_MIKE)
     k_dynamics_debug_mike<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(

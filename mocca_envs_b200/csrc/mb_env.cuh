@@ -328,7 +328,14 @@ template <class M> struct W3DEnv {
     MB_LANES(l)
       if (l == 0) { rec[ER_LINPOT] = lp; rec[ER_BODYX] = S.pos[0]; }
     MB_END
-    target_obs(d, a, obs);
+    if (M::planar_env()) {
+      // Walker2DCustomEnv.reset (env_locomotion.py:289-299): np.concatenate((robot_state, [0], [0]))
+      MB_LANES(l)
+        if (l == 0) { obs[ROBOT_OBS] = 0.0f; obs[ROBOT_OBS + 1] = 0.0f; }
+      MB_END
+    } else {
+      target_obs(d, a, obs);
+    }
   }
 
   // Walker3DCustomEnv.step (env_locomotion.py:111-141) for one env; obs/reward/done follow the VecEnv
@@ -391,6 +398,10 @@ template <class M> struct W3DEnv {
     const float height_obs = mb_clip5(o.height);
     const float tall = height_obs > M::term_height() ? 2.0f : -1.0f;  // env_locomotion.py:44,195,320
     if (tall < 0.0f) env_done = 1;
+    // Walker2DCustomEnv.step (env_locomotion.py:301-305) overwrites done with False: only the TimeLimit ends an
+    // episode (the reward keeps the -1 "tall bonus").  A non-finite state still resets here (the reference would
+    // stay broken for the rest of the episode).
+    if (M::planar_env()) env_done = o.nonfinite ? 1 : 0;
     float target_bonus = 0.0f;
     int close = rec_i(rec, ER_CLOSE);
     if (dist < 0.15f) { close += 1; target_bonus = 2.0f; }

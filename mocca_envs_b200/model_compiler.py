@@ -182,6 +182,7 @@ class MJCFCompiler:
         self.links: List[Link] = []
         self.base: Optional[Link] = None
         self.anon = 0
+        self.planar = False
 
         root = ET.parse(path).getroot()
         comp = root.find("compiler")
@@ -248,7 +249,14 @@ class MJCFCompiler:
         children = [c for c in body if c.tag == "body"]
 
         if is_root:
-            assert not joints, "root body with joints is not a floating base"
+            # walker2d.xml / crab2d.xml: the root carries slide-x, slide-z and hinge-y joints named "ignore*"
+            # (skipped by robots.py:163-172).  Bullet imports them as a fixed base with two massless dummy links,
+            # which is the same mechanism as a free base confined to the x-z plane: every joint axis is y and every
+            # COM has y = 0, so the out-of-plane coordinates of a free base stay exactly zero (tested) -- the root
+            # is compiled as the ordinary floating base and the table is flagged planar.
+            assert all((j.get("name") or "").startswith("ignore") for j in joints), \
+                "root body with joints is not a floating base"
+            self.planar = bool(joints)
             link = Link(name, -2, "", JOINT_FIXED, np.zeros(3), np.array([0, 0, 0, 1.0]), np.zeros(3), np.zeros(3))
             link.geoms = [self._parse_geom(g, np.zeros(3)) for g in geoms]
             self.base = link
@@ -365,6 +373,7 @@ def compile_mjcf(path: str, name: str, power_coef: Dict[str, float], base_power:
 
     table = dict(
         name=name,
+        planar=bool(c.planar),
         source=path.split("/mocca_envs/")[-1],
         conventions=dict(density=DENSITY, mjcf_damping=use_mjcf_damping, mjcf_armature=use_mjcf_armature,
                          inertia="aabb-of-compound", com="body-origin"),
@@ -551,6 +560,48 @@ MIKE_POWER = {  # mocca_envs/robots.py:477-499
     "right_shoulder_x": 30, "right_shoulder_z": 30, "right_shoulder_y": 25, "right_elbow": 30,
     "left_shoulder_x": 30, "left_shoulder_z": 30, "left_shoulder_y": 25, "left_elbow": 30,
 }
+
+
+WALKER2D_POWER = {  # mocca_envs/robots.py:342-350
+    "torso_joint": 100, "thigh_joint": 100, "leg_joint": 100, "foot_joint": 50,
+    "thigh_left_joint": 100, "leg_left_joint": 100, "foot_left_joint": 50,
+}
+CRAB2D_POWER = {  # mocca_envs/robots.py:380-387
+    "thigh_left_joint": 100, "leg_left_joint": 100, "foot_left_joint": 50,
+    "thigh_joint": 100, "leg_joint": 100, "foot_joint": 50,
+}
+
+
+def _planar_family(t: dict, right, left) -> dict:
+    """Walker2D / Crab2D (robots.py:338-404): zero base pose (set_base_pose :352-354), identity orientation, no negated
+    joints.  coordinate="global" is not understood by Bullet's MJCF importer (the reference's xml says so: "CHANGES:
+    see hopper.xml"), it reads every pos / fromto as body-local; all nested bodies have no pos, so every link frame
+    (= inertial frame, convention "com": "body-origin") coincides with the pelvis origin at zero joint angles.  The
+    pelvis body sits at z = -1.35 under the fixed base and Walker2DCustomEnv resets that base to z = +1.35
+    (env_locomotion.py:287, robots.py:198-200 -> resetBasePositionAndOrientation on the multibody), so the pelvis
+    origin starts at the world origin and the geoms stand where the xml's global coordinates put them."""
+    assert t.get("planar")
+    t["base_joint_angles"] = [0.0] * t["n_dof"]
+    t["base_position"] = [0.0, 0.0, 0.0]
+    t["right_joint_indices"] = list(right)
+    t["left_joint_indices"] = list(left)
+    t["negation_joint_indices"] = []
+    t["self_pairs"], t["self_pairs_candidates"] = self_collision_pairs(t)
+    t.setdefault("conventions", {})["planar_base"] = (
+        "ignorex / ignorez / ignorey root joints = free base confined to the x-z plane (exact: all axes are y)")
+    return t
+
+
+def compile_walker2d(data_dir: str, **kw) -> dict:
+    """Walker2D (robots.py:338-370): 7 hinges about y, feet "foot" / "foot_left", no self-collision flag."""
+    t = compile_mjcf(data_dir + "/robots/walker2d.xml", "walker2d", WALKER2D_POWER, 1.0, ["foot", "foot_left"], **kw)
+    return _planar_family(t, [1, 2, 3], [4, 5, 6])
+
+
+def compile_crab2d(data_dir: str, **kw) -> dict:
+    """Crab2D (robots.py:373-404): 6 hinges about +-y, loaded with the self-collision flags."""
+    t = compile_mjcf(data_dir + "/robots/crab2d.xml", "crab2d", CRAB2D_POWER, 1.0, ["foot", "foot_left"], **kw)
+    return _planar_family(t, [0, 1, 2], [3, 4, 5])
 
 
 def _walker_family(t: dict) -> dict:

@@ -29,6 +29,8 @@ MONKEY_ID = "Monkey3DCustomEnv-v0"
 CASSIE_ID = "CassieEnv-v0"
 CHILD_ID = "Child3DCustomEnv-v0"
 MIKE_ID = "MikeStepperEnv-v0"
+WALKER2D_ID = "Walker2DCustomEnv-v0"
+CRAB2D_ID = "Crab2DCustomEnv-v0"
 _MODELS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models")
 
 
@@ -352,6 +354,24 @@ class Child3DCustomVecEnv(Walker3DCustomVecEnv):
     model = "child3d"
 
 
+class Walker2DCustomVecEnv(Walker3DCustomVecEnv):
+    """Batched Walker2DCustomEnv-v0 (reference env_locomotion.py:285-310, robots.py:338-370): Walker3DCustomEnv's
+    logic on the planar walker2d model (7 hinges about y; the root's "ignore*" slide / hinge joints are a free base
+    that stays exactly in the x-z plane).  The reference forces done to False (:303), so only the 1000-step
+    TimeLimit ends an episode, and reset() returns zeros in the two target slots (:298)."""
+
+    env_id = WALKER2D_ID
+    model = "walker2d"
+
+
+class Crab2DCustomVecEnv(Walker2DCustomVecEnv):
+    """Batched Crab2DCustomEnv-v0 (reference env_locomotion.py:312-314, robots.py:373-404): the same env on crab2d.xml
+    (6 hinges, self-collision flags on)."""
+
+    env_id = CRAB2D_ID
+    model = "crab2d"
+
+
 class MikeStepperVecEnv(Walker3DStepperVecEnv):
     """Batched MikeStepperEnv-v0 (reference env_locomotion.py:843-851, robots.py:474-513): Walker3DStepperEnv's
     logic on the mike model (own power table, waist mass 8), started at (0.3, 0, 1.0)."""
@@ -511,6 +531,18 @@ class Child3DCustomEnv(Walker3DCustomEnv):
     vec_class = Child3DCustomVecEnv
 
 
+class Walker2DCustomEnv(Walker3DCustomEnv):
+    """gym-protocol facade of Walker2DCustomEnv-v0."""
+
+    vec_class = Walker2DCustomVecEnv
+
+
+class Crab2DCustomEnv(Walker3DCustomEnv):
+    """gym-protocol facade of Crab2DCustomEnv-v0."""
+
+    vec_class = Crab2DCustomVecEnv
+
+
 class MikeStepperEnv(Walker3DStepperEnv):
     """gym-protocol facade of MikeStepperEnv-v0."""
 
@@ -554,7 +586,8 @@ class CassieEnv(Walker3DCustomEnv):
 
 _REGISTRY = {ENV_ID: (Walker3DCustomEnv, Walker3DCustomVecEnv), STEPPER_ID: (Walker3DStepperEnv, Walker3DStepperVecEnv),
              MONKEY_ID: (Monkey3DCustomEnv, Monkey3DCustomVecEnv), CASSIE_ID: (CassieEnv, CassieVecEnv),
-             CHILD_ID: (Child3DCustomEnv, Child3DCustomVecEnv), MIKE_ID: (MikeStepperEnv, MikeStepperVecEnv)}
+             CHILD_ID: (Child3DCustomEnv, Child3DCustomVecEnv), MIKE_ID: (MikeStepperEnv, MikeStepperVecEnv),
+             WALKER2D_ID: (Walker2DCustomEnv, Walker2DCustomVecEnv), CRAB2D_ID: (Crab2DCustomEnv, Crab2DCustomVecEnv)}
 
 
 def make(env_id: str, num_envs: int | None = None, **kwargs):

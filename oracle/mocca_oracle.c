@@ -1352,6 +1352,11 @@ void orc_w3d_reset(const orc_model* m, const orc_params* p, orc_w3d_env* e, doub
   w3d_robot_reset(m, e, m->base_position);
   w3d_calc_potential(e, p->dt * p->substeps);
   w3d_obs(m, e, obs);
+  if (m->planar_env != 0) { /* Walker2DCustomEnv.reset (env_locomotion.py:289-299): (robot_state, [0], [0]) */
+    int n = 6 + 2 * m->n_dof + m->n_feet;
+    obs[n] = 0;
+    obs[n + 1] = 0;
+  }
 }
 
 void orc_w3d_step(const orc_model* m, const orc_params* p, orc_w3d_env* e, const double* action, double* obs,
@@ -1389,6 +1394,13 @@ void orc_w3d_step(const orc_model* m, const orc_params* p, orc_w3d_env* e, const
   e->joints_penalty = 0.1 * e->joints_at_limit;
   e->tall_bonus = e->robot_state[0] > m->termination_height ? 2.0 : -1.0;
   if (e->tall_bonus < 0) e->done = 1;
+  if (m->planar_env != 0) {
+    /* Walker2DCustomEnv.step (env_locomotion.py:301-305): "self.done = False" after super().step(); a non-finite
+     * state still ends the episode here (shared deviation with the kernel: the reference would stay broken) */
+    e->done = 0;
+    for (int k = 0; k < nstate; k++)
+      if (!isfinite(e->robot_state[k])) e->done = 1;
+  }
   e->target_bonus = 0;
   if (e->distance_to_target < 0.15) { e->close_count++; e->target_bonus = 2; }
   if (e->close_count >= e->stop_frames) {

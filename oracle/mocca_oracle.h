@@ -57,6 +57,8 @@ typedef struct {
   double base_position[3];
   double base_orientation[4];       /* xyzw; set_base_pose (robots.py:276,311-323) */
   double termination_height;        /* env class attribute (env_locomotion.py:44,320) */
+  double planar_env;                /* != 0: Walker2DCustomEnv / Crab2DCustomEnv (env_locomotion.py:285-314): done forced
+                                       to False, reset() returns zeros in the target slots */
   double stepper_init_position[3];  /* robot_init_position of the stepper env (env_locomotion.py:339,845) */
   int n_right, right_idx[ORC_MAXD], left_idx[ORC_MAXD]; /* mirroring tables robots.py:282-290 */
   int n_neg, neg_idx[8];

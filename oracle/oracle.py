@@ -38,7 +38,7 @@ class Model(C.Structure):
         ("geom_size", (d * 3) * MAXG), ("geom_friction", d * MAXG),
         ("foot_link", i32 * 4),
         ("base_joint_angles", d * MAXD), ("base_position", d * 3),
-        ("base_orientation", d * 4), ("termination_height", d), ("stepper_init_position", d * 3),
+        ("base_orientation", d * 4), ("termination_height", d), ("planar_env", d), ("stepper_init_position", d * 3),
         ("n_right", i32), ("right_idx", i32 * MAXD), ("left_idx", i32 * MAXD),
         ("n_neg", i32), ("neg_idx", i32 * 8),
         ("palm_link", i32 * 2),
@@ -203,6 +203,7 @@ def model_from_table(t: dict) -> Model:
     _fill(m.base_position, np.array(t["base_position"], dtype=np.float64))
     _fill(m.base_orientation, np.array(t.get("base_orientation", [0, 0, 0, 1]), dtype=np.float64))
     m.termination_height = float(t.get("termination_height", 0.7))
+    m.planar_env = 1.0 if t.get("planar") else 0.0
     _fill(m.stepper_init_position, np.array(t.get("stepper_init_position", [0.3, 0.0, 1.32]), dtype=np.float64))
     m.n_right = len(t["right_joint_indices"])
     _fill(m.right_idx, np.array(t["right_joint_indices"], dtype=np.int64))

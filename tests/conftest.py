@@ -49,6 +49,20 @@ def mike_table():
 
 
 @pytest.fixture(scope="session")
+def walker2d_table():
+    from mocca_envs_b200.model_compiler import load_table
+
+    return load_table(os.path.join(ROOT, "mocca_envs_b200", "models", "walker2d.json"))
+
+
+@pytest.fixture(scope="session")
+def crab2d_table():
+    from mocca_envs_b200.model_compiler import load_table
+
+    return load_table(os.path.join(ROOT, "mocca_envs_b200", "models", "crab2d.json"))
+
+
+@pytest.fixture(scope="session")
 def cassie_table():
     from mocca_envs_b200.model_compiler import load_table
 

@@ -8,6 +8,8 @@
 #include "../../mocca_envs_b200/csrc/generated/cassie_model.h"
 #include "../../mocca_envs_b200/csrc/generated/child3d_model.h"
 #include "../../mocca_envs_b200/csrc/generated/mike_model.h"
+#include "../../mocca_envs_b200/csrc/generated/walker2d_model.h"
+#include "../../mocca_envs_b200/csrc/generated/crab2d_model.h"
 #include "../../mocca_envs_b200/csrc/mb_env.cuh"
 
 typedef W3D_Model WM;
@@ -300,6 +302,9 @@ void emu_cassie_mass_matrix(const MbPhysics* p, const float* state, float* Mout,
   }
 EMU_ENV(child, CH3D_Model, W3DEnv<CH3D_Model>, 0)
 EMU_ENV(mike, MIKE_Model, StepperEnv<MIKE_Model>, MB_OBST_BOXES)
+// the planar walkers (Walker2DCustomEnv-v0, Crab2DCustomEnv-v0)
+EMU_ENV(walker2d, W2D_Model, W3DEnv<W2D_Model>, 0)
+EMU_ENV(crab2d, CR2D_Model, W3DEnv<CR2D_Model>, 0)
 // plank_class = "Pillar": the PILLAR instantiation of the stepper template
 typedef StepperEnv<WM, true> SEnvPillar;
 EMU_ENV(pillar, WM, SEnvPillar, MB_OBST_CYLS)

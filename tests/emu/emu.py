@@ -10,7 +10,8 @@ _LIB = os.path.join(_HERE, "libmb_emu.so")
 _SRC = [os.path.join(_HERE, "emu.cpp")] + [
     os.path.join(_HERE, "..", "..", "mocca_envs_b200", "csrc", f)
     for f in ("mb_core.cuh", "mb_env.cuh", "mb_tables.h", "generated/walker3d_model.h", "generated/monkey3d_model.h",
-              "generated/cassie_model.h", "generated/child3d_model.h", "generated/mike_model.h")]
+              "generated/cassie_model.h", "generated/child3d_model.h", "generated/mike_model.h",
+              "generated/walker2d_model.h", "generated/crab2d_model.h")]
 
 
 class Phys(C.Structure):
@@ -103,6 +104,22 @@ class EmuW3D:
 class EmuChild(EmuW3D):
     """Child3DCustomEnv-v0: the Walker3DCustomEnv template on the child3d table."""
     prefix = "child"
+
+
+class EmuWalker2D(EmuW3D):
+    """Walker2DCustomEnv-v0: the Walker3DCustomEnv template on the planar walker2d table."""
+    prefix = "walker2d"
+
+    def __init__(self, mt_state, phys=None):
+        super().__init__(mt_state, obs_dim=24, act_dim=7, phys=phys)
+
+
+class EmuCrab2D(EmuW3D):
+    """Crab2DCustomEnv-v0."""
+    prefix = "crab2d"
+
+    def __init__(self, mt_state, phys=None):
+        super().__init__(mt_state, obs_dim=22, act_dim=6, phys=phys)
 
 
 def model_step_physics(prefix, p, state, tau, rec=None):

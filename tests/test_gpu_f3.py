@@ -220,7 +220,8 @@ def test_env_param_accessors(torch_mod):
 @pytest.mark.gpu
 @pytest.mark.parametrize("env_id,kwargs", [("Walker3DStepperEnv-v0", {}), ("Walker3DStepperEnv-v0", {"plank_class": "Pillar"}),
                                            ("Monkey3DCustomEnv-v0", {}), ("CassieEnv-v0", {}),
-                                           ("Child3DCustomEnv-v0", {}), ("MikeStepperEnv-v0", {})])
+                                           ("Child3DCustomEnv-v0", {}), ("MikeStepperEnv-v0", {}),
+                                           ("Walker2DCustomEnv-v0", {}), ("Crab2DCustomEnv-v0", {})])
 def test_step_host_pinned_matches_device_every_env(env_id, kwargs):
     """The `_host` instantiation of every step kernel (zero-copy result stores into pinned host buffers, actions read
     from the pinned host buffer in place) returns exactly what the device-buffer step returns."""

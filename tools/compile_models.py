@@ -21,7 +21,8 @@ def main(data_dir="/root/reference/mocca_envs/data"):
     mc.save_table(w, os.path.join(out, "walker3d.json"))
     m = mc.compile_monkey3d(data_dir)
     mc.save_table(m, os.path.join(out, "monkey3d.json"))
-    for fn, nm in ((mc.compile_child3d, "child3d"), (mc.compile_mike, "mike")):
+    for fn, nm in ((mc.compile_child3d, "child3d"), (mc.compile_mike, "mike"), (mc.compile_walker2d, "walker2d"),
+                   (mc.compile_crab2d, "crab2d")):
         t = fn(data_dir)
         mc.save_table(t, os.path.join(out, nm + ".json"))
         print("%-9s links=%d dof=%d mass=%.3f self pairs %d of %d" % (nm + ":", t["n_links"], t["n_dof"], t["total_mass"],
