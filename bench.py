@@ -204,7 +204,27 @@ def cpu_reference_run(n_envs, steps, warmup, threads, time_budget=None, kind="cu
     return n_envs * done_steps / dt, dt, done_steps
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." at
+    communicator creation): keep a private handle on the real stdout and point fd 1 at stderr for the rest of the run."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
@@ -244,7 +264,7 @@ def main():
                                        "port (PyBullet itself is not installable: no wheel, no network)" % (sample_envs, ks)},
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line))
+        _emit(line)
         return
 
     import numpy as np
@@ -475,7 +495,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                 "sample": str(ce) + " envs x %d control steps (%.1f s), same action distribution; float64 "
                                           "oracle port with OpenMP over envs (PyBullet not installable here)" % (ks, dt)}
-    print(json.dumps(line))
+    _emit(line)
     if dist:
         dist.destroy_process_group()
 
