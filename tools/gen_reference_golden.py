@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Golden traces of the reference's OWN Python env layer (tests/golden/ref_*.npz).
+
+The reference (/root/reference/mocca_envs, read-only, only present in the build container) cannot run as shipped:
+its arithmetic below the env layer is the third-party `pybullet` C extension, which is not installable here.  This
+script imports the reference's unmodified modules (env_base.py, env_locomotion.py, robots.py, bullet_utils.py) with
+stand-ins for `gym` (spaces, seeding) and `pybullet`: the stand-in Bullet client answers the calls the env layer makes
+(loadMJCF / getJointInfo / getJointStates / getLinkState / getBasePositionAndOrientation / getBaseVelocity /
+getContactPoints / resetJointState / resetBase... / setJointMotorControlArray / stepSimulation ...) from the float64
+CPU oracle's physics (oracle/mocca_oracle.c).  Everything ABOVE that boundary -- apply_action, calc_state, reset draws,
+target logic, rewards, termination, the stepping-stone terrain generator -- is then computed by the reference's real
+code, and recorded.
+
+What the traces pin: the oracle's restatement of the env layer against the reference's own
+code on identical physics (tests/test_reference_golden.py replays the recorded actions through the oracle env and
+compares observation, reward and done).  What they do not pin: Bullet's arithmetic (still "parity unpinned").
+
+usage: python tools/gen_reference_golden.py            (writes tests/golden/ref_*.npz)
+"""
+import ctypes as C
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+from mocca_envs_b200.model_compiler import JOINT_REVOLUTE as MC_REVOLUTE, load_table  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+MODELS = os.path.join(ROOT, "mocca_envs_b200", "models")
+JOINT_REVOLUTE, JOINT_FIXED = 0, 4  # pybullet constants
+
+
+# ----------------------------------------------------------------------------------------------- gym stand-in
+def install_gym():
+    gym = types.ModuleType("gym")
+
+    class Env:
+        metadata = {}
+
+    class Box:
+        def __init__(self, low, high, dtype=np.float32):
+            self.low, self.high = np.asarray(low, dtype=dtype), np.asarray(high, dtype=dtype)
+            self.shape, self.dtype = self.low.shape, np.dtype(dtype)
+
+    spaces = types.ModuleType("gym.spaces")
+    spaces.Box = Box
+    utils = types.ModuleType("gym.utils")
+    seeding = types.ModuleType("gym.utils.seeding")
+
+    def np_random(seed=None):  # gym <= 0.21: RandomState seeded with _int_list_from_bigint(hash_seed(seed))
+        assert seed is not None, "the generator always seeds explicitly"
+        rng = np.random.RandomState()
+        rng.seed(O.gym_seed_words(seed))
+        return rng, seed
+
+    seeding.np_random = np_random
+    utils.seeding = seeding
+    envs = types.ModuleType("gym.envs")
+    registration = types.ModuleType("gym.envs.registration")
+    registration.register = lambda id, **kw: None
+    registration.registry = types.SimpleNamespace(env_specs={})
+    envs.registration = registration
+    envs.registry = types.SimpleNamespace(env_specs={})
+    gym.Env, gym.spaces, gym.utils, gym.envs = Env, spaces, utils, envs
+    for name, mod in (("gym", gym), ("gym.spaces", spaces), ("gym.utils", utils), ("gym.utils.seeding", seeding),
+                      ("gym.envs", envs), ("gym.envs.registration", registration)):
+        sys.modules[name] = mod
+
+
+# ----------------------------------------------------------------------------------------------- pybullet stand-in
+def mat_to_quat(R):
+    from mocca_envs_b200.model_compiler import mat_to_quat as m2q
+
+    return m2q(np.asarray(R))
+
+
+class FakeWorld:
+    """One Bullet world: the robot (a model table + an oracle state) on the ground plane or on stepping stones."""
+
+    def __init__(self):
+        self.bodies = {}  # id -> dict(kind=...)
+        self.next_id = 0
+        self.params = O.default_params()
+        self.robot = None
+        self.tau = None
+        self.contacts = None
+        self.warm = None
+        self.saved = {}
+
+    def new_body(self, **kw):
+        i = self.next_id
+        self.next_id += 1
+        self.bodies[i] = kw
+        return i
+
+
+W = None  # the world of the env under construction (one env at a time)
+
+
+def install_pybullet():
+    pb = types.ModuleType("pybullet")
+    pb.error = RuntimeError
+    for k, v in dict(DIRECT=2, GUI=1, SHARED_MEMORY=3, POSITION_CONTROL=2, VELOCITY_CONTROL=0, TORQUE_CONTROL=1,
+                     JOINT_REVOLUTE=0, JOINT_PRISMATIC=1, JOINT_FIXED=4, MJCF_COLORS_FROM_FILE=512,
+                     URDF_USE_SELF_COLLISION=8, URDF_USE_SELF_COLLISION_EXCLUDE_ALL_PARENTS=32,
+                     URDF_USE_SELF_COLLISION_EXCLUDE_PARENT=16, URDF_USE_INERTIA_FROM_FILE=2,
+                     COV_ENABLE_RENDERING=7, COV_ENABLE_GUI=1, COV_ENABLE_KEYBOARD_SHORTCUTS=9,
+                     COV_ENABLE_SEGMENTATION_MARK_PREVIEW=5, COV_ENABLE_DEPTH_BUFFER_PREVIEW=4,
+                     COV_ENABLE_RGB_BUFFER_PREVIEW=3, GEOM_SPHERE=2, GEOM_MESH=5).items():
+        setattr(pb, k, v)
+
+    def connect(mode, options=""):
+        global W
+        W = FakeWorld()
+        return 0
+
+    pb.connect = connect
+    pb.disconnect = lambda **kw: None
+    pb.configureDebugVisualizer = lambda *a, **kw: None
+    pb.setGravity = lambda x, y, z: setattr(W.params, "gravity", -z)
+    pb.setDefaultContactERP = lambda erp: setattr(W.params, "erp_contact", erp)
+
+    def setPhysicsEngineParameter(fixedTimeStep=None, numSolverIterations=None, numSubSteps=None, **kw):
+        W.params.dt = fixedTimeStep / numSubSteps
+        W.params.substeps = numSubSteps
+        W.params.iterations = numSolverIterations
+
+    pb.setPhysicsEngineParameter = setPhysicsEngineParameter
+    pb.saveState = lambda: 0
+    pb.restoreState = lambda *a, **kw: None
+
+    def loadSDF(filename):
+        assert filename.endswith("plane_stadium.sdf")
+        W.params.has_ground = 1
+        return (W.new_body(kind="ground"),)
+
+    pb.loadSDF = loadSDF
+
+    def loadMJCF(path, flags=0):
+        name = os.path.splitext(os.path.basename(path))[0]
+        t = load_table(os.path.join(MODELS, name + ".json"))
+        assert not t.get("planar"), "planar tables fold the root joints into the base; not servable joint by joint"
+        W.params.self_collision = 1 if flags & pb.URDF_USE_SELF_COLLISION else 0
+        A = t["n_dof"]
+        W.robot = dict(table=t, model=O.model_from_table(t), A=A,
+                       state=O.make_state(A, t["base"]["init_pos"], [0, 0, 0, 1], [0] * 3, [0] * 3, [0] * A, [0] * A))
+        W.tau = np.zeros(A)
+        W.warm = (C.c_double * O.MAXW)()
+        W.contacts = None
+        return (W.new_body(kind="robot"),)
+
+    pb.loadMJCF = loadMJCF
+
+    def changeDynamics(body, link, **kw):
+        b = W.bodies[body]
+        if b["kind"] == "ground":  # bullet_utils.py:371: lateralFriction 0.8, restitution 0.5
+            assert kw == dict(lateralFriction=0.8, restitution=0.5)
+            W.params.ground_friction = kw["lateralFriction"]
+        else:
+            raise NotImplementedError(kw)
+
+    pb.changeDynamics = changeDynamics
+    pb.getNumJoints = lambda body: W.robot["table"]["n_links"] if W.bodies[body]["kind"] == "robot" else 0
+
+    def getJointInfo(body, j):
+        t = W.robot["table"]
+        rev = t["joint_type"][j] == MC_REVOLUTE
+        d = t["dof_of_link"][j]
+        lo, hi = (t["lower"][d], t["upper"][d]) if rev else (0.0, -1.0)
+        info = [j, t["joint_names_all"][j].encode(), JOINT_REVOLUTE if rev else JOINT_FIXED, 0, 0, 0, 0.0, 0.0, lo, hi,
+                0.0, 0.0, t["link_names"][j].encode(), tuple(t["axis"][j]), (0, 0, 0), (0, 0, 0, 1), t["parent"][j]]
+        return tuple(info)
+
+    pb.getJointInfo = getJointInfo
+
+    def _dof(j):
+        return W.robot["table"]["dof_of_link"][j]
+
+    def getJointState(body, j):
+        s, d = W.robot["state"], _dof(j)
+        return (s.q[d], s.qd[d], (0,) * 6, 0.0) if d >= 0 else (0.0, 0.0, (0,) * 6, 0.0)
+
+    pb.getJointState = getJointState
+    pb.getJointStates = lambda body, js: [getJointState(body, j) for j in js]
+
+    def resetJointState(body, j, targetValue=0.0, targetVelocity=0.0):
+        s, d = W.robot["state"], _dof(j)
+        if d >= 0:
+            s.q[d], s.qd[d] = float(targetValue), float(targetVelocity)
+
+    pb.resetJointState = resetJointState
+
+    def setJointMotorControl2(*a, **kw):  # only ever used to switch the default motors off (force = 0)
+        assert kw.get("force", 0) == 0
+
+    pb.setJointMotorControl2 = setJointMotorControl2
+
+    def setJointMotorControlArray(bodyIndex, jointIndices, controlMode, forces=None, **kw):
+        if controlMode == pb.TORQUE_CONTROL:
+            for j, f in zip(jointIndices, forces):
+                W.tau[_dof(j)] = float(f)
+        else:  # POSITION_CONTROL with zero force: motors off
+            assert all(f == 0 for f in forces)
+            for j in jointIndices:
+                W.tau[_dof(j)] = 0.0
+
+    pb.setJointMotorControlArray = setJointMotorControlArray
+
+    def getBasePositionAndOrientation(body):
+        s = W.robot["state"]
+        return tuple(s.pos[:]), tuple(s.quat[:])
+
+    pb.getBasePositionAndOrientation = getBasePositionAndOrientation
+    pb.getBaseVelocity = lambda body: (tuple(W.robot["state"].vel[:]), tuple(W.robot["state"].omega[:]))
+
+    def resetBasePositionAndOrientation(body, pos, orn):
+        assert W.bodies[body]["kind"] == "robot"
+        s = W.robot["state"]
+        for k in range(3):
+            s.pos[k] = float(pos[k])
+        for k in range(4):
+            s.quat[k] = float(orn[k])
+        W.warm = (C.c_double * O.MAXW)()
+        W.contacts = None
+
+    pb.resetBasePositionAndOrientation = resetBasePositionAndOrientation
+
+    def resetBaseVelocity(body, lin, ang):
+        s = W.robot["state"]
+        for k in range(3):
+            s.vel[k], s.omega[k] = float(lin[k]), float(ang[k])
+
+    pb.resetBaseVelocity = resetBaseVelocity
+
+    def getLinkState(body, link, computeLinkVelocity=0):
+        assert not computeLinkVelocity
+        pos, rot = O.fk(W.robot["model"], W.robot["state"])  # index 0 = base, link i -> i + 1: COM (inertial) frames
+        q = mat_to_quat(rot[link + 1])
+        return tuple(pos[link + 1]), tuple(q), (0,) * 3, (0, 0, 0, 1), tuple(pos[link + 1]), tuple(q)
+
+    pb.getLinkState = getLinkState
+
+    def stepSimulation():
+        r = W.robot
+        W.contacts, _ = O.step_physics(r["model"], W.params, r["state"], W.tau, warm=W.warm)
+
+    pb.stepSimulation = stepSimulation
+
+    def getContactPoints(bodyA=None, linkIndexA=None, **kw):
+        out = []
+        c = W.contacts
+        if c is None:
+            return out
+        ground = [i for i, b in W.bodies.items() if b["kind"] == "ground"]
+        for k in range(c.n):
+            if linkIndexA is not None and c.link[k] != linkIndexA:
+                continue
+            if c.partner[k] == 0:  # the ground plane
+                out.append((0, bodyA, ground[0], c.link[k], -1))
+            elif c.partner[k] >= 1000:  # self-contact: both bodies are the robot
+                out.append((0, bodyA, bodyA, c.link[k], c.link_b[k]))
+        return out
+
+    pb.getContactPoints = getContactPoints
+
+    def getEulerFromQuaternion(qin):  # Bullet's b3GetEulerFromQuaternion semantics (restated as in the oracle)
+        q = np.asarray(qin, dtype=np.float64)
+        q = q / np.sqrt((q * q).sum())
+        sqx, sqy, sqz, squ = q[0] * q[0], q[1] * q[1], q[2] * q[2], q[3] * q[3]
+        sarg = -2 * (q[0] * q[2] - q[3] * q[1])
+        if sarg <= -0.99999:
+            return (0.0, -0.5 * np.pi, 2 * np.arctan2(q[0], -q[1]))
+        if sarg >= 0.99999:
+            return (0.0, 0.5 * np.pi, 2 * np.arctan2(-q[0], q[1]))
+        return (np.arctan2(2 * (q[1] * q[2] + q[3] * q[0]), squ - sqx - sqy + sqz), np.arcsin(sarg),
+                np.arctan2(2 * (q[0] * q[1] + q[3] * q[2]), squ + sqx - sqy - sqz))
+
+    pb.getEulerFromQuaternion = getEulerFromQuaternion
+    sys.modules["pybullet"] = pb
+    return pb
+
+
+# ----------------------------------------------------------------------------------------------- traces
+def trace_walker3d_custom(seed, steps, action_seed, eval_mode=False):
+    from mocca_envs.env_locomotion import Walker3DCustomEnv
+
+    env = Walker3DCustomEnv()
+    env.seed(seed)  # the quirk-Q1 path: np_random rebound, the robot keeps the stream it got at construction
+    if eval_mode:
+        env.evaluation_mode()
+    rs = np.random.RandomState(action_seed)
+    A = env.action_space.shape[0]
+    obs = [env.reset()]
+    acts, rews, dones, targets, resets = [], [], [], [], []
+    for t in range(steps):
+        a = rs.uniform(-1.2, 1.2, A)
+        o, r, d, info = env.step(a)
+        acts.append(a); rews.append(r); dones.append(d); targets.append(np.array(env.walk_target, dtype=np.float64))
+        if d:
+            resets.append(t)
+            obs.append(o)          # terminal observation
+            o = env.reset()
+        obs.append(o)
+    return dict(seed=seed, action_seed=action_seed, eval_mode=int(eval_mode), actions=np.array(acts),
+                obs=np.array(obs, dtype=np.float64), rewards=np.array(rews), dones=np.array(dones),
+                walk_target=np.array(targets), resets=np.array(resets, dtype=np.int64),
+                mirror=np.concatenate([np.asarray(x, dtype=np.int64).ravel() for x in env.get_mirror_indices()]),
+                construction_seed=CONSTRUCTION_SEED)
+
+
+CONSTRUCTION_SEED = 12345  # EnvBase.__init__ calls self.seed() with no argument: fixed here instead of os.urandom
+
+
+def main():
+    assert os.path.isdir(REF), "the reference tree is only present in the build container"
+    install_gym()
+    install_pybullet()
+    sys.path.insert(0, REF)
+    import gym.utils.seeding as seeding
+
+    real = seeding.np_random
+    seeding.np_random = lambda seed=None: real(CONSTRUCTION_SEED if seed is None else seed)
+    out = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out, exist_ok=True)
+    for seed, steps, aseed, ev in ((0, 160, 1, False), (7, 160, 2, False), (3, 60, 3, True)):
+        g = trace_walker3d_custom(seed, steps, aseed, ev)
+        fn = os.path.join(out, "ref_walker3d_custom_seed%d%s.npz" % (seed, "_eval" if ev else ""))
+        np.savez_compressed(fn, **g)
+        print("wrote %s: %d steps, %d episodes ended, reward sum %.6f" % (fn, steps, len(g["resets"]),
+                                                                          g["rewards"].sum()))
+
+
+if __name__ == "__main__":
+    main()
