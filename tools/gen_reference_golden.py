@@ -86,6 +86,8 @@ class FakeWorld:
         self.bodies = {}  # id -> dict(kind=...)
         self.next_id = 0
         self.params = O.default_params()
+        self.params.has_ground = 0  # until plane_stadium.sdf is loaded (remove_ground=True envs never load it)
+        self.planks = []  # body ids of the stepping stones, in creation order
         self.robot = None
         self.tau = None
         self.contacts = None
@@ -100,6 +102,7 @@ class FakeWorld:
 
 
 W = None  # the world of the env under construction (one env at a time)
+W_plank_boxes = [None]
 
 
 def install_pybullet():
@@ -156,16 +159,95 @@ def install_pybullet():
 
     pb.loadMJCF = loadMJCF
 
+    def quat_to_mat(q):
+        x, y, z, w = [float(v) for v in q]
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+    def loadURDF(filename, basePosition=(0, 0, 0), baseOrientation=(0, 0, 0, 1), useFixedBase=False,
+                 globalScaling=1.0, **kw):
+        """A stepping stone (data/objects/steps/*.urdf): static links with one box (or cylinder) collision shape each,
+        joined by fixed joints at the origin.  Geometry is read from the URDF, nothing is taken from the oracle."""
+        import xml.etree.ElementTree as ET
+
+        root = ET.parse(filename).getroot()
+        links = []
+        for l in root.findall("link"):
+            f3 = lambda e: np.array([float(v) for v in e.get("xyz", "0 0 0").split()])
+            iner = f3(l.find("inertial").find("origin")) * globalScaling
+            col = l.find("collision")
+            corg = f3(col.find("origin")) * globalScaling
+            geo = col.find("geometry")
+            if geo.find("box") is not None:
+                half = 0.5 * globalScaling * np.array([float(v) for v in geo.find("box").get("size").split()])
+                cyl = 0
+            else:
+                c = geo.find("cylinder")
+                r, h = float(c.get("radius")) * globalScaling, float(c.get("length")) * globalScaling
+                half, cyl = np.array([r, r, 0.5 * h]), 1
+            assert float(l.find("inertial").find("mass").get("value")) == 0  # static
+            links.append(dict(inertial=iner, col=corg, half=half, cyl=cyl))
+        for j in root.findall("joint"):
+            assert j.get("type") == "fixed" and j.find("origin").get("xyz") == "0 0 0"
+        R = quat_to_mat(baseOrientation)
+        b = W.new_body(kind="plank", links=links, com=np.asarray(basePosition, dtype=np.float64) + R @ links[0]["inertial"],
+                       quat=np.asarray(baseOrientation, dtype=np.float64), dyn={})
+        W.planks.append(b)
+        return b
+
+    pb.loadURDF = loadURDF
+
+    def getQuaternionFromEuler(e):  # Bullet: yaw-pitch-roll (ZYX) composition
+        roll, pitch, yaw = [float(v) for v in e]
+        cr, sr, cp, sp = np.cos(roll * 0.5), np.sin(roll * 0.5), np.cos(pitch * 0.5), np.sin(pitch * 0.5)
+        cy, sy = np.cos(yaw * 0.5), np.sin(yaw * 0.5)
+        return (sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy,
+                cr * cp * cy + sr * sp * sy)
+
+    pb.getQuaternionFromEuler = getQuaternionFromEuler
+
+    def plank_boxes():
+        """The stones as the oracle's static obstacles: link box centre = base COM + R (collision origin - base
+        inertial origin); soft contact from changeDynamics (bullet_objects.py:64-72)."""
+        if not W.planks:
+            return None
+        out = []
+        for pi, b in enumerate(W.planks):
+            body = W.bodies[b]
+            R = quat_to_mat(body["quat"])
+            for k, l in enumerate(body["links"]):
+                bx = O.Box()
+                c = body["com"] + R @ (l["col"] - body["links"][0]["inertial"])
+                for i in range(3):
+                    bx.center[i] = c[i]
+                    bx.half[i] = l["half"][i]
+                    for j in range(3):
+                        bx.R[i][j] = R[i, j]
+                dyn = body["dyn"][k - 1]
+                bx.friction = dyn["lateralFriction"]
+                bx.stiffness = dyn["contactStiffness"]
+                bx.damping = dyn["contactDamping"] + 0.1  # Bullet adds the other body's contact damping (link default 0.1)
+                bx.id = 10 + 2 * pi + k
+                bx.cylinder = l["cyl"]
+                out.append(bx)
+        return (O.Box * len(out))(*out)
+
+    W_plank_boxes[0] = plank_boxes
+
     def changeDynamics(body, link, **kw):
         b = W.bodies[body]
         if b["kind"] == "ground":  # bullet_utils.py:371: lateralFriction 0.8, restitution 0.5
             assert kw == dict(lateralFriction=0.8, restitution=0.5)
             W.params.ground_friction = kw["lateralFriction"]
+        elif b["kind"] == "plank":
+            b["dyn"][link] = dict(kw)
         else:
             raise NotImplementedError(kw)
 
     pb.changeDynamics = changeDynamics
-    pb.getNumJoints = lambda body: W.robot["table"]["n_links"] if W.bodies[body]["kind"] == "robot" else 0
+    pb.getNumJoints = lambda body: (W.robot["table"]["n_links"] if W.bodies[body]["kind"] == "robot"
+                                    else len(W.bodies[body]["links"]) - 1)
 
     def getJointInfo(body, j):
         t = W.robot["table"]
@@ -212,13 +294,20 @@ def install_pybullet():
     pb.setJointMotorControlArray = setJointMotorControlArray
 
     def getBasePositionAndOrientation(body):
+        if W.bodies[body]["kind"] == "plank":
+            return tuple(W.bodies[body]["com"]), tuple(W.bodies[body]["quat"])
         s = W.robot["state"]
         return tuple(s.pos[:]), tuple(s.quat[:])
 
     pb.getBasePositionAndOrientation = getBasePositionAndOrientation
     pb.getBaseVelocity = lambda body: (tuple(W.robot["state"].vel[:]), tuple(W.robot["state"].omega[:]))
 
-    def resetBasePositionAndOrientation(body, pos, orn):
+    def resetBasePositionAndOrientation(body, posObj=None, ornObj=None):
+        pos, orn = posObj, ornObj
+        if W.bodies[body]["kind"] == "plank":  # sets the pose of the base link's INERTIAL frame
+            W.bodies[body]["com"] = np.asarray(pos, dtype=np.float64).copy()
+            W.bodies[body]["quat"] = np.asarray(orn, dtype=np.float64).copy()
+            return
         assert W.bodies[body]["kind"] == "robot"
         s = W.robot["state"]
         for k in range(3):
@@ -247,7 +336,7 @@ def install_pybullet():
 
     def stepSimulation():
         r = W.robot
-        W.contacts, _ = O.step_physics(r["model"], W.params, r["state"], W.tau, warm=W.warm)
+        W.contacts, _ = O.step_physics(r["model"], W.params, r["state"], W.tau, boxes=W_plank_boxes[0](), warm=W.warm)
 
     pb.stepSimulation = stepSimulation
 
@@ -258,12 +347,19 @@ def install_pybullet():
             return out
         ground = [i for i, b in W.bodies.items() if b["kind"] == "ground"]
         for k in range(c.n):
+            if c.partner[k] >= 1000:  # self-contact: both bodies are the robot; Bullet reports it for either link
+                if linkIndexA is None or c.link[k] == linkIndexA:
+                    out.append((0, bodyA, bodyA, c.link[k], c.link_b[k]))
+                elif c.link_b[k] == linkIndexA:
+                    out.append((0, bodyA, bodyA, c.link_b[k], c.link[k]))
+                continue
             if linkIndexA is not None and c.link[k] != linkIndexA:
                 continue
             if c.partner[k] == 0:  # the ground plane
                 out.append((0, bodyA, ground[0], c.link[k], -1))
-            elif c.partner[k] >= 1000:  # self-contact: both bodies are the robot
-                out.append((0, bodyA, bodyA, c.link[k], c.link_b[k]))
+            elif 10 <= c.partner[k] < 20:  # a stepping stone: box id 10 + 2 * plank + (0 base | 1 cover)
+                pi, kk = divmod(c.partner[k] - 10, 2)
+                out.append((0, bodyA, W.planks[pi], c.link[k], kk - 1))
         return out
 
     pb.getContactPoints = getContactPoints
@@ -313,6 +409,36 @@ def trace_walker3d_custom(seed, steps, action_seed, eval_mode=False):
                 construction_seed=CONSTRUCTION_SEED)
 
 
+def trace_stepper(env_name, seed, steps, action_seed, curriculum, **kwargs):
+    import mocca_envs.env_locomotion as EL
+
+    env = getattr(EL, env_name)(**kwargs)
+    env.seed(seed)
+    env.set_env_params({"curriculum": curriculum})
+    rs = np.random.RandomState(action_seed)
+    A = env.action_space.shape[0]
+    obs = [env.reset()]
+    terrain = [env.terrain_info.copy()]
+    acts, rews, dones, nexts, resets, reached = [], [], [], [], [], []
+    for t in range(steps):
+        a = rs.uniform(-1.0, 1.0, A) * 0.6   # gentler than the flat-ground traces: walkers stay on the stones longer
+        o, r, d, info = env.step(a)
+        acts.append(a); rews.append(r); dones.append(d); nexts.append(env.next_step_index)
+        reached.append(info.get("steps_reached", -1))
+        if d:
+            resets.append(t)
+            obs.append(o)
+            o = env.reset()
+            terrain.append(env.terrain_info.copy())
+        obs.append(o)
+    return dict(seed=seed, action_seed=action_seed, curriculum=curriculum, actions=np.array(acts),
+                obs=np.array(obs, dtype=np.float64), rewards=np.array(rews, dtype=np.float64), dones=np.array(dones),
+                next_step_index=np.array(nexts), steps_reached=np.array(reached), terrain=np.array(terrain),
+                resets=np.array(resets, dtype=np.int64), construction_seed=CONSTRUCTION_SEED,
+                mirror=np.concatenate([np.asarray(x, dtype=np.int64).ravel() for x in env.get_mirror_indices()]),
+                plank_class=str(kwargs.get("plank_class") or "LargePlank"), random_reward=int(kwargs.get("random_reward", False)))
+
+
 CONSTRUCTION_SEED = 12345  # EnvBase.__init__ calls self.seed() with no argument: fixed here instead of os.urandom
 
 
@@ -333,6 +459,14 @@ def main():
         np.savez_compressed(fn, **g)
         print("wrote %s: %d steps, %d episodes ended, reward sum %.6f" % (fn, steps, len(g["resets"]),
                                                                           g["rewards"].sum()))
+    for tag, seed, steps, aseed, cur, kw in (("c0", 0, 200, 5, 0, {}), ("c9", 4, 200, 6, 9, {}),
+                                              ("c5_plank", 2, 150, 7, 5, {"plank_class": "Plank"}),
+                                              ("c3_rr", 5, 150, 8, 3, {"random_reward": True})):
+        g = trace_stepper("Walker3DStepperEnv", seed, steps, aseed, cur, **kw)
+        fn = os.path.join(out, "ref_walker3d_stepper_%s.npz" % tag)
+        np.savez_compressed(fn, **g)
+        print("wrote %s: %d steps, %d episodes ended, max next_step_index %d, reward sum %.6f"
+              % (fn, steps, len(g["resets"]), g["next_step_index"].max(), g["rewards"].sum()))
 
 
 if __name__ == "__main__":
