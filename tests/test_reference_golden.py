@@ -12,17 +12,20 @@ import os
 import numpy as np
 import pytest
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_walker3d_custom_*.npz")))
+_G = os.path.join(os.path.dirname(__file__), "golden")
+GOLDEN = sorted(glob.glob(os.path.join(_G, "ref_walker3d_custom_*.npz")) + glob.glob(os.path.join(_G, "ref_child3d_custom_*.npz")))
 
 
 def test_fixtures_present():
-    assert len(GOLDEN) >= 3
+    assert len(GOLDEN) >= 4
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
-def test_walker3d_custom_env_layer_matches_reference(path, walker_table, oracle_mod):
+def test_walker3d_custom_env_layer_matches_reference(path, walker_table, child_table, oracle_mod):
+    """Walker3DCustomEnv, and Child3DCustomEnv (crawl start pose, power 0.4, termination height 0.1) on its table."""
     O, g = oracle_mod, np.load(path)
-    env = O.Walker3DCustomOracle(walker_table, seed=int(g["construction_seed"]))  # EnvBase.__init__: self.seed()
+    table = child_table if "child3d" in os.path.basename(path) else walker_table
+    env = O.Walker3DCustomOracle(table, seed=int(g["construction_seed"]))  # EnvBase.__init__: self.seed()
     env.seed(int(g["seed"]))  # env_base.py:164-166: the robot keeps the construction stream (quirk Q1)
     if int(g["eval_mode"]):
         env.e.eval_mode = 1
@@ -58,22 +61,23 @@ def test_mirror_indices_match_reference(walker_table):
     assert np.array_equal(ours, g["mirror"])
 
 
-STEPPER = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_walker3d_stepper_*.npz")))
+STEPPER = sorted(glob.glob(os.path.join(_G, "ref_walker3d_stepper_*.npz")) + glob.glob(os.path.join(_G, "ref_mike_stepper_*.npz")))
 
 
 def test_stepper_fixtures_present():
-    assert len(STEPPER) >= 4
+    assert len(STEPPER) >= 6
 
 
 @pytest.mark.parametrize("path", STEPPER, ids=[os.path.basename(p) for p in STEPPER])
-def test_walker3d_stepper_env_layer_matches_reference(path, walker_table, oracle_mod):
+def test_walker3d_stepper_env_layer_matches_reference(path, walker_table, mike_table, oracle_mod):
     """Walker3DStepperEnv (env_locomotion.py:330-840) as the reference's own code computes it -- terrain generator,
     plank placement (bullet_objects.py:47-103: geometry read from the URDFs by the stand-in, not from the oracle), foot /
     target contact logic, step bonus, curriculum gains and terminal heights, `random_reward`, `plank_class`,
     `steps_reached` -- against the oracle's restatement, on identical physics."""
     O, g = oracle_mod, np.load(path)
     pc = str(g["plank_class"])
-    env = O.Walker3DStepperOracle(walker_table, seed=int(g["construction_seed"]), curriculum=0,
+    table = mike_table if "mike" in os.path.basename(path) else walker_table  # MikeStepperEnv: start (0.3, 0, 1.0)
+    env = O.Walker3DStepperOracle(table, seed=int(g["construction_seed"]), curriculum=0,
                                   random_reward=bool(int(g["random_reward"])),
                                   plank_class=None if pc == "LargePlank" else pc)
     env.seed(int(g["seed"]))

@@ -242,6 +242,9 @@ def install_pybullet():
             W.params.ground_friction = kw["lateralFriction"]
         elif b["kind"] == "plank":
             b["dyn"][link] = dict(kw)
+        elif b["kind"] == "robot" and set(kw) == {"mass"}:
+            # Mike: changeDynamics(waist, mass=8) (robots.py:506-510) -- the compiled table already carries it
+            assert abs(W.robot["table"]["mass"][link] - kw["mass"]) < 1e-12
         else:
             raise NotImplementedError(kw)
 
@@ -382,10 +385,10 @@ def install_pybullet():
 
 
 # ----------------------------------------------------------------------------------------------- traces
-def trace_walker3d_custom(seed, steps, action_seed, eval_mode=False):
-    from mocca_envs.env_locomotion import Walker3DCustomEnv
+def trace_walker3d_custom(seed, steps, action_seed, eval_mode=False, env_name="Walker3DCustomEnv"):
+    import mocca_envs.env_locomotion as EL
 
-    env = Walker3DCustomEnv()
+    env = getattr(EL, env_name)()
     env.seed(seed)  # the quirk-Q1 path: np_random rebound, the robot keeps the stream it got at construction
     if eval_mode:
         env.evaluation_mode()
@@ -459,11 +462,19 @@ def main():
         np.savez_compressed(fn, **g)
         print("wrote %s: %d steps, %d episodes ended, reward sum %.6f" % (fn, steps, len(g["resets"]),
                                                                           g["rewards"].sum()))
-    for tag, seed, steps, aseed, cur, kw in (("c0", 0, 200, 5, 0, {}), ("c9", 4, 200, 6, 9, {}),
-                                              ("c5_plank", 2, 150, 7, 5, {"plank_class": "Plank"}),
-                                              ("c3_rr", 5, 150, 8, 3, {"random_reward": True})):
-        g = trace_stepper("Walker3DStepperEnv", seed, steps, aseed, cur, **kw)
-        fn = os.path.join(out, "ref_walker3d_stepper_%s.npz" % tag)
+    g = trace_walker3d_custom(1, 120, 4, False, env_name="Child3DCustomEnv")
+    fn = os.path.join(out, "ref_child3d_custom_seed1.npz")
+    np.savez_compressed(fn, **g)
+    print("wrote %s: %d episodes ended, reward sum %.6f" % (fn, len(g["resets"]), g["rewards"].sum()))
+    for name, tag, seed, steps, aseed, cur, kw in (
+            ("Walker3DStepperEnv", "walker3d_stepper_c0", 0, 200, 5, 0, {}),
+            ("Walker3DStepperEnv", "walker3d_stepper_c9", 4, 200, 6, 9, {}),
+            ("Walker3DStepperEnv", "walker3d_stepper_c5_plank", 2, 150, 7, 5, {"plank_class": "Plank"}),
+            ("Walker3DStepperEnv", "walker3d_stepper_c7_pillar", 6, 150, 9, 7, {"plank_class": "Pillar"}),
+            ("Walker3DStepperEnv", "walker3d_stepper_c3_rr", 5, 150, 8, 3, {"random_reward": True}),
+            ("MikeStepperEnv", "mike_stepper_c4", 8, 150, 10, 4, {})):
+        g = trace_stepper(name, seed, steps, aseed, cur, **kw)
+        fn = os.path.join(out, "ref_%s.npz" % tag)
         np.savez_compressed(fn, **g)
         print("wrote %s: %d steps, %d episodes ended, max next_step_index %d, reward sum %.6f"
               % (fn, steps, len(g["resets"]), g["next_step_index"].max(), g["rewards"].sum()))
