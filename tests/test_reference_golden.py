@@ -102,3 +102,39 @@ def test_walker3d_stepper_env_layer_matches_reference(path, walker_table, mike_t
     assert np.abs(obs - g["obs"]).max() < 1e-9
     assert worst_r < 1e-9
     assert g["dones"].sum() >= 2 and g["next_step_index"].max() >= 2
+
+
+MONKEY = sorted(glob.glob(os.path.join(_G, "ref_monkey3d_custom_*.npz")))
+
+
+@pytest.mark.parametrize("path", MONKEY, ids=[os.path.basename(p) for p in MONKEY])
+def test_monkey3d_env_layer_matches_reference(path, monkey_table, oracle_mod):
+    """Monkey3DCustomEnv (env_locomotion.py:1136-1516) as the reference computes it -- bar layout generator from the
+    hand positions, bar placement (bullet_objects.py:148-187), scripted finger actions, palm / hand contact logic, swing
+    potential, free-fall and 180-step terminations -- against the oracle's restatement, on identical physics."""
+    O, g = oracle_mod, np.load(path)
+    env = O.Monkey3DOracle(monkey_table, seed=int(g["construction_seed"]))
+    env.seed(int(g["seed"]))
+    obs = [env.reset()]
+    terrain = [np.array(env.e.terrain[:])]
+    worst_r = 0.0
+    for t, a in enumerate(g["actions"]):
+        o, r, d, info = env.step(a)
+        assert d == bool(g["dones"][t]), t
+        assert env.e.next_step_index == int(g["next_step_index"][t]) or d, t
+        worst_r = max(worst_r, abs(r - g["rewards"][t]))
+        if d:
+            obs.append(o)
+            o = env.reset()
+            terrain.append(np.array(env.e.terrain[:]))
+        obs.append(o)
+    obs = np.array(obs)
+    assert np.abs(np.array(terrain) - g["terrain"]).max() < 1e-9
+    assert obs.shape == g["obs"].shape
+    assert np.abs(obs[:, :65] - g["obs"][:, :65]).max() < 1e-9
+    # the swing palm's quaternion (last four entries): its overall sign comes from below the env layer (the stand-in
+    # client converts the oracle's rotation matrix, Bullet multiplies quaternions down the chain) -- compare as rotations
+    qa, qb = obs[:, 65:], g["obs"][:, 65:]
+    assert np.minimum(np.abs(qa - qb).max(axis=1), np.abs(qa + qb).max(axis=1)).max() < 1e-9
+    assert worst_r < 1e-9
+    assert g["dones"].sum() >= 1

@@ -88,6 +88,8 @@ class FakeWorld:
         self.params = O.default_params()
         self.params.has_ground = 0  # until plane_stadium.sdf is loaded (remove_ground=True envs never load it)
         self.planks = []  # body ids of the stepping stones, in creation order
+        self.bars = []    # body ids of the monkey bars, in creation order
+        self.shapes = []
         self.robot = None
         self.tau = None
         self.contacts = None
@@ -206,6 +208,45 @@ def install_pybullet():
                 cr * cp * cy + sr * sp * sy)
 
     pb.getQuaternionFromEuler = getQuaternionFromEuler
+    pb.GEOM_CYLINDER = 4
+
+    def createCollisionShape(shapeType, radius=None, height=None, **kw):
+        assert shapeType == pb.GEOM_CYLINDER
+        W.shapes.append(dict(radius=float(radius), height=float(height)))
+        return len(W.shapes) - 1
+
+    pb.createCollisionShape = createCollisionShape
+    pb.createVisualShape = lambda *a, **kw: -1
+
+    def createMultiBody(baseMass=0.0, baseCollisionShapeIndex=-1, baseVisualShapeIndex=-1, basePosition=(0, 0, 0), **kw):
+        """MonkeyBar (bullet_objects.py:148-187): a static cylinder about its local z axis; default dynamics
+        (lateral friction 0.5: the changeDynamics call in the reference is commented out)."""
+        assert baseMass == 0.0
+        sh = W.shapes[baseCollisionShapeIndex]
+        b = W.new_body(kind="bar", radius=sh["radius"], height=sh["height"], friction=0.5,
+                       com=np.asarray(basePosition, dtype=np.float64).copy(), quat=np.array([0.0, 0, 0, 1]))
+        W.bars.append(b)
+        return b
+
+    pb.createMultiBody = createMultiBody
+    pb.getNumConstraints = lambda: 0
+    pb.getConstraintUniqueId = lambda i: i
+    pb.removeConstraint = lambda i: None
+
+    def bar_array():
+        out = []
+        for bi, b in enumerate(W.bars):
+            body = W.bodies[b]
+            bar = O.Bar()
+            ax = quat_to_mat(body["quat"])[:, 2]
+            for i in range(3):
+                bar.center[i] = body["com"][i]
+                bar.axis[i] = ax[i]
+            bar.halflen, bar.radius, bar.friction, bar.id = 0.5 * body["height"], body["radius"], body["friction"], 20 + bi
+            out.append(bar)
+        return (O.Bar * len(out))(*out)
+
+    W_plank_boxes.append(bar_array)
 
     def plank_boxes():
         """The stones as the oracle's static obstacles: link box centre = base COM + R (collision origin - base
@@ -307,7 +348,7 @@ def install_pybullet():
 
     def resetBasePositionAndOrientation(body, posObj=None, ornObj=None):
         pos, orn = posObj, ornObj
-        if W.bodies[body]["kind"] == "plank":  # sets the pose of the base link's INERTIAL frame
+        if W.bodies[body]["kind"] in ("plank", "bar"):  # sets the pose of the base link's INERTIAL frame
             W.bodies[body]["com"] = np.asarray(pos, dtype=np.float64).copy()
             W.bodies[body]["quat"] = np.asarray(orn, dtype=np.float64).copy()
             return
@@ -339,11 +380,14 @@ def install_pybullet():
 
     def stepSimulation():
         r = W.robot
-        W.contacts, _ = O.step_physics(r["model"], W.params, r["state"], W.tau, boxes=W_plank_boxes[0](), warm=W.warm)
+        if W.bars:
+            W.contacts, _ = O.step_physics_bars(r["model"], W.params, r["state"], W.tau, W_plank_boxes[1]())
+        else:
+            W.contacts, _ = O.step_physics(r["model"], W.params, r["state"], W.tau, boxes=W_plank_boxes[0](), warm=W.warm)
 
     pb.stepSimulation = stepSimulation
 
-    def getContactPoints(bodyA=None, linkIndexA=None, **kw):
+    def getContactPoints(bodyA=None, bodyB=None, linkIndexA=None, **kw):
         out = []
         c = W.contacts
         if c is None:
@@ -363,6 +407,8 @@ def install_pybullet():
             elif 10 <= c.partner[k] < 20:  # a stepping stone: box id 10 + 2 * plank + (0 base | 1 cover)
                 pi, kk = divmod(c.partner[k] - 10, 2)
                 out.append((0, bodyA, W.planks[pi], c.link[k], kk - 1))
+            elif 20 <= c.partner[k] < 30:  # a monkey bar
+                out.append((0, bodyA, W.bars[c.partner[k] - 20], c.link[k], -1))
         return out
 
     pb.getContactPoints = getContactPoints
@@ -410,6 +456,32 @@ def trace_walker3d_custom(seed, steps, action_seed, eval_mode=False, env_name="W
                 walk_target=np.array(targets), resets=np.array(resets, dtype=np.int64),
                 mirror=np.concatenate([np.asarray(x, dtype=np.int64).ravel() for x in env.get_mirror_indices()]),
                 construction_seed=CONSTRUCTION_SEED)
+
+
+def trace_monkey(seed, steps, action_seed):
+    from mocca_envs.env_locomotion import Monkey3DCustomEnv
+
+    env = Monkey3DCustomEnv()
+    env.seed(seed)
+    rs = np.random.RandomState(action_seed)
+    A = env.action_space.shape[0]
+    obs = [env.reset()]
+    terrain = [env.terrain_info.copy()]
+    acts, rews, dones, nexts, resets = [], [], [], [], []
+    for t in range(steps):
+        a = rs.uniform(-1.0, 1.0, A)
+        sent = a.copy()
+        o, r, d, info = env.step(a)  # overwrites the two finger entries of `a` in place (quirk Q11)
+        acts.append(sent); rews.append(r); dones.append(d); nexts.append(env.next_step_index)
+        if d:
+            resets.append(t)
+            obs.append(o)
+            o = env.reset()
+            terrain.append(env.terrain_info.copy())
+        obs.append(o)
+    return dict(seed=seed, action_seed=action_seed, actions=np.array(acts), obs=np.array(obs, dtype=np.float64),
+                rewards=np.array(rews, dtype=np.float64), dones=np.array(dones), next_step_index=np.array(nexts),
+                terrain=np.array(terrain), resets=np.array(resets, dtype=np.int64), construction_seed=CONSTRUCTION_SEED)
 
 
 def trace_stepper(env_name, seed, steps, action_seed, curriculum, **kwargs):
@@ -466,6 +538,12 @@ def main():
     fn = os.path.join(out, "ref_child3d_custom_seed1.npz")
     np.savez_compressed(fn, **g)
     print("wrote %s: %d episodes ended, reward sum %.6f" % (fn, len(g["resets"]), g["rewards"].sum()))
+    for seed, steps, aseed in ((0, 260, 11), (5, 260, 12)):
+        g = trace_monkey(seed, steps, aseed)
+        fn = os.path.join(out, "ref_monkey3d_custom_seed%d.npz" % seed)
+        np.savez_compressed(fn, **g)
+        print("wrote %s: %d steps, %d episodes ended, max next_step_index %d, reward sum %.6f"
+              % (fn, steps, len(g["resets"]), g["next_step_index"].max(), g["rewards"].sum()))
     for name, tag, seed, steps, aseed, cur, kw in (
             ("Walker3DStepperEnv", "walker3d_stepper_c0", 0, 200, 5, 0, {}),
             ("Walker3DStepperEnv", "walker3d_stepper_c9", 4, 200, 6, 9, {}),
