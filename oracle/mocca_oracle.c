@@ -1961,7 +1961,9 @@ static void cassie_calc_state(const orc_model* m, orc_cassie_env* e) {
     float sp = (float)b->s.qd[d];
     st[6 + k] = nrm;
     st[6 + A + k] = sp;
-    e->rad_angles[k] = (hi - lo) * ((double)nrm + 1) / 2 + lo; /* to_radians, float64 weights */
+    /* to_radians (env_cassie.py:204-213): float64 weights, but `thetas + 1` is a float32 array plus a Python int and
+     * stays float32 -- pinned by the reference-generated trace tests/golden/ref_cassie_*.npz */
+    e->rad_angles[k] = (hi - lo) * (double)(float)(nrm + 1.0f) / 2 + lo;
     e->speeds[k] = sp;
     if (fabsf(nrm) > 0.99f) b->joints_at_limit++;
   }
@@ -2027,7 +2029,10 @@ void orc_cassie_step(const orc_model* m, const orc_params* p, orc_cassie_env* e,
   for (int k = 0; k < A; k++) jpos0[k] = e->rad_angles[k];
   int rows_total = 0;
   for (int it = 0; it < 50; it++) { /* llc_frame_skip (env_cassie.py:288,450) */
-    for (int k = 0; k < A; k++) e->jvel[k] = (1 - 0.2) * e->jvel[k] + 0.2 * e->speeds[k]; /* jvel_alpha = 10/50 */
+    /* jvel_alpha = 10/50 (env_cassie.py:319,451-453).  `alpha * joint_speeds` is a Python float times a float32
+     * array: the product is rounded to float32 before it joins the float64 running value (pinned by the
+     * reference-generated trace tests/golden/ref_cassie_*.npz) */
+    for (int k = 0; k < A; k++) e->jvel[k] = (1 - 0.2) * e->jvel[k] + (double)(0.2f * (float)e->speeds[k]);
     double tau[ORC_MAXD];
     for (int d = 0; d < m->n_dof; d++) tau[d] = 0;
     for (int k = 0; k < NP; k++) { /* pd_control (env_cassie.py:380-393) + apply_action clip (:225-230) */

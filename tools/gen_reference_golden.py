@@ -136,8 +136,36 @@ def install_pybullet():
         W.params.iterations = numSolverIterations
 
     pb.setPhysicsEngineParameter = setPhysicsEngineParameter
-    pb.saveState = lambda: 0
-    pb.restoreState = lambda *a, **kw: None
+    def saveState():
+        r = W.robot
+        if r is not None:
+            W.saved[0] = (O.state_vector(r["state"], r["A"]).copy(), W.tau.copy())
+        return 0
+
+    def restoreState(stateId=0, **kw):
+        r = W.robot
+        sv, tau = W.saved[0]
+        A = r["A"]
+        r["state"] = O.make_state(A, sv[0:3], sv[3:7], sv[7:10], sv[10:13], sv[13:13 + A], sv[13 + A:13 + 2 * A])
+        W.tau[:] = tau
+        W.warm = (C.c_double * O.MAXW)()
+        W.contacts = None
+
+    pb.saveState = saveState
+    pb.restoreState = restoreState
+    pb.JOINT_POINT2POINT = 5
+
+    def createConstraint(parentBody, parentLink, childBody, childLink, jointType=None, jointAxis=None,
+                         parentFramePosition=None, childFramePosition=None, **kw):
+        """Cassie's loop closures (env_cassie.py:114-137): must be the ones compiled into the table."""
+        assert jointType == pb.JOINT_POINT2POINT
+        c = [q for q in W.robot["table"]["p2p"] if q["link_a"] == parentLink and q["link_b"] == childLink]
+        assert len(c) == 1 and np.allclose(c[0]["pivot_a"], parentFramePosition, atol=0) \
+            and np.allclose(c[0]["pivot_b"], childFramePosition, atol=0)
+        return 0
+
+    pb.createConstraint = createConstraint
+    pb.setCollisionFilterGroupMask = lambda *a, **kw: None
 
     def loadSDF(filename):
         assert filename.endswith("plane_stadium.sdf")
@@ -146,18 +174,21 @@ def install_pybullet():
 
     pb.loadSDF = loadSDF
 
-    def loadMJCF(path, flags=0):
-        name = os.path.splitext(os.path.basename(path))[0]
+    def load_robot_table(name, flags=0, base_pos=None):
         t = load_table(os.path.join(MODELS, name + ".json"))
         assert not t.get("planar"), "planar tables fold the root joints into the base; not servable joint by joint"
         W.params.self_collision = 1 if flags & pb.URDF_USE_SELF_COLLISION else 0
         A = t["n_dof"]
         W.robot = dict(table=t, model=O.model_from_table(t), A=A,
-                       state=O.make_state(A, t["base"]["init_pos"], [0, 0, 0, 1], [0] * 3, [0] * 3, [0] * A, [0] * A))
+                       state=O.make_state(A, t["base"]["init_pos"] if base_pos is None else base_pos, [0, 0, 0, 1],
+                                          [0] * 3, [0] * 3, [0] * A, [0] * A))
         W.tau = np.zeros(A)
         W.warm = (C.c_double * O.MAXW)()
         W.contacts = None
-        return (W.new_body(kind="robot"),)
+        return W.new_body(kind="robot")
+
+    def loadMJCF(path, flags=0):
+        return (load_robot_table(os.path.splitext(os.path.basename(path))[0], flags),)
 
     pb.loadMJCF = loadMJCF
 
@@ -173,6 +204,8 @@ def install_pybullet():
         joined by fixed joints at the origin.  Geometry is read from the URDF, nothing is taken from the oracle."""
         import xml.etree.ElementTree as ET
 
+        if "cassie" in os.path.basename(filename):
+            return load_robot_table("cassie", flags=kw.get("flags", 0), base_pos=basePosition)
         root = ET.parse(filename).getroot()
         links = []
         for l in root.findall("link"):
@@ -283,6 +316,9 @@ def install_pybullet():
             W.params.ground_friction = kw["lateralFriction"]
         elif b["kind"] == "plank":
             b["dyn"][link] = dict(kw)
+        elif b["kind"] == "robot" and set(kw) == {"jointDamping"}:
+            # Cassie: changeDynamics(jointDamping=...) per ordered joint (env_cassie.py:197-201) -- compiled into the table
+            assert W.robot["table"]["damping"][W.robot["table"]["dof_of_link"][link]] == kw["jointDamping"]
         elif b["kind"] == "robot" and set(kw) == {"mass"}:
             # Mike: changeDynamics(waist, mass=8) (robots.py:506-510) -- the compiled table already carries it
             assert abs(W.robot["table"]["mass"][link] - kw["mass"]) < 1e-12
@@ -321,8 +357,16 @@ def install_pybullet():
 
     pb.resetJointState = resetJointState
 
-    def setJointMotorControl2(*a, **kw):  # only ever used to switch the default motors off (force = 0)
-        assert kw.get("force", 0) == 0
+    def setJointMotorControl2(*a, **kw):
+        args = dict(zip(("bodyIndex", "jointIndex", "controlMode"), a))
+        args.update(kw)
+        d = _dof(args["jointIndex"])
+        if args["controlMode"] == pb.TORQUE_CONTROL:  # Cassie applies its PD torques joint by joint
+            W.tau[d] = float(args["force"])
+        else:  # POSITION_CONTROL with zero force: the default motor switched off
+            assert args.get("force", 0) == 0
+            if d >= 0:
+                W.tau[d] = 0.0
 
     pb.setJointMotorControl2 = setJointMotorControl2
 
@@ -484,6 +528,46 @@ def trace_monkey(seed, steps, action_seed):
                 terrain=np.array(terrain), resets=np.array(resets, dtype=np.int64), construction_seed=CONSTRUCTION_SEED)
 
 
+def trace_cassie(steps, action_seed):
+    """CassieEnv-v0.  env_cassie.py does not import as shipped; the three defects are fixed by intent, nothing else:
+    Q7 the missing `.loadstep` module (only the mocap variants use it), Q8 BodyPart / Joint not imported, Q9 the
+    EnvBase.__init__ call that passes `render` as robot_kwargs and drops `power`."""
+    import mocca_envs  # noqa: F401
+    import gym
+    from mocca_envs import bullet_utils
+    from mocca_envs.env_base import EnvBase
+
+    sys.modules["mocca_envs.loadstep"] = types.SimpleNamespace(CassieTrajectory=None)
+    from mocca_envs import env_cassie as EC
+
+    EC.BodyPart, EC.Joint = bullet_utils.BodyPart, bullet_utils.Joint
+
+    class CassieEnv(EC.CassieEnv):
+        def __init__(self, render=False, planar=False, power_coef=1.0, residual_control=True, rsi=True):
+            self.planar, self.residual_control, self.rsi = planar, residual_control, rsi
+            EnvBase.__init__(self, EC.Cassie, robot_kwargs={"power": power_coef}, render=render)
+            high = np.inf * np.ones(self.robot.observation_space.shape[0] + 2)
+            self.observation_space = gym.spaces.Box(-high, high, dtype=np.float32)
+            self.action_space = self.robot.action_space
+
+    env = CassieEnv()
+    rs = np.random.RandomState(action_seed)
+    obs = [env.reset()]
+    acts, rews, dones, alive, prog, resets = [], [], [], [], [], []
+    for t in range(steps):
+        a = rs.uniform(-1, 1, 10) * (0.1 if t % 40 < 25 else 0.6)  # mostly the standing residual, bursts that topple it
+        o, r, d, info = env.step(a)
+        acts.append(a); rews.append(r); dones.append(d); alive.append(info["AliveRew"]); prog.append(info["ProgressRew"])
+        if d:
+            resets.append(t)
+            obs.append(o)
+            o = env.reset()
+        obs.append(o)
+    return dict(action_seed=action_seed, actions=np.array(acts), obs=np.array(obs, dtype=np.float64),
+                rewards=np.array(rews, dtype=np.float64), dones=np.array(dones), alive=np.array(alive),
+                progress=np.array(prog), resets=np.array(resets, dtype=np.int64))
+
+
 def trace_stepper(env_name, seed, steps, action_seed, curriculum, **kwargs):
     import mocca_envs.env_locomotion as EL
 
@@ -538,6 +622,11 @@ def main():
     fn = os.path.join(out, "ref_child3d_custom_seed1.npz")
     np.savez_compressed(fn, **g)
     print("wrote %s: %d episodes ended, reward sum %.6f" % (fn, len(g["resets"]), g["rewards"].sum()))
+    g = trace_cassie(60, 21)
+    fn = os.path.join(out, "ref_cassie_a21.npz")
+    np.savez_compressed(fn, **g)
+    print("wrote %s: %d env steps (x50 substeps), %d episodes ended, reward sum %.6f"
+          % (fn, len(g["actions"]), len(g["resets"]), g["rewards"].sum()))
     for seed, steps, aseed in ((0, 260, 11), (5, 260, 12)):
         g = trace_monkey(seed, steps, aseed)
         fn = os.path.join(out, "ref_monkey3d_custom_seed%d.npz" % seed)
