@@ -1,6 +1,7 @@
 /*
  * mocca_oracle.c -- CPU float64 restatement of the mocca_envs hot path.  TEST INFRASTRUCTURE ONLY.
- * See mocca_oracle.h for the "parity unpinned" statement and the list of what may call this file.
+ * See mocca_oracle.h for the parity statement (env layer pinned by reference-run traces, Bullet arithmetic unpinned)
+ * and the list of what may call this file.
  *
  * Layout of this file
  *   1. small linear algebra

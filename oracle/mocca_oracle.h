@@ -1,14 +1,21 @@
 /*
  * mocca_oracle.h -- CPU float64 restatement of the mocca_envs hot path.  TEST INFRASTRUCTURE ONLY.
  *
- * PARITY UNPINNED: the arithmetic of the reference's hot path lives in the third-party `pybullet`
- * C-extension (reference setup.py:11, un-pinned, not vendored, not installable here), reached through
- * `stepSimulation` (reference mocca_envs/bullet_utils.py:352-353).  The reference ships no tests or golden
- * vectors.  This file restates Bullet's published multibody pipeline (btMultiBody ABA,
- * btMultiBodyConstraintSolver PGS, semi-implicit Euler) and the reference's Python
- * env logic (robots.py, env_locomotion.py).  It is pinned against: NumPy RandomState streams (bit-exact),
- * an independent Jacobian-based mass matrix, ID(FD(tau)) round trips and conservation laws
- * (tests/test_oracle_*.py) -- NOT against PyBullet outputs.
+ * PARITY, two layers:
+ *   - ENV LAYER (everything the reference's Python computes: apply_action, calc_state, reset draws, targets, terrain
+ *     and bar generators, foot / palm contact logic, rewards, termination, Cassie's PD loop): PINNED against the
+ *     reference's own code.  tools/gen_reference_golden.py imports the unmodified env_base.py / env_locomotion.py /
+ *     robots.py / bullet_utils.py / bullet_objects.py / env_cassie.py with stand-ins for gym and pybullet whose Bullet
+ *     client is served by this file's physics, and records traces (tests/golden/ref_*.npz); replaying the recorded
+ *     actions through the orc_*_env functions reproduces observation / reward / done to float64 rounding (1e-15;
+ *     Cassie bit-identical) for all six env classes (tests/test_reference_golden.py).
+ *   - BULLET ARITHMETIC: PARITY UNPINNED.  It lives in the third-party `pybullet` C-extension (reference setup.py:11,
+ *     un-pinned, not vendored, not installable here), reached through `stepSimulation` (reference
+ *     mocca_envs/bullet_utils.py:352-353); the reference ships no tests or golden vectors.  This file
+ *     restates Bullet's published multibody pipeline (btMultiBody ABA, btMultiBodyConstraintSolver PGS, semi-implicit
+ *     Euler).  That part is pinned only against: NumPy RandomState streams (bit-exact), an
+ *     independent Jacobian-based mass matrix, ID(FD(tau)) round trips and conservation laws (tests/test_oracle_*.py)
+ *     -- NOT against PyBullet outputs.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
  */
