@@ -12,23 +12,28 @@ from tests.helpers import oracle_record
 
 pytestmark = pytest.mark.gpu
 _G = os.path.join(os.path.dirname(__file__), "golden")
-CUSTOM = sorted(glob.glob(os.path.join(_G, "ref_walker3d_custom_*.npz")) + glob.glob(os.path.join(_G, "ref_child3d_custom_*.npz")))
+CUSTOM = sorted(glob.glob(os.path.join(_G, "ref_walker3d_custom_*.npz")) + glob.glob(os.path.join(_G, "ref_child3d_custom_*.npz"))
+                + glob.glob(os.path.join(_G, "ref_walker2d_custom_*.npz")) + glob.glob(os.path.join(_G, "ref_crab2d_custom_*.npz")))
 
 
 @pytest.mark.parametrize("path", CUSTOM, ids=[os.path.basename(p) for p in CUSTOM])
-def test_device_env_step_vs_reference_trace(path, walker_table, child_table, oracle_mod):
+def test_device_env_step_vs_reference_trace(path, walker_table, child_table, walker2d_table, crab2d_table, oracle_mod):
     """Teacher-forced Walker3DCustomEnv / Child3DCustomEnv steps on the device vs the reference's recorded
     observation (5e-3) / reward (5e-2 + 1e-3 |r|) / done: >= 95 % of the steps (>= 88 % for the child, whose f32
     factorisation is good to ~3e-3 at full torque, see test_f3_emulation.py), median observation error < 5e-4."""
     import torch
-    from mocca_envs_b200.vec_env import Child3DCustomVecEnv, Walker3DCustomVecEnv
+    from mocca_envs_b200.vec_env import (Child3DCustomVecEnv, Crab2DCustomVecEnv, Walker2DCustomVecEnv,
+                                         Walker3DCustomVecEnv)
 
     O, g = oracle_mod, np.load(path)
-    child = "child3d" in os.path.basename(path)
-    table = child_table if child else walker_table
+    b = os.path.basename(path)
+    child = "child3d" in b
+    table, cls = ((child_table, Child3DCustomVecEnv) if child else (walker2d_table, Walker2DCustomVecEnv)
+                  if "walker2d" in b else (crab2d_table, Crab2DCustomVecEnv) if "crab2d" in b
+                  else (walker_table, Walker3DCustomVecEnv))
     o = O.Walker3DCustomOracle(table, seed=int(g["construction_seed"]))
     o.seed(int(g["seed"]))
-    env = (Child3DCustomVecEnv if child else Walker3DCustomVecEnv)(1, device="cuda:0", seed=0, return_final_obs=True)
+    env = cls(1, device="cuda:0", seed=0, return_final_obs=True)
     if int(g["eval_mode"]):
         o.e.eval_mode = 1
         env.evaluation_mode()

@@ -13,18 +13,25 @@ import numpy as np
 import pytest
 
 _G = os.path.join(os.path.dirname(__file__), "golden")
-GOLDEN = sorted(glob.glob(os.path.join(_G, "ref_walker3d_custom_*.npz")) + glob.glob(os.path.join(_G, "ref_child3d_custom_*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(_G, "ref_walker3d_custom_*.npz")) + glob.glob(os.path.join(_G, "ref_child3d_custom_*.npz"))
+                + glob.glob(os.path.join(_G, "ref_walker2d_custom_*.npz")) + glob.glob(os.path.join(_G, "ref_crab2d_custom_*.npz")))
 
 
 def test_fixtures_present():
-    assert len(GOLDEN) >= 4
+    assert len(GOLDEN) >= 6
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
-def test_walker3d_custom_env_layer_matches_reference(path, walker_table, child_table, oracle_mod):
-    """Walker3DCustomEnv, and Child3DCustomEnv (crawl start pose, power 0.4, termination height 0.1) on its table."""
+def test_walker3d_custom_env_layer_matches_reference(path, walker_table, child_table, walker2d_table, crab2d_table,
+                                                     oracle_mod):
+    """Walker3DCustomEnv; Child3DCustomEnv (crawl start pose, power 0.4, termination height 0.1) on its table; the
+    planar Walker2DCustomEnv / Crab2DCustomEnv (done forced to False, zeros in the target slots at reset, pelvis link
+    accessors, restoreState at every reset: env_locomotion.py:285-314)."""
     O, g = oracle_mod, np.load(path)
-    table = child_table if "child3d" in os.path.basename(path) else walker_table
+    b = os.path.basename(path)
+    planar = "2d_" in b
+    table = (child_table if "child3d" in b else walker2d_table if "walker2d" in b else crab2d_table if "crab2d" in b
+             else walker_table)
     env = O.Walker3DCustomOracle(table, seed=int(g["construction_seed"]))  # EnvBase.__init__: self.seed()
     env.seed(int(g["seed"]))  # env_base.py:164-166: the robot keeps the construction stream (quirk Q1)
     if int(g["eval_mode"]):
@@ -44,7 +51,7 @@ def test_walker3d_custom_env_layer_matches_reference(path, walker_table, child_t
     assert obs.shape == g["obs"].shape
     assert np.abs(obs - g["obs"]).max() < 1e-12
     assert worst_r < 1e-12
-    assert g["dones"].sum() >= 2  # the traces run through episode ends and resets
+    assert g["dones"].sum() >= (0 if planar else 2)  # the traces run through episode ends and resets
 
 
 def test_mirror_indices_match_reference(walker_table):

@@ -139,12 +139,13 @@ def install_pybullet():
     def saveState():
         r = W.robot
         if r is not None:
-            W.saved[0] = (O.state_vector(r["state"], r["A"]).copy(), W.tau.copy())
+            W.saved[0] = (O.state_vector(r["state"], r["A"]).copy(), W.tau.copy(), W.base_world.copy())
         return 0
 
     def restoreState(stateId=0, **kw):
         r = W.robot
-        sv, tau = W.saved[0]
+        sv, tau, bw = W.saved[0]
+        W.base_world = bw.copy()
         A = r["A"]
         r["state"] = O.make_state(A, sv[0:3], sv[3:7], sv[7:10], sv[10:13], sv[13:13 + A], sv[13 + A:13 + 2 * A])
         W.tau[:] = tau
@@ -176,11 +177,16 @@ def install_pybullet():
 
     def load_robot_table(name, flags=0, base_pos=None):
         t = load_table(os.path.join(MODELS, name + ".json"))
-        assert not t.get("planar"), "planar tables fold the root joints into the base; not servable joint by joint"
+        # Planar tables (walker2d / crab2d) fold the root's ignorex / ignorez / ignorey joints into a free base.  Towards
+        # the env layer the stand-in presents them the way Bullet does: joints 0..2 on a fixed base, the pelvis as link 2,
+        # every table link shifted by 3; the base frame sits 1.35 above the pelvis origin (body pos "0 0 -1.35").
+        W.shift = 3 if t.get("planar") else 0
+        W.base_world = np.zeros(3)
         W.params.self_collision = 1 if flags & pb.URDF_USE_SELF_COLLISION else 0
         A = t["n_dof"]
         W.robot = dict(table=t, model=O.model_from_table(t), A=A,
-                       state=O.make_state(A, t["base"]["init_pos"] if base_pos is None else base_pos, [0, 0, 0, 1],
+                       state=O.make_state(A, ([0, 0, -1.35] if t.get("planar") else t["base"]["init_pos"])
+                                          if base_pos is None else base_pos, [0, 0, 0, 1],
                                           [0] * 3, [0] * 3, [0] * A, [0] * A))
         W.tau = np.zeros(A)
         W.warm = (C.c_double * O.MAXW)()
@@ -326,11 +332,17 @@ def install_pybullet():
             raise NotImplementedError(kw)
 
     pb.changeDynamics = changeDynamics
-    pb.getNumJoints = lambda body: (W.robot["table"]["n_links"] if W.bodies[body]["kind"] == "robot"
+    pb.getNumJoints = lambda body: (W.robot["table"]["n_links"] + W.shift if W.bodies[body]["kind"] == "robot"
                                     else len(W.bodies[body]["links"]) - 1)
 
     def getJointInfo(body, j):
         t = W.robot["table"]
+        if j < W.shift:  # the planar root joints: slide x, slide z, hinge y, unlimited (lower > upper)
+            nm = ("ignorex", "ignorez", "ignorey")[j]
+            ln = ("link_dummy_pelvis_0", "link_dummy_pelvis_1", t["base"]["name"])[j]
+            return (j, nm.encode(), 1 if j < 2 else 0, 0, 0, 0, 0.0, 0.0, 1.0, -1.0, 0.0, 0.0, ln.encode(),
+                    ((1, 0, 0), (0, 0, 1), (0, 1, 0))[j], (0, 0, 0), (0, 0, 0, 1), j - 1)
+        j -= W.shift
         rev = t["joint_type"][j] == MC_REVOLUTE
         d = t["dof_of_link"][j]
         lo, hi = (t["lower"][d], t["upper"][d]) if rev else (0.0, -1.0)
@@ -341,7 +353,7 @@ def install_pybullet():
     pb.getJointInfo = getJointInfo
 
     def _dof(j):
-        return W.robot["table"]["dof_of_link"][j]
+        return W.robot["table"]["dof_of_link"][j - W.shift] if j >= W.shift else -1
 
     def getJointState(body, j):
         s, d = W.robot["state"], _dof(j)
@@ -382,6 +394,8 @@ def install_pybullet():
     pb.setJointMotorControlArray = setJointMotorControlArray
 
     def getBasePositionAndOrientation(body):
+        if W.bodies[body]["kind"] == "robot" and W.shift:
+            return tuple(W.base_world), (0.0, 0.0, 0.0, 1.0)
         if W.bodies[body]["kind"] == "plank":
             return tuple(W.bodies[body]["com"]), tuple(W.bodies[body]["quat"])
         s = W.robot["state"]
@@ -398,6 +412,15 @@ def install_pybullet():
             return
         assert W.bodies[body]["kind"] == "robot"
         s = W.robot["state"]
+        if W.shift:  # fixed base of a planar robot: the whole chain moves with it, the root joints keep their values
+            assert tuple(orn) == (0, 0, 0, 1)
+            delta = np.asarray(pos, dtype=np.float64) - W.base_world
+            W.base_world = np.asarray(pos, dtype=np.float64).copy()
+            for k in range(3):
+                s.pos[k] += delta[k]
+            W.warm = (C.c_double * O.MAXW)()
+            W.contacts = None
+            return
         for k in range(3):
             s.pos[k] = float(pos[k])
         for k in range(4):
@@ -408,6 +431,8 @@ def install_pybullet():
     pb.resetBasePositionAndOrientation = resetBasePositionAndOrientation
 
     def resetBaseVelocity(body, lin, ang):
+        if W.shift:  # a fixed base has no velocity to set
+            return
         s = W.robot["state"]
         for k in range(3):
             s.vel[k], s.omega[k] = float(lin[k]), float(ang[k])
@@ -415,8 +440,13 @@ def install_pybullet():
     pb.resetBaseVelocity = resetBaseVelocity
 
     def getLinkState(body, link, computeLinkVelocity=0):
+        s = W.robot["state"]
+        if W.shift and link == W.shift - 1:  # the pelvis of a planar robot = the table's base
+            out = (tuple(s.pos[:]), tuple(s.quat[:]), (0,) * 3, (0, 0, 0, 1), tuple(s.pos[:]), tuple(s.quat[:]))
+            return out + (tuple(s.vel[:]), tuple(s.omega[:])) if computeLinkVelocity else out
         assert not computeLinkVelocity
-        pos, rot = O.fk(W.robot["model"], W.robot["state"])  # index 0 = base, link i -> i + 1: COM (inertial) frames
+        link -= W.shift
+        pos, rot = O.fk(W.robot["model"], s)  # index 0 = base, link i -> i + 1: COM (inertial) frames
         q = mat_to_quat(rot[link + 1])
         return tuple(pos[link + 1]), tuple(q), (0,) * 3, (0, 0, 0, 1), tuple(pos[link + 1]), tuple(q)
 
@@ -437,17 +467,20 @@ def install_pybullet():
         if c is None:
             return out
         ground = [i for i, b in W.bodies.items() if b["kind"] == "ground"]
+        sh = W.shift
+        if linkIndexA is not None:
+            linkIndexA -= sh  # env-layer link index -> table link index (the pelvis of a planar robot becomes -1)
         for k in range(c.n):
             if c.partner[k] >= 1000:  # self-contact: both bodies are the robot; Bullet reports it for either link
                 if linkIndexA is None or c.link[k] == linkIndexA:
-                    out.append((0, bodyA, bodyA, c.link[k], c.link_b[k]))
+                    out.append((0, bodyA, bodyA, c.link[k] + sh, c.link_b[k] + sh))
                 elif c.link_b[k] == linkIndexA:
-                    out.append((0, bodyA, bodyA, c.link_b[k], c.link[k]))
+                    out.append((0, bodyA, bodyA, c.link_b[k] + sh, c.link[k] + sh))
                 continue
             if linkIndexA is not None and c.link[k] != linkIndexA:
                 continue
             if c.partner[k] == 0:  # the ground plane
-                out.append((0, bodyA, ground[0], c.link[k], -1))
+                out.append((0, bodyA, ground[0], c.link[k] + sh, -1))
             elif 10 <= c.partner[k] < 20:  # a stepping stone: box id 10 + 2 * plank + (0 base | 1 cover)
                 pi, kk = divmod(c.partner[k] - 10, 2)
                 out.append((0, bodyA, W.planks[pi], c.link[k], kk - 1))
@@ -622,6 +655,12 @@ def main():
     fn = os.path.join(out, "ref_child3d_custom_seed1.npz")
     np.savez_compressed(fn, **g)
     print("wrote %s: %d episodes ended, reward sum %.6f" % (fn, len(g["resets"]), g["rewards"].sum()))
+    for env_name, tag, seed, aseed in (("Walker2DCustomEnv", "walker2d", 2, 31), ("Crab2DCustomEnv", "crab2d", 4, 32)):
+        g = trace_walker3d_custom(seed, 200, aseed, False, env_name=env_name)
+        fn = os.path.join(out, "ref_%s_custom_seed%d.npz" % (tag, seed))
+        np.savez_compressed(fn, **g)
+        print("wrote %s: %d episodes ended (the reference forces done = False), reward sum %.6f, feet contacts %d"
+              % (fn, len(g["resets"]), g["rewards"].sum(), int(g["obs"][:, -4:-2].sum())))
     g = trace_cassie(60, 21)
     fn = os.path.join(out, "ref_cassie_a21.npz")
     np.savez_compressed(fn, **g)
