@@ -691,7 +691,7 @@ template <class M, bool PILLAR = false> struct StepperEnv {
 #pragma unroll 1
     for (int k = 0; k < P.substeps; ++k) {
       load_boxes(S, rec);  // the obstacle staging area is reused by the constraint rows of every substep
-      rows += S_::template substep<MB_OBST_BOXES>(S, P, C, &nc, &overflow);
+      rows += S_::template substep<OBST>(S, P, C, &nc, &overflow);
       ncsum += nc;
     }
     const int timestep = rec_i(rec, ES_TIMESTEP) + 1;

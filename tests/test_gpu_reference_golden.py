@@ -63,3 +63,66 @@ def test_device_env_step_vs_reference_trace(path, walker_table, child_table, wal
     assert bad <= (0.12 if child else 0.05) * len(errs), (bad, len(errs))
     assert np.median(errs) < 5e-4
     env.close()
+
+
+STEPPER = sorted(p for p in glob.glob(os.path.join(_G, "ref_walker3d_stepper_*.npz")) + glob.glob(os.path.join(_G, "ref_mike_stepper_*.npz"))
+                 if "_rr" not in p)  # random_reward draws from the env stream, which teacher forcing does not carry
+
+
+@pytest.mark.parametrize("path", STEPPER, ids=[os.path.basename(p) for p in STEPPER])
+def test_device_stepper_step_vs_reference_trace(path, walker_table, mike_table, oracle_mod):
+    """Walker3DStepperEnv / MikeStepperEnv (LargePlank, Plank, Pillar stones) teacher-forced on the device along the
+    reference's recorded traces: >= 95 % of the steps within 5e-3 (obs) / 5e-2 (reward) of the RECORDED values with the
+    recorded done flag, median observation error < 5e-4."""
+    import torch
+    from mocca_envs_b200.vec_env import MikeStepperVecEnv, Walker3DStepperVecEnv
+
+    O, g = oracle_mod, np.load(path)
+    mike = "mike" in os.path.basename(path)
+    pc = str(g["plank_class"])
+    kw = {} if pc == "LargePlank" else {"plank_class": pc}
+    o = O.Walker3DStepperOracle(mike_table if mike else walker_table, seed=int(g["construction_seed"]), **kw)
+    o.seed(int(g["seed"]))
+    cur = int(g["curriculum"])
+    o.set_env_params({"curriculum": cur})
+    env = (MikeStepperVecEnv if mike else Walker3DStepperVecEnv)(1, device="cuda:0", seed=0, return_final_obs=True, **kw)
+    env.set_env_params({"curriculum": cur})
+    env.reset()
+    o.reset()
+    k, bad, errs = 1, 0, []
+    for t, a in enumerate(g["actions"]):
+        b = o.e.base
+        sv = o.state_vector().astype(np.float32)
+        env.set_state(torch.tensor(sv[None]))
+        rec = env.get_record().cpu().numpy()
+        ri = rec.view(np.int32)
+        rec[0, 0:3] = np.array(b.walk_target[:], dtype=np.float32)
+        rec[0, 7] = b.linear_potential
+        rec[0, 9], rec[0, 10] = b.feet_contact[0], b.feet_contact[1]
+        ri[0, 8] = b.elapsed
+        ri[0, 22:27] = (o.e.next_step_index, o.e.target_reached_count, o.e.stop_on_next_step,
+                        o.e.set_stop_on_next_step, o.e.timestep)
+        ri[0, 6] = o.e.gain_curriculum
+        for p in range(3):
+            bx = o.e.boxes[2 * p]
+            rec[0, 32 + 12 * p:32 + 12 * p + 3] = np.array(bx.center[:], dtype=np.float32)
+            rec[0, 32 + 12 * p + 3:32 + 12 * p + 12] = np.array([list(r) for r in bx.R], dtype=np.float32).ravel()
+        rec[0, 68:188] = np.array(o.e.terrain[:], dtype=np.float32).ravel()
+        env.set_record(torch.tensor(rec))
+        obs, rew, done, info = env.step(torch.tensor(a[None].astype(np.float32)))
+        d = bool(done[0].item())
+        got = (info["terminal_observation"] if d else obs)[0].double().cpu().numpy()
+        ref_obs, ref_r, ref_d = g["obs"][k], float(g["rewards"][t]), bool(g["dones"][t])
+        e_obs = float(np.abs(got - ref_obs).max())
+        ok = d == ref_d and e_obs < 5e-3 and abs(float(rew[0].item()) - ref_r) < 5e-2 + 1e-3 * abs(ref_r)
+        bad += 0 if ok else 1
+        errs.append(e_obs)
+        _, _, d1, _ = o.step(a)
+        assert d1 == ref_d
+        k += 1
+        if d1:
+            o.reset()
+            k += 1
+    assert bad <= 0.05 * len(errs), (bad, len(errs))
+    assert np.median(errs) < 5e-4
+    env.close()

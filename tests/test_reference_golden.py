@@ -211,3 +211,61 @@ def test_kernel_source_vs_reference_trace(path, walker_table, oracle_mod):
             k += 1
     assert bad <= 0.05 * len(errs), (bad, len(errs))
     assert np.median(errs) < 5e-4
+
+
+@pytest.mark.parametrize("path", [p for p in STEPPER if "_rr" not in p], ids=lambda p: os.path.basename(p))
+def test_stepper_kernel_source_vs_reference_trace(path, walker_table, mike_table, oracle_mod):
+    """The stepper kernel source (LargePlank / Plank / Pillar instantiations, Walker3D and Mike tables; g++ lane loop)
+    teacher-forced along the reference traces: obs / reward / done per step against the RECORDED reference values
+    (5e-3 / 5e-2, >= 95 % of the steps, median < 5e-4).  This test caught the Pillar env step running its substeps with
+    the box narrow phase (fixed: StepperEnv::step uses its own OBST).  GPU twin: test_gpu_reference_golden.py."""
+    from tests.emu import emu as E
+
+    O, g = oracle_mod, np.load(path)
+    mike = "mike" in os.path.basename(path)
+    pc = str(g["plank_class"])
+    kw = {} if pc == "LargePlank" else {"plank_class": pc}
+    o = O.Walker3DStepperOracle(mike_table if mike else walker_table, seed=int(g["construction_seed"]), **kw)
+    o.seed(int(g["seed"]))
+    cur = int(g["curriculum"])
+    o.set_env_params({"curriculum": cur})
+
+    class EmuPillar(E.EmuStepper):
+        prefix = "pillar"
+
+    st = np.random.RandomState(O.gym_seed_words(0)).get_state()
+    cls = E.EmuMike if mike else (EmuPillar if pc == "Pillar" else E.EmuStepper)
+    e = cls(np.concatenate([st[1], [st[2]]]).astype(np.uint32), curriculum=cur)
+    e.reset()
+    o.reset()
+    k, bad, errs = 1, 0, []
+    for t, a in enumerate(g["actions"]):
+        b = o.e.base
+        e.state[:55] = o.state_vector().astype(np.float32)
+        rec, ri = e.rec, e.rec.view(np.int32)
+        rec[0:3] = np.array(b.walk_target[:], dtype=np.float32)
+        rec[7] = b.linear_potential
+        rec[9], rec[10] = b.feet_contact[0], b.feet_contact[1]
+        ri[8] = b.elapsed
+        ri[22:27] = (o.e.next_step_index, o.e.target_reached_count, o.e.stop_on_next_step, o.e.set_stop_on_next_step,
+                     o.e.timestep)
+        ri[6] = o.e.gain_curriculum
+        ri[4] = o.e.plank_class  # ES_PLANK_CLASS
+        for p in range(3):
+            bx = o.e.boxes[2 * p]
+            rec[32 + 12 * p:32 + 12 * p + 3] = np.array(bx.center[:], dtype=np.float32)
+            rec[32 + 12 * p + 3:32 + 12 * p + 12] = np.array([list(r) for r in bx.R], dtype=np.float32).ravel()
+        rec[68:188] = np.array(o.e.terrain[:], dtype=np.float32).ravel()
+        o2, r2, d2, tr2, fin = e.step(a)
+        got = fin if d2 else o2
+        ref_obs, ref_r, ref_d = g["obs"][k], float(g["rewards"][t]), bool(g["dones"][t])
+        err = float(np.abs(got - ref_obs).max())
+        bad += 0 if (d2 == ref_d and err < 5e-3 and abs(r2 - ref_r) < 5e-2 + 1e-3 * abs(ref_r)) else 1
+        errs.append(err)
+        _, _, d1, _ = o.step(a)
+        k += 1
+        if d1:
+            o.reset()
+            k += 1
+    assert bad <= 0.05 * len(errs), (bad, len(errs))
+    assert np.median(errs) < 5e-4
