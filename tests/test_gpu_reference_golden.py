@@ -89,8 +89,13 @@ def test_device_stepper_step_vs_reference_trace(path, walker_table, mike_table, 
     env.set_env_params({"curriculum": cur})
     env.reset()
     o.reset()
+    from tests.test_reference_golden import _teleport
+
+    tele = {int(r[0]): r[1:4] for r in g["teleports"]} if "teleports" in g.files else {}
     k, bad, errs = 1, 0, []
     for t, a in enumerate(g["actions"]):
+        if t in tele:
+            _teleport(o, mike_table if mike else walker_table, tele[t])
         b = o.e.base
         sv = o.state_vector().astype(np.float32)
         env.set_state(torch.tensor(sv[None]))

@@ -601,7 +601,11 @@ def trace_cassie(steps, action_seed):
                 progress=np.array(prog), resets=np.array(resets, dtype=np.int64))
 
 
-def trace_stepper(env_name, seed, steps, action_seed, curriculum, **kwargs):
+def trace_stepper(env_name, seed, steps, action_seed, curriculum, teleport_every=0, **kwargs):
+    """teleport_every > 0: every so many steps the walker is put back on its feet above the NEXT stepping stone (base
+    pose, zero velocity, through the env's own robot / Bullet-client calls), so that the trace walks the target-advance,
+    plank-recycling, step-bonus and stop-on-step logic that a random policy never reaches.  The teleports are recorded;
+    the replay applies the same state override to the oracle."""
     import mocca_envs.env_locomotion as EL
 
     env = getattr(EL, env_name)(**kwargs)
@@ -611,9 +615,16 @@ def trace_stepper(env_name, seed, steps, action_seed, curriculum, **kwargs):
     A = env.action_space.shape[0]
     obs = [env.reset()]
     terrain = [env.terrain_info.copy()]
-    acts, rews, dones, nexts, resets, reached = [], [], [], [], [], []
+    acts, rews, dones, nexts, resets, reached, teleports = [], [], [], [], [], [], []
     for t in range(steps):
         a = rs.uniform(-1.0, 1.0, A) * 0.6   # gentler than the flat-ground traces: walkers stay on the stones longer
+        if teleport_every and t > 0 and t % teleport_every == 0:
+            tgt = env.terrain_info[env.next_step_index, 0:3] + np.array([0.0, 0.0, 1.36])
+            env.robot.reset_joint_states(env.robot.base_joint_angles, env.robot.base_joint_speeds)
+            env.robot.robot_body.reset_pose([float(v) for v in tgt], [0.0, 0.0, 0.0, 1.0])
+            env.robot.robot_body.reset_velocity([0.0, 0.0, 0.0], [0.0, 0.0, 0.0])
+            teleports.append([t, *tgt])
+            a = a * 0.1
         o, r, d, info = env.step(a)
         acts.append(a); rews.append(r); dones.append(d); nexts.append(env.next_step_index)
         reached.append(info.get("steps_reached", -1))
@@ -627,6 +638,7 @@ def trace_stepper(env_name, seed, steps, action_seed, curriculum, **kwargs):
                 obs=np.array(obs, dtype=np.float64), rewards=np.array(rews, dtype=np.float64), dones=np.array(dones),
                 next_step_index=np.array(nexts), steps_reached=np.array(reached), terrain=np.array(terrain),
                 resets=np.array(resets, dtype=np.int64), construction_seed=CONSTRUCTION_SEED,
+                teleports=np.array(teleports, dtype=np.float64).reshape(-1, 4),
                 mirror=np.concatenate([np.asarray(x, dtype=np.int64).ravel() for x in env.get_mirror_indices()]),
                 plank_class=str(kwargs.get("plank_class") or "LargePlank"), random_reward=int(kwargs.get("random_reward", False)))
 
@@ -678,7 +690,8 @@ def main():
             ("Walker3DStepperEnv", "walker3d_stepper_c5_plank", 2, 150, 7, 5, {"plank_class": "Plank"}),
             ("Walker3DStepperEnv", "walker3d_stepper_c7_pillar", 6, 150, 9, 7, {"plank_class": "Pillar"}),
             ("Walker3DStepperEnv", "walker3d_stepper_c3_rr", 5, 150, 8, 3, {"random_reward": True}),
-            ("MikeStepperEnv", "mike_stepper_c4", 8, 150, 10, 4, {})):
+            ("MikeStepperEnv", "mike_stepper_c4", 8, 150, 10, 4, {}),
+            ("Walker3DStepperEnv", "walker3d_stepper_c6_walk", 9, 420, 13, 6, {"teleport_every": 14})):
         g = trace_stepper(name, seed, steps, aseed, cur, **kw)
         fn = os.path.join(out, "ref_%s.npz" % tag)
         np.savez_compressed(fn, **g)
