@@ -39,8 +39,13 @@ def test_device_env_step_vs_reference_trace(path, walker_table, child_table, wal
         env.evaluation_mode()
     env.reset()
     o.reset()
+    from tests.test_reference_golden import _teleport
+
+    tele = {int(r[0]): r[1:4] for r in g["teleports"]} if "teleports" in g.files else {}
     k, bad, errs = 1, 0, []
     for t, a in enumerate(g["actions"]):
+        if t in tele:
+            _teleport(o, table, tele[t])
         sv = o.state_vector().astype(np.float32)
         env.set_state(torch.tensor(sv[None]))
         rec = env.get_record().cpu().numpy()

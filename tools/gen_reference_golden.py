@@ -508,7 +508,10 @@ def install_pybullet():
 
 
 # ----------------------------------------------------------------------------------------------- traces
-def trace_walker3d_custom(seed, steps, action_seed, eval_mode=False, env_name="Walker3DCustomEnv"):
+def trace_walker3d_custom(seed, steps, action_seed, eval_mode=False, env_name="Walker3DCustomEnv", hold_at_target=False):
+    """hold_at_target: before every step the walker is put on its feet AT the walk target (recorded state override
+    through the reference's own robot calls), so that close_count runs up to stop_frames and the mid-episode target
+    re-randomisation (env_locomotion.py:196-222) is exercised, which no random policy reaches."""
     import mocca_envs.env_locomotion as EL
 
     env = getattr(EL, env_name)()
@@ -518,9 +521,16 @@ def trace_walker3d_custom(seed, steps, action_seed, eval_mode=False, env_name="W
     rs = np.random.RandomState(action_seed)
     A = env.action_space.shape[0]
     obs = [env.reset()]
-    acts, rews, dones, targets, resets = [], [], [], [], []
+    acts, rews, dones, targets, resets, teleports = [], [], [], [], [], []
     for t in range(steps):
         a = rs.uniform(-1.2, 1.2, A)
+        if hold_at_target:
+            tgt = np.array([env.walk_target[0], env.walk_target[1], 1.33])
+            env.robot.reset_joint_states(env.robot.base_joint_angles, env.robot.base_joint_speeds)
+            env.robot.robot_body.reset_pose([float(v) for v in tgt], [0.0, 0.0, 0.0, 1.0])
+            env.robot.robot_body.reset_velocity([0.0, 0.0, 0.0], [0.0, 0.0, 0.0])
+            teleports.append([t, *tgt])
+            a = a * 0.05
         o, r, d, info = env.step(a)
         acts.append(a); rews.append(r); dones.append(d); targets.append(np.array(env.walk_target, dtype=np.float64))
         if d:
@@ -531,6 +541,7 @@ def trace_walker3d_custom(seed, steps, action_seed, eval_mode=False, env_name="W
     return dict(seed=seed, action_seed=action_seed, eval_mode=int(eval_mode), actions=np.array(acts),
                 obs=np.array(obs, dtype=np.float64), rewards=np.array(rews), dones=np.array(dones),
                 walk_target=np.array(targets), resets=np.array(resets, dtype=np.int64),
+                teleports=np.array(teleports, dtype=np.float64).reshape(-1, 4),
                 mirror=np.concatenate([np.asarray(x, dtype=np.int64).ravel() for x in env.get_mirror_indices()]),
                 construction_seed=CONSTRUCTION_SEED)
 
@@ -663,6 +674,11 @@ def main():
         np.savez_compressed(fn, **g)
         print("wrote %s: %d steps, %d episodes ended, reward sum %.6f" % (fn, steps, len(g["resets"]),
                                                                           g["rewards"].sum()))
+    g = trace_walker3d_custom(11, 200, 14, False, hold_at_target=True)
+    fn = os.path.join(out, "ref_walker3d_custom_seed11_target.npz")
+    np.savez_compressed(fn, **g)
+    print("wrote %s: %d episodes ended, %d distinct walk targets, reward sum %.6f"
+          % (fn, len(g["resets"]), len(np.unique(g["walk_target"][:, 0])), g["rewards"].sum()))
     g = trace_walker3d_custom(1, 120, 4, False, env_name="Child3DCustomEnv")
     fn = os.path.join(out, "ref_child3d_custom_seed1.npz")
     np.savez_compressed(fn, **g)
