@@ -187,3 +187,61 @@ def test_device_cassie_step_vs_reference_trace(path, cassie_table, oracle_mod):
     assert bad <= 0.10 * len(errs), (bad, len(errs), sorted(errs)[-6:])
     assert np.median(errs) < 3e-3
     env.close()
+
+
+MONKEY = sorted(glob.glob(os.path.join(_G, "ref_monkey3d_custom_*.npz")))
+
+
+@pytest.mark.parametrize("path", MONKEY, ids=[os.path.basename(p) for p in MONKEY])
+def test_device_monkey_step_vs_reference_trace(path, monkey_table, oracle_mod):
+    """Monkey3DCustomEnv on the device, teacher-forced along the reference's recorded traces: >= 92 % of the steps
+    within 5e-3 (obs, the swing palm's quaternion compared up to its overall sign) / 5e-2 (reward) of the RECORDED
+    values with the recorded done flag (a hanging monkey under full-scale random torques: hand-on-bar contacts)."""
+    import torch
+    from mocca_envs_b200.vec_env import Monkey3DCustomVecEnv
+
+    O, g, t = oracle_mod, np.load(path), monkey_table
+    A = 23
+    o = O.Monkey3DOracle(t, seed=int(g["construction_seed"]))
+    o.seed(int(g["seed"]))
+    env = Monkey3DCustomVecEnv(1, device="cuda:0", seed=0, return_final_obs=True)
+    env.reset()
+    o.reset()
+    k, bad, errs = 1, 0, []
+    for step, a in enumerate(g["actions"]):
+        sv = o.state_vector().astype(np.float32)
+        rec = env.get_record().cpu().numpy()
+        ri = rec.view(np.int32)
+        b = o.e.base
+        rec[0, 0:3] = np.array(b.walk_target[:], dtype=np.float32)
+        rec[0, 9], rec[0, 10] = b.feet_contact[0], b.feet_contact[1]
+        ri[0, 8] = b.elapsed
+        ri[0, env.EM_NEXT], ri[0, env.EM_FREEFALL], ri[0, env.EM_TIMESTEP] = (o.e.next_step_index, o.e.free_fall_count,
+                                                                              o.e.timestep)
+        ri[0, env.EM_SWING], ri[0, env.EM_PIVOT] = o.e.swing_leg, o.e.pivot_leg
+        rec[0, 27] = o.e.swing_potential
+        rec[0, env.EM_TERRAIN:env.EM_TERRAIN + 128] = np.array([list(r) for r in o.e.terrain], dtype=np.float32).ravel()
+        for kk in range(4):
+            bar = o.e.bars[kk]
+            rec[0, env.EM_BAR + 8 * kk:env.EM_BAR + 8 * kk + 8] = np.array(
+                list(bar.center) + list(bar.axis) + [bar.halflen, bar.radius], dtype=np.float32)
+        env.set_state(torch.tensor(sv[None]))
+        env.set_record(torch.tensor(rec))
+        obs, rew, done, info = env.step(torch.tensor(a[None].astype(np.float32)))
+        d = bool(done[0].item())
+        got = (info["terminal_observation"] if d else obs)[0].double().cpu().numpy()
+        ref_obs, ref_r, ref_d = g["obs"][k], float(g["rewards"][step]), bool(g["dones"][step])
+        err = float(np.abs(got[:65] - ref_obs[:65]).max())
+        err = max(err, float(min(np.abs(got[65:] - ref_obs[65:]).max(), np.abs(got[65:] + ref_obs[65:]).max())))
+        ok = d == ref_d and err < 5e-3 and abs(float(rew[0].item()) - ref_r) < 5e-2 + 1e-3 * abs(ref_r)
+        bad += 0 if ok else 1
+        errs.append(err)
+        _, _, d1, _ = o.step(a)
+        assert d1 == ref_d
+        k += 1
+        if d1:
+            o.reset()
+            k += 1
+    assert bad <= 0.08 * len(errs), (bad, len(errs), sorted(errs)[-6:])
+    assert np.median(errs) < 5e-4
+    env.close()
