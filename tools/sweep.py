@@ -17,17 +17,21 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-from mocca_envs_b200.vec_env import (CassieVecEnv, Monkey3DCustomVecEnv, Walker3DCustomVecEnv,  # noqa: E402
-                                     Walker3DStepperVecEnv)
+from mocca_envs_b200.vec_env import (CassieVecEnv, Child3DCustomVecEnv, Crab2DCustomVecEnv,  # noqa: E402
+                                     MikeStepperVecEnv, Monkey3DCustomVecEnv, Walker2DCustomVecEnv,
+                                     Walker3DCustomVecEnv, Walker3DStepperVecEnv)
 
 KINDS = {"custom": (Walker3DCustomVecEnv, 1.0), "stepper": (Walker3DStepperVecEnv, 1.0),
          "monkey": (Monkey3DCustomVecEnv, 1.0), "cassie": (CassieVecEnv, 0.1)}
+# SURVEY 8 f3 envs: swept alone, not part of the mixed run (BASELINE config 5 names the four envs above)
+EXTRA = {"child": (Child3DCustomVecEnv, 1.0), "mike": (MikeStepperVecEnv, 1.0),
+         "walker2d": (Walker2DCustomVecEnv, 1.0), "crab2d": (Crab2DCustomVecEnv, 1.0)}
 
 
 def make(kind, n, dev):
-    cls, scale = KINDS[kind]
+    cls, scale = {**KINDS, **EXTRA}[kind]
     env = cls(n, device=dev, seed=1234)
-    if kind == "stepper":
+    if kind in ("stepper", "mike"):
         import numpy as np
 
         env.set_env_params({"curriculum": np.array([0, 5, 9] * (n // 3 + 1))[:n]})
@@ -89,7 +93,7 @@ def main():
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     out = {"steps": args.steps, "single": {}, "mixed": {}}
-    for kind in KINDS:
+    for kind in list(KINDS) + list(EXTRA):
         out["single"][kind] = {}
         for n in (1024, 2048, 4096, 8192, 16384, 32768, 65536):
             k = args.steps if kind != "cassie" else max(20, args.steps // 10)
