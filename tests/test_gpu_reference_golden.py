@@ -207,8 +207,13 @@ def test_device_monkey_step_vs_reference_trace(path, monkey_table, oracle_mod):
     env = Monkey3DCustomVecEnv(1, device="cuda:0", seed=0, return_final_obs=True)
     env.reset()
     o.reset()
+    from tests.test_reference_golden import _monkey_grab
+
+    tele = {int(r[0]): r[1:4] for r in g["teleports"]} if "teleports" in g.files else {}
     k, bad, errs = 1, 0, []
     for step, a in enumerate(g["actions"]):
+        if step in tele:
+            _monkey_grab(o, tele[step])
         sv = o.state_vector().astype(np.float32)
         rec = env.get_record().cpu().numpy()
         ri = rec.view(np.int32)

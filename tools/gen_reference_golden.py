@@ -546,7 +546,10 @@ def trace_walker3d_custom(seed, steps, action_seed, eval_mode=False, env_name="W
                 construction_seed=CONSTRUCTION_SEED)
 
 
-def trace_monkey(seed, steps, action_seed):
+def trace_monkey(seed, steps, action_seed, grab_every=0):
+    """grab_every > 0: every so many steps the whole monkey is translated (velocities zeroed, pose kept; through the
+    reference's own robot calls) so that its swing palm sits on the target bar -- the trace then walks the palm-contact /
+    swing-pivot swap / bar-recycling logic that random torques never reach.  The new base positions are recorded."""
     from mocca_envs.env_locomotion import Monkey3DCustomEnv
 
     env = Monkey3DCustomEnv()
@@ -555,9 +558,18 @@ def trace_monkey(seed, steps, action_seed):
     A = env.action_space.shape[0]
     obs = [env.reset()]
     terrain = [env.terrain_info.copy()]
-    acts, rews, dones, nexts, resets = [], [], [], [], []
+    acts, rews, dones, nexts, resets, teleports = [], [], [], [], [], []
     for t in range(steps):
         a = rs.uniform(-1.0, 1.0, A)
+        if grab_every and t > 0 and t % grab_every == 0:
+            palm = env.robot.parts["right_palm" if env.swing_leg == 0 else "left_palm"].pose().xyz()
+            new = np.array(env.robot.robot_body.pose().xyz()) + (env.terrain_info[env.next_step_index, 0:3] - palm)
+            js = env._p.getJointStates(env.robot.id, env.robot.ordered_joint_ids)
+            env.robot.reset_joint_states([x[0] for x in js], [0.0 for _ in js])
+            env.robot.robot_body.reset_pose([float(v) for v in new], env.robot.robot_body.pose().orientation())
+            env.robot.robot_body.reset_velocity([0.0, 0.0, 0.0], [0.0, 0.0, 0.0])
+            teleports.append([t, *new])
+            a = a * 0.2
         sent = a.copy()
         o, r, d, info = env.step(a)  # overwrites the two finger entries of `a` in place (quirk Q11)
         acts.append(sent); rews.append(r); dones.append(d); nexts.append(env.next_step_index)
@@ -569,7 +581,8 @@ def trace_monkey(seed, steps, action_seed):
         obs.append(o)
     return dict(seed=seed, action_seed=action_seed, actions=np.array(acts), obs=np.array(obs, dtype=np.float64),
                 rewards=np.array(rews, dtype=np.float64), dones=np.array(dones), next_step_index=np.array(nexts),
-                terrain=np.array(terrain), resets=np.array(resets, dtype=np.int64), construction_seed=CONSTRUCTION_SEED)
+                terrain=np.array(terrain), resets=np.array(resets, dtype=np.int64), construction_seed=CONSTRUCTION_SEED,
+                teleports=np.array(teleports, dtype=np.float64).reshape(-1, 4))
 
 
 def trace_cassie(steps, action_seed):
@@ -694,9 +707,9 @@ def main():
     np.savez_compressed(fn, **g)
     print("wrote %s: %d env steps (x50 substeps), %d episodes ended, reward sum %.6f"
           % (fn, len(g["actions"]), len(g["resets"]), g["rewards"].sum()))
-    for seed, steps, aseed in ((0, 260, 11), (5, 260, 12)):
-        g = trace_monkey(seed, steps, aseed)
-        fn = os.path.join(out, "ref_monkey3d_custom_seed%d.npz" % seed)
+    for seed, steps, aseed, grab in ((0, 260, 11, 0), (5, 260, 12, 0), (8, 200, 15, 10)):
+        g = trace_monkey(seed, steps, aseed, grab)
+        fn = os.path.join(out, "ref_monkey3d_custom_seed%d%s.npz" % (seed, "_grab" if grab else ""))
         np.savez_compressed(fn, **g)
         print("wrote %s: %d steps, %d episodes ended, max next_step_index %d, reward sum %.6f"
               % (fn, steps, len(g["resets"]), g["next_step_index"].max(), g["rewards"].sum()))
