@@ -312,3 +312,24 @@ def test_stepper_kernel_source_vs_reference_trace(path, walker_table, mike_table
             k += 1
     assert bad <= 0.05 * len(errs), (bad, len(errs))
     assert np.median(errs) < 5e-4
+
+
+def test_fixtures_regenerate_identically_from_the_reference(tmp_path):
+    """Where the reference tree is present (the build container), re-running tools/gen_reference_golden.py in a fresh
+    process reproduces every committed fixture array for array: the fixtures are what the reference's code computes
+    today, not stale files."""
+    import subprocess
+    import sys
+
+    if not os.path.isdir("/root/reference/mocca_envs"):
+        pytest.skip("reference tree not present on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "gen_reference_golden.py"), str(tmp_path)],
+                          stdout=subprocess.DEVNULL)
+    names = sorted(os.path.basename(p) for p in glob.glob(os.path.join(_G, "ref_*.npz")))
+    assert names == sorted(os.path.basename(p) for p in glob.glob(os.path.join(str(tmp_path), "ref_*.npz")))
+    for n in names:
+        a, b = np.load(os.path.join(_G, n)), np.load(os.path.join(str(tmp_path), n))
+        assert sorted(a.files) == sorted(b.files), n
+        for k in a.files:
+            assert np.array_equal(a[k], b[k]), (n, k)

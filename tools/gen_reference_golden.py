@@ -670,7 +670,7 @@ def trace_stepper(env_name, seed, steps, action_seed, curriculum, teleport_every
 CONSTRUCTION_SEED = 12345  # EnvBase.__init__ calls self.seed() with no argument: fixed here instead of os.urandom
 
 
-def main():
+def main(out=None):
     assert os.path.isdir(REF), "the reference tree is only present in the build container"
     install_gym()
     install_pybullet()
@@ -679,7 +679,7 @@ def main():
 
     real = seeding.np_random
     seeding.np_random = lambda seed=None: real(CONSTRUCTION_SEED if seed is None else seed)
-    out = os.path.join(ROOT, "tests", "golden")
+    out = out or os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
     for seed, steps, aseed, ev in ((0, 160, 1, False), (7, 160, 2, False), (3, 60, 3, True)):
         g = trace_walker3d_custom(seed, steps, aseed, ev)
@@ -729,4 +729,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(*sys.argv[1:2])
