@@ -333,3 +333,91 @@ def test_fixtures_regenerate_identically_from_the_reference(tmp_path):
         assert sorted(a.files) == sorted(b.files), n
         for k in a.files:
             assert np.array_equal(a[k], b[k]), (n, k)
+
+
+@pytest.mark.parametrize("path", MONKEY, ids=[os.path.basename(p) for p in MONKEY])
+def test_monkey_kernel_source_vs_reference_trace(path, monkey_table, oracle_mod):
+    """The Monkey3D kernel source (g++ lane loop) teacher-forced along the reference traces vs the RECORDED values:
+    >= 92 % of the compared steps within 5e-3 (obs; palm quaternion up to sign) / 5e-2 (reward) with the recorded done
+    flag.  Grab steps (the palm starts centred on the bar, see the GPU twin) are stepped but not compared."""
+    from tests.emu import emu as E
+
+    O, g = oracle_mod, np.load(path)
+    A = 23
+    o = O.Monkey3DOracle(monkey_table, seed=int(g["construction_seed"]))
+    o.seed(int(g["seed"]))
+    st = np.random.RandomState(O.gym_seed_words(0)).get_state()
+    e = E.EmuMonkey(np.concatenate([st[1], [st[2]]]).astype(np.uint32))
+    e.reset()
+    o.reset()
+    M = E.EmuMonkey
+    tele = {int(r[0]): r[1:4] for r in g["teleports"]} if "teleports" in g.files else {}
+    k, bad, errs = 1, 0, []
+    for t, a in enumerate(g["actions"]):
+        if t in tele:
+            _monkey_grab(o, tele[t])
+        b = o.e.base
+        e.state[:13 + 2 * A] = o.state_vector().astype(np.float32)
+        ri = e.rec.view(np.int32)
+        e.rec[0:3] = np.array(b.walk_target[:], dtype=np.float32)
+        e.rec[9], e.rec[10] = b.feet_contact[0], b.feet_contact[1]
+        ri[8] = b.elapsed
+        ri[M.EM_NEXT], ri[M.EM_FREEFALL], ri[M.EM_TIMESTEP] = o.e.next_step_index, o.e.free_fall_count, o.e.timestep
+        ri[M.EM_SWING], ri[M.EM_PIVOT] = o.e.swing_leg, o.e.pivot_leg
+        e.rec[M.EM_SWINGPOT] = o.e.swing_potential
+        e.rec[M.EM_TERRAIN:M.EM_TERRAIN + 128] = np.array([list(r) for r in o.e.terrain], dtype=np.float32).ravel()
+        for kk in range(4):
+            bar = o.e.bars[kk]
+            e.rec[M.EM_BAR + 8 * kk:M.EM_BAR + 8 * kk + 8] = np.array(
+                list(bar.center) + list(bar.axis) + [bar.halflen, bar.radius], dtype=np.float32)
+        o2, r2, d2, tr2, fin = e.step(a)
+        got = (fin if d2 else o2).astype(np.float64)
+        ref_obs, ref_r, ref_d = g["obs"][k], float(g["rewards"][t]), bool(g["dones"][t])
+        err = float(np.abs(got[:65] - ref_obs[:65]).max())
+        err = max(err, float(min(np.abs(got[65:] - ref_obs[65:]).max(), np.abs(got[65:] + ref_obs[65:]).max())))
+        if t not in tele:
+            bad += 0 if (d2 == ref_d and err < 5e-3 and abs(r2 - ref_r) < 5e-2 + 1e-3 * abs(ref_r)) else 1
+            errs.append(err)
+        _, _, d1, _ = o.step(a)
+        k += 1
+        if d1:
+            o.reset()
+            k += 1
+    assert bad <= 0.08 * len(errs), (bad, len(errs), sorted(errs)[-6:])
+    assert np.median(errs) < 5e-4
+
+
+@pytest.mark.parametrize("path", CASSIE, ids=[os.path.basename(p) for p in CASSIE])
+def test_cassie_kernel_source_vs_reference_trace(path, cassie_table, oracle_mod):
+    """The Cassie kernel source (g++ lane loop; 50 PD substeps per env step) teacher-forced along the reference trace vs
+    the RECORDED values: >= 90 % of the env steps within 1e-2 (obs) / 2e-3 (reward) with the recorded done flag."""
+    from tests.emu import emu as E
+
+    O, g = oracle_mod, np.load(path)
+    A = cassie_table["n_dof"]
+    o = O.CassieOracle(cassie_table)
+    e = E.EmuCassie()
+    e.reset()
+    o.reset()
+    k, bad, errs = 1, 0, []
+    for t, a in enumerate(g["actions"]):
+        sv = o.state_vector().astype(np.float32)
+        e.state[:13 + 2 * A] = sv
+        ri = e.rec.view(np.int32)
+        ri[8] = o.e.base.elapsed
+        e.rec[E.EmuCassie.EC_POTENTIAL] = o.e.potential
+        e.rec[23], e.rec[24] = sv[0], sv[1]  # EC_PREVX / EC_PREVY: position at the last calc_potential
+        e.rec[E.EmuCassie.EC_JVEL:E.EmuCassie.EC_JVEL + 14] = np.array(o.e.jvel[:14], dtype=np.float32)
+        o2, r2, d2, tr2, fin = e.step(a)
+        got = fin if d2 else o2
+        ref_obs, ref_r, ref_d = g["obs"][k], float(g["rewards"][t]), bool(g["dones"][t])
+        err = float(np.abs(got - ref_obs).max())
+        bad += 0 if (d2 == ref_d and err < 1e-2 and abs(r2 - ref_r) < 2e-3) else 1
+        errs.append(err)
+        _, _, d1, _ = o.step(a)
+        k += 1
+        if d1:
+            o.reset()
+            k += 1
+    assert bad <= 0.10 * len(errs), (bad, len(errs), sorted(errs)[-6:])
+    assert np.median(errs) < 3e-3
