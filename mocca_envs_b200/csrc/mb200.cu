@@ -551,6 +551,20 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   }
   e->warps = kind == KIND_MONKEY ? MB_WARPS_MONKEY : kind == KIND_CASSIE ? MB_WARPS_CASSIE
              : kind == KIND_CUSTOM ? MB_WARPS_CUSTOM : MB_WARPS_STEPPER;
+  {
+    // Small batches: with 14-warp CTAs 1 024 envs occupy 74 of the 148 SMs and the step takes the latency of one
+    // env-step; narrower CTAs spread the envs over every SM (2 resident CTAs each).  Pure scheduling (MB_WARPS is the
+    // launch's own blockDim), results are unchanged.  MB200_WARPS overrides (tuning / A-B runs).
+    const int slots = 2 * prop.multiProcessorCount;
+    int w = (n_envs + slots - 1) / slots;
+    if (w < 4) w = 4;
+    if (w < e->warps) e->warps = w;
+    if (const char* ov = getenv("MB200_WARPS")) {
+      const int v = atoi(ov);
+      if (v >= 1 && v <= e->warps) e->warps = v;
+      else if (v > e->warps && v <= MB_WARPS_MAX && kind != KIND_MONKEY) e->warps = v;
+    }
+  }
   e->state_dim = 13 + 2 * nj;
   e->nu = 6 + nj;
   mb200_physics p;
