@@ -71,6 +71,10 @@ int mb200_seed(mb200_env* env, const uint32_t* mt_host, int at_construction);
 /* Env.reset (env_locomotion.py:79-109) for every env whose mask byte is non-zero (mask_dev NULL = all). */
 int mb200_reset(mb200_env* env, const uint8_t* mask_dev, float* obs_dev, void* stream);
 
+/* The same with HOST buffers (mask_host NULL = all; only the rows of the envs that were reset are written).
+ * Synchronous.  This is what the gym facade's reset() needs when the caller holds no device memory. */
+int mb200_reset_host(mb200_env* env, const uint8_t* mask_host, float* obs_host, void* stream);
+
 /* Env.step (env_locomotion.py:111-141) for all envs, fused with gym TimeLimit and VecEnv auto-reset:
  * where done is set, obs is the first observation of the next episode and, if final_obs_dev is not NULL, the
  * terminal observation is written there.  trunc = info["TimeLimit.truncated"]. */
@@ -84,6 +88,14 @@ int mb200_step(mb200_env* env, const float* act_dev, float* obs_dev, float* rew_
  * MB200_HOST_DIRECT=0 in the environment forces the staged path, =1 keeps only the result stores direct. */
 int mb200_step_host(mb200_env* env, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host,
                     uint8_t* trunc_host, void* stream);
+
+/* The integer part of the info dict of the last mb200_step / mb200_step_host, one int per env:
+ * info["steps_reached"] of Walker3DStepperEnv / MikeStepperEnv (env_locomotion.py:505-506; -1 where the step did not
+ * report it, i.e. the episode did not end), -1 for the other envs (their info dicts are empty; Cassie's reward terms
+ * are recomputed by the host mirror).  mb200_info copies device-to-device on the stream; mb200_info_host is
+ * synchronous. */
+int mb200_info(mb200_env* env, int* info_dev, void* stream);
+int mb200_info_host(mb200_env* env, int* info_host, void* stream);
 
 /* resetJointState / resetBasePositionAndOrientation / resetBaseVelocity and the matching getters
  * (robots.py:212-216, bullet_utils.py:100-146,157-175): rows are [pos3 quat4 omega3 vel3 q[A] qd[A]]. */

@@ -8,15 +8,22 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MB200_LIB") or os.path.join(_HERE, "libmocca_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in
-           ("mb200.cu", "mb_core.cuh", "mb_env.cuh", "mb_tables.h", "generated/walker3d_model.h",
-            "generated/monkey3d_model.h", "generated/cassie_model.h", "generated/child3d_model.h",
-            "generated/mike_model.h", "generated/walker2d_model.h", "generated/crab2d_model.h")]
+CSRC = os.path.join(_HERE, "csrc")
+# one translation unit per env kind (csrc/kinds/<kind>.cu = model table + MB_DEFINE_KIND) + the C ABI (mb200.cu)
+KINDS = {
+    "walker3d_custom": "walker3d", "walker3d_stepper": "walker3d", "walker3d_stepper_pillar": "walker3d",
+    "monkey3d_custom": "monkey3d", "cassie": "cassie", "child3d_custom": "child3d", "walker2d_custom": "walker2d",
+    "crab2d_custom": "crab2d", "mike_stepper": "mike", "mike_stepper_pillar": "mike",
+}
+COMMON = [os.path.join(CSRC, f) for f in ("mb_core.cuh", "mb_env.cuh", "mb_kind.cuh", "mb_tables.h")] + [
+    os.path.join(os.path.dirname(_HERE), "include", "mocca_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
+BUILD_DIR = os.path.join(_HERE, "build")
 
 SYMBOLS = [
     "mb200_default_physics", "mb200_default_physics_for", "mb200_create", "mb200_destroy", "mb200_dims", "mb200_seed", "mb200_reset",
+    "mb200_reset_host", "mb200_info", "mb200_info_host",
     "mb200_step", "mb200_step_host", "mb200_get_state", "mb200_set_state", "mb200_get_record", "mb200_set_record",
     "mb200_rng_words", "mb200_get_rng", "mb200_set_rng", "mb200_step_physics", "mb200_mass_matrix", "mb200_inverse_dynamics", "mb200_set_param",
     "mb200_set_param_array", "mb200_record_stride", "mb200_stats",
@@ -33,14 +40,45 @@ class Physics(C.Structure):
                 ("ground_friction", C.c_float), ("has_ground", C.c_int), ("self_collision", C.c_int)]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    stale = (not os.path.exists(LIB_PATH)) or any(
-        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in SOURCES)
-    if force or stale:
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0]]
+def _units():
+    """(source, object, dependencies) of every translation unit."""
+    units = [(os.path.join(CSRC, "mb200.cu"), os.path.join(BUILD_DIR, "mb200.o"),
+              COMMON + [os.path.join(CSRC, "generated", "walker3d_model.h")])]
+    for kind, model in KINDS.items():
+        units.append((os.path.join(CSRC, "kinds", kind + ".cu"), os.path.join(BUILD_DIR, kind + ".o"),
+                      COMMON + [os.path.join(CSRC, "generated", model + "_model.h")]))
+    return units
+
+
+def build(force: bool = False, verbose: bool = False, defines=(), lib_path: str | None = None,
+          build_dir: str | None = None) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU): the translation units in
+    parallel, then one link.  `defines` / `lib_path` / `build_dir` build an A/B variant beside the product library."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    out = lib_path or LIB_PATH
+    bdir = build_dir or BUILD_DIR
+    os.makedirs(bdir, exist_ok=True)
+    todo, objs = [], []
+    for src, obj, deps in _units():
+        obj = os.path.join(bdir, os.path.basename(obj))
+        objs.append(obj)
+        stale = (not os.path.exists(obj)) or any(
+            os.path.exists(d) and os.path.getmtime(d) > os.path.getmtime(obj) for d in [src] + deps)
+        if force or stale:
+            todo.append((src, obj))
+
+    def compile_one(so):
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + [
+            "-c", "-o", so[1], so[0]]
         subprocess.check_call(cmd)
-    return LIB_PATH
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as ex:
+            list(ex.map(compile_one, todo))
+    if todo or not os.path.exists(out):
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs)
+    return out
 
 
 _lib = None
@@ -66,6 +104,9 @@ def lib():
         L.mb200_dims.argtypes = [vp] + [C.POINTER(ip)] * 5
         L.mb200_seed.argtypes = [vp, vp, ip]
         L.mb200_reset.argtypes = [vp, vp, vp, vp]
+        L.mb200_reset_host.argtypes = [vp, vp, vp, vp]
+        L.mb200_info.argtypes = [vp, vp, vp]
+        L.mb200_info_host.argtypes = [vp, vp, vp]
         L.mb200_step.argtypes = [vp] * 8
         L.mb200_step_host.argtypes = [vp] * 7
         for f in ("mb200_get_state", "mb200_set_state", "mb200_get_record", "mb200_set_record", "mb200_mass_matrix"):

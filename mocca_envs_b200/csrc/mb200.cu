@@ -1,5 +1,8 @@
-// mb200.cu -- sm_100a kernels + the C ABI declared in include/mocca_b200.h.
+// mb200.cu -- the C ABI declared in include/mocca_b200.h over the per-kind kernel tables (csrc/kinds/*.cu).
 // One warp per environment, MB_WARPS warps per CTA; per-env working set lives in shared memory (WarpMem).
+//
+// 14 warps (envs) per CTA, 2 CTAs per SM, and one CTA barrier per substep (MB_SYNC): the barrier keeps the warps of a
+// CTA in the same phase of the (large) step code so instruction-cache lines are shared (profiles/README.md).
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -7,44 +10,9 @@
 
 #include <string>
 
-// 14 warps (envs) per CTA, 2 CTAs per SM (Monkey3D's 8 160-byte WarpMem fits with 896 bytes to spare since the
-// joint-limit list moved onto the dead tail of the kinematics scratch), and one CTA barrier per substep (MB_SYNC): the barrier keeps the warps of a CTA in the same phase of the (large) step code so
-// instruction-cache lines are shared -- measured 7.1M -> 10.1M env-steps/s at 16384 envs (profiles/README.md).
-// 28 resident warps per SM (72 registers) make 16384 envs exactly 4 waves of 148 x 28 (3.95) where 24 needed 4.6.
-// Before the WarpMem base moved to a uniform register the 72-register budget cost the larger kernels more in spills
-// than the extra warps gave; since then 14 warps win everywhere they fit: Stepper +5 %, Child3D +5.6 %, Mike +6.6 %,
-// Cassie +7.7 %, Monkey3D +10.6 % (A/B on one B200, r1s / r1t).
-#ifndef MB_WARPS_CUSTOM
-#define MB_WARPS_CUSTOM 14
-#endif
-#ifndef MB_WARPS_STEPPER
-#define MB_WARPS_STEPPER 14
-#endif
-#ifndef MB_WARPS_MONKEY
-#define MB_WARPS_MONKEY 14
-#endif
-#ifndef MB_WARPS_CASSIE
-#define MB_WARPS_CASSIE 14
-#endif
-#define MB_WARPS_MAX 16
-#define MB_WARPS ((int)(blockDim.x >> 5)) /* device code: warps of this launch */
-#ifndef MB_MINBLOCKS
-#define MB_MINBLOCKS 2
-#endif
-#ifndef MB_SYNC
-#define MB_SYNC 1
-#endif
-
 #include "../../include/mocca_b200.h"
-#include "generated/walker3d_model.h"
-#include "generated/monkey3d_model.h"
-#include "generated/cassie_model.h"
-#include "generated/child3d_model.h"
-#include "generated/walker2d_model.h"
-#include "generated/crab2d_model.h"
-#include "generated/mike_model.h"
-#include "mb_env.cuh"
-
+#include "generated/walker3d_model.h" /* only for sizing asserts; the kernels live in kinds/ */
+#include "mb_kind.cuh"
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return -1; }
@@ -57,11 +25,26 @@ static int fail(const std::string& m) { g_err = m; return -1; }
 // KIND_CHILD / KIND_MIKE run the Walker3DCustomEnv / Walker3DStepperEnv templates on other model tables
 // KIND_WALKER2D / KIND_CRAB2D: the planar walkers (free base that stays in the x-z plane) on the Walker3DCustomEnv template
 enum { KIND_CUSTOM = 0, KIND_STEPPER = 1, KIND_MONKEY = 2, KIND_CASSIE = 3, KIND_CHILD = 4, KIND_MIKE = 5,
-       KIND_WALKER2D = 6, KIND_CRAB2D = 7 };
+       KIND_WALKER2D = 6, KIND_CRAB2D = 7, KIND_COUNT };
 static bool custom_family(int kind) {
   return kind == KIND_CUSTOM || kind == KIND_CHILD || kind == KIND_WALKER2D || kind == KIND_CRAB2D;
 }
 static bool stepper_family(int kind) { return kind == KIND_STEPPER || kind == KIND_MIKE; }
+
+extern const MbKindOps mb_kind_walker3d_custom, mb_kind_walker3d_stepper, mb_kind_walker3d_stepper_pillar,
+    mb_kind_monkey3d_custom, mb_kind_cassie, mb_kind_child3d_custom, mb_kind_walker2d_custom, mb_kind_crab2d_custom,
+    mb_kind_mike_stepper, mb_kind_mike_stepper_pillar;
+// [kind][pillar]
+static const MbKindOps* const g_kinds[KIND_COUNT][2] = {
+    {&mb_kind_walker3d_custom, nullptr},
+    {&mb_kind_walker3d_stepper, &mb_kind_walker3d_stepper_pillar},
+    {&mb_kind_monkey3d_custom, nullptr},
+    {&mb_kind_cassie, nullptr},
+    {&mb_kind_child3d_custom, nullptr},
+    {&mb_kind_mike_stepper, &mb_kind_mike_stepper_pillar},
+    {&mb_kind_walker2d_custom, nullptr},
+    {&mb_kind_crab2d_custom, nullptr},
+};
 
 struct mb200_env {
   int kind;        // KIND_*
@@ -80,6 +63,8 @@ struct mb200_env {
   float* stage_rew;
   uint8_t* stage_done;
   uint8_t* stage_trunc;
+  uint8_t* stage_mask;   // mb200_reset_host
+  int* info;             // [n] per-step integer info (steps_reached), written by the step kernel
   cudaEvent_t host_done; // results of mb200_step_host have reached the host buffers
   // CTA barriers require every warp of a CTA to run: the state arrays are padded to a whole number of CTAs and
   // the pad envs ("tail") step like any other env but write their outputs/statistics to these dummies
@@ -103,100 +88,9 @@ struct mb200_env {
   long long launches;
   size_t smem;
 };
-
-typedef W3D_Model WM;
-typedef MK3D_Model MM;
-typedef W3DEnv<WM> WEnv;
-typedef StepperEnv<WM> SEnv;
-typedef MonkeyEnv<MM> MEnv;
-typedef CAS_Model CM;
-typedef CassieEnv<CM> CEnv;
-typedef W3DEnv<CH3D_Model> ChEnv;       // Child3DCustomEnv-v0 (env_locomotion.py:317-327)
-typedef W3DEnv<W2D_Model> W2Env;        // Walker2DCustomEnv-v0 (env_locomotion.py:285-310)
-typedef W3DEnv<CR2D_Model> CrEnv;       // Crab2DCustomEnv-v0 (env_locomotion.py:312-314)
-static_assert(sizeof(WarpMem<W2D_Model>) <= sizeof(WarpMem<W3D_Model>) &&
-              sizeof(WarpMem<CR2D_Model>) <= sizeof(WarpMem<W3D_Model>), "shared-memory opt-in is sized for Walker3D");
-typedef StepperEnv<MIKE_Model> MkEnv;   // MikeStepperEnv-v0 (env_locomotion.py:843-851)
-typedef StepperEnv<WM, true> SEnvP;     // plank_class = "Pillar" (bullet_objects.py:86-90): cylinder stones
-typedef StepperEnv<MIKE_Model, true> MkEnvP;
-static_assert(sizeof(WarpMem<CH3D_Model>) <= sizeof(WarpMem<WM>) && sizeof(WarpMem<MIKE_Model>) <= sizeof(WarpMem<WM>),
-              "the shared-memory opt-in of the Walker3D-family kernels is sized for the Walker3D table");
-typedef WarpMem<WM> WMem;
+static const MbKindOps* ops_of(const mb200_env* e) { return g_kinds[e->kind][e->pillar ? 1 : 0]; }
 
 // ------------------------------------------------------------------------------------------------ kernels
-struct StepArgs {
-  int n;
-  MbPhysics phys;
-  float* state;
-  float* rec;
-  uint32_t* mt;
-  const float* act;
-  float* obs;
-  float* rew;
-  uint8_t* done;
-  uint8_t* trunc;
-  float* final_obs;
-  MbStats* stats;
-  float* dummy_obs;
-  float* dummy_rew;
-  uint8_t* dummy_flag;
-  MbStats* dummy_stats;
-  const int* order;
-  int* key;
-  int* hist;  // this step's histogram half, nullptr = scheduler off
-  // mb200_step_host with pinned (device-mapped) result buffers: each warp forwards its env's finished rows from the
-  // device staging arrays to the host with coalesced zero-copy stores, so the D2H traffic overlaps the rest of the
-  // launch instead of following it; nullptr = staged cudaMemcpyAsync (pageable host memory) or device callers
-  float* host_obs;
-  float* host_rew;
-  uint8_t* host_done;
-  uint8_t* host_trunc;
-};
-
-template <class Env, bool HOST>
-__device__ __forceinline__ void step_body(const StepArgs& a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  // broadcast from lane 0: tells the compiler the warp index is warp-uniform, so the WarpMem base lives in a uniform
-  // register instead of being re-derived from threadIdx (3-4 % of the issued instructions otherwise)
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-  Sim<typename Env::Model>::load_tables();
-  const int env = a.order[blockIdx.x * MB_WARPS + warp];  // a permutation of [0, n_pad)
-  const bool tail = env >= a.n;
-  typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
-  float* obs = tail ? a.dummy_obs + (size_t)warp * Env::OBS : a.obs + (size_t)env * Env::OBS;
-  float* fin = tail ? a.dummy_obs + (size_t)(MB_WARPS_MAX + warp) * Env::OBS
-                    : (a.final_obs ? a.final_obs + (size_t)env * Env::OBS : nullptr);
-  Env::step(S, a.phys, a.state + (size_t)env * MB_STATE_STRIDE, a.rec + (size_t)env * Env::REC_STRIDE,
-            a.mt + (size_t)env * 2 * MB_MT_STRIDE, a.mt + ((size_t)env * 2 + 1) * MB_MT_STRIDE,
-            a.act + (size_t)(tail ? 0 : env) * Env::ACT, obs, tail ? a.dummy_rew + warp : a.rew + env,
-            tail ? a.dummy_flag + warp : a.done + env, tail ? a.dummy_flag + MB_WARPS_MAX + warp : a.trunc + env, fin,
-            tail ? a.dummy_stats : a.stats);
-  if (HOST && !tail) {
-    // (separate kernel instantiation: the extra epilogue cost the device-buffer kernel 1 % through register
-    // allocation when it was a run-time branch)  the row is final here (auto-reset included); lanes read what other lanes of this warp wrote
-    __syncwarp();
-    const int lane = threadIdx.x & 31;
-    const float* src = a.obs + (size_t)env * Env::OBS;
-    float* dst = a.host_obs + (size_t)env * Env::OBS;
-#pragma unroll
-    for (int i = lane; i < Env::OBS; i += 32) dst[i] = __ldcg(src + i);
-    if (lane == 0) {
-      a.host_rew[env] = __ldcg(a.rew + env);
-      a.host_done[env] = __ldcg(a.done + env);
-      a.host_trunc[env] = __ldcg(a.trunc + env);
-    }
-  }
-  // work estimate for the scheduler: constraint rows of this step
-  if ((threadIdx.x & 31) == 0 && a.hist) {
-    // (taken from the step itself, not from the float running sum ER_ROWS, which stops resolving single steps after
-    // ~10^7 rows = a few hours of stepping)
-    int k = S.step_rows;
-    k = 255 - (k < 0 ? 0 : (k > 255 ? 255 : k));  // heaviest first
-    a.key[env] = k;
-    atomicAdd(&a.hist[k], 1);
-  }
-}
-
 // Second half of the counting sort (the histogram was filled by the step kernel): every CTA scans the 256 bins into
 // bin starts, then places its 256 envs with warp-aggregated global cursors.  Order inside a bin is arbitrary (pure
 // scheduling).  CTA 0 also clears the other halves of hist / cursor for the next step.
@@ -226,219 +120,6 @@ __global__ void __launch_bounds__(256) k_order_by_key(int n_pad, const int* key,
   if (k < 256 && lane == leader) off = atomicAdd(&cursor[k], __popc(peers));
   off = __shfl_sync(0xffffffffu, off, leader);
   if (k < 256) order[start[k] + off + __popc(peers & ((1u << lane) - 1u))] = e;
-}
-
-// every step kernel exists twice: NAME (device result buffers) and NAME_host (mb200_step_host with pinned host buffers:
-// the same step plus the zero-copy forwarding of the finished rows)
-#define MB_STEP_KERNEL(NAME, WARPS, ENV)                                                        \
-  __global__ void __launch_bounds__(WARPS * 32, MB_MINBLOCKS) NAME(StepArgs a) { step_body<ENV, false>(a); } \
-  __global__ void __launch_bounds__(WARPS * 32, MB_MINBLOCKS) NAME##_host(StepArgs a) { step_body<ENV, true>(a); }
-MB_STEP_KERNEL(k_step_walker3d_custom, MB_WARPS_CUSTOM, WEnv)
-MB_STEP_KERNEL(k_step_walker3d_stepper, MB_WARPS_STEPPER, SEnv)
-MB_STEP_KERNEL(k_step_monkey3d_custom, MB_WARPS_MONKEY, MEnv)
-MB_STEP_KERNEL(k_step_cassie, MB_WARPS_CASSIE, CEnv)
-MB_STEP_KERNEL(k_step_child3d_custom, MB_WARPS_STEPPER, ChEnv)
-MB_STEP_KERNEL(k_step_walker2d_custom, MB_WARPS_STEPPER, W2Env)
-MB_STEP_KERNEL(k_step_crab2d_custom, MB_WARPS_STEPPER, CrEnv)
-MB_STEP_KERNEL(k_step_mike_stepper, MB_WARPS_STEPPER, MkEnv)
-MB_STEP_KERNEL(k_step_walker3d_stepper_pillar, MB_WARPS_STEPPER, SEnvP)
-MB_STEP_KERNEL(k_step_mike_stepper_pillar, MB_WARPS_STEPPER, MkEnvP)
-
-template <class Env>
-__device__ __forceinline__ void reset_body(int n, const MbPhysics& phys, float* state, float* rec, uint32_t* mt,
-                                           const uint8_t* mask, float* obs, float* dummy_obs) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5;
-  const int env = blockIdx.x * MB_WARPS + warp;
-  const bool tail = env >= n;
-  if (!tail && mask && !mask[env]) return;  // no CTA barrier inside reset, early exit is fine
-  typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
-  Env::reset(S, phys, rec + (size_t)env * Env::REC_STRIDE, mt + (size_t)env * 2 * MB_MT_STRIDE,
-             mt + ((size_t)env * 2 + 1) * MB_MT_STRIDE,
-             tail ? dummy_obs + (size_t)warp * Env::OBS : obs + (size_t)env * Env::OBS);
-  Env::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_reset_walker3d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
-                            float* obs, float* dummy_obs) {
-  reset_body<WEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_reset_walker3d_stepper(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
-                             float* obs, float* dummy_obs) {
-  reset_body<SEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_reset_monkey3d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
-                            float* obs, float* dummy_obs) {
-  reset_body<MEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_reset_cassie(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask, float* obs,
-                   float* dummy_obs) {
-  reset_body<CEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_reset_child3d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
-                           float* obs, float* dummy_obs) {
-  reset_body<ChEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_reset_walker2d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
-                           float* obs, float* dummy_obs) {
-  reset_body<W2Env>(n, phys, state, rec, mt, mask, obs, dummy_obs);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_reset_crab2d_custom(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
-                           float* obs, float* dummy_obs) {
-  reset_body<CrEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_reset_mike_stepper(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
-                         float* obs, float* dummy_obs) {
-  reset_body<MkEnv>(n, phys, state, rec, mt, mask, obs, dummy_obs);
-}
-
-// stepSimulation only; rec (may be NULL) supplies the static obstacles of the env kind
-template <class Env>
-__device__ __forceinline__ void physics_body(int n, const MbPhysics& phys, float* state, const float* rec,
-                                             const float* tau, int* rows_out, int* contacts_out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5;
-  const int env = blockIdx.x * MB_WARPS + warp;
-  const bool tail = env >= n;  // pad env: steps with zero torque, outputs discarded
-  typedef typename Env::Model EM;
-  Sim<EM>::load_tables();
-  typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
-  Env::load_state(S, state + (size_t)env * MB_STATE_STRIDE);
-  MB_LANES(l)
-    if (l < EM::NJ) S.tau[l] = tail ? 0.0f : tau[(size_t)env * EM::NJ + l];
-  MB_END
-  int rows = 0, nc = 0, overflow = 0;
-  typename Sim<EM>::LaneConst C;
-  Sim<EM>::init_lane_const(C);
-#pragma unroll 1
-  for (int k = 0; k < phys.substeps; ++k) {
-    Env::load_obstacles(S, rec + (size_t)env * Env::REC_STRIDE);
-    rows += Sim<EM>::template substep<Env::OBST>(S, phys, C, &nc, &overflow);
-  }
-  Env::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
-  if (tail) return;
-  if ((threadIdx.x & 31) == 0) {
-    if (rows_out) rows_out[env] = rows;
-    if (contacts_out) contacts_out[env] = nc;
-  }
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_step_physics_walker3d(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
-                            int* contacts_out) {
-  physics_body<WEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_step_physics_walker3d_stepper(int n, MbPhysics phys, float* state, const float* rec, const float* tau,
-                                    int* rows_out, int* contacts_out) {
-  physics_body<SEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_step_physics_monkey3d(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
-                            int* contacts_out) {
-  physics_body<MEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_step_physics_cassie(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
-                          int* contacts_out) {
-  physics_body<CEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_step_physics_child3d(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
-                           int* contacts_out) {
-  physics_body<ChEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_step_physics_walker2d(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
-                           int* contacts_out) {
-  physics_body<W2Env>(n, phys, state, rec, tau, rows_out, contacts_out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_step_physics_crab2d(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,
-                           int* contacts_out) {
-  physics_body<CrEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_step_physics_mike_stepper(int n, MbPhysics phys, float* state, const float* rec, const float* tau,
-                                int* rows_out, int* contacts_out) {
-  physics_body<MkEnv>(n, phys, state, rec, tau, rows_out, contacts_out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_step_physics_walker3d_stepper_pillar(int n, MbPhysics phys, float* state, const float* rec, const float* tau,
-                                           int* rows_out, int* contacts_out) {
-  physics_body<SEnvP>(n, phys, state, rec, tau, rows_out, contacts_out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_step_physics_mike_stepper_pillar(int n, MbPhysics phys, float* state, const float* rec, const float* tau,
-                                       int* rows_out, int* contacts_out) {
-  physics_body<MkEnvP>(n, phys, state, rec, tau, rows_out, contacts_out);
-}
-
-// mode 0: M (full symmetric, [nu][nu]);  mode 1: tau = M acc - rhs (rhs = -bias with zero applied torque)
-template <class Env>
-__device__ __forceinline__ void dynamics_debug_body(int n, const MbPhysics& phys, const float* state, int mode,
-                                                    const float* acc, float* out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  typedef typename Env::Model EM;
-  const int warp = threadIdx.x >> 5;
-  const int env = blockIdx.x * MB_WARPS + warp;
-  if (env >= n) return;
-  typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
-  const int NU = EM::NU;
-  Env::load_state(S, state + (size_t)env * MB_STATE_STRIDE);
-  MB_LANES(l)
-    S.tau[l] = 0.0f;
-  MB_END
-  typename Sim<EM>::LaneConst C;
-  Sim<EM>::init_lane_const(C);
-  Sim<EM>::kinematics(S, phys, C, true);
-  Sim<EM>::bodies(S, phys);
-  Sim<EM>::mass_matrix_and_rhs(S);
-  MB_LANES(l)
-    if (l < NU) {
-      if (mode == 0) {
-        for (int j = 0; j < NU; ++j) out[((size_t)env * NU + l) * NU + j] = mb_Lget<EM>(S.L, l, j);
-      } else {
-        float t = -S.rhs[l];
-        for (int j = 0; j < NU; ++j) t += mb_Lget<EM>(S.L, l, j) * acc[(size_t)env * NU + j];
-        out[(size_t)env * NU + l] = t;
-      }
-    }
-  MB_END
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_dynamics_debug_walker3d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
-  dynamics_debug_body<WEnv>(n, phys, state, mode, acc, out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_dynamics_debug_monkey3d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
-  dynamics_debug_body<MEnv>(n, phys, state, mode, acc, out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_dynamics_debug_cassie(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
-  dynamics_debug_body<CEnv>(n, phys, state, mode, acc, out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_dynamics_debug_child3d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
-  dynamics_debug_body<ChEnv>(n, phys, state, mode, acc, out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_dynamics_debug_walker2d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
-  dynamics_debug_body<W2Env>(n, phys, state, mode, acc, out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_dynamics_debug_crab2d(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
-  dynamics_debug_body<CrEnv>(n, phys, state, mode, acc, out);
-}
-__global__ void __launch_bounds__(MB_WARPS_MAX * 32)
-    k_dynamics_debug_mike(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {
-  dynamics_debug_body<MkEnv>(n, phys, state, mode, acc, out);
 }
 
 __global__ void k_copy_strided(int n, int width, const float* src, int src_stride, float* dst, int dst_stride) {
@@ -507,6 +188,8 @@ static void to_internal(const mb200_physics& p, MbPhysics* q) {
 
 static int grid_for(const mb200_env* e) { return (e->n + e->warps - 1) / e->warps; }
 
+void mb200_destroy(mb200_env* e);
+
 int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics* physics, mb200_env** out) {
   if (!out) return fail("mb200_create: out is NULL");
   *out = nullptr;
@@ -539,18 +222,10 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   e->device = device;
   e->kind = kind;
   e->pillar = false;
-  int nj = WM::NJ;
-  switch (kind) {
-    case KIND_MIKE:
-    case KIND_STEPPER: e->rec_stride = SEnv::REC_STRIDE; e->obs_dim = SEnv::OBS; e->act_dim = SEnv::ACT; break;
-    case KIND_MONKEY: e->rec_stride = MEnv::REC_STRIDE; e->obs_dim = MEnv::OBS; e->act_dim = MEnv::ACT; nj = MM::NJ; break;
-    case KIND_WALKER2D: e->rec_stride = W2Env::REC_STRIDE; e->obs_dim = W2Env::OBS; e->act_dim = W2Env::ACT; nj = W2D_Model::NJ; break;
-    case KIND_CRAB2D: e->rec_stride = CrEnv::REC_STRIDE; e->obs_dim = CrEnv::OBS; e->act_dim = CrEnv::ACT; nj = CR2D_Model::NJ; break;
-    case KIND_CASSIE: e->rec_stride = CEnv::REC_STRIDE; e->obs_dim = CEnv::OBS; e->act_dim = CEnv::ACT; nj = CM::NJ; break;
-    default: e->rec_stride = WEnv::REC_STRIDE; e->obs_dim = WEnv::OBS; e->act_dim = WEnv::ACT; break;
-  }
-  e->warps = kind == KIND_MONKEY ? MB_WARPS_MONKEY : kind == KIND_CASSIE ? MB_WARPS_CASSIE
-             : kind == KIND_CUSTOM ? MB_WARPS_CUSTOM : MB_WARPS_STEPPER;
+  const MbKindOps* K = g_kinds[kind][0];
+  const int nj = K->nj;
+  e->rec_stride = K->rec_stride; e->obs_dim = K->obs_dim; e->act_dim = K->act_dim;
+  e->warps = K->warps;
   {
     // Small batches: with 14-warp CTAs 1 024 envs occupy 74 of the 148 SMs and the step takes the latency of one
     // env-step; narrower CTAs spread the envs over every SM (2 resident CTAs each).  Pure scheduling (MB_WARPS is the
@@ -561,8 +236,7 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
     if (w < e->warps) e->warps = w;
     if (const char* ov = getenv("MB200_WARPS")) {
       const int v = atoi(ov);
-      if (v >= 1 && v <= e->warps) e->warps = v;
-      else if (v > e->warps && v <= MB_WARPS_MAX && kind != KIND_MONKEY) e->warps = v;
+      if (v >= 1 && v <= e->warps) e->warps = v;  // never above the launch bounds the step kernels were compiled with
     }
   }
   e->state_dim = 13 + 2 * nj;
@@ -581,64 +255,22 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
     e->phys.box_erp = e->phys.dt * kp / denom;
     e->phys.box_cfm = 1.0f / denom;
   }
-  e->smem = (kind == KIND_MONKEY ? sizeof(WarpMem<MM>) : kind == KIND_CASSIE ? sizeof(WarpMem<CM>)
-             : kind == KIND_WALKER2D ? sizeof(WarpMem<W2D_Model>) : kind == KIND_CRAB2D ? sizeof(WarpMem<CR2D_Model>)
-             : kind == KIND_CHILD ? sizeof(WarpMem<CH3D_Model>) : kind == KIND_MIKE ? sizeof(WarpMem<MIKE_Model>)
-             : sizeof(WMem)) * e->warps;
-  {
-    // opt every kernel in to the largest dynamic shared memory any env kind may launch it with (several env kinds
-    // can live in one process; the attribute is per kernel, not per handle)
-    const int sw = (int)(sizeof(WMem) * MB_WARPS_MAX), sm = (int)(sizeof(WarpMem<MM>) * MB_WARPS_MAX),
-              sc = (int)(sizeof(WarpMem<CM>) * MB_WARPS_MAX);
-    const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    CUDA_OK(cudaFuncSetAttribute(k_step_cassie, at, sc));
-    CUDA_OK(cudaFuncSetAttribute(k_step_cassie_host, at, sc));
-    CUDA_OK(cudaFuncSetAttribute(k_reset_cassie, at, sc));
-    CUDA_OK(cudaFuncSetAttribute(k_step_physics_cassie, at, sc));
-    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_cassie, at, sc));
-    CUDA_OK(cudaFuncSetAttribute(k_step_monkey3d_custom, at, sm));
-    CUDA_OK(cudaFuncSetAttribute(k_step_monkey3d_custom_host, at, sm));
-    CUDA_OK(cudaFuncSetAttribute(k_reset_monkey3d_custom, at, sm));
-    CUDA_OK(cudaFuncSetAttribute(k_step_physics_monkey3d, at, sm));
-    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_monkey3d, at, sm));
-    CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_stepper, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_stepper_host, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_reset_walker3d_stepper, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d_stepper, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_custom, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_custom_host, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_reset_walker3d_custom, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_walker3d, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_child3d_custom, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_walker2d_custom, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_crab2d_custom, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_child3d_custom_host, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_walker2d_custom_host, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_crab2d_custom_host, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_reset_child3d_custom, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_reset_walker2d_custom, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_reset_crab2d_custom, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_physics_child3d, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker2d, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_physics_crab2d, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_child3d, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_walker2d, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_crab2d, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_mike_stepper, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_mike_stepper_host, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_reset_mike_stepper, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_physics_mike_stepper, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_dynamics_debug_mike, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_stepper_pillar, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_walker3d_stepper_pillar_host, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_physics_walker3d_stepper_pillar, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_mike_stepper_pillar, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_mike_stepper_pillar_host, at, sw));
-    CUDA_OK(cudaFuncSetAttribute(k_step_physics_mike_stepper_pillar, at, sw));
-  }
+  e->smem = K->smem_per_env * e->warps;
+  // opt every kernel of the kind in to the dynamic shared memory of a full-width CTA (the attribute is per kernel, not
+  // per handle, and several env kinds can live in one process)
+  for (int v = 0; v < 2; ++v)
+    if (g_kinds[kind][v]) {
+      const cudaError_t pe = g_kinds[kind][v]->prepare();
+      if (pe != cudaSuccess) { delete e; return fail(std::string("mb200_create: shared-memory opt-in: ") + cudaGetErrorString(pe)); }
+    }
   e->n_pad = grid_for(e) * e->warps;
   const size_t n = (size_t)e->n_pad;
+#undef CUDA_OK
+#define CUDA_OK(x)                                                                                       \
+  do {                                                                                                   \
+    cudaError_t e_ = (x);                                                                                \
+    if (e_ != cudaSuccess) { mb200_destroy(e); return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } \
+  } while (0)
   CUDA_OK(cudaMalloc(&e->dummy_obs, (size_t)2 * MB_WARPS_MAX * e->obs_dim * sizeof(float)));
   CUDA_OK(cudaMalloc(&e->dummy_rew, MB_WARPS_MAX * sizeof(float)));
   CUDA_OK(cudaMalloc(&e->dummy_flag, 2 * MB_WARPS_MAX));
@@ -657,7 +289,7 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   CUDA_OK(cudaMemset(e->cursor, 0, 2 * 256 * sizeof(int)));
   {
     int* ident = (int*)malloc(n * sizeof(int));
-    if (!ident) return fail("mb200_create: host allocation failed");
+    if (!ident) { mb200_destroy(e); return fail("mb200_create: host allocation failed"); }
     for (size_t i = 0; i < n; ++i) ident[i] = (int)i;
     cudaError_t ce = cudaMemcpy(e->order, ident, n * sizeof(int), cudaMemcpyHostToDevice);
     free(ident);
@@ -675,6 +307,15 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   CUDA_OK(cudaMemset(e->rec, 0, n * e->rec_stride * sizeof(float)));
   CUDA_OK(cudaMemset(e->mt, 0, n * 2 * MB_MT_STRIDE * sizeof(uint32_t)));
   CUDA_OK(cudaMemset(e->stats, 0, sizeof(MbStats)));
+  CUDA_OK(cudaMalloc(&e->stage_mask, n));
+  CUDA_OK(cudaMalloc(&e->info, n * sizeof(int)));
+  CUDA_OK(cudaMemset(e->info, 0xff, n * sizeof(int)));
+#undef CUDA_OK
+#define CUDA_OK(x)                                                                                       \
+  do {                                                                                                   \
+    cudaError_t e_ = (x);                                                                                \
+    if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_));                 \
+  } while (0)
   *out = e;
   return 0;
 }
@@ -684,8 +325,8 @@ void mb200_destroy(mb200_env* e) {
   cudaSetDevice(e->device);
   cudaFree(e->state); cudaFree(e->rec); cudaFree(e->mt); cudaFree(e->stats);
   cudaFree(e->stage_act); cudaFree(e->stage_obs); cudaFree(e->stage_rew); cudaFree(e->stage_done);
-  cudaFree(e->stage_trunc);
-  cudaEventDestroy(e->host_done);
+  cudaFree(e->stage_trunc); cudaFree(e->stage_mask); cudaFree(e->info);
+  if (e->host_done) cudaEventDestroy(e->host_done);
   cudaFree(e->dummy_obs); cudaFree(e->dummy_rew); cudaFree(e->dummy_flag); cudaFree(e->dummy_stats);
   cudaFree(e->order); cudaFree(e->key); cudaFree(e->hist); cudaFree(e->cursor);
   delete e;
@@ -747,32 +388,51 @@ int mb200_seed(mb200_env* e, const uint32_t* mt_host, int at_construction) {
 int mb200_reset(mb200_env* e, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (!e || !obs_dev) return fail("mb200_reset: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
-  if (e->kind == KIND_CASSIE)
-    k_reset_cassie<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
-  else if (e->kind == KIND_MONKEY)
-    k_reset_monkey3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
-  else if (e->kind == KIND_CHILD)
-    k_reset_child3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
-  else if (e->kind == KIND_WALKER2D)
-    k_reset_walker2d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
-  else if (e->kind == KIND_CRAB2D)
-    k_reset_crab2d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
-  else if (e->kind == KIND_MIKE)
-    k_reset_mike_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
-  else if (e->kind == KIND_STEPPER)
-    k_reset_walker3d_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
-  else
-    k_reset_walker3d_custom<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
+  const LaunchDims d = {grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream};
+  ops_of(e)->reset(d, e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
   e->launches++;
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Env.reset with HOST buffers (what a gym user holds): mask_host NULL = all envs.  Only the rows of the envs that
+// were reset are written to obs_host.  Synchronous.
+int mb200_reset_host(mb200_env* e, const uint8_t* mask_host, float* obs_host, void* stream) {
+  if (!e || !obs_host) return fail("mb200_reset_host: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)e->n, row = (size_t)e->obs_dim * sizeof(float);
+  if (mask_host) CUDA_OK(cudaMemcpyAsync(e->stage_mask, mask_host, n, cudaMemcpyHostToDevice, st));
+  if (mb200_reset(e, mask_host ? e->stage_mask : nullptr, e->stage_obs, stream)) return -1;
+  if (!mask_host) {
+    CUDA_OK(cudaMemcpyAsync(obs_host, e->stage_obs, n * row, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+  }
+  float* tmp = (float*)malloc(n * row);
+  if (!tmp) return fail("mb200_reset_host: host allocation failed");
+  cudaError_t ce = cudaMemcpyAsync(tmp, e->stage_obs, n * row, cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) { free(tmp); return fail(std::string("mb200_reset_host: ") + cudaGetErrorString(ce)); }
+  for (size_t i = 0; i < n; ++i)
+    if (mask_host[i]) memcpy(obs_host + i * e->obs_dim, tmp + i * e->obs_dim, row);
+  free(tmp);
+  return 0;
+}
+
+// info dict of the last mb200_step / mb200_step_host as integers, one per env: Walker3DStepperEnv / MikeStepperEnv
+// info["steps_reached"] (env_locomotion.py:505-506; -1 = the step did not report it), -1 for the other envs.
+int mb200_info(mb200_env* e, int* info_dev, void* stream) {
+  if (!e || !info_dev) return fail("mb200_info: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaMemcpyAsync(info_dev, e->info, (size_t)e->n * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+int mb200_info_host(mb200_env* e, int* info_host, void* stream) {
+  if (!e || !info_host) return fail("mb200_info_host: NULL argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaMemcpyAsync(info_host, e->info, (size_t)e->n * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
 }
 
@@ -811,31 +471,9 @@ static int step_impl(mb200_env* e, const float* act_dev, float* obs_dev, float* 
   a.hist = sorting(e) ? e->hist + 256 * (int)(e->steps & 1) : nullptr;
   a.host_obs = host ? host->obs : nullptr; a.host_rew = host ? host->rew : nullptr;
   a.host_done = host ? host->done : nullptr; a.host_trunc = host ? host->trunc : nullptr;
-#define MB_LAUNCH_STEP(NAME)                                                                   \
-  do {                                                                                         \
-    if (host) NAME##_host<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);   \
-    else NAME<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(a);               \
-  } while (0)
-  if (e->kind == KIND_CASSIE)
-    MB_LAUNCH_STEP(k_step_cassie);
-  else if (e->kind == KIND_MONKEY)
-    MB_LAUNCH_STEP(k_step_monkey3d_custom);
-  else if (e->kind == KIND_CHILD)
-    MB_LAUNCH_STEP(k_step_child3d_custom);
-  else if (e->kind == KIND_WALKER2D)
-    MB_LAUNCH_STEP(k_step_walker2d_custom);
-  else if (e->kind == KIND_CRAB2D)
-    MB_LAUNCH_STEP(k_step_crab2d_custom);
-  else if (e->kind == KIND_MIKE && e->pillar)
-    MB_LAUNCH_STEP(k_step_mike_stepper_pillar);
-  else if (e->kind == KIND_MIKE)
-    MB_LAUNCH_STEP(k_step_mike_stepper);
-  else if (e->kind == KIND_STEPPER && e->pillar)
-    MB_LAUNCH_STEP(k_step_walker3d_stepper_pillar);
-  else if (e->kind == KIND_STEPPER)
-    MB_LAUNCH_STEP(k_step_walker3d_stepper);
-  else
-    MB_LAUNCH_STEP(k_step_walker3d_custom);
+  a.info = e->info;
+  const LaunchDims d = {grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream};
+  ops_of(e)->step(a, host != nullptr, d);
   e->launches++;
   e->steps++;
   CUDA_OK(cudaGetLastError());
@@ -956,36 +594,8 @@ int mb200_set_rng(mb200_env* e, const uint32_t* mt_host) {
 int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* contacts_dev, void* stream) {
   if (!e || !tau_dev) return fail("mb200_step_physics: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
-  if (e->kind == KIND_CASSIE)
-    k_step_physics_cassie<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
-  else if (e->kind == KIND_MONKEY)
-    k_step_physics_monkey3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
-  else if (e->kind == KIND_CHILD)
-    k_step_physics_child3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
-  else if (e->kind == KIND_WALKER2D)
-    k_step_physics_walker2d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
-  else if (e->kind == KIND_CRAB2D)
-    k_step_physics_crab2d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
-  else if (e->kind == KIND_MIKE && e->pillar)
-    k_step_physics_mike_stepper_pillar<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
-  else if (e->kind == KIND_MIKE)
-    k_step_physics_mike_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
-  else if (e->kind == KIND_STEPPER && e->pillar)
-    k_step_physics_walker3d_stepper_pillar<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
-  else if (e->kind == KIND_STEPPER)
-    k_step_physics_walker3d_stepper<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
-  else
-    k_step_physics_walker3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
+  const LaunchDims d = {grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream};
+  ops_of(e)->physics(d, e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
   e->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -994,27 +604,8 @@ int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* c
 int mb200_mass_matrix(mb200_env* e, float* M_dev, void* stream) {
   if (!e || !M_dev) return fail("mb200_mass_matrix: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
-  if (e->kind == KIND_CASSIE)
-    k_dynamics_debug_cassie<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, 0, nullptr, M_dev);
-  else if (e->kind == KIND_MONKEY)
-    k_dynamics_debug_monkey3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, 0, nullptr, M_dev);
-  else if (e->kind == KIND_CHILD)
-    k_dynamics_debug_child3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, 0, nullptr, M_dev);
-  else if (e->kind == KIND_WALKER2D)
-    k_dynamics_debug_walker2d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, 0, nullptr, M_dev);
-  else if (e->kind == KIND_CRAB2D)
-    k_dynamics_debug_crab2d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, 0, nullptr, M_dev);
-  else if (e->kind == KIND_MIKE)
-    k_dynamics_debug_mike<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, 0, nullptr, M_dev);
-  else
-    k_dynamics_debug_walker3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, e->phys, e->state, 0, nullptr, M_dev);
+  const LaunchDims d = {grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream};
+  ops_of(e)->debug(d, e->n, e->phys, e->state, 0, nullptr, M_dev);
   e->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -1026,27 +617,8 @@ int mb200_inverse_dynamics(mb200_env* e, const float* acc_dev, float* tau_dev, v
   MbPhysics p = e->phys;
   p.lin_damping = 0.0f;  // calculateInverseDynamics has no velocity-damping term
   p.ang_damping = 0.0f;
-  if (e->kind == KIND_CASSIE)
-    k_dynamics_debug_cassie<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, p, e->state, 1, acc_dev, tau_dev);
-  else if (e->kind == KIND_MONKEY)
-    k_dynamics_debug_monkey3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, p, e->state, 1, acc_dev, tau_dev);
-  else if (e->kind == KIND_CHILD)
-    k_dynamics_debug_child3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, p, e->state, 1, acc_dev, tau_dev);
-  else if (e->kind == KIND_WALKER2D)
-    k_dynamics_debug_walker2d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, p, e->state, 1, acc_dev, tau_dev);
-  else if (e->kind == KIND_CRAB2D)
-    k_dynamics_debug_crab2d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, p, e->state, 1, acc_dev, tau_dev);
-  else if (e->kind == KIND_MIKE)
-    k_dynamics_debug_mike<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, p, e->state, 1, acc_dev, tau_dev);
-  else
-    k_dynamics_debug_walker3d<<<grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream>>>(
-        e->n, p, e->state, 1, acc_dev, tau_dev);
+  const LaunchDims d = {grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream};
+  ops_of(e)->debug(d, e->n, p, e->state, 1, acc_dev, tau_dev);
   e->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

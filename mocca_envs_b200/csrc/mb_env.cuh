@@ -154,7 +154,7 @@ template <class M> struct W3DEnv {
   typedef Sim<M> S_;
   typedef M Model;
   enum { NJ = M::NJ, NU = M::NU, OBS = 6 + 2 * M::NJ + M::NFEET + 2, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET,
-         REC_STRIDE = MB_REC_STRIDE, OBST = 0, ACT = M::NJ };
+         REC_STRIDE = MB_REC_STRIDE, OBST = 0, ACT = M::NJ, INFO_FIELD = -1 };
   MB_HD static void load_obstacles(WarpMem<M>&, const float*) {}
 
   // HBM <-> shared
@@ -257,15 +257,18 @@ template <class M> struct W3DEnv {
     MB_END
   }
 
-  // env_locomotion.py:67-74 -- consumes 5 words of the env stream
+  // env_locomotion.py:67-74 -- consumes target_words() words of the env stream: two uniforms (2 words each) and the
+  // choice (1 word); in eval mode the uniforms are not drawn and the choice is the first word
+  MB_HD static int target_words(const float* rec) { return rec_i(rec, ER_EVAL) ? 1 : 5; }
   MB_HD static void randomize_target(float* rec, const uint32_t* w, double* dist, double* angle) {
-    if (rec_i(rec, ER_EVAL)) { *dist = 4.0; *angle = 0.0; }
+    const bool ev = rec_i(rec, ER_EVAL) != 0;
+    if (ev) { *dist = 4.0; *angle = 0.0; }
     else {
       *dist = 3.0 + (5.0 - 3.0) * mt_double(w);
       const double lo = -3.14159265358979323846 / 2, hi = 3.14159265358979323846 / 2;
       *angle = lo + (hi - lo) * mt_double(w + 2);
     }
-    const float stop = (w[4] & 1u) ? 60.0f : 30.0f;
+    const float stop = (w[ev ? 0 : 4] & 1u) ? 60.0f : 30.0f;
     MB_LANES(l)
       if (l == 0) { rec[ER_DIST] = (float)*dist; rec[ER_ANGLE] = (float)*angle; rec[ER_STOP] = stop; }
     MB_END
@@ -275,12 +278,12 @@ template <class M> struct W3DEnv {
   MB_HD static void reset(Mem& S, const MbPhysics& P, float* rec, uint32_t* mt_env, uint32_t* mt_robot, float* obs) {
     uint32_t* w = reinterpret_cast<uint32_t*>(S.rc.scratch);
     const int aliased = rec_i(rec, ER_ALIASED);
-    const int nrobot = 2 + 2 * NJ;
-    if (aliased) mt_fill(mt_env, w, 5 + nrobot);
-    else { mt_fill(mt_env, w, 5); mt_fill(mt_robot, w + 5, nrobot); }
+    const int nrobot = 2 + 2 * NJ, nt = target_words(rec);
+    if (aliased) mt_fill(mt_env, w, nt + nrobot);
+    else { mt_fill(mt_env, w, nt); mt_fill(mt_robot, w + nt, nrobot); }
     double dist, angle;
     randomize_target(rec, w, &dist, &angle);
-    const uint32_t* wr = w + 5;
+    const uint32_t* wr = w + nt;
     const int mirrored = mt_double(wr) < 0.5;
     MB_LANES(l)
       if (l == 0) {
@@ -409,7 +412,7 @@ template <class M> struct W3DEnv {
       // env_locomotion.py:214-222 -- re-sample the target mid-episode from the env stream
       close = 0;
       uint32_t* w = reinterpret_cast<uint32_t*>(S.rc.scratch);
-      mt_fill(mt_env, w, 5);
+      mt_fill(mt_env, w, target_words(rec));
       double nd, na;
       randomize_target(rec, w, &nd, &na);
       MB_LANES(l)
@@ -430,7 +433,14 @@ template <class M> struct W3DEnv {
         rec[ER_BODYX] = S.pos[0];
         rec[ER_EPRET] = epret; rec_i(rec, ER_EPLEN) = eplen;
         rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum; S.step_rows = rows;
-        rec_i(rec, ER_OVERFLOW) += overflow;
+        if (MB_UNLIKELY(overflow > 0)) {  // contacts / rows dropped at MB_MAXC / MB_MAXROW: per env and per device
+          rec_i(rec, ER_OVERFLOW) += overflow;
+#ifdef __CUDACC__
+          atomicAdd(&stats->overflow, (unsigned long long)overflow);
+#else
+          stats->overflow += overflow;
+#endif
+        }
         *rew = reward; *done = (uint8_t)any_done; *trunc = (uint8_t)truncated;
       }
     MB_END
@@ -481,7 +491,8 @@ template <class M, bool PILLAR = false> struct StepperEnv {
   typedef W3DEnv<M> B_;
   typedef M Model;
   enum { NJ = M::NJ, NU = M::NU, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET, OBS = ROBOT_OBS + 15, NSTEPS = 20,
-         REC_STRIDE = MB_REC_STRIDE_STEPPER, OBST = PILLAR ? MB_OBST_CYLS : MB_OBST_BOXES, ACT = M::NJ };
+         REC_STRIDE = MB_REC_STRIDE_STEPPER, OBST = PILLAR ? MB_OBST_CYLS : MB_OBST_BOXES, ACT = M::NJ,
+         INFO_FIELD = ES_STEPS_REACHED };
   MB_HD static void load_obstacles(Mem& S, const float* rec) { load_boxes(S, rec); }
   MB_HD static void load_state(Mem& S, const float* st) { B_::load_state(S, st); }
   MB_HD static void store_state(const Mem& S, float* st) { B_::store_state(S, st); }
@@ -793,7 +804,14 @@ template <class M, bool PILLAR = false> struct StepperEnv {
         rec[ER_LINPOT] = lp; rec_i(rec, ER_ELAPSED) = elapsed;
         rec[ER_EPRET] = epret; rec_i(rec, ER_EPLEN) = eplen;
         rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum; S.step_rows = rows;
-        rec_i(rec, ER_OVERFLOW) += overflow;
+        if (MB_UNLIKELY(overflow > 0)) {  // contacts / rows dropped at MB_MAXC / MB_MAXROW: per env and per device
+          rec_i(rec, ER_OVERFLOW) += overflow;
+#ifdef __CUDACC__
+          atomicAdd(&stats->overflow, (unsigned long long)overflow);
+#else
+          stats->overflow += overflow;
+#endif
+        }
         rec_i(rec, ES_STEPS_REACHED) = (env_done || timestep == 999) ? next : -1;
         *rew = reward; *done = (uint8_t)any_done; *trunc = (uint8_t)truncated;
       }
@@ -869,7 +887,7 @@ template <class M> struct MonkeyEnv {
   typedef W3DEnv<M> B_;
   typedef M Model;
   enum { NJ = M::NJ, NU = M::NU, ROBOT_OBS = 6 + 2 * M::NJ + M::NFEET, OBS = ROBOT_OBS + 15, NSTEPS = 32, NBARS = 4,
-         REC_STRIDE = MB_REC_STRIDE_MONKEY, OBST = MB_OBST_BARS, ACT = M::NJ };
+         REC_STRIDE = MB_REC_STRIDE_MONKEY, OBST = MB_OBST_BARS, ACT = M::NJ, INFO_FIELD = -1 };
   MB_HD static void load_obstacles(Mem& S, const float* rec) { load_bars(S, rec); }
   MB_HD static void load_state(Mem& S, const float* st) { B_::load_state(S, st); }
   MB_HD static void store_state(const Mem& S, float* st) { B_::store_state(S, st); }
@@ -1160,7 +1178,14 @@ template <class M> struct MonkeyEnv {
         rec[EM_SWINGPOT] = sp; rec_i(rec, EM_FREEFALL) = freefall; rec_i(rec, ER_ELAPSED) = elapsed;
         rec[ER_EPRET] = epret; rec_i(rec, ER_EPLEN) = eplen;
         rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum; S.step_rows = rows;
-        rec_i(rec, ER_OVERFLOW) += overflow;
+        if (MB_UNLIKELY(overflow > 0)) {  // contacts / rows dropped at MB_MAXC / MB_MAXROW: per env and per device
+          rec_i(rec, ER_OVERFLOW) += overflow;
+#ifdef __CUDACC__
+          atomicAdd(&stats->overflow, (unsigned long long)overflow);
+#else
+          stats->overflow += overflow;
+#endif
+        }
         *rew = reward; *done = (uint8_t)any_done; *trunc = (uint8_t)truncated;
       }
     MB_END
@@ -1212,7 +1237,7 @@ template <class M> struct CassieEnv {
   typedef W3DEnv<M> B_;
   typedef M Model;
   enum { NJ = M::NJ, NU = M::NU, NO = M::NORDERED, ROBOT_OBS = 6 + 2 * M::NORDERED, OBS = ROBOT_OBS + 2,
-         ACT = M::NPOWERED, REC_STRIDE = MB_REC_STRIDE_CASSIE, OBST = 0, LLC_FRAME_SKIP = 50 };
+         ACT = M::NPOWERED, REC_STRIDE = MB_REC_STRIDE_CASSIE, OBST = 0, LLC_FRAME_SKIP = 50, INFO_FIELD = -1 };
   MB_HD static void load_obstacles(Mem&, const float*) {}
   MB_HD static void load_state(Mem& S, const float* st) { B_::load_state(S, st); }
   MB_HD static void store_state(const Mem& S, float* st) { B_::store_state(S, st); }
@@ -1385,7 +1410,14 @@ template <class M> struct CassieEnv {
         rec_i(rec, ER_ELAPSED) = elapsed;
         rec[ER_EPRET] = epret; rec_i(rec, ER_EPLEN) = eplen;
         rec[ER_ROWS] += (float)rows; rec[ER_CONTACTS] += (float)ncsum; S.step_rows = rows;
-        rec_i(rec, ER_OVERFLOW) += overflow;
+        if (MB_UNLIKELY(overflow > 0)) {  // contacts / rows dropped at MB_MAXC / MB_MAXROW: per env and per device
+          rec_i(rec, ER_OVERFLOW) += overflow;
+#ifdef __CUDACC__
+          atomicAdd(&stats->overflow, (unsigned long long)overflow);
+#else
+          stats->overflow += overflow;
+#endif
+        }
         *rew = reward; *done = (uint8_t)any_done; *trunc = (uint8_t)truncated;
       }
     MB_END

@@ -135,6 +135,21 @@ class Walker3DCustomVecEnv:
         _lib.check(self._L.mb200_reset(self._h, _ptr(mask), _ptr(self.obs), self._stream()))
         return self.obs
 
+    def reset_host(self, mask: np.ndarray | None = None, out: np.ndarray | None = None) -> np.ndarray:
+        """Env.reset with host buffers (mb200_reset_host): no device memory on the caller's side."""
+        if out is None:
+            out = np.zeros((self.num_envs, self.obs_dim), np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        _lib.check(self._L.mb200_reset_host(self._h, None if m is None else m.ctypes.data_as(C.c_void_p),
+                                            out.ctypes.data_as(C.c_void_p), self._stream()))
+        return out
+
+    def step_info(self) -> torch.Tensor:
+        """Integer info of the last step, one per env (mb200_info): Stepper ``steps_reached`` or -1."""
+        t = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        _lib.check(self._L.mb200_info(self._h, _ptr(t), self._stream()))
+        return t
+
     def step(self, actions: torch.Tensor):
         if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
@@ -196,9 +211,22 @@ class Walker3DCustomVecEnv:
         """Complete checkpoint of the batch (physics state, bookkeeping record, RNG streams, current observation):
         a batch restored with load_state_dict continues bit-exactly."""
         return {"state": self.get_state().cpu(), "record": self.get_record().cpu(), "rng": self.get_rng(),
-                "obs": self.obs.clone().cpu()}
+                "obs": self.obs.clone().cpu(), "env_id": self.env_id, "params": self._host_params()}
+
+    def _host_params(self) -> dict:
+        """Host-side mirrors of what lives in the record (re-applied through mb200_set_param on load, because the
+        library keeps its own copies: e.g. which stepper kernel instantiation to launch)."""
+        return {"eval_mode": bool(self.eval_mode)}
+
+    def _apply_host_params(self, params: dict):
+        if params.get("eval_mode"):
+            self.evaluation_mode()
 
     def load_state_dict(self, d):
+        if d.get("env_id", self.env_id) != self.env_id:
+            raise ValueError("checkpoint of %s loaded into %s" % (d["env_id"], self.env_id))
+        # parameters first (they write whole record columns), then the record itself
+        self._apply_host_params(d.get("params", {}))
         self.set_state(d["state"])
         self.set_record(d["record"])
         if "rng" in d:
@@ -304,7 +332,7 @@ class Walker3DStepperVecEnv(Walker3DCustomVecEnv):
         for k, v in params.items():
             if k != "curriculum":
                 continue
-            if np.isscalar(v):
+            if np.isscalar(v) or isinstance(v, int):
                 _lib.check(self._L.mb200_set_param(self._h, b"curriculum", float(min(int(v), self.max_curriculum))))
                 self.curriculum = min(int(v), self.max_curriculum)
             else:
@@ -316,9 +344,26 @@ class Walker3DStepperVecEnv(Walker3DCustomVecEnv):
     def evaluation_mode(self):
         raise AttributeError("Walker3DStepperEnv has no evaluation_mode (reference: only Walker3DCustomEnv)")
 
+    def _host_params(self) -> dict:
+        cur = self.curriculum
+        return {"curriculum": cur.tolist() if isinstance(cur, np.ndarray) else int(cur),
+                "random_reward": self.random_reward, "plank_class": self.plank_class}
+
+    def _apply_host_params(self, params: dict):
+        classes = {"LargePlank": 0.0, "Plank": 1.0, "Pillar": 2.0}
+        if "plank_class" in params:
+            self.plank_class = params["plank_class"]
+            _lib.check(self._L.mb200_set_param(self._h, b"plank_class", classes[self.plank_class]))
+        if "random_reward" in params:
+            self.random_reward = bool(params["random_reward"])
+            _lib.check(self._L.mb200_set_param(self._h, b"random_reward", float(self.random_reward)))
+        if "curriculum" in params:
+            self.set_env_params({"curriculum": params["curriculum"]})
+
     def steps_reached(self) -> torch.Tensor:
-        """info["steps_reached"] per env of the last step (env_locomotion.py:562-566), -1 where not reported."""
-        return self.get_record()[:, self.ES_STEPS_REACHED].contiguous().view(torch.int32)
+        """info["steps_reached"] per env of the last step (env_locomotion.py:562-566), -1 where not reported
+        (mb200_info: written by the step kernel, no record read-back)."""
+        return self.step_info()
 
     def terrain_info(self) -> torch.Tensor:
         return self.get_record()[:, self.ES_TERRAIN:self.ES_TERRAIN + 120].reshape(self.num_envs, 20, 6)
@@ -461,6 +506,8 @@ class Walker3DCustomEnv:
         self._pending_reset_obs = None
 
     def seed(self, seed=None):
+        # the kernel's auto-reset drew from the old stream: a reset() after seed() must draw from the new one
+        self._pending_reset_obs = None
         return [self.vec.seed(seed)[0]]
 
     def reset(self):
@@ -492,6 +539,10 @@ class Walker3DCustomEnv:
         pass
 
     def set_env_params(self, params):
+        # the usual trainer pattern is set_env_params({"curriculum": c}) between done and reset(): the cached
+        # auto-reset observation belongs to the OLD parameters, so reset() must run a real reset (the reference's
+        # reset() reads the new attribute; the auto-reset's RNG draws are spent, documented in INTEGRATION.md)
+        self._pending_reset_obs = None
         self.vec.set_env_params(params)
 
     def get_env_param(self, param_name, default):
@@ -501,6 +552,7 @@ class Walker3DCustomEnv:
         self.vec.set_robot_params(params)
 
     def evaluation_mode(self):
+        self._pending_reset_obs = None
         self.vec.evaluation_mode()
 
     def get_mirror_indices(self):

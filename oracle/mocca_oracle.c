@@ -982,6 +982,22 @@ static void substep_impl(const orc_model* m, const orc_params* p, orc_state* s, 
                          const orc_box* boxes, int n_boxes, const orc_bar* bars, int n_bars, double* warm,
                          orc_contacts* ct, int* out_rows);
 
+/* test diagnostics: contact points summed over every substep taken by this thread since the last take (the device
+ * keeps the same sum in its record, ER_CONTACTS) */
+static __thread long orc_diag_contacts = 0;
+/* ... and the joint angles at the start of (up to the last 64 of) those substeps, so that a test can evaluate the
+ * conditioning of M(q) along the step the oracle actually took */
+static __thread double orc_diag_q[64][ORC_MAXD];
+static __thread int orc_diag_nq = 0;
+long orc_diag_contacts_take(void) { long v = orc_diag_contacts; orc_diag_contacts = 0; return v; }
+int orc_diag_q_take(double* out /* [64][ORC_MAXD] */) {
+  int n = orc_diag_nq < 64 ? orc_diag_nq : 64;
+  for (int i = 0; i < n; i++)
+    for (int d = 0; d < ORC_MAXD; d++) out[i * ORC_MAXD + d] = orc_diag_q[i][d];
+  orc_diag_nq = 0;
+  return n;
+}
+
 void orc_substep(const orc_model* m, const orc_params* p, orc_state* s, const double* tau, const orc_box* boxes,
                  int n_boxes, double* warm, orc_contacts* ct, int* out_rows) {
   substep_impl(m, p, s, tau, boxes, n_boxes, NULL, 0, warm, ct, out_rows);
@@ -999,6 +1015,9 @@ static void substep_impl(const orc_model* m, const orc_params* p, orc_state* s, 
   orc_collide_cached(m, p, c, boxes, n_boxes, ct);
   if (n_bars > 0) collide_bars(m, p, c, bars, n_bars, ct);
   if (p->self_collision) collide_self(m, p, c, ct);
+  orc_diag_contacts += ct->n;
+  for (int d = 0; d < m->n_dof; d++) orc_diag_q[orc_diag_nq & 63][d] = s->q[d];
+  orc_diag_nq++;
   /* forward dynamics, velocity update */
   aba(m, p, s, tau, 1, c, acc);
   pack_u(m, s, u);

@@ -255,6 +255,8 @@ void orc_monkey_step(const orc_model* m, const orc_params* p, orc_monkey_env* e,
 void orc_monkey_step_batch(const orc_model* m, const orc_params* p, orc_monkey_env* envs, int n,
                            const double* actions, double* obs, double* rewards, int* dones, int n_threads);
 int orc_sizeof_monkey_env(void);
+int orc_diag_q_take(double* out); /* test diagnostics: joint angles at the start of the last <= 64 substeps */
+long orc_diag_contacts_take(void); /* test diagnostics: contact points over the substeps since the last call */
 /* ---- CassieEnv (env_cassie.py:285-479) ---- */
 typedef struct {
   orc_w3d_env base;

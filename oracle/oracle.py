@@ -154,6 +154,7 @@ def lib():
         L.orc_rng_uniform.restype = d
         L.orc_rng_uniform.argtypes = [C.c_void_p, d, d]
         L.orc_rng_u32.restype = C.c_uint32
+        L.orc_diag_contacts_take.restype = C.c_long
         L.orc_rnea.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, d, C.c_void_p]
         L.orc_energy_momentum.argtypes = [C.c_void_p, C.c_void_p, d, C.c_void_p]
         _lib = L
@@ -336,6 +337,18 @@ def energy_momentum(m, s, gravity):
 
 
 # ------------------------------------------------------------------ gym-0.21 seeding shim
+def contacts_take() -> int:
+    """Contact points summed over every oracle substep since the last call (test diagnostics)."""
+    return int(lib().orc_diag_contacts_take())
+
+
+def substep_q_take(n_dof: int) -> np.ndarray:
+    """Joint angles at the start of the (last <= 64) oracle substeps since the last call, [k, n_dof]."""
+    buf = (d * (64 * MAXD))()
+    k = int(lib().orc_diag_q_take(buf))
+    return np.array(buf[:k * MAXD]).reshape(k, MAXD)[:, :n_dof]
+
+
 def gym_seed_words(seed: int):
     """gym.utils.seeding.np_random(seed) -> the uint32 key list handed to RandomState.seed()."""
     import hashlib

@@ -73,42 +73,16 @@ def test_child_contact_step(child_table, oracle_mod):
     assert worst < 2e-3, worst
 
 
-def test_child_env_step_teacher_forced(child_table, oracle_mod):
-    """Child3DCustomEnv.step (termination height 0.1, power 0.4) from identical states and bookkeeping.
-    The child's links are small (30 kg in total, waist inertias ~1e-3 kg m^2, no armature in Bullet): full torque
-    drives the abdomen joints to the +-100 rad/s clamp within one substep and the f32 factorisation of the
-    ill-conditioned mass matrix is good to ~3e-3 there, so the stated bound is >= 90 % of env-steps (Walker3D: 97 %)."""
-    O, t = oracle_mod, child_table
-    N = 4
-    oracles = [O.Walker3DCustomOracle(t, seed=5 + i) for i in range(N)]
-    emus = [E.EmuChild(_mt_row(O, 5 + i)) for i in range(N)]
-    for o, e in zip(oracles, emus):
-        o.reset()
-        e.reset()
-    arng = np.random.RandomState(7)
-    bad, total, errs, lens = 0, 0, [], []
-    for step in range(40):
-        for o, e in zip(oracles, emus):
-            a = arng.uniform(-1.2, 1.2, 21)
-            sv = o.state_vector().astype(np.float32)
-            e.state[:55] = sv
-            oracle_record(o, e.rec)
-            force_oracle_state(o, sv.astype(np.float64))
-            o1, r1, d1, _ = o.step(a)
-            o2, r2, d2, tr2, fin = e.step(a)
-            ocmp = fin if d2 else o2
-            err = float(np.abs(o1 - ocmp).max())
-            ok = d1 == d2 and err < 5e-3 and abs(r1 - r2) < 5e-2 + 1e-3 * abs(r1)
-            total += 1
-            bad += 0 if ok else 1
-            errs.append(err)
-            if d1:
-                lens.append(o.e.elapsed)
-                o.reset()
-                if not d2:
-                    e.reset()
-    assert bad <= 0.10 * total, (bad, total)
-    assert np.median(errs) < 5e-4
+def test_child_env_step_teacher_forced(oracle_mod):
+    """Child3DCustomEnv.step (termination height 0.1, power 0.4) from f32-identical states and bookkeeping.  The child's
+    links are small (30 kg in total, waist inertias ~1e-3 kg m^2, no armature in Bullet): its mass matrix is
+    ill-conditioned more often than Walker3D's, which the judge verifies step by step (cond(M) >= 1e6).  Steps outside 1e-3 (obs) / 1e-2 (reward) must be explained by a verified
+    discontinuity and bounded (tests/teacher.py), else the test fails; integer bookkeeping read back and compared
+    exactly after every structurally identical step."""
+    from tests import teacher as T
+
+    js = T.run_vs_oracle(oracle_mod, "child3d", "emu", range(5, 9), 40, lambda rng, k: rng.uniform(-1.2, 1.2, 21))
+    assert np.median(np.concatenate([j.errs for j in js])) < 2e-4
 
 
 def test_mike_reset_and_terrain(mike_table, oracle_mod):
@@ -124,50 +98,11 @@ def test_mike_reset_and_terrain(mike_table, oracle_mod):
         assert np.abs(o1 - o2).max() < 1e-6
 
 
-def test_mike_env_step_teacher_forced(mike_table, oracle_mod):
-    """MikeStepperEnv.step (Mike's power table, waist mass 8) from identical states and bookkeeping."""
-    O, t = oracle_mod, mike_table
-    bad, total, errs = 0, 0, []
+def test_mike_env_step_teacher_forced(oracle_mod):
+    """MikeStepperEnv.step (Mike's power table, waist mass 8) from f32-identical states and bookkeeping.  Steps outside 1e-3 (obs) / 1e-2 (reward) must be explained by a verified
+    discontinuity and bounded (tests/teacher.py), else the test fails; integer bookkeeping read back and compared
+    exactly after every structurally identical step."""
+    from tests import teacher as T
+
     for seed, cur in ((3, 5), (4, 0)):
-        env = O.Walker3DStepperOracle(t, seed=seed, curriculum=cur)
-        emu = E.EmuMike(_mt_row(O, seed), curriculum=cur)
-        env.reset()
-        emu.reset()
-        arng = np.random.RandomState(seed)
-        for i in range(50):
-            a = 0.3 * arng.uniform(-1, 1, 21)
-            sv = env.state_vector().astype(np.float32)
-            emu.state[:55] = sv
-            b = env.e.base
-            force_oracle_state(env, sv.astype(np.float64)) if hasattr(env.e, "s") else None
-            for k in range(3):
-                b.s.pos[k] = float(sv[k]); b.s.omega[k] = float(sv[7 + k]); b.s.vel[k] = float(sv[10 + k])
-            for k in range(4):
-                b.s.quat[k] = float(sv[3 + k])
-            for k in range(21):
-                b.s.q[k] = float(sv[13 + k]); b.s.qd[k] = float(sv[34 + k])
-            ri = emu.rec.view(np.int32)
-            emu.rec[0:3] = np.array(b.walk_target[:], dtype=np.float32)
-            emu.rec[7] = b.linear_potential
-            emu.rec[9], emu.rec[10] = b.feet_contact[0], b.feet_contact[1]
-            ri[8] = b.elapsed
-            ri[22], ri[23], ri[24], ri[25], ri[26] = (env.e.next_step_index, env.e.target_reached_count,
-                                                      env.e.stop_on_next_step, env.e.set_stop_on_next_step,
-                                                      env.e.timestep)
-            for pl in range(3):
-                bx = env.e.boxes[2 * pl]
-                emu.rec[32 + 12 * pl:32 + 12 * pl + 3] = np.array(bx.center[:], dtype=np.float32)
-                emu.rec[32 + 12 * pl + 3:32 + 12 * pl + 12] = np.array([list(r) for r in bx.R], dtype=np.float32).ravel()
-            o1, r1, d1, _ = env.step(a)
-            o2, r2, d2, tr2, fin = emu.step(a)
-            ocmp = fin if d2 else o2
-            err = float(np.abs(o1 - ocmp).max())
-            ok = d1 == d2 and err < 5e-3 and abs(r1 - r2) < 5e-2 + 1e-3 * abs(r1)
-            total += 1
-            bad += 0 if ok else 1
-            errs.append(err)
-            if d1:
-                env.reset()
-                emu.reset() if not d2 else None
-    assert bad <= 0.05 * total, (bad, total)
-    assert np.median(errs) < 5e-4
+        T.run_vs_oracle(oracle_mod, "mike", "emu", [seed], 50, lambda rng, k: 0.3 * rng.uniform(-1, 1, 21), curriculum=cur)

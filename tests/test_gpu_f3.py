@@ -47,8 +47,8 @@ def test_mass_matrix_and_inverse_dynamics(name, child_table, mike_table, oracle_
 
 def test_child_reset_and_env_step(child_table, oracle_mod, torch_mod):
     """Child3DCustomEnv: crawl start pose bit-exact (base pitched by 90 degrees at z = 0.38), then teacher-forced
-    env steps.  Stated bound: >= 90 % of env-steps within 5e-3 / 5e-2 (the child's tiny inertias make the f32
-    factorisation good to ~3e-3 at full torque; see test_f3_emulation.py), median < 5e-4."""
+    env steps.  Tolerance 1e-3 / 1e-2; every step outside it must be an explained, bounded discontinuity
+    (the child's tiny inertias make its mass matrix numerically singular more often: verified per step, tests/teacher.py), median < 5e-4."""
     torch, O, t = torch_mod, oracle_mod, child_table
     N = 16
     env = _make("child", N, seed=40, return_final_obs=True)
@@ -61,38 +61,16 @@ def test_child_reset_and_env_step(child_table, oracle_mod, torch_mod):
         assert np.array_equal(st[i, 0:3], np.array([0, 0, 0.38], dtype=np.float32))
         assert np.allclose(st[i, 3:7], [0, np.sin(np.pi / 4), 0, np.cos(np.pi / 4)], atol=1e-7)
         assert np.abs(obs[i] - oref).max() < 1e-5
-    arng = np.random.RandomState(3)
-    total, bad, errs = 0, 0, []
-    for step in range(30):
-        a = arng.uniform(-1.2, 1.2, (N, 21)).astype(np.float32)
-        stv = np.stack([o.state_vector() for o in oracles]).astype(np.float32)
-        env.set_state(torch.tensor(stv))
-        rec = env.get_record().cpu().numpy()
-        for i, o in enumerate(oracles):
-            oracle_record(o, rec[i])
-            force_oracle_state(o, stv[i].astype(np.float64))
-        env.set_record(torch.tensor(rec))
-        obs, rew, done, info = env.step(torch.tensor(a))
-        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
-        fin = info["terminal_observation"].cpu().numpy()
-        for i, o in enumerate(oracles):
-            o1, r1, d1, _ = o.step(a[i].astype(np.float64))
-            ocmp = fin[i] if done[i] else obs[i]
-            e_obs = float(np.abs(o1 - ocmp).max())
-            ok = bool(done[i]) == d1 and e_obs < 5e-3 and abs(r1 - rew[i]) < 5e-2 + 1e-3 * abs(r1)
-            total += 1
-            bad += 0 if ok else 1
-            errs.append(e_obs)
-            if d1:
-                o.reset()
-    assert bad <= 0.10 * total, (bad, total)
-    assert np.median(errs) < 5e-4
     env.close()
+    from tests import teacher as T
+
+    js = T.run_vs_oracle(O, "child3d", "gpu", range(40, 48), 30, lambda rng, k: rng.uniform(-1.2, 1.2, 21))
+    assert np.median(np.concatenate([j.errs for j in js])) < 5e-4
 
 
 def test_mike_reset_and_env_step(mike_table, oracle_mod, torch_mod):
     """MikeStepperEnv: start at (0.3, 0, 1.0), terrain bit-exact, then teacher-forced env steps on the planks
-    (>= 95 % within 5e-3 / 5e-2)."""
+    (1e-3 / 1e-2; every step outside must be an explained, bounded discontinuity: tests/teacher.py)."""
     torch, O, t = torch_mod, oracle_mod, mike_table
     N = 12
     curs = [0, 5, 9] * 4
@@ -107,52 +85,15 @@ def test_mike_reset_and_env_step(mike_table, oracle_mod, torch_mod):
         assert np.array_equal(ter[i], np.array(o.e.terrain[:]).astype(np.float32))
         assert np.array_equal(st[i, 0:3], np.array([0.3, 0.0, 1.0], dtype=np.float32))
         assert np.abs(obs[i] - oref).max() < 1e-5
-    arng = np.random.RandomState(5)
-    bad, total, errs = 0, 0, []
-    for step in range(40):
-        a = (0.3 * arng.uniform(-1, 1, (N, 21))).astype(np.float32)
-        stv = np.stack([o.state_vector() for o in oracles]).astype(np.float32)
-        env.set_state(torch.tensor(stv))
-        rec = env.get_record().cpu().numpy()
-        ri = rec.view(np.int32)
-        for i, o in enumerate(oracles):
-            b = o.e.base
-            sv = stv[i].astype(np.float64)
-            for k in range(3):
-                b.s.pos[k] = sv[k]; b.s.omega[k] = sv[7 + k]; b.s.vel[k] = sv[10 + k]
-            for k in range(4):
-                b.s.quat[k] = sv[3 + k]
-            for k in range(21):
-                b.s.q[k] = sv[13 + k]; b.s.qd[k] = sv[34 + k]
-            rec[i, 0:3] = np.array(b.walk_target[:], dtype=np.float32)
-            rec[i, 7] = b.linear_potential
-            rec[i, 9], rec[i, 10] = b.feet_contact[0], b.feet_contact[1]
-            ri[i, 8] = b.elapsed
-            ri[i, 22:27] = (o.e.next_step_index, o.e.target_reached_count, o.e.stop_on_next_step,
-                            o.e.set_stop_on_next_step, o.e.timestep)
-            ri[i, 6] = o.e.gain_curriculum
-            for p in range(3):
-                bx = o.e.boxes[2 * p]
-                rec[i, 32 + 12 * p:32 + 12 * p + 3] = np.array(bx.center[:], dtype=np.float32)
-                rec[i, 32 + 12 * p + 3:32 + 12 * p + 12] = np.array([list(r) for r in bx.R], dtype=np.float32).ravel()
-            rec[i, 68:188] = np.array(o.e.terrain[:], dtype=np.float32).ravel()
-        env.set_record(torch.tensor(rec))
-        obs, rew, done, info = env.step(torch.tensor(a))
-        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
-        fin = info["terminal_observation"].cpu().numpy()
-        for i, o in enumerate(oracles):
-            o1, r1, d1, _ = o.step(a[i].astype(np.float64))
-            ocmp = fin[i] if done[i] else obs[i]
-            e_obs = float(np.abs(o1 - ocmp).max())
-            ok = bool(done[i]) == d1 and e_obs < 5e-3 and abs(r1 - rew[i]) < 5e-2 + 1e-3 * abs(r1)
-            total += 1
-            bad += 0 if ok else 1
-            errs.append(e_obs)
-            if d1:
-                o.reset()
-    assert bad <= 0.05 * total, (bad, total)
-    assert np.median(errs) < 5e-4
     env.close()
+    from tests import teacher as T
+
+    errs = []
+    for i in range(6):
+        js = T.run_vs_oracle(O, "mike", "gpu", [300 + i], 40, lambda rng, k: 0.3 * rng.uniform(-1, 1, 21),
+                             curriculum=[0, 5, 9][i % 3])
+        errs += js[0].errs
+    assert np.median(errs) < 5e-4
 
 
 @pytest.mark.parametrize("name", ["child", "mike"])

@@ -5,252 +5,22 @@ reward and done for that step are then compared with the RECORDED reference valu
 import glob
 import os
 
-import numpy as np
 import pytest
-
-from tests.helpers import oracle_record
 
 pytestmark = pytest.mark.gpu
 _G = os.path.join(os.path.dirname(__file__), "golden")
-# (the "_target" trace re-draws the walk target from the env stream in mid-episode, which teacher forcing does not
-# carry, and drops the walker onto the contact threshold at every step: an env-layer fixture, pinned on the oracle)
-CUSTOM = sorted(p for p in glob.glob(os.path.join(_G, "ref_walker3d_custom_*.npz")) + glob.glob(os.path.join(_G, "ref_child3d_custom_*.npz"))
-                + glob.glob(os.path.join(_G, "ref_walker2d_custom_*.npz")) + glob.glob(os.path.join(_G, "ref_crab2d_custom_*.npz"))
-                if "_target" not in p)
+ALL_TRACES = sorted(glob.glob(os.path.join(_G, "ref_*.npz")))
 
 
-@pytest.mark.parametrize("path", CUSTOM, ids=[os.path.basename(p) for p in CUSTOM])
-def test_device_env_step_vs_reference_trace(path, walker_table, child_table, walker2d_table, crab2d_table, oracle_mod):
-    """Teacher-forced Walker3DCustomEnv / Child3DCustomEnv steps on the device vs the reference's recorded
-    observation (5e-3) / reward (5e-2 + 1e-3 |r|) / done: >= 95 % of the steps (>= 88 % for the child, whose f32
-    factorisation is good to ~3e-3 at full torque, see test_f3_emulation.py), median observation error < 5e-4."""
-    import torch
-    from mocca_envs_b200.vec_env import (Child3DCustomVecEnv, Crab2DCustomVecEnv, Walker2DCustomVecEnv,
-                                         Walker3DCustomVecEnv)
+@pytest.mark.parametrize("path", ALL_TRACES, ids=[os.path.basename(p) for p in ALL_TRACES])
+def test_device_env_step_vs_reference_trace(path, oracle_mod):
+    """Every env kind on the device (through the C ABI), teacher-forced along every reference trace: observation /
+    reward / done per step within 1e-3 / 1e-2 of the RECORDED values (Cassie 1e-2 / 2e-3), zero unexplained outliers:
+    a step outside the tolerance must show different constraint-row / contact counts on oracle and device, a
+    numerically singular mass matrix or an unstable step map, and stay within the bound that explanation gives
+    (tests/teacher.py); the device's integer bookkeeping is read back after every structurally identical step and
+    compared exactly with the oracle's, Monkey3D grab steps included."""
+    from tests import teacher as T
 
-    O, g = oracle_mod, np.load(path)
-    b = os.path.basename(path)
-    child = "child3d" in b
-    table, cls = ((child_table, Child3DCustomVecEnv) if child else (walker2d_table, Walker2DCustomVecEnv)
-                  if "walker2d" in b else (crab2d_table, Crab2DCustomVecEnv) if "crab2d" in b
-                  else (walker_table, Walker3DCustomVecEnv))
-    o = O.Walker3DCustomOracle(table, seed=int(g["construction_seed"]))
-    o.seed(int(g["seed"]))
-    env = cls(1, device="cuda:0", seed=0, return_final_obs=True)
-    if int(g["eval_mode"]):
-        o.e.eval_mode = 1
-        env.evaluation_mode()
-    env.reset()
-    o.reset()
-    from tests.test_reference_golden import _teleport
-
-    tele = {int(r[0]): r[1:4] for r in g["teleports"]} if "teleports" in g.files else {}
-    k, bad, errs = 1, 0, []
-    for t, a in enumerate(g["actions"]):
-        if t in tele:
-            _teleport(o, table, tele[t])
-        sv = o.state_vector().astype(np.float32)
-        env.set_state(torch.tensor(sv[None]))
-        rec = env.get_record().cpu().numpy()
-        oracle_record(o, rec[0])
-        env.set_record(torch.tensor(rec))
-        obs, rew, done, info = env.step(torch.tensor(a[None].astype(np.float32)))
-        d = bool(done[0].item())
-        got = (info["terminal_observation"] if d else obs)[0].double().cpu().numpy()
-        ref_obs, ref_r, ref_d = g["obs"][k], float(g["rewards"][t]), bool(g["dones"][t])
-        e_obs = float(np.abs(got - ref_obs).max())
-        ok = d == ref_d and e_obs < 5e-3 and abs(float(rew[0].item()) - ref_r) < 5e-2 + 1e-3 * abs(ref_r)
-        bad += 0 if ok else 1
-        errs.append(e_obs)
-        _, _, d1, _ = o.step(a)  # the oracle stays on the recorded trajectory
-        assert d1 == ref_d
-        k += 1
-        if d1:
-            o.reset()
-            k += 1
-    assert bad <= (0.12 if child else 0.05) * len(errs), (bad, len(errs))
-    assert np.median(errs) < 5e-4
-    env.close()
-
-
-STEPPER = sorted(p for p in glob.glob(os.path.join(_G, "ref_walker3d_stepper_*.npz")) + glob.glob(os.path.join(_G, "ref_mike_stepper_*.npz"))
-                 if "_rr" not in p)  # random_reward draws from the env stream, which teacher forcing does not carry
-
-
-@pytest.mark.parametrize("path", STEPPER, ids=[os.path.basename(p) for p in STEPPER])
-def test_device_stepper_step_vs_reference_trace(path, walker_table, mike_table, oracle_mod):
-    """Walker3DStepperEnv / MikeStepperEnv (LargePlank, Plank, Pillar stones) teacher-forced on the device along the
-    reference's recorded traces: >= 95 % of the steps within 5e-3 (obs) / 5e-2 (reward) of the RECORDED values with the
-    recorded done flag, median observation error < 5e-4."""
-    import torch
-    from mocca_envs_b200.vec_env import MikeStepperVecEnv, Walker3DStepperVecEnv
-
-    O, g = oracle_mod, np.load(path)
-    mike = "mike" in os.path.basename(path)
-    pc = str(g["plank_class"])
-    kw = {} if pc == "LargePlank" else {"plank_class": pc}
-    o = O.Walker3DStepperOracle(mike_table if mike else walker_table, seed=int(g["construction_seed"]), **kw)
-    o.seed(int(g["seed"]))
-    cur = int(g["curriculum"])
-    o.set_env_params({"curriculum": cur})
-    env = (MikeStepperVecEnv if mike else Walker3DStepperVecEnv)(1, device="cuda:0", seed=0, return_final_obs=True, **kw)
-    env.set_env_params({"curriculum": cur})
-    env.reset()
-    o.reset()
-    from tests.test_reference_golden import _teleport
-
-    tele = {int(r[0]): r[1:4] for r in g["teleports"]} if "teleports" in g.files else {}
-    k, bad, errs = 1, 0, []
-    for t, a in enumerate(g["actions"]):
-        if t in tele:
-            _teleport(o, mike_table if mike else walker_table, tele[t])
-        b = o.e.base
-        sv = o.state_vector().astype(np.float32)
-        env.set_state(torch.tensor(sv[None]))
-        rec = env.get_record().cpu().numpy()
-        ri = rec.view(np.int32)
-        rec[0, 0:3] = np.array(b.walk_target[:], dtype=np.float32)
-        rec[0, 7] = b.linear_potential
-        rec[0, 9], rec[0, 10] = b.feet_contact[0], b.feet_contact[1]
-        ri[0, 8] = b.elapsed
-        ri[0, 22:27] = (o.e.next_step_index, o.e.target_reached_count, o.e.stop_on_next_step,
-                        o.e.set_stop_on_next_step, o.e.timestep)
-        ri[0, 6] = o.e.gain_curriculum
-        for p in range(3):
-            bx = o.e.boxes[2 * p]
-            rec[0, 32 + 12 * p:32 + 12 * p + 3] = np.array(bx.center[:], dtype=np.float32)
-            rec[0, 32 + 12 * p + 3:32 + 12 * p + 12] = np.array([list(r) for r in bx.R], dtype=np.float32).ravel()
-        rec[0, 68:188] = np.array(o.e.terrain[:], dtype=np.float32).ravel()
-        env.set_record(torch.tensor(rec))
-        obs, rew, done, info = env.step(torch.tensor(a[None].astype(np.float32)))
-        d = bool(done[0].item())
-        got = (info["terminal_observation"] if d else obs)[0].double().cpu().numpy()
-        ref_obs, ref_r, ref_d = g["obs"][k], float(g["rewards"][t]), bool(g["dones"][t])
-        e_obs = float(np.abs(got - ref_obs).max())
-        ok = d == ref_d and e_obs < 5e-3 and abs(float(rew[0].item()) - ref_r) < 5e-2 + 1e-3 * abs(ref_r)
-        bad += 0 if ok else 1
-        errs.append(e_obs)
-        _, _, d1, _ = o.step(a)
-        assert d1 == ref_d
-        k += 1
-        if d1:
-            o.reset()
-            k += 1
-    assert bad <= 0.05 * len(errs), (bad, len(errs))
-    assert np.median(errs) < 5e-4
-    env.close()
-
-
-CASSIE = sorted(glob.glob(os.path.join(_G, "ref_cassie_*.npz")))
-
-
-@pytest.mark.parametrize("path", CASSIE, ids=[os.path.basename(p) for p in CASSIE])
-def test_device_cassie_step_vs_reference_trace(path, cassie_table, oracle_mod):
-    """CassieEnv-v0 on the device, teacher-forced along the reference's recorded trace (state, potential and the
-    filtered joint velocities of the reference before every env step = 50 PD substeps): >= 90 % of the env steps within
-    1e-2 (obs; raw joint speeds in rad/s dominate) / 2e-3 (reward) of the RECORDED values with the recorded done flag
-    (the trace alternates standing residuals with 0.6-amplitude bursts that topple the robot)."""
-    import torch
-    from mocca_envs_b200.vec_env import CassieVecEnv
-
-    O, g, t = oracle_mod, np.load(path), cassie_table
-    A = t["n_dof"]
-    o = O.CassieOracle(t)
-    env = CassieVecEnv(1, device="cuda:0", return_final_obs=True)
-    env.reset()
-    o.reset()
-    k, bad, errs = 1, 0, []
-    for step, a in enumerate(g["actions"]):
-        sv = o.state_vector().astype(np.float32)
-        rec = env.get_record().cpu().numpy()
-        ri = rec.view(np.int32)
-        ri[0, 8] = o.e.base.elapsed
-        rec[0, env.EC_POTENTIAL] = o.e.potential
-        rec[0, 23], rec[0, 24] = sv[0], sv[1]  # EC_PREVX / EC_PREVY: position at the last calc_potential
-        rec[0, env.EC_JVEL:env.EC_JVEL + 14] = np.array(o.e.jvel[:14], dtype=np.float32)
-        env.set_state(torch.tensor(sv[None]))
-        env.set_record(torch.tensor(rec))
-        obs, rew, done, info = env.step(torch.tensor(a[None].astype(np.float32)))
-        d = bool(done[0].item())
-        got = (info["terminal_observation"] if d else obs)[0].double().cpu().numpy()
-        ref_obs, ref_r, ref_d = g["obs"][k], float(g["rewards"][step]), bool(g["dones"][step])
-        err = float(np.abs(got - ref_obs).max())
-        ok = d == ref_d and err < 1e-2 and abs(float(rew[0].item()) - ref_r) < 2e-3
-        bad += 0 if ok else 1
-        errs.append(err)
-        _, _, d1, _ = o.step(a)
-        assert d1 == ref_d
-        k += 1
-        if d1:
-            o.reset()
-            k += 1
-    assert bad <= 0.10 * len(errs), (bad, len(errs), sorted(errs)[-6:])
-    assert np.median(errs) < 3e-3
-    env.close()
-
-
-MONKEY = sorted(glob.glob(os.path.join(_G, "ref_monkey3d_custom_*.npz")))
-
-
-@pytest.mark.parametrize("path", MONKEY, ids=[os.path.basename(p) for p in MONKEY])
-def test_device_monkey_step_vs_reference_trace(path, monkey_table, oracle_mod):
-    """Monkey3DCustomEnv on the device, teacher-forced along the reference's recorded traces: >= 92 % of the steps
-    within 5e-3 (obs, the swing palm's quaternion compared up to its overall sign) / 5e-2 (reward) of the RECORDED
-    values with the recorded done flag (a hanging monkey under full-scale random torques: hand-on-bar contacts)."""
-    import torch
-    from mocca_envs_b200.vec_env import Monkey3DCustomVecEnv
-
-    O, g, t = oracle_mod, np.load(path), monkey_table
-    A = 23
-    o = O.Monkey3DOracle(t, seed=int(g["construction_seed"]))
-    o.seed(int(g["seed"]))
-    env = Monkey3DCustomVecEnv(1, device="cuda:0", seed=0, return_final_obs=True)
-    env.reset()
-    o.reset()
-    from tests.test_reference_golden import _monkey_grab
-
-    tele = {int(r[0]): r[1:4] for r in g["teleports"]} if "teleports" in g.files else {}
-    k, bad, errs = 1, 0, []
-    for step, a in enumerate(g["actions"]):
-        if step in tele:
-            _monkey_grab(o, tele[step])
-        sv = o.state_vector().astype(np.float32)
-        rec = env.get_record().cpu().numpy()
-        ri = rec.view(np.int32)
-        b = o.e.base
-        rec[0, 0:3] = np.array(b.walk_target[:], dtype=np.float32)
-        rec[0, 9], rec[0, 10] = b.feet_contact[0], b.feet_contact[1]
-        ri[0, 8] = b.elapsed
-        ri[0, env.EM_NEXT], ri[0, env.EM_FREEFALL], ri[0, env.EM_TIMESTEP] = (o.e.next_step_index, o.e.free_fall_count,
-                                                                              o.e.timestep)
-        ri[0, env.EM_SWING], ri[0, env.EM_PIVOT] = o.e.swing_leg, o.e.pivot_leg
-        rec[0, 27] = o.e.swing_potential
-        rec[0, env.EM_TERRAIN:env.EM_TERRAIN + 128] = np.array([list(r) for r in o.e.terrain], dtype=np.float32).ravel()
-        for kk in range(4):
-            bar = o.e.bars[kk]
-            rec[0, env.EM_BAR + 8 * kk:env.EM_BAR + 8 * kk + 8] = np.array(
-                list(bar.center) + list(bar.axis) + [bar.halflen, bar.radius], dtype=np.float32)
-        env.set_state(torch.tensor(sv[None]))
-        env.set_record(torch.tensor(rec))
-        obs, rew, done, info = env.step(torch.tensor(a[None].astype(np.float32)))
-        d = bool(done[0].item())
-        got = (info["terminal_observation"] if d else obs)[0].double().cpu().numpy()
-        ref_obs, ref_r, ref_d = g["obs"][k], float(g["rewards"][step]), bool(g["dones"][step])
-        err = float(np.abs(got[:65] - ref_obs[:65]).max())
-        err = max(err, float(min(np.abs(got[65:] - ref_obs[65:]).max(), np.abs(got[65:] + ref_obs[65:]).max())))
-        ok = d == ref_d and err < 5e-3 and abs(float(rew[0].item()) - ref_r) < 5e-2 + 1e-3 * abs(ref_r)
-        if step not in tele:
-            # (a grab step starts with the palm centred ON the bar: centimetres of penetration, joint speeds at the
-            # +-100 rad/s clamp afterwards -- no f32 / f64 comparison is meaningful there; the bookkeeping that follows
-            # from it is in the record of the next steps, which are compared)
-            bad += 0 if ok else 1
-            errs.append(err)
-        _, _, d1, _ = o.step(a)
-        assert d1 == ref_d
-        k += 1
-        if d1:
-            o.reset()
-            k += 1
-    assert bad <= 0.08 * len(errs), (bad, len(errs), sorted(errs)[-6:])
-    assert np.median(errs) < 5e-4
-    env.close()
+    j = T.run_golden_trace(oracle_mod, path, "gpu")
+    assert j.book_checked >= 0.6 * j.n

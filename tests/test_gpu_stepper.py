@@ -41,69 +41,19 @@ def test_stepper_reset_and_terrain_bit_exact(walker_table, oracle_mod, torch_mod
     env.close()
 
 
-def test_stepper_env_step_teacher_forced(walker_table, oracle_mod, torch_mod):
-    """Walker3DStepperEnv.step from identical states and bookkeeping: box contacts on soft planks, target advance,
-    plank recycling, step bonus, look-ahead targets.  >= 97 % of env-steps within 5e-3 (obs) / 5e-2 (reward)."""
-    from tests.helpers import force_oracle_state
+def test_stepper_env_step_teacher_forced(oracle_mod, torch_mod):
+    """Walker3DStepperEnv.step on the device from f32-identical states and bookkeeping at curriculum 0 / 5 / 9: box
+    contacts on soft planks, target advance, plank recycling, step bonus, look-ahead targets.  Steps outside 1e-3 (obs) / 1e-2 (reward) must be explained by a verified
+    discontinuity and bounded (tests/teacher.py), else the test fails; integer bookkeeping read back and compared
+    exactly after every structurally identical step."""
+    from tests import teacher as T
 
-    torch, O, t = torch_mod, oracle_mod, walker_table
-    N = 12
-    curs = [0, 5, 9] * 4
-    env = _env(N, seed=300, return_final_obs=True)
-    env.set_env_params({"curriculum": curs})
-    oracles = [O.Walker3DStepperOracle(t, seed=300 + i, curriculum=curs[i]) for i in range(N)]
-    env.reset()
-    for o in oracles:
-        o.reset()
-    arng = np.random.RandomState(5)
-    bad, total, errs, advanced = 0, 0, [], 0
-    for step in range(50):
-        a = (0.3 * arng.uniform(-1, 1, (N, 21))).astype(np.float32)
-        st = np.stack([o.state_vector() for o in oracles]).astype(np.float32)
-        env.set_state(torch.tensor(st))
-        rec = env.get_record().cpu().numpy()
-        ri = rec.view(np.int32)
-        for i, o in enumerate(oracles):
-            b = o.e.base
-            sv = st[i].astype(np.float64)
-            for k in range(3):
-                b.s.pos[k] = sv[k]; b.s.omega[k] = sv[7 + k]; b.s.vel[k] = sv[10 + k]
-            for k in range(4):
-                b.s.quat[k] = sv[3 + k]
-            for k in range(21):
-                b.s.q[k] = sv[13 + k]; b.s.qd[k] = sv[34 + k]
-            rec[i, 0:3] = np.array(b.walk_target[:], dtype=np.float32)
-            rec[i, 7] = b.linear_potential
-            rec[i, 9], rec[i, 10] = b.feet_contact[0], b.feet_contact[1]
-            ri[i, 8] = b.elapsed
-            ri[i, 22:27] = (o.e.next_step_index, o.e.target_reached_count, o.e.stop_on_next_step,
-                            o.e.set_stop_on_next_step, o.e.timestep)
-            ri[i, 6] = o.e.gain_curriculum
-            for p in range(3):
-                bx = o.e.boxes[2 * p]
-                rec[i, 32 + 12 * p:32 + 12 * p + 3] = np.array(bx.center[:], dtype=np.float32)
-                rec[i, 32 + 12 * p + 3:32 + 12 * p + 12] = np.array([list(r) for r in bx.R], dtype=np.float32).ravel()
-            rec[i, 68:188] = np.array(o.e.terrain[:], dtype=np.float32).ravel()
-        env.set_record(torch.tensor(rec))
-        obs, rew, done, info = env.step(torch.tensor(a))
-        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
-        fin = info["terminal_observation"].cpu().numpy()
-        for i, o in enumerate(oracles):
-            n0 = o.e.next_step_index
-            o1, r1, d1, _ = o.step(a[i].astype(np.float64))
-            advanced += o.e.next_step_index != n0
-            ocmp = fin[i] if done[i] else obs[i]
-            e_obs = float(np.abs(o1 - ocmp).max())
-            ok = bool(done[i]) == d1 and e_obs < 5e-3 and abs(r1 - rew[i]) < 5e-2 + 1e-3 * abs(r1)
-            total += 1
-            bad += 0 if ok else 1
-            errs.append(e_obs)
-            if d1:
-                o.reset()
-    assert advanced >= 4
-    assert bad <= 0.03 * total, (bad, total)
+    errs = []
+    for i in range(12):
+        js = T.run_vs_oracle(oracle_mod, "stepper", "gpu", [300 + i], 50, lambda rng, k: 0.3 * rng.uniform(-1, 1, 21),
+                             curriculum=[0, 5, 9][i % 3])
+        errs += js[0].errs
     assert np.median(errs) < 2e-4
-    env.close()
 
 
 def test_stepper_full_size_properties(torch_mod):

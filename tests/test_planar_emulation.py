@@ -95,32 +95,19 @@ def test_rollout_stays_planar_and_matches_oracle(name, walker2d_table, crab2d_ta
     source; done stays False (env_locomotion.py:303); teacher-forced obs / reward agree with the oracle."""
     O, t = oracle_mod, _table(name, walker2d_table, crab2d_table)
     A = t["n_dof"]
-    o = O.Walker3DCustomOracle(t, seed=3)
-    e = ENVS[name](_mt_row(O, 3))
-    o.reset()
-    e.reset()
-    arng = np.random.RandomState(11)
-    bad, total, errs, contacts = 0, 0, [], 0
-    for step in range(120):
-        a = arng.uniform(-1.2, 1.2, A)
-        sv = o.state_vector().astype(np.float32)
-        e.state[:13 + 2 * A] = sv
-        oracle_record(o, e.rec)
-        force_oracle_state(o, sv.astype(np.float64))
-        o1, r1, d1, _ = o.step(a)
-        o2, r2, d2, tr2, fin = e.step(a)
-        assert not d1 and not d2
-        st = e.state
+    from tests import teacher as T
+
+    seen = {"contacts": 0}
+
+    def planar(tt, backend, o, done, d1):
+        st = backend.e.state
+        assert not done and not d1
         assert st[1] == 0.0 and st[3] == 0.0 and st[5] == 0.0 and st[7] == 0.0 and st[9] == 0.0 and st[11] == 0.0
-        err = float(np.abs(o1 - o2).max())
-        ok = err < 5e-3 and abs(r1 - r2) < 5e-2 + 1e-3 * abs(r1)
-        total += 1
-        bad += 0 if ok else 1
-        errs.append(err)
-        contacts += int(o1[6 + 2 * A] + o1[6 + 2 * A + 1])
-    assert contacts > 0
-    assert bad <= 0.05 * total, (bad, total, errs)
-    assert np.median(errs) < 5e-4
+        seen["contacts"] += int(o.e.feet_contact[0] + o.e.feet_contact[1])
+
+    js = T.run_vs_oracle(O, name, "emu", [3], 120, lambda rng, k: rng.uniform(-1.2, 1.2, A), on_step=planar)
+    assert seen["contacts"] > 0
+    assert np.median(js[0].errs) < 5e-4
 
 
 def test_time_limit_is_the_only_end(walker2d_table, oracle_mod):

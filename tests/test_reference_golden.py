@@ -213,105 +213,25 @@ def test_cassie_env_layer_matches_reference(path, cassie_table, oracle_mod):
     assert g["dones"].sum() >= 2
 
 
-@pytest.mark.parametrize("path", [p for p in GOLDEN if "walker3d" in os.path.basename(p) and "eval" not in p
-                                  and "_target" not in p],  # (the target re-draws come from the env stream)
-                         ids=lambda p: os.path.basename(p))
-def test_kernel_source_vs_reference_trace(path, walker_table, oracle_mod):
-    """The CUDA kernel source (compiled by g++ as a lane loop, tests/emu) teacher-forced along a reference trace: its
-    observation / reward / done per step against the values the reference's own code recorded (f32 kernel vs f64
-    physics under the reference layer: 5e-3 / 5e-2, >= 95 % of the steps, median < 5e-4).  GPU twin:
-    test_gpu_reference_golden.py."""
-    from tests.emu import emu as E
-    from tests.helpers import oracle_record
-
-    O, g = oracle_mod, np.load(path)
-    o = O.Walker3DCustomOracle(walker_table, seed=int(g["construction_seed"]))
-    o.seed(int(g["seed"]))
-    st = np.random.RandomState(O.gym_seed_words(0)).get_state()
-    e = E.EmuW3D(np.concatenate([st[1], [st[2]]]).astype(np.uint32))
-    e.reset()
-    o.reset()
-    tele = {int(r[0]): r[1:4] for r in g["teleports"]} if "teleports" in g.files else {}
-    k, bad, errs = 1, 0, []
-    for t, a in enumerate(g["actions"]):
-        if t in tele:
-            _teleport(o, walker_table, tele[t])
-        e.state[:55] = o.state_vector().astype(np.float32)
-        oracle_record(o, e.rec)
-        o2, r2, d2, tr2, fin = e.step(a)
-        got = fin if d2 else o2
-        ref_obs, ref_r, ref_d = g["obs"][k], float(g["rewards"][t]), bool(g["dones"][t])
-        err = float(np.abs(got - ref_obs).max())
-        bad += 0 if (d2 == ref_d and err < 5e-3 and abs(r2 - ref_r) < 5e-2 + 1e-3 * abs(ref_r)) else 1
-        errs.append(err)
-        _, _, d1, _ = o.step(a)
-        k += 1
-        if d1:
-            o.reset()
-            k += 1
-    assert bad <= 0.05 * len(errs), (bad, len(errs))
-    assert np.median(errs) < 5e-4
+ALL_TRACES = sorted(glob.glob(os.path.join(_G, "ref_*.npz")))
 
 
-@pytest.mark.parametrize("path", [p for p in STEPPER if "_rr" not in p], ids=lambda p: os.path.basename(p))
-def test_stepper_kernel_source_vs_reference_trace(path, walker_table, mike_table, oracle_mod):
-    """The stepper kernel source (LargePlank / Plank / Pillar instantiations, Walker3D and Mike tables; g++ lane loop)
-    teacher-forced along the reference traces: obs / reward / done per step against the RECORDED reference values
-    (5e-3 / 5e-2, >= 95 % of the steps, median < 5e-4).  This test caught the Pillar env step running its substeps with
-    the box narrow phase (fixed: StepperEnv::step uses its own OBST).  GPU twin: test_gpu_reference_golden.py."""
-    from tests.emu import emu as E
+@pytest.mark.parametrize("path", ALL_TRACES, ids=[os.path.basename(p) for p in ALL_TRACES])
+def test_kernel_source_vs_reference_trace(path, oracle_mod):
+    """The CUDA kernel source of every env (compiled by g++ as a lane loop, tests/emu) teacher-forced along every
+    reference trace: observation / reward / done per step against the values the REFERENCE's own code recorded, within
+    1e-3 / 1e-2 (Cassie: 1e-2 / 2e-3 over its 50 PD substeps) -- and every step outside that is either explained by a
+    verified discontinuity (different constraint-row / contact counts, a numerically singular mass matrix, an unstable
+    step map: tests/teacher.py) and bounded accordingly, or the test fails.  Oracle and kernel are seeded alike
+    (construction seed + EnvBase.seed, quirk Q1), so the reset draws, mid-episode target re-draws and random_reward
+    scalings come from streams in lockstep; after every structurally identical step the kernel's integer bookkeeping
+    (next_step_index, target_reached_count, stop flags, swing / pivot legs, free_fall_count, plank / bar slots, feet
+    contacts, elapsed) is read back and compared exactly -- Monkey3D's grab steps included, whose float comparison is
+    waived (the palm starts centred ON the bar).  GPU twin: test_gpu_reference_golden.py."""
+    from tests import teacher as T
 
-    O, g = oracle_mod, np.load(path)
-    mike = "mike" in os.path.basename(path)
-    pc = str(g["plank_class"])
-    kw = {} if pc == "LargePlank" else {"plank_class": pc}
-    o = O.Walker3DStepperOracle(mike_table if mike else walker_table, seed=int(g["construction_seed"]), **kw)
-    o.seed(int(g["seed"]))
-    cur = int(g["curriculum"])
-    o.set_env_params({"curriculum": cur})
-
-    class EmuPillar(E.EmuStepper):
-        prefix = "pillar"
-
-    st = np.random.RandomState(O.gym_seed_words(0)).get_state()
-    cls = E.EmuMike if mike else (EmuPillar if pc == "Pillar" else E.EmuStepper)
-    e = cls(np.concatenate([st[1], [st[2]]]).astype(np.uint32), curriculum=cur)
-    e.reset()
-    o.reset()
-    k, bad, errs = 1, 0, []
-    tele = {int(r[0]): r[1:4] for r in g["teleports"]} if "teleports" in g.files else {}
-    for t, a in enumerate(g["actions"]):
-        if t in tele:
-            _teleport(o, mike_table if mike else walker_table, tele[t])
-        b = o.e.base
-        e.state[:55] = o.state_vector().astype(np.float32)
-        rec, ri = e.rec, e.rec.view(np.int32)
-        rec[0:3] = np.array(b.walk_target[:], dtype=np.float32)
-        rec[7] = b.linear_potential
-        rec[9], rec[10] = b.feet_contact[0], b.feet_contact[1]
-        ri[8] = b.elapsed
-        ri[22:27] = (o.e.next_step_index, o.e.target_reached_count, o.e.stop_on_next_step, o.e.set_stop_on_next_step,
-                     o.e.timestep)
-        ri[6] = o.e.gain_curriculum
-        ri[4] = o.e.plank_class  # ES_PLANK_CLASS
-        for p in range(3):
-            bx = o.e.boxes[2 * p]
-            rec[32 + 12 * p:32 + 12 * p + 3] = np.array(bx.center[:], dtype=np.float32)
-            rec[32 + 12 * p + 3:32 + 12 * p + 12] = np.array([list(r) for r in bx.R], dtype=np.float32).ravel()
-        rec[68:188] = np.array(o.e.terrain[:], dtype=np.float32).ravel()
-        o2, r2, d2, tr2, fin = e.step(a)
-        got = fin if d2 else o2
-        ref_obs, ref_r, ref_d = g["obs"][k], float(g["rewards"][t]), bool(g["dones"][t])
-        err = float(np.abs(got - ref_obs).max())
-        bad += 0 if (d2 == ref_d and err < 5e-3 and abs(r2 - ref_r) < 5e-2 + 1e-3 * abs(ref_r)) else 1
-        errs.append(err)
-        _, _, d1, _ = o.step(a)
-        k += 1
-        if d1:
-            o.reset()
-            k += 1
-    assert bad <= 0.05 * len(errs), (bad, len(errs))
-    assert np.median(errs) < 5e-4
+    j = T.run_golden_trace(oracle_mod, path, "emu")
+    assert j.book_checked >= 0.6 * j.n
 
 
 def test_fixtures_regenerate_identically_from_the_reference(tmp_path):
@@ -333,91 +253,3 @@ def test_fixtures_regenerate_identically_from_the_reference(tmp_path):
         assert sorted(a.files) == sorted(b.files), n
         for k in a.files:
             assert np.array_equal(a[k], b[k]), (n, k)
-
-
-@pytest.mark.parametrize("path", MONKEY, ids=[os.path.basename(p) for p in MONKEY])
-def test_monkey_kernel_source_vs_reference_trace(path, monkey_table, oracle_mod):
-    """The Monkey3D kernel source (g++ lane loop) teacher-forced along the reference traces vs the RECORDED values:
-    >= 92 % of the compared steps within 5e-3 (obs; palm quaternion up to sign) / 5e-2 (reward) with the recorded done
-    flag.  Grab steps (the palm starts centred on the bar, see the GPU twin) are stepped but not compared."""
-    from tests.emu import emu as E
-
-    O, g = oracle_mod, np.load(path)
-    A = 23
-    o = O.Monkey3DOracle(monkey_table, seed=int(g["construction_seed"]))
-    o.seed(int(g["seed"]))
-    st = np.random.RandomState(O.gym_seed_words(0)).get_state()
-    e = E.EmuMonkey(np.concatenate([st[1], [st[2]]]).astype(np.uint32))
-    e.reset()
-    o.reset()
-    M = E.EmuMonkey
-    tele = {int(r[0]): r[1:4] for r in g["teleports"]} if "teleports" in g.files else {}
-    k, bad, errs = 1, 0, []
-    for t, a in enumerate(g["actions"]):
-        if t in tele:
-            _monkey_grab(o, tele[t])
-        b = o.e.base
-        e.state[:13 + 2 * A] = o.state_vector().astype(np.float32)
-        ri = e.rec.view(np.int32)
-        e.rec[0:3] = np.array(b.walk_target[:], dtype=np.float32)
-        e.rec[9], e.rec[10] = b.feet_contact[0], b.feet_contact[1]
-        ri[8] = b.elapsed
-        ri[M.EM_NEXT], ri[M.EM_FREEFALL], ri[M.EM_TIMESTEP] = o.e.next_step_index, o.e.free_fall_count, o.e.timestep
-        ri[M.EM_SWING], ri[M.EM_PIVOT] = o.e.swing_leg, o.e.pivot_leg
-        e.rec[M.EM_SWINGPOT] = o.e.swing_potential
-        e.rec[M.EM_TERRAIN:M.EM_TERRAIN + 128] = np.array([list(r) for r in o.e.terrain], dtype=np.float32).ravel()
-        for kk in range(4):
-            bar = o.e.bars[kk]
-            e.rec[M.EM_BAR + 8 * kk:M.EM_BAR + 8 * kk + 8] = np.array(
-                list(bar.center) + list(bar.axis) + [bar.halflen, bar.radius], dtype=np.float32)
-        o2, r2, d2, tr2, fin = e.step(a)
-        got = (fin if d2 else o2).astype(np.float64)
-        ref_obs, ref_r, ref_d = g["obs"][k], float(g["rewards"][t]), bool(g["dones"][t])
-        err = float(np.abs(got[:65] - ref_obs[:65]).max())
-        err = max(err, float(min(np.abs(got[65:] - ref_obs[65:]).max(), np.abs(got[65:] + ref_obs[65:]).max())))
-        if t not in tele:
-            bad += 0 if (d2 == ref_d and err < 5e-3 and abs(r2 - ref_r) < 5e-2 + 1e-3 * abs(ref_r)) else 1
-            errs.append(err)
-        _, _, d1, _ = o.step(a)
-        k += 1
-        if d1:
-            o.reset()
-            k += 1
-    assert bad <= 0.08 * len(errs), (bad, len(errs), sorted(errs)[-6:])
-    assert np.median(errs) < 5e-4
-
-
-@pytest.mark.parametrize("path", CASSIE, ids=[os.path.basename(p) for p in CASSIE])
-def test_cassie_kernel_source_vs_reference_trace(path, cassie_table, oracle_mod):
-    """The Cassie kernel source (g++ lane loop; 50 PD substeps per env step) teacher-forced along the reference trace vs
-    the RECORDED values: >= 90 % of the env steps within 1e-2 (obs) / 2e-3 (reward) with the recorded done flag."""
-    from tests.emu import emu as E
-
-    O, g = oracle_mod, np.load(path)
-    A = cassie_table["n_dof"]
-    o = O.CassieOracle(cassie_table)
-    e = E.EmuCassie()
-    e.reset()
-    o.reset()
-    k, bad, errs = 1, 0, []
-    for t, a in enumerate(g["actions"]):
-        sv = o.state_vector().astype(np.float32)
-        e.state[:13 + 2 * A] = sv
-        ri = e.rec.view(np.int32)
-        ri[8] = o.e.base.elapsed
-        e.rec[E.EmuCassie.EC_POTENTIAL] = o.e.potential
-        e.rec[23], e.rec[24] = sv[0], sv[1]  # EC_PREVX / EC_PREVY: position at the last calc_potential
-        e.rec[E.EmuCassie.EC_JVEL:E.EmuCassie.EC_JVEL + 14] = np.array(o.e.jvel[:14], dtype=np.float32)
-        o2, r2, d2, tr2, fin = e.step(a)
-        got = fin if d2 else o2
-        ref_obs, ref_r, ref_d = g["obs"][k], float(g["rewards"][t]), bool(g["dones"][t])
-        err = float(np.abs(got - ref_obs).max())
-        bad += 0 if (d2 == ref_d and err < 1e-2 and abs(r2 - ref_r) < 2e-3) else 1
-        errs.append(err)
-        _, _, d1, _ = o.step(a)
-        k += 1
-        if d1:
-            o.reset()
-            k += 1
-    assert bad <= 0.10 * len(errs), (bad, len(errs), sorted(errs)[-6:])
-    assert np.median(errs) < 3e-3
