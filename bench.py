@@ -21,6 +21,10 @@ WORKLOAD = "Walker3DCustomEnv-v0 batched 16384 envs/GPU, flat ground"
 METRIC = "env-steps/sec (Walker3DCustomEnv-v0, 16384 envs/GPU, random actions)"
 
 
+# DRAM bytes per launch of k_step_walker3d_custom at 16384 envs from the last committed ncu --set full capture
+NCU_TRAFFIC = {"bytes": 8.05e6, "source": "ncu --set full capture profiles/r1v_step_kernel_raw.csv (8.05 MB read, < 0.01 MB "
+                                          "written per launch), not measured by this run"}
+
 ENV_NAMES = {"custom": "Walker3DCustomEnv", "stepper": "Walker3DStepperEnv", "monkey": "Monkey3DCustomEnv",
              "cassie": "CassieEnv", "child": "Child3DCustomEnv", "mike": "MikeStepperEnv",
              "walker2d": "Walker2DCustomEnv", "crab2d": "Crab2DCustomEnv"}
@@ -237,6 +241,9 @@ def main():
                          "child / mike = SURVEY 8 f3 (Child3DCustomEnv-v0, MikeStepperEnv-v0)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", dest="also", action="store_false",
+                    help="skip the short runs of BASELINE configs 2-5 (scripted PD, Stepper, Monkey3D, Cassie at 8192 envs) "
+                         "that the default headline run appends under \"also\"")
     ap.add_argument("--self-collision", type=int, default=1, choices=[0, 1],
                     help="1 = the reference's URDF_USE_SELF_COLLISION flags (robots.py:259-264); 0 = ablation")
     args = ap.parse_args()
@@ -258,7 +265,10 @@ def main():
             "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": ks, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(ks, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs, "actions": "random-uniform U(-1,1)^21"},
+            "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs, "actions": "random-uniform U(-1,1)^21",
+                       "envs_stepped_per_sample": sample_envs,
+                       "note": "a CPU loop over independent envs: throughput does not depend on the batch size, so each "
+                               "timed step advances a bounded sample of %d envs of the %d-env workload" % (sample_envs, args.envs)},
             "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": "%d envs x %d control steps per step-sample, OpenMP over envs; float64 oracle "
                                        "port (PyBullet itself is not installable: no wheel, no network)" % (sample_envs, ks)},
@@ -286,21 +296,65 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     N, K, W = args.envs, args.steps, max(args.warmup, 3)
+    ctx = dict(np=np, torch=torch, _lib=_lib, dist=dist, dev=dev, rank=rank, world=world, local_rank=local_rank)
+    line = measure(ctx, args.env, N, K, W, args.actions, args.self_collision)
+    if args.also and args.env == "custom" and args.actions == "random" and args.self_collision:
+        # BASELINE configs 2-5 next to the headline, every default run (so the 1/2/4/8-GPU scaling runs carry them):
+        # short device + e2e measurements with their own roofline fractions
+        also = {}
+        Ka, Wa = max(200, min(K, 400)), 20
+        for name, kind, n_envs, acts in (("walker3d_custom_pd", "custom", N, "pd"),
+                                         ("walker3d_stepper", "stepper", N, "random"),
+                                         ("monkey3d", "monkey", N, "random"),
+                                         ("cassie_8192", "cassie", min(N, 8192), "random")):
+            r = measure(ctx, kind, n_envs, Ka, Wa, acts, 1)
+            if r is not None:
+                also[name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "roofline",
+                                                "e2e", "gpu_launches", "episodes")}
+                also[name]["config"] = {k: r["config"][k] for k in ("workload", "envs_per_gpu", "actions", "frame_skip")}
+        if line is not None:
+            line["also"] = also
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    if not args.no_cpu_baseline:
+        ce = 256 if args.env == "cassie" else 2048
+        v, dt, ks = cpu_reference_run(ce, 2000, 2, cores, time_budget=15.0, kind=args.env)
+        line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                "sample": str(ce) + " envs x %d control steps (%.1f s), same action distribution; float64 "
+                                          "oracle port with OpenMP over envs (PyBullet not installable here)" % (ks, dt)}
+    _emit(line)
+    if dist:
+        dist.destroy_process_group()
+
+
+
+
+def measure(ctx, env_kind, N, K, W, actions, self_collision):
+    """One workload: W warm-up steps, K device-timed steps (CUDA events, L2 flushed in between, max over ranks) and the
+    host-buffer e2e leg.  Returns the JSON line (rank 0) or None."""
+    np, torch, _lib, dist, dev = ctx["np"], ctx["torch"], ctx["_lib"], ctx["dist"], ctx["dev"]
+    rank, world, local_rank = ctx["rank"], ctx["world"], ctx["local_rank"]
+    from mocca_envs_b200.distributed import shard_seed
+    from mocca_envs_b200.vec_env import (CassieVecEnv, Child3DCustomVecEnv, MikeStepperVecEnv, Monkey3DCustomVecEnv,
+                                         Walker3DCustomVecEnv, Walker3DStepperVecEnv)
+
     # env i of rank r is global env r*N + i: seeds are independent of the GPU count (SURVEY 8e)
-    phys = {"self_collision": args.self_collision}
-    if args.env in ("stepper", "mike"):
-        cls = Walker3DStepperVecEnv if args.env == "stepper" else MikeStepperVecEnv
+    phys = {"self_collision": self_collision}
+    if env_kind in ("stepper", "mike"):
+        cls = Walker3DStepperVecEnv if env_kind == "stepper" else MikeStepperVecEnv
         env = cls(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
         env.set_env_params({"curriculum": np.array([0, 5, 9] * (N // 3 + 1))[:N]})
-    elif args.env == "child":
+    elif env_kind == "child":
         env = Child3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
-    elif args.env in ("walker2d", "crab2d"):
+    elif env_kind in ("walker2d", "crab2d"):
         from mocca_envs_b200.vec_env import Crab2DCustomVecEnv, Walker2DCustomVecEnv
-        cls = Walker2DCustomVecEnv if args.env == "walker2d" else Crab2DCustomVecEnv
+        cls = Walker2DCustomVecEnv if env_kind == "walker2d" else Crab2DCustomVecEnv
         env = cls(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
-    elif args.env == "monkey":
+    elif env_kind == "monkey":
         env = Monkey3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
-    elif args.env == "cassie":
+    elif env_kind == "cassie":
         env = CassieVecEnv(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
     else:
         env = Walker3DCustomVecEnv(N, device=dev, seed=shard_seed(1234, rank, N), physics=phys)
@@ -309,16 +363,16 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     pool = 64
     act_pool = torch.rand(pool, N, A, device=dev, generator=gen) * 2 - 1
-    if args.env == "cassie":
+    if env_kind == "cassie":
         act_pool *= 0.1  # a ~ U(-0.1, 0.1)^10 residual on the PD targets
-    if args.actions == "pd":
+    if actions == "pd":
         q_ref = torch.tensor(env.table["base_joint_angles"], device=dev, dtype=torch.float32)
         lo = torch.tensor(env.table["lower"], device=dev, dtype=torch.float32)
         hi = torch.tensor(env.table["upper"], device=dev, dtype=torch.float32)
         ref_norm = 2 * (q_ref - lo) / (hi - lo) - 1
 
     def action(i, obs):
-        if args.actions == "random":
+        if actions == "random":
             return act_pool[i % pool]
         # scripted PD toward the running_start pose in normalised units (kp=1, kd=0.1)
         return torch.clamp(1.0 * (ref_norm - obs[:, 6:6 + A]) - 0.1 * (obs[:, 6 + A:6 + 2 * A] * 10.0), -1, 1)
@@ -408,27 +462,27 @@ def main():
     h2d = N * A * 4
     d2h = N * (env.obs_dim * 4 + 4 + 1 + 1)
 
+    env.close()
+    del flush, act_pool, h_pool
     if rank != 0:
-        if dist:
-            dist.destroy_process_group()
-        return
+        return None
 
     ms_per_step = total_ms_max / K
     value = N * world * K / (total_ms_max * 1e-3)
-    S_sub = 50 * env.physics.substeps if args.env == "cassie" else env.physics.substeps  # substeps per env step
+    S_sub = 50 * env.physics.substeps if env_kind == "cassie" else env.physics.substeps  # substeps per env step
     R_mean = rows_all / (K * N * world * S_sub)
-    n_self = len(env.table.get("self_pairs", [])) if args.self_collision else 0
-    if args.env == "cassie":  # Cassie: 50 x 1 substeps, n = 24 generalised coordinates, 17 massive links, 158 points
+    n_self = len(env.table.get("self_pairs", [])) if self_collision else 0
+    if env_kind == "cassie":  # Cassie: 50 x 1 substeps, n = 24 generalised coordinates, 17 massive links, 158 points
         F = flops_per_env_step(R_mean, S=S_sub, n=24, L=17, G=158)
         B_step = bytes_per_env_step(S_state=49, A=10, O=36, S_env=20)
-    elif args.env == "monkey":  # Monkey3D: n = 29 generalised coordinates, 20 massive links, 29 geoms, obs 69
+    elif env_kind == "monkey":  # Monkey3D: n = 29 generalised coordinates, 20 massive links, 29 geoms, obs 69
         F = flops_per_env_step(R_mean, n=29, L=20, G=29, P=n_self)
         B_step = bytes_per_env_step(S_state=59, A=23, O=69, S_env=40)
-    elif args.env in ("stepper", "mike"):
+    elif env_kind in ("stepper", "mike"):
         F = flops_per_env_step(R_mean, L=len([x for x in env.table["mass"] if x > 0]) + 1, G=len(env.table["geoms"]),
                                P=n_self)
         B_step = bytes_per_env_step(O=65, S_env=40)
-    elif args.env in ("walker2d", "crab2d"):  # planar walkers: n = 6 + A, every link massive
+    elif env_kind in ("walker2d", "crab2d"):  # planar walkers: n = 6 + A, every link massive
         F = flops_per_env_step(R_mean, n=6 + A, L=len(env.table["mass"]) + 1, G=len(env.table["geoms"]), P=n_self)
         B_step = bytes_per_env_step(S_state=13 + 2 * A, A=A, O=env.obs_dim)
     else:
@@ -436,7 +490,9 @@ def main():
         B_step = bytes_per_env_step()
     kernel_s = (total_ms / K) * 1e-3  # this rank's average launch duration (one kernel per step)
     achieved_tf = F * N / kernel_s / 1e12
-    peak = C_peak(_lib, local_rank)
+    if "fp32_peak" not in ctx:
+        ctx["fp32_peak"] = C_peak(_lib, local_rank)
+    peak = ctx["fp32_peak"]
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -446,7 +502,7 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_ach = B_step * N / kernel_s / 1e9
     line = {
-        "metric": METRIC.replace("Walker3DCustomEnv", ENV_NAMES[args.env]
+        "metric": METRIC.replace("Walker3DCustomEnv", ENV_NAMES[env_kind]
                                  ).replace("16384", str(N)),
         "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -459,9 +515,9 @@ def main():
                                 "child": "Child3DCustomEnv-v0 batched, flat ground, crawl start pose",
                                 "walker2d": "Walker2DCustomEnv-v0 batched, flat ground, planar base (SURVEY 8 f3)",
                                 "crab2d": "Crab2DCustomEnv-v0 batched, flat ground, planar base (SURVEY 8 f3)",
-                                "mike": "MikeStepperEnv-v0 batched, seeded stepping stones, curriculum 0/5/9"}[args.env],
+                                "mike": "MikeStepperEnv-v0 batched, seeded stepping stones, curriculum 0/5/9"}[env_kind],
                    "envs_per_gpu": N, "actions": "random-uniform U(-1,1)^%d (device pool)" % A
-                   if args.actions == "random" else "scripted PD toward running_start (kp=1, kd=0.1, normalised)",
+                   if actions == "random" else "scripted PD toward running_start (kp=1, kd=0.1, normalised)",
                    "frame_skip": S_sub, "solver_iterations": 5,
                    "self_collision": "on, %d candidate geom pairs per substep" % n_self if n_self else "off", "rng": "mt19937 (NumPy-compatible)",
                    "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs)",
@@ -469,10 +525,11 @@ def main():
                    "parallelism": "env-sharded x%d, no data-path collective" % world},
         "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak if peak else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at 16384 envs from the
-                     # committed ncu --set full capture (profiles/r1u_step_kernel_raw.csv: 8.05 MB read, < 0.01 MB
-                     # written); null for other workloads
-                     "traffic": 8.05e6 if (args.env == "custom" and N == 16384 and args.self_collision) else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at 16384 envs: NOT measured
+                     # by this run (ncu cannot run inside a timed bench) -- the figure of the committed ncu --set full
+                     # capture named in traffic_source; null for other workloads
+                     "traffic": NCU_TRAFFIC["bytes"] if (env_kind == "custom" and N == 16384 and self_collision and actions == "random") else None,
+                     "traffic_source": NCU_TRAFFIC["source"] if (env_kind == "custom" and N == 16384 and self_collision and actions == "random") else None,
                      "peak_source": "FP32 FMA probe kernel measured in this run (mb200_measure_fp32_peak)",
                      "flops_per_env_step": F, "rows_per_substep": R_mean,
                      "contacts_per_substep": conts_all / (K * N * world * S_sub),
@@ -489,15 +546,7 @@ def main():
                      "cap_overflows": overflow, "reduced_with": "nccl all_reduce" if dist else "single rank"},
         "wall_s": wall,
     }
-    if not args.no_cpu_baseline:
-        ce = 256 if args.env == "cassie" else 2048
-        v, dt, ks = cpu_reference_run(ce, 2000, 2, cores, time_budget=15.0, kind=args.env)
-        line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                "sample": str(ce) + " envs x %d control steps (%.1f s), same action distribution; float64 "
-                                          "oracle port with OpenMP over envs (PyBullet not installable here)" % (ks, dt)}
-    _emit(line)
-    if dist:
-        dist.destroy_process_group()
+    return line
 
 
 def C_peak(_lib, device):

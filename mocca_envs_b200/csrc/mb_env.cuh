@@ -367,7 +367,7 @@ template <class M> struct W3DEnv {
     S_::init_lane_const(C);
 #pragma unroll 1
     for (int k = 0; k < P.substeps; ++k) {
-      rows += S_::template substep<0>(S, P, C, &nc, &overflow);
+      rows += S_::template substep<0>(S, P, C, &nc, &overflow, k);
       ncsum += nc;
     }
     // feet_contact from the last collision pass (robots.py:74-86 via getContactPoints)
@@ -702,7 +702,7 @@ template <class M, bool PILLAR = false> struct StepperEnv {
 #pragma unroll 1
     for (int k = 0; k < P.substeps; ++k) {
       load_boxes(S, rec);  // the obstacle staging area is reused by the constraint rows of every substep
-      rows += S_::template substep<OBST>(S, P, C, &nc, &overflow);
+      rows += S_::template substep<OBST>(S, P, C, &nc, &overflow, k);
       ncsum += nc;
     }
     const int timestep = rec_i(rec, ES_TIMESTEP) + 1;
@@ -1104,7 +1104,7 @@ template <class M> struct MonkeyEnv {
 #pragma unroll 1
     for (int k = 0; k < P.substeps; ++k) {
       load_bars(S, rec);  // the obstacle staging area is reused by the constraint rows of every substep
-      rows += S_::template substep<MB_OBST_BARS>(S, P, C, &nc, &overflow);
+      rows += S_::template substep<MB_OBST_BARS>(S, P, C, &nc, &overflow, k);
       ncsum += nc;
     }
     const int timestep = rec_i(rec, EM_TIMESTEP) + 1;
@@ -1373,7 +1373,7 @@ template <class M> struct CassieEnv {
           S.tau[pdd[l]] += fminf(fmaxf(t, -lim[l]), lim[l]);                       // apply_action clip (:225-230)
         }
       MB_END
-      rows += S_::template substep<0>(S, P, C, &nc, &overflow);
+      rows += S_::template substep<0>(S, P, C, &nc, &overflow, it);
       ncsum += nc;
     }
     S_::kinematics(S, P, C, false);

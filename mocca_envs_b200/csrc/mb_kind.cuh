@@ -156,7 +156,7 @@ __device__ __forceinline__ void physics_body(int n, const MbPhysics& phys, float
 #pragma unroll 1
   for (int k = 0; k < phys.substeps; ++k) {
     Env::load_obstacles(S, rec + (size_t)env * Env::REC_STRIDE);
-    rows += Sim<EM>::template substep<Env::OBST>(S, phys, C, &nc, &overflow);
+    rows += Sim<EM>::template substep<Env::OBST>(S, phys, C, &nc, &overflow, k);
   }
   Env::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
   if (tail) return;

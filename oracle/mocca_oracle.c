@@ -1007,8 +1007,10 @@ static void substep_impl(const orc_model* m, const orc_params* p, orc_state* s, 
                          const orc_box* boxes, int n_boxes, const orc_bar* bars, int n_bars, double* warm,
                          orc_contacts* ct, int* out_rows) {
   int nu = 6 + m->n_dof;
-  orc_cache* c = (orc_cache*)malloc(sizeof(orc_cache));
-  orc_rows* rows = (orc_rows*)malloc(sizeof(orc_rows));
+  /* per-thread scratch, allocated once (the CPU baseline steps millions of substeps: no malloc in the loop) */
+  static __thread orc_cache* c = NULL;
+  static __thread orc_rows* rows = NULL;
+  if (!c) { c = (orc_cache*)malloc(sizeof(orc_cache)); rows = (orc_rows*)malloc(sizeof(orc_rows)); }
   double u[ORC_MAXU], acc[ORC_MAXU], dv[ORC_MAXU];
   /* collision detection at start-of-substep poses */
   kin(m, s, c);
@@ -1126,8 +1128,6 @@ static void substep_impl(const orc_model* m, const orc_params* p, orc_state* s, 
   for (int k = 0; k < nc; k++) ct->impulse[k] = rows->normal[k].applied;
   if (out_rows) *out_rows = nlim + 3 * nc;
   integrate_positions(m, p, s);
-  free(rows);
-  free(c);
 }
 
 /* one pybullet.stepSimulation(): applied torques + PyBullet's joint damping torque are computed once and
