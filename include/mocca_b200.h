@@ -118,6 +118,17 @@ int mb200_set_rng(mb200_env* env, const uint32_t* mt_host);
  * last substep); either may be NULL. */
 int mb200_step_physics(mb200_env* env, const float* tau_dev, int* rows_dev, int* contacts_dev, void* stream);
 
+/* The same stepSimulation, also returning what pybullet.getContactPoints reports afterwards (robots.py:74-86 reads it
+ * for feet_contact; bullet_utils.py:177-181): the contact points of the LAST collision pass with the normal impulse the
+ * solver applied to each.  points_dev is [n][mb200_max_contact_points()][mb200_contact_point_width()] float32:
+ * {world position on the robot link (3), contact normal on the partner pointing to the link (3), distance, normal
+ * impulse, robot link index (-1 = base, -2 = unused slot), partner (0 ground plane, 10 + k plank box k, 20 + k bar k,
+ * 1000 + p self-collision pair p)}.  Parity / golden-vector entry point; the env step kernels do not produce it. */
+int mb200_max_contact_points(void);
+int mb200_contact_point_width(void);
+int mb200_step_physics_points(mb200_env* env, const float* tau_dev, int* rows_dev, int* contacts_dev, float* points_dev,
+                              void* stream);
+
 /* pybullet.calculateMassMatrix / calculateInverseDynamics analogues at the current state, in PyBullet's
  * generalised coordinates u = [omega_world, v_world, qd]:  M_dev [n][nu][nu];  tau = M acc + C + G, [n][nu]. */
 int mb200_mass_matrix(mb200_env* env, float* M_dev, void* stream);

@@ -23,7 +23,8 @@ BUILD_DIR = os.path.join(_HERE, "build")
 
 SYMBOLS = [
     "mb200_default_physics", "mb200_default_physics_for", "mb200_create", "mb200_destroy", "mb200_dims", "mb200_seed", "mb200_reset",
-    "mb200_reset_host", "mb200_info", "mb200_info_host",
+    "mb200_reset_host", "mb200_info", "mb200_info_host", "mb200_step_physics_points", "mb200_max_contact_points",
+    "mb200_contact_point_width",
     "mb200_step", "mb200_step_host", "mb200_get_state", "mb200_set_state", "mb200_get_record", "mb200_set_record",
     "mb200_rng_words", "mb200_get_rng", "mb200_set_rng", "mb200_step_physics", "mb200_mass_matrix", "mb200_inverse_dynamics", "mb200_set_param",
     "mb200_set_param_array", "mb200_record_stride", "mb200_stats",
@@ -112,6 +113,7 @@ def lib():
         for f in ("mb200_get_state", "mb200_set_state", "mb200_get_record", "mb200_set_record", "mb200_mass_matrix"):
             getattr(L, f).argtypes = [vp, vp, vp]
         L.mb200_step_physics.argtypes = [vp, vp, vp, vp, vp]
+        L.mb200_step_physics_points.argtypes = [vp, vp, vp, vp, vp, vp]
         L.mb200_rng_words.argtypes = [vp]
         L.mb200_get_rng.argtypes = [vp, vp]
         L.mb200_set_rng.argtypes = [vp, vp]

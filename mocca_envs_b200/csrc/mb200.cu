@@ -230,7 +230,7 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
     // Small batches: with 14-warp CTAs 1 024 envs occupy 74 of the 148 SMs and the step takes the latency of one
     // env-step; narrower CTAs spread the envs over every SM (2 resident CTAs each).  Pure scheduling (MB_WARPS is the
     // launch's own blockDim), results are unchanged.  MB200_WARPS overrides (tuning / A-B runs).
-    const int slots = 2 * prop.multiProcessorCount;
+    const int slots = MB_MINBLOCKS * prop.multiProcessorCount;
     int w = (n_envs + slots - 1) / slots;
     if (w < 4) w = 4;
     if (w < e->warps) e->warps = w;
@@ -591,14 +591,28 @@ int mb200_set_rng(mb200_env* e, const uint32_t* mt_host) {
   return 0;
 }
 
-int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* contacts_dev, void* stream) {
+static int step_physics_impl(mb200_env* e, const float* tau_dev, int* rows_dev, int* contacts_dev, float* points_dev,
+                             void* stream) {
   if (!e || !tau_dev) return fail("mb200_step_physics: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
   const LaunchDims d = {grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream};
-  ops_of(e)->physics(d, e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev);
+  ops_of(e)->physics(d, e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev, points_dev);
   e->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int mb200_step_physics(mb200_env* e, const float* tau_dev, int* rows_dev, int* contacts_dev, void* stream) {
+  return step_physics_impl(e, tau_dev, rows_dev, contacts_dev, nullptr, stream);
+}
+
+int mb200_contact_point_width(void) { return MB_POINT_WIDTH; }
+int mb200_max_contact_points(void) { return MB_MAXC; }
+
+int mb200_step_physics_points(mb200_env* e, const float* tau_dev, int* rows_dev, int* contacts_dev, float* points_dev,
+                              void* stream) {
+  if (!points_dev) return fail("mb200_step_physics_points: NULL argument");
+  return step_physics_impl(e, tau_dev, rows_dev, contacts_dev, points_dev, stream);
 }
 
 int mb200_mass_matrix(mb200_env* e, float* M_dev, void* stream) {

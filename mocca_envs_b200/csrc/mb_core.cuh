@@ -100,9 +100,6 @@ inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #endif
 
 #define MB_UNLIKELY(x) __builtin_expect(!!(x), 0)
-#ifndef MB_USE_GRAM
-#define MB_USE_GRAM 1 /* impulse-space PGS over the Gram matrix of the rows when it fits (solve_constraints_gram) */
-#endif
 #ifdef __CUDACC__
 #define MB_ASSUME_SHARED(S) __builtin_assume(__isShared(&(S)))  /* out-of-line helpers keep LDS/STS addressing */
 #define MB_FDIV(a, b) __fdividef((a), (b))
@@ -129,6 +126,7 @@ MB_HD void mb_sincos(float x, float* s, float* c) {
 }
 
 #define MB_MAXC 16    /* contact points kept per substep */
+#define MB_POINT_WIDTH 10 /* floats per contact point of the debug output (substep points_out) */
 #define MB_MAXROW 48  /* constraint rows per substep (limits + 3 per contact) */
 #define MB_YSTRIDE 15 /* compact row: 6 base + <= 8 chain entries (+1 pad, odd stride = conflict-free) */
 #define MB_ROW_DUAL 0x80000000u /* r_mask flag: the row continues in a second compact row (other link, same multiplier) */
@@ -1530,181 +1528,6 @@ template <class M> struct Sim {
     }
   }
 
-  // ---- H2. the same projected Gauss-Seidel in IMPULSE space ----------------------------------------------------------
-  // J_r dv = Y_r . z with z = sum_s Y_s lambda_s, i.e. J_r dv = sum_s G_rs lambda_s with the Gram matrix G = Y Y^T of the
-  // compact rows.  With G at hand a row visit no longer touches a 27-wide vector: lane c carries w_c = sum_s G_cs lambda_s
-  // of compact row c in ONE register, a visit of row a is  w_a -> (one shuffle) -> delta (uniform, all lanes) ->
-  // w_c += G_ac delta (one LDS + one FFMA per lane).  No 5-stage butterfly reduction and no Y loads per visit: ~20
-  // instructions and ~50 cycles of dependent latency instead of ~50 and ~220 -- and the visiting order, clamps, cone
-  // projection and early exit are exactly those of solve_constraints (btMultiBodyConstraintSolver::solveSingleIteration).
-  // G (lower triangle, packed) lives in the unused tail of the row matrix, so the path needs Rc (Rc + 1) / 2 <=
-  // (MB_MAXROW - Rc) * MB_YSTRIDE, i.e. Rc <= 25 compact rows and at most one row per lane; substeps with more rows
-  // (a walker lying on the ground) and the loop-closure models take the z-space solver above.
-  // The common support of two compact rows is the base block plus the common prefix of their chains (a tree), and a
-  // coordinate sits in the same slot of every row that contains it, so G_rs = sum_{t < popc(mask_r & mask_s)} Y_r[t] Y_s[t].
-  MB_HD static bool gram_fits(int Rc) { return Rc <= 25 && Rc * (Rc + 1) <= 2 * (MB_MAXROW - Rc) * MB_YSTRIDE; }
-  MB_HD static void build_gram(Mem& S, int Rc) {
-    float* G = &S.w.Yc[0][0] + Rc * MB_YSTRIDE;
-    const int npair = (Rc * (Rc + 1)) >> 1;
-#pragma unroll 1
-    for (int base = 0; base < npair; base += 32) {
-      MB_LANES(l)
-        const int pidx = base + l;
-        if (pidx < npair) {
-          int r = (int)((sqrtf(8.0f * (float)pidx + 1.0f) - 1.0f) * 0.5f);
-          if (((r + 1) * (r + 2)) >> 1 <= pidx) ++r;
-          if ((r * (r + 1)) >> 1 > pidx) --r;
-          const int c = pidx - ((r * (r + 1)) >> 1);
-          const int n = mb_popc(S.rc.r.r_mask[r] & S.rc.r.r_mask[c] & MB_ROW_SUP);
-          const float* a = S.w.Yc[r];
-          const float* b = S.w.Yc[c];
-          float acc = 0.0f;
-#pragma unroll
-          for (int t = 0; t < M::MAXSUP; ++t)
-            if (t < n) acc = fmaf(a[t], b[t], acc);
-          G[pidx] = acc;
-        }
-      MB_END
-    }
-  }
-  // G(a, lane): lower-triangle lookup; tri_l = l (l + 1) / 2 of the lane
-  MB_HD static float gram_at(const float* G, int a, int tri_a, int l, int tri_l) {
-    return G[l <= a ? tri_a + l : tri_l + a];
-  }
-  // one row (DUAL as in pgs_single: the multiplier's second compact row is ra + 1)
-  template <int DUAL>
-  MB_HD static float gram_single(Mem& S, const float* G, const LaneVar<int>& tril, int Rc, int ra, float lo, float hi,
-                                 LaneVar<float>& w) {
-    const bool dual = DUAL == 1 || (DUAL == 2 && (S.rc.r.r_mask[ra] & MB_ROW_DUAL));
-    float dotA = warp_bcast(w, ra);
-    if (dual) dotA += warp_bcast(w, ra + 1);
-    const MbRowPar pA = S.rc.r.r_par[ra];
-    const float appA = S.rc.r.r_app[ra];
-    float dA = pA.rhs - appA * pA.cfm - dotA * pA.jinv;
-    const float sumA = appA + dA;
-    float nA = sumA;
-    if (sumA < lo) { dA = lo - appA; nA = lo; }
-    else if (sumA > hi) { dA = hi - appA; nA = hi; }
-    const int tra = (ra * (ra + 1)) >> 1, trb = ((ra + 1) * (ra + 2)) >> 1;
-    MB_LANES(l)
-      if (l < Rc) {
-        float g = gram_at(G, ra, tra, l, tril[l]);
-        if (dual) g += gram_at(G, ra + 1, trb, l, tril[l]);
-        w[l] = fmaf(g, dA, w[l]);
-      }
-      if (l == 0) S.rc.r.r_app[ra] = nA;
-    MB_END
-    return dA * pA.den;
-  }
-  // friction pair (rows ra, ra + 1; a self-contact's pair continues in ra + 2, ra + 3), cone projection as pgs_pair
-  MB_HD static float gram_pair(Mem& S, const float* G, const LaneVar<int>& tril, int Rc, int ra, float cone,
-                               LaneVar<float>& w) {
-    const int rb = ra + 1;
-    const bool dual = NSELF > 0 && (S.rc.r.r_mask[ra] & MB_ROW_DUAL);
-    float dotA = warp_bcast(w, ra), dotB = warp_bcast(w, rb);
-    if (dual) { dotA += warp_bcast(w, ra + 2); dotB += warp_bcast(w, ra + 3); }
-    const MbRowPar pA = S.rc.r.r_par[ra], pB = S.rc.r.r_par[rb];
-    const float appA = S.rc.r.r_app[ra], appB = S.rc.r.r_app[rb];
-    float dA = pA.rhs - appA * pA.cfm - dotA * pA.jinv;
-    float dB = pB.rhs - appB * pB.cfm - dotB * pB.jinv;
-    const float sumA = appA + dA, sumB = appB + dB;
-    float nA = sumA, nB = sumB;
-    const float n2 = sumA * sumA + sumB * sumB;
-    if (n2 >= cone * cone) {
-      const float sc = n2 > 0.0f ? fabsf(cone) * rsqrtf(n2) : 0.0f;
-      const float clipA = fabsf(sumA) * sc, clipB = fabsf(sumB) * sc;
-      if (sumA < -clipA) { dA = -clipA - appA; nA = -clipA; }
-      else if (sumA > clipA) { dA = clipA - appA; nA = clipA; }
-      if (sumB < -clipB) { dB = -clipB - appB; nB = -clipB; }
-      else if (sumB > clipB) { dB = clipB - appB; nB = clipB; }
-    }
-    const int tra = (ra * (ra + 1)) >> 1, trb = (rb * (rb + 1)) >> 1;
-    MB_LANES(l)
-      if (l < Rc) {
-        float ga = gram_at(G, ra, tra, l, tril[l]), gb = gram_at(G, rb, trb, l, tril[l]);
-        if (dual) {
-          ga += gram_at(G, ra + 2, ((ra + 2) * (ra + 3)) >> 1, l, tril[l]);
-          gb += gram_at(G, ra + 3, ((ra + 3) * (ra + 4)) >> 1, l, tril[l]);
-        }
-        w[l] = fmaf(ga, dA, fmaf(gb, dB, w[l]));
-      }
-      if (l == 0) { S.rc.r.r_app[ra] = nA; S.rc.r.r_app[rb] = nB; }
-    MB_END
-    return dA * pA.den + dB * pB.den;
-  }
-  // Runs the PGS and leaves z = sum_r Y_r lambda_r (what solve_constraints accumulates on the fly) in `z`.
-  MB_HD static void solve_constraints_gram(Mem& S, const MbPhysics& P, const LaneConst& C, int nlim, int nc, int ncs,
-                                           int Rc, LaneVar<float>& z) {
-    const int nnc = nlim + NLC / 2, n0 = nlim + NLC, S0 = n0 + 3 * nc, nct = nc + (NSELF > 0 ? ncs : 0);
-    build_gram(S, Rc);
-    const float* G = &S.w.Yc[0][0] + Rc * MB_YSTRIDE;
-    LaneVar<float> w;
-    LaneVar<int> tril;
-    MB_LANES(l)
-      w[l] = 0.0f;
-      tril[l] = (l * (l + 1)) >> 1;
-    MB_END_REG
-#pragma unroll 1
-    for (int it = 0; it < P.iterations; ++it) {
-      float res2 = 0.0f;
-#pragma unroll 1
-      for (int v = 0; v < nnc; ++v) {
-        const int idx = (it & 1) ? v : nnc - 1 - v;
-        float rr;
-        if (NLC == 0 || idx < nlim) rr = gram_single<0>(S, G, tril, Rc, idx, 0.0f, P.limit_max_impulse, w);
-        else {
-          const int ra = nlim + 2 * (idx - nlim);
-          const float lim = S.rc.r.r_mu[ra];
-          rr = gram_single<1>(S, G, tril, Rc, ra, -lim, lim, w);
-        }
-        res2 = fmaxf(res2, rr * rr);
-      }
-#pragma unroll 1
-      for (int k = 0; k < nct; ++k) {
-        const int ra = (NSELF > 0 && k >= nc) ? S0 + 2 * (k - nc) : n0 + k;
-        const float rr = gram_single<(NSELF > 0 ? 2 : 0)>(S, G, tril, Rc, ra, 0.0f, 1e10f, w);
-        res2 = fmaxf(res2, rr * rr);
-      }
-#pragma unroll 1
-      for (int k = 0; k < nct; ++k) {
-        const bool self = NSELF > 0 && k >= nc;
-        const int ra = self ? S0 + 2 * ncs + 4 * (k - nc) : n0 + nc + 2 * k;
-        const int rn = self ? S0 + 2 * (k - nc) : n0 + k;
-        const float cone = S.rc.r.r_mu[ra] * S.rc.r.r_app[rn];
-        if (cone == 0.0f && S.rc.r.r_app[ra] == 0.0f && S.rc.r.r_app[ra + 1] == 0.0f) continue;  // exact skip, see above
-        const float rr = gram_pair(S, G, tril, Rc, ra, cone, w);
-        res2 = fmaxf(res2, rr * rr);
-      }
-      if (res2 <= P.residual_threshold) break;
-    }
-    // the second compact row of a dual row carries the same multiplier
-    if (NLC > 0 || NSELF > 0) {
-      MB_LANES(l)
-        if (NLC > 0 && l < NLC / 2) S.rc.r.r_app[nlim + 2 * l + 1] = S.rc.r.r_app[nlim + 2 * l];
-        if (NSELF > 0) {
-          for (int i = l; i < 3 * ncs; i += 32) {
-            const int sidx = i / 3, wq = i - 3 * sidx;
-            const int ra = S0 + (wq == 0 ? 2 * sidx : 2 * ncs + 4 * sidx + (wq - 1));
-            S.rc.r.r_app[ra + (wq == 0 ? 1 : 2)] = S.rc.r.r_app[ra];
-          }
-        }
-      MB_END
-    }
-    // z = sum_r Y_r lambda_r, one generalised coordinate per lane
-    MB_LANES(l)
-      z[l] = 0.0f;
-    MB_END_REG
-#pragma unroll 1
-    for (int r = 0; r < Rc; ++r) {
-      const unsigned sup = S.rc.r.r_mask[r];
-      const float lam = S.rc.r.r_app[r];
-      if (lam == 0.0f) continue;  // speculative contacts and their friction rows: nothing applied
-      MB_LANES(l)
-        if (l < NU && ((sup >> l) & 1u)) z[l] = fmaf(S.w.Yc[r][C.tl[l]], lam, z[l]);
-      MB_END_REG
-    }
-  }
-
   // ---- I. integrate positions (btMultiBody::stepPositionsMultiDof) --------------------------------------------
   MB_HD static void integrate(Mem& S, const MbPhysics& P) {
     MB_LANES(l)
@@ -1734,7 +1557,12 @@ template <class M> struct Sim {
 
   // ---- one Bullet substep.  Returns the number of constraint rows; contact list of this substep stays in S ----
   template <int OBST>
-  MB_HD static int substep(Mem& S, const MbPhysics& P, LaneConst& C, int* nc_out, int* overflow, int sub = 0) {
+  // points_out (debug / golden-vector kernels only; nullptr in the env step kernels, where the block folds away):
+  // [MB_MAXC][MB_POINT_WIDTH] = world position on the robot link, normal (on the partner, towards the link), distance,
+  // applied normal impulse, link index (-1 = base), partner code (0 ground, 10 + box, 20 + bar, 1000 + self pair) --
+  // the fields pybullet.getContactPoints reports ([5..9], [3], [2 / 4]); unused slots carry link = -2.
+  MB_HD static int substep(Mem& S, const MbPhysics& P, LaneConst& C, int* nc_out, int* overflow, int sub = 0,
+                           float* points_out = nullptr) {
     MB_BLOCK_BARRIER(sub);  // keeps the warps of a CTA in the same phase so instruction-cache lines are shared
     kinematics(S, P, C, true);
     int ns_all = 0;
@@ -1771,19 +1599,35 @@ template <class M> struct Sim {
         setup_self_rows(S, nlim + NLC + 3 * nc, nc, ncs, P.linear_slop, 1.0f / P.dt);
         init_lane_const(C);  // dead across the call by construction: recomputed, not saved
       }
+      // (an impulse-space variant of the PGS -- Gram matrix G = Y Y^T of the rows in the unused tail of the row matrix,
+      // one register w_c = sum_s G_cs lambda_s per lane, a row visit = one shuffle + uniform delta + one LDS / FFMA per
+      // lane -- was measured in round 2: 26 instead of 31 instructions per visit, but building G and assembling z cost
+      // what the visits saved: -3 % on every Walker-family env (profiles/README.md, r2d); the z-space solver stays)
       LaneVar<float> z;
-      const int Rc = nlim + NLC + 3 * nc + 6 * ncs;  // compact rows
-      if (MB_USE_GRAM && NLC == 0 && gram_fits(Rc)) {
-        solve_constraints_gram(S, P, C, nlim, nc, ncs, Rc, z);
-      } else {
-        MB_LANES(l)
-          z[l] = 0.0f;
-        MB_END
-        solve_constraints(S, P, C, nlim, nc, ncs, z);
-      }
+      MB_LANES(l)
+        z[l] = 0.0f;
+      MB_END
+      solve_constraints(S, P, C, nlim, nc, ncs, z);
       solve_L<false>(S, C, z);
       MB_LANES(l)
         if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + z[l], -P.max_coord_vel), P.max_coord_vel);
+      MB_END
+    }
+    if (points_out) {
+      const int n0 = nlim + NLC, S0 = n0 + 3 * nc;
+      MB_LANES(l)
+        if (l < MB_MAXC) {
+          float* o = points_out + MB_POINT_WIDTH * l;
+          const bool live = l < nc + ncs;  // (contacts dropped at the row cap carry no row)
+          const int row = l < nc ? n0 + l : S0 + 2 * (l - nc);
+          o[0] = live ? S.cP[l][0] + S.pos[0] : 0.0f; o[1] = live ? S.cP[l][1] + S.pos[1] : 0.0f;
+          o[2] = live ? S.cP[l][2] + S.pos[2] : 0.0f;
+          o[3] = live ? S.cn[l][0] : 0.0f; o[4] = live ? S.cn[l][1] : 0.0f; o[5] = live ? S.cn[l][2] : 0.0f;
+          o[6] = live ? S.cdist[l] : 0.0f;
+          o[7] = live && R > 0 ? S.rc.r.r_app[row] : 0.0f;
+          o[8] = live ? (float)S.clink[l] : -2.0f;
+          o[9] = live ? (float)S.cpartner[l] : 0.0f;
+        }
       MB_END
     }
     integrate(S, P);

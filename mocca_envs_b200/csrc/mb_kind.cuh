@@ -9,7 +9,9 @@
 #ifndef MB_WARPS_DEFAULT
 #define MB_WARPS_DEFAULT 14 /* envs (warps) per CTA of the step kernels; 2 CTAs per SM (72 registers, <= 114 KB smem) */
 #endif
+#ifndef MB_WARPS_MAX
 #define MB_WARPS_MAX 16
+#endif
 #define MB_WARPS ((int)(blockDim.x >> 5)) /* device code: warps of this launch */
 #ifndef MB_MINBLOCKS
 #define MB_MINBLOCKS 2
@@ -67,7 +69,7 @@ struct MbKindOps {
   void (*reset)(const LaunchDims&, int n, const MbPhysics&, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
                 float* obs, float* dummy_obs);
   void (*physics)(const LaunchDims&, int n, const MbPhysics&, float* state, const float* rec, const float* tau,
-                  int* rows_out, int* contacts_out);
+                  int* rows_out, int* contacts_out, float* points_out);
   void (*debug)(const LaunchDims&, int n, const MbPhysics&, const float* state, int mode, const float* acc, float* out);
 };
 
@@ -138,7 +140,7 @@ __device__ __forceinline__ void reset_body(int n, const MbPhysics& phys, float* 
 // stepSimulation only; rec supplies the static obstacles of the env kind
 template <class Env>
 __device__ __forceinline__ void physics_body(int n, const MbPhysics& phys, float* state, const float* rec,
-                                             const float* tau, int* rows_out, int* contacts_out) {
+                                             const float* tau, int* rows_out, int* contacts_out, float* points_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * MB_WARPS + warp;
@@ -156,7 +158,10 @@ __device__ __forceinline__ void physics_body(int n, const MbPhysics& phys, float
 #pragma unroll 1
   for (int k = 0; k < phys.substeps; ++k) {
     Env::load_obstacles(S, rec + (size_t)env * Env::REC_STRIDE);
-    rows += Sim<EM>::template substep<Env::OBST>(S, phys, C, &nc, &overflow, k);
+    // the contact points of the LAST collision pass (what getContactPoints reports after stepSimulation)
+    float* pts = points_out && !tail && k == phys.substeps - 1
+                     ? points_out + (size_t)env * MB_MAXC * MB_POINT_WIDTH : nullptr;
+    rows += Sim<EM>::template substep<Env::OBST>(S, phys, C, &nc, &overflow, k, pts);
   }
   Env::store_state(S, state + (size_t)env * MB_STATE_STRIDE);
   if (tail) return;
@@ -212,15 +217,15 @@ __device__ __forceinline__ void dynamics_debug_body(int n, const MbPhysics& phys
   }                                                                                                                   \
   __global__ void __launch_bounds__(MB_WARPS_MAX * 32)                                                                \
       k_step_physics_##ID(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,    \
-                          int* contacts_out) {                                                                        \
-    physics_body<ENV>(n, phys, state, rec, tau, rows_out, contacts_out);                                              \
+                          int* contacts_out, float* points_out) {                                                     \
+    physics_body<ENV>(n, phys, state, rec, tau, rows_out, contacts_out, points_out);                                  \
   }                                                                                                                   \
   __global__ void __launch_bounds__(MB_WARPS_MAX * 32)                                                                \
       k_dynamics_debug_##ID(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {     \
     dynamics_debug_body<ENV>(n, phys, state, mode, acc, out);                                                         \
   }                                                                                                                   \
   static cudaError_t prepare_##ID(void) {                                                                             \
-    const int bytes = (int)(sizeof(typename ENV::Mem) * MB_WARPS_MAX);                                                \
+    const int bytes = (int)(sizeof(typename ENV::Mem) * WARPS);                                                \
     const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;                                         \
     cudaError_t e;                                                                                                    \
     if ((e = cudaFuncSetAttribute(k_step_##ID, at, bytes)) != cudaSuccess) return e;                                  \
@@ -238,8 +243,9 @@ __device__ __forceinline__ void dynamics_debug_body(int n, const MbPhysics& phys
     k_reset_##ID<<<d.grid, d.threads, d.smem, d.stream>>>(n, p, state, rec, mt, mask, obs, dummy_obs);                \
   }                                                                                                                   \
   static void launch_physics_##ID(const LaunchDims& d, int n, const MbPhysics& p, float* state, const float* rec,    \
-                                  const float* tau, int* rows_out, int* contacts_out) {                               \
-    k_step_physics_##ID<<<d.grid, d.threads, d.smem, d.stream>>>(n, p, state, rec, tau, rows_out, contacts_out);      \
+                                  const float* tau, int* rows_out, int* contacts_out, float* points_out) {            \
+    k_step_physics_##ID<<<d.grid, d.threads, d.smem, d.stream>>>(n, p, state, rec, tau, rows_out, contacts_out,       \
+                                                                 points_out);                                         \
   }                                                                                                                   \
   static void launch_debug_##ID(const LaunchDims& d, int n, const MbPhysics& p, const float* state, int mode,        \
                                 const float* acc, float* out) {                                                       \

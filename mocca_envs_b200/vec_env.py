@@ -242,6 +242,17 @@ class Walker3DCustomVecEnv:
         _lib.check(self._L.mb200_step_physics(self._h, _ptr(tau), _ptr(rows), _ptr(nc), self._stream()))
         return rows, nc
 
+    def step_physics_points(self, tau: torch.Tensor):
+        """stepSimulation + pybullet.getContactPoints: returns (rows, contacts, points[n, max_points, width]); per point
+        {world position (3), normal (3), distance, normal impulse, link index (-2 = unused), partner code}."""
+        tau = tau.to(device=self.device, dtype=torch.float32).contiguous()
+        rows = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        nc = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        pts = torch.zeros(self.num_envs, int(self._L.mb200_max_contact_points()),
+                          int(self._L.mb200_contact_point_width()), dtype=torch.float32, device=self.device)
+        _lib.check(self._L.mb200_step_physics_points(self._h, _ptr(tau), _ptr(rows), _ptr(nc), _ptr(pts), self._stream()))
+        return rows, nc, pts
+
     def mass_matrix(self) -> torch.Tensor:
         M = torch.empty(self.num_envs, self.nu, self.nu, dtype=torch.float32, device=self.device)
         _lib.check(self._L.mb200_mass_matrix(self._h, _ptr(M), self._stream()))

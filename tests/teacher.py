@@ -279,6 +279,16 @@ def _perturbed_response(O, o, pre, a, base_obs, A, rng):
     return worst
 
 
+def _set_oracle_state(o, A, sv):
+    s = _w3d_base(o).s
+    for k in range(3):
+        s.pos[k], s.omega[k], s.vel[k] = float(sv[k]), float(sv[7 + k]), float(sv[10 + k])
+    for k in range(4):
+        s.quat[k] = float(sv[3 + k])
+    for k in range(A):
+        s.q[k], s.qd[k] = float(sv[13 + k]), float(sv[13 + A + k])
+
+
 def _round_oracle_state(o, A):
     """Overwrite the oracle's physics state with its own float32 rounding (what the backend is given)."""
     s = _w3d_base(o).s
@@ -288,7 +298,7 @@ def _round_oracle_state(o, A):
 
 
 def run_teacher_forced(kind, O, table, o, backend, actions, judge, refs=None, teleports=None, obs_err=None,
-                       skip_compare=(), book_on_done=False, round_oracle=False, on_step=None):
+                       skip_compare=(), book_on_done=False, round_oracle=False, on_step=None, force_states=False):
     """Drive oracle `o` along `actions`; before every step hand the backend the oracle's state and bookkeeping; compare
     the backend's observation / reward / done with `refs` (the reference-recorded obs / rewards / dones of a golden
     trace) or, when refs is None, with the oracle's own.  `skip_compare`: steps whose float comparison is waived (their
@@ -300,6 +310,10 @@ def run_teacher_forced(kind, O, table, o, backend, actions, judge, refs=None, te
     for t, a in enumerate(actions):
         if teleports and t in teleports:
             teleports[t](o)
+        if refs is not None and "states" in getattr(refs, "files", refs) and force_states:
+            # a trace recorded from another physics engine (PyBullet): oracle and backend both restart every step from
+            # the RECORDED state, so the comparison is one env step deep and errors do not accumulate
+            _set_oracle_state(o, A, refs["states"][k - 1])
         if round_oracle:
             _round_oracle_state(o, A)
         rows0, nc0 = backend.force(kind, o)
@@ -315,7 +329,7 @@ def run_teacher_forced(kind, O, table, o, backend, actions, judge, refs=None, te
         rows, nc = rec[15] - rows0, rec[16] - nc0
         if refs is not None:
             ref_obs, ref_r, ref_d = refs["obs"][k], float(refs["rewards"][t]), bool(refs["dones"][t])
-            assert d1 == ref_d, "the oracle left the recorded trajectory at step %d" % t
+            assert force_states or d1 == ref_d, "the oracle left the recorded trajectory at step %d" % t
         else:
             ref_obs, ref_r, ref_d = o1, r1, d1
         e_obs = obs_err(got, ref_obs)
@@ -426,7 +440,8 @@ def make_pair(O, env_name, backend, seed, seed2=None, plank_class=None, curricul
 
 
 def env_name_of_fixture(basename):
-    for key, name in (("child3d", "child3d"), ("walker2d", "walker2d"), ("crab2d", "crab2d"), ("mike", "mike"),
+    for key, name in (("Walker3DCustomEnv", "walker3d"), ("Walker3DStepperEnv", "stepper"), ("Monkey3DCustomEnv", "monkey"),
+                      ("CassieEnv", "cassie"), ("child3d", "child3d"), ("walker2d", "walker2d"), ("crab2d", "crab2d"), ("mike", "mike"),
                       ("walker3d_stepper", "stepper"), ("monkey3d", "monkey"), ("cassie", "cassie"),
                       ("walker3d_custom", "walker3d")):
         if key in basename:
@@ -439,7 +454,7 @@ def env_name_of_fixture(basename):
 TOL = {"custom": (1e-3, 1e-2), "stepper": (1e-3, 1e-2), "monkey": (1e-3, 1e-2), "cassie": (1e-2, 2e-3)}
 
 
-def run_golden_trace(O, path, backend):
+def run_golden_trace(O, path, backend, force_states=False):
     """One reference-recorded fixture (tests/golden/ref_*.npz) teacher-forced through `backend` ("emu" / "gpu"): the
     backend's observation / reward / done per step against the values the REFERENCE's own code recorded."""
     import os
@@ -479,7 +494,7 @@ def run_golden_trace(O, path, backend):
                   max_explained=0.30 if "_target" in base else 0.10)
     run_teacher_forced(kind, O, t, o, b, g["actions"], judge, refs=g, teleports=tele,
                        obs_err=monkey_obs_err if kind == "monkey" else None,
-                       skip_compare=set(tele) if kind == "monkey" else ())
+                       skip_compare=set(tele) if kind == "monkey" else (), force_states=force_states)
     b.close()
     return judge.finish(median_below=3e-3 if kind == "cassie" else 5e-4)
 

@@ -1,0 +1,133 @@
+"""Analytic pins on the device: facts that follow from the reference's Bullet parameters alone, checked on
+the CUDA path through the C ABI -- no oracle in the loop, so they hold whatever the restatement got wrong.
+
+  free fall         explicit-Euler recursion v <- v + dt (-g - k v (1 + |v|)), k = 0.04 (btMultiBody link damping): every
+                    link has the same velocity, so the joints do not move and the base follows the scalar recursion;
+  resting contact   ERP 0.9 + linear slop 1e-5 without split impulse: a loaded resting contact sits at distance -slop
+                    (the positional term removes 90 % of the excess penetration per substep), and the ground's normal
+                    impulses sum to M g dt per substep (momentum balance of the whole multibody; M from the model table);
+  soft planks       contactStiffness 30000 / contactDamping 1000 (bullet_objects.py:64-72) -> erp = dt kp / (dt kp + kd),
+                    cfm = 1 / (dt kp + kd): at rest every loaded contact obeys the spring law impulse = dt kp depth, and
+                    the vertical components of the plank impulses sum to M g dt.
+
+(A pendulum-period pin needs a fixed base; every model of the path has a floating base -- DESIGN.md section 10.)"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+G, K_DAMP = 9.8, 0.04
+
+
+def _free_fall_reference(dt, n):
+    v, z = 0.0, 0.0
+    for _ in range(n):
+        v = v + dt * (-G - K_DAMP * v * (1.0 + abs(v)))
+        z = z + dt * v
+    return v, z
+
+
+@pytest.mark.parametrize("name", ["walker3d", "monkey", "cassie"])
+def test_free_fall_follows_the_damped_euler_recursion(name):
+    import torch
+
+    from mocca_envs_b200 import vec_env as V
+    from tests.teacher import SPECS, table_of
+
+    cls = getattr(V, SPECS[name][4])
+    t = table_of(SPECS[name][1])
+    A = t["n_dof"]
+    N = 8
+    env = cls(N, device="cuda:0", seed=0, physics={"self_collision": 0})
+    env.reset()
+    st = env.get_state().cpu().numpy()
+    st[:, 0:3] = [0.0, 0.0, 50.0]
+    st[:, 3:7] = [0, 0, 0, 1]
+    st[:, 7:13] = 0.0
+    st[:, 13 + A:] = 0.0
+    z0 = st[:, 2].copy()
+    q0 = st[:, 13:13 + A].copy()
+    env.set_state(torch.tensor(st))
+    calls = 30
+    for _ in range(calls):
+        env.step_physics(torch.zeros(N, A, device="cuda:0"))
+    out = env.get_state().cpu().numpy()
+    n = calls * env.physics.substeps
+    v_ref, dz_ref = _free_fall_reference(env.physics.dt, n)
+    assert np.abs(out[:, 12] - v_ref).max() < 2e-5 * abs(v_ref), (out[:, 12], v_ref)
+    assert np.abs((out[:, 2] - z0) - dz_ref).max() < 2e-5 * abs(dz_ref) + 1e-5
+    assert np.abs(out[:, 10:12]).max() < 1e-5 and np.abs(out[:, 7:10]).max() < 1e-5
+    # no relative motion: the joints keep their angles (Cassie: the loop-closure rows stay idle)
+    assert np.abs(out[:, 13:13 + A] - q0).max() < 2e-4, np.abs(out[:, 13:13 + A] - q0).max()
+    env.close()
+
+
+def _settle(env, A, calls):
+    import torch
+
+    zero = torch.zeros(env.num_envs, A, device="cuda:0")
+    for _ in range(calls):
+        env.step_physics(zero)
+    rows, nc, pts = env.step_physics_points(zero)
+    return pts.cpu().numpy(), env.get_state().cpu().numpy()
+
+
+def test_resting_on_the_ground_plane(walker_table):
+    """A collapsed Walker3D at rest on the stadium plane: sum of the ground's normal impulses = M g dt (0.5 %), every
+    loaded contact rests at distance -slop (within [-1e-4, 2e-5])."""
+    import torch
+
+    from mocca_envs_b200.vec_env import Walker3DCustomVecEnv
+
+    t = walker_table
+    A, M = 21, t["total_mass"]
+    N = 16
+    env = Walker3DCustomVecEnv(N, device="cuda:0", seed=5)
+    env.reset()  # 16 different noisy start poses: 16 different heaps on the ground
+    pts, st = _settle(env, A, 450)
+    dt = env.physics.dt
+    assert np.abs(st[:, 7:13]).max() < 2e-2 and np.abs(st[:, 13 + A:]).max() < 0.2, "not at rest"
+    for i in range(N):
+        p = pts[i]
+        ground = (p[:, 8] > -2) & (p[:, 9] == 0)
+        assert ground.sum() >= 3
+        ratio = p[ground, 7].sum() / (M * G * dt)
+        assert abs(ratio - 1.0) < 5e-3, (i, ratio)
+        loaded = ground & (p[:, 7] > 0.02 * M * G * dt)
+        assert loaded.any()
+        assert p[loaded, 6].min() > -1e-4 and p[loaded, 6].max() < 2e-5, (i, p[loaded, 6])
+    env.close()
+
+
+def test_resting_on_a_soft_plank(walker_table):
+    """A collapsed Walker3D at rest on its first stepping stone (kp = 30000, kd = 1000): the vertical components of the
+    plank impulses sum to M g dt (3 %) and every contact carrying > 10 % of the weight obeys impulse = dt kp depth
+    (each within 20 %, their median within 3 %; five un-warm-started PGS iterations per substep do not converge further)."""
+    import torch
+
+    from mocca_envs_b200.vec_env import Walker3DStepperVecEnv
+
+    t = walker_table
+    A, M, KP = 21, t["total_mass"], 30000.0
+    N = 16
+    env = Walker3DStepperVecEnv(N, device="cuda:0", seed=5)
+    env.reset()
+    pts, st = _settle(env, A, 900)
+    dt, slop = env.physics.dt, env.physics.linear_slop
+    ratios = []
+    rested = 0
+    for i in range(N):
+        if np.abs(st[i, 7:13]).max() > 2e-2 or np.abs(st[i, 13 + A:]).max() > 0.2 or st[i, 2] < -1.0:
+            continue  # still rocking on the plank's edge, or slid off it (there is no ground in this env)
+        rested += 1
+        p = pts[i]
+        plank = (p[:, 8] > -2) & (p[:, 9] >= 10) & (p[:, 9] < 20)
+        vertical = (p[plank, 7] * p[plank, 5]).sum() / (M * G * dt)
+        assert abs(vertical - 1.0) < 3e-2, (i, vertical)
+        loaded = plank & (p[:, 7] > 0.10 * M * G * dt)
+        depth = -(p[loaded, 6] + slop)
+        r = p[loaded, 7] / (dt * KP * depth)
+        assert np.all(np.abs(r - 1.0) < 0.2), (i, r)
+        ratios += list(r)
+    assert rested >= N // 2, rested
+    assert abs(np.median(ratios) - 1.0) < 3e-2, np.median(ratios)
+    env.close()

@@ -24,3 +24,12 @@ def test_device_env_step_vs_reference_trace(path, oracle_mod):
 
     j = T.run_golden_trace(oracle_mod, path, "gpu")
     assert j.book_checked >= 0.6 * j.n
+
+
+def test_device_follows_config1_trace(oracle_mod):
+    """BASELINE configs[0]: the 1000-step single-env random-action trace (recorded from the oracle, labelled
+    "restatement": tools/gen_config1_trace.py) teacher-forced on the device, explained-or-fatal."""
+    from tests import teacher as T
+
+    j = T.run_golden_trace(oracle_mod, os.path.join(_G, "restatement_walker3d_custom_config1.npz"), "gpu")
+    assert j.n == 1000 and j.book_checked >= 900

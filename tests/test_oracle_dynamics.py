@@ -190,3 +190,23 @@ def test_self_contact_is_an_internal_force(walker_table, oracle_mod):
         # the friction impulses act at the two surface points, |penetration| apart: a small couple remains
         assert np.abs(mom[0]["L"] - mom[1]["L"]).max() / (np.abs(e0["L"]).max() + 1.0) < 5e-2
     assert changed >= 3
+
+
+def test_resting_contact_pins(walker_table, oracle_mod):
+    """Analytic pins of the contact model on the oracle (device twin: tests/test_gpu_analytic.py): a collapsed Walker3D
+    at rest on the ground plane receives M g dt of normal impulse per substep from the ground (self-contacts are internal)
+    and its loaded contacts rest at distance -slop (ERP 0.9, no split impulse)."""
+    O, t = oracle_mod, walker_table
+    A, M = 21, t["total_mass"]
+    m = O.model_from_table(t)
+    p = O.default_params()
+    p.substeps = 1
+    s = O.make_state(A, [0, 0, 1.32], [0, 0, 0, 1], [0] * 3, [0] * 3, np.array(t["base_joint_angles"]), np.zeros(A))
+    for _ in range(1300):
+        c, _ = O.step_physics(m, p, s, np.zeros(A))
+    assert abs(s.vel[2]) < 1e-2
+    ground = [i for i in range(c.n) if c.partner[i] == 0]
+    ratio = sum(c.impulse[i] for i in ground) / (M * 9.8 * p.dt)
+    assert abs(ratio - 1.0) < 5e-3, ratio
+    loaded = [c.dist[i] for i in ground if c.impulse[i] > 0.02 * M * 9.8 * p.dt]
+    assert loaded and min(loaded) > -1e-4 and max(loaded) < 2e-5, loaded

@@ -253,3 +253,28 @@ def test_fixtures_regenerate_identically_from_the_reference(tmp_path):
         assert sorted(a.files) == sorted(b.files), n
         for k in a.files:
             assert np.array_equal(a[k], b[k]), (n, k)
+
+
+CONFIG1 = os.path.join(_G, "restatement_walker3d_custom_config1.npz")
+
+
+def test_config1_trace_regenerates_and_kernel_source_follows_it(oracle_mod):
+    """BASELINE configs[0]: the 1000-step single-env random-action trace.  Recorded from the ORACLE
+    and labelled "restatement" (PyBullet is not installable; tools/gen_pybullet_golden.py records the PyBullet twin
+    where it is): the oracle regenerates it bit for bit, and the kernel source (g++ lane loop) follows it teacher-forced
+    under the explained-or-fatal rules of tests/teacher.py.  GPU twin: test_gpu_reference_golden.py."""
+    import importlib.util
+
+    from tests import teacher as T
+
+    g = np.load(CONFIG1)
+    assert "restatement" in str(g["source"])
+    spec = importlib.util.spec_from_file_location("gen_config1", os.path.join(os.path.dirname(_G), "..", "tools", "gen_config1_trace.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    d = mod.record()
+    for k in ("actions", "obs", "states", "rewards", "dones"):
+        assert np.array_equal(d[k], g[k]), k
+    assert len(g["actions"]) == 1000 and g["dones"].sum() > 20
+    j = T.run_golden_trace(oracle_mod, CONFIG1, "emu")
+    assert j.n == 1000 and j.book_checked >= 900

@@ -503,6 +503,57 @@ def install_pybullet():
                 np.arctan2(2 * (q[0] * q[1] + q[3] * q[2]), squ + sqx - sqy - sqz))
 
     pb.getEulerFromQuaternion = getEulerFromQuaternion
+
+    # ---- calls only tools/gen_pybullet_golden.py --standin makes (the env layer never does): model dump, dynamics
+    # queries and the full 10-field contact tuples, all answered from the oracle
+    pb.getAPIVersion = lambda: "standin"
+
+    def getDynamicsInfo(body, link):
+        t = W.robot["table"]
+        if link < 0:
+            b = t["base"]
+            return (b["mass"], 1.0, tuple(b.get("inertia_diag", (0, 0, 0))), (0, 0, 0), (0, 0, 0, 1), 0.0, 0.0, 0.0, -1.0, -1.0)
+        l = link - W.shift
+        return (t["mass"][l], 1.0, tuple(t["inertia_diag"][l]) if "inertia_diag" in t else (0, 0, 0), (0, 0, 0),
+                (0, 0, 0, 1), 0.0, 0.0, 0.0, -1.0, -1.0)
+
+    pb.getDynamicsInfo = getDynamicsInfo
+    pb.getCollisionShapeData = lambda body, link: tuple(
+        (body, link, g["type"], tuple(g["size"])) for g in W.robot["table"]["geoms"] if g["link"] == link - W.shift)
+
+    def calculateMassMatrix(body, q):
+        r = W.robot
+        A = r["table"]["n_dof"]
+        s = O.make_state(A, list(r["state"].pos), list(r["state"].quat), [0] * 3, [0] * 3, list(q), [0.0] * A)
+        return O.mass_matrix(r["model"], s).tolist()
+
+    pb.calculateMassMatrix = calculateMassMatrix
+
+    def calculateInverseDynamics(body, q, qd, acc):
+        r = W.robot
+        A = r["table"]["n_dof"]
+        st = r["state"]
+        s = O.make_state(A, list(st.pos), list(st.quat), list(st.omega), list(st.vel), list(q), list(qd))
+        return O.rnea(r["model"], s, np.concatenate([np.zeros(6), acc]), W.params.gravity)[6:].tolist()
+
+    pb.calculateInverseDynamics = calculateInverseDynamics
+    _five = pb.getContactPoints
+
+    def getContactPointsFull(bodyA=None, bodyB=None, linkIndexA=None, **kw):
+        """the env layer's 5-field tuples extended by positionOnA, positionOnB, contactNormalOnB, distance, normalForce"""
+        c = W.contacts
+        short = _five(bodyA=bodyA, bodyB=bodyB, linkIndexA=linkIndexA, **kw)
+        if c is None or linkIndexA is not None:
+            return short
+        out = []
+        for k, tup in zip([k for k in range(c.n)], short):
+            pa = tuple(c.pos_a[k])
+            n = tuple(c.normal[k])
+            pbp = tuple(pa[i] - c.dist[k] * n[i] for i in range(3))
+            out.append(tuple(tup) + (pa, pbp, n, c.dist[k], c.impulse[k] / (W.params.dt)))
+        return out
+
+    pb.getContactPoints = getContactPointsFull
     sys.modules["pybullet"] = pb
     return pb
 
@@ -585,7 +636,7 @@ def trace_monkey(seed, steps, action_seed, grab_every=0):
                 teleports=np.array(teleports, dtype=np.float64).reshape(-1, 4))
 
 
-def trace_cassie(steps, action_seed):
+def make_cassie_env():
     """CassieEnv-v0.  env_cassie.py does not import as shipped; the three defects are fixed by intent, nothing else:
     Q7 the missing `.loadstep` module (only the mocap variants use it), Q8 BodyPart / Joint not imported, Q9 the
     EnvBase.__init__ call that passes `render` as robot_kwargs and drops `power`."""
@@ -607,7 +658,12 @@ def trace_cassie(steps, action_seed):
             self.observation_space = gym.spaces.Box(-high, high, dtype=np.float32)
             self.action_space = self.robot.action_space
 
-    env = CassieEnv()
+    return CassieEnv()
+
+
+def trace_cassie(steps, action_seed):
+    """CassieEnv-v0 through make_cassie_env()."""
+    env = make_cassie_env()
     rs = np.random.RandomState(action_seed)
     obs = [env.reset()]
     acts, rews, dones, alive, prog, resets = [], [], [], [], [], []

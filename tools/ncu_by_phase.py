@@ -6,7 +6,7 @@ csv_path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/src_r1s.csv"
 cubin = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/sass/mb200.sm_100a.cubin"
 core_src = sys.argv[3] if len(sys.argv) > 3 else "mocca_envs_b200/csrc/mb_core.cuh"
 kname = sys.argv[4] if len(sys.argv) > 4 else "_Z22k_step_walker3d_custom8StepArgs"
-if cubin.endswith(".so"):
+if cubin.endswith(".so") or cubin.endswith(".o"):
     d = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(cubin)], cwd=d, check=True, capture_output=True)
     cubin = os.path.join(d, sorted(f for f in os.listdir(d) if f.endswith(".cubin"))[0])
