@@ -40,6 +40,10 @@ typedef struct mb200_physics {
   int has_ground;           /* 1      bullet_utils.py:361-371 plane_stadium.sdf (0 = remove_ground)       */
   int self_collision;       /* 1      robots.py:259-264 URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS (Walker3D,
                                       Monkey3D sphere / capsule geoms; Cassie's mesh hulls: not modelled)          */
+  float warmstart;          /* 0      Bullet-version switch: multibody contact warm starting.
+                                      0 = off (btMultiBodyConstraintSolver disables it); f > 0 = every contact normal row
+                                      starts from f x the impulse its candidate point carried in the previous substep
+                                      (m_warmstartingFactor), across env steps too (per-env impulses kept in HBM)   */
 } mb200_physics;
 
 void mb200_default_physics(mb200_physics* p);
@@ -112,6 +116,12 @@ int mb200_set_record(mb200_env* env, const float* rec_dev, void* stream);
 int mb200_rng_words(const mb200_env* env);
 int mb200_get_rng(mb200_env* env, uint32_t* mt_host);
 int mb200_set_rng(mb200_env* env, const uint32_t* mt_host);
+
+/* The contact impulses kept for warm starting (mb200_physics.warmstart > 0), [n_envs][mb200_warm_width()] float32 on the
+ * device, one slot per contact candidate id: the fourth part of a checkpoint when the switch is on.  Width 0 = off. */
+int mb200_warm_width(const mb200_env* env);
+int mb200_get_warm(mb200_env* env, float* warm_dev, void* stream);
+int mb200_set_warm(mb200_env* env, const float* warm_dev, void* stream);
 
 /* stepSimulation only (bullet_utils.py:352-353): hold tau_dev [n][nu - 6] over `substeps` substeps, no env logic.
  * Outputs per env: rows_dev (constraint rows summed over the substeps) and contacts_dev (contact points of the

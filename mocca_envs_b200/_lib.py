@@ -24,7 +24,7 @@ BUILD_DIR = os.path.join(_HERE, "build")
 SYMBOLS = [
     "mb200_default_physics", "mb200_default_physics_for", "mb200_create", "mb200_destroy", "mb200_dims", "mb200_seed", "mb200_reset",
     "mb200_reset_host", "mb200_info", "mb200_info_host", "mb200_step_physics_points", "mb200_max_contact_points",
-    "mb200_contact_point_width",
+    "mb200_contact_point_width", "mb200_warm_width", "mb200_get_warm", "mb200_set_warm",
     "mb200_step", "mb200_step_host", "mb200_get_state", "mb200_set_state", "mb200_get_record", "mb200_set_record",
     "mb200_rng_words", "mb200_get_rng", "mb200_set_rng", "mb200_step_physics", "mb200_mass_matrix", "mb200_inverse_dynamics", "mb200_set_param",
     "mb200_set_param_array", "mb200_record_stride", "mb200_stats",
@@ -38,7 +38,8 @@ class Physics(C.Structure):
                 ("erp_contact", C.c_float), ("erp_joint", C.c_float), ("linear_slop", C.c_float),
                 ("lin_damping", C.c_float), ("ang_damping", C.c_float), ("max_coord_vel", C.c_float),
                 ("limit_max_impulse", C.c_float), ("split_threshold", C.c_float), ("residual_threshold", C.c_float),
-                ("ground_friction", C.c_float), ("has_ground", C.c_int), ("self_collision", C.c_int)]
+                ("ground_friction", C.c_float), ("has_ground", C.c_int), ("self_collision", C.c_int),
+                ("warmstart", C.c_float)]
 
 
 def _units():
@@ -110,7 +111,9 @@ def lib():
         L.mb200_info_host.argtypes = [vp, vp, vp]
         L.mb200_step.argtypes = [vp] * 8
         L.mb200_step_host.argtypes = [vp] * 7
-        for f in ("mb200_get_state", "mb200_set_state", "mb200_get_record", "mb200_set_record", "mb200_mass_matrix"):
+        L.mb200_warm_width.argtypes = [vp]
+        for f in ("mb200_get_state", "mb200_set_state", "mb200_get_record", "mb200_set_record", "mb200_mass_matrix",
+                  "mb200_get_warm", "mb200_set_warm"):
             getattr(L, f).argtypes = [vp, vp, vp]
         L.mb200_step_physics.argtypes = [vp, vp, vp, vp, vp]
         L.mb200_step_physics_points.argtypes = [vp, vp, vp, vp, vp, vp]

@@ -314,6 +314,7 @@ def emit_header(t: dict, prefix: str) -> str:
                               thresh=0)]
     out.append(_iarr(P + "_xowner", [b["owner"] for b in xb]))
     out.append(_iarr(P + "_xfoot", [b["foot"] for b in xb]))
+    out.append(_iarr(P + "_xpid", [2 * b.get("geom", 0) for b in xb]))
     out.append(_farr(P + "_xpos", [b["pos"] for b in xb]))
     out.append(_farr(P + "_xrot", [b["rot"] for b in xb]))
     out.append(_farr(P + "_xhalf", [b["half"] for b in xb]))
@@ -353,7 +354,7 @@ def emit_header(t: dict, prefix: str) -> str:
                        ("cdepth", "int"), ("canc0", "unsigned"), ("canc1", "unsigned"),
                        ("jaxk", "int"), ("jident", "int"),
                        ("bowner", "int"), ("powner", "int"), ("pfoot", "int"), ("pid", "int"), ("foot_body", "int"),
-                       ("palm_body", "int"), ("xowner", "int"), ("xfoot", "int"),
+                       ("palm_body", "int"), ("xowner", "int"), ("xfoot", "int"), ("xpid", "int"),
                        ("lc_owner", "int"), ("ordered", "int"), ("pd_dof", "int"), ("pd_ordered", "int"),
                        ("right", "int"), ("left", "int"), ("neg", "int"), ("sp_pack", "unsigned"), ("sp_own", "int")]:
         out.append("  MB_HD static %s %s(int i) { return %s_%s[i]; }\n" % (ctype, fld, P, fld))

@@ -65,6 +65,7 @@ struct mb200_env {
   uint8_t* stage_trunc;
   uint8_t* stage_mask;   // mb200_reset_host
   int* info;             // [n] per-step integer info (steps_reached), written by the step kernel
+  float* warm;           // [n_pad][MB_NWARM] warm-start impulses (allocated when phys.warmstart > 0)
   cudaEvent_t host_done; // results of mb200_step_host have reached the host buffers
   // CTA barriers require every warp of a CTA to run: the state arrays are padded to a whole number of CTAs and
   // the pad envs ("tail") step like any other env but write their outputs/statistics to these dummies
@@ -164,6 +165,7 @@ void mb200_default_physics(mb200_physics* p) {
   p->ground_friction = 0.8f;
   p->has_ground = 1;
   p->self_collision = 1;
+  p->warmstart = 0.0f;
 }
 
 void mb200_default_physics_for(const char* env_id, mb200_physics* p) {
@@ -184,6 +186,7 @@ static void to_internal(const mb200_physics& p, MbPhysics* q) {
   q->residual_threshold = p.residual_threshold; q->ground_friction = p.ground_friction; q->has_ground = p.has_ground;
   q->box_friction = 1.0f; q->box_erp = p.erp_contact; q->box_cfm = 0.0f; q->bar_friction = 0.5f;
   q->self_collision = p.self_collision;
+  q->warmstart = p.warmstart > 0.0f ? p.warmstart : 0.0f;
 }
 
 static int grid_for(const mb200_env* e) { return (e->n + e->warps - 1) / e->warps; }
@@ -308,6 +311,10 @@ int mb200_create(const char* env_id, int n_envs, int device, const mb200_physics
   CUDA_OK(cudaMemset(e->mt, 0, n * 2 * MB_MT_STRIDE * sizeof(uint32_t)));
   CUDA_OK(cudaMemset(e->stats, 0, sizeof(MbStats)));
   CUDA_OK(cudaMalloc(&e->stage_mask, n));
+  if (e->phys.warmstart > 0.0f) {
+    CUDA_OK(cudaMalloc(&e->warm, n * MB_NWARM * sizeof(float)));
+    CUDA_OK(cudaMemset(e->warm, 0, n * MB_NWARM * sizeof(float)));
+  }
   CUDA_OK(cudaMalloc(&e->info, n * sizeof(int)));
   CUDA_OK(cudaMemset(e->info, 0xff, n * sizeof(int)));
 #undef CUDA_OK
@@ -325,7 +332,7 @@ void mb200_destroy(mb200_env* e) {
   cudaSetDevice(e->device);
   cudaFree(e->state); cudaFree(e->rec); cudaFree(e->mt); cudaFree(e->stats);
   cudaFree(e->stage_act); cudaFree(e->stage_obs); cudaFree(e->stage_rew); cudaFree(e->stage_done);
-  cudaFree(e->stage_trunc); cudaFree(e->stage_mask); cudaFree(e->info);
+  cudaFree(e->stage_trunc); cudaFree(e->stage_mask); cudaFree(e->info); cudaFree(e->warm);
   if (e->host_done) cudaEventDestroy(e->host_done);
   cudaFree(e->dummy_obs); cudaFree(e->dummy_rew); cudaFree(e->dummy_flag); cudaFree(e->dummy_stats);
   cudaFree(e->order); cudaFree(e->key); cudaFree(e->hist); cudaFree(e->cursor);
@@ -389,7 +396,7 @@ int mb200_reset(mb200_env* e, const uint8_t* mask_dev, float* obs_dev, void* str
   if (!e || !obs_dev) return fail("mb200_reset: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
   const LaunchDims d = {grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream};
-  ops_of(e)->reset(d, e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs);
+  ops_of(e)->reset(d, e->n, e->phys, e->state, e->rec, e->mt, mask_dev, obs_dev, e->dummy_obs, e->warm);
   e->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -472,6 +479,7 @@ static int step_impl(mb200_env* e, const float* act_dev, float* obs_dev, float* 
   a.host_obs = host ? host->obs : nullptr; a.host_rew = host ? host->rew : nullptr;
   a.host_done = host ? host->done : nullptr; a.host_trunc = host ? host->trunc : nullptr;
   a.info = e->info;
+  a.warm = e->warm;
   const LaunchDims d = {grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream};
   ops_of(e)->step(a, host != nullptr, d);
   e->launches++;
@@ -575,6 +583,23 @@ int mb200_set_record(mb200_env* e, const float* rec_dev, void* stream) {
   return 0;
 }
 
+// warm-start impulses (phys.warmstart > 0): part of the checkpoint of a batch; width 0 = warm starting off
+int mb200_warm_width(const mb200_env* e) { return e && e->warm ? MB_NWARM : 0; }
+int mb200_get_warm(mb200_env* e, float* warm_dev, void* stream) {
+  if (!e || !warm_dev || !e->warm) return fail("mb200_get_warm: NULL argument or warm starting off");
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaMemcpyAsync(warm_dev, e->warm, (size_t)e->n * MB_NWARM * sizeof(float), cudaMemcpyDeviceToDevice,
+                          (cudaStream_t)stream));
+  return 0;
+}
+int mb200_set_warm(mb200_env* e, const float* warm_dev, void* stream) {
+  if (!e || !warm_dev || !e->warm) return fail("mb200_set_warm: NULL argument or warm starting off");
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaMemcpyAsync(e->warm, warm_dev, (size_t)e->n * MB_NWARM * sizeof(float), cudaMemcpyDeviceToDevice,
+                          (cudaStream_t)stream));
+  return 0;
+}
+
 int mb200_rng_words(const mb200_env* e) { return e ? 2 * MB_MT_STRIDE : 0; }
 int mb200_get_rng(mb200_env* e, uint32_t* mt_host) {
   if (!e || !mt_host) return fail("mb200_get_rng: NULL argument");
@@ -596,7 +621,7 @@ static int step_physics_impl(mb200_env* e, const float* tau_dev, int* rows_dev, 
   if (!e || !tau_dev) return fail("mb200_step_physics: NULL argument");
   CUDA_OK(cudaSetDevice(e->device));
   const LaunchDims d = {grid_for(e), e->warps * 32, e->smem, (cudaStream_t)stream};
-  ops_of(e)->physics(d, e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev, points_dev);
+  ops_of(e)->physics(d, e->n, e->phys, e->state, e->rec, tau_dev, rows_dev, contacts_dev, points_dev, e->warm);
   e->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

@@ -46,6 +46,7 @@
 #define MB_LANES(l) { const int l = (int)(threadIdx.x & 31);
 #define MB_END } __syncwarp();
 #define MB_END_REG }  /* the block touched registers only: no memory ordering needed */
+#define MB_WARP_SYNC() __syncwarp()
 template <typename T> struct LaneVar {
   T v;
   MB_HD T& operator[](int) { return v; }
@@ -68,6 +69,7 @@ MB_HD int mb_popc(unsigned x) { return __popc(x); }
 #define MB_LANES(l) for (int l = 0; l < 32; ++l) {
 #define MB_END }
 #define MB_END_REG }
+#define MB_WARP_SYNC()
 template <typename T> struct LaneVar {
   T v[32];
   T& operator[](int l) { return v[l]; }
@@ -162,8 +164,19 @@ struct MbPhysics {
   float box_cfm;
   float bar_friction;  // MonkeyBar keeps Bullet's default lateral friction (bullet_objects.py:172-179 is commented out)
   int self_collision;  // robots.py:259-264 URDF_USE_SELF_COLLISION | URDF_USE_SELF_COLLISION_EXCLUDE_ALL_PARENTS
+  // Bullet-version switch: multibody contact warm starting.  0 = off (Bullet <= 2.8x and the
+  // "(DISABLES CODE)" of later versions, the default); f > 0: a contact normal row starts from f times the impulse
+  // its candidate point carried in the previous substep (btContactSolverInfo::m_warmstartingFactor), also across env
+  // steps: the impulses live in HBM (mb200_env::warm, one slot per candidate id).
+  float warmstart;
 };
 
+// contact bookkeeping word cfoot: low byte = foot index of the point (-1 = not a foot), upper bits = candidate id of
+// the point (2 * geom + end, the key of the warm-start impulses)
+MB_HD int mb_pack_foot(int foot, int pid) { return (foot & 255) | (pid << 8); }
+MB_HD int mb_foot(int v) { return (int)(signed char)(v & 255); }
+MB_HD int mb_pid(int v) { return v >> 8; }
+#define MB_NWARM 384 /* warm-start slots per env: candidate ids 2 * geom + end, geoms <= 192 */
 MB_HD constexpr int tri(int i, int j) { return (i * (i + 1)) / 2 + j; }  // packed lower-triangular index, j <= i
 MB_HD int chain_at(unsigned long long pack, int t) { return (int)((pack >> (5 * t)) & 31ull); }
 MB_HD bool mb_finite(float x) { return fabsf(x) <= 3.402823466e38f; }   // false for NaN and +-inf
@@ -256,6 +269,7 @@ template <class M> struct WarpMem {
   int nbox;
   int nbar;
   int step_rows;  // constraint rows of the env step just taken: the scheduler's sort key (mb200.cu step_body)
+  float* warm;    // this env's warm-start impulses in HBM [MB_NWARM], nullptr = warm starting off (MbPhysics::warmstart)
   // ---- loop-closure pivots (btMultiBodyPoint2Point, Cassie): world axes, relative to the base COM; [2c] on link A,
   // [2c + 1] on link B
   float lcP[(M::NLOOP > 0 ? 2 * M::NLOOP : 1)][3];
@@ -869,7 +883,7 @@ template <class M> struct Sim {
           S.cerp[k] = erp;
           S.ccfm[k] = 0.0f;
           S.clink[k] = (M::sp_own(pr) & 255) - 1;
-          S.cfoot[k] = -1;
+          S.cfoot[k] = mb_pack_foot(-1, M::pid((int)(M::sp_pack(pr) & 255u)));
           S.cpartner[k] = 1000 + pr;
         }
       }
@@ -1008,7 +1022,7 @@ template <class M> struct Sim {
               S.cerp[k] = ob < 0 ? P.erp_contact : P.box_erp;
               S.ccfm[k] = ob < 0 ? 0.0f : P.box_cfm;
               S.clink[k] = M::powner(pt);
-              S.cfoot[k] = M::pfoot(pt);
+              S.cfoot[k] = mb_pack_foot(M::pfoot(pt), M::pid(pt));
               S.cpartner[k] = ob < 0 ? 0 : 10 + ob;
             }
           }
@@ -1056,7 +1070,7 @@ template <class M> struct Sim {
                 S.cerp[k] = P.erp_contact;
                 S.ccfm[k] = 0.0f;
                 S.clink[k] = M::powner(pt);
-                S.cfoot[k] = M::pfoot(pt);
+                S.cfoot[k] = mb_pack_foot(M::pfoot(pt), M::pid(pt));
                 S.cpartner[k] = 20 + ob;
               }
             }
@@ -1101,7 +1115,7 @@ template <class M> struct Sim {
                   S.cerp[k] = P.erp_contact;
                   S.ccfm[k] = 0.0f;
                   S.clink[k] = M::xowner(l);
-                  S.cfoot[k] = M::xfoot(l);
+                  S.cfoot[k] = mb_pack_foot(M::xfoot(l), M::xpid(l));
                   S.cpartner[k] = 20 + ob;
                 }
               }
@@ -1407,6 +1421,48 @@ template <class M> struct Sim {
   }
 
 
+  // ---- G3. contact warm starting (cold path: MbPhysics::warmstart > 0 only) --------------------------------------------
+  // setupMultiBodyContactConstraint with SOLVER_USE_WARMSTARTING: appliedImpulse = factor * previous impulse of the point,
+  // applied to the velocity before the first iteration (z += Y_r lambda_r); friction rows start from zero.
+  MB_NOINLINE static void warm_start(Mem& S, float factor, int n0, int S0, int nc, int ncs, float* zout) {
+    MB_ASSUME_SHARED(S);
+    LaneVar<float> z;
+    MB_LANES(l)
+      z[l] = 0.0f;
+    MB_END_REG
+#pragma unroll 1
+    for (int k = 0; k < nc + ncs; ++k) {
+      const int ra = k < nc ? n0 + k : S0 + 2 * (k - nc);
+      const float imp = factor * S.warm[mb_pid(S.cfoot[k])];
+      if (imp == 0.0f) continue;
+      const bool dual = k >= nc;
+      const unsigned supA = S.rc.r.r_mask[ra] & MB_ROW_SUP, supB = dual ? S.rc.r.r_mask[ra + 1] : 0u;
+      MB_LANES(l)
+        const int tl = l < NU ? M::rowlen(l) - 1 : 0;
+        if ((supA >> l) & 1u) z[l] = fmaf(S.w.Yc[ra][tl], imp, z[l]);
+        if ((supB >> l) & 1u) z[l] = fmaf(S.w.Yc[ra + 1][tl], imp, z[l]);
+        if (l == 0) S.rc.r.r_app[ra] = imp;
+      MB_END
+    }
+    MB_LANES(l)
+      zout[l] = z[l];
+    MB_END
+  }
+  MB_NOINLINE static void warm_store(Mem& S, int n0, int S0, int nc, int ncs, bool solved) {
+    MB_ASSUME_SHARED(S);
+    MB_LANES(l)
+      for (int i = l; i < MB_NWARM; i += 32) S.warm[i] = 0.0f;
+    MB_END
+    if (!solved) return;
+#pragma unroll 1
+    for (int k = 0; k < nc + ncs; ++k) {  // in contact order: a later contact of the same candidate overwrites
+      const int ra = k < nc ? n0 + k : S0 + 2 * (k - nc);
+      MB_LANES(l)
+        if (l == 0) S.warm[mb_pid(S.cfoot[k])] = S.rc.r.r_app[ra];
+      MB_END
+    }
+  }
+
   // ---- H. projected Gauss-Seidel in z-space (btMultiBodyConstraintSolver::solveSingleIteration order) --------
   // Row r of Y is stored over its support; the entry of coordinate l sits at slot tl(l) (prefix property).
   // DUAL: 0 = the row is one compact row (joint limits; contacts of a model without self-collision), 1 = always two
@@ -1435,6 +1491,7 @@ template <class M> struct Sim {
     float nA = sumA;
     if (sumA < lo) { dA = lo - appA; nA = lo; }
     else if (sumA > hi) { dA = hi - appA; nA = hi; }
+    MB_WARP_SYNC();  // every lane has read r_app[ra] before lane 0 replaces it (compute-sanitizer racecheck: WAR)
     MB_LANES(l)
       z[l] += ya[l] * dA;
       if (l == 0) S.rc.r.r_app[ra] = nA;
@@ -1478,6 +1535,7 @@ template <class M> struct Sim {
       if (sumB < -clipB) { dB = -clipB - appB; nB = -clipB; }
       else if (sumB > clipB) { dB = clipB - appB; nB = clipB; }
     }
+    MB_WARP_SYNC();
     MB_LANES(l)
       z[l] += ya[l] * dA + yb[l] * dB;
       if (l == 0) { S.rc.r.r_app[ra] = nA; S.rc.r.r_app[rb] = nB; }
@@ -1607,11 +1665,22 @@ template <class M> struct Sim {
       MB_LANES(l)
         z[l] = 0.0f;
       MB_END
+      if (MB_UNLIKELY(S.warm != nullptr)) {
+        warm_start(S, P.warmstart, nlim + NLC, nlim + NLC + 3 * nc, nc, ncs, S.rhs);  // (S.rhs is free after the FD solve)
+        init_lane_const(C);
+        MB_LANES(l)
+          z[l] = S.rhs[l];
+        MB_END
+      }
       solve_constraints(S, P, C, nlim, nc, ncs, z);
       solve_L<false>(S, C, z);
       MB_LANES(l)
         if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + z[l], -P.max_coord_vel), P.max_coord_vel);
       MB_END
+    }
+    if (MB_UNLIKELY(S.warm != nullptr)) {
+      warm_store(S, nlim + NLC, nlim + NLC + 3 * nc, nc, ncs, R > 0);
+      init_lane_const(C);
     }
     if (points_out) {
       const int n0 = nlim + NLC, S0 = n0 + 3 * nc;

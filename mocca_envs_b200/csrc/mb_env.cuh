@@ -77,6 +77,15 @@ struct MbStats {  // per-device accumulators, all-reduced across ranks by the ho
   double len_sum;
 };
 
+// warm-start impulses of an env (HBM, MbPhysics::warmstart > 0): zeroed at every reset
+MB_HD void mb_clear_warm(float* warm) {
+  if (MB_UNLIKELY(warm != nullptr)) {
+    MB_LANES(l)
+      for (int i = l; i < MB_NWARM; i += 32) warm[i] = 0.0f;
+    MB_END
+  }
+}
+
 MB_HD int& rec_i(float* rec, int k) { return reinterpret_cast<int*>(rec)[k]; }
 MB_HD int rec_i(const float* rec, int k) { return reinterpret_cast<const int*>(rec)[k]; }
 
@@ -276,6 +285,7 @@ template <class M> struct W3DEnv {
 
   // Walker3DCustomEnv.reset (env_locomotion.py:79-109) + WalkerBase.reset (robots.py:179-210)
   MB_HD static void reset(Mem& S, const MbPhysics& P, float* rec, uint32_t* mt_env, uint32_t* mt_robot, float* obs) {
+    mb_clear_warm(S.warm);  // (robot reset: the cached contact impulses die with the episode)
     uint32_t* w = reinterpret_cast<uint32_t*>(S.rc.scratch);
     const int aliased = rec_i(rec, ER_ALIASED);
     const int nrobot = 2 + 2 * NJ, nt = target_words(rec);
@@ -373,8 +383,8 @@ template <class M> struct W3DEnv {
     // feet_contact from the last collision pass (robots.py:74-86 via getContactPoints)
     float fc0 = 0.0f, fc1 = 0.0f;
     for (int k = 0; k < nc; ++k) {
-      if (S.cpartner[k] == 0 && S.cfoot[k] == 0) fc0 = 1.0f;
-      if (S.cpartner[k] == 0 && S.cfoot[k] == 1) fc1 = 1.0f;
+      if (S.cpartner[k] == 0 && mb_foot(S.cfoot[k]) == 0) fc0 = 1.0f;
+      if (S.cpartner[k] == 0 && mb_foot(S.cfoot[k]) == 1) fc1 = 1.0f;
     }
     const float prev_bodyx = rec[ER_BODYX];
     const int eval_mode = rec_i(rec, ER_EVAL);
@@ -617,6 +627,7 @@ template <class M, bool PILLAR = false> struct StepperEnv {
 
   // Walker3DStepperEnv.reset (env_locomotion.py:481-513)
   MB_HD static void reset(Mem& S, const MbPhysics& P, float* rec, uint32_t* mt_env, uint32_t* mt_robot, float* obs) {
+    mb_clear_warm(S.warm);  // (robot reset: the cached contact impulses die with the episode)
     // 44 robot words + 200 terrain words; the row storage is free between steps and serves as scratch
     uint32_t* w = reinterpret_cast<uint32_t*>(&S.w);
     double* dbuf = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(w + 256) + 7) & ~(uintptr_t)7);
@@ -713,9 +724,9 @@ template <class M, bool PILLAR = false> struct StepperEnv {
     float fc0 = 0.0f, fc1 = 0.0f;
     int reached = 0;
     for (int k = 0; k < nc; ++k) {
-      if (S.cfoot[k] == 0) fc0 = 1.0f;
-      if (S.cfoot[k] == 1) fc1 = 1.0f;
-      if (S.cfoot[k] >= 0 && S.cpartner[k] == cover_id) reached = 1;
+      if (mb_foot(S.cfoot[k]) == 0) fc0 = 1.0f;
+      if (mb_foot(S.cfoot[k]) == 1) fc1 = 1.0f;
+      if (mb_foot(S.cfoot[k]) >= 0 && S.cpartner[k] == cover_id) reached = 1;
       if (M::NSELF > 0 && S.cpartner[k] >= 1000) {
         // "contact = 1.0 if contact_ids" (env_locomotion.py:645-646): a self-contact of the foot link counts too
         const int feet = M::sp_own(S.cpartner[k] - 1000) >> 16;
@@ -1021,6 +1032,7 @@ template <class M> struct MonkeyEnv {
 
   // Monkey3DCustomEnv.reset (env_locomotion.py:1283-1316); robot.reset(random_pose=False) still draws the coin
   MB_HD static void reset(Mem& S, const MbPhysics& P, float* rec, uint32_t* mt_env, uint32_t* mt_robot, float* obs) {
+    mb_clear_warm(S.warm);  // (robot reset: the cached contact impulses die with the episode)
     uint32_t* w = reinterpret_cast<uint32_t*>(S.L);  // 2 + 192 words; the factor storage is free between steps
     // kinematics(with_vel = false) writes jR / jp / js only: the body scratch behind them is free for the doubles
     double* dbuf = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(&S.w.k.u2) + 7) & ~(uintptr_t)7);
@@ -1115,7 +1127,7 @@ template <class M> struct MonkeyEnv {
     float fc[2] = {0.0f, 0.0f};
     int palm_hit[2] = {0, 0};
     for (int k = 0; k < nc; ++k) {
-      const int f = S.cfoot[k];
+      const int f = mb_foot(S.cfoot[k]);
       if (f == 0 || f == 1) fc[f] = 1.0f;
       if ((f == 2 || f == 3) && S.cpartner[k] == target_id) palm_hit[f - 2] = 1;
     }
@@ -1300,6 +1312,7 @@ template <class M> struct CassieEnv {
   }
 
   MB_HD static void reset(Mem& S, const MbPhysics& P, float* rec, uint32_t*, uint32_t*, float* obs) {
+    mb_clear_warm(S.warm);  // (robot reset: the cached contact impulses die with the episode)
     MB_LANES(l)
       if (l == 0) {
         rec[ER_TX] = 1000.0f; rec[ER_TY] = 0.0f; rec[ER_TZ] = 0.0f;

@@ -50,6 +50,7 @@ struct StepArgs {
   uint8_t* host_done;
   uint8_t* host_trunc;
   int* info;  // [n] per-step integer info (Stepper: steps_reached, -1 = not reported), may be nullptr
+  float* warm;  // [n_pad][MB_NWARM] contact impulses of the previous substep, nullptr = warm starting off
 };
 
 struct LaunchDims {
@@ -67,9 +68,9 @@ struct MbKindOps {
   cudaError_t (*prepare)(void);  // shared-memory opt-in of every kernel of the kind
   void (*step)(const StepArgs&, bool host, const LaunchDims&);
   void (*reset)(const LaunchDims&, int n, const MbPhysics&, float* state, float* rec, uint32_t* mt, const uint8_t* mask,
-                float* obs, float* dummy_obs);
+                float* obs, float* dummy_obs, float* warm);
   void (*physics)(const LaunchDims&, int n, const MbPhysics&, float* state, const float* rec, const float* tau,
-                  int* rows_out, int* contacts_out, float* points_out);
+                  int* rows_out, int* contacts_out, float* points_out, float* warm);
   void (*debug)(const LaunchDims&, int n, const MbPhysics&, const float* state, int mode, const float* acc, float* out);
 };
 
@@ -83,6 +84,8 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   const int env = a.order[blockIdx.x * MB_WARPS + warp];  // a permutation of [0, n_pad)
   const bool tail = env >= a.n;
   typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
+  if ((threadIdx.x & 31) == 0) S.warm = a.warm ? a.warm + (size_t)env * MB_NWARM : nullptr;
+  __syncwarp();
   float* obs = tail ? a.dummy_obs + (size_t)warp * Env::OBS : a.obs + (size_t)env * Env::OBS;
   float* fin = tail ? a.dummy_obs + (size_t)(MB_WARPS_MAX + warp) * Env::OBS
                     : (a.final_obs ? a.final_obs + (size_t)env * Env::OBS : nullptr);
@@ -124,13 +127,15 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
 
 template <class Env>
 __device__ __forceinline__ void reset_body(int n, const MbPhysics& phys, float* state, float* rec, uint32_t* mt,
-                                           const uint8_t* mask, float* obs, float* dummy_obs) {
+                                           const uint8_t* mask, float* obs, float* dummy_obs, float* warm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * MB_WARPS + warp;
   const bool tail = env >= n;
   if (!tail && mask && !mask[env]) return;  // no CTA barrier inside reset, early exit is fine
   typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
+  if ((threadIdx.x & 31) == 0) S.warm = warm ? warm + (size_t)env * MB_NWARM : nullptr;
+  __syncwarp();
   Env::reset(S, phys, rec + (size_t)env * Env::REC_STRIDE, mt + (size_t)env * 2 * MB_MT_STRIDE,
              mt + ((size_t)env * 2 + 1) * MB_MT_STRIDE,
              tail ? dummy_obs + (size_t)warp * Env::OBS : obs + (size_t)env * Env::OBS);
@@ -140,7 +145,8 @@ __device__ __forceinline__ void reset_body(int n, const MbPhysics& phys, float* 
 // stepSimulation only; rec supplies the static obstacles of the env kind
 template <class Env>
 __device__ __forceinline__ void physics_body(int n, const MbPhysics& phys, float* state, const float* rec,
-                                             const float* tau, int* rows_out, int* contacts_out, float* points_out) {
+                                             const float* tau, int* rows_out, int* contacts_out, float* points_out,
+                                             float* warm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * MB_WARPS + warp;
@@ -148,6 +154,8 @@ __device__ __forceinline__ void physics_body(int n, const MbPhysics& phys, float
   typedef typename Env::Model EM;
   Sim<EM>::load_tables();
   typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
+  if ((threadIdx.x & 31) == 0) S.warm = warm ? warm + (size_t)env * MB_NWARM : nullptr;
+  __syncwarp();
   Env::load_state(S, state + (size_t)env * MB_STATE_STRIDE);
   MB_LANES(l)
     if (l < EM::NJ) S.tau[l] = tail ? 0.0f : tau[(size_t)env * EM::NJ + l];
@@ -182,6 +190,8 @@ __device__ __forceinline__ void dynamics_debug_body(int n, const MbPhysics& phys
   if (env >= n) return;
   typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
   const int NU = EM::NU;
+  if ((threadIdx.x & 31) == 0) S.warm = nullptr;
+  __syncwarp();
   Env::load_state(S, state + (size_t)env * MB_STATE_STRIDE);
   MB_LANES(l)
     S.tau[l] = 0.0f;
@@ -212,13 +222,13 @@ __device__ __forceinline__ void dynamics_debug_body(int n, const MbPhysics& phys
   }                                                                                                                   \
   __global__ void __launch_bounds__(MB_WARPS_MAX * 32)                                                                \
       k_reset_##ID(int n, MbPhysics phys, float* state, float* rec, uint32_t* mt, const uint8_t* mask, float* obs,   \
-                   float* dummy_obs) {                                                                                \
-    reset_body<ENV>(n, phys, state, rec, mt, mask, obs, dummy_obs);                                                   \
+                   float* dummy_obs, float* warm) {                                                                   \
+    reset_body<ENV>(n, phys, state, rec, mt, mask, obs, dummy_obs, warm);                                             \
   }                                                                                                                   \
   __global__ void __launch_bounds__(MB_WARPS_MAX * 32)                                                                \
       k_step_physics_##ID(int n, MbPhysics phys, float* state, const float* rec, const float* tau, int* rows_out,    \
-                          int* contacts_out, float* points_out) {                                                     \
-    physics_body<ENV>(n, phys, state, rec, tau, rows_out, contacts_out, points_out);                                  \
+                          int* contacts_out, float* points_out, float* warm) {                                        \
+    physics_body<ENV>(n, phys, state, rec, tau, rows_out, contacts_out, points_out, warm);                            \
   }                                                                                                                   \
   __global__ void __launch_bounds__(MB_WARPS_MAX * 32)                                                                \
       k_dynamics_debug_##ID(int n, MbPhysics phys, const float* state, int mode, const float* acc, float* out) {     \
@@ -239,13 +249,14 @@ __device__ __forceinline__ void dynamics_debug_body(int n, const MbPhysics& phys
     else k_step_##ID<<<d.grid, d.threads, d.smem, d.stream>>>(a);                                                     \
   }                                                                                                                   \
   static void launch_reset_##ID(const LaunchDims& d, int n, const MbPhysics& p, float* state, float* rec,            \
-                                uint32_t* mt, const uint8_t* mask, float* obs, float* dummy_obs) {                    \
-    k_reset_##ID<<<d.grid, d.threads, d.smem, d.stream>>>(n, p, state, rec, mt, mask, obs, dummy_obs);                \
+                                uint32_t* mt, const uint8_t* mask, float* obs, float* dummy_obs, float* warm) {       \
+    k_reset_##ID<<<d.grid, d.threads, d.smem, d.stream>>>(n, p, state, rec, mt, mask, obs, dummy_obs, warm);          \
   }                                                                                                                   \
   static void launch_physics_##ID(const LaunchDims& d, int n, const MbPhysics& p, float* state, const float* rec,    \
-                                  const float* tau, int* rows_out, int* contacts_out, float* points_out) {            \
+                                  const float* tau, int* rows_out, int* contacts_out, float* points_out,              \
+                                  float* warm) {                                                                      \
     k_step_physics_##ID<<<d.grid, d.threads, d.smem, d.stream>>>(n, p, state, rec, tau, rows_out, contacts_out,       \
-                                                                 points_out);                                         \
+                                                                 points_out, warm);                                   \
   }                                                                                                                   \
   static void launch_debug_##ID(const LaunchDims& d, int n, const MbPhysics& p, const float* state, int mode,        \
                                 const float* acc, float* out) {                                                       \

@@ -210,8 +210,14 @@ class Walker3DCustomVecEnv:
     def state_dict(self):
         """Complete checkpoint of the batch (physics state, bookkeeping record, RNG streams, current observation):
         a batch restored with load_state_dict continues bit-exactly."""
-        return {"state": self.get_state().cpu(), "record": self.get_record().cpu(), "rng": self.get_rng(),
-                "obs": self.obs.clone().cpu(), "env_id": self.env_id, "params": self._host_params()}
+        d = {"state": self.get_state().cpu(), "record": self.get_record().cpu(), "rng": self.get_rng(),
+             "obs": self.obs.clone().cpu(), "env_id": self.env_id, "params": self._host_params()}
+        w = int(self._L.mb200_warm_width(self._h))
+        if w:  # physics["warmstart"] > 0: the cached contact impulses are state too
+            t = torch.empty(self.num_envs, w, dtype=torch.float32, device=self.device)
+            _lib.check(self._L.mb200_get_warm(self._h, _ptr(t), self._stream()))
+            d["warm"] = t.cpu()
+        return d
 
     def _host_params(self) -> dict:
         """Host-side mirrors of what lives in the record (re-applied through mb200_set_param on load, because the
@@ -231,6 +237,10 @@ class Walker3DCustomVecEnv:
         self.set_record(d["record"])
         if "rng" in d:
             self.set_rng(d["rng"])
+        if "warm" in d and int(self._L.mb200_warm_width(self._h)):
+            t = d["warm"].to(device=self.device, dtype=torch.float32).contiguous()
+            _lib.check(self._L.mb200_set_warm(self._h, _ptr(t), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
         if "obs" in d:
             self.obs.copy_(d["obs"].to(self.device))
 

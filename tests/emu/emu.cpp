@@ -30,6 +30,7 @@ static void default_phys(MbPhysics* p) {
   p->residual_threshold = 1e-7f; p->ground_friction = 0.8f; p->has_ground = 1;
   p->box_friction = 1.0f; p->box_erp = 0.9f; p->box_cfm = 0.0f; p->bar_friction = 0.5f;
   p->self_collision = 1;
+  p->warmstart = 0.0f;
 }
 
 extern "C" {
@@ -40,6 +41,22 @@ void emu_default_phys(MbPhysics* p) { default_phys(p); }
 void emu_step_physics(const MbPhysics* p, float* state, const float* tau, int* rows, int* contacts) {
   static WMem S;
   memset(&S, 0, sizeof(S));
+  WEnv::load_state(S, state);
+  for (int j = 0; j < WM::NJ; ++j) S.tau[j] = tau[j];
+  int r = 0, nc = 0, ov = 0;
+  Sim<WM>::LaneConst C;
+  Sim<WM>::init_lane_const(C);
+  for (int k = 0; k < p->substeps; ++k) r += Sim<WM>::substep<0>(S, *p, C, &nc, &ov);
+  WEnv::store_state(S, state);
+  *rows = r;
+  *contacts = nc;
+}
+
+// stepSimulation with the warm-start switch: `warm` [MB_NWARM] plays the env's HBM impulse array
+void emu_step_physics_warm(const MbPhysics* p, float* state, const float* tau, float* warm, int* rows, int* contacts) {
+  static WMem S;
+  memset(&S, 0, sizeof(S));
+  S.warm = warm;
   WEnv::load_state(S, state);
   for (int j = 0; j < WM::NJ; ++j) S.tau[j] = tau[j];
   int r = 0, nc = 0, ov = 0;

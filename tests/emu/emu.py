@@ -20,7 +20,8 @@ class Phys(C.Structure):
                 ("lin_damping", C.c_float), ("ang_damping", C.c_float), ("max_coord_vel", C.c_float),
                 ("limit_max_impulse", C.c_float), ("split_threshold", C.c_float), ("residual_threshold", C.c_float),
                 ("ground_friction", C.c_float), ("has_ground", C.c_int), ("box_friction", C.c_float),
-                ("box_erp", C.c_float), ("box_cfm", C.c_float), ("bar_friction", C.c_float), ("self_collision", C.c_int)]
+                ("box_erp", C.c_float), ("box_cfm", C.c_float), ("bar_friction", C.c_float), ("self_collision", C.c_int),
+                ("warmstart", C.c_float)]
 
 
 _lib = None
@@ -55,6 +56,17 @@ def step_physics(p, state, tau):
     tau = np.ascontiguousarray(tau, dtype=np.float32)
     rows, nc = C.c_int(0), C.c_int(0)
     lib().emu_step_physics(C.byref(p), _fp(buf), _fp(tau), C.byref(rows), C.byref(nc))
+    return buf[: len(state)].copy(), rows.value, nc.value
+
+
+def step_physics_warm(p, state, tau, warm):
+    """stepSimulation with MbPhysics.warmstart: `warm` (float32[384], updated in place) carries the contact impulses."""
+    state = np.ascontiguousarray(state, dtype=np.float32).copy()
+    buf = np.zeros(64, dtype=np.float32)
+    buf[: len(state)] = state
+    tau = np.ascontiguousarray(tau, dtype=np.float32)
+    rows, nc = C.c_int(0), C.c_int(0)
+    lib().emu_step_physics_warm(C.byref(p), _fp(buf), _fp(tau), _fp(warm), C.byref(rows), C.byref(nc))
     return buf[: len(state)].copy(), rows.value, nc.value
 
 

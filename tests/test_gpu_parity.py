@@ -366,3 +366,42 @@ def test_checkpoint_resume_bit_exact(torch_mod):
         o, r, d = ref[k - 15]
         assert torch.equal(obs, o) and torch.equal(rew, r) and torch.equal(done, d), k
     env2.close()
+
+
+def test_warm_start_switch(walker_table, oracle_mod, torch_mod):
+    """Bullet-version switch mb200_physics.warmstart on the device: persistent per-candidate
+    contact impulses in HBM, across stepSimulation calls.  Flipping the switch moves the oracle and the device TOGETHER:
+    three consecutive steps from in-contact states agree within the contact-frame tolerance (2e-3) with the switch on, the
+    impulse arrays agree, and the switched-on states differ from the switched-off ones by far more than the tolerance."""
+    import ctypes as C
+
+    torch, O, t = torch_mod, oracle_mod, walker_table
+    A = 21
+    m = O.model_from_table(t)
+    rng = np.random.RandomState(5)
+    N = 32
+    st = contact_states(O, t, rng, N).astype(np.float32)
+    tau = (0.3 * np.array(t["gain"]) * rng.uniform(-1, 1, (N, A))).astype(np.float32)
+    outs = {}
+    for f in (0.0, 0.85):
+        env = _env(N, physics={"warmstart": f})
+        env.set_state(torch.tensor(st))
+        for k in range(3):
+            env.step_physics(torch.tensor(tau))
+        outs[f] = env.get_state().cpu().numpy()
+        if f > 0:
+            warm_dev = env.state_dict()["warm"].numpy()
+            p = O.default_params()
+            p.warmstart = f
+            worst = 0.0
+            for i in range(N):
+                s = oracle_state(O, A, st[i].astype(np.float64))
+                warm = (C.c_double * 384)()
+                for k in range(3):
+                    O.step_physics(m, p, s, tau[i].astype(np.float64), warm=warm)
+                worst = max(worst, state_error(outs[f][i], O.state_vector(s, A)))
+                wo = np.array(warm[:])
+                assert np.abs(warm_dev[i] - wo).max() < 2e-3 * max(1.0, np.abs(wo).max()), i
+            assert worst < 2e-3, worst
+        env.close()
+    assert max(state_error(outs[0.85][i], outs[0.0][i]) for i in range(N)) > 2e-2

@@ -1,6 +1,8 @@
 """CPU checks of the CUDA kernel SOURCE: mb_core.cuh / mb_env.cuh compiled by g++ as a 32-lane loop
 (tests/emu) and diffed against the float64 oracle.  The GPU tests (-m gpu) repeat these through the C ABI on the
 real device; this file exists so that kernel-logic regressions are caught on a box without a GPU."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -262,3 +264,40 @@ def test_stepper_pillar_class(walker_table, oracle_mod):
         assert worst < 2e-3, (cls, worst)
         outs[cls] = O.state_vector(s, 21)
     assert np.abs(outs["Pillar"] - outs["LargePlank"]).max() > 1e-2
+
+
+def test_warm_start_switch(walker_table, oracle_mod):
+    """Bullet-version switch MbPhysics.warmstart: contact normal rows start from f x the impulse
+    of the same candidate point in the previous substep.  Flipping it changes the oracle and the kernel source TOGETHER:
+    three consecutive stepSimulations from in-contact states agree within the contact-frame tolerance (2e-3) with the
+    switch on, and the switched-on result differs from the switched-off one by far more than that."""
+    from tests.helpers import contact_states, oracle_state, state_error
+
+    O, t = oracle_mod, walker_table
+    A = 21
+    m = O.model_from_table(t)
+    rng = np.random.RandomState(5)
+    states = contact_states(O, t, rng, 12).astype(np.float32)
+    worst_on, moved = 0.0, 0.0
+    for st in states:
+        tau = (0.3 * np.array(t["gain"]) * rng.uniform(-1, 1, A)).astype(np.float32)
+        outs = {}
+        for f in (0.0, 0.85):
+            p = O.default_params()
+            p.warmstart = f
+            pe = E.default_phys()
+            pe.warmstart = f
+            s = oracle_state(O, A, st.astype(np.float64))
+            warm_o = (C.c_double * 384)()
+            warm_e = np.zeros(384, dtype=np.float32)
+            se = st.copy()
+            for k in range(3):
+                O.step_physics(m, p, s, tau.astype(np.float64), warm=warm_o)
+                se, _, _ = (E.step_physics_warm(pe, se, tau, warm_e) if f > 0 else E.step_physics(pe, se, tau))
+            outs[f] = (O.state_vector(s, A), se)
+            if f > 0:
+                worst_on = max(worst_on, state_error(se, O.state_vector(s, A)))
+                assert np.abs(warm_e - np.array(warm_o[:], dtype=np.float32)).max() < 2e-3 * max(1.0, np.abs(warm_e).max())
+        moved = max(moved, state_error(outs[0.85][1], outs[0.0][1]))
+    assert worst_on < 2e-3, worst_on
+    assert moved > 2e-2, moved
