@@ -208,8 +208,9 @@ template <class M> struct WarpMem {
       float jV[M::NJ + 1][6];  // [0] = base
       float jA[M::NJ + 1][6];
       union {
-        struct {
-          // ---- bodies
+        struct alignas(8) {
+          // ---- bodies (8-byte aligned: ptxas pairs neighbouring floats into LDS.64; unaligned, such a pair straddles
+          // the end of bF and touches L[0], which compute-sanitizer racecheck reports as a hazard)
           float bI[M::NB][10];  // m, h[3], I_O{xx,yy,zz,xy,xz,yz}
           float bF[M::NB][6];   // bias wrench about O (n, f)  (one 64-byte record + 128-bit loads measured no gain)
         } b;
@@ -421,6 +422,16 @@ template <class M> struct Sim {
         }
       }
     MB_END
+    // sin / cos of every joint angle once, one joint per lane (the level loop below reads them back: three lanes per
+    // joint would otherwise each run the 30-instruction polynomial).  Scratch: Ldinv / Ldi2, dead until factorize().
+    MB_LANES(l)
+      if (l < NJ) {
+        float sn, cs;
+        mb_sincos(S.q[l], &sn, &cs);
+        S.Ldinv[l] = sn;
+        S.Ldi2[l] = cs;
+      }
+    MB_END
     // Level by level down the tree; within a level lane 3*slot + c handles component c (matrix row / vector
     // entry) of the slot-th joint of that level -- three lanes per joint, lanes of a warp are free.
 #pragma unroll 1
@@ -442,8 +453,7 @@ template <class M> struct Sim {
             const float n2 = b0 * M::jrot(j, 2) + b1 * M::jrot(j, 5) + b2 * M::jrot(j, 8);
             b0 = n0; b1 = n1; b2 = n2;
           }
-          float sn, cs;
-          mb_sincos(S.q[j], &sn, &cs);
+          const float sn = S.Ldinv[j], cs = S.Ldi2[j];
           const int kax = M::jaxk(j);
           float r0, r1, r2, ac;
           if (M::ALL_ALIGNED || kax >= 0) {  // coordinate-aligned axis: two columns mix
@@ -471,27 +481,24 @@ template <class M> struct Sim {
         const int j = jj[l];
         if (j >= 0) {
           const int slot = l / 3, c = l - 3 * slot;
+          const int i1 = c == 2 ? 0 : c + 1, i2 = c == 0 ? 2 : c - 1;  // cyclic successors: (x y)_c = x[i1] y[i2] - x[i2] y[i1]
           const float* p = S.w.k.jp[j];
           const float* a = S.js[j];
-          float sl[3];
-          mb_cross(p, a, sl);  // linear part of the motion subspace, all three entries (needed by the crosses)
-          const float slc = c == 0 ? sl[0] : (c == 1 ? sl[1] : sl[2]);
+          // linear part of the motion subspace sl = p x a: own component for the store, the two others for the crosses
+          const float pc_ = p[c], p1 = p[i1], p2 = p[i2], ac_ = a[c], a1 = a[i1], a2 = a[i2];
+          const float slc = p1 * a2 - p2 * a1;
           S.js[j][3 + c] = slc;
           if (with_vel) {
+            const float sl1 = p2 * ac_ - pc_ * a2, sl2 = pc_ * a1 - p1 * ac_;
             const int pj = M::jparent(j);
             const float qd = S.u[6 + j];
             const float* Vp = S.w.k.jV[pj + 1];
             const float* Ap = S.w.k.jA[pj + 1];
-            const float vw[3] = {a[0] * qd, a[1] * qd, a[2] * qd};
-            const float vv[3] = {sl[0] * qd, sl[1] * qd, sl[2] * qd};
-            float c1[3], c2[3], c3[3];
-            mb_cross(Vp, vw, c1);      // A = Ap + Vp x vj   (motion cross; vj x vj = 0)
-            mb_cross(Vp, vv, c2);
-            mb_cross(Vp + 3, vw, c3);
-            const float c1c = c == 0 ? c1[0] : (c == 1 ? c1[1] : c1[2]);
-            const float c23 = c == 0 ? c2[0] + c3[0] : (c == 1 ? c2[1] + c3[1] : c2[2] + c3[2]);
-            const float vwc = c == 0 ? vw[0] : (c == 1 ? vw[1] : vw[2]);
-            S.w.k.jV[j + 1][c] = Vp[c] + vwc;
+            const float w1 = Vp[i1], w2 = Vp[i2], v1 = Vp[3 + i1], v2 = Vp[3 + i2];
+            // A = Ap + Vp x vj (motion cross; vj x vj = 0), component c only: vj = (a, sl) qd
+            const float c1c = (w1 * a2 - w2 * a1) * qd;
+            const float c23 = (w1 * sl2 - w2 * sl1 + v1 * a2 - v2 * a1) * qd;
+            S.w.k.jV[j + 1][c] = Vp[c] + ac_ * qd;
             S.w.k.jV[j + 1][3 + c] = Vp[3 + c] + slc * qd;
             S.w.k.jA[j + 1][c] = Ap[c] + c1c;
             S.w.k.jA[j + 1][3 + c] = Ap[3 + c] + c23;
@@ -1257,7 +1264,7 @@ template <class M> struct Sim {
           par.rhs = rel_vel; par.cfm = 0.0f; par.jinv = dd; par.den = 0.0f;
           S.rc.r.r_par[r] = par;
           S.rc.r.r_app[r] = 0.0f;
-          S.rc.r.r_mu[r] = S.cmu[k];
+          S.rc.r.r_mu[r] = fr >= 0 ? S.cmu[k] : 0.0f;  // (normal rows: idle threshold 0 = never skipped)
         }
       MB_END
     }
@@ -1395,7 +1402,13 @@ template <class M> struct Sim {
           par.cfm = cfm * jinv;
           S.rc.r.r_par[r] = par;
           S.rc.r.r_app[r] = 0.0f;
-          S.rc.r.r_mu[r] = mu;
+          // A contact normal row whose right-hand side b = positional + verr is negative (a speculative contact the
+          // link is not closing fast enough to reach, or a separating one) stays at zero impulse while Y_r . z > b.
+          // |Y_r . z| <= |Y_r| |z|, so it PROVABLY stays idle while |z| < -b / |Y_r|: that threshold goes where friction
+          // rows keep mu (a normal row has no use for the slot); solve_constraints carries an upper bound of |z| and
+          // skips the visit -- the skipped visit would have computed a zero delta, so results are bit-identical.
+          S.rc.r.r_mu[r] = kind == 1 ? ((positional + verr) < 0.0f && dd > 0.0f ? -(positional + verr) * rsqrtf(dd) * 0.999f : 0.0f)
+                                     : mu;
         }
       MB_END
     }
@@ -1467,8 +1480,9 @@ template <class M> struct Sim {
   // Row r of Y is stored over its support; the entry of coordinate l sits at slot tl(l) (prefix property).
   // DUAL: 0 = the row is one compact row (joint limits; contacts of a model without self-collision), 1 = always two
   // (loop closures), 2 = look at the row's MB_ROW_DUAL flag (contacts of a model with self-collision)
+  // zb: running upper bound of |z| (each visit adds |Y_r| |delta|; a dual row's |Y_A + Y_B| <= sqrt(2 den))
   template <int DUAL>
-  MB_HD static float pgs_single(Mem& S, const LaneConst& C, int ra, float lo, float hi, LaneVar<float>& z) {
+  MB_HD static float pgs_single(Mem& S, const LaneConst& C, int ra, float lo, float hi, LaneVar<float>& z, float& zb) {
     const unsigned supA = S.rc.r.r_mask[ra];
     LaneVar<float> ya, ta;
     MB_LANES(l)
@@ -1496,11 +1510,12 @@ template <class M> struct Sim {
       z[l] += ya[l] * dA;
       if (l == 0) S.rc.r.r_app[ra] = nA;
     MB_END
+    zb += fabsf(dA) * sqrtf((DUAL ? 2.0f : 1.0f) * pA.den) * 1.001f;
     return dA * pA.den;  // deltaImpulse * (1 / jacDiagABInv)
   }
   // friction pair with btMultiBodyConstraintSolver::resolveConeFrictionConstraintRows' projection;
   // sin/cos(atan2(a, b)) are written as a/|(a,b)|, b/|(a,b)|.  A self-contact's pair continues in rows ra + 2, ra + 3.
-  MB_HD static float pgs_pair(Mem& S, const LaneConst& C, int ra, float cone, LaneVar<float>& z) {
+  MB_HD static float pgs_pair(Mem& S, const LaneConst& C, int ra, float cone, LaneVar<float>& z, float& zb) {
     const int rb = ra + 1;
     const unsigned supA = S.rc.r.r_mask[ra];  // both rows of a contact share the support
     LaneVar<float> ya, yb, ta, tb;
@@ -1540,6 +1555,7 @@ template <class M> struct Sim {
       z[l] += ya[l] * dA + yb[l] * dB;
       if (l == 0) { S.rc.r.r_app[ra] = nA; S.rc.r.r_app[rb] = nB; }
     MB_END
+    zb += (fabsf(dA) * sqrtf((NSELF > 0 ? 2.0f : 1.0f) * pA.den) + fabsf(dB) * sqrtf((NSELF > 0 ? 2.0f : 1.0f) * pB.den)) * 1.001f;
     return dA * pA.den + dB * pB.den;
   }
 
@@ -1547,7 +1563,7 @@ template <class M> struct Sim {
   // alternating direction), normals, friction.  Contact k < nc is a static-world contact, nc <= k < nc + ncs a
   // self-contact (rows behind S0, see setup_self_rows); one loop serves both so that the row code exists once.
   MB_HD static void solve_constraints(Mem& S, const MbPhysics& P, const LaneConst& C, int nlim, int nc, int ncs,
-                                      LaneVar<float>& z) {
+                                      LaneVar<float>& z, float zb) {
     const int nnc = nlim + NLC / 2, n0 = nlim + NLC, S0 = n0 + 3 * nc, nct = nc + (NSELF > 0 ? ncs : 0);
 #pragma unroll 1
     for (int it = 0; it < P.iterations; ++it) {
@@ -1556,18 +1572,20 @@ template <class M> struct Sim {
       for (int v = 0; v < nnc; ++v) {
         const int idx = (it & 1) ? v : nnc - 1 - v;
         float rr;
-        if (NLC == 0 || idx < nlim) rr = pgs_single<0>(S, C, idx, 0.0f, P.limit_max_impulse, z);
+        if (NLC == 0 || idx < nlim) rr = pgs_single<0>(S, C, idx, 0.0f, P.limit_max_impulse, z, zb);
         else {
           const int ra = nlim + 2 * (idx - nlim);
           const float lim = S.rc.r.r_mu[ra];
-          rr = pgs_single<1>(S, C, ra, -lim, lim, z);
+          rr = pgs_single<1>(S, C, ra, -lim, lim, z, zb);
         }
         res2 = fmaxf(res2, rr * rr);
       }
 #pragma unroll 1
       for (int k = 0; k < nct; ++k) {
         const int ra = (NSELF > 0 && k >= nc) ? S0 + 2 * (k - nc) : n0 + k;
-        const float rr = pgs_single<(NSELF > 0 ? 2 : 0)>(S, C, ra, 0.0f, 1e10f, z);
+        // idle row (see setup_rows): nothing applied yet and |z| provably too small to activate it -> zero delta
+        if (zb < S.rc.r.r_mu[ra] && S.rc.r.r_app[ra] == 0.0f) continue;
+        const float rr = pgs_single<(NSELF > 0 ? 2 : 0)>(S, C, ra, 0.0f, 1e10f, z, zb);
         res2 = fmaxf(res2, rr * rr);
       }
 #pragma unroll 1
@@ -1579,7 +1597,7 @@ template <class M> struct Sim {
         // a contact that carries no normal impulse has a zero friction cone: with nothing applied yet the projection
         // returns exactly zero for both rows (deltas 0, residual 0), so the visit can be skipped -- bit-identical
         if (cone == 0.0f && S.rc.r.r_app[ra] == 0.0f && S.rc.r.r_app[ra + 1] == 0.0f) continue;
-        const float rr = pgs_pair(S, C, ra, cone, z);
+        const float rr = pgs_pair(S, C, ra, cone, z, zb);
         res2 = fmaxf(res2, rr * rr);
       }
       if (res2 <= P.residual_threshold) break;
@@ -1665,20 +1683,22 @@ template <class M> struct Sim {
       MB_LANES(l)
         z[l] = 0.0f;
       MB_END
-      if (MB_UNLIKELY(S.warm != nullptr)) {
+      float zb = 0.0f;  // upper bound of |z| for the idle-row skip
+      if (MB_UNLIKELY(P.warmstart > 0.0f)) {  // (a kernel parameter: the test costs the default path one predicate)
         warm_start(S, P.warmstart, nlim + NLC, nlim + NLC + 3 * nc, nc, ncs, S.rhs);  // (S.rhs is free after the FD solve)
         init_lane_const(C);
         MB_LANES(l)
           z[l] = S.rhs[l];
         MB_END
+        zb = 3.0e38f;  // z starts non-zero: no row is skipped
       }
-      solve_constraints(S, P, C, nlim, nc, ncs, z);
+      solve_constraints(S, P, C, nlim, nc, ncs, z, zb);
       solve_L<false>(S, C, z);
       MB_LANES(l)
         if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + z[l], -P.max_coord_vel), P.max_coord_vel);
       MB_END
     }
-    if (MB_UNLIKELY(S.warm != nullptr)) {
+    if (MB_UNLIKELY(P.warmstart > 0.0f)) {
       warm_store(S, nlim + NLC, nlim + NLC + 3 * nc, nc, ncs, R > 0);
       init_lane_const(C);
     }
