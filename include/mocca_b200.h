@@ -38,8 +38,9 @@ typedef struct mb200_physics {
   float residual_threshold; /* 1e-7   m_leastSquaresResidualThreshold (PGS early exit)                    */
   float ground_friction;    /* 0.8    bullet_utils.py:371 changeDynamics(lateralFriction=0.8)             */
   int has_ground;           /* 1      bullet_utils.py:361-371 plane_stadium.sdf (0 = remove_ground)       */
-  int self_collision;       /* 1      robots.py:259-264 URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS (Walker3D,
-                                      Monkey3D sphere / capsule geoms; Cassie's mesh hulls: not modelled)          */
+  int self_collision;       /* 1      robots.py:259-264, env_cassie.py:81-85 URDF_USE_SELF_COLLISION |
+                                      ..._EXCLUDE_ALL_PARENTS: Walker3D / Monkey3D sphere and capsule geoms (closest points
+                                      of segments), Cassie's mesh hulls (GJK on 32-vertex link hulls, left vs right leg) */
   float warmstart;          /* 0      Bullet-version switch: multibody contact warm starting.
                                       0 = off (btMultiBodyConstraintSolver disables it); f > 0 = every contact normal row
                                       starts from f x the impulse its candidate point carried in the previous substep

@@ -132,6 +132,27 @@ def reduce_table(t: dict) -> dict:
         spairs.append(dict(reach=reach * (1 + 1e-5) + 1e-6, pack=pa[0] | (pa[-1] << 8) | (pb[0] << 16) | (pb[-1] << 24), thresh=min(A["thresh"], B["thresh"]),
                            mu=A["friction"] * B["friction"], own_a=A["owner"], own_b=B["owner"], feet=feet))
         assert A["owner"] != B["owner"]
+    # mesh-hull self-collision (Cassie, urdf_compiler.hull_collision_pairs): hull vertices and bounding spheres in the
+    # owner joint frames; the pairs ride in the same sp_* tables as the segment pairs (pack = hull a | hull b << 8)
+    hulls = []
+    for h in t.get("hulls", []):
+        link = h["link"]
+        oj = owner_joint(link)
+        Ro, oo = frame(oj)
+        vw = [Ro.T @ (pl[link + 1] + Rl[link + 1] @ np.array(v) - oo) for v in h["verts"]]
+        c = np.mean(vw, axis=0)
+        hulls.append(dict(link=link, owner=oj, verts=vw, center=c, radius=max(float(np.linalg.norm(v - c)) for v in vw),
+                          thresh=thresh[link + 1], friction=t["link_friction"][link + 1],
+                          foot=foot_links.index(link) if link in foot_links else -1))
+    for ha, hb in t.get("hull_pairs", []):
+        A, B = hulls[ha], hulls[hb]
+        assert not spairs or "hull" in spairs[0], "a model has segment pairs or hull pairs, not both"
+        feet = sum(1 << f for f in range(2) for x in (A, B) if x["foot"] == f)
+        th = min(A["thresh"], B["thresh"])
+        spairs.append(dict(hull=1, reach=(A["radius"] + B["radius"] + th + 2 * t["hull_margin"]) * (1 + 1e-5) + 1e-6,
+                           pack=ha | (hb << 8), thresh=th, mu=A["friction"] * B["friction"], own_a=A["owner"],
+                           own_b=B["owner"], feet=feet))
+        assert A["owner"] != B["owner"]
     # ancestor chains (root -> self) packed 5 bits per entry, and the compact (chain-ordered) factor layout:
     # row i of L stores only its support [base block | ancestors root->parent | diagonal]
     chains = []
@@ -164,7 +185,8 @@ def reduce_table(t: dict) -> dict:
         extras = dict(ordered=t["ordered_dofs"], pd_dof=[t["ordered_dofs"][k] for k in pd], pd_ordered=pd,
                       pd_kp=t["pd_kp"], pd_kd=t["pd_kd"], npowered=len(t["powered_joint_inds"]))
     return dict(name=t["name"], nj=nj, nb=nb, nu=6 + nj, npt=len(points), nlevel=max(jlevel) + 1,
-                xboxes=xboxes, palm_body=palm_body, p2p=p2p, extras=extras, spairs=spairs,
+                xboxes=xboxes, palm_body=palm_body, p2p=p2p, extras=extras, spairs=spairs, hulls=hulls,
+                hull_margin=t.get("hull_margin", 0.0),
                 jparent=jparent, joff=joff, jrot=jrot, jaxis=jaxis, jlevel=jlevel, janc=janc,
                 lower=t["lower"], upper=t["upper"], gain=t["gain"], damping=t["damping"], armature=t["armature"],
                 bodies=bodies, bstart=bstart, bend=bend, points=points, foot_body=foot_body,
@@ -303,6 +325,11 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append(_farr(P + "_sp_thresh", [x["thresh"] for x in sp] or [0]))
     out.append(_farr(P + "_sp_mu", [x["mu"] for x in sp] or [0]))
     out.append(_farr(P + "_sp_reach", [x["reach"] for x in sp] or [0]))
+    hl = r["hulls"] or [dict(owner=-1, verts=[np.zeros(3)] * 32, center=np.zeros(3), radius=0.0)]
+    out.append(_iarr(P + "_hown", [h["owner"] for h in hl]))
+    out.append(_farr(P + "_hcen", [list(h["center"]) + [h["radius"]] for h in hl]))
+    out.append("MB_TABLE float %s_hv[%d][32][3] = {\n%s};\n" % (P, len(hl), ",\n".join(
+        "  {" + ", ".join("{%s, %s, %s}" % tuple(_f(x) for x in v) for v in h["verts"]) + "}" for h in hl)))
     ex = r["extras"]
     out.append(_iarr(P + "_ordered", ex.get("ordered", [])))
     out.append(_iarr(P + "_pd_dof", ex.get("pd_dof", [])))
@@ -337,11 +364,16 @@ def emit_header(t: dict, prefix: str) -> str:
                " ".join("i == %d ? %du :" % (i, m) for i, m in enumerate(rowmask)) + " 0u;\n  }\n")
     out.append("  enum { NJ = %d, NB = %d, NU = %d, NPT = %d, NLEVEL = %d, NFEET = %d, NMIRROR = %d, NNEG = %d,\n"
                "         LSIZE = %d, MAXSUP = %d, NXBOX = %d, NLOOP = %d, NORDERED = %d, NPD = %d, NPOWERED = %d, NSELF = %d,\n"
-               "         ALL_ALIGNED = %d, ALL_IDENT = %d };  // every joint axis is a coordinate axis / every zero-pose rotation is 1\n"
+               "         ALL_ALIGNED = %d, ALL_IDENT = %d,  // every joint axis is a coordinate axis / every zero-pose rotation is 1\n"
+               "         NHULL = %d, SELF_HULLS = %d };  // the self-collision pairs are mesh-hull pairs (hull-vs-hull narrow phase)\n"
                % (r["nj"], r["nb"], r["nu"], r["npt"], r["nlevel"], r["nfeet"], len(r["right"]), len(r["neg"]),
                   r["lsize"], r["maxsup"], len(r["xboxes"]), len(r["p2p"]), len(ex.get("ordered", [])),
                   len(ex.get("pd_dof", [])), ex.get("npowered", 0), len(sp),
-                  int(all(k >= 0 for k in jaxk)), int(all(jident))))
+                  int(all(k >= 0 for k in jaxk)), int(all(jident)), len(r["hulls"]), int(bool(r["hulls"]) and bool(sp))))
+    out.append("  MB_HD static float hull_margin() { return %s; }\n" % _f(r["hull_margin"]))
+    out.append("  MB_HD static int hown(int i) { return %s_hown[i]; }\n" % P)
+    out.append("  MB_HD static float hcen(int i, int k) { return %s_hcen[i][k]; }\n" % P)
+    out.append("  MB_HD static float hv(int h, int v, int k) { return %s_hv[h][v][k]; }\n" % P)
     out.append("  MB_HD static unsigned long long chainpack(int j) { return %s_chainpack[j]; }\n" % P)
     out.append("  MB_HD static int facoff(int k, int t) { return %s_facoff[k][t]; }\n" % P)
     out.append("  MB_HD static int fcol(int k, int t) { return %s_fcol[k][t]; }\n" % P)

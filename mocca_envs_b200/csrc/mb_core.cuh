@@ -64,6 +64,18 @@ MB_HD void warp_gather(const LaneVar<float>& x, const LaneVar<int>& src, LaneVar
 }
 MB_HD unsigned warp_ballot(const LaneVar<int>& p) { return __ballot_sync(0xffffffffu, p.v != 0); }
 MB_HD int mb_popc(unsigned x) { return __popc(x); }
+// lane holding the largest value (the lowest such lane on ties)
+MB_HD int warp_argmax(const LaneVar<float>& x) {
+  float v = x.v;
+  int i = (int)(threadIdx.x & 31);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+    if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; }
+  }
+  return i;
+}
 #else
 #define MB_NOINLINE
 #define MB_LANES(l) for (int l = 0; l < 32; ++l) {
@@ -98,6 +110,12 @@ inline unsigned warp_ballot(const LaneVar<int>& p) {
   return m;
 }
 inline int mb_popc(unsigned x) { return __builtin_popcount(x); }
+inline int warp_argmax(const LaneVar<float>& x) {
+  int best = 0;
+  for (int l = 1; l < 32; ++l)
+    if (x.v[l] > x.v[best]) best = l;
+  return best;
+}
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #endif
 
@@ -944,6 +962,240 @@ template <class M> struct Sim {
     return ns;
   }
 
+  // ---- F1b. mesh-hull self-collision (Cassie: env_cassie.py:81-85 loads the URDF with URDF_USE_SELF_COLLISION |
+  // ..._EXCLUDE_ALL_PARENTS; the only non-ancestor link pairs are left-leg vs right-leg links) -------------------------
+  // Bullet runs GJK between the two btConvexHullShapes (margin 1 mm each) and reports one point per frame.  Here a hull
+  // is the convex hull of <= 32 support vertices of the mesh (urdf_compiler.hull_fan_vertices), ONE VERTEX PER LANE: the
+  // support function of GJK is a dot product per lane and a warp arg-max.  The sub-distance step enumerates the <= 15
+  // faces of the <= 4-point simplex (closest point of each face's affine hull, valid if its barycentric weights are
+  // non-negative; the nearest valid one is the closest point of the simplex).  Contact distance = core distance - 2
+  // margins; cores that overlap (deeper than 2 mm: ERP 0.9 pushes contacts out long before) fall back to the overlap of
+  // the two hulls along the line of their bounding-sphere centres.  Cold path, written for size; scratch in S.rc.
+  struct Gjk {  // view of S.rc.scratch: simplex points of the Minkowski difference and their A-side points, weights
+    float* w;    // [4][3]
+    float* a;    // [4][3]
+    float* lam;  // [4]
+  };
+  // closest point of the simplex (n points) to the origin: writes v, compacts the simplex to the supporting face
+  MB_HD static int gjk_closest(const Gjk& g, int n, float* v) {
+    float best = 3.0e38f, bl[4] = {0, 0, 0, 0};
+    int bmask = 0;
+#pragma unroll 1
+    for (int mask = 1; mask < (1 << n); ++mask) {
+      int id[4], k = 0;
+      for (int i = 0; i < n; ++i)
+        if ((mask >> i) & 1) id[k++] = i;
+      const float* p0 = g.w + 3 * id[0];
+      float mu[3] = {0, 0, 0};
+      bool ok = true;
+      if (k > 1) {
+        float e[3][3], G[3][3], b[3];
+        for (int i = 0; i < k - 1; ++i)
+          for (int c = 0; c < 3; ++c) e[i][c] = g.w[3 * id[i + 1] + c] - p0[c];
+        for (int i = 0; i < k - 1; ++i) {
+          b[i] = -(e[i][0] * p0[0] + e[i][1] * p0[1] + e[i][2] * p0[2]);
+          for (int j = 0; j < k - 1; ++j) G[i][j] = e[i][0] * e[j][0] + e[i][1] * e[j][1] + e[i][2] * e[j][2];
+        }
+        if (k == 2) {
+          ok = G[0][0] > 1e-20f;
+          mu[0] = ok ? b[0] / G[0][0] : 0.0f;
+        } else if (k == 3) {
+          const float det = G[0][0] * G[1][1] - G[0][1] * G[1][0];
+          ok = det > 1e-12f * G[0][0] * G[1][1];
+          if (ok) { mu[0] = (b[0] * G[1][1] - b[1] * G[0][1]) / det; mu[1] = (G[0][0] * b[1] - G[1][0] * b[0]) / det; }
+        } else {
+          const float c00 = G[1][1] * G[2][2] - G[1][2] * G[2][1], c01 = G[1][2] * G[2][0] - G[1][0] * G[2][2];
+          const float c02 = G[1][0] * G[2][1] - G[1][1] * G[2][0];
+          const float det = G[0][0] * c00 + G[0][1] * c01 + G[0][2] * c02;
+          ok = det > 1e-10f * G[0][0] * G[1][1] * G[2][2];
+          if (ok) {
+            mu[0] = (b[0] * c00 + b[1] * (G[0][2] * G[2][1] - G[0][1] * G[2][2]) + b[2] * (G[0][1] * G[1][2] - G[0][2] * G[1][1])) / det;
+            mu[1] = (b[0] * c01 + b[1] * (G[0][0] * G[2][2] - G[0][2] * G[2][0]) + b[2] * (G[0][2] * G[1][0] - G[0][0] * G[1][2])) / det;
+            mu[2] = (b[0] * c02 + b[1] * (G[0][1] * G[2][0] - G[0][0] * G[2][1]) + b[2] * (G[0][0] * G[1][1] - G[0][1] * G[1][0])) / det;
+          }
+        }
+      }
+      if (!ok) continue;
+      float l4[4] = {1.0f - mu[0] - mu[1] - mu[2], mu[0], mu[1], mu[2]};
+      bool inside = true;
+      for (int i = 0; i < k; ++i)
+        if (l4[i] < -1e-6f) inside = false;
+      if (!inside) continue;
+      float p[3] = {0, 0, 0};
+      if (k == 3) {
+        // triangle interior: the foot of the perpendicular through the plane normal (the barycentric combination
+        // squares the condition number of the edge matrix; the normal of the contact is this vector's direction)
+        const float* q1 = g.w + 3 * id[1];
+        const float* q2 = g.w + 3 * id[2];
+        const float e0[3] = {q1[0] - p0[0], q1[1] - p0[1], q1[2] - p0[2]}, e1[3] = {q2[0] - p0[0], q2[1] - p0[1], q2[2] - p0[2]};
+        float nn[3];
+        mb_cross(e0, e1, nn);
+        const float sc = (nn[0] * p0[0] + nn[1] * p0[1] + nn[2] * p0[2]) / (nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+        p[0] = nn[0] * sc; p[1] = nn[1] * sc; p[2] = nn[2] * sc;
+      } else {
+        for (int i = 0; i < k; ++i)
+          for (int c = 0; c < 3; ++c) p[c] += l4[i] * g.w[3 * id[i] + c];
+      }
+      const float d2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+      if (d2 < best) {
+        best = d2; bmask = mask;
+        for (int i = 0; i < 4; ++i) bl[i] = i < k ? fmaxf(l4[i], 0.0f) : 0.0f;
+        v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+      }
+    }
+    // compact the simplex to the supporting face
+    int k = 0;
+    for (int i = 0; i < n; ++i)
+      if ((bmask >> i) & 1) {
+        for (int c = 0; c < 3; ++c) { g.w[3 * k + c] = g.w[3 * i + c]; g.a[3 * k + c] = g.a[3 * i + c]; }
+        g.lam[k] = bl[k];
+        ++k;
+      }
+    return k;
+  }
+  // narrow phase of one hull pair; appends a contact at slot `at` (returns 1) or nothing (0)
+  MB_HD static int hull_pair(Mem& S, int pr, int at, float erp) {
+    const unsigned pk = M::sp_pack(pr);
+    const int ha = pk & 255u, hb = (pk >> 8) & 255u;
+    LaneVar<float> ax, ay, az, bx, by, bz, key;
+    MB_LANES(l)
+      {
+        const int o = M::hown(ha);
+        const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
+        const float loc[3] = {M::hv(ha, l, 0), M::hv(ha, l, 1), M::hv(ha, l, 2)};
+        float c[3];
+        mb_matvec(R, loc, c);
+        if (o >= 0) { c[0] += S.w.k.jp[o][0]; c[1] += S.w.k.jp[o][1]; c[2] += S.w.k.jp[o][2]; }
+        ax[l] = c[0]; ay[l] = c[1]; az[l] = c[2];
+      }
+      {
+        const int o = M::hown(hb);
+        const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
+        const float loc[3] = {M::hv(hb, l, 0), M::hv(hb, l, 1), M::hv(hb, l, 2)};
+        float c[3];
+        mb_matvec(R, loc, c);
+        if (o >= 0) { c[0] += S.w.k.jp[o][0]; c[1] += S.w.k.jp[o][1]; c[2] += S.w.k.jp[o][2]; }
+        bx[l] = c[0]; by[l] = c[1]; bz[l] = c[2];
+      }
+    MB_END_REG
+    Gjk g;
+    g.w = S.rc.scratch; g.a = S.rc.scratch + 12; g.lam = S.rc.scratch + 24;
+    float v[3] = {warp_bcast(ax, 0) - warp_bcast(bx, 0), warp_bcast(ay, 0) - warp_bcast(by, 0),
+                  warp_bcast(az, 0) - warp_bcast(bz, 0)};
+    int n = 0;
+    bool overlap = false;
+#pragma unroll 1
+    for (int it = 0; it < 32; ++it) {
+      const float vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+      if (vv < 1e-14f) { overlap = true; break; }
+      MB_LANES(l)
+        key[l] = -(ax[l] * v[0] + ay[l] * v[1] + az[l] * v[2]);
+      MB_END_REG
+      const int sa = warp_argmax(key);
+      MB_LANES(l)
+        key[l] = bx[l] * v[0] + by[l] * v[1] + bz[l] * v[2];
+      MB_END_REG
+      const int sb = warp_argmax(key);
+      const float pa[3] = {warp_bcast(ax, sa), warp_bcast(ay, sa), warp_bcast(az, sa)};
+      const float w[3] = {pa[0] - warp_bcast(bx, sb), pa[1] - warp_bcast(by, sb), pa[2] - warp_bcast(bz, sb)};
+      if (vv - (v[0] * w[0] + v[1] * w[1] + v[2] * w[2]) <= 1e-7f * vv && n > 0) break;  // no progress: v is the closest point
+      MB_LANES(l)
+        if (l < 3) { g.w[3 * n + l] = l == 0 ? w[0] : (l == 1 ? w[1] : w[2]); g.a[3 * n + l] = l == 0 ? pa[0] : (l == 1 ? pa[1] : pa[2]); }
+      MB_END
+      n = gjk_closest(g, n + 1, v);
+      MB_WARP_SYNC();
+      if (n == 4) { overlap = true; break; }  // the origin is inside the tetrahedron
+    }
+    const float margin = M::hull_margin();
+    float nrm[3], pA[3], dist;
+    if (!overlap) {
+      const float len = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+      dist = len - 2.0f * margin;
+      if (dist >= M::sp_thresh(pr)) return 0;
+      const float il = 1.0f / len;
+      for (int c = 0; c < 3; ++c) {
+        nrm[c] = v[c] * il;
+        float acc = 0.0f;
+        for (int i = 0; i < n; ++i) acc += g.lam[i] * g.a[3 * i + c];
+        pA[c] = acc - margin * nrm[c];
+      }
+    } else {
+      // overlapping cores: separate along the line of the bounding-sphere centres
+      float ca[3], cb[3];
+      for (int side = 0; side < 2; ++side) {
+        const int h = side ? hb : ha, o = M::hown(h);
+        const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
+        const float loc[3] = {M::hcen(h, 0), M::hcen(h, 1), M::hcen(h, 2)};
+        float* c = side ? cb : ca;
+        mb_matvec(R, loc, c);
+        if (o >= 0) { c[0] += S.w.k.jp[o][0]; c[1] += S.w.k.jp[o][1]; c[2] += S.w.k.jp[o][2]; }
+      }
+      const float d[3] = {ca[0] - cb[0], ca[1] - cb[1], ca[2] - cb[2]};
+      const float len = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      if (len < 1e-9f) return 0;
+      for (int c = 0; c < 3; ++c) nrm[c] = d[c] / len;
+      MB_LANES(l)
+        key[l] = -(ax[l] * nrm[0] + ay[l] * nrm[1] + az[l] * nrm[2]);
+      MB_END_REG
+      const int sa = warp_argmax(key);
+      MB_LANES(l)
+        key[l] = bx[l] * nrm[0] + by[l] * nrm[1] + bz[l] * nrm[2];
+      MB_END_REG
+      const int sb = warp_argmax(key);
+      const float pa[3] = {warp_bcast(ax, sa), warp_bcast(ay, sa), warp_bcast(az, sa)};
+      const float pb[3] = {warp_bcast(bx, sb), warp_bcast(by, sb), warp_bcast(bz, sb)};
+      dist = (pa[0] - pb[0]) * nrm[0] + (pa[1] - pb[1]) * nrm[1] + (pa[2] - pb[2]) * nrm[2] - 2.0f * margin;
+      for (int c = 0; c < 3; ++c) pA[c] = pa[c] - margin * nrm[c];
+    }
+    if (at >= MB_MAXC) return 1;
+    MB_LANES(l)
+      if (l == 0) {
+        S.cP[at][0] = pA[0]; S.cP[at][1] = pA[1]; S.cP[at][2] = pA[2];
+        S.cn[at][0] = nrm[0]; S.cn[at][1] = nrm[1]; S.cn[at][2] = nrm[2];
+        S.cdist[at] = dist;
+        S.cmu[at] = M::sp_mu(pr);
+        S.cerp[at] = erp;
+        S.ccfm[at] = 0.0f;
+        S.clink[at] = (M::sp_own(pr) & 255) - 1;
+        S.cfoot[at] = mb_pack_foot(-1, 320 + pr);  // (warm-start slots 320.. : behind every candidate id 2 * geom + end)
+        S.cpartner[at] = 1000 + pr;
+      }
+    MB_END
+    return 1;
+  }
+  MB_NOINLINE static int collide_self_hulls(Mem& S, float erp_contact, int nc) {
+    MB_ASSUME_SHARED(S);
+    static_assert(NSELF <= 32, "one hull pair per lane in the broad phase");
+    LaneVar<int> near;
+    MB_LANES(l)
+      near[l] = 0;
+      if (l < NSELF) {
+        const unsigned pk = M::sp_pack(l);
+        float c[2][3];
+        for (int side = 0; side < 2; ++side) {
+          const int h = side ? (int)((pk >> 8) & 255u) : (int)(pk & 255u), o = M::hown(h);
+          const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
+          const float loc[3] = {M::hcen(h, 0), M::hcen(h, 1), M::hcen(h, 2)};
+          mb_matvec(R, loc, c[side]);
+          if (o >= 0) { c[side][0] += S.w.k.jp[o][0]; c[side][1] += S.w.k.jp[o][1]; c[side][2] += S.w.k.jp[o][2]; }
+        }
+        const float dx = c[0][0] - c[1][0], dy = c[0][1] - c[1][1], dz = c[0][2] - c[1][2];
+        const float reach = M::sp_reach(l);
+        near[l] = dx * dx + dy * dy + dz * dz < reach * reach;
+      }
+    MB_END_REG
+    unsigned mask = warp_ballot(near);
+    int ns = 0;
+#pragma unroll 1
+    while (mask) {
+      int pr = 0;
+      while (!((mask >> pr) & 1u)) ++pr;
+      mask &= mask - 1u;
+      ns += hull_pair(S, pr, nc + ns, erp_contact);
+    }
+    return ns;
+  }
+
   template <int OBST> MB_HD static int collide(Mem& S, const MbPhysics& P, int* overflow, int* ns_out) {
     constexpr bool BOXES = (OBST & (MB_OBST_BOXES | MB_OBST_CYLS)) != 0;
     constexpr bool CYLS = (OBST & MB_OBST_CYLS) != 0;
@@ -1134,9 +1386,17 @@ template <class M> struct Sim {
     }
     if (nc > MB_MAXC) { *overflow += 1; nc = MB_MAXC; }
     int ns = 0;
-    if (NSELF > 0 && STORE && P.self_collision) {
-      ns = collide_self(S, P.erp_contact, nc);
-      if (nc + ns > MB_MAXC) { *overflow += 1; ns = MB_MAXC - nc; }
+    if constexpr (NSELF > 0 && M::SELF_HULLS) {
+      static_assert(OBST == 0, "the hull narrow phase borrows the obstacle staging area as scratch");
+      if (P.self_collision) {
+        ns = collide_self_hulls(S, P.erp_contact, nc);
+        if (nc + ns > MB_MAXC) { *overflow += 1; ns = MB_MAXC - nc; }
+      }
+    } else if constexpr (NSELF > 0 && STORE) {
+      if (P.self_collision) {
+        ns = collide_self(S, P.erp_contact, nc);
+        if (nc + ns > MB_MAXC) { *overflow += 1; ns = MB_MAXC - nc; }
+      }
     }
     *ns_out = ns;
     return nc + ns;
@@ -1264,7 +1524,7 @@ template <class M> struct Sim {
           par.rhs = rel_vel; par.cfm = 0.0f; par.jinv = dd; par.den = 0.0f;
           S.rc.r.r_par[r] = par;
           S.rc.r.r_app[r] = 0.0f;
-          S.rc.r.r_mu[r] = fr >= 0 ? S.cmu[k] : 0.0f;  // (normal rows: idle threshold 0 = never skipped)
+          S.rc.r.r_mu[r] = S.cmu[k];
         }
       MB_END
     }
@@ -1402,13 +1662,7 @@ template <class M> struct Sim {
           par.cfm = cfm * jinv;
           S.rc.r.r_par[r] = par;
           S.rc.r.r_app[r] = 0.0f;
-          // A contact normal row whose right-hand side b = positional + verr is negative (a speculative contact the
-          // link is not closing fast enough to reach, or a separating one) stays at zero impulse while Y_r . z > b.
-          // |Y_r . z| <= |Y_r| |z|, so it PROVABLY stays idle while |z| < -b / |Y_r|: that threshold goes where friction
-          // rows keep mu (a normal row has no use for the slot); solve_constraints carries an upper bound of |z| and
-          // skips the visit -- the skipped visit would have computed a zero delta, so results are bit-identical.
-          S.rc.r.r_mu[r] = kind == 1 ? ((positional + verr) < 0.0f && dd > 0.0f ? -(positional + verr) * rsqrtf(dd) * 0.999f : 0.0f)
-                                     : mu;
+          S.rc.r.r_mu[r] = mu;
         }
       MB_END
     }
@@ -1480,9 +1734,8 @@ template <class M> struct Sim {
   // Row r of Y is stored over its support; the entry of coordinate l sits at slot tl(l) (prefix property).
   // DUAL: 0 = the row is one compact row (joint limits; contacts of a model without self-collision), 1 = always two
   // (loop closures), 2 = look at the row's MB_ROW_DUAL flag (contacts of a model with self-collision)
-  // zb: running upper bound of |z| (each visit adds |Y_r| |delta|; a dual row's |Y_A + Y_B| <= sqrt(2 den))
   template <int DUAL>
-  MB_HD static float pgs_single(Mem& S, const LaneConst& C, int ra, float lo, float hi, LaneVar<float>& z, float& zb) {
+  MB_HD static float pgs_single(Mem& S, const LaneConst& C, int ra, float lo, float hi, LaneVar<float>& z) {
     const unsigned supA = S.rc.r.r_mask[ra];
     LaneVar<float> ya, ta;
     MB_LANES(l)
@@ -1510,12 +1763,11 @@ template <class M> struct Sim {
       z[l] += ya[l] * dA;
       if (l == 0) S.rc.r.r_app[ra] = nA;
     MB_END
-    zb += fabsf(dA) * sqrtf((DUAL ? 2.0f : 1.0f) * pA.den) * 1.001f;
     return dA * pA.den;  // deltaImpulse * (1 / jacDiagABInv)
   }
   // friction pair with btMultiBodyConstraintSolver::resolveConeFrictionConstraintRows' projection;
   // sin/cos(atan2(a, b)) are written as a/|(a,b)|, b/|(a,b)|.  A self-contact's pair continues in rows ra + 2, ra + 3.
-  MB_HD static float pgs_pair(Mem& S, const LaneConst& C, int ra, float cone, LaneVar<float>& z, float& zb) {
+  MB_HD static float pgs_pair(Mem& S, const LaneConst& C, int ra, float cone, LaneVar<float>& z) {
     const int rb = ra + 1;
     const unsigned supA = S.rc.r.r_mask[ra];  // both rows of a contact share the support
     LaneVar<float> ya, yb, ta, tb;
@@ -1555,7 +1807,6 @@ template <class M> struct Sim {
       z[l] += ya[l] * dA + yb[l] * dB;
       if (l == 0) { S.rc.r.r_app[ra] = nA; S.rc.r.r_app[rb] = nB; }
     MB_END
-    zb += (fabsf(dA) * sqrtf((NSELF > 0 ? 2.0f : 1.0f) * pA.den) + fabsf(dB) * sqrtf((NSELF > 0 ? 2.0f : 1.0f) * pB.den)) * 1.001f;
     return dA * pA.den + dB * pB.den;
   }
 
@@ -1563,7 +1814,7 @@ template <class M> struct Sim {
   // alternating direction), normals, friction.  Contact k < nc is a static-world contact, nc <= k < nc + ncs a
   // self-contact (rows behind S0, see setup_self_rows); one loop serves both so that the row code exists once.
   MB_HD static void solve_constraints(Mem& S, const MbPhysics& P, const LaneConst& C, int nlim, int nc, int ncs,
-                                      LaneVar<float>& z, float zb) {
+                                      LaneVar<float>& z) {
     const int nnc = nlim + NLC / 2, n0 = nlim + NLC, S0 = n0 + 3 * nc, nct = nc + (NSELF > 0 ? ncs : 0);
 #pragma unroll 1
     for (int it = 0; it < P.iterations; ++it) {
@@ -1572,20 +1823,18 @@ template <class M> struct Sim {
       for (int v = 0; v < nnc; ++v) {
         const int idx = (it & 1) ? v : nnc - 1 - v;
         float rr;
-        if (NLC == 0 || idx < nlim) rr = pgs_single<0>(S, C, idx, 0.0f, P.limit_max_impulse, z, zb);
+        if (NLC == 0 || idx < nlim) rr = pgs_single<0>(S, C, idx, 0.0f, P.limit_max_impulse, z);
         else {
           const int ra = nlim + 2 * (idx - nlim);
           const float lim = S.rc.r.r_mu[ra];
-          rr = pgs_single<1>(S, C, ra, -lim, lim, z, zb);
+          rr = pgs_single<1>(S, C, ra, -lim, lim, z);
         }
         res2 = fmaxf(res2, rr * rr);
       }
 #pragma unroll 1
       for (int k = 0; k < nct; ++k) {
         const int ra = (NSELF > 0 && k >= nc) ? S0 + 2 * (k - nc) : n0 + k;
-        // idle row (see setup_rows): nothing applied yet and |z| provably too small to activate it -> zero delta
-        if (zb < S.rc.r.r_mu[ra] && S.rc.r.r_app[ra] == 0.0f) continue;
-        const float rr = pgs_single<(NSELF > 0 ? 2 : 0)>(S, C, ra, 0.0f, 1e10f, z, zb);
+        const float rr = pgs_single<(NSELF > 0 ? 2 : 0)>(S, C, ra, 0.0f, 1e10f, z);
         res2 = fmaxf(res2, rr * rr);
       }
 #pragma unroll 1
@@ -1597,7 +1846,7 @@ template <class M> struct Sim {
         // a contact that carries no normal impulse has a zero friction cone: with nothing applied yet the projection
         // returns exactly zero for both rows (deltas 0, residual 0), so the visit can be skipped -- bit-identical
         if (cone == 0.0f && S.rc.r.r_app[ra] == 0.0f && S.rc.r.r_app[ra + 1] == 0.0f) continue;
-        const float rr = pgs_pair(S, C, ra, cone, z, zb);
+        const float rr = pgs_pair(S, C, ra, cone, z);
         res2 = fmaxf(res2, rr * rr);
       }
       if (res2 <= P.residual_threshold) break;
@@ -1683,16 +1932,16 @@ template <class M> struct Sim {
       MB_LANES(l)
         z[l] = 0.0f;
       MB_END
-      float zb = 0.0f;  // upper bound of |z| for the idle-row skip
+      // (an exact skip of idle speculative rows -- |Y_r . z| <= |Y_r| |z| with a running bound of |z| -- was measured in
+      // round 2: the bound is too loose to fire often and its bookkeeping cost 6 % (Walker3D) to 11 % (Cassie): dropped)
       if (MB_UNLIKELY(P.warmstart > 0.0f)) {  // (a kernel parameter: the test costs the default path one predicate)
         warm_start(S, P.warmstart, nlim + NLC, nlim + NLC + 3 * nc, nc, ncs, S.rhs);  // (S.rhs is free after the FD solve)
         init_lane_const(C);
         MB_LANES(l)
           z[l] = S.rhs[l];
         MB_END
-        zb = 3.0e38f;  // z starts non-zero: no row is skipped
       }
-      solve_constraints(S, P, C, nlim, nc, ncs, z, zb);
+      solve_constraints(S, P, C, nlim, nc, ncs, z);
       solve_L<false>(S, C, z);
       MB_LANES(l)
         if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + z[l], -P.max_coord_vel), P.max_coord_vel);

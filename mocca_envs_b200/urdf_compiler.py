@@ -119,6 +119,77 @@ def hull_support_points(verts, level):
     return hv[sorted(idx)], hv
 
 
+HULL_VERTS = 32  # vertices kept per link hull for the hull-vs-hull narrow phase (one per lane of a warp)
+
+
+def hull_fan_vertices(hv, n=HULL_VERTS):
+    """Support vertices of the hull `hv` along n spherical-Fibonacci directions (duplicates removed, then padded by
+    repeating the first vertex): the convex hull of these is the link's shape in the hull-vs-hull narrow phase -- an
+    inner approximation of Bullet's btConvexHullShape (which keeps every mesh vertex), millimetres off at most."""
+    idx = []
+    ga = math.pi * (3.0 - math.sqrt(5.0))
+    for k in range(n):
+        z = 1.0 - 2.0 * (k + 0.5) / n
+        r = math.sqrt(max(0.0, 1.0 - z * z))
+        d = np.array([r * math.cos(ga * k), r * math.sin(ga * k), z])
+        i = int(np.argmax(hv @ d))
+        if i not in idx:
+            idx.append(i)
+    v = hv[idx]
+    pad = np.repeat(v[:1], n - len(v), axis=0)
+    return np.concatenate([v, pad]), len(v)
+
+
+def hull_distance(A, B, iters=64):
+    """Distance between the convex hulls of two vertex sets (Gilbert's iteration on the Minkowski difference)."""
+    v = A[0] - B[0]
+    for _ in range(iters):
+        s = A[int(np.argmax(A @ -v))] - B[int(np.argmax(B @ v))]
+        if v @ v - v @ s < 1e-12:
+            break
+        e = s - v
+        v = v + min(1.0, max(0.0, -(v @ e) / (e @ e))) * e
+    return float(np.linalg.norm(v))
+
+
+def hull_collision_pairs(t, samples=3000, margin=0.08, seed=0):
+    """Link pairs whose mesh hulls can touch under URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS (env_cassie.py:81-85):
+    neither link an ancestor of the other, both with a collision hull (the achilles rods carry none and are filtered
+    out anyway, env_cassie.py:140-149); pairs that never come within `margin` in `samples` poses drawn inside the joint
+    limits are dropped (the same documented reduction as model_compiler.self_collision_pairs)."""
+    from .model_compiler import fk_links
+
+    par = t["parent"]
+
+    def ancestors(l):
+        out = set()
+        while l >= 0:
+            l = par[l]
+            out.add(l)
+        return out
+
+    H = t["hulls"]
+    cand = [(a, b) for a in range(len(H)) for b in range(a + 1, len(H))
+            if H[a]["link"] not in ancestors(H[b]["link"]) and H[b]["link"] not in ancestors(H[a]["link"])
+            and H[a]["link"] != H[b]["link"]]
+    rng = np.random.RandomState(seed)
+    lo, hi = np.array(t["lower"]), np.array(t["upper"])
+    verts = [np.array(h["verts"]) for h in H]
+    cen = [v.mean(0) for v in verts]
+    rad = [float(np.linalg.norm(v - c, axis=1).max()) for v, c in zip(verts, cen)]
+    mind = np.full(len(cand), np.inf)
+    for _ in range(samples):
+        q = lo + (hi - lo) * rng.uniform(0, 1, len(lo))
+        pos, rot = fk_links(t, q)
+        W = [v @ rot[h["link"] + 1].T + pos[h["link"] + 1] for v, h in zip(verts, H)]
+        C = [rot[h["link"] + 1] @ c + pos[h["link"] + 1] for c, h in zip(cen, H)]
+        for k, (a, b) in enumerate(cand):
+            if np.linalg.norm(C[a] - C[b]) - rad[a] - rad[b] > min(mind[k], margin):
+                continue
+            mind[k] = min(mind[k], hull_distance(W[a], W[b]))
+    return [[a, b] for k, (a, b) in enumerate(cand) if mind[k] < margin], len(cand)
+
+
 def compile_urdf(path, name, fan_level=None, mesh_root=None):
     fan_level = fan_level or {}
     root = ET.parse(path).getroot()
@@ -194,13 +265,17 @@ def compile_urdf(path, name, fan_level=None, mesh_root=None):
 
     mesh_root = mesh_root or os.path.dirname(path)
 
-    def link_points(link):
+    hulls = []
+
+    def link_points(link, li):
         pts, lo, hi = [], None, None
+        allv = []
         for fn, cx, cr, scale in link["meshes"]:
             v = load_stl_vertices(os.path.normpath(os.path.join(mesh_root, fn))) * scale
             v = v @ rpy_to_mat(cr).T + cx  # collision frame -> link frame
             v = (v - link["xyz"]) @ link["R"]  # link frame -> inertial frame
             sp, hv = hull_support_points(v, fan_level.get(link["name"], 0))
+            allv.append(hv)
             pts.extend(sp.tolist())
             l2, h2 = hv.min(0) - HULL_MARGIN, hv.max(0) + HULL_MARGIN
             lo = l2 if lo is None else np.minimum(lo, l2)
@@ -208,12 +283,15 @@ def compile_urdf(path, name, fan_level=None, mesh_root=None):
         thr = 0.0
         if lo is not None:
             thr = CONTACT_BREAKING_THRESHOLD * (0.5 * float(np.linalg.norm(hi - lo)) + float(np.linalg.norm(0.5 * (lo + hi))))
+        if allv and li >= 1:  # (the base is an ancestor of every link: never a partner under EXCLUDE_ALL_PARENTS)
+            fv, n = hull_fan_vertices(np.concatenate(allv))
+            hulls.append(dict(link=li - 1, verts=fv.tolist(), n=n))
         return pts, thr
 
     geoms = []
     thresholds = []
     for li, link in enumerate([base] + [f[0] for f in flat]):
-        pts, thr = link_points(link)
+        pts, thr = link_points(link, li)
         thresholds.append(thr)
         for k, p in enumerate(pts):
             geoms.append(dict(name="%s_v%d" % (link["name"], k), link=li - 1, type=GEOM_SPHERE, pos=list(p),
@@ -232,6 +310,7 @@ def compile_urdf(path, name, fan_level=None, mesh_root=None):
         joint_type=[JOINT_REVOLUTE if f[2]["type"] in ("revolute", "continuous") else JOINT_FIXED for f in flat],
         mass=[f[0]["mass"] for f in flat], inertia=[f[0]["inertia"].tolist() for f in flat],
         contact_threshold=thresholds[1:], group=[1] * len(flat), mask=[1] * len(flat), geoms=geoms,
+        hulls=hulls, hull_margin=HULL_MARGIN, link_friction=[base["friction"]] + [f[0]["friction"] for f in flat],
     )
     axis, rot, ev, dv = [], [], [], []
     for link, pidx, jd in flat:
@@ -308,4 +387,6 @@ def compile_cassie(data_dir: str) -> dict:
     kp = [100, 100, 88, 96, 50, 100, 100, 88, 96, 50, 400, 400]
     t["pd_kp"] = [k / 1.9 for k in kp]
     t["pd_kd"] = [k / 1.9 / 10 for k in kp]
+    # mesh-hull self-collision (env_cassie.py:81-85): left-leg vs right-leg links are the only non-ancestor pairs
+    t["hull_pairs"], t["hull_pairs_considered"] = hull_collision_pairs(t)
     return t

@@ -796,12 +796,160 @@ int orc_collide_cached(const orc_model* m, const orc_params* p, const orc_cache*
   return out->n;
 }
 
+/* ---- mesh-hull self-collision (Cassie): GJK distance between the <= 32-vertex hulls of two links, Bullet's
+ * btGjkPairDetector on two btConvexHullShapes with margin m->hull_margin each.  Sub-distance step: every face of the
+ * <= 4-point simplex (closest point of its affine hull, valid when its barycentric weights are >= 0; the nearest valid one
+ * is the closest point of the simplex).  Cores that overlap fall back to the overlap along the centre line. */
+static int gjk_closest(double w[4][3], double a[4][3], double lam[4], int n, v3 v) {
+  double best = 1e300, bl[4] = {0, 0, 0, 0};
+  int bmask = 0;
+  for (int mask = 1; mask < (1 << n); mask++) {
+    int id[4], k = 0;
+    for (int i = 0; i < n; i++)
+      if ((mask >> i) & 1) id[k++] = i;
+    const double* p0 = w[id[0]];
+    double mu[3] = {0, 0, 0};
+    int ok = 1;
+    if (k > 1) {
+      double e[3][3], G[3][3], b[3];
+      for (int i = 0; i < k - 1; i++)
+        for (int c = 0; c < 3; c++) e[i][c] = w[id[i + 1]][c] - p0[c];
+      for (int i = 0; i < k - 1; i++) {
+        b[i] = -v3dot(e[i], p0);
+        for (int j = 0; j < k - 1; j++) G[i][j] = v3dot(e[i], e[j]);
+      }
+      if (k == 2) {
+        ok = G[0][0] > 1e-20;
+        mu[0] = ok ? b[0] / G[0][0] : 0.0;
+      } else if (k == 3) {
+        double det = G[0][0] * G[1][1] - G[0][1] * G[1][0];
+        ok = det > 1e-12 * G[0][0] * G[1][1];
+        if (ok) { mu[0] = (b[0] * G[1][1] - b[1] * G[0][1]) / det; mu[1] = (G[0][0] * b[1] - G[1][0] * b[0]) / det; }
+      } else {
+        double c00 = G[1][1] * G[2][2] - G[1][2] * G[2][1], c01 = G[1][2] * G[2][0] - G[1][0] * G[2][2];
+        double c02 = G[1][0] * G[2][1] - G[1][1] * G[2][0];
+        double det = G[0][0] * c00 + G[0][1] * c01 + G[0][2] * c02;
+        ok = det > 1e-10 * G[0][0] * G[1][1] * G[2][2];
+        if (ok) {
+          mu[0] = (b[0] * c00 + b[1] * (G[0][2] * G[2][1] - G[0][1] * G[2][2]) + b[2] * (G[0][1] * G[1][2] - G[0][2] * G[1][1])) / det;
+          mu[1] = (b[0] * c01 + b[1] * (G[0][0] * G[2][2] - G[0][2] * G[2][0]) + b[2] * (G[0][2] * G[1][0] - G[0][0] * G[1][2])) / det;
+          mu[2] = (b[0] * c02 + b[1] * (G[0][1] * G[2][0] - G[0][0] * G[2][1]) + b[2] * (G[0][0] * G[1][1] - G[0][1] * G[1][0])) / det;
+        }
+      }
+    }
+    if (!ok) continue;
+    double l4[4] = {1.0 - mu[0] - mu[1] - mu[2], mu[0], mu[1], mu[2]};
+    int inside = 1;
+    for (int i = 0; i < k; i++)
+      if (l4[i] < -1e-6) inside = 0;
+    if (!inside) continue;
+    v3 pnt = {0, 0, 0};
+    if (k == 3) { /* triangle interior: foot of the perpendicular through the plane normal (better conditioned) */
+      v3 e0, e1, nn;
+      for (int c = 0; c < 3; c++) { e0[c] = w[id[1]][c] - p0[c]; e1[c] = w[id[2]][c] - p0[c]; }
+      v3cross(e0, e1, nn);
+      double sc = v3dot(nn, p0) / v3dot(nn, nn);
+      for (int c = 0; c < 3; c++) pnt[c] = nn[c] * sc;
+    } else {
+      for (int i = 0; i < k; i++)
+        for (int c = 0; c < 3; c++) pnt[c] += l4[i] * w[id[i]][c];
+    }
+    double d2 = v3dot(pnt, pnt);
+    if (d2 < best) {
+      best = d2; bmask = mask;
+      for (int i = 0; i < 4; i++) bl[i] = i < k ? (l4[i] > 0 ? l4[i] : 0.0) : 0.0;
+      v3copy(v, pnt);
+    }
+  }
+  int k = 0;
+  for (int i = 0; i < n; i++)
+    if ((bmask >> i) & 1) {
+      for (int c = 0; c < 3; c++) { w[k][c] = w[i][c]; a[k][c] = a[i][c]; }
+      lam[k] = bl[k];
+      k++;
+    }
+  return k;
+}
+
+static int hull_support(double V[ORC_HULLV][3], const v3 d) {
+  int best = 0;
+  double bv = v3dot(V[0], d);
+  for (int i = 1; i < ORC_HULLV; i++) {
+    double x = v3dot(V[i], d);
+    if (x > bv) { bv = x; best = i; }
+  }
+  return best;
+}
+
+static void collide_hulls(const orc_model* m, const orc_params* p, const orc_cache* c, orc_contacts* out) {
+  for (int k = 0; k < m->n_hpairs; k++) {
+    int ha = m->hpair_a[k], hb = m->hpair_b[k];
+    int la = m->hull_link[ha], lb = m->hull_link[hb];
+    double thresh = m->link_thresh[la + 1] < m->link_thresh[lb + 1] ? m->link_thresh[la + 1] : m->link_thresh[lb + 1];
+    v3 ca, cb, t;
+    m3Tvec(c->Rw[la + 1], m->hull_center[ha], t);
+    for (int i = 0; i < 3; i++) ca[i] = c->pw[la + 1][i] + t[i];
+    m3Tvec(c->Rw[lb + 1], m->hull_center[hb], t);
+    for (int i = 0; i < 3; i++) cb[i] = c->pw[lb + 1][i] + t[i];
+    double reach = m->hull_radius[ha] + m->hull_radius[hb] + thresh + 2 * m->hull_margin;
+    v3 dc = {ca[0] - cb[0], ca[1] - cb[1], ca[2] - cb[2]};
+    if (v3dot(dc, dc) >= reach * reach) continue;
+    double A[ORC_HULLV][3], B[ORC_HULLV][3];
+    for (int i = 0; i < ORC_HULLV; i++) {
+      m3Tvec(c->Rw[la + 1], m->hull_verts[ha][i], t);
+      for (int j = 0; j < 3; j++) A[i][j] = c->pw[la + 1][j] + t[j];
+      m3Tvec(c->Rw[lb + 1], m->hull_verts[hb][i], t);
+      for (int j = 0; j < 3; j++) B[i][j] = c->pw[lb + 1][j] + t[j];
+    }
+    double w[4][3], a[4][3], lam[4];
+    v3 v = {A[0][0] - B[0][0], A[0][1] - B[0][1], A[0][2] - B[0][2]};
+    int n = 0, overlap = 0;
+    for (int it = 0; it < 32; it++) {
+      double vv = v3dot(v, v);
+      if (vv < 1e-14) { overlap = 1; break; }
+      v3 nv = {-v[0], -v[1], -v[2]};
+      int sa = hull_support(A, nv), sb = hull_support(B, v);
+      v3 ws = {A[sa][0] - B[sb][0], A[sa][1] - B[sb][1], A[sa][2] - B[sb][2]};
+      if (vv - v3dot(v, ws) <= 1e-7 * vv && n > 0) break;
+      v3copy(w[n], ws); v3copy(a[n], A[sa]);
+      n = gjk_closest(w, a, lam, n + 1, v);
+      if (n == 4) { overlap = 1; break; }
+    }
+    v3 nrm, pa;
+    double dist;
+    if (!overlap) {
+      double len = v3norm(v);
+      dist = len - 2 * m->hull_margin;
+      if (dist >= thresh) continue;
+      for (int i = 0; i < 3; i++) {
+        nrm[i] = v[i] / len;
+        double acc = 0;
+        for (int j = 0; j < n; j++) acc += lam[j] * a[j][i];
+        pa[i] = acc - m->hull_margin * nrm[i];
+      }
+    } else {
+      double len = v3norm(dc);
+      if (len < 1e-9) continue;
+      for (int i = 0; i < 3; i++) nrm[i] = dc[i] / len;
+      v3 nn = {-nrm[0], -nrm[1], -nrm[2]};
+      int sa = hull_support(A, nn), sb = hull_support(B, nrm);
+      dist = (A[sa][0] - B[sb][0]) * nrm[0] + (A[sa][1] - B[sb][1]) * nrm[1] + (A[sa][2] - B[sb][2]) * nrm[2] - 2 * m->hull_margin;
+      for (int i = 0; i < 3; i++) pa[i] = A[sa][i] - m->hull_margin * nrm[i];
+    }
+    if (out->n >= ORC_MAXP) return;
+    int idx = out->n;
+    add_point(out, 320 + k, la, 1000 + lb + 1, pa, nrm, dist, m->hull_friction[ha] * m->hull_friction[hb], p->erp_contact, 0.0);
+    out->link_b[idx] = lb;
+    for (int i = 0; i < 3; i++) out->pos_b[idx][i] = pa[i] - dist * nrm[i];
+  }
+}
+
 int orc_collide(const orc_model* m, const orc_params* p, const orc_state* s, const orc_box* boxes, int n_boxes,
                 orc_contacts* out) {
   orc_cache* c = (orc_cache*)malloc(sizeof(orc_cache));
   kin(m, s, c);
   orc_collide_cached(m, p, c, boxes, n_boxes, out);
-  if (p->self_collision) collide_self(m, p, c, out);
+  if (p->self_collision) { collide_self(m, p, c, out); collide_hulls(m, p, c, out); }
   free(c);
   return out->n;
 }
@@ -1016,7 +1164,7 @@ static void substep_impl(const orc_model* m, const orc_params* p, orc_state* s, 
   kin(m, s, c);
   orc_collide_cached(m, p, c, boxes, n_boxes, ct);
   if (n_bars > 0) collide_bars(m, p, c, bars, n_bars, ct);
-  if (p->self_collision) collide_self(m, p, c, ct);
+  if (p->self_collision) { collide_self(m, p, c, ct); collide_hulls(m, p, c, ct); }
   orc_diag_contacts += ct->n;
   for (int d = 0; d < m->n_dof; d++) orc_diag_q[orc_diag_nq & 63][d] = s->q[d];
   orc_diag_nq++;

@@ -31,6 +31,9 @@
 #define ORC_MAXROW (3 * ORC_MAXP + 2 * ORC_MAXD)
 #define ORC_MAXU (6 + ORC_MAXD)
 #define ORC_MAXSP 256 /* self-collision candidate pairs */
+#define ORC_MAXHULL 24 /* links with a mesh hull */
+#define ORC_HULLV 32   /* vertices per hull */
+#define ORC_MAXHPAIR 64
 #define ORC_MAXSTEPS 32 /* stepping stones / bars in a terrain table */
 
 enum { ORC_GEOM_SPHERE = 0, ORC_GEOM_CAPSULE = 1, ORC_GEOM_BOX = 2 };
@@ -77,6 +80,13 @@ typedef struct {
   /* Cassie bookkeeping (env_cassie.py:59-60,192-202): dofs of the 14 ordered joints, PD joint list, gains */
   /* self-collision candidate geom pairs (robots.py:259-264; compiled by model_compiler.self_collision_pairs) */
   int n_self, self_a[ORC_MAXSP], self_b[ORC_MAXSP];
+  /* mesh-hull self-collision (Cassie, env_cassie.py:81-85): per link hull ORC_HULLV support vertices in the link's
+   * inertial frame (urdf_compiler.hull_fan_vertices), candidate hull pairs, collision margin of a hull */
+  int n_hulls, hull_link[ORC_MAXHULL];
+  double hull_verts[ORC_MAXHULL][ORC_HULLV][3];
+  double hull_center[ORC_MAXHULL][3], hull_radius[ORC_MAXHULL], hull_friction[ORC_MAXHULL];
+  int n_hpairs, hpair_a[ORC_MAXHPAIR], hpair_b[ORC_MAXHPAIR];
+  double hull_margin;
   int n_ordered, ordered_dof[ORC_MAXD];
   int n_pd, pd_ordered_index[16]; /* powered + spring joints, as indices into the ordered joints */
   double pd_kp[16], pd_kd[16];

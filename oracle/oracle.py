@@ -19,6 +19,7 @@ MAXL, MAXD, MAXG, MAXP = 40, 40, 192, 96
 MAXW = 2 * MAXG
 MAXU = 6 + MAXD
 MAXSP = 256
+MAXHULL, HULLV, MAXHPAIR = 24, 32, 64
 
 d = C.c_double
 i32 = C.c_int
@@ -45,6 +46,9 @@ class Model(C.Structure):
         ("n_p2p", i32), ("p2p_link_a", i32 * 2), ("p2p_link_b", i32 * 2),
         ("p2p_pivot_a", (d * 3) * 2), ("p2p_pivot_b", (d * 3) * 2), ("p2p_max_impulse", d * 2),
         ("n_self", i32), ("self_a", i32 * MAXSP), ("self_b", i32 * MAXSP),
+        ("n_hulls", i32), ("hull_link", i32 * MAXHULL), ("hull_verts", ((d * 3) * HULLV) * MAXHULL),
+        ("hull_center", (d * 3) * MAXHULL), ("hull_radius", d * MAXHULL), ("hull_friction", d * MAXHULL),
+        ("n_hpairs", i32), ("hpair_a", i32 * MAXHPAIR), ("hpair_b", i32 * MAXHPAIR), ("hull_margin", d),
         ("n_ordered", i32), ("ordered_dof", i32 * MAXD),
         ("n_pd", i32), ("pd_ordered_index", i32 * 16), ("pd_kp", d * 16), ("pd_kd", d * 16),
     ]
@@ -225,6 +229,25 @@ def model_from_table(t: dict) -> Model:
     m.n_self = len(pairs)
     for k, (a, b) in enumerate(pairs):
         m.self_a[k], m.self_b[k] = a, b
+    hulls = t.get("hulls", [])
+    assert len(hulls) <= MAXHULL and len(t.get("hull_pairs", [])) <= MAXHPAIR
+    m.n_hulls = len(hulls)
+    m.hull_margin = float(t.get("hull_margin", 0.0))
+    for k, h in enumerate(hulls):
+        v = np.array(h["verts"], dtype=np.float64)
+        assert v.shape == (HULLV, 3)
+        m.hull_link[k] = h["link"]
+        cen = v.mean(0)
+        for i in range(HULLV):
+            for j in range(3):
+                m.hull_verts[k][i][j] = v[i, j]
+        for j in range(3):
+            m.hull_center[k][j] = cen[j]
+        m.hull_radius[k] = float(np.linalg.norm(v - cen, axis=1).max())
+        m.hull_friction[k] = float(t["link_friction"][h["link"] + 1])
+    m.n_hpairs = len(t.get("hull_pairs", []))
+    for k, (a, b) in enumerate(t.get("hull_pairs", [])):
+        m.hpair_a[k], m.hpair_b[k] = a, b
     if "ordered_dofs" in t:
         m.n_ordered = len(t["ordered_dofs"])
         _fill(m.ordered_dof, np.array(t["ordered_dofs"], dtype=np.int64))

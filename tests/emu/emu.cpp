@@ -249,6 +249,23 @@ void emu_cassie_step_physics(const MbPhysics* p, float* state, const float* tau,
   *contacts = nc;
 }
 
+// the same with the contact points of the last collision pass ([MB_MAXC][MB_POINT_WIDTH], see Sim::substep)
+void emu_cassie_step_physics_points(const MbPhysics* p, float* state, const float* tau, int* rows, int* contacts,
+                                    float* points) {
+  static CMem S;
+  memset(&S, 0, sizeof(S));
+  CEnv::load_state(S, state);
+  for (int j = 0; j < CM::NJ; ++j) S.tau[j] = tau[j];
+  int r = 0, nc = 0, ov = 0;
+  Sim<CM>::LaneConst C;
+  Sim<CM>::init_lane_const(C);
+  for (int k = 0; k < p->substeps; ++k)
+    r += Sim<CM>::substep<0>(S, *p, C, &nc, &ov, k, k == p->substeps - 1 ? points : nullptr);
+  CEnv::store_state(S, state);
+  *rows = r;
+  *contacts = nc;
+}
+
 void emu_cassie_mass_matrix(const MbPhysics* p, const float* state, float* Mout, float* bias) {
   static CMem S;
   memset(&S, 0, sizeof(S));

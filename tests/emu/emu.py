@@ -308,6 +308,17 @@ class EmuCassie:
         return rows.value, nc.value
 
 
+def cassie_step_physics_points(p, state, tau):
+    """(state after, rows, contacts, points[16, 10]) of one Cassie stepSimulation through the kernel source."""
+    buf = np.zeros(64, dtype=np.float32)
+    buf[: len(state)] = state
+    tau = np.ascontiguousarray(tau, dtype=np.float32)
+    rows, nc = C.c_int(0), C.c_int(0)
+    pts = np.zeros((16, 10), dtype=np.float32)
+    lib().emu_cassie_step_physics_points(C.byref(p), _fp(buf), _fp(tau), C.byref(rows), C.byref(nc), _fp(pts))
+    return buf[: len(state)].copy(), rows.value, nc.value, pts
+
+
 def cassie_mass_matrix(p, state, nu=24):
     buf = np.zeros(64, dtype=np.float32)
     buf[: len(state)] = state

@@ -98,3 +98,25 @@ def self_contact_states(O, table, rng, n, max_tries=4000):
                 break
     assert len(out) == n
     return np.array(out)
+
+
+def cassie_hull_contact_states(O, table, rng, n, deepest=-1.0e-3, max_tries=40000):
+    """Airborne Cassie poses (zero velocity) inside the joint limits whose left-leg / right-leg mesh hulls are in
+    shallow contact according to the oracle (every hull contact no deeper than `deepest`: the GJK path; deeper overlaps
+    take the centre-line fallback)."""
+    A = table["n_dof"]
+    m = O.model_from_table(table)
+    p = O.cassie_params()
+    lo, hi = np.array(table["lower"]), np.array(table["upper"])
+    base = np.array(table["base_joint_angles"])
+    out = []
+    for _ in range(max_tries):
+        q = np.clip(base + rng.uniform(-1, 1, A) * 0.5 * (hi - lo) * rng.uniform(0.2, 1.0), lo + 1e-3, hi - 1e-3)
+        s = O.make_state(A, [0, 0, 3.0], [0, 0, 0, 1], [0] * 3, [0] * 3, q, np.zeros(A))
+        c = O.collide(m, p, s)
+        d = [c.dist[k] for k in range(c.n) if c.partner[k] >= 1000]
+        if d and min(d) > deepest:
+            out.append(np.concatenate([[0, 0, 3.0], [0, 0, 0, 1], np.zeros(6), q, np.zeros(A)]))
+            if len(out) == n:
+                return np.array(out, dtype=np.float32)
+    raise AssertionError("not enough hull-contact states")

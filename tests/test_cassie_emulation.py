@@ -120,3 +120,55 @@ def test_cassie_env_free_running(cassie_table, oracle_mod):
         prev = emu.rec[15]
         if d1:
             break
+
+
+def test_cassie_hull_self_collision(cassie_table, oracle_mod):
+    """Mesh-hull self-collision (env_cassie.py:81-85: URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS; the non-ancestor
+    pairs are left-leg vs right-leg links): warp-cooperative GJK on the 32-vertex link hulls in the kernel source against
+    the oracle's float64 GJK on the same hulls.  Contact geometry (distance 2e-6, point 2e-4 (barycentric weights of a float32 Gram solve), normal 2e-3: the normal
+    is a millimetre-long difference of metre-sized float32 coordinates), contact and row counts, the state after one
+    0.6 ms stepSimulation (5e-3, median 5e-4) -- and with self_collision = 0 the same states come out differently, so
+    the feature is live."""
+    from tests.helpers import cassie_hull_contact_states, oracle_state, state_error
+
+    O, t = oracle_mod, cassie_table
+    A = t["n_dof"]
+    m = O.model_from_table(t)
+    p = O.cassie_params()
+    p_off = O.cassie_params()
+    p_off.self_collision = 0
+    pe = E.cassie_phys()
+    rng = np.random.RandomState(3)
+    states = cassie_hull_contact_states(O, t, rng, 24)
+    errs, effect = [], []
+    for st in states:
+        s = oracle_state(O, A, st.astype(np.float64))
+        c0 = O.collide(m, p, s)
+        c, rows_ref = O.step_physics(m, p, s, np.zeros(A))
+        out, rows, nc, pts = E.cassie_step_physics_points(pe, st, np.zeros(A, dtype=np.float32))
+        assert nc == c.n and rows == rows_ref
+        for k in range(c0.n):
+            if c0.partner[k] >= 1000:
+                assert int(pts[k, 9]) >= 1000
+                assert abs(pts[k, 6] - c0.dist[k]) < 2e-6
+                assert np.abs(pts[k, 0:3] - np.array(c0.pos_a[k][:])).max() < 2e-4
+                assert np.abs(pts[k, 3:6] - np.array(c0.normal[k][:])).max() < 2e-3
+        ref = O.state_vector(s, A)
+        errs.append(state_error(out, ref))
+        s_off = oracle_state(O, A, st.astype(np.float64))
+        O.step_physics(m, p_off, s_off, np.zeros(A))
+        effect.append(state_error(O.state_vector(s_off, A), ref))
+    assert max(errs) < 5e-3 and np.median(errs) < 5e-4, sorted(errs)[-5:]
+    assert np.median(effect) > 0.1, np.median(effect)
+
+
+def test_cassie_hull_pairs_of_the_table(cassie_table):
+    """The compiled hull tables: 16 link hulls of exactly 32 vertices, only left-leg vs right-leg candidate pairs (every
+    other pair is an ancestor pair under EXCLUDE_ALL_PARENTS; the achilles rods carry no collision hull)."""
+    t = cassie_table
+    assert len(t["hulls"]) == 16 and all(len(h["verts"]) == 32 for h in t["hulls"])
+    names = t["link_names"]
+    assert 10 <= len(t["hull_pairs"]) <= 32
+    for a, b in t["hull_pairs"]:
+        na, nb = names[t["hulls"][a]["link"]], names[t["hulls"][b]["link"]]
+        assert {na.split("_")[0], nb.split("_")[0]} == {"left", "right"}, (na, nb)

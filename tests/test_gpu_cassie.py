@@ -106,3 +106,42 @@ def test_cassie_determinism_and_gym_facade(torch_mod):
     o, r, d, info = env.step(np.zeros(10))
     assert set(info) >= {"AliveRew", "ProgressRew"} and abs(info["AliveRew"] + info["ProgressRew"] - r) < 1e-6
     env.close()
+
+
+def test_cassie_hull_self_collision(cassie_table, oracle_mod, torch_mod):
+    """Mesh-hull self-collision on the device (warp-cooperative GJK, one hull vertex per lane; env_cassie.py:81-85)
+    against the oracle's float64 GJK: contact geometry through mb200_step_physics_points (distance 2e-6, point 2e-6,
+    normal 2e-3), contact / row counts, the state after one stepSimulation (5e-3, median 5e-4); with
+    physics={"self_collision": 0} the same states disagree (the feature is live on the device)."""
+    from tests.helpers import cassie_hull_contact_states, oracle_state, state_error
+
+    torch, O, t = torch_mod, oracle_mod, cassie_table
+    A = t["n_dof"]
+    m = O.model_from_table(t)
+    p = O.cassie_params()
+    rng = np.random.RandomState(3)
+    N = 32
+    st = cassie_hull_contact_states(O, t, rng, N)
+    outs = {}
+    for flag in (1, 0):
+        env = _env(N, physics={"self_collision": flag})
+        env.set_state(torch.tensor(st))
+        rows, nc, pts = env.step_physics_points(torch.zeros(N, A))
+        outs[flag] = (env.get_state().cpu().numpy(), rows.cpu().numpy(), nc.cpu().numpy(), pts.cpu().numpy())
+        env.close()
+    out, rows, nc, pts = outs[1]
+    errs = []
+    for i in range(N):
+        s = oracle_state(O, A, st[i].astype(np.float64))
+        c0 = O.collide(m, p, s)
+        c, rows_ref = O.step_physics(m, p, s, np.zeros(A))
+        assert nc[i] == c.n and rows[i] == rows_ref
+        for k in range(c0.n):
+            if c0.partner[k] >= 1000:
+                assert int(pts[i, k, 9]) >= 1000
+                assert abs(pts[i, k, 6] - c0.dist[k]) < 2e-6
+                assert np.abs(pts[i, k, 0:3] - np.array(c0.pos_a[k][:])).max() < 2e-4
+                assert np.abs(pts[i, k, 3:6] - np.array(c0.normal[k][:])).max() < 2e-3
+        errs.append(state_error(out[i], O.state_vector(s, A)))
+    assert max(errs) < 5e-3 and np.median(errs) < 5e-4, sorted(errs)[-5:]
+    assert np.median([state_error(outs[0][0][i], out[i]) for i in range(N)]) > 0.1
