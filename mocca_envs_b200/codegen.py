@@ -141,7 +141,14 @@ def reduce_table(t: dict) -> dict:
         Ro, oo = frame(oj)
         vw = [Ro.T @ (pl[link + 1] + Rl[link + 1] @ np.array(v) - oo) for v in h["verts"]]
         c = np.mean(vw, axis=0)
+        # bounding capsule for the broad phase: principal axis of the vertices, radius = largest distance to it
+        V = np.array(vw) - c
+        u = np.linalg.eigh(V.T @ V)[1][:, -1]
+        tt = V @ u
+        seg = (c + tt.min() * u, c + tt.max() * u)
+        crad = float(np.linalg.norm(V - np.outer(tt, u), axis=1).max())
         hulls.append(dict(link=link, owner=oj, verts=vw, center=c, radius=max(float(np.linalg.norm(v - c)) for v in vw),
+                          seg=seg, crad=crad,
                           thresh=thresh[link + 1], friction=t["link_friction"][link + 1],
                           foot=foot_links.index(link) if link in foot_links else -1))
     for ha, hb in t.get("hull_pairs", []):
@@ -149,7 +156,7 @@ def reduce_table(t: dict) -> dict:
         assert not spairs or "hull" in spairs[0], "a model has segment pairs or hull pairs, not both"
         feet = sum(1 << f for f in range(2) for x in (A, B) if x["foot"] == f)
         th = min(A["thresh"], B["thresh"])
-        spairs.append(dict(hull=1, reach=(A["radius"] + B["radius"] + th + 2 * t["hull_margin"]) * (1 + 1e-5) + 1e-6,
+        spairs.append(dict(hull=1, reach=(A["crad"] + B["crad"] + th + 2 * t["hull_margin"]) * (1 + 1e-5) + 1e-6,
                            pack=ha | (hb << 8), thresh=th, mu=A["friction"] * B["friction"], own_a=A["owner"],
                            own_b=B["owner"], feet=feet))
         assert A["owner"] != B["owner"]
@@ -325,9 +332,11 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append(_farr(P + "_sp_thresh", [x["thresh"] for x in sp] or [0]))
     out.append(_farr(P + "_sp_mu", [x["mu"] for x in sp] or [0]))
     out.append(_farr(P + "_sp_reach", [x["reach"] for x in sp] or [0]))
-    hl = r["hulls"] or [dict(owner=-1, verts=[np.zeros(3)] * 32, center=np.zeros(3), radius=0.0)]
+    hl = r["hulls"] or [dict(owner=-1, verts=[np.zeros(3)] * 32, center=np.zeros(3), radius=0.0,
+                             seg=(np.zeros(3), np.zeros(3)))]
     out.append(_iarr(P + "_hown", [h["owner"] for h in hl]))
     out.append(_farr(P + "_hcen", [list(h["center"]) + [h["radius"]] for h in hl]))
+    out.append(_farr(P + "_hseg", [list(h["seg"][0]) + list(h["seg"][1]) for h in hl]))
     out.append("MB_TABLE float %s_hv[%d][32][3] = {\n%s};\n" % (P, len(hl), ",\n".join(
         "  {" + ", ".join("{%s, %s, %s}" % tuple(_f(x) for x in v) for v in h["verts"]) + "}" for h in hl)))
     ex = r["extras"]
@@ -373,6 +382,7 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append("  MB_HD static float hull_margin() { return %s; }\n" % _f(r["hull_margin"]))
     out.append("  MB_HD static int hown(int i) { return %s_hown[i]; }\n" % P)
     out.append("  MB_HD static float hcen(int i, int k) { return %s_hcen[i][k]; }\n" % P)
+    out.append("  MB_HD static float hseg(int i, int k) { return %s_hseg[i][k]; }\n" % P)
     out.append("  MB_HD static float hv(int h, int v, int k) { return %s_hv[h][v][k]; }\n" % P)
     out.append("  MB_HD static unsigned long long chainpack(int j) { return %s_chainpack[j]; }\n" % P)
     out.append("  MB_HD static int facoff(int k, int t) { return %s_facoff[k][t]; }\n" % P)

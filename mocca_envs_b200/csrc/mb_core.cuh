@@ -1001,13 +1001,13 @@ template <class M> struct Sim {
           mu[0] = ok ? b[0] / G[0][0] : 0.0f;
         } else if (k == 3) {
           const float det = G[0][0] * G[1][1] - G[0][1] * G[1][0];
-          ok = det > 1e-12f * G[0][0] * G[1][1];
+          ok = det > 1e-5f * G[0][0] * G[1][1];  /* (a float32 determinant is noise below that) */
           if (ok) { mu[0] = (b[0] * G[1][1] - b[1] * G[0][1]) / det; mu[1] = (G[0][0] * b[1] - G[1][0] * b[0]) / det; }
         } else {
           const float c00 = G[1][1] * G[2][2] - G[1][2] * G[2][1], c01 = G[1][2] * G[2][0] - G[1][0] * G[2][2];
           const float c02 = G[1][0] * G[2][1] - G[1][1] * G[2][0];
           const float det = G[0][0] * c00 + G[0][1] * c01 + G[0][2] * c02;
-          ok = det > 1e-10f * G[0][0] * G[1][1] * G[2][2];
+          ok = det > 1e-4f * G[0][0] * G[1][1] * G[2][2];
           if (ok) {
             mu[0] = (b[0] * c00 + b[1] * (G[0][2] * G[2][1] - G[0][1] * G[2][2]) + b[2] * (G[0][1] * G[1][2] - G[0][2] * G[1][1])) / det;
             mu[1] = (b[0] * c01 + b[1] * (G[0][0] * G[2][2] - G[0][2] * G[2][0]) + b[2] * (G[0][2] * G[1][0] - G[0][0] * G[1][2])) / det;
@@ -1163,28 +1163,8 @@ template <class M> struct Sim {
     MB_END
     return 1;
   }
-  MB_NOINLINE static int collide_self_hulls(Mem& S, float erp_contact, int nc) {
+  MB_NOINLINE static int collide_self_hulls_narrow(Mem& S, unsigned mask, float erp_contact, int nc) {
     MB_ASSUME_SHARED(S);
-    static_assert(NSELF <= 32, "one hull pair per lane in the broad phase");
-    LaneVar<int> near;
-    MB_LANES(l)
-      near[l] = 0;
-      if (l < NSELF) {
-        const unsigned pk = M::sp_pack(l);
-        float c[2][3];
-        for (int side = 0; side < 2; ++side) {
-          const int h = side ? (int)((pk >> 8) & 255u) : (int)(pk & 255u), o = M::hown(h);
-          const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
-          const float loc[3] = {M::hcen(h, 0), M::hcen(h, 1), M::hcen(h, 2)};
-          mb_matvec(R, loc, c[side]);
-          if (o >= 0) { c[side][0] += S.w.k.jp[o][0]; c[side][1] += S.w.k.jp[o][1]; c[side][2] += S.w.k.jp[o][2]; }
-        }
-        const float dx = c[0][0] - c[1][0], dy = c[0][1] - c[1][1], dz = c[0][2] - c[1][2];
-        const float reach = M::sp_reach(l);
-        near[l] = dx * dx + dy * dy + dz * dz < reach * reach;
-      }
-    MB_END_REG
-    unsigned mask = warp_ballot(near);
     int ns = 0;
 #pragma unroll 1
     while (mask) {
@@ -1194,6 +1174,37 @@ template <class M> struct Sim {
       ns += hull_pair(S, pr, nc + ns, erp_contact);
     }
     return ns;
+  }
+  // broad phase inline (every substep), narrow phase out of line (only when two capsules come within reach)
+  MB_HD static int collide_self_hulls(Mem& S, float erp_contact, int nc) {
+    static_assert(NSELF <= 32, "one hull pair per lane in the broad phase");
+    // broad phase, one pair per lane: bounding capsules (principal-axis segment + radius of each hull; the links are
+    // elongated, bounding spheres of two shins side by side overlap all the time) -- distance of the two segments
+    // against the tabulated reach = both radii + breaking threshold + both margins
+    LaneVar<int> near;
+    MB_LANES(l)
+      near[l] = 0;
+      if (l < NSELF) {
+        const unsigned pk = M::sp_pack(l);
+        float e[2][2][3];
+        for (int side = 0; side < 2; ++side) {
+          const int h = side ? (int)((pk >> 8) & 255u) : (int)(pk & 255u), o = M::hown(h);
+          const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
+          for (int end = 0; end < 2; ++end) {
+            const float loc[3] = {M::hseg(h, 3 * end), M::hseg(h, 3 * end + 1), M::hseg(h, 3 * end + 2)};
+            mb_matvec(R, loc, e[side][end]);
+            if (o >= 0) { e[side][end][0] += S.w.k.jp[o][0]; e[side][end][1] += S.w.k.jp[o][1]; e[side][end][2] += S.w.k.jp[o][2]; }
+          }
+        }
+        float c1[3], c2[3];
+        seg_seg(e[0][0], e[0][1], e[1][0], e[1][1], c1, c2);
+        const float dx = c1[0] - c2[0], dy = c1[1] - c2[1], dz = c1[2] - c2[2];
+        const float reach = M::sp_reach(l);
+        near[l] = dx * dx + dy * dy + dz * dz < reach * reach;
+      }
+    MB_END_REG
+    const unsigned mask = warp_ballot(near);
+    return MB_UNLIKELY(mask != 0u) ? collide_self_hulls_narrow(S, mask, erp_contact, nc) : 0;
   }
 
   template <int OBST> MB_HD static int collide(Mem& S, const MbPhysics& P, int* overflow, int* ns_out) {
@@ -1767,16 +1778,17 @@ template <class M> struct Sim {
   }
   // friction pair with btMultiBodyConstraintSolver::resolveConeFrictionConstraintRows' projection;
   // sin/cos(atan2(a, b)) are written as a/|(a,b)|, b/|(a,b)|.  A self-contact's pair continues in rows ra + 2, ra + 3.
+  template <bool SELF>
   MB_HD static float pgs_pair(Mem& S, const LaneConst& C, int ra, float cone, LaneVar<float>& z) {
     const int rb = ra + 1;
     const unsigned supA = S.rc.r.r_mask[ra];  // both rows of a contact share the support
     LaneVar<float> ya, yb, ta, tb;
     MB_LANES(l)
-      const bool in = (((NSELF > 0 ? supA & MB_ROW_SUP : supA) >> l) & 1u) != 0u;
+      const bool in = (((SELF ? supA & MB_ROW_SUP : supA) >> l) & 1u) != 0u;
       ya[l] = in ? S.w.Yc[ra][C.tl[l]] : 0.0f;
       yb[l] = in ? S.w.Yc[rb][C.tl[l]] : 0.0f;
     MB_END_REG
-    if (NSELF > 0 && (supA & MB_ROW_DUAL)) {
+    if (SELF && (supA & MB_ROW_DUAL)) {
       const unsigned supB = S.rc.r.r_mask[ra + 2];
       MB_LANES(l)
         if ((supB >> l) & 1u) { ya[l] += S.w.Yc[ra + 2][C.tl[l]]; yb[l] += S.w.Yc[ra + 3][C.tl[l]]; }
@@ -1813,9 +1825,13 @@ template <class M> struct Sim {
   // btMultiBodyConstraintSolver::solveSingleIteration order: non-contact rows (limits, then loop closures;
   // alternating direction), normals, friction.  Contact k < nc is a static-world contact, nc <= k < nc + ncs a
   // self-contact (rows behind S0, see setup_self_rows); one loop serves both so that the row code exists once.
+  // SELF: the model has self-collision pairs, so a contact row may be a dual row.  (Running substeps without
+  // self-contacts through a SELF = false instantiation and keeping the SELF = true copy out of line was measured in
+  // round 2: the extra call site cost Walker3D 8 % through register allocation, profiles/README.md r2l.)
+  template <bool SELF>
   MB_HD static void solve_constraints(Mem& S, const MbPhysics& P, const LaneConst& C, int nlim, int nc, int ncs,
                                       LaneVar<float>& z) {
-    const int nnc = nlim + NLC / 2, n0 = nlim + NLC, S0 = n0 + 3 * nc, nct = nc + (NSELF > 0 ? ncs : 0);
+    const int nnc = nlim + NLC / 2, n0 = nlim + NLC, S0 = n0 + 3 * nc, nct = nc + (SELF ? ncs : 0);
 #pragma unroll 1
     for (int it = 0; it < P.iterations; ++it) {
       float res2 = 0.0f;
@@ -1833,26 +1849,25 @@ template <class M> struct Sim {
       }
 #pragma unroll 1
       for (int k = 0; k < nct; ++k) {
-        const int ra = (NSELF > 0 && k >= nc) ? S0 + 2 * (k - nc) : n0 + k;
-        const float rr = pgs_single<(NSELF > 0 ? 2 : 0)>(S, C, ra, 0.0f, 1e10f, z);
+        const int ra = (SELF && k >= nc) ? S0 + 2 * (k - nc) : n0 + k;
+        const float rr = pgs_single<(SELF ? 2 : 0)>(S, C, ra, 0.0f, 1e10f, z);
         res2 = fmaxf(res2, rr * rr);
       }
 #pragma unroll 1
       for (int k = 0; k < nct; ++k) {
-        const bool self = NSELF > 0 && k >= nc;
+        const bool self = SELF && k >= nc;
         const int ra = self ? S0 + 2 * ncs + 4 * (k - nc) : n0 + nc + 2 * k;
         const int rn = self ? S0 + 2 * (k - nc) : n0 + k;
         const float cone = S.rc.r.r_mu[ra] * S.rc.r.r_app[rn];
         // a contact that carries no normal impulse has a zero friction cone: with nothing applied yet the projection
         // returns exactly zero for both rows (deltas 0, residual 0), so the visit can be skipped -- bit-identical
         if (cone == 0.0f && S.rc.r.r_app[ra] == 0.0f && S.rc.r.r_app[ra + 1] == 0.0f) continue;
-        const float rr = pgs_pair(S, C, ra, cone, z);
+        const float rr = pgs_pair<SELF>(S, C, ra, cone, z);
         res2 = fmaxf(res2, rr * rr);
       }
       if (res2 <= P.residual_threshold) break;
     }
   }
-
   // ---- I. integrate positions (btMultiBody::stepPositionsMultiDof) --------------------------------------------
   MB_HD static void integrate(Mem& S, const MbPhysics& P) {
     MB_LANES(l)
@@ -1941,7 +1956,10 @@ template <class M> struct Sim {
           z[l] = S.rhs[l];
         MB_END
       }
-      solve_constraints(S, P, C, nlim, nc, ncs, z);
+      // (hull models -- Cassie, 34 rows per substep -- run substeps without self-contacts through the SELF = false
+      // instantiation: +3.6 %; for the segment-pair models the second inline copy costs 2 % of instruction cache, r2n)
+      if (M::SELF_HULLS && ncs == 0) solve_constraints<false>(S, P, C, nlim, nc, 0, z);
+      else solve_constraints<(NSELF > 0)>(S, P, C, nlim, nc, ncs, z);
       solve_L<false>(S, C, z);
       MB_LANES(l)
         if (l < NU) S.u[l] = fminf(fmaxf(S.u[l] + z[l], -P.max_coord_vel), P.max_coord_vel);

@@ -823,13 +823,13 @@ static int gjk_closest(double w[4][3], double a[4][3], double lam[4], int n, v3 
         mu[0] = ok ? b[0] / G[0][0] : 0.0;
       } else if (k == 3) {
         double det = G[0][0] * G[1][1] - G[0][1] * G[1][0];
-        ok = det > 1e-12 * G[0][0] * G[1][1];
+        ok = det > 1e-5 * G[0][0] * G[1][1];  /* (a float32 determinant is noise below that) */
         if (ok) { mu[0] = (b[0] * G[1][1] - b[1] * G[0][1]) / det; mu[1] = (G[0][0] * b[1] - G[1][0] * b[0]) / det; }
       } else {
         double c00 = G[1][1] * G[2][2] - G[1][2] * G[2][1], c01 = G[1][2] * G[2][0] - G[1][0] * G[2][2];
         double c02 = G[1][0] * G[2][1] - G[1][1] * G[2][0];
         double det = G[0][0] * c00 + G[0][1] * c01 + G[0][2] * c02;
-        ok = det > 1e-10 * G[0][0] * G[1][1] * G[2][2];
+        ok = det > 1e-4 * G[0][0] * G[1][1] * G[2][2];
         if (ok) {
           mu[0] = (b[0] * c00 + b[1] * (G[0][2] * G[2][1] - G[0][1] * G[2][2]) + b[2] * (G[0][1] * G[1][2] - G[0][2] * G[1][1])) / det;
           mu[1] = (b[0] * c01 + b[1] * (G[0][0] * G[2][2] - G[0][2] * G[2][0]) + b[2] * (G[0][2] * G[1][0] - G[0][0] * G[1][2])) / det;
