@@ -88,9 +88,9 @@ def test_resting_on_the_ground_plane(walker_table):
 
     t = walker_table
     A, M = 21, t["total_mass"]
-    N = 16
+    N = 64
     env = Walker3DCustomVecEnv(N, device="cuda:0", seed=5)
-    env.reset()  # 16 different noisy start poses: 16 different heaps on the ground
+    env.reset()  # 64 different noisy start poses: 64 different heaps on the ground
     pts, st = _settle(env, A, 700)
     dt = env.physics.dt
     rested = 0
@@ -107,7 +107,9 @@ def test_resting_on_the_ground_plane(walker_table):
             assert loaded.any()
             assert np.abs(p[loaded, 6]).max() < 5e-4, (i, p[loaded, 6])
         assert abs(np.mean(ratios) - 1.0) < 5e-3, (i, ratios)
-    assert rested >= 6, rested
+    # about a third of the heaps has stopped rocking by then (the count moves by a few from build to build: a heap's
+    # way to the ground is chaotic); the pins above are asserted for every one that has
+    assert rested >= N // 8, rested
     env.close()
 
 
@@ -121,7 +123,7 @@ def test_resting_on_a_soft_plank(walker_table):
 
     t = walker_table
     A, M, KP = 21, t["total_mass"], 30000.0
-    N = 16
+    N = 64
     env = Walker3DStepperVecEnv(N, device="cuda:0", seed=5)
     env.reset()
     pts, st = _settle(env, A, 1200)
@@ -143,7 +145,7 @@ def test_resting_on_a_soft_plank(walker_table):
             ratios += list(r)
         assert abs(np.mean(vs) - 1.0) < 0.15, (i, vs)
         verticals.append(np.mean(vs))
-    assert rested >= 4, rested
+    assert rested >= N // 16, rested
     assert abs(np.median(ratios) - 1.0) < 3e-2, np.median(ratios)
     assert abs(np.median(verticals) - 1.0) < 3e-2, np.median(verticals)
     env.close()

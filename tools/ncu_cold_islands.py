@@ -9,7 +9,10 @@ kname = sys.argv[3] if len(sys.argv) > 3 else "_Z22k_step_walker3d_custom8StepAr
 if cubin.endswith(".so"):
     d = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(cubin)], cwd=d, check=True, capture_output=True)
-    cubin = os.path.join(d, sorted(f for f in os.listdir(d) if f.endswith(".cubin"))[0])
+    # one cubin per env kind since round 2: take the one that defines the kernel
+    _kn = (sys.argv[4] if len(sys.argv) > 4 else "_Z22k_step_walker3d_custom8StepArgs") if "by_phase" in __file__ else (sys.argv[3] if len(sys.argv) > 3 else "_Z22k_step_walker3d_custom8StepArgs")
+    cubin = next(os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(".cubin") and
+                 (".text." + _kn) in subprocess.run(["cuobjdump", "-elf", os.path.join(d, f)], capture_output=True, text=True).stdout)
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
 start = next(i for i, l in enumerate(dis) if l.startswith(".text." + kname + ":"))
 lines, cur = [], ("?", 0)
