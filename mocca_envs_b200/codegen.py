@@ -87,6 +87,22 @@ def reduce_table(t: dict) -> dict:
         bstart.append(idx[0])
         bend.append(idx[-1] + 1)
 
+    # body forest for the leaf-to-root accumulation of the composite inertias: parent = the latest previous body whose
+    # owner joint is the base, the same joint, or an ancestor of the body's owner.  The composite of joint j is then the
+    # accumulated record of body bstart(j) -- asserted: its descendants are exactly the range [bstart(j), bend(j)).
+    bparent = []
+    for k, b in enumerate(bodies):
+        cand = [k2 for k2 in range(k) if bodies[k2]["owner"] < 0 or
+                (b["owner"] >= 0 and (janc[b["owner"]] >> bodies[k2]["owner"]) & 1)]
+        bparent.append(cand[-1] if cand else -1)
+    assert bparent[0] == -1 and all(pb >= 0 for pb in bparent[1:]), "body 0 must be the base"
+    desc = [{k} for k in range(nb)]
+    for k in range(nb - 1, 0, -1):
+        desc[bparent[k]] |= desc[k]
+    assert desc[0] == set(range(nb))
+    for j in range(nj):
+        assert desc[bstart[j]] == set(range(bstart[j], bend[j])), "joint %d: subtree is not one body's subtree" % j
+
     thresh = [t["base"]["contact_threshold"]] + t["contact_threshold"]
     foot_links = t["foot_links"]
     palm_links = t.get("palm_links", [])
@@ -196,7 +212,7 @@ def reduce_table(t: dict) -> dict:
                 hull_margin=t.get("hull_margin", 0.0),
                 jparent=jparent, joff=joff, jrot=jrot, jaxis=jaxis, jlevel=jlevel, janc=janc,
                 lower=t["lower"], upper=t["upper"], gain=t["gain"], damping=t["damping"], armature=t["armature"],
-                bodies=bodies, bstart=bstart, bend=bend, points=points, foot_body=foot_body,
+                bodies=bodies, bstart=bstart, bend=bend, bparent=bparent, points=points, foot_body=foot_body,
                 nfeet=len(foot_links), base_joint_angles=t["base_joint_angles"], base_position=t["base_position"],
                 right=t["right_joint_indices"], left=t["left_joint_indices"], neg=t["negation_joint_indices"],
                 jdepth=jdepth, chainpack=chainpack, rowlen=rowlen, rowoff=rowoff, rowmask_rt=rowmask_rt,
@@ -265,6 +281,29 @@ def emit_header(t: dict, prefix: str) -> str:
         fcol.append(cols + [0] * (maxoff - len(cols)))
     out.append("MB_TABLE int %s_fcol[%d][%d] = {\n  %s};\n" % (
         P, r["nu"], maxoff, ",\n  ".join("{" + ", ".join(str(v) for v in row) + "}" for row in fcol)))
+    # Affine form of the two tables (round 2): the rows along a chain are stored like a packed dense triangle, so for the
+    # pair (t, s) with packed index p = t (t + 1) / 2 + s the update lands at  p + delta_k(t)  and slot t belongs to column
+    # t + cdelta_k(t), where both deltas are piecewise constant in t with one step per branch point the chain passes
+    # after leaving the first-stored path: fstep[k][i] = (t_i, increment of delta, increment of cdelta), t_i = 15 = unused.
+    fsteps = []
+    for k in range(r["nu"]):
+        nk = r["rowlen"][k] - 1
+        dd_ = [fac[k][tt] - tt * (tt + 1) // 2 for tt in range(nk)]
+        dc_ = [fcol[k][tt] - tt for tt in range(nk)]
+        st_, pd_, pc_ = [], 0, 0
+        for tt in range(nk):
+            if dd_[tt] != pd_ or dc_[tt] != pc_:
+                st_.append((tt, dd_[tt] - pd_, dc_[tt] - pc_))
+                pd_, pc_ = dd_[tt], dc_[tt]
+        fsteps.append(st_)
+    nsteps = max(1, max(len(x) for x in fsteps))
+    assert nsteps <= 2, "factorize() supports two steps per pivot row"
+    for i in range(nsteps):
+        out.append(_iarr(P + "_c_ft%d" % (i + 1), [x[i][0] if len(x) > i else 15 for x in fsteps]).replace("MB_TABLE", "MB_CTABLE"))
+        out.append(_iarr(P + "_c_fd%d" % (i + 1), [x[i][1] if len(x) > i else 0 for x in fsteps]).replace("MB_TABLE", "MB_CTABLE"))
+        out.append(_iarr(P + "_c_fc%d" % (i + 1), [x[i][2] if len(x) > i else 0 for x in fsteps]).replace("MB_TABLE", "MB_CTABLE"))
+    r["fsteps"] = nsteps
+    r["fsteps_list"] = fsteps
     # per coordinate: depth in the joint tree (-1 for the six base coordinates) and its ancestors' coordinate
     # indices by level, 5 bits each (levels 0-5 in word 0, 6-11 in word 1)
     cdepth = [-1] * 6 + list(r["jdepth"])
@@ -311,6 +350,7 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append(_iarr(P + "_bstart", r["bstart"]))
     out.append(_iarr(P + "_bend", r["bend"]))
     out.append(_iarr(P + "_bowner", [b["owner"] for b in r["bodies"]]))
+    out.append(_iarr(P + "_c_bparent", [max(v, 0) for v in r["bparent"]]).replace("MB_TABLE", "MB_CTABLE"))
     out.append(_farr(P + "_bcom", [b["com"] for b in r["bodies"]]))
     out.append(_farr(P + "_bmass", [b["mass"] for b in r["bodies"]]))
     out.append(_farr(P + "_binertia", [b["inertia"] for b in r["bodies"]]))
@@ -388,7 +428,22 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append("  MB_HD static int facoff(int k, int t) { return %s_facoff[k][t]; }\n" % P)
     out.append("  MB_HD static int fcol(int k, int t) { return %s_fcol[k][t]; }\n" % P)
     out.append("  MB_HD static int lvjoint(int lev, int slot) { return %s_lvjoint[lev][slot]; }\n" % P)
+    out.append("  enum { FSTEPS = %d };  // steps of the affine factorisation addressing (c_ft / c_fd / c_fc)\n" % r["fsteps"])
+    # compile-time copies for the unrolled factorisation (template-indexed: every per-pivot scalar becomes an immediate)
+    out.append("  static constexpr int k_rowoff[%d] = {%s};\n" % (r["nu"], ", ".join(str(v) for v in r["rowoff"])))
+    out.append("  static constexpr int k_rowlen[%d] = {%s};\n" % (r["nu"], ", ".join(str(v) for v in r["rowlen"])))
+    for i in range(2):
+        for nm, col, dflt in (("ft", 0, 15), ("fd", 1, 0), ("fc", 2, 0)):
+            out.append("  static constexpr int k_%s%d[%d] = {%s};\n" % (nm, i + 1, r["nu"], ", ".join(
+                str(x[i][col] if len(x) > i else dflt) for x in r["fsteps_list"])))
+    for i in range(r["fsteps"]):
+        for nm in ("ft", "fd", "fc"):
+            out.append("  MB_HD static int c_%s%d(int k) { return %s_c_%s%d[k]; }\n" % (nm, i + 1, P, nm, i + 1))
+    if r["fsteps"] < 2:
+        out.append("  MB_HD static int c_ft2(int) { return 15; }\n  MB_HD static int c_fd2(int) { return 0; }\n"
+                   "  MB_HD static int c_fc2(int) { return 0; }\n")
     out.append("  MB_HD static int c_rowoff(int i) { return %s_c_rowoff[i]; }\n" % P)
+    out.append("  MB_HD static int c_bparent(int i) { return %s_c_bparent[i]; }\n" % P)
     out.append("  MB_HD static int c_rowlen(int i) { return %s_c_rowlen[i]; }\n" % P)
     out.append("  MB_HD static unsigned c_rowmask(int i) { return %s_c_rowmask[i]; }\n" % P)
     for fld, ctype in [("jparent", "int"), ("jlevel", "int"), ("janc", "unsigned"), ("bstart", "int"), ("bend", "int"),

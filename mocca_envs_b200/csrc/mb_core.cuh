@@ -197,6 +197,24 @@ MB_HD int mb_pid(int v) { return v >> 8; }
 #define MB_NWARM 384 /* warm-start slots per env: candidate ids 2 * geom + end, geoms <= 192 */
 MB_HD constexpr int tri(int i, int j) { return (i * (i + 1)) / 2 + j; }  // packed lower-triangular index, j <= i
 MB_HD int chain_at(unsigned long long pack, int t) { return (int)((pack >> (5 * t)) & 31ull); }
+// 1 / sqrt(x) for a pivot (positive, normal): the bare MUFU.RSQ -- rsqrtf() wraps it in a denormal-range rescue (a
+// compare and two predicated multiplies on the critical path of every pivot)
+MB_HD float mb_rsqrt_pivot(float x) {
+#ifdef __CUDACC__
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+MB_HD unsigned mb_byte(unsigned x, int r) {  // byte r of x, zero-extended (one PRMT)
+#ifdef __CUDACC__
+  return __byte_perm(x, 0u, 0x4440u | (unsigned)r);
+#else
+  return (x >> (8 * r)) & 255u;
+#endif
+}
 MB_HD bool mb_finite(float x) { return fabsf(x) <= 3.402823466e38f; }   // false for NaN and +-inf
 
 // per-row solver constants, read with one 128-bit shared-memory load per row visit
@@ -226,11 +244,11 @@ template <class M> struct WarpMem {
       float jV[M::NJ + 1][6];  // [0] = base
       float jA[M::NJ + 1][6];
       union {
-        struct alignas(8) {
-          // ---- bodies (8-byte aligned: ptxas pairs neighbouring floats into LDS.64; unaligned, such a pair straddles
-          // the end of bF and touches L[0], which compute-sanitizer racecheck reports as a hazard)
-          float bI[M::NB][10];  // m, h[3], I_O{xx,yy,zz,xy,xz,yz}
-          float bF[M::NB][6];   // bias wrench about O (n, f)  (one 64-byte record + 128-bit loads measured no gain)
+        struct alignas(16) {
+          // ---- bodies: one 64-byte record per body, [0..9] = m, h[3], I_O{xx,yy,zz,xy,xz,yz}, [10..15] = bias wrench
+          // about O (n, f).  composites() then sums the records up the body forest in place, one component per lane,
+          // so that the record of body bstart(j) becomes the composite of joint j's subtree.
+          float bIF[M::NB][16];
         } b;
         // contact candidate points (collision runs before the body pass); models with many candidates (hull
         // vertices, Cassie) test them on the fly against the ground plane and store nothing
@@ -346,15 +364,6 @@ template <class M> MB_HD float mb_Lget(const float* L, int i, int j) {
   return ((sup >> j) & 1u) ? L[M::rowoff(i) + mb_popc(sup & ((1u << j) - 1u))] : 0.0f;
 }
 
-// Per-CTA copy of the two factorisation tables (facoff: offset of the compact row an update lands in, fcol: column of
-// a slot), as bytes: [which][k][16].  They are read with a lane-dependent index at every pivot of every substep; from
-// global memory that was 470 of the 10 700 instructions of a substep (64-bit address arithmetic) and a 35-cycle L1 hit
-// on the critical path of a sequential 27-pivot loop: +3 % Walker3D, +5 % Monkey3D.  Filled by Sim::load_tables() at
-// kernel start.  (The same treatment of the per-joint kinematics tables measured within noise and was dropped.)
-#ifdef __CUDACC__
-static __shared__ unsigned char mb_s_fac[2 * 32 * 16];
-#endif
-
 // ------------------------------------------------------------------------------------------------ simulator
 template <class M> struct Sim {
   typedef WarpMem<M> Mem;
@@ -369,7 +378,7 @@ template <class M> struct Sim {
     LaneVar<int> tl;        // |support(l)| = slot of column l in every descendant's compact row = rowlen(l) - 1
     LaneVar<int> off;       // rowoff(l)
     LaneVar<unsigned> sup;  // rowmask(l)
-    LaneVar<int> pairs;     // (t, s) of the lower-triangle entries p = l, l + 32, l + 64 (4 bits each)
+    LaneVar<unsigned> pt4, ps4;  // 4 t and 4 s of the lower-triangle entries p = l, l + 32, l + 64 (one byte per round)
     LaneVar<int> dep;       // tree depth of coordinate l (-1 base block, 99 unused lane)
     LaneVar<unsigned> anc0, anc1;  // coordinate index of l's ancestor at each level, 5 bits per level
   };
@@ -381,45 +390,19 @@ template <class M> struct Sim {
       C.dep[l] = l < NU ? M::cdepth(l) : 99;
       C.anc0[l] = l < NU ? M::canc0(l) : 0u;
       C.anc1[l] = l < NU ? M::canc1(l) : 0u;
-      int packed = 0;
+      unsigned pt = 0u, ps = 0u;
       for (int r = 0; r < 3; ++r) {
         const int pidx = l + 32 * r;
         int t = (int)((sqrtf(8.0f * (float)pidx + 1.0f) - 1.0f) * 0.5f);
         if ((t + 1) * (t + 2) / 2 <= pidx) ++t;
         if (t * (t + 1) / 2 > pidx) --t;
         const int s2 = pidx - t * (t + 1) / 2;
-        packed |= (t | (s2 << 4)) << (8 * r);
+        pt |= (unsigned)(4 * t) << (8 * r);
+        ps |= (unsigned)(4 * s2) << (8 * r);
       }
-      C.pairs[l] = packed;
+      C.pt4[l] = pt;
+      C.ps4[l] = ps;
     MB_END
-  }
-
-  // every kernel that runs substeps calls this once (all threads of the CTA)
-  MB_HD static void load_tables() {
-#ifdef __CUDACC__
-    static_assert(M::NU <= 32 && M::MAXSUP - 1 <= 16 && M::LSIZE <= 255, "byte tables");
-    for (int i = (int)threadIdx.x; i < 2 * 32 * 16; i += (int)blockDim.x) {
-      const int which = i >> 9, k = (i >> 4) & 31, t = i & 15;
-      int v = 0;
-      if (k < NU && t < M::MAXSUP - 1) v = which ? M::fcol(k, t) : M::facoff(k, t);
-      mb_s_fac[i] = (unsigned char)v;
-    }
-    __syncthreads();
-#endif
-  }
-  MB_HD static int t_facoff(int k, int t) {
-#ifdef __CUDACC__
-    return mb_s_fac[(k << 4) + t];
-#else
-    return M::facoff(k, t);
-#endif
-  }
-  MB_HD static int t_fcol(int k, int t) {
-#ifdef __CUDACC__
-    return mb_s_fac[512 + (k << 4) + t];
-#else
-    return M::fcol(k, t);
-#endif
   }
 
   // ---- A. kinematics (+ velocities / bias accelerations when with_vel) --------------------------------------
@@ -571,36 +554,45 @@ template <class M> struct Sim {
         }
         mb_cross(c, f, nO);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { S.w.k.u2.b.bF[l][k] = nc[k] + nO[k]; S.w.k.u2.b.bF[l][3 + k] = f[k]; }
+        float* rec = S.w.k.u2.b.bIF[l];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { rec[10 + k] = nc[k] + nO[k]; rec[13 + k] = f[k]; }
         const float cc = mb_dot3(c, c);
-        S.w.k.u2.b.bI[l][0] = m;
-        S.w.k.u2.b.bI[l][1] = m * c[0]; S.w.k.u2.b.bI[l][2] = m * c[1]; S.w.k.u2.b.bI[l][3] = m * c[2];
-        S.w.k.u2.b.bI[l][4] = Ic[0] + m * (cc - c[0] * c[0]);
-        S.w.k.u2.b.bI[l][5] = Ic[4] + m * (cc - c[1] * c[1]);
-        S.w.k.u2.b.bI[l][6] = Ic[8] + m * (cc - c[2] * c[2]);
-        S.w.k.u2.b.bI[l][7] = Ic[1] - m * c[0] * c[1];
-        S.w.k.u2.b.bI[l][8] = Ic[2] - m * c[0] * c[2];
-        S.w.k.u2.b.bI[l][9] = Ic[5] - m * c[1] * c[2];
+        rec[0] = m;
+        rec[1] = m * c[0]; rec[2] = m * c[1]; rec[3] = m * c[2];
+        rec[4] = Ic[0] + m * (cc - c[0] * c[0]);
+        rec[5] = Ic[4] + m * (cc - c[1] * c[1]);
+        rec[6] = Ic[8] + m * (cc - c[2] * c[2]);
+        rec[7] = Ic[1] - m * c[0] * c[1];
+        rec[8] = Ic[2] - m * c[0] * c[2];
+        rec[9] = Ic[5] - m * c[1] * c[2];
+      }
+    MB_END
+  }
+
+  // ---- B2. composite inertias and summed bias wrenches, leaf to root over the body forest (codegen: c_bparent), in
+  // place, one of the 16 components per lane: NB - 1 dependent adds instead of every joint lane summing its whole
+  // subtree (round 2: the per-lane sums were 4.8 % of the step kernel's instructions at 5 active lanes).
+  MB_HD static void composites(Mem& S) {
+    MB_LANES(l)
+      if (l < 16) {
+#pragma unroll 1
+        for (int b = NB - 1; b > 0; --b) S.w.k.u2.b.bIF[M::c_bparent(b)][l] += S.w.k.u2.b.bIF[b][l];
       }
     MB_END
   }
 
   // ---- C. composite inertias -> mass matrix rows (packed lower) and generalised rhs = tau - bias ------------
   MB_HD static void mass_matrix_and_rhs(Mem& S) {
+    composites(S);
     MB_LANES(l)
       if (l <= NJ) {
-        const int b0 = l < NJ ? M::bstart(l) : 0, b1 = l < NJ ? M::bend(l) : NB;
+        const float* rec = S.w.k.u2.b.bIF[l < NJ ? M::bstart(l) : 0];  // composite record (composites())
         float I[10], F[6];
 #pragma unroll
-        for (int k = 0; k < 10; ++k) I[k] = 0.0f;
+        for (int k = 0; k < 10; ++k) I[k] = rec[k];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) F[k] = 0.0f;
-        for (int b = b0; b < b1; ++b) {
-#pragma unroll
-          for (int k = 0; k < 10; ++k) I[k] += S.w.k.u2.b.bI[b][k];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) F[k] += S.w.k.u2.b.bF[b][k];
-        }
+        for (int k = 0; k < 6; ++k) F[k] = rec[10 + k];
         const float m = I[0];
         const float* h = &I[1];
         if (l < NJ) {
@@ -655,28 +647,90 @@ template <class M> struct Sim {
   // With RHS the backward substitution L^T y = rhs rides along (same visiting order, k descending): the pivot row
   // pushes rhs_col -= U[k][col] rhs_k / d_k.  S.rhs is left holding d^1/2 y, which is exactly the pre-scaled input
   // solve_L<true> wants, so the forward-dynamics solve never touches a square root besides the pivot's rsqrt.
+  // Addressing (round 2): the rows along a chain are stored like a packed dense triangle, so the pair (t, s) with packed
+  // index p = t (t + 1) / 2 + s = l + 32 r updates word p of L, shifted by a per-pivot constant behind each branch point
+  // of the pivot's chain (codegen: c_ft / c_fd / c_fc, at most FSTEPS = 2 steps): no table look-up on the lane path.
   template <bool RHS> MB_HD static void factorize(Mem& S, const LaneConst& C) {
+#if !defined(MB_FACT_UNROLL) || MB_FACT_UNROLL
+    if (true) { pivots_from<RHS, NU - 1>(S, C); return; }
+#endif
 #pragma unroll 1
     for (int k = NU - 1; k >= 0; --k) {
       const int offk = M::c_rowoff(k), nk = M::c_rowlen(k) - 1;
+      const int t1 = M::c_ft1(k), d1 = M::c_fd1(k), c1 = M::c_fc1(k), p1 = (t1 * (t1 + 1)) >> 1;
+      const int t2 = M::FSTEPS > 1 ? M::c_ft2(k) : 15, d2 = M::FSTEPS > 1 ? M::c_fd2(k) : 0;
+      const int c2 = M::FSTEPS > 1 ? M::c_fc2(k) : 0, p2 = (t2 * (t2 + 1)) >> 1;
       const float dkk = S.L[offk + nk];
-      const float inv = rsqrtf(dkk), invd = inv * inv;
+      const float inv = mb_rsqrt_pivot(dkk), invd = inv * inv;
       const float ck = RHS ? S.rhs[k] * invd : 0.0f;
       const int npairs = (nk * (nk + 1)) >> 1;
+      // byte addressing throughout: one add per operand address (the 4 t / 4 s fields are lane constants, the row base
+      // and the step sizes are per-pivot uniforms).  Lanes behind the last pair compute on in-bounds garbage (at most
+      // word LSIZE + 53 of the L / Ldinv / Ldi2 block) and only their store is predicated: no divergence in the loop.
+      const char* Lk = (const char*)&S.L[offk];
+      char* L0 = (char*)&S.L[0];
+      const int d14 = 4 * d1, d24 = 4 * d2;
       MB_LANES(l)
         if (l == 31) { S.Ldinv[k] = inv; S.Ldi2[k] = invd; }
-        if (RHS && l < nk) S.rhs[t_fcol(k, l)] -= S.L[offk + l] * ck;
+        if (RHS && l < nk) {
+          int col = l + (l >= t1 ? c1 : 0);
+          if (M::FSTEPS > 1) col += l >= t2 ? c2 : 0;
+          S.rhs[col] -= *(const float*)(Lk + 4 * l) * ck;
+        }
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           if (32 * r < npairs) {  // uniform: whole rounds are skipped for short rows
-            if (l + 32 * r < npairs) {
-              const int t = (C.pairs[l] >> (8 * r)) & 15, s2 = (C.pairs[l] >> (8 * r + 4)) & 15;
-              S.L[t_facoff(k, t) + s2] -= (S.L[offk + t] * invd) * S.L[offk + s2];
-            }
+            const int p = l + 32 * r;
+            const unsigned t4 = mb_byte(C.pt4[l], r), s4 = mb_byte(C.ps4[l], r);
+            int dst4 = 4 * p + (p >= p1 ? d14 : 0);
+            if (M::FSTEPS > 1) dst4 += p >= p2 ? d24 : 0;
+            float* dst = (float*)(L0 + dst4);
+            const float v = *dst - (*(const float*)(Lk + t4) * invd) * *(const float*)(Lk + s4);
+            if (p < npairs) *dst = v;
           }
         }
       MB_END
     }
+  }
+
+  // Unrolled form (MB_FACT_UNROLL, the default): one template instance per pivot, so the row offset, the row length,
+  // the number of rounds, the branch-point steps and every shared-memory offset are immediates -- no constant-bank
+  // loads, no index arithmetic, no loop: ~32 instead of ~65 instructions per pivot for 14 KB of straight-line code.
+  template <bool RHS, int K> MB_HD static void pivot(Mem& S, const LaneConst& C) {
+    constexpr int offk = M::k_rowoff[K], nk = M::k_rowlen[K] - 1, npairs = (nk * (nk + 1)) / 2;
+    constexpr int t1 = M::k_ft1[K], c1 = M::k_fc1[K], p1 = (t1 * (t1 + 1)) / 2, d14 = 4 * M::k_fd1[K];
+    constexpr int t2 = M::k_ft2[K], c2 = M::k_fc2[K], p2 = (t2 * (t2 + 1)) / 2, d24 = 4 * M::k_fd2[K];
+    const float dkk = S.L[offk + nk];
+    const float inv = mb_rsqrt_pivot(dkk), invd = inv * inv;
+    const float ck = RHS ? S.rhs[K] * invd : 0.0f;
+    const char* Lk = (const char*)&S.L[offk];
+    char* L0 = (char*)&S.L[0];
+    MB_LANES(l)
+      if (l == 31) { S.Ldinv[K] = inv; S.Ldi2[K] = invd; }
+      if (RHS && nk > 0 && l < nk) {
+        int col = l;
+        if (t1 < nk) col += l >= t1 ? c1 : 0;
+        if (t2 < nk) col += l >= t2 ? c2 : 0;
+        S.rhs[col] -= *(const float*)(Lk + 4 * l) * ck;
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        if (32 * r < npairs) {
+          const int p = l + 32 * r;
+          const unsigned t4 = mb_byte(C.pt4[l], r), s4 = mb_byte(C.ps4[l], r);
+          int dst4 = 4 * p;
+          if (p1 < npairs) dst4 += p >= p1 ? d14 : 0;
+          if (p2 < npairs) dst4 += p >= p2 ? d24 : 0;
+          float* dst = (float*)(L0 + dst4);
+          const float v = *dst - (*(const float*)(Lk + t4) * invd) * *(const float*)(Lk + s4);
+          if (32 * r + 32 <= npairs || p < npairs) *dst = v;
+        }
+      }
+    MB_END
+  }
+  template <bool RHS, int K> MB_HD static void pivots_from(Mem& S, const LaneConst& C) {
+    pivot<RHS, K>(S, C);
+    if constexpr (K > 0) pivots_from<RHS, K - 1>(S, C);
   }
 
   // ---- E. single right-hand-side solve, one generalised coordinate per lane ----------------------------------

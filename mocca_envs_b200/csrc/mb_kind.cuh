@@ -80,7 +80,6 @@ __device__ __forceinline__ void step_body(const StepArgs& a) {
   // broadcast from lane 0: tells the compiler the warp index is warp-uniform, so the WarpMem base lives in a uniform
   // register instead of being re-derived from threadIdx (3-4 % of the issued instructions otherwise)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-  Sim<typename Env::Model>::load_tables();
   const int env = a.order[blockIdx.x * MB_WARPS + warp];  // a permutation of [0, n_pad)
   const bool tail = env >= a.n;
   typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
@@ -152,7 +151,6 @@ __device__ __forceinline__ void physics_body(int n, const MbPhysics& phys, float
   const int env = blockIdx.x * MB_WARPS + warp;
   const bool tail = env >= n;  // pad env: steps with zero torque, outputs discarded
   typedef typename Env::Model EM;
-  Sim<EM>::load_tables();
   typename Env::Mem& S = reinterpret_cast<typename Env::Mem*>(smem_raw)[warp];
   if ((threadIdx.x & 31) == 0) S.warm = warm ? warm + (size_t)env * MB_NWARM : nullptr;
   __syncwarp();
