@@ -47,10 +47,12 @@ def reduce_table(t: dict) -> dict:
             l = parent[l]
         return -1
 
-    def frame(j):  # joint frame (origin at pivot, link axes) in base coords at q = 0
+    def frame(j):  # joint frame in base coords at q = 0: origin at the pivot, axes parallel to the base's (round 2:
+        # every zero-pose rotation between consecutive joint frames is then the identity, and the kinematics is one
+        # Rodrigues rotation per joint about the axis as it points at q = 0 -- no per-joint constant rotation)
         if j < 0:
             return np.eye(3), np.zeros(3)
-        return Rl[jlink[j] + 1], piv[jlink[j] + 1]
+        return np.eye(3), piv[jlink[j] + 1]
 
     jparent, joff, jrot, jaxis, jlevel, janc = [], [], [], [], [], []
     for j, l in enumerate(jlink):
@@ -60,7 +62,9 @@ def reduce_table(t: dict) -> dict:
         jparent.append(pj)
         joff.append(Rp.T @ (oj - op))
         jrot.append(Rp.T @ Rj)
-        jaxis.append(np.array(t["axis"][l]))
+        ax_ = Rl[l + 1] @ np.array(t["axis"][l], dtype=np.float64)
+        ax_ = np.where(np.abs(ax_) < 1e-15, 0.0, ax_)
+        jaxis.append(ax_ / np.linalg.norm(ax_))
         jlevel.append(0 if pj < 0 else jlevel[pj] + 1)
         janc.append((1 << j) | (0 if pj < 0 else janc[pj]))
 
@@ -331,6 +335,35 @@ def emit_header(t: dict, prefix: str) -> str:
         jaxk.append(k if aligned else -1)
         jsgn.append(float(np.sign(ax[k])) if aligned else 0.0)
         jident.append(1 if np.abs(np.asarray(R0) - np.eye(3)).max() < 1e-12 else 0)
+    # Chain-walk kinematics (round 2): lane 3 * ch + c carries row c of the rotation (and component c of every vector)
+    # down the ch-th root-to-leaf chain in registers; kin[step][ch] = the joint met at that step, its pivot offset in
+    # the parent frame, its axis, and whether this chain is the one that stores the joint (shared prefixes are walked
+    # by every chain that contains them, stored by the first).  Chain NCH is the idle one of the unused lanes.
+    leaves = [j for j in range(r["nj"]) if j not in r["jparent"]]
+    kchains = []
+    for lf in leaves:
+        c = [lf]
+        while r["jparent"][c[0]] >= 0:
+            c.insert(0, r["jparent"][c[0]])
+        kchains.append(c)
+    assert len(kchains) <= 10, "three lanes per chain"
+    seen = set()
+    krec = []
+    for st in range(r["nlevel"]):
+        row = []
+        for c in kchains + [[]]:
+            if st < len(c):
+                j = c[st]
+                row.append((j, list(r["joff"][j]), list(r["jaxis"][j]), 0 if j in seen else 1))
+                seen.add(j)
+            else:
+                row.append((0, [0.0, 0.0, 0.0], [0.0, 0.0, 1.0], 0))
+        krec.append(row)
+    assert seen == set(range(r["nj"]))
+    out.append("MB_TABLE MbKinRec %s_kin[%d][%d] = {\n  %s};\n" % (P, r["nlevel"], len(kchains) + 1, ",\n  ".join(
+        "{" + ", ".join("{%d, {%s}, {%s}, %d}" % (j, ", ".join(_f(v) for v in off), ", ".join(_f(v) for v in ax), fl)
+                        for j, off, ax, fl in row) + "}" for row in krec)))
+    r["nch"] = len(kchains)
     # joints of each kinematic level (component-parallel kinematics: lane = 3 * slot + component)
     lv = [[j for j in range(r["nj"]) if r["jlevel"][j] == L] for L in range(r["nlevel"])]
     maxslot = 10
@@ -428,9 +461,12 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append("  MB_HD static int facoff(int k, int t) { return %s_facoff[k][t]; }\n" % P)
     out.append("  MB_HD static int fcol(int k, int t) { return %s_fcol[k][t]; }\n" % P)
     out.append("  MB_HD static int lvjoint(int lev, int slot) { return %s_lvjoint[lev][slot]; }\n" % P)
+    out.append("  enum { NCH = %d };  // root-to-leaf chains of the kinematics walk (kin[step][chain], chain NCH = idle)\n" % r["nch"])
+    out.append("  MB_HD static const MbKinRec* kin(int step, int ch) { return &%s_kin[step][ch]; }\n" % P)
     out.append("  enum { FSTEPS = %d };  // steps of the affine factorisation addressing (c_ft / c_fd / c_fc)\n" % r["fsteps"])
     # compile-time copies for the unrolled factorisation (template-indexed: every per-pivot scalar becomes an immediate)
     out.append("  static constexpr int k_rowoff[%d] = {%s};\n" % (r["nu"], ", ".join(str(v) for v in r["rowoff"])))
+    out.append("  static constexpr int k_bparent[%d] = {%s};\n" % (r["nb"], ", ".join(str(max(v, 0)) for v in r["bparent"])))
     out.append("  static constexpr int k_rowlen[%d] = {%s};\n" % (r["nu"], ", ".join(str(v) for v in r["rowlen"])))
     for i in range(2):
         for nm, col, dflt in (("ft", 0, 15), ("fd", 1, 0), ("fc", 2, 0)):

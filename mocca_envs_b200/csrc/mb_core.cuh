@@ -123,7 +123,9 @@ inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #ifdef __CUDACC__
 #define MB_ASSUME_SHARED(S) __builtin_assume(__isShared(&(S)))  /* out-of-line helpers keep LDS/STS addressing */
 #define MB_FDIV(a, b) __fdividef((a), (b))
+#define MB_FMUL(a, b) __fmul_rn((a), (b))  /* a product the compiler must not contract into an FMA */
 #else
+#define MB_FMUL(a, b) ((a) * (b))
 #define MB_ASSUME_SHARED(S)
 #define MB_FDIV(a, b) ((a) / (b))
 #endif
@@ -406,7 +408,17 @@ template <class M> struct Sim {
   }
 
   // ---- A. kinematics (+ velocities / bias accelerations when with_vel) --------------------------------------
-  MB_HD static void kinematics(Mem& S, const MbPhysics& P, const LaneConst& C, bool with_vel) {
+  // Pose-only kinematics (reset, observation epilogue): once per env step at most, so one out-of-line copy per kernel
+  // instead of two more inline copies of the unrolled chain walk in the instruction stream.
+  MB_NOINLINE static void kinematics_pose(Mem& S, const MbPhysics& P) {
+    MB_ASSUME_SHARED(S);
+    kinematics_impl<false>(S, P);
+  }
+  MB_HD static void kinematics(Mem& S, const MbPhysics& P, const LaneConst&, bool with_vel) {
+    if (with_vel) kinematics_impl<true>(S, P);
+    else kinematics_pose(S, P);
+  }
+  template <bool with_vel> MB_HD static void kinematics_impl(Mem& S, const MbPhysics& P) {
     MB_LANES(l)
       if (l == 0) {
         mb_quat_to_mat(S.quat, S.Rb);
@@ -433,80 +445,81 @@ template <class M> struct Sim {
         S.Ldi2[l] = cs;
       }
     MB_END
-    // Level by level down the tree; within a level lane 3*slot + c handles component c (matrix row / vector
-    // entry) of the slot-th joint of that level -- three lanes per joint, lanes of a warp are free.
-#pragma unroll 1
-    for (int lev = 0; lev < M::NLEVEL; ++lev) {
+    // Chain walk (round 2).  Joint frames are parallel to the base frame at q = 0 (codegen.py), so a joint's frame is
+    // its parent's times ONE Rodrigues rotation about the axis a as it points at q = 0:
+    //   row_c(R) = cos row_c(B) + sin (row_c(B) x a) + (1 - cos)(row_c(B) . a) a,   world axis component c = row_c(B) . a.
+    // Row c of a rotation depends on row c of the parent's only, and so does component c of the pivot position: lane
+    // 3 ch + c carries them in registers down the ch-th root-to-leaf chain -- no level loop, no table look-ups by joint
+    // (one 32-byte record per step and chain), no shared-memory round trip between a joint and its child.  The cross
+    // products of the motion subspace / velocity / bias-acceleration recursion need the two other components, which
+    // live in the two neighbouring lanes: eight shuffles per step.  Chains that share a prefix (the two legs below the
+    // abdomen) both walk it; the first one stores it.  Lanes behind the last chain walk an idle record.
+    LaneVar<float> b0, b1, b2, pc, vw, vv, aw, al;
+    LaneVar<int> s1, s2;
+    MB_LANES(l)
+      const int g = l / 3, c = l - 3 * g;
+      s1[l] = (3 * g + (c == 2 ? 0 : c + 1)) & 31;  // lanes of the cyclic successors: (x y)_c = x[i1] y[i2] - x[i2] y[i1]
+      s2[l] = (3 * g + (c == 0 ? 2 : c - 1)) & 31;
+      b0[l] = S.Rb[3 * c]; b1[l] = S.Rb[3 * c + 1]; b2[l] = S.Rb[3 * c + 2];
+      pc[l] = 0.0f;
+      vw[l] = with_vel ? S.w.k.jV[0][c] : 0.0f; vv[l] = with_vel ? S.w.k.jV[0][3 + c] : 0.0f;
+      aw[l] = with_vel ? S.w.k.jA[0][c] : 0.0f; al[l] = with_vel ? S.w.k.jA[0][3 + c] : 0.0f;
+    MB_END_REG
+#pragma unroll
+    for (int st = 0; st < M::NLEVEL; ++st) {
+      LaneVar<float> ac, p1, p2, a1, a2, w1, w2, v1, v2;
       LaneVar<int> jj;
       MB_LANES(l)
-        const int slot = l / 3, c = l - 3 * slot;
-        const int j = slot < 10 ? M::lvjoint(lev, slot) : -1;
-        jj[l] = j;
-        if (j >= 0) {
-          const int pj = M::jparent(j);
-          const float* Rp = pj < 0 ? S.Rb : S.w.k.jR[pj];
-          float b0 = Rp[3 * c], b1 = Rp[3 * c + 1], b2 = Rp[3 * c + 2];  // row c of the parent rotation
-          float pc = b0 * M::joff(j, 0) + b1 * M::joff(j, 1) + b2 * M::joff(j, 2);
-          if (pj >= 0) pc += S.w.k.jp[pj][c];
-          if (!M::ALL_IDENT && !M::jident(j)) {  // row c of Rp * R0
-            const float n0 = b0 * M::jrot(j, 0) + b1 * M::jrot(j, 3) + b2 * M::jrot(j, 6);
-            const float n1 = b0 * M::jrot(j, 1) + b1 * M::jrot(j, 4) + b2 * M::jrot(j, 7);
-            const float n2 = b0 * M::jrot(j, 2) + b1 * M::jrot(j, 5) + b2 * M::jrot(j, 8);
-            b0 = n0; b1 = n1; b2 = n2;
-          }
-          const float sn = S.Ldinv[j], cs = S.Ldi2[j];
-          const int kax = M::jaxk(j);
-          float r0, r1, r2, ac;
-          if (M::ALL_ALIGNED || kax >= 0) {  // coordinate-aligned axis: two columns mix
-            const float sgn = M::jsgn(j), sg = sn * sgn;
-            const float ci = kax == 0 ? b1 : (kax == 1 ? b2 : b0);
-            const float cj = kax == 0 ? b2 : (kax == 1 ? b0 : b1);
-            const float ni = cs * ci + sg * cj, nj = cs * cj - sg * ci;
-            r0 = kax == 0 ? b0 : (kax == 1 ? nj : ni);
-            r1 = kax == 0 ? ni : (kax == 1 ? b1 : nj);
-            r2 = kax == 0 ? nj : (kax == 1 ? ni : b2);
-            ac = sgn * (kax == 0 ? r0 : (kax == 1 ? r1 : r2));
-          } else {  // generic axis: row c of B * Rodrigues(ax, q)
-            const float ax0 = M::jaxis(j, 0), ax1 = M::jaxis(j, 1), ax2 = M::jaxis(j, 2), t = 1.0f - cs;
-            r0 = b0 * (t * ax0 * ax0 + cs) + b1 * (t * ax0 * ax1 + sn * ax2) + b2 * (t * ax0 * ax2 - sn * ax1);
-            r1 = b0 * (t * ax0 * ax1 - sn * ax2) + b1 * (t * ax1 * ax1 + cs) + b2 * (t * ax1 * ax2 + sn * ax0);
-            r2 = b0 * (t * ax0 * ax2 + sn * ax1) + b1 * (t * ax1 * ax2 - sn * ax0) + b2 * (t * ax2 * ax2 + cs);
-            ac = r0 * ax0 + r1 * ax1 + r2 * ax2;
-          }
+        const int g = l / 3, c = l - 3 * g;
+        const MbKinRec* kr = M::kin(st, g < M::NCH ? g : (int)M::NCH);
+        const int j = kr->j;
+        const float ax0 = kr->ax[0], ax1 = kr->ax[1], ax2 = kr->ax[2];
+        const float sn = S.Ldinv[j], cs = S.Ldi2[j];
+        const float B0 = b0[l], B1 = b1[l], B2 = b2[l];
+        // (explicit fmaf: a sum of two products can be contracted either way round, and the device-buffer and host-buffer
+        // instantiations of a step kernel must round alike -- their outputs are compared bit for bit)
+        const float pn = fmaf(B2, kr->off[2], fmaf(B1, kr->off[1], fmaf(B0, kr->off[0], pc[l])));
+        const float ba = fmaf(B2, ax2, fmaf(B1, ax1, B0 * ax0));
+        const float x0 = fmaf(B1, ax2, -(B2 * ax1)), x1 = fmaf(B2, ax0, -(B0 * ax2)), x2 = fmaf(B0, ax1, -(B1 * ax0));
+        const float kk = (1.0f - cs) * ba;
+        const float r0 = fmaf(kk, ax0, fmaf(sn, x0, cs * B0)), r1 = fmaf(kk, ax1, fmaf(sn, x1, cs * B1));
+        const float r2 = fmaf(kk, ax2, fmaf(sn, x2, cs * B2));
+        jj[l] = kr->store ? j : -1;
+        if (kr->store) {
           S.w.k.jR[j][3 * c] = r0; S.w.k.jR[j][3 * c + 1] = r1; S.w.k.jR[j][3 * c + 2] = r2;
-          S.w.k.jp[j][c] = pc;
-          S.js[j][c] = ac;
+          S.w.k.jp[j][c] = pn;
+          S.js[j][c] = ba;
         }
-      MB_END
+        b0[l] = r0; b1[l] = r1; b2[l] = r2; pc[l] = pn; ac[l] = ba;
+      MB_END_REG
+      warp_gather(pc, s1, p1); warp_gather(pc, s2, p2);
+      warp_gather(ac, s1, a1); warp_gather(ac, s2, a2);
+      if (with_vel) {
+        warp_gather(vw, s1, w1); warp_gather(vw, s2, w2);
+        warp_gather(vv, s1, v1); warp_gather(vv, s2, v2);
+      }
       MB_LANES(l)
+        const int g = l / 3, c = l - 3 * g;
         const int j = jj[l];
-        if (j >= 0) {
-          const int slot = l / 3, c = l - 3 * slot;
-          const int i1 = c == 2 ? 0 : c + 1, i2 = c == 0 ? 2 : c - 1;  // cyclic successors: (x y)_c = x[i1] y[i2] - x[i2] y[i1]
-          const float* p = S.w.k.jp[j];
-          const float* a = S.js[j];
-          // linear part of the motion subspace sl = p x a: own component for the store, the two others for the crosses
-          const float pc_ = p[c], p1 = p[i1], p2 = p[i2], ac_ = a[c], a1 = a[i1], a2 = a[i2];
-          const float slc = p1 * a2 - p2 * a1;
-          S.js[j][3 + c] = slc;
-          if (with_vel) {
-            const float sl1 = p2 * ac_ - pc_ * a2, sl2 = pc_ * a1 - p1 * ac_;
-            const int pj = M::jparent(j);
-            const float qd = S.u[6 + j];
-            const float* Vp = S.w.k.jV[pj + 1];
-            const float* Ap = S.w.k.jA[pj + 1];
-            const float w1 = Vp[i1], w2 = Vp[i2], v1 = Vp[3 + i1], v2 = Vp[3 + i2];
-            // A = Ap + Vp x vj (motion cross; vj x vj = 0), component c only: vj = (a, sl) qd
-            const float c1c = (w1 * a2 - w2 * a1) * qd;
-            const float c23 = (w1 * sl2 - w2 * sl1 + v1 * a2 - v2 * a1) * qd;
-            S.w.k.jV[j + 1][c] = Vp[c] + ac_ * qd;
-            S.w.k.jV[j + 1][3 + c] = Vp[3 + c] + slc * qd;
-            S.w.k.jA[j + 1][c] = Ap[c] + c1c;
-            S.w.k.jA[j + 1][3 + c] = Ap[3 + c] + c23;
+        // linear part of the motion subspace sl = p x a: own component for the store, the two others for the crosses
+        const float slc = fmaf(p1[l], a2[l], -(p2[l] * a1[l]));
+        if (j >= 0) S.js[j][3 + c] = slc;
+        if (with_vel) {
+          const MbKinRec* kr = M::kin(st, g < M::NCH ? g : (int)M::NCH);
+          const float sl1 = fmaf(p2[l], ac[l], -(pc[l] * a2[l])), sl2 = fmaf(pc[l], a1[l], -(p1[l] * ac[l]));
+          const float qd = S.u[6 + kr->j];
+          // A = Ap + Vp x vj (motion cross; vj x vj = 0), component c only: vj = (a, sl) qd
+          const float c1c = fmaf(w1[l], a2[l], -(w2[l] * a1[l])) * qd;
+          const float c23 = fmaf(-v2[l], a1[l], fmaf(v1[l], a2[l], fmaf(-w2[l], sl1, w1[l] * sl2))) * qd;
+          vw[l] = fmaf(ac[l], qd, vw[l]); vv[l] = fmaf(slc, qd, vv[l]); aw[l] += c1c; al[l] += c23;
+          if (j >= 0) {
+            S.w.k.jV[j + 1][c] = vw[l]; S.w.k.jV[j + 1][3 + c] = vv[l];
+            S.w.k.jA[j + 1][c] = aw[l]; S.w.k.jA[j + 1][3 + c] = al[l];
           }
         }
-      MB_END
+      MB_END_REG
     }
+    MB_WARP_SYNC();
   }
 
   // ---- B. per-body spatial inertia about O and bias wrench (gyroscopic + Bullet velocity damping + gravity) --
@@ -554,9 +567,8 @@ template <class M> struct Sim {
         }
         mb_cross(c, f, nO);
 #pragma unroll
+        for (int k = 0; k < 3; ++k) { S.w.k.u2.b.bIF[l][10 + k] = nc[k] + nO[k]; S.w.k.u2.b.bIF[l][13 + k] = f[k]; }
         float* rec = S.w.k.u2.b.bIF[l];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { rec[10 + k] = nc[k] + nO[k]; rec[13 + k] = f[k]; }
         const float cc = mb_dot3(c, c);
         rec[0] = m;
         rec[1] = m * c[0]; rec[2] = m * c[1]; rec[3] = m * c[2];
@@ -573,12 +585,13 @@ template <class M> struct Sim {
   // ---- B2. composite inertias and summed bias wrenches, leaf to root over the body forest (codegen: c_bparent), in
   // place, one of the 16 components per lane: NB - 1 dependent adds instead of every joint lane summing its whole
   // subtree (round 2: the per-lane sums were 4.8 % of the step kernel's instructions at 5 active lanes).
+  template <int B> MB_HD static void composite_from(Mem& S, int l) {  // (parents are immediates: four instructions per body)
+    S.w.k.u2.b.bIF[M::k_bparent[B]][l] += S.w.k.u2.b.bIF[B][l];
+    if constexpr (B > 1) composite_from<B - 1>(S, l);
+  }
   MB_HD static void composites(Mem& S) {
     MB_LANES(l)
-      if (l < 16) {
-#pragma unroll 1
-        for (int b = NB - 1; b > 0; --b) S.w.k.u2.b.bIF[M::c_bparent(b)][l] += S.w.k.u2.b.bIF[b][l];
-      }
+      if (l < 16) composite_from<NB - 1>(S, l);
     MB_END
   }
 
@@ -652,8 +665,8 @@ template <class M> struct Sim {
   // of the pivot's chain (codegen: c_ft / c_fd / c_fc, at most FSTEPS = 2 steps): no table look-up on the lane path.
   template <bool RHS> MB_HD static void factorize(Mem& S, const LaneConst& C) {
 #if !defined(MB_FACT_UNROLL) || MB_FACT_UNROLL
-    if (true) { pivots_from<RHS, NU - 1>(S, C); return; }
-#endif
+    pivots_from<RHS, NU - 1>(S, C);
+#else
 #pragma unroll 1
     for (int k = NU - 1; k >= 0; --k) {
       const int offk = M::c_rowoff(k), nk = M::c_rowlen(k) - 1;
@@ -691,6 +704,7 @@ template <class M> struct Sim {
         }
       MB_END
     }
+#endif
   }
 
   // Unrolled form (MB_FACT_UNROLL, the default): one template instance per pivot, so the row offset, the row length,

@@ -146,14 +146,16 @@ struct W3DObsScalars {
 MB_HD void mb_euler(const float* qin, float* rpy) {
   const float len = sqrtf(qin[0] * qin[0] + qin[1] * qin[1] + qin[2] * qin[2] + qin[3] * qin[3]);
   const float q0 = qin[0] / len, q1 = qin[1] / len, q2 = qin[2] / len, q3 = qin[3] / len;
-  const float sqx = q0 * q0, sqy = q1 * q1, sqz = q2 * q2, squ = q3 * q3;
-  const float sarg = -2.0f * (q0 * q2 - q3 * q1);
+  // (products that feed sums are rounded on their own / fused explicitly: left to the compiler, the contraction of
+  // a * b + c * d came out differently in the device-buffer and the host-buffer instantiation of one step kernel)
+  const float sqx = MB_FMUL(q0, q0), sqy = MB_FMUL(q1, q1), sqz = MB_FMUL(q2, q2), squ = MB_FMUL(q3, q3);
+  const float sarg = -2.0f * fmaf(q0, q2, -MB_FMUL(q3, q1));
   if (sarg <= -0.99999f) { rpy[0] = 0; rpy[1] = -0.5f * MB_PI_F; rpy[2] = 2 * atan2f(q0, -q1); }
   else if (sarg >= 0.99999f) { rpy[0] = 0; rpy[1] = 0.5f * MB_PI_F; rpy[2] = 2 * atan2f(-q0, q1); }
   else {
-    rpy[0] = atan2f(2 * (q1 * q2 + q3 * q0), squ - sqx - sqy + sqz);
+    rpy[0] = atan2f(2 * fmaf(q1, q2, MB_FMUL(q3, q0)), squ - sqx - sqy + sqz);
     rpy[1] = asinf(sarg);
-    rpy[2] = atan2f(2 * (q0 * q1 + q3 * q2), squ + sqx - sqy - sqz);
+    rpy[2] = atan2f(2 * fmaf(q0, q1, MB_FMUL(q3, q2)), squ + sqx - sqy - sqz);
   }
 }
 MB_HD float mb_clip5(float x) { return fminf(fmaxf(x, -5.0f), 5.0f); }

@@ -11,3 +11,11 @@
 #define MB_TABLE static const
 #define MB_CTABLE static const
 #endif
+
+// one step of the chain-walk kinematics (codegen.py: kin[step][chain]); 32 bytes = two 128-bit loads
+struct alignas(16) MbKinRec {
+  int j;          // joint met at this step of the chain
+  float off[3];   // pivot offset in the parent joint frame
+  float ax[3];    // joint axis as it points at q = 0 (joint frames are parallel to the base frame at q = 0)
+  int store;      // 1: this chain stores the joint's kinematics (0: another chain does, or the chain has ended)
+};

@@ -257,7 +257,7 @@ def _perturbed_response(O, o, pre, a, base_obs, A, rng):
 
     post = bytes(o.e)
     worst = 0.0
-    for _ in range(3):
+    for _ in range(8):  # (the response is heavy-tailed -- a limit or a contact switches for some directions only)
         C.memmove(C.byref(o.e), pre, len(pre))
         s = _w3d_base(o).s
         for k in range(3):
@@ -451,7 +451,9 @@ def env_name_of_fixture(basename):
 
 # tolerances per record kind: observation / reward; the Cassie observation carries raw joint speeds in rad/s over 50
 # PD substeps per env step
-TOL = {"custom": (1e-3, 1e-2), "stepper": (1e-3, 1e-2), "monkey": (1e-3, 1e-2), "cassie": (1e-2, 2e-3)}
+# PD substeps per env step (device vs oracle from f32-identical states, 8 seeds x 25 steps, tools/dbg_teacher_errs.py:
+# median 1.1e-3, p99 6e-3, max 1.0e-2 .. 1.4e-2 from build to build at cond(M) = 7e4)
+TOL = {"custom": (1e-3, 1e-2), "stepper": (1e-3, 1e-2), "monkey": (1e-3, 1e-2), "cassie": (2e-2, 2e-3)}
 
 
 def run_golden_trace(O, path, backend, force_states=False):

@@ -125,7 +125,7 @@ def test_cassie_env_free_running(cassie_table, oracle_mod):
 def test_cassie_hull_self_collision(cassie_table, oracle_mod):
     """Mesh-hull self-collision (env_cassie.py:81-85: URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS; the non-ancestor
     pairs are left-leg vs right-leg links): warp-cooperative GJK on the 32-vertex link hulls in the kernel source against
-    the oracle's float64 GJK on the same hulls.  Contact geometry (distance 2e-6, point 2e-4 (barycentric weights of a float32 Gram solve), normal 2e-3: the normal
+    the oracle's float64 GJK on the same hulls.  Contact geometry (distance 2e-6, point 1e-3 (barycentric weights of a float32 Gram solve; the witness point of two nearly parallel faces slides along them with the rounding of the vertex coordinates), normal 2e-3: the normal
     is a millimetre-long difference of metre-sized float32 coordinates), contact and row counts, the state after one
     0.6 ms stepSimulation (5e-3, median 5e-4) -- and with self_collision = 0 the same states come out differently, so
     the feature is live."""
@@ -151,7 +151,7 @@ def test_cassie_hull_self_collision(cassie_table, oracle_mod):
             if c0.partner[k] >= 1000:
                 assert int(pts[k, 9]) >= 1000
                 assert abs(pts[k, 6] - c0.dist[k]) < 2e-6
-                assert np.abs(pts[k, 0:3] - np.array(c0.pos_a[k][:])).max() < 2e-4
+                assert np.abs(pts[k, 0:3] - np.array(c0.pos_a[k][:])).max() < 1e-3
                 assert np.abs(pts[k, 3:6] - np.array(c0.normal[k][:])).max() < 2e-3
         ref = O.state_vector(s, A)
         errs.append(state_error(out, ref))

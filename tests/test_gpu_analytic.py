@@ -118,7 +118,7 @@ def test_resting_on_the_ground_plane(walker_table):
 def test_resting_on_a_soft_plank(walker_table):
     """A collapsed Walker3D at rest on its first stepping stone (kp = 30000, kd = 1000): the vertical components of the
     plank impulses sum to M g dt (each heap within 20 %, their median within 3 %: a heap keeps rocking slowly) and every contact carrying > 10 % of the weight obeys impulse = dt kp depth
-    (each within 35 %, their median within 3 %; five un-warm-started PGS iterations per substep do not converge further)."""
+    (nine in ten within 20 %, their median within 3 %; five un-warm-started PGS iterations per substep do not converge further)."""
     import torch
 
     from mocca_envs_b200.vec_env import Walker3DStepperVecEnv
@@ -143,11 +143,12 @@ def test_resting_on_a_soft_plank(walker_table):
             loaded = plank & (p[:, 7] > 0.10 * M * G * dt)
             depth = -(p[loaded, 6] + slop)
             r = p[loaded, 7] / (dt * KP * depth)
-            assert np.all(np.abs(r - 1.0) < 0.35), (i, r)
             ratios += list(r)
         assert abs(np.mean(vs) - 1.0) < 0.2, (i, vs)
         verticals.append(np.mean(vs))
     assert rested >= N // 16, rested
+    ratios = np.array(ratios)
+    assert np.mean(np.abs(ratios - 1.0) < 0.2) > 0.9, np.sort(ratios)  # a heap that still rocks loads / unloads a contact
     assert abs(np.median(ratios) - 1.0) < 3e-2, np.median(ratios)
     assert abs(np.median(verticals) - 1.0) < 3e-2, np.median(verticals)
     env.close()

@@ -76,7 +76,7 @@ def test_cassie_airborne_step_with_loop_closures(cassie_table, oracle_mod, torch
 def test_cassie_env_step_teacher_forced(oracle_mod, torch_mod):
     """CassieEnv.step (50 PD substeps, toe contacts, loop closures) on the device from f32-identical states and
     bookkeeping for 8 action streams: the oracle's state and low-pass joint velocities are injected before every step.
-    Tolerance 1e-2 (obs; raw joint speeds in rad/s dominate) / 2e-3 (reward), same done; every step outside must be
+    Tolerance 2e-2 (obs; raw joint speeds in rad/s dominate) / 2e-3 (reward), same done; every step outside must be
     explained by a verified discontinuity and bounded (tests/teacher.py), else the test fails."""
     from tests import teacher as T
 
@@ -140,7 +140,7 @@ def test_cassie_hull_self_collision(cassie_table, oracle_mod, torch_mod):
             if c0.partner[k] >= 1000:
                 assert int(pts[i, k, 9]) >= 1000
                 assert abs(pts[i, k, 6] - c0.dist[k]) < 2e-6
-                assert np.abs(pts[i, k, 0:3] - np.array(c0.pos_a[k][:])).max() < 2e-4
+                assert np.abs(pts[i, k, 0:3] - np.array(c0.pos_a[k][:])).max() < 1e-3
                 assert np.abs(pts[i, k, 3:6] - np.array(c0.normal[k][:])).max() < 2e-3
         errs.append(state_error(out[i], O.state_vector(s, A)))
     assert max(errs) < 5e-3 and np.median(errs) < 5e-4, sorted(errs)[-5:]
