@@ -380,12 +380,14 @@ template <class M> struct Sim {
     LaneVar<int> tl;        // |support(l)| = slot of column l in every descendant's compact row = rowlen(l) - 1
     LaneVar<int> off;       // rowoff(l)
     LaneVar<unsigned> sup;  // rowmask(l)
+    LaneVar<unsigned> bit;       // 1 << l: "is coordinate l in the row's support" is one LOP3 with predicate output
     LaneVar<unsigned> pt4, ps4;  // 4 t and 4 s of the lower-triangle entries p = l, l + 32, l + 64 (one byte per round)
     LaneVar<int> dep;       // tree depth of coordinate l (-1 base block, 99 unused lane)
     LaneVar<unsigned> anc0, anc1;  // coordinate index of l's ancestor at each level, 5 bits per level
   };
   MB_HD static void init_lane_const(LaneConst& C) {
     MB_LANES(l)
+      C.bit[l] = 1u << l;
       C.tl[l] = l < NU ? M::rowlen(l) - 1 : 0;
       C.off[l] = l < NU ? M::rowoff(l) : 0;
       C.sup[l] = l < NU ? M::rowmask(l) : 0u;
@@ -1526,113 +1528,17 @@ template <class M> struct Sim {
   // as TWO compact rows (the part on link A and the part on link B -- their union is a tree, not a chain) that share
   // one multiplier; then contact normals and friction pairs.
   enum { NLC = 6 * M::NLOOP };
-  // ---- G2. self-contact rows (cold path: ~0.3 self-contacts per env step under random actions) --------------------
-  // A self-contact couples two links, so like a loop row each of its three rows is stored as two compact rows
-  // sharing one multiplier (flag MB_ROW_DUAL on the first): normals at S0 + 2s + {A, B}, friction at
-  // S0 + 2 ncs + 4s + {t1 A, t2 A, t1 B, t2 B} (S0 = first row after the static-world contacts, s = self-contact
-  // index, contact slot nc + s).  Written for SIZE, not speed: the step kernel's hot loop already exceeds the 32 KB
-  // L1.5 instruction cache, so every instruction executed off the common path evicts hot code.  Rolled loops, the
-  // half solve runs in place in the row's own shared-memory slot; out of line, and the caller re-derives its lane
-  // constants afterwards instead of keeping them live across the call.
-  MB_NOINLINE static void setup_self_rows(Mem& S, int S0, int nc, int ncs, float slop, float inv_dt) {
-    MB_ASSUME_SHARED(S);
-    const int R = 6 * ncs;
-#pragma unroll 1
-    for (int base = 0; base < R; base += 32) {
-      MB_LANES(l)
-        const int i = base + l;
-        if (i < R) {
-          int k, fr = -1;
-          bool sideB;
-          if (i < 2 * ncs) { k = nc + (i >> 1); sideB = (i & 1) != 0; }
-          else { const int i2 = i - 2 * ncs; k = nc + (i2 >> 2); fr = i2 & 1; sideB = (i2 & 2) != 0; }
-          float dirv[3] = {S.cn[k][0], S.cn[k][1], S.cn[k][2]};
-          if (fr >= 0) {
-            float t1[3], t2[3];
-            mb_plane_space(S.cn[k], t1, t2);
-            dirv[0] = fr ? t2[0] : t1[0]; dirv[1] = fr ? t2[1] : t1[1]; dirv[2] = fr ? t2[2] : t1[2];
-          }
-          int cj = S.clink[k];
-          float pc[3] = {S.cP[k][0], S.cP[k][1], S.cP[k][2]};
-          if (sideB) {
-            // setupMultiBodyContactConstraint: jacobian B is built with -direction at the point on B = pA - dist n
-            const float dk = S.cdist[k];
-            pc[0] -= dk * S.cn[k][0]; pc[1] -= dk * S.cn[k][1]; pc[2] -= dk * S.cn[k][2];
-            dirv[0] = -dirv[0]; dirv[1] = -dirv[1]; dirv[2] = -dirv[2];
-            cj = ((M::sp_own(S.cpartner[k] - 1000) >> 8) & 255) - 1;
-          }
-          float W[6];
-          mb_cross(pc, dirv, W);
-          W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
-          const unsigned long long pack = cj >= 0 ? M::chainpack(cj) : 0ull;
-          const int depth = cj >= 0 ? M::jdepth(cj) : -1;
-          const int n = 7 + depth;
-          const int r = S0 + i;
-          float* Yr = S.w.Yc[r];
-          float rel_vel = 0.0f;
-#pragma unroll 1
-          for (int t = 0; t < n; ++t) {
-            float v, uu;
-            if (t < 6) {  // (a select chain: a dynamic index would push W into local memory)
-              v = t == 0 ? W[0] : (t == 1 ? W[1] : (t == 2 ? W[2] : (t == 3 ? W[3] : (t == 4 ? W[4] : W[5]))));
-              uu = S.u[t];
-            } else {
-              const int a = chain_at(pack, t - 6);
-              const float* sj = S.js[a];
-              v = sj[0] * W[0] + sj[1] * W[1] + sj[2] * W[2] + sj[3] * W[3] + sj[4] * W[4] + sj[5] * W[5];
-              uu = S.u[6 + a];
-            }
-            rel_vel += v * uu;
-            Yr[t] = v;
-          }
-          // half solve L^T y = J^T in place (prefix property of the compact factor)
-#pragma unroll 1
-          for (int t = n - 1; t >= 0; --t) {
-            const int it = t < 6 ? t : 6 + chain_at(pack, t - 6);
-            const float bt = Yr[t], ci = bt * S.Ldi2[it];
-            Yr[t] = bt * S.Ldinv[it];
-            const float* Li = &S.L[M::rowoff(it)];
-#pragma unroll 1
-            for (int s2 = 0; s2 < t; ++s2) Yr[s2] -= Li[s2] * ci;
-          }
-          float dd = 0.0f;
-#pragma unroll 1
-          for (int t = 0; t < n; ++t) dd += Yr[t] * Yr[t];
-          S.rc.r.r_mask[r] = 0x3Fu | (cj >= 0 ? (M::janc(cj) << 6) : 0u);
-          MbRowPar par;  // partial sums, combined below
-          par.rhs = rel_vel; par.cfm = 0.0f; par.jinv = dd; par.den = 0.0f;
-          S.rc.r.r_par[r] = par;
-          S.rc.r.r_app[r] = 0.0f;
-          S.rc.r.r_mu[r] = S.cmu[k];
-        }
-      MB_END
-    }
-    // fillMultiBodyConstraint: denominator = JA M^-1 JA^T + JB M^-1 JB^T (no coupling term, as for loop closures)
-    MB_LANES(l)
-      for (int i = l; i < 3 * ncs; i += 32) {
-        const int sidx = i / 3, w = i - 3 * sidx;  // w: 0 normal, 1 / 2 friction directions
-        const int ra = S0 + (w == 0 ? 2 * sidx : 2 * ncs + 4 * sidx + (w - 1));
-        const int rb = ra + (w == 0 ? 1 : 2);
-        const float dd = S.rc.r.r_par[ra].jinv + S.rc.r.r_par[rb].jinv;
-        const float jinv = dd > 1.1920929e-07f ? 1.0f / dd : 0.0f;
-        const float rel_vel = S.rc.r.r_par[ra].rhs + S.rc.r.r_par[rb].rhs;
-        float positional = 0.0f, verr = -rel_vel;
-        if (w == 0) {
-          const float dist = S.cdist[nc + sidx] + slop;
-          if (dist > 0.0f) verr -= dist * inv_dt;
-          else positional = -dist * S.cerp[nc + sidx] * inv_dt;
-        }
-        MbRowPar par;
-        par.rhs = (positional + verr) * jinv; par.cfm = 0.0f; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
-        S.rc.r.r_par[ra] = par;
-        if (w < 2) S.rc.r.r_mask[ra] |= MB_ROW_DUAL;  // friction pairs carry the flag on their first row
-      }
-    MB_END
-  }
-
-  MB_HD static void setup_rows(Mem& S, const MbPhysics& P, int nlim, int nc) {
+  // ---- G2. self-contact rows.  A self-contact couples two links, so like a loop row each of its three rows is stored
+  // as two compact rows sharing one multiplier (flag MB_ROW_DUAL on the first): normals at S0 + 2s + {A, B}, friction
+  // at S0 + 2 ncs + 4s + {t1 A, t2 A, t1 B, t2 B} (S0 = first row after the static-world contacts, s = self-contact
+  // index, contact slot nc + s).  They are built by setup_rows() in the same pass as every other row -- one more lane
+  // each, the unrolled register code is shared.  (Until round 2 a size-optimised out-of-line routine built them in
+  // ~1 500 instructions; a substep with a self-contact then made its whole CTA wait at the next barrier, and with 14
+  // envs per CTA nearly every substep had one.)
+  MB_HD static void setup_rows(Mem& S, const MbPhysics& P, int nlim, int nc, int ncs) {
     const int n0 = nlim + NLC;
-    const int R = n0 + 3 * nc;
+    const int S0 = n0 + 3 * nc;
+    const int R = S0 + (NSELF > 0 ? 6 * ncs : 0);
     const float inv_dt = 1.0f / P.dt;
 #pragma unroll 1
     for (int base = 0; base < R; base += 32) {
@@ -1663,23 +1569,35 @@ template <class M> struct Sim {
             W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
             cj = M::lc_owner(sd);
           } else {
-            int k;
-            float dirv[3];
-            if (r < n0 + nc) {
-              kind = 1; k = r - n0;
-              dirv[0] = S.cn[k][0]; dirv[1] = S.cn[k][1]; dirv[2] = S.cn[k][2];
-              cfm = S.ccfm[k] * inv_dt; erp = S.cerp[k]; dist = S.cdist[k] + P.linear_slop;
-            } else {
-              kind = 2; k = (r - n0 - nc) >> 1;
+            int k, fr = -1;       // contact slot; friction direction (-1 = the normal)
+            bool sideB = false;   // the part of a self-contact row on the partner link
+            if (r < n0 + nc) { kind = 1; k = r - n0; }
+            else if (NSELF == 0 || r < S0) { kind = 2; k = (r - n0 - nc) >> 1; fr = (r - n0 - nc) & 1; }
+            else {
+              kind = 4;
+              const int i = r - S0;
+              if (i < 2 * ncs) { k = nc + (i >> 1); sideB = (i & 1) != 0; }
+              else { const int i2 = i - 2 * ncs; k = nc + (i2 >> 2); fr = i2 & 1; sideB = (i2 & 2) != 0; }
+            }
+            float dirv[3] = {S.cn[k][0], S.cn[k][1], S.cn[k][2]};
+            if (fr >= 0) {
               float t1[3], t2[3];
               mb_plane_space(S.cn[k], t1, t2);
-              const bool second = ((r - n0 - nc) & 1) != 0;
-              dirv[0] = second ? t2[0] : t1[0]; dirv[1] = second ? t2[1] : t1[1]; dirv[2] = second ? t2[2] : t1[2];
+              dirv[0] = fr ? t2[0] : t1[0]; dirv[1] = fr ? t2[1] : t1[1]; dirv[2] = fr ? t2[2] : t1[2];
             }
+            if (kind == 1) { cfm = S.ccfm[k] * inv_dt; erp = S.cerp[k]; dist = S.cdist[k] + P.linear_slop; }
             mu = S.cmu[k];
-            mb_cross(S.cP[k], dirv, W);
-            W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
             cj = S.clink[k];
+            float pcv[3] = {S.cP[k][0], S.cP[k][1], S.cP[k][2]};
+            if (NSELF > 0 && sideB) {
+              // setupMultiBodyContactConstraint: jacobian B is built with -direction at the point on B = pA - dist n
+              const float dk = S.cdist[k];
+              pcv[0] -= dk * S.cn[k][0]; pcv[1] -= dk * S.cn[k][1]; pcv[2] -= dk * S.cn[k][2];
+              dirv[0] = -dirv[0]; dirv[1] = -dirv[1]; dirv[2] = -dirv[2];
+              cj = ((M::sp_own(S.cpartner[k] - 1000) >> 8) & 255) - 1;
+            }
+            mb_cross(pcv, dirv, W);
+            W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
           }
           const unsigned long long pack = cj >= 0 ? M::chainpack(cj) : 0ull;
           const int depth = cj >= 0 ? M::jdepth(cj) : -1;
@@ -1733,7 +1651,7 @@ template <class M> struct Sim {
             if (t < n) Yr[t] = b[t];
           S.rc.r.r_mask[r] = 0x3Fu | (cj >= 0 ? (M::janc(cj) << 6) : 0u);
           MbRowPar par;
-          if (kind == 3) {  // partial sums; the two parts of a loop row are combined below
+          if (kind >= 3) {  // partial sums; the two parts of a loop / self-contact row are combined below
             par.rhs = rel_vel; par.jinv = dd; par.den = 0.0f;
           } else {
             par.rhs = (positional + verr) * jinv; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
@@ -1761,6 +1679,29 @@ template <class M> struct Sim {
           S.rc.r.r_par[ra] = par;
           S.rc.r.r_mu[ra] = M::lc_maximp(c);
           S.rc.r.r_mask[ra] |= MB_ROW_DUAL;
+        }
+      MB_END
+    }
+    if (NSELF > 0 && ncs > 0) {
+      // fillMultiBodyConstraint: denominator = JA M^-1 JA^T + JB M^-1 JB^T (no coupling term, as for loop closures)
+      MB_LANES(l)
+        for (int i = l; i < 3 * ncs; i += 32) {
+          const int sidx = i / 3, w = i - 3 * sidx;  // w: 0 normal, 1 / 2 friction directions
+          const int ra = S0 + (w == 0 ? 2 * sidx : 2 * ncs + 4 * sidx + (w - 1));
+          const int rb = ra + (w == 0 ? 1 : 2);
+          const float dd = S.rc.r.r_par[ra].jinv + S.rc.r.r_par[rb].jinv;
+          const float jinv = dd > 1.1920929e-07f ? 1.0f / dd : 0.0f;
+          const float rel_vel = S.rc.r.r_par[ra].rhs + S.rc.r.r_par[rb].rhs;
+          float positional = 0.0f, verr = -rel_vel;
+          if (w == 0) {
+            const float dist = S.cdist[nc + sidx] + P.linear_slop;
+            if (dist > 0.0f) verr -= dist * inv_dt;
+            else positional = -dist * S.cerp[nc + sidx] * inv_dt;
+          }
+          MbRowPar par;
+          par.rhs = (positional + verr) * jinv; par.cfm = 0.0f; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
+          S.rc.r.r_par[ra] = par;
+          if (w < 2) S.rc.r.r_mask[ra] |= MB_ROW_DUAL;  // friction pairs carry the flag on their first row
         }
       MB_END
     }
@@ -1818,12 +1759,12 @@ template <class M> struct Sim {
     const unsigned supA = S.rc.r.r_mask[ra];
     LaneVar<float> ya, ta;
     MB_LANES(l)
-      ya[l] = (((DUAL ? supA & MB_ROW_SUP : supA) >> l) & 1u) ? S.w.Yc[ra][C.tl[l]] : 0.0f;
+      ya[l] = ((DUAL ? supA & MB_ROW_SUP : supA) & C.bit[l]) ? S.w.Yc[ra][C.tl[l]] : 0.0f;
     MB_END_REG
     if (DUAL == 1 || (DUAL == 2 && (supA & MB_ROW_DUAL))) {  // loop closure / self-contact: part on the other link
       const unsigned supB = S.rc.r.r_mask[ra + 1];
       MB_LANES(l)
-        if ((supB >> l) & 1u) ya[l] += S.w.Yc[ra + 1][C.tl[l]];
+        if (supB & C.bit[l]) ya[l] += S.w.Yc[ra + 1][C.tl[l]];
       MB_END_REG
     }
     MB_LANES(l)
@@ -1834,9 +1775,10 @@ template <class M> struct Sim {
     const float appA = S.rc.r.r_app[ra];
     float dA = pA.rhs - appA * pA.cfm - dotA * pA.jinv;
     const float sumA = appA + dA;
-    float nA = sumA;
-    if (sumA < lo) { dA = lo - appA; nA = lo; }
-    else if (sumA > hi) { dA = hi - appA; nA = hi; }
+    // clamp to [lo, hi]; the delta is recomputed only when the clamp bites (same values as the if / else if chain of
+    // btMultiBodyConstraintSolver::resolveSingleConstraintRowGeneric, five instructions instead of twelve)
+    const float nA = fminf(fmaxf(sumA, lo), hi);
+    if (nA != sumA) dA = nA - appA;
     MB_WARP_SYNC();  // every lane has read r_app[ra] before lane 0 replaces it (compute-sanitizer racecheck: WAR)
     MB_LANES(l)
       z[l] += ya[l] * dA;
@@ -1852,14 +1794,14 @@ template <class M> struct Sim {
     const unsigned supA = S.rc.r.r_mask[ra];  // both rows of a contact share the support
     LaneVar<float> ya, yb, ta, tb;
     MB_LANES(l)
-      const bool in = (((SELF ? supA & MB_ROW_SUP : supA) >> l) & 1u) != 0u;
+      const bool in = ((SELF ? supA & MB_ROW_SUP : supA) & C.bit[l]) != 0u;
       ya[l] = in ? S.w.Yc[ra][C.tl[l]] : 0.0f;
       yb[l] = in ? S.w.Yc[rb][C.tl[l]] : 0.0f;
     MB_END_REG
     if (SELF && (supA & MB_ROW_DUAL)) {
       const unsigned supB = S.rc.r.r_mask[ra + 2];
       MB_LANES(l)
-        if ((supB >> l) & 1u) { ya[l] += S.w.Yc[ra + 2][C.tl[l]]; yb[l] += S.w.Yc[ra + 3][C.tl[l]]; }
+        if (supB & C.bit[l]) { ya[l] += S.w.Yc[ra + 2][C.tl[l]]; yb[l] += S.w.Yc[ra + 3][C.tl[l]]; }
       MB_END_REG
     }
     MB_LANES(l)
@@ -1892,7 +1834,7 @@ template <class M> struct Sim {
 
   // btMultiBodyConstraintSolver::solveSingleIteration order: non-contact rows (limits, then loop closures;
   // alternating direction), normals, friction.  Contact k < nc is a static-world contact, nc <= k < nc + ncs a
-  // self-contact (rows behind S0, see setup_self_rows); one loop serves both so that the row code exists once.
+  // self-contact (rows behind S0, see setup_rows); one loop serves both so that the row code exists once.
   // SELF: the model has self-collision pairs, so a contact row may be a dual row.  (Running substeps without
   // self-contacts through a SELF = false instantiation and keeping the SELF = true copy out of line was measured in
   // round 2: the extra call site cost Walker3D 8 % through register allocation, profiles/README.md r2l.)
@@ -2002,11 +1944,7 @@ template <class M> struct Sim {
     if (R > 0) {
       // (a size-optimised rolled version of setup_rows serving every row kind was measured too: 12.7 KB less hot
       // code, but 9 % slower on Walker3D and 11 % on Cassie -- the unrolled register version stays)
-      setup_rows(S, P, nlim, nc);
-      if (NSELF > 0 && MB_UNLIKELY(ncs > 0)) {
-        setup_self_rows(S, nlim + NLC + 3 * nc, nc, ncs, P.linear_slop, 1.0f / P.dt);
-        init_lane_const(C);  // dead across the call by construction: recomputed, not saved
-      }
+      setup_rows(S, P, nlim, nc, ncs);
       // (an impulse-space variant of the PGS -- Gram matrix G = Y Y^T of the rows in the unused tail of the row matrix,
       // one register w_c = sum_s G_cs lambda_s per lane, a row visit = one shuffle + uniform delta + one LDS / FFMA per
       // lane -- was measured in round 2: 26 instead of 31 instructions per visit, but building G and assembling z cost
