@@ -306,6 +306,26 @@ def emit_header(t: dict, prefix: str) -> str:
         out.append(_iarr(P + "_c_ft%d" % (i + 1), [x[i][0] if len(x) > i else 15 for x in fsteps]).replace("MB_TABLE", "MB_CTABLE"))
         out.append(_iarr(P + "_c_fd%d" % (i + 1), [x[i][1] if len(x) > i else 0 for x in fsteps]).replace("MB_TABLE", "MB_CTABLE"))
         out.append(_iarr(P + "_c_fc%d" % (i + 1), [x[i][2] if len(x) > i else 0 for x in fsteps]).replace("MB_TABLE", "MB_CTABLE"))
+    # lane-indexed variant (global memory) for setup_rows(): the support of a constraint row on coordinate k is row k's
+    # support PLUS k itself (slot nk), so the steps are taken over t = 0 .. nk inclusive
+    rsteps = []
+    for k in range(r["nu"]):
+        nk = r["rowlen"][k] - 1
+        cols_ = fcol[k][:nk] + [k]
+        offs_ = fac[k][:nk] + [r["rowoff"][k]]
+        st_, pd_, pc_ = [], 0, 0
+        for tt in range(nk + 1):
+            dd_, dc_ = offs_[tt] - tt * (tt + 1) // 2, cols_[tt] - tt
+            if dd_ != pd_ or dc_ != pc_:
+                st_.append((tt, dd_ - pd_, dc_ - pc_))
+                pd_, pc_ = dd_, dc_
+        rsteps.append(st_)
+    assert max(len(x) for x in rsteps) <= 2, "setup_rows() supports two steps per row"
+    r["rsteps"] = max(1, max(len(x) for x in rsteps))
+    for i in range(2):
+        out.append(_iarr(P + "_ft%d" % (i + 1), [x[i][0] if len(x) > i else 15 for x in rsteps]))
+        out.append(_iarr(P + "_fd%d" % (i + 1), [x[i][1] if len(x) > i else 0 for x in rsteps]))
+        out.append(_iarr(P + "_fc%d" % (i + 1), [x[i][2] if len(x) > i else 0 for x in rsteps]))
     r["fsteps"] = nsteps
     r["fsteps_list"] = fsteps
     # per coordinate: depth in the joint tree (-1 for the six base coordinates) and its ancestors' coordinate
@@ -475,6 +495,10 @@ def emit_header(t: dict, prefix: str) -> str:
     for i in range(r["fsteps"]):
         for nm in ("ft", "fd", "fc"):
             out.append("  MB_HD static int c_%s%d(int k) { return %s_c_%s%d[k]; }\n" % (nm, i + 1, P, nm, i + 1))
+    out.append("  enum { RSTEPS = %d };  // steps of the affine chain addressing of a constraint row (ft / fd / fc)\n" % r["rsteps"])
+    for i in range(2):
+        for nm in ("ft", "fd", "fc"):
+            out.append("  MB_HD static int %s%d(int k) { return %s_%s%d[k]; }\n" % (nm, i + 1, P, nm, i + 1))
     if r["fsteps"] < 2:
         out.append("  MB_HD static int c_ft2(int) { return 15; }\n  MB_HD static int c_fd2(int) { return 0; }\n"
                    "  MB_HD static int c_fc2(int) { return 0; }\n")

@@ -64,6 +64,7 @@ MB_HD void warp_gather(const LaneVar<float>& x, const LaneVar<int>& src, LaneVar
 }
 MB_HD unsigned warp_ballot(const LaneVar<int>& p) { return __ballot_sync(0xffffffffu, p.v != 0); }
 MB_HD int mb_popc(unsigned x) { return __popc(x); }
+MB_HD int mb_ffs(unsigned x) { return __ffs((int)x); }  // 1-based index of the lowest set bit, 0 for x = 0
 // lane holding the largest value (the lowest such lane on ties)
 MB_HD int warp_argmax(const LaneVar<float>& x) {
   float v = x.v;
@@ -110,6 +111,7 @@ inline unsigned warp_ballot(const LaneVar<int>& p) {
   return m;
 }
 inline int mb_popc(unsigned x) { return __builtin_popcount(x); }
+inline int mb_ffs(unsigned x) { return __builtin_ffs((int)x); }
 inline int warp_argmax(const LaneVar<float>& x) {
   int best = 0;
   for (int l = 1; l < 32; ++l)
@@ -1295,26 +1297,11 @@ template <class M> struct Sim {
       }
     MB_END
     int nc = 0;
-    const int nbox = BOXES ? S.nbox : 0;
-#pragma unroll 1
-    for (int ob = P.has_ground ? -1 : 0; ob < nbox; ++ob) {
-      if (ob >= 0) {
-        // cheap uniform cull: the robot (all points within ~1.2 m of the base) cannot reach a plank whose local
-        // x / z slab is farther away than that
-        const float* bx = S.rc.box[ob];
-        const float d[3] = {S.pos[0] - bx[0], S.pos[1] - bx[1], S.pos[2] - bx[2]};
-        bool far = false;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float cl = bx[3 + k] * d[0] + bx[6 + k] * d[1] + bx[9 + k] * d[2];
-          if (fabsf(cl) > bx[12 + k] + 1.6f) far = true;
-        }
-        if (far) continue;
-      }
+    if (P.has_ground) {  // the stadium plane z = 0
 #pragma unroll 1
       for (int pass = 0; pass * 32 < NPT; ++pass) {
         LaneVar<int> hit;
-        LaneVar<float> px, py, pz, nx, ny, nz, dd;
+        LaneVar<float> px, py, pz, dd;
         MB_LANES(l)
           const int pt = pass * 32 + l;
           hit[l] = 0;
@@ -1329,22 +1316,10 @@ template <class M> struct Sim {
               if (o >= 0) { cfly[0] += S.w.k.jp[o][0]; cfly[1] += S.w.k.jp[o][1]; cfly[2] += S.w.k.jp[o][2]; }
             }
             const float* c = STORE ? S.w.k.u2.pt[STORE ? pt : 0] : cfly;
-            if (ob < 0) {
-              const float dist = (S.pos[2] + c[2]) - r;
-              if (dist < M::pthresh(pt)) {
-                hit[l] = 1;
-                px[l] = c[0]; py[l] = c[1]; pz[l] = c[2] - r; dd[l] = dist;
-                nx[l] = 0.0f; ny[l] = 0.0f; nz[l] = 1.0f;
-              }
-            } else {
-              const float cw[3] = {c[0] + S.pos[0], c[1] + S.pos[1], c[2] + S.pos[2]};
-              float pa[3], n[3], dist;
-              if (CYLS ? sphere_cyl(cw, r, S.rc.box[ob], M::pthresh(pt), pa, n, &dist)
-                       : sphere_box(cw, r, S.rc.box[ob], M::pthresh(pt), pa, n, &dist)) {
-                hit[l] = 1;
-                px[l] = pa[0] - S.pos[0]; py[l] = pa[1] - S.pos[1]; pz[l] = pa[2] - S.pos[2]; dd[l] = dist;
-                nx[l] = n[0]; ny[l] = n[1]; nz[l] = n[2];
-              }
+            const float dist = (S.pos[2] + c[2]) - r;
+            if (dist < M::pthresh(pt)) {
+              hit[l] = 1;
+              px[l] = c[0]; py[l] = c[1]; pz[l] = c[2] - r; dd[l] = dist;
             }
           }
         MB_END
@@ -1356,14 +1331,79 @@ template <class M> struct Sim {
             const int k = nc + mb_popc(mask & ((1u << l) - 1u));
             if (k < MB_MAXC) {
               S.cP[k][0] = px[l]; S.cP[k][1] = py[l]; S.cP[k][2] = pz[l];
-              S.cn[k][0] = nx[l]; S.cn[k][1] = ny[l]; S.cn[k][2] = nz[l];
+              S.cn[k][0] = 0.0f; S.cn[k][1] = 0.0f; S.cn[k][2] = 1.0f;
               S.cdist[k] = dd[l];
-              S.cmu[k] = M::pfriction(pt) * (ob < 0 ? P.ground_friction : P.box_friction);
-              S.cerp[k] = ob < 0 ? P.erp_contact : P.box_erp;
-              S.ccfm[k] = ob < 0 ? 0.0f : P.box_cfm;
+              S.cmu[k] = M::pfriction(pt) * P.ground_friction;
+              S.cerp[k] = P.erp_contact;
+              S.ccfm[k] = 0.0f;
               S.clink[k] = M::powner(pt);
               S.cfoot[k] = mb_pack_foot(M::pfoot(pt), M::pid(pt));
-              S.cpartner[k] = ob < 0 ? 0 : 10 + ob;
+              S.cpartner[k] = 0;
+            }
+          }
+        MB_END
+        nc += mb_popc(mask);
+      }
+    }
+    if (BOXES) {
+      // Static boxes (stepping stones).  A cheap uniform cull first: the robot (all points within ~1.2 m of the base)
+      // cannot reach a box whose local slab is farther away than that.  The (box, point) pairs of the boxes in reach are
+      // then flattened over the lanes, box-major like the oracle's contact list (round 2: NPT = 34 points per box took
+      // two passes with two live lanes in the second one).
+      unsigned boxlist = 0u;
+      int nact = 0;
+      const int nbox = S.nbox;
+#pragma unroll 1
+      for (int ob = 0; ob < nbox; ++ob) {
+        const float* bx = S.rc.box[ob];
+        const float d[3] = {S.pos[0] - bx[0], S.pos[1] - bx[1], S.pos[2] - bx[2]};
+        bool far = false;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float cl = bx[3 + k] * d[0] + bx[6 + k] * d[1] + bx[9 + k] * d[2];
+          if (fabsf(cl) > bx[12 + k] + 1.6f) far = true;
+        }
+        if (!far) { boxlist |= (unsigned)ob << (4 * nact); ++nact; }
+      }
+      const int ntask = nact * NPT;
+#pragma unroll 1
+      for (int base = 0; base < ntask; base += 32) {
+        LaneVar<int> hit, ptl, obl;
+        LaneVar<float> px, py, pz, nx, ny, nz, dd;
+        MB_LANES(l)
+          const int idx = base + l;
+          hit[l] = 0;
+          if (idx < ntask) {
+            const int bi = idx / NPT, pt = idx - bi * NPT, ob = (int)((boxlist >> (4 * bi)) & 15u);
+            ptl[l] = pt; obl[l] = ob;
+            const float r = M::pradius(pt);
+            const float* c = S.w.k.u2.pt[STORE ? pt : 0];
+            const float cw[3] = {c[0] + S.pos[0], c[1] + S.pos[1], c[2] + S.pos[2]};
+            float pa[3], n[3], dist;
+            if (CYLS ? sphere_cyl(cw, r, S.rc.box[ob], M::pthresh(pt), pa, n, &dist)
+                     : sphere_box(cw, r, S.rc.box[ob], M::pthresh(pt), pa, n, &dist)) {
+              hit[l] = 1;
+              px[l] = pa[0] - S.pos[0]; py[l] = pa[1] - S.pos[1]; pz[l] = pa[2] - S.pos[2]; dd[l] = dist;
+              nx[l] = n[0]; ny[l] = n[1]; nz[l] = n[2];
+            }
+          }
+        MB_END
+        const unsigned mask = warp_ballot(hit);
+        if (mask == 0u) continue;
+        MB_LANES(l)
+          if (hit[l]) {
+            const int pt = ptl[l];
+            const int k = nc + mb_popc(mask & ((1u << l) - 1u));
+            if (k < MB_MAXC) {
+              S.cP[k][0] = px[l]; S.cP[k][1] = py[l]; S.cP[k][2] = pz[l];
+              S.cn[k][0] = nx[l]; S.cn[k][1] = ny[l]; S.cn[k][2] = nz[l];
+              S.cdist[k] = dd[l];
+              S.cmu[k] = M::pfriction(pt) * P.box_friction;
+              S.cerp[k] = P.box_erp;
+              S.ccfm[k] = P.box_cfm;
+              S.clink[k] = M::powner(pt);
+              S.cfoot[k] = mb_pack_foot(M::pfoot(pt), M::pid(pt));
+              S.cpartner[k] = 10 + obl[l];
             }
           }
         MB_END
@@ -1599,9 +1639,15 @@ template <class M> struct Sim {
             mb_cross(pcv, dirv, W);
             W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
           }
-          const unsigned long long pack = cj >= 0 ? M::chainpack(cj) : 0ull;
           const int depth = cj >= 0 ? M::jdepth(cj) : -1;
           const int n = 7 + depth;  // support size
+          // Affine chain addressing (see factorize()): slot t of the row's support is coordinate t, and its compact row
+          // of L starts at word t (t + 1) / 2 -- both shifted by a per-row constant behind each branch point of the
+          // chain.  No per-slot table look-up sits on the serial path of the half solve.
+          const int kc = 6 + (cj >= 0 ? cj : 0);
+          const int t1 = cj >= 0 ? M::ft1(kc) : 15, d1 = cj >= 0 ? M::fd1(kc) : 0, c1 = cj >= 0 ? M::fc1(kc) : 0;
+          const int t2 = (M::RSTEPS > 1 && cj >= 0) ? M::ft2(kc) : 15, d2 = (M::RSTEPS > 1 && cj >= 0) ? M::fd2(kc) : 0;
+          const int c2 = (M::RSTEPS > 1 && cj >= 0) ? M::fc2(kc) : 0;
           float rel_vel = 0.0f;
 #pragma unroll
           for (int t = 0; t < 6; ++t) { b[t] = W[t]; rel_vel += W[t] * S.u[t]; }
@@ -1609,7 +1655,8 @@ template <class M> struct Sim {
           for (int t = 0; t < M::MAXSUP - 6; ++t) {
             float v = 0.0f;
             if (t <= depth) {
-              const int a = chain_at(pack, t);
+              int a = t + (6 + t >= t1 ? c1 : 0);
+              if (M::RSTEPS > 1) a += 6 + t >= t2 ? c2 : 0;
               if (kind == 0) v = t == depth ? dir : 0.0f;
               else {
                 const float* sj = S.js[a];
@@ -1623,10 +1670,14 @@ template <class M> struct Sim {
 #pragma unroll
           for (int t = M::MAXSUP - 1; t >= 0; --t) {
             if (t < n) {
-              const int it = t < 6 ? t : 6 + chain_at(pack, t - 6);
+              int it = t, ro = (t * (t + 1)) / 2;
+              if (t >= 6) {
+                if (t >= t1) { it += c1; ro += d1; }
+                if (M::RSTEPS > 1 && t >= t2) { it += c2; ro += d2; }
+              }
               const float ci = b[t] * S.Ldi2[it];  // rows are unscaled: L[it][s] y = U[it][s] (b_t / d_it)
               b[t] *= S.Ldinv[it];
-              const float* Li = &S.L[M::rowoff(it)];
+              const float* Li = &S.L[ro];
 #pragma unroll
               for (int s2 = 0; s2 < t; ++s2) b[s2] -= Li[s2] * ci;
             }
@@ -1755,7 +1806,7 @@ template <class M> struct Sim {
   // DUAL: 0 = the row is one compact row (joint limits; contacts of a model without self-collision), 1 = always two
   // (loop closures), 2 = look at the row's MB_ROW_DUAL flag (contacts of a model with self-collision)
   template <int DUAL>
-  MB_HD static float pgs_single(Mem& S, const LaneConst& C, int ra, float lo, float hi, LaneVar<float>& z) {
+  MB_HD static float pgs_single(Mem& S, const LaneConst& C, int ra, float lo, float hi, LaneVar<float>& z, float& applied) {
     const unsigned supA = S.rc.r.r_mask[ra];
     LaneVar<float> ya, ta;
     MB_LANES(l)
@@ -1784,12 +1835,13 @@ template <class M> struct Sim {
       z[l] += ya[l] * dA;
       if (l == 0) S.rc.r.r_app[ra] = nA;
     MB_END
+    applied = nA;
     return dA * pA.den;  // deltaImpulse * (1 / jacDiagABInv)
   }
   // friction pair with btMultiBodyConstraintSolver::resolveConeFrictionConstraintRows' projection;
   // sin/cos(atan2(a, b)) are written as a/|(a,b)|, b/|(a,b)|.  A self-contact's pair continues in rows ra + 2, ra + 3.
   template <bool SELF>
-  MB_HD static float pgs_pair(Mem& S, const LaneConst& C, int ra, float cone, LaneVar<float>& z) {
+  MB_HD static float pgs_pair(Mem& S, const LaneConst& C, int ra, float cone, LaneVar<float>& z, bool& loaded) {
     const int rb = ra + 1;
     const unsigned supA = S.rc.r.r_mask[ra];  // both rows of a contact share the support
     LaneVar<float> ya, yb, ta, tb;
@@ -1829,6 +1881,7 @@ template <class M> struct Sim {
       z[l] += ya[l] * dA + yb[l] * dB;
       if (l == 0) { S.rc.r.r_app[ra] = nA; S.rc.r.r_app[rb] = nB; }
     MB_END
+    loaded = nA != 0.0f || nB != 0.0f;
     return dA * pA.den + dB * pB.den;
   }
 
@@ -1843,36 +1896,45 @@ template <class M> struct Sim {
                                       LaneVar<float>& z) {
     const int nnc = nlim + NLC / 2, n0 = nlim + NLC, S0 = n0 + 3 * nc, nct = nc + (SELF ? ncs : 0);
 #pragma unroll 1
+    // A contact that carries no normal impulse has a zero friction cone: with nothing applied on its friction pair
+    // either, the projection returns exactly zero for both rows (deltas 0, residual 0), so the visit is skipped with
+    // identical results.  Which contacts are loaded is kept in two bit masks (normal impulse / friction impulses non-zero,
+    // refreshed by the visits themselves), and the friction sweep walks the set bits: an idle contact costs nothing
+    // (round 2; until then every contact paid 13 instructions per iteration to find out -- Cassie's speculative
+    // hull-vertex contacts are mostly idle).
+    unsigned nmask = 0u, fmask = 0u;
+#pragma unroll 1
     for (int it = 0; it < P.iterations; ++it) {
-      float res2 = 0.0f;
+      float res2 = 0.0f, app;
 #pragma unroll 1
       for (int v = 0; v < nnc; ++v) {
         const int idx = (it & 1) ? v : nnc - 1 - v;
         float rr;
-        if (NLC == 0 || idx < nlim) rr = pgs_single<0>(S, C, idx, 0.0f, P.limit_max_impulse, z);
+        if (NLC == 0 || idx < nlim) rr = pgs_single<0>(S, C, idx, 0.0f, P.limit_max_impulse, z, app);
         else {
           const int ra = nlim + 2 * (idx - nlim);
           const float lim = S.rc.r.r_mu[ra];
-          rr = pgs_single<1>(S, C, ra, -lim, lim, z);
+          rr = pgs_single<1>(S, C, ra, -lim, lim, z, app);
         }
         res2 = fmaxf(res2, rr * rr);
       }
 #pragma unroll 1
       for (int k = 0; k < nct; ++k) {
         const int ra = (SELF && k >= nc) ? S0 + 2 * (k - nc) : n0 + k;
-        const float rr = pgs_single<(SELF ? 2 : 0)>(S, C, ra, 0.0f, 1e10f, z);
+        const float rr = pgs_single<(SELF ? 2 : 0)>(S, C, ra, 0.0f, 1e10f, z, app);
+        nmask = app != 0.0f ? nmask | (1u << k) : nmask & ~(1u << k);
         res2 = fmaxf(res2, rr * rr);
       }
 #pragma unroll 1
-      for (int k = 0; k < nct; ++k) {
+      for (unsigned m = nmask | fmask; m != 0u; m &= m - 1u) {
+        const int k = mb_ffs(m) - 1;
         const bool self = SELF && k >= nc;
         const int ra = self ? S0 + 2 * ncs + 4 * (k - nc) : n0 + nc + 2 * k;
         const int rn = self ? S0 + 2 * (k - nc) : n0 + k;
         const float cone = S.rc.r.r_mu[ra] * S.rc.r.r_app[rn];
-        // a contact that carries no normal impulse has a zero friction cone: with nothing applied yet the projection
-        // returns exactly zero for both rows (deltas 0, residual 0), so the visit can be skipped -- bit-identical
-        if (cone == 0.0f && S.rc.r.r_app[ra] == 0.0f && S.rc.r.r_app[ra + 1] == 0.0f) continue;
-        const float rr = pgs_pair<SELF>(S, C, ra, cone, z);
+        bool loaded;
+        const float rr = pgs_pair<SELF>(S, C, ra, cone, z, loaded);
+        fmask = loaded ? fmask | (1u << k) : fmask & ~(1u << k);
         res2 = fmaxf(res2, rr * rr);
       }
       if (res2 <= P.residual_threshold) break;
