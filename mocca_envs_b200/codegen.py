@@ -258,33 +258,25 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append("// Source model: reference mocca_envs/%s.\n" % t["source"])
     out.append("#pragma once\n#include \"../mb_tables.h\"\n\n")
     out.append(_iarr(P + "_jparent", r["jparent"]))
-    out.append(_iarr(P + "_jlevel", r["jlevel"]))
     out.append(_iarr(P + "_janc", r["janc"], "unsigned"))
     out.append(_iarr(P + "_jdepth", r["jdepth"]))
-    out.append("MB_TABLE unsigned long long %s_chainpack[%d] = {%s};\n"
-               % (P, len(r["chainpack"]), ", ".join("%dull" % v for v in r["chainpack"])))
     out.append(_iarr(P + "_rowoff", r["rowoff"]))
     out.append(_iarr(P + "_rowlen", r["rowlen"]))
     out.append(_iarr(P + "_rowmask", r["rowmask_rt"], "unsigned"))
     # uniform-indexed copies in constant memory (one LDC instead of a global load in the sequential loops)
     out.append(_iarr(P + "_c_rowoff", r["rowoff"]).replace("MB_TABLE", "MB_CTABLE"))
     out.append(_iarr(P + "_c_rowlen", r["rowlen"]).replace("MB_TABLE", "MB_CTABLE"))
-    out.append(_iarr(P + "_c_rowmask", r["rowmask_rt"], "unsigned").replace("MB_TABLE", "MB_CTABLE"))
     # facoff[k][t]: offset of the compact row that entry t of row k updates (its column index' own row)
     maxoff = r["maxsup"] - 1
     fac = []
     for k in range(r["nu"]):
         cols = sorted(j for j in range(k) if (r["rowmask_rt"][k] >> j) & 1)
         fac.append([r["rowoff"][c] for c in cols] + [0] * (maxoff - len(cols)))
-    out.append("MB_TABLE int %s_facoff[%d][%d] = {\n  %s};\n" % (
-        P, r["nu"], maxoff, ",\n  ".join("{" + ", ".join(str(v) for v in row) + "}" for row in fac)))
     # fcol[k][t]: generalised coordinate whose column sits in slot t of compact row k
     fcol = []
     for k in range(r["nu"]):
         cols = sorted(j for j in range(k) if (r["rowmask_rt"][k] >> j) & 1)
         fcol.append(cols + [0] * (maxoff - len(cols)))
-    out.append("MB_TABLE int %s_fcol[%d][%d] = {\n  %s};\n" % (
-        P, r["nu"], maxoff, ",\n  ".join("{" + ", ".join(str(v) for v in row) + "}" for row in fcol)))
     # Affine form of the two tables (round 2): the rows along a chain are stored like a packed dense triangle, so for the
     # pair (t, s) with packed index p = t (t + 1) / 2 + s the update lands at  p + delta_k(t)  and slot t belongs to column
     # t + cdelta_k(t), where both deltas are piecewise constant in t with one step per branch point the chain passes
@@ -343,18 +335,6 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append(_iarr(P + "_cdepth", cdepth))
     out.append(_iarr(P + "_canc0", anc0, "unsigned"))
     out.append(_iarr(P + "_canc1", anc1, "unsigned"))
-    out.append(_farr(P + "_joff", r["joff"]))
-    out.append(_farr(P + "_jrot", [np.asarray(m).reshape(9) for m in r["jrot"]]))
-    out.append(_farr(P + "_jaxis", r["jaxis"]))
-    # fast paths: coordinate-aligned joint axes (index, sign; -1 = generic) and identity zero-pose rotations
-    jaxk, jsgn, jident = [], [], []
-    for ax, R0 in zip(r["jaxis"], r["jrot"]):
-        ax = np.asarray(ax)
-        k = int(np.argmax(np.abs(ax)))
-        aligned = abs(abs(ax[k]) - 1.0) < 1e-12 and np.abs(np.delete(ax, k)).max() < 1e-12
-        jaxk.append(k if aligned else -1)
-        jsgn.append(float(np.sign(ax[k])) if aligned else 0.0)
-        jident.append(1 if np.abs(np.asarray(R0) - np.eye(3)).max() < 1e-12 else 0)
     # Chain-walk kinematics (round 2): lane 3 * ch + c carries row c of the rotation (and component c of every vector)
     # down the ch-th root-to-leaf chain in registers; kin[step][ch] = the joint met at that step, its pivot offset in
     # the parent frame, its axis, and whether this chain is the one that stores the joint (shared prefixes are walked
@@ -384,15 +364,6 @@ def emit_header(t: dict, prefix: str) -> str:
         "{" + ", ".join("{%d, {%s}, {%s}, %d}" % (j, ", ".join(_f(v) for v in off), ", ".join(_f(v) for v in ax), fl)
                         for j, off, ax, fl in row) + "}" for row in krec)))
     r["nch"] = len(kchains)
-    # joints of each kinematic level (component-parallel kinematics: lane = 3 * slot + component)
-    lv = [[j for j in range(r["nj"]) if r["jlevel"][j] == L] for L in range(r["nlevel"])]
-    maxslot = 10
-    assert max(len(x) for x in lv) <= maxslot
-    out.append("MB_TABLE int %s_lvjoint[%d][%d] = {\n  %s};\n" % (
-        P, r["nlevel"], maxslot, ",\n  ".join("{" + ", ".join(str(v) for v in (x + [-1] * (maxslot - len(x)))) + "}" for x in lv)))
-    out.append(_iarr(P + "_jaxk", jaxk))
-    out.append(_farr(P + "_jsgn", jsgn))
-    out.append(_iarr(P + "_jident", jident))
     # float32 limits exactly as robots.py:126-130 builds them (weight = f32(upper - lower), bias = f32(lower))
     out.append(_farr(P + "_lower", r["lower"]))
     out.append(_farr(P + "_upper", r["upper"]))
@@ -403,7 +374,6 @@ def emit_header(t: dict, prefix: str) -> str:
     out.append(_iarr(P + "_bstart", r["bstart"]))
     out.append(_iarr(P + "_bend", r["bend"]))
     out.append(_iarr(P + "_bowner", [b["owner"] for b in r["bodies"]]))
-    out.append(_iarr(P + "_c_bparent", [max(v, 0) for v in r["bparent"]]).replace("MB_TABLE", "MB_CTABLE"))
     out.append(_farr(P + "_bcom", [b["com"] for b in r["bodies"]]))
     out.append(_farr(P + "_bmass", [b["mass"] for b in r["bodies"]]))
     out.append(_farr(P + "_binertia", [b["inertia"] for b in r["bodies"]]))
@@ -466,21 +436,16 @@ def emit_header(t: dict, prefix: str) -> str:
                " ".join("i == %d ? %du :" % (i, m) for i, m in enumerate(rowmask)) + " 0u;\n  }\n")
     out.append("  enum { NJ = %d, NB = %d, NU = %d, NPT = %d, NLEVEL = %d, NFEET = %d, NMIRROR = %d, NNEG = %d,\n"
                "         LSIZE = %d, MAXSUP = %d, NXBOX = %d, NLOOP = %d, NORDERED = %d, NPD = %d, NPOWERED = %d, NSELF = %d,\n"
-               "         ALL_ALIGNED = %d, ALL_IDENT = %d,  // every joint axis is a coordinate axis / every zero-pose rotation is 1\n"
                "         NHULL = %d, SELF_HULLS = %d };  // the self-collision pairs are mesh-hull pairs (hull-vs-hull narrow phase)\n"
                % (r["nj"], r["nb"], r["nu"], r["npt"], r["nlevel"], r["nfeet"], len(r["right"]), len(r["neg"]),
                   r["lsize"], r["maxsup"], len(r["xboxes"]), len(r["p2p"]), len(ex.get("ordered", [])),
                   len(ex.get("pd_dof", [])), ex.get("npowered", 0), len(sp),
-                  int(all(k >= 0 for k in jaxk)), int(all(jident)), len(r["hulls"]), int(bool(r["hulls"]) and bool(sp))))
+                  len(r["hulls"]), int(bool(r["hulls"]) and bool(sp))))
     out.append("  MB_HD static float hull_margin() { return %s; }\n" % _f(r["hull_margin"]))
     out.append("  MB_HD static int hown(int i) { return %s_hown[i]; }\n" % P)
     out.append("  MB_HD static float hcen(int i, int k) { return %s_hcen[i][k]; }\n" % P)
     out.append("  MB_HD static float hseg(int i, int k) { return %s_hseg[i][k]; }\n" % P)
     out.append("  MB_HD static float hv(int h, int v, int k) { return %s_hv[h][v][k]; }\n" % P)
-    out.append("  MB_HD static unsigned long long chainpack(int j) { return %s_chainpack[j]; }\n" % P)
-    out.append("  MB_HD static int facoff(int k, int t) { return %s_facoff[k][t]; }\n" % P)
-    out.append("  MB_HD static int fcol(int k, int t) { return %s_fcol[k][t]; }\n" % P)
-    out.append("  MB_HD static int lvjoint(int lev, int slot) { return %s_lvjoint[lev][slot]; }\n" % P)
     out.append("  enum { NCH = %d };  // root-to-leaf chains of the kinematics walk (kin[step][chain], chain NCH = idle)\n" % r["nch"])
     out.append("  MB_HD static const MbKinRec* kin(int step, int ch) { return &%s_kin[step][ch]; }\n" % P)
     out.append("  enum { FSTEPS = %d };  // steps of the affine factorisation addressing (c_ft / c_fd / c_fc)\n" % r["fsteps"])
@@ -503,13 +468,10 @@ def emit_header(t: dict, prefix: str) -> str:
         out.append("  MB_HD static int c_ft2(int) { return 15; }\n  MB_HD static int c_fd2(int) { return 0; }\n"
                    "  MB_HD static int c_fc2(int) { return 0; }\n")
     out.append("  MB_HD static int c_rowoff(int i) { return %s_c_rowoff[i]; }\n" % P)
-    out.append("  MB_HD static int c_bparent(int i) { return %s_c_bparent[i]; }\n" % P)
     out.append("  MB_HD static int c_rowlen(int i) { return %s_c_rowlen[i]; }\n" % P)
-    out.append("  MB_HD static unsigned c_rowmask(int i) { return %s_c_rowmask[i]; }\n" % P)
-    for fld, ctype in [("jparent", "int"), ("jlevel", "int"), ("janc", "unsigned"), ("bstart", "int"), ("bend", "int"),
+    for fld, ctype in [("jparent", "int"), ("janc", "unsigned"), ("bstart", "int"), ("bend", "int"),
                        ("jdepth", "int"), ("rowoff", "int"), ("rowlen", "int"), ("rowmask", "unsigned"),
                        ("cdepth", "int"), ("canc0", "unsigned"), ("canc1", "unsigned"),
-                       ("jaxk", "int"), ("jident", "int"),
                        ("bowner", "int"), ("powner", "int"), ("pfoot", "int"), ("pid", "int"), ("foot_body", "int"),
                        ("palm_body", "int"), ("xowner", "int"), ("xfoot", "int"), ("xpid", "int"),
                        ("lc_owner", "int"), ("ordered", "int"), ("pd_dof", "int"), ("pd_ordered", "int"),
@@ -517,9 +479,9 @@ def emit_header(t: dict, prefix: str) -> str:
         out.append("  MB_HD static %s %s(int i) { return %s_%s[i]; }\n" % (ctype, fld, P, fld))
     out.append("  MB_HD static double base_angles(int i) { return %s_base_angles[i]; }\n" % P)
     for fld in ["lower", "upper", "weight", "gain", "damping", "armature", "bmass", "pradius", "pfriction", "pthresh",
-                "jsgn", "xfriction", "xthresh", "lc_maximp", "pd_kp", "pd_kd", "sp_thresh", "sp_mu", "sp_reach"]:
+                "xfriction", "xthresh", "lc_maximp", "pd_kp", "pd_kd", "sp_thresh", "sp_mu", "sp_reach"]:
         out.append("  MB_HD static float %s(int i) { return %s_%s[i]; }\n" % (fld, P, fld))
-    for fld in ["joff", "jrot", "jaxis", "bcom", "binertia", "ppos", "xpos", "xrot", "xhalf", "lc_pos"]:
+    for fld in ["bcom", "binertia", "ppos", "xpos", "xrot", "xhalf", "lc_pos"]:
         out.append("  MB_HD static float %s(int i, int k) { return %s_%s[i][k]; }\n" % (fld, P, fld))
     out.append("  MB_HD static float base_x() { return %s; }\n" % _f(r["base_position"][0]))
     out.append("  MB_HD static float base_y() { return %s; }\n" % _f(r["base_position"][1]))

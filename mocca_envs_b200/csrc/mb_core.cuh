@@ -200,7 +200,6 @@ MB_HD int mb_foot(int v) { return (int)(signed char)(v & 255); }
 MB_HD int mb_pid(int v) { return v >> 8; }
 #define MB_NWARM 384 /* warm-start slots per env: candidate ids 2 * geom + end, geoms <= 192 */
 MB_HD constexpr int tri(int i, int j) { return (i * (i + 1)) / 2 + j; }  // packed lower-triangular index, j <= i
-MB_HD int chain_at(unsigned long long pack, int t) { return (int)((pack >> (5 * t)) & 31ull); }
 // 1 / sqrt(x) for a pivot (positive, normal): the bare MUFU.RSQ -- rsqrtf() wraps it in a denormal-range rescue (a
 // compare and two predicated multiplies on the critical path of every pivot)
 MB_HD float mb_rsqrt_pivot(float x) {
@@ -629,10 +628,10 @@ template <class M> struct Sim {
           float* Lr = &S.L[M::rowoff(row)];
 #pragma unroll
           for (int k = 0; k < 6; ++k) Lr[k] = G[k];
-          const unsigned long long pack = M::chainpack(l);
           const int depth = M::jdepth(l);
-          for (int t = 0; t <= depth; ++t) {
-            const float* si = S.js[chain_at(pack, t)];
+          const int t1 = M::ft1(row), c1 = M::fc1(row), t2 = M::RSTEPS > 1 ? M::ft2(row) : 15, c2 = M::RSTEPS > 1 ? M::fc2(row) : 0;
+          for (int t = 0; t <= depth; ++t) {  // (chain joint t = t + the affine steps of row 6 + l, see setup_rows())
+            const float* si = S.js[t + (6 + t >= t1 ? c1 : 0) + (M::RSTEPS > 1 && 6 + t >= t2 ? c2 : 0)];
             float v = 0.0f;
 #pragma unroll
             for (int k = 0; k < 6; ++k) v += si[k] * G[k];
@@ -725,11 +724,12 @@ template <class M> struct Sim {
     char* L0 = (char*)&S.L[0];
     MB_LANES(l)
       if (l == 31) { S.Ldinv[K] = inv; S.Ldi2[K] = invd; }
-      if (RHS && nk > 0 && l < nk) {
+      if (RHS && nk > 0) {  // (branch-free like the rounds: lanes behind the row compute on in-bounds garbage)
         int col = l;
         if (t1 < nk) col += l >= t1 ? c1 : 0;
         if (t2 < nk) col += l >= t2 ? c2 : 0;
-        S.rhs[col] -= *(const float*)(Lk + 4 * l) * ck;
+        const float v = S.rhs[col] - *(const float*)(Lk + 4 * l) * ck;
+        if (l < nk) S.rhs[col] = v;
       }
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
