@@ -1347,19 +1347,12 @@ template <class M> struct CassieEnv {
     B_::load_state(S, state);
     // PD targets, one lane per PD joint: base angle + residual action for the 10 powered joints, 0 for the two
     // knee_to_shin "springs" (env_cassie.py:434-443)
-    LaneVar<float> target, jvel, kp, kd, lim, jpos0;
-    LaneVar<int> pdo, pdd, badact;
+    // (the PD gains, targets and index maps are re-read from the tables in every substep instead of living in eight
+    // registers across the 50-substep loop: the Cassie kernel is register-starved in its constraint solver, round 2)
+    LaneVar<float> jvel, jpos0;
+    LaneVar<int> badact;
     MB_LANES(l)
-      target[l] = 0.0f; kp[l] = 0.0f; kd[l] = 0.0f; lim[l] = 0.0f; pdo[l] = 0; pdd[l] = 0; badact[l] = 0;
-      if (l < M::NPD) {
-        pdo[l] = M::pd_ordered(l); pdd[l] = M::pd_dof(l);
-        kp[l] = M::pd_kp(l); kd[l] = M::pd_kd(l); lim[l] = M::gain(pdd[l]);
-        if (l < M::NPOWERED) {
-          float a = act[l];
-          if (!mb_finite(a)) { a = 0.0f; badact[l] = 1; }
-          target[l] = (float)M::base_angles(pdd[l]) + a;
-        }
-      }
+      badact[l] = l < M::NPOWERED && !mb_finite(act[l]);
       float nrm;
       jpos0[l] = l < NO ? rad_angle(S, l, &nrm) : 0.0f;
       jvel[l] = l < NO ? rec[EC_JVEL + l] : 0.0f;  // lane k < 14 holds ordered joint k
@@ -1381,11 +1374,18 @@ template <class M> struct CassieEnv {
       MB_END
       MB_LANES(l)
         if (l < M::NPD) {
+          const int pdo = M::pd_ordered(l), pdd = M::pd_dof(l);
+          float target = 0.0f;
+          if (l < M::NPOWERED) {
+            const float a = act[l];
+            target = (float)M::base_angles(pdd) + (mb_finite(a) ? a : 0.0f);
+          }
+          const float lim = M::gain(pdd);
           float nrm;
-          const float q = rad_angle(S, pdo[l], &nrm);
-          const float verr = fminf(fmaxf(0.0f - S.rc.scratch[pdo[l]], -5.0f), 5.0f);  // env_cassie.py:380-393
-          const float t = kp[l] * (target[l] - q) + kd[l] * verr;
-          S.tau[pdd[l]] += fminf(fmaxf(t, -lim[l]), lim[l]);                       // apply_action clip (:225-230)
+          const float q = rad_angle(S, pdo, &nrm);
+          const float verr = fminf(fmaxf(0.0f - S.rc.scratch[pdo], -5.0f), 5.0f);  // env_cassie.py:380-393
+          const float t = M::pd_kp(l) * (target - q) + M::pd_kd(l) * verr;
+          S.tau[pdd] += fminf(fmaxf(t, -lim), lim);                                // apply_action clip (:225-230)
         }
       MB_END
       rows += S_::template substep<0>(S, P, C, &nc, &overflow, it);
