@@ -367,6 +367,25 @@ template <class M> MB_HD float mb_Lget(const float* L, int i, int j) {
   return ((sup >> j) & 1u) ? L[M::rowoff(i) + mb_popc(sup & ((1u << j) - 1u))] : 0.0f;
 }
 
+// (t, s) of the packed lower-triangle entries p = l, l + 32, l + 64, as byte offsets 4 t / 4 s, one byte per round
+struct MbPairTab {
+  unsigned t4[32], s4[32];
+  constexpr MbPairTab() : t4(), s4() {
+    for (int l = 0; l < 32; ++l) {
+      unsigned pt = 0u, ps = 0u;
+      for (int r = 0; r < 3; ++r) {
+        const int p = l + 32 * r;
+        int t = 0;
+        while ((t + 1) * (t + 2) / 2 <= p) ++t;
+        pt |= (unsigned)(4 * t) << (8 * r);
+        ps |= (unsigned)(4 * (p - t * (t + 1) / 2)) << (8 * r);
+      }
+      t4[l] = pt; s4[l] = ps;
+    }
+  }
+};
+MB_TABLE MbPairTab mb_pairtab = MbPairTab();
+
 // ------------------------------------------------------------------------------------------------ simulator
 template <class M> struct Sim {
   typedef WarpMem<M> Mem;
@@ -377,37 +396,18 @@ template <class M> struct Sim {
 #endif
 
   // ---- lane constants: computed once per kernel, live in registers -------------------------------------------
+  // Only what the constraint solver's inner loop reads per row visit stays in registers for the whole kernel; the
+  // factorisation's pair table and the forward substitution's tree tables are (re)loaded where they are used -- the
+  // Cassie and Monkey3D kernels are register-starved in the solver (round 2).
   struct LaneConst {
     LaneVar<int> tl;        // |support(l)| = slot of column l in every descendant's compact row = rowlen(l) - 1
-    LaneVar<int> off;       // rowoff(l)
-    LaneVar<unsigned> sup;  // rowmask(l)
-    LaneVar<unsigned> bit;       // 1 << l: "is coordinate l in the row's support" is one LOP3 with predicate output
-    LaneVar<unsigned> pt4, ps4;  // 4 t and 4 s of the lower-triangle entries p = l, l + 32, l + 64 (one byte per round)
-    LaneVar<int> dep;       // tree depth of coordinate l (-1 base block, 99 unused lane)
-    LaneVar<unsigned> anc0, anc1;  // coordinate index of l's ancestor at each level, 5 bits per level
+    LaneVar<unsigned> bit;  // 1 << l: "is coordinate l in the row's support" is one LOP3 with predicate output
   };
   MB_HD static void init_lane_const(LaneConst& C) {
     MB_LANES(l)
       C.bit[l] = 1u << l;
       C.tl[l] = l < NU ? M::rowlen(l) - 1 : 0;
-      C.off[l] = l < NU ? M::rowoff(l) : 0;
-      C.sup[l] = l < NU ? M::rowmask(l) : 0u;
-      C.dep[l] = l < NU ? M::cdepth(l) : 99;
-      C.anc0[l] = l < NU ? M::canc0(l) : 0u;
-      C.anc1[l] = l < NU ? M::canc1(l) : 0u;
-      unsigned pt = 0u, ps = 0u;
-      for (int r = 0; r < 3; ++r) {
-        const int pidx = l + 32 * r;
-        int t = (int)((sqrtf(8.0f * (float)pidx + 1.0f) - 1.0f) * 0.5f);
-        if ((t + 1) * (t + 2) / 2 <= pidx) ++t;
-        if (t * (t + 1) / 2 > pidx) --t;
-        const int s2 = pidx - t * (t + 1) / 2;
-        pt |= (unsigned)(4 * t) << (8 * r);
-        ps |= (unsigned)(4 * s2) << (8 * r);
-      }
-      C.pt4[l] = pt;
-      C.ps4[l] = ps;
-    MB_END
+    MB_END_REG
   }
 
   // ---- A. kinematics (+ velocities / bias accelerations when with_vel) --------------------------------------
@@ -697,7 +697,7 @@ template <class M> struct Sim {
         for (int r = 0; r < 3; ++r) {
           if (32 * r < npairs) {  // uniform: whole rounds are skipped for short rows
             const int p = l + 32 * r;
-            const unsigned t4 = mb_byte(C.pt4[l], r), s4 = mb_byte(C.ps4[l], r);
+            const unsigned t4 = mb_byte(mb_pairtab.t4[l], r), s4 = mb_byte(mb_pairtab.s4[l], r);
             int dst4 = 4 * p + (p >= p1 ? d14 : 0);
             if (M::FSTEPS > 1) dst4 += p >= p2 ? d24 : 0;
             float* dst = (float*)(L0 + dst4);
@@ -735,7 +735,7 @@ template <class M> struct Sim {
       for (int r = 0; r < 3; ++r) {
         if (32 * r < npairs) {
           const int p = l + 32 * r;
-          const unsigned t4 = mb_byte(C.pt4[l], r), s4 = mb_byte(C.ps4[l], r);
+          const unsigned t4 = mb_byte(mb_pairtab.t4[l], r), s4 = mb_byte(mb_pairtab.s4[l], r);
           int dst4 = 4 * p;
           if (p1 < npairs) dst4 += p >= p1 ? d14 : 0;
           if (p2 < npairs) dst4 += p >= p2 ? d24 : 0;
@@ -759,16 +759,22 @@ template <class M> struct Sim {
   // (one indexed shuffle) and subtracts U[l][ancestor], which sits at slot 6 + level of the lane's own compact row.
   template <bool PRESCALED> MB_HD static void solve_L(Mem& S, const LaneConst& C, LaneVar<float>& x) {
     LaneVar<float> di2;
+    LaneVar<int> off, dep;
+    LaneVar<unsigned> anc0, anc1;
     MB_LANES(l)
       di2[l] = S.Ldi2[l];
-      if (!PRESCALED && l < NU) x[l] *= S.L[C.off[l] + C.tl[l]] * S.Ldinv[l];
+      off[l] = l < NU ? M::rowoff(l) : 0;
+      dep[l] = l < NU ? M::cdepth(l) : 99;   // tree depth of coordinate l (-1 base block, 99 unused lane)
+      anc0[l] = l < NU ? M::canc0(l) : 0u;   // coordinate index of l's ancestor at each level, 5 bits per level
+      anc1[l] = l < NU ? M::canc1(l) : 0u;
+      if (!PRESCALED && l < NU) x[l] *= S.L[off[l] + C.tl[l]] * S.Ldinv[l];
     MB_END_REG
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const float xi = warp_bcast(x, i) * S.Ldi2[i];
       MB_LANES(l)
         if (l == i) x[l] = xi;
-        else if (l > i && l < NU) x[l] -= S.L[C.off[l] + i] * xi;
+        else if (l > i && l < NU) x[l] -= S.L[off[l] + i] * xi;
       MB_END_REG
     }
 #pragma unroll
@@ -776,12 +782,12 @@ template <class M> struct Sim {
       LaneVar<int> src;
       LaneVar<float> xa;
       MB_LANES(l)
-        if (C.dep[l] == d) x[l] *= di2[l];
-        src[l] = (int)(((d < 6 ? C.anc0[l] >> (5 * d) : C.anc1[l] >> (5 * (d - 6)))) & 31u);
+        if (dep[l] == d) x[l] *= di2[l];
+        src[l] = (int)(((d < 6 ? anc0[l] >> (5 * d) : anc1[l] >> (5 * (d - 6)))) & 31u);
       MB_END_REG
       warp_gather(x, src, xa);
       MB_LANES(l)
-        if (C.dep[l] > d && C.dep[l] < 99) x[l] -= S.L[C.off[l] + 6 + d] * xa[l];
+        if (dep[l] > d && dep[l] < 99) x[l] -= S.L[off[l] + 6 + d] * xa[l];
       MB_END_REG
     }
   }
