@@ -22,7 +22,7 @@ METRIC = "env-steps/sec (Walker3DCustomEnv-v0, 16384 envs/GPU, random actions)"
 
 
 # DRAM bytes per launch of k_step_walker3d_custom at 16384 envs from the last committed ncu --set full capture
-NCU_TRAFFIC = {"bytes": 8.05e6, "source": "ncu --set full capture profiles/r1v_step_kernel_raw.csv (8.05 MB read, < 0.01 MB "
+NCU_TRAFFIC = {"bytes": 8.06e6, "source": "ncu --set full capture profiles/r3z_step_kernel_raw.csv (8.06 MB read, < 0.01 MB "
                                           "written per launch), not measured by this run"}
 
 ENV_NAMES = {"custom": "Walker3DCustomEnv", "stepper": "Walker3DStepperEnv", "monkey": "Monkey3DCustomEnv",
