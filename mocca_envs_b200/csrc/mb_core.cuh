@@ -65,6 +65,7 @@ MB_HD void warp_gather(const LaneVar<float>& x, const LaneVar<int>& src, LaneVar
 MB_HD unsigned warp_ballot(const LaneVar<int>& p) { return __ballot_sync(0xffffffffu, p.v != 0); }
 MB_HD int mb_popc(unsigned x) { return __popc(x); }
 MB_HD int mb_ffs(unsigned x) { return __ffs((int)x); }  // 1-based index of the lowest set bit, 0 for x = 0
+MB_HD int mb_nth_bit(unsigned x, int n) { return (int)__fns(x, 0u, n + 1); }  // position of the n-th (0-based) set bit
 // lane holding the largest value (the lowest such lane on ties)
 MB_HD int warp_argmax(const LaneVar<float>& x) {
   float v = x.v;
@@ -112,6 +113,10 @@ inline unsigned warp_ballot(const LaneVar<int>& p) {
 }
 inline int mb_popc(unsigned x) { return __builtin_popcount(x); }
 inline int mb_ffs(unsigned x) { return __builtin_ffs((int)x); }
+inline int mb_nth_bit(unsigned x, int n) {
+  for (int i = 0; i < n; ++i) x &= x - 1u;
+  return __builtin_ffs((int)x) - 1;
+}
 inline int warp_argmax(const LaneVar<float>& x) {
   int best = 0;
   for (int l = 1; l < 32; ++l)
@@ -304,6 +309,12 @@ template <class M> struct WarpMem {
     float box[MB_MAXBOX][16];
     // static bars (MonkeyBar, bullet_objects.py:148-187): centre[3], unit axis[3], half length, radius
     float bar[MB_MAXBAR][8];
+    // behind the bars: the robot's own box geoms (Monkey3D fingers / hands) in world axes, staged once per substep by
+    // collide(): centre[3] relative to the base COM, axes R[9], half[3], bounding radius
+    struct {
+      float bars_[MB_MAXBAR][8];
+      float xbox[(M::NXBOX > 0 ? M::NXBOX : 1)][16];
+    } xb;
     float scratch[64];
   } rc;
   int nbox;
@@ -896,31 +907,7 @@ template <class M> struct Sim {
 
   // robot box geom (Monkey3D fingers / hands) vs bar.  Bullet runs GJK/EPA (one point per frame); restated as the
   // deepest of 5 spheres of the bar's radius sampled 3 cm apart along its axis around the point nearest to the box
-  // centre (same restatement as the oracle's box_bar)
-  MB_HD static bool box_bar(const float* bx, const float* bc, const float* bar, float thresh, float* pa, float* n,
-                            float* dist) {
-    const float d[3] = {bx[0] - bc[0], bx[1] - bc[1], bx[2] - bc[2]};
-    const float t0 = d[0] * bar[3] + d[1] * bar[4] + d[2] * bar[5];
-    bool found = false;
-    float best = 1e30f;
-#pragma unroll 1
-    for (int kk = 0; kk < 5; ++kk) {
-      // visiting order 0, -1, +1, -2, +2; an outer sample wins only if deeper by more than 1e-5 m, so a bar lying
-      // parallel to a box face (all samples equally deep) yields the central point
-      const int k = kk == 0 ? 0 : ((kk & 1) ? -((kk + 1) >> 1) : (kk >> 1));
-      const float t = fminf(fmaxf(t0 + 0.03f * k, -bar[6]), bar[6]);
-      const float q[3] = {bc[0] + t * bar[3], bc[1] + t * bar[4], bc[2] + t * bar[5]};
-      float ps[3], ns[3], ds;
-      if (sphere_box(q, bar[7], bx, thresh, ps, ns, &ds) && ds < best - 1e-5f) {
-        best = ds;
-        found = true;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { n[i] = -ns[i]; pa[i] = ps[i] - ds * ns[i]; }
-      }
-    }
-    *dist = best;
-    return found;
-  }
+  // centre (same restatement as the oracle's box_bar) -- evaluated five lanes per box inside collide().
 
   // closest points of two segments (Ericson, Real-Time Collision Detection 5.1.9; same restatement as the oracle's
   // seg_seg): Bullet's sphere-sphere, capsuleCapsuleDistance and GJK on two capsules all reduce to this
@@ -1037,6 +1024,7 @@ template <class M> struct Sim {
       cnt += add;
     }
     if (cnt > 0) ns += collide_self_narrow(S, cnt, nc + ns, erp_contact);
+    MB_WARP_SYNC();  // the candidate points are dead from here on: bodies() overwrites them (union u2)
     return ns;
   }
 
@@ -1121,15 +1109,21 @@ template <class M> struct Sim {
         v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
       }
     }
-    // compact the simplex to the supporting face
-    int k = 0;
-    for (int i = 0; i < n; ++i)
-      if ((bmask >> i) & 1) {
-        for (int c = 0; c < 3; ++c) { g.w[3 * k + c] = g.w[3 * i + c]; g.a[3 * k + c] = g.a[3 * i + c]; }
-        g.lam[k] = bl[k];
-        ++k;
+    // compact the simplex to the supporting face: one lane writes (the enumeration above ran redundantly on every lane;
+    // 32 lanes storing the same words is what compute-sanitizer racecheck reports as intra-warp hazards)
+    MB_WARP_SYNC();
+    MB_LANES(l)
+      if (l == 0) {
+        int k = 0;
+        for (int i = 0; i < n; ++i)
+          if ((bmask >> i) & 1) {
+            for (int c = 0; c < 3; ++c) { g.w[3 * k + c] = g.w[3 * i + c]; g.a[3 * k + c] = g.a[3 * i + c]; }
+            g.lam[k] = bl[k];
+            ++k;
+          }
       }
-    return k;
+    MB_END
+    return mb_popc((unsigned)bmask & ((1u << n) - 1u));
   }
   // narrow phase of one hull pair; appends a contact at slot `at` (returns 1) or nothing (0)
   MB_HD static int hull_pair(Mem& S, int pr, int at, float erp) {
@@ -1417,6 +1411,26 @@ template <class M> struct Sim {
       }
     }
     if (OBST & MB_OBST_BARS) {
+      if (M::NXBOX > 0) {  // the robot's box geoms in world axes, once per substep (they do not depend on the bar)
+        MB_LANES(l)
+          if (l < M::NXBOX) {
+            const int o = M::xowner(l);
+            const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
+            float bx[16];
+            const float loc[3] = {M::xpos(l, 0), M::xpos(l, 1), M::xpos(l, 2)};
+            mb_matvec(R, loc, bx);
+            if (o >= 0) { bx[0] += S.w.k.jp[o][0]; bx[1] += S.w.k.jp[o][1]; bx[2] += S.w.k.jp[o][2]; }
+            float Rx[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rx[i] = M::xrot(l, i);
+            mb_matmul(R, Rx, bx + 3);
+            bx[12] = M::xhalf(l, 0); bx[13] = M::xhalf(l, 1); bx[14] = M::xhalf(l, 2);
+            bx[15] = sqrtf(bx[12] * bx[12] + bx[13] * bx[13] + bx[14] * bx[14]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) S.rc.xb.xbox[l][i] = bx[i];
+          }
+        MB_END
+      }
 #pragma unroll 1
       for (int ob = 0; ob < S.nbar; ++ob) {
         const float* bar = S.rc.bar[ob];
@@ -1464,49 +1478,91 @@ template <class M> struct Sim {
           nc += mb_popc(mask);
         }
         if (M::NXBOX > 0) {
-          LaneVar<int> hit;
-          LaneVar<float> px, py, pz, nx, ny, nz, dd;
+          // Robot box geoms vs this bar (box_bar: the deepest of five bar-radius spheres sampled along the axis).  A
+          // conservative reach test per box first -- no sample can touch a box whose centre is farther from the axis
+          // segment than its bounding radius + bar radius + threshold -- and a uniform skip when no box is near (the
+          // bars the monkey is not holding); the (box, sample) pairs of the near boxes are then flattened over the lanes,
+          // five neighbouring lanes per box, and the sequential "deeper by 1e-5 wins" choice is replayed from the five
+          // distances (round 2: 8 live lanes walking 5 samples in turn were 16 % of the Monkey3D kernel).
+          LaneVar<int> near;
           MB_LANES(l)
-            hit[l] = 0;
+            near[l] = 0;
             if (l < M::NXBOX) {
-              const int o = M::xowner(l);
-              const float* R = o < 0 ? S.Rb : S.w.k.jR[o];
-              float bx[16];
-              const float loc[3] = {M::xpos(l, 0), M::xpos(l, 1), M::xpos(l, 2)};
-              mb_matvec(R, loc, bx);
-              if (o >= 0) { bx[0] += S.w.k.jp[o][0]; bx[1] += S.w.k.jp[o][1]; bx[2] += S.w.k.jp[o][2]; }
-              float Rx[9];
-#pragma unroll
-              for (int i = 0; i < 9; ++i) Rx[i] = M::xrot(l, i);
-              mb_matmul(R, Rx, bx + 3);
-              bx[12] = M::xhalf(l, 0); bx[13] = M::xhalf(l, 1); bx[14] = M::xhalf(l, 2);
-              float pa[3], n[3], dist;
-              if (box_bar(bx, bc, bar, M::xthresh(l), pa, n, &dist)) {
-                hit[l] = 1;
-                px[l] = pa[0]; py[l] = pa[1]; pz[l] = pa[2]; dd[l] = dist;
-                nx[l] = n[0]; ny[l] = n[1]; nz[l] = n[2];
-              }
+              const float* bx = S.rc.xb.xbox[l];
+              const float d[3] = {bx[0] - bc[0], bx[1] - bc[1], bx[2] - bc[2]};
+              const float t = fminf(fmaxf(d[0] * bar[3] + d[1] * bar[4] + d[2] * bar[5], -bar[6]), bar[6]);
+              const float e[3] = {d[0] - t * bar[3], d[1] - t * bar[4], d[2] - t * bar[5]};
+              const float reach = bx[15] + bar[7] + M::xthresh(l) + 1e-4f;
+              near[l] = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] < reach * reach;
             }
-          MB_END
-          const unsigned mask = warp_ballot(hit);
-          if (mask != 0u) {
+          MB_END_REG
+          const unsigned nearmask = warp_ballot(near);
+          const int nnear = mb_popc(nearmask);
+#pragma unroll 1
+          for (int base = 0; base < nnear; base += 6) {
+            LaneVar<int> hit, boxl, src0;
+            LaneVar<float> px, py, pz, nx, ny, nz, dd, dse, e0, e1, e2, e3, e4;
             MB_LANES(l)
-              if (hit[l]) {
-                const int k = nc + mb_popc(mask & ((1u << l) - 1u));
-                if (k < MB_MAXC) {
-                  S.cP[k][0] = px[l]; S.cP[k][1] = py[l]; S.cP[k][2] = pz[l];
-                  S.cn[k][0] = nx[l]; S.cn[k][1] = ny[l]; S.cn[k][2] = nz[l];
-                  S.cdist[k] = dd[l];
-                  S.cmu[k] = M::xfriction(l) * P.bar_friction;
-                  S.cerp[k] = P.erp_contact;
-                  S.ccfm[k] = 0.0f;
-                  S.clink[k] = M::xowner(l);
-                  S.cfoot[k] = mb_pack_foot(M::xfoot(l), M::xpid(l));
-                  S.cpartner[k] = 20 + ob;
+              const int slot = l / 5, kk = l - 5 * slot;
+              hit[l] = 0; dse[l] = 1e30f; boxl[l] = 0; src0[l] = (5 * slot) & 31;
+              if (slot < 6 && base + slot < nnear) {
+                const int bxi = mb_nth_bit(nearmask, base + slot);
+                boxl[l] = bxi;
+                const float* bx = S.rc.xb.xbox[bxi];
+                const float d[3] = {bx[0] - bc[0], bx[1] - bc[1], bx[2] - bc[2]};
+                const float t0 = d[0] * bar[3] + d[1] * bar[4] + d[2] * bar[5];
+                // visiting order 0, -1, +1, -2, +2
+                const int k = kk == 0 ? 0 : ((kk & 1) ? -((kk + 1) >> 1) : (kk >> 1));
+                const float t = fminf(fmaxf(t0 + 0.03f * k, -bar[6]), bar[6]);
+                const float q[3] = {bc[0] + t * bar[3], bc[1] + t * bar[4], bc[2] + t * bar[5]};
+                float ps[3], ns[3], ds;
+                if (sphere_box(q, bar[7], bx, M::xthresh(bxi), ps, ns, &ds)) {
+                  dse[l] = ds; dd[l] = ds;
+                  nx[l] = -ns[0]; ny[l] = -ns[1]; nz[l] = -ns[2];
+                  px[l] = ps[0] - ds * ns[0]; py[l] = ps[1] - ds * ns[1]; pz[l] = ps[2] - ds * ns[2];
                 }
               }
-            MB_END
-            nc += mb_popc(mask);
+            MB_END_REG
+            LaneVar<int> s1, s2, s3, s4;
+            MB_LANES(l)
+              s1[l] = (src0[l] + 1) & 31; s2[l] = (src0[l] + 2) & 31; s3[l] = (src0[l] + 3) & 31; s4[l] = (src0[l] + 4) & 31;
+            MB_END_REG
+            warp_gather(dse, src0, e0); warp_gather(dse, s1, e1); warp_gather(dse, s2, e2);
+            warp_gather(dse, s3, e3); warp_gather(dse, s4, e4);
+            MB_LANES(l)
+              const int slot = l / 5, kk = l - 5 * slot;
+              // an outer sample wins only if deeper by more than 1e-5 m, so a bar lying parallel to a box face (all
+              // samples equally deep) yields the central point
+              float best = 1e30f;
+              int sel = -1;
+              if (e0[l] < best - 1e-5f) { best = e0[l]; sel = 0; }
+              if (e1[l] < best - 1e-5f) { best = e1[l]; sel = 1; }
+              if (e2[l] < best - 1e-5f) { best = e2[l]; sel = 2; }
+              if (e3[l] < best - 1e-5f) { best = e3[l]; sel = 3; }
+              if (e4[l] < best - 1e-5f) { best = e4[l]; sel = 4; }
+              hit[l] = slot < 6 && base + slot < nnear && sel == kk;
+            MB_END_REG
+            const unsigned mask = warp_ballot(hit);
+            if (mask != 0u) {
+              MB_LANES(l)
+                if (hit[l]) {
+                  const int bxi = boxl[l];
+                  const int k = nc + mb_popc(mask & ((1u << l) - 1u));
+                  if (k < MB_MAXC) {
+                    S.cP[k][0] = px[l]; S.cP[k][1] = py[l]; S.cP[k][2] = pz[l];
+                    S.cn[k][0] = nx[l]; S.cn[k][1] = ny[l]; S.cn[k][2] = nz[l];
+                    S.cdist[k] = dd[l];
+                    S.cmu[k] = M::xfriction(bxi) * P.bar_friction;
+                    S.cerp[k] = P.erp_contact;
+                    S.ccfm[k] = 0.0f;
+                    S.clink[k] = M::xowner(bxi);
+                    S.cfoot[k] = mb_pack_foot(M::xfoot(bxi), M::xpid(bxi));
+                    S.cpartner[k] = 20 + ob;
+                  }
+                }
+              MB_END
+              nc += mb_popc(mask);
+            }
           }
         }
       }
@@ -1901,7 +1957,6 @@ template <class M> struct Sim {
   MB_HD static void solve_constraints(Mem& S, const MbPhysics& P, const LaneConst& C, int nlim, int nc, int ncs,
                                       LaneVar<float>& z) {
     const int nnc = nlim + NLC / 2, n0 = nlim + NLC, S0 = n0 + 3 * nc, nct = nc + (SELF ? ncs : 0);
-#pragma unroll 1
     // A contact that carries no normal impulse has a zero friction cone: with nothing applied on its friction pair
     // either, the projection returns exactly zero for both rows (deltas 0, residual 0), so the visit is skipped with
     // identical results.  Which contacts are loaded is kept in two bit masks (normal impulse / friction impulses non-zero,

@@ -1063,11 +1063,12 @@ template <class M> struct MonkeyEnv {
         }
         S.q[l] = sign * (float)M::base_angles(src);
       }
-      if (l < NU) S.u[l] = 0.0f;
+      // base_velocity (3, 0, -1) (env_locomotion.py:1154): every lane writes its own coordinate (racecheck: no second
+      // writer for u[3..5])
+      if (l < NU) S.u[l] = l == 3 ? 3.0f : (l == 5 ? -1.0f : 0.0f);
       if (l == 31) {
         S.pos[0] = 0.0f; S.pos[1] = 0.0f; S.pos[2] = 20.0f;  // initial_height (env_locomotion.py:1142,1153)
         S.quat[0] = 0.0f; S.quat[1] = 0.0f; S.quat[2] = 0.0f; S.quat[3] = 1.0f;
-        S.u[3] = 3.0f; S.u[4] = 0.0f; S.u[5] = -1.0f;        // base_velocity (env_locomotion.py:1154)
       }
     MB_END
     typename S_::LaneConst C;
