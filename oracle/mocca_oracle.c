@@ -394,6 +394,7 @@ void orc_default_params(orc_params* p) {
   p->has_ground = 1;
   p->ground_friction = 0.8;
   p->self_collision = 1;
+  p->persistent_manifold = 0;
 }
 
 void orc_forward_dynamics(const orc_model* m, const orc_params* p, const orc_state* s, const double* tau,
@@ -753,11 +754,117 @@ static void collide_self(const orc_model* m, const orc_params* p, const orc_cach
   }
 }
 
+/* ---- persistent_manifold switch: btPersistentManifold semantics for robot link vs ground plane (oracle only) ----------
+ * State per link in man[16 * (link + 1)]: 4 slots x {candidate id + 1, cached plane point x, y, pad}, compact at the front.
+ * Per substep, as btCollisionDispatcher / btCompoundCollisionAlgorithm / btConvexPlaneCollisionAlgorithm do it:
+ *   refreshContactPoints: a cached point is dropped when its distance exceeds the link's breaking threshold or when it has
+ *     drifted along the plane by more than the threshold from where it was cached (removeContactPoint swaps the last in);
+ *   every child shape reports ONE point, its support vertex towards the plane (a capsule: the deeper end), if closer than
+ *     the threshold; getCacheEntry replaces the cached point nearest to it within the threshold, else it is appended, and
+ *     a fifth point replaces the slot sortCachedPoints picks (keep the deepest, maximise calcArea4Points). */
+static __thread double* orc_tls_manifold = NULL;
+
+static double area4(const v3 p0, const v3 p1, const v3 p2, const v3 p3) {
+  v3 a[3], b[3], t;
+  for (int k = 0; k < 3; k++) {
+    a[0][k] = p0[k] - p1[k]; b[0][k] = p2[k] - p3[k];
+    a[1][k] = p0[k] - p2[k]; b[1][k] = p1[k] - p3[k];
+    a[2][k] = p0[k] - p3[k]; b[2][k] = p1[k] - p2[k];
+  }
+  double best = 0;
+  for (int i = 0; i < 3; i++) {
+    v3cross(a[i], b[i], t);
+    double l2 = v3dot(t, t);
+    if (l2 > best) best = l2;
+  }
+  return best;
+}
+
+static void candidate_now(const orc_model* m, const orc_cache* c, int id, v3 pa, double* dist) {
+  int g = id >> 1, e = id & 1;
+  v3 cw;
+  point_world(m, c, g, e, cw);
+  double r = m->geom_size[g][0];
+  pa[0] = cw[0]; pa[1] = cw[1]; pa[2] = cw[2] - r;
+  *dist = cw[2] - r;
+}
+
+static void collide_ground_manifold(const orc_model* m, const orc_params* p, const orc_cache* c, double* man,
+                                    orc_contacts* out) {
+  for (int li = -1; li < m->n_links; li++) {
+    double* M = man + 16 * (li + 1);
+    double thresh = m->link_thresh[li + 1];
+    int n = 0;
+    while (n < 4 && M[4 * n] > 0) n++;
+    /* refreshContactPoints (back to front, like Bullet) */
+    for (int k = n - 1; k >= 0; k--) {
+      v3 pa;
+      double dist;
+      candidate_now(m, c, (int)M[4 * k] - 1, pa, &dist);
+      double dx = pa[0] - M[4 * k + 1], dy = pa[1] - M[4 * k + 2];
+      if (dist > thresh || dx * dx + dy * dy > thresh * thresh) {
+        n--;
+        for (int q = 0; q < 4; q++) { M[4 * k + q] = M[4 * n + q]; M[4 * n + q] = 0; }
+      }
+    }
+    /* narrow phase: one support point per child shape */
+    for (int g = 0; g < m->n_geoms; g++) {
+      if (m->geom_link[g] != li || m->geom_type[g] == ORC_GEOM_BOX) continue;
+      int nends = m->geom_type[g] == ORC_GEOM_CAPSULE ? 2 : 1, id = 2 * g;
+      v3 pa, pb;
+      double dist, d1;
+      candidate_now(m, c, 2 * g, pa, &dist);
+      if (nends == 2) {
+        candidate_now(m, c, 2 * g + 1, pb, &d1);
+        if (d1 < dist) { dist = d1; id = 2 * g + 1; v3copy(pa, pb); }
+      }
+      if (!(dist < thresh)) continue;
+      int idx = -1;
+      double shortest = thresh * thresh;
+      v3 q[4];
+      double qd[4];
+      for (int k = 0; k < n; k++) {
+        candidate_now(m, c, (int)M[4 * k] - 1, q[k], &qd[k]);
+        double d2 = (q[k][0] - pa[0]) * (q[k][0] - pa[0]) + (q[k][1] - pa[1]) * (q[k][1] - pa[1]) +
+                    (q[k][2] - pa[2]) * (q[k][2] - pa[2]);
+        if (d2 < shortest) { shortest = d2; idx = k; }
+      }
+      if (idx < 0) {
+        if (n < 4) idx = n++;
+        else { /* sortCachedPoints */
+          int deepest = -1;
+          double maxpen = dist;
+          for (int k = 0; k < 4; k++)
+            if (qd[k] < maxpen) { deepest = k; maxpen = qd[k]; }
+          double res[4] = {0, 0, 0, 0};
+          if (deepest != 0) res[0] = area4(pa, q[1], q[2], q[3]);
+          if (deepest != 1) res[1] = area4(pa, q[0], q[2], q[3]);
+          if (deepest != 2) res[2] = area4(pa, q[0], q[1], q[3]);
+          if (deepest != 3) res[3] = area4(pa, q[0], q[1], q[2]);
+          idx = 0;
+          for (int k = 1; k < 4; k++)
+            if (res[k] > res[idx]) idx = k;
+        }
+      }
+      M[4 * idx] = id + 1; M[4 * idx + 1] = pa[0]; M[4 * idx + 2] = pa[1]; M[4 * idx + 3] = 0;
+    }
+    /* the manifold's points are this link's contacts */
+    for (int k = 0; k < n; k++) {
+      int id = (int)M[4 * k] - 1;
+      v3 pa, nrm = {0, 0, 1};
+      double dist;
+      candidate_now(m, c, id, pa, &dist);
+      add_point(out, id, li, 0, pa, nrm, dist, m->geom_friction[id >> 1] * p->ground_friction, p->erp_contact, 0.0);
+    }
+  }
+}
+
 int orc_collide_cached(const orc_model* m, const orc_params* p, const orc_cache* c, const orc_box* boxes,
                        int n_boxes, orc_contacts* out) {
   out->n = 0;
   for (int ob = -1; ob < n_boxes; ob++) {
     if (ob < 0 && !p->has_ground) continue;
+    if (ob < 0 && orc_tls_manifold) { collide_ground_manifold(m, p, c, orc_tls_manifold, out); continue; }
     for (int g = 0; g < m->n_geoms; g++) {
       int link = m->geom_link[g];
       if (m->geom_type[g] == ORC_GEOM_BOX) continue; /* robot box geoms (Monkey3D) not handled yet */
@@ -1162,7 +1269,9 @@ static void substep_impl(const orc_model* m, const orc_params* p, orc_state* s, 
   double u[ORC_MAXU], acc[ORC_MAXU], dv[ORC_MAXU];
   /* collision detection at start-of-substep poses */
   kin(m, s, c);
+  orc_tls_manifold = (p->persistent_manifold && warm) ? warm + ORC_MAXW : NULL;
   orc_collide_cached(m, p, c, boxes, n_boxes, ct);
+  orc_tls_manifold = NULL;
   if (n_bars > 0) collide_bars(m, p, c, bars, n_bars, ct);
   if (p->self_collision) { collide_self(m, p, c, ct); collide_hulls(m, p, c, ct); }
   orc_diag_contacts += ct->n;
@@ -1479,7 +1588,7 @@ static void robot_reset_ex(const orc_model* m, orc_w3d_env* e, const double* pos
   /* "quat = quat or self.base_orientation" (robots.py:199): the un-mirrored attribute, not the mirrored copy */
   for (int k = 0; k < 4; k++) e->s.quat[k] = m->base_orientation[k];
   for (int f = 0; f < 4; f++) { e->feet_contact[f] = 0; v3set(e->feet_xyz[f], 0, 0, 0); }
-  for (int i = 0; i < ORC_MAXW; i++) e->warm[i] = 0;
+  for (int i = 0; i < ORC_WARMSZ; i++) e->warm[i] = 0;
   w3d_calc_state(m, e, NULL);
 }
 
@@ -2176,7 +2285,7 @@ void orc_cassie_reset(const orc_model* m, const orc_params* p, orc_cassie_env* e
   for (int d = 0; d < m->n_dof; d++) { b->s.q[d] = m->base_joint_angles[d]; b->s.qd[d] = 0; }
   for (int k = 0; k < 3; k++) { b->s.pos[k] = m->base_position[k]; b->s.omega[k] = 0; b->s.vel[k] = 0; }
   b->s.quat[0] = b->s.quat[1] = b->s.quat[2] = 0; b->s.quat[3] = 1;
-  for (int i = 0; i < ORC_MAXW; i++) b->warm[i] = 0;
+  for (int i = 0; i < ORC_WARMSZ; i++) b->warm[i] = 0;
   for (int k = 0; k < 16; k++) e->jvel[k] = 0;
   e->initial_z = NAN;
   cassie_calc_state(m, e);

@@ -28,6 +28,9 @@
 #define ORC_MAXG 192  /* geoms (Cassie: 158 hull support vertices) */
 #define ORC_MAXP 96   /* contact points kept per substep */
 #define ORC_MAXW (2 * ORC_MAXG) /* warm-start slots, indexed by candidate id = 2 * geom + end */
+/* per-env persistent contact state: [0, ORC_MAXW) the impulses above; behind them the ground-plane manifolds of the
+ * persistent_manifold switch, 4 slots x {candidate id + 1 (0 = empty), cached point on the plane x, y, pad} per link */
+#define ORC_WARMSZ (ORC_MAXW + 16 * (ORC_MAXL + 1))
 #define ORC_MAXROW (3 * ORC_MAXP + 2 * ORC_MAXD)
 #define ORC_MAXU (6 + ORC_MAXD)
 #define ORC_MAXSP 256 /* self-collision candidate pairs */
@@ -112,6 +115,11 @@ typedef struct {
   int has_ground;            /* 1: infinite plane z=0 (plane_stadium.sdf) */
   double ground_friction;    /* 0.8 bullet_utils.py:371 */
   int self_collision;        /* 1: URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS (robots.py:259-264) */
+  int persistent_manifold;   /* 0 (default): every sphere / capsule end within the breaking threshold is a contact, as the
+                                CUDA kernel has it.  1: btPersistentManifold semantics against the ground plane (SURVEY App.
+                                B.2, OQ8): per link <= 4 cached points, refreshed every substep (dropped beyond the breaking
+                                threshold or after drifting more than it along the plane), and each geom reports only its
+                                deepest point per substep.  Oracle-only hypothesis switch (tools/switch_deltas.py). */
 } orc_params;
 
 typedef struct {
@@ -175,7 +183,7 @@ int orc_collide(const orc_model* m, const orc_params* p, const orc_state* s, con
 void orc_step_physics_bars(const orc_model* m, const orc_params* p, orc_state* s, const double* tau_applied,
                            const orc_bar* bars, int n_bars, orc_contacts* last_contacts, int* rows_sum);
 void orc_substep(const orc_model* m, const orc_params* p, orc_state* s, const double* tau, const orc_box* boxes,
-                 int n_boxes, double* warm /* [ORC_MAXW] */, orc_contacts* out_contacts, int* out_rows);
+                 int n_boxes, double* warm /* [ORC_MAXW], or [ORC_WARMSZ] with persistent_manifold */, orc_contacts* out_contacts, int* out_rows);
 void orc_step_physics(const orc_model* m, const orc_params* p, orc_state* s, const double* tau_applied,
                       const orc_box* boxes, int n_boxes, double* warm, orc_contacts* last_contacts, int* rows_sum);
 void orc_energy_momentum(const orc_model* m, const orc_state* s, double gravity, double* out /* KE,PE,P[3],L[3] */);
@@ -189,7 +197,7 @@ double orc_rng_uniform(orc_rng* r, double lo, double hi);
 /* ---- Walker3DCustomEnv (env_locomotion.py:37-282) ---- */
 typedef struct {
   orc_state s;
-  double warm[ORC_MAXW];
+  double warm[ORC_WARMSZ];
   /* robot (robots.py:13-227) */
   double feet_contact[4];
   double feet_xyz[4][3];

@@ -17,6 +17,7 @@ _LIB_PATH = os.path.join(_HERE, "libmocca_oracle.so")
 
 MAXL, MAXD, MAXG, MAXP = 40, 40, 192, 96
 MAXW = 2 * MAXG
+WARMSZ = MAXW + 16 * (MAXL + 1)  # + the ground-plane manifolds of the persistent_manifold switch
 MAXU = 6 + MAXD
 MAXSP = 256
 MAXHULL, HULLV, MAXHPAIR = 24, 32, 64
@@ -60,7 +61,7 @@ class Params(C.Structure):
         ("erp_contact", d), ("erp_joint", d), ("linear_slop", d), ("lin_damping", d), ("ang_damping", d),
         ("max_coord_vel", d), ("warmstart", d), ("limit_max_impulse", d), ("split_threshold", d),
         ("residual_threshold", d), ("limit_rows_always", i32), ("gyro", i32), ("has_ground", i32),
-        ("ground_friction", d), ("self_collision", i32),
+        ("ground_friction", d), ("self_collision", i32), ("persistent_manifold", i32),
     ]
 
 
@@ -87,7 +88,7 @@ class Rng(C.Structure):
 
 class W3DEnv(C.Structure):
     _fields_ = [
-        ("s", State), ("warm", d * MAXW),
+        ("s", State), ("warm", d * WARMSZ),
         ("feet_contact", d * 4), ("feet_xyz", (d * 3) * 4), ("body_xyz", d * 3), ("body_rpy", d * 3),
         ("body_vel", d * 3), ("joint_speeds", d * MAXD), ("joints_at_limit", i32), ("mirrored", i32),
         ("robot_state", d * (6 + 2 * MAXD + 4)),

@@ -210,3 +210,47 @@ def test_resting_contact_pins(walker_table, oracle_mod):
     assert abs(ratio - 1.0) < 5e-3, ratio
     loaded = [c.dist[i] for i in ground if c.impulse[i] > 0.02 * M * 9.8 * p.dt]
     assert loaded and min(loaded) > -1e-4 and max(loaded) < 2e-5, loaded
+
+
+def test_persistent_manifold_switch(walker_table, oracle_mod):
+    """Oracle-only hypothesis switch orc_params.persistent_manifold (btPersistentManifold semantics against the ground
+    plane): a walker dropped onto the plane keeps at most four cached points per link, every one of
+    them a candidate the default mode would also report (within the link's breaking threshold), each geom adds at most
+    its deeper end per substep -- and with the switch off the persistent buffer's manifold region stays untouched."""
+    import ctypes as C
+
+    O, t = oracle_mod, walker_table
+    A = t["n_dof"]
+    m = O.model_from_table(t)
+    rng = np.random.RandomState(0)
+
+    def drop(pm, steps=160):
+        p = O.default_params()
+        p.persistent_manifold = pm
+        p.self_collision = 0
+        q0 = np.array(t["base_joint_angles"]) + rng.uniform(-0.2, 0.2, A)
+        s = O.make_state(A, [0, 0, 1.0], [0.3, 0.1, 0, 0.95], [0] * 3, [0] * 3, q0, np.zeros(A))
+        warm = (C.c_double * O.WARMSZ)()
+        seen_fewer = False
+        for _ in range(steps):
+            c, _ = O.step_physics(m, p, s, np.zeros(A), warm=warm)
+            ids = [int(c.point_id[i]) for i in range(c.n)]
+            links = [int(c.link[i]) for i in range(c.n)]
+            if pm:
+                assert len(set(ids)) == len(ids)
+                assert max([links.count(x) for x in set(links)] or [0]) <= 4
+                for i in range(c.n):  # a cached point is still within its link's breaking threshold
+                    assert c.dist[i] <= m.link_thresh[links[i] + 1] + 1e-12
+            man = np.array(warm[O.MAXW:])
+            if not pm:
+                assert not man.any()
+            else:
+                seen_fewer = seen_fewer or (0 < c.n)
+        return np.array(warm[O.MAXW:]), O.state_vector(s, A), seen_fewer
+
+    rng = np.random.RandomState(0)
+    man_off, s_off, _ = drop(0)
+    rng = np.random.RandomState(0)
+    man_on, s_on, touched = drop(1)
+    assert touched and man_on.any() and not man_off.any()
+    assert s_on[2] < 0.3 and s_off[2] < 0.3  # both heaps ended on the ground

@@ -5,6 +5,9 @@ return of Walker3DCustomEnv-v0 under the random and the scripted-PD policy, floa
   warmstart          multibody contact warm starting (oracle AND kernel: mb200_physics.warmstart)
   limit_rows_always  joint-limit rows created for every limited joint, not only violated ones (Bullet < 2.88; oracle
                      only: 42 always-on rows do not fit the kernel's 48-row budget next to the contacts)
+  persistent_manifold  btPersistentManifold semantics against the ground plane: <= 4 cached points per link, refreshed
+                     per substep, one new (deepest) point per geom per substep (oracle only; the kernel and the default
+                     oracle take every sphere / capsule end within the breaking threshold)
 
 usage: python tools/switch_deltas.py [n_envs]"""
 import os
@@ -56,7 +59,7 @@ def main(n=1024):
 
     print("%-28s %-8s %12s %12s %14s %14s" % ("setting", "policy", "mean length", "(s.e.)", "mean return", "(s.e.)"))
     for name, kw in (("reference defaults", {}), ("warmstart = 0.85", {"warmstart": 0.85}), ("warmstart = 0.1", {"warmstart": 0.1}),
-                     ("limit_rows_always = 1", {"limit_rows_always": 1})):
+                     ("limit_rows_always = 1", {"limit_rows_always": 1}), ("persistent_manifold = 1", {"persistent_manifold": 1})):
         for policy in ("random", "pd"):
             p = O.default_params()
             for k, v in kw.items():
