@@ -406,7 +406,7 @@ template <class M> struct Sim {
   enum { NJ = M::NJ, NB = M::NB, NU = M::NU, NPT = M::NPT, NSELF = M::NSELF };
 #endif
 
-  // ---- lane constants: computed once per kernel, live in registers -------------------------------------------
+  // ---- lane constants -----------------------------------------------------------------------------------------
   // Only what the constraint solver's inner loop reads per row visit stays in registers for the whole kernel; the
   // factorisation's pair table and the forward substitution's tree tables are (re)loaded where they are used -- the
   // Cassie and Monkey3D kernels are register-starved in the solver (round 2).
@@ -449,8 +449,8 @@ template <class M> struct Sim {
         }
       }
     MB_END
-    // sin / cos of every joint angle once, one joint per lane (the level loop below reads them back: three lanes per
-    // joint would otherwise each run the 30-instruction polynomial).  Scratch: Ldinv / Ldi2, dead until factorize().
+    // sin / cos of every joint angle once, one joint per lane (the chain walk below reads them back: the three lanes of
+    // a chain would otherwise each run the 30-instruction polynomial).  Scratch: Ldinv / Ldi2, dead until factorize().
     MB_LANES(l)
       if (l < NJ) {
         float sn, cs;
