@@ -1637,16 +1637,16 @@ template <class M> struct Sim {
   // each, the unrolled register code is shared.  (Until round 2 a size-optimised out-of-line routine built them in
   // ~1 500 instructions; a substep with a self-contact then made its whole CTA wait at the next barrier, and with 14
   // envs per CTA nearly every substep had one.)
-  MB_HD static void setup_rows(Mem& S, const MbPhysics& P, int nlim, int nc, int ncs) {
+  // number of compact rows the row pass builds for (nlim, nc, ncs)
+  MB_HD static int compact_rows(int nlim, int nc, int ncs) { return nlim + NLC + 3 * nc + (NSELF > 0 ? 6 * ncs : 0); }
+
+  // One compact row, one lane: J over the row's support, Y = L^-T J^T in registers, effective mass, right-hand side.
+  // S is the env the row belongs to -- under the cooperative row pass (coop_rows) that is not the calling warp's env.
+  MB_HD static void row_build(Mem& S, const MbPhysics& P, int nlim, int nc, int ncs, int r) {
     const int n0 = nlim + NLC;
     const int S0 = n0 + 3 * nc;
-    const int R = S0 + (NSELF > 0 ? 6 * ncs : 0);
     const float inv_dt = 1.0f / P.dt;
-#pragma unroll 1
-    for (int base = 0; base < R; base += 32) {
-      MB_LANES(l)
-        const int r = base + l;
-        if (r < R) {
+        {
           // everything lives on the row's support: base block + chain (root -> constrained joint)
           float b[M::MAXSUP];
           float W[6];
@@ -1774,8 +1774,67 @@ template <class M> struct Sim {
           S.rc.r.r_app[r] = 0.0f;
           S.rc.r.r_mu[r] = mu;
         }
+  }
+
+  // the rows of one env, built by its own warp (lane-loop emulation; kernels without the cooperative pass)
+  MB_HD static void setup_rows(Mem& S, const MbPhysics& P, int nlim, int nc, int ncs) {
+    const int R = compact_rows(nlim, nc, ncs);
+#pragma unroll 1
+    for (int base = 0; base < R; base += 32) {
+      MB_LANES(l)
+        if (base + l < R) row_build(S, P, nlim, nc, ncs, base + l);
       MB_END
     }
+    rows_combine(S, P, nlim, nc, ncs);
+  }
+
+#if defined(__CUDACC__) && defined(MB_COOP_ROWS) && MB_COOP_ROWS
+  // Cooperative row pass (round 2; compile with -DMB_COOP_ROWS=1 -- measured and NOT kept as the default: Walker3D +-0,
+  // Stepper +1.3 %, Monkey3D +-0, Cassie -1.8 %, profiles/r3o_coop_rows_ab.txt: the instructions it saves are paid back
+  // by the two extra CTA barriers and by the few working warps running latency-bound while the others wait).
+  // One lane builds one row in ~800 instructions, and an env has ~8 rows (Walker3D) to ~40
+  // (Cassie): a warp building only its own env's rows runs the pass a quarter full.  The warps of a CTA are in lockstep
+  // anyway (barrier per substep), so the CTA pools its rows: every warp publishes its env's row count, and warp w builds
+  // the pooled rows 32 w .. 32 w + 31 -- of whichever envs they belong to, through those envs' WarpMem -- while the warps
+  // without a share wait at the closing barrier and issue nothing.  Same arithmetic per row, fewer instructions per CTA.
+  // EVERY warp of the CTA must call this once per substep (it contains two __syncthreads()).
+  MB_HD static void coop_rows(Mem& S, const MbPhysics& P, int nlim, int nc, int ncs, int Rc) {
+    __shared__ int s_cnt[32], s_par[32];
+    const int lane = (int)(threadIdx.x & 31), W = (int)(blockDim.x >> 5);
+    const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    if (lane == 0) { s_cnt[w] = Rc; s_par[w] = nlim | (nc << 8) | (ncs << 16); }
+    __syncthreads();
+    const int c = lane < W ? s_cnt[lane] : 0;
+    int inc = c;  // inclusive prefix sum of the counts over the warps, one warp per lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    const int T = __shfl_sync(0xffffffffu, inc, 31);
+    Mem* const S0 = &S - w;
+#pragma unroll 1
+    for (int base = 32 * w; base < T; base += 32 * W) {
+      const int g = base + lane;
+      int e = 0;  // owner of pooled row g: the number of warps whose rows end at or before it
+#pragma unroll 1
+      for (int k = 0; k < W; ++k) e += g >= __shfl_sync(0xffffffffu, inc, k) ? 1 : 0;
+      e = e < W ? e : W - 1;
+      const int first = __shfl_sync(0xffffffffu, inc - c, e);
+      if (g < T) {
+        const int par = s_par[e];
+        row_build(S0[e], P, par & 255, (par >> 8) & 255, par >> 16, g - first);
+      }
+    }
+    __syncthreads();
+  }
+#endif
+
+  // second, short pass of the dual rows (loop closures, self-contacts): the two parts' partial sums -> one multiplier
+  MB_HD static void rows_combine(Mem& S, const MbPhysics& P, int nlim, int nc, int ncs) {
+    const int n0 = nlim + NLC;
+    const int S0 = n0 + 3 * nc;
+    const float inv_dt = 1.0f / P.dt;
     if (NLC > 0) {
       // fillMultiBodyConstraint: denominator = JA M^-1 JA^T + JB M^-1 JB^T (no coupling term, even for two links of
       // the same multibody), erp = m_erp, impulse bounds +-maxAppliedImpulse
@@ -2064,10 +2123,17 @@ template <class M> struct Sim {
       *overflow += 1;
     }
     const int R = nlim + NLC / 2 + 3 * (nc + ncs);  // as Bullet counts them (a loop / self-contact row is one row)
+#if defined(__CUDACC__) && defined(MB_COOP_ROWS) && MB_COOP_ROWS
+    coop_rows(S, P, nlim, nc, ncs, R > 0 ? compact_rows(nlim, nc, ncs) : 0);
+#endif
     if (R > 0) {
       // (a size-optimised rolled version of setup_rows serving every row kind was measured too: 12.7 KB less hot
       // code, but 9 % slower on Walker3D and 11 % on Cassie -- the unrolled register version stays)
+#if defined(__CUDACC__) && defined(MB_COOP_ROWS) && MB_COOP_ROWS
+      rows_combine(S, P, nlim, nc, ncs);
+#else
       setup_rows(S, P, nlim, nc, ncs);
+#endif
       // (an impulse-space variant of the PGS -- Gram matrix G = Y Y^T of the rows in the unused tail of the row matrix,
       // one register w_c = sum_s G_cs lambda_s per lane, a row visit = one shuffle + uniform delta + one LDS / FFMA per
       // lane -- was measured in round 2: 26 instead of 31 instructions per visit, but building G and assembling z cost
