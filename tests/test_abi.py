@@ -69,3 +69,29 @@ def test_model_table_matches_reference_files():
     import json
 
     assert json.loads(json.dumps(t, default=float)) == have
+
+
+def test_device_and_host_step_kernels_round_alike():
+    """mb200_step and mb200_step_host run two instantiations of each step kernel whose outputs are compared bit for bit on
+    the GPU (tests/test_gpu_f3.py).  Checked here without a GPU: per source line both kernels carry the same multiset of
+    FFMA / FMUL / FADD / MUFU opcodes with the same negation pattern, i.e. the compiler contracted every a * b + c * d the
+    same way round in both (it once did not: mb_euler, round 2)."""
+    import importlib.util
+    import shutil
+
+    from mocca_envs_b200 import _lib
+
+    if not (shutil.which("cuobjdump") and shutil.which("nvdisasm")) or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("CUDA binary utilities or the built library are not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("sass_fp_diff", os.path.join(root, "tools", "sass_fp_diff.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    cubins = tool.extract(_lib.LIB_PATH)
+    kinds = [k for k in cubins if re.fullmatch(r"_Z\d+k_step_\w+_host8StepArgs", k)]
+    assert len(kinds) == len(_lib.KINDS)
+    for kh in kinds:
+        name = re.fullmatch(r"_Z\d+(k_step_\w+)_host8StepArgs", kh).group(1)
+        kd = "_Z%d%s8StepArgs" % (len(name), name)
+        assert kd in cubins, kd
+        assert tool.differences(cubins, kd, kh) == [], name
