@@ -2026,9 +2026,11 @@ template <class M> struct Sim {
 #pragma unroll 1
     for (int it = 0; it < P.iterations; ++it) {
       float res2 = 0.0f, app;
+      // (alternating sweep direction over the non-contact rows, as solveSingleIteration does)
+      int idx = (it & 1) ? 0 : nnc - 1;
+      const int dir = (it & 1) ? 1 : -1;
 #pragma unroll 1
-      for (int v = 0; v < nnc; ++v) {
-        const int idx = (it & 1) ? v : nnc - 1 - v;
+      for (int v = 0; v < nnc; ++v, idx += dir) {
         float rr;
         if (NLC == 0 || idx < nlim) rr = pgs_single<0>(S, C, idx, 0.0f, P.limit_max_impulse, z, app);
         else {
