@@ -1646,134 +1646,132 @@ template <class M> struct Sim {
     const int n0 = nlim + NLC;
     const int S0 = n0 + 3 * nc;
     const float inv_dt = 1.0f / P.dt;
-        {
-          // everything lives on the row's support: base block + chain (root -> constrained joint)
-          float b[M::MAXSUP];
-          float W[6];
-          float cfm = 0.0f, mu = 0.0f, pen = 0.0f, dist = 0.0f, erp = 0.0f, dir = 0.0f;
-          int kind;  // 0 limit, 1 normal, 2 friction
-          int cj;    // constrained joint, -1 = base link
-          if (r < nlim) {
-            kind = 0;
-            cj = S.w.t.r_dof[r];
-            dir = S.w.t.r_dir[r];
-            pen = dir > 0.0f ? S.q[cj] - M::lower(cj) : M::upper(cj) - S.q[cj];
+    // everything lives on the row's support: base block + chain (root -> constrained joint)
+    float b[M::MAXSUP];
+    float W[6];
+    float cfm = 0.0f, mu = 0.0f, pen = 0.0f, dist = 0.0f, erp = 0.0f, dir = 0.0f;
+    int kind;  // 0 limit, 1 normal, 2 friction
+    int cj;    // constrained joint, -1 = base link
+    if (r < nlim) {
+      kind = 0;
+      cj = S.w.t.r_dof[r];
+      dir = S.w.t.r_dir[r];
+      pen = dir > 0.0f ? S.q[cj] - M::lower(cj) : M::upper(cj) - S.q[cj];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) W[i] = 0.0f;
-          } else if (r < n0) {
-            // btMultiBodyPoint2Point::createConstraintRows: contactNormalOnB = -e_ax for link A, +e_ax for link B
-            kind = 3;
-            const int i = r - nlim, side = i & 1, ax = (i % 6) >> 1, sd = 2 * (i / 6) + side;
-            float dirv[3] = {0.0f, 0.0f, 0.0f};
-            const float sg = side ? 1.0f : -1.0f;
-            if (ax == 0) dirv[0] = sg; else if (ax == 1) dirv[1] = sg; else dirv[2] = sg;
-            mb_cross(S.lcP[sd], dirv, W);
-            W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
-            cj = M::lc_owner(sd);
-          } else {
-            int k, fr = -1;       // contact slot; friction direction (-1 = the normal)
-            bool sideB = false;   // the part of a self-contact row on the partner link
-            if (r < n0 + nc) { kind = 1; k = r - n0; }
-            else if (NSELF == 0 || r < S0) { kind = 2; k = (r - n0 - nc) >> 1; fr = (r - n0 - nc) & 1; }
-            else {
-              kind = 4;
-              const int i = r - S0;
-              if (i < 2 * ncs) { k = nc + (i >> 1); sideB = (i & 1) != 0; }
-              else { const int i2 = i - 2 * ncs; k = nc + (i2 >> 2); fr = i2 & 1; sideB = (i2 & 2) != 0; }
-            }
-            float dirv[3] = {S.cn[k][0], S.cn[k][1], S.cn[k][2]};
-            if (fr >= 0) {
-              float t1[3], t2[3];
-              mb_plane_space(S.cn[k], t1, t2);
-              dirv[0] = fr ? t2[0] : t1[0]; dirv[1] = fr ? t2[1] : t1[1]; dirv[2] = fr ? t2[2] : t1[2];
-            }
-            if (kind == 1) { cfm = S.ccfm[k] * inv_dt; erp = S.cerp[k]; dist = S.cdist[k] + P.linear_slop; }
-            mu = S.cmu[k];
-            cj = S.clink[k];
-            float pcv[3] = {S.cP[k][0], S.cP[k][1], S.cP[k][2]};
-            if (NSELF > 0 && sideB) {
-              // setupMultiBodyContactConstraint: jacobian B is built with -direction at the point on B = pA - dist n
-              const float dk = S.cdist[k];
-              pcv[0] -= dk * S.cn[k][0]; pcv[1] -= dk * S.cn[k][1]; pcv[2] -= dk * S.cn[k][2];
-              dirv[0] = -dirv[0]; dirv[1] = -dirv[1]; dirv[2] = -dirv[2];
-              cj = ((M::sp_own(S.cpartner[k] - 1000) >> 8) & 255) - 1;
-            }
-            mb_cross(pcv, dirv, W);
-            W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
-          }
-          const int depth = cj >= 0 ? M::jdepth(cj) : -1;
-          const int n = 7 + depth;  // support size
-          // Affine chain addressing (see factorize()): slot t of the row's support is coordinate t, and its compact row
-          // of L starts at word t (t + 1) / 2 -- both shifted by a per-row constant behind each branch point of the
-          // chain.  No per-slot table look-up sits on the serial path of the half solve.
-          const int kc = 6 + (cj >= 0 ? cj : 0);
-          const int t1 = cj >= 0 ? M::ft1(kc) : 15, d1 = cj >= 0 ? M::fd1(kc) : 0, c1 = cj >= 0 ? M::fc1(kc) : 0;
-          const int t2 = (M::RSTEPS > 1 && cj >= 0) ? M::ft2(kc) : 15, d2 = (M::RSTEPS > 1 && cj >= 0) ? M::fd2(kc) : 0;
-          const int c2 = (M::RSTEPS > 1 && cj >= 0) ? M::fc2(kc) : 0;
-          float rel_vel = 0.0f;
+      for (int i = 0; i < 6; ++i) W[i] = 0.0f;
+    } else if (r < n0) {
+      // btMultiBodyPoint2Point::createConstraintRows: contactNormalOnB = -e_ax for link A, +e_ax for link B
+      kind = 3;
+      const int i = r - nlim, side = i & 1, ax = (i % 6) >> 1, sd = 2 * (i / 6) + side;
+      float dirv[3] = {0.0f, 0.0f, 0.0f};
+      const float sg = side ? 1.0f : -1.0f;
+      if (ax == 0) dirv[0] = sg; else if (ax == 1) dirv[1] = sg; else dirv[2] = sg;
+      mb_cross(S.lcP[sd], dirv, W);
+      W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
+      cj = M::lc_owner(sd);
+    } else {
+      int k, fr = -1;       // contact slot; friction direction (-1 = the normal)
+      bool sideB = false;   // the part of a self-contact row on the partner link
+      if (r < n0 + nc) { kind = 1; k = r - n0; }
+      else if (NSELF == 0 || r < S0) { kind = 2; k = (r - n0 - nc) >> 1; fr = (r - n0 - nc) & 1; }
+      else {
+        kind = 4;
+        const int i = r - S0;
+        if (i < 2 * ncs) { k = nc + (i >> 1); sideB = (i & 1) != 0; }
+        else { const int i2 = i - 2 * ncs; k = nc + (i2 >> 2); fr = i2 & 1; sideB = (i2 & 2) != 0; }
+      }
+      float dirv[3] = {S.cn[k][0], S.cn[k][1], S.cn[k][2]};
+      if (fr >= 0) {
+        float t1[3], t2[3];
+        mb_plane_space(S.cn[k], t1, t2);
+        dirv[0] = fr ? t2[0] : t1[0]; dirv[1] = fr ? t2[1] : t1[1]; dirv[2] = fr ? t2[2] : t1[2];
+      }
+      if (kind == 1) { cfm = S.ccfm[k] * inv_dt; erp = S.cerp[k]; dist = S.cdist[k] + P.linear_slop; }
+      mu = S.cmu[k];
+      cj = S.clink[k];
+      float pcv[3] = {S.cP[k][0], S.cP[k][1], S.cP[k][2]};
+      if (NSELF > 0 && sideB) {
+        // setupMultiBodyContactConstraint: jacobian B is built with -direction at the point on B = pA - dist n
+        const float dk = S.cdist[k];
+        pcv[0] -= dk * S.cn[k][0]; pcv[1] -= dk * S.cn[k][1]; pcv[2] -= dk * S.cn[k][2];
+        dirv[0] = -dirv[0]; dirv[1] = -dirv[1]; dirv[2] = -dirv[2];
+        cj = ((M::sp_own(S.cpartner[k] - 1000) >> 8) & 255) - 1;
+      }
+      mb_cross(pcv, dirv, W);
+      W[3] = dirv[0]; W[4] = dirv[1]; W[5] = dirv[2];
+    }
+    const int depth = cj >= 0 ? M::jdepth(cj) : -1;
+    const int n = 7 + depth;  // support size
+    // Affine chain addressing (see factorize()): slot t of the row's support is coordinate t, and its compact row
+    // of L starts at word t (t + 1) / 2 -- both shifted by a per-row constant behind each branch point of the
+    // chain.  No per-slot table look-up sits on the serial path of the half solve.
+    const int kc = 6 + (cj >= 0 ? cj : 0);
+    const int t1 = cj >= 0 ? M::ft1(kc) : 15, d1 = cj >= 0 ? M::fd1(kc) : 0, c1 = cj >= 0 ? M::fc1(kc) : 0;
+    const int t2 = (M::RSTEPS > 1 && cj >= 0) ? M::ft2(kc) : 15, d2 = (M::RSTEPS > 1 && cj >= 0) ? M::fd2(kc) : 0;
+    const int c2 = (M::RSTEPS > 1 && cj >= 0) ? M::fc2(kc) : 0;
+    float rel_vel = 0.0f;
 #pragma unroll
-          for (int t = 0; t < 6; ++t) { b[t] = W[t]; rel_vel += W[t] * S.u[t]; }
+    for (int t = 0; t < 6; ++t) { b[t] = W[t]; rel_vel += W[t] * S.u[t]; }
 #pragma unroll
-          for (int t = 0; t < M::MAXSUP - 6; ++t) {
-            float v = 0.0f;
-            if (t <= depth) {
-              int a = t + (6 + t >= t1 ? c1 : 0);
-              if (M::RSTEPS > 1) a += 6 + t >= t2 ? c2 : 0;
-              if (kind == 0) v = t == depth ? dir : 0.0f;
-              else {
-                const float* sj = S.js[a];
-                v = sj[0] * W[0] + sj[1] * W[1] + sj[2] * W[2] + sj[3] * W[3] + sj[4] * W[4] + sj[5] * W[5];
-              }
-              rel_vel += v * S.u[6 + a];
-            }
-            b[6 + t] = v;
-          }
-          // half solve L^T y = J^T restricted to the support (prefix property of the compact factor)
-#pragma unroll
-          for (int t = M::MAXSUP - 1; t >= 0; --t) {
-            if (t < n) {
-              int it = t, ro = (t * (t + 1)) / 2;
-              if (t >= 6) {
-                if (t >= t1) { it += c1; ro += d1; }
-                if (M::RSTEPS > 1 && t >= t2) { it += c2; ro += d2; }
-              }
-              const float ci = b[t] * S.Ldi2[it];  // rows are unscaled: L[it][s] y = U[it][s] (b_t / d_it)
-              b[t] *= S.Ldinv[it];
-              const float* Li = &S.L[ro];
-#pragma unroll
-              for (int s2 = 0; s2 < t; ++s2) b[s2] -= Li[s2] * ci;
-            }
-          }
-          float dd = cfm;
-#pragma unroll
-          for (int t = 0; t < M::MAXSUP; ++t) dd += b[t] * b[t];
-          const float jinv = dd > 1.1920929e-07f ? 1.0f / dd : 0.0f;
-          float positional = 0.0f, verr = -rel_vel;
-          if (kind == 0) {
-            // btMultiBodyJointLimitConstraint: erp = m_erp unless deeper than the split-impulse threshold, in
-            // which case the positional part is routed to the (never applied) split impulse
-            if (pen > 0.0f) verr = -pen * inv_dt;
-            else if (pen > P.split_threshold) positional = -pen * P.erp_joint * inv_dt;
-          } else if (kind == 1) {
-            if (dist > 0.0f) verr -= dist * inv_dt;
-            else positional = -dist * erp * inv_dt;
-          }
-          float* Yr = S.w.Yc[r];
-#pragma unroll
-          for (int t = 0; t < M::MAXSUP; ++t)
-            if (t < n) Yr[t] = b[t];
-          S.rc.r.r_mask[r] = 0x3Fu | (cj >= 0 ? (M::janc(cj) << 6) : 0u);
-          MbRowPar par;
-          if (kind >= 3) {  // partial sums; the two parts of a loop / self-contact row are combined below
-            par.rhs = rel_vel; par.jinv = dd; par.den = 0.0f;
-          } else {
-            par.rhs = (positional + verr) * jinv; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
-          }
-          par.cfm = cfm * jinv;
-          S.rc.r.r_par[r] = par;
-          S.rc.r.r_app[r] = 0.0f;
-          S.rc.r.r_mu[r] = mu;
+    for (int t = 0; t < M::MAXSUP - 6; ++t) {
+      float v = 0.0f;
+      if (t <= depth) {
+        int a = t + (6 + t >= t1 ? c1 : 0);
+        if (M::RSTEPS > 1) a += 6 + t >= t2 ? c2 : 0;
+        if (kind == 0) v = t == depth ? dir : 0.0f;
+        else {
+          const float* sj = S.js[a];
+          v = sj[0] * W[0] + sj[1] * W[1] + sj[2] * W[2] + sj[3] * W[3] + sj[4] * W[4] + sj[5] * W[5];
         }
+        rel_vel += v * S.u[6 + a];
+      }
+      b[6 + t] = v;
+    }
+    // half solve L^T y = J^T restricted to the support (prefix property of the compact factor)
+#pragma unroll
+    for (int t = M::MAXSUP - 1; t >= 0; --t) {
+      if (t < n) {
+        int it = t, ro = (t * (t + 1)) / 2;
+        if (t >= 6) {
+          if (t >= t1) { it += c1; ro += d1; }
+          if (M::RSTEPS > 1 && t >= t2) { it += c2; ro += d2; }
+        }
+        const float ci = b[t] * S.Ldi2[it];  // rows are unscaled: L[it][s] y = U[it][s] (b_t / d_it)
+        b[t] *= S.Ldinv[it];
+        const float* Li = &S.L[ro];
+#pragma unroll
+        for (int s2 = 0; s2 < t; ++s2) b[s2] -= Li[s2] * ci;
+      }
+    }
+    float dd = cfm;
+#pragma unroll
+    for (int t = 0; t < M::MAXSUP; ++t) dd += b[t] * b[t];
+    const float jinv = dd > 1.1920929e-07f ? 1.0f / dd : 0.0f;
+    float positional = 0.0f, verr = -rel_vel;
+    if (kind == 0) {
+      // btMultiBodyJointLimitConstraint: erp = m_erp unless deeper than the split-impulse threshold, in
+      // which case the positional part is routed to the (never applied) split impulse
+      if (pen > 0.0f) verr = -pen * inv_dt;
+      else if (pen > P.split_threshold) positional = -pen * P.erp_joint * inv_dt;
+    } else if (kind == 1) {
+      if (dist > 0.0f) verr -= dist * inv_dt;
+      else positional = -dist * erp * inv_dt;
+    }
+    float* Yr = S.w.Yc[r];
+#pragma unroll
+    for (int t = 0; t < M::MAXSUP; ++t)
+      if (t < n) Yr[t] = b[t];
+    S.rc.r.r_mask[r] = 0x3Fu | (cj >= 0 ? (M::janc(cj) << 6) : 0u);
+    MbRowPar par;
+    if (kind >= 3) {  // partial sums; the two parts of a loop / self-contact row are combined below
+      par.rhs = rel_vel; par.jinv = dd; par.den = 0.0f;
+    } else {
+      par.rhs = (positional + verr) * jinv; par.jinv = jinv; par.den = jinv != 0.0f ? dd : 0.0f;
+    }
+    par.cfm = cfm * jinv;
+    S.rc.r.r_par[r] = par;
+    S.rc.r.r_app[r] = 0.0f;
+    S.rc.r.r_mu[r] = mu;
   }
 
   // the rows of one env, built by its own warp (lane-loop emulation; kernels without the cooperative pass)
